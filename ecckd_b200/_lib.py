@@ -1,0 +1,128 @@
+"""Loader for the C-ABI shared library (include/ecckd_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a) as
+``ecckd_b200/lib/libecckd_b200.so``.  There is no fallback of any kind: if the
+library is missing, or no sm_100 device is usable, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libecckd_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ecckd_b200.h")
+
+_lib = None
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_void_pp = C.POINTER(C.c_void_p)
+
+
+class GasTable(C.Structure):
+    """struct ecckd_gas_table (include/ecckd_b200.h)."""
+
+    _fields_ = [
+        ("conc_dependence", C.c_int32),
+        ("nconc", C.c_int32),
+        ("vmr_lut", C.c_void_p),
+        ("reference_vmr", C.c_double),
+        ("molar_abs", C.c_void_p),
+    ]
+
+
+def header_symbols(path: str = HEADER_PATH):
+    """Names of every function the header declares."""
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ecckd_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    """Return the loaded library, loading it on first use."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  ecckd_b200 has no CPU fallback."
+            )
+        _lib = C.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L):
+    vp, i32, i64, dbl, sz = C.c_void_p, C.c_int, C.c_int64, C.c_double, C.c_size_t
+    L.ecckd_version.restype = C.c_int
+    L.ecckd_last_error.restype = C.c_char_p
+    L.ecckd_device_count.restype = C.c_int
+    L.ecckd_kernel_launch_count.restype = C.c_int64
+    L.ecckd_kernel_launch_count.argtypes = [vp]
+    L.ecckd_averaging_method_from_string.argtypes = [C.c_char_p]
+    sigs = {
+        "ecckd_ctx_create": [i32, vp, c_void_pp],
+        "ecckd_ctx_destroy": [vp],
+        "ecckd_ctx_set_stream": [vp, vp],
+        "ecckd_synchronize": [vp],
+        "ecckd_device_malloc": [vp, sz, c_void_pp],
+        "ecckd_device_free": [vp, vp],
+        "ecckd_host_malloc_pinned": [sz, c_void_pp],
+        "ecckd_host_free_pinned": [vp],
+        "ecckd_memcpy_h2d": [vp, vp, vp, sz],
+        "ecckd_memcpy_d2h": [vp, vp, vp, sz],
+        "ecckd_planck_function_dev": [vp, i32, vp, i64, vp, vp, vp, i64],
+        "ecckd_planck_function": [vp, i32, vp, i64, vp, vp, vp, i64],
+        "ecckd_gpoint_plan_create": [vp, vp, i64, i32, c_void_pp],
+        "ecckd_gpoint_plan_destroy": [vp],
+        "ecckd_gpoint_plan_counts": [vp, vp],
+        "ecckd_average_optical_depth_to_g_point_dev": [vp, vp, dbl, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp,
+                                                       i32, vp, vp, vp, i64, vp],
+        "ecckd_average_optical_depth_batch_dev": [vp, vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp,
+                                                  i32, vp, vp, vp, i64, vp],
+        "ecckd_average_optical_depth_to_g_point": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, i64, C.c_char_p,
+                                                   vp, vp, vp, i64, vp],
+        "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],
+        "ecckd_gpoint_fraction_dev": [vp, i32, i64, vp, vp, vp, i32, vp, vp, vp],
+        "ecckd_ssi_intervals_dev": [vp, i64, vp, vp, i32, vp, vp, vp],
+        "ecckd_planck_lut_dev": [vp, vp, vp, vp, i32, vp, vp],
+        "ecckd_compact_g_points_dev": [vp, i32, i64, vp, vp, C.POINTER(C.c_int)],
+        "ecckd_sort_key_lw_dev": [vp, i32, i64, vp, vp, vp, vp, i64, dbl, vp, vp],
+        "ecckd_sort_key_sw_dev": [vp, i32, i64, vp, vp, i64, dbl, vp, vp],
+        "ecckd_rank_bands_dev": [vp, i64, vp, vp, i32, vp, vp, vp, vp, vp],
+        "ecckd_store_g_points_dev": [vp, i64, vp, i32, vp, vp, vp],
+        "ecckd_overlap_g_points": [i32, i32, vp, vp, vp, i32, vp, vp, vp, C.POINTER(C.c_int)],
+        "ecckd_assign_g_points_dev": [vp, i32, i64, vp, i32, i32, vp, vp, vp, vp],
+        "ecckd_ckd_model_create": [vp, i32, vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, c_void_pp],
+        "ecckd_ckd_model_destroy": [vp],
+        "ecckd_ckd_calc_optical_depth_dev": [vp, vp, i32, i32, i32, vp, vp, vp, vp, i32],
+        "ecckd_ckd_calc_planck_function_dev": [vp, vp, i64, vp, vp],
+        "ecckd_ckd_calc_rayleigh_optical_depth_dev": [vp, vp, i32, i32, vp, vp],
+        "ecckd_radiative_transfer_lw_dev": [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp],
+        "ecckd_radiative_transfer_sw_dev": [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp],
+        "ecckd_heating_rate_dev": [vp, i32, i32, i64, vp, vp, vp, vp],
+        "ecckd_run_ckd_dev": [vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "ecckd_run_ckd": [vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+    }
+    for name, argtypes in sigs.items():
+        if hasattr(L, name):  # symbol-completeness is asserted by tests/test_abi.py
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+
+
+class EcckdError(RuntimeError):
+    """A non-zero status from the C ABI; .code carries the ESA exit code."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"[{code}] {message}")
+        self.code = code
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = lib().ecckd_last_error()
+        raise EcckdError(rc, msg.decode() if msg else "")

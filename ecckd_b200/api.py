@@ -1,0 +1,503 @@
+"""Host-side Python mirror of the reference's operator interface.
+
+Function names and argument meaning follow the reference's C++ free functions
+(average_optical_depth_to_g_point, planck_function, radiative_transfer_lw, ...),
+so tests read like calls into the reference.  Everything here only marshals
+pointers into the C ABI (include/ecckd_b200.h); all arithmetic runs in the
+sm_100a kernels.  Arrays on the device are ``DeviceArray`` (a raw device pointer
+plus shape); any object exposing ``data_ptr()`` (a torch CUDA tensor) is accepted
+wherever a device array is expected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import EcckdError, GasTable, check
+
+AVERAGING_METHODS = (
+    "linear",
+    "transmission",
+    "transmission-2",
+    "transmission-3",
+    "transmission-10",
+    "square-root",
+    "logarithmic",
+    "hybrid-logarithmic-transmission-3",
+)
+WEIGHT_MATRIX, WEIGHT_VECTOR, WEIGHT_PLANCK = 0, 1, 2
+CONC_NONE, CONC_LINEAR, CONC_LUT, CONC_RELATIVE_LINEAR = 0, 1, 2, 3
+
+
+def _ptr(x) -> Optional[int]:
+    """Device pointer of a DeviceArray / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, DeviceArray):
+        return x.ptr
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    return int(x)
+
+
+def _h(x, dtype=np.float64):
+    """Contiguous host array + its pointer (keeps the array alive via return)."""
+    if x is None:
+        return None, None
+    a = np.ascontiguousarray(x, dtype=dtype)
+    return a, a.ctypes.data
+
+
+class DeviceArray:
+    """A typed view of device memory owned by a Context."""
+
+    def __init__(self, ctx: "Context", shape, dtype=np.float64, ptr: Optional[int] = None):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in (shape if hasattr(shape, "__len__") else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        self._owned = ptr is None
+        if ptr is None:
+            p = C.c_void_p()
+            check(_lib.lib().ecckd_device_malloc(ctx.handle, max(self.nbytes, 1), C.byref(p)))
+            ptr = p.value
+        self.ptr = int(ptr)
+
+    def copy_from(self, a: np.ndarray):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        check(_lib.lib().ecckd_memcpy_h2d(self.ctx.handle, self.ptr, a.ctypes.data, a.nbytes))
+        self.ctx.synchronize()  # `a` may be a temporary
+        return self
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, dtype=self.dtype)
+        check(_lib.lib().ecckd_memcpy_d2h(self.ctx.handle, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def free(self):
+        if self._owned and self.ptr and self.ctx.handle:
+            _lib.lib().ecckd_device_free(self.ctx.handle, self.ptr)
+        self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """ecckd_ctx: one device + one stream."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        self.handle = None
+        h = C.c_void_p()
+        check(_lib.lib().ecckd_ctx_create(device, stream, C.byref(h)))
+        self.handle = h.value
+        self.device = device
+
+    def set_stream(self, stream: Optional[int]):
+        check(_lib.lib().ecckd_ctx_set_stream(self.handle, stream))
+
+    def synchronize(self):
+        check(_lib.lib().ecckd_synchronize(self.handle))
+
+    def empty(self, shape, dtype=np.float64) -> DeviceArray:
+        return DeviceArray(self, shape, dtype)
+
+    def zeros(self, shape, dtype=np.float64) -> DeviceArray:
+        d = DeviceArray(self, shape, dtype)
+        return d.copy_from(np.zeros(d.shape, dtype=dtype))
+
+    def to_device(self, a, dtype=None) -> DeviceArray:
+        a = np.ascontiguousarray(a, dtype=dtype)
+        return DeviceArray(self, a.shape, a.dtype).copy_from(a)
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(_lib.lib().ecckd_kernel_launch_count(self.handle))
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_count() -> int:
+    return int(_lib.lib().ecckd_device_count())
+
+
+# ----------------------------------------------------------------- stage 1
+def planck_function(ctx: Context, temperature, wavenumber_cm_1, d_wavenumber_cm_1) -> np.ndarray:
+    """planck_function (planck_function.cpp:22-54), host arrays in and out."""
+    t, tp = _h(temperature)
+    wn, wnp = _h(wavenumber_cm_1)
+    dwn, dwnp = _h(d_wavenumber_cm_1)
+    if wn.size != dwn.size:  # planck_function.cpp:35-38
+        raise EcckdError(147, "wavenumber_cm_1 and d_wavenumber_cm_1 must have the same length")
+    out = np.empty((t.size, wn.size))
+    check(_lib.lib().ecckd_planck_function(ctx.handle, t.size, tp, wn.size, wnp, dwnp, out.ctypes.data, wn.size))
+    return out
+
+
+def planck_function_dev(ctx: Context, temperature, d_wavenumber, d_d_wavenumber, nwav: int, d_ans, ans_stride=None):
+    t, tp = _h(temperature)
+    check(_lib.lib().ecckd_planck_function_dev(ctx.handle, t.size, tp, nwav, _ptr(d_wavenumber), _ptr(d_d_wavenumber),
+                                               _ptr(d_ans), ans_stride or nwav))
+
+
+class GPointPlan:
+    """ecckd_gpoint_plan: per-chunk g-sorted visiting order for one g-point map."""
+
+    def __init__(self, ctx: Context, d_g_point, nwav: int, ng: int):
+        self.ctx, self.nwav, self.ng = ctx, int(nwav), int(ng)
+        self.handle = None
+        h = C.c_void_p()
+        check(_lib.lib().ecckd_gpoint_plan_create(ctx.handle, _ptr(d_g_point), self.nwav, self.ng, C.byref(h)))
+        self.handle = h.value
+
+    def counts(self) -> np.ndarray:
+        out = np.zeros(self.ng, dtype=np.int64)
+        check(_lib.lib().ecckd_gpoint_plan_counts(self.handle, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_gpoint_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _method_id(averaging_method) -> int:
+    if isinstance(averaging_method, str):
+        mid = _lib.lib().ecckd_averaging_method_from_string(averaging_method.encode())
+        if mid < 0:  # average_optical_depth.cpp:130-133
+            raise EcckdError(147, f'averaging_method "{averaging_method}" not understood')
+        return mid
+    return int(averaging_method)
+
+
+def average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_vmr, pressure_fl, pressure_hl, g_point,
+                                     optical_depth, planck_fl, averaging_method, want_minmax=True):
+    """Host-array form with the reference's argument list (average_optical_depth.h:19-30).
+
+    planck_fl may be [nlay][nwav] or a single [nwav] row (spread<0>(ssi, nlay)).
+    Returns (molar_abs, min_molar_abs, max_molar_abs, warn).
+    """
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, nwav = od.shape
+    w = np.ascontiguousarray(planck_fl, dtype=np.float64)
+    w_stride = 0 if w.ndim == 1 else nwav
+    gp = np.ascontiguousarray(g_point, dtype=np.int32)
+    pf, pfp = _h(pressure_fl)
+    ph, php = _h(pressure_hl)
+    out = np.zeros((nlay, ng))
+    omin = np.zeros((nlay, ng)) if want_minmax else None
+    omax = np.zeros((nlay, ng)) if want_minmax else None
+    warn = np.zeros(ng, dtype=np.int32)
+    if not isinstance(averaging_method, str):
+        averaging_method = AVERAGING_METHODS[int(averaging_method)]
+    check(_lib.lib().ecckd_average_optical_depth_to_g_point(
+        ctx.handle, ng, float(reference_surface_vmr), nlay, nwav, pfp, php, gp.ctypes.data, od.ctypes.data, nwav,
+        w.ctypes.data, w_stride, averaging_method.encode(), out.ctypes.data,
+        omin.ctypes.data if want_minmax else None, omax.ctypes.data if want_minmax else None, ng, warn.ctypes.data))
+    return out, omin, omax, warn
+
+
+def average_optical_depth_to_g_point_dev(ctx: Context, plan: GPointPlan, reference_surface_vmr, pressure_fl,
+                                         pressure_hl, d_od, od_stride, weight_mode, d_weight, w_stride, temperature,
+                                         d_wavenumber, d_d_wavenumber, averaging_method, d_molar_abs, d_min=None,
+                                         d_max=None, out_stride=None, d_warn=None):
+    pf, pfp = _h(pressure_fl)
+    ph, php = _h(pressure_hl)
+    t, tp = _h(temperature)
+    check(_lib.lib().ecckd_average_optical_depth_to_g_point_dev(
+        ctx.handle, plan.handle, float(reference_surface_vmr), pf.size, pfp, php, _ptr(d_od), od_stride, weight_mode,
+        _ptr(d_weight), w_stride, tp, _ptr(d_wavenumber), _ptr(d_d_wavenumber), _method_id(averaging_method),
+        _ptr(d_molar_abs), _ptr(d_min), _ptr(d_max), out_stride or plan.ng, _ptr(d_warn)))
+
+
+def _ptr_array(items: Optional[Sequence]):
+    if items is None:
+        return None, None
+    arr = (C.c_void_p * len(items))(*[_ptr(x) for x in items])
+    return arr, C.cast(arr, C.c_void_p).value
+
+
+def average_optical_depth_batch_dev(ctx: Context, plan: GPointPlan, reference_surface_vmr: Sequence[float], pressure_fl,
+                                    pressure_hl, d_ods: Sequence, od_stride, weight_mode, d_weight, w_stride,
+                                    temperature, d_wavenumber, d_d_wavenumber, averaging_method, d_molar_abs: Sequence,
+                                    d_min: Optional[Sequence] = None, d_max: Optional[Sequence] = None,
+                                    out_stride=None, d_warn: Optional[Sequence] = None):
+    pf, pfp = _h(pressure_fl)
+    ph, php = _h(pressure_hl)
+    t, tp = _h(temperature)
+    v, vp = _h(reference_surface_vmr)
+    a_od, p_od = _ptr_array(d_ods)
+    a_out, p_out = _ptr_array(d_molar_abs)
+    a_min, p_min = _ptr_array(d_min)
+    a_max, p_max = _ptr_array(d_max)
+    a_w, p_w = _ptr_array(d_warn)
+    check(_lib.lib().ecckd_average_optical_depth_batch_dev(
+        ctx.handle, plan.handle, len(d_ods), vp, pf.size, pfp, php, p_od, od_stride, weight_mode, _ptr(d_weight),
+        w_stride, tp, _ptr(d_wavenumber), _ptr(d_d_wavenumber), _method_id(averaging_method), p_out, p_min, p_max,
+        out_stride or plan.ng, p_w))
+
+
+def merge_axpy_dev(ctx: Context, nlay, nwav, d_optical_depth, stride, d_od, od_stride, scaling=1.0,
+                   scaling_profile=None):
+    sp, spp = _h(scaling_profile)
+    check(_lib.lib().ecckd_merge_axpy_dev(ctx.handle, nlay, nwav, _ptr(d_optical_depth), stride, _ptr(d_od), od_stride,
+                                          float(scaling), spp))
+
+
+def gpoint_fraction_dev(ctx: Context, ng, nwav, d_g_point, d_wavenumber, d_d_wavenumber, wavenumber1, wavenumber2,
+                        d_out):
+    w1, w1p = _h(wavenumber1)
+    w2, w2p = _h(wavenumber2)
+    check(_lib.lib().ecckd_gpoint_fraction_dev(ctx.handle, ng, nwav, _ptr(d_g_point), _ptr(d_wavenumber),
+                                               _ptr(d_d_wavenumber), w1.size, w1p, w2p, _ptr(d_out)))
+
+
+def ssi_intervals_dev(ctx: Context, nwav, d_wavenumber, d_ssi, wavenumber1, wavenumber2, d_out):
+    w1, w1p = _h(wavenumber1)
+    w2, w2p = _h(wavenumber2)
+    check(_lib.lib().ecckd_ssi_intervals_dev(ctx.handle, nwav, _ptr(d_wavenumber), _ptr(d_ssi), w1.size, w1p, w2p,
+                                             _ptr(d_out)))
+
+
+def planck_lut_dev(ctx: Context, plan: GPointPlan, d_wavenumber, d_d_wavenumber, temperature_lut, d_out):
+    t, tp = _h(temperature_lut)
+    check(_lib.lib().ecckd_planck_lut_dev(ctx.handle, plan.handle, _ptr(d_wavenumber), _ptr(d_d_wavenumber), t.size, tp,
+                                          _ptr(d_out)))
+
+
+def compact_g_points_dev(ctx: Context, ng, nwav, d_g_point):
+    """Returns (new_ng, g_point_map[new_ng]); d_g_point renumbered in place."""
+    gmap = np.zeros(ng, dtype=np.int32)
+    n = C.c_int(0)
+    check(_lib.lib().ecckd_compact_g_points_dev(ctx.handle, ng, nwav, _ptr(d_g_point), gmap.ctypes.data, C.byref(n)))
+    return n.value, gmap[: n.value].copy()
+
+
+# ----------------------------------------------------------------- ranking
+def sort_key_lw_dev(ctx, nlay, nwav, pressure_hl, d_wavenumber, d_d_wavenumber, d_od, od_stride, threshold, d_key,
+                    d_column_od=None):
+    ph, php = _h(pressure_hl)
+    check(_lib.lib().ecckd_sort_key_lw_dev(ctx.handle, nlay, nwav, php, _ptr(d_wavenumber), _ptr(d_d_wavenumber),
+                                           _ptr(d_od), od_stride, float(threshold), _ptr(d_key), _ptr(d_column_od)))
+
+
+def sort_key_sw_dev(ctx, nlay, nwav, pressure_hl, d_od, od_stride, threshold, d_key, d_column_od=None):
+    ph, php = _h(pressure_hl)
+    check(_lib.lib().ecckd_sort_key_sw_dev(ctx.handle, nlay, nwav, php, _ptr(d_od), od_stride, float(threshold),
+                                           _ptr(d_key), _ptr(d_column_od)))
+
+
+def rank_bands_dev(ctx, nwav, d_wavenumber, d_key, band_bound1, band_bound2, d_iband=None, d_rank=None,
+                   d_ordered_index=None):
+    b1, b1p = _h(band_bound1)
+    b2, b2p = _h(band_bound2)
+    check(_lib.lib().ecckd_rank_bands_dev(ctx.handle, nwav, _ptr(d_wavenumber), _ptr(d_key), b1.size, b1p, b2p,
+                                          _ptr(d_iband), _ptr(d_rank), _ptr(d_ordered_index)))
+
+
+def store_g_points_dev(ctx, nwav, d_rank, rank1, rank2, d_g_point):
+    r1, r1p = _h(rank1, np.int32)
+    r2, r2p = _h(rank2, np.int32)
+    check(_lib.lib().ecckd_store_g_points_dev(ctx.handle, nwav, _ptr(d_rank), r1.size, r1p, r2p, _ptr(d_g_point)))
+
+
+def overlap_g_points(n_g_points, sorting_variables: Sequence[np.ndarray]):
+    """overlap_g_points (single_gas_data.cpp:23-124) -> (ng, g_min[ngas][ng], g_max[ngas][ng], band_number[ng])."""
+    n_g = np.ascontiguousarray(n_g_points, dtype=np.int32)
+    ngas, nband = n_g.shape
+    sv = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.float64) for s in sorting_variables]))
+    offs = np.zeros(ngas, dtype=np.int32)
+    offs[1:] = np.cumsum([len(s) for s in sorting_variables])[:-1]
+    cap = int(n_g.sum()) + 1
+    g_min = np.zeros((ngas, cap), dtype=np.int32)
+    g_max = np.zeros((ngas, cap), dtype=np.int32)
+    band = np.zeros(cap, dtype=np.int32)
+    ng = C.c_int(0)
+    check(_lib.lib().ecckd_overlap_g_points(ngas, nband, n_g.ctypes.data, sv.ctypes.data, offs.ctypes.data, cap,
+                                            g_min.ctypes.data, g_max.ctypes.data, band.ctypes.data, C.byref(ng)))
+    n = ng.value
+    return n, g_min[:, :n].copy(), g_max[:, :n].copy(), band[:n].copy()
+
+
+def assign_g_points_dev(ctx, nwav, d_gas_g_point, g_min, g_max, d_g_point) -> int:
+    gmin = np.ascontiguousarray(g_min, dtype=np.int32)
+    gmax = np.ascontiguousarray(g_max, dtype=np.int32)
+    ngas, ng = gmin.shape
+    n_un = C.c_int64(0)
+    check(_lib.lib().ecckd_assign_g_points_dev(ctx.handle, ngas, nwav, _ptr(d_gas_g_point), ng, ng, gmin.ctypes.data,
+                                               gmax.ctypes.data, _ptr(d_g_point), C.byref(n_un)))
+    return int(n_un.value)
+
+
+# ----------------------------------------------------------------- stage 2
+class CkdModel:
+    """ecckd_ckd_model: the look-up tables of a CKD definition on the device.
+
+    gases: sequence of dicts with keys conc_dependence, molar_abs and, as
+    needed, vmr_lut and reference_vmr (the per-gas variables of
+    ckd_model.cpp:288-641).
+    """
+
+    def __init__(self, ctx: Context, gases, log_pressure, temperature, temperature_planck=None, planck_lut=None,
+                 solar_irradiance=None, rayleigh_molar_scat=None):
+        self.ctx = ctx
+        self.handle = None
+        keep = []
+        tabs = (GasTable * len(gases))()
+        for i, g in enumerate(gases):
+            k, kp = _h(g["molar_abs"])
+            v, vp = _h(g.get("vmr_lut"))
+            keep += [k, v]
+            tabs[i].conc_dependence = int(g["conc_dependence"])
+            tabs[i].nconc = 0 if v is None else v.size
+            tabs[i].vmr_lut = vp
+            tabs[i].reference_vmr = float(g.get("reference_vmr", 0.0))
+            tabs[i].molar_abs = kp
+        lp, lpp = _h(log_pressure)
+        t, tp = _h(temperature)
+        tpl, tplp = _h(temperature_planck)
+        pl, plp = _h(planck_lut)
+        si, sip = _h(solar_irradiance)
+        ra, rap = _h(rayleigh_molar_scat)
+        self.nt, self.np = t.shape
+        self.ng = int(np.asarray(gases[0]["molar_abs"]).shape[-1])
+        self.ngas = len(gases)
+        self.is_sw = si is not None
+        h = C.c_void_p()
+        check(_lib.lib().ecckd_ckd_model_create(ctx.handle, len(gases), C.cast(tabs, C.c_void_p).value, self.nt,
+                                                self.np, self.ng, lpp, tp, 0 if tpl is None else tpl.size, tplp, plp,
+                                                sip, rap, C.byref(h)))
+        self.handle = h.value
+
+    def calc_optical_depth_dev(self, igas, ncol, nlay, d_pressure_hl, d_temperature_fl, d_vmr_fl, d_od,
+                               accumulate=False):
+        check(_lib.lib().ecckd_ckd_calc_optical_depth_dev(self.ctx.handle, self.handle, igas, ncol, nlay,
+                                                          _ptr(d_pressure_hl), _ptr(d_temperature_fl), _ptr(d_vmr_fl),
+                                                          _ptr(d_od), 1 if accumulate else 0))
+
+    def calc_planck_function_dev(self, n, d_temperature, d_planck):
+        check(_lib.lib().ecckd_ckd_calc_planck_function_dev(self.ctx.handle, self.handle, n, _ptr(d_temperature),
+                                                            _ptr(d_planck)))
+
+    def calc_rayleigh_optical_depth_dev(self, ncol, nlay, d_pressure_hl, d_od):
+        check(_lib.lib().ecckd_ckd_calc_rayleigh_optical_depth_dev(self.ctx.handle, self.handle, ncol, nlay,
+                                                                   _ptr(d_pressure_hl), _ptr(d_od)))
+
+    def run_ckd_dev(self, d_vmr_fl: Sequence, tsi, ncol, nlay, d_pressure_hl, d_temperature_hl, d_od=None,
+                    d_planck_hl=None, d_planck_surf=None, d_flux_dn=None, d_flux_up=None, d_bb_flux_dn=None,
+                    d_bb_flux_up=None):
+        arr, p = _ptr_array(d_vmr_fl)
+        check(_lib.lib().ecckd_run_ckd_dev(self.ctx.handle, self.handle, p, float(tsi), ncol, nlay, _ptr(d_pressure_hl),
+                                           _ptr(d_temperature_hl), _ptr(d_od), _ptr(d_planck_hl), _ptr(d_planck_surf),
+                                           _ptr(d_flux_dn), _ptr(d_flux_up), _ptr(d_bb_flux_dn), _ptr(d_bb_flux_up)))
+
+    def run_ckd(self, vmr_fl: Sequence[Optional[np.ndarray]], pressure_hl, temperature_hl, tsi=1361.0):
+        """Numerical core of run_ckd (run_ckd.cpp:119-367) on host arrays -> dict of outputs."""
+        ph = np.ascontiguousarray(pressure_hl, dtype=np.float64)
+        th = np.ascontiguousarray(temperature_hl, dtype=np.float64)
+        ncol, nhl = ph.shape
+        nlay, ng = nhl - 1, self.ng
+        keep = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in vmr_fl]
+        arr = (C.c_void_p * len(keep))(*[None if v is None else v.ctypes.data for v in keep])
+        out = {"optical_depth": np.zeros((ncol, nlay, ng)), "flux_dn": np.zeros((ncol, nhl, ng)),
+               "bb_flux_dn": np.zeros((ncol, nhl))}
+        if not self.is_sw:
+            out.update(planck_hl=np.zeros((ncol, nhl, ng)), planck_surf=np.zeros((ncol, ng)),
+                       flux_up=np.zeros((ncol, nhl, ng)), bb_flux_up=np.zeros((ncol, nhl)))
+        g = lambda k: out[k].ctypes.data if k in out else None
+        check(_lib.lib().ecckd_run_ckd(self.ctx.handle, self.handle, C.cast(arr, C.c_void_p).value, float(tsi), ncol,
+                                       nlay, ph.ctypes.data, th.ctypes.data, g("optical_depth"), g("planck_hl"),
+                                       g("planck_surf"), g("flux_dn"), g("flux_up"), g("bb_flux_dn"), g("bb_flux_up")))
+        return out
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_ckd_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def radiative_transfer_lw_dev(ctx, ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck, d_flux_dn,
+                              d_flux_up):
+    check(_lib.lib().ecckd_radiative_transfer_lw_dev(ctx.handle, ncol, nlay, n, _ptr(d_planck), _ptr(d_od),
+                                                     _ptr(d_surf_emissivity), _ptr(d_surf_planck), _ptr(d_flux_dn),
+                                                     _ptr(d_flux_up)))
+
+
+def radiative_transfer_sw_dev(ctx, ncol, nlay, n, cos_sza, d_ssi, d_od, d_albedo, d_flux_dn, d_flux_up=None):
+    mu, mup = _h(np.broadcast_to(np.asarray(cos_sza, dtype=np.float64), (ncol,)))
+    check(_lib.lib().ecckd_radiative_transfer_sw_dev(ctx.handle, ncol, nlay, n, mup, _ptr(d_ssi), _ptr(d_od),
+                                                     _ptr(d_albedo), _ptr(d_flux_dn), _ptr(d_flux_up)))
+
+
+def heating_rate_dev(ctx, ncol, nlay, n, d_pressure_hl, d_flux_dn, d_flux_up, d_hr):
+    check(_lib.lib().ecckd_heating_rate_dev(ctx.handle, ncol, nlay, n, _ptr(d_pressure_hl), _ptr(d_flux_dn),
+                                            _ptr(d_flux_up), _ptr(d_hr)))
+
+
+# Convenience host-array wrappers that mirror the reference call signatures.
+def radiative_transfer_lw(ctx, planck, optical_depth, surf_emissivity, surf_planck):
+    """radiative_transfer_lw<false> (radiative_transfer_lw.cpp:25-60) -> (flux_dn, flux_up)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, n = od.shape
+    d = [ctx.to_device(np.asarray(a, dtype=np.float64)) for a in (planck, od, surf_emissivity, surf_planck)]
+    dn, up = ctx.empty((nlay + 1, n)), ctx.empty((nlay + 1, n))
+    radiative_transfer_lw_dev(ctx, 1, nlay, n, d[0], d[1], d[2], d[3], dn, up)
+    return dn.numpy(), up.numpy()
+
+
+def radiative_transfer_direct_sw(ctx, cos_sza, ssi, optical_depth):
+    """radiative_transfer_direct_sw<false> (radiative_transfer_sw.cpp:24-43)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, n = od.shape
+    d_ssi, d_od, dn = ctx.to_device(np.asarray(ssi, dtype=np.float64)), ctx.to_device(od), ctx.empty((nlay + 1, n))
+    radiative_transfer_sw_dev(ctx, 1, nlay, n, cos_sza, d_ssi, d_od, None, dn, None)
+    return dn.numpy()
+
+
+def radiative_transfer_norayleigh_sw(ctx, cos_sza, ssi, optical_depth, albedo):
+    """radiative_transfer_norayleigh_sw<false> (radiative_transfer_sw.cpp:47-77)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, n = od.shape
+    d_ssi, d_od, d_al = (ctx.to_device(np.asarray(a, dtype=np.float64)) for a in (ssi, od, albedo))
+    dn, up = ctx.empty((nlay + 1, n)), ctx.empty((nlay + 1, n))
+    radiative_transfer_sw_dev(ctx, 1, nlay, n, cos_sza, d_ssi, d_od, d_al, dn, up)
+    return dn.numpy(), up.numpy()
+
+
+def heating_rate(ctx, pressure_hl, flux_dn, flux_up=None):
+    """heating_rate<false> (heating_rate.h:25-49)."""
+    fd = np.ascontiguousarray(flux_dn, dtype=np.float64)
+    nhl, n = fd.shape
+    d_p, d_dn = ctx.to_device(np.asarray(pressure_hl, dtype=np.float64)), ctx.to_device(fd)
+    d_up = None if flux_up is None else ctx.to_device(np.asarray(flux_up, dtype=np.float64))
+    hr = ctx.empty((nhl - 1, n))
+    heating_rate_dev(ctx, 1, nhl - 1, n, d_p, d_dn, d_up, hr)
+    return hr.numpy()

@@ -1,0 +1,211 @@
+// capi.cu - context, memory and error plumbing of the C ABI (include/ecckd_b200.h)
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace ecckd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int ws_reserve(ecckd_ctx* ctx, int slot, size_t bytes, void** out) {
+  Workspace& w = ctx->ws[slot];
+  if (w.bytes < bytes) {
+    // All users are stream-ordered on ctx->stream; drain before freeing.
+    if (w.ptr) {
+      ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      ECCKD_CUDA_OK(cudaFree(w.ptr));
+      w.ptr = nullptr;
+      w.bytes = 0;
+    }
+    size_t want = (bytes + 255) & ~size_t(255);
+    ECCKD_CUDA_OK(cudaMalloc(&w.ptr, want));
+    w.bytes = want;
+  }
+  *out = w.ptr;
+  return ECCKD_OK;
+}
+
+int upload_small(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (bytes == 0) return ECCKD_OK;
+  if (bytes > ctx->pinned_bytes) {
+    // too big for the staging ring: synchronous pageable copy
+    ECCKD_CUDA_OK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    return ECCKD_OK;
+  }
+  size_t off = (ctx->pinned_off + 63) & ~size_t(63);
+  if (off + bytes > ctx->pinned_bytes) {
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    off = 0;
+  }
+  char* stage = static_cast<char*>(ctx->pinned) + off;
+  memcpy(stage, h_src, bytes);
+  ctx->pinned_off = off + bytes;
+  ECCKD_CUDA_OK(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ECCKD_OK;
+}
+
+}  // namespace ecckd
+
+using namespace ecckd;
+
+ECCKD_API int ecckd_version(void) { return ECCKD_B200_VERSION; }
+
+ECCKD_API const char* ecckd_last_error(void) { return g_err; }
+
+ECCKD_API int ecckd_averaging_method_from_string(const char* name) {
+  // strings of src/ecckd/average_optical_depth.cpp:43-129
+  static const char* names[] = {"linear",          "transmission", "transmission-2",
+                                "transmission-3",  "transmission-10", "square-root",
+                                "logarithmic",     "hybrid-logarithmic-transmission-3"};
+  if (!name) return -1;
+  for (int i = 0; i < 8; ++i) {
+    if (strcmp(name, names[i]) == 0) return i;
+  }
+  return -1;
+}
+
+ECCKD_API int ecckd_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int usable = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++usable;
+  }
+  return usable;
+}
+
+ECCKD_API int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out) {
+  ECCKD_REQUIRE(out != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_ctx_create: out is NULL");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_error("ecckd_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  ECCKD_REQUIRE(device >= 0 && device < n, ECCKD_PARAMETER_ERROR, "ecckd_ctx_create: device %d out of range [0,%d)",
+                device, n);
+  cudaDeviceProp prop;
+  ECCKD_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  ECCKD_REQUIRE(prop.major == 10, ECCKD_UNEXPECTED_EXCEPTION,
+                "ecckd_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
+                prop.major, prop.minor);
+  ECCKD_CUDA_OK(cudaSetDevice(device));
+  ecckd_ctx* ctx = new ecckd_ctx();
+  ctx->device = device;
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  if (stream) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+    ctx->owns_stream = false;
+  } else {
+    cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+      delete ctx;
+      set_error("cudaStreamCreateWithFlags failed: %s", cudaGetErrorString(se));
+      return ECCKD_UNEXPECTED_EXCEPTION;
+    }
+    ctx->owns_stream = true;
+  }
+  ctx->pinned_bytes = size_t(4) << 20;
+  cudaError_t pe = cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault);
+  if (pe != cudaSuccess) {
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    set_error("cudaHostAlloc failed: %s", cudaGetErrorString(pe));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  *out = ctx;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
+  if (!ctx) return ECCKD_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& w : ctx->ws) {
+    if (w.ptr) cudaFree(w.ptr);
+  }
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ctx_set_stream(ecckd_ctx* ctx, void* stream) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_ctx_set_stream: ctx is NULL");
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->owns_stream) {
+    cudaStreamDestroy(ctx->stream);
+    ctx->owns_stream = false;
+  }
+  if (stream) {
+    ctx->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    ECCKD_CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->owns_stream = true;
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_synchronize(ecckd_ctx* ctx) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_synchronize: ctx is NULL");
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_device_malloc(ecckd_ctx* ctx, size_t bytes, void** d_ptr) {
+  ECCKD_REQUIRE(ctx && d_ptr, ECCKD_PARAMETER_ERROR, "ecckd_device_malloc: NULL argument");
+  ECCKD_CUDA_OK(cudaSetDevice(ctx->device));
+  ECCKD_CUDA_OK(cudaMalloc(d_ptr, bytes ? bytes : 1));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_device_free(ecckd_ctx* ctx, void* d_ptr) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_device_free: ctx is NULL");
+  if (d_ptr) {
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ECCKD_CUDA_OK(cudaFree(d_ptr));
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_host_malloc_pinned(size_t bytes, void** h_ptr) {
+  ECCKD_REQUIRE(h_ptr != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_host_malloc_pinned: NULL argument");
+  ECCKD_CUDA_OK(cudaHostAlloc(h_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_host_free_pinned(void* h_ptr) {
+  if (h_ptr) ECCKD_CUDA_OK(cudaFreeHost(h_ptr));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_memcpy_h2d(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_memcpy_h2d: ctx is NULL");
+  ECCKD_CUDA_OK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_memcpy_d2h: ctx is NULL");
+  ECCKD_CUDA_OK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return ECCKD_OK;
+}
+
+ECCKD_API int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx) { return ctx ? ctx->launches : 0; }

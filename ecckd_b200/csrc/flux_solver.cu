@@ -1,0 +1,743 @@
+// flux_solver.cu - stage 2 of the hot path: CKD optical depths from the
+// look-up table and the forward flux solvers that run_ckd and the forward pass
+// of optimize_lut evaluate (reference: ckd_model.cpp:923-1145,
+// radiative_transfer_{lw,sw}.cpp, heating_rate.h, run_ckd.cpp:119-367).
+//
+// Layout: every 3-D array is [column][layer or half-level][g] with g fastest,
+// exactly as the reference's Array3D.  Threads map to g (fastest) so each warp
+// reads/writes contiguous 256-512 B rows; one thread walks the layers of one
+// column x g-point, carrying the flux recurrence in registers.  All kernels are
+// HBM-bound streams: 32 B per column x layer x g for the LW solver.
+#include <algorithm>
+
+#include "common.cuh"
+
+struct ecckd_ckd_model {
+  ecckd_ctx* ctx = nullptr;
+  int ngas = 0, nt = 0, np = 0, ng = 0, nlut = 0;
+  bool is_sw = false;
+  std::vector<int> conc_dependence, nconc;
+  std::vector<double> reference_vmr;
+  std::vector<double*> d_molar_abs;  // per gas
+  std::vector<double*> d_vmr_lut;    // per gas (LUT only)
+  std::vector<double> log_vmr0, d_log_c;  // per gas (LUT only), host-computed as in ckd_model.cpp:1003-1005
+  double* d_log_pressure = nullptr;
+  double* d_temperature = nullptr;
+  double* d_temperature_planck = nullptr;
+  double* d_planck_lut = nullptr;
+  double* d_solar_irradiance = nullptr;
+  double* d_rayleigh = nullptr;
+  double log_p_0 = 0, d_log_p = 0, d_t = 0;          // ckd_model.cpp:948-952
+  double planck_t0 = 0, planck_dt = 0;               // ckd_model.cpp:1123-1124
+  double solar_sum = 0;                              // sum(solar_irradiance), run_ckd.cpp:98
+  void* d_gasdesc = nullptr;                         // device array of GasDev
+};
+
+namespace ecckd {
+
+struct GasDev {
+  const double* molar_abs;
+  const double* vmr;  // per-call: [ncol][nlay] or NULL
+  double reference_vmr;
+  double log_vmr0;
+  double d_log_c;
+  int32_t conc_dependence;
+  int32_t nconc;
+};
+
+// interpolation state of one (column, layer): ckd_model.cpp:962-980
+struct Interp {
+  int ip0, it0;
+  double pw0, pw1, tw0, tw1, simple_weight;
+};
+
+__device__ __forceinline__ Interp make_interp(double p0, double p1, double t_fl, double log_p_0, double d_log_p,
+                                              double d_t, int nt, int np, const double* __restrict__ temperature) {
+  Interp it;
+  const double log_pressure_fl = log(0.5 * (p1 + p0));
+  double pindex0 = (log_pressure_fl - log_p_0) / d_log_p;
+  pindex0 = fmax(0.0, fmin(pindex0, np - 1.0001));
+  it.ip0 = (int)pindex0;
+  it.pw1 = pindex0 - it.ip0;
+  it.pw0 = 1.0 - it.pw1;
+  const double t_0 = it.pw0 * temperature[it.ip0] + it.pw1 * temperature[it.ip0 + 1];
+  double tindex0 = (t_fl - t_0) / d_t;
+  tindex0 = fmax(0.0, fmin(tindex0, nt - 1.0001));
+  it.it0 = (int)tindex0;
+  it.tw1 = tindex0 - it.it0;
+  it.tw0 = 1.0 - it.tw1;
+  it.simple_weight = (1.0 / (ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR)) * (p1 - p0);
+  return it;
+}
+
+// optical depth of one gas at one (column, layer, g): ckd_model.cpp:982-1088
+__device__ __forceinline__ double gas_od(const GasDev& gs, const Interp& it, double vmr, bool have_vmr, int nt, int np,
+                                         int ng, int g) {
+  const size_t sP = (size_t)ng, sT = (size_t)np * ng;
+  double weight = 0.0;
+  if (have_vmr) {
+    weight = (gs.conc_dependence == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - gs.reference_vmr)
+                                                                : it.simple_weight * vmr;
+  }
+  if (gs.conc_dependence == ECCKD_CONC_LUT) {
+    double cindex0 = (log(vmr) - gs.log_vmr0) / gs.d_log_c;
+    cindex0 = fmax(0.0, fmin(cindex0, gs.nconc - 1.0001));
+    const int ic0 = (int)cindex0;
+    const double cw1 = cindex0 - ic0;
+    const double cw0 = 1.0 - cw1;
+    const size_t sC = (size_t)nt * sT;
+    const double* k = gs.molar_abs + ic0 * sC + it.it0 * sT + it.ip0 * sP + g;
+    const double a = it.tw0 * (it.pw0 * k[0] + it.pw1 * k[sP]) + it.tw1 * (it.pw0 * k[sT] + it.pw1 * k[sT + sP]);
+    k += sC;
+    const double b = it.tw0 * (it.pw0 * k[0] + it.pw1 * k[sP]) + it.tw1 * (it.pw0 * k[sT] + it.pw1 * k[sT + sP]);
+    return weight * (cw0 * a + cw1 * b);
+  }
+  const double* k = gs.molar_abs + it.it0 * sT + it.ip0 * sP + g;
+  const double v = it.tw0 * (it.pw0 * k[0] + it.pw1 * k[sP]) + it.tw1 * (it.pw0 * k[sT] + it.pw1 * k[sT + sP]);
+  return ((gs.conc_dependence == ECCKD_CONC_NONE) ? it.simple_weight : weight) * v;
+}
+
+// CkdModel::calc_planck_function for one temperature and g: ckd_model.cpp:1124-1142
+__device__ __forceinline__ double planck_interp(double t, double t0, double d_t, int nlut, int ng, int g,
+                                                const double* __restrict__ lut) {
+  const double tindex0 = (t - t0) / d_t;
+  if (tindex0 >= 0) {
+    const int it0 = min((int)tindex0, nlut - 2);
+    const double w1 = tindex0 - it0;
+    const double w0 = 1.0 - w1;
+    return w0 * lut[(size_t)it0 * ng + g] + w1 * lut[(size_t)(it0 + 1) * ng + g];
+  }
+  return (t / t0) * lut[g];
+}
+
+// LW layer emissivity and Planck-gradient factor: radiative_transfer_lw.cpp:41-43
+__device__ __forceinline__ void lw_layer(double tau, double& e, double& f) {
+  e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+  f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+}
+
+// ------------------------------------------------------------------ kernels
+// thread = (column*nlay + layer, g)
+__global__ void ckd_od_kernel(GasDev gs, int nt, int np, int ng, double log_p_0, double d_log_p, double d_t,
+                              const double* __restrict__ temperature, int ncol, int nlay,
+                              const double* __restrict__ pressure_hl, const double* __restrict__ temperature_fl,
+                              double* __restrict__ od, int accumulate) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t cl = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (g >= ng || cl >= (int64_t)ncol * nlay) return;
+  const int icol = (int)(cl / nlay), ip = (int)(cl - (int64_t)icol * nlay);
+  const double p0 = pressure_hl[(int64_t)icol * (nlay + 1) + ip];
+  const double p1 = pressure_hl[(int64_t)icol * (nlay + 1) + ip + 1];
+  const Interp it = make_interp(p0, p1, temperature_fl[cl], log_p_0, d_log_p, d_t, nt, np, temperature);
+  const bool have = gs.vmr != nullptr;
+  const double v = gas_od(gs, it, have ? gs.vmr[cl] : 0.0, have, nt, np, ng, g);
+  double* o = od + cl * ng + g;
+  *o = accumulate ? (*o + v) : v;
+}
+
+__global__ void clamp_zero_kernel(int64_t n, double* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = fmax(x[i], 0.0);  // run_ckd.cpp:317
+}
+
+__global__ void ckd_planck_kernel(int nlut, int ng, double t0, double d_t, const double* __restrict__ lut, int64_t n,
+                                  const double* __restrict__ temperature, double* __restrict__ planck) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (g >= ng || i >= n) return;
+  planck[i * ng + g] = planck_interp(temperature[i], t0, d_t, nlut, ng, g, lut);
+}
+
+__global__ void rayleigh_od_kernel(int ncol, int nlay, int ng, const double* __restrict__ pressure_hl,
+                                   const double* __restrict__ molar_scat, double* __restrict__ od) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t cl = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  if (g >= ng || cl >= (int64_t)ncol * nlay) return;
+  const int icol = (int)(cl / nlay), ip = (int)(cl - (int64_t)icol * nlay);
+  const double dp = pressure_hl[(int64_t)icol * (nlay + 1) + ip + 1] - pressure_hl[(int64_t)icol * (nlay + 1) + ip];
+  // ckd_model.h:246-250: dp * (1/(g*0.001*M)) * sigma
+  od[cl * ng + g] = (dp * (1.0 / (ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR))) * molar_scat[g];
+}
+
+__global__ void temperature_fl_kernel(int ncol, int nlay, const double* __restrict__ t_hl,
+                                      const double* __restrict__ p_hl, double* __restrict__ t_fl) {
+  const int64_t cl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cl >= (int64_t)ncol * nlay) return;
+  const int icol = (int)(cl / nlay), i = (int)(cl - (int64_t)icol * nlay);
+  const double* t = t_hl + (int64_t)icol * (nlay + 1);
+  const double* p = p_hl + (int64_t)icol * (nlay + 1);
+  t_fl[cl] = (t[i] * p[i] + t[i + 1] * p[i + 1]) / (p[i] + p[i + 1]);  // run_ckd.cpp:119-122
+}
+
+// radiative_transfer_lw.cpp:36-59; thread = (column, spectral index)
+__global__ void rt_lw_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ planck,
+                             const double* __restrict__ od, const double* __restrict__ surf_emissivity,
+                             const double* __restrict__ surf_planck, double* __restrict__ flux_dn,
+                             double* __restrict__ flux_up) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int icol = blockIdx.y;
+  if (i >= n) return;
+  const double* pl = planck + (int64_t)icol * (nlay + 1) * n + i;
+  const double* tau = od + (int64_t)icol * nlay * n + i;
+  double* dn = flux_dn + (int64_t)icol * (nlay + 1) * n + i;
+  double* up = flux_up + (int64_t)icol * (nlay + 1) * n + i;
+  double f_dn = 0.0;
+  dn[0] = 0.0;
+  double b_top = pl[0];
+#pragma unroll 4
+  for (int l = 0; l < nlay; ++l) {
+    double e, f;
+    lw_layer(tau[(int64_t)l * n], e, f);
+    const double b_bot = pl[(int64_t)(l + 1) * n];
+    f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
+    dn[(int64_t)(l + 1) * n] = f_dn;
+    b_top = b_bot;
+  }
+  const double es = surf_emissivity[i];
+  double f_up = surf_planck[(int64_t)icol * n + i] * es + (1.0 - es) * f_dn;
+  up[(int64_t)nlay * n] = f_up;
+  double b_bot = b_top;
+#pragma unroll 4
+  for (int l = nlay - 1; l >= 0; --l) {
+    double e, f;
+    lw_layer(tau[(int64_t)l * n], e, f);
+    const double b_t = pl[(int64_t)l * n];
+    f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
+    up[(int64_t)l * n] = f_up;
+    b_bot = b_t;
+  }
+}
+
+// radiative_transfer_sw.cpp:36-42 and :61-76
+__global__ void rt_sw_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ cos_sza,
+                             const double* __restrict__ ssi, const double* __restrict__ od,
+                             const double* __restrict__ albedo, double* __restrict__ flux_dn,
+                             double* __restrict__ flux_up) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int icol = blockIdx.y;
+  if (i >= n) return;
+  const double mu0 = cos_sza[icol];
+  const double minus_sec_sza = -1.0 / mu0;
+  const double* tau = od + (int64_t)icol * nlay * n + i;
+  double* dn = flux_dn + (int64_t)icol * (nlay + 1) * n + i;
+  double f = mu0 * ssi[i];
+  dn[0] = f;
+#pragma unroll 4
+  for (int l = 0; l < nlay; ++l) {
+    f = f * exp(minus_sec_sza * tau[(int64_t)l * n]);
+    dn[(int64_t)(l + 1) * n] = f;
+  }
+  if (flux_up) {
+    double* up = flux_up + (int64_t)icol * (nlay + 1) * n + i;
+    f = f * albedo[i];
+    up[(int64_t)nlay * n] = f;
+#pragma unroll 4
+    for (int l = nlay - 1; l >= 0; --l) {
+      f = f * exp(-2.0 * tau[(int64_t)l * n]);
+      up[(int64_t)l * n] = f;
+    }
+  }
+}
+
+// heating_rate.h:38-48
+__global__ void heating_rate_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ pressure_hl,
+                                    const double* __restrict__ flux_dn, const double* __restrict__ flux_up,
+                                    double* __restrict__ hr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t cl = blockIdx.y;
+  if (i >= n) return;
+  const int icol = (int)(cl / nlay), l = (int)(cl - (int64_t)icol * nlay);
+  const double* p = pressure_hl + (int64_t)icol * (nlay + 1);
+  const double conv = -(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p[l + 1] - p[l]);
+  const int64_t a = ((int64_t)icol * (nlay + 1) + l) * n + i;
+  double v;
+  if (flux_up) v = conv * (flux_dn[a + n] - flux_dn[a] - flux_up[a + n] + flux_up[a]);
+  else v = conv * (flux_dn[a + n] - flux_dn[a]);
+  hr[cl * n + i] = v;
+}
+
+// sum(flux, 2): run_ckd.cpp:355-356,367.  One warp per (column, level) row.
+__global__ void sum_g_kernel(int64_t nrows, int ng, const double* __restrict__ flux, double* __restrict__ out) {
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  // fixed order: lane partial sums over g = lane, lane+32, ... then a shuffle tree
+  double s = 0.0;
+  for (int g = lane; g < ng; g += 32) s += flux[row * ng + g];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+
+// Fused run_ckd core (run_ckd.cpp:119-132,261-367): block = one column,
+// thread = g point.  Interpolation state per (layer, gas) is computed once per
+// column into shared memory, then each thread walks the layers.
+struct RunCkdParams {
+  const GasDev* gases;
+  int ngas, nt, np, ng, nlut, is_sw;
+  double log_p_0, d_log_p, d_t, planck_t0, planck_dt, tsi_scaling;
+  const double* temperature;       // [nt][np]
+  const double* planck_lut;        // [nlut][ng]
+  const double* solar_irradiance;  // [ng]
+  const double* rayleigh;          // [ng]
+  int ncol, nlay;
+  const double* pressure_hl;
+  const double* temperature_hl;
+  double* od;
+  double* planck_hl;
+  double* planck_surf;
+  double* flux_dn;
+  double* flux_up;
+  double* bb_flux_dn;
+  double* bb_flux_up;
+  double* scratch_od;  // [ncol][nlay][ng] when od == NULL
+};
+
+__global__ void run_ckd_kernel(const RunCkdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int icol = blockIdx.x;
+  const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
+  Interp* s_it = reinterpret_cast<Interp*>(smem_raw);                              // [nlay]
+  double* s_vmr = reinterpret_cast<double*>(s_it + nlay);                          // [nlay][ngas]
+  double* s_bb = s_vmr + (size_t)nlay * ngas;                                      // [2][nlay+1]
+  const double* p_hl = p.pressure_hl + (int64_t)icol * (nlay + 1);
+  const double* t_hl = p.temperature_hl + (int64_t)icol * (nlay + 1);
+  for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
+    const double t_fl = (t_hl[l] * p_hl[l] + t_hl[l + 1] * p_hl[l + 1]) / (p_hl[l] + p_hl[l + 1]);
+    s_it[l] = make_interp(p_hl[l], p_hl[l + 1], t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+    for (int ig = 0; ig < ngas; ++ig) {
+      const double* v = p.gases[ig].vmr;
+      s_vmr[l * ngas + ig] = v ? v[(int64_t)icol * nlay + l] : 0.0;
+    }
+  }
+  for (int l = threadIdx.x; l < 2 * (nlay + 1); l += blockDim.x) s_bb[l] = 0.0;
+  __syncthreads();
+
+  double* od_col = (p.od ? p.od : p.scratch_od) + (int64_t)icol * nlay * ng;
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    // optical depth: sum over gases, clamp (run_ckd.cpp:265-317)
+    for (int l = 0; l < nlay; ++l) {
+      double tau = 0.0;
+      for (int ig = 0; ig < ngas; ++ig) {
+        const GasDev gs = p.gases[ig];
+        tau += gas_od(gs, s_it[l], s_vmr[l * ngas + ig], gs.vmr != nullptr, p.nt, p.np, ng, g);
+      }
+      od_col[(int64_t)l * ng + g] = fmax(tau, 0.0);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    const int64_t hl0 = (int64_t)icol * (nlay + 1) * ng + g;
+    if (!p.is_sw) {
+      // Planck function at half levels and surface (run_ckd.cpp:131-132)
+      double b_top = planck_interp(t_hl[0], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+      if (p.planck_hl) p.planck_hl[hl0] = b_top;
+      const double b_surf = planck_interp(t_hl[nlay], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+      if (p.planck_surf) p.planck_surf[(int64_t)icol * ng + g] = b_surf;
+      if (!(p.flux_dn && p.flux_up)) {
+        if (p.planck_hl) {
+          for (int l = 1; l <= nlay; ++l)
+            p.planck_hl[hl0 + (int64_t)l * ng] = planck_interp(t_hl[l], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+        }
+        continue;
+      }
+      double f_dn = 0.0;
+      p.flux_dn[hl0] = 0.0;
+      for (int l = 0; l < nlay; ++l) {
+        double e, f;
+        lw_layer(od_col[(int64_t)l * ng + g], e, f);
+        const double b_bot = planck_interp(t_hl[l + 1], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+        if (p.planck_hl) p.planck_hl[hl0 + (int64_t)(l + 1) * ng] = b_bot;
+        f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
+        p.flux_dn[hl0 + (int64_t)(l + 1) * ng] = f_dn;
+        if (p.bb_flux_dn) atomicAdd(&s_bb[l + 1], f_dn);
+        b_top = b_bot;
+      }
+      // surface emissivity 1 (run_ckd.cpp:344-345): up = B_s*1 + (1-1)*dn
+      double f_up = b_surf * 1.0 + (1.0 - 1.0) * f_dn;
+      p.flux_up[hl0 + (int64_t)nlay * ng] = f_up;
+      if (p.bb_flux_up) atomicAdd(&s_bb[(nlay + 1) + nlay], f_up);
+      double b_bot = b_top;
+      for (int l = nlay - 1; l >= 0; --l) {
+        double e, f;
+        lw_layer(od_col[(int64_t)l * ng + g], e, f);
+        const double b_t = planck_interp(t_hl[l], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+        f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
+        p.flux_up[hl0 + (int64_t)l * ng] = f_up;
+        if (p.bb_flux_up) atomicAdd(&s_bb[(nlay + 1) + l], f_up);
+        b_bot = b_t;
+      }
+    } else if (p.flux_dn) {
+      // direct beam at mu0 = 0.5 through gas + Rayleigh (run_ckd.cpp:360-365)
+      const double mu0 = 0.5;
+      const double minus_sec = -1.0 / mu0;
+      double f = mu0 * (p.tsi_scaling * p.solar_irradiance[g]);
+      p.flux_dn[hl0] = f;
+      if (p.bb_flux_dn) atomicAdd(&s_bb[0], f);
+      const double sig = p.rayleigh[g];
+      for (int l = 0; l < nlay; ++l) {
+        const double ray = ((p_hl[l + 1] - p_hl[l]) * (1.0 / (ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR))) * sig;
+        f = f * exp(minus_sec * (od_col[(int64_t)l * ng + g] + ray));
+        p.flux_dn[hl0 + (int64_t)(l + 1) * ng] = f;
+        if (p.bb_flux_dn) atomicAdd(&s_bb[l + 1], f);
+      }
+    }
+  }
+  (void)s_bb;
+}
+
+}  // namespace ecckd
+
+using namespace ecckd;
+
+static int upload_new(const double* h, size_t n, double** d) {
+  *d = nullptr;
+  if (!h || n == 0) return ECCKD_OK;
+  ECCKD_CUDA_OK(cudaMalloc(d, n * sizeof(double)));
+  ECCKD_CUDA_OK(cudaMemcpy(*d, h, n * sizeof(double), cudaMemcpyHostToDevice));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ckd_model_destroy(ecckd_ckd_model* m) {
+  if (!m) return ECCKD_OK;
+  if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
+  for (double* p : m->d_molar_abs) cudaFree(p);
+  for (double* p : m->d_vmr_lut) cudaFree(p);
+  cudaFree(m->d_log_pressure);
+  cudaFree(m->d_temperature);
+  cudaFree(m->d_temperature_planck);
+  cudaFree(m->d_planck_lut);
+  cudaFree(m->d_solar_irradiance);
+  cudaFree(m->d_rayleigh);
+  cudaFree(m->d_gasdesc);
+  delete m;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ckd_model_create(ecckd_ctx* ctx, int ngas, const ecckd_gas_table* gases, int nt, int np, int ng,
+                                     const double* log_pressure, const double* temperature, int nlut,
+                                     const double* temperature_planck, const double* planck_lut,
+                                     const double* solar_irradiance, const double* rayleigh_molar_scat,
+                                     ecckd_ckd_model** out) {
+  ECCKD_REQUIRE(ctx && gases && log_pressure && temperature && out, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_model_create: NULL argument");
+  ECCKD_REQUIRE(ngas > 0 && nt >= 2 && np >= 2 && ng > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_model_create: need ngas>0, nt>=2, np>=2, ng>0");
+  const bool is_sw = solar_irradiance != nullptr;
+  ECCKD_REQUIRE(is_sw || (planck_lut && temperature_planck && nlut >= 2), ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_model_create: longwave model needs a Planck look-up table");
+  ECCKD_REQUIRE(!is_sw || rayleigh_molar_scat, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_model_create: shortwave model needs rayleigh_molar_scat");
+  *out = nullptr;
+  ecckd_ckd_model* m = new ecckd_ckd_model();
+  m->ctx = ctx;
+  m->ngas = ngas;
+  m->nt = nt;
+  m->np = np;
+  m->ng = ng;
+  m->nlut = nlut;
+  m->is_sw = is_sw;
+  int rc = ECCKD_OK;
+  for (int i = 0; i < ngas && rc == ECCKD_OK; ++i) {
+    const ecckd_gas_table& g = gases[i];
+    m->conc_dependence.push_back(g.conc_dependence);
+    m->nconc.push_back(g.nconc);
+    m->reference_vmr.push_back(g.reference_vmr);
+    double *d_k = nullptr, *d_v = nullptr;
+    size_t n = (size_t)nt * np * ng;
+    double lv0 = 0.0, dlc = 1.0;
+    if (g.conc_dependence == ECCKD_CONC_LUT) {
+      if (g.nconc < 2 || !g.vmr_lut) {
+        set_error("gas %d: a LUT gas needs nconc >= 2 mole fractions", i);
+        rc = ECCKD_PARAMETER_ERROR;
+        break;
+      }
+      n *= (size_t)g.nconc;
+      rc = upload_new(g.vmr_lut, g.nconc, &d_v);
+      lv0 = log(g.vmr_lut[0]);                  // ckd_model.cpp:1005
+      dlc = log(g.vmr_lut[1] / g.vmr_lut[0]);   // ckd_model.cpp:1004
+    } else if (g.conc_dependence < 0 || g.conc_dependence > 3) {
+      set_error("gas %d: conc_dependence %d not understood", i, g.conc_dependence);
+      rc = ECCKD_PARAMETER_ERROR;
+      break;
+    }
+    if (rc == ECCKD_OK) rc = upload_new(g.molar_abs, n, &d_k);
+    m->d_molar_abs.push_back(d_k);
+    m->d_vmr_lut.push_back(d_v);
+    m->log_vmr0.push_back(lv0);
+    m->d_log_c.push_back(dlc);
+  }
+  if (rc == ECCKD_OK) rc = upload_new(log_pressure, np, &m->d_log_pressure);
+  if (rc == ECCKD_OK) rc = upload_new(temperature, (size_t)nt * np, &m->d_temperature);
+  if (rc == ECCKD_OK && !is_sw) rc = upload_new(temperature_planck, nlut, &m->d_temperature_planck);
+  if (rc == ECCKD_OK && !is_sw) rc = upload_new(planck_lut, (size_t)nlut * ng, &m->d_planck_lut);
+  if (rc == ECCKD_OK && is_sw) rc = upload_new(solar_irradiance, ng, &m->d_solar_irradiance);
+  if (rc == ECCKD_OK && is_sw) rc = upload_new(rayleigh_molar_scat, ng, &m->d_rayleigh);
+  if (rc == ECCKD_OK) {
+    cudaError_t e = cudaMalloc(&m->d_gasdesc, (size_t)ngas * sizeof(GasDev));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
+      rc = ECCKD_UNEXPECTED_EXCEPTION;
+    }
+  }
+  if (rc != ECCKD_OK) {
+    ecckd_ckd_model_destroy(m);
+    return rc;
+  }
+  m->log_p_0 = log_pressure[0];
+  m->d_log_p = log_pressure[1] - log_pressure[0];
+  m->d_t = temperature[(size_t)1 * np + 0] - temperature[0];
+  if (!is_sw) {
+    m->planck_t0 = temperature_planck[0];
+    m->planck_dt = temperature_planck[1] - temperature_planck[0];
+  } else {
+    double s = 0.0;
+    for (int g = 0; g < ng; ++g) s += solar_irradiance[g];
+    m->solar_sum = s;
+  }
+  *out = m;
+  return ECCKD_OK;
+}
+
+static GasDev make_gasdev(const ecckd_ckd_model* m, int igas, const double* d_vmr) {
+  GasDev g;
+  g.molar_abs = m->d_molar_abs[igas];
+  g.vmr = d_vmr;
+  g.reference_vmr = m->reference_vmr[igas];
+  g.log_vmr0 = m->log_vmr0[igas];
+  g.d_log_c = m->d_log_c[igas];
+  g.conc_dependence = m->conc_dependence[igas];
+  g.nconc = m->nconc[igas];
+  return g;
+}
+
+static int check_vmr(const ecckd_ckd_model* m, int igas, const double* d_vmr) {
+  // ckd_model.cpp:1011-1014, 1048-1051: THROW(1)
+  if (m->conc_dependence[igas] != ECCKD_CONC_NONE && d_vmr == nullptr) {
+    set_error("Concentration of gas %d not provided", igas);
+    return 1;
+  }
+  return ECCKD_OK;
+}
+
+static dim3 g_block(int ng) { return dim3(ng <= 32 ? 32 : (ng <= 64 ? 64 : 128), ng <= 32 ? 8 : (ng <= 64 ? 4 : 2)); }
+
+ECCKD_API int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int igas, int ncol, int nlay,
+                                               const double* d_pressure_hl, const double* d_temperature_fl,
+                                               const double* d_vmr_fl, double* d_od, int accumulate) {
+  ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_temperature_fl && d_od, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_calc_optical_depth: NULL argument");
+  ECCKD_REQUIRE(igas >= 0 && igas < m->ngas && ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_calc_optical_depth: bad gas index or dimensions");
+  ECCKD_TRY(check_vmr(m, igas, d_vmr_fl));
+  const dim3 block = g_block(m->ng);
+  const int64_t ncl = (int64_t)ncol * nlay;
+  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((ncl + block.y - 1) / block.y));
+  ckd_od_kernel<<<grid, block, 0, ctx->stream>>>(make_gasdev(m, igas, d_vmr_fl), m->nt, m->np, m->ng, m->log_p_0,
+                                                 m->d_log_p, m->d_t, m->d_temperature, ncol, nlay, d_pressure_hl,
+                                                 d_temperature_fl, d_od, accumulate);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int64_t n,
+                                                 const double* d_temperature, double* d_planck) {
+  ECCKD_REQUIRE(ctx && m && d_temperature && d_planck && n > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_calc_planck_function: bad argument");
+  ECCKD_REQUIRE(!m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_planck_function: shortwave model has no Planck table");
+  const dim3 block = g_block(m->ng);
+  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((n + block.y - 1) / block.y));
+  ckd_planck_kernel<<<grid, block, 0, ctx->stream>>>(m->nlut, m->ng, m->planck_t0, m->planck_dt, m->d_planck_lut, n,
+                                                     d_temperature, d_planck);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ckd_calc_rayleigh_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int ncol, int nlay,
+                                                        const double* d_pressure_hl, double* d_od) {
+  ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_od && ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_ckd_calc_rayleigh_optical_depth: bad argument");
+  ECCKD_REQUIRE(m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_rayleigh_optical_depth: longwave model");
+  const dim3 block = g_block(m->ng);
+  const int64_t ncl = (int64_t)ncol * nlay;
+  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((ncl + block.y - 1) / block.y));
+  rayleigh_od_kernel<<<grid, block, 0, ctx->stream>>>(ncol, nlay, m->ng, d_pressure_hl, m->d_rayleigh, d_od);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck,
+                                              const double* d_od, const double* d_surf_emissivity,
+                                              const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+  ECCKD_REQUIRE(ctx && d_planck && d_od && d_surf_emissivity && d_surf_planck && d_flux_dn && d_flux_up,
+                ECCKD_PARAMETER_ERROR, "ecckd_radiative_transfer_lw: NULL argument");
+  ECCKD_REQUIRE(ncol > 0 && ncol <= 65535 && nlay > 0 && n > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_radiative_transfer_lw: bad dimensions");
+  const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
+  rt_lw_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol), bs, 0, ctx->stream>>>(
+      ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck, d_flux_dn, d_flux_up);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* h_cos_sza,
+                                              const double* d_ssi, const double* d_od, const double* d_albedo,
+                                              double* d_flux_dn, double* d_flux_up) {
+  ECCKD_REQUIRE(ctx && h_cos_sza && d_ssi && d_od && d_flux_dn, ECCKD_PARAMETER_ERROR,
+                "ecckd_radiative_transfer_sw: NULL argument");
+  ECCKD_REQUIRE((d_albedo == nullptr) == (d_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                "ecckd_radiative_transfer_sw: albedo and flux_up must both be given or both be NULL");
+  ECCKD_REQUIRE(ncol > 0 && ncol <= 65535 && nlay > 0 && n > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_radiative_transfer_sw: bad dimensions");
+  void* d_mu = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, (size_t)ncol * sizeof(double), &d_mu));
+  ECCKD_TRY(upload_small(ctx, d_mu, h_cos_sza, (size_t)ncol * sizeof(double)));
+  const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
+  rt_sw_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol), bs, 0, ctx->stream>>>(
+      ncol, nlay, n, static_cast<const double*>(d_mu), d_ssi, d_od, d_albedo, d_flux_dn, d_flux_up);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_heating_rate_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_pressure_hl,
+                                     const double* d_flux_dn, const double* d_flux_up, double* d_hr) {
+  ECCKD_REQUIRE(ctx && d_pressure_hl && d_flux_dn && d_hr, ECCKD_PARAMETER_ERROR, "ecckd_heating_rate: NULL argument");
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && (int64_t)ncol * nlay <= 65535, ECCKD_PARAMETER_ERROR,
+                "ecckd_heating_rate: bad dimensions (ncol*nlay must be <= 65535)");
+  const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
+  heating_rate_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol * nlay), bs, 0, ctx->stream>>>(
+      ncol, nlay, n, d_pressure_hl, d_flux_dn, d_flux_up, d_hr);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* const* h_d_vmr_fl, double tsi,
+                                int ncol, int nlay, const double* d_pressure_hl, const double* d_temperature_hl,
+                                double* d_od, double* d_planck_hl, double* d_planck_surf, double* d_flux_dn,
+                                double* d_flux_up, double* d_bb_flux_dn, double* d_bb_flux_up) {
+  ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_temperature_hl, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: NULL argument");
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: bad dimensions");
+  std::vector<GasDev> gd(m->ngas);
+  for (int i = 0; i < m->ngas; ++i) {
+    const double* v = h_d_vmr_fl ? h_d_vmr_fl[i] : nullptr;
+    ECCKD_TRY(check_vmr(m, i, v));
+    gd[i] = make_gasdev(m, i, v);
+  }
+  ECCKD_TRY(upload_small(ctx, m->d_gasdesc, gd.data(), gd.size() * sizeof(GasDev)));
+  RunCkdParams p;
+  p.gases = static_cast<const GasDev*>(m->d_gasdesc);
+  p.ngas = m->ngas;
+  p.nt = m->nt;
+  p.np = m->np;
+  p.ng = m->ng;
+  p.nlut = m->nlut;
+  p.is_sw = m->is_sw ? 1 : 0;
+  p.log_p_0 = m->log_p_0;
+  p.d_log_p = m->d_log_p;
+  p.d_t = m->d_t;
+  p.planck_t0 = m->planck_t0;
+  p.planck_dt = m->planck_dt;
+  p.tsi_scaling = m->is_sw ? tsi / m->solar_sum : 0.0;  // run_ckd.cpp:98
+  p.temperature = m->d_temperature;
+  p.planck_lut = m->d_planck_lut;
+  p.solar_irradiance = m->d_solar_irradiance;
+  p.rayleigh = m->d_rayleigh;
+  p.ncol = ncol;
+  p.nlay = nlay;
+  p.pressure_hl = d_pressure_hl;
+  p.temperature_hl = d_temperature_hl;
+  p.od = d_od;
+  p.planck_hl = d_planck_hl;
+  p.planck_surf = d_planck_surf;
+  p.flux_dn = d_flux_dn;
+  p.flux_up = m->is_sw ? nullptr : d_flux_up;
+  p.bb_flux_dn = nullptr;  // broadband sums are done by sum_g_kernel below (fixed order)
+  p.bb_flux_up = nullptr;
+  p.scratch_od = nullptr;
+  if (!d_od) {
+    void* s = nullptr;
+    ECCKD_TRY(ws_reserve(ctx, 1, (size_t)ncol * nlay * m->ng * sizeof(double), &s));
+    p.scratch_od = static_cast<double*>(s);
+  }
+  const int threads = m->ng <= 32 ? 32 : (m->ng <= 64 ? 64 : 128);
+  const size_t smem = (size_t)nlay * sizeof(Interp) + (size_t)nlay * m->ngas * sizeof(double) +
+                      (size_t)2 * (nlay + 1) * sizeof(double);
+  ECCKD_REQUIRE(smem <= 48 * 1024, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: nlay*ngas too large for shared memory");
+  run_ckd_kernel<<<ncol, threads, smem, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  const int64_t nrows = (int64_t)ncol * (nlay + 1);
+  if (d_flux_dn && d_bb_flux_dn) {
+    sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, m->ng, d_flux_dn, d_bb_flux_dn);
+    ECCKD_LAUNCH_CHECK(ctx);
+  }
+  if (!m->is_sw && d_flux_up && d_bb_flux_up) {
+    sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, m->ng, d_flux_up, d_bb_flux_up);
+    ECCKD_LAUNCH_CHECK(ctx);
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* const* vmr_fl, double tsi, int ncol,
+                            int nlay, const double* pressure_hl, const double* temperature_hl, double* od,
+                            double* planck_hl, double* planck_surf, double* flux_dn, double* flux_up,
+                            double* bb_flux_dn, double* bb_flux_up) {
+  ECCKD_REQUIRE(ctx && m && pressure_hl && temperature_hl, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: NULL argument");
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: bad dimensions");
+  const int ng = m->ng, ngas = m->ngas;
+  const size_t n_hl = (size_t)ncol * (nlay + 1), n_fl = (size_t)ncol * nlay;
+  // one device arena: inputs then outputs
+  size_t n_in = 2 * n_hl + (size_t)ngas * n_fl;
+  size_t n_out = n_fl * ng + n_hl * ng * 3 + (size_t)ncol * ng + 2 * n_hl;
+  double* arena = nullptr;
+  ECCKD_CUDA_OK(cudaMalloc(&arena, (n_in + n_out) * sizeof(double)));
+  cudaStream_t st = ctx->stream;
+  double* d_p = arena;
+  double* d_t = d_p + n_hl;
+  double* d_v = d_t + n_hl;
+  double* d_od = d_v + (size_t)ngas * n_fl;
+  double* d_plh = d_od + n_fl * ng;
+  double* d_dn = d_plh + n_hl * ng;
+  double* d_up = d_dn + n_hl * ng;
+  double* d_pls = d_up + n_hl * ng;
+  double* d_bdn = d_pls + (size_t)ncol * ng;
+  double* d_bup = d_bdn + n_hl;
+  int rc = ECCKD_OK;
+  cudaError_t e = cudaMemcpyAsync(d_p, pressure_hl, n_hl * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, temperature_hl, n_hl * sizeof(double), cudaMemcpyHostToDevice, st);
+  std::vector<const double*> dv(ngas, nullptr);
+  for (int i = 0; i < ngas && e == cudaSuccess; ++i) {
+    if (vmr_fl && vmr_fl[i]) {
+      dv[i] = d_v + (size_t)i * n_fl;
+      e = cudaMemcpyAsync(d_v + (size_t)i * n_fl, vmr_fl[i], n_fl * sizeof(double), cudaMemcpyHostToDevice, st);
+    }
+  }
+  const bool want_flux = flux_dn != nullptr && (m->is_sw || flux_up != nullptr);
+  if (e == cudaSuccess) {
+    rc = ecckd_run_ckd_dev(ctx, m, dv.data(), tsi, ncol, nlay, d_p, d_t, d_od, m->is_sw ? nullptr : d_plh,
+                           m->is_sw ? nullptr : d_pls, want_flux ? d_dn : nullptr,
+                           (want_flux && !m->is_sw) ? d_up : nullptr, (want_flux && bb_flux_dn) ? d_bdn : nullptr,
+                           (want_flux && bb_flux_up && !m->is_sw) ? d_bup : nullptr);
+  }
+  auto back = [&](double* h, const double* d, size_t n) {
+    if (h && e == cudaSuccess && rc == ECCKD_OK) e = cudaMemcpyAsync(h, d, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+  };
+  back(od, d_od, n_fl * ng);
+  if (!m->is_sw) {
+    back(planck_hl, d_plh, n_hl * ng);
+    back(planck_surf, d_pls, (size_t)ncol * ng);
+  }
+  if (want_flux) {
+    back(flux_dn, d_dn, n_hl * ng);
+    if (!m->is_sw) back(flux_up, d_up, n_hl * ng);
+    back(bb_flux_dn, d_bdn, n_hl);
+    if (!m->is_sw) back(bb_flux_up, d_bup, n_hl);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(st);
+  cudaFree(arena);
+  if (rc != ECCKD_OK) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ecckd_run_ckd: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  return ECCKD_OK;
+}

@@ -1,0 +1,588 @@
+// ranking.cu - g-point ranking and assignment (reference: reorder_spectrum.cpp
+// :111-300, single_gas_data.h:56-62, single_gas_data.cpp:23-124,
+// find_g_points.cpp:1455-1481).
+//
+//  * sort keys: one thread per wavenumber walks the layers (coalesced across
+//    wavenumbers), upward fluxes parked in shared memory [level][thread].
+//  * rank: std::stable_sort(key[i] < key[j]) per band == a stable LSD radix
+//    sort of an order-preserving 64-bit image of the key (with -0.0 folded onto
+//    +0.0, which the comparator treats as equal).  8-bit digits, per-tile
+//    histograms, one exclusive scan, stable in-tile multi-split with
+//    __match_any_sync.  Passes whose digit is constant over the range are skipped.
+//  * g-point assignment: integer per-wavenumber loops, tables in shared memory.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ecckd {
+
+__device__ __forceinline__ double planck_elem_r(double t, double nu, double dnu) {
+  // planck_function.cpp:29-33,47-53
+  const double h = 6.62606896e-34;
+  const double c = 2.99792458e8;
+  const double k = 1.3806504e-23;
+  const double inv_cm_2_Hz = 100.0 * c;
+  const double pi = 3.14159265358979323846;
+  const double freq = nu * inv_cm_2_Hz;
+  const double prefactor = (dnu * 2.0 * h * inv_cm_2_Hz * pi / (c * c)) * (freq * freq * freq);
+  return prefactor / (exp((h / k) * (freq / t)) - 1.0);
+}
+
+__device__ __forceinline__ void lw_layer_r(double tau, double& e, double& f) {
+  e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+  f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+}
+
+// per-layer constants uploaded by the host: [0..nlay] T_hl, then conv[nlay],
+// dh[nlay], dhh[nlay]  (reorder_spectrum.cpp:121-124, 178-183; heating_rate.h:38)
+__global__ void sort_key_lw_kernel(int nlay, int64_t nwav, const double* __restrict__ lay, const double* __restrict__ wn,
+                                   const double* __restrict__ dwn, const double* __restrict__ od, int64_t od_stride,
+                                   double thr, double* __restrict__ key, double* __restrict__ column_od) {
+  extern __shared__ double s_up[];  // [nlay+1][blockDim.x]
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  const int bs = blockDim.x, tx = threadIdx.x;
+  const double* t_hl = lay;
+  const double* conv = lay + (nlay + 1);
+  const double* dh = conv + nlay;
+  const double* dhh = dh + nlay;
+  const double nu = wn[w], dnu = dwn[w];
+  // upward sweep first: with surface emissivity 1 (reorder_spectrum.cpp:138-139)
+  // flux_up(nlay) = surf_planck*1 + (1-1)*flux_dn(nlay), independent of flux_dn
+  double b_bot = planck_elem_r(t_hl[nlay], nu, dnu);
+  double f_up = b_bot * 1.0;
+  s_up[nlay * bs + tx] = f_up;
+  for (int l = nlay - 1; l >= 0; --l) {
+    double e, f;
+    lw_layer_r(od[(int64_t)l * od_stride + w], e, f);
+    const double b_t = planck_elem_r(t_hl[l], nu, dnu);
+    f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
+    s_up[l * bs + tx] = f_up;
+    b_bot = b_t;
+  }
+  // downward sweep, heating rate and the two weighted sums in ascending layer order
+  double f_dn = 0.0, col = 0.0, num = 0.0, den = 0.0;
+  double b_top = b_bot;  // planck at level 0
+  for (int l = 0; l < nlay; ++l) {
+    const double tau = od[(int64_t)l * od_stride + w];
+    col += tau;
+    double e, f;
+    lw_layer_r(tau, e, f);
+    const double b_b = planck_elem_r(t_hl[l + 1], nu, dnu);
+    const double f_next = f_dn * (1.0 - e) + b_top * (e - f) + b_b * f;
+    double hr = conv[l] * (f_next - f_dn - s_up[(l + 1) * bs + tx] + s_up[l * bs + tx]);
+    if (hr > 0.0) hr = 0.0;  // reorder_spectrum.cpp:175
+    num += hr * dhh[l];
+    den += hr * dh[l];
+    f_dn = f_next;
+    b_top = b_b;
+  }
+  double k = num / den;
+  if (thr > 0.0 && col < thr) k = -thr + col;  // reorder_spectrum.cpp:187-190
+  key[w] = k;
+  if (column_od) column_od[w] = col;
+}
+
+// reorder_spectrum.cpp:197-228; lay = pseudo_height_hl[nlay+1]
+__global__ void sort_key_sw_kernel(int nlay, int64_t nwav, const double* __restrict__ h_hl, const double* __restrict__ od,
+                                   int64_t od_stride, double thr, double* __restrict__ key,
+                                   double* __restrict__ column_od, int* __restrict__ err) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  double col = 0.0;
+  for (int l = 0; l < nlay; ++l) col += od[(int64_t)l * od_stride + w];
+  if (column_od) column_od[w] = col;
+  double k;
+  if (col <= thr) {
+    k = col - thr;
+  } else {
+    double cum = 0.0;
+    k = 0.0;
+    for (int l = 0; l < nlay; ++l) {
+      const double tau = od[(int64_t)l * od_stride + w];
+      const double next = cum + tau;
+      if (next >= thr) {
+        k = ((thr - cum) * h_hl[l + 1] + (next - thr) * h_hl[l]) / fmax(1.0e-12, tau);
+        if (k > 30.0) *err = 1;  // the reference throws here (:214-216)
+        break;
+      }
+      cum = next;
+    }
+  }
+  key[w] = k;
+}
+
+// ------------------------------------------------------------------ bands
+__global__ void band_kernel(int64_t nwav, const double* __restrict__ wn, int nband, const double* __restrict__ b1,
+                            const double* __restrict__ b2, int32_t* __restrict__ iband, int* __restrict__ first,
+                            int* __restrict__ last, int32_t* __restrict__ g_index) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  const double nu = wn[w];
+  int ib = -1;
+  for (int j = 0; j < nband; ++j) {
+    const bool in = (j < nband - 1) ? (nu >= b1[j] && nu < b2[j]) : (nu >= b1[j] && nu <= b2[j]);
+    if (in) {
+      ib = j;  // later bands overwrite (iband(index) = jband, reorder_spectrum.cpp:290)
+      atomicMin(&first[j], (int)w);
+      atomicMax(&last[j], (int)w);
+    }
+  }
+  if (iband) iband[w] = ib;
+  g_index[w] = (int32_t)w;
+}
+
+// order-preserving image of a double under `a < b`, with -0.0 == +0.0
+__device__ __forceinline__ unsigned long long key_image(double x) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  if ((b << 1) == 0ull) b = 0ull;  // fold -0.0 onto +0.0
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void gather_keys_kernel(int64_t n, const int32_t* __restrict__ g_index, const double* __restrict__ key,
+                                   unsigned long long* __restrict__ k_out, uint32_t* __restrict__ v_out,
+                                   unsigned long long* __restrict__ or_bits, unsigned long long* __restrict__ and_bits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long img = 0ull, img_and = ~0ull;
+  if (i < n) {
+    const int32_t idx = g_index[i];
+    img = key_image(key[idx]);
+    img_and = img;
+    k_out[i] = img;
+    v_out[i] = (uint32_t)idx;
+  }
+  // which bits vary over the range: OR and AND reductions
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    img |= __shfl_xor_sync(0xffffffffu, img, o);
+    img_and &= __shfl_xor_sync(0xffffffffu, img_and, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(or_bits, img);
+    atomicAnd(and_bits, img_and);
+  }
+}
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ROUNDS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+
+// per-tile digit histogram -> hist[digit][tile]
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(int64_t n, const unsigned long long* __restrict__ keys,
+                                                                int shift, int ntiles, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_h[256];
+  s_h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    const int64_t i = base + r * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_h[threadIdx.x];
+}
+
+// exclusive scan of hist (256*ntiles entries, digit-major) by a single block
+__global__ void __launch_bounds__(1024) radix_scan_kernel(int64_t total, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < total; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = (i < total) ? hist[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t t = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;  // inclusive over warps
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    const uint32_t warp_off = (warp == 0) ? 0u : s_warp[warp - 1];
+    if (i < total) hist[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + x;
+    __syncthreads();
+  }
+}
+
+// stable scatter of one tile
+__global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(int64_t n, const unsigned long long* __restrict__ keys,
+                                                                   const uint32_t* __restrict__ vals, int shift,
+                                                                   int ntiles, const uint32_t* __restrict__ offs,
+                                                                   unsigned long long* __restrict__ keys_out,
+                                                                   uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t s_run[256];        // next free global position per digit
+  __shared__ uint32_t s_wcnt[8][256];    // per-warp digit counts of the current round
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  s_run[threadIdx.x] = offs[(size_t)threadIdx.x * ntiles + blockIdx.x];
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  for (int r = 0; r < RS_ROUNDS; ++r) {
+    for (int j = threadIdx.x; j < 8 * 256; j += RS_THREADS) (&s_wcnt[0][0])[j] = 0;
+    __syncthreads();
+    const int64_t i = base + r * RS_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    unsigned long long k = 0;
+    uint32_t v = 0;
+    // out-of-range lanes get digit 256 (their own match group), never counted
+    int digit = 256;
+    if (valid) {
+      k = keys[i];
+      v = vals[i];
+      digit = (int)((k >> shift) & 0xFF);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0) s_wcnt[warp][digit] = (uint32_t)__popc(peers);
+    __syncthreads();
+    {  // digit = threadIdx.x: exclusive prefix over warps, advance the running offset
+      uint32_t run = s_run[threadIdx.x];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const uint32_t c = s_wcnt[w][threadIdx.x];
+        s_wcnt[w][threadIdx.x] = run;
+        run += c;
+      }
+      s_run[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (valid) {
+      const uint32_t pos = s_wcnt[warp][digit] + (uint32_t)rank_in_warp;
+      keys_out[pos] = k;
+      vals_out[pos] = v;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void write_back_kernel(int64_t n, const uint32_t* __restrict__ vals, int32_t* __restrict__ g_index) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) g_index[i] = (int32_t)vals[i];
+}
+
+__global__ void rank_from_order_kernel(int64_t nwav, const int32_t* __restrict__ g_index, int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nwav) rank[g_index[i]] = (int32_t)i;  // reorder_spectrum.cpp:299-300
+}
+
+// ------------------------------------------------------------------ g points
+__global__ void store_g_points_kernel(int64_t nwav, const int32_t* __restrict__ rank, int ng,
+                                      const int32_t* __restrict__ r12, int32_t* __restrict__ g_point) {
+  extern __shared__ int32_t s_r[];  // rank1[ng], rank2[ng]
+  for (int j = threadIdx.x; j < 2 * ng; j += blockDim.x) s_r[j] = r12[j];
+  __syncthreads();
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  const int32_t r = rank[w];
+  int g = -1;
+  for (int ig = 0; ig < ng; ++ig) {
+    if (r >= s_r[ig] && r <= s_r[ng + ig]) g = ig;  // later ig overwrites (single_gas_data.h:59-61)
+  }
+  g_point[w] = g;
+}
+
+__global__ void assign_g_points_kernel(int ngas, int64_t nwav, const int32_t* __restrict__ gas_g, int ng, int cap,
+                                       const int32_t* __restrict__ gmm, int32_t* __restrict__ g_point,
+                                       unsigned long long* __restrict__ n_unassigned) {
+  extern __shared__ int32_t s_t[];  // g_min[ngas][ng], g_max[ngas][ng]
+  for (int j = threadIdx.x; j < 2 * ngas * ng; j += blockDim.x) {
+    const int which = j / (ngas * ng), rem = j - which * ngas * ng;
+    const int igas = rem / ng, ig = rem - igas * ng;
+    s_t[j] = gmm[(size_t)which * ngas * cap + (size_t)igas * cap + ig];
+  }
+  __syncthreads();
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  int g = -1;
+  for (int ig = 0; ig < ng; ++ig) {
+    bool found = true;
+    for (int igas = 0; igas < ngas; ++igas) {
+      const int32_t v = gas_g[(size_t)igas * nwav + w];
+      if (v < s_t[igas * ng + ig] || v > s_t[ngas * ng + igas * ng + ig]) found = false;
+    }
+    if (found) g = ig;  // ascending ig, later overwrites (find_g_points.cpp:1463-1470)
+  }
+  g_point[w] = g;
+  if (g < 0) atomicAdd(n_unassigned, 1ull);
+}
+
+// Stable LSD radix sort of n (key image, value) pairs in place in (k0, v0),
+// using (k1, v1) as the ping-pong buffers; `vary` = bits that differ somewhere.
+static int radix_sort_pairs(ecckd_ctx* ctx, int64_t n, unsigned long long* k0, uint32_t* v0, unsigned long long* k1,
+                            uint32_t* v1, uint32_t* hist, unsigned long long vary, uint32_t** v_result) {
+  const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  unsigned long long* kin = k0;
+  unsigned long long* kout = k1;
+  uint32_t* vin = v0;
+  uint32_t* vout = v1;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = pass * 8;
+    if (((vary >> shift) & 0xFFull) == 0ull) continue;  // digit constant over the range: identity pass
+    radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(n, kin, shift, ntiles, hist);
+    ECCKD_LAUNCH_CHECK(ctx);
+    radix_scan_kernel<<<1, 1024, 0, ctx->stream>>>((int64_t)256 * ntiles, hist);
+    ECCKD_LAUNCH_CHECK(ctx);
+    radix_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(n, kin, vin, shift, ntiles, hist, kout, vout);
+    ECCKD_LAUNCH_CHECK(ctx);
+    std::swap(kin, kout);
+    std::swap(vin, vout);
+  }
+  *v_result = vin;
+  return ECCKD_OK;
+}
+
+}  // namespace ecckd
+
+using namespace ecckd;
+
+ECCKD_API int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
+                                    const double* d_wn, const double* d_dwn, const double* d_od, int64_t od_stride,
+                                    double thr, double* d_key, double* d_column_od) {
+  ECCKD_REQUIRE(ctx && h_pressure_hl && d_wn && d_dwn && d_od && d_key, ECCKD_PARAMETER_ERROR,
+                "ecckd_sort_key_lw: NULL argument");
+  ECCKD_REQUIRE(nlay > 0 && nlay <= 400 && nwav > 0 && od_stride >= nwav, ECCKD_PARAMETER_ERROR,
+                "ecckd_sort_key_lw: bad dimensions");
+  // per-layer constants (reorder_spectrum.cpp:119-124,178-183; heating_rate.h:38)
+  std::vector<double> lay((size_t)(nlay + 1) + 3 * (size_t)nlay);
+  const double x0 = log(1.0), x1 = log(100000.0), y0 = 273.15 - 100.0, y1 = 273.15 + 15.0;
+  for (int i = 0; i <= nlay; ++i) {
+    const double x = log(h_pressure_hl[i]);
+    lay[i] = (x <= x0) ? y0 : (x >= x1) ? y1 : y0 + (y1 - y0) * (x - x0) / (x1 - x0);
+  }
+  double* conv = lay.data() + (nlay + 1);
+  double* dh = conv + nlay;
+  double* dhh = dh + nlay;
+  for (int i = 0; i < nlay; ++i) {
+    conv[i] = -(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (h_pressure_hl[i + 1] - h_pressure_hl[i]);
+    const double ph = log(h_pressure_hl[nlay]) - 0.5 * (log(h_pressure_hl[i]) + log(h_pressure_hl[i + 1]));
+    dh[i] = log(h_pressure_hl[i + 1]) - log(h_pressure_hl[i]);
+    dhh[i] = dh[i] * ph;
+  }
+  void* d_lay = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, lay.size() * sizeof(double), &d_lay));
+  ECCKD_TRY(upload_small(ctx, d_lay, lay.data(), lay.size() * sizeof(double)));
+  const int bs = 128;
+  const size_t smem = (size_t)(nlay + 1) * bs * sizeof(double);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(sort_key_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sort_key_lw_kernel<<<(unsigned)((nwav + bs - 1) / bs), bs, smem, ctx->stream>>>(
+      nlay, nwav, static_cast<const double*>(d_lay), d_wn, d_dwn, d_od, od_stride, thr, d_key, d_column_od);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_sort_key_sw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
+                                    const double* d_od, int64_t od_stride, double thr, double* d_key,
+                                    double* d_column_od) {
+  ECCKD_REQUIRE(ctx && h_pressure_hl && d_od && d_key, ECCKD_PARAMETER_ERROR, "ecckd_sort_key_sw: NULL argument");
+  ECCKD_REQUIRE(nlay > 0 && nwav > 0 && od_stride >= nwav, ECCKD_PARAMETER_ERROR, "ecckd_sort_key_sw: bad dimensions");
+  std::vector<double> h_hl(nlay + 1);
+  for (int i = 0; i <= nlay; ++i) h_hl[i] = log(h_pressure_hl[nlay]) - log(h_pressure_hl[i]);
+  void* d_lay = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, (size_t)(nlay + 2) * sizeof(double), &d_lay));
+  ECCKD_TRY(upload_small(ctx, d_lay, h_hl.data(), h_hl.size() * sizeof(double)));
+  int* d_err = reinterpret_cast<int*>(static_cast<double*>(d_lay) + (nlay + 1));
+  ECCKD_CUDA_OK(cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream));
+  sort_key_sw_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(
+      nlay, nwav, static_cast<const double*>(d_lay), d_od, od_stride, thr, d_key, d_column_od, d_err);
+  ECCKD_LAUNCH_CHECK(ctx);
+  int err = 0;
+  ECCKD_CUDA_OK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (err) {
+    set_error("sorting variable exceeds 30 (reorder_spectrum.cpp:214-216)");
+    return ECCKD_PROCESSING_ERROR;
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wn, const double* d_key, int nband,
+                                   const double* h_b1, const double* h_b2, int32_t* d_iband, int32_t* d_rank,
+                                   int32_t* d_ordered_index) {
+  ECCKD_REQUIRE(ctx && d_wn && d_key && h_b1 && h_b2, ECCKD_PARAMETER_ERROR, "ecckd_rank_bands: NULL argument");
+  ECCKD_REQUIRE(nwav > 0 && nwav < (int64_t)1 << 31, ECCKD_PARAMETER_ERROR, "ecckd_rank_bands: nwav out of range");
+  // reorder_spectrum.cpp:245-248
+  ECCKD_REQUIRE(nband > 0, ECCKD_PARAMETER_ERROR,
+                "Failure to interpret wavenumber1 and wavenumber2 as a list of band boundaries");
+  // scratch layout (slot 1): k0 | k1 | v0 | v1 | g_index | hist | band meta
+  const int ntiles_max = (int)((nwav + RS_TILE - 1) / RS_TILE);
+  const size_t kbytes = (size_t)nwav * sizeof(unsigned long long);
+  const size_t vbytes = ((size_t)nwav * sizeof(uint32_t) + 255) & ~size_t(255);
+  const size_t hbytes = ((size_t)256 * ntiles_max * sizeof(uint32_t) + 255) & ~size_t(255);
+  const size_t mbytes = ((size_t)nband * (2 * sizeof(double) + 2 * sizeof(int)) + 2 * sizeof(unsigned long long) + 255) &
+                        ~size_t(255);
+  void* base = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, 2 * kbytes + 3 * vbytes + hbytes + mbytes + 1024, &base));
+  char* pch = static_cast<char*>(base);
+  unsigned long long* k0 = reinterpret_cast<unsigned long long*>(pch);
+  unsigned long long* k1 = reinterpret_cast<unsigned long long*>(pch + kbytes);
+  pch += 2 * kbytes;
+  uint32_t* v0 = reinterpret_cast<uint32_t*>(pch);
+  uint32_t* v1 = reinterpret_cast<uint32_t*>(pch + vbytes);
+  int32_t* g_index = d_ordered_index ? d_ordered_index : reinterpret_cast<int32_t*>(pch + 2 * vbytes);
+  pch += 3 * vbytes;
+  uint32_t* hist = reinterpret_cast<uint32_t*>(pch);
+  pch += hbytes;
+  double* d_b1 = reinterpret_cast<double*>(pch);
+  double* d_b2 = d_b1 + nband;
+  unsigned long long* d_bits = reinterpret_cast<unsigned long long*>(d_b2 + nband);  // [or, and]
+  int* d_first = reinterpret_cast<int*>(d_bits + 2);
+  int* d_last = d_first + nband;
+
+  ECCKD_TRY(upload_small(ctx, d_b1, h_b1, (size_t)nband * sizeof(double)));
+  ECCKD_TRY(upload_small(ctx, d_b2, h_b2, (size_t)nband * sizeof(double)));
+  std::vector<int> init(2 * nband);
+  for (int j = 0; j < nband; ++j) {
+    init[j] = 0x7fffffff;
+    init[nband + j] = -1;
+  }
+  ECCKD_TRY(upload_small(ctx, d_first, init.data(), init.size() * sizeof(int)));
+  const unsigned nb = (unsigned)((nwav + 255) / 256);
+  band_kernel<<<nb, 256, 0, ctx->stream>>>(nwav, d_wn, nband, d_b1, d_b2, d_iband, d_first, d_last, g_index);
+  ECCKD_LAUNCH_CHECK(ctx);
+  std::vector<int> fl(2 * nband);
+  ECCKD_CUDA_OK(cudaMemcpyAsync(fl.data(), d_first, fl.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int j = 0; j < nband; ++j) {
+    const int i1 = fl[j], i2 = fl[nband + j];
+    // the reference indexes an empty vector here (reorder_spectrum.cpp:291)
+    ECCKD_REQUIRE(i2 >= 0 && i1 <= i2, ECCKD_PARAMETER_ERROR, "band %d (%g-%g cm-1) contains no wavenumbers", j, h_b1[j],
+                  h_b2[j]);
+    const int64_t n = (int64_t)i2 - i1 + 1;
+    if (n < 2) continue;
+    const unsigned long long bits_init[2] = {0ull, ~0ull};
+    ECCKD_TRY(upload_small(ctx, d_bits, bits_init, sizeof(bits_init)));
+    gather_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, g_index + i1, d_key, k0, v0, d_bits,
+                                                                              d_bits + 1);
+    ECCKD_LAUNCH_CHECK(ctx);
+    unsigned long long bits[2];
+    ECCKD_CUDA_OK(cudaMemcpyAsync(bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long vary = bits[0] & ~bits[1];
+    uint32_t* v_sorted = nullptr;
+    ECCKD_TRY(radix_sort_pairs(ctx, n, k0, v0, k1, v1, hist, vary, &v_sorted));
+    write_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, v_sorted, g_index + i1);
+    ECCKD_LAUNCH_CHECK(ctx);
+  }
+  if (d_rank) {
+    rank_from_order_kernel<<<nb, 256, 0, ctx->stream>>>(nwav, g_index, d_rank);
+    ECCKD_LAUNCH_CHECK(ctx);
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_store_g_points_dev(ecckd_ctx* ctx, int64_t nwav, const int32_t* d_rank, int ng,
+                                       const int32_t* h_rank1, const int32_t* h_rank2, int32_t* d_g_point) {
+  ECCKD_REQUIRE(ctx && d_rank && h_rank1 && h_rank2 && d_g_point, ECCKD_PARAMETER_ERROR,
+                "ecckd_store_g_points: NULL argument");
+  ECCKD_REQUIRE(nwav > 0 && ng > 0 && ng <= 4096, ECCKD_PARAMETER_ERROR, "ecckd_store_g_points: bad dimensions");
+  std::vector<int32_t> r12(2 * (size_t)ng);
+  memcpy(r12.data(), h_rank1, (size_t)ng * sizeof(int32_t));
+  memcpy(r12.data() + ng, h_rank2, (size_t)ng * sizeof(int32_t));
+  void* d_r = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, r12.size() * sizeof(int32_t), &d_r));
+  ECCKD_TRY(upload_small(ctx, d_r, r12.data(), r12.size() * sizeof(int32_t)));
+  store_g_points_kernel<<<(unsigned)((nwav + 255) / 256), 256, r12.size() * sizeof(int32_t), ctx->stream>>>(
+      nwav, d_rank, ng, static_cast<const int32_t*>(d_r), d_g_point);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+// Hypercube partition of Hogan (2010): single_gas_data.cpp:23-124.
+ECCKD_API int ecckd_overlap_g_points(int ngas, int nband, const int32_t* n_g, const double* sort_var,
+                                     const int32_t* gas_offset, int cap, int32_t* g_min, int32_t* g_max,
+                                     int32_t* band_number, int* ng_out) {
+  ECCKD_REQUIRE(n_g && sort_var && gas_offset && g_min && g_max && band_number && ng_out, ECCKD_PARAMETER_ERROR,
+                "ecckd_overlap_g_points: NULL argument");
+  ECCKD_REQUIRE(ngas > 0 && nband > 0, ECCKD_PARAMETER_ERROR, "ecckd_overlap_g_points: bad dimensions");
+  // merged g points per band: 1 - ngas + sum_gas n_g (Eq. 7 of Hogan 2010)
+  int total = 0;
+  std::vector<int> per_band(nband);
+  for (int b = 0; b < nband; ++b) {
+    int s = 1 - ngas;
+    for (int a = 0; a < ngas; ++a) s += n_g[a * nband + b];
+    per_band[b] = s;
+    total += s;
+  }
+  ECCKD_REQUIRE(total <= cap, ECCKD_PARAMETER_ERROR, "ecckd_overlap_g_points: capacity %d < %d merged g points", cap,
+                total);
+  std::vector<int> cur(ngas, 0);  // current g point of each gas
+  int m = 0;                      // current merged g point
+  for (int b = 0; b < nband; ++b) {
+    const std::vector<int> start = cur;
+    // first merged point of the band: every gas at its weakest interval
+    for (int a = 0; a < ngas; ++a) g_min[a * cap + m] = g_max[a * cap + m] = start[a];
+    band_number[m] = b;
+    for (int step = 1; step < per_band[b]; ++step) {
+      // advance the gas whose next interval has the smallest sorting variable
+      int pick = -1;
+      double best = 1.0e30;
+      for (int a = 0; a < ngas; ++a) {
+        const bool can_advance = cur[a] < start[a] + n_g[a * nband + b] - 1;
+        const double v = can_advance ? sort_var[gas_offset[a] + cur[a] + 1] : 1.0e30;
+        if (v < best) {
+          best = v;
+          pick = a;
+        }
+      }
+      if (pick < 0) {
+        set_error("Could not locate next gas to advance");  // single_gas_data.cpp:92-95
+        return ECCKD_PROCESSING_ERROR;
+      }
+      ++cur[pick];
+      ++m;
+      band_number[m] = b;
+      for (int a = 0; a < ngas; ++a) {
+        g_min[a * cap + m] = (a == pick) ? cur[a] : start[a];
+        g_max[a * cap + m] = cur[a];
+      }
+    }
+    ++m;
+    for (int a = 0; a < ngas; ++a) ++cur[a];
+  }
+  *ng_out = total;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_assign_g_points_dev(ecckd_ctx* ctx, int ngas, int64_t nwav, const int32_t* d_gas_g_point, int ng,
+                                        int cap, const int32_t* h_g_min, const int32_t* h_g_max, int32_t* d_g_point,
+                                        int64_t* h_n_unassigned) {
+  ECCKD_REQUIRE(ctx && d_gas_g_point && h_g_min && h_g_max && d_g_point, ECCKD_PARAMETER_ERROR,
+                "ecckd_assign_g_points: NULL argument");
+  ECCKD_REQUIRE(ngas > 0 && nwav > 0 && ng > 0 && cap >= ng, ECCKD_PARAMETER_ERROR, "ecckd_assign_g_points: bad dimensions");
+  const size_t tab = (size_t)ngas * cap;
+  const size_t smem = (size_t)2 * ngas * ng * sizeof(int32_t);
+  ECCKD_REQUIRE(smem <= 48 * 1024, ECCKD_PARAMETER_ERROR, "ecckd_assign_g_points: ngas*ng too large");
+  std::vector<int32_t> gmm(2 * tab);
+  memcpy(gmm.data(), h_g_min, tab * sizeof(int32_t));
+  memcpy(gmm.data() + tab, h_g_max, tab * sizeof(int32_t));
+  void* d_t = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, gmm.size() * sizeof(int32_t) + 64, &d_t));
+  unsigned long long* d_cnt = static_cast<unsigned long long*>(d_t);
+  int32_t* d_gmm = reinterpret_cast<int32_t*>(d_cnt + 1);
+  ECCKD_CUDA_OK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), ctx->stream));
+  ECCKD_TRY(upload_small(ctx, d_gmm, gmm.data(), gmm.size() * sizeof(int32_t)));
+  assign_g_points_kernel<<<(unsigned)((nwav + 255) / 256), 256, smem, ctx->stream>>>(ngas, nwav, d_gas_g_point, ng, cap,
+                                                                                     d_gmm, d_g_point, d_cnt);
+  ECCKD_LAUNCH_CHECK(ctx);
+  if (h_n_unassigned) {
+    unsigned long long c = 0;
+    ECCKD_CUDA_OK(cudaMemcpyAsync(&c, d_cnt, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *h_n_unassigned = (int64_t)c;
+  }
+  return ECCKD_OK;
+}

@@ -1,0 +1,335 @@
+/* ecckd_b200.h - C ABI of the B200-native (sm_100a) implementation of ecCKD's
+ * data-parallel hot path.
+ *
+ * The reference (ecmwf-ifs/ecckd v1.6) has no FFI/plugin layer: its tool
+ * mains call plain C++ free functions taking adept::Vector/Matrix arguments.
+ * Each entry point below replaces one such function (or one inline hot loop of
+ * a tool main) and cites it as path:line relative to the reference root.
+ * A maintainer of the reference binds them as shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Plain pointers and sizes only; row-major arrays, last index fastest,
+ *    explicit row strides (in elements) where the reference passes slices.
+ *  - Names ending in _dev take DEVICE pointers for every array marked d_ and
+ *    HOST pointers for the small per-layer vectors marked h_; they enqueue work
+ *    on the context's stream and do not synchronise unless stated.
+ *    Names without _dev take HOST pointers only (the reference-facing call):
+ *    they copy in, run the same kernels, copy out and synchronise.
+ *  - Every function returns an int status: 0 = OK, otherwise the reference's
+ *    ESA exit codes (src/include/EsaExitCodes.h:16-51): 147 PARAMETER_ERROR,
+ *    148 PROCESSING_ERROR; CUDA failures give 131 UNEXPECTED_EXCEPTION.
+ *    ecckd_last_error() returns the message of the calling thread's last error.
+ *    Nothing throws across this ABI.
+ *  - There is no CPU fallback: every compute entry point fails with 131 when no
+ *    sm_100 device is usable.
+ */
+#ifndef ECCKD_B200_H
+#define ECCKD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECCKD_B200_VERSION 100 /* 0.1.0 */
+
+typedef struct ecckd_ctx ecckd_ctx;
+typedef struct ecckd_gpoint_plan ecckd_gpoint_plan;
+typedef struct ecckd_ckd_model ecckd_ckd_model;
+
+/* src/include/EsaExitCodes.h:16-51 */
+enum ecckd_status {
+  ECCKD_OK = 0,
+  ECCKD_UNEXPECTED_EXCEPTION = 131,
+  ECCKD_PARAMETER_ERROR = 147,
+  ECCKD_PROCESSING_ERROR = 148
+};
+
+/* averaging_method strings of src/ecckd/average_optical_depth.cpp:43-129 */
+enum ecckd_averaging_method {
+  ECCKD_AVG_LINEAR = 0,             /* "linear" */
+  ECCKD_AVG_TRANSMISSION = 1,       /* "transmission" */
+  ECCKD_AVG_TRANSMISSION_2 = 2,     /* "transmission-2" */
+  ECCKD_AVG_TRANSMISSION_3 = 3,     /* "transmission-3" */
+  ECCKD_AVG_TRANSMISSION_10 = 4,    /* "transmission-10" */
+  ECCKD_AVG_SQUARE_ROOT = 5,        /* "square-root" */
+  ECCKD_AVG_LOGARITHMIC = 6,        /* "logarithmic" */
+  ECCKD_AVG_HYBRID_LOG_TRANS3 = 7   /* "hybrid-logarithmic-transmission-3" */
+};
+
+/* Returns the enum for a reference averaging_method string, or -1
+ * (the reference throws PARAMETER_ERROR, average_optical_depth.cpp:130-133). */
+int ecckd_averaging_method_from_string(const char* name);
+
+/* How the averaging weights are supplied (create_look_up_table.cpp:323-339). */
+enum ecckd_weight_mode {
+  ECCKD_WEIGHT_MATRIX = 0, /* d_weight[nwrow][nwav], e.g. planck_fl             */
+  ECCKD_WEIGHT_VECTOR = 1, /* d_weight[nwav] for all layers: spread<0>(ssi,nlay) */
+  ECCKD_WEIGHT_PLANCK = 2  /* Planck function of h_temperature[nwrow] computed in
+                              the kernel (fuses planck_function.cpp:47-53)       */
+};
+
+/* per-g-point warning bits, the WARNINGs of average_optical_depth.cpp:136,154,159 */
+enum ecckd_warning {
+  ECCKD_WARN_EMPTY_G = 1,
+  ECCKD_WARN_MIN_GT_FIT = 2,
+  ECCKD_WARN_MIN_GE_MAX = 4
+};
+
+/* conc_dependence codes written by src/ecckd/ckd_model.cpp:409-413 */
+enum ecckd_conc_dependence {
+  ECCKD_CONC_NONE = 0,
+  ECCKD_CONC_LINEAR = 1,
+  ECCKD_CONC_LUT = 2,
+  ECCKD_CONC_RELATIVE_LINEAR = 3
+};
+
+/* ------------------------------------------------------------------ context */
+int ecckd_version(void);
+const char* ecckd_last_error(void);
+/* Number of usable sm_100 devices (0 if none or no driver). */
+int ecckd_device_count(void);
+/* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
+ * for a private non-blocking stream owned by the context. */
+int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out);
+int ecckd_ctx_destroy(ecckd_ctx* ctx);
+int ecckd_ctx_set_stream(ecckd_ctx* ctx, void* stream);
+int ecckd_synchronize(ecckd_ctx* ctx);
+int ecckd_device_malloc(ecckd_ctx* ctx, size_t bytes, void** d_ptr);
+int ecckd_device_free(ecckd_ctx* ctx, void* d_ptr);
+int ecckd_host_malloc_pinned(size_t bytes, void** h_ptr);
+int ecckd_host_free_pinned(void* h_ptr);
+int ecckd_memcpy_h2d(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+/* Number of kernels this library has launched on this context so far. */
+int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx);
+
+/* -------------------------------------------------- stage 1: spectra -> LUT */
+
+/* planck_function: src/ecckd/planck_function.cpp:22-54.
+ * d_ans[nt][nwav] with row stride ans_stride. */
+int ecckd_planck_function_dev(ecckd_ctx* ctx, int nt, const double* h_temperature, int64_t nwav,
+                              const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1,
+                              double* d_ans, int64_t ans_stride);
+int ecckd_planck_function(ecckd_ctx* ctx, int nt, const double* temperature, int64_t nwav,
+                          const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, double* ans,
+                          int64_t ans_stride);
+
+/* The g-point map is the same for every (gas, concentration, temperature)
+ * block of a LUT build (create_look_up_table.cpp:89-107 reads it once), so the
+ * per-chunk g-sorted visiting order that the reduction kernel uses is computed
+ * once and reused.  d_g_point[nwav] int32; entries outside [0,ng) belong to no
+ * g point (they never match `g_point == ig`, average_optical_depth.cpp:40). */
+int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
+                             ecckd_gpoint_plan** out);
+int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan);
+/* Number of wavenumbers in each g point (h_count[ng], host). */
+int ecckd_gpoint_plan_counts(ecckd_gpoint_plan* plan, int64_t* h_count);
+
+/* average_optical_depth_to_g_point: src/ecckd/average_optical_depth.cpp:22-197
+ * (declaration average_optical_depth.h:19-30).
+ *   d_od[nlay][nwav] row stride od_stride;
+ *   weights per weight_mode: MATRIX d_weight[nlay][nwav] row stride w_stride;
+ *     VECTOR d_weight[nwav]; PLANCK h_temperature[nlay] with d_wavenumber_cm_1,
+ *     d_d_wavenumber_cm_1[nwav] (d_weight ignored);
+ *   outputs d_molar_abs, d_min_molar_abs, d_max_molar_abs [nlay][ng] with row
+ *     stride out_stride (min/max may both be NULL), d_warn[ng] int32 bit flags
+ *     (may be NULL; OR-ed into, caller zeroes).
+ *   h_pressure_fl[nlay], h_pressure_hl[nlay+1] host vectors.
+ * reference_surface_vmr <= 0 returns mean optical depth instead of molar
+ * absorption (:186-193). */
+int ecckd_average_optical_depth_to_g_point_dev(
+    ecckd_ctx* ctx, ecckd_gpoint_plan* plan, double reference_surface_vmr, int nlay,
+    const double* h_pressure_fl, const double* h_pressure_hl, const double* d_od, int64_t od_stride,
+    int weight_mode, const double* d_weight, int64_t w_stride, const double* h_temperature,
+    const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1, int averaging_method,
+    double* d_molar_abs, double* d_min_molar_abs, double* d_max_molar_abs, int64_t out_stride,
+    int32_t* d_warn);
+
+/* Same reduction for nspec spectra that share g points, weights and pressure
+ * grid (all the (gas, concentration) blocks of one temperature index of the
+ * create_look_up_table.cpp:249-505 loops): one pass streams every spectrum
+ * once and the weights once.  h_d_od[nspec] are device pointers to
+ * [nlay][nwav] arrays (row stride od_stride); h_reference_surface_vmr[nspec];
+ * h_d_molar_abs / h_d_min / h_d_max [nspec] device pointers to [nlay][ng]
+ * outputs (row stride out_stride; min/max arrays may be NULL); h_d_warn[nspec]
+ * device pointers to int32[ng] (array or entries may be NULL). */
+int ecckd_average_optical_depth_batch_dev(
+    ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nspec, const double* h_reference_surface_vmr, int nlay,
+    const double* h_pressure_fl, const double* h_pressure_hl, const double* const* h_d_od,
+    int64_t od_stride, int weight_mode, const double* d_weight, int64_t w_stride,
+    const double* h_temperature, const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1,
+    int averaging_method, double* const* h_d_molar_abs, double* const* h_d_min_molar_abs,
+    double* const* h_d_max_molar_abs, int64_t out_stride, int32_t* const* h_d_warn);
+
+/* Host-buffer form with exactly the reference's argument list
+ * (average_optical_depth.h:19-30): g_point, optical_depth and planck_fl are
+ * host arrays; planck_fl row stride 0 broadcasts one row over layers
+ * (spread<0>(ssi,nlay), create_look_up_table.cpp:335).  warn[ng] may be NULL. */
+int ecckd_average_optical_depth_to_g_point(
+    ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav,
+    const double* pressure_fl, const double* pressure_hl, const int32_t* g_point,
+    const double* optical_depth, int64_t od_stride, const double* planck_fl, int64_t planck_stride,
+    const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs,
+    int64_t out_stride, int32_t* warn);
+
+/* Merge of several spectra: src/ecckd/read_merged_spectrum.cpp:149-168.
+ * d_optical_depth += d_od * scaling, or * h_scaling_profile[layer] if non-NULL. */
+int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
+                         const double* d_od, int64_t od_stride, double scaling,
+                         const double* h_scaling_profile);
+
+/* gpoint_fraction: src/ecckd/create_look_up_table.cpp:512-548.
+ * Bin i is (h_wavenumber1[i], h_wavenumber2[i]]; bins must be the contiguous
+ * uniform grid the reference builds (:526-535).  d_out[ng][nbin]. */
+int ecckd_gpoint_fraction_dev(ecckd_ctx* ctx, int ng, int64_t nwav, const int32_t* d_g_point,
+                              const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1, int nbin,
+                              const double* h_wavenumber1, const double* h_wavenumber2, double* d_out);
+
+/* Solar irradiance per bin: src/ecckd/create_look_up_table.cpp:555-561. d_out[nbin]. */
+int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenumber_cm_1,
+                            const double* d_ssi, int nbin, const double* h_wavenumber1,
+                            const double* h_wavenumber2, double* d_out);
+
+/* Planck look-up table per g point: src/ecckd/create_look_up_table.cpp:579-591.
+ * d_out[nlut][ng] = sum over the g point's wavenumbers of planck(T_lut, nu). */
+int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const double* d_wavenumber_cm_1,
+                         const double* d_d_wavenumber_cm_1, int nlut, const double* h_temperature_lut,
+                         double* d_out);
+
+/* Remove g points that occupy none of the spectrum, renumbering in place:
+ * src/ecckd/create_look_up_table.cpp:111-160.  h_g_point_map[>=ng] (host)
+ * receives the old index of each kept g point; *new_ng the new count.
+ * Returns 1 (the reference's THROW(1), :148) if a point is left unassigned. */
+int ecckd_compact_g_points_dev(ecckd_ctx* ctx, int ng, int64_t nwav, int32_t* d_g_point,
+                               int32_t* h_g_point_map, int* new_ng);
+
+/* ------------------------------------------ ranking / g-point assignment */
+
+/* Sorting variable of reorder_spectrum: LW pseudo-height of peak cooling
+ * (src/ecckd/reorder_spectrum.cpp:111-190) and SW height where the optical
+ * depth from TOA reaches the threshold (:197-228).  d_od[nlay][nwav];
+ * outputs d_key[nwav], d_column_od[nwav] (may be NULL).  The SW form returns
+ * PROCESSING_ERROR where the reference throws (key > 30, :214-216). */
+int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
+                          const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1,
+                          const double* d_od, int64_t od_stride, double threshold_optical_depth, double* d_key,
+                          double* d_column_od);
+int ecckd_sort_key_sw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
+                          const double* d_od, int64_t od_stride, double threshold_optical_depth, double* d_key,
+                          double* d_column_od);
+
+/* Band membership and per-band std::stable_sort of the sorting variable:
+ * src/ecckd/reorder_spectrum.cpp:30-34,262-300.  Outputs (any may be NULL)
+ * d_iband[nwav], d_rank[nwav], d_ordered_index[nwav], all int32.  Bit-exact
+ * with std::stable_sort(key[i] < key[j]) for NaN-free keys. */
+int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenumber_cm_1, const double* d_key,
+                         int nband, const double* h_band_bound1, const double* h_band_bound2,
+                         int32_t* d_iband, int32_t* d_rank, int32_t* d_ordered_index);
+
+/* SingleGasData::store_g_points: src/ecckd/single_gas_data.h:56-62. */
+int ecckd_store_g_points_dev(ecckd_ctx* ctx, int64_t nwav, const int32_t* d_rank, int ng,
+                             const int32_t* h_rank1, const int32_t* h_rank2, int32_t* d_g_point);
+
+/* overlap_g_points (hypercube partition): src/ecckd/single_gas_data.cpp:23-124.
+ * Host integer logic over a few dozen entries; all pointers are HOST.
+ * h_n_g_points[ngas][nband]; h_sorting_variable is the concatenation of each
+ * gas's per-g array with h_gas_offset[ngas] the start of each slice;
+ * h_g_min/h_g_max[ngas][cap], h_band_number[cap].  *ng_out = merged count. */
+int ecckd_overlap_g_points(int ngas, int nband, const int32_t* h_n_g_points, const double* h_sorting_variable,
+                           const int32_t* h_gas_offset, int cap, int32_t* h_g_min, int32_t* h_g_max,
+                           int32_t* h_band_number, int* ng_out);
+
+/* Final multi-gas assignment: src/ecckd/find_g_points.cpp:1459-1475.
+ * d_gas_g_point[ngas][nwav]; h_g_min/h_g_max[ngas][cap] (host);
+ * d_g_point[nwav]; *h_n_unassigned (host, may be NULL) counts -1 entries. */
+int ecckd_assign_g_points_dev(ecckd_ctx* ctx, int ngas, int64_t nwav, const int32_t* d_gas_g_point, int ng,
+                              int cap, const int32_t* h_g_min, const int32_t* h_g_max, int32_t* d_g_point,
+                              int64_t* h_n_unassigned);
+
+/* ------------------------------------------------ stage 2: CKD flux solver */
+
+/* One gas of a CKD model as stored by src/ecckd/ckd_model.cpp:288-641.
+ * All pointers HOST; copied to the device by ecckd_ckd_model_create. */
+typedef struct ecckd_gas_table {
+  int32_t conc_dependence;  /* enum ecckd_conc_dependence */
+  int32_t nconc;            /* LUT only: number of mole fractions */
+  const double* vmr_lut;    /* LUT only: [nconc] */
+  double reference_vmr;     /* relative-linear only */
+  const double* molar_abs;  /* [nt][np][ng], or [nconc][nt][np][ng] for LUT */
+} ecckd_gas_table;
+
+/* LW: planck_lut[nlut][ng] with temperature_planck[nlut]; solar_irradiance and
+ * rayleigh_molar_scat NULL.  SW: solar_irradiance[ng], rayleigh_molar_scat[ng];
+ * planck tables NULL/0.  log_pressure[np] (evenly spaced), temperature[nt][np]. */
+int ecckd_ckd_model_create(ecckd_ctx* ctx, int ngas, const ecckd_gas_table* gases, int nt, int np, int ng,
+                           const double* log_pressure, const double* temperature, int nlut,
+                           const double* temperature_planck, const double* planck_lut,
+                           const double* solar_irradiance, const double* rayleigh_molar_scat,
+                           ecckd_ckd_model** out);
+int ecckd_ckd_model_destroy(ecckd_ckd_model* model);
+
+/* CkdModel::calc_optical_depth: src/ecckd/ckd_model.cpp:923-1102.
+ * d_pressure_hl[ncol][nlay+1], d_temperature_fl[ncol][nlay], d_vmr_fl[ncol][nlay]
+ * (NULL = "not provided"); d_od[ncol][nlay][ng] is overwritten
+ * (accumulate = 0) or added to (accumulate != 0, run_ckd.cpp:312). */
+int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, int igas, int ncol, int nlay,
+                                     const double* d_pressure_hl, const double* d_temperature_fl,
+                                     const double* d_vmr_fl, double* d_od, int accumulate);
+
+/* CkdModel::calc_planck_function: src/ecckd/ckd_model.cpp:1105-1145.
+ * d_temperature[n] -> d_planck[n][ng]. */
+int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, int64_t n,
+                                       const double* d_temperature, double* d_planck);
+
+/* CkdModel::calc_rayleigh_optical_depth: src/ecckd/ckd_model.h:242-252. */
+int ecckd_ckd_calc_rayleigh_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, int ncol, int nlay,
+                                              const double* d_pressure_hl, double* d_od);
+
+/* radiative_transfer_lw<false>: src/ecckd/radiative_transfer_lw.cpp:25-60,
+ * batched over ncol independent columns (ncol = 1 is the reference call).
+ * d_planck[ncol][nlay+1][n], d_od[ncol][nlay][n], d_surf_emissivity[n] (shared
+ * by all columns, run_ckd.cpp:344-345), d_surf_planck[ncol][n],
+ * d_flux_dn/up[ncol][nlay+1][n]. */
+int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck,
+                                    const double* d_od, const double* d_surf_emissivity,
+                                    const double* d_surf_planck, double* d_flux_dn, double* d_flux_up);
+
+/* radiative_transfer_direct_sw<false> (d_albedo, d_flux_up NULL):
+ * src/ecckd/radiative_transfer_sw.cpp:24-43; radiative_transfer_norayleigh_sw
+ * <false> (both non-NULL): :47-77.  d_ssi[n], d_albedo[n] shared by columns;
+ * h_cos_sza[ncol] per column (host). */
+int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* h_cos_sza,
+                                    const double* d_ssi, const double* d_od, const double* d_albedo,
+                                    double* d_flux_dn, double* d_flux_up);
+
+/* heating_rate<false>: src/ecckd/heating_rate.h:25-49, batched over columns.
+ * d_pressure_hl[ncol][nlay+1]; d_flux_up may be NULL; d_hr[ncol][nlay][n]. */
+int ecckd_heating_rate_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_pressure_hl,
+                           const double* d_flux_dn, const double* d_flux_up, double* d_hr);
+
+/* Numerical core of run_ckd: src/ecckd/run_ckd.cpp:119-132,261-367 in one
+ * fused pass per column x g point: full-level temperature, LUT interpolation of
+ * every gas, sum, clamp at zero, Planck interpolation (LW) or Rayleigh +
+ * incoming solar (SW, mu0 = 0.5), flux sweep, sums over g.
+ * h_d_vmr_fl[ngas]: device pointers [ncol][nlay] per gas, NULL entry = variable
+ * absent from the input file (:277-281).  Outputs (device, any may be NULL):
+ * d_od[ncol][nlay][ng], d_planck_hl[ncol][nlay+1][ng], d_planck_surf[ncol][ng],
+ * d_flux_dn, d_flux_up[ncol][nlay+1][ng] (SW: d_flux_dn = direct flux, d_flux_up
+ * ignored), d_bb_flux_dn, d_bb_flux_up[ncol][nlay+1]. */
+int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, const double* const* h_d_vmr_fl, double tsi,
+                      int ncol, int nlay, const double* d_pressure_hl, const double* d_temperature_hl,
+                      double* d_od, double* d_planck_hl, double* d_planck_surf, double* d_flux_dn,
+                      double* d_flux_up, double* d_bb_flux_dn, double* d_bb_flux_up);
+/* Host-buffer form: same arguments, all arrays on the host. */
+int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* model, const double* const* vmr_fl, double tsi, int ncol,
+                  int nlay, const double* pressure_hl, const double* temperature_hl, double* od,
+                  double* planck_hl, double* planck_surf, double* flux_dn, double* flux_up,
+                  double* bb_flux_dn, double* bb_flux_up);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECCKD_B200_H */

@@ -1,0 +1,60 @@
+"""The C-ABI library loads and exports every symbol include/ecckd_b200.h declares
+(no compute calls: this file runs without a GPU)."""
+import ctypes
+import os
+
+import pytest
+
+from ecckd_b200 import _lib
+
+
+def test_library_exists_and_loads():
+    assert os.path.exists(_lib.LIB_PATH), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    L = _lib.lib()
+    assert L.ecckd_version() == 100
+
+
+def test_exports_every_header_symbol():
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    syms = _lib.header_symbols()
+    assert len(syms) >= 40
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_method_strings():
+    L = _lib.lib()
+    names = ["linear", "transmission", "transmission-2", "transmission-3", "transmission-10", "square-root",
+             "logarithmic", "hybrid-logarithmic-transmission-3"]
+    for i, n in enumerate(names):
+        assert L.ecckd_averaging_method_from_string(n.encode()) == i
+    assert L.ecckd_averaging_method_from_string(b"total-transmission") == -1
+    assert L.ecckd_averaging_method_from_string(b"nonsense") == -1
+
+
+def test_overlap_g_points_is_host_only(O):
+    """ecckd_overlap_g_points is integer host logic: it must run without a device
+    and match the oracle (single_gas_data.cpp:23-124)."""
+    import numpy as np
+
+    import ecckd_b200 as E
+
+    rng = np.random.default_rng(4)
+    for ngas, nband in [(1, 1), (2, 1), (3, 4), (5, 13)]:
+        n_g = rng.integers(1, 6, size=(ngas, nband)).astype(np.int32)
+        sv = [np.sort(rng.uniform(0, 10, n_g[a].sum())) for a in range(ngas)]
+        ng, gmin, gmax, band = E.overlap_g_points(n_g, sv)
+        ng_o, gmin_o, gmax_o, band_o = O.overlap_g_points(n_g, sv)
+        assert ng == ng_o == int((1 - ngas) * nband + n_g.sum())  # Eq. 7 of Hogan (2010)
+        assert np.array_equal(gmin, gmin_o) and np.array_equal(gmax, gmax_o) and np.array_equal(band, band_o)
+
+
+@pytest.mark.skipif(_lib.lib().ecckd_device_count() > 0, reason="a B200 is present")
+def test_no_cpu_fallback_without_gpu():
+    """Without a device the product path must fail loudly, never compute on the CPU."""
+    import ecckd_b200 as E
+
+    with pytest.raises(E.EcckdError) as ei:
+        E.Context(0)
+    assert ei.value.code == 131
+    assert "no CPU fallback" in str(ei.value)
