@@ -79,6 +79,11 @@ def _declare(L):
         "ecckd_gpoint_plan_create": [vp, vp, i64, i32, c_void_pp],
         "ecckd_gpoint_plan_destroy": [vp],
         "ecckd_gpoint_plan_counts": [vp, vp],
+        "ecckd_gpoint_plan_counts_dev": [vp, c_void_pp],
+        "ecckd_average_optical_depth_partial_dev": [vp, vp, i32, i32, vp, vp, i64, i32, vp, i64, vp, vp, vp, i32, vp,
+                                                    vp],
+        "ecckd_average_optical_depth_finalize_dev": [vp, i32, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, i64,
+                                                     vp],
         "ecckd_average_optical_depth_to_g_point_dev": [vp, vp, dbl, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp,
                                                        i32, vp, vp, vp, i64, vp],
         "ecckd_average_optical_depth_batch_dev": [vp, vp, i32, vp, i32, vp, vp, vp, i64, i32, vp, i64, vp, vp, vp,

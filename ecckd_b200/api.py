@@ -171,6 +171,12 @@ class GPointPlan:
         check(_lib.lib().ecckd_gpoint_plan_counts(self.handle, out.ctypes.data))
         return out
 
+    def counts_dev(self) -> int:
+        """Device pointer to int64[ng] counts (summed across ranks when sharded)."""
+        p = C.c_void_p()
+        check(_lib.lib().ecckd_gpoint_plan_counts_dev(self.handle, C.byref(p)))
+        return int(p.value)
+
     def close(self):
         if self.handle:
             _lib.lib().ecckd_gpoint_plan_destroy(self.handle)
@@ -257,6 +263,34 @@ def average_optical_depth_batch_dev(ctx: Context, plan: GPointPlan, reference_su
         ctx.handle, plan.handle, len(d_ods), vp, pf.size, pfp, php, p_od, od_stride, weight_mode, _ptr(d_weight),
         w_stride, tp, _ptr(d_wavenumber), _ptr(d_d_wavenumber), _method_id(averaging_method), p_out, p_min, p_max,
         out_stride or plan.ng, p_w))
+
+
+def average_optical_depth_partial_dev(ctx: Context, plan: GPointPlan, nlay, pressure_fl, d_ods: Sequence, od_stride,
+                                      weight_mode, d_weight, w_stride, temperature, d_wavenumber, d_d_wavenumber,
+                                      averaging_method, d_sums, d_minmax):
+    """Per-shard streaming stage; d_sums [nlay][nspec][ng][3], d_minmax [nlay][nspec][ng][2]."""
+    pf, pfp = _h(pressure_fl)
+    t, tp = _h(temperature)
+    a_od, p_od = _ptr_array(d_ods)
+    check(_lib.lib().ecckd_average_optical_depth_partial_dev(
+        ctx.handle, plan.handle, len(d_ods), nlay, pfp, p_od, od_stride, weight_mode, _ptr(d_weight), w_stride, tp,
+        _ptr(d_wavenumber), _ptr(d_d_wavenumber), _method_id(averaging_method), _ptr(d_sums), _ptr(d_minmax)))
+
+
+def average_optical_depth_finalize_dev(ctx: Context, ng, d_count, reference_surface_vmr: Sequence[float], pressure_fl,
+                                       pressure_hl, averaging_method, d_sums, d_minmax, d_molar_abs: Sequence,
+                                       d_min: Optional[Sequence] = None, d_max: Optional[Sequence] = None,
+                                       out_stride=None, d_warn: Optional[Sequence] = None):
+    pf, pfp = _h(pressure_fl)
+    ph, php = _h(pressure_hl)
+    v, vp = _h(reference_surface_vmr)
+    a_out, p_out = _ptr_array(d_molar_abs)
+    a_min, p_min = _ptr_array(d_min)
+    a_max, p_max = _ptr_array(d_max)
+    a_w, p_w = _ptr_array(d_warn)
+    check(_lib.lib().ecckd_average_optical_depth_finalize_dev(
+        ctx.handle, ng, _ptr(d_count), len(d_molar_abs), vp, pf.size, pfp, php, _method_id(averaging_method),
+        _ptr(d_sums), _ptr(d_minmax), p_out, p_min, p_max, out_stride or ng, p_w))
 
 
 def merge_axpy_dev(ctx: Context, nlay, nwav, d_optical_depth, stride, d_od, od_stride, scaling=1.0,

@@ -296,10 +296,9 @@ __global__ void __launch_bounds__(128) reduce_kernel(const ReduceParams p) {
   for (int i = lane; i < ng * 128; i += 32) out[i] = acc[i];
 }
 
-// ------------------------------------------------------------------ epilogue
-// average_optical_depth.cpp:43-193 after the sums: inverse transform, empty-g
-// handling, min/max clamp and fixes, conversion to molar absorption.
-__global__ void epilogue_kernel(const EpilogueParams p) {
+// ------------------------------------------------------------------ combine + finalize
+// Combine the span partials of every (row, g) in fixed span order (deterministic).
+__global__ void combine_kernel(const CombineParams p) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (int64_t)p.nslots * p.ng) return;
   const int slot = (int)(tid / p.ng);
@@ -309,29 +308,50 @@ __global__ void epilogue_kernel(const EpilogueParams p) {
   const int group = slot >> 5, lane = slot & 31;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
-  for (int s = 0; s < p.nspans; ++s) {  // fixed order: deterministic
+  for (int s = 0; s < p.nspans; ++s) {
     const double* a = p.partial + ((size_t)(group * p.nspans + s) * p.ng + g) * 128 + lane;
     s0 += a[0];
     s1 += a[32];
     mn = fmin(mn, a[64]);
     mx = fmax(mx, a[96]);
   }
-  if (rd.method == M_SUMW) {  // planck look-up table: sum of weights only
-    rd.out[g] = s1;
+  double* so = p.sums + ((size_t)rd.row * p.ng + g) * NSUM;
+  so[0] = s0;
+  so[1] = s1;
+  so[2] = (rd.method == M_LOG) ? (double)p.zcount[(size_t)slot * p.ng + g] : 0.0;
+  double* mo = p.minmax + ((size_t)rd.row * p.ng + g) * NMINMAX;
+  mo[0] = mn;
+  mo[1] = -mx;
+}
+
+// average_optical_depth.cpp:43-193 after the sums: inverse transform, empty-g
+// handling, min/max clamp and fixes, conversion to molar absorption.
+__global__ void finalize_kernel(const FinalizeParams p) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (int64_t)p.nrows * p.ng) return;
+  const int row = (int)(tid / p.ng);
+  const int g = (int)(tid - (int64_t)row * p.ng);
+  const OutDesc od = p.outs[row];
+  const double* so = p.sums + ((size_t)row * p.ng + g) * NSUM;
+  const double* mo = p.minmax + ((size_t)row * p.ng + g) * NMINMAX;
+  const double s0 = so[0], s1 = so[1];
+  double mn = mo[0], mx = -mo[1];
+  if (od.method == M_SUMW) {  // planck look-up table: sum of weights only
+    od.out[g] = s1;
     return;
   }
-  const unsigned long long n = p.count[g];
+  const long long n = p.count[g];
   double fit;
-  if (rd.method == M_LINEAR) {
+  if (od.method == M_LINEAR) {
     fit = s0 / s1;
-  } else if (rd.method == M_TRANS) {
+  } else if (od.method == M_TRANS) {
     const double x = fmin(0.9999999999999999, s0 / s1);
     fit = fabs(-log(1.0 - x) / p.kd);
-  } else if (rd.method == M_SQRT) {
+  } else if (od.method == M_SQRT) {
     const double r = s0 / s1;
     fit = r * r;
-  } else {  // M_LOG
-    const unsigned long long nnz = n - (unsigned long long)p.zcount[(size_t)slot * p.ng + g];
+  } else {  // M_LOG (average_optical_depth.cpp:79-96)
+    const long long nnz = n - (long long)so[2];
     if (nnz == n) fit = exp(s0 / s1);
     else if (nnz == 0) fit = 0.0;
     else fit = exp(s0 / s1) * ((double)nnz / (double)n);
@@ -354,16 +374,16 @@ __global__ void epilogue_kernel(const EpilogueParams p) {
       mx *= 1.01;
     }
   }
-  if (rd.factor > 0.0) {
-    rd.out[g] = rd.factor * fit / rd.dp;
-    if (rd.out_min) rd.out_min[g] = rd.factor * mn / rd.dp;
-    if (rd.out_max) rd.out_max[g] = rd.factor * mx / rd.dp;
+  if (od.factor > 0.0) {
+    od.out[g] = od.factor * fit / od.dp;
+    if (od.out_min) od.out_min[g] = od.factor * mn / od.dp;
+    if (od.out_max) od.out_max[g] = od.factor * mx / od.dp;
   } else {
-    rd.out[g] = fit;
-    if (rd.out_min) rd.out_min[g] = mn;
-    if (rd.out_max) rd.out_max[g] = mx;
+    od.out[g] = fit;
+    if (od.out_min) od.out_min[g] = mn;
+    if (od.out_max) od.out_max[g] = mx;
   }
-  if (rd.warn && wflag) atomicOr(&rd.warn[g], wflag);
+  if (od.warn && wflag) atomicOr(&od.warn[g], wflag);
 }
 
 // ------------------------------------------------------------------ small kernels
@@ -485,11 +505,13 @@ static void launch_reduce(int fkind, int wmode, int vec, dim3 grid, dim3 block, 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// Core driver: reduce `rows` (any mix of spectra/layers sharing one plan and one
-// weight definition) to per-g-point outputs.
-static int reduce_rows(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, std::vector<RowDesc>& rows, int fkind, double kd,
-                       int wmode, const double* d_weight, int64_t w_stride, const double* h_temperature,
-                       int n_temperature, const double* d_wn, const double* d_dwn) {
+// Streaming stage: reduce `rows` (any mix of spectra/layers sharing one plan and
+// one weight definition) to per-(row, g) partial results in d_sums / d_minmax
+// (layouts in spectral_reduce.cuh), rows[i].row giving each row's index there.
+static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::vector<RowDesc>& rows, int fkind,
+                          double kd, int wmode, const double* d_weight, int64_t w_stride,
+                          const double* h_temperature, int n_temperature, const double* d_wn, const double* d_dwn,
+                          double* d_sums, double* d_minmax) {
   const int nrows = (int)rows.size();
   if (nrows == 0) return ECCKD_OK;
   const int ng = plan->ng;
@@ -510,7 +532,7 @@ static int reduce_rows(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, std::vector<RowD
     if (!aligned16(d_wn) || !aligned16(d_dwn)) vec = 8;
   }
 
-  // group descriptors
+  // group descriptors: 32 consecutive rows per warp
   std::vector<GroupDesc> groups(ngroups);
   std::vector<RowDesc> slots(nslots);
   int maxw = 1;
@@ -556,25 +578,24 @@ static int reduce_rows(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, std::vector<RowD
   ECCKD_REQUIRE(per_warp <= smem_max, ECCKD_PARAMETER_ERROR,
                 "average_optical_depth: ng = %d needs %zu B of shared memory per warp (limit %zu)", ng, per_warp,
                 smem_max);
-  int warps = (int)std::min<size_t>(4, smem_max / per_warp);
-  // prefer two CTAs per SM when a 2-warp CTA leaves room for it
+  const int warps = (int)std::min<size_t>(4, smem_max / per_warp);
   const size_t smem = per_warp * warps;
 
-  // spans: fill the machine with one wave of warps
+  // spans of the wavenumber axis: one wave of warps fills the machine
   const int64_t total_warps = (int64_t)ctx->num_sms * warps;
   int nspans = (int)std::max<int64_t>(1, total_warps / ngroups);
   nspans = (int)std::min<int64_t>(nspans, std::max<int64_t>(1, plan->nchunks));
   const int ntasks = ngroups * nspans;
   const int nblocks = (ntasks + warps - 1) / warps;
 
-  // device scratch: [groups | slots] in ws0, partial in ws1, zcount in ws2, temperatures in ws3
+  // device scratch: [groups | slots] in ws0, span partials in ws1, zcount in ws2, temperatures in ws3
   void* d_desc = nullptr;
-  const size_t groups_bytes = (size_t)ngroups * sizeof(GroupDesc);
+  const size_t groups_bytes = ((size_t)ngroups * sizeof(GroupDesc) + 255) & ~size_t(255);
   const size_t slots_bytes = (size_t)nslots * sizeof(RowDesc);
-  ECCKD_TRY(ws_reserve(ctx, 0, groups_bytes + slots_bytes + 256, &d_desc));
+  ECCKD_TRY(ws_reserve(ctx, 0, groups_bytes + slots_bytes, &d_desc));
   GroupDesc* d_groups = static_cast<GroupDesc*>(d_desc);
-  RowDesc* d_slots = reinterpret_cast<RowDesc*>(static_cast<char*>(d_desc) + ((groups_bytes + 255) & ~size_t(255)));
-  ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), groups_bytes));
+  RowDesc* d_slots = reinterpret_cast<RowDesc*>(static_cast<char*>(d_desc) + groups_bytes);
+  ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), (size_t)ngroups * sizeof(GroupDesc)));
   ECCKD_TRY(upload_small(ctx, d_slots, slots.data(), slots_bytes));
 
   void* d_partial = nullptr;
@@ -615,22 +636,45 @@ static int reduce_rows(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, std::vector<RowD
   ECCKD_CUDA_OK(attr_err);
   ECCKD_LAUNCH_CHECK(ctx);
 
-  EpilogueParams ep;
-  ep.rows = d_slots;
-  ep.nslots = nslots;
-  ep.nspans = nspans;
-  ep.ng = ng;
-  ep.partial = static_cast<const double*>(d_partial);
-  ep.zcount = static_cast<const int32_t*>(d_z);
-  ep.count = plan->d_count;
-  ep.kd = kd;
+  CombineParams cp;
+  cp.rows = d_slots;
+  cp.nslots = nslots;
+  cp.nspans = nspans;
+  cp.ng = ng;
+  cp.partial = static_cast<const double*>(d_partial);
+  cp.zcount = static_cast<const int32_t*>(d_z);
+  cp.sums = d_sums;
+  cp.minmax = d_minmax;
   const int64_t nthreads = (int64_t)nslots * ng;
-  epilogue_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(ep);
+  combine_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(cp);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
 
-// Resolve the public averaging method into (kernel f kind, kd, per-layer method).
+// Finalize stage: partial results -> outputs (average_optical_depth.cpp:43-193).
+// d_count[ng]: wavenumbers per g point over the WHOLE spectrum (all shards).
+static int finalize_rows(ecckd_ctx* ctx, int ng, const long long* d_count, const std::vector<OutDesc>& outs, double kd,
+                         const double* d_sums, const double* d_minmax) {
+  const int nrows = (int)outs.size();
+  if (nrows == 0) return ECCKD_OK;
+  void* d_outs = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 0, (size_t)nrows * sizeof(OutDesc), &d_outs));
+  ECCKD_TRY(upload_small(ctx, d_outs, outs.data(), (size_t)nrows * sizeof(OutDesc)));
+  FinalizeParams fp;
+  fp.outs = static_cast<const OutDesc*>(d_outs);
+  fp.nrows = nrows;
+  fp.ng = ng;
+  fp.sums = d_sums;
+  fp.minmax = d_minmax;
+  fp.count = d_count;
+  fp.kd = kd;
+  const int64_t nthreads = (int64_t)nrows * ng;
+  finalize_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(fp);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+// Resolve the public averaging method into (kernel f kind, kd).
 static int resolve_method(int averaging_method, int* fkind, double* kd) {
   const double OD_SCALING = 1.0;  // average_optical_depth.cpp:35
   switch (averaging_method) {
@@ -657,6 +701,26 @@ static int row_method(int fkind, double pressure_fl) {
     case F_LOG: return M_LOG;
     default: return (pressure_fl > 100.0e2) ? M_LOG : M_TRANS;  // average_optical_depth.cpp:101
   }
+}
+
+static int resolve_weights(const ecckd_gpoint_plan* plan, int weight_mode, const double* d_weight, int64_t w_stride,
+                           const double* h_temperature, const double* d_wn, const double* d_dwn, int* wmode) {
+  if (weight_mode == ECCKD_WEIGHT_MATRIX) {
+    ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight matrix is NULL");
+    *wmode = (w_stride == 0) ? W_VECTOR : W_TILE_MATRIX;  // stride 0 == spread<0>(ssi, nlay)
+    ECCKD_REQUIRE(w_stride == 0 || w_stride >= plan->nwav, ECCKD_PARAMETER_ERROR, "weight stride smaller than nwav");
+  } else if (weight_mode == ECCKD_WEIGHT_VECTOR) {
+    ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight vector is NULL");
+    *wmode = W_VECTOR;
+  } else if (weight_mode == ECCKD_WEIGHT_PLANCK) {
+    ECCKD_REQUIRE(h_temperature && d_wn && d_dwn, ECCKD_PARAMETER_ERROR,
+                  "Planck weights need temperature, wavenumber and d_wavenumber");
+    *wmode = W_TILE_PLANCK;
+  } else {
+    set_error("weight_mode %d not understood", weight_mode);
+    return ECCKD_PARAMETER_ERROR;
+  }
+  return ECCKD_OK;
 }
 
 }  // namespace ecckd
@@ -711,6 +775,7 @@ ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
   if (plan->ctx) cudaStreamSynchronize(plan->ctx->stream);
   cudaFree(plan->d_slots);
   cudaFree(plan->d_count);
+  cudaFree(plan->d_scratch);
   delete plan;
   return ECCKD_OK;
 }
@@ -718,6 +783,12 @@ ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
 ECCKD_API int ecckd_gpoint_plan_counts(ecckd_gpoint_plan* plan, int64_t* h_count) {
   ECCKD_REQUIRE(plan && h_count, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_counts: NULL argument");
   for (int g = 0; g < plan->ng; ++g) h_count[g] = plan->h_count[g];
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_gpoint_plan_counts_dev(ecckd_gpoint_plan* plan, int64_t** d_count) {
+  ECCKD_REQUIRE(plan && d_count, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_counts_dev: NULL argument");
+  *d_count = reinterpret_cast<int64_t*>(plan->d_count);
   return ECCKD_OK;
 }
 
@@ -740,58 +811,101 @@ ECCKD_API int ecckd_planck_function_dev(ecckd_ctx* ctx, int nt, const double* h_
   return ECCKD_OK;
 }
 
+ECCKD_API int ecckd_average_optical_depth_partial_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nspec, int nlay,
+                                                      const double* h_pressure_fl, const double* const* h_d_od,
+                                                      int64_t od_stride, int weight_mode, const double* d_weight,
+                                                      int64_t w_stride, const double* h_temperature,
+                                                      const double* d_wn, const double* d_dwn, int averaging_method,
+                                                      double* d_sums, double* d_minmax) {
+  ECCKD_REQUIRE(ctx && plan && h_pressure_fl && h_d_od && d_sums && d_minmax, ECCKD_PARAMETER_ERROR,
+                "ecckd_average_optical_depth_partial: NULL argument");
+  ECCKD_REQUIRE(nspec > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: nspec and nlay must be > 0");
+  ECCKD_REQUIRE(od_stride >= plan->nwav, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: od_stride < nwav");
+  int fkind, wmode;
+  double kd;
+  ECCKD_TRY(resolve_method(averaging_method, &fkind, &kd));
+  ECCKD_TRY(resolve_weights(plan, weight_mode, d_weight, w_stride, h_temperature, d_wn, d_dwn, &wmode));
+  // rows ordered layer-major so that the 32 rows of a warp share few weight rows
+  std::vector<RowDesc> rows;
+  rows.reserve((size_t)nspec * nlay);
+  for (int l = 0; l < nlay; ++l) {
+    for (int s = 0; s < nspec; ++s) {
+      ECCKD_REQUIRE(h_d_od[s] != nullptr, ECCKD_PARAMETER_ERROR, "spectrum %d: NULL device pointer", s);
+      RowDesc r;
+      r.od = h_d_od[s] + (int64_t)l * od_stride;
+      r.method = row_method(fkind, h_pressure_fl[l]);
+      r.wrow = l;
+      r.row = l * nspec + s;
+      r.pad_ = 0;
+      rows.push_back(r);
+    }
+  }
+  return reduce_partial(ctx, plan, rows, fkind, kd, wmode, d_weight, w_stride, h_temperature, nlay, d_wn, d_dwn, d_sums,
+                        d_minmax);
+}
+
+ECCKD_API int ecckd_average_optical_depth_finalize_dev(ecckd_ctx* ctx, int ng, const int64_t* d_count, int nspec,
+                                                       const double* h_reference_surface_vmr, int nlay,
+                                                       const double* h_pressure_fl, const double* h_pressure_hl,
+                                                       int averaging_method, const double* d_sums,
+                                                       const double* d_minmax, double* const* h_d_molar_abs,
+                                                       double* const* h_d_min, double* const* h_d_max,
+                                                       int64_t out_stride, int32_t* const* h_d_warn) {
+  ECCKD_REQUIRE(ctx && d_count && h_reference_surface_vmr && h_pressure_fl && h_pressure_hl && d_sums && d_minmax &&
+                    h_d_molar_abs,
+                ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth_finalize: NULL argument");
+  ECCKD_REQUIRE(nspec > 0 && nlay > 0 && ng > 0 && out_stride >= ng, ECCKD_PARAMETER_ERROR,
+                "ecckd_average_optical_depth_finalize: bad dimensions");
+  int fkind;
+  double kd;
+  ECCKD_TRY(resolve_method(averaging_method, &fkind, &kd));
+  std::vector<OutDesc> outs((size_t)nspec * nlay);
+  for (int l = 0; l < nlay; ++l) {
+    for (int s = 0; s < nspec; ++s) {
+      ECCKD_REQUIRE(h_d_molar_abs[s] != nullptr, ECCKD_PARAMETER_ERROR, "spectrum %d: NULL output pointer", s);
+      OutDesc& o = outs[(size_t)l * nspec + s];
+      o.out = h_d_molar_abs[s] + (int64_t)l * out_stride;
+      const bool mm = h_d_min && h_d_max && h_d_min[s] && h_d_max[s];
+      o.out_min = mm ? h_d_min[s] + (int64_t)l * out_stride : nullptr;
+      o.out_max = mm ? h_d_max[s] + (int64_t)l * out_stride : nullptr;
+      o.warn = (h_d_warn && h_d_warn[s]) ? h_d_warn[s] : nullptr;
+      const double vmr = h_reference_surface_vmr[s];
+      o.factor = (vmr > 0.0) ? ((ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR) / vmr) : 0.0;
+      o.dp = h_pressure_hl[l + 1] - h_pressure_hl[l];
+      o.method = row_method(fkind, h_pressure_fl[l]);
+      o.pad_ = 0;
+    }
+  }
+  return finalize_rows(ctx, ng, reinterpret_cast<const long long*>(d_count), outs, kd, d_sums, d_minmax);
+}
+
 ECCKD_API int ecckd_average_optical_depth_batch_dev(
     ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nspec, const double* h_reference_surface_vmr, int nlay,
     const double* h_pressure_fl, const double* h_pressure_hl, const double* const* h_d_od, int64_t od_stride,
     int weight_mode, const double* d_weight, int64_t w_stride, const double* h_temperature, const double* d_wn,
     const double* d_dwn, int averaging_method, double* const* h_d_molar_abs, double* const* h_d_min,
     double* const* h_d_max, int64_t out_stride, int32_t* const* h_d_warn) {
-  ECCKD_REQUIRE(ctx && plan && h_reference_surface_vmr && h_pressure_fl && h_pressure_hl && h_d_od && h_d_molar_abs,
-                ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: NULL argument");
+  ECCKD_REQUIRE(ctx && plan, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: NULL argument");
   ECCKD_REQUIRE(nspec > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: nspec and nlay must be > 0");
-  ECCKD_REQUIRE(od_stride >= plan->nwav && out_stride >= plan->ng, ECCKD_PARAMETER_ERROR,
-                "ecckd_average_optical_depth: strides smaller than row length");
-  int fkind;
-  double kd;
-  ECCKD_TRY(resolve_method(averaging_method, &fkind, &kd));
-  int wmode;
-  if (weight_mode == ECCKD_WEIGHT_MATRIX) {
-    ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight matrix is NULL");
-    wmode = (w_stride == 0) ? W_VECTOR : W_TILE_MATRIX;  // stride 0 == spread<0>(ssi, nlay)
-    ECCKD_REQUIRE(w_stride == 0 || w_stride >= plan->nwav, ECCKD_PARAMETER_ERROR, "weight stride smaller than nwav");
-  } else if (weight_mode == ECCKD_WEIGHT_VECTOR) {
-    ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight vector is NULL");
-    wmode = W_VECTOR;
-  } else if (weight_mode == ECCKD_WEIGHT_PLANCK) {
-    ECCKD_REQUIRE(h_temperature && d_wn && d_dwn, ECCKD_PARAMETER_ERROR,
-                  "Planck weights need temperature, wavenumber and d_wavenumber");
-    wmode = W_TILE_PLANCK;
-  } else {
-    set_error("weight_mode %d not understood", weight_mode);
-    return ECCKD_PARAMETER_ERROR;
+  // partial sums live in the plan-independent scratch slot 3 tail; sized [nrows][ng][NSUM + NMINMAX]
+  const size_t nrg = (size_t)nspec * nlay * plan->ng;
+  if (plan->scratch_bytes < nrg * (NSUM + NMINMAX) * sizeof(double)) {
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(plan->d_scratch);
+    plan->d_scratch = nullptr;
+    plan->scratch_bytes = 0;
+    ECCKD_CUDA_OK(cudaMalloc(&plan->d_scratch, nrg * (NSUM + NMINMAX) * sizeof(double)));
+    plan->scratch_bytes = nrg * (NSUM + NMINMAX) * sizeof(double);
   }
-  // rows ordered layer-major so that the 32 rows of a warp share few weight rows
-  std::vector<RowDesc> rows;
-  rows.reserve((size_t)nspec * nlay);
-  for (int l = 0; l < nlay; ++l) {
-    for (int s = 0; s < nspec; ++s) {
-      ECCKD_REQUIRE(h_d_od[s] && h_d_molar_abs[s], ECCKD_PARAMETER_ERROR, "spectrum %d: NULL device pointer", s);
-      RowDesc r;
-      r.od = h_d_od[s] + (int64_t)l * od_stride;
-      r.out = h_d_molar_abs[s] + (int64_t)l * out_stride;
-      const bool mm = h_d_min && h_d_max && h_d_min[s] && h_d_max[s];
-      r.out_min = mm ? h_d_min[s] + (int64_t)l * out_stride : nullptr;
-      r.out_max = mm ? h_d_max[s] + (int64_t)l * out_stride : nullptr;
-      r.warn = (h_d_warn && h_d_warn[s]) ? h_d_warn[s] : nullptr;
-      const double vmr = h_reference_surface_vmr[s];
-      r.factor = (vmr > 0.0) ? ((ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR) / vmr) : 0.0;
-      r.dp = h_pressure_hl[l + 1] - h_pressure_hl[l];
-      r.method = row_method(fkind, h_pressure_fl[l]);
-      r.wrow = l;
-      rows.push_back(r);
-    }
-  }
-  return reduce_rows(ctx, plan, rows, fkind, kd, wmode, d_weight, w_stride, h_temperature, nlay, d_wn, d_dwn);
+  double* d_sums = plan->d_scratch;
+  double* d_minmax = d_sums + nrg * NSUM;
+  ECCKD_TRY(ecckd_average_optical_depth_partial_dev(ctx, plan, nspec, nlay, h_pressure_fl, h_d_od, od_stride,
+                                                    weight_mode, d_weight, w_stride, h_temperature, d_wn, d_dwn,
+                                                    averaging_method, d_sums, d_minmax));
+  return ecckd_average_optical_depth_finalize_dev(ctx, plan->ng, reinterpret_cast<const int64_t*>(plan->d_count), nspec,
+                                                  h_reference_surface_vmr, nlay, h_pressure_fl, h_pressure_hl,
+                                                  averaging_method, d_sums, d_minmax, h_d_molar_abs, h_d_min, h_d_max,
+                                                  out_stride, h_d_warn);
 }
 
 ECCKD_API int ecckd_average_optical_depth_to_g_point_dev(
@@ -950,17 +1064,33 @@ ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, cons
                                    int nlut, const double* h_temperature_lut, double* d_out) {
   ECCKD_REQUIRE(ctx && plan && d_wn && d_dwn && h_temperature_lut && d_out && nlut > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_planck_lut: bad argument");
+  // sum over each g point of planck(T, nu): the reduction with f = 1 and Planck weights
   std::vector<RowDesc> rows(nlut);
+  std::vector<OutDesc> outs(nlut);
   for (int t = 0; t < nlut; ++t) {
-    RowDesc r;
-    memset(&r, 0, sizeof(r));
+    RowDesc& r = rows[t];
     r.od = d_wn;  // any valid row: F_NONE ignores the values
-    r.out = d_out + (int64_t)t * plan->ng;
     r.method = M_SUMW;
     r.wrow = t;
-    rows[t] = r;
+    r.row = t;
+    r.pad_ = 0;
+    OutDesc& o = outs[t];
+    memset(&o, 0, sizeof(o));
+    o.out = d_out + (int64_t)t * plan->ng;
+    o.method = M_SUMW;
   }
-  return reduce_rows(ctx, plan, rows, F_NONE, 1.0, W_TILE_PLANCK, nullptr, 0, h_temperature_lut, nlut, d_wn, d_dwn);
+  void* scratch = nullptr;
+  const size_t nrg = (size_t)nlut * plan->ng;
+  ECCKD_CUDA_OK(cudaMalloc(&scratch, nrg * (NSUM + NMINMAX) * sizeof(double)));
+  double* d_sums = static_cast<double*>(scratch);
+  double* d_minmax = d_sums + nrg * NSUM;
+  int rc = reduce_partial(ctx, plan, rows, F_NONE, 1.0, W_TILE_PLANCK, nullptr, 0, h_temperature_lut, nlut, d_wn, d_dwn,
+                          d_sums, d_minmax);
+  if (rc == ECCKD_OK)
+    rc = finalize_rows(ctx, plan->ng, reinterpret_cast<const long long*>(plan->d_count), outs, 1.0, d_sums, d_minmax);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(scratch);
+  return rc;
 }
 
 ECCKD_API int ecckd_compact_g_points_dev(ecckd_ctx* ctx, int ng, int64_t nwav, int32_t* d_g_point,

@@ -17,9 +17,17 @@ enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };
 enum { F_LINEAR = 0, F_TRANS = 1, F_SQRT = 2, F_LOG = 3, F_HYBRID = 4, F_NONE = 5 };
 enum { W_TILE_MATRIX = 0, W_VECTOR = 1, W_TILE_PLANCK = 2 };
 
-// One (spectrum, layer) row of the reduction.
+// One (spectrum, layer) row of the streaming reduction.
 struct RowDesc {
-  const double* od;   // row base (nwav doubles)
+  const double* od;   // row base (nwav doubles); NULL = unused slot
+  int32_t method;     // M_*
+  int32_t wrow;       // weight row (layer index / temperature index)
+  int32_t row;        // index of this row in the partial-sum arrays
+  int32_t pad_;
+};
+
+// Where and how one row's result is written by the finalize kernel.
+struct OutDesc {
   double* out;        // &molar_abs[layer][0]
   double* out_min;    // may be NULL
   double* out_max;    // may be NULL
@@ -27,8 +35,14 @@ struct RowDesc {
   double factor;      // (g*0.001*M_air)/vmr_ref, or <= 0 for "raw optical depth"
   double dp;          // p_hl[l+1]-p_hl[l]
   int32_t method;     // M_*
-  int32_t wrow;       // weight row (layer index / temperature index)
+  int32_t pad_;
 };
+
+// Per-(row, g) partial results, the only data that crosses GPUs when the
+// wavenumber axis is sharded: sums[row][g] = {sum f*w, sum w, count(tau<=0)}
+// (allreduce SUM) and minmax[row][g] = {min tau, -max tau} (allreduce MIN).
+constexpr int NSUM = 3;
+constexpr int NMINMAX = 2;
 
 // 32 rows handled by one warp (row = lane).
 struct GroupDesc {
@@ -61,14 +75,24 @@ struct ReduceParams {
   int smem_per_warp;
 };
 
-struct EpilogueParams {
+struct CombineParams {
   const RowDesc* rows;  // indexed by row slot = group*32 + lane; od == NULL for inactive
   int nslots;
   int nspans;
   int ng;
   const double* partial;
   const int32_t* zcount;
-  const unsigned long long* count;  // [ng] wavenumbers per g point
+  double* sums;    // [nrows][ng][NSUM]
+  double* minmax;  // [nrows][ng][NMINMAX]
+};
+
+struct FinalizeParams {
+  const OutDesc* outs;  // [nrows]
+  int nrows;
+  int ng;
+  const double* sums;
+  const double* minmax;
+  const long long* count;  // [ng] wavenumbers per g point (global)
   double kd;
 };
 
@@ -82,4 +106,6 @@ struct ecckd_gpoint_plan {
   uint16_t* d_slots = nullptr;           // [nchunks][CHUNK]
   unsigned long long* d_count = nullptr; // [ng]
   std::vector<int64_t> h_count;
+  double* d_scratch = nullptr;           // per-(row, g) partial results of the single-GPU path
+  size_t scratch_bytes = 0;
 };

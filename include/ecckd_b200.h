@@ -127,6 +127,9 @@ int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t n
 int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan);
 /* Number of wavenumbers in each g point (h_count[ng], host). */
 int ecckd_gpoint_plan_counts(ecckd_gpoint_plan* plan, int64_t* h_count);
+/* Device pointer to the same counts as int64[ng] (for a cross-GPU sum when the
+ * wavenumber axis is sharded). */
+int ecckd_gpoint_plan_counts_dev(ecckd_gpoint_plan* plan, int64_t** d_count);
 
 /* average_optical_depth_to_g_point: src/ecckd/average_optical_depth.cpp:22-197
  * (declaration average_optical_depth.h:19-30).
@@ -163,6 +166,30 @@ int ecckd_average_optical_depth_batch_dev(
     const double* h_temperature, const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1,
     int averaging_method, double* const* h_d_molar_abs, double* const* h_d_min_molar_abs,
     double* const* h_d_max_molar_abs, int64_t out_stride, int32_t* const* h_d_warn);
+
+/* The same reduction split in two for wavenumber sharding across GPUs
+ * (BASELINE north_star: only the small per-g-point partial accumulators cross
+ * NVLink).  Each rank runs _partial_dev on its own wavenumber range (its own
+ * plan), the ranks all-reduce
+ *   d_sums  [nlay][nspec][ng][3] = {sum f(tau)*w, sum w, count(tau <= 0)}  with SUM,
+ *   d_minmax[nlay][nspec][ng][2] = {min tau, -max tau}                      with MIN,
+ *   the plan counts int64[ng]                                               with SUM,
+ * and every rank runs _finalize_dev (average_optical_depth.cpp:43-193 after the
+ * sums) on the reduced arrays.  _batch_dev above is exactly _partial_dev
+ * followed by _finalize_dev on one device. */
+int ecckd_average_optical_depth_partial_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nspec, int nlay,
+                                            const double* h_pressure_fl, const double* const* h_d_od,
+                                            int64_t od_stride, int weight_mode, const double* d_weight,
+                                            int64_t w_stride, const double* h_temperature,
+                                            const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1,
+                                            int averaging_method, double* d_sums, double* d_minmax);
+int ecckd_average_optical_depth_finalize_dev(ecckd_ctx* ctx, int ng, const int64_t* d_count, int nspec,
+                                             const double* h_reference_surface_vmr, int nlay,
+                                             const double* h_pressure_fl, const double* h_pressure_hl,
+                                             int averaging_method, const double* d_sums, const double* d_minmax,
+                                             double* const* h_d_molar_abs, double* const* h_d_min_molar_abs,
+                                             double* const* h_d_max_molar_abs, int64_t out_stride,
+                                             int32_t* const* h_d_warn);
 
 /* Host-buffer form with exactly the reference's argument list
  * (average_optical_depth.h:19-30): g_point, optical_depth and planck_fl are

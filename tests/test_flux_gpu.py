@@ -1,0 +1,136 @@
+"""GPU parity of the CKD flux solver (ckd_model.cpp:923-1145, radiative_transfer_*.cpp,
+heating_rate.h, run_ckd.cpp:119-367) against the CPU oracle.  Flux tolerance: 1e-6 W m-2
+(north_star); optical depths and Planck functions relative 1e-12."""
+import numpy as np
+import pytest
+
+import ecckd_b200 as E
+from tests import synthetic as S
+
+pytestmark = pytest.mark.gpu
+FLUX_ATOL = S.FLUX_ATOL
+
+
+def _model(ctx, c, sw=False):
+    if sw:
+        return E.CkdModel(ctx, c["gases"], c["log_pressure"], c["temperature"],
+                          solar_irradiance=c["solar_irradiance"], rayleigh_molar_scat=c["rayleigh_molar_scat"])
+    return E.CkdModel(ctx, c["gases"], c["log_pressure"], c["temperature"], c["temperature_planck"], c["planck_lut"])
+
+
+def test_rt_lw_spectral(ctx, O):
+    rng = np.random.default_rng(0)
+    nlay, n = 54, 3000
+    od = np.exp(rng.normal(-3, 3, (nlay, n)))
+    od[rng.uniform(size=od.shape) < 0.1] = 0.0
+    planck = rng.uniform(0.0, 30.0, (nlay + 1, n))
+    emis, sp = rng.uniform(0.8, 1.0, n), rng.uniform(0.0, 30.0, n)
+    dn, up = E.radiative_transfer_lw(ctx, planck, od, emis, sp)
+    dn_o, up_o = O.radiative_transfer_lw(planck, od, emis, sp)
+    assert np.max(np.abs(dn - dn_o)) <= FLUX_ATOL * 1e-3 and np.max(np.abs(up - up_o)) <= FLUX_ATOL * 1e-3
+    # limits: opaque isothermal and transparent columns
+    pl = np.full((nlay + 1, n), 3.0)
+    dn, up = E.radiative_transfer_lw(ctx, pl, np.full((nlay, n), 50.0), np.ones(n), np.full(n, 3.0))
+    np.testing.assert_allclose(dn[1:], 3.0, rtol=1e-13)
+    dn, up = E.radiative_transfer_lw(ctx, pl, np.zeros((nlay, n)), np.ones(n), np.full(n, 3.0))
+    assert np.all(dn == 0.0) and np.all(up == 3.0)
+
+
+def test_rt_sw(ctx, O):
+    rng = np.random.default_rng(2)
+    nlay, n = 54, 2000
+    od = np.exp(rng.normal(-2, 2, (nlay, n)))
+    ssi, alb = rng.uniform(0.1, 2.0, n), rng.uniform(0, 0.5, n)
+    for mu0 in (0.5, 0.1, 1.0):
+        dn = E.radiative_transfer_direct_sw(ctx, mu0, ssi, od)
+        assert np.max(np.abs(dn - O.radiative_transfer_direct_sw(mu0, ssi, od))) <= FLUX_ATOL * 1e-3
+        dn2, up2 = E.radiative_transfer_norayleigh_sw(ctx, mu0, ssi, od, alb)
+        dn_o, up_o = O.radiative_transfer_norayleigh_sw(mu0, ssi, od, alb)
+        assert np.max(np.abs(dn2 - dn_o)) <= FLUX_ATOL * 1e-3 and np.max(np.abs(up2 - up_o)) <= FLUX_ATOL * 1e-3
+    cum = np.concatenate([np.zeros((1, n)), np.cumsum(od, axis=0)])
+    np.testing.assert_allclose(E.radiative_transfer_direct_sw(ctx, 0.5, ssi, od), 0.5 * ssi * np.exp(-cum / 0.5),
+                               rtol=1e-12, atol=1e-300)
+
+
+def test_heating_rate(ctx, O):
+    rng = np.random.default_rng(3)
+    p = S.pressure_grid(54)
+    dn, up = rng.uniform(0, 400, (55, 777)), rng.uniform(0, 400, (55, 777))
+    np.testing.assert_allclose(E.heating_rate(ctx, p, dn, up), O.heating_rate(p, dn, up), rtol=1e-14, atol=1e-18)
+    np.testing.assert_allclose(E.heating_rate(ctx, p, dn), O.heating_rate(p, dn), rtol=1e-14, atol=1e-18)
+
+
+def test_ckd_optical_depth_each_gas(ctx, O):
+    c = S.ckd_model_case(ncol=7, nlay=54, ng=32, seed=9)
+    m = _model(ctx, c)
+    t_fl = O.temperature_fl(c["temperature_hl"], c["pressure_hl"])
+    d_p, d_t = ctx.to_device(c["pressure_hl"]), ctx.to_device(t_fl)
+    d_od = ctx.empty((7, 54, 32))
+    total = np.zeros((7, 54, 32))
+    d_tot = ctx.zeros((7, 54, 32))
+    for i, (gas, vmr) in enumerate(zip(c["gases"], c["vmr_fl"])):
+        d_v = None if vmr is None else ctx.to_device(vmr)
+        m.calc_optical_depth_dev(i, 7, 54, d_p, d_t, d_v, d_od)
+        ref = O.ckd_calc_optical_depth(gas, c["log_pressure"], c["temperature"], c["pressure_hl"], t_fl, vmr)
+        # index weights are differences (pindex0 - ip0): last-bit differences of log() are amplified
+        np.testing.assert_allclose(d_od.numpy(), ref, rtol=5e-12, atol=1e-300, err_msg=gas["name"])
+        m.calc_optical_depth_dev(i, 7, 54, d_p, d_t, d_v, d_tot, accumulate=True)
+        total += ref
+    np.testing.assert_allclose(d_tot.numpy(), total, rtol=1e-11, atol=1e-18)
+    with pytest.raises(E.EcckdError) as ei:  # concentration not provided: THROW(1)
+        m.calc_optical_depth_dev(2, 7, 54, d_p, d_t, None, d_od)
+    assert ei.value.code == 1
+
+
+def test_ckd_planck_function(ctx, O):
+    c = S.ckd_model_case(ncol=9, nlay=54, ng=64, seed=3)
+    m = _model(ctx, c)
+    d_t = ctx.to_device(c["temperature_hl"])
+    d_pl = ctx.empty((9, 55, 64))
+    m.calc_planck_function_dev(9 * 55, d_t, d_pl)
+    ref = O.ckd_calc_planck_function(c["temperature_planck"], c["planck_lut"], c["temperature_hl"])
+    np.testing.assert_allclose(d_pl.numpy(), ref, rtol=1e-14)
+
+
+@pytest.mark.parametrize("ng", [32, 64, 20])
+def test_run_ckd_lw_config_a(ctx, O, ng):
+    """BASELINE config A: 50 columns x 54 layers x 32 g points, 8 gases."""
+    c = S.ckd_model_case(ncol=50, nlay=54, ng=ng, seed=1234)
+    m = _model(ctx, c)
+    got = m.run_ckd(c["vmr_fl"], c["pressure_hl"], c["temperature_hl"])
+    ref = O.run_ckd(c, is_sw=False)
+    np.testing.assert_allclose(got["optical_depth"], ref["optical_depth"], rtol=2e-11, atol=1e-18)
+    np.testing.assert_allclose(got["planck_hl"], ref["planck_hl"], rtol=1e-14)
+    np.testing.assert_allclose(got["planck_surf"], ref["planck_surf"], rtol=1e-14)
+    for k in ("flux_dn", "flux_up", "bb_flux_dn", "bb_flux_up"):
+        err = np.max(np.abs(got[k] - ref[k]))
+        assert err <= FLUX_ATOL, (k, err)
+    assert np.all(got["optical_depth"] >= 0.0)
+    assert ref["bb_flux_up"].max() > 100.0  # fluxes of physical magnitude: the 1e-6 W m-2 tolerance is meaningful
+
+
+def test_run_ckd_sw(ctx, O):
+    c = S.ckd_model_case(ncol=50, nlay=54, ng=32, seed=77, sw=True)
+    m = _model(ctx, c, sw=True)
+    got = m.run_ckd(c["vmr_fl"], c["pressure_hl"], c["temperature_hl"], tsi=1361.0)
+    ref = O.run_ckd(c, is_sw=True, tsi=1361.0)
+    np.testing.assert_allclose(got["optical_depth"], ref["optical_depth"], rtol=2e-11, atol=1e-18)
+    for k in ("flux_dn", "bb_flux_dn"):
+        err = np.max(np.abs(got[k] - ref[k]))
+        assert err <= FLUX_ATOL, (k, err)
+    np.testing.assert_allclose(got["bb_flux_dn"][:, 0], 0.5 * 1361.0, rtol=1e-13)
+
+
+def test_run_ckd_negative_od_is_clamped(ctx, O):
+    """relative-linear gases below their reference concentration give negative optical
+    depth; the sum is clamped at zero (run_ckd.cpp:317)."""
+    c = S.ckd_model_case(ncol=6, nlay=20, ng=8, seed=5)
+    for i in (0, 1, 2, 3, 6, 7):
+        c["gases"][i]["molar_abs"] = c["gases"][i]["molar_abs"] * 1e-9
+    c["vmr_fl"][4] = c["vmr_fl"][4] * 0.01
+    m = _model(ctx, c)
+    got = m.run_ckd(c["vmr_fl"], c["pressure_hl"], c["temperature_hl"])
+    ref = O.run_ckd(c, is_sw=False)
+    assert (ref["optical_depth"] == 0.0).any()
+    assert np.array_equal(got["optical_depth"] == 0.0, ref["optical_depth"] == 0.0)
+    assert np.max(np.abs(got["flux_up"] - ref["flux_up"])) <= FLUX_ATOL

@@ -1,0 +1,203 @@
+"""GPU parity of the spectral reduction (average_optical_depth.cpp:22-197 and
+companions) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+
+import ecckd_b200 as E
+from tests import synthetic as S
+from tests.oracle_lib import METHODS
+
+pytestmark = pytest.mark.gpu
+
+
+def _planck(O, c):
+    return O.planck_function(c["temperature_fl"], c["wavenumber"], c["d_wavenumber"])
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_avg_host_api_all_methods(ctx, O, method):
+    c = S.lw_spectrum_case(nlay=13, nwav=6000, ng=10, nband=3, seed=21)
+    planck = _planck(O, c)
+    got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                             c["od"], planck, method)
+    ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                             c["od"], planck, method)
+    S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c), what=method + " ")
+
+
+@pytest.mark.parametrize("nwav", [1, 2, 63, 64, 65, 127, 4097])
+def test_avg_ragged_sizes(ctx, O, nwav):
+    """Chunk boundaries, odd lengths (8-byte copy path) and tiny spectra."""
+    c = S.lw_spectrum_case(nlay=5, nwav=max(nwav, 8), ng=3, nband=1, seed=nwav)
+    sl = slice(0, nwav)
+    od, g = np.ascontiguousarray(c["od"][:, sl]), c["g_point"][sl]
+    planck = np.ascontiguousarray(_planck(O, c)[:, sl])
+    for method in ("transmission", "logarithmic"):
+        got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], g, od,
+                                                 planck, method)
+        ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], g, od, planck,
+                                                 method)
+        S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c), what=f"nwav={nwav} {method} ")
+
+
+def test_avg_empty_unassigned_and_all_zero(ctx, O):
+    c = S.lw_spectrum_case(nlay=7, nwav=3000, ng=6, nband=2, seed=4)
+    g = c["g_point"].copy()
+    g[g == 3] = 2       # empty g point
+    g[::13] = -1        # wavenumbers in no g point
+    g[5::97] = 99       # out-of-range index also belongs to no g point
+    od = c["od"].copy()
+    od[2, g == 1] = 0.0  # a (layer, g) with no positive optical depth at all
+    planck = _planck(O, c)
+    for method in METHODS:
+        got = E.average_optical_depth_to_g_point(ctx, 6, c["vmr"], c["pressure_fl"], c["pressure_hl"], g, od, planck,
+                                                 method)
+        ref = O.average_optical_depth_to_g_point(6, c["vmr"], c["pressure_fl"], c["pressure_hl"], g, od, planck,
+                                                 method)
+        S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c), what=method + " ")
+        assert got[3][3] & 1 and np.all(got[0][:, 3] == 0.0)
+
+
+def test_avg_raw_optical_depth_and_solar_weight(ctx, O):
+    """reference_surface_vmr <= 0 returns optical depth (:186-193); SW weights are one
+    row broadcast over layers (create_look_up_table.cpp:335)."""
+    c = S.sw_spectrum_case(nlay=9, nwav=5000, ng=8, nband=2, seed=6)
+    for vmr in (-1.0, 2.0e-3):
+        got = E.average_optical_depth_to_g_point(ctx, c["ng"], vmr, c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                                 c["od"], c["ssi"], "transmission")
+        ref = O.average_optical_depth_to_g_point(c["ng"], vmr, c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                                 c["od"], c["ssi"], "transmission")
+        cc = dict(c, vmr=vmr)
+        S.assert_avg_close(got, ref, method="transmission", scale=S.out_scale(cc))
+
+
+def test_avg_bad_method_is_parameter_error(ctx):
+    c = S.lw_spectrum_case(nlay=3, nwav=100, ng=2, nband=1, seed=5)
+    with pytest.raises(E.EcckdError) as ei:
+        E.average_optical_depth_to_g_point(ctx, 2, 1.0, c["pressure_fl"], c["pressure_hl"], c["g_point"], c["od"],
+                                           c["od"], "total-transmission")
+    assert ei.value.code == 147
+
+
+def test_avg_known_answer_constant_od(ctx):
+    c = S.lw_spectrum_case(nlay=6, nwav=1200, ng=5, nband=1, seed=2, zero_frac=0.0)
+    tau_g = np.array([1e-6, 3e-3, 0.2, 1.5, 4.0])
+    lay = np.linspace(0.5, 2.0, 6)
+    od = np.ascontiguousarray(np.broadcast_to(tau_g[c["g_point"]], c["od"].shape) * lay[:, None])
+    w = np.abs(np.sin(np.arange(1200.0)))[None, :] + 0.1 * np.arange(1, 7)[:, None]
+    for m in METHODS:
+        out, mn, mx, warn = E.average_optical_depth_to_g_point(ctx, 5, -1.0, c["pressure_fl"], c["pressure_hl"],
+                                                               c["g_point"], od, w, m)
+        np.testing.assert_allclose(out, lay[:, None] * tau_g[None, :], rtol=1e-9, err_msg=m)
+        assert np.all(warn & 4)
+
+
+def _device_case(ctx, c):
+    d = dict(od=ctx.to_device(c["od"]), g=ctx.to_device(c["g_point"], np.int32), wn=ctx.to_device(c["wavenumber"]),
+             dwn=ctx.to_device(c["d_wavenumber"]))
+    d["plan"] = E.GPointPlan(ctx, d["g"], c["nwav"], c["ng"])
+    return d
+
+
+def test_plan_counts(ctx):
+    c = S.lw_spectrum_case(nlay=2, nwav=7001, ng=9, nband=3, seed=8)
+    d = _device_case(ctx, c)
+    assert np.array_equal(d["plan"].counts(), np.bincount(c["g_point"], minlength=c["ng"]))
+
+
+@pytest.mark.parametrize("method", ["transmission", "hybrid-logarithmic-transmission-3", "linear"])
+def test_avg_fused_planck_weights(ctx, O, method):
+    """ECCKD_WEIGHT_PLANCK fuses planck_function (planck_function.cpp:47-53) into the
+    reduction; result must equal planck_function followed by the averaging."""
+    c = S.lw_spectrum_case(nlay=40, nwav=9000, ng=12, nband=3, seed=31)
+    d = _device_case(ctx, c)
+    nlay, ng = c["nlay"], c["ng"]
+    out, omin, omax = ctx.empty((nlay, ng)), ctx.empty((nlay, ng)), ctx.empty((nlay, ng))
+    warn = ctx.zeros(ng, np.int32)
+    E.average_optical_depth_to_g_point_dev(ctx, d["plan"], c["vmr"], c["pressure_fl"], c["pressure_hl"], d["od"],
+                                           c["nwav"], E.WEIGHT_PLANCK, None, 0, c["temperature_fl"], d["wn"], d["dwn"],
+                                           method, out, omin, omax, ng, warn)
+    ref = O.average_optical_depth_to_g_point(ng, c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], c["od"],
+                                             _planck(O, c), method)
+    S.assert_avg_close((out.numpy(), omin.numpy(), omax.numpy(), warn.numpy()), ref, method=method,
+                       scale=S.out_scale(c))
+
+
+@pytest.mark.parametrize("weight_mode", ["planck", "matrix", "vector"])
+def test_avg_batch_matches_single_calls(ctx, O, weight_mode):
+    """All (gas, concentration) blocks of one temperature index in one pass: identical
+    to nspec separate reference calls."""
+    nspec = 5
+    base = S.lw_spectrum_case(nlay=11, nwav=7000, ng=9, nband=2, seed=40)
+    rng = np.random.default_rng(1)
+    ods = [base["od"] * np.exp(rng.normal(0, 1.0, base["od"].shape)) for _ in range(nspec)]
+    vmrs = [1.0, 3e-4, 1e-6, -1.0, 2.5e-2]
+    d = _device_case(ctx, base)
+    nlay, ng, nwav = base["nlay"], base["ng"], base["nwav"]
+    planck = _planck(O, base)
+    ssi = np.abs(np.sin(np.arange(nwav) * 0.01)) + 0.2
+    if weight_mode == "planck":
+        mode, d_w, wstride, w_ref = E.WEIGHT_PLANCK, None, 0, planck
+    elif weight_mode == "matrix":
+        mode, d_w, wstride, w_ref = E.WEIGHT_MATRIX, ctx.to_device(planck), nwav, planck
+    else:
+        mode, d_w, wstride, w_ref = E.WEIGHT_VECTOR, ctx.to_device(ssi), 0, ssi
+    d_ods = [ctx.to_device(o) for o in ods]
+    outs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    mins = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    maxs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    warns = [ctx.zeros(ng, np.int32) for _ in range(nspec)]
+    E.average_optical_depth_batch_dev(ctx, d["plan"], vmrs, base["pressure_fl"], base["pressure_hl"], d_ods, nwav,
+                                      mode, d_w, wstride, base["temperature_fl"], d["wn"], d["dwn"], "transmission",
+                                      outs, mins, maxs, ng, warns)
+    for s in range(nspec):
+        ref = O.average_optical_depth_to_g_point(ng, vmrs[s], base["pressure_fl"], base["pressure_hl"],
+                                                 base["g_point"], ods[s], w_ref, "transmission")
+        cc = dict(base, vmr=vmrs[s])
+        S.assert_avg_close((outs[s].numpy(), mins[s].numpy(), maxs[s].numpy(), warns[s].numpy()), ref,
+                           method="transmission", scale=S.out_scale(cc), what=f"spec {s} ")
+
+
+def test_avg_incoherent_g_map(ctx, O):
+    """A g map with no spectral coherence (every chunk holds most g points)."""
+    c = S.lw_spectrum_case(nlay=8, nwav=8000, ng=40, nband=1, seed=12, coherent=False)
+    planck = _planck(O, c)
+    got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                             c["od"], planck, "transmission")
+    ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                             c["od"], planck, "transmission")
+    S.assert_avg_close(got, ref, method="transmission", scale=S.out_scale(c))
+
+
+def test_avg_linearity_property_full_width(ctx):
+    """Size-independent property at a larger size than the oracle is run at: the
+    'linear' average of a*od1 + b*od2 equals a*avg(od1) + b*avg(od2) (raw optical depth),
+    and the result does not depend on how the kernel splits the spectrum (determinism)."""
+    nlay, nwav, ng = 53, 1 << 18, 64
+    rng = np.random.default_rng(0)
+    wn = np.linspace(0.0002, 3260.0, nwav)
+    key = np.log(S.smooth_spectrum(wn, rng, ncomp=40))
+    g, ng = S.g_point_map(wn, key, np.linspace(wn[0], wn[-1], 14), S.split_g_points(ng, 13), rng)
+    od1 = np.exp(rng.normal(-2, 1.5, (nlay, nwav)))
+    od2 = np.exp(rng.normal(-1, 1.0, (nlay, nwav)))
+    w = rng.uniform(0.5, 1.5, (nlay, nwav))
+    p_hl = S.pressure_grid(nlay)
+    p_fl = 0.5 * (p_hl[1:] + p_hl[:-1])
+    run = lambda od: E.average_optical_depth_to_g_point(ctx, ng, -1.0, p_fl, p_hl, g, od, w, "linear")
+    a1, a2 = run(od1), run(od2)
+    a3 = run(2.0 * od1 + 0.5 * od2)
+    np.testing.assert_allclose(a3[0], 2.0 * a1[0] + 0.5 * a2[0], rtol=1e-12)
+    od3 = 2.0 * od1 + 0.5 * od2
+    mn_ref = np.full((nlay, ng), np.inf)
+    for l in range(nlay):
+        np.minimum.at(mn_ref[l], g, od3[l])
+    assert np.array_equal(a3[1], mn_ref)  # minima are selections: exact
+    again = run(od1)
+    assert np.array_equal(again[0], a1[0])  # bitwise reproducible
+    # weighted mean from NumPy directly
+    sums = np.zeros((nlay, ng))
+    wsum = np.zeros((nlay, ng))
+    for l in range(nlay):
+        sums[l] = np.bincount(g, weights=od1[l] * w[l], minlength=ng)
+        wsum[l] = np.bincount(g, weights=w[l], minlength=ng)
+    np.testing.assert_allclose(a1[0], sums / wsum, rtol=1e-12)
