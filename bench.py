@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py - throughput of ecCKD's hot path on B200 (one JSON line on stdout).
+
+Workload (BASELINE.json configs[1], "create_look_up_table LW, 7 gases, 64 g
+points"): the spectral reduction of one temperature index of the look-up-table
+build = the 19 (gas, concentration) spectra that share that temperature's
+Planck weights (composite, H2O x 12 concentrations, O3, CO2, CH4, N2O, CFC-11,
+CFC-12; test/create_lut_lw.sh:146-200), each [53 layers][nwav = 2^23] FP64, 64 g
+points over 13 bands, averaging_method "transmission", Planck weights computed
+in the kernel.  The whole config is 6 such steps (114 blocks, 405 GB of optical
+depth), which does not fit one GPU's HBM at once; one temperature index
+(67.6 GB) does.  All data are synthetic and CKDMIP-shaped (no CKDMIP database).
+
+  value  = point.layers/s of the device-resident reduction, whole job (all ranks).
+  e2e    = the same metric through the reference-facing host-buffer call
+           (planck_function + average_optical_depth_to_g_point on one block,
+           host pinned buffers, H2D/D2H inside the timed region).
+  N > 1  = the wavenumber axis is sharded (each rank owns its own range, weak
+           scaling); per step the ranks all-reduce the per-g-point partial
+           accumulators over NCCL and finalize redundantly.
+
+`--impl reference` times the CPU oracle port of the reference algorithm
+(oracle/, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LW_BAND_EDGES = [0.0, 350.0, 500.0, 630.0, 700.0, 820.0, 980.0, 1080.0, 1180.0, 1390.0, 1480.0, 1800.0, 2080.0,
+                 3260.0]  # 13 "narrow" longwave bands (CKDMIP/RRTMG-like)
+NG_PER_BAND = [6, 5, 5, 5, 5, 5, 4, 4, 5, 4, 5, 5, 6]  # 64 g points
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log2-nwav", type=int, default=23)
+    ap.add_argument("--nspec", type=int, default=19)
+    ap.add_argument("--nlay", type=int, default=53)
+    ap.add_argument("--gmap", default="ranked", choices=["ranked", "random"],
+                    help="ranked: g points from ranking a smooth synthetic spectrum (as find_g_points does); "
+                         "random: no spectral coherence at all (adversarial)")
+    ap.add_argument("--weights", default="planck", choices=["planck", "matrix"])
+    ap.add_argument("--method", default="transmission")
+    ap.add_argument("--cpu-log2-nwav", type=int, default=22, help="CPU baseline sample size")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-flux", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ helpers
+def pressure_grid(nlay):
+    return np.exp(np.linspace(np.log(1.0), np.log(1.0e5), nlay + 1))
+
+
+def temperature_profile(p_hl, offset=0.0):
+    return 200.0 + 90.0 * (np.log(p_hl) / np.log(1.0e5)) + offset
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampler running during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ------------------------------------------------------------------ synthetic data on the device
+def smooth_key(torch, wn, seed, ncomp=40):
+    """Smooth multi-scale function of wavenumber (log of a synthetic absorption spectrum)."""
+    rng = np.random.default_rng(seed)
+    x = wn / 3260.0
+    f = torch.zeros_like(wn)
+    for _ in range(ncomp):
+        freq = 2.0 ** rng.uniform(0, 17)  # features from the whole spectrum down to ~0.02 cm-1
+        f += float(rng.normal() / np.sqrt(ncomp)) * torch.sin((2 * np.pi * freq) * x + float(rng.uniform(0, 2 * np.pi)))
+    return f
+
+
+def make_g_point(torch, wn, key, mode, seed):
+    """g-point map: rank `key` inside each band, cut the rank axis at seeded fractions."""
+    rng = np.random.default_rng(seed)
+    g = torch.full((wn.numel(),), -1, dtype=torch.int32, device=wn.device)
+    if mode == "random":
+        key = torch.rand(wn.numel(), dtype=torch.float64, device=wn.device,
+                         generator=torch.Generator(device=wn.device).manual_seed(seed))
+    g0 = 0
+    edges = LW_BAND_EDGES
+    for b in range(len(edges) - 1):
+        cuts = np.sort(rng.uniform(0.05, 0.95, NG_PER_BAND[b] - 1))
+        if b < len(edges) - 2:
+            m = (wn >= edges[b]) & (wn < edges[b + 1])
+        else:
+            m = (wn >= edges[b]) & (wn <= edges[b + 1])
+        idx = torch.nonzero(m).flatten()
+        n = idx.numel()
+        if n > 0:
+            order = torch.argsort(key[idx], stable=True)
+            frac = (torch.arange(n, device=wn.device, dtype=torch.float64) + 0.5) / n
+            gb = torch.bucketize(frac, torch.tensor(cuts, device=wn.device)).to(torch.int32) + g0
+            g[idx[order]] = gb
+        g0 += NG_PER_BAND[b]
+    return g, g0
+
+
+def make_spectrum(torch, wn, nlay, p_hl, seed, vmr):
+    """One synthetic spectrum [nlay][nwav]: smooth absorption x layer mass x lognormal noise, 2 % zeros."""
+    dev = wn.device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    base = torch.exp(2.5 * smooth_key(torch, wn, seed))
+    mass = torch.tensor((p_hl[1:] - p_hl[:-1]) * vmr / (9.80665 * 0.001 * 28.970), device=dev)
+    od = torch.empty((nlay, wn.numel()), dtype=torch.float64, device=dev)
+    od.normal_(0.0, 0.3, generator=gen)
+    od.exp_()
+    od.mul_(base[None, :])
+    od.mul_((3.0e-4 * mass)[:, None])
+    for l in range(nlay):  # zeros sprinkled in (exercise the zero-handling branches), row by row to bound memory
+        z = torch.rand(wn.numel(), device=dev, generator=gen) < 0.02
+        od[l].masked_fill_(z, 0.0)
+    return od
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+class CpuSample:
+    """The oracle port of planck_function + average_optical_depth_to_g_point (the reference's
+    per-block call pair, create_look_up_table.cpp:320-331) on a sample of the workload."""
+
+    def __init__(self, args, log2_nwav):
+        from tests.oracle_lib import oracle
+        from tests import synthetic as S
+
+        self.O = oracle()
+        self.method = args.method
+        self.nwav = nwav = 1 << log2_nwav
+        self.nlay = nlay = args.nlay
+        rng = np.random.default_rng(7)
+        self.p_hl = pressure_grid(nlay)
+        self.p_fl = 0.5 * (self.p_hl[1:] + self.p_hl[:-1])
+        t_hl = temperature_profile(self.p_hl)
+        self.t_fl = 0.5 * (t_hl[:-1] * self.p_hl[:-1] + t_hl[1:] * self.p_hl[1:]) / self.p_fl
+        self.wn = np.linspace(0.0002, 3260.0, nwav)
+        self.dwn = np.full(nwav, self.wn[1] - self.wn[0])
+        key = np.log(S.smooth_spectrum(self.wn, rng, ncomp=40))
+        self.g, self.ng = S.g_point_map(self.wn, key, np.array(LW_BAND_EDGES), NG_PER_BAND, rng)
+        row = np.exp(rng.normal(-3.0, 1.5, nwav))
+        self.od = np.ascontiguousarray(row[None, :] * np.linspace(0.2, 3.0, nlay)[:, None])
+
+    def run(self):
+        t0 = time.perf_counter()
+        planck = self.O.planck_function(self.t_fl, self.wn, self.dwn)
+        self.O.average_optical_depth_to_g_point(self.ng, 4.0e-4, self.p_fl, self.p_hl, self.g, self.od, planck,
+                                                self.method)
+        return time.perf_counter() - t0
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps, warm = args.steps, args.warmup
+    sample = CpuSample(args, args.cpu_log2_nwav)
+    for _ in range(warm):
+        sample.run()
+    total_t = sum(sample.run() for _ in range(steps))
+    value = steps * args.nlay * sample.nwav / total_t
+    line = {
+        "impl": "reference", "metric": "LBL spectral points*layers/s reduced to LUT", "value": value,
+        "unit": "point*layers/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "create_look_up_table LW block: planck_function + average_optical_depth_to_g_point "
+                               f"('{args.method}'), {args.nlay} layers x 2^{args.cpu_log2_nwav} wavenumbers, 64 g points "
+                               "(bounded sample of the 2^23-wavenumber block of BASELINE configs[1])"},
+        "cpu_baseline": {"value": value, "unit": "point*layers/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.nlay} x 2^{args.cpu_log2_nwav} per step; oracle/ecckd_oracle.cpp "
+                                   "(C++/OpenMP restatement incl. the reference's per-g rescans), all host threads"},
+        "e2e": {"value": value, "unit": "point*layers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import ecckd_b200 as E
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    # One explicit non-default stream for everything (torch ops, NCCL, our kernels, the timing
+    # events): the legacy default stream has handle 0, which the C ABI reads as "make a private stream".
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+    assert stream != 0
+    ctx = E.Context(local_rank, stream)
+
+    nlay, nspec = args.nlay, args.nspec
+    nwav = 1 << args.log2_nwav
+    # this rank's wavenumber range of the (world * nwav)-point spectrum
+    dnu = (3260.0 - 0.0002) / (world * nwav - 1)
+    wn = 0.0002 + dnu * (torch.arange(nwav, device=dev, dtype=torch.float64) + float(rank * nwav))
+    dwn = torch.full((nwav,), dnu, dtype=torch.float64, device=dev)
+    key = smooth_key(torch, wn, seed=7)
+    g_point, ng = make_g_point(torch, wn, key, args.gmap, seed=7)
+    del key
+    p_hl = pressure_grid(nlay)
+    p_fl = 0.5 * (p_hl[1:] + p_hl[:-1])
+    t_hl = temperature_profile(p_hl)
+    t_fl = 0.5 * (t_hl[:-1] * p_hl[:-1] + t_hl[1:] * p_hl[1:]) / p_fl
+    vmrs = [1.0] + [1e-7 * 10 ** (0.5 * i) for i in range(12)] + [5e-6, 4.15e-4, 1.9e-6, 3.3e-7, 2.3e-10, 5e-10]
+    vmrs = (vmrs * ((nspec + len(vmrs) - 1) // len(vmrs)))[:nspec]
+    ods = [make_spectrum(torch, wn, nlay, p_hl, 1000 + s + 100 * rank, vmrs[s]) for s in range(nspec)]
+    weight = None
+    if args.weights == "matrix":
+        weight = torch.empty((nlay, nwav), dtype=torch.float64, device=dev)
+        E.planck_function_dev(ctx, t_fl, wn, dwn, nwav, weight)
+    plan = E.GPointPlan(ctx, g_point, nwav, ng)
+    count = torch.zeros(ng, dtype=torch.int64, device=dev)
+    count.copy_(torch.from_numpy(plan.counts()))
+    if world > 1:
+        dist.all_reduce(count)
+    sums = torch.empty((nlay, nspec, ng, 3), dtype=torch.float64, device=dev)
+    minmax = torch.empty((nlay, nspec, ng, 2), dtype=torch.float64, device=dev)
+    outs = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
+    mins = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
+    maxs = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
+    wmode = E.WEIGHT_PLANCK if weight is None else E.WEIGHT_MATRIX
+
+    def step():
+        E.average_optical_depth_partial_dev(ctx, plan, nlay, p_fl, ods, nwav, wmode, weight, nwav, t_fl, wn, dwn,
+                                            args.method, sums, minmax)
+        if world > 1:  # the only cross-GPU traffic: per-(layer, spectrum, g) partial accumulators
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(minmax, op=dist.ReduceOp.MIN)
+        E.average_optical_depth_finalize_dev(ctx, ng, count, vmrs, p_fl, p_hl, args.method, sums, minmax, outs, mins,
+                                             maxs, ng)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ctx.set_timing(True)
+    ctx.reduce_kernel_time()
+    launches0 = ctx.kernel_launches
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    kms, klaunch = ctx.reduce_kernel_time()
+    ctx.set_timing(False)
+    launches = ctx.kernel_launches - launches0
+    kstat = torch.tensor([kms / max(klaunch, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kstat, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    units_per_step = world * nspec * nlay * nwav
+    value = units_per_step * args.steps / (total_ms * 1e-3)
+
+    # roofline of the dominant kernel (reduce_kernel), algorithmic bytes per launch per GPU:
+    # 8 B per point.layer of optical depth; per wavenumber 4 B g point + 8 B nu + 8 B dnu (Planck
+    # weights recomputed) or + 8 B per point.layer of weights per distinct weight row (streamed).
+    alg_bytes = nspec * nlay * nwav * 8 + nwav * 20
+    if weight is not None:
+        alg_bytes = nspec * nlay * nwav * 8 + nlay * nwav * 8 + nwav * 4
+    k_ms = float(kstat.item())
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak_gbs()
+
+    # ---- end to end through the reference-facing host call (one block per step)
+    e2e = None
+    if not args.no_e2e:
+        h_od = torch.empty((nlay, nwav), dtype=torch.float64, pin_memory=True)
+        h_od.copy_(ods[1])
+        h_wn, h_dwn = wn.cpu().numpy(), dwn.cpu().numpy()
+        h_g = g_point.cpu().numpy()
+        od_np = h_od.numpy()
+        res = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
+        for _ in range(2):
+            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od_np, t_fl, h_wn, h_dwn,
+                                                      args.method, out=res)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(2, min(args.steps, 5))
+        e0.record()
+        for _ in range(e2e_steps):
+            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od_np, t_fl, h_wn, h_dwn,
+                                                      args.method, out=res)
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nlay * nwav * e2e_steps / (float(ems.item()) * 1e-3), "unit": "point*layers/s",
+               "h2d_bytes_per_step": int(nlay * nwav * 8 + nwav * (8 + 8 + 4)),
+               "d2h_bytes_per_step": int(3 * nlay * ng * 8 + ng * 4),
+               "call": "ecckd_planck_average_optical_depth_to_g_point (one [53][2^%d] block per step, pinned host "
+                       "buffers)" % args.log2_nwav,
+               "ms_per_step": float(ems.item()) / e2e_steps}
+        del h_od
+
+    # ---- metric 2: CKD flux columns.g-points/s (run_ckd LW, config A LUT with columns replicated)
+    flux = None
+    if not args.no_flux and rank == 0:
+        try:
+            flux = bench_flux(torch, E, ctx, dev, peak)
+        except Exception as exc:  # secondary metric must not hide the primary one
+            flux = {"error": repr(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = CpuSample(args, args.cpu_log2_nwav)
+        sample.run()
+        dt = min(sample.run(), sample.run())
+        v = nlay * sample.nwav / dt
+        cpu = {"value": v, "unit": "point*layers/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"one block of {nlay} x 2^{args.cpu_log2_nwav} (planck_function + "
+                         f"average_optical_depth_to_g_point, oracle/ecckd_oracle.cpp, OpenMP all threads), {dt:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "LBL spectral points*layers/s reduced to LUT", "value": value, "unit": "point*layers/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": f"create_look_up_table LW (BASELINE configs[1]), one temperature index: {nspec} spectra x "
+                            f"{nlay} layers x 2^{args.log2_nwav} wavenumbers per GPU, {ng} g points / 13 bands, "
+                            f"'{args.method}', weights={args.weights}, g map={args.gmap}",
+                "sharding": "wavenumber ranges per rank; NCCL allreduce of per-g partial accumulators only",
+                "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" % (nspec * nlay * nwav * 8 / 1e9),
+                "reduce_partial_bytes_allreduced_per_step": int(sums.numel() * 8 + minmax.numel() * 8) if world > 1 else 0,
+            },
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "reduce_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes)},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches) * world,
+            "clocks": clocks,
+        }
+        if flux is not None:
+            line["flux_solver"] = flux
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_flux(torch, E, ctx, dev, peak):
+    """CKD flux columns.g-points/s: fused run_ckd LW core on 2^16 columns x 54 layers x 32 g points."""
+    from tests import synthetic as S
+
+    ncol, nlay, ng = 1 << 16, 54, 32
+    c = S.ckd_model_case(ncol=64, nlay=nlay, ng=ng, seed=1234)
+    model = E.CkdModel(ctx, c["gases"], c["log_pressure"], c["temperature"], c["temperature_planck"], c["planck_lut"])
+    rep = ncol // 64
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a, (rep, 1)))).to(dev)
+    p_hl, t_hl = t(c["pressure_hl"]), t(c["temperature_hl"])
+    vmr = [None if v is None else t(v) for v in c["vmr_fl"]]
+    od = torch.empty((ncol, nlay, ng), dtype=torch.float64, device=dev)
+    plh = torch.empty((ncol, nlay + 1, ng), dtype=torch.float64, device=dev)
+    pls = torch.empty((ncol, ng), dtype=torch.float64, device=dev)
+    dn, up = torch.empty_like(plh), torch.empty_like(plh)
+    bdn = torch.empty((ncol, nlay + 1), dtype=torch.float64, device=dev)
+    bup = torch.empty_like(bdn)
+    run = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls, dn, up, bdn, bup)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 10
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    bytes_per = 8 * (54 + 3 * 55) + 8  # 1760 B per column.g-point
+    return {"metric": "CKD flux columns*g-points/s", "value": ncol * ng / (ms * 1e-3), "unit": "column*g-points/s",
+            "ms_per_step": ms, "config": f"run_ckd LW fused core, {ncol} columns x {nlay} layers x {ng} g points, 8 gases",
+            "roofline": {"bound": "hbm", "achieved": ncol * ng * bytes_per / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": ncol * ng * bytes_per / (ms * 1e-3) / 1e9 / peak}}
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,10 @@ def _declare(L):
                                                   i32, vp, vp, vp, i64, vp],
         "ecckd_average_optical_depth_to_g_point": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, i64, C.c_char_p,
                                                    vp, vp, vp, i64, vp],
+        "ecckd_planck_average_optical_depth_to_g_point": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp,
+                                                          C.c_char_p, vp, vp, vp, i64, vp],
+        "ecckd_ctx_set_timing": [vp, i32],
+        "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],
         "ecckd_gpoint_fraction_dev": [vp, i32, i64, vp, vp, vp, i32, vp, vp, vp],
         "ecckd_ssi_intervals_dev": [vp, i64, vp, vp, i32, vp, vp, vp],

@@ -117,6 +117,15 @@ class Context:
         a = np.ascontiguousarray(a, dtype=dtype)
         return DeviceArray(self, a.shape, a.dtype).copy_from(a)
 
+    def set_timing(self, on: bool):
+        check(_lib.lib().ecckd_ctx_set_timing(self.handle, 1 if on else 0))
+
+    def reduce_kernel_time(self):
+        """(total ms, launches) of the streaming reduction kernel since the last call."""
+        ms, n = C.c_double(0.0), C.c_int64(0)
+        check(_lib.lib().ecckd_ctx_reduce_kernel_time(self.handle, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     @property
     def kernel_launches(self) -> int:
         return int(_lib.lib().ecckd_kernel_launch_count(self.handle))
@@ -223,6 +232,29 @@ def average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_vmr, pr
         w.ctypes.data, w_stride, averaging_method.encode(), out.ctypes.data,
         omin.ctypes.data if want_minmax else None, omax.ctypes.data if want_minmax else None, ng, warn.ctypes.data))
     return out, omin, omax, warn
+
+
+def planck_average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_vmr, pressure_fl, pressure_hl, g_point,
+                                            optical_depth, temperature_fl, wavenumber_cm_1, d_wavenumber_cm_1,
+                                            averaging_method, out=None):
+    """planck_function + average_optical_depth_to_g_point (create_look_up_table.cpp:320-331) on host
+    arrays in one call; `out` may hold preallocated (molar_abs, min, max, warn) arrays."""
+    od = optical_depth if isinstance(optical_depth, np.ndarray) and optical_depth.flags.c_contiguous and \
+        optical_depth.dtype == np.float64 else np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, nwav = od.shape
+    gp = np.ascontiguousarray(g_point, dtype=np.int32)
+    pf, pfp = _h(pressure_fl)
+    ph, php = _h(pressure_hl)
+    tf, tfp = _h(temperature_fl)
+    wn, wnp = _h(wavenumber_cm_1)
+    dwn, dwnp = _h(d_wavenumber_cm_1)
+    if out is None:
+        out = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
+    check(_lib.lib().ecckd_planck_average_optical_depth_to_g_point(
+        ctx.handle, ng, float(reference_surface_vmr), nlay, nwav, pfp, php, gp.ctypes.data, od.ctypes.data, nwav, tfp,
+        wnp, dwnp, averaging_method.encode(), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
+        out[3].ctypes.data))
+    return out
 
 
 def average_optical_depth_to_g_point_dev(ctx: Context, plan: GPointPlan, reference_surface_vmr, pressure_fl,

@@ -140,6 +140,10 @@ ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
   for (auto& w : ctx->ws) {
     if (w.ptr) cudaFree(w.ptr);
   }
+  for (auto& ev : ctx->reduce_events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -209,3 +213,26 @@ ECCKD_API int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, s
 }
 
 ECCKD_API int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+ECCKD_API int ecckd_ctx_set_timing(ecckd_ctx* ctx, int on) {
+  ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_ctx_set_timing: ctx is NULL");
+  ctx->timing = on != 0;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_ctx_reduce_kernel_time(ecckd_ctx* ctx, double* total_ms, int64_t* launches) {
+  ECCKD_REQUIRE(ctx && total_ms && launches, ECCKD_PARAMETER_ERROR, "ecckd_ctx_reduce_kernel_time: NULL argument");
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double sum = 0.0;
+  for (auto& ev : ctx->reduce_events) {
+    float ms = 0.f;
+    ECCKD_CUDA_OK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+    sum += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *total_ms = sum;
+  *launches = (int64_t)ctx->reduce_events.size();
+  ctx->reduce_events.clear();
+  return ECCKD_OK;
+}

@@ -40,7 +40,9 @@ struct ecckd_ctx {
   int num_sms = 148;
   size_t smem_optin = 0;
   int64_t launches = 0;
-  ecckd::Workspace ws[4];   // device scratch slots
+  ecckd::Workspace ws[8];   // device scratch slots (0-3 kernels' descriptors/partials, 4-5 host-API staging)
+  bool timing = false;      // record CUDA events around the streaming reduction kernel
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> reduce_events;
   void* pinned = nullptr;   // small pinned staging buffer for descriptor uploads
   size_t pinned_bytes = 0;
   size_t pinned_off = 0;    // bump offset; wraps after a stream synchronise

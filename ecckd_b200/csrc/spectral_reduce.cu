@@ -4,22 +4,27 @@
 // Planck LUT).
 //
 // Kernel design (B200, sm_100a) -- see DESIGN.md section 3:
-//   * A "row" is one (spectrum, layer) vector of nwav FP64 optical depths.  One
-//     warp owns 32 rows (row = lane) and sweeps a span of wavenumber chunks.
-//   * Chunks of CHUNK wavenumbers are staged into shared memory with
-//     asynchronous copies (coalesced 512 B per row per request, double
-//     buffered), so every HBM byte is read once, with full sectors.
+//   * A "row" is one (spectrum, layer) vector of nwav FP64 optical depths.  Rows
+//     that share a weight row (all spectra of one layer) form a group; a CTA
+//     gives each row of a group its own consumer warp and walks chunks of CH
+//     wavenumbers.  Consumer warps stage their row's chunk in shared memory
+//     with one bulk asynchronous copy (cp.async.bulk + mbarrier, NS stages
+//     deep): every HBM byte is read exactly once, 1792 contiguous bytes at a time.
+//   * The Planck weights of a chunk are computed once per CTA by two producer
+//     warps into a shared-memory tile that all rows of the group use (the
+//     reference recomputes planck_function for every block); matrix / vector
+//     weights are bulk-copied into the same tile.
 //   * The g-point map is identical for every row and every call of a LUT build,
-//     so a "plan" holds, per chunk, the local indices in g-sorted order.  The
-//     warp visits a chunk in that order: the g index is warp-uniform, each lane
-//     accumulates its row's running sums in registers, and only at a g change
-//     (warp-uniform branch) are they folded into lane-private shared-memory
-//     accumulators [g][4][lane] -- no atomics, no bank conflicts, deterministic
-//     summation order.
-//   * Spans of the wavenumber axis go to different warps/CTAs; their partial
-//     accumulators are combined in fixed span order by the epilogue kernel,
-//     which also applies the inverse transform, the min/max clamps and the
-//     conversion to molar absorption.
+//     so a "plan" assigns, per chunk, every wavenumber to a (lane, slot) such
+//     that each lane only sees one g point per round and lanes of one g point are
+//     adjacent.  A lane therefore accumulates its 8 slots in registers with no
+//     branches; a static segmented shuffle reduction (5 steps) then folds the
+//     lanes of each g point and the head lane adds the result to the warp's
+//     private shared-memory accumulator [ng][4].  No atomics anywhere; the
+//     summation order is fixed by the plan and the launch geometry.
+//   * The (group, chunk) space is cut into equal contiguous pieces, one per
+//     resident CTA; a CTA flushes its accumulators when it crosses into the
+//     next group.  A small combine kernel adds the pieces in fixed order.
 #include "spectral_reduce.cuh"
 
 #include <algorithm>
@@ -27,19 +32,40 @@
 namespace ecckd {
 
 // ------------------------------------------------------------------ helpers
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk asynchronous copy global -> shared (SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
 // planck_function.cpp:29-33,47-53, one element
 __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
@@ -54,272 +80,427 @@ __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
 }
 
 // ------------------------------------------------------------------ plan
-// One block of CHUNK threads per chunk: stable counting sort of the chunk's
-// local indices by g point; slot = (g << 6) | local index, SLOT_END padding.
-__global__ void __launch_bounds__(CHUNK) plan_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
-                                                      uint16_t* __restrict__ slots,
-                                                      unsigned long long* __restrict__ count) {
-  __shared__ int sg[CHUNK];
-  const int64_t c = blockIdx.x;
+// One block of CH threads per chunk.  Thread i owns local wavenumber i and
+// finds its (round, lane, slot): g points in ascending order, each padded to a
+// whole number of lanes; inside a g point, the k-th wavenumber goes to lane
+// (k mod L), slot (k div L), so that consecutive wavenumbers sit in consecutive
+// lanes (conflict-free shared-memory reads).
+struct PlanPos {
+  int g;       // -1: belongs to no g point
+  int vlane;   // virtual lane over all rounds of the chunk
+  int slot;
+  int nvlanes; // total virtual lanes of the chunk
+  int first;   // first wavenumber of its g point in the chunk
+  int count;   // wavenumbers of its g point in the chunk
+};
+
+__device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_point, int64_t nwav, int ng, int64_t c,
+                                                 int* sg, int* sl) {
   const int i = threadIdx.x;
-  const int64_t w = c * CHUNK + i;
+  const int64_t w = c * CH + i;
   int g = -1;
   if (w < nwav) {
     g = g_point[w];
     if (g < 0 || g >= ng) g = -1;
   }
   sg[i] = g;
-  slots[c * CHUNK + i] = (uint16_t)SLOT_END;
   __syncthreads();
-  if (g >= 0) {
-    int pos = 0, same_before = 0, same = 0;
-#pragma unroll 8
-    for (int j = 0; j < CHUNK; ++j) {
-      const int gj = sg[j];
-      if (gj >= 0) {
-        pos += (gj < g) || (gj == g && j < i);
-        same += (gj == g);
-        same_before += (gj == g && j < i);
-      }
-    }
-    slots[c * CHUNK + pos] = (uint16_t)((g << 6) | i);
-    if (same_before == 0) atomicAdd(&count[g], (unsigned long long)same);
+  int k = 0, n = 0;
+  for (int j = 0; j < CH; ++j) {
+    const int same = (sg[j] == g);
+    n += same;
+    k += same & (j < i);
   }
+  const int L = (n + SLOTS_PER_LANE - 1) / SLOTS_PER_LANE;
+  sl[i] = (g >= 0 && k == 0) ? L : 0;
+  __syncthreads();
+  int a = 0, total = 0;
+  for (int j = 0; j < CH; ++j) {
+    const int lj = sl[j];
+    total += lj;
+    a += (sg[j] < g) ? lj : 0;  // sl[j] is non-zero only for valid first occurrences
+  }
+  PlanPos p;
+  p.g = g;
+  p.nvlanes = total;
+  p.first = (k == 0);
+  p.count = n;
+  p.vlane = (g >= 0) ? a + (k % L) : 0;
+  p.slot = (g >= 0) ? (k / L) : 0;
+  return p;
+}
+
+__global__ void __launch_bounds__(CH) plan_count_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
+                                                         uint32_t* __restrict__ nrounds,
+                                                         unsigned long long* __restrict__ count) {
+  __shared__ int sg[CH];
+  __shared__ int sl[CH];
+  const int64_t c = blockIdx.x;
+  const PlanPos p = plan_position(g_point, nwav, ng, c, sg, sl);
+  if (threadIdx.x == 0) nrounds[c] = (uint32_t)((p.nvlanes + 31) / 32);
+  if (p.g >= 0 && p.first) atomicAdd(&count[p.g], (unsigned long long)p.count);
+}
+
+__global__ void __launch_bounds__(CH) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
+                                                        const uint32_t* __restrict__ round_off,
+                                                        uint8_t* __restrict__ slots, uint16_t* __restrict__ lane_g) {
+  __shared__ int sg[CH];
+  __shared__ int sl[CH];
+  const int64_t c = blockIdx.x;
+  const PlanPos p = plan_position(g_point, nwav, ng, c, sg, sl);
+  if (p.g < 0) return;
+  const size_t round = (size_t)round_off[c] + (size_t)(p.vlane >> 5);
+  const int lane = p.vlane & 31;
+  slots[(round * 32 + lane) * SLOTS_PER_LANE + p.slot] = (uint8_t)threadIdx.x;
+  if (p.slot == 0) lane_g[round * 32 + lane] = (uint16_t)p.g;
+}
+
+// exclusive scan of n uint32 by one block (n is a few 10^4 .. 10^5)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(int64_t n, const uint32_t* __restrict__ in,
+                                                              uint32_t* __restrict__ out) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t base = 0; base < n; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = (i < n) ? in[i] : 0u;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t t = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp[lane] = t;
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    const uint32_t warp_off = (warp == 0) ? 0u : s_warp[warp - 1];
+    if (i < n) out[i] = carry + warp_off + x - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = carry + warp_off + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[n] = s_carry;
 }
 
 // ------------------------------------------------------------------ reduce
 template <int FKIND>
-__device__ __forceinline__ double f_transform(double tau, double kd, bool is_log, bool& valid) {
-  valid = true;
+__device__ __forceinline__ double f_transform(double tau, double kd, bool is_log, bool& positive) {
+  positive = true;
   if (FKIND == F_LINEAR) return tau;
   if (FKIND == F_TRANS) return 1.0 - exp(-tau * kd);
   if (FKIND == F_SQRT) return sqrt(tau);
   if (FKIND == F_LOG) {
-    valid = tau > 0.0;
-    return valid ? log(tau) : 0.0;
+    positive = tau > 0.0;
+    return positive ? log(tau) : 0.0;
   }
   if (FKIND == F_HYBRID) {
     if (is_log) {
-      valid = tau > 0.0;
-      return valid ? log(tau) : 0.0;
+      positive = tau > 0.0;
+      return positive ? log(tau) : 0.0;
     }
     return 1.0 - exp(-tau * kd);
   }
   return 1.0;  // F_NONE: only the weight sum is wanted
 }
 
-struct WarpStage {
-  double* data;    // [32][PITCH]
-  double* wt;      // TILE: [maxw][PITCH]; VECTOR: [CHUNK]
-  double* nu;      // PLANCK only: [CHUNK]
-  double* dnu;     // PLANCK only: [CHUNK]
-  uint16_t* plan;  // [CHUNK]
+// Shared-memory layout of one CTA (byte offsets computed identically on the host)
+struct SmemLayout {
+  int bars;    // mbarriers: full_d[nw][NS], full_w[NSW], empty_w[NSW]
+  int wt;      // weight tiles [NSW][CH] doubles
+  int data;    // data stages [nw][NS][CH] doubles
+  int acc;     // accumulators [nw][ng][4] doubles
+  int accz;    // zero counters [nw][ng] int32
+  int total;
 };
-
-template <int VEC>
-__device__ __forceinline__ void stage_row(double* dst, const double* src, int64_t w0, int64_t nwav, int lane) {
-  // dst: CHUNK doubles in shared memory; src: row base in global memory
-  if (VEC == 16) {
-    const int col = lane * 2;
-    if (w0 + col + 1 < nwav) cp_async16(dst + col, src + w0 + col);
-    else if (w0 + col < nwav) cp_async8(dst + col, src + w0 + col);
-  } else {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int col = lane + 32 * h;
-      if (w0 + col < nwav) cp_async8(dst + col, src + w0 + col);
-    }
-  }
+__host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
+  SmemLayout L;
+  int off = 0;
+  L.bars = off;
+  off += (nw * NS + 2 * NSW) * 8;
+  off = (off + 127) & ~127;
+  L.wt = off;
+  off += NSW * CH * 8;
+  L.data = off;
+  off += nw * NS * CH * 8;
+  L.acc = off;
+  off += nw * ng * 4 * 8;
+  L.accz = off;
+  off += nw * ng * 4;
+  L.total = (off + 15) & ~15;
+  return L;
 }
 
-template <int FKIND, int WMODE, int VEC>
-__global__ void __launch_bounds__(128) reduce_kernel(const ReduceParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+template <int FKIND, int WMODE>
+__global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const ReduceParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int task = blockIdx.x * (blockDim.x >> 5) + warp;
-  if (task >= p.ntasks) return;  // no block-wide barriers below
-  const int group = task / p.nspans;
-  const int span = task - group * p.nspans;
-  const int64_t c0 = (p.nchunks * span) / p.nspans;
-  const int64_t c1 = (p.nchunks * (span + 1)) / p.nspans;
-  const int ng = p.ng;
+  const int nw = p.nw, ng = p.ng;
+  const SmemLayout L = smem_layout(nw, ng);
+  uint64_t* full_d = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [nw][NS]
+  uint64_t* full_w = full_d + nw * NS;                                 // [NSW]
+  uint64_t* empty_w = full_w + NSW;                                    // [NSW]
+  double* wt = reinterpret_cast<double*>(smem_raw + L.wt);
 
-  unsigned char* my = smem_raw + (size_t)warp * p.smem_per_warp;
-  double* acc = reinterpret_cast<double*>(my);  // [ng][4][32]
-  size_t off = (size_t)ng * 4 * 32 * sizeof(double);
-  WarpStage st[NSTAGE];
-  const int wt_doubles = (WMODE == W_VECTOR) ? CHUNK : p.maxw * PITCH;
-#pragma unroll
-  for (int s = 0; s < NSTAGE; ++s) {
-    st[s].data = reinterpret_cast<double*>(my + off);
-    off += (size_t)32 * PITCH * sizeof(double);
-    st[s].wt = reinterpret_cast<double*>(my + off);
-    off += (size_t)wt_doubles * sizeof(double);
-    st[s].nu = reinterpret_cast<double*>(my + off);
-    st[s].dnu = st[s].nu + CHUNK;
-    if (WMODE == W_TILE_PLANCK) off += (size_t)2 * CHUNK * sizeof(double);
-    st[s].plan = reinterpret_cast<uint16_t*>(my + off);
-    off += CHUNK * sizeof(uint16_t);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nw * NS; ++i) mbar_init(&full_d[i], 1);
+    for (int i = 0; i < NSW; ++i) {
+      mbar_init(&full_w[i], NPW);
+      mbar_init(&empty_w[i], nw);
+    }
+    fence_mbar_init();
   }
+  __syncthreads();
 
-  const GroupDesc* __restrict__ gd = p.groups + group;
-  const double* my_od = gd->od[lane];
-  const bool active = my_od != nullptr;
-  const int my_wslot = gd->wslot[lane];
-  const bool my_is_log = (FKIND == F_HYBRID) ? (gd->is_log[lane] != 0) : (FKIND == F_LOG);
-  const int n_w = gd->n_wrows;
-  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
+  // this CTA's contiguous piece of the (group, chunk) space
+  const int64_t T = (int64_t)p.ngroups * p.nchunks;
+  const int64_t lo = (T * blockIdx.x) / p.ncta;
+  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
+  const int first_group = (int)(lo / p.nchunks);
 
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  for (int g = 0; g < ng; ++g) {
-    double* a = acc + (size_t)g * 128 + lane;
-    a[0] = 0.0;
-    a[32] = 0.0;
-    a[64] = inf;
-    a[96] = -inf;
-  }
-
-  auto issue = [&](int s, int64_t c) {
-    const int64_t w0 = c * CHUNK;
-    for (int r = 0; r < 32; ++r) {
-      const double* src = gd->od[r];  // warp-uniform
-      if (src) stage_row<VEC>(st[s].data + r * PITCH, src, w0, p.nwav, lane);
-    }
-    if (WMODE == W_TILE_MATRIX) {
-      for (int t = 0; t < n_w; ++t) {
-        stage_row<VEC>(st[s].wt + t * PITCH, p.weight + (int64_t)gd->wrows[t] * p.w_stride, w0, p.nwav, lane);
-      }
-    } else if (WMODE == W_VECTOR) {
-      stage_row<VEC>(st[s].wt, p.weight, w0, p.nwav, lane);
-    } else {
-      stage_row<VEC>(st[s].nu, p.wn, w0, p.nwav, lane);
-      stage_row<VEC>(st[s].dnu, p.dwn, w0, p.nwav, lane);
-    }
-    if (lane < 8) cp_async16(st[s].plan + lane * 8, p.plan + c * CHUNK + lane * 8);
-  };
-
-  // running sums of the current g run (registers)
-  int gcur = -1;
-  double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
-  int zc = 0;
-  const int slot_row = group * 32 + lane;
-
-  auto flush = [&]() {
-    if (gcur >= 0) {
-      double* a = acc + (size_t)gcur * 128 + lane;
-      a[0] += s0;
-      a[32] += s1;
-      a[64] = fmin(a[64], mn);
-      a[96] = fmax(a[96], mx);
-      if (LOGKIND && zc != 0 && active) atomicAdd(&p.zcount[(size_t)slot_row * ng + gcur], zc);
-    }
-    s0 = 0.0;
-    s1 = 0.0;
-    mn = inf;
-    mx = -inf;
-    zc = 0;
-  };
-
-  if (c0 < c1) issue(0, c0);
-  cp_async_commit();
-  for (int64_t c = c0; c < c1; ++c) {
-    const int s = (int)((c - c0) & 1);
-    if (c + 1 < c1) issue(s ^ 1, c + 1);
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
-
-    const int64_t w0 = c * CHUNK;
-    if (WMODE == W_TILE_PLANCK) {
-      // weights of this chunk for the group's distinct temperatures
-      for (int e = lane; e < n_w * CHUNK; e += 32) {
-        const int t = e >> 6, i = e & (CHUNK - 1);
-        if (w0 + i < p.nwav) {
-          st[s].wt[t * PITCH + i] = planck_elem(p.temperature[gd->wrows[t]], st[s].nu[i], st[s].dnu[i]);
+  if (warp >= nw) {
+    // ===================== weight producers =====================
+    const int pw = warp - nw;
+    int64_t k = 0;
+    for (int64_t gc = lo; gc < hi; ++gc, ++k) {
+      const int grp = (int)(gc / p.nchunks);
+      const int64_t c = gc - (int64_t)grp * p.nchunks;
+      const int ws = (int)(k % NSW);
+      if (k >= NSW) mbar_wait(&empty_w[ws], (unsigned)(((k / NSW) - 1) & 1));
+      const int64_t w0 = c * CH;
+      const int n_c = (int)min((int64_t)CH, p.nwav - w0);
+      double* tile = wt + ws * CH;
+      if (WMODE == W_PLANCK) {
+        const double t = p.temperature[p.groups[grp].wrow];
+        for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = planck_elem(t, p.wn[w0 + j], p.dwn[w0 + j]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full_w[ws]);
+      } else {
+        const double* src = (WMODE == W_VECTOR) ? (p.weight + w0)
+                                                : (p.weight + (int64_t)p.groups[grp].wrow * p.w_stride + w0);
+        const bool bulk = p.weight_bulk_ok && ((n_c & 1) == 0);
+        if (bulk) {
+          if (lane == 0) {
+            if (pw == 0) {
+              fence_proxy_async();
+              mbar_arrive_expect_tx(&full_w[ws], (unsigned)(n_c * 8));
+              bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
+            } else {
+              mbar_arrive(&full_w[ws]);
+            }
+          }
+        } else {
+          for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full_w[ws]);
         }
       }
+    }
+    return;
+  }
+
+  // ===================== consumers: warp = one row of the group =====================
+  double* data = reinterpret_cast<double*>(smem_raw + L.data) + (size_t)warp * NS * CH;
+  double* acc = reinterpret_cast<double*>(smem_raw + L.acc) + (size_t)warp * ng * 4;
+  int32_t* accz = reinterpret_cast<int32_t*>(smem_raw + L.accz) + (size_t)warp * ng;
+  uint64_t* my_full = full_d + warp * NS;
+  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+  auto init_acc = [&]() {
+    for (int g = lane; g < ng; g += 32) {
+      acc[g * 4 + 0] = 0.0;
+      acc[g * 4 + 1] = 0.0;
+      acc[g * 4 + 2] = inf;
+      acc[g * 4 + 3] = -inf;
+      accz[g] = 0;
+    }
+    __syncwarp();
+  };
+  auto flush_partial = [&](int grp) {
+    __syncwarp();
+    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)(grp - first_group)) * nw + warp;
+    double* out = p.partial + slot * ng * 4;
+    for (int i = lane; i < ng * 4; i += 32) out[i] = acc[i];
+    int32_t* outz = p.partial_z + slot * ng;
+    for (int i = lane; i < ng; i += 32) outz[i] = accz[i];
+    __syncwarp();
+  };
+  // is chunk gc of this warp's row fetched with a bulk copy?
+  auto chunk_info = [&](int64_t gc, const double*& src, int& n_c, bool& active, bool& bulk) {
+    const int grp = (int)(gc / p.nchunks);
+    const int64_t c = gc - (int64_t)grp * p.nchunks;
+    const GroupDesc* gd = p.groups + grp;
+    active = warp < gd->nrows;
+    const int64_t w0 = c * CH;
+    n_c = (int)min((int64_t)CH, p.nwav - w0);
+    src = active ? gd->od[warp] + w0 : nullptr;
+    bulk = active && gd->bulk_ok[warp] && ((n_c & 1) == 0);
+  };
+  auto issue = [&](int64_t gc, int stage) {
+    const double* src;
+    int n_c;
+    bool active, bulk;
+    chunk_info(gc, src, n_c, active, bulk);
+    if (bulk && lane == 0) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&my_full[stage], (unsigned)(n_c * 8));
+      bulk_g2s(data + stage * CH, src, (unsigned)(n_c * 8), &my_full[stage]);
+    }
+  };
+
+  for (int j = 0; j < NS; ++j) {
+    if (lo + j < hi) issue(lo + j, j);
+  }
+  unsigned phase_bits = 0;  // bit s: parity to wait for on my_full[s]
+  int cur_grp = -1;
+  bool my_is_log = (FKIND == F_LOG);
+  int64_t k = 0;
+  for (int64_t gc = lo; gc < hi; ++gc, ++k) {
+    const int grp = (int)(gc / p.nchunks);
+    const int64_t c = gc - (int64_t)grp * p.nchunks;
+    if (grp != cur_grp) {
+      if (cur_grp >= 0) flush_partial(cur_grp);
+      init_acc();
+      cur_grp = grp;
+      if (FKIND == F_HYBRID) my_is_log = (warp < p.groups[grp].nrows) && (p.groups[grp].is_log[warp] != 0);
+    }
+    const int s = (int)(k % NS);
+    const int ws = (int)(k % NSW);
+    const double* src;
+    int n_c;
+    bool active, bulk;
+    chunk_info(gc, src, n_c, active, bulk);
+    double* stage = data + s * CH;
+    // the plan of this chunk (read-only, shared by every row: L1/L2 hits)
+    const uint32_t r0 = p.round_off[c], r1 = p.round_off[c + 1];
+    if (bulk) {
+      mbar_wait(&my_full[s], (phase_bits >> s) & 1u);
+      phase_bits ^= (1u << s);
+    } else if (active) {
+      for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
       __syncwarp();
     }
+    mbar_wait(&full_w[ws], (unsigned)((k / NSW) & 1));
+    const double* wtile = wt + ws * CH;
 
-    const double* myrow = st[s].data + (active ? lane : 0) * PITCH;
-    const double* myw = (WMODE == W_VECTOR) ? st[s].wt : (st[s].wt + my_wslot * PITCH);
-    const uint4* plan4 = reinterpret_cast<const uint4*>(st[s].plan);
-    bool done = false;
-#pragma unroll 1
-    for (int j0 = 0; j0 < CHUNK && !done; j0 += 8) {
-      const uint4 pk = plan4[j0 >> 3];
-      unsigned sl[8];
-      sl[0] = pk.x & 0xFFFFu; sl[1] = pk.x >> 16;
-      sl[2] = pk.y & 0xFFFFu; sl[3] = pk.y >> 16;
-      sl[4] = pk.z & 0xFFFFu; sl[5] = pk.z >> 16;
-      sl[6] = pk.w & 0xFFFFu; sl[7] = pk.w >> 16;
-      double tau[8], ww[8], f[8];
-      bool valid[8];
+    if (active) {
+      for (uint32_t r = r0; r < r1; ++r) {
+        const uint2 sl = p.slots[(size_t)r * 32 + lane];
+        const unsigned g = p.lane_g[(size_t)r * 32 + lane];
+        double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
+        int zc = 0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int idx = sl[u] & (CHUNK - 1);
-        tau[u] = myrow[idx];
-        ww[u] = myw[idx];
-      }
+        for (int half = 0; half < 2; ++half) {
+          const unsigned word = half ? sl.y : sl.x;
+          double tau[4], ww[4], f[4];
+          bool ok[4], pos[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) f[u] = f_transform<FKIND>(tau[u], p.kd, my_is_log, valid[u]);
+          for (int u = 0; u < 4; ++u) {
+            const unsigned idx = (word >> (8 * u)) & 0xFFu;
+            ok[u] = idx != PAD_SLOT;
+            const unsigned ii = ok[u] ? idx : 0u;
+            tau[u] = stage[ii];
+            ww[u] = wtile[ii];
+          }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (sl[u] == SLOT_END) {  // warp-uniform: only trailing slots are invalid
-          done = true;
-          break;
+          for (int u = 0; u < 4; ++u) f[u] = f_transform<FKIND>(tau[u], p.kd, my_is_log, pos[u]);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const bool use = LOGKIND ? (ok[u] && pos[u]) : ok[u];
+            const double we = use ? ww[u] : 0.0;
+            s0 += (use ? f[u] : 0.0) * we;
+            s1 += we;
+            mn = ok[u] ? fmin(mn, tau[u]) : mn;
+            mx = ok[u] ? fmax(mx, tau[u]) : mx;
+            if (LOGKIND) zc += (ok[u] && !pos[u]) ? 1 : 0;
+          }
         }
-        const int g = (int)(sl[u] >> 6);
-        if (g != gcur) {  // warp-uniform
-          flush();
-          gcur = g;
+        // segmented suffix reduction over adjacent lanes of the same g point
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
+          const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
+          const double t1 = __shfl_down_sync(0xffffffffu, s1, d);
+          const double tn = __shfl_down_sync(0xffffffffu, mn, d);
+          const double tx = __shfl_down_sync(0xffffffffu, mx, d);
+          const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
+          if (lane + d < 32 && go == g) {
+            s0 += t0;
+            s1 += t1;
+            mn = fmin(mn, tn);
+            mx = fmax(mx, tx);
+            zc += tz;
+          }
         }
-        if (LOGKIND) {
-          const double we = valid[u] ? ww[u] : 0.0;
-          s0 += f[u] * we;
-          s1 += we;
-          zc += valid[u] ? 0 : 1;
-        } else {
-          s0 += f[u] * ww[u];
-          s1 += ww[u];
+        const unsigned gprev = __shfl_up_sync(0xffffffffu, g, 1);
+        if (g != NO_G && (lane == 0 || gprev != g)) {  // head lane of its g point in this round
+          double* a = acc + g * 4;
+          a[0] += s0;
+          a[1] += s1;
+          a[2] = fmin(a[2], mn);
+          a[3] = fmax(a[3], mx);
+          if (LOGKIND) accz[g] += zc;
         }
-        mn = fmin(mn, tau[u]);
-        mx = fmax(mx, tau[u]);
+        __syncwarp();
       }
     }
-    __syncwarp();  // everyone has finished reading stage s before it is refilled
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_w[ws]);
+    if (lo + k + NS < hi) issue(lo + k + NS, s);
   }
-  flush();
-  __syncwarp();
-  double* out = p.partial + (size_t)task * ng * 128;
-  for (int i = lane; i < ng * 128; i += 32) out[i] = acc[i];
+  if (cur_grp >= 0) flush_partial(cur_grp);
 }
 
 // ------------------------------------------------------------------ combine + finalize
-// Combine the span partials of every (row, g) in fixed span order (deterministic).
+// Add the CTA pieces of every (row, g) in fixed CTA order (deterministic).
 __global__ void combine_kernel(const CombineParams p) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (int64_t)p.nslots * p.ng) return;
-  const int slot = (int)(tid / p.ng);
-  const int g = (int)(tid - (int64_t)slot * p.ng);
-  const RowDesc rd = p.rows[slot];
-  if (rd.od == nullptr) return;
-  const int group = slot >> 5, lane = slot & 31;
+  const int64_t total = (int64_t)p.ngroups * p.nw * p.ng;
+  if (tid >= total) return;
+  const int g = (int)(tid % p.ng);
+  const int w = (int)((tid / p.ng) % p.nw);
+  const int grp = (int)(tid / ((int64_t)p.ng * p.nw));
+  const GroupDesc* gd = p.groups + grp;
+  if (w >= gd->nrows) return;
+  const int64_t T = (int64_t)p.ngroups * p.nchunks;
+  const int64_t glo = (int64_t)grp * p.nchunks, ghi = glo + p.nchunks;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
-  for (int s = 0; s < p.nspans; ++s) {
-    const double* a = p.partial + ((size_t)(group * p.nspans + s) * p.ng + g) * 128 + lane;
+  long long zc = 0;
+  int b = (int)((glo * p.ncta) / T);
+  if (b > 0) --b;
+  for (; b < p.ncta; ++b) {
+    const int64_t lo = (T * b) / p.ncta, hi = (T * (b + 1)) / p.ncta;
+    if (lo >= ghi) break;
+    if (hi <= glo || hi <= lo) continue;
+    const int first_group = (int)(lo / p.nchunks);
+    const size_t slot = ((size_t)b * p.maxg + (size_t)(grp - first_group)) * p.nw + w;
+    const double* a = p.partial + (slot * p.ng + g) * 4;
     s0 += a[0];
-    s1 += a[32];
-    mn = fmin(mn, a[64]);
-    mx = fmax(mx, a[96]);
+    s1 += a[1];
+    mn = fmin(mn, a[2]);
+    mx = fmax(mx, a[3]);
+    zc += p.partial_z[slot * p.ng + g];
   }
-  double* so = p.sums + ((size_t)rd.row * p.ng + g) * NSUM;
+  const int row = gd->row[w];
+  double* so = p.sums + ((size_t)row * p.ng + g) * NSUM;
   so[0] = s0;
   so[1] = s1;
-  so[2] = (rd.method == M_LOG) ? (double)p.zcount[(size_t)slot * p.ng + g] : 0.0;
-  double* mo = p.minmax + ((size_t)rd.row * p.ng + g) * NMINMAX;
+  so[2] = (double)zc;
+  double* mo = p.minmax + ((size_t)row * p.ng + g) * NMINMAX;
   mo[0] = mn;
   mo[1] = -mx;
 }
@@ -470,36 +651,39 @@ __global__ void compact_remap_kernel(int ng, int64_t nwav, int32_t* __restrict__
 
 // ------------------------------------------------------------------ host side
 template <int FKIND, int WMODE>
-static void launch_reduce_vec(int vec, dim3 grid, dim3 block, size_t smem, cudaStream_t st, const ReduceParams& p,
-                              cudaError_t* attr_err) {
-  if (vec == 16) {
-    *attr_err = cudaFuncSetAttribute(reduce_kernel<FKIND, WMODE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem);
-    if (*attr_err == cudaSuccess) reduce_kernel<FKIND, WMODE, 16><<<grid, block, smem, st>>>(p);
-  } else {
-    *attr_err = cudaFuncSetAttribute(reduce_kernel<FKIND, WMODE, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem);
-    if (*attr_err == cudaSuccess) reduce_kernel<FKIND, WMODE, 8><<<grid, block, smem, st>>>(p);
+static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta_out,
+                                   bool dry_run) {
+  cudaError_t e = cudaFuncSetAttribute(reduce_kernel<FKIND, WMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return e;
+  if (dry_run) {
+    int nb = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, reduce_kernel<FKIND, WMODE>, threads, smem);
+    if (e != cudaSuccess) return e;
+    *ncta_out = std::max(1, nb) * ctx->num_sms;
+    return cudaSuccess;
   }
+  reduce_kernel<FKIND, WMODE><<<p.ncta, threads, smem, ctx->stream>>>(p);
+  return cudaGetLastError();
 }
 
 template <int FKIND>
-static void launch_reduce_w(int wmode, int vec, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                            const ReduceParams& p, cudaError_t* e) {
-  if (wmode == W_TILE_MATRIX) launch_reduce_vec<FKIND, W_TILE_MATRIX>(vec, grid, block, smem, st, p, e);
-  else if (wmode == W_VECTOR) launch_reduce_vec<FKIND, W_VECTOR>(vec, grid, block, smem, st, p, e);
-  else launch_reduce_vec<FKIND, W_TILE_PLANCK>(vec, grid, block, smem, st, p, e);
+static cudaError_t launch_reduce_w(int wmode, ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta,
+                                   bool dry) {
+  if (wmode == W_MATRIX) return launch_reduce_t<FKIND, W_MATRIX>(ctx, p, threads, smem, ncta, dry);
+  if (wmode == W_VECTOR) return launch_reduce_t<FKIND, W_VECTOR>(ctx, p, threads, smem, ncta, dry);
+  return launch_reduce_t<FKIND, W_PLANCK>(ctx, p, threads, smem, ncta, dry);
 }
 
-static void launch_reduce(int fkind, int wmode, int vec, dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                          const ReduceParams& p, cudaError_t* e) {
+static cudaError_t launch_reduce(int fkind, int wmode, ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem,
+                                 int* ncta, bool dry) {
   switch (fkind) {
-    case F_LINEAR: launch_reduce_w<F_LINEAR>(wmode, vec, grid, block, smem, st, p, e); break;
-    case F_TRANS: launch_reduce_w<F_TRANS>(wmode, vec, grid, block, smem, st, p, e); break;
-    case F_SQRT: launch_reduce_w<F_SQRT>(wmode, vec, grid, block, smem, st, p, e); break;
-    case F_LOG: launch_reduce_w<F_LOG>(wmode, vec, grid, block, smem, st, p, e); break;
-    case F_HYBRID: launch_reduce_w<F_HYBRID>(wmode, vec, grid, block, smem, st, p, e); break;
-    default: launch_reduce_w<F_NONE>(wmode, vec, grid, block, smem, st, p, e); break;
+    case F_LINEAR: return launch_reduce_w<F_LINEAR>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_TRANS: return launch_reduce_w<F_TRANS>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_SQRT: return launch_reduce_w<F_SQRT>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_LOG: return launch_reduce_w<F_LOG>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_HYBRID: return launch_reduce_w<F_HYBRID>(wmode, ctx, p, threads, smem, ncta, dry);
+    default: return launch_reduce_w<F_NONE>(wmode, ctx, p, threads, smem, ncta, dry);
   }
 }
 
@@ -508,6 +692,7 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 // Streaming stage: reduce `rows` (any mix of spectra/layers sharing one plan and
 // one weight definition) to per-(row, g) partial results in d_sums / d_minmax
 // (layouts in spectral_reduce.cuh), rows[i].row giving each row's index there.
+// Consecutive rows with the same weight row are grouped into one CTA-wide group.
 static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::vector<RowDesc>& rows, int fkind,
                           double kd, int wmode, const double* d_weight, int64_t w_stride,
                           const double* h_temperature, int n_temperature, const double* d_wn, const double* d_dwn,
@@ -516,136 +701,117 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   if (nrows == 0) return ECCKD_OK;
   const int ng = plan->ng;
   const int64_t nwav = plan->nwav;
-  const int ngroups = (nrows + 31) / 32;
-  const int nslots = ngroups * 32;
 
-  // vector width: 16 B copies need 16 B aligned rows and an even nwav
-  int vec = (nwav % 2 == 0) ? 16 : 8;
-  for (const RowDesc& r : rows) {
-    if (!aligned16(r.od)) vec = 8;
+  // consumer warps per CTA: as many rows as share a weight row, capped by NW_MAX and shared memory
+  int longest = 1;
+  for (int i = 0, run = 0; i < nrows; ++i) {
+    run = (i > 0 && rows[i].wrow == rows[i - 1].wrow) ? run + 1 : 1;
+    longest = std::max(longest, run);
   }
-  if (wmode == W_TILE_MATRIX) {
-    if (!aligned16(d_weight) || (w_stride % 2) != 0) vec = 8;
-  } else if (wmode == W_VECTOR) {
-    if (!aligned16(d_weight)) vec = 8;
-  } else {
-    if (!aligned16(d_wn) || !aligned16(d_dwn)) vec = 8;
-  }
-
-  // group descriptors: 32 consecutive rows per warp
-  std::vector<GroupDesc> groups(ngroups);
-  std::vector<RowDesc> slots(nslots);
-  int maxw = 1;
-  for (int gi = 0; gi < ngroups; ++gi) {
-    GroupDesc& gd = groups[gi];
-    memset(&gd, 0, sizeof(gd));
-    for (int l = 0; l < 32; ++l) {
-      const int r = gi * 32 + l;
-      RowDesc& sd = slots[r];
-      if (r < nrows) {
-        sd = rows[r];
-        gd.od[l] = sd.od;
-        gd.is_log[l] = (sd.method == M_LOG) ? 1 : 0;
-        int ws = -1;
-        for (int t = 0; t < gd.n_wrows; ++t) {
-          if (gd.wrows[t] == sd.wrow) ws = t;
-        }
-        if (ws < 0) {
-          ws = gd.n_wrows++;
-          gd.wrows[ws] = sd.wrow;
-        }
-        gd.wslot[l] = (uint8_t)ws;
-      } else {
-        memset(&sd, 0, sizeof(sd));
-      }
-    }
-    if (gd.n_wrows == 0) {
-      gd.n_wrows = 1;
-      gd.wrows[0] = 0;
-    }
-    maxw = std::max(maxw, gd.n_wrows);
-  }
-
-  // shared memory per warp
-  const size_t acc_bytes = (size_t)ng * 4 * 32 * sizeof(double);
-  const size_t wt_bytes = (wmode == W_VECTOR ? (size_t)CHUNK : (size_t)maxw * PITCH) * sizeof(double);
-  const size_t stage_bytes = (size_t)32 * PITCH * sizeof(double) + wt_bytes +
-                             (wmode == W_TILE_PLANCK ? (size_t)2 * CHUNK * sizeof(double) : 0) +
-                             CHUNK * sizeof(uint16_t);
-  size_t per_warp = acc_bytes + NSTAGE * stage_bytes;
-  per_warp = (per_warp + 127) & ~size_t(127);
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
-  ECCKD_REQUIRE(per_warp <= smem_max, ECCKD_PARAMETER_ERROR,
-                "average_optical_depth: ng = %d needs %zu B of shared memory per warp (limit %zu)", ng, per_warp,
-                smem_max);
-  const int warps = (int)std::min<size_t>(4, smem_max / per_warp);
-  const size_t smem = per_warp * warps;
-
-  // spans of the wavenumber axis: one wave of warps fills the machine
-  const int64_t total_warps = (int64_t)ctx->num_sms * warps;
-  int nspans = (int)std::max<int64_t>(1, total_warps / ngroups);
-  nspans = (int)std::min<int64_t>(nspans, std::max<int64_t>(1, plan->nchunks));
-  const int ntasks = ngroups * nspans;
-  const int nblocks = (ntasks + warps - 1) / warps;
-
-  // device scratch: [groups | slots] in ws0, span partials in ws1, zcount in ws2, temperatures in ws3
-  void* d_desc = nullptr;
-  const size_t groups_bytes = ((size_t)ngroups * sizeof(GroupDesc) + 255) & ~size_t(255);
-  const size_t slots_bytes = (size_t)nslots * sizeof(RowDesc);
-  ECCKD_TRY(ws_reserve(ctx, 0, groups_bytes + slots_bytes, &d_desc));
-  GroupDesc* d_groups = static_cast<GroupDesc*>(d_desc);
-  RowDesc* d_slots = reinterpret_cast<RowDesc*>(static_cast<char*>(d_desc) + groups_bytes);
-  ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), (size_t)ngroups * sizeof(GroupDesc)));
-  ECCKD_TRY(upload_small(ctx, d_slots, slots.data(), slots_bytes));
-
-  void* d_partial = nullptr;
-  ECCKD_TRY(ws_reserve(ctx, 1, (size_t)ntasks * ng * 128 * sizeof(double), &d_partial));
-  void* d_z = nullptr;
-  const bool logkind = (fkind == F_LOG || fkind == F_HYBRID);
-  const size_t z_bytes = (size_t)nslots * ng * sizeof(int32_t);
-  ECCKD_TRY(ws_reserve(ctx, 2, z_bytes, &d_z));
-  if (logkind) ECCKD_CUDA_OK(cudaMemsetAsync(d_z, 0, z_bytes, ctx->stream));
-  void* d_temp = nullptr;
-  if (wmode == W_TILE_PLANCK) {
-    ECCKD_TRY(ws_reserve(ctx, 3, (size_t)n_temperature * sizeof(double), &d_temp));
-    ECCKD_TRY(upload_small(ctx, d_temp, h_temperature, (size_t)n_temperature * sizeof(double)));
+  int nw = std::min(NW_MAX, longest);
+  while (nw > 1 && (size_t)smem_layout(nw, ng).total > smem_max) --nw;
+  ECCKD_REQUIRE((size_t)smem_layout(nw, ng).total <= smem_max, ECCKD_PARAMETER_ERROR,
+                "average_optical_depth: ng = %d needs %d B of shared memory (limit %zu)", ng,
+                smem_layout(nw, ng).total, smem_max);
+  // balance: split a run of n rows into ceil(n/nw) groups of nearly equal size
+  std::vector<GroupDesc> groups;
+  for (int i = 0; i < nrows;) {
+    int j = i;
+    while (j < nrows && rows[j].wrow == rows[i].wrow) ++j;
+    const int n = j - i;
+    const int pieces = (n + nw - 1) / nw;
+    for (int q = 0; q < pieces; ++q) {
+      const int b0 = i + (int)(((int64_t)n * q) / pieces), b1 = i + (int)(((int64_t)n * (q + 1)) / pieces);
+      GroupDesc gd;
+      memset(&gd, 0, sizeof(gd));
+      gd.nrows = b1 - b0;
+      gd.wrow = rows[i].wrow;
+      for (int r = b0; r < b1; ++r) {
+        gd.od[r - b0] = rows[r].od;
+        gd.row[r - b0] = rows[r].row;
+        gd.is_log[r - b0] = (rows[r].method == M_LOG) ? 1 : 0;
+        gd.bulk_ok[r - b0] = aligned16(rows[r].od) ? 1 : 0;
+      }
+      groups.push_back(gd);
+    }
+    i = j;
   }
+  const int ngroups = (int)groups.size();
+  const int threads = (nw + NPW) * 32;
+  const size_t smem = (size_t)smem_layout(nw, ng).total;
 
   ReduceParams rp;
-  rp.groups = d_groups;
+  memset(&rp, 0, sizeof(rp));
   rp.ngroups = ngroups;
-  rp.nspans = nspans;
-  rp.ntasks = ntasks;
-  rp.plan = plan->d_slots;
-  rp.nwav = nwav;
+  rp.nw = nw;
   rp.nchunks = plan->nchunks;
+  rp.nwav = nwav;
   rp.ng = ng;
+  rp.round_off = plan->d_round_off;
+  rp.slots = plan->d_slots;
+  rp.lane_g = plan->d_lane_g;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
-  rp.temperature = static_cast<const double*>(d_temp);
+  rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
   rp.wn = d_wn;
   rp.dwn = d_dwn;
   rp.kd = kd;
-  rp.partial = static_cast<double*>(d_partial);
-  rp.zcount = static_cast<int32_t*>(d_z);
-  rp.maxw = maxw;
-  rp.smem_per_warp = (int)per_warp;
 
-  cudaError_t attr_err = cudaSuccess;
-  launch_reduce(fkind, wmode, vec, dim3(nblocks), dim3(32 * warps), smem, ctx->stream, rp, &attr_err);
-  ECCKD_CUDA_OK(attr_err);
-  ECCKD_LAUNCH_CHECK(ctx);
+  int ncta = 0;
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, ctx, rp, threads, smem, &ncta, true));
+  const int64_t T = (int64_t)ngroups * plan->nchunks;
+  ncta = (int)std::min<int64_t>(ncta, std::max<int64_t>(1, T));
+  const int64_t per_cta = (T + ncta - 1) / ncta;
+  const int maxg = (int)((per_cta + plan->nchunks - 1) / plan->nchunks) + 1;
+  rp.ncta = ncta;
+  rp.maxg = maxg;
+
+  // device scratch: groups in ws0, CTA pieces in ws1/ws2, temperatures in ws3
+  void* d_groups = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 0, (size_t)ngroups * sizeof(GroupDesc), &d_groups));
+  ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), (size_t)ngroups * sizeof(GroupDesc)));
+  const size_t npieces = (size_t)ncta * maxg * nw;
+  void* d_partial = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, npieces * ng * 4 * sizeof(double), &d_partial));
+  void* d_pz = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 2, npieces * ng * sizeof(int32_t), &d_pz));
+  void* d_temp = nullptr;
+  if (wmode == W_PLANCK) {
+    ECCKD_TRY(ws_reserve(ctx, 3, (size_t)n_temperature * sizeof(double), &d_temp));
+    ECCKD_TRY(upload_small(ctx, d_temp, h_temperature, (size_t)n_temperature * sizeof(double)));
+  }
+  rp.groups = static_cast<const GroupDesc*>(d_groups);
+  rp.temperature = static_cast<const double*>(d_temp);
+  rp.partial = static_cast<double*>(d_partial);
+  rp.partial_z = static_cast<int32_t*>(d_pz);
+
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->timing) {
+    ECCKD_CUDA_OK(cudaEventCreate(&ev0));
+    ECCKD_CUDA_OK(cudaEventCreate(&ev1));
+    ECCKD_CUDA_OK(cudaEventRecord(ev0, ctx->stream));
+  }
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, ctx, rp, threads, smem, &ncta, false));
+  ctx->launches++;
+  if (ctx->timing) {
+    ECCKD_CUDA_OK(cudaEventRecord(ev1, ctx->stream));
+    ctx->reduce_events.emplace_back(ev0, ev1);
+  }
 
   CombineParams cp;
-  cp.rows = d_slots;
-  cp.nslots = nslots;
-  cp.nspans = nspans;
+  cp.groups = rp.groups;
+  cp.ngroups = ngroups;
+  cp.nw = nw;
+  cp.ncta = ncta;
+  cp.maxg = maxg;
+  cp.nchunks = plan->nchunks;
   cp.ng = ng;
-  cp.partial = static_cast<const double*>(d_partial);
-  cp.zcount = static_cast<const int32_t*>(d_z);
+  cp.partial = rp.partial;
+  cp.partial_z = rp.partial_z;
   cp.sums = d_sums;
   cp.minmax = d_minmax;
-  const int64_t nthreads = (int64_t)nslots * ng;
+  const int64_t nthreads = (int64_t)ngroups * nw * ng;
   combine_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(cp);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
@@ -707,7 +873,7 @@ static int resolve_weights(const ecckd_gpoint_plan* plan, int weight_mode, const
                            const double* h_temperature, const double* d_wn, const double* d_dwn, int* wmode) {
   if (weight_mode == ECCKD_WEIGHT_MATRIX) {
     ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight matrix is NULL");
-    *wmode = (w_stride == 0) ? W_VECTOR : W_TILE_MATRIX;  // stride 0 == spread<0>(ssi, nlay)
+    *wmode = (w_stride == 0) ? W_VECTOR : W_MATRIX;  // stride 0 == spread<0>(ssi, nlay)
     ECCKD_REQUIRE(w_stride == 0 || w_stride >= plan->nwav, ECCKD_PARAMETER_ERROR, "weight stride smaller than nwav");
   } else if (weight_mode == ECCKD_WEIGHT_VECTOR) {
     ECCKD_REQUIRE(d_weight != nullptr, ECCKD_PARAMETER_ERROR, "weight vector is NULL");
@@ -715,7 +881,7 @@ static int resolve_weights(const ecckd_gpoint_plan* plan, int weight_mode, const
   } else if (weight_mode == ECCKD_WEIGHT_PLANCK) {
     ECCKD_REQUIRE(h_temperature && d_wn && d_dwn, ECCKD_PARAMETER_ERROR,
                   "Planck weights need temperature, wavenumber and d_wavenumber");
-    *wmode = W_TILE_PLANCK;
+    *wmode = W_PLANCK;
   } else {
     set_error("weight_mode %d not understood", weight_mode);
     return ECCKD_PARAMETER_ERROR;
@@ -728,41 +894,67 @@ static int resolve_weights(const ecckd_gpoint_plan* plan, int weight_mode, const
 using namespace ecckd;
 
 // ------------------------------------------------------------------ C ABI
+static void plan_free(ecckd_gpoint_plan* p) {
+  cudaFree(p->d_round_off);
+  cudaFree(p->d_slots);
+  cudaFree(p->d_lane_g);
+  cudaFree(p->d_count);
+  cudaFree(p->d_scratch);
+  delete p;
+}
+
 ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
                                        ecckd_gpoint_plan** out) {
   ECCKD_REQUIRE(ctx && d_g_point && out, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: NULL argument");
   ECCKD_REQUIRE(nwav > 0 && ng > 0 && ng <= MAX_NG, ECCKD_PARAMETER_ERROR,
                 "ecckd_gpoint_plan_create: need nwav > 0 and 0 < ng <= %d (got nwav=%lld ng=%d)", MAX_NG,
                 (long long)nwav, ng);
+  *out = nullptr;
   ecckd_gpoint_plan* p = new ecckd_gpoint_plan();
   p->ctx = ctx;
   p->nwav = nwav;
   p->ng = ng;
-  p->nchunks = (nwav + CHUNK - 1) / CHUNK;
-  *out = nullptr;
-  cudaError_t e = cudaMalloc(&p->d_slots, (size_t)p->nchunks * CHUNK * sizeof(uint16_t));
+  p->nchunks = (nwav + CH - 1) / CH;
+  ECCKD_REQUIRE(p->nchunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
+  uint32_t* d_nrounds = nullptr;
+  cudaError_t e = cudaMalloc(&p->d_round_off, (size_t)(p->nchunks + 1) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_nrounds, (size_t)p->nchunks * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_count, (size_t)ng * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_count, 0, (size_t)ng * sizeof(unsigned long long), ctx->stream);
-  if (e != cudaSuccess) {
-    set_error("ecckd_gpoint_plan_create: %s", cudaGetErrorString(e));
-    cudaFree(p->d_slots);
-    cudaFree(p->d_count);
-    delete p;
-    return ECCKD_UNEXPECTED_EXCEPTION;
-  }
-  plan_kernel<<<(unsigned)p->nchunks, CHUNK, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_slots, p->d_count);
-  ctx->launches++;
+  uint32_t total = 0;
   std::vector<unsigned long long> cnt(ng);
-  e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    plan_count_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, d_nrounds, p->d_count);
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->nchunks, d_nrounds, p->d_round_off);
+    ctx->launches += 2;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(&total, p->d_round_off + p->nchunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(cnt.data(), p->d_count, (size_t)ng * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                         ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) {
+    p->nrounds = total;
+    const size_t nr = std::max<size_t>(1, total);
+    e = cudaMalloc(&p->d_slots, nr * 32 * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_lane_g, nr * 32 * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_slots, 0xFF, nr * 32 * sizeof(uint2), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_lane_g, 0xFF, nr * 32 * sizeof(uint16_t), ctx->stream);
+    if (e == cudaSuccess) {
+      plan_fill_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
+                                                                     reinterpret_cast<uint8_t*>(p->d_slots),
+                                                                     p->d_lane_g);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller
+  }
+  cudaFree(d_nrounds);
   if (e != cudaSuccess) {
     set_error("ecckd_gpoint_plan_create: %s", cudaGetErrorString(e));
-    cudaFree(p->d_slots);
-    cudaFree(p->d_count);
-    delete p;
+    plan_free(p);
     return ECCKD_UNEXPECTED_EXCEPTION;
   }
   p->h_count.assign(cnt.begin(), cnt.end());
@@ -773,10 +965,7 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
 ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
   if (!plan) return ECCKD_OK;
   if (plan->ctx) cudaStreamSynchronize(plan->ctx->stream);
-  cudaFree(plan->d_slots);
-  cudaFree(plan->d_count);
-  cudaFree(plan->d_scratch);
-  delete plan;
+  plan_free(plan);
   return ECCKD_OK;
 }
 
@@ -924,6 +1113,85 @@ ECCKD_API int ecckd_average_optical_depth_to_g_point_dev(
                                                out_stride, warns);
 }
 
+// Host-buffer driver shared by the two reference-facing entry points below.
+// Weights: either planck_fl (matrix, or one row when planck_stride == 0) or
+// Planck function of temperature_fl computed in the kernel.
+static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav,
+                        const double* pressure_fl, const double* pressure_hl, const int32_t* g_point,
+                        const double* optical_depth, int64_t od_stride, const double* planck_fl,
+                        int64_t planck_stride, const double* temperature_fl, const double* wavenumber_cm_1,
+                        const double* d_wavenumber_cm_1, const char* averaging_method, double* molar_abs,
+                        double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn) {
+  const int method = ecckd_averaging_method_from_string(averaging_method);
+  if (method < 0) {
+    set_error("averaging_method \"%s\" not understood", averaging_method ? averaging_method : "(null)");
+    return ECCKD_PARAMETER_ERROR;
+  }
+  ECCKD_REQUIRE(nlay > 0 && nwav > 0 && ng > 0 && od_stride >= nwav && out_stride >= ng, ECCKD_PARAMETER_ERROR,
+                "ecckd_average_optical_depth_to_g_point: bad dimensions");
+  cudaStream_t st = ctx->stream;
+  const bool fused = planck_fl == nullptr;
+  const bool vecw = !fused && planck_stride == 0;
+  // device staging (even row strides so 16 B copies are legal), cached in the context
+  const int64_t dstride = (nwav + 1) & ~int64_t(1);
+  const size_t od_elems = (size_t)nlay * dstride;
+  const size_t w_elems = fused ? (size_t)2 * dstride : (vecw ? (size_t)dstride : (size_t)nlay * dstride);
+  const size_t out_elems = (size_t)nlay * ng;
+  void* arena = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 4, (od_elems + w_elems + 3 * out_elems) * sizeof(double), &arena));
+  double* d_od = static_cast<double*>(arena);
+  double* d_w = d_od + od_elems;
+  double* d_out = d_w + w_elems;
+  void* iarena = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 5, (size_t)(nwav + ng) * sizeof(int32_t), &iarena));
+  int32_t* d_g = static_cast<int32_t*>(iarena);
+  int32_t* d_warn = d_g + nwav;
+  ECCKD_CUDA_OK(cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  ECCKD_CUDA_OK(cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), st));
+  ECCKD_CUDA_OK(cudaMemcpy2DAsync(d_od, dstride * sizeof(double), optical_depth, od_stride * sizeof(double),
+                                  nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st));
+  if (fused) {
+    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
+    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else if (vecw) {
+    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
+  } else {
+    ECCKD_CUDA_OK(cudaMemcpy2DAsync(d_w, dstride * sizeof(double), planck_fl, planck_stride * sizeof(double),
+                                    nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st));
+  }
+  ecckd_gpoint_plan* plan = nullptr;
+  ECCKD_TRY(ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan));
+  const bool mm = min_molar_abs && max_molar_abs;
+  int rc = ecckd_average_optical_depth_to_g_point_dev(
+      ctx, plan, reference_surface_vmr, nlay, pressure_fl, pressure_hl, d_od, dstride,
+      fused ? ECCKD_WEIGHT_PLANCK : (vecw ? ECCKD_WEIGHT_VECTOR : ECCKD_WEIGHT_MATRIX), fused ? nullptr : d_w,
+      (fused || vecw) ? 0 : dstride, fused ? temperature_fl : nullptr, fused ? d_w : nullptr,
+      fused ? d_w + dstride : nullptr, method, d_out, mm ? d_out + out_elems : nullptr,
+      mm ? d_out + 2 * out_elems : nullptr, ng, d_warn);
+  cudaError_t e = cudaSuccess;
+  if (rc == ECCKD_OK) {
+    e = cudaMemcpy2DAsync(molar_abs, out_stride * sizeof(double), d_out, ng * sizeof(double), ng * sizeof(double), nlay,
+                          cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && mm) {
+      e = cudaMemcpy2DAsync(min_molar_abs, out_stride * sizeof(double), d_out + out_elems, ng * sizeof(double),
+                            ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(max_molar_abs, out_stride * sizeof(double), d_out + 2 * out_elems, ng * sizeof(double),
+                              ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess && warn)
+      e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  }
+  const cudaError_t e2 = cudaStreamSynchronize(st);
+  ecckd_gpoint_plan_destroy(plan);
+  if (rc != ECCKD_OK) return rc;
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  return ECCKD_OK;
+}
+
 ECCKD_API int ecckd_average_optical_depth_to_g_point(ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay,
                                                      int64_t nwav, const double* pressure_fl,
                                                      const double* pressure_hl, const int32_t* g_point,
@@ -934,68 +1202,23 @@ ECCKD_API int ecckd_average_optical_depth_to_g_point(ecckd_ctx* ctx, int ng, dou
                                                      int32_t* warn) {
   ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && planck_fl && molar_abs,
                 ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth_to_g_point: NULL argument");
-  const int method = ecckd_averaging_method_from_string(averaging_method);
-  if (method < 0) {
-    set_error("averaging_method \"%s\" not understood", averaging_method ? averaging_method : "(null)");
-    return ECCKD_PARAMETER_ERROR;
-  }
-  ECCKD_REQUIRE(nlay > 0 && nwav > 0 && ng > 0 && od_stride >= nwav && out_stride >= ng, ECCKD_PARAMETER_ERROR,
-                "ecckd_average_optical_depth_to_g_point: bad dimensions");
-  cudaStream_t st = ctx->stream;
-  const bool vecw = (planck_stride == 0);
-  // device staging (even row strides so 16 B copies are legal)
-  const int64_t dstride = (nwav + 1) & ~int64_t(1);
-  double *d_od = nullptr, *d_w = nullptr, *d_out = nullptr;
-  int32_t *d_g = nullptr, *d_warn = nullptr;
-  const size_t od_bytes = (size_t)nlay * dstride * sizeof(double);
-  const size_t w_bytes = (vecw ? (size_t)dstride : (size_t)nlay * dstride) * sizeof(double);
-  const size_t out_elems = (size_t)nlay * ng;
-  ECCKD_CUDA_OK(cudaMalloc(&d_od, od_bytes + w_bytes + 3 * out_elems * sizeof(double)));
-  d_w = d_od + (size_t)nlay * dstride;
-  d_out = d_w + w_bytes / sizeof(double);
-  int rc = ECCKD_OK;
-  ecckd_gpoint_plan* plan = nullptr;
-  do {
-    if (cudaMalloc(&d_g, (size_t)(nwav + ng) * sizeof(int32_t)) != cudaSuccess) { rc = ECCKD_UNEXPECTED_EXCEPTION; set_error("cudaMalloc failed"); break; }
-    d_warn = d_g + nwav;
-    cudaError_t e = cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), st);
-    if (e == cudaSuccess)
-      e = cudaMemcpy2DAsync(d_od, dstride * sizeof(double), optical_depth, od_stride * sizeof(double),
-                            nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess) {
-      if (vecw) e = cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
-      else
-        e = cudaMemcpy2DAsync(d_w, dstride * sizeof(double), planck_fl, planck_stride * sizeof(double),
-                              nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st);
-    }
-    if (e != cudaSuccess) { rc = ECCKD_UNEXPECTED_EXCEPTION; set_error("H2D copy failed: %s", cudaGetErrorString(e)); break; }
-    rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
-    if (rc) break;
-    const bool mm = min_molar_abs && max_molar_abs;
-    rc = ecckd_average_optical_depth_to_g_point_dev(
-        ctx, plan, reference_surface_vmr, nlay, pressure_fl, pressure_hl, d_od, dstride,
-        vecw ? ECCKD_WEIGHT_VECTOR : ECCKD_WEIGHT_MATRIX, d_w, vecw ? 0 : dstride, nullptr, nullptr, nullptr, method,
-        d_out, mm ? d_out + out_elems : nullptr, mm ? d_out + 2 * out_elems : nullptr, ng, d_warn);
-    if (rc) break;
-    e = cudaMemcpy2DAsync(molar_abs, out_stride * sizeof(double), d_out, ng * sizeof(double), ng * sizeof(double), nlay,
-                          cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && mm) {
-      e = cudaMemcpy2DAsync(min_molar_abs, out_stride * sizeof(double), d_out + out_elems, ng * sizeof(double),
-                            ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(max_molar_abs, out_stride * sizeof(double), d_out + 2 * out_elems, ng * sizeof(double),
-                              ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
-    }
-    if (e == cudaSuccess && warn) e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess) { rc = ECCKD_UNEXPECTED_EXCEPTION; set_error("D2H copy failed: %s", cudaGetErrorString(e)); break; }
-  } while (0);
-  cudaStreamSynchronize(st);
-  if (plan) ecckd_gpoint_plan_destroy(plan);
-  cudaFree(d_g);
-  cudaFree(d_od);
-  return rc;
+  return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, pressure_fl, pressure_hl, g_point, optical_depth,
+                      od_stride, planck_fl, planck_stride, nullptr, nullptr, nullptr, averaging_method, molar_abs,
+                      min_molar_abs, max_molar_abs, out_stride, warn);
+}
+
+ECCKD_API int ecckd_planck_average_optical_depth_to_g_point(
+    ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav, const double* pressure_fl,
+    const double* pressure_hl, const int32_t* g_point, const double* optical_depth, int64_t od_stride,
+    const double* temperature_fl, const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
+    const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride,
+    int32_t* warn) {
+  ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && temperature_fl && wavenumber_cm_1 &&
+                    d_wavenumber_cm_1 && molar_abs,
+                ECCKD_PARAMETER_ERROR, "ecckd_planck_average_optical_depth_to_g_point: NULL argument");
+  return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, pressure_fl, pressure_hl, g_point, optical_depth,
+                      od_stride, nullptr, 0, temperature_fl, wavenumber_cm_1, d_wavenumber_cm_1, averaging_method,
+                      molar_abs, min_molar_abs, max_molar_abs, out_stride, warn);
 }
 
 ECCKD_API int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
@@ -1084,7 +1307,7 @@ ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, cons
   ECCKD_CUDA_OK(cudaMalloc(&scratch, nrg * (NSUM + NMINMAX) * sizeof(double)));
   double* d_sums = static_cast<double*>(scratch);
   double* d_minmax = d_sums + nrg * NSUM;
-  int rc = reduce_partial(ctx, plan, rows, F_NONE, 1.0, W_TILE_PLANCK, nullptr, 0, h_temperature_lut, nlut, d_wn, d_dwn,
+  int rc = reduce_partial(ctx, plan, rows, F_NONE, 1.0, W_PLANCK, nullptr, 0, h_temperature_lut, nlut, d_wn, d_dwn,
                           d_sums, d_minmax);
   if (rc == ECCKD_OK)
     rc = finalize_rows(ctx, plan->ng, reinterpret_cast<const long long*>(plan->d_count), outs, 1.0, d_sums, d_minmax);

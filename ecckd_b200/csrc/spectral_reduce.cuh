@@ -5,21 +5,25 @@
 
 namespace ecckd {
 
-constexpr int CHUNK = 64;          // wavenumbers staged per pipeline stage
-constexpr int PITCH = CHUNK + 2;   // doubles per staged row (16 B pad: at most 2-way bank conflicts)
-constexpr int NSTAGE = 2;
-constexpr unsigned SLOT_END = 0xFFFFu;
-constexpr int MAX_NG = 1023;       // slot = (g << 6) | local index, 0xFFFF reserved
+constexpr int CH = 224;            // wavenumbers per chunk (1792 B per row: a multiple of 16 B)
+constexpr int SLOTS_PER_LANE = 8;  // plan slots per lane per round
+constexpr int NS = 3;              // data stages per consumer warp
+constexpr int NSW = 3;             // weight stages per CTA
+constexpr int NPW = 2;             // producer (weight) warps per CTA
+constexpr int NW_MAX = 20;         // consumer warps (= rows) per CTA
+constexpr unsigned PAD_SLOT = 255u;
+constexpr unsigned NO_G = 0xFFFFu;
+constexpr int MAX_NG = 4096;
 
 // internal per-row method ids (public enum resolved per layer for hybrid)
 enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };
 // kernel "f kind": which transform the streaming kernel applies
 enum { F_LINEAR = 0, F_TRANS = 1, F_SQRT = 2, F_LOG = 3, F_HYBRID = 4, F_NONE = 5 };
-enum { W_TILE_MATRIX = 0, W_VECTOR = 1, W_TILE_PLANCK = 2 };
+enum { W_MATRIX = 0, W_VECTOR = 1, W_PLANCK = 2 };
 
 // One (spectrum, layer) row of the streaming reduction.
 struct RowDesc {
-  const double* od;   // row base (nwav doubles); NULL = unused slot
+  const double* od;   // row base (nwav doubles)
   int32_t method;     // M_*
   int32_t wrow;       // weight row (layer index / temperature index)
   int32_t row;        // index of this row in the partial-sum arrays
@@ -44,44 +48,49 @@ struct OutDesc {
 constexpr int NSUM = 3;
 constexpr int NMINMAX = 2;
 
-// 32 rows handled by one warp (row = lane).
+// Up to NW_MAX rows that share one weight row: one consumer warp each.
 struct GroupDesc {
-  const double* od[32];  // NULL = inactive lane
-  int32_t wrows[32];     // distinct weight rows used by this group
-  int32_t n_wrows;
-  int32_t pad_[3];
-  uint8_t wslot[32];     // lane -> index into wrows
-  uint8_t is_log[32];    // lane uses logarithmic averaging (hybrid)
+  const double* od[NW_MAX];
+  int32_t row[NW_MAX];     // index in the partial-sum arrays
+  uint8_t is_log[NW_MAX];  // row uses logarithmic averaging (hybrid method)
+  uint8_t bulk_ok[NW_MAX]; // row base is 16-byte aligned: bulk async copies allowed
+  int32_t nrows;
+  int32_t wrow;
 };
 
 struct ReduceParams {
   const GroupDesc* groups;
   int ngroups;
-  int nspans;
-  int ntasks;
-  const uint16_t* plan;  // [nchunks][CHUNK]
-  int64_t nwav;
+  int nw;                  // consumer warps per CTA
+  int ncta;                // grid size P
+  int maxg;                // partial slots per CTA (groups a CTA can touch)
   int64_t nchunks;
+  int64_t nwav;
   int ng;
-  const double* weight;  // MATRIX: [wrow][nwav] (stride w_stride); VECTOR: [nwav]
+  const uint32_t* round_off;  // [nchunks+1]
+  const uint2* slots;         // [nrounds][32] 8 byte-sized local indices per lane
+  const uint16_t* lane_g;     // [nrounds][32]
+  const double* weight;       // MATRIX: [wrow][nwav] (stride w_stride); VECTOR: [nwav]
   int64_t w_stride;
+  int weight_bulk_ok;
   const double* temperature;  // PLANCK: device [n weight rows]
   const double* wn;
   const double* dwn;
-  double kd;        // transmission exponent scale (LW_DIFFUSIVITY*OD_SCALING*k)
-  double* partial;  // [ntasks][ng][4][32]
-  int32_t* zcount;  // [ngroups*32][ng] count of tau <= 0 (log modes)
-  int maxw;         // weight rows staged per warp stage
-  int smem_per_warp;
+  double kd;                  // transmission exponent scale (LW_DIFFUSIVITY*OD_SCALING*k)
+  double* partial;            // [ncta][maxg][nw][ng][4]
+  int32_t* partial_z;         // [ncta][maxg][nw][ng]
 };
 
 struct CombineParams {
-  const RowDesc* rows;  // indexed by row slot = group*32 + lane; od == NULL for inactive
-  int nslots;
-  int nspans;
+  const GroupDesc* groups;
+  int ngroups;
+  int nw;
+  int ncta;
+  int maxg;
+  int64_t nchunks;
   int ng;
   const double* partial;
-  const int32_t* zcount;
+  const int32_t* partial_z;
   double* sums;    // [nrows][ng][NSUM]
   double* minmax;  // [nrows][ng][NMINMAX]
 };
@@ -102,8 +111,11 @@ struct ecckd_gpoint_plan {
   ecckd_ctx* ctx = nullptr;
   int64_t nwav = 0;
   int64_t nchunks = 0;
+  int64_t nrounds = 0;
   int ng = 0;
-  uint16_t* d_slots = nullptr;           // [nchunks][CHUNK]
+  uint32_t* d_round_off = nullptr;       // [nchunks+1]
+  uint2* d_slots = nullptr;              // [nrounds][32]
+  uint16_t* d_lane_g = nullptr;          // [nrounds][32]
   unsigned long long* d_count = nullptr; // [ng]
   std::vector<int64_t> h_count;
   double* d_scratch = nullptr;           // per-(row, g) partial results of the single-GPU path

@@ -105,6 +105,12 @@ int ecckd_memcpy_h2d(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t byte
 int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
 /* Number of kernels this library has launched on this context so far. */
 int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx);
+/* Measurement hook: when on, CUDA events are recorded on the context stream
+ * around every launch of the streaming reduction kernel;
+ * ecckd_ctx_reduce_kernel_time synchronises, returns their summed duration and
+ * launch count since the last call, and clears them. */
+int ecckd_ctx_set_timing(ecckd_ctx* ctx, int on);
+int ecckd_ctx_reduce_kernel_time(ecckd_ctx* ctx, double* total_ms, int64_t* launches);
 
 /* -------------------------------------------------- stage 1: spectra -> LUT */
 
@@ -201,6 +207,18 @@ int ecckd_average_optical_depth_to_g_point(
     const double* optical_depth, int64_t od_stride, const double* planck_fl, int64_t planck_stride,
     const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs,
     int64_t out_stride, int32_t* warn);
+
+/* The pair planck_function + average_optical_depth_to_g_point that
+ * create_look_up_table calls for every longwave block
+ * (src/ecckd/create_look_up_table.cpp:320-331, 394-405, 474-485) in one host
+ * call: the Planck weights of temperature_fl[nlay] are computed inside the
+ * reduction kernel, so planck_fl[nlay][nwav] is never formed or transferred. */
+int ecckd_planck_average_optical_depth_to_g_point(
+    ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav,
+    const double* pressure_fl, const double* pressure_hl, const int32_t* g_point,
+    const double* optical_depth, int64_t od_stride, const double* temperature_fl,
+    const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, const char* averaging_method,
+    double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn);
 
 /* Merge of several spectra: src/ecckd/read_merged_spectrum.cpp:149-168.
  * d_optical_depth += d_od * scaling, or * h_scaling_profile[layer] if non-NULL. */
