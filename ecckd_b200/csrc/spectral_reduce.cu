@@ -67,7 +67,48 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
-// planck_function.cpp:29-33,47-53, one element
+// exp(x) without branches: Cody-Waite reduction by ln 2 and a degree-11 polynomial; maximum
+// error 0.90 ulp on [-690, 700] (checked against a long-double reference on the host, see
+// DESIGN.md).  Below -693 the result is clamped near 1e-301 instead of underflowing gradually,
+// which is exact for its only uses here: 1 - exp(x) with x <= 0 (1 - 1e-301 == 1) and
+// exp(x) - 1 with x >= 0.  Coefficients live in constant memory so that the DFMAs take them
+// as constant-bank operands instead of re-materialising 64-bit immediates.
+__constant__ double EXP_C[12] = {2.5052097064908941e-8, 2.7626262793835868e-7, 2.7557414788000726e-6,
+                                 2.4801504602132958e-5, 1.9841269707468915e-4, 1.3888888932258898e-3,
+                                 8.3333333333978320e-3, 4.1666666666573905e-2, 1.6666666666666563e-1,
+                                 5.0000000000000056e-1, 1.0,                   1.0};
+__constant__ double EXP_K[4] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
+                                -1.90821492927058770002e-10};
+
+__device__ __forceinline__ double fast_exp(double x) {
+  const double t = fma(x, EXP_K[0], EXP_K[1]);
+  int k = __double2loint(t);
+  const double kf = t - EXP_K[1];
+  double r = fma(kf, EXP_K[2], x);
+  r = fma(kf, EXP_K[3], r);
+  double q = EXP_C[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) q = fma(q, r, EXP_C[i]);
+  k = max(-1000, min(k, 1000));
+  return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
+}
+
+// planck_function.cpp:29-33,47-53, one element.  The reference evaluates
+// prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) (one rounding more in the
+// exponent argument, i.e. a relative change of the weight below 1e-14, far inside the 1e-12
+// tolerance of the averages the weights feed).
+__device__ __forceinline__ double planck_elem_fast(double inv_t, double nu, double dnu) {
+  const double h = 6.62606896e-34;
+  const double c = 2.99792458e8;
+  const double k = 1.3806504e-23;
+  const double inv_cm_2_Hz = 100.0 * c;
+  const double pi = 3.14159265358979323846;
+  const double freq = nu * inv_cm_2_Hz;
+  const double prefactor = (dnu * 2.0 * h * inv_cm_2_Hz * pi / (c * c)) * (freq * freq * freq);
+  return prefactor / (fast_exp((h / k) * (freq * inv_t)) - 1.0);
+}
+
+// exact evaluation order of planck_function.cpp:47-53 (used by the standalone planck kernel)
 __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
   const double h = 6.62606896e-34;
   const double c = 2.99792458e8;
@@ -91,6 +132,7 @@ struct PlanPos {
   int slot;
   int nvlanes; // total virtual lanes of the chunk
   int first;   // first wavenumber of its g point in the chunk
+  int kth;     // index of this wavenumber inside its g point (chunk-local)
   int count;   // wavenumbers of its g point in the chunk
 };
 
@@ -124,6 +166,7 @@ __device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_p
   p.g = g;
   p.nvlanes = total;
   p.first = (k == 0);
+  p.kth = k;
   p.count = n;
   p.vlane = (g >= 0) ? a + (k % L) : 0;
   p.slot = (g >= 0) ? (k / L) : 0;
@@ -143,7 +186,8 @@ __global__ void __launch_bounds__(CH) plan_count_kernel(const int32_t* __restric
 
 __global__ void __launch_bounds__(CH) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
                                                         const uint32_t* __restrict__ round_off,
-                                                        uint8_t* __restrict__ slots, uint16_t* __restrict__ lane_g) {
+                                                        uint8_t* __restrict__ slots, uint16_t* __restrict__ lane_g,
+                                                        uint32_t* __restrict__ round_steps) {
   __shared__ int sg[CH];
   __shared__ int sl[CH];
   const int64_t c = blockIdx.x;
@@ -151,8 +195,25 @@ __global__ void __launch_bounds__(CH) plan_fill_kernel(const int32_t* __restrict
   if (p.g < 0) return;
   const size_t round = (size_t)round_off[c] + (size_t)(p.vlane >> 5);
   const int lane = p.vlane & 31;
-  slots[(round * 32 + lane) * SLOTS_PER_LANE + p.slot] = (uint8_t)threadIdx.x;
-  if (p.slot == 0) lane_g[round * 32 + lane] = (uint16_t)p.g;
+  uint8_t* my = slots + (round * 32 + lane) * SLOTS_PER_LANE;
+  my[p.slot] = (uint8_t)threadIdx.x;
+  if (p.slot == 0) {
+    // this thread owns the lane: valid slots form a prefix of length nv; the padding slots repeat
+    // slot 0 (harmless for min/max, masked out of the sums by nv)
+    const int L = (p.count + SLOTS_PER_LANE - 1) / SLOTS_PER_LANE;
+    const int k = p.kth;  // k < L here
+    const int nv = (p.count - 1 - k) / L + 1;
+    for (int e = nv; e < SLOTS_PER_LANE; ++e) my[e] = (uint8_t)threadIdx.x;
+    lane_g[round * 32 + lane] = (uint16_t)((unsigned)p.g | ((unsigned)nv << 12));
+    int steps = 0;
+    while ((1 << steps) < min(L, 32)) ++steps;
+    if (steps > 0) atomicMax(&round_steps[round], (uint32_t)steps);
+  }
+}
+
+__global__ void narrow_steps_kernel(int64_t n, const uint32_t* __restrict__ in, uint8_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (uint8_t)in[i];
 }
 
 // exclusive scan of n uint32 by one block (n is a few 10^4 .. 10^5)
@@ -199,7 +260,7 @@ template <int FKIND>
 __device__ __forceinline__ double f_transform(double tau, double kd, bool is_log, bool& positive) {
   positive = true;
   if (FKIND == F_LINEAR) return tau;
-  if (FKIND == F_TRANS) return 1.0 - exp(-tau * kd);
+  if (FKIND == F_TRANS) return 1.0 - fast_exp(-tau * kd);
   if (FKIND == F_SQRT) return sqrt(tau);
   if (FKIND == F_LOG) {
     positive = tau > 0.0;
@@ -210,7 +271,7 @@ __device__ __forceinline__ double f_transform(double tau, double kd, bool is_log
       positive = tau > 0.0;
       return positive ? log(tau) : 0.0;
     }
-    return 1.0 - exp(-tau * kd);
+    return 1.0 - fast_exp(-tau * kd);
   }
   return 1.0;  // F_NONE: only the weight sum is wanted
 }
@@ -265,31 +326,63 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   __syncthreads();
 
   // this CTA's contiguous piece of the (group, chunk) space
+  const int nchunks = (int)p.nchunks;
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
   const int64_t lo = (T * blockIdx.x) / p.ncta;
   const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
+  const int niter = (int)(hi - lo);
   const int first_group = (int)(lo / p.nchunks);
+  const int first_chunk = (int)(lo - (int64_t)first_group * p.nchunks);
+  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * CH);  // length of the last chunk of a row
 
   if (warp >= nw) {
     // ===================== weight producers =====================
     const int pw = warp - nw;
-    int64_t k = 0;
-    for (int64_t gc = lo; gc < hi; ++gc, ++k) {
-      const int grp = (int)(gc / p.nchunks);
-      const int64_t c = gc - (int64_t)grp * p.nchunks;
-      const int ws = (int)(k % NSW);
-      if (k >= NSW) mbar_wait(&empty_w[ws], (unsigned)(((k / NSW) - 1) & 1));
-      const int64_t w0 = c * CH;
-      const int n_c = (int)min((int64_t)CH, p.nwav - w0);
+    constexpr int PER = (CH + NPW * 32 - 1) / (NPW * 32);  // elements per producer lane per chunk
+    int grp = first_group, c = first_chunk, ws = 0;
+    unsigned epar = 0;
+    double inv_t = (WMODE == W_PLANCK) ? 1.0 / p.temperature[p.groups[grp].wrow] : 0.0;
+    const double* wrow_ptr = (WMODE == W_MATRIX) ? p.weight + (int64_t)p.groups[grp].wrow * p.w_stride : p.weight;
+    // wavenumbers of the next chunk, fetched one chunk ahead
+    double nu_n[PER], dnu_n[PER];
+    auto fetch = [&](int cc) {
+      const int64_t w0 = (int64_t)cc * CH;
+#pragma unroll
+      for (int m = 0; m < PER; ++m) {
+        const int64_t w = w0 + pw * 32 + lane + m * NPW * 32;
+        const bool ok = (pw * 32 + lane + m * NPW * 32) < CH && w < p.nwav;
+        nu_n[m] = ok ? p.wn[w] : 1.0;
+        dnu_n[m] = ok ? p.dwn[w] : 0.0;
+      }
+    };
+    if (WMODE == W_PLANCK && niter > 0) fetch(c);
+    for (int k = 0; k < niter; ++k) {
+      const int64_t w0 = (int64_t)c * CH;
+      const int n_c = (c == nchunks - 1) ? last_n : CH;
       double* tile = wt + ws * CH;
+      const int c_next = (c + 1 == nchunks) ? 0 : c + 1;
       if (WMODE == W_PLANCK) {
-        const double t = p.temperature[p.groups[grp].wrow];
-        for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = planck_elem(t, p.wn[w0 + j], p.dwn[w0 + j]);
+        double nu[PER], dnu[PER];
+#pragma unroll
+        for (int m = 0; m < PER; ++m) {
+          nu[m] = nu_n[m];
+          dnu[m] = dnu_n[m];
+        }
+        if (k + 1 < niter) fetch(c_next);
+        double val[PER];
+#pragma unroll
+        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, nu[m], dnu[m]);
+        if (k >= NSW) mbar_wait(&empty_w[ws], epar);
+#pragma unroll
+        for (int m = 0; m < PER; ++m) {
+          const int j = pw * 32 + lane + m * NPW * 32;
+          if (j < n_c) tile[j] = val[m];
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_w[ws]);
       } else {
-        const double* src = (WMODE == W_VECTOR) ? (p.weight + w0)
-                                                : (p.weight + (int64_t)p.groups[grp].wrow * p.w_stride + w0);
+        if (k >= NSW) mbar_wait(&empty_w[ws], epar);
+        const double* src = wrow_ptr + w0;
         const bool bulk = p.weight_bulk_ok && ((n_c & 1) == 0);
         if (bulk) {
           if (lane == 0) {
@@ -307,6 +400,18 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
           if (lane == 0) mbar_arrive(&full_w[ws]);
         }
       }
+      if (++ws == NSW) {
+        ws = 0;
+        if (k >= NSW) epar ^= 1u;  // first pass over the stages needs no wait; parity 0 comes first
+      }
+      if (++c == nchunks) {
+        c = 0;
+        ++grp;
+        if (k + 1 < niter) {
+          if (WMODE == W_PLANCK) inv_t = 1.0 / p.temperature[p.groups[grp].wrow];
+          if (WMODE == W_MATRIX) wrow_ptr = p.weight + (int64_t)p.groups[grp].wrow * p.w_stride;
+        }
+      }
     }
     return;
   }
@@ -318,6 +423,9 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   uint64_t* my_full = full_d + warp * NS;
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const uint2* slots_lane = p.slots + lane;
+  const uint16_t* meta_lane = p.lane_g + lane;
+  const int lim = 32 - lane;
 
   auto init_acc = [&]() {
     for (int g = lane; g < ng; g += 32) {
@@ -338,120 +446,144 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
     for (int i = lane; i < ng; i += 32) outz[i] = accz[i];
     __syncwarp();
   };
-  // is chunk gc of this warp's row fetched with a bulk copy?
-  auto chunk_info = [&](int64_t gc, const double*& src, int& n_c, bool& active, bool& bulk) {
-    const int grp = (int)(gc / p.nchunks);
-    const int64_t c = gc - (int64_t)grp * p.nchunks;
-    const GroupDesc* gd = p.groups + grp;
-    active = warp < gd->nrows;
-    const int64_t w0 = c * CH;
-    n_c = (int)min((int64_t)CH, p.nwav - w0);
-    src = active ? gd->od[warp] + w0 : nullptr;
-    bulk = active && gd->bulk_ok[warp] && ((n_c & 1) == 0);
+
+  // issue cursor (runs NS chunks ahead of the compute cursor)
+  int grp_i = first_group, c_i = first_chunk;
+  const double* od_i = nullptr;
+  bool bulk_row_i = false;
+  auto load_issue_group = [&]() {
+    const GroupDesc* gd = p.groups + grp_i;
+    const bool act = warp < gd->nrows;
+    od_i = act ? gd->od[warp] : nullptr;
+    bulk_row_i = act && gd->bulk_ok[warp];
   };
-  auto issue = [&](int64_t gc, int stage) {
-    const double* src;
-    int n_c;
-    bool active, bulk;
-    chunk_info(gc, src, n_c, active, bulk);
-    if (bulk && lane == 0) {
+  auto issue = [&](int stage) {
+    const int n_c = (c_i == nchunks - 1) ? last_n : CH;
+    if (bulk_row_i && ((n_c & 1) == 0) && lane == 0) {
       fence_proxy_async();
       mbar_arrive_expect_tx(&my_full[stage], (unsigned)(n_c * 8));
-      bulk_g2s(data + stage * CH, src, (unsigned)(n_c * 8), &my_full[stage]);
+      bulk_g2s(data + stage * CH, od_i + (int64_t)c_i * CH, (unsigned)(n_c * 8), &my_full[stage]);
+    }
+    if (++c_i == nchunks) {
+      c_i = 0;
+      ++grp_i;
+      if (grp_i < p.ngroups) load_issue_group();
     }
   };
+  load_issue_group();
+  for (int j = 0; j < NS && j < niter; ++j) issue(j);
 
-  for (int j = 0; j < NS; ++j) {
-    if (lo + j < hi) issue(lo + j, j);
-  }
   unsigned phase_bits = 0;  // bit s: parity to wait for on my_full[s]
-  int cur_grp = -1;
-  bool my_is_log = (FKIND == F_LOG);
-  int64_t k = 0;
-  for (int64_t gc = lo; gc < hi; ++gc, ++k) {
-    const int grp = (int)(gc / p.nchunks);
-    const int64_t c = gc - (int64_t)grp * p.nchunks;
-    if (grp != cur_grp) {
-      if (cur_grp >= 0) flush_partial(cur_grp);
+  unsigned wpar = 0;
+  int grp = first_group, c = first_chunk, s = 0, ws = 0;
+  const double* od_c = nullptr;
+  bool active = false, bulk_row = false, my_is_log = (FKIND == F_LOG);
+  bool need_group = true;
+  // plan words of the current chunk's first round, fetched one iteration ahead so that their
+  // global-memory latency is off the critical path
+  uint32_t r0 = p.round_off[c], r1 = p.round_off[c + 1];
+  uint2 sl_cur = slots_lane[(size_t)r0 * 32];
+  unsigned meta_cur = meta_lane[(size_t)r0 * 32];
+  int steps_cur = p.round_steps[r0];
+  for (int k = 0; k < niter; ++k) {
+    if (need_group) {
+      const GroupDesc* gd = p.groups + grp;
+      active = warp < gd->nrows;
+      od_c = active ? gd->od[warp] : nullptr;
+      bulk_row = active && gd->bulk_ok[warp];
+      if (FKIND == F_HYBRID) my_is_log = active && (gd->is_log[warp] != 0);
       init_acc();
-      cur_grp = grp;
-      if (FKIND == F_HYBRID) my_is_log = (warp < p.groups[grp].nrows) && (p.groups[grp].is_log[warp] != 0);
+      need_group = false;
     }
-    const int s = (int)(k % NS);
-    const int ws = (int)(k % NSW);
-    const double* src;
-    int n_c;
-    bool active, bulk;
-    chunk_info(gc, src, n_c, active, bulk);
+    // prefetch the next chunk's plan
+    const int c_next = (c + 1 == nchunks) ? 0 : c + 1;
+    const uint32_t r0_next = p.round_off[c_next], r1_next = p.round_off[c_next + 1];
+    const uint2 sl_next = slots_lane[(size_t)r0_next * 32];
+    const unsigned meta_next = meta_lane[(size_t)r0_next * 32];
+    const int steps_next = p.round_steps[r0_next];
+
+    const int n_c = (c == nchunks - 1) ? last_n : CH;
     double* stage = data + s * CH;
-    // the plan of this chunk (read-only, shared by every row: L1/L2 hits)
-    const uint32_t r0 = p.round_off[c], r1 = p.round_off[c + 1];
-    if (bulk) {
+    if (bulk_row && ((n_c & 1) == 0)) {
       mbar_wait(&my_full[s], (phase_bits >> s) & 1u);
       phase_bits ^= (1u << s);
     } else if (active) {
+      const double* src = od_c + (int64_t)c * CH;
       for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
       __syncwarp();
     }
-    mbar_wait(&full_w[ws], (unsigned)((k / NSW) & 1));
+    mbar_wait(&full_w[ws], wpar);
     const double* wtile = wt + ws * CH;
 
     if (active) {
       for (uint32_t r = r0; r < r1; ++r) {
-        const uint2 sl = p.slots[(size_t)r * 32 + lane];
-        const unsigned g = p.lane_g[(size_t)r * 32 + lane];
+        uint2 sl = sl_cur;
+        unsigned meta = meta_cur;
+        int nsteps = steps_cur;
+        if (r != r0) {  // chunks needing more than one round (many g points per chunk): rare
+          sl = slots_lane[(size_t)r * 32];
+          meta = meta_lane[(size_t)r * 32];
+          nsteps = p.round_steps[r];
+        }
+        const unsigned g = meta & 0xFFFu;
+        const int nv = (int)(meta >> 12);
         double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
         int zc = 0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const unsigned word = half ? sl.y : sl.x;
           double tau[4], ww[4], f[4];
-          bool ok[4], pos[4];
+          bool pos[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const unsigned idx = (word >> (8 * u)) & 0xFFu;
-            ok[u] = idx != PAD_SLOT;
-            const unsigned ii = ok[u] ? idx : 0u;
-            tau[u] = stage[ii];
-            ww[u] = wtile[ii];
+            tau[u] = stage[idx];
+            ww[u] = wtile[idx];
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) f[u] = f_transform<FKIND>(tau[u], p.kd, my_is_log, pos[u]);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const bool use = LOGKIND ? (ok[u] && pos[u]) : ok[u];
+            const bool valid = (half * 4 + u) < nv;  // padding slots repeat slot 0
+            const bool use = LOGKIND ? (valid && pos[u]) : valid;
             const double we = use ? ww[u] : 0.0;
-            s0 += (use ? f[u] : 0.0) * we;
+            s0 = fma(f[u], we, s0);
             s1 += we;
-            mn = ok[u] ? fmin(mn, tau[u]) : mn;
-            mx = ok[u] ? fmax(mx, tau[u]) : mx;
-            if (LOGKIND) zc += (ok[u] && !pos[u]) ? 1 : 0;
+            mn = (tau[u] < mn) ? tau[u] : mn;
+            mx = (tau[u] > mx) ? tau[u] : mx;
+            if (LOGKIND) zc += (valid && !pos[u]) ? 1 : 0;
           }
         }
         // segmented suffix reduction over adjacent lanes of the same g point
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
-          const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
-          const double t1 = __shfl_down_sync(0xffffffffu, s1, d);
-          const double tn = __shfl_down_sync(0xffffffffu, mn, d);
-          const double tx = __shfl_down_sync(0xffffffffu, mx, d);
-          const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
-          if (lane + d < 32 && go == g) {
-            s0 += t0;
-            s1 += t1;
-            mn = fmin(mn, tn);
-            mx = fmax(mx, tx);
-            zc += tz;
+        for (int st = 0; st < 5; ++st) {
+          if (st < nsteps) {  // warp-uniform
+            const int d = 1 << st;
+            const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
+            const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
+            const double t1 = __shfl_down_sync(0xffffffffu, s1, d);
+            const double tn = __shfl_down_sync(0xffffffffu, mn, d);
+            const double tx = __shfl_down_sync(0xffffffffu, mx, d);
+            const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
+            if (d < lim && go == g) {
+              s0 += t0;
+              s1 += t1;
+              mn = (tn < mn) ? tn : mn;
+              mx = (tx > mx) ? tx : mx;
+              zc += tz;
+            }
           }
         }
         const unsigned gprev = __shfl_up_sync(0xffffffffu, g, 1);
         if (g != NO_G && (lane == 0 || gprev != g)) {  // head lane of its g point in this round
-          double* a = acc + g * 4;
-          a[0] += s0;
-          a[1] += s1;
-          a[2] = fmin(a[2], mn);
-          a[3] = fmax(a[3], mx);
+          double2* a = reinterpret_cast<double2*>(acc + g * 4);
+          double2 a01 = a[0], a23 = a[1];
+          a01.x += s0;
+          a01.y += s1;
+          a23.x = (mn < a23.x) ? mn : a23.x;
+          a23.y = (mx > a23.y) ? mx : a23.y;
+          a[0] = a01;
+          a[1] = a23;
           if (LOGKIND) accz[g] += zc;
         }
         __syncwarp();
@@ -459,9 +591,25 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_w[ws]);
-    if (lo + k + NS < hi) issue(lo + k + NS, s);
+    if (k + NS < niter) issue(s);
+    r0 = r0_next;
+    r1 = r1_next;
+    sl_cur = sl_next;
+    meta_cur = meta_next;
+    steps_cur = steps_next;
+    if (++s == NS) s = 0;
+    if (++ws == NSW) {
+      ws = 0;
+      wpar ^= 1u;
+    }
+    if (++c == nchunks) {
+      flush_partial(grp);
+      c = 0;
+      ++grp;
+      need_group = true;
+    }
   }
-  if (cur_grp >= 0) flush_partial(cur_grp);
+  if (!need_group) flush_partial(grp);
 }
 
 // ------------------------------------------------------------------ combine + finalize
@@ -751,6 +899,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.round_off = plan->d_round_off;
   rp.slots = plan->d_slots;
   rp.lane_g = plan->d_lane_g;
+  rp.round_steps = plan->d_round_steps;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
@@ -898,6 +1047,8 @@ static void plan_free(ecckd_gpoint_plan* p) {
   cudaFree(p->d_round_off);
   cudaFree(p->d_slots);
   cudaFree(p->d_lane_g);
+  cudaFree(p->d_round_steps32);
+  cudaFree(p->d_round_steps);
   cudaFree(p->d_count);
   cudaFree(p->d_scratch);
   delete p;
@@ -940,13 +1091,19 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
     const size_t nr = std::max<size_t>(1, total);
     e = cudaMalloc(&p->d_slots, nr * 32 * sizeof(uint2));
     if (e == cudaSuccess) e = cudaMalloc(&p->d_lane_g, nr * 32 * sizeof(uint16_t));
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_slots, 0xFF, nr * 32 * sizeof(uint2), ctx->stream);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_round_steps32, nr * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_round_steps, nr);
+    // unused lanes: slots 0 (any valid index), meta 0xFFFF (g = NO_G)
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_slots, 0, nr * 32 * sizeof(uint2), ctx->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(p->d_lane_g, 0xFF, nr * 32 * sizeof(uint16_t), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_round_steps32, 0, nr * sizeof(uint32_t), ctx->stream);
     if (e == cudaSuccess) {
       plan_fill_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
                                                                      reinterpret_cast<uint8_t*>(p->d_slots),
-                                                                     p->d_lane_g);
-      ctx->launches++;
+                                                                     p->d_lane_g, p->d_round_steps32);
+      narrow_steps_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_round_steps32,
+                                                                                 p->d_round_steps);
+      ctx->launches += 2;
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller

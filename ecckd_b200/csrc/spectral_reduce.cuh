@@ -10,10 +10,10 @@ constexpr int SLOTS_PER_LANE = 8;  // plan slots per lane per round
 constexpr int NS = 3;              // data stages per consumer warp
 constexpr int NSW = 3;             // weight stages per CTA
 constexpr int NPW = 2;             // producer (weight) warps per CTA
-constexpr int NW_MAX = 20;         // consumer warps (= rows) per CTA
-constexpr unsigned PAD_SLOT = 255u;
-constexpr unsigned NO_G = 0xFFFFu;
-constexpr int MAX_NG = 4096;
+constexpr int NW_MAX = 19;         // consumer warps (= rows) per CTA: 23 warps x 88 registers fill the register file
+// lane meta word of the plan: bits 0-11 g point (0xFFF = lane unused), bits 12-15 valid slots (1..8)
+constexpr unsigned NO_G = 0xFFFu;
+constexpr int MAX_NG = 4094;
 
 // internal per-row method ids (public enum resolved per layer for hybrid)
 enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };
@@ -69,7 +69,8 @@ struct ReduceParams {
   int ng;
   const uint32_t* round_off;  // [nchunks+1]
   const uint2* slots;         // [nrounds][32] 8 byte-sized local indices per lane
-  const uint16_t* lane_g;     // [nrounds][32]
+  const uint16_t* lane_g;     // [nrounds][32] lane meta words
+  const uint8_t* round_steps; // [nrounds] shuffle steps the segmented reduction needs
   const double* weight;       // MATRIX: [wrow][nwav] (stride w_stride); VECTOR: [nwav]
   int64_t w_stride;
   int weight_bulk_ok;
@@ -116,6 +117,8 @@ struct ecckd_gpoint_plan {
   uint32_t* d_round_off = nullptr;       // [nchunks+1]
   uint2* d_slots = nullptr;              // [nrounds][32]
   uint16_t* d_lane_g = nullptr;          // [nrounds][32]
+  uint32_t* d_round_steps32 = nullptr;   // [nrounds] (atomicMax target)
+  uint8_t* d_round_steps = nullptr;      // [nrounds]
   unsigned long long* d_count = nullptr; // [ng]
   std::vector<int64_t> h_count;
   double* d_scratch = nullptr;           // per-(row, g) partial results of the single-GPU path
