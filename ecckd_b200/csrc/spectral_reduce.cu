@@ -80,7 +80,8 @@ __constant__ double EXP_C[12] = {2.5052097064908941e-8, 2.7626262793835868e-7, 2
 __constant__ double EXP_K[4] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
                                 -1.90821492927058770002e-10};
 
-__device__ __forceinline__ double fast_exp(double x) {
+template <bool CLAMP_HIGH>
+__device__ __forceinline__ double fast_exp_t(double x) {
   const double t = fma(x, EXP_K[0], EXP_K[1]);
   int k = __double2loint(t);
   const double kf = t - EXP_K[1];
@@ -89,9 +90,13 @@ __device__ __forceinline__ double fast_exp(double x) {
   double q = EXP_C[0];
 #pragma unroll
   for (int i = 1; i < 12; ++i) q = fma(q, r, EXP_C[i]);
-  k = max(-1000, min(k, 1000));
+  k = CLAMP_HIGH ? max(-1000, min(k, 1000)) : max(-1000, k);
   return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
 }
+__device__ __forceinline__ double fast_exp(double x) { return fast_exp_t<true>(x); }
+// for arguments known to be <= 0 up to unphysical inputs (x = -kd*tau with tau >= 0): no upper
+// clamp, i.e. optical depths below -700/kd would give garbage instead of the reference's -inf
+__device__ __forceinline__ double fast_exp_nonpos(double x) { return fast_exp_t<false>(x); }
 
 // planck_function.cpp:29-33,47-53, one element.  The reference evaluates
 // prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) (one rounding more in the
@@ -184,36 +189,45 @@ __global__ void __launch_bounds__(CH) plan_count_kernel(const int32_t* __restric
   if (p.g >= 0 && p.first) atomicAdd(&count[p.g], (unsigned long long)p.count);
 }
 
+__global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds) {
+  // unused lanes: offsets 0 (a valid address), weight offsets at the zero entry, meta = NO_G
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nrounds * 32) return;
+  PlanRound& r = rounds[i >> 5];
+  const int lane = (int)(i & 31);
+  r.tau_off[lane] = make_uint4(0, 0, 0, 0);
+  const unsigned z = (unsigned)(CH * 8) | ((unsigned)(CH * 8) << 16);
+  r.w_off[lane] = make_uint4(z, z, z, z);
+  r.meta[lane] = 0xFFFFu;
+  if (lane == 0) r.steps = 0;
+}
+
 __global__ void __launch_bounds__(CH) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
                                                         const uint32_t* __restrict__ round_off,
-                                                        uint8_t* __restrict__ slots, uint16_t* __restrict__ lane_g,
-                                                        uint32_t* __restrict__ round_steps) {
+                                                        PlanRound* __restrict__ rounds) {
   __shared__ int sg[CH];
   __shared__ int sl[CH];
   const int64_t c = blockIdx.x;
   const PlanPos p = plan_position(g_point, nwav, ng, c, sg, sl);
   if (p.g < 0) return;
-  const size_t round = (size_t)round_off[c] + (size_t)(p.vlane >> 5);
+  PlanRound& rd = rounds[(size_t)round_off[c] + (size_t)(p.vlane >> 5)];
   const int lane = p.vlane & 31;
-  uint8_t* my = slots + (round * 32 + lane) * SLOTS_PER_LANE;
-  my[p.slot] = (uint8_t)threadIdx.x;
+  uint16_t* tau_off = reinterpret_cast<uint16_t*>(&rd.tau_off[lane]);
+  uint16_t* w_off = reinterpret_cast<uint16_t*>(&rd.w_off[lane]);
+  const uint16_t off = (uint16_t)(threadIdx.x * 8);
+  tau_off[p.slot] = off;
+  w_off[p.slot] = off;
   if (p.slot == 0) {
-    // this thread owns the lane: valid slots form a prefix of length nv; the padding slots repeat
-    // slot 0 (harmless for min/max, masked out of the sums by nv)
+    // this thread owns the lane: valid slots form a prefix of length nv; padding slots repeat slot 0
+    // for the optical depth (harmless for min/max) and keep the zero weight entry
     const int L = (p.count + SLOTS_PER_LANE - 1) / SLOTS_PER_LANE;
-    const int k = p.kth;  // k < L here
-    const int nv = (p.count - 1 - k) / L + 1;
-    for (int e = nv; e < SLOTS_PER_LANE; ++e) my[e] = (uint8_t)threadIdx.x;
-    lane_g[round * 32 + lane] = (uint16_t)((unsigned)p.g | ((unsigned)nv << 12));
+    const int nv = (p.count - 1 - p.kth) / L + 1;  // kth < L here
+    for (int e = nv; e < SLOTS_PER_LANE; ++e) tau_off[e] = off;
+    rd.meta[lane] = (uint16_t)((unsigned)p.g | ((unsigned)nv << 12));
     int steps = 0;
     while ((1 << steps) < min(L, 32)) ++steps;
-    if (steps > 0) atomicMax(&round_steps[round], (uint32_t)steps);
+    if (steps > 0) atomicMax(&rd.steps, (uint32_t)steps);
   }
-}
-
-__global__ void narrow_steps_kernel(int64_t n, const uint32_t* __restrict__ in, uint8_t* __restrict__ out) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (uint8_t)in[i];
 }
 
 // exclusive scan of n uint32 by one block (n is a few 10^4 .. 10^5)
@@ -260,7 +274,7 @@ template <int FKIND>
 __device__ __forceinline__ double f_transform(double tau, double kd, bool is_log, bool& positive) {
   positive = true;
   if (FKIND == F_LINEAR) return tau;
-  if (FKIND == F_TRANS) return 1.0 - fast_exp(-tau * kd);
+  if (FKIND == F_TRANS) return 1.0 - fast_exp_nonpos(-tau * kd);
   if (FKIND == F_SQRT) return sqrt(tau);
   if (FKIND == F_LOG) {
     positive = tau > 0.0;
@@ -271,7 +285,7 @@ __device__ __forceinline__ double f_transform(double tau, double kd, bool is_log
       positive = tau > 0.0;
       return positive ? log(tau) : 0.0;
     }
-    return 1.0 - fast_exp(-tau * kd);
+    return 1.0 - fast_exp_nonpos(-tau * kd);
   }
   return 1.0;  // F_NONE: only the weight sum is wanted
 }
@@ -279,20 +293,22 @@ __device__ __forceinline__ double f_transform(double tau, double kd, bool is_log
 // Shared-memory layout of one CTA (byte offsets computed identically on the host)
 struct SmemLayout {
   int bars;    // mbarriers: full_d[nw][NS], full_w[NSW], empty_w[NSW]
-  int wt;      // weight tiles [NSW][CH] doubles
+  int wt;      // weight stages [NSW]: {double tile[WT_STRIDE]; PlanRound plan}
   int data;    // data stages [nw][NS][CH] doubles
   int acc;     // accumulators [nw][ng][4] doubles
   int accz;    // zero counters [nw][ng] int32
   int total;
 };
+constexpr int WSTAGE_BYTES = WT_STRIDE * 8 + (int)sizeof(PlanRound);
+static_assert(WSTAGE_BYTES % 16 == 0 && (WT_STRIDE * 8) % 16 == 0, "weight stage alignment");
 __host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
   SmemLayout L;
   int off = 0;
   L.bars = off;
-  off += (nw * NS + 2 * NSW) * 8;
+  off += (nw * NS + 2 * NSW) * 8 + NSW * 4;
   off = (off + 127) & ~127;
   L.wt = off;
-  off += NSW * CH * 8;
+  off += NSW * WSTAGE_BYTES;
   L.data = off;
   off += nw * NS * CH * 8;
   L.acc = off;
@@ -301,6 +317,87 @@ __host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
   off += nw * ng * 4;
   L.total = (off + 15) & ~15;
   return L;
+}
+
+// One round of one row: 8 slots per lane in registers, segmented shuffle reduction, head lanes
+// fold into the warp's accumulators.  DO_S1: also accumulate the weight sum (only the first row
+// of a group needs to: all rows of a group share the weights).
+template <int FKIND, bool DO_S1>
+__device__ __forceinline__ void reduce_round(const unsigned char* __restrict__ stage_b,
+                                             const unsigned char* __restrict__ wtile_b, const uint4 to, const uint4 wo,
+                                             const unsigned meta, const int nsteps, const double kd,
+                                             const bool my_is_log, const int lane, double* __restrict__ acc,
+                                             int32_t* __restrict__ accz) {
+  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const unsigned g = meta & 0xFFFu;
+  const int nv = (int)(meta >> 12);
+  const int lim = 32 - lane;
+  double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
+  int zc = 0;
+  const unsigned tw[4] = {to.x, to.y, to.z, to.w};
+  const unsigned ww4[4] = {wo.x, wo.y, wo.z, wo.w};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    double tau[4], ww[4], f[4];
+    bool pos[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = half * 4 + u;
+      const unsigned toff = (e & 1) ? (tw[e >> 1] >> 16) : (tw[e >> 1] & 0xFFFFu);
+      const unsigned woff = (e & 1) ? (ww4[e >> 1] >> 16) : (ww4[e >> 1] & 0xFFFFu);
+      tau[u] = *reinterpret_cast<const double*>(stage_b + toff);
+      ww[u] = *reinterpret_cast<const double*>(wtile_b + woff);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) f[u] = f_transform<FKIND>(tau[u], kd, my_is_log, pos[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      double we = ww[u];  // zero for padding slots
+      if (LOGKIND) {
+        const bool valid = (half * 4 + u) < nv;
+        we = pos[u] ? we : 0.0;
+        zc += (valid && !pos[u]) ? 1 : 0;
+      }
+      s0 = fma(f[u], we, s0);
+      if (DO_S1) s1 += we;
+      mn = (tau[u] < mn) ? tau[u] : mn;
+      mx = (tau[u] > mx) ? tau[u] : mx;
+    }
+  }
+  // segmented suffix reduction over adjacent lanes of the same g point
+#pragma unroll
+  for (int st = 0; st < 5; ++st) {
+    if (st < nsteps) {  // warp-uniform
+      const int d = 1 << st;
+      const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
+      const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
+      const double t1 = DO_S1 ? __shfl_down_sync(0xffffffffu, s1, d) : 0.0;
+      const double tn = __shfl_down_sync(0xffffffffu, mn, d);
+      const double tx = __shfl_down_sync(0xffffffffu, mx, d);
+      const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
+      if (d < lim && go == g) {
+        s0 += t0;
+        if (DO_S1) s1 += t1;
+        mn = (tn < mn) ? tn : mn;
+        mx = (tx > mx) ? tx : mx;
+        zc += tz;
+      }
+    }
+  }
+  const unsigned gprev = __shfl_up_sync(0xffffffffu, g, 1);
+  if (g != NO_G && (lane == 0 || gprev != g)) {  // head lane of its g point in this round
+    double2* a = reinterpret_cast<double2*>(acc + g * 4);
+    double2 a01 = a[0], a23 = a[1];
+    a01.x += s0;
+    if (DO_S1) a01.y += s1;
+    a23.x = (mn < a23.x) ? mn : a23.x;
+    a23.y = (mx > a23.y) ? mx : a23.y;
+    a[0] = a01;
+    a[1] = a23;
+    if (LOGKIND) accz[g] += zc;
+  }
+  __syncwarp();
 }
 
 template <int FKIND, int WMODE>
@@ -313,7 +410,9 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   uint64_t* full_d = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [nw][NS]
   uint64_t* full_w = full_d + nw * NS;                                 // [NSW]
   uint64_t* empty_w = full_w + NSW;                                    // [NSW]
-  double* wt = reinterpret_cast<double*>(smem_raw + L.wt);
+  uint32_t* wrounds = reinterpret_cast<uint32_t*>(empty_w + NSW);      // [NSW] rounds of the staged chunk
+  unsigned char* wstages = smem_raw + L.wt;
+  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nw * NS; ++i) mbar_init(&full_d[i], 1);
@@ -322,6 +421,11 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
       mbar_init(&empty_w[i], nw);
     }
     fence_mbar_init();
+  }
+  if (threadIdx.x < NSW) {  // the zero weight that padding slots read
+    double* tile = reinterpret_cast<double*>(wstages + threadIdx.x * WSTAGE_BYTES);
+    tile[CH] = 0.0;
+    tile[CH + 1] = 0.0;
   }
   __syncthreads();
 
@@ -336,31 +440,42 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * CH);  // length of the last chunk of a row
 
   if (warp >= nw) {
-    // ===================== weight producers =====================
+    // ===================== producers: weight tile + plan record of every chunk =====================
     const int pw = warp - nw;
     constexpr int PER = (CH + NPW * 32 - 1) / (NPW * 32);  // elements per producer lane per chunk
     int grp = first_group, c = first_chunk, ws = 0;
     unsigned epar = 0;
     double inv_t = (WMODE == W_PLANCK) ? 1.0 / p.temperature[p.groups[grp].wrow] : 0.0;
     const double* wrow_ptr = (WMODE == W_MATRIX) ? p.weight + (int64_t)p.groups[grp].wrow * p.w_stride : p.weight;
-    // wavenumbers of the next chunk, fetched one chunk ahead
-    double nu_n[PER], dnu_n[PER];
+    double nu_n[PER], dnu_n[PER];  // wavenumbers of the next chunk, fetched one chunk ahead
     auto fetch = [&](int cc) {
       const int64_t w0 = (int64_t)cc * CH;
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
-        const int64_t w = w0 + pw * 32 + lane + m * NPW * 32;
-        const bool ok = (pw * 32 + lane + m * NPW * 32) < CH && w < p.nwav;
-        nu_n[m] = ok ? p.wn[w] : 1.0;
-        dnu_n[m] = ok ? p.dwn[w] : 0.0;
+        const int j = pw * 32 + lane + m * NPW * 32;
+        const bool ok = j < CH && (w0 + j) < p.nwav;
+        nu_n[m] = ok ? p.wn[w0 + j] : 1.0;
+        dnu_n[m] = ok ? p.dwn[w0 + j] : 0.0;
       }
     };
     if (WMODE == W_PLANCK && niter > 0) fetch(c);
+    uint32_t r0 = 0, r1 = 0;
+    if (niter > 0) {
+      r0 = p.round_off[c];
+      r1 = p.round_off[c + 1];
+    }
     for (int k = 0; k < niter; ++k) {
       const int64_t w0 = (int64_t)c * CH;
       const int n_c = (c == nchunks - 1) ? last_n : CH;
-      double* tile = wt + ws * CH;
+      unsigned char* wstage = wstages + ws * WSTAGE_BYTES;
+      double* tile = reinterpret_cast<double*>(wstage);
       const int c_next = (c + 1 == nchunks) ? 0 : c + 1;
+      uint32_t r0_next = 0, r1_next = 0;
+      if (k + 1 < niter) {
+        r0_next = p.round_off[c_next];
+        r1_next = p.round_off[c_next + 1];
+      }
+      double val[PER];
       if (WMODE == W_PLANCK) {
         double nu[PER], dnu[PER];
 #pragma unroll
@@ -369,37 +484,39 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
           dnu[m] = dnu_n[m];
         }
         if (k + 1 < niter) fetch(c_next);
-        double val[PER];
 #pragma unroll
         for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, nu[m], dnu[m]);
-        if (k >= NSW) mbar_wait(&empty_w[ws], epar);
+      }
+      if (k >= NSW) mbar_wait(&empty_w[ws], epar);
+      const double* src = (WMODE == W_PLANCK) ? nullptr : wrow_ptr + w0;
+      const bool wbulk = (WMODE != W_PLANCK) && p.weight_bulk_ok && ((n_c & 1) == 0);
+      if (WMODE == W_PLANCK) {
 #pragma unroll
         for (int m = 0; m < PER; ++m) {
           const int j = pw * 32 + lane + m * NPW * 32;
           if (j < n_c) tile[j] = val[m];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_w[ws]);
-      } else {
-        if (k >= NSW) mbar_wait(&empty_w[ws], epar);
-        const double* src = wrow_ptr + w0;
-        const bool bulk = p.weight_bulk_ok && ((n_c & 1) == 0);
-        if (bulk) {
-          if (lane == 0) {
-            if (pw == 0) {
-              fence_proxy_async();
-              mbar_arrive_expect_tx(&full_w[ws], (unsigned)(n_c * 8));
-              bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
-            } else {
-              mbar_arrive(&full_w[ws]);
-            }
-          }
+      } else if (!wbulk) {
+        for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (pw == 0) {
+          // bulk copies: the plan record of the chunk's first round (if it has one), and the
+          // weights themselves unless they were computed above
+          const bool has_round = r1 > r0;
+          wrounds[ws] = r1 - r0;
+          fence_proxy_async();
+          const unsigned bytes = (has_round ? (unsigned)sizeof(PlanRound) : 0u) + (wbulk ? (unsigned)(n_c * 8) : 0u);
+          mbar_arrive_expect_tx(&full_w[ws], bytes);
+          if (has_round) bulk_g2s(wstage + WT_STRIDE * 8, p.rounds + r0, (unsigned)sizeof(PlanRound), &full_w[ws]);
+          if (wbulk) bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
         } else {
-          for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full_w[ws]);
+          mbar_arrive(&full_w[ws]);
         }
       }
+      r0 = r0_next;
+      r1 = r1_next;
       if (++ws == NSW) {
         ws = 0;
         if (k >= NSW) epar ^= 1u;  // first pass over the stages needs no wait; parity 0 comes first
@@ -421,11 +538,10 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   double* acc = reinterpret_cast<double*>(smem_raw + L.acc) + (size_t)warp * ng * 4;
   int32_t* accz = reinterpret_cast<int32_t*>(smem_raw + L.accz) + (size_t)warp * ng;
   uint64_t* my_full = full_d + warp * NS;
-  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const uint2* slots_lane = p.slots + lane;
-  const uint16_t* meta_lane = p.lane_g + lane;
-  const int lim = 32 - lane;
+  // only the first row of a group accumulates the weight sums (shared by the group's rows),
+  // except where they depend on the row (logarithmic kinds) or are the result (F_NONE)
+  const bool do_s1 = LOGKIND || FKIND == F_NONE || warp == 0;
 
   auto init_acc = [&]() {
     for (int g = lane; g < ng; g += 32) {
@@ -479,12 +595,6 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
   const double* od_c = nullptr;
   bool active = false, bulk_row = false, my_is_log = (FKIND == F_LOG);
   bool need_group = true;
-  // plan words of the current chunk's first round, fetched one iteration ahead so that their
-  // global-memory latency is off the critical path
-  uint32_t r0 = p.round_off[c], r1 = p.round_off[c + 1];
-  uint2 sl_cur = slots_lane[(size_t)r0 * 32];
-  unsigned meta_cur = meta_lane[(size_t)r0 * 32];
-  int steps_cur = p.round_steps[r0];
   for (int k = 0; k < niter; ++k) {
     if (need_group) {
       const GroupDesc* gd = p.groups + grp;
@@ -495,13 +605,6 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
       init_acc();
       need_group = false;
     }
-    // prefetch the next chunk's plan
-    const int c_next = (c + 1 == nchunks) ? 0 : c + 1;
-    const uint32_t r0_next = p.round_off[c_next], r1_next = p.round_off[c_next + 1];
-    const uint2 sl_next = slots_lane[(size_t)r0_next * 32];
-    const unsigned meta_next = meta_lane[(size_t)r0_next * 32];
-    const int steps_next = p.round_steps[r0_next];
-
     const int n_c = (c == nchunks - 1) ? last_n : CH;
     double* stage = data + s * CH;
     if (bulk_row && ((n_c & 1) == 0)) {
@@ -513,90 +616,34 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
       __syncwarp();
     }
     mbar_wait(&full_w[ws], wpar);
-    const double* wtile = wt + ws * CH;
+    const unsigned char* wstage = wstages + ws * WSTAGE_BYTES;
 
-    if (active) {
-      for (uint32_t r = r0; r < r1; ++r) {
-        uint2 sl = sl_cur;
-        unsigned meta = meta_cur;
-        int nsteps = steps_cur;
-        if (r != r0) {  // chunks needing more than one round (many g points per chunk): rare
-          sl = slots_lane[(size_t)r * 32];
-          meta = meta_lane[(size_t)r * 32];
-          nsteps = p.round_steps[r];
+    const uint32_t nrounds_c = wrounds[ws];
+    if (active && nrounds_c > 0) {
+      const PlanRound* pr = reinterpret_cast<const PlanRound*>(wstage + WT_STRIDE * 8);
+      const uint4 to = pr->tau_off[lane];
+      const uint4 wo = pr->w_off[lane];
+      const unsigned meta = pr->meta[lane];
+      const int nsteps = (int)pr->steps;
+      if (do_s1)
+        reduce_round<FKIND, true>(reinterpret_cast<const unsigned char*>(stage), wstage, to, wo, meta, nsteps, p.kd,
+                                  my_is_log, lane, acc, accz);
+      else
+        reduce_round<FKIND, false>(reinterpret_cast<const unsigned char*>(stage), wstage, to, wo, meta, nsteps, p.kd,
+                                   my_is_log, lane, acc, accz);
+      if (nrounds_c > 1) {
+        // chunks with more g points than one round holds (rare): further rounds straight from global memory
+        const uint32_t r0 = p.round_off[c];
+        for (uint32_t r = r0 + 1; r < r0 + nrounds_c; ++r) {
+          const PlanRound* gr = p.rounds + r;
+          reduce_round<FKIND, true>(reinterpret_cast<const unsigned char*>(stage), wstage, gr->tau_off[lane],
+                                    gr->w_off[lane], gr->meta[lane], (int)gr->steps, p.kd, my_is_log, lane, acc, accz);
         }
-        const unsigned g = meta & 0xFFFu;
-        const int nv = (int)(meta >> 12);
-        double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
-        int zc = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const unsigned word = half ? sl.y : sl.x;
-          double tau[4], ww[4], f[4];
-          bool pos[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const unsigned idx = (word >> (8 * u)) & 0xFFu;
-            tau[u] = stage[idx];
-            ww[u] = wtile[idx];
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) f[u] = f_transform<FKIND>(tau[u], p.kd, my_is_log, pos[u]);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const bool valid = (half * 4 + u) < nv;  // padding slots repeat slot 0
-            const bool use = LOGKIND ? (valid && pos[u]) : valid;
-            const double we = use ? ww[u] : 0.0;
-            s0 = fma(f[u], we, s0);
-            s1 += we;
-            mn = (tau[u] < mn) ? tau[u] : mn;
-            mx = (tau[u] > mx) ? tau[u] : mx;
-            if (LOGKIND) zc += (valid && !pos[u]) ? 1 : 0;
-          }
-        }
-        // segmented suffix reduction over adjacent lanes of the same g point
-#pragma unroll
-        for (int st = 0; st < 5; ++st) {
-          if (st < nsteps) {  // warp-uniform
-            const int d = 1 << st;
-            const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
-            const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
-            const double t1 = __shfl_down_sync(0xffffffffu, s1, d);
-            const double tn = __shfl_down_sync(0xffffffffu, mn, d);
-            const double tx = __shfl_down_sync(0xffffffffu, mx, d);
-            const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
-            if (d < lim && go == g) {
-              s0 += t0;
-              s1 += t1;
-              mn = (tn < mn) ? tn : mn;
-              mx = (tx > mx) ? tx : mx;
-              zc += tz;
-            }
-          }
-        }
-        const unsigned gprev = __shfl_up_sync(0xffffffffu, g, 1);
-        if (g != NO_G && (lane == 0 || gprev != g)) {  // head lane of its g point in this round
-          double2* a = reinterpret_cast<double2*>(acc + g * 4);
-          double2 a01 = a[0], a23 = a[1];
-          a01.x += s0;
-          a01.y += s1;
-          a23.x = (mn < a23.x) ? mn : a23.x;
-          a23.y = (mx > a23.y) ? mx : a23.y;
-          a[0] = a01;
-          a[1] = a23;
-          if (LOGKIND) accz[g] += zc;
-        }
-        __syncwarp();
       }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_w[ws]);
     if (k + NS < niter) issue(s);
-    r0 = r0_next;
-    r1 = r1_next;
-    sl_cur = sl_next;
-    meta_cur = meta_next;
-    steps_cur = steps_next;
     if (++s == NS) s = 0;
     if (++ws == NSW) {
       ws = 0;
@@ -623,6 +670,7 @@ __global__ void combine_kernel(const CombineParams p) {
   const int grp = (int)(tid / ((int64_t)p.ng * p.nw));
   const GroupDesc* gd = p.groups + grp;
   if (w >= gd->nrows) return;
+  const int w_s1 = p.shared_s1 ? 0 : w;  // weight sums live in the group's first row
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
   const int64_t glo = (int64_t)grp * p.nchunks, ghi = glo + p.nchunks;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -635,13 +683,13 @@ __global__ void combine_kernel(const CombineParams p) {
     if (lo >= ghi) break;
     if (hi <= glo || hi <= lo) continue;
     const int first_group = (int)(lo / p.nchunks);
-    const size_t slot = ((size_t)b * p.maxg + (size_t)(grp - first_group)) * p.nw + w;
-    const double* a = p.partial + (slot * p.ng + g) * 4;
+    const size_t base = ((size_t)b * p.maxg + (size_t)(grp - first_group)) * p.nw;
+    const double* a = p.partial + ((base + w) * p.ng + g) * 4;
     s0 += a[0];
-    s1 += a[1];
+    s1 += p.partial[((base + w_s1) * p.ng + g) * 4 + 1];
     mn = fmin(mn, a[2]);
     mx = fmax(mx, a[3]);
-    zc += p.partial_z[slot * p.ng + g];
+    zc += p.partial_z[(base + w) * p.ng + g];
   }
   const int row = gd->row[w];
   double* so = p.sums + ((size_t)row * p.ng + g) * NSUM;
@@ -897,9 +945,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.nwav = nwav;
   rp.ng = ng;
   rp.round_off = plan->d_round_off;
-  rp.slots = plan->d_slots;
-  rp.lane_g = plan->d_lane_g;
-  rp.round_steps = plan->d_round_steps;
+  rp.rounds = plan->d_rounds;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
@@ -956,6 +1002,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.maxg = maxg;
   cp.nchunks = plan->nchunks;
   cp.ng = ng;
+  cp.shared_s1 = !(fkind == F_LOG || fkind == F_HYBRID || fkind == F_NONE);
   cp.partial = rp.partial;
   cp.partial_z = rp.partial_z;
   cp.sums = d_sums;
@@ -1045,10 +1092,7 @@ using namespace ecckd;
 // ------------------------------------------------------------------ C ABI
 static void plan_free(ecckd_gpoint_plan* p) {
   cudaFree(p->d_round_off);
-  cudaFree(p->d_slots);
-  cudaFree(p->d_lane_g);
-  cudaFree(p->d_round_steps32);
-  cudaFree(p->d_round_steps);
+  cudaFree(p->d_rounds);
   cudaFree(p->d_count);
   cudaFree(p->d_scratch);
   delete p;
@@ -1089,20 +1133,10 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   if (e == cudaSuccess) {
     p->nrounds = total;
     const size_t nr = std::max<size_t>(1, total);
-    e = cudaMalloc(&p->d_slots, nr * 32 * sizeof(uint2));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_lane_g, nr * 32 * sizeof(uint16_t));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_round_steps32, nr * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&p->d_round_steps, nr);
-    // unused lanes: slots 0 (any valid index), meta 0xFFFF (g = NO_G)
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_slots, 0, nr * 32 * sizeof(uint2), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_lane_g, 0xFF, nr * 32 * sizeof(uint16_t), ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(p->d_round_steps32, 0, nr * sizeof(uint32_t), ctx->stream);
+    e = cudaMalloc(&p->d_rounds, (nr + 1) * sizeof(PlanRound));
     if (e == cudaSuccess) {
-      plan_fill_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
-                                                                     reinterpret_cast<uint8_t*>(p->d_slots),
-                                                                     p->d_lane_g, p->d_round_steps32);
-      narrow_steps_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_round_steps32,
-                                                                                 p->d_round_steps);
+      plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds);
+      plan_fill_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off, p->d_rounds);
       ctx->launches += 2;
       e = cudaGetLastError();
     }

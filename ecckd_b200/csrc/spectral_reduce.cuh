@@ -14,6 +14,20 @@ constexpr int NW_MAX = 19;         // consumer warps (= rows) per CTA: 23 warps 
 // lane meta word of the plan: bits 0-11 g point (0xFFF = lane unused), bits 12-15 valid slots (1..8)
 constexpr unsigned NO_G = 0xFFFu;
 constexpr int MAX_NG = 4094;
+constexpr int WT_STRIDE = CH + 2;  // weight tile: CH weights + a zero entry that padding slots point at
+
+// One round of the plan: for each lane, 8 byte offsets into the row stage (padding repeats
+// slot 0), 8 byte offsets into the weight tile (padding -> the zero entry), the lane meta word
+// and the number of shuffle steps the segmented reduction needs.  1104 bytes, copied to shared
+// memory with one bulk copy.
+struct PlanRound {
+  uint4 tau_off[32];
+  uint4 w_off[32];
+  uint16_t meta[32];
+  uint32_t steps;
+  uint32_t pad_[3];
+};
+static_assert(sizeof(PlanRound) == 1104, "PlanRound layout");
 
 // internal per-row method ids (public enum resolved per layer for hybrid)
 enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };
@@ -68,9 +82,7 @@ struct ReduceParams {
   int64_t nwav;
   int ng;
   const uint32_t* round_off;  // [nchunks+1]
-  const uint2* slots;         // [nrounds][32] 8 byte-sized local indices per lane
-  const uint16_t* lane_g;     // [nrounds][32] lane meta words
-  const uint8_t* round_steps; // [nrounds] shuffle steps the segmented reduction needs
+  const PlanRound* rounds;    // [nrounds]
   const double* weight;       // MATRIX: [wrow][nwav] (stride w_stride); VECTOR: [nwav]
   int64_t w_stride;
   int weight_bulk_ok;
@@ -90,6 +102,7 @@ struct CombineParams {
   int maxg;
   int64_t nchunks;
   int ng;
+  int shared_s1;   // weight sums are accumulated by the first row of each group only
   const double* partial;
   const int32_t* partial_z;
   double* sums;    // [nrows][ng][NSUM]
@@ -115,10 +128,7 @@ struct ecckd_gpoint_plan {
   int64_t nrounds = 0;
   int ng = 0;
   uint32_t* d_round_off = nullptr;       // [nchunks+1]
-  uint2* d_slots = nullptr;              // [nrounds][32]
-  uint16_t* d_lane_g = nullptr;          // [nrounds][32]
-  uint32_t* d_round_steps32 = nullptr;   // [nrounds] (atomicMax target)
-  uint8_t* d_round_steps = nullptr;      // [nrounds]
+  ecckd::PlanRound* d_rounds = nullptr;  // [nrounds]
   unsigned long long* d_count = nullptr; // [ng]
   std::vector<int64_t> h_count;
   double* d_scratch = nullptr;           // per-(row, g) partial results of the single-GPU path
