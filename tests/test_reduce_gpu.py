@@ -201,3 +201,44 @@ def test_avg_linearity_property_full_width(ctx):
         sums[l] = np.bincount(g, weights=od1[l] * w[l], minlength=ng)
         wsum[l] = np.bincount(g, weights=w[l], minlength=ng)
     np.testing.assert_allclose(a1[0], sums / wsum, rtol=1e-12)
+
+
+@pytest.mark.parametrize("method", ["transmission", "logarithmic"])
+def test_avg_wavenumber_shards_emulated_on_one_device(ctx, O, method):
+    """The multi-GPU decomposition (partial per wavenumber shard -> SUM/MIN reduction of the
+    partial accumulators -> finalize) with three shards emulated on one device; the reduction
+    across shards is done here in NumPy exactly as NCCL would (sum, min)."""
+    from ecckd_b200 import sharding
+
+    c = S.lw_spectrum_case(nlay=9, nwav=6007, ng=11, nband=2, seed=77)
+    nlay, ng, nwav, nspec = c["nlay"], c["ng"], c["nwav"], 2
+    ods = [c["od"], c["od"][::-1].copy() * 0.5]
+    vmrs = [c["vmr"], -1.0]
+    sums_tot, mm_tot, cnt_tot = None, None, None
+    for r in range(3):
+        lo, hi = sharding.shard_range(nwav, r, 3)
+        d_g = ctx.to_device(c["g_point"][lo:hi], np.int32)
+        plan = E.GPointPlan(ctx, d_g, hi - lo, ng)
+        d_ods = [ctx.to_device(np.ascontiguousarray(o[:, lo:hi])) for o in ods]
+        d_wn, d_dwn = ctx.to_device(c["wavenumber"][lo:hi]), ctx.to_device(c["d_wavenumber"][lo:hi])
+        d_s, d_m = ctx.empty((nlay, nspec, ng, 3)), ctx.empty((nlay, nspec, ng, 2))
+        E.average_optical_depth_partial_dev(ctx, plan, nlay, c["pressure_fl"], d_ods, hi - lo, E.WEIGHT_PLANCK, None, 0,
+                                            c["temperature_fl"], d_wn, d_dwn, method, d_s, d_m)
+        s_r, m_r, c_r = d_s.numpy(), d_m.numpy(), plan.counts()
+        sums_tot = s_r if sums_tot is None else sums_tot + s_r
+        mm_tot = m_r if mm_tot is None else np.minimum(mm_tot, m_r)
+        cnt_tot = c_r if cnt_tot is None else cnt_tot + c_r
+    assert np.array_equal(cnt_tot, np.bincount(c["g_point"], minlength=ng))
+    d_s, d_m, d_c = ctx.to_device(sums_tot), ctx.to_device(mm_tot), ctx.to_device(cnt_tot, np.int64)
+    outs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    mins = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    maxs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    warns = [ctx.zeros(ng, np.int32) for _ in range(nspec)]
+    E.average_optical_depth_finalize_dev(ctx, ng, d_c, vmrs, c["pressure_fl"], c["pressure_hl"], method, d_s, d_m, outs,
+                                         mins, maxs, ng, warns)
+    planck = O.planck_function(c["temperature_fl"], c["wavenumber"], c["d_wavenumber"])
+    for s in range(nspec):
+        ref = O.average_optical_depth_to_g_point(ng, vmrs[s], c["pressure_fl"], c["pressure_hl"], c["g_point"], ods[s],
+                                                 planck, method)
+        S.assert_avg_close((outs[s].numpy(), mins[s].numpy(), maxs[s].numpy(), warns[s].numpy()), ref, method=method,
+                           scale=S.out_scale(dict(c, vmr=vmrs[s])), what=f"spec {s} ")
