@@ -5,29 +5,35 @@
 //
 // Kernel design (B200, sm_100a) -- see DESIGN.md section 3:
 //   * A "row" is one (spectrum, layer) vector of nwav FP64 optical depths.  Rows
-//     that share a weight row (all spectra of one layer) form a group; a CTA
-//     gives each row of a group its own consumer warp and walks chunks of CH
-//     wavenumbers.  Consumer warps stage their row's chunk in shared memory
-//     with one bulk asynchronous copy (cp.async.bulk + mbarrier, NS stages
-//     deep): every HBM byte is read exactly once, 1792 contiguous bytes at a time.
-//   * The Planck weights of a chunk are computed once per CTA by two producer
-//     warps into a shared-memory tile that all rows of the group use (the
-//     reference recomputes planck_function for every block); matrix / vector
-//     weights are bulk-copied into the same tile.
+//     that share a weight row (all spectra of one layer) form a group of up to
+//     20; a CTA gives every consumer warp two rows of the group and walks chunks
+//     of `ch` (<= 480) wavenumbers.  A consumer warp stages its rows' chunks in
+//     shared memory with bulk asynchronous copies (cp.async.bulk + mbarrier,
+//     two chunk visits deep, L2 evict-first): every optical depth is read from
+//     HBM exactly once, 3.8 KB at a time, ~75 KB in flight per SM.
+//   * The weights of a chunk (Planck function, or a streamed row) are produced
+//     once per CTA by two producer warps into a 4-slot ring together with the
+//     chunk's plan record.
 //   * The g-point map is identical for every row and every call of a LUT build,
 //     so a "plan" assigns, per chunk, every wavenumber to a (lane, slot) such
-//     that each lane only sees one g point per round and lanes of one g point are
-//     adjacent.  A lane therefore accumulates its 8 slots in registers with no
-//     branches; a static segmented shuffle reduction (5 steps) then folds the
-//     lanes of each g point and the head lane adds the result to the warp's
-//     private shared-memory accumulator [ng][4].  No atomics anywhere; the
-//     summation order is fixed by the plan and the launch geometry.
-//   * The (group, chunk) space is cut into equal contiguous pieces, one per
-//     resident CTA; a CTA flushes its accumulators when it crosses into the
-//     next group.  A small combine kernel adds the pieces in fixed order.
+//     that each lane only sees one g point per round (32 lanes x 16 slots), the
+//     lanes of a g point are adjacent and consecutive wavenumbers sit in
+//     consecutive lanes.  A lane keeps its 16 shared-memory addresses and 16
+//     weights in registers for both of its rows, evaluates the slots with no
+//     branches (trans_core.cuh: 12 FP64 instructions per 1 - exp), then a
+//     segmented shuffle reduction whose lane predicates come from the plan
+//     folds the lanes of each g point and the head lane adds the result to the
+//     warp's shared-memory accumulators [row][ng][4].  No atomics anywhere;
+//     the summation order is fixed by the plan and the launch geometry.
+//   * Work items are ordered (wavenumber window, group, chunk) and cut into
+//     equal contiguous pieces, one per CTA, so that the per-wavenumber data of
+//     a window (wavenumbers, plan) are re-read from L2, not HBM, by the next
+//     group.  A CTA flushes its accumulators when it crosses into the next
+//     (window, group); a small combine kernel adds the pieces in fixed order.
 #include "spectral_reduce.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace ecckd {
 
@@ -64,15 +70,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// the same with an L2 cache policy (optical depths are read once: evict-first keeps the
+// per-wavenumber data that every group re-reads resident in L2)
+__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar,
+                                              uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+  return pol;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
 
 // exp(x) without branches: Cody-Waite reduction by ln 2 and a degree-11 polynomial; maximum
 // error 0.90 ulp on [-690, 700] (checked against a long-double reference on the host, see
-// DESIGN.md).  Below -693 the result is clamped near 1e-301 instead of underflowing gradually,
-// which is exact for its only uses here: 1 - exp(x) with x <= 0 (1 - 1e-301 == 1) and
-// exp(x) - 1 with x >= 0.  Coefficients live in constant memory so that the DFMAs take them
-// as constant-bank operands instead of re-materialising 64-bit immediates.
+// DESIGN.md).  Used by the Planck weights of the producer warps.
 __constant__ double EXP_C[12] = {2.5052097064908941e-8, 2.7626262793835868e-7, 2.7557414788000726e-6,
                                  2.4801504602132958e-5, 1.9841269707468915e-4, 1.3888888932258898e-3,
                                  8.3333333333978320e-3, 4.1666666666573905e-2, 1.6666666666666563e-1,
@@ -80,8 +98,7 @@ __constant__ double EXP_C[12] = {2.5052097064908941e-8, 2.7626262793835868e-7, 2
 __constant__ double EXP_K[4] = {1.4426950408889634074, 6755399441055744.0, -6.93147180369123816490e-01,
                                 -1.90821492927058770002e-10};
 
-template <bool CLAMP_HIGH>
-__device__ __forceinline__ double fast_exp_t(double x) {
+__device__ __forceinline__ double fast_exp(double x) {
   const double t = fma(x, EXP_K[0], EXP_K[1]);
   int k = __double2loint(t);
   const double kf = t - EXP_K[1];
@@ -90,13 +107,9 @@ __device__ __forceinline__ double fast_exp_t(double x) {
   double q = EXP_C[0];
 #pragma unroll
   for (int i = 1; i < 12; ++i) q = fma(q, r, EXP_C[i]);
-  k = CLAMP_HIGH ? max(-1000, min(k, 1000)) : max(-1000, k);
+  k = max(-1000, min(k, 1000));
   return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
 }
-__device__ __forceinline__ double fast_exp(double x) { return fast_exp_t<true>(x); }
-// for arguments known to be <= 0 up to unphysical inputs (x = -kd*tau with tau >= 0): no upper
-// clamp, i.e. optical depths below -700/kd would give garbage instead of the reference's -inf
-__device__ __forceinline__ double fast_exp_nonpos(double x) { return fast_exp_t<false>(x); }
 
 // planck_function.cpp:29-33,47-53, one element.  The reference evaluates
 // prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) (one rounding more in the
@@ -126,7 +139,7 @@ __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
 }
 
 // ------------------------------------------------------------------ plan
-// One block of CH threads per chunk.  Thread i owns local wavenumber i and
+// One block of `ch` threads per chunk.  Thread i owns local wavenumber i and
 // finds its (round, lane, slot): g points in ascending order, each padded to a
 // whole number of lanes; inside a g point, the k-th wavenumber goes to lane
 // (k mod L), slot (k div L), so that consecutive wavenumbers sit in consecutive
@@ -136,15 +149,15 @@ struct PlanPos {
   int vlane;   // virtual lane over all rounds of the chunk
   int slot;
   int nvlanes; // total virtual lanes of the chunk
-  int first;   // first wavenumber of its g point in the chunk
   int kth;     // index of this wavenumber inside its g point (chunk-local)
   int count;   // wavenumbers of its g point in the chunk
+  int L;       // lanes of its g point
 };
 
-__device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_point, int64_t nwav, int ng, int64_t c,
-                                                 int* sg, int* sl) {
+__device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_point, int64_t nwav, int ng, int ch,
+                                                 int64_t c, int* sg, int* sl) {
   const int i = threadIdx.x;
-  const int64_t w = c * CH + i;
+  const int64_t w = c * ch + i;
   int g = -1;
   if (w < nwav) {
     g = g_point[w];
@@ -153,16 +166,16 @@ __device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_p
   sg[i] = g;
   __syncthreads();
   int k = 0, n = 0;
-  for (int j = 0; j < CH; ++j) {
+  for (int j = 0; j < ch; ++j) {
     const int same = (sg[j] == g);
     n += same;
     k += same & (j < i);
   }
-  const int L = (n + SLOTS_PER_LANE - 1) / SLOTS_PER_LANE;
+  const int L = (n + SLOTS - 1) / SLOTS;
   sl[i] = (g >= 0 && k == 0) ? L : 0;
   __syncthreads();
   int a = 0, total = 0;
-  for (int j = 0; j < CH; ++j) {
+  for (int j = 0; j < ch; ++j) {
     const int lj = sl[j];
     total += lj;
     a += (sg[j] < g) ? lj : 0;  // sl[j] is non-zero only for valid first occurrences
@@ -170,62 +183,82 @@ __device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_p
   PlanPos p;
   p.g = g;
   p.nvlanes = total;
-  p.first = (k == 0);
   p.kth = k;
   p.count = n;
+  p.L = L;
   p.vlane = (g >= 0) ? a + (k % L) : 0;
   p.slot = (g >= 0) ? (k / L) : 0;
   return p;
 }
 
-__global__ void __launch_bounds__(CH) plan_count_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
-                                                         uint32_t* __restrict__ nrounds,
-                                                         unsigned long long* __restrict__ count) {
-  __shared__ int sg[CH];
-  __shared__ int sl[CH];
+// rounds per chunk (at least one, so that every chunk visit has a ring entry) and, optionally,
+// the wavenumbers per g point
+__global__ void __launch_bounds__(CH_MAX) plan_count_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
+                                                             uint32_t* __restrict__ nrounds,
+                                                             unsigned long long* __restrict__ count) {
+  __shared__ int sg[CH_MAX];
+  __shared__ int sl[CH_MAX];
   const int64_t c = blockIdx.x;
-  const PlanPos p = plan_position(g_point, nwav, ng, c, sg, sl);
-  if (threadIdx.x == 0) nrounds[c] = (uint32_t)((p.nvlanes + 31) / 32);
-  if (p.g >= 0 && p.first) atomicAdd(&count[p.g], (unsigned long long)p.count);
+  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, sg, sl);
+  if (threadIdx.x == 0) nrounds[c] = (uint32_t)max(1, (p.nvlanes + 31) / 32);
+  if (count != nullptr && p.g >= 0 && p.kth == 0) atomicAdd(&count[p.g], (unsigned long long)p.count);
 }
 
 __global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds) {
-  // unused lanes: offsets 0 (a valid address), weight offsets at the zero entry, meta = NO_G
+  // unused lanes: offsets 0 (a valid address), no valid slots, meta = NO_G
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrounds * 32) return;
   PlanRound& r = rounds[i >> 5];
   const int lane = (int)(i & 31);
-  r.tau_off[lane] = make_uint4(0, 0, 0, 0);
-  const unsigned z = (unsigned)(CH * 8) | ((unsigned)(CH * 8) << 16);
-  r.w_off[lane] = make_uint4(z, z, z, z);
-  r.meta[lane] = 0xFFFFu;
-  if (lane == 0) r.steps = 0;
+  r.off[0][lane] = make_uint4(0, 0, 0, 0);
+  r.off[1][lane] = make_uint4(0, 0, 0, 0);
+  r.meta[lane] = NO_G;
+  if (lane == 0) {
+    r.steps = 0;
+    r.chunk = 0;
+    r.flags = 0;
+    r.pad_ = 0;
+  }
 }
 
-__global__ void __launch_bounds__(CH) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
-                                                        const uint32_t* __restrict__ round_off,
-                                                        PlanRound* __restrict__ rounds) {
-  __shared__ int sg[CH];
-  __shared__ int sl[CH];
+__global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
+                                                            const uint32_t* __restrict__ round_off,
+                                                            PlanRound* __restrict__ rounds) {
+  __shared__ int sg[CH_MAX];
+  __shared__ int sl[CH_MAX];
   const int64_t c = blockIdx.x;
-  const PlanPos p = plan_position(g_point, nwav, ng, c, sg, sl);
+  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, sg, sl);
+  const uint32_t r0 = round_off[c], r1 = round_off[c + 1];
+  if (threadIdx.x == 0) {
+    for (uint32_t r = r0; r < r1; ++r) {
+      rounds[r].chunk = (uint32_t)c;
+      rounds[r].flags = (r == r0 ? 1u : 0u) | (r + 1 == r1 ? 2u : 0u);
+    }
+  }
   if (p.g < 0) return;
-  PlanRound& rd = rounds[(size_t)round_off[c] + (size_t)(p.vlane >> 5)];
+  PlanRound& rd = rounds[(size_t)r0 + (size_t)(p.vlane >> 5)];
   const int lane = p.vlane & 31;
-  uint16_t* tau_off = reinterpret_cast<uint16_t*>(&rd.tau_off[lane]);
-  uint16_t* w_off = reinterpret_cast<uint16_t*>(&rd.w_off[lane]);
-  const uint16_t off = (uint16_t)(threadIdx.x * 8);
-  tau_off[p.slot] = off;
-  w_off[p.slot] = off;
+  uint16_t* off = reinterpret_cast<uint16_t*>(&rd.off[0][0]);
+  const uint16_t my = (uint16_t)(threadIdx.x * 8);
+  auto slot_ref = [&](int slot) -> uint16_t& { return off[((slot >> 3) * 32 + lane) * 8 + (slot & 7)]; };
+  slot_ref(p.slot) = my;
   if (p.slot == 0) {
     // this thread owns the lane: valid slots form a prefix of length nv; padding slots repeat slot 0
-    // for the optical depth (harmless for min/max) and keep the zero weight entry
-    const int L = (p.count + SLOTS_PER_LANE - 1) / SLOTS_PER_LANE;
-    const int nv = (p.count - 1 - p.kth) / L + 1;  // kth < L here
-    for (int e = nv; e < SLOTS_PER_LANE; ++e) tau_off[e] = off;
-    rd.meta[lane] = (uint16_t)((unsigned)p.g | ((unsigned)nv << 12));
+    const int li = p.kth;  // lane index inside the g point (kth < L here)
+    const int nv = (p.count - 1 - li) / p.L + 1;
+    for (int e = nv; e < SLOTS; ++e) slot_ref(e) = my;
+    // lanes of the same g point that follow this one inside the round
+    const int follow = min(p.L - 1 - li, 31 - lane);
+    unsigned mask = 0;
     int steps = 0;
-    while ((1 << steps) < min(L, 32)) ++steps;
+    for (int s = 0; s < 5; ++s) {
+      if ((1 << s) <= follow) {
+        mask |= 1u << s;
+        steps = s + 1;
+      }
+    }
+    const unsigned head = (lane == 0 || li == 0) ? 1u : 0u;
+    rd.meta[lane] = (unsigned)p.g | ((unsigned)nv << 12) | (mask << 17) | (head << 22);
     if (steps > 0) atomicMax(&rd.steps, (uint32_t)steps);
   }
 }
@@ -270,210 +303,235 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(int64_t n, const u
 }
 
 // ------------------------------------------------------------------ reduce
+// Shared-memory layout of one CTA (byte offsets computed identically on the host)
+struct SmemLayout {
+  int bars;    // mbarriers: full_d[nw][NSETS*RPW], full_w[NSW], empty_w[NSW]
+  int ring;    // ring slots [NSW]: {double tile[CH_MAX]; PlanRound plan}
+  int data;    // data stages [nw][NSETS*RPW][CH_MAX] doubles
+  int acc;     // accumulators [nw][RPW][ng][4] doubles: {sum f*w, sum w, min, max}
+  int accz;    // zero counters [nw][RPW][ng] int32
+  int total;
+};
+static_assert(RING_SLOT_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "stage alignment");
+__host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
+  SmemLayout L;
+  int off = 0;
+  L.bars = off;
+  off += (nw * NSETS * RPW + 2 * NSW) * 8;
+  off = (off + 127) & ~127;
+  L.ring = off;
+  off += NSW * RING_SLOT_BYTES;
+  L.data = off;
+  off += nw * NSETS * RPW * STAGE_BYTES;
+  L.acc = off;
+  off += nw * RPW * ng * 4 * 8;
+  L.accz = off;
+  off += nw * RPW * ng * 4;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+// position of a CTA in the (window, group, chunk) item order
+struct Cursor {
+  int v, l, c, c_begin, c_end;
+};
+__device__ __forceinline__ Cursor cursor_at(int64_t item, int ngroups, int cw, int nchunks) {
+  Cursor q;
+  const int64_t per_win = (int64_t)ngroups * cw;  // every window but the last holds cw chunks
+  q.v = (int)(item / per_win);
+  const int64_t rem = item - (int64_t)q.v * per_win;
+  q.c_begin = q.v * cw;
+  q.c_end = min(nchunks, q.c_begin + cw);
+  const int n_v = q.c_end - q.c_begin;
+  q.l = (int)(rem / n_v);
+  q.c = q.c_begin + (int)(rem - (int64_t)q.l * n_v);
+  return q;
+}
+// returns true when the step entered a new (window, group)
+__device__ __forceinline__ bool cursor_next(Cursor& q, int ngroups, int cw, int nchunks) {
+  if (++q.c < q.c_end) return false;
+  if (++q.l == ngroups) {
+    q.l = 0;
+    ++q.v;
+    q.c_begin = q.v * cw;
+    q.c_end = min(nchunks, q.c_begin + cw);
+  }
+  q.c = q.c_begin;
+  return true;
+}
+
 template <int FKIND>
-__device__ __forceinline__ double f_transform(double tau, double kd, bool is_log, bool& positive) {
+__device__ __forceinline__ double f_transform(double tau, const TransConst& K, const TransLane& tl, bool is_log,
+                                              bool& positive) {
   positive = true;
   if (FKIND == F_LINEAR) return tau;
-  if (FKIND == F_TRANS) return 1.0 - fast_exp_nonpos(-tau * kd);
+  if (FKIND == F_TRANS) return trans_one_minus_exp(tau, K, tl);
   if (FKIND == F_SQRT) return sqrt(tau);
   if (FKIND == F_LOG) {
     positive = tau > 0.0;
     return positive ? log(tau) : 0.0;
   }
   if (FKIND == F_HYBRID) {
+    // warp-uniform branch (is_log is a property of the row): the shuffles inside stay converged
     if (is_log) {
       positive = tau > 0.0;
       return positive ? log(tau) : 0.0;
     }
-    return 1.0 - fast_exp_nonpos(-tau * kd);
+    return trans_one_minus_exp(tau, K, tl);
   }
   return 1.0;  // F_NONE: only the weight sum is wanted
 }
 
-// Shared-memory layout of one CTA (byte offsets computed identically on the host)
-struct SmemLayout {
-  int bars;    // mbarriers: full_d[nw][NS], full_w[NSW], empty_w[NSW]
-  int wt;      // weight stages [NSW]: {double tile[WT_STRIDE]; PlanRound plan}
-  int data;    // data stages [nw][NS][CH] doubles
-  int acc;     // accumulators [nw][ng][4] doubles
-  int accz;    // zero counters [nw][ng] int32
-  int total;
+// Per-lane partial result of one row over the 16 slots of a round.
+struct Partial {
+  double s0, s1, mn, mx;
+  int zc;
 };
-constexpr int WSTAGE_BYTES = WT_STRIDE * 8 + (int)sizeof(PlanRound);
-static_assert(WSTAGE_BYTES % 16 == 0 && (WT_STRIDE * 8) % 16 == 0, "weight stage alignment");
-__host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
-  SmemLayout L;
-  int off = 0;
-  L.bars = off;
-  off += (nw * NS + 2 * NSW) * 8 + NSW * 4;
-  off = (off + 127) & ~127;
-  L.wt = off;
-  off += NSW * WSTAGE_BYTES;
-  L.data = off;
-  off += nw * NS * CH * 8;
-  L.acc = off;
-  off += nw * ng * 4 * 8;
-  L.accz = off;
-  off += nw * ng * 4;
-  L.total = (off + 15) & ~15;
-  return L;
-}
 
-// One round of one row: 8 slots per lane in registers, segmented shuffle reduction, head lanes
-// fold into the warp's accumulators.  DO_S1: also accumulate the weight sum (only the first row
-// of a group needs to: all rows of a group share the weights).
-template <int FKIND, bool DO_S1>
-__device__ __forceinline__ void reduce_round(const unsigned char* __restrict__ stage_b,
-                                             const unsigned char* __restrict__ wtile_b, const uint4 to, const uint4 wo,
-                                             const unsigned meta, const int nsteps, const double kd,
-                                             const bool my_is_log, const int lane, double* __restrict__ acc,
-                                             int32_t* __restrict__ accz) {
+// The 16 slots of one row: `sbase + addr[k]` is the shared-memory location of slot k in the row's
+// stage.  One copy of this body serves every row and stage set: the unrolled 16-slot sequence is
+// ~8 KB of SASS and the instruction cache has to hold it for all warps of the SM.
+template <int FKIND>
+__device__ __forceinline__ Partial row_slots(const unsigned char* __restrict__ sbase, const unsigned (&addr)[SLOTS],
+                                             const double (&w)[SLOTS], const int nv, const TransConst& K,
+                                             const TransLane& tl, const bool is_log) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  const unsigned g = meta & 0xFFFu;
-  const int nv = (int)(meta >> 12);
-  const int lim = 32 - lane;
-  double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
-  int zc = 0;
-  const unsigned tw[4] = {to.x, to.y, to.z, to.w};
-  const unsigned ww4[4] = {wo.x, wo.y, wo.z, wo.w};
+  Partial a;
+  a.s0 = 0.0;
+  a.s1 = 0.0;
+  a.mn = inf;
+  a.mx = -inf;
+  a.zc = 0;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    double tau[4], ww[4], f[4];
-    bool pos[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = half * 4 + u;
-      const unsigned toff = (e & 1) ? (tw[e >> 1] >> 16) : (tw[e >> 1] & 0xFFFFu);
-      const unsigned woff = (e & 1) ? (ww4[e >> 1] >> 16) : (ww4[e >> 1] & 0xFFFFu);
-      tau[u] = *reinterpret_cast<const double*>(stage_b + toff);
-      ww[u] = *reinterpret_cast<const double*>(wtile_b + woff);
+  for (int k = 0; k < SLOTS; ++k) {
+    const double tau = *reinterpret_cast<const double*>(sbase + addr[k]);
+    bool pos;
+    const double f = f_transform<FKIND>(tau, K, tl, is_log, pos);
+    double we = w[k];  // zero for padding slots
+    if (LOGKIND) {
+      we = pos ? we : 0.0;
+      a.zc += (k < nv && !pos) ? 1 : 0;
+      a.s1 += we;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) f[u] = f_transform<FKIND>(tau[u], kd, my_is_log, pos[u]);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      double we = ww[u];  // zero for padding slots
-      if (LOGKIND) {
-        const bool valid = (half * 4 + u) < nv;
-        we = pos[u] ? we : 0.0;
-        zc += (valid && !pos[u]) ? 1 : 0;
-      }
-      s0 = fma(f[u], we, s0);
-      if (DO_S1) s1 += we;
-      mn = (tau[u] < mn) ? tau[u] : mn;
-      mx = (tau[u] > mx) ? tau[u] : mx;
-    }
+    a.s0 = fma(f, we, a.s0);
+    a.mn = (tau < a.mn) ? tau : a.mn;
+    a.mx = (tau > a.mx) ? tau : a.mx;
   }
-  // segmented suffix reduction over adjacent lanes of the same g point
+  return a;
+}
+
+// Segmented suffix reduction over adjacent lanes of the same g point (lane predicates from the
+// plan), then the head lane of every g point folds the result into the row's accumulators.
+template <bool S0, bool S1, bool MM, bool ZC>
+__device__ __forceinline__ void fold_partial(Partial a, const unsigned meta, const int nsteps, double* __restrict__ acc,
+                                             int32_t* __restrict__ accz) {
 #pragma unroll
   for (int st = 0; st < 5; ++st) {
     if (st < nsteps) {  // warp-uniform
       const int d = 1 << st;
-      const unsigned go = __shfl_down_sync(0xffffffffu, g, d);
-      const double t0 = __shfl_down_sync(0xffffffffu, s0, d);
-      const double t1 = DO_S1 ? __shfl_down_sync(0xffffffffu, s1, d) : 0.0;
-      const double tn = __shfl_down_sync(0xffffffffu, mn, d);
-      const double tx = __shfl_down_sync(0xffffffffu, mx, d);
-      const int tz = LOGKIND ? __shfl_down_sync(0xffffffffu, zc, d) : 0;
-      if (d < lim && go == g) {
-        s0 += t0;
-        if (DO_S1) s1 += t1;
-        mn = (tn < mn) ? tn : mn;
-        mx = (tx > mx) ? tx : mx;
-        zc += tz;
+      const double t0 = S0 ? __shfl_down_sync(0xffffffffu, a.s0, d) : 0.0;
+      const double t1 = S1 ? __shfl_down_sync(0xffffffffu, a.s1, d) : 0.0;
+      const double tn = MM ? __shfl_down_sync(0xffffffffu, a.mn, d) : 0.0;
+      const double tx = MM ? __shfl_down_sync(0xffffffffu, a.mx, d) : 0.0;
+      const int tz = ZC ? __shfl_down_sync(0xffffffffu, a.zc, d) : 0;
+      if ((meta >> (17 + st)) & 1u) {
+        if (S0) a.s0 += t0;
+        if (S1) a.s1 += t1;
+        if (MM) {
+          a.mn = (tn < a.mn) ? tn : a.mn;
+          a.mx = (tx > a.mx) ? tx : a.mx;
+        }
+        if (ZC) a.zc += tz;
       }
     }
   }
-  const unsigned gprev = __shfl_up_sync(0xffffffffu, g, 1);
-  if (g != NO_G && (lane == 0 || gprev != g)) {  // head lane of its g point in this round
-    double2* a = reinterpret_cast<double2*>(acc + g * 4);
-    double2 a01 = a[0], a23 = a[1];
-    a01.x += s0;
-    if (DO_S1) a01.y += s1;
-    a23.x = (mn < a23.x) ? mn : a23.x;
-    a23.y = (mx > a23.y) ? mx : a23.y;
-    a[0] = a01;
-    a[1] = a23;
-    if (LOGKIND) accz[g] += zc;
+  const unsigned g = meta & 0xFFFu;
+  if (g != NO_G && ((meta >> 22) & 1u)) {  // head lane of its g point in this round
+    double2* q = reinterpret_cast<double2*>(acc + g * 4);
+    if (S0 || S1) {
+      double2 a01 = q[0];
+      if (S0) a01.x += a.s0;
+      if (S1) a01.y += a.s1;
+      q[0] = a01;
+    }
+    if (MM) {
+      double2 a23 = q[1];
+      a23.x = (a.mn < a23.x) ? a.mn : a23.x;
+      a23.y = (a.mx > a23.y) ? a.mx : a23.y;
+      q[1] = a23;
+    }
+    if (ZC) accz[g] += a.zc;
   }
-  __syncwarp();
 }
 
 template <int FKIND, int WMODE>
-__global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const ReduceParams p) {
+__global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __grid_constant__ ReduceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nw = p.nw, ng = p.ng;
   const SmemLayout L = smem_layout(nw, ng);
-  uint64_t* full_d = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [nw][NS]
-  uint64_t* full_w = full_d + nw * NS;                                 // [NSW]
-  uint64_t* empty_w = full_w + NSW;                                    // [NSW]
-  uint32_t* wrounds = reinterpret_cast<uint32_t*>(empty_w + NSW);      // [NSW] rounds of the staged chunk
-  unsigned char* wstages = smem_raw + L.wt;
+  uint64_t* full_d = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [nw][NSETS*RPW]
+  uint64_t* full_w = full_d + nw * NSETS * RPW;                       // [NSW]
+  uint64_t* empty_w = full_w + NSW;                                   // [NSW]
+  unsigned char* ring = smem_raw + L.ring;
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
+  constexpr bool USES_TAU = (FKIND != F_NONE);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nw * NS; ++i) mbar_init(&full_d[i], 1);
+    for (int i = 0; i < nw * NSETS * RPW; ++i) mbar_init(&full_d[i], 1);
     for (int i = 0; i < NSW; ++i) {
       mbar_init(&full_w[i], NPW);
       mbar_init(&empty_w[i], nw);
     }
     fence_mbar_init();
   }
-  if (threadIdx.x < NSW) {  // the zero weight that padding slots read
-    double* tile = reinterpret_cast<double*>(wstages + threadIdx.x * WSTAGE_BYTES);
-    tile[CH] = 0.0;
-    tile[CH + 1] = 0.0;
-  }
   __syncthreads();
 
-  // this CTA's contiguous piece of the (group, chunk) space
+  // this CTA's contiguous piece of the (window, group, chunk) space
   const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
   const int64_t lo = (T * blockIdx.x) / p.ncta;
   const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
   const int niter = (int)(hi - lo);
-  const int first_group = (int)(lo / p.nchunks);
-  const int first_chunk = (int)(lo - (int64_t)first_group * p.nchunks);
-  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * CH);  // length of the last chunk of a row
+  if (niter == 0) return;
+  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
+  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
 
   if (warp >= nw) {
-    // ===================== producers: weight tile + plan record of every chunk =====================
+    // ===================== producers: weight tile + plan record of every round =====================
     const int pw = warp - nw;
-    constexpr int PER = (CH + NPW * 32 - 1) / (NPW * 32);  // elements per producer lane per chunk
-    int grp = first_group, c = first_chunk, ws = 0;
+    constexpr int PER = (CH_MAX + NPW * 32 - 1) / (NPW * 32);  // elements per producer lane per chunk
+    Cursor q = first;
+    int ws = 0, filled = 0;
     unsigned epar = 0;
-    double inv_t = (WMODE == W_PLANCK) ? 1.0 / p.temperature[p.groups[grp].wrow] : 0.0;
-    const double* wrow_ptr = (WMODE == W_MATRIX) ? p.weight + (int64_t)p.groups[grp].wrow * p.w_stride : p.weight;
+    double inv_t = (WMODE == W_PLANCK) ? 1.0 / p.temperature[p.groups[q.l].wrow] : 0.0;
+    const double* wrow_ptr = (WMODE == W_MATRIX) ? p.weight + (int64_t)p.groups[q.l].wrow * p.w_stride : p.weight;
     double nu_n[PER], dnu_n[PER];  // wavenumbers of the next chunk, fetched one chunk ahead
     auto fetch = [&](int cc) {
-      const int64_t w0 = (int64_t)cc * CH;
+      const int64_t w0 = (int64_t)cc * ch;
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
         const int j = pw * 32 + lane + m * NPW * 32;
-        const bool ok = j < CH && (w0 + j) < p.nwav;
+        const bool ok = j < ch && (w0 + j) < p.nwav;
         nu_n[m] = ok ? p.wn[w0 + j] : 1.0;
         dnu_n[m] = ok ? p.dwn[w0 + j] : 0.0;
       }
     };
-    if (WMODE == W_PLANCK && niter > 0) fetch(c);
-    uint32_t r0 = 0, r1 = 0;
-    if (niter > 0) {
-      r0 = p.round_off[c];
-      r1 = p.round_off[c + 1];
-    }
+    if (WMODE == W_PLANCK) fetch(q.c);
+    uint32_t r0 = p.round_off[q.c], r1 = p.round_off[q.c + 1];
     for (int k = 0; k < niter; ++k) {
-      const int64_t w0 = (int64_t)c * CH;
-      const int n_c = (c == nchunks - 1) ? last_n : CH;
-      unsigned char* wstage = wstages + ws * WSTAGE_BYTES;
-      double* tile = reinterpret_cast<double*>(wstage);
-      const int c_next = (c + 1 == nchunks) ? 0 : c + 1;
+      const int c = q.c;
+      const int64_t w0 = (int64_t)c * ch;
+      const int n_c = (c == nchunks - 1) ? last_n : ch;
+      Cursor qn = q;
+      const bool new_group = cursor_next(qn, p.ngroups, p.cw, nchunks);
       uint32_t r0_next = 0, r1_next = 0;
       if (k + 1 < niter) {
-        r0_next = p.round_off[c_next];
-        r1_next = p.round_off[c_next + 1];
+        r0_next = p.round_off[qn.c];
+        r1_next = p.round_off[qn.c + 1];
       }
       double val[PER];
       if (WMODE == W_PLANCK) {
@@ -483,215 +541,265 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const Re
           nu[m] = nu_n[m];
           dnu[m] = dnu_n[m];
         }
-        if (k + 1 < niter) fetch(c_next);
+        if (k + 1 < niter) fetch(qn.c);
 #pragma unroll
         for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, nu[m], dnu[m]);
       }
-      if (k >= NSW) mbar_wait(&empty_w[ws], epar);
       const double* src = (WMODE == W_PLANCK) ? nullptr : wrow_ptr + w0;
       const bool wbulk = (WMODE != W_PLANCK) && p.weight_bulk_ok && ((n_c & 1) == 0);
-      if (WMODE == W_PLANCK) {
+      for (uint32_t r = r0; r < r1; ++r) {  // one ring entry per round (a second round of a chunk is rare)
+        unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+        double* tile = reinterpret_cast<double*>(slot);
+        if (filled >= NSW) mbar_wait(&empty_w[ws], epar);
+        if (WMODE == W_PLANCK) {
 #pragma unroll
-        for (int m = 0; m < PER; ++m) {
-          const int j = pw * 32 + lane + m * NPW * 32;
-          if (j < n_c) tile[j] = val[m];
+          for (int m = 0; m < PER; ++m) {
+            const int j = pw * 32 + lane + m * NPW * 32;
+            if (j < n_c) tile[j] = val[m];
+          }
+        } else if (!wbulk) {
+          for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
         }
-      } else if (!wbulk) {
-        for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
-      }
-      __syncwarp();
-      if (lane == 0) {
-        if (pw == 0) {
-          // bulk copies: the plan record of the chunk's first round (if it has one), and the
-          // weights themselves unless they were computed above
-          const bool has_round = r1 > r0;
-          wrounds[ws] = r1 - r0;
-          fence_proxy_async();
-          const unsigned bytes = (has_round ? (unsigned)sizeof(PlanRound) : 0u) + (wbulk ? (unsigned)(n_c * 8) : 0u);
-          mbar_arrive_expect_tx(&full_w[ws], bytes);
-          if (has_round) bulk_g2s(wstage + WT_STRIDE * 8, p.rounds + r0, (unsigned)sizeof(PlanRound), &full_w[ws]);
-          if (wbulk) bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
-        } else {
-          mbar_arrive(&full_w[ws]);
+        __syncwarp();
+        if (lane == 0) {
+          if (pw == 0) {
+            fence_proxy_async();
+            const unsigned bytes = (unsigned)sizeof(PlanRound) + (wbulk ? (unsigned)(n_c * 8) : 0u);
+            mbar_arrive_expect_tx(&full_w[ws], bytes);
+            bulk_g2s(slot + STAGE_BYTES, p.rounds + r, (unsigned)sizeof(PlanRound), &full_w[ws]);
+            if (wbulk) bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
+          } else {
+            mbar_arrive(&full_w[ws]);
+          }
+        }
+        ++filled;
+        if (++ws == NSW) {
+          ws = 0;
+          if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
         }
       }
       r0 = r0_next;
       r1 = r1_next;
-      if (++ws == NSW) {
-        ws = 0;
-        if (k >= NSW) epar ^= 1u;  // first pass over the stages needs no wait; parity 0 comes first
-      }
-      if (++c == nchunks) {
-        c = 0;
-        ++grp;
-        if (k + 1 < niter) {
-          if (WMODE == W_PLANCK) inv_t = 1.0 / p.temperature[p.groups[grp].wrow];
-          if (WMODE == W_MATRIX) wrow_ptr = p.weight + (int64_t)p.groups[grp].wrow * p.w_stride;
-        }
+      q = qn;
+      if (new_group && k + 1 < niter) {
+        if (WMODE == W_PLANCK) inv_t = 1.0 / p.temperature[p.groups[q.l].wrow];
+        if (WMODE == W_MATRIX) wrow_ptr = p.weight + (int64_t)p.groups[q.l].wrow * p.w_stride;
       }
     }
     return;
   }
 
-  // ===================== consumers: warp = one row of the group =====================
-  double* data = reinterpret_cast<double*>(smem_raw + L.data) + (size_t)warp * NS * CH;
-  double* acc = reinterpret_cast<double*>(smem_raw + L.acc) + (size_t)warp * ng * 4;
-  int32_t* accz = reinterpret_cast<int32_t*>(smem_raw + L.accz) + (size_t)warp * ng;
-  uint64_t* my_full = full_d + warp * NS;
+  // ===================== consumers: warp = RPW rows of the group =====================
+  const TransLane tl = trans_lane_init();
+  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE_BYTES;
+  double* acc = reinterpret_cast<double*>(smem_raw + L.acc) + (size_t)warp * RPW * ng * 4;
+  int32_t* accz = reinterpret_cast<int32_t*>(smem_raw + L.accz) + (size_t)warp * RPW * ng;
+  uint64_t* my_full = full_d + warp * NSETS * RPW;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  // only the first row of a group accumulates the weight sums (shared by the group's rows),
-  // except where they depend on the row (logarithmic kinds) or are the result (F_NONE)
-  const bool do_s1 = LOGKIND || FKIND == F_NONE || warp == 0;
+  const uint64_t pol = policy_evict_first();
+  // the weight sums do not depend on the row: the last consumer warp (the one with the fewest rows)
+  // accumulates them once per group into the s1 field of its row 0, except where they depend on
+  // the row (logarithmic kinds)
+  const bool s1_duty = !LOGKIND && warp == nw - 1;
 
   auto init_acc = [&]() {
-    for (int g = lane; g < ng; g += 32) {
-      acc[g * 4 + 0] = 0.0;
-      acc[g * 4 + 1] = 0.0;
-      acc[g * 4 + 2] = inf;
-      acc[g * 4 + 3] = -inf;
-      accz[g] = 0;
+    for (int i = lane; i < RPW * ng; i += 32) {
+      acc[i * 4 + 0] = 0.0;
+      acc[i * 4 + 1] = 0.0;
+      acc[i * 4 + 2] = inf;
+      acc[i * 4 + 3] = -inf;
+      accz[i] = 0;
     }
     __syncwarp();
   };
-  auto flush_partial = [&](int grp) {
+  auto flush_partial = [&](int vg) {
     __syncwarp();
-    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)(grp - first_group)) * nw + warp;
+    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (nw * RPW) + warp * RPW;
     double* out = p.partial + slot * ng * 4;
-    for (int i = lane; i < ng * 4; i += 32) out[i] = acc[i];
+    for (int i = lane; i < RPW * ng * 4; i += 32) out[i] = acc[i];
     int32_t* outz = p.partial_z + slot * ng;
-    for (int i = lane; i < ng; i += 32) outz[i] = accz[i];
+    for (int i = lane; i < RPW * ng; i += 32) outz[i] = accz[i];
     __syncwarp();
   };
 
-  // issue cursor (runs NS chunks ahead of the compute cursor)
-  int grp_i = first_group, c_i = first_chunk;
-  const double* od_i = nullptr;
-  bool bulk_row_i = false;
+  // issue cursor (runs NSETS chunk visits ahead of the compute cursor)
+  Cursor qi = first;
+  const double* od_i[RPW];
+  bool bulk_i[RPW];
   auto load_issue_group = [&]() {
-    const GroupDesc* gd = p.groups + grp_i;
-    const bool act = warp < gd->nrows;
-    od_i = act ? gd->od[warp] : nullptr;
-    bulk_row_i = act && gd->bulk_ok[warp];
-  };
-  auto issue = [&](int stage) {
-    const int n_c = (c_i == nchunks - 1) ? last_n : CH;
-    if (bulk_row_i && ((n_c & 1) == 0) && lane == 0) {
-      fence_proxy_async();
-      mbar_arrive_expect_tx(&my_full[stage], (unsigned)(n_c * 8));
-      bulk_g2s(data + stage * CH, od_i + (int64_t)c_i * CH, (unsigned)(n_c * 8), &my_full[stage]);
-    }
-    if (++c_i == nchunks) {
-      c_i = 0;
-      ++grp_i;
-      if (grp_i < p.ngroups) load_issue_group();
+    const GroupDesc* gd = p.groups + qi.l;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = warp + r * nw;
+      const bool act = USES_TAU && i < gd->nrows;
+      od_i[r] = act ? gd->od[i] : nullptr;
+      bulk_i[r] = act && gd->bulk_ok[i];
     }
   };
-  load_issue_group();
-  for (int j = 0; j < NS && j < niter; ++j) issue(j);
-
-  unsigned phase_bits = 0;  // bit s: parity to wait for on my_full[s]
-  unsigned wpar = 0;
-  int grp = first_group, c = first_chunk, s = 0, ws = 0;
-  const double* od_c = nullptr;
-  bool active = false, bulk_row = false, my_is_log = (FKIND == F_LOG);
-  bool need_group = true;
-  for (int k = 0; k < niter; ++k) {
-    if (need_group) {
-      const GroupDesc* gd = p.groups + grp;
-      active = warp < gd->nrows;
-      od_c = active ? gd->od[warp] : nullptr;
-      bulk_row = active && gd->bulk_ok[warp];
-      if (FKIND == F_HYBRID) my_is_log = active && (gd->is_log[warp] != 0);
-      init_acc();
-      need_group = false;
-    }
-    const int n_c = (c == nchunks - 1) ? last_n : CH;
-    double* stage = data + s * CH;
-    if (bulk_row && ((n_c & 1) == 0)) {
-      mbar_wait(&my_full[s], (phase_bits >> s) & 1u);
-      phase_bits ^= (1u << s);
-    } else if (active) {
-      const double* src = od_c + (int64_t)c * CH;
-      for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
-      __syncwarp();
-    }
-    mbar_wait(&full_w[ws], wpar);
-    const unsigned char* wstage = wstages + ws * WSTAGE_BYTES;
-
-    const uint32_t nrounds_c = wrounds[ws];
-    if (active && nrounds_c > 0) {
-      const PlanRound* pr = reinterpret_cast<const PlanRound*>(wstage + WT_STRIDE * 8);
-      const uint4 to = pr->tau_off[lane];
-      const uint4 wo = pr->w_off[lane];
-      const unsigned meta = pr->meta[lane];
-      const int nsteps = (int)pr->steps;
-      if (do_s1)
-        reduce_round<FKIND, true>(reinterpret_cast<const unsigned char*>(stage), wstage, to, wo, meta, nsteps, p.kd,
-                                  my_is_log, lane, acc, accz);
-      else
-        reduce_round<FKIND, false>(reinterpret_cast<const unsigned char*>(stage), wstage, to, wo, meta, nsteps, p.kd,
-                                   my_is_log, lane, acc, accz);
-      if (nrounds_c > 1) {
-        // chunks with more g points than one round holds (rare): further rounds straight from global memory
-        const uint32_t r0 = p.round_off[c];
-        for (uint32_t r = r0 + 1; r < r0 + nrounds_c; ++r) {
-          const PlanRound* gr = p.rounds + r;
-          reduce_round<FKIND, true>(reinterpret_cast<const unsigned char*>(stage), wstage, gr->tau_off[lane],
-                                    gr->w_off[lane], gr->meta[lane], (int)gr->steps, p.kd, my_is_log, lane, acc, accz);
+  auto issue = [&](int set) {
+    const int n_c = (qi.c == nchunks - 1) ? last_n : ch;
+    if (lane == 0 && ((n_c & 1) == 0)) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        if (bulk_i[r]) {
+          uint64_t* bar = &my_full[set * RPW + r];
+          mbar_arrive_expect_tx(bar, (unsigned)(n_c * 8));
+          bulk_g2s_hint(data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_w[ws]);
-    if (k + NS < niter) issue(s);
-    if (++s == NS) s = 0;
-    if (++ws == NSW) {
-      ws = 0;
-      wpar ^= 1u;
+    if (cursor_next(qi, p.ngroups, p.cw, nchunks)) load_issue_group();
+  };
+  load_issue_group();
+  for (int j = 0; j < NSETS && j < niter; ++j) issue(j);
+
+  Cursor q = first;
+  int ws = 0, vg = 0;
+  unsigned wpar = 0;
+  unsigned phase_bits = 0;  // bit (set*RPW + r): parity to wait for on that stage's mbarrier
+  const double* od_c[RPW];
+  bool active[RPW], bulk_row[RPW], is_log[RPW];
+  bool need_group = true;
+
+  // one chunk visit on stage set `set`
+  auto visit = [&](const int set, const int k) {
+    if (need_group) {
+      const GroupDesc* gd = p.groups + q.l;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int i = warp + r * nw;
+        active[r] = USES_TAU && i < gd->nrows;
+        od_c[r] = active[r] ? gd->od[i] : nullptr;
+        bulk_row[r] = active[r] && gd->bulk_ok[i];
+        is_log[r] = (FKIND == F_LOG) || (FKIND == F_HYBRID && active[r] && gd->is_log[i] != 0);
+      }
+      init_acc();
+      need_group = false;
     }
-    if (++c == nchunks) {
-      flush_partial(grp);
-      c = 0;
-      ++grp;
+    const int n_c = (q.c == nchunks - 1) ? last_n : ch;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int st = set * RPW + r;
+      if (bulk_row[r] && ((n_c & 1) == 0)) {
+        mbar_wait(&my_full[st], (phase_bits >> st) & 1u);
+        phase_bits ^= 1u << st;
+      } else if (active[r]) {
+        const double* src = od_c[r] + (int64_t)q.c * ch;
+        double* stage = reinterpret_cast<double*>(data + st * STAGE_BYTES);
+        for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
+      }
+    }
+    __syncwarp();
+    bool last_round = false;
+    while (!last_round) {
+      mbar_wait(&full_w[ws], wpar);
+      const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + STAGE_BYTES);
+      const uint4 o0 = pr->off[0][lane];
+      const uint4 o1 = pr->off[1][lane];
+      const unsigned meta = pr->meta[lane];
+      const int nsteps = (int)pr->steps;
+      last_round = (pr->flags & 2u) != 0;
+      const int nv = (int)((meta >> 12) & 31u);
+      const unsigned packed[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+      unsigned off[SLOTS];
+      double w[SLOTS];
+#pragma unroll
+      for (int e = 0; e < SLOTS; ++e) {
+        off[e] = (e & 1) ? (packed[e >> 1] >> 16) : (packed[e >> 1] & 0xFFFFu);
+        w[e] = (e < nv) ? *reinterpret_cast<const double*>(slot + off[e]) : 0.0;
+      }
+      if (s1_duty) {
+        Partial a;
+        a.s0 = 0.0;
+        a.mn = 0.0;
+        a.mx = 0.0;
+        a.zc = 0;
+        double s = 0.0;
+#pragma unroll
+        for (int e = 0; e < SLOTS; ++e) s += w[e];
+        a.s1 = s;
+        fold_partial<false, true, false, false>(a, meta, nsteps, acc, accz);
+        __syncwarp();
+      }
+      if (USES_TAU) {
+#pragma unroll 1
+        for (int r = 0; r < RPW; ++r) {
+          if (!active[r]) continue;
+          const unsigned char* stage = data + (set * RPW + r) * STAGE_BYTES;
+          const Partial a = row_slots<FKIND>(stage, off, w, nv, p.tc, tl, is_log[r]);
+          fold_partial<true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc + r * ng * 4, accz + r * ng);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_w[ws]);
+      if (++ws == NSW) {
+        ws = 0;
+        wpar ^= 1u;
+      }
+    }
+    if (k + NSETS < niter) {
+      fence_proxy_async();  // the stage was read through the generic proxy; the next copy writes it asynchronously
+      issue(set);
+    }
+    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
+      flush_partial(vg);
+      ++vg;
       need_group = true;
     }
-  }
-  if (!need_group) flush_partial(grp);
+  };
+
+#pragma unroll 1
+  for (int k = 0; k < niter; ++k) visit(k & (NSETS - 1), k);
+  if (!need_group) flush_partial(vg);
 }
 
 // ------------------------------------------------------------------ combine + finalize
-// Add the CTA pieces of every (row, g) in fixed CTA order (deterministic).
+// Add the CTA pieces of every (row, g) in fixed (window, CTA) order (deterministic).
 __global__ void combine_kernel(const CombineParams p) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)p.ngroups * p.nw * p.ng;
+  const int64_t total = (int64_t)p.ngroups * p.nw * RPW * p.ng;
   if (tid >= total) return;
   const int g = (int)(tid % p.ng);
-  const int w = (int)((tid / p.ng) % p.nw);
-  const int grp = (int)(tid / ((int64_t)p.ng * p.nw));
+  const int i = (int)((tid / p.ng) % (p.nw * RPW));  // row of the group
+  const int grp = (int)(tid / ((int64_t)p.ng * p.nw * RPW));
   const GroupDesc* gd = p.groups + grp;
-  if (w >= gd->nrows) return;
-  const int w_s1 = p.shared_s1 ? 0 : w;  // weight sums live in the group's first row
+  if (i >= gd->nrows) return;
+  const int piece = (i % p.nw) * RPW + (i / p.nw);                   // (warp, row of the warp)
+  const int piece_s1 = p.shared_s1 ? (p.nw - 1) * RPW : piece;       // weight sums: last warp, row 0
+  const int nrw = p.nw * RPW;
+  const int nchunks = (int)p.nchunks;
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
-  const int64_t glo = (int64_t)grp * p.nchunks, ghi = glo + p.nchunks;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   double s0 = 0.0, s1 = 0.0, mn = inf, mx = -inf;
   long long zc = 0;
-  int b = (int)((glo * p.ncta) / T);
-  if (b > 0) --b;
-  for (; b < p.ncta; ++b) {
-    const int64_t lo = (T * b) / p.ncta, hi = (T * (b + 1)) / p.ncta;
-    if (lo >= ghi) break;
-    if (hi <= glo || hi <= lo) continue;
-    const int first_group = (int)(lo / p.nchunks);
-    const size_t base = ((size_t)b * p.maxg + (size_t)(grp - first_group)) * p.nw;
-    const double* a = p.partial + ((base + w) * p.ng + g) * 4;
-    s0 += a[0];
-    s1 += p.partial[((base + w_s1) * p.ng + g) * 4 + 1];
-    mn = fmin(mn, a[2]);
-    mx = fmax(mx, a[3]);
-    zc += p.partial_z[(base + w) * p.ng + g];
+  for (int v = 0; v < p.nwin; ++v) {
+    const int c_begin = v * p.cw, c_end = min(nchunks, c_begin + p.cw);
+    const int n_v = c_end - c_begin;
+    if (n_v <= 0) break;
+    const int64_t glo = (int64_t)p.ngroups * c_begin + (int64_t)grp * n_v, ghi = glo + n_v;
+    const int vg = v * p.ngroups + grp;
+    int b = (int)((glo * p.ncta) / T);
+    if (b > 0) --b;
+    for (; b < p.ncta; ++b) {
+      const int64_t lo = (T * b) / p.ncta, hi = (T * (b + 1)) / p.ncta;
+      if (lo >= ghi) break;
+      if (hi <= glo || hi <= lo) continue;
+      // (window, group) index of the CTA's first item
+      const int64_t per_win = (int64_t)p.ngroups * p.cw;
+      const int fv = (int)(lo / per_win);
+      const int fn = min(nchunks, fv * p.cw + p.cw) - fv * p.cw;
+      const int fvg = fv * p.ngroups + (int)((lo - (int64_t)fv * per_win) / fn);
+      const size_t base = ((size_t)b * p.maxg + (size_t)(vg - fvg)) * nrw;
+      const double* a = p.partial + ((base + piece) * p.ng + g) * 4;
+      s0 += a[0];
+      s1 += p.partial[((base + piece_s1) * p.ng + g) * 4 + 1];
+      mn = fmin(mn, a[2]);
+      mx = fmax(mx, a[3]);
+      zc += p.partial_z[(base + piece) * p.ng + g];
+    }
   }
-  const int row = gd->row[w];
+  const int row = gd->row[i];
   double* so = p.sums + ((size_t)row * p.ng + g) * NSUM;
   so[0] = s0;
   so[1] = s1;
@@ -898,25 +1006,27 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   const int ng = plan->ng;
   const int64_t nwav = plan->nwav;
 
-  // consumer warps per CTA: as many rows as share a weight row, capped by NW_MAX and shared memory
+  // consumer warps per CTA: RPW rows each; as many as the longest run of rows sharing a weight row
+  // needs, capped by NW_MAX and shared memory
   int longest = 1;
   for (int i = 0, run = 0; i < nrows; ++i) {
     run = (i > 0 && rows[i].wrow == rows[i - 1].wrow) ? run + 1 : 1;
     longest = std::max(longest, run);
   }
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
-  int nw = std::min(NW_MAX, longest);
+  int nw = std::min(NW_MAX, (longest + RPW - 1) / RPW);
   while (nw > 1 && (size_t)smem_layout(nw, ng).total > smem_max) --nw;
   ECCKD_REQUIRE((size_t)smem_layout(nw, ng).total <= smem_max, ECCKD_PARAMETER_ERROR,
                 "average_optical_depth: ng = %d needs %d B of shared memory (limit %zu)", ng,
                 smem_layout(nw, ng).total, smem_max);
-  // balance: split a run of n rows into ceil(n/nw) groups of nearly equal size
+  // balance: split a run of n rows into ceil(n/(nw*RPW)) groups of nearly equal size
+  const int cap = nw * RPW;
   std::vector<GroupDesc> groups;
   for (int i = 0; i < nrows;) {
     int j = i;
     while (j < nrows && rows[j].wrow == rows[i].wrow) ++j;
     const int n = j - i;
-    const int pieces = (n + nw - 1) / nw;
+    const int pieces = (n + cap - 1) / cap;
     for (int q = 0; q < pieces; ++q) {
       const int b0 = i + (int)(((int64_t)n * q) / pieces), b1 = i + (int)(((int64_t)n * (q + 1)) / pieces);
       GroupDesc gd;
@@ -944,6 +1054,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.nchunks = plan->nchunks;
   rp.nwav = nwav;
   rp.ng = ng;
+  rp.ch = plan->ch;
   rp.round_off = plan->d_round_off;
   rp.rounds = plan->d_rounds;
   rp.weight = d_weight;
@@ -951,14 +1062,37 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
   rp.wn = d_wn;
   rp.dwn = d_dwn;
-  rp.kd = kd;
+  trans_const_init(&rp.tc, kd);
+  // wavenumber windows: the per-wavenumber data a group re-reads (wavenumber grids or weight vector,
+  // plan records: ~20 B per wavenumber) should stay in L2 between groups; 24 MB per window does
+  int nwin = 1;
+  if (ngroups > 1) {
+    const double per_wav = (wmode == W_PLANCK ? 16.0 : (wmode == W_VECTOR ? 8.0 : 0.0)) + (double)sizeof(PlanRound) / plan->ch;
+    nwin = (int)std::min<int64_t>(64, std::max<int64_t>(1, (int64_t)(per_wav * (double)nwav / 24.0e6 + 0.999)));
+    if (const char* e = getenv("ECCKD_NWIN")) nwin = std::max(1, atoi(e));
+    nwin = (int)std::min<int64_t>(nwin, plan->nchunks);
+  }
+  const int cw = (int)((plan->nchunks + nwin - 1) / nwin);
+  nwin = (int)((plan->nchunks + cw - 1) / cw);
+  rp.nwin = nwin;
+  rp.cw = cw;
 
   int ncta = 0;
   ECCKD_CUDA_OK(launch_reduce(fkind, wmode, ctx, rp, threads, smem, &ncta, true));
   const int64_t T = (int64_t)ngroups * plan->nchunks;
   ncta = (int)std::min<int64_t>(ncta, std::max<int64_t>(1, T));
-  const int64_t per_cta = (T + ncta - 1) / ncta;
-  const int maxg = (int)((per_cta + plan->nchunks - 1) / plan->nchunks) + 1;
+  // (window, group) pairs a CTA's contiguous piece can touch
+  auto vg_of = [&](int64_t item) {
+    const int64_t per_win = (int64_t)ngroups * cw;
+    const int64_t v = item / per_win;
+    const int64_t n_v = std::min<int64_t>(plan->nchunks, v * cw + cw) - v * cw;
+    return v * ngroups + (item - v * per_win) / n_v;
+  };
+  int maxg = 1;
+  for (int b = 0; b < ncta; ++b) {
+    const int64_t lo = (T * b) / ncta, hi = (T * (b + 1)) / ncta;
+    if (hi > lo) maxg = std::max(maxg, (int)(vg_of(hi - 1) - vg_of(lo) + 1));
+  }
   rp.ncta = ncta;
   rp.maxg = maxg;
 
@@ -966,7 +1100,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   void* d_groups = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 0, (size_t)ngroups * sizeof(GroupDesc), &d_groups));
   ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), (size_t)ngroups * sizeof(GroupDesc)));
-  const size_t npieces = (size_t)ncta * maxg * nw;
+  const size_t npieces = (size_t)ncta * maxg * nw * RPW;
   void* d_partial = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 1, npieces * ng * 4 * sizeof(double), &d_partial));
   void* d_pz = nullptr;
@@ -1000,14 +1134,16 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.nw = nw;
   cp.ncta = ncta;
   cp.maxg = maxg;
+  cp.nwin = nwin;
+  cp.cw = cw;
   cp.nchunks = plan->nchunks;
   cp.ng = ng;
-  cp.shared_s1 = !(fkind == F_LOG || fkind == F_HYBRID || fkind == F_NONE);
+  cp.shared_s1 = !(fkind == F_LOG || fkind == F_HYBRID);
   cp.partial = rp.partial;
   cp.partial_z = rp.partial_z;
   cp.sums = d_sums;
   cp.minmax = d_minmax;
-  const int64_t nthreads = (int64_t)ngroups * nw * ng;
+  const int64_t nthreads = (int64_t)ngroups * nw * RPW * ng;
   combine_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(cp);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
@@ -1109,23 +1245,53 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   p->ctx = ctx;
   p->nwav = nwav;
   p->ng = ng;
-  p->nchunks = (nwav + CH - 1) / CH;
-  ECCKD_REQUIRE(p->nchunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
+  // Chunk length: the plan packs every chunk into rounds of 32 lanes x 16 slots with each g point
+  // padded to whole lanes, so the longest chunk whose g points still fit one round is the cheapest;
+  // it depends on how many g points meet inside a chunk.  Count the rounds for a few candidates
+  // (longest first) and keep the one needing the fewest rounds per wavenumber.
+  static const int candidates[] = {CH_MAX, 448, 384, 320, 256};
+  const int64_t max_chunks = (nwav + 255) / 256;
+  ECCKD_REQUIRE(max_chunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
   uint32_t* d_nrounds = nullptr;
-  cudaError_t e = cudaMalloc(&p->d_round_off, (size_t)(p->nchunks + 1) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_nrounds, (size_t)p->nchunks * sizeof(uint32_t));
+  cudaError_t e = cudaMalloc(&p->d_round_off, (size_t)(max_chunks + 1) * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_nrounds, (size_t)max_chunks * sizeof(uint32_t));
   if (e == cudaSuccess) e = cudaMalloc(&p->d_count, (size_t)ng * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_count, 0, (size_t)ng * sizeof(unsigned long long), ctx->stream);
   uint32_t total = 0;
   std::vector<unsigned long long> cnt(ng);
-  if (e == cudaSuccess) {
-    plan_count_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, d_nrounds, p->d_count);
-    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(p->nchunks, d_nrounds, p->d_round_off);
+  int best_ch = 0;
+  if (const char* env = getenv("ECCKD_CH")) best_ch = std::min(CH_MAX, std::max(2, atoi(env) & ~1));
+  auto count_rounds = [&](int ch, bool with_counts, uint32_t* h_total) {
+    const int64_t nch = (nwav + ch - 1) / ch;
+    plan_count_kernel<<<(unsigned)nch, ch, 0, ctx->stream>>>(d_g_point, nwav, ng, d_nrounds,
+                                                              with_counts ? p->d_count : nullptr);
+    exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(nch, d_nrounds, p->d_round_off);
     ctx->launches += 2;
-    e = cudaGetLastError();
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(h_total, p->d_round_off + nch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    return err;
+  };
+  if (e == cudaSuccess && best_ch == 0) {
+    double best_cost = 0.0;
+    for (int ch : candidates) {
+      uint32_t tot = 0;
+      e = count_rounds(ch, false, &tot);
+      if (e != cudaSuccess) break;
+      const double cost = (double)tot;  // every round costs the same 32 x 16 slots per row
+      if (best_ch == 0 || cost < best_cost * 0.995) {
+        best_ch = ch;
+        best_cost = cost;
+      }
+      if ((int64_t)tot == (nwav + ch - 1) / ch) break;  // one round per chunk: shorter chunks cannot win
+    }
   }
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(&total, p->d_round_off + p->nchunks, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) {
+    p->ch = best_ch;
+    p->nchunks = (nwav + best_ch - 1) / best_ch;
+    e = count_rounds(best_ch, true, &total);
+  }
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(cnt.data(), p->d_count, (size_t)ng * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                         ctx->stream);
@@ -1136,7 +1302,8 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
     e = cudaMalloc(&p->d_rounds, (nr + 1) * sizeof(PlanRound));
     if (e == cudaSuccess) {
       plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds);
-      plan_fill_kernel<<<(unsigned)p->nchunks, CH, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off, p->d_rounds);
+      plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
+                                                                          p->d_rounds);
       ctx->launches += 2;
       e = cudaGetLastError();
     }

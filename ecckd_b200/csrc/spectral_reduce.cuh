@@ -2,32 +2,38 @@
 // (LBL spectra -> per-g-point averages) host code and kernels.
 #pragma once
 #include "common.cuh"
+#include "trans_core.cuh"
 
 namespace ecckd {
 
-constexpr int CH = 224;            // wavenumbers per chunk (1792 B per row: a multiple of 16 B)
-constexpr int SLOTS_PER_LANE = 8;  // plan slots per lane per round
-constexpr int NS = 3;              // data stages per consumer warp
-constexpr int NSW = 3;             // weight stages per CTA
+constexpr int SLOTS = 16;          // plan slots per lane per round
+constexpr int CH_MAX = 480;        // longest chunk (wavenumbers); chunk bytes stay a multiple of 16
+constexpr int STAGE_BYTES = CH_MAX * 8;
+constexpr int RPW = 2;             // rows per consumer warp (they share the lane's offsets and weights)
+constexpr int NSETS = 2;           // stage sets per consumer warp: chunk visit k uses set k & 1
+constexpr int NSW = 4;             // ring slots of (weight tile, plan round) per CTA
 constexpr int NPW = 2;             // producer (weight) warps per CTA
-constexpr int NW_MAX = 19;         // consumer warps (= rows) per CTA: 23 warps x 88 registers fill the register file
-// lane meta word of the plan: bits 0-11 g point (0xFFF = lane unused), bits 12-15 valid slots (1..8)
+constexpr int NW_MAX = 10;         // consumer warps per CTA: 12 warps x 168 registers fill the register file
+constexpr int GROUP_ROWS = NW_MAX * RPW;
+// lane meta word of the plan: bits 0-11 g point (0xFFF = lane unused), 12-16 valid slots (0..16),
+// 17-21 "lane + 2^s belongs to the same g point in this round" for shuffle step s, 22 head lane of its g point
 constexpr unsigned NO_G = 0xFFFu;
 constexpr int MAX_NG = 4094;
-constexpr int WT_STRIDE = CH + 2;  // weight tile: CH weights + a zero entry that padding slots point at
 
-// One round of the plan: for each lane, 8 byte offsets into the row stage (padding repeats
-// slot 0), 8 byte offsets into the weight tile (padding -> the zero entry), the lane meta word
-// and the number of shuffle steps the segmented reduction needs.  1104 bytes, copied to shared
-// memory with one bulk copy.
+// One round of the plan (32 lanes x 16 slots): per lane 16 byte offsets into the chunk (padding slots
+// repeat slot 0: neutral for min/max, their weight is forced to zero through the valid-slot count) and
+// the lane meta word; per round the number of shuffle steps, its chunk and first/last-of-chunk flags.
+// 1168 bytes, copied to shared memory with one bulk copy.
 struct PlanRound {
-  uint4 tau_off[32];
-  uint4 w_off[32];
-  uint16_t meta[32];
+  uint4 off[2][32];   // off[h][lane]: slots 8h .. 8h+7 as uint16
+  uint32_t meta[32];
   uint32_t steps;
-  uint32_t pad_[3];
+  uint32_t chunk;
+  uint32_t flags;     // bit 0: first round of its chunk, bit 1: last round of its chunk
+  uint32_t pad_;
 };
-static_assert(sizeof(PlanRound) == 1104, "PlanRound layout");
+static_assert(sizeof(PlanRound) == 1168, "PlanRound layout");
+constexpr int RING_SLOT_BYTES = STAGE_BYTES + (int)sizeof(PlanRound);
 
 // internal per-row method ids (public enum resolved per layer for hybrid)
 enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };
@@ -62,12 +68,13 @@ struct OutDesc {
 constexpr int NSUM = 3;
 constexpr int NMINMAX = 2;
 
-// Up to NW_MAX rows that share one weight row: one consumer warp each.
+// Up to GROUP_ROWS rows that share one weight row.  Row i of a group is handled by consumer warp
+// i % nw as its row i / nw.
 struct GroupDesc {
-  const double* od[NW_MAX];
-  int32_t row[NW_MAX];     // index in the partial-sum arrays
-  uint8_t is_log[NW_MAX];  // row uses logarithmic averaging (hybrid method)
-  uint8_t bulk_ok[NW_MAX]; // row base is 16-byte aligned: bulk async copies allowed
+  const double* od[GROUP_ROWS];
+  int32_t row[GROUP_ROWS];     // index in the partial-sum arrays
+  uint8_t is_log[GROUP_ROWS];  // row uses logarithmic averaging (hybrid method)
+  uint8_t bulk_ok[GROUP_ROWS]; // row base is 16-byte aligned: bulk async copies allowed
   int32_t nrows;
   int32_t wrow;
 };
@@ -77,7 +84,10 @@ struct ReduceParams {
   int ngroups;
   int nw;                  // consumer warps per CTA
   int ncta;                // grid size P
-  int maxg;                // partial slots per CTA (groups a CTA can touch)
+  int maxg;                // partial slots per CTA ((window, group) pairs a CTA can touch)
+  int ch;                  // chunk length of the plan
+  int nwin;                // wavenumber windows: items are ordered (window, group, chunk) so that the
+  int cw;                  //   per-wavenumber data of a window (cw chunks) stay in L2 across groups
   int64_t nchunks;
   int64_t nwav;
   int ng;
@@ -89,9 +99,9 @@ struct ReduceParams {
   const double* temperature;  // PLANCK: device [n weight rows]
   const double* wn;
   const double* dwn;
-  double kd;                  // transmission exponent scale (LW_DIFFUSIVITY*OD_SCALING*k)
-  double* partial;            // [ncta][maxg][nw][ng][4]
-  int32_t* partial_z;         // [ncta][maxg][nw][ng]
+  TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
+  double* partial;            // [ncta][maxg][nw*RPW][ng][4]
+  int32_t* partial_z;         // [ncta][maxg][nw*RPW][ng]
 };
 
 struct CombineParams {
@@ -100,9 +110,11 @@ struct CombineParams {
   int nw;
   int ncta;
   int maxg;
+  int nwin;
+  int cw;
   int64_t nchunks;
   int ng;
-  int shared_s1;   // weight sums are accumulated by the first row of each group only
+  int shared_s1;   // weight sums are accumulated once per group (by the last consumer warp)
   const double* partial;
   const int32_t* partial_z;
   double* sums;    // [nrows][ng][NSUM]
@@ -127,6 +139,7 @@ struct ecckd_gpoint_plan {
   int64_t nchunks = 0;
   int64_t nrounds = 0;
   int ng = 0;
+  int ch = 0;                            // chunk length chosen for this g-point map
   uint32_t* d_round_off = nullptr;       // [nchunks+1]
   ecckd::PlanRound* d_rounds = nullptr;  // [nrounds]
   unsigned long long* d_count = nullptr; // [ng]

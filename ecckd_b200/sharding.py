@@ -13,7 +13,7 @@ from __future__ import annotations
 
 from typing import Tuple
 
-CHUNK = 224  # wavenumbers per kernel chunk (ecckd_b200/csrc/spectral_reduce.cuh: CH)
+CHUNK = 480  # shard boundaries are multiples of the longest kernel chunk (spectral_reduce.cuh: CH_MAX), hence 16-byte aligned
 
 
 def shard_range(nwav: int, rank: int, world: int, align: int = CHUNK) -> Tuple[int, int]:
