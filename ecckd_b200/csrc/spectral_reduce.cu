@@ -111,11 +111,12 @@ __device__ __forceinline__ double fast_exp(double x) {
   return __hiloint2double(__double2hiint(q) + (k << 20), __double2loint(q));
 }
 
-// planck_function.cpp:29-33,47-53, one element.  The reference evaluates
-// prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) (one rounding more in the
-// exponent argument, i.e. a relative change of the weight below 1e-14, far inside the 1e-12
-// tolerance of the averages the weights feed).
-__device__ __forceinline__ double planck_elem_fast(double inv_t, double nu, double dnu) {
+// planck_function.cpp:29-33,47-53, one element, for the producer warps (all 32 lanes call it
+// together: the exponential looks its 2^(j/32) factor up by warp shuffle, trans_core.cuh).  The
+// reference evaluates prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) and the
+// division is a reciprocal refined by two Newton steps: the weight differs from the reference's
+// by a few ulp, far inside the 1e-12 tolerance of the averages the weights feed.
+__device__ __forceinline__ double planck_elem_fast(double inv_t, double nu, double dnu, const TransLane& tl) {
   const double h = 6.62606896e-34;
   const double c = 2.99792458e8;
   const double k = 1.3806504e-23;
@@ -123,7 +124,12 @@ __device__ __forceinline__ double planck_elem_fast(double inv_t, double nu, doub
   const double pi = 3.14159265358979323846;
   const double freq = nu * inv_cm_2_Hz;
   const double prefactor = (dnu * 2.0 * h * inv_cm_2_Hz * pi / (c * c)) * (freq * freq * freq);
-  return prefactor / (fast_exp((h / k) * (freq * inv_t)) - 1.0);
+  const double e = exp_table((h / k) * (freq * inv_t), tl) - 1.0;
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(e));  // ~20 bits
+  x = fma(x, fma(-e, x, 1.0), x);
+  x = fma(x, fma(-e, x, 1.0), x);
+  return prefactor * x;
 }
 
 // exact evaluation order of planck_function.cpp:47-53 (used by the standalone planck kernel)
@@ -210,8 +216,7 @@ __global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds
   if (i >= nrounds * 32) return;
   PlanRound& r = rounds[i >> 5];
   const int lane = (int)(i & 31);
-  r.off[0][lane] = make_uint4(0, 0, 0, 0);
-  r.off[1][lane] = make_uint4(0, 0, 0, 0);
+  for (int k = 0; k < SLOTS; ++k) r.off[k][lane] = 0;
   r.meta[lane] = NO_G;
   if (lane == 0) {
     r.steps = 0;
@@ -238,9 +243,8 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __rest
   if (p.g < 0) return;
   PlanRound& rd = rounds[(size_t)r0 + (size_t)(p.vlane >> 5)];
   const int lane = p.vlane & 31;
-  uint16_t* off = reinterpret_cast<uint16_t*>(&rd.off[0][0]);
   const uint16_t my = (uint16_t)(threadIdx.x * 8);
-  auto slot_ref = [&](int slot) -> uint16_t& { return off[((slot >> 3) * 32 + lane) * 8 + (slot & 7)]; };
+  auto slot_ref = [&](int slot) -> uint16_t& { return rd.off[slot][lane]; };
   slot_ref(p.slot) = my;
   if (p.slot == 0) {
     // this thread owns the lane: valid slots form a prefix of length nv; padding slots repeat slot 0
@@ -388,80 +392,105 @@ struct Partial {
   int zc;
 };
 
-// The 16 slots of one row: `sbase + addr[k]` is the shared-memory location of slot k in the row's
-// stage.  One copy of this body serves every row and stage set: the unrolled 16-slot sequence is
-// ~8 KB of SASS and the instruction cache has to hold it for all warps of the SM.
-template <int FKIND>
-__device__ __forceinline__ Partial row_slots(const unsigned char* __restrict__ sbase, const unsigned (&addr)[SLOTS],
-                                             const double (&w)[SLOTS], const int nv, const TransConst& K,
-                                             const TransLane& tl, const bool is_log) {
+// The 16 slots of NR rows of one round, evaluated together: the rows share the lane's offsets and
+// weights (read once per slot from the ring slot) and give the FP64 pipe NR x 4 independent
+// dependency chains.  `stage0` is the first row's chunk in shared memory, row r is STAGE_BYTES
+// further.  The slot loop is only unrolled by 4 so that the body (~4 KB of SASS for two rows) stays
+// resident in the instruction cache for all warps of the SM.
+template <int FKIND, int NR>
+__device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char* __restrict__ stage0,
+                                           const uint16_t* __restrict__ offp, const double* __restrict__ wp,
+                                           const int nv, const TransConst& K, const TransLane& tl,
+                                           const bool (&is_log)[NR]) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  Partial a;
-  a.s0 = 0.0;
-  a.s1 = 0.0;
-  a.mn = inf;
-  a.mx = -inf;
-  a.zc = 0;
 #pragma unroll
-  for (int k = 0; k < SLOTS; ++k) {
-    const double tau = *reinterpret_cast<const double*>(sbase + addr[k]);
-    bool pos;
-    const double f = f_transform<FKIND>(tau, K, tl, is_log, pos);
-    double we = w[k];  // zero for padding slots
-    if (LOGKIND) {
-      we = pos ? we : 0.0;
-      a.zc += (k < nv && !pos) ? 1 : 0;
-      a.s1 += we;
-    }
-    a.s0 = fma(f, we, a.s0);
-    a.mn = (tau < a.mn) ? tau : a.mn;
-    a.mx = (tau > a.mx) ? tau : a.mx;
+  for (int r = 0; r < NR; ++r) {
+    a[r].s0 = 0.0;
+    a[r].s1 = 0.0;
+    a[r].mn = inf;
+    a[r].mx = -inf;
+    a[r].zc = 0;
   }
-  return a;
+#pragma unroll 1
+  for (int kk = 0; kk < SLOTS; kk += 4) {
+    double tau[NR][4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned o = offp[(kk + j) * 32];
+      w[j] = wp[(kk + j) * 32];  // zero for padding slots
+#pragma unroll
+      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double f[4];
+      bool pos[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = f_transform<FKIND>(tau[r][j], K, tl, is_log[r], pos[j]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double we = w[j];
+        if (LOGKIND) {
+          we = pos[j] ? we : 0.0;
+          a[r].zc += (kk + j < nv && !pos[j]) ? 1 : 0;
+          a[r].s1 += we;
+        }
+        a[r].s0 = fma(f[j], we, a[r].s0);
+        a[r].mn = (tau[r][j] < a[r].mn) ? tau[r][j] : a[r].mn;
+        a[r].mx = (tau[r][j] > a[r].mx) ? tau[r][j] : a[r].mx;
+      }
+    }
+  }
 }
 
 // Segmented suffix reduction over adjacent lanes of the same g point (lane predicates from the
-// plan), then the head lane of every g point folds the result into the row's accumulators.
-template <bool S0, bool S1, bool MM, bool ZC>
-__device__ __forceinline__ void fold_partial(Partial a, const unsigned meta, const int nsteps, double* __restrict__ acc,
-                                             int32_t* __restrict__ accz) {
+// plan) for NR rows at once, then the head lane of every g point folds the results into the rows'
+// accumulators (row r at acc + r*acc_stride).
+template <int NR, bool S0, bool S1, bool MM, bool ZC>
+__device__ __forceinline__ void fold_partials(Partial (&a)[NR], const unsigned meta, const int nsteps,
+                                              double* __restrict__ acc, int32_t* __restrict__ accz, const int ng) {
 #pragma unroll
   for (int st = 0; st < 5; ++st) {
     if (st < nsteps) {  // warp-uniform
       const int d = 1 << st;
-      const double t0 = S0 ? __shfl_down_sync(0xffffffffu, a.s0, d) : 0.0;
-      const double t1 = S1 ? __shfl_down_sync(0xffffffffu, a.s1, d) : 0.0;
-      const double tn = MM ? __shfl_down_sync(0xffffffffu, a.mn, d) : 0.0;
-      const double tx = MM ? __shfl_down_sync(0xffffffffu, a.mx, d) : 0.0;
-      const int tz = ZC ? __shfl_down_sync(0xffffffffu, a.zc, d) : 0;
-      if ((meta >> (17 + st)) & 1u) {
-        if (S0) a.s0 += t0;
-        if (S1) a.s1 += t1;
+      const bool take = (meta >> (17 + st)) & 1u;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const double t0 = S0 ? __shfl_down_sync(0xffffffffu, a[r].s0, d) : 0.0;
+        const double t1 = S1 ? __shfl_down_sync(0xffffffffu, a[r].s1, d) : 0.0;
+        const double tn = MM ? __shfl_down_sync(0xffffffffu, a[r].mn, d) : 0.0;
+        const double tx = MM ? __shfl_down_sync(0xffffffffu, a[r].mx, d) : 0.0;
+        const int tz = ZC ? __shfl_down_sync(0xffffffffu, a[r].zc, d) : 0;
+        if (S0) a[r].s0 += take ? t0 : 0.0;
+        if (S1) a[r].s1 += take ? t1 : 0.0;
         if (MM) {
-          a.mn = (tn < a.mn) ? tn : a.mn;
-          a.mx = (tx > a.mx) ? tx : a.mx;
+          a[r].mn = (take && tn < a[r].mn) ? tn : a[r].mn;
+          a[r].mx = (take && tx > a[r].mx) ? tx : a[r].mx;
         }
-        if (ZC) a.zc += tz;
+        if (ZC) a[r].zc += take ? tz : 0;
       }
     }
   }
   const unsigned g = meta & 0xFFFu;
   if (g != NO_G && ((meta >> 22) & 1u)) {  // head lane of its g point in this round
-    double2* q = reinterpret_cast<double2*>(acc + g * 4);
-    if (S0 || S1) {
-      double2 a01 = q[0];
-      if (S0) a01.x += a.s0;
-      if (S1) a01.y += a.s1;
-      q[0] = a01;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double2* q = reinterpret_cast<double2*>(acc + ((size_t)r * ng + g) * 4);
+      if (S0 || S1) {
+        double2 a01 = q[0];
+        if (S0) a01.x += a[r].s0;
+        if (S1) a01.y += a[r].s1;
+        q[0] = a01;
+      }
+      if (MM) {
+        double2 a23 = q[1];
+        a23.x = (a[r].mn < a23.x) ? a[r].mn : a23.x;
+        a23.y = (a[r].mx > a23.y) ? a[r].mx : a23.y;
+        q[1] = a23;
+      }
+      if (ZC) accz[r * ng + g] += a[r].zc;
     }
-    if (MM) {
-      double2 a23 = q[1];
-      a23.x = (a.mn < a23.x) ? a.mn : a23.x;
-      a23.y = (a.mx > a23.y) ? a.mx : a23.y;
-      q[1] = a23;
-    }
-    if (ZC) accz[g] += a.zc;
   }
 }
 
@@ -501,89 +530,118 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
 
   if (warp >= nw) {
-    // ===================== producers: weight tile + plan record of every round =====================
+    // ===================== producers: permuted weights + plan record of every round =====================
+    // Producer lane `lane` of warp pw fills wperm[k][lane] for the slots k = pw, pw + NPW, ...: the
+    // weight of the wavenumber the plan puts there (zero for padding slots).  Consecutive
+    // wavenumbers sit in consecutive lanes of a slot, so the gathers below are nearly coalesced.
+    // Software pipeline over ring entries (= plan rounds): plan offsets are fetched two entries
+    // ahead, wavenumbers / weights one entry ahead.
     const int pw = warp - nw;
-    constexpr int PER = (CH_MAX + NPW * 32 - 1) / (NPW * 32);  // elements per producer lane per chunk
+    constexpr int PER = SLOTS / NPW;  // slots per producer lane per round
+    static_assert(SLOTS % NPW == 0, "slots must split evenly over the producer warps");
+    const TransLane ptl = trans_lane_init();
+    struct Entry {
+      uint32_t r;       // plan round
+      int64_t w0;       // first wavenumber of its chunk
+      int wrow;         // weight row (temperature index / matrix row)
+      bool valid;
+    };
     Cursor q = first;
-    int ws = 0, filled = 0;
-    unsigned epar = 0;
-    double inv_t = (WMODE == W_PLANCK) ? 1.0 / p.temperature[p.groups[q.l].wrow] : 0.0;
-    const double* wrow_ptr = (WMODE == W_MATRIX) ? p.weight + (int64_t)p.groups[q.l].wrow * p.w_stride : p.weight;
-    double nu_n[PER], dnu_n[PER];  // wavenumbers of the next chunk, fetched one chunk ahead
-    auto fetch = [&](int cc) {
-      const int64_t w0 = (int64_t)cc * ch;
+    int visit = 0;
+    uint32_t r_cur = p.round_off[q.c], r_end = p.round_off[q.c + 1];
+    auto next_entry = [&]() {
+      Entry e;
+      e.valid = visit < niter;
+      e.r = r_cur;
+      e.w0 = (int64_t)q.c * ch;
+      e.wrow = e.valid ? p.groups[q.l].wrow : 0;
+      if (e.valid && ++r_cur == r_end) {
+        ++visit;
+        if (visit < niter) {
+          cursor_next(q, p.ngroups, p.cw, nchunks);
+          r_cur = p.round_off[q.c];
+          r_end = p.round_off[q.c + 1];
+        }
+      }
+      return e;
+    };
+    auto load_plan = [&](const Entry& e, unsigned (&off)[PER], unsigned& meta) {
+      if (!e.valid) return;
+      const PlanRound* pr = p.rounds + e.r;
+      meta = pr->meta[lane];
+#pragma unroll
+      for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
+    };
+    auto load_src = [&](const Entry& e, const unsigned (&off)[PER], double (&x)[PER], double (&y)[PER]) {
+      if (!e.valid) return;
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
-        const int j = pw * 32 + lane + m * NPW * 32;
-        const bool ok = j < ch && (w0 + j) < p.nwav;
-        nu_n[m] = ok ? p.wn[w0 + j] : 1.0;
-        dnu_n[m] = ok ? p.dwn[w0 + j] : 0.0;
+        const int64_t w = e.w0 + (off[m] >> 3);
+        if (WMODE == W_PLANCK) {
+          x[m] = p.wn[w];
+          y[m] = p.dwn[w];
+        } else if (WMODE == W_MATRIX) {
+          x[m] = p.weight[(int64_t)e.wrow * p.w_stride + w];
+        } else {
+          x[m] = p.weight[w];
+        }
       }
     };
-    if (WMODE == W_PLANCK) fetch(q.c);
-    uint32_t r0 = p.round_off[q.c], r1 = p.round_off[q.c + 1];
-    for (int k = 0; k < niter; ++k) {
-      const int c = q.c;
-      const int64_t w0 = (int64_t)c * ch;
-      const int n_c = (c == nchunks - 1) ? last_n : ch;
-      Cursor qn = q;
-      const bool new_group = cursor_next(qn, p.ngroups, p.cw, nchunks);
-      uint32_t r0_next = 0, r1_next = 0;
-      if (k + 1 < niter) {
-        r0_next = p.round_off[qn.c];
-        r1_next = p.round_off[qn.c + 1];
-      }
+    Entry e0 = next_entry(), e1 = next_entry();
+    unsigned off0[PER], off1[PER], off2[PER], meta0 = NO_G, meta1 = NO_G, meta2 = NO_G;
+    double x0[PER], y0[PER], x1[PER], y1[PER];
+    load_plan(e0, off0, meta0);
+    load_plan(e1, off1, meta1);
+    load_src(e0, off0, x0, y0);
+    int ws = 0, filled = 0;
+    unsigned epar = 0;
+    while (e0.valid) {
+      const Entry e2 = next_entry();
+      load_src(e1, off1, x1, y1);
+      load_plan(e2, off2, meta2);
+      const int nv = (int)((meta0 >> 12) & 31u);
       double val[PER];
       if (WMODE == W_PLANCK) {
-        double nu[PER], dnu[PER];
+        const double inv_t = 1.0 / p.temperature[e0.wrow];
 #pragma unroll
-        for (int m = 0; m < PER; ++m) {
-          nu[m] = nu_n[m];
-          dnu[m] = dnu_n[m];
-        }
-        if (k + 1 < niter) fetch(qn.c);
+        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, x0[m], y0[m], ptl);
+      } else {
 #pragma unroll
-        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, nu[m], dnu[m]);
+        for (int m = 0; m < PER; ++m) val[m] = x0[m];
       }
-      const double* src = (WMODE == W_PLANCK) ? nullptr : wrow_ptr + w0;
-      const bool wbulk = (WMODE != W_PLANCK) && p.weight_bulk_ok && ((n_c & 1) == 0);
-      for (uint32_t r = r0; r < r1; ++r) {  // one ring entry per round (a second round of a chunk is rare)
-        unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-        double* tile = reinterpret_cast<double*>(slot);
-        if (filled >= NSW) mbar_wait(&empty_w[ws], epar);
-        if (WMODE == W_PLANCK) {
+      unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+      double* wperm = reinterpret_cast<double*>(slot);
+      if (filled >= NSW) mbar_wait(&empty_w[ws], epar);
 #pragma unroll
-          for (int m = 0; m < PER; ++m) {
-            const int j = pw * 32 + lane + m * NPW * 32;
-            if (j < n_c) tile[j] = val[m];
-          }
-        } else if (!wbulk) {
-          for (int j = pw * 32 + lane; j < n_c; j += NPW * 32) tile[j] = src[j];
-        }
-        __syncwarp();
-        if (lane == 0) {
-          if (pw == 0) {
-            fence_proxy_async();
-            const unsigned bytes = (unsigned)sizeof(PlanRound) + (wbulk ? (unsigned)(n_c * 8) : 0u);
-            mbar_arrive_expect_tx(&full_w[ws], bytes);
-            bulk_g2s(slot + STAGE_BYTES, p.rounds + r, (unsigned)sizeof(PlanRound), &full_w[ws]);
-            if (wbulk) bulk_g2s(tile, src, (unsigned)(n_c * 8), &full_w[ws]);
-          } else {
-            mbar_arrive(&full_w[ws]);
-          }
-        }
-        ++filled;
-        if (++ws == NSW) {
-          ws = 0;
-          if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
+      for (int m = 0; m < PER; ++m) {
+        const int k = pw + NPW * m;
+        wperm[k * 32 + lane] = (k < nv) ? val[m] : 0.0;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        if (pw == 0) {
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&full_w[ws], (unsigned)sizeof(PlanRound));
+          bulk_g2s(slot + WPERM_BYTES, p.rounds + e0.r, (unsigned)sizeof(PlanRound), &full_w[ws]);
+        } else {
+          mbar_arrive(&full_w[ws]);
         }
       }
-      r0 = r0_next;
-      r1 = r1_next;
-      q = qn;
-      if (new_group && k + 1 < niter) {
-        if (WMODE == W_PLANCK) inv_t = 1.0 / p.temperature[p.groups[q.l].wrow];
-        if (WMODE == W_MATRIX) wrow_ptr = p.weight + (int64_t)p.groups[q.l].wrow * p.w_stride;
+      ++filled;
+      if (++ws == NSW) {
+        ws = 0;
+        if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
+      }
+      e0 = e1;
+      e1 = e2;
+      meta0 = meta1;
+      meta1 = meta2;
+#pragma unroll
+      for (int m = 0; m < PER; ++m) {
+        off0[m] = off1[m];
+        off1[m] = off2[m];
+        x0[m] = x1[m];
+        y0[m] = y1[m];
       }
     }
     return;
@@ -694,41 +752,37 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     while (!last_round) {
       mbar_wait(&full_w[ws], wpar);
       const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + STAGE_BYTES);
-      const uint4 o0 = pr->off[0][lane];
-      const uint4 o1 = pr->off[1][lane];
+      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
+      const double* wp = reinterpret_cast<const double*>(slot) + lane;
+      const uint16_t* offp = &pr->off[0][lane];
       const unsigned meta = pr->meta[lane];
       const int nsteps = (int)pr->steps;
       last_round = (pr->flags & 2u) != 0;
       const int nv = (int)((meta >> 12) & 31u);
-      const unsigned packed[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-      unsigned off[SLOTS];
-      double w[SLOTS];
-#pragma unroll
-      for (int e = 0; e < SLOTS; ++e) {
-        off[e] = (e & 1) ? (packed[e >> 1] >> 16) : (packed[e >> 1] & 0xFFFFu);
-        w[e] = (e < nv) ? *reinterpret_cast<const double*>(slot + off[e]) : 0.0;
-      }
       if (s1_duty) {
-        Partial a;
-        a.s0 = 0.0;
-        a.mn = 0.0;
-        a.mx = 0.0;
-        a.zc = 0;
+        Partial a[1];
+        a[0].s0 = 0.0;
+        a[0].mn = 0.0;
+        a[0].mx = 0.0;
+        a[0].zc = 0;
         double s = 0.0;
 #pragma unroll
-        for (int e = 0; e < SLOTS; ++e) s += w[e];
-        a.s1 = s;
-        fold_partial<false, true, false, false>(a, meta, nsteps, acc, accz);
+        for (int e = 0; e < SLOTS; ++e) s += wp[e * 32];
+        a[0].s1 = s;
+        fold_partials<1, false, true, false, false>(a, meta, nsteps, acc, accz, ng);
         __syncwarp();
       }
-      if (USES_TAU) {
-#pragma unroll 1
-        for (int r = 0; r < RPW; ++r) {
-          if (!active[r]) continue;
-          const unsigned char* stage = data + (set * RPW + r) * STAGE_BYTES;
-          const Partial a = row_slots<FKIND>(stage, off, w, nv, p.tc, tl, is_log[r]);
-          fold_partial<true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc + r * ng * 4, accz + r * ng);
+      if (USES_TAU && active[0]) {
+        const unsigned char* stage0 = data + (set * RPW) * STAGE_BYTES;
+        if (active[RPW - 1]) {
+          Partial a[RPW];
+          rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log);
+          fold_partials<RPW, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
+        } else {
+          Partial a[1];
+          const bool il[1] = {is_log[0]};
+          rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il);
+          fold_partials<1, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
         }
       }
       __syncwarp();

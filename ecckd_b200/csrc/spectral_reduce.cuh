@@ -21,11 +21,11 @@ constexpr unsigned NO_G = 0xFFFu;
 constexpr int MAX_NG = 4094;
 
 // One round of the plan (32 lanes x 16 slots): per lane 16 byte offsets into the chunk (padding slots
-// repeat slot 0: neutral for min/max, their weight is forced to zero through the valid-slot count) and
+// repeat slot 0: neutral for min/max; the producers give them zero weight) and
 // the lane meta word; per round the number of shuffle steps, its chunk and first/last-of-chunk flags.
 // 1168 bytes, copied to shared memory with one bulk copy.
 struct PlanRound {
-  uint4 off[2][32];   // off[h][lane]: slots 8h .. 8h+7 as uint16
+  uint16_t off[SLOTS][32];  // byte offset of (slot, lane) into the chunk
   uint32_t meta[32];
   uint32_t steps;
   uint32_t chunk;
@@ -33,7 +33,8 @@ struct PlanRound {
   uint32_t pad_;
 };
 static_assert(sizeof(PlanRound) == 1168, "PlanRound layout");
-constexpr int RING_SLOT_BYTES = STAGE_BYTES + (int)sizeof(PlanRound);
+constexpr int WPERM_BYTES = SLOTS * 32 * 8;  // weights of a round in (slot, lane) order, zero for padding slots
+constexpr int RING_SLOT_BYTES = WPERM_BYTES + (int)sizeof(PlanRound);
 
 // internal per-row method ids (public enum resolved per layer for hybrid)
 enum { M_LINEAR = 0, M_TRANS = 1, M_SQRT = 2, M_LOG = 3, M_SUMW = 4 };

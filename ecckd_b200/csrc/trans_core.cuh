@@ -95,4 +95,26 @@ __device__ __forceinline__ double trans_one_minus_exp(double tau, const TransCon
   return fma(-T, p, om);
 }
 
+// exp(x) for 0 <= x < 708 with the same table: x = (32 k + j) ln2/32 + r (two-constant
+// Cody-Waite reduction), exp(x) = 2^k 2^(j/32) (1 + p(r)).  Below 1 ulp; used for the Planck weights.
+__device__ __forceinline__ double exp_table(double x, const TransLane& tl) {
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 0x1.71547652b82fep+5, magic);  // 32/ln2
+  const int n = __double2loint(t);
+  const double nf = t - magic;
+  double r = fma(nf, -0x1.62e42fee00000p-6, x);  // -ln2/32, high part (21 trailing zero bits)
+  r = fma(nf, -0x1.a39ef35793c76p-38, r);  // low part
+  double q = 1.0 / 720.0;
+  q = fma(q, r, 1.0 / 120.0);
+  q = fma(q, r, 1.0 / 24.0);
+  q = fma(q, r, 1.0 / 6.0);
+  q = fma(q, r, 0.5);
+  q = fma(q, r, 1.0);
+  const double pr = q * r;
+  const int thi = __shfl_sync(0xffffffffu, tl.hi_adj, n);
+  const int tlo = __shfl_sync(0xffffffffu, tl.lo, n);
+  const double T = __hiloint2double(thi + (n << 15), tlo);
+  return fma(T, pr, T);
+}
+
 }  // namespace ecckd
