@@ -31,6 +31,7 @@
 //     group.  A CTA flushes its accumulators when it crosses into the next
 //     (window, group); a small combine kernel adds the pieces in fixed order.
 #include "spectral_reduce.cuh"
+#include "reduce_rows.cuh"
 
 #include <algorithm>
 #include <type_traits>
@@ -56,11 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra.uni WAIT_DONE;\n\t"
       "bra.uni WAIT_LOOP;\n"
       "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
       : "memory");
 }
 // 1-D bulk asynchronous copy global -> shared (SASS: UBLKCP), completion on an mbarrier
@@ -113,18 +114,19 @@ __device__ __forceinline__ double fast_exp(double x) {
 
 // planck_function.cpp:29-33,47-53, one element, for the producer warps (all 32 lanes call it
 // together: the exponential looks its 2^(j/32) factor up by warp shuffle, trans_core.cuh).  The
-// reference evaluates prefactor / (exp((h/k)*(freq/T)) - 1); here freq/T is freq * (1/T) and the
-// division is a reciprocal refined by two Newton steps: the weight differs from the reference's
-// by a few ulp, far inside the 1e-12 tolerance of the averages the weights feed.
-__device__ __forceinline__ double planck_elem_fast(double inv_t, double nu, double dnu, const TransLane& tl) {
+// reference evaluates prefactor / (exp((h/k)*(freq/T)) - 1) with prefactor =
+// (dnu*2*h*inv_cm_2_Hz*pi/(c*c)) * freq^3; here the constants are folded (hk_over_t = (h/k)/T is
+// formed on the host), and the division is a reciprocal refined by two Newton steps: the weight
+// differs from the reference's by a few ulp, far inside the 1e-12 tolerance of the averages.
+__device__ __forceinline__ double planck_elem_fast(double hk_over_t, double nu, double dnu, const TransLane& tl) {
   const double h = 6.62606896e-34;
   const double c = 2.99792458e8;
-  const double k = 1.3806504e-23;
   const double inv_cm_2_Hz = 100.0 * c;
   const double pi = 3.14159265358979323846;
+  const double c1 = 2.0 * h * inv_cm_2_Hz * pi / (c * c);
   const double freq = nu * inv_cm_2_Hz;
-  const double prefactor = (dnu * 2.0 * h * inv_cm_2_Hz * pi / (c * c)) * (freq * freq * freq);
-  const double e = exp_table((h / k) * (freq * inv_t), tl) - 1.0;
+  const double prefactor = (dnu * c1) * (freq * freq * freq);
+  const double e = exp_table(freq * hk_over_t, tl) - 1.0;
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(e));  // ~20 bits
   x = fma(x, fma(-e, x, 1.0), x);
@@ -364,136 +366,6 @@ __device__ __forceinline__ bool cursor_next(Cursor& q, int ngroups, int cw, int 
   return true;
 }
 
-template <int FKIND>
-__device__ __forceinline__ double f_transform(double tau, const TransConst& K, const TransLane& tl, bool is_log,
-                                              bool& positive) {
-  positive = true;
-  if (FKIND == F_LINEAR) return tau;
-  if (FKIND == F_TRANS) return trans_one_minus_exp(tau, K, tl);
-  if (FKIND == F_SQRT) return sqrt(tau);
-  if (FKIND == F_LOG) {
-    positive = tau > 0.0;
-    return positive ? log(tau) : 0.0;
-  }
-  if (FKIND == F_HYBRID) {
-    // warp-uniform branch (is_log is a property of the row): the shuffles inside stay converged
-    if (is_log) {
-      positive = tau > 0.0;
-      return positive ? log(tau) : 0.0;
-    }
-    return trans_one_minus_exp(tau, K, tl);
-  }
-  return 1.0;  // F_NONE: only the weight sum is wanted
-}
-
-// Per-lane partial result of one row over the 16 slots of a round.
-struct Partial {
-  double s0, s1, mn, mx;
-  int zc;
-};
-
-// The 16 slots of NR rows of one round, evaluated together: the rows share the lane's offsets and
-// weights (read once per slot from the ring slot) and give the FP64 pipe NR x 4 independent
-// dependency chains.  `stage0` is the first row's chunk in shared memory, row r is STAGE_BYTES
-// further.  The slot loop is only unrolled by 4 so that the body (~4 KB of SASS for two rows) stays
-// resident in the instruction cache for all warps of the SM.
-template <int FKIND, int NR>
-__device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char* __restrict__ stage0,
-                                           const uint16_t* __restrict__ offp, const double* __restrict__ wp,
-                                           const int nv, const TransConst& K, const TransLane& tl,
-                                           const bool (&is_log)[NR]) {
-  constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-#pragma unroll
-  for (int r = 0; r < NR; ++r) {
-    a[r].s0 = 0.0;
-    a[r].s1 = 0.0;
-    a[r].mn = inf;
-    a[r].mx = -inf;
-    a[r].zc = 0;
-  }
-#pragma unroll 1
-  for (int kk = 0; kk < SLOTS; kk += 4) {
-    double tau[NR][4], w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned o = offp[(kk + j) * 32];
-      w[j] = wp[(kk + j) * 32];  // zero for padding slots
-#pragma unroll
-      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
-    }
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      double f[4];
-      bool pos[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = f_transform<FKIND>(tau[r][j], K, tl, is_log[r], pos[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double we = w[j];
-        if (LOGKIND) {
-          we = pos[j] ? we : 0.0;
-          a[r].zc += (kk + j < nv && !pos[j]) ? 1 : 0;
-          a[r].s1 += we;
-        }
-        a[r].s0 = fma(f[j], we, a[r].s0);
-        a[r].mn = (tau[r][j] < a[r].mn) ? tau[r][j] : a[r].mn;
-        a[r].mx = (tau[r][j] > a[r].mx) ? tau[r][j] : a[r].mx;
-      }
-    }
-  }
-}
-
-// Segmented suffix reduction over adjacent lanes of the same g point (lane predicates from the
-// plan) for NR rows at once, then the head lane of every g point folds the results into the rows'
-// accumulators (row r at acc + r*acc_stride).
-template <int NR, bool S0, bool S1, bool MM, bool ZC>
-__device__ __forceinline__ void fold_partials(Partial (&a)[NR], const unsigned meta, const int nsteps,
-                                              double* __restrict__ acc, int32_t* __restrict__ accz, const int ng) {
-#pragma unroll
-  for (int st = 0; st < 5; ++st) {
-    if (st < nsteps) {  // warp-uniform
-      const int d = 1 << st;
-      const bool take = (meta >> (17 + st)) & 1u;
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const double t0 = S0 ? __shfl_down_sync(0xffffffffu, a[r].s0, d) : 0.0;
-        const double t1 = S1 ? __shfl_down_sync(0xffffffffu, a[r].s1, d) : 0.0;
-        const double tn = MM ? __shfl_down_sync(0xffffffffu, a[r].mn, d) : 0.0;
-        const double tx = MM ? __shfl_down_sync(0xffffffffu, a[r].mx, d) : 0.0;
-        const int tz = ZC ? __shfl_down_sync(0xffffffffu, a[r].zc, d) : 0;
-        if (S0) a[r].s0 += take ? t0 : 0.0;
-        if (S1) a[r].s1 += take ? t1 : 0.0;
-        if (MM) {
-          a[r].mn = (take && tn < a[r].mn) ? tn : a[r].mn;
-          a[r].mx = (take && tx > a[r].mx) ? tx : a[r].mx;
-        }
-        if (ZC) a[r].zc += take ? tz : 0;
-      }
-    }
-  }
-  const unsigned g = meta & 0xFFFu;
-  if (g != NO_G && ((meta >> 22) & 1u)) {  // head lane of its g point in this round
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      double2* q = reinterpret_cast<double2*>(acc + ((size_t)r * ng + g) * 4);
-      if (S0 || S1) {
-        double2 a01 = q[0];
-        if (S0) a01.x += a[r].s0;
-        if (S1) a01.y += a[r].s1;
-        q[0] = a01;
-      }
-      if (MM) {
-        double2 a23 = q[1];
-        a23.x = (a[r].mn < a23.x) ? a[r].mn : a23.x;
-        a23.y = (a[r].mx > a23.y) ? a[r].mx : a23.y;
-        q[1] = a23;
-      }
-      if (ZC) accz[r * ng + g] += a[r].zc;
-    }
-  }
-}
-
 template <int FKIND, int WMODE>
 __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __grid_constant__ ReduceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -588,23 +460,23 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       }
     };
     Entry e0 = next_entry(), e1 = next_entry();
-    unsigned off0[PER], off1[PER], off2[PER], meta0 = NO_G, meta1 = NO_G, meta2 = NO_G;
+    unsigned off1[PER], meta0 = NO_G, meta1 = NO_G, meta2 = NO_G;
     double x0[PER], y0[PER], x1[PER], y1[PER];
-    load_plan(e0, off0, meta0);
+    load_plan(e0, off1, meta0);
+    load_src(e0, off1, x0, y0);
     load_plan(e1, off1, meta1);
-    load_src(e0, off0, x0, y0);
     int ws = 0, filled = 0;
     unsigned epar = 0;
     while (e0.valid) {
       const Entry e2 = next_entry();
       load_src(e1, off1, x1, y1);
-      load_plan(e2, off2, meta2);
+      load_plan(e2, off1, meta2);  // off1 is free again: the gathers above have their addresses
       const int nv = (int)((meta0 >> 12) & 31u);
       double val[PER];
       if (WMODE == W_PLANCK) {
-        const double inv_t = 1.0 / p.temperature[e0.wrow];
+        const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
 #pragma unroll
-        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(inv_t, x0[m], y0[m], ptl);
+        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(hkt, x0[m], y0[m], ptl);
       } else {
 #pragma unroll
         for (int m = 0; m < PER; ++m) val[m] = x0[m];
@@ -638,8 +510,6 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       meta1 = meta2;
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
-        off0[m] = off1[m];
-        off1[m] = off2[m];
         x0[m] = x1[m];
         y0[m] = y1[m];
       }
@@ -759,12 +629,11 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       const int nsteps = (int)pr->steps;
       last_round = (pr->flags & 2u) != 0;
       const int nv = (int)((meta >> 12) & 31u);
+      const bool lane_used = (meta & 0xFFFu) != NO_G;
+      const unsigned gsafe = lane_used ? (meta & 0xFFFu) : 0u;
       if (s1_duty) {
         Partial a[1];
-        a[0].s0 = 0.0;
-        a[0].mn = 0.0;
-        a[0].mx = 0.0;
-        a[0].zc = 0;
+        partial_begin(a[0], acc, false);
         double s = 0.0;
 #pragma unroll
         for (int e = 0; e < SLOTS; ++e) s += wp[e * 32];
@@ -772,15 +641,19 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
         fold_partials<1, false, true, false, false>(a, meta, nsteps, acc, accz, ng);
         __syncwarp();
       }
-      if (USES_TAU && active[0]) {
+      if (USES_TAU && active[0] && !(p.debug & 1)) {
         const unsigned char* stage0 = data + (set * RPW) * STAGE_BYTES;
         if (active[RPW - 1]) {
           Partial a[RPW];
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) partial_begin(a[r], acc + ((size_t)r * ng + gsafe) * 4, lane_used);
           rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log);
-          fold_partials<RPW, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
+          if (!(p.debug & 2)) fold_partials<RPW, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
+          else if (a[0].s0 == 1.2345e-300) acc[0] = a[0].s0 + a[RPW - 1].mn + a[0].mx + a[RPW - 1].s0 + a[0].upd;
         } else {
           Partial a[1];
           const bool il[1] = {is_log[0]};
+          partial_begin(a[0], acc + (size_t)gsafe * 4, lane_used);
           rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il);
           fold_partials<1, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
         }
@@ -1117,6 +990,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.wn = d_wn;
   rp.dwn = d_dwn;
   trans_const_init(&rp.tc, kd);
+  if (const char* e = getenv("ECCKD_DEBUG")) rp.debug = atoi(e);
   // wavenumber windows: the per-wavenumber data a group re-reads (wavenumber grids or weight vector,
   // plan records: ~20 B per wavenumber) should stay in L2 between groups; 24 MB per window does
   int nwin = 1;
@@ -1162,7 +1036,10 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   void* d_temp = nullptr;
   if (wmode == W_PLANCK) {
     ECCKD_TRY(ws_reserve(ctx, 3, (size_t)n_temperature * sizeof(double), &d_temp));
-    ECCKD_TRY(upload_small(ctx, d_temp, h_temperature, (size_t)n_temperature * sizeof(double)));
+    // the kernel wants (h/k)/T per weight row (planck_function.cpp:31-33,50)
+    std::vector<double> hkt((size_t)n_temperature);
+    for (int i = 0; i < n_temperature; ++i) hkt[i] = (6.62606896e-34 / 1.3806504e-23) / h_temperature[i];
+    ECCKD_TRY(upload_small(ctx, d_temp, hkt.data(), (size_t)n_temperature * sizeof(double)));
   }
   rp.groups = static_cast<const GroupDesc*>(d_groups);
   rp.temperature = static_cast<const double*>(d_temp);

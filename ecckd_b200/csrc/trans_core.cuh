@@ -95,6 +95,41 @@ __device__ __forceinline__ double trans_one_minus_exp(double tau, const TransCon
   return fma(-T, p, om);
 }
 
+// The same in three phases, so that a caller evaluating several values can run phase 1 for all
+// of them, then all the shuffles (one convergence check), then phase 3: with the single-call form
+// ptxas serialises the first value's polynomial in front of the shuffle block.
+struct TransMid {
+  double rho;
+  int n;
+};
+__device__ __forceinline__ TransMid trans_phase1(double tau, const TransConst& K) {
+  const double magic = 6755399441055744.0;
+  const double tc = __hiloint2double(min(__double2hiint(tau), K.hi_max), __double2loint(tau));
+  const double t = fma(tc, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma(t - magic, K.b, tc);
+  return m;
+}
+__device__ __forceinline__ double trans_phase2(const TransMid& m, const TransLane& tl) {
+#ifdef ECCKD_UBENCH_NOSHFL  // timing experiment only (tools/ubench): no table look-up
+  return __hiloint2double(tl.hi_adj + (m.n << 15), tl.lo);
+#endif
+  const int thi = __shfl_sync(0xffffffffu, tl.hi_adj, m.n);
+  const int tlo = __shfl_sync(0xffffffffu, tl.lo, m.n);
+  return __hiloint2double(thi + (m.n << 15), tlo);
+}
+__device__ __forceinline__ double trans_phase3(const TransMid& m, const double T, const TransConst& K) {
+  double q = K.c[5];
+  q = fma(q, m.rho, K.c[4]);
+  q = fma(q, m.rho, K.c[3]);
+  q = fma(q, m.rho, K.c[2]);
+  q = fma(q, m.rho, K.c[1]);
+  q = fma(q, m.rho, K.c[0]);
+  // 1 - T*(1 + p): two FMAs; absolute error ~1e-16 like the reference's 1 - exp()
+  return fma(-T, fma(q, m.rho, 1.0), 1.0);
+}
+
 // exp(x) for 0 <= x < 708 with the same table: x = (32 k + j) ln2/32 + r (two-constant
 // Cody-Waite reduction), exp(x) = 2^k 2^(j/32) (1 + p(r)).  Below 1 ulp; used for the Planck weights.
 __device__ __forceinline__ double exp_table(double x, const TransLane& tl) {
