@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--log2-nwav", type=int, default=23)
     ap.add_argument("--nspec", type=int, default=19)
     ap.add_argument("--nlay", type=int, default=53)
-    ap.add_argument("--gmap", default="ranked", choices=["ranked", "random"],
+    ap.add_argument("--gmap", default="ranked", choices=["ranked", "random", "bands"],
                     help="ranked: g points from ranking a smooth synthetic spectrum (as find_g_points does); "
                          "random: no spectral coherence at all (adversarial)")
     ap.add_argument("--weights", default="planck", choices=["planck", "matrix"])
@@ -164,7 +164,9 @@ def make_g_point(torch, wn, key, mode, seed):
             m = (wn >= edges[b]) & (wn <= edges[b + 1])
         idx = torch.nonzero(m).flatten()
         n = idx.numel()
-        if n > 0:
+        if n > 0 and mode == "bands":  # one g point per band: a single lane segment per round (diagnostic)
+            g[idx] = g0
+        elif n > 0:
             order = torch.argsort(key[idx], stable=True)
             frac = (torch.arange(n, device=wn.device, dtype=torch.float64) + 0.5) / n
             gb = torch.bucketize(frac, torch.tensor(cuts, device=wn.device)).to(torch.int32) + g0

@@ -42,43 +42,44 @@ namespace ecckd {
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
   return static_cast<unsigned>(__cvta_generic_to_shared(p));
 }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+// The mbarrier / bulk-copy helpers take shared-window byte addresses (smem_u32 of the dynamic
+// shared-memory base, computed once per thread, plus an offset): converting a generic pointer at
+// every call costs an S2R of the CTA-in-cluster id each time.
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
-  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(smem_u32(bar)),
-               "r"(bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(bar), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra.uni WAIT_DONE;\n\t"
       "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "WAIT_DONE:\n\t}\n" ::"r"(bar),
       "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning
       : "memory");
 }
 // 1-D bulk asynchronous copy global -> shared (SASS: UBLKCP), completion on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gmem_src), "r"(bytes), "r"(bar)
                : "memory");
 }
 // the same with an L2 cache policy (optical depths are read once: evict-first keeps the
 // per-wavenumber data that every group re-reads resident in L2)
-__device__ __forceinline__ void bulk_g2s_hint(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar,
+__device__ __forceinline__ void bulk_g2s_hint(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned bar,
                                               uint64_t policy) {
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;\n" ::
-          "r"(smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+          "r"(smem_dst),
+      "l"(gmem_src), "r"(bytes), "r"(bar), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
@@ -373,18 +374,19 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   const int lane = threadIdx.x & 31;
   const int nw = p.nw, ng = p.ng;
   const SmemLayout L = smem_layout(nw, ng);
-  uint64_t* full_d = reinterpret_cast<uint64_t*>(smem_raw + L.bars);  // [nw][NSETS*RPW]
-  uint64_t* full_w = full_d + nw * NSETS * RPW;                       // [NSW]
-  uint64_t* empty_w = full_w + NSW;                                   // [NSW]
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned full_d = sbase + L.bars;                // mbarriers [nw][NSETS*RPW], 8 bytes each
+  const unsigned full_w = full_d + nw * NSETS * RPW * 8; // [NSW]
+  const unsigned empty_w = full_w + NSW * 8;             // [NSW]
   unsigned char* ring = smem_raw + L.ring;
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   constexpr bool USES_TAU = (FKIND != F_NONE);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nw * NSETS * RPW; ++i) mbar_init(&full_d[i], 1);
+    for (int i = 0; i < nw * NSETS * RPW; ++i) mbar_init(full_d + i * 8, 1);
     for (int i = 0; i < NSW; ++i) {
-      mbar_init(&full_w[i], NPW);
-      mbar_init(&empty_w[i], nw);
+      mbar_init(full_w + i * 8, NPW);
+      mbar_init(empty_w + i * 8, nw);
     }
     fence_mbar_init();
   }
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       }
       unsigned char* slot = ring + ws * RING_SLOT_BYTES;
       double* wperm = reinterpret_cast<double*>(slot);
-      if (filled >= NSW) mbar_wait(&empty_w[ws], epar);
+      if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
 #pragma unroll
       for (int m = 0; m < PER; ++m) {
         const int k = pw + NPW * m;
@@ -492,11 +494,13 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       __syncwarp();
       if (lane == 0) {
         if (pw == 0) {
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&full_w[ws], (unsigned)sizeof(PlanRound));
-          bulk_g2s(slot + WPERM_BYTES, p.rounds + e0.r, (unsigned)sizeof(PlanRound), &full_w[ws]);
+          // (no proxy fence: the consumers only READ the old record through the generic proxy, and
+          // their release of the slot is ordered before this copy by the empty barrier)
+          mbar_arrive_expect_tx(full_w + ws * 8, (unsigned)sizeof(PlanRound));
+          bulk_g2s(sbase + L.ring + ws * RING_SLOT_BYTES + WPERM_BYTES, p.rounds + e0.r, (unsigned)sizeof(PlanRound),
+                   full_w + ws * 8);
         } else {
-          mbar_arrive(&full_w[ws]);
+          mbar_arrive(full_w + ws * 8);
         }
       }
       ++filled;
@@ -522,7 +526,8 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE_BYTES;
   double* acc = reinterpret_cast<double*>(smem_raw + L.acc) + (size_t)warp * RPW * ng * 4;
   int32_t* accz = reinterpret_cast<int32_t*>(smem_raw + L.accz) + (size_t)warp * RPW * ng;
-  uint64_t* my_full = full_d + warp * NSETS * RPW;
+  const unsigned my_full = full_d + warp * NSETS * RPW * 8;
+  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * STAGE_BYTES;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const uint64_t pol = policy_evict_first();
   // the weight sums do not depend on the row: the last consumer warp (the one with the fewest rows)
@@ -540,7 +545,10 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     }
     __syncwarp();
   };
+  PendingFold pend;
+  pend.valid = false;
   auto flush_partial = [&](int vg) {
+    pending_finish(pend, 0, acc, ng);  // the last round's sums are still parked
     __syncwarp();
     const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (nw * RPW) + warp * RPW;
     double* out = p.partial + slot * ng * 4;
@@ -570,9 +578,9 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
         if (bulk_i[r]) {
-          uint64_t* bar = &my_full[set * RPW + r];
+          const unsigned bar = my_full + (set * RPW + r) * 8;
           mbar_arrive_expect_tx(bar, (unsigned)(n_c * 8));
-          bulk_g2s_hint(data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
+          bulk_g2s_hint(my_data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
         }
       }
     }
@@ -609,7 +617,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     for (int r = 0; r < RPW; ++r) {
       const int st = set * RPW + r;
       if (bulk_row[r] && ((n_c & 1) == 0)) {
-        mbar_wait(&my_full[st], (phase_bits >> st) & 1u);
+        mbar_wait(my_full + st * 8, (phase_bits >> st) & 1u);
         phase_bits ^= 1u << st;
       } else if (active[r]) {
         const double* src = od_c[r] + (int64_t)q.c * ch;
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     __syncwarp();
     bool last_round = false;
     while (!last_round) {
-      mbar_wait(&full_w[ws], wpar);
+      mbar_wait(full_w + ws * 8, wpar);
       const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
       const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
       const double* wp = reinterpret_cast<const double*>(slot) + lane;
@@ -647,28 +655,50 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
           Partial a[RPW];
 #pragma unroll
           for (int r = 0; r < RPW; ++r) partial_begin(a[r], acc + ((size_t)r * ng + gsafe) * 4, lane_used);
-          rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log);
-          if (!(p.debug & 2)) fold_partials<RPW, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
-          else if (a[0].s0 == 1.2345e-300) acc[0] = a[0].s0 + a[RPW - 1].mn + a[0].mx + a[RPW - 1].s0 + a[0].upd;
+          if (LOGKIND) {
+            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log);
+            fold_partials<RPW, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
+          } else {
+            // the sums of the previous round are reduced inside this round's slot loop
+            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, &pend);
+            pending_finish(pend, SLOTS / 4, acc, ng);
+            fold_partials<RPW, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
+#pragma unroll
+            for (int r = 0; r < RPW; ++r) pend.s0[r] = a[r].s0;
+            pend.meta = meta;
+            pend.nsteps = nsteps;
+            pend.valid = true;
+          }
         } else {
           Partial a[1];
           const bool il[1] = {is_log[0]};
           partial_begin(a[0], acc + (size_t)gsafe * 4, lane_used);
-          rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il);
-          fold_partials<1, true, LOGKIND, true, LOGKIND>(a, meta, nsteps, acc, accz, ng);
+          if (LOGKIND) {
+            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il);
+            fold_partials<1, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
+          } else {
+            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, &pend);
+            pending_finish(pend, SLOTS / 4, acc, ng);
+            fold_partials<1, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
+            pend.s0[0] = a[0].s0;
+#pragma unroll
+            for (int r = 1; r < RPW; ++r) pend.s0[r] = 0.0;
+            pend.meta = meta;
+            pend.nsteps = nsteps;
+            pend.valid = true;
+          }
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_w[ws]);
+      if (lane == 0) mbar_arrive(empty_w + ws * 8);
       if (++ws == NSW) {
         ws = 0;
         wpar ^= 1u;
       }
     }
-    if (k + NSETS < niter) {
-      fence_proxy_async();  // the stage was read through the generic proxy; the next copy writes it asynchronously
-      issue(set);
-    }
+    // re-arm the set for the visit after next.  No proxy fence: the stage was only READ through the
+    // generic proxy, and those loads completed before the __syncwarp above (their values were used).
+    if (k + NSETS < niter) issue(set);
     if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
       flush_partial(vg);
       ++vg;

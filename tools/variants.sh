@@ -1,5 +1,4 @@
 run() { echo "== $ECCKD_DEBUG $*"; timeout 300 python bench.py --steps 3 --warmup 3 --log2-nwav 20 --no-e2e --no-cpu --no-flux "$@" 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('%.1f G/s  kernel_ms %.3f frac %.3f' % (d['value']/1e9, d['roofline']['kernel_ms'], d['roofline']['frac']))"; }
 run
 run --weights matrix
-run --method linear --weights matrix
-ECCKD_DEBUG=2 run --weights matrix
+run --gmap bands --weights matrix
