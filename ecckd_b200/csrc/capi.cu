@@ -145,6 +145,7 @@ ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
     cudaEventDestroy(ev.second);
   }
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return ECCKD_OK;

@@ -43,6 +43,7 @@ struct ecckd_ctx {
   ecckd::Workspace ws[8];   // device scratch slots (0-3 kernels' descriptors/partials, 4-5 host-API staging)
   bool timing = false;      // record CUDA events around the streaming reduction kernel
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> reduce_events;
+  cudaStream_t copy_stream = nullptr;  // host-buffer entry points: H2D copies overlapped with the kernels
   void* pinned = nullptr;   // small pinned staging buffer for descriptor uploads
   size_t pinned_bytes = 0;
   size_t pinned_off = 0;    // bump offset; wraps after a stream synchronise

@@ -122,8 +122,8 @@ __global__ void ckd_od_kernel(GasDev gs, int nt, int np, int ng, double log_p_0,
                               const double* __restrict__ temperature, int ncol, int nlay,
                               const double* __restrict__ pressure_hl, const double* __restrict__ temperature_fl,
                               double* __restrict__ od, int accumulate) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t cl = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;  // grid.x runs over rows (no 65535 limit), grid.y over g
+  const int64_t cl = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   if (g >= ng || cl >= (int64_t)ncol * nlay) return;
   const int icol = (int)(cl / nlay), ip = (int)(cl - (int64_t)icol * nlay);
   const double p0 = pressure_hl[(int64_t)icol * (nlay + 1) + ip];
@@ -142,16 +142,16 @@ __global__ void clamp_zero_kernel(int64_t n, double* __restrict__ x) {
 
 __global__ void ckd_planck_kernel(int nlut, int ng, double t0, double d_t, const double* __restrict__ lut, int64_t n,
                                   const double* __restrict__ temperature, double* __restrict__ planck) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   if (g >= ng || i >= n) return;
   planck[i * ng + g] = planck_interp(temperature[i], t0, d_t, nlut, ng, g, lut);
 }
 
 __global__ void rayleigh_od_kernel(int ncol, int nlay, int ng, const double* __restrict__ pressure_hl,
                                    const double* __restrict__ molar_scat, double* __restrict__ od) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t cl = (int64_t)blockIdx.y * blockDim.y + threadIdx.y;
+  const int g = blockIdx.y * blockDim.x + threadIdx.x;  // grid.x runs over rows (no 65535 limit), grid.y over g
+  const int64_t cl = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
   if (g >= ng || cl >= (int64_t)ncol * nlay) return;
   const int icol = (int)(cl / nlay), ip = (int)(cl - (int64_t)icol * nlay);
   const double dp = pressure_hl[(int64_t)icol * (nlay + 1) + ip + 1] - pressure_hl[(int64_t)icol * (nlay + 1) + ip];
@@ -169,13 +169,18 @@ __global__ void temperature_fl_kernel(int ncol, int nlay, const double* __restri
   t_fl[cl] = (t[i] * p[i] + t[i + 1] * p[i + 1]) / (p[i] + p[i + 1]);  // run_ckd.cpp:119-122
 }
 
-// radiative_transfer_lw.cpp:36-59; thread = (column, spectral index)
+// radiative_transfer_lw.cpp:36-59; thread = (column, spectral index), one warp-wide block per
+// 32 spectral points of a column so that 32 blocks (1024 independent recurrences, ~64 KB of loads in
+// flight) are resident per SM.  The upward sweep re-reads optical depth and Planck function: parking
+// the per-layer terms in shared memory instead was measured at half the speed (27 KB per warp leaves
+// 8 warps per SM, too few loads in flight), see profiles/README.md.
 __global__ void rt_lw_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ planck,
                              const double* __restrict__ od, const double* __restrict__ surf_emissivity,
                              const double* __restrict__ surf_planck, double* __restrict__ flux_dn,
                              double* __restrict__ flux_up) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int icol = blockIdx.y;
+  const unsigned nchunk = (unsigned)((n + blockDim.x - 1) / blockDim.x);  // 1-D grid: block = (column, spectral chunk)
+  const int icol = (int)(blockIdx.x / nchunk);
+  const int64_t i = (int64_t)(blockIdx.x - (unsigned)icol * nchunk) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double* pl = planck + (int64_t)icol * (nlay + 1) * n + i;
   const double* tau = od + (int64_t)icol * nlay * n + i;
@@ -213,8 +218,9 @@ __global__ void rt_sw_kernel(int ncol, int nlay, int64_t n, const double* __rest
                              const double* __restrict__ ssi, const double* __restrict__ od,
                              const double* __restrict__ albedo, double* __restrict__ flux_dn,
                              double* __restrict__ flux_up) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int icol = blockIdx.y;
+  const unsigned nchunk = (unsigned)((n + blockDim.x - 1) / blockDim.x);
+  const int icol = (int)(blockIdx.x / nchunk);
+  const int64_t i = (int64_t)(blockIdx.x - (unsigned)icol * nchunk) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double mu0 = cos_sza[icol];
   const double minus_sec_sza = -1.0 / mu0;
@@ -243,8 +249,9 @@ __global__ void rt_sw_kernel(int ncol, int nlay, int64_t n, const double* __rest
 __global__ void heating_rate_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ pressure_hl,
                                     const double* __restrict__ flux_dn, const double* __restrict__ flux_up,
                                     double* __restrict__ hr) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t cl = blockIdx.y;
+  const unsigned nchunk = (unsigned)((n + blockDim.x - 1) / blockDim.x);
+  const int64_t cl = blockIdx.x / nchunk;
+  const int64_t i = (int64_t)(blockIdx.x - (unsigned)cl * nchunk) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int icol = (int)(cl / nlay), l = (int)(cl - (int64_t)icol * nlay);
   const double* p = pressure_hl + (int64_t)icol * (nlay + 1);
@@ -532,7 +539,7 @@ ECCKD_API int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* 
   ECCKD_TRY(check_vmr(m, igas, d_vmr_fl));
   const dim3 block = g_block(m->ng);
   const int64_t ncl = (int64_t)ncol * nlay;
-  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((ncl + block.y - 1) / block.y));
+  const dim3 grid((unsigned)((ncl + block.y - 1) / block.y), (m->ng + block.x - 1) / block.x);
   ckd_od_kernel<<<grid, block, 0, ctx->stream>>>(make_gasdev(m, igas, d_vmr_fl), m->nt, m->np, m->ng, m->log_p_0,
                                                  m->d_log_p, m->d_t, m->d_temperature, ncol, nlay, d_pressure_hl,
                                                  d_temperature_fl, d_od, accumulate);
@@ -546,7 +553,7 @@ ECCKD_API int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model
                 "ecckd_ckd_calc_planck_function: bad argument");
   ECCKD_REQUIRE(!m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_planck_function: shortwave model has no Planck table");
   const dim3 block = g_block(m->ng);
-  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((n + block.y - 1) / block.y));
+  const dim3 grid((unsigned)((n + block.y - 1) / block.y), (m->ng + block.x - 1) / block.x);
   ckd_planck_kernel<<<grid, block, 0, ctx->stream>>>(m->nlut, m->ng, m->planck_t0, m->planck_dt, m->d_planck_lut, n,
                                                      d_temperature, d_planck);
   ECCKD_LAUNCH_CHECK(ctx);
@@ -560,7 +567,7 @@ ECCKD_API int ecckd_ckd_calc_rayleigh_optical_depth_dev(ecckd_ctx* ctx, ecckd_ck
   ECCKD_REQUIRE(m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_rayleigh_optical_depth: longwave model");
   const dim3 block = g_block(m->ng);
   const int64_t ncl = (int64_t)ncol * nlay;
-  const dim3 grid((m->ng + block.x - 1) / block.x, (unsigned)((ncl + block.y - 1) / block.y));
+  const dim3 grid((unsigned)((ncl + block.y - 1) / block.y), (m->ng + block.x - 1) / block.x);
   rayleigh_od_kernel<<<grid, block, 0, ctx->stream>>>(ncol, nlay, m->ng, d_pressure_hl, m->d_rayleigh, d_od);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
@@ -571,11 +578,12 @@ ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay
                                               const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
   ECCKD_REQUIRE(ctx && d_planck && d_od && d_surf_emissivity && d_surf_planck && d_flux_dn && d_flux_up,
                 ECCKD_PARAMETER_ERROR, "ecckd_radiative_transfer_lw: NULL argument");
-  ECCKD_REQUIRE(ncol > 0 && ncol <= 65535 && nlay > 0 && n > 0, ECCKD_PARAMETER_ERROR,
-                "ecckd_radiative_transfer_lw: bad dimensions");
   const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
-  rt_lw_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol), bs, 0, ctx->stream>>>(
-      ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck, d_flux_dn, d_flux_up);
+  const int64_t nblk = (int64_t)ncol * ((n + bs - 1) / bs);
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && nblk < 2147483647LL, ECCKD_PARAMETER_ERROR,
+                "ecckd_radiative_transfer_lw: bad dimensions");
+  rt_lw_kernel<<<(unsigned)nblk, bs, 0, ctx->stream>>>(ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck,
+                                                       d_flux_dn, d_flux_up);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
@@ -587,13 +595,13 @@ ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay
                 "ecckd_radiative_transfer_sw: NULL argument");
   ECCKD_REQUIRE((d_albedo == nullptr) == (d_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
                 "ecckd_radiative_transfer_sw: albedo and flux_up must both be given or both be NULL");
-  ECCKD_REQUIRE(ncol > 0 && ncol <= 65535 && nlay > 0 && n > 0, ECCKD_PARAMETER_ERROR,
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && (int64_t)ncol * ((n + 31) / 32) < 2147483647LL, ECCKD_PARAMETER_ERROR,
                 "ecckd_radiative_transfer_sw: bad dimensions");
   void* d_mu = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 3, (size_t)ncol * sizeof(double), &d_mu));
   ECCKD_TRY(upload_small(ctx, d_mu, h_cos_sza, (size_t)ncol * sizeof(double)));
   const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
-  rt_sw_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol), bs, 0, ctx->stream>>>(
+  rt_sw_kernel<<<(unsigned)((int64_t)ncol * ((n + bs - 1) / bs)), bs, 0, ctx->stream>>>(
       ncol, nlay, n, static_cast<const double*>(d_mu), d_ssi, d_od, d_albedo, d_flux_dn, d_flux_up);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
@@ -602,10 +610,11 @@ ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay
 ECCKD_API int ecckd_heating_rate_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_pressure_hl,
                                      const double* d_flux_dn, const double* d_flux_up, double* d_hr) {
   ECCKD_REQUIRE(ctx && d_pressure_hl && d_flux_dn && d_hr, ECCKD_PARAMETER_ERROR, "ecckd_heating_rate: NULL argument");
-  ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && (int64_t)ncol * nlay <= 65535, ECCKD_PARAMETER_ERROR,
-                "ecckd_heating_rate: bad dimensions (ncol*nlay must be <= 65535)");
   const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
-  heating_rate_kernel<<<dim3((unsigned)((n + bs - 1) / bs), ncol * nlay), bs, 0, ctx->stream>>>(
+  const int64_t nblk = (int64_t)ncol * nlay * ((n + bs - 1) / bs);
+  ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && nblk < 2147483647LL, ECCKD_PARAMETER_ERROR,
+                "ecckd_heating_rate: bad dimensions");
+  heating_rate_kernel<<<(unsigned)nblk, bs, 0, ctx->stream>>>(
       ncol, nlay, n, d_pressure_hl, d_flux_dn, d_flux_up, d_hr);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;

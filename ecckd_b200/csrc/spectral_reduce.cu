@@ -1187,11 +1187,15 @@ static int resolve_weights(const ecckd_gpoint_plan* plan, int weight_mode, const
 using namespace ecckd;
 
 // ------------------------------------------------------------------ C ABI
+// Plan buffers come from the stream-ordered allocator: cudaMalloc/cudaFree synchronise the whole
+// device, which would serialise a plan built on the compute stream with the host-to-device copies
+// the host-buffer entry points run concurrently on their copy stream.
 static void plan_free(ecckd_gpoint_plan* p) {
-  cudaFree(p->d_round_off);
-  cudaFree(p->d_rounds);
-  cudaFree(p->d_count);
-  cudaFree(p->d_scratch);
+  cudaStream_t st = p->ctx ? p->ctx->stream : nullptr;
+  if (p->d_round_off) cudaFreeAsync(p->d_round_off, st);
+  if (p->d_rounds) cudaFreeAsync(p->d_rounds, st);
+  if (p->d_count) cudaFreeAsync(p->d_count, st);
+  if (p->d_scratch) cudaFreeAsync(p->d_scratch, st);
   delete p;
 }
 
@@ -1214,9 +1218,9 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   const int64_t max_chunks = (nwav + 255) / 256;
   ECCKD_REQUIRE(max_chunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
   uint32_t* d_nrounds = nullptr;
-  cudaError_t e = cudaMalloc(&p->d_round_off, (size_t)(max_chunks + 1) * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_nrounds, (size_t)max_chunks * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_count, (size_t)ng * sizeof(unsigned long long));
+  cudaError_t e = cudaMallocAsync(&p->d_round_off, (size_t)(max_chunks + 1) * sizeof(uint32_t), ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_nrounds, (size_t)max_chunks * sizeof(uint32_t), ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&p->d_count, (size_t)ng * sizeof(unsigned long long), ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_count, 0, (size_t)ng * sizeof(unsigned long long), ctx->stream);
   uint32_t total = 0;
   std::vector<unsigned long long> cnt(ng);
@@ -1236,7 +1240,7 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   };
   if (e == cudaSuccess && best_ch == 0) {
     double best_cost = 0.0;
-    for (int ch : candidates) {
+    for (const int& ch : candidates) {
       uint32_t tot = 0;
       e = count_rounds(ch, false, &tot);
       if (e != cudaSuccess) break;
@@ -1245,7 +1249,11 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
         best_ch = ch;
         best_cost = cost;
       }
-      if ((int64_t)tot == (nwav + ch - 1) / ch) break;  // one round per chunk: shorter chunks cannot win
+      // the next (shorter) candidate needs at least one round per chunk: stop when that cannot win
+      const size_t idx = (size_t)(&ch - candidates);
+      if (idx + 1 < sizeof(candidates) / sizeof(candidates[0]) &&
+          (double)tot <= 0.995 * (double)((nwav + candidates[idx + 1] - 1) / candidates[idx + 1]))
+        break;
     }
   }
   if (e == cudaSuccess) {
@@ -1260,7 +1268,7 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   if (e == cudaSuccess) {
     p->nrounds = total;
     const size_t nr = std::max<size_t>(1, total);
-    e = cudaMalloc(&p->d_rounds, (nr + 1) * sizeof(PlanRound));
+    e = cudaMallocAsync(&p->d_rounds, (nr + 1) * sizeof(PlanRound), ctx->stream);
     if (e == cudaSuccess) {
       plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds);
       plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
@@ -1270,7 +1278,7 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller
   }
-  cudaFree(d_nrounds);
+  if (d_nrounds) cudaFreeAsync(d_nrounds, ctx->stream);
   if (e != cudaSuccess) {
     set_error("ecckd_gpoint_plan_create: %s", cudaGetErrorString(e));
     plan_free(p);
@@ -1398,11 +1406,10 @@ ECCKD_API int ecckd_average_optical_depth_batch_dev(
   // partial sums live in the plan-independent scratch slot 3 tail; sized [nrows][ng][NSUM + NMINMAX]
   const size_t nrg = (size_t)nspec * nlay * plan->ng;
   if (plan->scratch_bytes < nrg * (NSUM + NMINMAX) * sizeof(double)) {
-    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(plan->d_scratch);
+    if (plan->d_scratch) ECCKD_CUDA_OK(cudaFreeAsync(plan->d_scratch, ctx->stream));
     plan->d_scratch = nullptr;
     plan->scratch_bytes = 0;
-    ECCKD_CUDA_OK(cudaMalloc(&plan->d_scratch, nrg * (NSUM + NMINMAX) * sizeof(double)));
+    ECCKD_CUDA_OK(cudaMallocAsync(&plan->d_scratch, nrg * (NSUM + NMINMAX) * sizeof(double), ctx->stream));
     plan->scratch_bytes = nrg * (NSUM + NMINMAX) * sizeof(double);
   }
   double* d_sums = plan->d_scratch;
@@ -1465,30 +1472,62 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   ECCKD_TRY(ws_reserve(ctx, 5, (size_t)(nwav + ng) * sizeof(int32_t), &iarena));
   int32_t* d_g = static_cast<int32_t*>(iarena);
   int32_t* d_warn = d_g + nwav;
-  ECCKD_CUDA_OK(cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  ECCKD_CUDA_OK(cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), st));
-  ECCKD_CUDA_OK(cudaMemcpy2DAsync(d_od, dstride * sizeof(double), optical_depth, od_stride * sizeof(double),
-                                  nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st));
-  if (fused) {
-    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
-    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
-  } else if (vecw) {
-    ECCKD_CUDA_OK(cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, st));
-  } else {
-    ECCKD_CUDA_OK(cudaMemcpy2DAsync(d_w, dstride * sizeof(double), planck_fl, planck_stride * sizeof(double),
-                                    nwav * sizeof(double), nlay, cudaMemcpyHostToDevice, st));
-  }
-  ecckd_gpoint_plan* plan = nullptr;
-  ECCKD_TRY(ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan));
-  const bool mm = min_molar_abs && max_molar_abs;
-  int rc = ecckd_average_optical_depth_to_g_point_dev(
-      ctx, plan, reference_surface_vmr, nlay, pressure_fl, pressure_hl, d_od, dstride,
-      fused ? ECCKD_WEIGHT_PLANCK : (vecw ? ECCKD_WEIGHT_VECTOR : ECCKD_WEIGHT_MATRIX), fused ? nullptr : d_w,
-      (fused || vecw) ? 0 : dstride, fused ? temperature_fl : nullptr, fused ? d_w : nullptr,
-      fused ? d_w + dstride : nullptr, method, d_out, mm ? d_out + out_elems : nullptr,
-      mm ? d_out + 2 * out_elems : nullptr, ng, d_warn);
+  // Layers are independent, so the optical depths (and a weight matrix) go up in slabs of layers on a
+  // second stream while the slabs already there are reduced: the call costs the PCIe transfer plus one
+  // slab's reduction instead of transfer + plan + reduction in sequence.
+  if (!ctx->copy_stream) ECCKD_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  cudaStream_t cs = ctx->copy_stream;
+  ECCKD_CUDA_OK(cudaStreamSynchronize(st));  // the staging arena may still be read by earlier work on st
+  const int nslab = std::min(nlay, 8);
+  std::vector<cudaEvent_t> ready(nslab, nullptr);
   cudaError_t e = cudaSuccess;
-  if (rc == ECCKD_OK) {
+  for (int s = 0; s < nslab && e == cudaSuccess; ++s) {
+    const int l0 = (int)(((int64_t)nlay * s) / nslab), l1 = (int)(((int64_t)nlay * (s + 1)) / nslab);
+    e = cudaMemcpy2DAsync(d_od + (size_t)l0 * dstride, dstride * sizeof(double), optical_depth + (size_t)l0 * od_stride,
+                          od_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess && !fused && !vecw)
+      e = cudaMemcpy2DAsync(d_w + (size_t)l0 * dstride, dstride * sizeof(double), planck_fl + (size_t)l0 * planck_stride,
+                            planck_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[s], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(ready[s], cs);
+  }
+  auto drop_events = [&]() {
+    for (cudaEvent_t ev : ready)
+      if (ev) cudaEventDestroy(ev);
+  };
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(cs);
+    drop_events();
+    set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  // small per-wavenumber inputs and the plan on the compute stream, concurrently with the slabs
+  int rc = ECCKD_OK;
+  ecckd_gpoint_plan* plan = nullptr;
+  e = cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), st);
+  if (e == cudaSuccess && fused) {
+    e = cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
+  } else if (e == cudaSuccess && vecw) {
+    e = cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess) rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
+  const bool mm = min_molar_abs && max_molar_abs;
+  for (int s = 0; s < nslab && e == cudaSuccess && rc == ECCKD_OK; ++s) {
+    const int l0 = (int)(((int64_t)nlay * s) / nslab), l1 = (int)(((int64_t)nlay * (s + 1)) / nslab);
+    e = cudaStreamWaitEvent(st, ready[s], 0);
+    if (e != cudaSuccess) break;
+    rc = ecckd_average_optical_depth_to_g_point_dev(
+        ctx, plan, reference_surface_vmr, l1 - l0, pressure_fl + l0, pressure_hl + l0, d_od + (size_t)l0 * dstride, dstride,
+        fused ? ECCKD_WEIGHT_PLANCK : (vecw ? ECCKD_WEIGHT_VECTOR : ECCKD_WEIGHT_MATRIX),
+        fused ? nullptr : (vecw ? d_w : d_w + (size_t)l0 * dstride), (fused || vecw) ? 0 : dstride,
+        fused ? temperature_fl + l0 : nullptr, fused ? d_w : nullptr, fused ? d_w + dstride : nullptr, method,
+        d_out + (size_t)l0 * ng, mm ? d_out + out_elems + (size_t)l0 * ng : nullptr,
+        mm ? d_out + 2 * out_elems + (size_t)l0 * ng : nullptr, ng, d_warn);
+  }
+  if (rc == ECCKD_OK && e == cudaSuccess) {
     e = cudaMemcpy2DAsync(molar_abs, out_stride * sizeof(double), d_out, ng * sizeof(double), ng * sizeof(double), nlay,
                           cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess && mm) {
@@ -1501,6 +1540,8 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     if (e == cudaSuccess && warn)
       e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   }
+  cudaStreamSynchronize(cs);
+  drop_events();
   const cudaError_t e2 = cudaStreamSynchronize(st);
   ecckd_gpoint_plan_destroy(plan);
   if (rc != ECCKD_OK) return rc;
