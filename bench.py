@@ -361,6 +361,15 @@ def main():
         alg_bytes = nspec * nlay * nwav * 8 + nlay * nwav * 8 + nwav * 4
     k_ms = float(kstat.item())
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None  # DRAM bytes of one launch from the committed ncu capture, if it is of this workload
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "reduce_traffic.json")))
+        w = t["workload"]
+        if (w["nspec"], w["nlay"], w["log2_nwav"], w["method"], w["weights"], w["gmap"]) == (
+                nspec, nlay, args.log2_nwav, args.method, args.weights, args.gmap):
+            traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     peak, peak_src = measured_peak_gbs()
 
     # ---- end to end through the reference-facing host call (one block per step)
@@ -428,7 +437,7 @@ def main():
                 "reduce_partial_bytes_allreduced_per_step": int(sums.numel() * 8 + minmax.numel() * 8) if world > 1 else 0,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "reduce_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                         "traffic": traffic, "kernel": "reduce_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes)},
             "cpu_baseline": cpu,
             "e2e": e2e,

@@ -74,6 +74,7 @@ def _declare(L):
         "ecckd_host_free_pinned": [vp],
         "ecckd_memcpy_h2d": [vp, vp, vp, sz],
         "ecckd_memcpy_d2h": [vp, vp, vp, sz],
+        "ecckd_debug_eval": [vp, i32, dbl, i64, vp, vp],
         "ecckd_planck_function_dev": [vp, i32, vp, i64, vp, vp, vp, i64],
         "ecckd_planck_function": [vp, i32, vp, i64, vp, vp, vp, i64],
         "ecckd_gpoint_plan_create": [vp, vp, i64, i32, c_void_pp],

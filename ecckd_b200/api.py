@@ -159,6 +159,14 @@ def planck_function(ctx: Context, temperature, wavenumber_cm_1, d_wavenumber_cm_
     return out
 
 
+def debug_eval(ctx: Context, which: int, kd: float, x) -> np.ndarray:
+    """ecckd_debug_eval: the kernels' 1 - exp(-kd*x) (which=0) or Planck weight at T=kd, nu=x, dnu=1 (which=1)."""
+    xa, xp = _h(x)
+    out = np.empty_like(xa)
+    check(_lib.lib().ecckd_debug_eval(ctx.handle, int(which), float(kd), xa.size, xp, out.ctypes.data))
+    return out
+
+
 def planck_function_dev(ctx: Context, temperature, d_wavenumber, d_d_wavenumber, nwav: int, d_ans, ans_stride=None):
     t, tp = _h(temperature)
     check(_lib.lib().ecckd_planck_function_dev(ctx.handle, t.size, tp, nwav, _ptr(d_wavenumber), _ptr(d_d_wavenumber),

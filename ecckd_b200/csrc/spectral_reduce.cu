@@ -1289,6 +1289,44 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   return ECCKD_OK;
 }
 
+namespace ecckd {
+__global__ void debug_eval_kernel(int which, TransConst K, double kd, int64_t n, const double* __restrict__ x,
+                                  double* __restrict__ out) {
+  const TransLane tl = trans_lane_init();
+  // whole warps stay in the loop (the evaluations shuffle): pad with a harmless argument
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const double v = i < n ? x[i] : 1.0;
+    const double r = which == 0 ? trans_one_minus_exp(v, K, tl)
+                                : planck_elem_fast((6.62606896e-34 / 1.3806504e-23) / kd, v, 1.0, tl);
+    if (i < n) out[i] = r;
+  }
+}
+}  // namespace ecckd
+
+ECCKD_API int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, const double* x, double* out) {
+  ECCKD_REQUIRE(ctx && x && out && n > 0 && (which == 0 || which == 1) && kd > 0.0, ECCKD_PARAMETER_ERROR,
+                "ecckd_debug_eval: bad argument");
+  double* d = nullptr;
+  ECCKD_CUDA_OK(cudaMalloc(&d, (size_t)2 * n * sizeof(double)));
+  TransConst K;
+  trans_const_init(&K, kd);
+  cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    debug_eval_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(which, K, kd, n, d, d + n);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_error("ecckd_debug_eval: %s", cudaGetErrorString(e));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  return ECCKD_OK;
+}
+
 ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
   if (!plan) return ECCKD_OK;
   if (plan->ctx) cudaStreamSynchronize(plan->ctx->stream);

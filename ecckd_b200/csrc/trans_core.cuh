@@ -1,6 +1,6 @@
 // trans_core.cuh - 1 - exp(-kd*tau) for the transmission averaging methods
 // (average_optical_depth.cpp:47-70: `1.0 - exp(-LW_DIFFUSIVITY*OD_SCALING*k * optical_depth)`),
-// written for the FP64 pipe of sm_100a: 12 FP64 instructions per value instead of ~18.
+// written for the FP64 pipe of sm_100a: 11 FP64 instructions per value instead of ~18.
 //
 //   x = -kd*tau = (32 k + j) ln2/32 + r,  |r| <= ln2/64
 //   exp(x) = 2^k * 2^(j/32) * (1 + p(r)),  p(r) = r + r^2/2 + ... + r^6/720   (|r^7/7!| < 4e-18)
@@ -11,10 +11,9 @@
 // * 2^(j/32) is a 32-entry table held one entry per LANE and looked up with two warp shuffles
 //   (a shared-memory table would bank-conflict ~3-way); the table's high words are stored minus
 //   (j << 15) so that adding (n << 15) to them applies 2^k and cancels j in one integer IMAD;
-// * 1 - exp(x) = (1 - T) - T*p with T = 2^k 2^(j/32): for tau -> 0 this is -p exactly, i.e. the
-//   result keeps full RELATIVE accuracy where the reference's 1 - exp() only has absolute accuracy
-//   1.1e-16; elsewhere the absolute error is below 1e-16 (tests/test_trans_core.py sweeps it
-//   against mpmath through the C ABI hook ecckd_debug_one_minus_exp).
+// * 1 - exp(x) = 1 - T*(1 + p) with T = 2^k 2^(j/32), two FMAs: absolute error below 2.3e-16 (two
+//   ulp of 1; the reference's 1.0 - exp() is within ~1.7e-16), swept against expm1 on the GPU by
+//   tests/test_trans_core_gpu.py through the C ABI hook ecckd_debug_eval.
 // * tau is clamped to 708/kd through its high word (one integer min): exp() would be below 1e-307
 //   there and 1 - exp() is exactly 1 long before.  Not handled (unphysical): tau < -708/kd and NaN.
 // All 32 lanes of the warp must call trans_one_minus_exp together (it shuffles).

@@ -114,6 +114,13 @@ int ecckd_ctx_reduce_kernel_time(ecckd_ctx* ctx, double* total_ms, int64_t* laun
 
 /* -------------------------------------------------- stage 1: spectra -> LUT */
 
+/* Test hook (no reference counterpart): the kernels' own 1 - exp(-kd*tau) of the transmission
+ * averaging methods (average_optical_depth.cpp:49,53,57,61: `1.0 - exp(-D*k*optical_depth)`) and
+ * their Planck weight (planck_function.cpp:47-53 with the folded constants of the fused path),
+ * evaluated element-wise on host arrays so that tests can sweep their accuracy.
+ * which = 0: out[i] = 1 - exp(-kd*x[i]);  which = 1: out[i] = planck(T = kd, nu = x[i], dnu = 1). */
+int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, const double* x, double* out);
+
 /* planck_function: src/ecckd/planck_function.cpp:22-54.
  * d_ans[nt][nwav] with row stride ans_stride. */
 int ecckd_planck_function_dev(ecckd_ctx* ctx, int nt, const double* h_temperature, int64_t nwav,

@@ -242,3 +242,87 @@ def test_avg_wavenumber_shards_emulated_on_one_device(ctx, O, method):
                                                  planck, method)
         S.assert_avg_close((outs[s].numpy(), mins[s].numpy(), maxs[s].numpy(), warns[s].numpy()), ref, method=method,
                            scale=S.out_scale(dict(c, vmr=vmrs[s])), what=f"spec {s} ")
+
+
+def test_avg_many_g_points_per_chunk(ctx, O):
+    """A chunk of 480 wavenumbers holding up to 150 g points needs several plan rounds (more lanes than a
+    warp); the shorter chunk lengths of the plan builder are exercised too."""
+    rng = np.random.default_rng(5)
+    c = S.lw_spectrum_case(nlay=6, nwav=9000, ng=8, nband=1, seed=31)
+    ng = 150
+    g = rng.integers(0, ng, size=c["g_point"].size).astype(np.int32)
+    g[:1500] = np.repeat(np.arange(ng, dtype=np.int32), 10)  # long runs too
+    planck = _planck(O, c)
+    for method in ("transmission", "linear", "logarithmic"):
+        got = E.average_optical_depth_to_g_point(ctx, ng, c["vmr"], c["pressure_fl"], c["pressure_hl"], g, c["od"], planck,
+                                                 method)
+        ref = O.average_optical_depth_to_g_point(ng, c["vmr"], c["pressure_fl"], c["pressure_hl"], g, c["od"], planck,
+                                                 method)
+        S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c), what=method + " ")
+
+
+def test_avg_extremes_are_exact_with_duplicates_huge_and_tiny_values(ctx, O):
+    """min/max are selections of input values: the range-check fast path must never lose an extreme that
+    shares its high word with the running one, repeats it, is zero, denormal, or enormous (optical depths
+    beyond 708/kd saturate 1 - exp exactly)."""
+    rng = np.random.default_rng(17)
+    c = S.lw_spectrum_case(nlay=9, nwav=20000, ng=6, nband=2, seed=8)
+    od = c["od"].copy()
+    od[0, :] = 0.5                                  # constant row: min == max
+    od[1, :] = 0.5 * (1.0 + 1e-9 * rng.random(od.shape[1]))  # all values share the extremes' high word
+    od[2, ::7] = 0.0                                # many exact zeros
+    od[3, 11::501] = 5e-324                         # denormal minimum
+    od[4, 3::997] = 1.0e5                           # beyond the exponent clamp
+    od[5, 123] = 3.0e12
+    od[6, :] = np.sort(od[6, :])                    # new maximum in every chunk
+    od[7, :] = np.sort(od[7, :])[::-1]              # new minimum in every chunk
+    planck = _planck(O, c)
+    for method in ("transmission", "linear"):
+        got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                                 od, planck, method)
+        ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], od,
+                                                 planck, method)
+        S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c), what=method + " ")
+
+
+def test_avg_negative_optical_depths_take_the_exact_path(ctx, O):
+    """Unphysical but legal input: the extremes of a g point holding negative values are still exact."""
+    c = S.lw_spectrum_case(nlay=4, nwav=5000, ng=4, nband=1, seed=12)
+    od = c["od"].copy()
+    od[1, ::5] *= -1.0
+    od[2, :] = -np.abs(od[2, :])
+    planck = _planck(O, c)
+    got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], od,
+                                             planck, "linear")
+    ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], od,
+                                             planck, "linear")
+    for i in (1, 2):  # min / max before the reference's clamping logic touches them: compare where both finite
+        ok = np.isfinite(ref[i]) & np.isfinite(got[i])
+        assert np.allclose(got[i][ok], ref[i][ok], rtol=1e-15, atol=0.0)
+
+
+def test_avg_group_of_twenty_spectra_and_wavenumber_windows(ctx, O, monkeypatch):
+    """Twenty spectra share each layer's weights (one full CTA group: two rows per consumer warp, the last
+    warp also sums the weights) and the work is cut into several wavenumber windows."""
+    monkeypatch.setenv("ECCKD_NWIN", "5")
+    nspec, nlay, nwav, ng = 20, 3, 30000, 12
+    c = S.lw_spectrum_case(nlay=nlay, nwav=nwav, ng=ng, nband=3, seed=44)
+    rng = np.random.default_rng(3)
+    ods = [np.ascontiguousarray(c["od"] * rng.uniform(0.2, 5.0)) for _ in range(nspec)]
+    vmrs = [float(v) for v in rng.uniform(1e-6, 1e-3, nspec)]
+    d_g = ctx.to_device(c["g_point"].astype(np.int32))
+    plan = E.GPointPlan(ctx, d_g, nwav, ng)
+    d_wn, d_dwn = ctx.to_device(c["wavenumber"]), ctx.to_device(c["d_wavenumber"])
+    d_ods = [ctx.to_device(o) for o in ods]
+    outs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    mins = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    maxs = [ctx.empty((nlay, ng)) for _ in range(nspec)]
+    E.average_optical_depth_batch_dev(ctx, plan, vmrs, c["pressure_fl"], c["pressure_hl"], d_ods, nwav, E.WEIGHT_PLANCK, None,
+                                      nwav, c["temperature_fl"], d_wn, d_dwn, "transmission", outs, mins, maxs, ng)
+    planck = _planck(O, c)
+    for s in range(nspec):
+        ref = O.average_optical_depth_to_g_point(ng, vmrs[s], c["pressure_fl"], c["pressure_hl"], c["g_point"], ods[s], planck,
+                                                 "transmission")
+        got = (outs[s].numpy(), mins[s].numpy(), maxs[s].numpy(), None)
+        scale = (9.80665 * 0.001 * 28.970 / vmrs[s]) / (c["pressure_hl"][1:] - c["pressure_hl"][:-1])
+        S.assert_avg_close(got, ref, method="transmission", scale=scale, what=f"spectrum {s} ")
