@@ -1024,3 +1024,473 @@ ORC_API int orc_assign_g_points(int ngas, int64_t nwav, const int32_t* gas_g_poi
 // Rayleigh molar scattering: src/ecckd/rayleigh_scattering.h:23-43 and
 // src/ecckd/ckd_model.h:368-385 are restated in oracle_extra.cpp together with
 // the find_g_points interval error (a13) and the forward cost functions (a22).
+
+// ===========================================================================
+// Rows a4b, a7b, a13, a15, a21, a22 of SURVEY.md section 8.
+// ===========================================================================
+
+// rayleigh_molar_scattering_coeff: src/ecckd/rayleigh_scattering.h:23-43
+// (Bucholtz 1995 two-branch power law, m2 mol-1).
+ORC_API int orc_rayleigh_molar_scattering_coeff(int64_t nwav, const double* wavenumber_cm_1,
+                                                double* scat_coeff) {
+  const double AVOGADRO_CONSTANT = 6.02214076e23;  // constants.h:26
+  for (int64_t i = 0; i < nwav; ++i) {
+    const double wl = 10000.0 / wavenumber_cm_1[i];
+    double s;
+    if (wl < 0.5) {
+      s = 3.01577e-32 * std::pow(wl, -(3.55212 + 1.35579 * wl + 0.11563 / wl));
+    } else {
+      s = 4.01061e-32 * std::pow(wl, -(3.99668 + 0.00110298 * wl + 0.0271393 / wl));
+    }
+    scat_coeff[i] = s * AVOGADRO_CONSTANT;
+  }
+  return ORC_OK;
+}
+
+// CkdModel::calc_rayleigh_molar_scat: src/ecckd/ckd_model.h:368-385.
+// gpoint_fraction[ng][nbin], ssi_intervals[nbin], wavenumber1/2[nbin] -> rayleigh_molar_scat[ng].
+ORC_API int orc_rayleigh_molar_scat_gpoints(int ng, int nbin, const double* wavenumber1,
+                                            const double* wavenumber2, const double* gpoint_fraction,
+                                            const double* ssi_intervals, double* rayleigh_molar_scat) {
+  const double REFERENCE_COS_SZA = 0.5;  // calc_cost_function_sw.h:20
+  std::vector<double> mid(nbin), scat(nbin), trans_hr(nbin);
+  for (int i = 0; i < nbin; ++i) mid[i] = 0.5 * (wavenumber1[i] + wavenumber2[i]);
+  orc_rayleigh_molar_scattering_coeff(nbin, mid.data(), scat.data());
+  const double molar_column = 1.0e5 / (ACCEL_GRAVITY * 0.001 * MOLAR_MASS_DRY_AIR);
+  for (int i = 0; i < nbin; ++i) trans_hr[i] = std::exp(-(molar_column * scat[i]) / REFERENCE_COS_SZA);
+  for (int ig = 0; ig < ng; ++ig) {
+    double num = 0.0, den = 0.0;
+    for (int i = 0; i < nbin; ++i) {
+      num += gpoint_fraction[(size_t)ig * nbin + i] * (ssi_intervals[i] * trans_hr[i]);
+      den += gpoint_fraction[(size_t)ig * nbin + i] * ssi_intervals[i];
+    }
+    const double transmission = num / den;
+    const double od = -std::log(std::max(1.0e-14, transmission)) * REFERENCE_COS_SZA;
+    rayleigh_molar_scat[ig] = od / molar_column;
+  }
+  return ORC_OK;
+}
+
+// Base g-point split: src/ecckd/create_look_up_table.cpp:162-224.
+// In/out: *ng, band_number[cap], g_point[nwav], solar_irradiance[cap] (NULL in the longwave,
+// together with ssi).  Returns PROCESSING_ERROR when cap is too small.
+// Note: for the LAST band the reference leaves new_band_number / new_solar_irradiance of the g
+// points above the split one uninitialised (:190-193 only copies them when iband < nband-1);
+// here they are copied for every band, which is what any initialised value would have to be.
+ORC_API int orc_split_base_g_points(int nband, const double* band_wn1, const double* band_wn2, int nbound,
+                                    const double* base_wavenumber_boundary, int64_t nwav,
+                                    const double* wavenumber_cm_1, const double* ssi, int cap, int* ng_io,
+                                    int32_t* band_number, int32_t* g_point, double* solar_irradiance) {
+  int ng = *ng_io;
+  for (int iband = 0; iband < nband; ++iband) {
+    std::vector<double> inside;
+    for (int k = 0; k < nbound; ++k) {
+      if (base_wavenumber_boundary[k] > band_wn1[iband] && base_wavenumber_boundary[k] < band_wn2[iband]) {
+        inside.push_back(base_wavenumber_boundary[k]);
+      }
+    }
+    const int nidx = (int)inside.size();
+    if (nidx == 0) continue;
+    int ig = -1;
+    for (int k = 0; k < ng; ++k) {
+      if (band_number[k] == iband) { ig = k; break; }
+    }
+    if (ig < 0) return ORC_PROCESSING_ERROR;  // minval of an empty find() in the reference
+    const int new_ng = ng + nidx;
+    if (new_ng > cap) return ORC_PROCESSING_ERROR;
+    std::vector<int32_t> new_band(new_ng);
+    std::vector<double> new_sol(new_ng, 0.0);
+    for (int k = 0; k <= ig; ++k) new_band[k] = band_number[k];
+    for (int k = ig + 1; k <= ig + nidx; ++k) new_band[k] = iband;
+    for (int k = 0; k < ig; ++k) if (solar_irradiance) new_sol[k] = solar_irradiance[k];
+    for (int k = ig + 1; k < ng; ++k) {
+      new_band[k + nidx] = band_number[k];
+      if (solar_irradiance) new_sol[k + nidx] = solar_irradiance[k];
+    }
+    std::vector<double> bounds(nidx + 2);
+    bounds[0] = band_wn1[iband];
+    for (int k = 0; k < nidx; ++k) bounds[k + 1] = inside[k];
+    bounds[nidx + 1] = band_wn2[iband];
+    std::vector<int32_t> new_g(nwav);
+    for (int64_t i = 0; i < nwav; ++i) new_g[i] = g_point[i] > ig ? g_point[i] + nidx : g_point[i];
+    for (int new_ig = ig; new_ig <= ig + nidx; ++new_ig) {
+      for (int64_t i = 0; i < nwav; ++i) {
+        if (g_point[i] == ig && wavenumber_cm_1[i] >= bounds[new_ig - ig] &&
+            wavenumber_cm_1[i] < bounds[new_ig - ig + 1]) {
+          new_g[i] = new_ig;
+        }
+      }
+    }
+    if (solar_irradiance && ssi) {
+      for (int new_ig = ig; new_ig <= ig + nidx; ++new_ig) {
+        double s = 0.0;
+        for (int64_t i = 0; i < nwav; ++i) if (new_g[i] == new_ig) s += ssi[i];
+        new_sol[new_ig] = s;
+      }
+    }
+    for (int k = 0; k < new_ng; ++k) {
+      band_number[k] = new_band[k];
+      if (solar_irradiance) solar_irradiance[k] = new_sol[k];
+    }
+    std::memcpy(g_point, new_g.data(), sizeof(int32_t) * nwav);
+    ng = new_ng;
+  }
+  *ng_io = ng;
+  return ORC_OK;
+}
+
+// fit_optical_depth_lw: src/ecckd/find_g_points.cpp:54-116.  metric[nlay][n], planck_hl[nlay+1][n]
+// (row stride n), interval [i1,i2] inclusive.  Methods: linear, transmission, transmission-2,
+// square-root, logarithmic (ids as above; others -> PARAMETER_ERROR).  Kept quirks: the weights
+// are planck_hl rows 1..nlay (:62), and the logarithmic branch divides by the sum of row iz while
+// weighting by row iz+1 (:88-89).
+ORC_API int orc_fit_optical_depth_lw(int method, int nlay, int64_t n, int64_t i1, int64_t i2, const double* planck_hl,
+                                     const double* metric, double* optical_depth_fit) {
+  if (!(method == AVG_LINEAR || method == AVG_TRANSMISSION || method == AVG_TRANSMISSION_2 ||
+        method == AVG_SQUARE_ROOT || method == AVG_LOGARITHMIC)) {
+    return ORC_PARAMETER_ERROR;
+  }
+  for (int iz = 0; iz < nlay; ++iz) {
+    const double* m = metric + (int64_t)iz * n;
+    const double* w = planck_hl + (int64_t)(iz + 1) * n;
+    if (method != AVG_LOGARITHMIC) {
+      double num = 0.0, den = 0.0;
+      for (int64_t i = i1; i <= i2; ++i) { num += m[i] * w[i]; den += w[i]; }
+      double x = num / den;
+      if (method == AVG_TRANSMISSION) {
+        x = std::min(0.9999999999999999, x);
+        x = std::fabs(-std::log(1.0 - x) / LW_DIFFUSIVITY);
+      } else if (method == AVG_TRANSMISSION_2) {
+        x = std::min(0.9999999999999999, x);
+        x = std::fabs(-std::log(1.0 - x) / (LW_DIFFUSIVITY * 2.0));
+      } else if (method == AVG_SQUARE_ROOT) {
+        x *= x;
+      }
+      optical_depth_fit[iz] = x;
+    } else {
+      const double* wden = planck_hl + (int64_t)iz * n;
+      double num = 0.0, den = 0.0;
+      int64_t nnz = 0;
+      for (int64_t i = i1; i <= i2; ++i) {
+        if (m[i] > 0.0) { num += std::log(m[i]) * w[i]; den += wden[i]; ++nnz; }
+      }
+      if (nnz == i2 - i1 + 1) optical_depth_fit[iz] = std::exp(num / den);
+      else if (nnz == 0) optical_depth_fit[iz] = 0.0;
+      else optical_depth_fit[iz] = std::exp(num / den) * ((double)nnz / (double)(i2 - i1 + 1));
+    }
+  }
+  return ORC_OK;
+}
+
+// fit_optical_depth_sw: src/ecckd/find_g_points.cpp:119-173.  Kept quirk: in the transmission
+// branches min(0.9999999999999999, .) is applied to the un-normalised sum (:131,:136).
+// AVG_TOTAL_TRANSMISSION takes the logarithmic branch (:146-147).
+ORC_API int orc_fit_optical_depth_sw(int method, int nlay, int64_t n, int64_t i1, int64_t i2, const double* ssi,
+                                     const double* metric, double* optical_depth_fit) {
+  if (!(method == AVG_LINEAR || method == AVG_TRANSMISSION || method == AVG_TRANSMISSION_2 ||
+        method == AVG_SQUARE_ROOT || method == AVG_LOGARITHMIC || method == AVG_TOTAL_TRANSMISSION)) {
+    return ORC_PARAMETER_ERROR;
+  }
+  double ssum = 0.0;
+  for (int64_t i = i1; i <= i2; ++i) ssum += ssi[i];
+  const double norm_factor = 1.0 / ssum;
+  for (int iz = 0; iz < nlay; ++iz) {
+    const double* m = metric + (int64_t)iz * n;
+    if (method != AVG_LOGARITHMIC && method != AVG_TOTAL_TRANSMISSION) {
+      double num = 0.0;
+      for (int64_t i = i1; i <= i2; ++i) num += m[i] * ssi[i];
+      double x;
+      if (method == AVG_TRANSMISSION) {
+        x = std::min(0.9999999999999999, num) * norm_factor;
+        x = std::fabs(-std::log(1.0 - x) / LW_DIFFUSIVITY);
+      } else if (method == AVG_TRANSMISSION_2) {
+        x = std::min(0.9999999999999999, num) * norm_factor;
+        x = std::fabs(-std::log(1.0 - x) / (LW_DIFFUSIVITY * 2.0));
+      } else if (method == AVG_SQUARE_ROOT) {
+        x = num * norm_factor;
+        x *= x;
+      } else {
+        x = num * norm_factor;
+      }
+      optical_depth_fit[iz] = x;
+    } else {
+      double num = 0.0, den = 0.0;
+      int64_t nnz = 0;
+      for (int64_t i = i1; i <= i2; ++i) {
+        if (m[i] > 0.0) { num += std::log(m[i]) * ssi[i]; den += ssi[i]; ++nnz; }
+      }
+      if (nnz == i2 - i1 + 1) optical_depth_fit[iz] = std::exp(num / den);
+      else if (nnz == 0) optical_depth_fit[iz] = 0.0;
+      else optical_depth_fit[iz] = std::exp(num / den) * ((double)nnz / (double)(i2 - i1 + 1));
+    }
+  }
+  return ORC_OK;
+}
+
+// fit_optical_depth_sw_total_trans: src/ecckd/find_g_points.cpp:176-204.  Kept quirk: when a
+// broadband flux underflows to zero the WHOLE profile is overwritten by the linear average (:197),
+// and later layers may overwrite their own entry again.
+ORC_API int orc_fit_optical_depth_sw_total_trans(int nlay, int64_t n, int64_t i1, int64_t i2, const double* ssi,
+                                                 const double* bg_od, const double* od, double* optical_depth_fit) {
+  const int64_t m = i2 - i1 + 1;
+  std::vector<double> flux_dn(m), bg_flux_dn(m);
+  double top = 0.0;
+  for (int64_t i = 0; i < m; ++i) { flux_dn[i] = bg_flux_dn[i] = ssi[i1 + i]; top += ssi[i1 + i]; }
+  double bb_flux_dn_top = top, bb_bg_flux_dn_top = top;
+  const double norm_factor = 1.0 / top;
+  for (int iz = 0; iz < nlay; ++iz) optical_depth_fit[iz] = 0.0;  // Vector(nz): unset in the reference
+  for (int iz = 0; iz < nlay; ++iz) {
+    double bb_bg = 0.0, bb = 0.0;
+    for (int64_t i = 0; i < m; ++i) {
+      const double b = bg_od[(int64_t)iz * n + i1 + i], o = od[(int64_t)iz * n + i1 + i];
+      bg_flux_dn[i] *= std::exp(-2.0 * b);
+      flux_dn[i] *= std::exp(-2.0 * (b + o));
+    }
+    for (int64_t i = 0; i < m; ++i) bb_bg += bg_flux_dn[i];
+    for (int64_t i = 0; i < m; ++i) bb += flux_dn[i];
+    if (bb_bg > 0.0 && bb > 0.0) {
+      const double bg_od_fit = -0.5 * std::log(bb_bg / bb_bg_flux_dn_top);
+      optical_depth_fit[iz] = -0.5 * std::log(bb / bb_flux_dn_top) - bg_od_fit;
+    } else {
+      for (int jz = 0; jz < nlay; ++jz) {
+        double s = 0.0;
+        for (int64_t i = 0; i < m; ++i) s += od[(int64_t)jz * n + i1 + i] * ssi[i1 + i];
+        optical_depth_fit[jz] = s * norm_factor;
+      }
+    }
+    bb_flux_dn_top = bb;
+    bb_bg_flux_dn_top = bb_bg;
+  }
+  return ORC_OK;
+}
+
+// calc_cost_function_lw: src/ecckd/calc_cost_function_lw.cpp:23-110 (index empty: the caller
+// passes interval slices).  Arrays hold the n wavenumbers of the interval.
+ORC_API int orc_calc_cost_function_lw(int nlay, int64_t n, const double* pressure_hl, const double* planck_hl,
+                                      const double* surf_emissivity, const double* surf_planck,
+                                      const double* bg_optical_depth, const double* optical_depth_fit,
+                                      const double* flux_dn_surf, const double* flux_up_toa, const double* hr,
+                                      double flux_weight, const double* layer_weight, double* cost) {
+  const double hr_weight = 3600.0 * 24.0;
+  std::vector<double> hr_true(nlay), dn(nlay + 1), up(nlay + 1), hr_fit(nlay);
+  for (int iz = 0; iz < nlay; ++iz) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += hr[(int64_t)iz * n + i];
+    hr_true[iz] = s;
+  }
+  double dn_true = 0.0, up_true = 0.0;
+  for (int64_t i = 0; i < n; ++i) dn_true += flux_dn_surf[i];
+  for (int64_t i = 0; i < n; ++i) up_true += flux_up_toa[i];
+  orc_radiative_transfer_lw_bb(nlay, n, planck_hl, bg_optical_depth, optical_depth_fit, surf_emissivity, surf_planck,
+                               dn.data(), up.data());
+  orc_heating_rate_single(nlay, pressure_hl, dn.data(), up.data(), hr_fit.data());
+  double s = 0.0;
+  for (int iz = 0; iz < nlay; ++iz) s += layer_weight[iz] * ((hr_fit[iz] - hr_true[iz]) * (hr_fit[iz] - hr_true[iz]));
+  *cost = std::sqrt(hr_weight * hr_weight * s +
+                    flux_weight * ((dn[nlay] - dn_true) * (dn[nlay] - dn_true) + (up[0] - up_true) * (up[0] - up_true)));
+  return ORC_OK;
+}
+
+// calc_cost_function_sw: src/ecckd/calc_cost_function_sw.cpp:20-110.  albedo <= 0: direct beam
+// only and flux_up_fit stays 0 (:56); the fitted heating rate never includes the upwelling (:87).
+ORC_API int orc_calc_cost_function_sw(int nlay, int64_t n, double cos_sza, const double* pressure_hl, const double* ssi,
+                                      double albedo, const double* bg_optical_depth, const double* optical_depth_fit,
+                                      const double* flux_dn_surf, const double* flux_up_toa, const double* hr,
+                                      double flux_weight, const double* layer_weight, double* cost) {
+  const double hr_weight = 3600.0 * 24.0;
+  std::vector<double> hr_true(nlay), dn(nlay + 1), up(nlay + 1, 0.0), hr_fit(nlay);
+  for (int iz = 0; iz < nlay; ++iz) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += hr[(int64_t)iz * n + i];
+    hr_true[iz] = s;
+  }
+  double dn_true = 0.0, up_true = 0.0;
+  for (int64_t i = 0; i < n; ++i) dn_true += flux_dn_surf[i];
+  for (int64_t i = 0; i < n; ++i) up_true += flux_up_toa[i];
+  orc_radiative_transfer_sw_bb(nlay, n, cos_sza, ssi, bg_optical_depth, optical_depth_fit, albedo, dn.data(),
+                               albedo <= 0.0 ? (double*)0 : up.data());
+  orc_heating_rate_single(nlay, pressure_hl, dn.data(), (const double*)0, hr_fit.data());
+  double s = 0.0;
+  for (int iz = 0; iz < nlay; ++iz) s += layer_weight[iz] * ((hr_fit[iz] - hr_true[iz]) * (hr_fit[iz] - hr_true[iz]));
+  *cost = std::sqrt(hr_weight * hr_weight * s +
+                    flux_weight * ((dn[nlay] - dn_true) * (dn[nlay] - dn_true) + (up[0] - up_true) * (up[0] - up_true)));
+  return ORC_OK;
+}
+
+// Shared tail of calc_cost_function_ckd_{lw,sw}: band sums, heating rates and the cost terms.
+// fdo/fuo[nlay+1][ng] are the forward g-point fluxes (already minus the relative-to fluxes).
+static double ckd_cost_terms(bool sw, bool up_in_bb, int nlay, int ng, int nband, const int32_t* band_mapping,
+                             const double* pressure_hl, const std::vector<double>& fdo, const std::vector<double>& fuo,
+                             const double* flux_dn, const double* flux_up, const double* hr, double flux_weight,
+                             double flux_profile_weight, double broadband_weight, const double* layer_weight,
+                             double* cost_fn_per_band) {
+  const double hr_weight = 3600.0 * 24.0;
+  const int nlev = nlay + 1;
+  std::vector<double> fd((size_t)nlev * nband), fu((size_t)nlev * nband), hrf((size_t)nlay * nband);
+  if (!band_mapping) {
+    fd = fdo;
+    fu = fuo;
+  } else {
+    for (int ib = 0; ib < nband; ++ib) {
+      for (int il = 0; il < nlev; ++il) {
+        double sd = 0.0, su = 0.0;
+        for (int ig = 0; ig < ng; ++ig) {
+          if (band_mapping[ig] == ib) { sd += fdo[(size_t)il * ng + ig]; su += fuo[(size_t)il * ng + ig]; }
+        }
+        fd[(size_t)il * nband + ib] = sd;
+        fu[(size_t)il * nband + ib] = su;
+      }
+    }
+  }
+  // heating_rate(): LW with upwelling, SW with aMatrix() i.e. downwelling only (calc_cost_function_sw.cpp:195)
+  orc_heating_rate(nlay, nband, pressure_hl, fd.data(), sw ? (const double*)0 : fu.data(), hrf.data());
+  std::vector<double> iw(nlay > 1 ? nlay - 1 : 0);
+  for (int iz = 0; iz + 1 < nlay; ++iz) iw[iz] = flux_profile_weight * 0.5 * (layer_weight[iz] + layer_weight[iz + 1]);
+  double cost = 0.0;
+  for (int ib = 0; ib < nband; ++ib) {
+    double s = 0.0;
+    for (int iz = 0; iz < nlay; ++iz) {
+      const double d = hrf[(size_t)iz * nband + ib] - hr[(size_t)iz * nband + ib];
+      s += layer_weight[iz] * d * d;
+    }
+    const double dd = fd[(size_t)nlay * nband + ib] - flux_dn[(size_t)nlay * nband + ib];
+    const double du = fu[ib] - flux_up[ib];
+    double local = hr_weight * hr_weight * s + flux_weight * (dd * dd + (sw ? 20.0 : 1.0) * du * du);
+    if (flux_profile_weight > 0.0) {
+      double t = 0.0;
+      for (int il = 1; il < nlay; ++il) {
+        const double a = fd[(size_t)il * nband + ib] - flux_dn[(size_t)il * nband + ib];
+        const double b = fu[(size_t)il * nband + ib] - flux_up[(size_t)il * nband + ib];
+        t += iw[il - 1] * (a * a + b * b);
+      }
+      local += t;
+    }
+    cost += local;
+    if (cost_fn_per_band) cost_fn_per_band[ib] += local;
+  }
+  if (!sw || broadband_weight > 0.0) {  // the LW applies the mix unconditionally (:205), the SW if > 0 (:243)
+    double s = 0.0;
+    for (int iz = 0; iz < nlay; ++iz) {
+      double e = 0.0;
+      for (int ib = 0; ib < nband; ++ib) e += hrf[(size_t)iz * nband + ib] - hr[(size_t)iz * nband + ib];
+      s += layer_weight[iz] * (e * e);
+    }
+    double ed = 0.0, eu = 0.0;
+    for (int ib = 0; ib < nband; ++ib) ed += fd[(size_t)nlay * nband + ib] - flux_dn[(size_t)nlay * nband + ib];
+    for (int ib = 0; ib < nband; ++ib) eu += fu[ib] - flux_up[ib];
+    if (!sw) {
+      cost = (cost * (1.0 - broadband_weight)) / nband + broadband_weight * hr_weight * hr_weight * s +
+             broadband_weight * flux_weight * (ed * ed + eu * eu);
+    } else {
+      cost = (cost * (1.0 - broadband_weight)) / nband + broadband_weight * hr_weight * hr_weight * s;
+      cost += broadband_weight * flux_weight * (ed * ed);
+      if (up_in_bb) cost += broadband_weight * flux_weight * (eu * eu);
+    }
+    if (flux_profile_weight > 0.0) {
+      double td = 0.0, tu = 0.0;
+      for (int il = 1; il < nlay; ++il) {
+        double a = 0.0, b = 0.0;
+        for (int ib = 0; ib < nband; ++ib) {
+          a += fd[(size_t)il * nband + ib] - flux_dn[(size_t)il * nband + ib];
+          b += fu[(size_t)il * nband + ib] - flux_up[(size_t)il * nband + ib];
+        }
+        td += iw[il - 1] * (a * a);
+        tu += iw[il - 1] * (b * b);
+      }
+      if (!sw) {
+        double t = 0.0;  // one sum of (dn^2 + up^2) in the LW (:216-217)
+        for (int il = 1; il < nlay; ++il) {
+          double a = 0.0, b = 0.0;
+          for (int ib = 0; ib < nband; ++ib) {
+            a += fd[(size_t)il * nband + ib] - flux_dn[(size_t)il * nband + ib];
+            b += fu[(size_t)il * nband + ib] - flux_up[(size_t)il * nband + ib];
+          }
+          t += iw[il - 1] * (a * a + b * b);
+        }
+        cost += broadband_weight * t;
+      } else {
+        cost += broadband_weight * td;
+        if (up_in_bb) cost += broadband_weight * tu;
+      }
+    }
+  }
+  return cost;
+}
+
+// calc_cost_function_ckd_lw (forward value): src/ecckd/calc_cost_function_lw.cpp:115-232.
+ORC_API int orc_calc_cost_function_ckd_lw(int nlay, int ng, int nband, const double* pressure_hl, const double* planck_hl,
+                                          const double* surf_emissivity, const double* surf_planck,
+                                          const double* optical_depth, const double* flux_dn, const double* flux_up,
+                                          const double* hr, const double* spectral_flux_dn_surf,
+                                          const double* spectral_flux_up_toa, double flux_weight,
+                                          double flux_profile_weight, double broadband_weight,
+                                          double spectral_boundary_weight, const double* layer_weight,
+                                          const double* relative_ckd_flux_dn, const double* relative_ckd_flux_up,
+                                          const int32_t* band_mapping, double* cost) {
+  const int nlev = nlay + 1;
+  if (!band_mapping && nband != ng) return ORC_PARAMETER_ERROR;
+  std::vector<double> emis(ng), fdo((size_t)nlev * ng), fuo((size_t)nlev * ng);
+  for (int ig = 0; ig < ng; ++ig) emis[ig] = band_mapping ? surf_emissivity[band_mapping[ig]] : surf_emissivity[ig];
+  orc_radiative_transfer_lw(nlay, ng, planck_hl, optical_depth, emis.data(), surf_planck, fdo.data(), fuo.data());
+  if (relative_ckd_flux_dn) {
+    for (size_t k = 0; k < fdo.size(); ++k) { fdo[k] -= relative_ckd_flux_dn[k]; fuo[k] -= relative_ckd_flux_up[k]; }
+  }
+  double c = ckd_cost_terms(false, true, nlay, ng, nband, band_mapping, pressure_hl, fdo, fuo, flux_dn, flux_up, hr,
+                            flux_weight, flux_profile_weight, broadband_weight, layer_weight, (double*)0);
+  if (spectral_boundary_weight > 0.0 && spectral_flux_dn_surf && spectral_flux_up_toa) {
+    double s = 0.0;
+    for (int ig = 0; ig < ng; ++ig) {
+      const double a = fdo[(size_t)nlay * ng + ig] - spectral_flux_dn_surf[ig];
+      const double b = fuo[ig] - spectral_flux_up_toa[ig];
+      s += a * a + b * b;
+    }
+    c += spectral_boundary_weight * s;
+  }
+  *cost = c;
+  return ORC_OK;
+}
+
+// calc_cost_function_ckd_sw (forward value): src/ecckd/calc_cost_function_sw.cpp:115-277.
+// The ">0.1 W m-2 incoming flux" warning (:232-237) is not part of the value and is not restated.
+ORC_API int orc_calc_cost_function_ckd_sw(int nlay, int ng, int nband, double cos_sza, const double* pressure_hl,
+                                          const double* ssi, int nalbedo, const double* albedo,
+                                          const double* optical_depth, const double* flux_dn, const double* flux_up,
+                                          const double* hr, const double* spectral_flux_dn_surf,
+                                          const double* spectral_flux_up_toa, double flux_weight,
+                                          double flux_profile_weight, double broadband_weight,
+                                          const double* spectral_boundary_weights, const double* layer_weight,
+                                          const double* relative_ckd_flux_dn, const double* relative_ckd_flux_up,
+                                          const int32_t* band_mapping, double* cost_fn_per_band, double* cost) {
+  (void)spectral_flux_up_toa;
+  const int nlev = nlay + 1;
+  if (!band_mapping && nband != ng) return ORC_PARAMETER_ERROR;
+  bool all_le0 = true, all_gt0 = true;
+  for (int k = 0; k < nalbedo; ++k) {
+    if (!(albedo[k] <= 0.0)) all_le0 = false;
+    if (!(albedo[k] > 0.0)) all_gt0 = false;
+  }
+  std::vector<double> fdo((size_t)nlev * ng), fuo((size_t)nlev * ng, 0.0);
+  if (all_le0) {
+    orc_radiative_transfer_direct_sw(nlay, ng, cos_sza, ssi, optical_depth, fdo.data());
+  } else {
+    if (!band_mapping) return ORC_PARAMETER_ERROR;  // albedo(band_mapping) would be empty: Adept size mismatch
+    std::vector<double> alb(ng);
+    for (int ig = 0; ig < ng; ++ig) alb[ig] = albedo[band_mapping[ig]];
+    orc_radiative_transfer_norayleigh_sw(nlay, ng, cos_sza, ssi, optical_depth, alb.data(), fdo.data(), fuo.data());
+  }
+  if (relative_ckd_flux_dn) {
+    for (size_t k = 0; k < fdo.size(); ++k) { fdo[k] -= relative_ckd_flux_dn[k]; fuo[k] -= relative_ckd_flux_up[k]; }
+  }
+  double c = ckd_cost_terms(true, all_gt0, nlay, ng, nband, band_mapping, pressure_hl, fdo, fuo, flux_dn, flux_up, hr,
+                            flux_weight, flux_profile_weight, broadband_weight, layer_weight, cost_fn_per_band);
+  if (spectral_boundary_weights && spectral_flux_dn_surf) {
+    double s = 0.0;
+    for (int ig = 0; ig < ng; ++ig) {
+      const double a = fdo[(size_t)nlay * ng + ig] - spectral_flux_dn_surf[ig];
+      s += spectral_boundary_weights[ig] * a * a;
+    }
+    c += s;
+  }
+  *cost = c;
+  return ORC_OK;
+}

@@ -14,6 +14,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "libecckd_oracle.so")
+# the reference's own translation units, compiled in place against oracle/adept_shim (oracle/build_ref_shim.sh)
+REFERENCE_LIB = os.path.join(ORACLE_DIR, "_ref", "libecckd_ref.so")
 
 METHODS = (
     "linear",
@@ -50,18 +52,25 @@ def _p(a):
 
 
 class Oracle:
-    def __init__(self):
-        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith(".cpp")]
-        stale = (not os.path.exists(ORACLE_LIB)) or any(
-            os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in srcs)
-        if stale:
-            env = dict(os.environ)
-            env.pop("CXX", None)
-            env.pop("CC", None)
-            subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, env=env, stdout=subprocess.DEVNULL)
-        self.L = C.CDLL(ORACLE_LIB)
-        for name in dir(self.L):
-            pass
+    """`Oracle()` binds the restated oracle; `Oracle(REFERENCE_LIB)` binds the same entry points
+    backed by the reference's own compiled sources (only the subset listed in oracle/ref_glue.cpp)."""
+
+    def __init__(self, lib=None):
+        if lib is None:
+            srcs = [os.path.join(ORACLE_DIR, "ecckd_oracle.cpp")]
+            stale = (not os.path.exists(ORACLE_LIB)) or any(
+                os.path.getmtime(s) > os.path.getmtime(ORACLE_LIB) for s in srcs)
+            if stale:
+                env = dict(os.environ)
+                env.pop("CXX", None)
+                env.pop("CC", None)
+                subprocess.run(["make", "-C", ORACLE_DIR, "all"], check=True, env=env, stdout=subprocess.DEVNULL)
+            lib = ORACLE_LIB
+        self.path = lib
+        self.L = C.CDLL(lib)
+
+    def has(self, name):
+        return hasattr(self.L, "orc_" + name)
 
     # -- stage 1
     def planck_function(self, temperature, wavenumber, d_wavenumber):
@@ -181,6 +190,107 @@ class Oracle:
         self.L.orc_heating_rate(C.c_int(nhl - 1), C.c_int64(n), C.c_void_p(_p(p)), C.c_void_p(_p(dn)),
                                 C.c_void_p(_p(up)), C.c_void_p(_p(hr)))
         return hr
+
+    def radiative_transfer_sw_bb(self, cos_sza, ssi, spectral_od, grey_od, albedo, direct_only=False):
+        s, od, go = _f64(ssi), _f64(spectral_od), _f64(grey_od)
+        nlay, n = od.shape
+        dn = np.zeros(nlay + 1)
+        up = None if direct_only else np.zeros(nlay + 1)
+        rc = self.L.orc_radiative_transfer_sw_bb(C.c_int(nlay), C.c_int64(n), C.c_double(cos_sza), C.c_void_p(_p(s)),
+                                                 C.c_void_p(_p(od)), C.c_void_p(_p(go)), C.c_double(albedo),
+                                                 C.c_void_p(_p(dn)), C.c_void_p(_p(up)))
+        assert rc == 0, rc
+        return dn, up
+
+    def heating_rate_single(self, pressure_hl, flux_dn, flux_up=None):
+        p, dn = _f64(pressure_hl), _f64(flux_dn)
+        up = None if flux_up is None else _f64(flux_up)
+        hr = np.zeros(dn.size - 1)
+        rc = self.L.orc_heating_rate_single(C.c_int(dn.size - 1), C.c_void_p(_p(p)), C.c_void_p(_p(dn)),
+                                            C.c_void_p(_p(up)), C.c_void_p(_p(hr)))
+        assert rc == 0, rc
+        return hr
+
+    def rayleigh_molar_scattering_coeff(self, wavenumber):
+        wn = _f64(wavenumber)
+        out = np.zeros(wn.size)
+        rc = self.L.orc_rayleigh_molar_scattering_coeff(C.c_int64(wn.size), C.c_void_p(_p(wn)), C.c_void_p(_p(out)))
+        assert rc == 0, rc
+        return out
+
+    # -- cost functions (interval error a13, forward cost a22)
+    def calc_cost_function_lw(self, pressure_hl, planck_hl, surf_emissivity, surf_planck, bg_od, od_fit, flux_dn_surf,
+                              flux_up_toa, hr, flux_weight, layer_weight):
+        ph, pl, se, sp, bg, fit, fds, fut, hr, lw = (_f64(a) for a in (
+            pressure_hl, planck_hl, surf_emissivity, surf_planck, bg_od, od_fit, flux_dn_surf, flux_up_toa, hr,
+            layer_weight))
+        nlay, n = bg.shape
+        cost = C.c_double(0.0)
+        rc = self.L.orc_calc_cost_function_lw(
+            C.c_int(nlay), C.c_int64(n), C.c_void_p(_p(ph)), C.c_void_p(_p(pl)), C.c_void_p(_p(se)), C.c_void_p(_p(sp)),
+            C.c_void_p(_p(bg)), C.c_void_p(_p(fit)), C.c_void_p(_p(fds)), C.c_void_p(_p(fut)), C.c_void_p(_p(hr)),
+            C.c_double(flux_weight), C.c_void_p(_p(lw)), C.byref(cost))
+        assert rc == 0, rc
+        return cost.value
+
+    def calc_cost_function_sw(self, cos_sza, pressure_hl, ssi, albedo, bg_od, od_fit, flux_dn_surf, flux_up_toa, hr,
+                              flux_weight, layer_weight):
+        ph, s, bg, fit, fds, fut, hr, lw = (_f64(a) for a in (
+            pressure_hl, ssi, bg_od, od_fit, flux_dn_surf, flux_up_toa, hr, layer_weight))
+        nlay, n = bg.shape
+        cost = C.c_double(0.0)
+        rc = self.L.orc_calc_cost_function_sw(
+            C.c_int(nlay), C.c_int64(n), C.c_double(cos_sza), C.c_void_p(_p(ph)), C.c_void_p(_p(s)), C.c_double(albedo),
+            C.c_void_p(_p(bg)), C.c_void_p(_p(fit)), C.c_void_p(_p(fds)), C.c_void_p(_p(fut)), C.c_void_p(_p(hr)),
+            C.c_double(flux_weight), C.c_void_p(_p(lw)), C.byref(cost))
+        assert rc == 0, rc
+        return cost.value
+
+    def calc_cost_function_ckd_lw(self, pressure_hl, planck_hl, surf_emissivity, surf_planck, od, flux_dn, flux_up, hr,
+                                  flux_weight, flux_profile_weight, broadband_weight, spectral_boundary_weight,
+                                  layer_weight, spectral_flux_dn_surf=None, spectral_flux_up_toa=None, rel_dn=None,
+                                  rel_up=None, band_mapping=None):
+        ph, pl, se, sp, od, fd, fu, hr, lw = (_f64(a) for a in (
+            pressure_hl, planck_hl, surf_emissivity, surf_planck, od, flux_dn, flux_up, hr, layer_weight))
+        nlay, ng = od.shape
+        nband = fd.shape[1]
+        opt = [None if a is None else _f64(a) for a in (spectral_flux_dn_surf, spectral_flux_up_toa, rel_dn, rel_up)]
+        bm = None if band_mapping is None else _i32(band_mapping)
+        cost = C.c_double(0.0)
+        rc = self.L.orc_calc_cost_function_ckd_lw(
+            C.c_int(nlay), C.c_int(ng), C.c_int(nband), C.c_void_p(_p(ph)), C.c_void_p(_p(pl)), C.c_void_p(_p(se)),
+            C.c_void_p(_p(sp)), C.c_void_p(_p(od)), C.c_void_p(_p(fd)), C.c_void_p(_p(fu)), C.c_void_p(_p(hr)),
+            C.c_void_p(_p(opt[0])), C.c_void_p(_p(opt[1])), C.c_double(flux_weight), C.c_double(flux_profile_weight),
+            C.c_double(broadband_weight), C.c_double(spectral_boundary_weight), C.c_void_p(_p(lw)),
+            C.c_void_p(_p(opt[2])), C.c_void_p(_p(opt[3])), C.c_void_p(_p(bm)), C.byref(cost))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return cost.value
+
+    def calc_cost_function_ckd_sw(self, cos_sza, pressure_hl, ssi, albedo, od, flux_dn, flux_up, hr, flux_weight,
+                                  flux_profile_weight, broadband_weight, layer_weight, spectral_boundary_weights=None,
+                                  spectral_flux_dn_surf=None, spectral_flux_up_toa=None, rel_dn=None, rel_up=None,
+                                  band_mapping=None, cost_fn_per_band=None):
+        ph, s, al, od, fd, fu, hr, lw = (_f64(a) for a in (
+            pressure_hl, ssi, np.atleast_1d(albedo), od, flux_dn, flux_up, hr, layer_weight))
+        nlay, ng = od.shape
+        nband = fd.shape[1]
+        opt = [None if a is None else _f64(a) for a in (
+            spectral_flux_dn_surf, spectral_flux_up_toa, spectral_boundary_weights, rel_dn, rel_up)]
+        bm = None if band_mapping is None else _i32(band_mapping)
+        cost = C.c_double(0.0)
+        if cost_fn_per_band is not None:
+            assert cost_fn_per_band.dtype == np.float64 and cost_fn_per_band.flags.c_contiguous
+        rc = self.L.orc_calc_cost_function_ckd_sw(
+            C.c_int(nlay), C.c_int(ng), C.c_int(nband), C.c_double(cos_sza), C.c_void_p(_p(ph)), C.c_void_p(_p(s)),
+            C.c_int(al.size), C.c_void_p(_p(al)), C.c_void_p(_p(od)), C.c_void_p(_p(fd)), C.c_void_p(_p(fu)),
+            C.c_void_p(_p(hr)), C.c_void_p(_p(opt[0])), C.c_void_p(_p(opt[1])), C.c_double(flux_weight),
+            C.c_double(flux_profile_weight), C.c_double(broadband_weight), C.c_void_p(_p(opt[2])), C.c_void_p(_p(lw)),
+            C.c_void_p(_p(opt[3])), C.c_void_p(_p(opt[4])), C.c_void_p(_p(bm)), C.c_void_p(_p(cost_fn_per_band)),
+            C.byref(cost))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return cost.value
 
     # -- CKD model
     def ckd_calc_optical_depth(self, gas, log_pressure, temperature, pressure_hl, temperature_fl, vmr_fl):
@@ -320,6 +430,19 @@ class Oracle:
         self.L.orc_assign_g_points(C.c_int(ngas), C.c_int64(nwav), C.c_void_p(_p(gg)), C.c_int(ng), C.c_int(ng),
                                    C.c_void_p(_p(gmin)), C.c_void_p(_p(gmax)), C.c_void_p(_p(g)), C.byref(n_un))
         return g, int(n_un.value)
+
+
+_reference = None
+
+
+def reference_oracle():
+    """The reference's own sources behind the oracle's entry points, or None when oracle/_ref has not
+    been built (it is built by __graft_entry__.build() wherever /root/reference exists and travels
+    to the GPU box as a prebuilt file)."""
+    global _reference
+    if _reference is None and os.path.exists(REFERENCE_LIB):
+        _reference = Oracle(REFERENCE_LIB)
+    return _reference
 
 
 _oracle = None

@@ -200,5 +200,5 @@ def assert_avg_close(got, ref, method="linear", scale=None, rtol=AVG_RTOL, what=
         rel = err[fin] / np.maximum(np.abs(b[fin]), 1e-300)
         assert not bad.any(), (f"{what}{name}: max rel err {np.max(rel):.3e}, "
                                f"{bad.sum()} of {bad.size} out of tolerance")
-    if got[3] is not None and ref[3] is not None:
+    if len(got) > 3 and len(ref) > 3 and got[3] is not None and ref[3] is not None:
         assert np.array_equal(got[3] & 1, ref[3] & 1), f"{what}empty-g warning flags differ"
