@@ -116,6 +116,20 @@ def _declare(L):
         "ecckd_heating_rate_dev": [vp, i32, i32, i64, vp, vp, vp, vp],
         "ecckd_run_ckd_dev": [vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
         "ecckd_run_ckd": [vp, vp, vp, dbl, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp],
+        "ecckd_split_base_g_points_dev": [vp, i32, vp, vp, i32, vp, i64, vp, vp, i32, C.POINTER(C.c_int), vp, vp, vp],
+        "ecckd_rayleigh_molar_scattering_coeff_dev": [vp, i64, vp, vp],
+        "ecckd_rayleigh_molar_scat_gpoints_dev": [vp, i32, i32, vp, vp, vp, vp, vp],
+        "ecckd_radiative_transfer_lw_bb_dev": [vp, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp],
+        "ecckd_radiative_transfer_sw_bb_dev": [vp, i32, i64, i64, dbl, vp, vp, vp, dbl, vp, vp],
+        "ecckd_interval_bounds_to_indices": [i64, i32, vp, vp, vp, vp],
+        "ecckd_interval_error_batch_lw_dev": [vp, i32, i32, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, vp, i32,
+                                              vp, vp, vp, vp],
+        "ecckd_interval_error_batch_sw_dev": [vp, i32, i32, i64, i64, dbl, vp, vp, dbl, vp, vp, vp, vp, vp, dbl, vp,
+                                              vp, vp, vp, vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp],
+        "ecckd_cost_function_ckd_lw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl,
+                                           dbl, dbl, vp, dbl, dbl, vp, vp, vp, vp, vp, vp],
+        "ecckd_cost_function_ckd_sw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dbl,
+                                           dbl, dbl, vp, vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp],
     }
     for name, argtypes in sigs.items():
         if hasattr(L, name):  # symbol-completeness is asserted by tests/test_abi.py

@@ -27,6 +27,7 @@ AVERAGING_METHODS = (
     "square-root",
     "logarithmic",
     "hybrid-logarithmic-transmission-3",
+    "total-transmission",  # interval fits of find_g_points only
 )
 WEIGHT_MATRIX, WEIGHT_VECTOR, WEIGHT_PLANCK = 0, 1, 2
 CONC_NONE, CONC_LINEAR, CONC_LUT, CONC_RELATIVE_LINEAR = 0, 1, 2, 3
@@ -575,3 +576,187 @@ def heating_rate(ctx, pressure_hl, flux_dn, flux_up=None):
     hr = ctx.empty((nhl - 1, n))
     heating_rate_dev(ctx, 1, nhl - 1, n, d_p, d_dn, d_up, hr)
     return hr.numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Stage-1 extras, broadband solvers, interval error batches, forward cost (rows a4b, a7b, a13,
+# a15, a21-a23 of SURVEY.md section 8)
+# ---------------------------------------------------------------------------------------------
+def _dev(ctx, a, dtype=np.float64):
+    return None if a is None else ctx.to_device(np.ascontiguousarray(a, dtype=dtype), dtype)
+
+
+def split_base_g_points_dev(ctx, band_wn1, band_wn2, base_wavenumber_boundary, nwav, d_wavenumber, d_ssi, ng,
+                            band_number, d_g_point, solar_irradiance=None, cap=None):
+    """create_look_up_table.cpp:162-224 -> (ng, band_number, solar_irradiance); d_g_point is updated in place."""
+    b1, b1p = _h(band_wn1)
+    b2, b2p = _h(band_wn2)
+    bb, bbp = _h(np.atleast_1d(np.asarray(base_wavenumber_boundary, dtype=np.float64)))
+    cap = int(cap if cap is not None else ng + bb.size)
+    bn = np.zeros(cap, dtype=np.int32)
+    bn[:ng] = np.asarray(band_number, dtype=np.int32)
+    sol = None
+    if solar_irradiance is not None:
+        sol = np.zeros(cap)
+        sol[:ng] = np.asarray(solar_irradiance, dtype=np.float64)
+    ng_io = C.c_int(int(ng))
+    check(_lib.lib().ecckd_split_base_g_points_dev(
+        ctx.handle, b1.size, b1p, b2p, bb.size, bbp, nwav, _ptr(d_wavenumber), _ptr(d_ssi), cap, C.byref(ng_io),
+        bn.ctypes.data, _ptr(d_g_point), None if sol is None else sol.ctypes.data))
+    n = ng_io.value
+    return n, bn[:n].copy(), (None if sol is None else sol[:n].copy())
+
+
+def rayleigh_molar_scattering_coeff(ctx, wavenumber_cm_1):
+    """rayleigh_scattering.h:23-43."""
+    d_wn = _dev(ctx, wavenumber_cm_1)
+    out = ctx.empty(d_wn.shape)
+    check(_lib.lib().ecckd_rayleigh_molar_scattering_coeff_dev(ctx.handle, int(np.prod(d_wn.shape)), d_wn.ptr, out.ptr))
+    return out.numpy()
+
+
+def rayleigh_molar_scat_gpoints(ctx, wavenumber1, wavenumber2, gpoint_fraction, ssi_intervals):
+    """CkdModel::calc_rayleigh_molar_scat, ckd_model.h:368-385."""
+    gf = np.ascontiguousarray(gpoint_fraction, dtype=np.float64)
+    ng, nbin = gf.shape
+    d = [_dev(ctx, a) for a in (wavenumber1, wavenumber2, gf, ssi_intervals)]
+    out = ctx.empty(ng)
+    check(_lib.lib().ecckd_rayleigh_molar_scat_gpoints_dev(ctx.handle, ng, nbin, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr,
+                                                          out.ptr))
+    return out.numpy()
+
+
+def radiative_transfer_lw_bb(ctx, planck, spectral_od, grey_od, surf_emissivity, surf_planck):
+    """radiative_transfer_lw_bb<false> (radiative_transfer_lw.cpp:85-142) -> (flux_dn, flux_up)[nlay+1]."""
+    od = np.ascontiguousarray(spectral_od, dtype=np.float64)
+    nlay, n = od.shape
+    d = [_dev(ctx, a) for a in (planck, od, grey_od, surf_emissivity, surf_planck)]
+    dn, up = ctx.empty(nlay + 1), ctx.empty(nlay + 1)
+    check(_lib.lib().ecckd_radiative_transfer_lw_bb_dev(ctx.handle, nlay, n, n, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr,
+                                                       d[4].ptr, dn.ptr, up.ptr))
+    return dn.numpy(), up.numpy()
+
+
+def radiative_transfer_sw_bb(ctx, cos_sza, ssi, spectral_od, grey_od, albedo, direct_only=False):
+    """radiative_transfer_{direct,norayleigh}_sw_bb<false> (radiative_transfer_sw.cpp:116-184)."""
+    od = np.ascontiguousarray(spectral_od, dtype=np.float64)
+    nlay, n = od.shape
+    d = [_dev(ctx, a) for a in (ssi, od, grey_od)]
+    dn = ctx.empty(nlay + 1)
+    up = None if direct_only else ctx.empty(nlay + 1)
+    check(_lib.lib().ecckd_radiative_transfer_sw_bb_dev(ctx.handle, nlay, n, n, float(cos_sza), d[0].ptr, d[1].ptr,
+                                                       d[2].ptr, float(albedo), dn.ptr, _ptr(up)))
+    return dn.numpy(), (None if up is None else up.numpy())
+
+
+def interval_bounds_to_indices(npoints, bound1, bound2):
+    """CkdEquipartition::lower_index/upper_index + the checks of calc_error (find_g_points.cpp:284-315)."""
+    b1, b1p = _h(np.atleast_1d(bound1))
+    b2, b2p = _h(np.atleast_1d(bound2))
+    i1, i2 = np.zeros(b1.size, dtype=np.int64), np.zeros(b1.size, dtype=np.int64)
+    check(_lib.lib().ecckd_interval_bounds_to_indices(int(npoints), b1.size, b1p, b2p, i1.ctypes.data, i2.ctypes.data))
+    return i1, i2
+
+
+def interval_error_batch_lw_dev(ctx, averaging_method, nlay, n, stride, d_pressure_hl, d_planck_hl, d_surf_emissivity,
+                                d_surf_planck, d_bg_od, d_metric, d_flux_dn_surf, d_flux_up_toa, d_hr, flux_weight,
+                                d_layer_weight, i1, i2, d_error, d_fit=None):
+    a1, a1p = _h(i1, np.int64)
+    a2, a2p = _h(i2, np.int64)
+    check(_lib.lib().ecckd_interval_error_batch_lw_dev(
+        ctx.handle, _method_id(averaging_method), nlay, n, stride, _ptr(d_pressure_hl), _ptr(d_planck_hl),
+        _ptr(d_surf_emissivity), _ptr(d_surf_planck), _ptr(d_bg_od), _ptr(d_metric), _ptr(d_flux_dn_surf),
+        _ptr(d_flux_up_toa), _ptr(d_hr), float(flux_weight), _ptr(d_layer_weight), a1.size, a1p, a2p, _ptr(d_error),
+        _ptr(d_fit)))
+
+
+def interval_error_batch_lw(ctx, averaging_method, pressure_hl, planck_hl, surf_emissivity, surf_planck, bg_od, metric,
+                            flux_dn_surf, flux_up_toa, hr, flux_weight, layer_weight, i1, i2):
+    """Batched CkdEquipartition::calc_error, longwave -> (error[nint], optical_depth_fit[nint][nlay])."""
+    bg = np.ascontiguousarray(bg_od, dtype=np.float64)
+    nlay, n = bg.shape
+    d = [_dev(ctx, a) for a in (pressure_hl, planck_hl, surf_emissivity, surf_planck, bg, metric, flux_dn_surf,
+                                flux_up_toa, hr, layer_weight)]
+    nint = len(np.atleast_1d(i1))
+    err, fit = ctx.empty(nint), ctx.empty((nint, nlay))
+    interval_error_batch_lw_dev(ctx, averaging_method, nlay, n, n, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8],
+                                flux_weight, d[9], i1, i2, err, fit)
+    return err.numpy(), fit.numpy()
+
+
+def interval_error_batch_sw_dev(ctx, averaging_method, nlay, n, stride, cos_sza, d_pressure_hl, d_ssi, albedo, d_bg_od,
+                                d_metric, d_flux_dn_surf, d_flux_up_toa, d_hr, flux_weight, d_layer_weight, i1, i2,
+                                d_error, d_fit=None, low=None, high=None, min_scaling=1.0, max_scaling=1.0):
+    a1, a1p = _h(i1, np.int64)
+    a2, a2p = _h(i2, np.int64)
+    low = low or (None, None, None)
+    high = high or (None, None, None)
+    check(_lib.lib().ecckd_interval_error_batch_sw_dev(
+        ctx.handle, _method_id(averaging_method), nlay, n, stride, float(cos_sza), _ptr(d_pressure_hl), _ptr(d_ssi),
+        float(albedo), _ptr(d_bg_od), _ptr(d_metric), _ptr(d_flux_dn_surf), _ptr(d_flux_up_toa), _ptr(d_hr),
+        float(flux_weight), _ptr(d_layer_weight), _ptr(low[0]), _ptr(low[1]), _ptr(low[2]), _ptr(high[0]),
+        _ptr(high[1]), _ptr(high[2]), float(min_scaling), float(max_scaling), a1.size, a1p, a2p, _ptr(d_error),
+        _ptr(d_fit)))
+
+
+def interval_error_batch_sw(ctx, averaging_method, cos_sza, pressure_hl, ssi, albedo, bg_od, metric, flux_dn_surf,
+                            flux_up_toa, hr, flux_weight, layer_weight, i1, i2, low=None, high=None, min_scaling=1.0,
+                            max_scaling=1.0):
+    """Batched CkdEquipartition::calc_error, shortwave; low/high = (flux_dn_surf, flux_up_toa, hr) sets."""
+    bg = np.ascontiguousarray(bg_od, dtype=np.float64)
+    nlay, n = bg.shape
+    d = [_dev(ctx, a) for a in (pressure_hl, ssi, bg, metric, flux_dn_surf, flux_up_toa, hr, layer_weight)]
+    dl = None if low is None else tuple(_dev(ctx, a) for a in low)
+    dh = None if high is None else tuple(_dev(ctx, a) for a in high)
+    nint = len(np.atleast_1d(i1))
+    err, fit = ctx.empty(nint), ctx.empty((nint, nlay))
+    interval_error_batch_sw_dev(ctx, averaging_method, nlay, n, n, cos_sza, d[0], d[1], albedo, d[2], d[3], d[4], d[5],
+                                d[6], flux_weight, d[7], i1, i2, err, fit, dl, dh, min_scaling, max_scaling)
+    return err.numpy(), fit.numpy()
+
+
+def cost_function_ckd_lw(ctx, pressure_hl, planck_hl, surf_emissivity, surf_planck, optical_depth, flux_dn, flux_up, hr,
+                         flux_weight, flux_profile_weight, broadband_weight, spectral_boundary_weight, layer_weight=None,
+                         pressure_weight_power=0.5, negative_od_penalty=1.0e4, spectral_flux_dn_surf=None,
+                         spectral_flux_up_toa=None, rel_dn=None, rel_up=None, band_mapping=None):
+    """calc_cost_function_ckd_lw for every profile of a scene (calc_cost_function_lw.cpp:115-232 as driven by
+    solve_adept.cpp:96-184) -> dict(cost_profile[nprof], cost_total, penalty)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nprof, nlay, ng = od.shape
+    nband = np.asarray(flux_dn).shape[-1]
+    d = [_dev(ctx, a) for a in (pressure_hl, planck_hl, surf_emissivity, surf_planck, od, flux_dn, flux_up, hr,
+                                spectral_flux_dn_surf, spectral_flux_up_toa, layer_weight, rel_dn, rel_up)]
+    d_bm = _dev(ctx, band_mapping, np.int32)
+    cp, ct, pt = ctx.empty(nprof), ctx.empty(1), ctx.empty(1)
+    check(_lib.lib().ecckd_cost_function_ckd_lw_dev(
+        ctx.handle, nprof, nlay, ng, nband, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, d[5].ptr, d[6].ptr,
+        d[7].ptr, _ptr(d[8]), _ptr(d[9]), float(flux_weight), float(flux_profile_weight), float(broadband_weight),
+        float(spectral_boundary_weight), _ptr(d[10]), float(pressure_weight_power), float(negative_od_penalty),
+        _ptr(d[11]), _ptr(d[12]), _ptr(d_bm), cp.ptr, ct.ptr, pt.ptr))
+    return dict(cost_profile=cp.numpy(), cost_total=float(ct.numpy()[0]), penalty=float(pt.numpy()[0]))
+
+
+def cost_function_ckd_sw(ctx, cos_sza, pressure_hl, ssi, albedo, optical_depth, flux_dn, flux_up, hr, flux_weight,
+                         flux_profile_weight, broadband_weight, layer_weight=None, pressure_weight_power=0.5,
+                         negative_od_penalty=1.0e4, spectral_boundary_weights=None, spectral_flux_dn_surf=None,
+                         spectral_flux_up_toa=None, rel_dn=None, rel_up=None, band_mapping=None, cost_fn_per_band=None):
+    """calc_cost_function_ckd_sw for every profile of a scene (calc_cost_function_sw.cpp:115-277)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nprof, nlay, ng = od.shape
+    nband = np.asarray(flux_dn).shape[-1]
+    mu = np.broadcast_to(np.asarray(cos_sza, dtype=np.float64), (nprof,))
+    d = [_dev(ctx, a) for a in (mu, pressure_hl, ssi, od, flux_dn, flux_up, hr, spectral_flux_dn_surf,
+                                spectral_flux_up_toa, spectral_boundary_weights, layer_weight, rel_dn, rel_up)]
+    d_bm = _dev(ctx, band_mapping, np.int32)
+    alb, albp = _h(np.atleast_1d(albedo))
+    d_pb = _dev(ctx, cost_fn_per_band)
+    cp, ct, pt = ctx.empty(nprof), ctx.empty(1), ctx.empty(1)
+    check(_lib.lib().ecckd_cost_function_ckd_sw_dev(
+        ctx.handle, nprof, nlay, ng, nband, d[0].ptr, d[1].ptr, d[2].ptr, alb.size, albp, d[3].ptr, d[4].ptr, d[5].ptr,
+        d[6].ptr, _ptr(d[7]), _ptr(d[8]), float(flux_weight), float(flux_profile_weight), float(broadband_weight),
+        _ptr(d[9]), _ptr(d[10]), float(pressure_weight_power), float(negative_od_penalty), _ptr(d[11]), _ptr(d[12]),
+        _ptr(d_bm), _ptr(d_pb), cp.ptr, ct.ptr, pt.ptr))
+    out = dict(cost_profile=cp.numpy(), cost_total=float(ct.numpy()[0]), penalty=float(pt.numpy()[0]))
+    if d_pb is not None:
+        out["cost_fn_per_band"] = d_pb.numpy()
+    return out

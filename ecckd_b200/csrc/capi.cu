@@ -64,9 +64,10 @@ ECCKD_API int ecckd_averaging_method_from_string(const char* name) {
   // strings of src/ecckd/average_optical_depth.cpp:43-129
   static const char* names[] = {"linear",          "transmission", "transmission-2",
                                 "transmission-3",  "transmission-10", "square-root",
-                                "logarithmic",     "hybrid-logarithmic-transmission-3"};
+                                "logarithmic",     "hybrid-logarithmic-transmission-3",
+                                "total-transmission"};  // find_g_points.cpp:146 (interval fits only)
   if (!name) return -1;
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 9; ++i) {
     if (strcmp(name, names[i]) == 0) return i;
   }
   return -1;

@@ -1,0 +1,985 @@
+// cost_function.cu - the error / cost evaluations built on the flux solvers:
+//   * broadband solvers radiative_transfer_lw_bb, radiative_transfer_{direct,norayleigh}_sw_bb
+//     (radiative_transfer_lw.cpp:85-142, radiative_transfer_sw.cpp:116-184),
+//   * the candidate-interval error of find_g_points, batched over intervals:
+//     fit_optical_depth_{lw,sw,sw_total_trans} (find_g_points.cpp:54-204),
+//     calc_cost_function_{lw,sw} (calc_cost_function_lw.cpp:23-110, calc_cost_function_sw.cpp:20-110),
+//     CkdEquipartition::calc_error (find_g_points.cpp:291-405),
+//   * the forward cost of optimize_lut, batched over profiles:
+//     calc_cost_function_ckd_{lw,sw} (calc_cost_function_lw.cpp:115-232, calc_cost_function_sw.cpp:115-277)
+//     with the layer weights and negative-optical-depth penalty of solve_adept.cpp:107-116,133-145.
+//
+// Interval batches.  The spectral arrays are [layer][n] in rank order, so a candidate interval is a
+// contiguous slab [i1,i2].  Every interval is cut into tiles of 256 wavenumbers; one CTA handles one
+// (interval, tile) item and writes partial sums, which a second tiny kernel adds in tile order:
+// the result does not depend on the launch geometry and is bitwise reproducible.  All kernels are
+// HBM streams (16-24 B per wavenumber x layer).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ecckd {
+
+constexpr int kTile = 256;  // wavenumbers per item == threads per CTA
+constexpr int kWarps = kTile / 32;
+
+struct IntervalParams {
+  int sw, method, nlay, nint, nitems;
+  int64_t n, stride;
+  const double* pressure_hl;      // [nlay+1]
+  const double* planck_hl;        // LW [nlay+1][n]
+  const double* ssi;              // SW [n]
+  const double* surf_emissivity;  // LW [n]
+  const double* surf_planck;      // LW [n]
+  const double* bg_od;            // [nlay][n]
+  const double* metric;           // [nlay][n]
+  const double* flux_dn_surf;     // [n]
+  const double* flux_up_toa;      // [n]
+  const double* hr;               // [nlay][n]
+  const double* layer_weight;     // [nlay]
+  double cos_sza, albedo, flux_weight, od_scale;
+  const int64_t* i1;          // [nint] inclusive bounds
+  const int64_t* i2;          // [nint]
+  const int64_t* item_start;  // [nint+1] first item of each interval
+  double* part_fit;           // [nitems][nlay][4]: fit numerator, denominator, count of tau>0, sum of hr
+  double* part_scal;          // [nitems][4]: sum flux_dn_surf, sum flux_up_toa, sum ssi
+  double* part_flux;          // [nitems][2][nlay+1]
+  double* fit;                // [nint][nlay]
+  double* truth;              // [nint][nlay+4]: hr_true[nlay], flux_dn_surf_true, flux_up_toa_true, sum ssi
+  double* bb_flux;            // [nint][2][nlay+1] (optional output)
+  double* error;              // [nint]
+  int error_mode;             // 0: store, 1: store 0.5*, 2: add 0.5*  (total-transmission low/high mean)
+};
+
+__device__ __forceinline__ int find_interval(const int64_t* __restrict__ item_start, int nint, int64_t item) {
+  int lo = 0, hi = nint - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (item_start[mid] <= item) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- phase A: per-tile partial sums of the fit and of the "true" quantities.
+// Warp w handles layers w, w+8, ...; lanes stride the tile (coalesced 256 B rows).
+__global__ void __launch_bounds__(kTile) interval_fit_partial_kernel(const IntervalParams p) {
+  const int64_t item = blockIdx.x;
+  const int k = find_interval(p.item_start, p.nint, item);
+  const int64_t a = p.i1[k] + (item - p.item_start[k]) * kTile;
+  const int64_t b = min(a + kTile, p.i2[k] + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool logm = p.method == ECCKD_AVG_LOGARITHMIC || (p.sw && p.method == ECCKD_AVG_TOTAL_TRANSMISSION);
+  const bool tt_linear = p.sw && p.method == ECCKD_AVG_TOTAL_TRANSMISSION;  // also wants the linear sums (fallback)
+  for (int l = warp; l < p.nlay; l += kWarps) {
+    const double* m = p.metric + (int64_t)l * p.stride;
+    const double* h = p.hr + (int64_t)l * p.stride;
+    // weights: LW planck_hl row l+1 (find_g_points.cpp:62); SW ssi
+    const double* w = p.sw ? p.ssi : p.planck_hl + (int64_t)(l + 1) * p.stride;
+    const double* wden = p.sw ? p.ssi : p.planck_hl + (int64_t)l * p.stride;  // log branch divides by row l (:89)
+    double num = 0.0, den = 0.0, cnt = 0.0, hs = 0.0;
+    for (int64_t i = a + lane; i < b; i += 32) {
+      const double mv = m[i];
+      hs += h[i];
+      if (logm && !tt_linear) {
+        if (mv > 0.0) { num += log(mv) * w[i]; den += wden[i]; cnt += 1.0; }
+      } else {
+        num += mv * w[i];
+        den += w[i];
+      }
+    }
+    num = warp_sum(num); den = warp_sum(den); cnt = warp_sum(cnt); hs = warp_sum(hs);
+    if (lane == 0) {
+      double* o = p.part_fit + ((size_t)item * p.nlay + l) * 4;
+      o[0] = num; o[1] = den; o[2] = cnt; o[3] = hs;
+    }
+  }
+  if (warp == 0) {
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t i = a + lane; i < b; i += 32) {
+      s0 += p.flux_dn_surf[i];
+      s1 += p.flux_up_toa[i];
+      if (p.sw) s2 += p.ssi[i];
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) {
+      double* o = p.part_scal + (size_t)item * 4;
+      o[0] = s0; o[1] = s1; o[2] = s2; o[3] = 0.0;
+    }
+  }
+}
+
+// ---- phase A2: add the tile partials in tile order and apply the fit formula.  CTA = interval.
+__global__ void interval_fit_finish_kernel(const IntervalParams p, int fit_from_sweep) {
+  const int k = blockIdx.x;
+  const int64_t it0 = p.item_start[k], it1 = p.item_start[k + 1];
+  const int64_t npts = p.i2[k] - p.i1[k] + 1;
+  __shared__ double s_scal[3];
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int64_t it = it0; it < it1; ++it) s += p.part_scal[(size_t)it * 4 + threadIdx.x];
+    s_scal[threadIdx.x] = s;
+    p.truth[(size_t)k * (p.nlay + 4) + p.nlay + threadIdx.x] = s;
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < p.nlay; l += blockDim.x) {
+    double num = 0.0, den = 0.0, cnt = 0.0, hs = 0.0;
+    for (int64_t it = it0; it < it1; ++it) {
+      const double* o = p.part_fit + ((size_t)it * p.nlay + l) * 4;
+      num += o[0]; den += o[1]; cnt += o[2]; hs += o[3];
+    }
+    p.truth[(size_t)k * (p.nlay + 4) + l] = hs;
+    if (fit_from_sweep == 2) continue;  // only the truth sums were wanted
+    double x;
+    if (!p.sw) {
+      switch (p.method) {
+        case ECCKD_AVG_LINEAR: x = num / den; break;
+        case ECCKD_AVG_TRANSMISSION:
+          x = fmin(0.9999999999999999, num / den);
+          x = fabs(-log(1.0 - x) / ECCKD_LW_DIFFUSIVITY);
+          break;
+        case ECCKD_AVG_TRANSMISSION_2:
+          x = fmin(0.9999999999999999, num / den);
+          x = fabs(-log(1.0 - x) / (ECCKD_LW_DIFFUSIVITY * 2.0));
+          break;
+        case ECCKD_AVG_SQUARE_ROOT: x = num / den; x *= x; break;
+        default:  // logarithmic (find_g_points.cpp:80-103)
+          if (cnt == (double)npts) x = exp(num / den);
+          else if (cnt == 0.0) x = 0.0;
+          else x = exp(num / den) * (cnt / (double)npts);
+      }
+    } else {
+      const double norm_factor = 1.0 / s_scal[2];
+      switch (p.method) {
+        case ECCKD_AVG_LINEAR: x = num * norm_factor; break;
+        case ECCKD_AVG_TRANSMISSION:  // min() before the normalisation, as the reference (:131)
+          x = fmin(0.9999999999999999, num) * norm_factor;
+          x = fabs(-log(1.0 - x) / ECCKD_LW_DIFFUSIVITY);
+          break;
+        case ECCKD_AVG_TRANSMISSION_2:
+          x = fmin(0.9999999999999999, num) * norm_factor;
+          x = fabs(-log(1.0 - x) / (ECCKD_LW_DIFFUSIVITY * 2.0));
+          break;
+        case ECCKD_AVG_SQUARE_ROOT: x = num * norm_factor; x *= x; break;
+        case ECCKD_AVG_TOTAL_TRANSMISSION: x = num * norm_factor; break;  // linear fallback profile, see below
+        default:
+          if (cnt == (double)npts) x = exp(num / den);
+          else if (cnt == 0.0) x = 0.0;
+          else x = exp(num / den) * (cnt / (double)npts);
+      }
+    }
+    p.fit[(size_t)k * p.nlay + l] = x;
+  }
+  if (!fit_from_sweep) return;
+  // fit_optical_depth_sw_total_trans (find_g_points.cpp:176-204): part_flux holds, per tile and level,
+  // the broadband direct flux with the background only [0] and with the gas added [1].
+  __syncthreads();
+  if (threadIdx.x == 0 && fit_from_sweep == 1) {
+    const int nlev = p.nlay + 1;
+    double top_bg = s_scal[2], top = s_scal[2];
+    bool fallback_used = false;
+    // the linear profile is already in fit[]; keep a copy semantics: layers not overwritten later keep it
+    // only if a fallback happened at or before... the reference overwrites the WHOLE profile at the failing
+    // layer and then continues, so layers after the failure are set individually again if they succeed.
+    // Walk the layers in order, tracking what the reference's vector would contain.
+    extern __shared__ double s_lin[];
+    for (int l = 0; l < p.nlay; ++l) s_lin[l] = p.fit[(size_t)k * p.nlay + l];
+    for (int l = 0; l < p.nlay; ++l) p.fit[(size_t)k * p.nlay + l] = 0.0;
+    for (int l = 0; l < p.nlay; ++l) {
+      double base_bg = 0.0, base = 0.0;
+      for (int64_t it = it0; it < it1; ++it) {
+        base_bg += p.part_flux[((size_t)it * 2 + 0) * nlev + l + 1];
+        base += p.part_flux[((size_t)it * 2 + 1) * nlev + l + 1];
+      }
+      if (base_bg > 0.0 && base > 0.0) {
+        const double bg_fit = -0.5 * log(base_bg / top_bg);
+        p.fit[(size_t)k * p.nlay + l] = -0.5 * log(base / top) - bg_fit;
+      } else {
+        for (int j = 0; j < p.nlay; ++j) p.fit[(size_t)k * p.nlay + j] = s_lin[j];
+        fallback_used = true;
+      }
+      top = base;
+      top_bg = base_bg;
+    }
+    (void)fallback_used;
+  }
+}
+
+// ---- sweep for the total-transmission fit: direct beam at secant 2 through background / background+gas.
+__global__ void __launch_bounds__(kTile) interval_tt_sweep_kernel(const IntervalParams p) {
+  extern __shared__ double s_part[];  // [2][nlev][kWarps]
+  const int64_t item = blockIdx.x;
+  const int k = find_interval(p.item_start, p.nint, item);
+  const int64_t i = p.i1[k] + (item - p.item_start[k]) * kTile + threadIdx.x;
+  const bool on = i <= p.i2[k];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nlev = p.nlay + 1;
+  double f_bg = on ? p.ssi[i] : 0.0, f = f_bg;
+  for (int l = 0; l < p.nlay; ++l) {
+    if (on) {
+      const double b = p.bg_od[(int64_t)l * p.stride + i], o = p.metric[(int64_t)l * p.stride + i];
+      f_bg *= exp(-2.0 * b);
+      f *= exp(-2.0 * (b + o));
+    }
+    const double s0 = warp_sum(f_bg), s1 = warp_sum(f);
+    if (lane == 0) {
+      s_part[(0 * nlev + l + 1) * kWarps + warp] = s0;
+      s_part[(1 * nlev + l + 1) * kWarps + warp] = s1;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * nlev; j += blockDim.x) {
+    double s = 0.0;
+    if (j % nlev != 0)
+      for (int w = 0; w < kWarps; ++w) s += s_part[j * kWarps + w];
+    p.part_flux[(size_t)item * 2 * nlev + j] = s;
+  }
+}
+
+// ---- phase B: broadband flux sweep of one tile (radiative_transfer_lw_bb / _sw_bb).
+template <bool SW>
+__global__ void __launch_bounds__(kTile) interval_flux_kernel(const IntervalParams p) {
+  extern __shared__ double s_part[];  // [2][nlev][kWarps]
+  const int64_t item = blockIdx.x;
+  const int k = find_interval(p.item_start, p.nint, item);
+  const int64_t i = p.i1[k] + (item - p.item_start[k]) * kTile + threadIdx.x;
+  const bool on = i <= p.i2[k];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nlev = p.nlay + 1;
+  const double* fit = p.fit + (size_t)k * p.nlay;
+  const double sc = p.od_scale;
+  double flux = 0.0;
+  if (!SW) {
+    const double THRESHOLD_EMISSIVITY = 1.0e-5;  // radiative_transfer_lw.cpp:98
+    double b_top = on ? p.planck_hl[i] : 0.0;
+    if (lane == 0) s_part[(0 * nlev + 0) * kWarps + warp] = 0.0;
+    for (int l = 0; l < p.nlay; ++l) {
+      double b_bot = 0.0;
+      if (on) {
+        const double tau = p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc;
+        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+        const double f = fmax(1.0 - (1.0 / ECCKD_LW_DIFFUSIVITY) * fmax(e, THRESHOLD_EMISSIVITY) /
+                                        fmax(tau, THRESHOLD_EMISSIVITY / ECCKD_LW_DIFFUSIVITY),
+                              0.5 * THRESHOLD_EMISSIVITY);
+        b_bot = p.planck_hl[(int64_t)(l + 1) * p.stride + i];
+        flux = flux * (1.0 - e) + b_top * (e - f) + b_bot * f;
+      }
+      const double s = warp_sum(flux);
+      if (lane == 0) s_part[(0 * nlev + l + 1) * kWarps + warp] = s;
+      b_top = b_bot;
+    }
+    double b_bot = b_top;
+    if (on) {
+      const double es = p.surf_emissivity[i];
+      flux = p.surf_planck[i] * es + (1.0 - es) * flux;
+    }
+    {
+      const double s = warp_sum(flux);
+      if (lane == 0) s_part[(1 * nlev + p.nlay) * kWarps + warp] = s;
+    }
+    for (int l = p.nlay - 1; l >= 0; --l) {
+      double b_t = 0.0;
+      if (on) {
+        const double tau = p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc;
+        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+        const double f = fmax(1.0 - (1.0 / ECCKD_LW_DIFFUSIVITY) * fmax(e, THRESHOLD_EMISSIVITY) /
+                                        fmax(tau, THRESHOLD_EMISSIVITY / ECCKD_LW_DIFFUSIVITY),
+                              0.5 * THRESHOLD_EMISSIVITY);
+        b_t = p.planck_hl[(int64_t)l * p.stride + i];
+        flux = flux * (1.0 - e) + b_bot * (e - f) + b_t * f;
+      }
+      const double s = warp_sum(flux);
+      if (lane == 0) s_part[(1 * nlev + l) * kWarps + warp] = s;
+      b_bot = b_t;
+    }
+  } else {
+    const double minus_sec_sza = -1.0 / p.cos_sza;
+    flux = on ? p.cos_sza * p.ssi[i] : 0.0;
+    if (lane == 0) s_part[(0 * nlev + 0) * kWarps + warp] = 0.0;  // level 0 is cos_sza*sum(ssi): set in phase C
+    for (int l = 0; l < p.nlay; ++l) {
+      if (on) flux = flux * exp(minus_sec_sza * (p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc));
+      const double s = warp_sum(flux);
+      if (lane == 0) s_part[(0 * nlev + l + 1) * kWarps + warp] = s;
+    }
+    if (p.albedo > 0.0) {
+      flux *= p.albedo;
+      {
+        const double s = warp_sum(flux);
+        if (lane == 0) s_part[(1 * nlev + p.nlay) * kWarps + warp] = s;
+      }
+      for (int l = p.nlay - 1; l >= 0; --l) {
+        if (on) flux = flux * exp(-2.0 * (p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc));
+        const double s = warp_sum(flux);
+        if (lane == 0) s_part[(1 * nlev + l) * kWarps + warp] = s;
+      }
+    } else {
+      for (int l = lane; l < nlev; l += 32) s_part[(1 * nlev + l) * kWarps + warp] = 0.0;
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < 2 * nlev; j += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < kWarps; ++w) s += s_part[j * kWarps + w];
+    p.part_flux[(size_t)item * 2 * nlev + j] = s;
+  }
+}
+
+// ---- phase C: broadband fluxes of each interval, heating rate, RMS error.  CTA = interval.
+__global__ void interval_error_kernel(const IntervalParams p) {
+  extern __shared__ double s_c[];  // dn[nlev], up[nlev], term[nlay]
+  const int k = blockIdx.x, nlev = p.nlay + 1;
+  double* dn = s_c;
+  double* up = s_c + nlev;
+  double* term = up + nlev;
+  const int64_t it0 = p.item_start[k], it1 = p.item_start[k + 1];
+  const double* truth = p.truth ? p.truth + (size_t)k * (p.nlay + 4) : nullptr;
+  for (int j = threadIdx.x; j < 2 * nlev; j += blockDim.x) {
+    double s = 0.0;
+    for (int64_t it = it0; it < it1; ++it) s += p.part_flux[(size_t)it * 2 * nlev + j];
+    if (p.sw && j == 0) s = p.cos_sza * truth[p.nlay + 2];  // flux_dn(0) = cos_sza*sum(ssi), radiative_transfer_sw.cpp:134
+    s_c[j] = s;
+    if (p.bb_flux) p.bb_flux[(size_t)k * 2 * nlev + j] = s;
+  }
+  if (!p.error) return;
+  __syncthreads();
+  const double hr_weight = 3600.0 * 24.0;
+  for (int l = threadIdx.x; l < p.nlay; l += blockDim.x) {
+    const double c = -((ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p.pressure_hl[l + 1] - p.pressure_hl[l]));
+    // LW: heating_rate_single with both fluxes; SW: Vector() for the upwelling (calc_cost_function_sw.cpp:87)
+    const double hr_fit = p.sw ? c * (dn[l + 1] - dn[l]) : c * (dn[l + 1] - dn[l] - up[l + 1] + up[l]);
+    const double d = hr_fit - truth[l];
+    term[l] = p.layer_weight[l] * (d * d);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int l = 0; l < p.nlay; ++l) s += term[l];
+    const double dd = dn[p.nlay] - truth[p.nlay], du = up[0] - truth[p.nlay + 1];
+    const double e = sqrt(hr_weight * hr_weight * s + p.flux_weight * (dd * dd + du * du));
+    if (p.error_mode == 0) p.error[k] = e;
+    else if (p.error_mode == 1) p.error[k] = 0.5 * e;
+    else p.error[k] += 0.5 * e;
+  }
+}
+
+// Host side of a batch: item table, scratch carving, launches.
+struct IntervalBatch {
+  IntervalParams p;
+  std::vector<int64_t> item_start;
+};
+
+static int setup_batch(ecckd_ctx* ctx, IntervalParams& p, int nint, const int64_t* h_i1, const int64_t* h_i2, int64_t n,
+                       const char* who) {
+  ECCKD_REQUIRE(nint > 0 && h_i1 && h_i2, ECCKD_PARAMETER_ERROR, "%s: no intervals", who);
+  std::vector<int64_t> host((size_t)3 * nint + 1);
+  int64_t* i1 = host.data();
+  int64_t* i2 = i1 + nint;
+  int64_t* start = i2 + nint;
+  int64_t items = 0;
+  for (int k = 0; k < nint; ++k) {
+    // find_g_points.cpp:297-312: indices outside the valid range or out of order are a PROCESSING_ERROR
+    ECCKD_REQUIRE(h_i1[k] >= 0 && h_i2[k] < n && h_i2[k] >= h_i1[k], ECCKD_PROCESSING_ERROR,
+                  "%s: interval %d = [%lld,%lld] outside 0-%lld or out of order", who, k, (long long)h_i1[k],
+                  (long long)h_i2[k], (long long)(n - 1));
+    i1[k] = h_i1[k];
+    i2[k] = h_i2[k];
+    start[k] = items;
+    items += (h_i2[k] - h_i1[k] + 1 + kTile - 1) / kTile;
+  }
+  start[nint] = items;
+  ECCKD_REQUIRE(items < 2147483647LL, ECCKD_PARAMETER_ERROR, "%s: too many tiles", who);
+  p.nint = nint;
+  p.nitems = (int)items;
+  const int nlev = p.nlay + 1;
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t b_idx = up256(host.size() * sizeof(int64_t));
+  const size_t b_fit = up256((size_t)items * p.nlay * 4 * sizeof(double));
+  const size_t b_scal = up256((size_t)items * 4 * sizeof(double));
+  const size_t b_flux = up256((size_t)items * 2 * nlev * sizeof(double));
+  const size_t b_truth = up256((size_t)nint * (p.nlay + 4) * sizeof(double));
+  const size_t b_fitout = up256((size_t)nint * p.nlay * sizeof(double));
+  void* base = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 2, b_idx + b_fit + b_scal + b_flux + b_truth + b_fitout, &base));
+  char* c = static_cast<char*>(base);
+  ECCKD_TRY(upload_small(ctx, c, host.data(), host.size() * sizeof(int64_t)));
+  p.i1 = reinterpret_cast<int64_t*>(c);
+  p.i2 = p.i1 + nint;
+  p.item_start = p.i2 + nint;
+  c += b_idx;
+  p.part_fit = reinterpret_cast<double*>(c); c += b_fit;
+  p.part_scal = reinterpret_cast<double*>(c); c += b_scal;
+  p.part_flux = reinterpret_cast<double*>(c); c += b_flux;
+  p.truth = reinterpret_cast<double*>(c); c += b_truth;
+  if (!p.fit) p.fit = reinterpret_cast<double*>(c);
+  return ECCKD_OK;
+}
+
+static int launch_flux_and_error(ecckd_ctx* ctx, const IntervalParams& p) {
+  const size_t smem = (size_t)2 * (p.nlay + 1) * kWarps * sizeof(double);
+  if (p.sw) interval_flux_kernel<true><<<p.nitems, kTile, smem, ctx->stream>>>(p);
+  else interval_flux_kernel<false><<<p.nitems, kTile, smem, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  interval_error_kernel<<<p.nint, 64, (size_t)(3 * p.nlay + 2) * sizeof(double), ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+// ------------------------------------------------------------------ forward cost of optimize_lut
+struct CkdCostParams {
+  int sw, nprof, nlay, ng, nband, nemis, nalbedo, up_in_bb, direct_only;
+  const double* pressure_hl;       // [nprof][nlay+1]
+  const double* planck_hl;         // LW [nprof][nlay+1][ng]
+  const double* surf_emissivity;   // LW [nprof][nemis]
+  const double* surf_planck;       // LW [nprof][ng]
+  const double* cos_sza;           // SW [nprof]
+  const double* ssi;               // SW [ng] (already scaled by tsi_scaling)
+  const double* albedo;            // SW [nalbedo]
+  const double* optical_depth;     // [nprof][nlay][ng]
+  const double* flux_dn;           // [nprof][nlay+1][nband]
+  const double* flux_up;           // [nprof][nlay+1][nband]
+  const double* hr;                // [nprof][nlay][nband]
+  const double* spectral_flux_dn_surf;  // [nprof][ng] or NULL
+  const double* spectral_flux_up_toa;   // [nprof][ng] or NULL
+  const double* spectral_boundary_weights;  // SW [ng] or NULL
+  const double* layer_weight;      // [nprof][nlay] or NULL (then from pressure_weight_power)
+  const double* rel_dn;            // [nprof][nlay+1][ng] or NULL
+  const double* rel_up;
+  const int32_t* band_mapping;     // [ng] or NULL
+  double flux_weight, flux_profile_weight, broadband_weight, spectral_boundary_weight, negative_od_penalty,
+      pressure_weight_power;
+  double* cost_profile;            // [nprof]
+  double* penalty_profile;         // [nprof]
+  double* cost_band_profile;       // [nprof][nband] or NULL
+};
+
+// CTA = profile, thread = g point for the sweep; the (tiny) cost terms follow the reference's
+// evaluation order with sequential sums.
+__global__ void ckd_cost_kernel(const CkdCostParams p) {
+  extern __shared__ double sm[];
+  const int ip = blockIdx.x, nlay = p.nlay, nlev = nlay + 1, ng = p.ng, nband = p.nband;
+  double* fdo = sm;                          // [nlev][ng]
+  double* fuo = fdo + (size_t)nlev * ng;     // [nlev][ng]
+  double* fd = fuo + (size_t)nlev * ng;      // [nlev][nband]
+  double* fu = fd + (size_t)nlev * nband;    // [nlev][nband]
+  double* hrf = fu + (size_t)nlev * nband;   // [nlay][nband]
+  double* lw = hrf + (size_t)nlay * nband;   // [nlay]
+  double* iw = lw + nlay;                    // [nlay]
+  double* tmp = iw + nlay;                   // [max(nband, nlev, ng)]
+  double* red = tmp + max(max(nband, nlev), ng);  // [8]
+  const double* p_hl = p.pressure_hl + (size_t)ip * nlev;
+  const double* od = p.optical_depth + (size_t)ip * nlay * ng;
+  const double hr_weight = 3600.0 * 24.0;
+
+  // layer weights (solve_adept.cpp:133-145)
+  if (threadIdx.x == 0) {
+    if (p.layer_weight) {
+      for (int l = 0; l < nlay; ++l) lw[l] = p.layer_weight[(size_t)ip * nlay + l];
+    } else {
+      double s = 0.0;
+      for (int l = 0; l < nlay; ++l) {
+        double v;
+        if (p.pressure_weight_power == 0.5) v = sqrt(p_hl[l + 1]) - sqrt(p_hl[l]);
+        else if (p.pressure_weight_power == 1.0) v = p_hl[l + 1] - p_hl[l];
+        else v = pow(p_hl[l + 1], p.pressure_weight_power) - pow(p_hl[l], p.pressure_weight_power);
+        lw[l] = v;
+        s += v;
+      }
+      for (int l = 0; l < nlay; ++l) lw[l] /= s;
+    }
+    for (int l = 0; l + 1 < nlay; ++l) iw[l] = p.flux_profile_weight * 0.5 * (lw[l] + lw[l + 1]);
+  }
+
+  // forward fluxes per g point, with the negative optical depths penalised and clamped
+  // (solve_adept.cpp:107-116)
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    double pen = 0.0;
+    if (!p.sw) {
+      const double* pl = p.planck_hl + (size_t)ip * nlev * ng + g;
+      double f_dn = 0.0, b_top = pl[0];
+      fdo[g] = 0.0;
+      for (int l = 0; l < nlay; ++l) {
+        double tau = od[(size_t)l * ng + g];
+        if (tau < 0.0) { pen += tau * tau; tau = 0.0; }
+        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+        const double f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+        const double b_bot = pl[(size_t)(l + 1) * ng];
+        f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
+        fdo[(size_t)(l + 1) * ng + g] = f_dn;
+        b_top = b_bot;
+      }
+      const int ie = p.band_mapping ? p.band_mapping[g] : g;
+      const double es = p.surf_emissivity[(size_t)ip * p.nemis + ie];
+      double f_up = p.surf_planck[(size_t)ip * ng + g] * es + (1.0 - es) * f_dn;
+      fuo[(size_t)nlay * ng + g] = f_up;
+      double b_bot = b_top;
+      for (int l = nlay - 1; l >= 0; --l) {
+        const double tau = fmax(od[(size_t)l * ng + g], 0.0);
+        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
+        const double f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+        const double b_t = pl[(size_t)l * ng];
+        f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
+        fuo[(size_t)l * ng + g] = f_up;
+        b_bot = b_t;
+      }
+    } else {
+      const double mu0 = p.cos_sza[ip];
+      const double minus_sec_sza = -1.0 / mu0;
+      double f = mu0 * p.ssi[g];
+      fdo[g] = f;
+      for (int l = 0; l < nlay; ++l) {
+        double tau = od[(size_t)l * ng + g];
+        if (tau < 0.0) { pen += tau * tau; tau = 0.0; }
+        f = f * exp(minus_sec_sza * tau);
+        fdo[(size_t)(l + 1) * ng + g] = f;
+      }
+      if (p.direct_only) {
+        for (int l = 0; l < nlev; ++l) fuo[(size_t)l * ng + g] = 0.0;
+      } else {
+        f = f * p.albedo[p.band_mapping[g]];
+        fuo[(size_t)nlay * ng + g] = f;
+        for (int l = nlay - 1; l >= 0; --l) {
+          f = f * exp(-2.0 * fmax(od[(size_t)l * ng + g], 0.0));
+          fuo[(size_t)l * ng + g] = f;
+        }
+      }
+    }
+    tmp[g] = pen;
+    if (p.rel_dn) {
+      const double* rd = p.rel_dn + (size_t)ip * nlev * ng + g;
+      const double* ru = p.rel_up + (size_t)ip * nlev * ng + g;
+      for (int l = 0; l < nlev; ++l) {
+        fdo[(size_t)l * ng + g] -= rd[(size_t)l * ng];
+        fuo[(size_t)l * ng + g] -= ru[(size_t)l * ng];
+      }
+    }
+  }
+  // penalty: per-g partial sums added in g order
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double pen = 0.0;
+    for (int g = 0; g < ng; ++g) pen += tmp[g];
+    p.penalty_profile[ip] = p.negative_od_penalty * pen;
+  }
+  __syncthreads();
+
+  // g points -> bands
+  for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
+    const int l = j / nband, ib = j - l * nband;
+    if (!p.band_mapping) {
+      fd[j] = fdo[(size_t)l * ng + ib];
+      fu[j] = fuo[(size_t)l * ng + ib];
+    } else {
+      double sd = 0.0, su = 0.0;
+      for (int g = 0; g < ng; ++g) {
+        if (p.band_mapping[g] == ib) { sd += fdo[(size_t)l * ng + g]; su += fuo[(size_t)l * ng + g]; }
+      }
+      fd[j] = sd;
+      fu[j] = su;
+    }
+  }
+  __syncthreads();
+  // heating rates (heating_rate.h:38-48; the SW passes an empty upwelling, calc_cost_function_sw.cpp:195)
+  for (int j = threadIdx.x; j < nlay * nband; j += blockDim.x) {
+    const int l = j / nband, ib = j - l * nband;
+    const double conv = -(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l + 1] - p_hl[l]);
+    const size_t a = (size_t)l * nband + ib;
+    hrf[j] = p.sw ? conv * (fd[a + nband] - fd[a]) : conv * (fd[a + nband] - fd[a] - fu[a + nband] + fu[a]);
+  }
+  __syncthreads();
+  const double* t_dn = p.flux_dn + (size_t)ip * nlev * nband;
+  const double* t_up = p.flux_up + (size_t)ip * nlev * nband;
+  const double* t_hr = p.hr + (size_t)ip * nlay * nband;
+  // per-band terms
+  for (int ib = threadIdx.x; ib < nband; ib += blockDim.x) {
+    double s = 0.0;
+    for (int l = 0; l < nlay; ++l) {
+      const double d = hrf[(size_t)l * nband + ib] - t_hr[(size_t)l * nband + ib];
+      s += lw[l] * d * d;
+    }
+    const double dd = fd[(size_t)nlay * nband + ib] - t_dn[(size_t)nlay * nband + ib];
+    const double du = fu[ib] - t_up[ib];
+    double local = hr_weight * hr_weight * s + p.flux_weight * (dd * dd + (p.sw ? 20.0 : 1.0) * du * du);
+    if (p.flux_profile_weight > 0.0) {
+      double t = 0.0;
+      for (int l = 1; l < nlay; ++l) {
+        const double a = fd[(size_t)l * nband + ib] - t_dn[(size_t)l * nband + ib];
+        const double b = fu[(size_t)l * nband + ib] - t_up[(size_t)l * nband + ib];
+        t += iw[l - 1] * (a * a + b * b);
+      }
+      local += t;
+    }
+    tmp[ib] = local;
+    if (p.cost_band_profile) p.cost_band_profile[(size_t)ip * nband + ib] = local;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    for (int ib = 0; ib < nband; ++ib) c += tmp[ib];
+    red[0] = c;
+  }
+  __syncthreads();
+  // broadband terms: errors summed over bands, per layer / level
+  for (int l = threadIdx.x; l < nlev; l += blockDim.x) {
+    double e = 0.0, a = 0.0, b = 0.0;
+    for (int ib = 0; ib < nband; ++ib) {
+      if (l < nlay) e += hrf[(size_t)l * nband + ib] - t_hr[(size_t)l * nband + ib];
+      a += fd[(size_t)l * nband + ib] - t_dn[(size_t)l * nband + ib];
+      b += fu[(size_t)l * nband + ib] - t_up[(size_t)l * nband + ib];
+    }
+    red[8 + 3 * l + 0] = e;
+    red[8 + 3 * l + 1] = a;
+    red[8 + 3 * l + 2] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double cost = red[0];
+    const double* bb = red + 8;
+    if (!p.sw || p.broadband_weight > 0.0) {
+      double s = 0.0;
+      for (int l = 0; l < nlay; ++l) s += lw[l] * (bb[3 * l] * bb[3 * l]);
+      const double ed = bb[3 * nlay + 1], eu = bb[2];
+      if (!p.sw) {
+        cost = (cost * (1.0 - p.broadband_weight)) / nband + p.broadband_weight * hr_weight * hr_weight * s +
+               p.broadband_weight * p.flux_weight * (ed * ed + eu * eu);
+      } else {
+        cost = (cost * (1.0 - p.broadband_weight)) / nband + p.broadband_weight * hr_weight * hr_weight * s;
+        cost += p.broadband_weight * p.flux_weight * (ed * ed);
+        if (p.up_in_bb) cost += p.broadband_weight * p.flux_weight * (eu * eu);
+      }
+      if (p.flux_profile_weight > 0.0) {
+        if (!p.sw) {
+          double t = 0.0;
+          for (int l = 1; l < nlay; ++l) t += iw[l - 1] * (bb[3 * l + 1] * bb[3 * l + 1] + bb[3 * l + 2] * bb[3 * l + 2]);
+          cost += p.broadband_weight * t;
+        } else {
+          double td = 0.0, tu = 0.0;
+          for (int l = 1; l < nlay; ++l) {
+            td += iw[l - 1] * (bb[3 * l + 1] * bb[3 * l + 1]);
+            tu += iw[l - 1] * (bb[3 * l + 2] * bb[3 * l + 2]);
+          }
+          cost += p.broadband_weight * td;
+          if (p.up_in_bb) cost += p.broadband_weight * tu;
+        }
+      }
+    }
+    // spectral boundary terms on the g-point fluxes
+    if (!p.sw) {
+      if (p.spectral_boundary_weight > 0.0 && p.spectral_flux_dn_surf && p.spectral_flux_up_toa) {
+        double s = 0.0;
+        for (int g = 0; g < ng; ++g) {
+          const double a = fdo[(size_t)nlay * ng + g] - p.spectral_flux_dn_surf[(size_t)ip * ng + g];
+          const double b = fuo[g] - p.spectral_flux_up_toa[(size_t)ip * ng + g];
+          s += a * a + b * b;
+        }
+        cost += p.spectral_boundary_weight * s;
+      }
+    } else if (p.spectral_boundary_weights && p.spectral_flux_dn_surf) {
+      double s = 0.0;
+      for (int g = 0; g < ng; ++g) {
+        const double a = fdo[(size_t)nlay * ng + g] - p.spectral_flux_dn_surf[(size_t)ip * ng + g];
+        s += p.spectral_boundary_weights[g] * a * a;
+      }
+      cost += s;
+    }
+    p.cost_profile[ip] = cost;
+  }
+}
+
+// cost = sum over profiles in profile order (solve_adept.cpp:96-199 `cost +=`), penalties first per scene
+__global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __restrict__ cost_profile,
+                                      const double* __restrict__ penalty_profile,
+                                      const double* __restrict__ cost_band_profile, double* __restrict__ cost_total,
+                                      double* __restrict__ penalty_total, double* __restrict__ cost_fn_per_band) {
+  if (threadIdx.x == 0) {
+    double pen = 0.0, c = 0.0;
+    for (int i = 0; i < nprof; ++i) pen += penalty_profile[i];
+    for (int i = 0; i < nprof; ++i) c += cost_profile[i];
+    if (penalty_total) *penalty_total = pen;
+    if (cost_total) *cost_total = pen + c;
+  }
+  if (cost_fn_per_band && cost_band_profile) {
+    for (int ib = threadIdx.x; ib < nband; ib += blockDim.x) {
+      double s = cost_fn_per_band[ib];
+      for (int i = 0; i < nprof; ++i) s += cost_band_profile[(size_t)i * nband + ib];
+      cost_fn_per_band[ib] = s;
+    }
+  }
+}
+
+static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_profile, double* d_cost_total,
+                           double* d_penalty_total, double* d_cost_fn_per_band, const char* who) {
+  const int nlev = p.nlay + 1;
+  ECCKD_REQUIRE(p.nprof > 0 && p.nlay > 0 && p.ng > 0 && p.nband > 0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
+  ECCKD_REQUIRE(p.band_mapping || p.nband == p.ng, ECCKD_PARAMETER_ERROR,
+                "%s: without band_mapping the truth arrays are per g point (nband must equal ng)", who);
+  const size_t ndbl = (size_t)2 * nlev * p.ng + (size_t)2 * nlev * p.nband + (size_t)p.nlay * p.nband + 2 * p.nlay +
+                      std::max(std::max(p.nband, nlev), p.ng) + 8 + 3 * nlev;
+  const size_t smem = ndbl * sizeof(double);
+  ECCKD_REQUIRE(smem <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
+                "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, p.ng, nlev, smem,
+                ctx->smem_optin);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  void* base = nullptr;
+  const size_t b_prof = ((size_t)p.nprof * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_band = d_cost_fn_per_band ? (size_t)p.nprof * p.nband * sizeof(double) : 0;
+  ECCKD_TRY(ws_reserve(ctx, 2, 2 * b_prof + b_band, &base));
+  char* c = static_cast<char*>(base);
+  p.penalty_profile = reinterpret_cast<double*>(c);
+  double* own_cost = reinterpret_cast<double*>(c + b_prof);
+  p.cost_profile = d_cost_profile ? d_cost_profile : own_cost;
+  p.cost_band_profile = d_cost_fn_per_band ? reinterpret_cast<double*>(c + 2 * b_prof) : nullptr;
+  const int threads = std::min(1024, std::max(64, (p.ng + 31) / 32 * 32));
+  ckd_cost_kernel<<<p.nprof, threads, smem, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  ckd_cost_total_kernel<<<1, 64, 0, ctx->stream>>>(p.nprof, p.nband, p.cost_profile, p.penalty_profile,
+                                                   p.cost_band_profile, d_cost_total, d_penalty_total,
+                                                   d_cost_fn_per_band);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+}  // namespace ecckd
+
+using namespace ecckd;
+
+// ------------------------------------------------------------------ C ABI
+ECCKD_API int ecckd_interval_bounds_to_indices(int64_t npoints, int nint, const double* bound1, const double* bound2,
+                                               int64_t* i1, int64_t* i2) {
+  ECCKD_REQUIRE(npoints > 0 && nint >= 0 && bound1 && bound2 && i1 && i2, ECCKD_PARAMETER_ERROR,
+                "ecckd_interval_bounds_to_indices: bad argument");
+  for (int k = 0; k < nint; ++k) {
+    // find_g_points.cpp:284-315
+    int64_t ib1 = (int64_t)std::ceil(bound1[k] * (double)(npoints - 1));
+    int64_t ib2 = (int64_t)std::floor(bound2[k] * (double)(npoints - 1));
+    ECCKD_REQUIRE(!(ib1 < 0 || ib2 >= npoints), ECCKD_PROCESSING_ERROR,
+                  "requested bounds %g-%g corresponding to indices %lld-%lld outside valid range 0-%lld", bound1[k],
+                  bound2[k], (long long)ib1, (long long)ib2, (long long)(npoints - 1));
+    ECCKD_REQUIRE(!(bound2[k] < bound1[k]), ECCKD_PROCESSING_ERROR, "requested bounds out of order: %g-%g", bound1[k],
+                  bound2[k]);
+    ECCKD_REQUIRE(!(ib2 + 1 < ib1), ECCKD_PROCESSING_ERROR, "requested indices out of order: %lld-%lld", (long long)ib1,
+                  (long long)ib2);
+    if (ib2 < ib1) ib2 = ib1;
+    i1[k] = ib1;
+    i2[k] = ib2;
+  }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_interval_error_batch_lw_dev(ecckd_ctx* ctx, int averaging_method, int nlay, int64_t n, int64_t stride,
+                                                const double* d_pressure_hl, const double* d_planck_hl,
+                                                const double* d_surf_emissivity, const double* d_surf_planck,
+                                                const double* d_bg_optical_depth, const double* d_metric,
+                                                const double* d_flux_dn_surf, const double* d_flux_up_toa,
+                                                const double* d_hr, double flux_weight, const double* d_layer_weight,
+                                                int nint, const int64_t* h_i1, const int64_t* h_i2, double* d_error,
+                                                double* d_optical_depth_fit) {
+  const char* who = "ecckd_interval_error_batch_lw";
+  ECCKD_REQUIRE(ctx && d_pressure_hl && d_planck_hl && d_surf_emissivity && d_surf_planck && d_bg_optical_depth &&
+                    d_metric && d_flux_dn_surf && d_flux_up_toa && d_hr && d_layer_weight && d_error,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE(averaging_method == ECCKD_AVG_LINEAR || averaging_method == ECCKD_AVG_TRANSMISSION ||
+                    averaging_method == ECCKD_AVG_TRANSMISSION_2 || averaging_method == ECCKD_AVG_SQUARE_ROOT ||
+                    averaging_method == ECCKD_AVG_LOGARITHMIC,
+                ECCKD_PARAMETER_ERROR, "Averaging method %d not understood", averaging_method);  // find_g_points.cpp:111-113
+  ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
+  IntervalParams p = {};
+  p.sw = 0; p.method = averaging_method; p.nlay = nlay; p.n = n; p.stride = stride;
+  p.pressure_hl = d_pressure_hl; p.planck_hl = d_planck_hl; p.surf_emissivity = d_surf_emissivity;
+  p.surf_planck = d_surf_planck; p.bg_od = d_bg_optical_depth; p.metric = d_metric; p.flux_dn_surf = d_flux_dn_surf;
+  p.flux_up_toa = d_flux_up_toa; p.hr = d_hr; p.layer_weight = d_layer_weight; p.flux_weight = flux_weight;
+  p.od_scale = 1.0; p.error = d_error; p.fit = d_optical_depth_fit;
+  ECCKD_TRY(setup_batch(ctx, p, nint, h_i1, h_i2, n, who));
+  interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 0);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return launch_flux_and_error(ctx, p);
+}
+
+ECCKD_API int ecckd_interval_error_batch_sw_dev(
+    ecckd_ctx* ctx, int averaging_method, int nlay, int64_t n, int64_t stride, double cos_sza,
+    const double* d_pressure_hl, const double* d_ssi, double albedo, const double* d_bg_optical_depth,
+    const double* d_metric, const double* d_flux_dn_surf, const double* d_flux_up_toa, const double* d_hr,
+    double flux_weight, const double* d_layer_weight, const double* d_flux_dn_surf_low,
+    const double* d_flux_up_toa_low, const double* d_hr_low, const double* d_flux_dn_surf_high,
+    const double* d_flux_up_toa_high, const double* d_hr_high, double min_scaling, double max_scaling, int nint,
+    const int64_t* h_i1, const int64_t* h_i2, double* d_error, double* d_optical_depth_fit) {
+  const char* who = "ecckd_interval_error_batch_sw";
+  ECCKD_REQUIRE(ctx && d_pressure_hl && d_ssi && d_bg_optical_depth && d_metric && d_layer_weight && d_error,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  const bool tt = averaging_method == ECCKD_AVG_TOTAL_TRANSMISSION;
+  ECCKD_REQUIRE(averaging_method == ECCKD_AVG_LINEAR || averaging_method == ECCKD_AVG_TRANSMISSION ||
+                    averaging_method == ECCKD_AVG_TRANSMISSION_2 || averaging_method == ECCKD_AVG_SQUARE_ROOT ||
+                    averaging_method == ECCKD_AVG_LOGARITHMIC || tt,
+                ECCKD_PARAMETER_ERROR, "Averaging method %d not understood", averaging_method);  // find_g_points.cpp:168-170
+  if (tt) {
+    ECCKD_REQUIRE(d_flux_dn_surf_low && d_flux_up_toa_low && d_hr_low && d_flux_dn_surf_high && d_flux_up_toa_high &&
+                      d_hr_high,
+                  ECCKD_PARAMETER_ERROR, "%s: total-transmission needs the low/high reference sets", who);
+  } else {
+    ECCKD_REQUIRE(d_flux_dn_surf && d_flux_up_toa && d_hr, ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  }
+  ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n && cos_sza > 0.0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
+  IntervalParams p = {};
+  p.sw = 1; p.method = averaging_method; p.nlay = nlay; p.n = n; p.stride = stride; p.cos_sza = cos_sza; p.albedo = albedo;
+  p.pressure_hl = d_pressure_hl; p.ssi = d_ssi; p.bg_od = d_bg_optical_depth; p.metric = d_metric;
+  p.layer_weight = d_layer_weight; p.flux_weight = flux_weight; p.od_scale = 1.0; p.error = d_error;
+  p.fit = d_optical_depth_fit;
+  p.flux_dn_surf = tt ? d_flux_dn_surf_low : d_flux_dn_surf;
+  p.flux_up_toa = tt ? d_flux_up_toa_low : d_flux_up_toa;
+  p.hr = tt ? d_hr_low : d_hr;
+  ECCKD_TRY(setup_batch(ctx, p, nint, h_i1, h_i2, n, who));
+  interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  if (!tt) {
+    interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 0);
+    ECCKD_LAUNCH_CHECK(ctx);
+    return launch_flux_and_error(ctx, p);
+  }
+  // total-transmission (find_g_points.cpp:334-384): one fit, errors against the low and high sets
+  const size_t smem = (size_t)2 * (nlay + 1) * kWarps * sizeof(double);
+  interval_tt_sweep_kernel<<<p.nitems, kTile, smem, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  interval_fit_finish_kernel<<<p.nint, 64, (size_t)nlay * sizeof(double), ctx->stream>>>(p, 1);
+  ECCKD_LAUNCH_CHECK(ctx);
+  p.od_scale = min_scaling;
+  p.error_mode = 1;
+  ECCKD_TRY(launch_flux_and_error(ctx, p));
+  // truth sums of the high set, then the second evaluation
+  p.flux_dn_surf = d_flux_dn_surf_high; p.flux_up_toa = d_flux_up_toa_high; p.hr = d_hr_high;
+  interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 2);
+  ECCKD_LAUNCH_CHECK(ctx);
+  p.od_scale = max_scaling;
+  p.error_mode = 2;
+  return launch_flux_and_error(ctx, p);
+}
+
+// Broadband solvers: one interval covering the whole array, fit = grey optical depth.
+static int bb_solver(ecckd_ctx* ctx, IntervalParams& p, const double* d_grey_od, double* d_flux_dn, double* d_flux_up,
+                     const char* who) {
+  const int nlev = p.nlay + 1;
+  const int64_t i1 = 0, i2 = p.n - 1;
+  p.od_scale = 1.0;
+  p.fit = const_cast<double*>(d_grey_od);
+  ECCKD_TRY(setup_batch(ctx, p, 1, &i1, &i2, p.n, who));
+  void* d_bb = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, (size_t)2 * nlev * sizeof(double), &d_bb));
+  p.bb_flux = static_cast<double*>(d_bb);
+  p.error = nullptr;
+  if (p.sw) {  // level 0 of the SW needs sum(ssi)
+    p.flux_dn_surf = p.ssi; p.flux_up_toa = p.ssi; p.hr = p.bg_od; p.metric = p.bg_od; p.method = ECCKD_AVG_LINEAR;
+    interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
+    ECCKD_LAUNCH_CHECK(ctx);
+    interval_fit_finish_kernel<<<1, 64, 0, ctx->stream>>>(p, 2);
+    ECCKD_LAUNCH_CHECK(ctx);
+  } else {
+    p.truth = nullptr;
+  }
+  ECCKD_TRY(launch_flux_and_error(ctx, p));
+  ECCKD_CUDA_OK(cudaMemcpyAsync(d_flux_dn, p.bb_flux, nlev * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (d_flux_up)
+    ECCKD_CUDA_OK(cudaMemcpyAsync(d_flux_up, p.bb_flux + nlev, nlev * sizeof(double), cudaMemcpyDeviceToDevice,
+                                  ctx->stream));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_radiative_transfer_lw_bb_dev(ecckd_ctx* ctx, int nlay, int64_t n, int64_t stride,
+                                                 const double* d_planck, const double* d_spectral_od,
+                                                 const double* d_grey_od, const double* d_surf_emissivity,
+                                                 const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+  const char* who = "ecckd_radiative_transfer_lw_bb";
+  ECCKD_REQUIRE(ctx && d_planck && d_spectral_od && d_grey_od && d_surf_emissivity && d_surf_planck && d_flux_dn &&
+                    d_flux_up,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
+  IntervalParams p = {};
+  p.sw = 0; p.nlay = nlay; p.n = n; p.stride = stride; p.planck_hl = d_planck; p.bg_od = d_spectral_od;
+  p.surf_emissivity = d_surf_emissivity; p.surf_planck = d_surf_planck;
+  return bb_solver(ctx, p, d_grey_od, d_flux_dn, d_flux_up, who);
+}
+
+ECCKD_API int ecckd_radiative_transfer_sw_bb_dev(ecckd_ctx* ctx, int nlay, int64_t n, int64_t stride, double cos_sza,
+                                                 const double* d_ssi, const double* d_spectral_od,
+                                                 const double* d_grey_od, double albedo, double* d_flux_dn,
+                                                 double* d_flux_up) {
+  const char* who = "ecckd_radiative_transfer_sw_bb";
+  ECCKD_REQUIRE(ctx && d_ssi && d_spectral_od && d_grey_od && d_flux_dn, ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n && cos_sza > 0.0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
+  IntervalParams p = {};
+  p.sw = 1; p.nlay = nlay; p.n = n; p.stride = stride; p.ssi = d_ssi; p.bg_od = d_spectral_od; p.cos_sza = cos_sza;
+  // radiative_transfer_direct_sw_bb has no upwelling; the norayleigh variant multiplies by the albedo as given
+  p.albedo = d_flux_up ? albedo : 0.0;
+  if (d_flux_up && !(albedo > 0.0)) p.albedo = 0.0;
+  return bb_solver(ctx, p, d_grey_od, d_flux_dn, d_flux_up, who);
+}
+
+ECCKD_API int ecckd_cost_function_ckd_lw_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_pressure_hl, const double* d_planck_hl,
+    const double* d_surf_emissivity, const double* d_surf_planck, const double* d_optical_depth,
+    const double* d_flux_dn, const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    double spectral_boundary_weight, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_cost_profile, double* d_cost_total, double* d_penalty_total) {
+  const char* who = "ecckd_cost_function_ckd_lw";
+  ECCKD_REQUIRE(ctx && d_pressure_hl && d_planck_hl && d_surf_emissivity && d_surf_planck && d_optical_depth &&
+                    d_flux_dn && d_flux_up && d_hr,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE((d_relative_ckd_flux_dn == nullptr) == (d_relative_ckd_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                "%s: relative-to fluxes must both be given or both be NULL", who);
+  CkdCostParams p = {};
+  p.sw = 0; p.nprof = nprof; p.nlay = nlay; p.ng = ng; p.nband = nband; p.nemis = d_band_mapping ? nband : ng;
+  p.up_in_bb = 1;
+  p.pressure_hl = d_pressure_hl; p.planck_hl = d_planck_hl; p.surf_emissivity = d_surf_emissivity;
+  p.surf_planck = d_surf_planck; p.optical_depth = d_optical_depth; p.flux_dn = d_flux_dn; p.flux_up = d_flux_up;
+  p.hr = d_hr; p.spectral_flux_dn_surf = d_spectral_flux_dn_surf; p.spectral_flux_up_toa = d_spectral_flux_up_toa;
+  p.layer_weight = d_layer_weight; p.rel_dn = d_relative_ckd_flux_dn; p.rel_up = d_relative_ckd_flux_up;
+  p.band_mapping = d_band_mapping; p.flux_weight = flux_weight; p.flux_profile_weight = flux_profile_weight;
+  p.broadband_weight = broadband_weight; p.spectral_boundary_weight = spectral_boundary_weight;
+  p.negative_od_penalty = negative_od_penalty; p.pressure_weight_power = pressure_weight_power;
+  return launch_ckd_cost(ctx, p, d_cost_profile, d_cost_total, d_penalty_total, nullptr, who);
+}
+
+ECCKD_API int ecckd_cost_function_ckd_sw_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_cos_sza, const double* d_pressure_hl,
+    const double* d_ssi, int nalbedo, const double* h_albedo, const double* d_optical_depth, const double* d_flux_dn,
+    const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    const double* d_spectral_boundary_weights, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_profile, double* d_cost_total,
+    double* d_penalty_total) {
+  const char* who = "ecckd_cost_function_ckd_sw";
+  (void)d_spectral_flux_up_toa;
+  ECCKD_REQUIRE(ctx && d_cos_sza && d_pressure_hl && d_ssi && h_albedo && nalbedo > 0 && d_optical_depth && d_flux_dn &&
+                    d_flux_up && d_hr,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE((d_relative_ckd_flux_dn == nullptr) == (d_relative_ckd_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                "%s: relative-to fluxes must both be given or both be NULL", who);
+  bool all_le0 = true, all_gt0 = true;  // calc_cost_function_sw.cpp:149,250
+  for (int k = 0; k < nalbedo; ++k) {
+    if (!(h_albedo[k] <= 0.0)) all_le0 = false;
+    if (!(h_albedo[k] > 0.0)) all_gt0 = false;
+  }
+  ECCKD_REQUIRE(all_le0 || d_band_mapping, ECCKD_PARAMETER_ERROR,
+                "%s: a non-zero albedo is indexed by band_mapping (calc_cost_function_sw.cpp:156)", who);
+  void* d_alb = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, (size_t)nalbedo * sizeof(double), &d_alb));
+  ECCKD_TRY(upload_small(ctx, d_alb, h_albedo, (size_t)nalbedo * sizeof(double)));
+  CkdCostParams p = {};
+  p.sw = 1; p.nprof = nprof; p.nlay = nlay; p.ng = ng; p.nband = nband; p.nalbedo = nalbedo;
+  p.up_in_bb = all_gt0 ? 1 : 0; p.direct_only = all_le0 ? 1 : 0;
+  p.cos_sza = d_cos_sza; p.pressure_hl = d_pressure_hl; p.ssi = d_ssi; p.albedo = static_cast<double*>(d_alb);
+  p.optical_depth = d_optical_depth; p.flux_dn = d_flux_dn; p.flux_up = d_flux_up; p.hr = d_hr;
+  p.spectral_flux_dn_surf = d_spectral_flux_dn_surf; p.spectral_boundary_weights = d_spectral_boundary_weights;
+  p.layer_weight = d_layer_weight; p.rel_dn = d_relative_ckd_flux_dn; p.rel_up = d_relative_ckd_flux_up;
+  p.band_mapping = d_band_mapping; p.flux_weight = flux_weight; p.flux_profile_weight = flux_profile_weight;
+  p.broadband_weight = broadband_weight; p.negative_od_penalty = negative_od_penalty;
+  p.pressure_weight_power = pressure_weight_power;
+  return launch_ckd_cost(ctx, p, d_cost_profile, d_cost_total, d_penalty_total, d_cost_fn_per_band, who);
+}

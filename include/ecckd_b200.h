@@ -56,7 +56,8 @@ enum ecckd_averaging_method {
   ECCKD_AVG_TRANSMISSION_10 = 4,    /* "transmission-10" */
   ECCKD_AVG_SQUARE_ROOT = 5,        /* "square-root" */
   ECCKD_AVG_LOGARITHMIC = 6,        /* "logarithmic" */
-  ECCKD_AVG_HYBRID_LOG_TRANS3 = 7   /* "hybrid-logarithmic-transmission-3" */
+  ECCKD_AVG_HYBRID_LOG_TRANS3 = 7,  /* "hybrid-logarithmic-transmission-3" */
+  ECCKD_AVG_TOTAL_TRANSMISSION = 8  /* "total-transmission": find_g_points only (find_g_points.cpp:146,334) */
 };
 
 /* Returns the enum for a reference averaging_method string, or -1
@@ -380,6 +381,121 @@ int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* model, const double* const* v
                   int nlay, const double* pressure_hl, const double* temperature_hl, double* od,
                   double* planck_hl, double* planck_surf, double* flux_dn, double* flux_up,
                   double* bb_flux_dn, double* bb_flux_up);
+
+/* ---------------------------------------------------------------------------
+ * Stage-1 extras
+ * ------------------------------------------------------------------------- */
+
+/* Base g-point split: src/ecckd/create_look_up_table.cpp:162-224.  For every band that contains
+ * base_wavenumber_boundary values strictly inside (band_wn1, band_wn2), the first g point of
+ * the band is cut at those wavenumbers; higher g points are renumbered.  In/out: *ng_io,
+ * h_band_number[cap] (host), d_g_point[nwav] (device), h_solar_irradiance[cap] (host; NULL
+ * together with d_ssi in the longwave).  PROCESSING_ERROR if cap < the new number of g points. */
+int ecckd_split_base_g_points_dev(ecckd_ctx* ctx, int nband, const double* h_band_wn1, const double* h_band_wn2,
+                                  int nbound, const double* h_base_wavenumber_boundary, int64_t nwav,
+                                  const double* d_wavenumber_cm_1, const double* d_ssi, int cap, int* ng_io,
+                                  int32_t* h_band_number, int32_t* d_g_point, double* h_solar_irradiance);
+
+/* rayleigh_molar_scattering_coeff: src/ecckd/rayleigh_scattering.h:23-43 (m2 mol-1). */
+int ecckd_rayleigh_molar_scattering_coeff_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenumber_cm_1,
+                                              double* d_scat_coeff);
+
+/* CkdModel::calc_rayleigh_molar_scat: src/ecckd/ckd_model.h:368-385.
+ * d_wavenumber1/2[nbin], d_gpoint_fraction[ng][nbin], d_ssi_intervals[nbin] -> [ng]. */
+int ecckd_rayleigh_molar_scat_gpoints_dev(ecckd_ctx* ctx, int ng, int nbin, const double* d_wavenumber1,
+                                          const double* d_wavenumber2, const double* d_gpoint_fraction,
+                                          const double* d_ssi_intervals, double* d_rayleigh_molar_scat);
+
+/* ---------------------------------------------------------------------------
+ * Broadband solvers and the candidate-interval error of find_g_points (rows a13, a15)
+ * ------------------------------------------------------------------------- */
+
+/* radiative_transfer_lw_bb<false>: src/ecckd/radiative_transfer_lw.cpp:85-142.
+ * d_planck[nlay+1][n], d_spectral_od[nlay][n] (row stride `stride`), d_grey_od[nlay],
+ * d_surf_emissivity[n], d_surf_planck[n] -> d_flux_dn, d_flux_up[nlay+1] (sums over n). */
+int ecckd_radiative_transfer_lw_bb_dev(ecckd_ctx* ctx, int nlay, int64_t n, int64_t stride, const double* d_planck,
+                                       const double* d_spectral_od, const double* d_grey_od,
+                                       const double* d_surf_emissivity, const double* d_surf_planck,
+                                       double* d_flux_dn, double* d_flux_up);
+
+/* radiative_transfer_direct_sw_bb<false> (d_flux_up NULL): src/ecckd/radiative_transfer_sw.cpp:116-141;
+ * radiative_transfer_norayleigh_sw_bb<false>: :145-184 (scalar albedo). */
+int ecckd_radiative_transfer_sw_bb_dev(ecckd_ctx* ctx, int nlay, int64_t n, int64_t stride, double cos_sza,
+                                       const double* d_ssi, const double* d_spectral_od, const double* d_grey_od,
+                                       double albedo, double* d_flux_dn, double* d_flux_up);
+
+/* CkdEquipartition::lower_index / upper_index and the bound checks of calc_error:
+ * src/ecckd/find_g_points.cpp:284-315.  bound1/2[nint] are fractions of the band's rank axis;
+ * returns PROCESSING_ERROR (148) exactly where the reference throws it. */
+int ecckd_interval_bounds_to_indices(int64_t npoints, int nint, const double* bound1, const double* bound2,
+                                     int64_t* i1, int64_t* i2);
+
+/* CkdEquipartition::calc_error for a BATCH of candidate intervals (the reference calls it from an
+ * OpenMP loop, equipartition.h:100-105): fit_optical_depth_lw (find_g_points.cpp:54-116, methods
+ * linear / transmission / transmission-2 / square-root / logarithmic) followed by
+ * calc_cost_function_lw (calc_cost_function_lw.cpp:23-110).  Spectral arrays are the band's
+ * slices in rank order: d_planck_hl[nlay+1][n], d_bg_optical_depth, d_metric, d_hr[nlay][n]
+ * (row stride `stride`), d_surf_emissivity, d_surf_planck, d_flux_dn_surf, d_flux_up_toa[n],
+ * d_pressure_hl[nlay+1], d_layer_weight[nlay].  h_i1/h_i2[nint]: inclusive index bounds (host).
+ * Outputs: d_error[nint]; d_optical_depth_fit[nint][nlay] (may be NULL). */
+int ecckd_interval_error_batch_lw_dev(ecckd_ctx* ctx, int averaging_method, int nlay, int64_t n, int64_t stride,
+                                      const double* d_pressure_hl, const double* d_planck_hl,
+                                      const double* d_surf_emissivity, const double* d_surf_planck,
+                                      const double* d_bg_optical_depth, const double* d_metric,
+                                      const double* d_flux_dn_surf, const double* d_flux_up_toa, const double* d_hr,
+                                      double flux_weight, const double* d_layer_weight, int nint,
+                                      const int64_t* h_i1, const int64_t* h_i2, double* d_error,
+                                      double* d_optical_depth_fit);
+
+/* Shortwave form: fit_optical_depth_sw (find_g_points.cpp:119-173) or, for
+ * ECCKD_AVG_TOTAL_TRANSMISSION, fit_optical_depth_sw_total_trans (:176-204) with the error taken as
+ * the mean of calc_cost_function_sw (calc_cost_function_sw.cpp:20-110) against the *_low set at
+ * min_scaling and the *_high set at max_scaling (find_g_points.cpp:334-384); the plain reference
+ * set may then be NULL, otherwise the low/high sets may be NULL. */
+int ecckd_interval_error_batch_sw_dev(
+    ecckd_ctx* ctx, int averaging_method, int nlay, int64_t n, int64_t stride, double cos_sza,
+    const double* d_pressure_hl, const double* d_ssi, double albedo, const double* d_bg_optical_depth,
+    const double* d_metric, const double* d_flux_dn_surf, const double* d_flux_up_toa, const double* d_hr,
+    double flux_weight, const double* d_layer_weight, const double* d_flux_dn_surf_low,
+    const double* d_flux_up_toa_low, const double* d_hr_low, const double* d_flux_dn_surf_high,
+    const double* d_flux_up_toa_high, const double* d_hr_high, double min_scaling, double max_scaling, int nint,
+    const int64_t* h_i1, const int64_t* h_i2, double* d_error, double* d_optical_depth_fit);
+
+/* ---------------------------------------------------------------------------
+ * Forward cost of optimize_lut (rows a21-a23), batched over the profiles of a scene
+ * ------------------------------------------------------------------------- */
+
+/* calc_cost_function_ckd_lw (forward value): src/ecckd/calc_cost_function_lw.cpp:115-232, for
+ * every profile of a training scene as solve_adept.cpp:96-184 drives it, including the layer
+ * weights (d_layer_weight[nprof][nlay], or NULL: computed from pressure_weight_power and
+ * normalised, solve_adept.cpp:133-145) and the negative-optical-depth penalty and clamp
+ * (solve_adept.cpp:107-116; the input array is not modified).
+ * d_planck_hl[nprof][nlay+1][ng], d_surf_emissivity[nprof][nband] (or [ng] without band_mapping),
+ * d_surf_planck[nprof][ng], d_optical_depth[nprof][nlay][ng], truth d_flux_dn/up[nprof][nlay+1][nband],
+ * d_hr[nprof][nlay][nband], optional d_spectral_flux_*[nprof][ng], d_relative_ckd_flux_*[nprof][nlay+1][ng],
+ * d_band_mapping[ng] (NULL: nband == ng).  Outputs (device, any may be NULL): d_cost_profile[nprof],
+ * d_cost_total[1] = penalty + sum of the profile costs in profile order, d_penalty_total[1]. */
+int ecckd_cost_function_ckd_lw_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_pressure_hl, const double* d_planck_hl,
+    const double* d_surf_emissivity, const double* d_surf_planck, const double* d_optical_depth,
+    const double* d_flux_dn, const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    double spectral_boundary_weight, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_cost_profile, double* d_cost_total, double* d_penalty_total);
+
+/* calc_cost_function_ckd_sw (forward value): src/ecckd/calc_cost_function_sw.cpp:115-277.
+ * d_cos_sza[nprof], d_ssi[ng] (already scaled to the scene's TSI, solve_adept.cpp:160-166),
+ * h_albedo[nalbedo] indexed by band_mapping; d_cost_fn_per_band[nband] (may be NULL) is added to. */
+int ecckd_cost_function_ckd_sw_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_cos_sza, const double* d_pressure_hl,
+    const double* d_ssi, int nalbedo, const double* h_albedo, const double* d_optical_depth, const double* d_flux_dn,
+    const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    const double* d_spectral_boundary_weights, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_profile, double* d_cost_total,
+    double* d_penalty_total);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,9 @@ METHODS = (
 )
 
 
+METHODS_FIT = METHODS + ("total-transmission",)
+
+
 class OrcGasTable(C.Structure):
     _fields_ = [
         ("conc_dependence", C.c_int32),
@@ -215,6 +218,70 @@ class Oracle:
         wn = _f64(wavenumber)
         out = np.zeros(wn.size)
         rc = self.L.orc_rayleigh_molar_scattering_coeff(C.c_int64(wn.size), C.c_void_p(_p(wn)), C.c_void_p(_p(out)))
+        assert rc == 0, rc
+        return out
+
+    def rayleigh_molar_scat_gpoints(self, wavenumber1, wavenumber2, gpoint_fraction, ssi_intervals):
+        w1, w2, gf, si = _f64(wavenumber1), _f64(wavenumber2), _f64(gpoint_fraction), _f64(ssi_intervals)
+        ng, nbin = gf.shape
+        out = np.zeros(ng)
+        rc = self.L.orc_rayleigh_molar_scat_gpoints(C.c_int(ng), C.c_int(nbin), C.c_void_p(_p(w1)), C.c_void_p(_p(w2)),
+                                                    C.c_void_p(_p(gf)), C.c_void_p(_p(si)), C.c_void_p(_p(out)))
+        assert rc == 0, rc
+        return out
+
+    def split_base_g_points(self, band_wn1, band_wn2, boundaries, wavenumber, ssi, ng, band_number, g_point,
+                            solar_irradiance=None):
+        b1, b2, bb, wn = _f64(band_wn1), _f64(band_wn2), _f64(np.atleast_1d(boundaries)), _f64(wavenumber)
+        s = None if ssi is None else _f64(ssi)
+        cap = int(ng) + bb.size
+        bn = np.zeros(cap, dtype=np.int32)
+        bn[:ng] = band_number
+        g = _i32(g_point).copy()
+        sol = None
+        if solar_irradiance is not None:
+            sol = np.zeros(cap)
+            sol[:ng] = solar_irradiance
+        ng_io = C.c_int(int(ng))
+        rc = self.L.orc_split_base_g_points(C.c_int(b1.size), C.c_void_p(_p(b1)), C.c_void_p(_p(b2)), C.c_int(bb.size),
+                                            C.c_void_p(_p(bb)), C.c_int64(wn.size), C.c_void_p(_p(wn)),
+                                            C.c_void_p(_p(s)), C.c_int(cap), C.byref(ng_io), C.c_void_p(_p(bn)),
+                                            C.c_void_p(_p(g)), C.c_void_p(_p(sol)))
+        if rc != 0:
+            raise RuntimeError(rc)
+        n = ng_io.value
+        return n, bn[:n].copy(), g, (None if sol is None else sol[:n].copy())
+
+    # -- interval fits of find_g_points (find_g_points.cpp:54-204)
+    def fit_optical_depth_lw(self, method, i1, i2, planck_hl, metric):
+        pl, m = _f64(planck_hl), _f64(metric)
+        nlay, n = m.shape
+        out = np.zeros(nlay)
+        mid = METHODS_FIT.index(method) if isinstance(method, str) else int(method)
+        rc = self.L.orc_fit_optical_depth_lw(C.c_int(mid), C.c_int(nlay), C.c_int64(n), C.c_int64(i1), C.c_int64(i2),
+                                             C.c_void_p(_p(pl)), C.c_void_p(_p(m)), C.c_void_p(_p(out)))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return out
+
+    def fit_optical_depth_sw(self, method, i1, i2, ssi, metric):
+        s, m = _f64(ssi), _f64(metric)
+        nlay, n = m.shape
+        out = np.zeros(nlay)
+        mid = METHODS_FIT.index(method) if isinstance(method, str) else int(method)
+        rc = self.L.orc_fit_optical_depth_sw(C.c_int(mid), C.c_int(nlay), C.c_int64(n), C.c_int64(i1), C.c_int64(i2),
+                                             C.c_void_p(_p(s)), C.c_void_p(_p(m)), C.c_void_p(_p(out)))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return out
+
+    def fit_optical_depth_sw_total_trans(self, i1, i2, ssi, bg_od, od):
+        s, b, o = _f64(ssi), _f64(bg_od), _f64(od)
+        nlay, n = o.shape
+        out = np.zeros(nlay)
+        rc = self.L.orc_fit_optical_depth_sw_total_trans(C.c_int(nlay), C.c_int64(n), C.c_int64(i1), C.c_int64(i2),
+                                                         C.c_void_p(_p(s)), C.c_void_p(_p(b)), C.c_void_p(_p(o)),
+                                                         C.c_void_p(_p(out)))
         assert rc == 0, rc
         return out
 

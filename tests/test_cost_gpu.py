@@ -1,0 +1,288 @@
+"""GPU parity for the rows of SURVEY.md section 8 that build on the flux solvers: broadband
+solvers (a15), the batched candidate-interval error of find_g_points (a13), the forward cost of
+optimize_lut (a21-a23), the base g-point split (a4b) and the Rayleigh coefficients (a7b).
+
+Every CUDA result is held against the CPU oracle on the same seeded inputs; the oracle itself is
+held against the reference's own compiled sources in tests/test_reference_sources.py.
+Tolerances: fluxes <= 1e-6 W m-2 (north_star), errors / costs relative 1e-11 (they are sums of
+squares of those fluxes, summed in a different but fixed order), integer outputs bit-exact.
+"""
+import numpy as np
+import pytest
+
+import ecckd_b200 as E
+from tests import synthetic as S
+from tests.test_reference_sources import ckd_cost_case, interval_case, rt_inputs
+
+pytestmark = pytest.mark.gpu
+
+FLUX_ATOL = 1e-6
+COST_RTOL = 1e-11
+
+
+def test_radiative_transfer_bb(ctx, O):
+    od, planck, emis, surf = rt_inputs(nlay=54, n=3001, seed=1)
+    grey = np.exp(np.random.default_rng(2).normal(-3, 2, od.shape[0]))
+    grey[3] = 0.0
+    a = E.radiative_transfer_lw_bb(ctx, planck, od, grey, emis, surf)
+    b = O.radiative_transfer_lw_bb(planck, od, grey, emis, surf)
+    assert np.max(np.abs(a[0] - b[0])) <= FLUX_ATOL and np.max(np.abs(a[1] - b[1])) <= FLUX_ATOL
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-12)
+    rng = np.random.default_rng(4)
+    ssi = rng.uniform(0.1, 3.0, od.shape[1])
+    for direct, albedo in ((False, 0.15), (True, 0.15), (False, 0.0)):
+        a = E.radiative_transfer_sw_bb(ctx, 0.5, ssi, od, grey * 0.1, albedo, direct_only=direct)
+        b = O.radiative_transfer_sw_bb(0.5, ssi, od, grey * 0.1, albedo, direct_only=direct)
+        np.testing.assert_allclose(a[0], b[0], rtol=1e-12, atol=1e-9)
+        if not direct:
+            np.testing.assert_allclose(a[1], b[1], rtol=1e-12, atol=1e-9)
+
+
+def test_interval_bounds_to_indices(ctx):
+    i1, i2 = E.interval_bounds_to_indices(1000, [0.0, 0.25, 0.5001, 0.3], [0.2499, 0.5, 0.5002, 1.0])
+    assert list(i1) == [0, 250, 500, 300] and list(i2) == [249, 499, 500, 999]  # empty range collapses to ibound1
+    for b1, b2 in (([-0.1], [0.5]), ([0.2], [1.1]), ([0.6], [0.5])):
+        with pytest.raises(E.EcckdError) as ei:
+            E.interval_bounds_to_indices(1000, b1, b2)
+        assert ei.value.code == 148  # PROCESSING_ERROR, find_g_points.cpp:297-312
+
+
+def _intervals(n, rng, k=9):
+    cuts = np.sort(rng.choice(np.arange(1, n - 1), k - 1, replace=False))
+    i1 = np.concatenate([[0], cuts])
+    i2 = np.concatenate([cuts - 1, [n - 1]])
+    # plus overlapping candidates, a single point and the whole band
+    i1 = np.concatenate([i1, [5, n // 3, 0]])
+    i2 = np.concatenate([i2, [5, n - 7, n - 1]])
+    return i1.astype(np.int64), i2.astype(np.int64)
+
+
+@pytest.mark.parametrize("method", ["linear", "transmission", "transmission-2", "square-root", "logarithmic"])
+def test_interval_error_batch_lw(ctx, O, method):
+    c = interval_case(nlay=20, n=3000, seed=7)
+    rng = c["rng"]
+    true_dn, true_up = O.radiative_transfer_lw(c["planck"], c["od"] * 1.3, c["emis"], c["surf"])
+    hr = O.heating_rate(c["p"], true_dn, true_up)
+    od_gas = c["od"] * rng.uniform(0.1, 2.0, c["od"].shape)
+    if method in ("transmission", "transmission-2"):
+        kd = 1.66 * (2.0 if method.endswith("2") else 1.0)
+        metric = 1.0 - np.exp(-kd * od_gas)
+    elif method == "square-root":
+        metric = np.sqrt(od_gas)
+    else:
+        metric = od_gas
+    i1, i2 = _intervals(c["od"].shape[1], rng)
+    err, fit = E.interval_error_batch_lw(ctx, method, c["p"], c["planck"], c["emis"], c["surf"], c["od"], metric,
+                                         true_dn[-1], true_up[0], hr, 0.2, c["lw"], i1, i2)
+    for k, (a, b) in enumerate(zip(i1, i2)):
+        f = O.fit_optical_depth_lw(method, a, b, c["planck"], metric)
+        np.testing.assert_allclose(fit[k], f, rtol=1e-11, atol=1e-300, err_msg=f"fit {k}")
+        sl = slice(a, b + 1)
+        e = O.calc_cost_function_lw(c["p"], c["planck"][:, sl], c["emis"][sl], c["surf"][sl], c["od"][:, sl], f,
+                                    true_dn[-1, sl], true_up[0, sl], hr[:, sl], 0.2, c["lw"])
+        assert abs(err[k] - e) <= COST_RTOL * abs(e) + 1e-12, (k, err[k], e)
+
+
+def test_interval_error_batch_lw_errors(ctx):
+    c = interval_case(nlay=5, n=300, seed=1)
+    z = np.zeros(300)
+    args = (c["p"], c["planck"], c["emis"], c["surf"], c["od"], c["od"], z, z, c["od"], 0.2, c["lw"])
+    with pytest.raises(E.EcckdError) as ei:
+        E.interval_error_batch_lw(ctx, "transmission-3", *args, [0], [10])
+    assert ei.value.code == 147  # method not understood, find_g_points.cpp:111-113
+    with pytest.raises(E.EcckdError) as ei:
+        E.interval_error_batch_lw(ctx, "linear", *args, [0], [300])
+    assert ei.value.code == 148
+
+
+@pytest.mark.parametrize("method", ["linear", "transmission", "transmission-2", "square-root", "logarithmic"])
+@pytest.mark.parametrize("albedo", [0.0, 0.15])
+def test_interval_error_batch_sw(ctx, O, method, albedo):
+    c = interval_case(nlay=20, n=2500, seed=9)
+    rng = c["rng"]
+    n = c["od"].shape[1]
+    ssi = rng.uniform(0.1, 2.0, n) * 1e-3
+    true_dn, true_up = O.radiative_transfer_norayleigh_sw(0.5, ssi, c["od"] * 1.2, np.full(n, 0.15))
+    hr = O.heating_rate(c["p"], true_dn, None)
+    od_gas = c["od"] * rng.uniform(0.1, 2.0, c["od"].shape) * 0.05
+    if method in ("transmission", "transmission-2"):
+        metric = 1.0 - np.exp(-1.66 * (2.0 if method.endswith("2") else 1.0) * od_gas)
+    elif method == "square-root":
+        metric = np.sqrt(od_gas)
+    else:
+        metric = od_gas
+    i1, i2 = _intervals(n, rng)
+    err, fit = E.interval_error_batch_sw(ctx, method, 0.5, c["p"], ssi, albedo, c["od"], metric, true_dn[-1],
+                                         true_up[0], hr, 0.2, c["lw"], i1, i2)
+    for k, (a, b) in enumerate(zip(i1, i2)):
+        f = O.fit_optical_depth_sw(method, a, b, ssi, metric)
+        np.testing.assert_allclose(fit[k], f, rtol=1e-11, atol=1e-300, err_msg=f"fit {k}")
+        sl = slice(a, b + 1)
+        e = O.calc_cost_function_sw(0.5, c["p"], ssi[sl], albedo, c["od"][:, sl], f, true_dn[-1, sl], true_up[0, sl],
+                                    hr[:, sl], 0.2, c["lw"])
+        assert abs(err[k] - e) <= COST_RTOL * abs(e) + 1e-12, (k, err[k], e)
+
+
+def test_interval_error_batch_sw_total_transmission(ctx, O):
+    c = interval_case(nlay=20, n=2500, seed=10)
+    rng = c["rng"]
+    n = c["od"].shape[1]
+    ssi = rng.uniform(0.1, 2.0, n) * 1e-3
+    od_gas = c["od"] * rng.uniform(0.1, 2.0, c["od"].shape) * 0.3
+    bg = c["od"] * 0.1
+    bg[:, 40:80] += 400.0  # an interval whose direct beam underflows: the linear fallback (find_g_points.cpp:196-198)
+    mins, maxs = 0.5, 2.5
+    sets = []
+    for scal in (mins, maxs):
+        dn, up = O.radiative_transfer_norayleigh_sw(0.5, ssi, bg + scal * od_gas, np.full(n, 0.15))
+        sets.append((dn[-1], up[0], O.heating_rate(c["p"], dn, None)))
+    i1, i2 = _intervals(n, rng)
+    i1 = np.concatenate([i1, [40]])
+    i2 = np.concatenate([i2, [79]])
+    err, fit = E.interval_error_batch_sw(ctx, "total-transmission", 0.5, c["p"], ssi, 0.15, bg, od_gas, None, None, None,
+                                         0.2, c["lw"], i1, i2, low=sets[0], high=sets[1], min_scaling=mins,
+                                         max_scaling=maxs)
+    for k, (a, b) in enumerate(zip(i1, i2)):
+        f = O.fit_optical_depth_sw_total_trans(a, b, ssi, bg, od_gas)
+        np.testing.assert_allclose(fit[k], f, rtol=1e-10, atol=1e-14, err_msg=f"fit {k}")
+        sl = slice(a, b + 1)
+        e = 0.0
+        for scal, st in zip((mins, maxs), sets):
+            e += 0.5 * O.calc_cost_function_sw(0.5, c["p"], ssi[sl], 0.15, bg[:, sl], f * scal, st[0][sl], st[1][sl],
+                                               st[2][:, sl], 0.2, c["lw"])
+        assert abs(err[k] - e) <= 1e-9 * abs(e) + 1e-12, (k, err[k], e)
+
+
+def _scene(nprof, nlay, ng, nband, seed, sw=False):
+    rng = np.random.default_rng(seed)
+    cases = [ckd_cost_case(nlay=nlay, ng=ng, nband=nband, seed=seed * 100 + i) for i in range(nprof)]
+    bm = cases[0]["bm"]
+    d = dict(p=np.stack([c["p"] for c in cases]), od=np.stack([c["od"] for c in cases]),
+             planck=np.stack([c["planck"] for c in cases]), surf=np.stack([c["surf"] for c in cases]), bm=bm, rng=rng)
+    d["od"][0, 2, 3] = -0.01  # negative optical depths: penalty + clamp (solve_adept.cpp:107-116)
+    d["od"][nprof - 1, 0, 0] = -0.2
+    return d
+
+
+@pytest.mark.parametrize("banded", [True, False])
+@pytest.mark.parametrize("weights", [(0.2, 0.2, 0.8, 0.1), (0.5, 0.0, 0.0, 0.0)])
+@pytest.mark.parametrize("power", [0.5, 1.0, 0.3])
+def test_cost_function_ckd_lw(ctx, O, banded, weights, power):
+    nprof, nlay, ng, nb = 7, 54, 64, 13
+    s = _scene(nprof, nlay, ng, nb, seed=3)
+    rng = s["rng"]
+    nband = nb if banded else ng
+    bm = s["bm"] if banded else None
+    emis = rng.uniform(0.9, 1.0, (nprof, nband))
+    t_dn, t_up, hr, lws = [], [], [], []
+    for i in range(nprof):
+        eg = emis[i][bm] if banded else emis[i]
+        dn, up = O.radiative_transfer_lw(s["planck"][i], np.maximum(s["od"][i], 0) * 1.1, eg, s["surf"][i])
+        if banded:
+            dn = np.stack([dn[:, bm == b].sum(1) for b in range(nband)], 1)
+            up = np.stack([up[:, bm == b].sum(1) for b in range(nband)], 1)
+        t_dn.append(dn), t_up.append(up), hr.append(O.heating_rate(s["p"][i], dn, up))
+        lw = np.diff(s["p"][i] ** power) if power != 0.5 else np.diff(np.sqrt(s["p"][i]))
+        lws.append(lw / lw.sum())
+    t_dn, t_up, hr = np.stack(t_dn), np.stack(t_up), np.stack(hr)
+    sfd, sfu = rng.uniform(0, 5, (nprof, ng)), rng.uniform(0, 5, (nprof, ng))
+    rel = rng.uniform(0, 1, (2, nprof, nlay + 1, ng))
+    got = E.cost_function_ckd_lw(ctx, s["p"], s["planck"], emis, s["surf"], s["od"], t_dn, t_up, hr, *weights,
+                                 pressure_weight_power=power, negative_od_penalty=1.0e4, spectral_flux_dn_surf=sfd,
+                                 spectral_flux_up_toa=sfu, rel_dn=rel[0], rel_up=rel[1], band_mapping=bm)
+    ref = [O.calc_cost_function_ckd_lw(s["p"][i], s["planck"][i], emis[i], s["surf"][i], np.maximum(s["od"][i], 0.0),
+                                       t_dn[i], t_up[i], hr[i], *weights, lws[i], spectral_flux_dn_surf=sfd[i],
+                                       spectral_flux_up_toa=sfu[i], rel_dn=rel[0][i], rel_up=rel[1][i], band_mapping=bm)
+           for i in range(nprof)]
+    np.testing.assert_allclose(got["cost_profile"], ref, rtol=COST_RTOL)
+    pen = 1.0e4 * float((np.minimum(s["od"], 0.0) ** 2).sum())
+    assert abs(got["penalty"] - pen) <= 1e-12 * pen
+    assert abs(got["cost_total"] - (pen + sum(ref))) <= COST_RTOL * (pen + sum(ref))
+    # explicit layer weights give the same answer as the in-kernel ones
+    got2 = E.cost_function_ckd_lw(ctx, s["p"], s["planck"], emis, s["surf"], s["od"], t_dn, t_up, hr, *weights,
+                                  layer_weight=np.stack(lws), spectral_flux_dn_surf=sfd, spectral_flux_up_toa=sfu,
+                                  rel_dn=rel[0], rel_up=rel[1], band_mapping=bm)
+    np.testing.assert_allclose(got2["cost_profile"], ref, rtol=COST_RTOL)
+
+
+@pytest.mark.parametrize("albedo_on", [True, False])
+@pytest.mark.parametrize("weights", [(0.2, 0.2, 0.8), (0.5, 0.0, 0.0)])
+def test_cost_function_ckd_sw(ctx, O, albedo_on, weights):
+    nprof, nlay, ng, nband = 6, 54, 32, 9
+    s = _scene(nprof, nlay, ng, nband, seed=5, sw=True)
+    rng, bm = s["rng"], s["bm"]
+    ssi = rng.uniform(1.0, 100.0, ng)
+    albedo = rng.uniform(0.05, 0.5, nband) if albedo_on else np.zeros(nband)
+    mu = rng.uniform(0.2, 1.0, nprof)
+    t_dn, t_up, hr, lws = [], [], [], []
+    for i in range(nprof):
+        dn, up = O.radiative_transfer_norayleigh_sw(mu[i], ssi, np.maximum(s["od"][i], 0) * 1.1, albedo[bm])
+        dn = np.stack([dn[:, bm == b].sum(1) for b in range(nband)], 1)
+        up = np.stack([up[:, bm == b].sum(1) for b in range(nband)], 1)
+        t_dn.append(dn), t_up.append(up), hr.append(O.heating_rate(s["p"][i], dn, None))
+        lw = np.diff(np.sqrt(s["p"][i]))
+        lws.append(lw / lw.sum())
+    t_dn, t_up, hr = np.stack(t_dn), np.stack(t_up), np.stack(hr)
+    sbw, sfd = rng.uniform(0, 1, ng), rng.uniform(0, 5, (nprof, ng))
+    per_band0 = rng.uniform(0, 1, nband)
+    got = E.cost_function_ckd_sw(ctx, mu, s["p"], ssi, albedo, s["od"], t_dn, t_up, hr, *weights,
+                                 spectral_boundary_weights=sbw, spectral_flux_dn_surf=sfd, band_mapping=bm,
+                                 cost_fn_per_band=per_band0)
+    per_band = per_band0.copy()
+    ref = [O.calc_cost_function_ckd_sw(mu[i], s["p"][i], ssi, albedo, np.maximum(s["od"][i], 0.0), t_dn[i], t_up[i],
+                                       hr[i], *weights, lws[i], spectral_boundary_weights=sbw,
+                                       spectral_flux_dn_surf=sfd[i], spectral_flux_up_toa=sfd[i], band_mapping=bm,
+                                       cost_fn_per_band=per_band) for i in range(nprof)]
+    np.testing.assert_allclose(got["cost_profile"], ref, rtol=COST_RTOL)
+    np.testing.assert_allclose(got["cost_fn_per_band"], per_band, rtol=COST_RTOL)
+
+
+def test_cost_function_errors(ctx):
+    s = _scene(2, 6, 8, 3, seed=1)
+    z = np.zeros((2, 7, 3))
+    with pytest.raises(E.EcckdError) as ei:  # truth arrays per band but no band_mapping
+        E.cost_function_ckd_lw(ctx, s["p"], s["planck"], np.ones((2, 3)), s["surf"], s["od"], z, z, np.zeros((2, 6, 3)),
+                               0.2, 0.2, 0.8, 0.1)
+    assert ei.value.code == 147
+
+
+def test_split_base_g_points_bit_exact(ctx, O):
+    c = S.sw_spectrum_case(nlay=4, nwav=20000, ng=9, nband=3, seed=6)
+    wn, g, ng = c["wavenumber"], c["g_point"], c["ng"]
+    edges = c["band_edges"]
+    b1, b2 = edges[:-1].copy(), edges[1:].copy()
+    band_number = np.repeat(np.arange(3), S.split_g_points(9, 3)).astype(np.int32)
+    solar = np.array([c["ssi"][g == k].sum() for k in range(ng)])
+    # two cuts in band 0, none in band 1, one in band 2, plus values outside every band / on an edge
+    bounds = np.array([edges[0] + 0.3 * (edges[1] - edges[0]), edges[0] + 0.6 * (edges[1] - edges[0]),
+                       0.5 * (edges[2] + edges[3]), edges[1], 1.0e9])
+    for use_ssi in (True, False):
+        ref = O.split_base_g_points(b1, b2, bounds, wn, c["ssi"] if use_ssi else None, ng, band_number, g,
+                                    solar if use_ssi else None)
+        d_g = ctx.to_device(g, np.int32)
+        got = E.split_base_g_points_dev(ctx, b1, b2, bounds, wn.size, ctx.to_device(wn),
+                                        ctx.to_device(c["ssi"]) if use_ssi else None, ng, band_number, d_g,
+                                        solar if use_ssi else None)
+        assert got[0] == ref[0] == ng + 3
+        assert np.array_equal(got[1], ref[1]) and np.array_equal(d_g.numpy(), ref[2])
+        if use_ssi:
+            np.testing.assert_allclose(got[2], ref[3], rtol=1e-13)
+    with pytest.raises(E.EcckdError) as ei:
+        E.split_base_g_points_dev(ctx, b1, b2, bounds, wn.size, ctx.to_device(wn), None, ng, band_number,
+                                  ctx.to_device(g, np.int32), None, cap=ng + 1)
+    assert ei.value.code == 148
+
+
+def test_rayleigh_coefficients(ctx, O):
+    wn = np.concatenate([np.linspace(275.0, 49975.0, 995), [19999.9, 20000.0, 20000.1]])
+    np.testing.assert_allclose(E.rayleigh_molar_scattering_coeff(ctx, wn), O.rayleigh_molar_scattering_coeff(wn),
+                               rtol=1e-13)
+    rng = np.random.default_rng(3)
+    w1 = 250.0 + 50.0 * np.arange(995)
+    w2 = w1 + 50.0
+    gf = rng.uniform(0, 1, (32, 995)) * (rng.uniform(size=(32, 995)) < 0.1)
+    gf[:, 0] += 1e-3
+    ssi_int = S.solar_spectrum(0.5 * (w1 + w2))
+    np.testing.assert_allclose(E.rayleigh_molar_scat_gpoints(ctx, w1, w2, gf, ssi_int),
+                               O.rayleigh_molar_scat_gpoints(w1, w2, gf, ssi_int), rtol=1e-12)
