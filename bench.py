@@ -73,7 +73,8 @@ def temperature_profile(p_hl, offset=0.0):
 
 
 class ClockSampler:
-    """nvidia-smi clock/throttle sampler running during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (2 ms
+    period, so even a 100 ms region gets tens of samples); `nvidia-smi -lms` as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -81,19 +82,65 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.stop_flag = False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
+
+    def _poll(self, nv, h):
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))]
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=float(max(self.mx)),
+                           reasons=sorted(self.reasons), samples=len(self.sm), source="nvml")
+            return out
         if self.p is None:
             return out
         self.p.terminate()
@@ -123,7 +170,7 @@ class ClockSampler:
             pass
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), source="nvidia-smi")
         return out
 
 
@@ -500,7 +547,7 @@ def bench_flux(torch, E, ctx, dev, peak):
             "config": f"radiative_transfer_lw (flux solver), {ncol} columns x {nlay} layers x {ng} g points, optical depth "
                       "and Planck arrays resident",
             "roofline": {"bound": "hbm", "achieved": gbs_rt, "peak": peak, "unit": "GB/s", "frac": gbs_rt / peak,
-                         "kernel": "rt_lw_kernel", "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
+                         "kernel": "rt_lw_staged_kernel", "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
             "fused_run_ckd": {"value": ncol * ng / (ms * 1e-3), "unit": "column*g-points/s", "ms_per_step": ms,
                               "config": "run_ckd LW core in one kernel: full-level temperature, LUT interpolation of 8 "
                                         "gases (36 LUT rows per layer.g point, L2-resident gathers), clamp, Planck "

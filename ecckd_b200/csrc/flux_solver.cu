@@ -11,6 +11,8 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "async_copy.cuh"
+#include "trans_core.cuh"
 
 struct ecckd_ckd_model {
   ecckd_ctx* ctx = nullptr;
@@ -210,6 +212,124 @@ __global__ void rt_lw_kernel(int ncol, int nlay, int64_t n, const double* __rest
     f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
     up[(int64_t)l * n] = f_up;
     b_bot = b_t;
+  }
+}
+
+// The same solver with the column staged in shared memory (the path taken when n is a multiple of
+// 32 and the arrays are 16-byte aligned).  One warp owns one (column, 32 spectral points) item at
+// a time: it pulls the item's optical depths and Planck functions into shared memory with bulk
+// asynchronous copies (two copies when n == 32, where a column is contiguous; one 256-byte copy per
+// layer row otherwise), walks down writing flux_dn and overwriting each layer's two inputs IN PLACE
+// with the two numbers the way up needs - the layer transmittance 1 - e and the source
+// B(l+1) (e - f) + B(l) f - and walks up with one FMA per layer.  Every input is read from HBM
+// once (32 B per column x layer x g, the algorithmic figure; the register-only kernel above re-reads
+// both inputs on the way up: 48 B), and the layer terms are evaluated once instead of twice, four
+// layers at a time (they are independent; only the flux recurrence is serial).
+// 1 - exp(-1.66 tau) is trans_core.cuh's table evaluation (2.3e-16 absolute error) and the division
+// by tau a reciprocal refined by two Newton steps: the fluxes differ from the kernel above by a
+// few ulp, nine orders of magnitude inside the 1e-6 W m-2 tolerance.
+struct RtLwStagedParams {
+  int ncol, nlay;
+  int64_t n;
+  const double* planck;
+  const double* od;
+  const double* surf_emissivity;
+  const double* surf_planck;
+  double* flux_dn;
+  double* flux_up;
+  TransConst tc;  // kd = LW_DIFFUSIVITY
+};
+
+__device__ __forceinline__ void lw_layer_fast(double tau, const TransConst& K, const TransLane& tl, double& e, double& f) {
+  e = trans_one_minus_exp(tau, K, tl);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(tau));  // ~20 bits
+  r = fma(r, fma(-tau, r, 1.0), r);
+  r = fma(r, fma(-tau, r, 1.0), r);
+  f = (e > 1.0e-5) ? (1.0 - (e * (1.0 / ECCKD_LW_DIFFUSIVITY)) * r) : (0.5 * e);
+}
+
+template <bool UNIT>
+__global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant__ RtLwStagedParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int nlay = p.nlay;
+  const int64_t n = p.n;
+  double* s_tau = reinterpret_cast<double*>(smem_raw);  // [nlay][32]  -> 1 - e
+  double* s_pl = s_tau + (size_t)nlay * 32;             // [nlay+1][32] -> source of the upward sweep in rows 0..nlay-1
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned bar = sbase + (unsigned)((2 * nlay + 1) * 32 * sizeof(double));
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const TransLane tl = trans_lane_init();
+  const int64_t nchunk = n >> 5;
+  const int64_t nitems = (int64_t)p.ncol * nchunk;
+  unsigned parity = 0;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t icol = item / nchunk;
+    const int64_t i0 = (item - icol * nchunk) << 5;
+    const double* g_tau = p.od + icol * nlay * n + i0;
+    const double* g_pl = p.planck + icol * (nlay + 1) * n + i0;
+    if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)((2 * nlay + 1) * 256));
+    __syncwarp();
+    if (UNIT) {
+      if (lane == 0) bulk_g2s(sbase, g_tau, (unsigned)(nlay * 256), bar);
+      if (lane == 1) bulk_g2s(sbase + (unsigned)(nlay * 256), g_pl, (unsigned)((nlay + 1) * 256), bar);
+    } else {
+      for (int r = lane; r < 2 * nlay + 1; r += 32) {
+        const double* src = r < nlay ? g_tau + (int64_t)r * n : g_pl + (int64_t)(r - nlay) * n;
+        bulk_g2s(sbase + (unsigned)(r * 256), src, 256u, bar);
+      }
+    }
+    double* dn = p.flux_dn + icol * (nlay + 1) * n + i0 + lane;
+    double* up = p.flux_up + icol * (nlay + 1) * n + i0 + lane;
+    const double es = p.surf_emissivity[i0 + lane];
+    const double bs = p.surf_planck[icol * n + i0 + lane];
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    double f_dn = 0.0;
+    dn[0] = 0.0;
+    double b_top = s_pl[lane];
+    int l = 0;
+    for (; l + 4 <= nlay; l += 4) {
+      double e[4], f[4], b[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        lw_layer_fast(s_tau[(l + j) * 32 + lane], p.tc, tl, e[j], f[j]);
+        b[j] = s_pl[(l + j + 1) * 32 + lane];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f_dn = f_dn * (1.0 - e[j]) + b_top * (e[j] - f[j]) + b[j] * f[j];
+        dn[(int64_t)(l + j + 1) * n] = f_dn;
+        s_tau[(l + j) * 32 + lane] = 1.0 - e[j];
+        s_pl[(l + j) * 32 + lane] = b[j] * (e[j] - f[j]) + b_top * f[j];
+        b_top = b[j];
+      }
+    }
+    for (; l < nlay; ++l) {
+      double e, f;
+      lw_layer_fast(s_tau[l * 32 + lane], p.tc, tl, e, f);
+      const double b_bot = s_pl[(l + 1) * 32 + lane];
+      f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
+      dn[(int64_t)(l + 1) * n] = f_dn;
+      s_tau[l * 32 + lane] = 1.0 - e;
+      s_pl[l * 32 + lane] = b_bot * (e - f) + b_top * f;
+      b_top = b_bot;
+    }
+    double f_up = bs * es + (1.0 - es) * f_dn;
+    up[(int64_t)nlay * n] = f_up;
+#pragma unroll 6
+    for (l = nlay - 1; l >= 0; --l) {
+      f_up = f_up * s_tau[l * 32 + lane] + s_pl[l * 32 + lane];
+      up[(int64_t)l * n] = f_up;
+    }
+    // the next item's bulk copies (async proxy) overwrite what this one wrote through the generic proxy
+    fence_proxy_async();
+    __syncwarp();
   }
 }
 
@@ -582,8 +702,29 @@ ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay
   const int64_t nblk = (int64_t)ncol * ((n + bs - 1) / bs);
   ECCKD_REQUIRE(ncol > 0 && nlay > 0 && n > 0 && nblk < 2147483647LL, ECCKD_PARAMETER_ERROR,
                 "ecckd_radiative_transfer_lw: bad dimensions");
-  rt_lw_kernel<<<(unsigned)nblk, bs, 0, ctx->stream>>>(ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck,
-                                                       d_flux_dn, d_flux_up);
+  const size_t staged_smem = (size_t)(2 * nlay + 1) * 256 + 16;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(d_planck) | reinterpret_cast<uintptr_t>(d_od)) & 15u) == 0;
+  if ((n & 31) == 0 && aligned && staged_smem <= ctx->smem_optin / 4 && !getenv("ECCKD_RT_PLAIN")) {
+    RtLwStagedParams sp;
+    sp.ncol = ncol; sp.nlay = nlay; sp.n = n; sp.planck = d_planck; sp.od = d_od; sp.surf_emissivity = d_surf_emissivity;
+    sp.surf_planck = d_surf_planck; sp.flux_dn = d_flux_dn; sp.flux_up = d_flux_up;
+    trans_const_init(&sp.tc, ECCKD_LW_DIFFUSIVITY);
+    const int per_sm = (int)std::min<size_t>(32, (ctx->smem_optin + 1024) / (staged_smem + 1024));
+    const int64_t items = (int64_t)ncol * (n >> 5);
+    const unsigned grid = (unsigned)std::min<int64_t>(items, (int64_t)ctx->num_sms * per_sm);
+    if (n == 32) {
+      ECCKD_CUDA_OK(cudaFuncSetAttribute(rt_lw_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)staged_smem));
+      rt_lw_staged_kernel<true><<<grid, 32, staged_smem, ctx->stream>>>(sp);
+    } else {
+      ECCKD_CUDA_OK(cudaFuncSetAttribute(rt_lw_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)staged_smem));
+      rt_lw_staged_kernel<false><<<grid, 32, staged_smem, ctx->stream>>>(sp);
+    }
+  } else {
+    rt_lw_kernel<<<(unsigned)nblk, bs, 0, ctx->stream>>>(ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck,
+                                                         d_flux_dn, d_flux_up);
+  }
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
