@@ -450,7 +450,31 @@ def main():
                "call": "ecckd_planck_average_optical_depth_to_g_point (one [53][2^%d] block per step, pinned host "
                        "buffers)" % args.log2_nwav,
                "ms_per_step": float(ems.item()) / e2e_steps}
-        del h_od
+        del h_od, od_np
+        # the same call fed the float32 values the CKDMIP files hold (widened on the device, bit-identical
+        # results): what a front-end reading the spectra files would pass.  Reported beside e2e, not as e2e.
+        h32 = torch.empty((nlay, nwav), dtype=torch.float32, pin_memory=True)
+        h32.copy_(ods[1])
+        od32 = h32.numpy()
+        for _ in range(2):
+            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od32, t_fl, h_wn, h_dwn,
+                                                      args.method, out=res)
+        barrier()
+        e0.record()
+        for _ in range(e2e_steps):
+            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od32, t_fl, h_wn, h_dwn,
+                                                      args.method, out=res)
+        e1.record()
+        barrier()
+        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e["float32_spectra"] = {
+            "value": world * nlay * nwav * e2e_steps / (float(ems.item()) * 1e-3), "unit": "point*layers/s",
+            "h2d_bytes_per_step": int(nlay * nwav * 4 + nwav * (8 + 8 + 4)),
+            "call": "ecckd_planck_average_optical_depth_to_g_point_f32 (float32 optical depths as stored in the "
+                    "spectra files, widened on the device)", "ms_per_step": float(ems.item()) / e2e_steps}
+        del h32, od32
 
     # ---- metric 2: CKD flux columns.g-points/s (run_ckd LW, config A LUT with columns replicated)
     flux = None

@@ -93,6 +93,8 @@ def _declare(L):
                                                    vp, vp, vp, i64, vp],
         "ecckd_planck_average_optical_depth_to_g_point": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp,
                                                           C.c_char_p, vp, vp, vp, i64, vp],
+        "ecckd_planck_average_optical_depth_to_g_point_f32": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp,
+                                                              C.c_char_p, vp, vp, vp, i64, vp],
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],
@@ -126,6 +128,7 @@ def _declare(L):
                                               vp, vp, vp, vp],
         "ecckd_interval_error_batch_sw_dev": [vp, i32, i32, i64, i64, dbl, vp, vp, dbl, vp, vp, vp, vp, vp, dbl, vp,
                                               vp, vp, vp, vp, vp, vp, dbl, dbl, i32, vp, vp, vp, vp],
+        "ecckd_calc_total_optical_depth_dev": [vp, vp, vp, i32, i32, vp, vp, vp],
         "ecckd_cost_function_ckd_lw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl,
                                            dbl, dbl, vp, dbl, dbl, vp, vp, vp, vp, vp, vp],
         "ecckd_cost_function_ckd_sw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dbl,

@@ -247,9 +247,14 @@ def planck_average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_
                                             optical_depth, temperature_fl, wavenumber_cm_1, d_wavenumber_cm_1,
                                             averaging_method, out=None):
     """planck_function + average_optical_depth_to_g_point (create_look_up_table.cpp:320-331) on host
-    arrays in one call; `out` may hold preallocated (molar_abs, min, max, warn) arrays."""
-    od = optical_depth if isinstance(optical_depth, np.ndarray) and optical_depth.flags.c_contiguous and \
-        optical_depth.dtype == np.float64 else np.ascontiguousarray(optical_depth, dtype=np.float64)
+    arrays in one call; `out` may hold preallocated (molar_abs, min, max, warn) arrays.  A float32
+    `optical_depth` (the precision the CKDMIP files hold) is uploaded as such and widened on the device."""
+    f32 = isinstance(optical_depth, np.ndarray) and optical_depth.dtype == np.float32
+    if f32:
+        od = np.ascontiguousarray(optical_depth)
+    else:
+        od = optical_depth if isinstance(optical_depth, np.ndarray) and optical_depth.flags.c_contiguous and \
+            optical_depth.dtype == np.float64 else np.ascontiguousarray(optical_depth, dtype=np.float64)
     nlay, nwav = od.shape
     gp = np.ascontiguousarray(g_point, dtype=np.int32)
     pf, pfp = _h(pressure_fl)
@@ -259,7 +264,9 @@ def planck_average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_
     dwn, dwnp = _h(d_wavenumber_cm_1)
     if out is None:
         out = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
-    check(_lib.lib().ecckd_planck_average_optical_depth_to_g_point(
+    fn = _lib.lib().ecckd_planck_average_optical_depth_to_g_point_f32 if f32 else \
+        _lib.lib().ecckd_planck_average_optical_depth_to_g_point
+    check(fn(
         ctx.handle, ng, float(reference_surface_vmr), nlay, nwav, pfp, php, gp.ctypes.data, od.ctypes.data, nwav, tfp,
         wnp, dwnp, averaging_method.encode(), out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
         out[3].ctypes.data))
@@ -487,6 +494,12 @@ class CkdModel:
         check(_lib.lib().ecckd_run_ckd_dev(self.ctx.handle, self.handle, p, float(tsi), ncol, nlay, _ptr(d_pressure_hl),
                                            _ptr(d_temperature_hl), _ptr(d_od), _ptr(d_planck_hl), _ptr(d_planck_surf),
                                            _ptr(d_flux_dn), _ptr(d_flux_up), _ptr(d_bb_flux_dn), _ptr(d_bb_flux_up)))
+
+    def calc_total_optical_depth_dev(self, d_vmr_fl: Sequence, ncol, nlay, d_pressure_hl, d_temperature_hl, d_od):
+        """calc_total_optical_depth (solve_adept.cpp:23-69); d_vmr_fl[igas] = device array or None."""
+        arr, p = _ptr_array(d_vmr_fl)
+        check(_lib.lib().ecckd_calc_total_optical_depth_dev(self.ctx.handle, self.handle, p, ncol, nlay,
+                                                            _ptr(d_pressure_hl), _ptr(d_temperature_hl), _ptr(d_od)))
 
     def run_ckd(self, vmr_fl: Sequence[Optional[np.ndarray]], pressure_hl, temperature_hl, tsi=1361.0):
         """Numerical core of run_ckd (run_ckd.cpp:119-367) on host arrays -> dict of outputs."""

@@ -122,6 +122,17 @@ ECCKD_API int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out) {
     }
     ctx->owns_stream = true;
   }
+  {
+    // plans and partial sums come from the stream-ordered pool (cudaMallocAsync): keep what it has
+    // instead of returning it to the driver at every synchronisation (the default threshold of 0
+    // made one host-buffer call in ten pay ~300 ms for a fresh allocation)
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      uint64_t keep = ~uint64_t(0);
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   ctx->pinned_bytes = size_t(4) << 20;
   cudaError_t pe = cudaHostAlloc(&ctx->pinned, ctx->pinned_bytes, cudaHostAllocDefault);
   if (pe != cudaSuccess) {

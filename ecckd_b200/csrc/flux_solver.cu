@@ -667,6 +667,33 @@ ECCKD_API int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* 
   return ECCKD_OK;
 }
 
+// calc_total_optical_depth: src/ecckd/solve_adept.cpp:23-69.  Rayleigh optical depth (shortwave
+// models), then every gas of the model: with its concentration when the training scene holds it,
+// without when it does not and the gas has no concentration dependence, skipped otherwise.
+ECCKD_API int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* const* h_d_vmr_fl,
+                                                 int ncol, int nlay, const double* d_pressure_hl,
+                                                 const double* d_temperature_hl, double* d_od) {
+  ECCKD_REQUIRE(ctx && m && h_d_vmr_fl && d_pressure_hl && d_temperature_hl && d_od && ncol > 0 && nlay > 0,
+                ECCKD_PARAMETER_ERROR, "ecckd_calc_total_optical_depth: bad argument");
+  const int64_t ncl = (int64_t)ncol * nlay;
+  void* d_tfl = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, (size_t)ncl * sizeof(double), &d_tfl));
+  temperature_fl_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, ctx->stream>>>(ncol, nlay, d_temperature_hl,
+                                                                              d_pressure_hl, static_cast<double*>(d_tfl));
+  ECCKD_LAUNCH_CHECK(ctx);
+  if (m->is_sw) {
+    ECCKD_TRY(ecckd_ckd_calc_rayleigh_optical_depth_dev(ctx, m, ncol, nlay, d_pressure_hl, d_od));
+  } else {
+    ECCKD_CUDA_OK(cudaMemsetAsync(d_od, 0, (size_t)ncl * m->ng * sizeof(double), ctx->stream));
+  }
+  for (int igas = 0; igas < m->ngas; ++igas) {
+    if (!h_d_vmr_fl[igas] && m->conc_dependence[igas] != ECCKD_CONC_NONE) continue;  // :62-66 "not present in LBL file"
+    ECCKD_TRY(ecckd_ckd_calc_optical_depth_dev(ctx, m, igas, ncol, nlay, d_pressure_hl, static_cast<double*>(d_tfl),
+                                               h_d_vmr_fl[igas], d_od, 1));
+  }
+  return ECCKD_OK;
+}
+
 ECCKD_API int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int64_t n,
                                                  const double* d_temperature, double* d_planck) {
   ECCKD_REQUIRE(ctx && m && d_temperature && d_planck && n > 0, ECCKD_PARAMETER_ERROR,

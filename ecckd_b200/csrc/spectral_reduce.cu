@@ -1426,6 +1426,18 @@ ECCKD_API int ecckd_average_optical_depth_to_g_point_dev(
                                                out_stride, warns);
 }
 
+// float32 spectra (how the CKDMIP files store optical depth, merge_spectra.cpp:108; the reference widens them
+// on read, DataFileEngineNetcdf.cpp:393-397) widened on the device: exact, and half the PCIe bytes.
+__global__ void widen_f32_kernel(int64_t n, const float* __restrict__ src, double* __restrict__ dst) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (i + 1 < n) {
+    const float2 v = *reinterpret_cast<const float2*>(src + i);
+    *reinterpret_cast<double2*>(dst + i) = make_double2((double)v.x, (double)v.y);
+  } else if (i < n) {
+    dst[i] = (double)src[i];
+  }
+}
+
 // Host-buffer driver shared by the two reference-facing entry points below.
 // Weights: either planck_fl (matrix, or one row when planck_stride == 0) or
 // Planck function of temperature_fl computed in the kernel.
@@ -1434,7 +1446,8 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
                         const double* optical_depth, int64_t od_stride, const double* planck_fl,
                         int64_t planck_stride, const double* temperature_fl, const double* wavenumber_cm_1,
                         const double* d_wavenumber_cm_1, const char* averaging_method, double* molar_abs,
-                        double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn) {
+                        double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn,
+                        const float* optical_depth_f32 = nullptr) {
   const int method = ecckd_averaging_method_from_string(averaging_method);
   if (method < 0) {
     set_error("averaging_method \"%s\" not understood", averaging_method ? averaging_method : "(null)");
@@ -1451,10 +1464,12 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   const size_t w_elems = fused ? (size_t)2 * dstride : (vecw ? (size_t)dstride : (size_t)nlay * dstride);
   const size_t out_elems = (size_t)nlay * ng;
   void* arena = nullptr;
-  ECCKD_TRY(ws_reserve(ctx, 4, (od_elems + w_elems + 3 * out_elems) * sizeof(double), &arena));
+  const size_t f32_elems = optical_depth_f32 ? (od_elems + 1) / 2 : 0;  // float staging, counted in doubles
+  ECCKD_TRY(ws_reserve(ctx, 4, (od_elems + w_elems + 3 * out_elems + f32_elems) * sizeof(double), &arena));
   double* d_od = static_cast<double*>(arena);
   double* d_w = d_od + od_elems;
   double* d_out = d_w + w_elems;
+  float* d_f32 = reinterpret_cast<float*>(d_out + 3 * out_elems);
   void* iarena = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 5, (size_t)(nwav + ng) * sizeof(int32_t), &iarena));
   int32_t* d_g = static_cast<int32_t*>(iarena);
@@ -1470,8 +1485,22 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   cudaError_t e = cudaSuccess;
   for (int s = 0; s < nslab && e == cudaSuccess; ++s) {
     const int l0 = (int)(((int64_t)nlay * s) / nslab), l1 = (int)(((int64_t)nlay * (s + 1)) / nslab);
-    e = cudaMemcpy2DAsync(d_od + (size_t)l0 * dstride, dstride * sizeof(double), optical_depth + (size_t)l0 * od_stride,
-                          od_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
+    if (optical_depth_f32) {
+      e = cudaMemcpy2DAsync(d_f32 + (size_t)l0 * dstride, dstride * sizeof(float),
+                            optical_depth_f32 + (size_t)l0 * od_stride, od_stride * sizeof(float), nwav * sizeof(float),
+                            l1 - l0, cudaMemcpyHostToDevice, cs);
+      if (e == cudaSuccess) {
+        const int64_t nel = (int64_t)(l1 - l0) * dstride;  // pad columns carry stale values nobody reads
+        widen_f32_kernel<<<(unsigned)((nel / 2 + 256) / 256), 256, 0, cs>>>(nel, d_f32 + (size_t)l0 * dstride,
+                                                                          d_od + (size_t)l0 * dstride);
+        ctx->launches++;
+        e = cudaGetLastError();
+      }
+    } else {
+      e = cudaMemcpy2DAsync(d_od + (size_t)l0 * dstride, dstride * sizeof(double),
+                            optical_depth + (size_t)l0 * od_stride, od_stride * sizeof(double), nwav * sizeof(double),
+                            l1 - l0, cudaMemcpyHostToDevice, cs);
+    }
     if (e == cudaSuccess && !fused && !vecw)
       e = cudaMemcpy2DAsync(d_w + (size_t)l0 * dstride, dstride * sizeof(double), planck_fl + (size_t)l0 * planck_stride,
                             planck_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
@@ -1566,6 +1595,20 @@ ECCKD_API int ecckd_planck_average_optical_depth_to_g_point(
   return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, pressure_fl, pressure_hl, g_point, optical_depth,
                       od_stride, nullptr, 0, temperature_fl, wavenumber_cm_1, d_wavenumber_cm_1, averaging_method,
                       molar_abs, min_molar_abs, max_molar_abs, out_stride, warn);
+}
+
+ECCKD_API int ecckd_planck_average_optical_depth_to_g_point_f32(
+    ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav, const double* pressure_fl,
+    const double* pressure_hl, const int32_t* g_point, const float* optical_depth, int64_t od_stride,
+    const double* temperature_fl, const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
+    const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride,
+    int32_t* warn) {
+  ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && temperature_fl && wavenumber_cm_1 &&
+                    d_wavenumber_cm_1 && molar_abs,
+                ECCKD_PARAMETER_ERROR, "ecckd_planck_average_optical_depth_to_g_point_f32: NULL argument");
+  return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, pressure_fl, pressure_hl, g_point, nullptr, od_stride,
+                      nullptr, 0, temperature_fl, wavenumber_cm_1, d_wavenumber_cm_1, averaging_method, molar_abs,
+                      min_molar_abs, max_molar_abs, out_stride, warn, optical_depth);
 }
 
 ECCKD_API int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,

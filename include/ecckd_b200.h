@@ -228,6 +228,17 @@ int ecckd_planck_average_optical_depth_to_g_point(
     const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, const char* averaging_method,
     double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn);
 
+/* The same with the optical depths as the float32 values the CKDMIP spectra files hold
+ * (merge_spectra.cpp:108; the reference widens them to Real on read,
+ * src/tools/DataFileEngineNetcdf.cpp:393-397).  The widening is done on the device: results are
+ * bit-identical to widening on the host, and the PCIe transfer is halved. */
+int ecckd_planck_average_optical_depth_to_g_point_f32(
+    ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav, const double* pressure_fl,
+    const double* pressure_hl, const int32_t* g_point, const float* optical_depth, int64_t od_stride,
+    const double* temperature_fl, const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
+    const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs,
+    int64_t out_stride, int32_t* warn);
+
 /* Merge of several spectra: src/ecckd/read_merged_spectrum.cpp:149-168.
  * d_optical_depth += d_od * scaling, or * h_scaling_profile[layer] if non-NULL. */
 int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
@@ -464,6 +475,14 @@ int ecckd_interval_error_batch_sw_dev(
 /* ---------------------------------------------------------------------------
  * Forward cost of optimize_lut (rows a21-a23), batched over the profiles of a scene
  * ------------------------------------------------------------------------- */
+
+/* calc_total_optical_depth: src/ecckd/solve_adept.cpp:23-69.  d_od[ncol][nlay][ng] = Rayleigh
+ * optical depth (shortwave models) + every gas of the model; h_d_vmr_fl[ngas] holds device
+ * pointers [ncol][nlay] or NULL for a gas the training scene does not hold: such a gas is
+ * included without concentration if it has no concentration dependence and skipped otherwise. */
+int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, const double* const* h_d_vmr_fl,
+                                       int ncol, int nlay, const double* d_pressure_hl,
+                                       const double* d_temperature_hl, double* d_od);
 
 /* calc_cost_function_ckd_lw (forward value): src/ecckd/calc_cost_function_lw.cpp:115-232, for
  * every profile of a training scene as solve_adept.cpp:96-184 drives it, including the layer

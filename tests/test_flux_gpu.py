@@ -134,3 +134,27 @@ def test_run_ckd_negative_od_is_clamped(ctx, O):
     assert (ref["optical_depth"] == 0.0).any()
     assert np.array_equal(got["optical_depth"] == 0.0, ref["optical_depth"] == 0.0)
     assert np.max(np.abs(got["flux_up"] - ref["flux_up"])) <= FLUX_ATOL
+
+
+@pytest.mark.parametrize("sw", [False, True])
+def test_calc_total_optical_depth(ctx, O, sw):
+    """calc_total_optical_depth (solve_adept.cpp:23-69): Rayleigh + gases; a gas missing from the training
+    scene is included only when it has no concentration dependence."""
+    c = S.ckd_model_case(ncol=6, nlay=54, ng=32, seed=17, sw=sw)
+    m = _model(ctx, c, sw=sw)
+    t_fl = O.temperature_fl(c["temperature_hl"], c["pressure_hl"])
+    vmr = list(c["vmr_fl"])
+    absent = [i for i, g in enumerate(c["gases"]) if g["conc_dependence"] != E.CONC_NONE][-1]
+    vmr[absent] = None  # "not present in LBL file": skipped
+    ref = np.zeros((6, 54, 32))
+    if sw:
+        dp = np.diff(c["pressure_hl"], axis=1)
+        ref += (dp * (1.0 / (9.80665 * 0.001 * 28.970)))[:, :, None] * c["rayleigh_molar_scat"][None, None, :]
+    for i, (gas, v) in enumerate(zip(c["gases"], vmr)):
+        if v is None and gas["conc_dependence"] != E.CONC_NONE:
+            continue
+        ref += O.ckd_calc_optical_depth(gas, c["log_pressure"], c["temperature"], c["pressure_hl"], t_fl, v)
+    d_od = ctx.empty((6, 54, 32))
+    m.calc_total_optical_depth_dev([None if v is None else ctx.to_device(v) for v in vmr], 6, 54,
+                                   ctx.to_device(c["pressure_hl"]), ctx.to_device(c["temperature_hl"]), d_od)
+    np.testing.assert_allclose(d_od.numpy(), ref, rtol=1e-11, atol=1e-18)

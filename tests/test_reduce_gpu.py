@@ -326,3 +326,18 @@ def test_avg_group_of_twenty_spectra_and_wavenumber_windows(ctx, O, monkeypatch)
         got = (outs[s].numpy(), mins[s].numpy(), maxs[s].numpy(), None)
         scale = (9.80665 * 0.001 * 28.970 / vmrs[s]) / (c["pressure_hl"][1:] - c["pressure_hl"][:-1])
         S.assert_avg_close(got, ref, method="transmission", scale=scale, what=f"spectrum {s} ")
+
+
+@pytest.mark.parametrize("method", ["transmission", "logarithmic"])
+def test_avg_host_call_float32_spectra_bit_identical(ctx, method):
+    """ecckd_planck_average_optical_depth_to_g_point_f32: float32 optical depths (what the CKDMIP files hold)
+    widened on the device give bit-identical results to widening on the host; odd nwav and a zero row."""
+    c = S.lw_spectrum_case(nlay=23, nwav=9001, ng=10, nband=2, seed=77)
+    od32 = c["od"].astype(np.float32)
+    od32[5] = 0.0
+    args = (c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"])
+    tail = (c["temperature_fl"], c["wavenumber"], c["d_wavenumber"], method)
+    a = E.planck_average_optical_depth_to_g_point(ctx, *args, od32, *tail)
+    b = E.planck_average_optical_depth_to_g_point(ctx, *args, od32.astype(np.float64), *tail)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)

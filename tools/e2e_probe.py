@@ -1,38 +1,56 @@
-"""Where does the host-buffer entry point spend its time?  (diagnostic)"""
-import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-import ecckd_b200 as E
-import bench
+"""Times the host-buffer averaging call with float64 and float32 spectra and the raw pinned H2D copies."""
+import os
+import sys
+import time
 
-log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 23
-nlay, nwav = 53, 1 << log2
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ecckd_b200 as E  # noqa: E402
+import bench  # noqa: E402
+
 dev = torch.device("cuda", 0)
-st = torch.cuda.Stream(device=dev); torch.cuda.set_stream(st)
+st = torch.cuda.Stream(device=dev)
+torch.cuda.set_stream(st)
 ctx = E.Context(0, st.cuda_stream)
+nlay, log2 = 53, int(sys.argv[1]) if len(sys.argv) > 1 else 23
+nwav = 1 << log2
 dnu = (3260.0 - 0.0002) / (nwav - 1)
 wn = 0.0002 + dnu * torch.arange(nwav, device=dev, dtype=torch.float64)
 dwn = torch.full((nwav,), dnu, dtype=torch.float64, device=dev)
 key = bench.smooth_key(torch, wn, seed=7)
 g_point, ng = bench.make_g_point(torch, wn, key, "ranked", seed=7)
-p_hl = bench.pressure_grid(nlay); p_fl = 0.5 * (p_hl[1:] + p_hl[:-1])
-t_hl = bench.temperature_profile(p_hl); t_fl = 0.5 * (t_hl[:-1] * p_hl[:-1] + t_hl[1:] * p_hl[1:]) / p_fl
-od = bench.make_spectrum(torch, wn, nlay, p_hl, 1001, 1e-3)
-h_od = torch.empty((nlay, nwav), dtype=torch.float64, pin_memory=True); h_od.copy_(od)
-torch.cuda.synchronize()
-def T(f, n=3):
-    f(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(n): f()
-    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
-print("H2D 53 x nwav pinned: %.1f ms" % T(lambda: od.copy_(h_od, non_blocking=True)))
-print("plan create: %.1f ms" % T(lambda: E.GPointPlan(ctx, g_point, nwav, ng).close()))
-plan = E.GPointPlan(ctx, g_point, nwav, ng)
-out = torch.empty((nlay, ng), dtype=torch.float64, device=dev); mn = torch.empty_like(out); mx = torch.empty_like(out)
-def devcall(n):
-    E.average_optical_depth_to_g_point_dev(ctx, plan, 1e-3, p_fl[:n], p_hl[:n + 1], od, nwav, E.WEIGHT_PLANCK, None, nwav,
-                                           t_fl[:n], wn, dwn, "transmission", out, mn, mx, ng)
-for n in (53, 27, 7, 1):
-    print("dev call, %2d layers x 1 spectrum: %.2f ms" % (n, T(lambda: devcall(n))))
-h_wn, h_dwn, h_g = wn.cpu().numpy(), dwn.cpu().numpy(), g_point.cpu().numpy()
+p_hl = bench.pressure_grid(nlay)
+p_fl = 0.5 * (p_hl[1:] + p_hl[:-1])
+t_hl = bench.temperature_profile(p_hl)
+t_fl = 0.5 * (t_hl[:-1] * p_hl[:-1] + t_hl[1:] * p_hl[1:]) / p_fl
+od = bench.make_spectrum(torch, wn, nlay, p_hl, 1001, 4.15e-4)
+pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)  # noqa: E731
+h64 = pin(od)
+h32 = torch.empty(od.shape, dtype=torch.float32, pin_memory=True)
+h32.copy_(od)
+h_wn, h_dwn, h_g = pin(wn).numpy(), pin(dwn).numpy(), pin(g_point).numpy()
 res = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
-print("host call: %.1f ms" % T(lambda: E.planck_average_optical_depth_to_g_point(ctx, ng, 1e-3, p_fl, p_hl, h_g, h_od.numpy(), t_fl, h_wn, h_dwn, "transmission", out=res)))
+d64 = torch.empty_like(od)
+d32 = torch.empty(od.shape, dtype=torch.float32, device=dev)
+for name, h, d in (("f64", h64, d64), ("f32", h32, d32)):
+    for _ in range(2):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(3):
+        d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / 3
+    print(f"raw pinned H2D {name}: {dt * 1e3:.1f} ms  {h.numel() * h.element_size() / dt / 1e9:.1f} GB/s")
+for name, h in (("f64", h64.numpy()), ("f32", h32.numpy()), ("f64", h64.numpy()), ("f32", h32.numpy())):
+    for _ in range(2):
+        E.planck_average_optical_depth_to_g_point(ctx, ng, 4.15e-4, p_fl, p_hl, h_g, h, t_fl, h_wn, h_dwn, "transmission", out=res)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(3):
+        E.planck_average_optical_depth_to_g_point(ctx, ng, 4.15e-4, p_fl, p_hl, h_g, h, t_fl, h_wn, h_dwn, "transmission", out=res)
+    torch.cuda.synchronize()
+    dt = (time.time() - t0) / 3
+    print(f"host call {name}: {dt * 1e3:.1f} ms  checksum {res[0].sum():.6e}")
