@@ -120,29 +120,18 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
                                            const bool (&is_log)[NR], PendingFold* pend = nullptr) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const bool have_pending = pend != nullptr && pend->valid;  // warp-uniform
-  // software pipeline: the offsets, weights and optical depths of the next 4 slots are loaded
-  // while the current 4 are evaluated
-  double tau_n[NR][4], w_n[4];
-  auto load4 = [&](const int kk) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned o = offp[(kk + j) * 32];
-      w_n[j] = wp[(kk + j) * 32];  // zero for padding slots
-#pragma unroll
-      for (int r = 0; r < NR; ++r) tau_n[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
-    }
-  };
-  load4(0);
+  // no register software pipeline: the loads of a trip are issued at its top and the other warps
+  // of the scheduler cover their latency (the rotating pipeline cost 52 register moves per trip)
 #pragma unroll 1
   for (int kk = 0; kk < SLOTS; kk += 4) {
     double tau[NR][4], w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      w[j] = w_n[j];
+      const unsigned o = offp[(kk + j) * 32];
+      w[j] = wp[(kk + j) * 32];  // zero for padding slots
 #pragma unroll
-      for (int r = 0; r < NR; ++r) tau[r][j] = tau_n[r][j];
+      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
     }
-    load4(min(kk + 4, SLOTS - 4));  // the last iteration reloads its own slots (no branch)
     if (have_pending) pending_step(*pend, kk >> 2);  // one step of the previous round's reduction
     // extremes: one range check per value, one (rare) branch per 4 x NR values
     bool outside = false;
