@@ -117,7 +117,8 @@ template <int FKIND, int NR>
 __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char* __restrict__ stage0,
                                            const uint16_t* __restrict__ offp, const double* __restrict__ wp,
                                            const int nv, const TransConst& K, const TransLane& tl,
-                                           const bool (&is_log)[NR], PendingFold* pend = nullptr) {
+                                           const bool (&is_log)[NR], const TransConst256& K2,
+                                           const unsigned char* __restrict__ tab, PendingFold* pend = nullptr) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   const bool have_pending = pend != nullptr && pend->valid;  // warp-uniform
   // no register software pipeline: the loads of a trip are issued at its top and the other warps
@@ -167,16 +168,16 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[r][j] = trans_phase1(tau[r][j], K);
+        for (int j = 0; j < 4; ++j) m[r][j] = trans256_phase1(tau[r][j], K2);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) T[r][j] = trans_phase2(m[r][j], tl);
+        for (int j = 0; j < 4; ++j) T[r][j] = trans256_phase2(m[r][j], tab);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[r][j] = trans_phase3(m[r][j], T[r][j], K);
+          f[r][j] = trans256_phase3(m[r][j], T[r][j], K2);
           pos[r][j] = true;
         }
     } else {

@@ -266,6 +266,7 @@ struct SmemLayout {
   int data;    // data stages [nw][NSETS*RPW][CH_MAX] doubles
   int acc;     // accumulators [nw][RPW][ng][4] doubles: {sum f*w, sum w, min, max}
   int accz;    // zero counters [nw][RPW][ng] int32
+  int tab;     // 2^(j/256) table of the consumer warps (trans_core.cuh)
   int total;
 };
 static_assert(RING_SLOT_BYTES % 16 == 0 && STAGE_BYTES % 16 == 0, "stage alignment");
@@ -283,6 +284,9 @@ __host__ __device__ inline SmemLayout smem_layout(int nw, int ng) {
   off += nw * RPW * ng * 4 * 8;
   L.accz = off;
   off += nw * RPW * ng * 4;
+  off = (off + 15) & ~15;
+  L.tab = off;
+  off += TRANS_TAB_BYTES;
   L.total = (off + 15) & ~15;
   return L;
 }
@@ -339,7 +343,9 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     }
     fence_mbar_init();
   }
+  if (FKIND == F_TRANS) trans_tab_init(reinterpret_cast<double*>(smem_raw + L.tab));
   __syncthreads();
+  const unsigned char* tab = smem_raw + L.tab;
 
   // this CTA's contiguous piece of the (window, group, chunk) space
   const int nchunks = (int)p.nchunks;
@@ -605,11 +611,11 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
 #pragma unroll
           for (int r = 0; r < RPW; ++r) partial_begin(a[r], acc + ((size_t)r * ng + gsafe) * 4, lane_used);
           if (LOGKIND) {
-            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log);
+            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, p.tc256, tab);
             fold_partials<RPW, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
           } else {
             // the sums of the previous round are reduced inside this round's slot loop
-            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, &pend);
+            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, p.tc256, tab, &pend);
             pending_finish(pend, SLOTS / 4, acc, ng);
             fold_partials<RPW, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
 #pragma unroll
@@ -623,10 +629,10 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
           const bool il[1] = {is_log[0]};
           partial_begin(a[0], acc + (size_t)gsafe * 4, lane_used);
           if (LOGKIND) {
-            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il);
+            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, p.tc256, tab);
             fold_partials<1, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
           } else {
-            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, &pend);
+            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, p.tc256, tab, &pend);
             pending_finish(pend, SLOTS / 4, acc, ng);
             fold_partials<1, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
             pend.s0[0] = a[0].s0;
@@ -969,6 +975,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.wn = d_wn;
   rp.dwn = d_dwn;
   trans_const_init(&rp.tc, kd);
+  trans_const256_init(&rp.tc256, kd);
   if (const char* e = getenv("ECCKD_DEBUG")) rp.debug = atoi(e);
   // wavenumber windows: the per-wavenumber data a group re-reads (wavenumber grids or weight vector,
   // plan records: ~20 B per wavenumber) should stay in L2 between groups; 24 MB per window does
@@ -1239,14 +1246,19 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
 }
 
 namespace ecckd {
-__global__ void debug_eval_kernel(int which, TransConst K, double kd, int64_t n, const double* __restrict__ x,
-                                  double* __restrict__ out) {
+__global__ void debug_eval_kernel(int which, TransConst K, TransConst256 K2, double kd, int64_t n,
+                                  const double* __restrict__ x, double* __restrict__ out) {
+  __shared__ __align__(16) double s_tab[256];
+  trans_tab_init(s_tab);
+  __syncthreads();
+  const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_tab);
   const TransLane tl = trans_lane_init();
   // whole warps stay in the loop (the evaluations shuffle): pad with a harmless argument
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
     const int64_t i = base + threadIdx.x;
     const double v = i < n ? x[i] : 1.0;
     const double r = which == 0 ? trans_one_minus_exp(v, K, tl)
+                   : which == 2 ? trans256_one_minus_exp(v, K2, tab)
                                 : planck_elem_fast((6.62606896e-34 / 1.3806504e-23) / kd, v, 1.0, tl);
     if (i < n) out[i] = r;
   }
@@ -1254,15 +1266,17 @@ __global__ void debug_eval_kernel(int which, TransConst K, double kd, int64_t n,
 }  // namespace ecckd
 
 ECCKD_API int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, const double* x, double* out) {
-  ECCKD_REQUIRE(ctx && x && out && n > 0 && (which == 0 || which == 1) && kd > 0.0, ECCKD_PARAMETER_ERROR,
+  ECCKD_REQUIRE(ctx && x && out && n > 0 && which >= 0 && which <= 2 && kd > 0.0, ECCKD_PARAMETER_ERROR,
                 "ecckd_debug_eval: bad argument");
   double* d = nullptr;
   ECCKD_CUDA_OK(cudaMalloc(&d, (size_t)2 * n * sizeof(double)));
   TransConst K;
   trans_const_init(&K, kd);
+  TransConst256 K2;
+  trans_const256_init(&K2, kd);
   cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    debug_eval_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(which, K, kd, n, d, d + n);
+    debug_eval_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(which, K, K2, kd, n, d, d + n);
     ctx->launches++;
     e = cudaGetLastError();
   }

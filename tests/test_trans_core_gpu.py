@@ -11,11 +11,12 @@ pytestmark = pytest.mark.gpu
 KD = [1.66, 2 * 1.66, 3 * 1.66, 10 * 1.66]  # transmission, -2, -3, -10
 
 
+@pytest.mark.parametrize("which", [0, 2])  # 0: 32-entry lane table, degree 6; 2: 256-entry shared table, degree 4
 @pytest.mark.parametrize("kd", KD)
-def test_one_minus_exp_absolute_error(ctx, kd):
+def test_one_minus_exp_absolute_error(ctx, kd, which):
     rng = np.random.default_rng(int(kd * 100))
     tau = np.concatenate([10.0 ** rng.uniform(-14, 3.5, 200000), [0.0, 5e-324, 1e-300, 1e-20, 426.0 / kd * 1.66, 1e6, 1e30]])
-    got = E.debug_eval(ctx, 0, kd, tau)
+    got = E.debug_eval(ctx, which, kd, tau)
     ref = -np.expm1(-kd * tau.astype(np.longdouble)).astype(np.float64)
     # the reference's 1.0 - exp(x) carries up to ~1.7e-16 (exp rounded at ulp(1)/2, the difference once more);
     # the table scheme with its two final FMAs stays within 2 ulp of 1
@@ -25,9 +26,10 @@ def test_one_minus_exp_absolute_error(ctx, kd):
     assert got[len(tau) - 7] == 0.0            # tau = 0
 
 
-def test_one_minus_exp_is_monotone_on_a_fine_grid(ctx):
+@pytest.mark.parametrize("which", [0, 2])
+def test_one_minus_exp_is_monotone_on_a_fine_grid(ctx, which):
     tau = np.linspace(0.0, 30.0, 400001)
-    got = E.debug_eval(ctx, 0, 1.66, tau)
+    got = E.debug_eval(ctx, which, 1.66, tau)
     assert np.all(np.diff(got) >= -2.3e-16)
 
 

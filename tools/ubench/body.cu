@@ -32,6 +32,11 @@ __global__ void __launch_bounds__(MAXT, 1) body_kernel(TransConst K, int iters, 
   for (int i = lane; i < 64 * 4 * NR; i += 32) acc[i] = (i & 3) == 2 ? 1e-5 : ((i & 3) == 3 ? 10.0 : 0.0);  // extremes established: the usual state
   __syncwarp();
   const TransLane tl = trans_lane_init();
+  __shared__ __align__(16) double s_tab[256];
+  trans_tab_init(s_tab);
+  TransConst256 K2;
+  K2.a = K.a * 8.0; K2.b = K.b / 8.0; K2.hi_max = K.hi_max;
+  for (int i = 0; i < 4; ++i) K2.c[i] = K.c[i];
   int32_t accz_dummy[2];
   const bool is_log[NR] = {};
   __syncthreads();
@@ -43,7 +48,7 @@ __global__ void __launch_bounds__(MAXT, 1) body_kernel(TransConst K, int iters, 
     const unsigned meta = pr->meta[lane];
     for (int r = 0; r < NR; ++r) partial_begin(a[r], acc + ((size_t)r * 64 + (meta & 0xFFFu)) * 4, true);
     rows_slots<F_TRANS, NR>(a, reinterpret_cast<const unsigned char*>(stage), &pr->off[0][lane], wperm + lane, 16, K, tl,
-                            is_log);
+                            is_log, K2, reinterpret_cast<const unsigned char*>(s_tab));
     if (FOLD) fold_partials<NR, true, false, true, false>(a, meta, 4, acc, accz_dummy, 64);
     else sink += a[0].s0 + a[NR - 1].mn;
     __syncwarp();
