@@ -75,52 +75,19 @@ __device__ __forceinline__ void partial_begin(Partial& p, const double* __restri
   }
 }
 
-// Deferred reduction of the weighted sums: the segmented shuffle reduction is a chain of five
-// dependent shuffle + add steps (~70 cycles each) with nothing else to do in between, so a round's
-// sums are parked here and reduced one step per 4-slot iteration of the NEXT round's slot loop,
-// where the FP64 work of that round hides the latency.  Always RPW rows (unused rows carry zeros).
-struct PendingFold {
-  double s0[RPW];
-  unsigned meta;
-  int nsteps;
-  bool valid;  // warp-uniform
-};
-__device__ __forceinline__ void pending_step(PendingFold& pf, const int st) {
-  if (st < pf.nsteps) {  // warp-uniform
-    const bool take = (pf.meta >> (17 + st)) & 1u;
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const double t = __shfl_down_sync(0xffffffffu, pf.s0[r], 1 << st);
-      pf.s0[r] += take ? t : 0.0;
-    }
-  }
-}
-// steps first_step.. and the head lane's update of the accumulators (row r at acc + r*ng*4)
-__device__ __forceinline__ void pending_finish(PendingFold& pf, const int first_step, double* __restrict__ acc,
-                                               const int ng) {
-  if (!pf.valid) return;
-  for (int st = first_step; st < 5; ++st) pending_step(pf, st);
-  const unsigned g = pf.meta & 0xFFFu;
-  if (g != NO_G && ((pf.meta >> 22) & 1u)) {
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) acc[((size_t)r * ng + g) * 4] += pf.s0[r];
-  }
-  pf.valid = false;
-}
-
 // The 16 slots of NR rows of one round, evaluated together: the rows share the lane's offsets and
 // weights (read once per slot from the ring slot) and give the FP64 pipe NR x 4 independent
 // dependency chains.  `stage0` is the first row's chunk in shared memory, row r is STAGE_BYTES
-// further.  The slot loop is only unrolled by 4 so that the body (~4 KB of SASS for two rows) stays
-// resident in the instruction cache for all warps of the SM.  `a` must come from partial_begin.
+// further.  The slot loop handles 4 slots per trip and is not unrolled further: measured on the B200,
+// every variant with a bigger body (8 slots per trip, a register software pipeline, a deferred fold
+// threaded through the loop) was slower than this plain form.  `a` must come from partial_begin.
 template <int FKIND, int NR>
 __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char* __restrict__ stage0,
                                            const uint16_t* __restrict__ offp, const double* __restrict__ wp,
                                            const int nv, const TransConst& K, const TransLane& tl,
                                            const bool (&is_log)[NR], const TransConst256& K2,
-                                           const unsigned char* __restrict__ tab, PendingFold* pend = nullptr) {
+                                           const unsigned char* __restrict__ tab) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
-  const bool have_pending = pend != nullptr && pend->valid;  // warp-uniform
   // no register software pipeline: the loads of a trip are issued at its top and the other warps
   // of the scheduler cover their latency (the rotating pipeline cost 52 register moves per trip)
 #pragma unroll 1
@@ -133,7 +100,6 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
 #pragma unroll
       for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
     }
-    if (have_pending) pending_step(*pend, kk >> 2);  // one step of the previous round's reduction
     // extremes: one range check per value, one (rare) branch per 4 x NR values
     bool outside = false;
 #pragma unroll

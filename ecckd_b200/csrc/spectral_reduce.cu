@@ -500,10 +500,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
     }
     __syncwarp();
   };
-  PendingFold pend;
-  pend.valid = false;
   auto flush_partial = [&](int vg) {
-    pending_finish(pend, 0, acc, ng);  // the last round's sums are still parked
     __syncwarp();
     const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (nw * RPW) + warp * RPW;
     double* out = p.partial + slot * ng * 4;
@@ -530,12 +527,17 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   auto issue = [&](int set) {
     const int n_c = (qi.c == nchunks - 1) ? last_n : ch;
     if (lane == 0 && ((n_c & 1) == 0)) {
+      // the rows of a set complete on ONE mbarrier (one wait per chunk visit instead of one per row)
+      const unsigned bar = my_full + (set * RPW) * 8;
+      int nb = 0;
 #pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        if (bulk_i[r]) {
-          const unsigned bar = my_full + (set * RPW + r) * 8;
-          mbar_arrive_expect_tx(bar, (unsigned)(n_c * 8));
-          bulk_g2s_hint(my_data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
+      for (int r = 0; r < RPW; ++r) nb += bulk_i[r] ? 1 : 0;
+      if (nb > 0) {
+        mbar_arrive_expect_tx(bar, (unsigned)(nb * n_c * 8));
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          if (bulk_i[r])
+            bulk_g2s_hint(my_data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
         }
       }
     }
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   Cursor q = first;
   int ws = 0, vg = 0;
   unsigned wpar = 0;
-  unsigned phase_bits = 0;  // bit (set*RPW + r): parity to wait for on that stage's mbarrier
+  unsigned phase_bits = 0;  // bit `set`: parity to wait for on that stage set's mbarrier
   const double* od_c[RPW];
   bool active[RPW], bulk_row[RPW], is_log[RPW];
   bool need_group = true;
@@ -568,13 +570,17 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       need_group = false;
     }
     const int n_c = (q.c == nchunks - 1) ? last_n : ch;
+    bool any_bulk = false;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) any_bulk = any_bulk || bulk_row[r];
+    if (any_bulk && ((n_c & 1) == 0)) {
+      mbar_wait(my_full + (set * RPW) * 8, (phase_bits >> set) & 1u);
+      phase_bits ^= 1u << set;
+    }
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int st = set * RPW + r;
-      if (bulk_row[r] && ((n_c & 1) == 0)) {
-        mbar_wait(my_full + st * 8, (phase_bits >> st) & 1u);
-        phase_bits ^= 1u << st;
-      } else if (active[r]) {
+      if (!(bulk_row[r] && ((n_c & 1) == 0)) && active[r]) {
         const double* src = od_c[r] + (int64_t)q.c * ch;
         double* stage = reinterpret_cast<double*>(data + st * STAGE_BYTES);
         for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
@@ -614,15 +620,8 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
             rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, p.tc256, tab);
             fold_partials<RPW, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
           } else {
-            // the sums of the previous round are reduced inside this round's slot loop
-            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, p.tc256, tab, &pend);
-            pending_finish(pend, SLOTS / 4, acc, ng);
-            fold_partials<RPW, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
-#pragma unroll
-            for (int r = 0; r < RPW; ++r) pend.s0[r] = a[r].s0;
-            pend.meta = meta;
-            pend.nsteps = nsteps;
-            pend.valid = true;
+            rows_slots<FKIND, RPW>(a, stage0, offp, wp, nv, p.tc, tl, is_log, p.tc256, tab);
+            fold_partials<RPW, true, false, true, false>(a, meta, nsteps, acc, accz, ng);
           }
         } else {
           Partial a[1];
@@ -632,15 +631,8 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
             rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, p.tc256, tab);
             fold_partials<1, true, true, true, true>(a, meta, nsteps, acc, accz, ng);
           } else {
-            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, p.tc256, tab, &pend);
-            pending_finish(pend, SLOTS / 4, acc, ng);
-            fold_partials<1, false, false, true, false>(a, meta, nsteps, acc, accz, ng);
-            pend.s0[0] = a[0].s0;
-#pragma unroll
-            for (int r = 1; r < RPW; ++r) pend.s0[r] = 0.0;
-            pend.meta = meta;
-            pend.nsteps = nsteps;
-            pend.valid = true;
+            rows_slots<FKIND, 1>(a, stage0, offp, wp, nv, p.tc, tl, il, p.tc256, tab);
+            fold_partials<1, true, false, true, false>(a, meta, nsteps, acc, accz, ng);
           }
         }
       }
