@@ -102,7 +102,7 @@ struct ReduceParams {
   const double* dwn;
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
   TransConst256 tc256;        // the same for the 256-entry shared-memory table of the consumer warps
-  int debug;                  // timing experiments only (ECCKD_DEBUG): 1 skip the row evaluation, 2 skip the fold
+  int debug;                  // timing experiments only (ECCKD_DEBUG): 1 skip the row evaluation, 4 skip only the slot loop
   double* partial;            // [ncta][maxg][nw*RPW][ng][4]
   int32_t* partial_z;         // [ncta][maxg][nw*RPW][ng]
 };
