@@ -566,11 +566,18 @@ def bench_flux(torch, E, ctx, dev, peak):
     torch.cuda.synchronize()
     ms_rt = e0.elapsed_time(e1) / n
     gbs_rt = ncol * ng * bytes_per / (ms_rt * 1e-3) / 1e9
+    rt_traffic = None
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "flux_traffic.json")))
+        if (t["workload"]["ncol"], t["workload"]["nlay"], t["workload"]["ng"]) == (ncol, nlay, ng):
+            rt_traffic = t["dram_bytes_per_launch"]
+    except Exception:
+        rt_traffic = None
     return {"metric": "CKD flux columns*g-points/s", "value": ncol * ng / (ms_rt * 1e-3), "unit": "column*g-points/s",
             "ms_per_step": ms_rt,
             "config": f"radiative_transfer_lw (flux solver), {ncol} columns x {nlay} layers x {ng} g points, optical depth "
                       "and Planck arrays resident",
-            "roofline": {"bound": "hbm", "achieved": gbs_rt, "peak": peak, "unit": "GB/s", "frac": gbs_rt / peak,
+            "roofline": {"bound": "hbm", "achieved": gbs_rt, "peak": peak, "unit": "GB/s", "frac": gbs_rt / peak, "traffic": rt_traffic,
                          "kernel": "rt_lw_staged_kernel", "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
             "fused_run_ckd": {"value": ncol * ng / (ms * 1e-3), "unit": "column*g-points/s", "ms_per_step": ms,
                               "config": "run_ckd LW core in one kernel: full-level temperature, LUT interpolation of 8 "
