@@ -16,7 +16,7 @@
 // this path, so it pins nothing itself.  This oracle is
 // pinned by (i) analytic known-answer tests, (ii) an independent NumPy
 // restatement (oracle/oracle_np.py) and (iii) the reference sources built
-// against the shim (oracle/_ref), all exercised in tests/test_oracle_*.py.
+// against the shim (oracle/_ref, tests/test_reference_sources.py, tests/test_golden_reference.py).
 //
 // Summation order: the reference's order is Adept-internal and unspecified;
 // this file sums sequentially in ascending index order.
