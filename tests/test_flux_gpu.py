@@ -158,3 +158,27 @@ def test_calc_total_optical_depth(ctx, O, sw):
     m.calc_total_optical_depth_dev([None if v is None else ctx.to_device(v) for v in vmr], 6, 54,
                                    ctx.to_device(c["pressure_hl"]), ctx.to_device(c["temperature_hl"]), d_od)
     np.testing.assert_allclose(d_od.numpy(), ref, rtol=1e-11, atol=1e-18)
+
+
+@pytest.mark.parametrize("ncol,nlay,n", [(3, 54, 32), (5, 54, 64), (2, 53, 96), (1, 1, 32), (2, 3, 3008), (1500, 7, 32)])
+def test_rt_lw_staged_kernel_shapes(ctx, O, ncol, nlay, n):
+    """radiative_transfer_lw through the shared-memory staged kernel (n a multiple of 32): contiguous
+    columns (n = 32, two bulk copies), per-row copies (n > 32), layer counts that are not a multiple
+    of the 4-layer batch, one layer, and more (column, chunk) items than resident warps.  Exact zeros,
+    optical depths under the 1e-5 emissivity threshold and opaque layers included."""
+    rng = np.random.default_rng(ncol * 1000 + nlay * 10 + n)
+    od = np.exp(rng.normal(-3, 3, (ncol, nlay, n)))
+    od[rng.uniform(size=od.shape) < 0.1] = 0.0
+    od[:, 0, :4] = 1e-9
+    od[:, -1, 4:8] = 300.0
+    planck = rng.uniform(0.0, 30.0, (ncol, nlay + 1, n))
+    emis, sp = rng.uniform(0.8, 1.0, n), rng.uniform(0.0, 30.0, (ncol, n))
+    d = [ctx.to_device(a) for a in (planck, od, emis, sp)]
+    dn, up = ctx.empty((ncol, nlay + 1, n)), ctx.empty((ncol, nlay + 1, n))
+    E.radiative_transfer_lw_dev(ctx, ncol, nlay, n, d[0], d[1], d[2], d[3], dn, up)
+    dn, up = dn.numpy(), up.numpy()
+    for c in rng.choice(ncol, min(ncol, 6), replace=False):
+        dn_o, up_o = O.radiative_transfer_lw(planck[c], od[c], emis, sp[c])
+        assert np.max(np.abs(dn[c] - dn_o)) <= FLUX_ATOL * 1e-3, (c, np.max(np.abs(dn[c] - dn_o)))
+        assert np.max(np.abs(up[c] - up_o)) <= FLUX_ATOL * 1e-3
+    assert np.all(dn[:, 0, :] == 0.0)
