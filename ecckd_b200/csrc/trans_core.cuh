@@ -246,7 +246,7 @@ __device__ __forceinline__ TransMid trans256_phase1(double tau, const TransConst
   return m;
 }
 __device__ __forceinline__ double trans256_phase2(const TransMid& m, const unsigned char* __restrict__ tab) {
-  const uint2 e = *reinterpret_cast<const uint2*>(tab + ((m.n & 255) << 3));
+  const uint2 e = *reinterpret_cast<const uint2*>(tab + (__byte_perm((unsigned)m.n, 0u, 0x4440u) << 3));  // (n & 255) * 8
   return __hiloint2double((int)e.y + (m.n << 12), (int)e.x);
 }
 __device__ __forceinline__ double trans256_phase3(const TransMid& m, const double T, const TransConst256& K) {
