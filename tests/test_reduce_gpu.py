@@ -341,3 +341,23 @@ def test_avg_host_call_float32_spectra_bit_identical(ctx, method):
     b = E.planck_average_optical_depth_to_g_point(ctx, *args, od32.astype(np.float64), *tail)
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("method", ["transmission", "transmission-10"])
+def test_avg_huge_optical_depths_saturate(ctx, O, method):
+    """Optical depths beyond 708/kd (where exp(-kd tau) underflows) scattered through every g point, as the first
+    values of a g point and as whole rows: the kernel's unclamped fast path must never see them."""
+    c = S.lw_spectrum_case(nlay=9, nwav=6000, ng=8, nband=2, seed=91, zero_frac=0.0)
+    od = c["od"].copy()
+    rng = np.random.default_rng(5)
+    od[rng.uniform(size=od.shape) < 0.03] = 1e3
+    od[rng.uniform(size=od.shape) < 0.01] = 1e30
+    od[2, :] = 5e4          # a whole layer opaque
+    od[3, :40] = 1e300      # the first values a lane sees
+    planck = _planck(O, c)
+    got = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], od,
+                                             planck, method)
+    ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"], c["g_point"], od,
+                                             planck, method)
+    assert np.all(np.isfinite(got[0]))
+    S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c))
