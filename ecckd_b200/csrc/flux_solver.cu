@@ -33,6 +33,7 @@ struct ecckd_ckd_model {
   double planck_t0 = 0, planck_dt = 0;               // ckd_model.cpp:1123-1124
   double solar_sum = 0;                              // sum(solar_irradiance), run_ckd.cpp:98
   void* d_gasdesc = nullptr;                         // device array of GasDev
+  double* d_ones = nullptr;                          // [ng] surface emissivity of run_ckd
 };
 
 namespace ecckd {
@@ -420,34 +421,86 @@ struct RunCkdParams {
   double* scratch_od;  // [ncol][nlay][ng] when od == NULL
 };
 
+// g-independent part of one gas's optical depth at one (column, layer)
+struct GasLayer {
+  double weight;   // what multiplies the interpolated absorption (ckd_model.cpp:980-999)
+  double cindex0;  // LUT gases: clamped concentration index (ic0 + cw1); -1 otherwise
+};
+constexpr int RUN_CKD_MAX_GAS = 16;
+__host__ __device__ inline size_t run_ckd_col_smem(int nlay, int ngas) {
+  return (((size_t)nlay * sizeof(Interp) + (size_t)nlay * ngas * sizeof(GasLayer)) + 15) & ~(size_t)15;
+}
+
 __global__ void run_ckd_kernel(const RunCkdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int icol = blockIdx.x;
+  __shared__ const double* s_molar_abs[RUN_CKD_MAX_GAS];
+  if (threadIdx.y == 0 && threadIdx.x < p.ngas) s_molar_abs[threadIdx.x] = p.gases[threadIdx.x].molar_abs;
+  // blockDim.y columns per block: neighbouring columns walk the layers at the same pace and read the
+  // same LUT rows (same pressure index, a handful of temperature indices), so the gathers of the
+  // block's warps hit in L1 instead of each going to L2.  A column past the end repeats the last one.
+  const int icol = min((int)(blockIdx.x * blockDim.y + threadIdx.y), p.ncol - 1);
   const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
-  Interp* s_it = reinterpret_cast<Interp*>(smem_raw);                              // [nlay]
-  double* s_vmr = reinterpret_cast<double*>(s_it + nlay);                          // [nlay][ngas]
-  double* s_bb = s_vmr + (size_t)nlay * ngas;                                      // [2][nlay+1]
+  const size_t col_bytes = run_ckd_col_smem(nlay, ngas);
+  unsigned char* my = smem_raw + threadIdx.y * col_bytes;
+  Interp* s_it = reinterpret_cast<Interp*>(my);                                    // [nlay]
+  GasLayer* s_gl = reinterpret_cast<GasLayer*>(s_it + nlay);                       // [nlay][ngas]
   const double* p_hl = p.pressure_hl + (int64_t)icol * (nlay + 1);
   const double* t_hl = p.temperature_hl + (int64_t)icol * (nlay + 1);
+  // everything of ckd_model.cpp:962-1009 that does not depend on the g point, once per (layer, gas):
+  // interpolation indices and weights, the concentration weight, and for a look-up-table gas its
+  // concentration index (one log() per layer instead of one per layer and g point)
   for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
     const double t_fl = (t_hl[l] * p_hl[l] + t_hl[l + 1] * p_hl[l + 1]) / (p_hl[l] + p_hl[l + 1]);
-    s_it[l] = make_interp(p_hl[l], p_hl[l + 1], t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+    const Interp it = make_interp(p_hl[l], p_hl[l + 1], t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+    s_it[l] = it;
     for (int ig = 0; ig < ngas; ++ig) {
-      const double* v = p.gases[ig].vmr;
-      s_vmr[l * ngas + ig] = v ? v[(int64_t)icol * nlay + l] : 0.0;
+      const GasDev gs = p.gases[ig];
+      const bool have = gs.vmr != nullptr;
+      const double vmr = have ? gs.vmr[(int64_t)icol * nlay + l] : 0.0;
+      double weight = 0.0;
+      if (have) {
+        weight = (gs.conc_dependence == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - gs.reference_vmr)
+                                                                    : it.simple_weight * vmr;
+      }
+      GasLayer gl;
+      gl.cindex0 = -1.0;
+      if (gs.conc_dependence == ECCKD_CONC_LUT) {
+        double cindex0 = (log(vmr) - gs.log_vmr0) / gs.d_log_c;
+        cindex0 = fmax(0.0, fmin(cindex0, gs.nconc - 1.0001));
+        gl.cindex0 = cindex0;
+        gl.weight = weight;
+      } else {
+        gl.weight = (gs.conc_dependence == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+      }
+      s_gl[l * ngas + ig] = gl;
     }
   }
-  for (int l = threadIdx.x; l < 2 * (nlay + 1); l += blockDim.x) s_bb[l] = 0.0;
   __syncthreads();
 
   double* od_col = (p.od ? p.od : p.scratch_od) + (int64_t)icol * nlay * ng;
+  const size_t sP = (size_t)ng, sT = (size_t)p.np * ng, sC = (size_t)p.nt * sT;
+  auto bilinear = [&](const Interp& it, double k00, double k01, double k10, double k11) {
+    return it.tw0 * (it.pw0 * k00 + it.pw1 * k01) + it.tw1 * (it.pw0 * k10 + it.pw1 * k11);  // as gas_od()
+  };
   for (int g = threadIdx.x; g < ng; g += blockDim.x) {
-    // optical depth: sum over gases, clamp (run_ckd.cpp:265-317)
+    // optical depth: sum over gases, clamp (run_ckd.cpp:265-317).  (Keeping the table values at ip0 + 1
+    // in registers for the next layer was measured slower: 7.1 vs 6.3 ms for 65536 x 54 x 32.)
     for (int l = 0; l < nlay; ++l) {
       double tau = 0.0;
+      const Interp it = s_it[l];
+      const size_t o00 = it.it0 * sT + it.ip0 * sP + g;
       for (int ig = 0; ig < ngas; ++ig) {
-        const GasDev gs = p.gases[ig];
-        tau += gas_od(gs, s_it[l], s_vmr[l * ngas + ig], gs.vmr != nullptr, p.nt, p.np, ng, g);
+        const GasLayer gl = s_gl[l * ngas + ig];
+        const int ic0 = (int)gl.cindex0;  // -1 for the gases without a concentration axis
+        const double* k = s_molar_abs[ig] + o00 + (ic0 >= 0 ? ic0 * sC : (size_t)0);
+        const double a = bilinear(it, k[0], k[sP], k[sT], k[sT + sP]);
+        if (ic0 >= 0) {
+          const double cw1 = gl.cindex0 - ic0;
+          k += sC;
+          tau += gl.weight * ((1.0 - cw1) * a + cw1 * bilinear(it, k[0], k[sP], k[sT], k[sT + sP]));
+        } else {
+          tau += gl.weight * a;
+        }
       }
       od_col[(int64_t)l * ng + g] = fmax(tau, 0.0);
     }
@@ -477,13 +530,11 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
         if (p.planck_hl) p.planck_hl[hl0 + (int64_t)(l + 1) * ng] = b_bot;
         f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
         p.flux_dn[hl0 + (int64_t)(l + 1) * ng] = f_dn;
-        if (p.bb_flux_dn) atomicAdd(&s_bb[l + 1], f_dn);
         b_top = b_bot;
       }
       // surface emissivity 1 (run_ckd.cpp:344-345): up = B_s*1 + (1-1)*dn
       double f_up = b_surf * 1.0 + (1.0 - 1.0) * f_dn;
       p.flux_up[hl0 + (int64_t)nlay * ng] = f_up;
-      if (p.bb_flux_up) atomicAdd(&s_bb[(nlay + 1) + nlay], f_up);
       double b_bot = b_top;
       for (int l = nlay - 1; l >= 0; --l) {
         double e, f;
@@ -491,7 +542,6 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
         const double b_t = planck_interp(t_hl[l], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
         f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
         p.flux_up[hl0 + (int64_t)l * ng] = f_up;
-        if (p.bb_flux_up) atomicAdd(&s_bb[(nlay + 1) + l], f_up);
         b_bot = b_t;
       }
     } else if (p.flux_dn) {
@@ -500,17 +550,14 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
       const double minus_sec = -1.0 / mu0;
       double f = mu0 * (p.tsi_scaling * p.solar_irradiance[g]);
       p.flux_dn[hl0] = f;
-      if (p.bb_flux_dn) atomicAdd(&s_bb[0], f);
       const double sig = p.rayleigh[g];
       for (int l = 0; l < nlay; ++l) {
         const double ray = ((p_hl[l + 1] - p_hl[l]) * (1.0 / (ECCKD_ACCEL_GRAVITY * 0.001 * ECCKD_MOLAR_MASS_DRY_AIR))) * sig;
         f = f * exp(minus_sec * (od_col[(int64_t)l * ng + g] + ray));
         p.flux_dn[hl0 + (int64_t)(l + 1) * ng] = f;
-        if (p.bb_flux_dn) atomicAdd(&s_bb[l + 1], f);
       }
     }
   }
-  (void)s_bb;
 }
 
 }  // namespace ecckd
@@ -537,6 +584,7 @@ ECCKD_API int ecckd_ckd_model_destroy(ecckd_ckd_model* m) {
   cudaFree(m->d_solar_irradiance);
   cudaFree(m->d_rayleigh);
   cudaFree(m->d_gasdesc);
+  cudaFree(m->d_ones);
   delete m;
   return ECCKD_OK;
 }
@@ -837,11 +885,46 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     p.scratch_od = static_cast<double*>(s);
   }
   const int threads = m->ng <= 32 ? 32 : (m->ng <= 64 ? 64 : 128);
-  const size_t smem = (size_t)nlay * sizeof(Interp) + (size_t)nlay * m->ngas * sizeof(double) +
-                      (size_t)2 * (nlay + 1) * sizeof(double);
-  ECCKD_REQUIRE(smem <= 48 * 1024, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: nlay*ngas too large for shared memory");
-  run_ckd_kernel<<<ncol, threads, smem, ctx->stream>>>(p);
+  const size_t col_smem = run_ckd_col_smem(nlay, m->ngas);
+  ECCKD_REQUIRE(m->ngas <= RUN_CKD_MAX_GAS && m->ngas <= threads, ECCKD_PARAMETER_ERROR,
+                "ecckd_run_ckd: more than %d gases", std::min(RUN_CKD_MAX_GAS, threads));
+  ECCKD_REQUIRE(col_smem <= ctx->smem_optin / 2, ECCKD_PARAMETER_ERROR,
+                "ecckd_run_ckd: nlay*ngas too large for shared memory");
+  // columns per block: as many resident warps per SM as shared memory allows, larger blocks on ties
+  int cols = 1, best = 0;
+  for (int c = std::min(256 / threads, ncol); c >= 1; --c) {
+    if (c * col_smem > ctx->smem_optin / 2) continue;
+    const int blocks = std::min<int>(32, (int)((ctx->smem_optin + 1024) / (c * col_smem + 1024)));
+    const int warps = std::min(64, blocks * c * (threads / 32));
+    if (warps > best) { best = warps; cols = c; }
+  }
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(run_ckd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(col_smem * cols)));
+  // Longwave fluxes: the kernel produces optical depth and Planck function (scratch arrays when the
+  // caller does not want them) and the sweep is the staged flux solver, which reads both once.
+  const bool lw_staged = !m->is_sw && d_flux_dn && d_flux_up;
+  if (lw_staged) {
+    const size_t n_hl = (size_t)ncol * (nlay + 1) * m->ng, n_s = (size_t)ncol * m->ng;
+    if (!d_planck_hl || !d_planck_surf) {
+      void* s = nullptr;
+      ECCKD_TRY(ws_reserve(ctx, 0, (n_hl + n_s) * sizeof(double), &s));
+      if (!d_planck_hl) p.planck_hl = static_cast<double*>(s);
+      if (!d_planck_surf) p.planck_surf = static_cast<double*>(s) + n_hl;
+    }
+    p.flux_dn = nullptr;
+    p.flux_up = nullptr;
+  }
+  run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols), col_smem * cols, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
+  if (lw_staged) {
+    if (!m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)
+      std::vector<double> ones(m->ng, 1.0);
+      ECCKD_CUDA_OK(cudaMalloc(&m->d_ones, m->ng * sizeof(double)));
+      ECCKD_CUDA_OK(cudaMemcpyAsync(m->d_ones, ones.data(), m->ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    }
+    ECCKD_TRY(ecckd_radiative_transfer_lw_dev(ctx, ncol, nlay, m->ng, p.planck_hl, d_od ? d_od : p.scratch_od, m->d_ones,
+                                              p.planck_surf, d_flux_dn, d_flux_up));
+  }
   const int64_t nrows = (int64_t)ncol * (nlay + 1);
   if (d_flux_dn && d_bb_flux_dn) {
     sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, m->ng, d_flux_dn, d_bb_flux_dn);
