@@ -580,10 +580,10 @@ def bench_flux(torch, E, ctx, dev, peak):
             "roofline": {"bound": "hbm", "achieved": gbs_rt, "peak": peak, "unit": "GB/s", "frac": gbs_rt / peak, "traffic": rt_traffic,
                          "kernel": "rt_lw_staged_kernel", "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
             "fused_run_ckd": {"value": ncol * ng / (ms * 1e-3), "unit": "column*g-points/s", "ms_per_step": ms,
-                              "config": "run_ckd LW core in one kernel: full-level temperature, LUT interpolation of 8 "
-                                        "gases (36 LUT rows per layer.g point, L2-resident gathers), clamp, Planck "
-                                        "interpolation and the sweep; bound by the L1/L2 traffic of the LUT gathers "
-                                        "(288 B per optical depth), not by HBM",
+                              "config": "run_ckd LW core (ecckd_run_ckd_dev): full-level temperature, LUT interpolation of 8 "
+                                        "gases (36 LUT rows per layer.g point gathered through L1/L2), clamp, Planck "
+                                        "interpolation, then the staged flux solver and the sums over g; bound by the "
+                                        "latency of the LUT gathers (288 B per optical depth), not by HBM",
                               "hbm_GBps_of_its_outputs": ncol * ng * bytes_per / (ms * 1e-3) / 1e9}}
 
 
