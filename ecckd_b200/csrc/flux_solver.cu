@@ -366,6 +366,98 @@ __global__ void rt_sw_kernel(int ncol, int nlay, int64_t n, const double* __rest
   }
 }
 
+// The shortwave solvers with the column's optical depths staged in shared memory, like
+// rt_lw_staged_kernel: tau is read from HBM once (24 B per column x layer x g with the upward
+// sweep instead of 32), the two exponentials of a layer are evaluated together on the way down
+// (exp(-tau/mu0) for the direct beam, exp(-2 tau) parked in place of tau for the way up) with
+// the table exponential of trans_core.cuh (exp_table: below 1 ulp relative, so that the deep,
+// tiny direct fluxes keep their relative accuracy), four layers at a time.
+struct RtSwStagedParams {
+  int ncol, nlay;
+  int64_t n;
+  const double* cos_sza;  // [ncol]
+  const double* ssi;      // [n]
+  const double* od;
+  const double* albedo;   // [n] or NULL (direct beam only)
+  double* flux_dn;
+  double* flux_up;
+};
+
+__global__ void __launch_bounds__(32) rt_sw_staged_kernel(const __grid_constant__ RtSwStagedParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x;
+  const int nlay = p.nlay;
+  const int64_t n = p.n;
+  double* s_tau = reinterpret_cast<double*>(smem_raw);  // [nlay][32] -> exp(-2 tau)
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned bar = sbase + (unsigned)(nlay * 32 * sizeof(double));
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const TransLane tl = trans_lane_init();
+  const int64_t nchunk = n >> 5;
+  const int64_t nitems = (int64_t)p.ncol * nchunk;
+  const bool contiguous = (n == 32);
+  unsigned parity = 0;
+  for (int64_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int64_t icol = item / nchunk;
+    const int64_t i0 = (item - icol * nchunk) << 5;
+    const double* g_tau = p.od + icol * nlay * n + i0;
+    if (lane == 0) mbar_arrive_expect_tx(bar, (unsigned)(nlay * 256));
+    __syncwarp();
+    if (contiguous) {
+      if (lane == 0) bulk_g2s(sbase, g_tau, (unsigned)(nlay * 256), bar);
+    } else {
+      for (int r = lane; r < nlay; r += 32) bulk_g2s(sbase + (unsigned)(r * 256), g_tau + (int64_t)r * n, 256u, bar);
+    }
+    double* dn = p.flux_dn + icol * (nlay + 1) * n + i0 + lane;
+    const double mu0 = p.cos_sza[icol];
+    const double minus_sec_sza = -1.0 / mu0;
+    double f = mu0 * p.ssi[i0 + lane];
+    const double alb = p.albedo ? p.albedo[i0 + lane] : 0.0;
+    dn[0] = f;
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    int l = 0;
+    for (; l + 4 <= nlay; l += 4) {
+      double t[4], u[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double tau = s_tau[(l + j) * 32 + lane];
+        // arguments below -700 give exp() < 1e-304: clamp (exp_table has no underflow handling)
+        t[j] = exp_table(fmax(minus_sec_sza * tau, -700.0), tl);
+        u[j] = p.albedo ? exp_table(fmax(-2.0 * tau, -700.0), tl) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f = f * t[j];
+        dn[(int64_t)(l + j + 1) * n] = f;
+        s_tau[(l + j) * 32 + lane] = u[j];
+      }
+    }
+    for (; l < nlay; ++l) {
+      const double tau = s_tau[l * 32 + lane];
+      f = f * exp_table(fmax(minus_sec_sza * tau, -700.0), tl);
+      dn[(int64_t)(l + 1) * n] = f;
+      s_tau[l * 32 + lane] = p.albedo ? exp_table(fmax(-2.0 * tau, -700.0), tl) : 0.0;
+    }
+    if (p.albedo) {
+      double* up = p.flux_up + icol * (nlay + 1) * n + i0 + lane;
+      f = f * alb;
+      up[(int64_t)nlay * n] = f;
+#pragma unroll 6
+      for (l = nlay - 1; l >= 0; --l) {
+        f = f * s_tau[l * 32 + lane];
+        up[(int64_t)l * n] = f;
+      }
+    }
+    fence_proxy_async();  // the next item's bulk copies overwrite what was written through the generic proxy
+    __syncwarp();
+  }
+}
+
 // heating_rate.h:38-48
 __global__ void heating_rate_kernel(int ncol, int nlay, int64_t n, const double* __restrict__ pressure_hl,
                                     const double* __restrict__ flux_dn, const double* __restrict__ flux_up,
@@ -816,9 +908,22 @@ ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay
   void* d_mu = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 3, (size_t)ncol * sizeof(double), &d_mu));
   ECCKD_TRY(upload_small(ctx, d_mu, h_cos_sza, (size_t)ncol * sizeof(double)));
-  const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
-  rt_sw_kernel<<<(unsigned)((int64_t)ncol * ((n + bs - 1) / bs)), bs, 0, ctx->stream>>>(
-      ncol, nlay, n, static_cast<const double*>(d_mu), d_ssi, d_od, d_albedo, d_flux_dn, d_flux_up);
+  const size_t staged_smem = (size_t)nlay * 256 + 16;
+  if ((n & 31) == 0 && (reinterpret_cast<uintptr_t>(d_od) & 15u) == 0 && staged_smem <= ctx->smem_optin / 4 &&
+      !getenv("ECCKD_RT_PLAIN")) {
+    RtSwStagedParams sp;
+    sp.ncol = ncol; sp.nlay = nlay; sp.n = n; sp.cos_sza = static_cast<const double*>(d_mu); sp.ssi = d_ssi; sp.od = d_od;
+    sp.albedo = d_albedo; sp.flux_dn = d_flux_dn; sp.flux_up = d_flux_up;
+    const int per_sm = (int)std::min<size_t>(32, (ctx->smem_optin + 1024) / (staged_smem + 1024));
+    const int64_t items = (int64_t)ncol * (n >> 5);
+    const unsigned grid = (unsigned)std::min<int64_t>(items, (int64_t)ctx->num_sms * per_sm);
+    ECCKD_CUDA_OK(cudaFuncSetAttribute(rt_sw_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_smem));
+    rt_sw_staged_kernel<<<grid, 32, staged_smem, ctx->stream>>>(sp);
+  } else {
+    const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
+    rt_sw_kernel<<<(unsigned)((int64_t)ncol * ((n + bs - 1) / bs)), bs, 0, ctx->stream>>>(
+        ncol, nlay, n, static_cast<const double*>(d_mu), d_ssi, d_od, d_albedo, d_flux_dn, d_flux_up);
+  }
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }

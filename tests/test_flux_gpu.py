@@ -182,3 +182,27 @@ def test_rt_lw_staged_kernel_shapes(ctx, O, ncol, nlay, n):
         assert np.max(np.abs(dn[c] - dn_o)) <= FLUX_ATOL * 1e-3, (c, np.max(np.abs(dn[c] - dn_o)))
         assert np.max(np.abs(up[c] - up_o)) <= FLUX_ATOL * 1e-3
     assert np.all(dn[:, 0, :] == 0.0)
+
+
+@pytest.mark.parametrize("ncol,nlay,n", [(3, 54, 32), (4, 54, 64), (2, 53, 96), (1, 1, 32), (700, 6, 32)])
+@pytest.mark.parametrize("with_up", [True, False])
+def test_rt_sw_staged_kernel_shapes(ctx, O, ncol, nlay, n, with_up):
+    """radiative_transfer_{direct,norayleigh}_sw through the shared-memory staged kernel (n a multiple of 32),
+    per-column cos_sza; deep columns whose direct beam underflows keep their RELATIVE accuracy."""
+    rng = np.random.default_rng(ncol * 100 + nlay + n)
+    od = np.exp(rng.normal(-2, 2, (ncol, nlay, n)))
+    od[rng.uniform(size=od.shape) < 0.1] = 0.0
+    od[0, :, :3] = 40.0  # cumulative optical depth in the thousands
+    ssi, alb = rng.uniform(0.1, 2.0, n), rng.uniform(0.0, 0.5, n)
+    mu = rng.uniform(0.1, 1.0, ncol)
+    dn, up = ctx.empty((ncol, nlay + 1, n)), ctx.empty((ncol, nlay + 1, n))
+    E.radiative_transfer_sw_dev(ctx, ncol, nlay, n, mu, ctx.to_device(ssi), ctx.to_device(od),
+                                ctx.to_device(alb) if with_up else None, dn, up if with_up else None)
+    dn = dn.numpy()
+    for c in rng.choice(ncol, min(ncol, 5), replace=False):
+        if with_up:
+            dn_o, up_o = O.radiative_transfer_norayleigh_sw(float(mu[c]), ssi, od[c], alb)
+            np.testing.assert_allclose(up.numpy()[c], up_o, rtol=1e-12, atol=1e-300)
+        else:
+            dn_o = O.radiative_transfer_direct_sw(float(mu[c]), ssi, od[c])
+        np.testing.assert_allclose(dn[c], dn_o, rtol=1e-12, atol=1e-300)

@@ -65,3 +65,26 @@ for name, env in (("plain ng=64", "1"), ("staged ng=64", None)):
     ms = e0.elapsed_time(e1) / 10
     gbs = ncol * ng * 1760 / (ms * 1e-3) / 1e9
     print(f"{name}: {ms:.3f} ms  {gbs:.0f} GB/s algorithmic  ({gbs / 6552.3:.3f} of peak)")
+
+# shortwave (direct + Lambertian up): 24 B per column.layer.g algorithmic
+ssi = torch.rand(ng, dtype=torch.float64, device=dev, generator=g).add_(0.5)
+alb = torch.rand(ng, dtype=torch.float64, device=dev, generator=g).mul_(0.4)
+import numpy as np
+mu = np.full(ncol, 0.5)
+for name, env in (("sw plain", "1"), ("sw staged", None)):
+    if env:
+        os.environ["ECCKD_RT_PLAIN"] = env
+    else:
+        os.environ.pop("ECCKD_RT_PLAIN", None)
+    for _ in range(3):
+        E.radiative_transfer_sw_dev(ctx, ncol, nlay, ng, mu, ssi, od, alb, dn, up)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        E.radiative_transfer_sw_dev(ctx, ncol, nlay, ng, mu, ssi, od, alb, dn, up)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    gbs = ncol * ng * (8 * nlay + 16 * (nlay + 1)) / (ms * 1e-3) / 1e9
+    print(f"{name}: {ms:.3f} ms  {gbs:.0f} GB/s algorithmic  ({gbs / 6552.3:.3f} of peak)")
