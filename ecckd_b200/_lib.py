@@ -95,6 +95,8 @@ def _declare(L):
                                                           C.c_char_p, vp, vp, vp, i64, vp],
         "ecckd_planck_average_optical_depth_to_g_point_f32": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp,
                                                               C.c_char_p, vp, vp, vp, i64, vp],
+        "ecckd_create_lut_block": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, C.c_char_p, vp, vp, vp, vp,
+                                   i64, vp],
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],

@@ -273,6 +273,27 @@ def planck_average_optical_depth_to_g_point(ctx: Context, ng, reference_surface_
     return out
 
 
+def create_lut_block(ctx: Context, ng, reference_surface_vmr, pressure_hl, temperature_hl, g_point, optical_depth,
+                     averaging_method, wavenumber_cm_1=None, d_wavenumber_cm_1=None, ssi=None):
+    """One block of the create_look_up_table driver loop (create_look_up_table.cpp:293-344)
+    -> (molar_abs, min, max, warn, temperature_fl)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nlay, nwav = od.shape
+    gp = np.ascontiguousarray(g_point, dtype=np.int32)
+    ph, php = _h(pressure_hl)
+    th, thp = _h(temperature_hl)
+    wn, wnp = _h(wavenumber_cm_1)
+    dwn, dwnp = _h(d_wavenumber_cm_1)
+    s, sp = _h(ssi)
+    out = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
+    t_fl = np.zeros(nlay)
+    check(_lib.lib().ecckd_create_lut_block(
+        ctx.handle, ng, float(reference_surface_vmr), nlay, nwav, php, thp, gp.ctypes.data, od.ctypes.data, nwav, wnp, dwnp,
+        sp, averaging_method.encode(), t_fl.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
+        out[3].ctypes.data))
+    return out + (t_fl,)
+
+
 def average_optical_depth_to_g_point_dev(ctx: Context, plan: GPointPlan, reference_surface_vmr, pressure_fl,
                                          pressure_hl, d_od, od_stride, weight_mode, d_weight, w_stride, temperature,
                                          d_wavenumber, d_d_wavenumber, averaging_method, d_molar_abs, d_min=None,

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "trans_core.cuh"
 
 namespace ecckd {
 
@@ -49,7 +50,23 @@ struct IntervalParams {
   double* bb_flux;            // [nint][2][nlay+1] (optional output)
   double* error;              // [nint]
   int error_mode;             // 0: store, 1: store 0.5*, 2: add 0.5*  (total-transmission low/high mean)
+  TransConst256 tc;           // 1 - exp(-LW_DIFFUSIVITY tau) by the table scheme of trans_core.cuh
 };
+
+// emissivity and Planck-gradient factor of radiative_transfer_lw_bb (radiative_transfer_lw.cpp:113-119)
+// with the table exponential and a Newton reciprocal instead of libm exp and a division (the broadband
+// fluxes change by parts in 1e13)
+__device__ __forceinline__ void lw_bb_layer(double tau, const TransConst256& K, const unsigned char* tab, double& e,
+                                            double& f) {
+  const double THRESHOLD_EMISSIVITY = 1.0e-5;  // radiative_transfer_lw.cpp:98
+  e = trans256_one_minus_exp(tau, K, tab);
+  const double den = fmax(tau, THRESHOLD_EMISSIVITY / ECCKD_LW_DIFFUSIVITY);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(den));
+  r = fma(r, fma(-den, r, 1.0), r);
+  r = fma(r, fma(-den, r, 1.0), r);
+  f = fmax(1.0 - ((1.0 / ECCKD_LW_DIFFUSIVITY) * fmax(e, THRESHOLD_EMISSIVITY)) * r, 0.5 * THRESHOLD_EMISSIVITY);
+}
 
 __device__ __forceinline__ int find_interval(const int64_t* __restrict__ item_start, int nint, int64_t item) {
   int lo = 0, hi = nint - 1;
@@ -243,7 +260,12 @@ __global__ void __launch_bounds__(kTile) interval_tt_sweep_kernel(const Interval
 // ---- phase B: broadband flux sweep of one tile (radiative_transfer_lw_bb / _sw_bb).
 template <bool SW>
 __global__ void __launch_bounds__(kTile) interval_flux_kernel(const IntervalParams p) {
-  extern __shared__ double s_part[];  // [2][nlev][kWarps]
+  extern __shared__ double s_part[];  // [2][nlev][kWarps], then the 2^(j/256) table (longwave)
+  const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_part + 2 * (p.nlay + 1) * kWarps);
+  if (!SW) {
+    trans_tab_init(s_part + 2 * (p.nlay + 1) * kWarps);
+    __syncthreads();
+  }
   const int64_t item = blockIdx.x;
   const int k = find_interval(p.item_start, p.nint, item);
   const int64_t i = p.i1[k] + (item - p.item_start[k]) * kTile + threadIdx.x;
@@ -253,17 +275,14 @@ __global__ void __launch_bounds__(kTile) interval_flux_kernel(const IntervalPara
   const double sc = p.od_scale;
   double flux = 0.0;
   if (!SW) {
-    const double THRESHOLD_EMISSIVITY = 1.0e-5;  // radiative_transfer_lw.cpp:98
     double b_top = on ? p.planck_hl[i] : 0.0;
     if (lane == 0) s_part[(0 * nlev + 0) * kWarps + warp] = 0.0;
     for (int l = 0; l < p.nlay; ++l) {
       double b_bot = 0.0;
       if (on) {
         const double tau = p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc;
-        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
-        const double f = fmax(1.0 - (1.0 / ECCKD_LW_DIFFUSIVITY) * fmax(e, THRESHOLD_EMISSIVITY) /
-                                        fmax(tau, THRESHOLD_EMISSIVITY / ECCKD_LW_DIFFUSIVITY),
-                              0.5 * THRESHOLD_EMISSIVITY);
+        double e, f;
+        lw_bb_layer(tau, p.tc, tab, e, f);
         b_bot = p.planck_hl[(int64_t)(l + 1) * p.stride + i];
         flux = flux * (1.0 - e) + b_top * (e - f) + b_bot * f;
       }
@@ -284,10 +303,8 @@ __global__ void __launch_bounds__(kTile) interval_flux_kernel(const IntervalPara
       double b_t = 0.0;
       if (on) {
         const double tau = p.bg_od[(int64_t)l * p.stride + i] + fit[l] * sc;
-        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
-        const double f = fmax(1.0 - (1.0 / ECCKD_LW_DIFFUSIVITY) * fmax(e, THRESHOLD_EMISSIVITY) /
-                                        fmax(tau, THRESHOLD_EMISSIVITY / ECCKD_LW_DIFFUSIVITY),
-                              0.5 * THRESHOLD_EMISSIVITY);
+        double e, f;
+        lw_bb_layer(tau, p.tc, tab, e, f);
         b_t = p.planck_hl[(int64_t)l * p.stride + i];
         flux = flux * (1.0 - e) + b_bot * (e - f) + b_t * f;
       }
@@ -418,7 +435,7 @@ static int setup_batch(ecckd_ctx* ctx, IntervalParams& p, int nint, const int64_
 }
 
 static int launch_flux_and_error(ecckd_ctx* ctx, const IntervalParams& p) {
-  const size_t smem = (size_t)2 * (p.nlay + 1) * kWarps * sizeof(double);
+  const size_t smem = (size_t)2 * (p.nlay + 1) * kWarps * sizeof(double) + (p.sw ? 0 : TRANS_TAB_BYTES);
   if (p.sw) interval_flux_kernel<true><<<p.nitems, kTile, smem, ctx->stream>>>(p);
   else interval_flux_kernel<false><<<p.nitems, kTile, smem, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
@@ -787,6 +804,7 @@ ECCKD_API int ecckd_interval_error_batch_lw_dev(ecckd_ctx* ctx, int averaging_me
   ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
   IntervalParams p = {};
   p.sw = 0; p.method = averaging_method; p.nlay = nlay; p.n = n; p.stride = stride;
+  trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
   p.pressure_hl = d_pressure_hl; p.planck_hl = d_planck_hl; p.surf_emissivity = d_surf_emissivity;
   p.surf_planck = d_surf_planck; p.bg_od = d_bg_optical_depth; p.metric = d_metric; p.flux_dn_surf = d_flux_dn_surf;
   p.flux_up_toa = d_flux_up_toa; p.hr = d_hr; p.layer_weight = d_layer_weight; p.flux_weight = flux_weight;
@@ -899,6 +917,7 @@ ECCKD_API int ecckd_radiative_transfer_lw_bb_dev(ecckd_ctx* ctx, int nlay, int64
   ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
   IntervalParams p = {};
   p.sw = 0; p.nlay = nlay; p.n = n; p.stride = stride; p.planck_hl = d_planck; p.bg_od = d_spectral_od;
+  trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
   p.surf_emissivity = d_surf_emissivity; p.surf_planck = d_surf_planck;
   return bb_solver(ctx, p, d_grey_od, d_flux_dn, d_flux_up, who);
 }

@@ -1619,6 +1619,39 @@ ECCKD_API int ecckd_planck_average_optical_depth_to_g_point_f32(
                       min_molar_abs, max_molar_abs, out_stride, warn, optical_depth);
 }
 
+// One (gas, concentration, temperature) block of the create_look_up_table driver loop:
+// src/ecckd/create_look_up_table.cpp:293-344 (and :368-415, :448-495 for the other concentration
+// dependences, which differ only in what is read).  From the half-level profile of the block it forms
+// pressure_fl (:305) and the pressure-weighted full-level temperature (:316-317), then averages with
+// Planck weights at that temperature (longwave, :320-331) or with the solar spectrum replicated over
+// the layers (shortwave, ssi != NULL, :333-341).
+ECCKD_API int ecckd_create_lut_block(ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav,
+                                     const double* pressure_hl, const double* temperature_hl, const int32_t* g_point,
+                                     const double* optical_depth, int64_t od_stride, const double* wavenumber_cm_1,
+                                     const double* d_wavenumber_cm_1, const double* ssi, const char* averaging_method,
+                                     double* temperature_fl, double* molar_abs, double* min_molar_abs,
+                                     double* max_molar_abs, int64_t out_stride, int32_t* warn) {
+  ECCKD_REQUIRE(ctx && pressure_hl && temperature_hl && g_point && optical_depth && molar_abs && nlay > 0,
+                ECCKD_PARAMETER_ERROR, "ecckd_create_lut_block: NULL argument");
+  ECCKD_REQUIRE(ssi || (wavenumber_cm_1 && d_wavenumber_cm_1), ECCKD_PARAMETER_ERROR,
+                "ecckd_create_lut_block: longwave blocks need the wavenumber grid, shortwave ones ssi");
+  std::vector<double> p_fl(nlay), t_fl(nlay);
+  for (int i = 0; i < nlay; ++i) {
+    p_fl[i] = 0.5 * (pressure_hl[i] + pressure_hl[i + 1]);                                   // :305
+    const double t_x_p0 = temperature_hl[i] * pressure_hl[i], t_x_p1 = temperature_hl[i + 1] * pressure_hl[i + 1];
+    t_fl[i] = 0.5 * (t_x_p0 + t_x_p1) / p_fl[i];                                             // :316-317
+    if (temperature_fl) temperature_fl[i] = t_fl[i];
+  }
+  if (ssi) {
+    return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, p_fl.data(), pressure_hl, g_point, optical_depth,
+                        od_stride, ssi, 0, nullptr, nullptr, nullptr, averaging_method, molar_abs, min_molar_abs,
+                        max_molar_abs, out_stride, warn);
+  }
+  return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, p_fl.data(), pressure_hl, g_point, optical_depth,
+                      od_stride, nullptr, 0, t_fl.data(), wavenumber_cm_1, d_wavenumber_cm_1, averaging_method, molar_abs,
+                      min_molar_abs, max_molar_abs, out_stride, warn);
+}
+
 ECCKD_API int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
                                    const double* d_od, int64_t od_stride, double scaling,
                                    const double* h_scaling_profile) {

@@ -228,6 +228,20 @@ int ecckd_planck_average_optical_depth_to_g_point(
     const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, const char* averaging_method,
     double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn);
 
+/* One (gas, concentration, temperature) block of the create_look_up_table driver loop:
+ * src/ecckd/create_look_up_table.cpp:293-344 (:368-415, :448-495).  Host arrays.  pressure_hl,
+ * temperature_hl[nlay+1] are the block's profile; pressure_fl (:305) and the pressure-weighted
+ * temperature_fl (:316-317, returned in temperature_fl[nlay] if not NULL) are formed here; weights
+ * are the Planck function at temperature_fl (ssi == NULL, :320-331) or ssi[nwav] replicated over
+ * the layers (:333-341).  The temperature loop itself is `for icol < (ncol + stride - 1) / stride`
+ * over profiles icol * stride (:293-300) in the caller, writing molar_abs(icol,__,__) slices. */
+int ecckd_create_lut_block(ecckd_ctx* ctx, int ng, double reference_surface_vmr, int nlay, int64_t nwav,
+                           const double* pressure_hl, const double* temperature_hl, const int32_t* g_point,
+                           const double* optical_depth, int64_t od_stride, const double* wavenumber_cm_1,
+                           const double* d_wavenumber_cm_1, const double* ssi, const char* averaging_method,
+                           double* temperature_fl, double* molar_abs, double* min_molar_abs,
+                           double* max_molar_abs, int64_t out_stride, int32_t* warn);
+
 /* The same with the optical depths as the float32 values the CKDMIP spectra files hold
  * (merge_spectra.cpp:108; the reference widens them to Real on read,
  * src/tools/DataFileEngineNetcdf.cpp:393-397).  The widening is done on the device: results are

@@ -361,3 +361,24 @@ def test_avg_huge_optical_depths_saturate(ctx, O, method):
                                              planck, method)
     assert np.all(np.isfinite(got[0]))
     S.assert_avg_close(got, ref, method=method, scale=S.out_scale(c))
+
+
+@pytest.mark.parametrize("sw", [False, True])
+def test_create_lut_block(ctx, O, sw):
+    """The body of the create_look_up_table temperature loop (create_look_up_table.cpp:293-344): full-level
+    pressure and pressure-weighted temperature from the block's half-level profile, then Planck- or
+    solar-weighted averaging."""
+    c = S.sw_spectrum_case(nlay=15, nwav=5000, ng=8, nband=2, seed=8) if sw else \
+        S.lw_spectrum_case(nlay=15, nwav=5000, ng=8, nband=2, seed=8)
+    p_hl, t_hl = c["pressure_hl"], c["temperature_hl"]
+    p_fl = 0.5 * (p_hl[:-1] + p_hl[1:])
+    t_x_p = t_hl * p_hl
+    t_fl = 0.5 * (t_x_p[:-1] + t_x_p[1:]) / p_fl
+    method = "transmission-3" if sw else "transmission"
+    got = E.create_lut_block(ctx, c["ng"], c["vmr"], p_hl, t_hl, c["g_point"], c["od"], method,
+                             wavenumber_cm_1=c["wavenumber"], d_wavenumber_cm_1=c["d_wavenumber"],
+                             ssi=c["ssi"] if sw else None)
+    assert np.array_equal(got[4], t_fl)
+    w = c["ssi"] if sw else O.planck_function(t_fl, c["wavenumber"], c["d_wavenumber"])
+    ref = O.average_optical_depth_to_g_point(c["ng"], c["vmr"], p_fl, p_hl, c["g_point"], c["od"], w, method)
+    S.assert_avg_close(got[:4], ref, method=method, scale=S.out_scale(dict(c, pressure_fl=p_fl)))
