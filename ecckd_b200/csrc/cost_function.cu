@@ -444,8 +444,21 @@ static int launch_flux_and_error(ecckd_ctx* ctx, const IntervalParams& p) {
   return ECCKD_OK;
 }
 
+// Layer emissivity and Planck-gradient factor of radiative_transfer_lw (radiative_transfer_lw.cpp:41-43) with the
+// table exponential and a Newton reciprocal (as rt_lw_staged_kernel; no shuffles, so any thread may call it)
+__device__ __forceinline__ void lw_layer_tab(double tau, const TransConst256& K, const unsigned char* tab, double& e,
+                                             double& f) {
+  e = trans256_one_minus_exp(tau, K, tab);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(tau));
+  r = fma(r, fma(-tau, r, 1.0), r);
+  r = fma(r, fma(-tau, r, 1.0), r);
+  f = (e > 1.0e-5) ? (1.0 - (e * (1.0 / ECCKD_LW_DIFFUSIVITY)) * r) : (0.5 * e);
+}
+
 // ------------------------------------------------------------------ forward cost of optimize_lut
 struct CkdCostParams {
+  TransConst256 tc;
   int sw, nprof, nlay, ng, nband, nemis, nalbedo, up_in_bb, direct_only;
   const double* pressure_hl;       // [nprof][nlay+1]
   const double* planck_hl;         // LW [nprof][nlay+1][ng]
@@ -489,6 +502,10 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
   const double* p_hl = p.pressure_hl + (size_t)ip * nlev;
   const double* od = p.optical_depth + (size_t)ip * nlay * ng;
   const double hr_weight = 3600.0 * 24.0;
+  double* s_tab = red + 8 + 3 * nlev + nband + 2;  // 2^(j/256) table of the longwave layer terms
+  if (!p.sw) trans_tab_init(s_tab);
+  const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_tab);
+  __syncthreads();
 
   // layer weights (solve_adept.cpp:133-145)
   if (threadIdx.x == 0) {
@@ -520,8 +537,8 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
       for (int l = 0; l < nlay; ++l) {
         double tau = od[(size_t)l * ng + g];
         if (tau < 0.0) { pen += tau * tau; tau = 0.0; }
-        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
-        const double f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+        double e, f;
+        lw_layer_tab(tau, p.tc, tab, e, f);
         const double b_bot = pl[(size_t)(l + 1) * ng];
         f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
         fdo[(size_t)(l + 1) * ng + g] = f_dn;
@@ -534,8 +551,8 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
       double b_bot = b_top;
       for (int l = nlay - 1; l >= 0; --l) {
         const double tau = fmax(od[(size_t)l * ng + g], 0.0);
-        const double e = 1.0 - exp(-ECCKD_LW_DIFFUSIVITY * tau);
-        const double f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
+        double e, f;
+        lw_layer_tab(tau, p.tc, tab, e, f);
         const double b_t = pl[(size_t)l * ng];
         f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
         fuo[(size_t)l * ng + g] = f_up;
@@ -582,7 +599,21 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
   }
   __syncthreads();
 
-  // g points -> bands
+  // g points -> bands.  The g points of a band are usually contiguous (iband_per_g is non-decreasing):
+  // then only that range is walked; either way the sum runs over the band's g points in ascending order.
+  int* s_rng = reinterpret_cast<int*>(red + 8 + 3 * nlev);  // [nband][2]: first g, last g (or -1: not contiguous)
+  if (p.band_mapping) {
+    for (int ib = threadIdx.x; ib < nband; ib += blockDim.x) {
+      int first = -1, last = -1, cnt = 0;
+      for (int g = 0; g < ng; ++g) {
+        if (p.band_mapping[g] == ib) { if (first < 0) first = g; last = g; ++cnt; }
+      }
+      const bool contig = cnt > 0 && last - first + 1 == cnt;
+      s_rng[2 * ib] = contig ? first : (cnt == 0 ? 0 : -1);
+      s_rng[2 * ib + 1] = contig ? last : (cnt == 0 ? -1 : 0);
+    }
+    __syncthreads();
+  }
   for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
     const int l = j / nband, ib = j - l * nband;
     if (!p.band_mapping) {
@@ -590,8 +621,13 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
       fu[j] = fuo[(size_t)l * ng + ib];
     } else {
       double sd = 0.0, su = 0.0;
-      for (int g = 0; g < ng; ++g) {
-        if (p.band_mapping[g] == ib) { sd += fdo[(size_t)l * ng + g]; su += fuo[(size_t)l * ng + g]; }
+      const int g0 = s_rng[2 * ib], g1 = s_rng[2 * ib + 1];
+      if (g0 >= 0) {
+        for (int g = g0; g <= g1; ++g) { sd += fdo[(size_t)l * ng + g]; su += fuo[(size_t)l * ng + g]; }
+      } else {
+        for (int g = 0; g < ng; ++g) {
+          if (p.band_mapping[g] == ib) { sd += fdo[(size_t)l * ng + g]; su += fuo[(size_t)l * ng + g]; }
+        }
       }
       fd[j] = sd;
       fu[j] = su;
@@ -729,11 +765,12 @@ __global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __rest
 static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_profile, double* d_cost_total,
                            double* d_penalty_total, double* d_cost_fn_per_band, const char* who) {
   const int nlev = p.nlay + 1;
+  trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
   ECCKD_REQUIRE(p.nprof > 0 && p.nlay > 0 && p.ng > 0 && p.nband > 0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
   ECCKD_REQUIRE(p.band_mapping || p.nband == p.ng, ECCKD_PARAMETER_ERROR,
                 "%s: without band_mapping the truth arrays are per g point (nband must equal ng)", who);
   const size_t ndbl = (size_t)2 * nlev * p.ng + (size_t)2 * nlev * p.nband + (size_t)p.nlay * p.nband + 2 * p.nlay +
-                      std::max(std::max(p.nband, nlev), p.ng) + 8 + 3 * nlev;
+                      std::max(std::max(p.nband, nlev), p.ng) + 8 + 3 * nlev + p.nband + 2 + 256;
   const size_t smem = ndbl * sizeof(double);
   ECCKD_REQUIRE(smem <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
                 "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, p.ng, nlev, smem,
@@ -748,7 +785,7 @@ static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_prof
   double* own_cost = reinterpret_cast<double*>(c + b_prof);
   p.cost_profile = d_cost_profile ? d_cost_profile : own_cost;
   p.cost_band_profile = d_cost_fn_per_band ? reinterpret_cast<double*>(c + 2 * b_prof) : nullptr;
-  const int threads = std::min(1024, std::max(64, (p.ng + 31) / 32 * 32));
+  const int threads = std::min(1024, std::max(128, (p.ng + 31) / 32 * 32));
   ckd_cost_kernel<<<p.nprof, threads, smem, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
   ckd_cost_total_kernel<<<1, 64, 0, ctx->stream>>>(p.nprof, p.nband, p.cost_profile, p.penalty_profile,
