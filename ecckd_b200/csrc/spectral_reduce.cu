@@ -35,6 +35,7 @@
 #include "async_copy.cuh"
 
 #include <algorithm>
+#include <ctime>
 #include <type_traits>
 
 namespace ecckd {
@@ -1488,11 +1489,55 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   if (!ctx->copy_stream) ECCKD_CUDA_OK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
   cudaStream_t cs = ctx->copy_stream;
   ECCKD_CUDA_OK(cudaStreamSynchronize(st));  // the staging arena may still be read by earlier work on st
+  // The small per-wavenumber inputs go FIRST and on the copy stream: host-to-device copies are served
+  // in submission order per stream, and queued on the compute stream they were only served after the
+  // last slab (measured: the plan and every reduction then started when all copies had landed, 12 ms
+  // per call).  The compute stream waits for them through an event.
+  int rc = ECCKD_OK;
+  ecckd_gpoint_plan* plan = nullptr;
+  const bool trace = getenv("ECCKD_TRACE") != nullptr;
+  auto now_ms = []() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  };
+  const double t_begin = now_ms();
+  cudaEvent_t small_ready = nullptr;
+  cudaError_t e = cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), cs);
+  if (e == cudaSuccess && fused) {
+    e = cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, cs);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, cs);
+  } else if (e == cudaSuccess && vecw) {
+    e = cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, cs);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&small_ready, trace ? cudaEventDefault : cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(small_ready, cs);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(st, small_ready, 0);
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(cs);
+    if (small_ready) cudaEventDestroy(small_ready);
+    set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  // slabs of decreasing size (weights nslab, nslab-1, ..., 1): what is left to do when the last copy
+  // lands is the reduction of a slab of one or two layers
   const int nslab = std::min(nlay, 8);
+  std::vector<int> slab_begin(nslab + 1, 0);
+  {
+    const int64_t tri = (int64_t)nslab * (nslab + 1) / 2;
+    int64_t acc_w = 0;
+    for (int s = 0; s < nslab; ++s) {
+      acc_w += nslab - s;
+      slab_begin[s + 1] = std::max(slab_begin[s] + 1, (int)((nlay * acc_w + tri / 2) / tri));
+    }
+    slab_begin[nslab] = nlay;
+    for (int s = nslab - 1; s > 0; --s) slab_begin[s] = std::min(slab_begin[s], slab_begin[s + 1] - 1);
+  }
   std::vector<cudaEvent_t> ready(nslab, nullptr);
-  cudaError_t e = cudaSuccess;
   for (int s = 0; s < nslab && e == cudaSuccess; ++s) {
-    const int l0 = (int)(((int64_t)nlay * s) / nslab), l1 = (int)(((int64_t)nlay * (s + 1)) / nslab);
+    const int l0 = slab_begin[s], l1 = slab_begin[s + 1];
     if (optical_depth_f32) {
       e = cudaMemcpy2DAsync(d_f32 + (size_t)l0 * dstride, dstride * sizeof(float),
                             optical_depth_f32 + (size_t)l0 * od_stride, od_stride * sizeof(float), nwav * sizeof(float),
@@ -1512,12 +1557,14 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     if (e == cudaSuccess && !fused && !vecw)
       e = cudaMemcpy2DAsync(d_w + (size_t)l0 * dstride, dstride * sizeof(double), planck_fl + (size_t)l0 * planck_stride,
                             planck_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[s], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[s], trace ? cudaEventDefault : cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(ready[s], cs);
   }
   auto drop_events = [&]() {
     for (cudaEvent_t ev : ready)
       if (ev) cudaEventDestroy(ev);
+    if (small_ready) cudaEventDestroy(small_ready);
+    small_ready = nullptr;
   };
   if (e != cudaSuccess) {
     cudaStreamSynchronize(cs);
@@ -1525,22 +1572,12 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
     return ECCKD_UNEXPECTED_EXCEPTION;
   }
-  // small per-wavenumber inputs and the plan on the compute stream, concurrently with the slabs
-  int rc = ECCKD_OK;
-  ecckd_gpoint_plan* plan = nullptr;
-  e = cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), st);
-  if (e == cudaSuccess && fused) {
-    e = cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
-    if (e == cudaSuccess)
-      e = cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
-  } else if (e == cudaSuccess && vecw) {
-    e = cudaMemcpyAsync(d_w, planck_fl, nwav * sizeof(double), cudaMemcpyHostToDevice, st);
-  }
+  const double t_enq = now_ms();
   if (e == cudaSuccess) rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
+  const double t_plan = now_ms();
   const bool mm = min_molar_abs && max_molar_abs;
   for (int s = 0; s < nslab && e == cudaSuccess && rc == ECCKD_OK; ++s) {
-    const int l0 = (int)(((int64_t)nlay * s) / nslab), l1 = (int)(((int64_t)nlay * (s + 1)) / nslab);
+    const int l0 = slab_begin[s], l1 = slab_begin[s + 1];
     e = cudaStreamWaitEvent(st, ready[s], 0);
     if (e != cudaSuccess) break;
     rc = ecckd_average_optical_depth_to_g_point_dev(
@@ -1564,10 +1601,26 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     if (e == cudaSuccess && warn)
       e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   }
+  const double t_launched = now_ms();
   cudaStreamSynchronize(cs);
+  const double t_copied = now_ms();
+  if (trace) {
+    cudaStreamSynchronize(st);
+    for (int s2 = 0; s2 < nslab; ++s2) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, small_ready, ready[s2]);
+      fprintf(stderr, "  slab %d (layers %d-%d) landed %.2f ms after the small inputs\n", s2, slab_begin[s2],
+              slab_begin[s2 + 1] - 1, ms);
+    }
+  }
   drop_events();
   const cudaError_t e2 = cudaStreamSynchronize(st);
+  const double t_done = now_ms();
   ecckd_gpoint_plan_destroy(plan);
+  if (trace)
+    fprintf(stderr, "host_average: enqueue copies %.2f, plan ready %.2f, launches done %.2f, copies landed %.2f, "
+            "all done %.2f, plan freed %.2f ms\n", t_enq - t_begin, t_plan - t_begin, t_launched - t_begin,
+            t_copied - t_begin, t_done - t_begin, now_ms() - t_begin);
   if (rc != ECCKD_OK) return rc;
   if (e != cudaSuccess || e2 != cudaSuccess) {
     set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
