@@ -1,6 +1,8 @@
 // capi.cu - context, memory and error plumbing of the C ABI (include/ecckd_b200.h)
 #include <cstdarg>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ecckd {
@@ -32,6 +34,18 @@ int ws_reserve(ecckd_ctx* ctx, int slot, size_t bytes, void** out) {
   return ECCKD_OK;
 }
 
+__global__ void stage_copy_kernel(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, size_t bytes) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15u) == 0) {
+    const size_t n16 = bytes >> 4;
+    for (size_t k = i; k < n16; k += stride) reinterpret_cast<uint4*>(dst)[k] = reinterpret_cast<const uint4*>(src)[k];
+    for (size_t k = (n16 << 4) + i; k < bytes; k += stride) dst[k] = src[k];
+  } else {
+    for (size_t k = i; k < bytes; k += stride) dst[k] = src[k];
+  }
+}
+
 int upload_small(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   if (bytes == 0) return ECCKD_OK;
   if (bytes > ctx->pinned_bytes) {
@@ -48,7 +62,14 @@ int upload_small(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
   char* stage = static_cast<char*>(ctx->pinned) + off;
   memcpy(stage, h_src, bytes);
   ctx->pinned_off = off + bytes;
-  ECCKD_CUDA_OK(cudaMemcpyAsync(d_dst, stage, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  // A kernel reads the pinned staging buffer over the bus (it is mapped into the device address space)
+  // instead of a host-to-device copy: copies are served by the copy engine in its own order, and a
+  // descriptor upload queued behind gigabytes of spectra (the host-buffer averaging call streams them
+  // on a second stream) held the kernels that needed it back until the last of them had landed.
+  const unsigned threads = 256, blocks = (unsigned)std::min<size_t>(64, (bytes + threads * 16 - 1) / (threads * 16));
+  stage_copy_kernel<<<blocks, threads, 0, ctx->stream>>>(static_cast<unsigned char*>(d_dst),
+                                                        reinterpret_cast<const unsigned char*>(stage), bytes);
+  ECCKD_CUDA_OK(cudaGetLastError());
   return ECCKD_OK;
 }
 

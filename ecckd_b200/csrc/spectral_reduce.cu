@@ -1535,8 +1535,23 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     slab_begin[nslab] = nlay;
     for (int s = nslab - 1; s > 0; --s) slab_begin[s] = std::min(slab_begin[s], slab_begin[s + 1] - 1);
   }
+  // One loop: enqueue the copy of slab s, then the reduction of slab s (the plan is built while slab 0
+  // is on its way).  The order matters: a reduction call uploads its small descriptors with host-to-device
+  // copies of its own, and those are served in submission order with the slabs - enqueued after ALL
+  // slab copies (as the first version did) every reduction waited for the last slab to land.
   std::vector<cudaEvent_t> ready(nslab, nullptr);
-  for (int s = 0; s < nslab && e == cudaSuccess; ++s) {
+  std::vector<cudaEvent_t> reduced;
+  auto drop_events = [&]() {
+    for (cudaEvent_t ev : ready)
+      if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : reduced) cudaEventDestroy(ev);
+    reduced.clear();
+    if (small_ready) cudaEventDestroy(small_ready);
+    small_ready = nullptr;
+  };
+  const bool mm = min_molar_abs && max_molar_abs;
+  double t_enq = 0.0, t_plan = 0.0;
+  for (int s = 0; s < nslab && e == cudaSuccess && rc == ECCKD_OK; ++s) {
     const int l0 = slab_begin[s], l1 = slab_begin[s + 1];
     if (optical_depth_f32) {
       e = cudaMemcpy2DAsync(d_f32 + (size_t)l0 * dstride, dstride * sizeof(float),
@@ -1559,25 +1574,13 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
                             planck_stride * sizeof(double), nwav * sizeof(double), l1 - l0, cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready[s], trace ? cudaEventDefault : cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(ready[s], cs);
-  }
-  auto drop_events = [&]() {
-    for (cudaEvent_t ev : ready)
-      if (ev) cudaEventDestroy(ev);
-    if (small_ready) cudaEventDestroy(small_ready);
-    small_ready = nullptr;
-  };
-  if (e != cudaSuccess) {
-    cudaStreamSynchronize(cs);
-    drop_events();
-    set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
-    return ECCKD_UNEXPECTED_EXCEPTION;
-  }
-  const double t_enq = now_ms();
-  if (e == cudaSuccess) rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
-  const double t_plan = now_ms();
-  const bool mm = min_molar_abs && max_molar_abs;
-  for (int s = 0; s < nslab && e == cudaSuccess && rc == ECCKD_OK; ++s) {
-    const int l0 = slab_begin[s], l1 = slab_begin[s + 1];
+    if (e != cudaSuccess) break;
+    if (s == 0) {
+      t_enq = now_ms();
+      rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
+      t_plan = now_ms();
+      if (rc != ECCKD_OK) break;
+    }
     e = cudaStreamWaitEvent(st, ready[s], 0);
     if (e != cudaSuccess) break;
     rc = ecckd_average_optical_depth_to_g_point_dev(
@@ -1587,19 +1590,50 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
         fused ? temperature_fl + l0 : nullptr, fused ? d_w : nullptr, fused ? d_w + dstride : nullptr, method,
         d_out + (size_t)l0 * ng, mm ? d_out + out_elems + (size_t)l0 * ng : nullptr,
         mm ? d_out + 2 * out_elems + (size_t)l0 * ng : nullptr, ng, d_warn);
-  }
-  if (rc == ECCKD_OK && e == cudaSuccess) {
-    e = cudaMemcpy2DAsync(molar_abs, out_stride * sizeof(double), d_out, ng * sizeof(double), ng * sizeof(double), nlay,
-                          cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess && mm) {
-      e = cudaMemcpy2DAsync(min_molar_abs, out_stride * sizeof(double), d_out + out_elems, ng * sizeof(double),
-                            ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpy2DAsync(max_molar_abs, out_stride * sizeof(double), d_out + 2 * out_elems, ng * sizeof(double),
-                              ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
+    if (trace) {
+      cudaEvent_t ev;
+      cudaEventCreate(&ev);
+      cudaEventRecord(ev, st);
+      reduced.push_back(ev);
     }
-    if (e == cudaSuccess && warn)
-      e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  }
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(cs);
+    cudaStreamSynchronize(st);
+    drop_events();
+    ecckd_gpoint_plan_destroy(plan);
+    set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
+    return ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  // Results: one contiguous device-to-host copy of {molar_abs, min, max} into the context's pinned
+  // staging buffer, rows copied to the caller's (possibly strided, pageable) arrays on the host after
+  // the synchronisation.  (Three 2-D copies into pageable memory, one row of 512 B at a time, cost ~4 ms.)
+  const size_t res_bytes = (mm ? 3 : 1) * out_elems * sizeof(double);
+  const bool staged_out = res_bytes + 256 + (size_t)ng * sizeof(int32_t) <= ctx->pinned_bytes;
+  double* h_res = nullptr;
+  int32_t* h_warn = nullptr;
+  if (rc == ECCKD_OK && e == cudaSuccess) {
+    if (staged_out) {
+      e = cudaStreamSynchronize(st);  // the staging ring may hold descriptor uploads still in flight
+      ctx->pinned_off = 0;
+      h_res = static_cast<double*>(ctx->pinned);
+      h_warn = reinterpret_cast<int32_t*>(static_cast<char*>(ctx->pinned) + ((res_bytes + 255) & ~(size_t)255));
+      if (e == cudaSuccess) e = cudaMemcpyAsync(h_res, d_out, res_bytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && warn)
+        e = cudaMemcpyAsync(h_warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    } else {
+      e = cudaMemcpy2DAsync(molar_abs, out_stride * sizeof(double), d_out, ng * sizeof(double), ng * sizeof(double), nlay,
+                            cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess && mm) {
+        e = cudaMemcpy2DAsync(min_molar_abs, out_stride * sizeof(double), d_out + out_elems, ng * sizeof(double),
+                              ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(max_molar_abs, out_stride * sizeof(double), d_out + 2 * out_elems, ng * sizeof(double),
+                                ng * sizeof(double), nlay, cudaMemcpyDeviceToHost, st);
+      }
+      if (e == cudaSuccess && warn)
+        e = cudaMemcpyAsync(warn, d_warn, (size_t)ng * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    }
   }
   const double t_launched = now_ms();
   cudaStreamSynchronize(cs);
@@ -1609,12 +1643,21 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     for (int s2 = 0; s2 < nslab; ++s2) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, small_ready, ready[s2]);
-      fprintf(stderr, "  slab %d (layers %d-%d) landed %.2f ms after the small inputs\n", s2, slab_begin[s2],
-              slab_begin[s2 + 1] - 1, ms);
+      float ms2 = 0.f;
+      if ((size_t)s2 < reduced.size()) cudaEventElapsedTime(&ms2, small_ready, reduced[s2]);
+      fprintf(stderr, "  slab %d (layers %d-%d) landed %.2f ms, reduced %.2f ms after the small inputs\n", s2,
+              slab_begin[s2], slab_begin[s2 + 1] - 1, ms, ms2);
     }
   }
   drop_events();
   const cudaError_t e2 = cudaStreamSynchronize(st);
+  if (h_res && rc == ECCKD_OK && e == cudaSuccess && e2 == cudaSuccess) {
+    double* dst[3] = {molar_abs, mm ? min_molar_abs : nullptr, mm ? max_molar_abs : nullptr};
+    for (int a = 0; a < (mm ? 3 : 1); ++a)
+      for (int l = 0; l < nlay; ++l)
+        memcpy(dst[a] + (size_t)l * out_stride, h_res + a * out_elems + (size_t)l * ng, (size_t)ng * sizeof(double));
+    if (warn) memcpy(warn, h_warn, (size_t)ng * sizeof(int32_t));
+  }
   const double t_done = now_ms();
   ecckd_gpoint_plan_destroy(plan);
   if (trace)
