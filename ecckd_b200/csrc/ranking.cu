@@ -163,36 +163,107 @@ __global__ void gather_keys_kernel(int64_t n, const int32_t* __restrict__ g_inde
   }
 }
 
+// All bands of a call at once (their index ranges [first, last] disjoint, sorted by position):
+// element i gets the image of its key if it lies in a band and 0 otherwise, the value i, and the
+// segment seg[i] = 2k+1 inside the k-th band, 2k in the gap before it.  After the stable sort by key
+// image and a last stable pass by segment every band is sorted within its own range and the
+// elements of the gaps have not moved.
+__global__ void gather_all_kernel(int64_t n, const double* __restrict__ key, int nseg_bands,
+                                  const int* __restrict__ first, const int* __restrict__ last,
+                                  unsigned long long* __restrict__ k_out, uint32_t* __restrict__ v_out,
+                                  uint8_t* __restrict__ seg, unsigned long long* __restrict__ or_bits,
+                                  unsigned long long* __restrict__ and_bits) {
+  __shared__ int s_first[128], s_last[128];
+  for (int j = threadIdx.x; j < nseg_bands; j += blockDim.x) {
+    s_first[j] = first[j];
+    s_last[j] = last[j];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long img = 0ull, img_and = ~0ull;
+  if (i < n) {
+    int lo = 0, hi = nseg_bands;  // number of bands with first <= i
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_first[mid] <= (int)i) lo = mid + 1; else hi = mid;
+    }
+    const bool inside = lo > 0 && (int)i <= s_last[lo - 1];
+    seg[i] = (uint8_t)(inside ? 2 * (lo - 1) + 1 : 2 * lo);
+    if (inside) {
+      img = key_image(key[i]);
+      img_and = img;
+    }
+    k_out[i] = img;
+    v_out[i] = (uint32_t)i;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    img |= __shfl_xor_sync(0xffffffffu, img, o);
+    img_and &= __shfl_xor_sync(0xffffffffu, img_and, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (img) atomicOr(or_bits, img);
+    if (~img_and) atomicAnd(and_bits, img_and);
+  }
+}
+
+// g_index[i] = sorted value, rank[sorted value] = i (reorder_spectrum.cpp:296-300)
+__global__ void order_and_rank_kernel(int64_t n, const uint32_t* __restrict__ vals, int32_t* __restrict__ g_index,
+                                      int32_t* __restrict__ rank) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t v = vals[i];
+  if (g_index) g_index[i] = (int32_t)v;
+  if (rank) rank[v] = (int32_t)i;
+}
+
 constexpr int RS_THREADS = 256;
-constexpr int RS_ROUNDS = 8;
-constexpr int RS_TILE = RS_THREADS * RS_ROUNDS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;  // elements per thread
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WSPAN = 32 * RS_ITEMS;  // a warp owns this many CONSECUTIVE elements of the tile
+// pass digit: bits [shift, shift+8) of the key image, or (shift == RS_SEG_PASS) the segment of the
+// element's original index (the bands of one ranking call sorted together, see ecckd_rank_bands_dev)
+constexpr int RS_SEG_PASS = 64;
+
+__device__ __forceinline__ int rs_digit(unsigned long long k, uint32_t v, int shift, const uint8_t* __restrict__ seg) {
+  return (shift == RS_SEG_PASS) ? (int)seg[v] : (int)((k >> shift) & 0xFFull);
+}
 
 // per-tile digit histogram -> hist[digit][tile]
 __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(int64_t n, const unsigned long long* __restrict__ keys,
-                                                                int shift, int ntiles, uint32_t* __restrict__ hist) {
+                                                                const uint32_t* __restrict__ vals,
+                                                                const uint8_t* __restrict__ seg, int shift, int ntiles,
+                                                                uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_h[256];
   s_h[threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-#pragma unroll
-  for (int r = 0; r < RS_ROUNDS; ++r) {
+#pragma unroll 4
+  for (int r = 0; r < RS_ITEMS; ++r) {
     const int64_t i = base + r * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 0xFF], 1u);
+    int digit = 256 + (int)(threadIdx.x & 31);  // out of range: a group of its own, not counted
+    if (i < n) digit = rs_digit(keys[i], shift == RS_SEG_PASS ? vals[i] : 0u, shift, seg);
+    // one shared-memory atomic per distinct digit of the warp (smooth keys put whole warps on one bin)
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    if (digit < 256 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&s_h[digit], (uint32_t)__popc(peers));
   }
   __syncthreads();
   hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_h[threadIdx.x];
 }
 
-// exclusive scan of hist (256*ntiles entries, digit-major) by a single block
-__global__ void __launch_bounds__(1024) radix_scan_kernel(int64_t total, uint32_t* __restrict__ hist) {
+// block d: exclusive scan of hist[d][0..ntiles) in place, the digit's total to totals[d]
+__global__ void __launch_bounds__(1024) radix_scan_kernel(int ntiles, uint32_t* __restrict__ hist,
+                                                          uint32_t* __restrict__ totals) {
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry;
   if (threadIdx.x == 0) s_carry = 0;
   __syncthreads();
+  uint32_t* h = hist + (size_t)blockIdx.x * ntiles;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t base = 0; base < total; base += 1024) {
-    const int64_t i = base + threadIdx.x;
-    const uint32_t v = (i < total) ? hist[i] : 0u;
+  for (int base = 0; base < ntiles; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = (i < ntiles) ? h[i] : 0u;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -213,59 +284,122 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(int64_t total, uint32_
     __syncthreads();
     const uint32_t carry = s_carry;
     const uint32_t warp_off = (warp == 0) ? 0u : s_warp[warp - 1];
-    if (i < total) hist[i] = carry + warp_off + x - v;
+    if (i < ntiles) h[i] = carry + warp_off + x - v;
     __syncthreads();
     if (threadIdx.x == 1023) s_carry = carry + warp_off + x;
     __syncthreads();
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = s_carry;
 }
 
-// stable scatter of one tile
+// exclusive scan of 256 values, one per thread of a 256-thread block (s_w: 8 words of scratch)
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t v, uint32_t* s_w) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) s_w[warp] = x;
+  __syncthreads();
+  uint32_t off = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) off += (w < warp) ? s_w[w] : 0u;
+  __syncthreads();
+  return off + x - v;
+}
+
+// Stable scatter of one tile.  A warp owns RS_WSPAN consecutive elements and ranks them round by round
+// (__match_any_sync + a per-warp running count per digit, warp-synchronous); the tile is then put in
+// digit order in shared memory and written out in runs of consecutive addresses.
+struct RsSmem {
+  unsigned long long key[RS_TILE];
+  uint32_t val[RS_TILE];
+  uint32_t wcnt[RS_WARPS][257];  // per warp: running count per digit, then exclusive prefix over warps
+  uint32_t dstart[256];          // first position of the digit in the sorted tile
+  uint32_t gofs[256];            // global position of sorted-tile position p with digit d: gofs[d] + p
+  uint32_t scratch[RS_WARPS];
+  uint8_t dig[RS_TILE];
+};
+
 __global__ void __launch_bounds__(RS_THREADS) radix_scatter_kernel(int64_t n, const unsigned long long* __restrict__ keys,
-                                                                   const uint32_t* __restrict__ vals, int shift,
+                                                                   const uint32_t* __restrict__ vals,
+                                                                   const uint8_t* __restrict__ seg, int shift,
                                                                    int ntiles, const uint32_t* __restrict__ offs,
+                                                                   const uint32_t* __restrict__ totals,
                                                                    unsigned long long* __restrict__ keys_out,
                                                                    uint32_t* __restrict__ vals_out) {
-  __shared__ uint32_t s_run[256];        // next free global position per digit
-  __shared__ uint32_t s_wcnt[8][256];    // per-warp digit counts of the current round
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  RsSmem& S = *reinterpret_cast<RsSmem*>(rs_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  s_run[threadIdx.x] = offs[(size_t)threadIdx.x * ntiles + blockIdx.x];
-  const int64_t base = (int64_t)blockIdx.x * RS_TILE;
-  for (int r = 0; r < RS_ROUNDS; ++r) {
-    for (int j = threadIdx.x; j < 8 * 256; j += RS_THREADS) (&s_wcnt[0][0])[j] = 0;
-    __syncthreads();
-    const int64_t i = base + r * RS_THREADS + threadIdx.x;
-    const bool valid = i < n;
-    unsigned long long k = 0;
-    uint32_t v = 0;
-    // out-of-range lanes get digit 256 (their own match group), never counted
-    int digit = 256;
-    if (valid) {
-      k = keys[i];
-      v = vals[i];
-      digit = (int)((k >> shift) & 0xFF);
-    }
-    const unsigned peers = __match_any_sync(0xffffffffu, digit);
-    const int rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-    if (valid && rank_in_warp == 0) s_wcnt[warp][digit] = (uint32_t)__popc(peers);
-    __syncthreads();
-    {  // digit = threadIdx.x: exclusive prefix over warps, advance the running offset
-      uint32_t run = s_run[threadIdx.x];
+  for (int j = threadIdx.x; j < RS_WARPS * 257; j += RS_THREADS) (&S.wcnt[0][0])[j] = 0;
+  // global base of every digit: exclusive scan of the digit totals + this tile's offset within the digit
+  const uint32_t dbase = block_exclusive_scan_256(totals[threadIdx.x], S.scratch) +
+                         offs[(size_t)threadIdx.x * ntiles + blockIdx.x];
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * RS_WSPAN;
+  unsigned long long k[RS_ITEMS];
+  uint32_t v[RS_ITEMS];
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        const uint32_t c = s_wcnt[w][threadIdx.x];
-        s_wcnt[w][threadIdx.x] = run;
-        run += c;
-      }
-      s_run[threadIdx.x] = run;
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t i = base + r * 32 + lane;
+    k[r] = 0ull;
+    v[r] = 0u;
+    if (i < n) {
+      k[r] = keys[i];
+      v[r] = vals[i];
     }
-    __syncthreads();
-    if (valid) {
-      const uint32_t pos = s_wcnt[warp][digit] + (uint32_t)rank_in_warp;
-      keys_out[pos] = k;
-      vals_out[pos] = v;
+  }
+  uint32_t dr[RS_ITEMS];  // digit | rank within (warp, digit) << 16
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int64_t i = base + r * 32 + lane;
+    const int digit = (i < n) ? rs_digit(k[r], v[r], shift, seg) : 256;
+    const unsigned peers = __match_any_sync(0xffffffffu, digit);
+    const uint32_t before = (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    const uint32_t old = S.wcnt[warp][digit];
+    __syncwarp();
+    if (before == 0u) S.wcnt[warp][digit] = old + (uint32_t)__popc(peers);
+    __syncwarp();
+    dr[r] = (uint32_t)digit | ((old + before) << 16);
+  }
+  __syncthreads();
+  uint32_t tile_count;
+  {  // digit = threadIdx.x: exclusive prefix over warps; then the digit's start in the sorted tile
+    uint32_t run = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) {
+      const uint32_t c = S.wcnt[w][threadIdx.x];
+      S.wcnt[w][threadIdx.x] = run;
+      run += c;
     }
-    __syncthreads();
+    tile_count = run;
+  }
+  const uint32_t dstart = block_exclusive_scan_256(tile_count, S.scratch);
+  S.dstart[threadIdx.x] = dstart;
+  S.gofs[threadIdx.x] = dbase - dstart;
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const uint32_t digit = dr[r] & 0xFFFFu;
+    if (digit < 256u) {
+      const uint32_t p = S.dstart[digit] + S.wcnt[warp][digit] + (dr[r] >> 16);
+      S.key[p] = k[r];
+      S.val[p] = v[r];
+      S.dig[p] = (uint8_t)digit;
+    }
+  }
+  __syncthreads();
+  const int64_t tile_n = min((int64_t)RS_TILE, n - (int64_t)blockIdx.x * RS_TILE);
+#pragma unroll 4
+  for (int r = 0; r < RS_ITEMS; ++r) {
+    const int p = r * RS_THREADS + (int)threadIdx.x;
+    if (p < tile_n) {
+      const uint32_t pos = S.gofs[S.dig[p]] + (uint32_t)p;
+      keys_out[pos] = S.key[p];
+      vals_out[pos] = S.val[p];
+    }
   }
 }
 
@@ -320,23 +454,31 @@ __global__ void assign_g_points_kernel(int ngas, int64_t nwav, const int32_t* __
   if (g < 0) atomicAdd(n_unassigned, 1ull);
 }
 
-// Stable LSD radix sort of n (key image, value) pairs in place in (k0, v0),
-// using (k1, v1) as the ping-pong buffers; `vary` = bits that differ somewhere.
+// Stable LSD radix sort of n (key image, value) pairs in place in (k0, v0), using (k1, v1) as the
+// ping-pong buffers; `vary` = key bits that differ somewhere (passes over constant digits are
+// skipped); with `seg` a last pass orders by seg[value] (the segments of a multi-band call).
+// hist: 256*ntiles + 256 words.
 static int radix_sort_pairs(ecckd_ctx* ctx, int64_t n, unsigned long long* k0, uint32_t* v0, unsigned long long* k1,
-                            uint32_t* v1, uint32_t* hist, unsigned long long vary, uint32_t** v_result) {
+                            uint32_t* v1, uint32_t* hist, unsigned long long vary, const uint8_t* seg,
+                            uint32_t** v_result) {
   const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  uint32_t* totals = hist + (size_t)256 * ntiles;
   unsigned long long* kin = k0;
   unsigned long long* kout = k1;
   uint32_t* vin = v0;
   uint32_t* vout = v1;
-  for (int pass = 0; pass < 8; ++pass) {
-    const int shift = pass * 8;
-    if (((vary >> shift) & 0xFFull) == 0ull) continue;  // digit constant over the range: identity pass
-    radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(n, kin, shift, ntiles, hist);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(RsSmem)));
+  for (int pass = 0; pass < 9; ++pass) {
+    const int shift = pass * 8;  // pass 8 = RS_SEG_PASS
+    if (pass < 8 && ((vary >> shift) & 0xFFull) == 0ull) continue;  // digit constant over the range: identity pass
+    if (pass == 8 && !seg) continue;
+    radix_hist_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(n, kin, vin, seg, shift, ntiles, hist);
     ECCKD_LAUNCH_CHECK(ctx);
-    radix_scan_kernel<<<1, 1024, 0, ctx->stream>>>((int64_t)256 * ntiles, hist);
+    radix_scan_kernel<<<256, 1024, 0, ctx->stream>>>(ntiles, hist, totals);
     ECCKD_LAUNCH_CHECK(ctx);
-    radix_scatter_kernel<<<ntiles, RS_THREADS, 0, ctx->stream>>>(n, kin, vin, shift, ntiles, hist, kout, vout);
+    radix_scatter_kernel<<<ntiles, RS_THREADS, sizeof(RsSmem), ctx->stream>>>(n, kin, vin, seg, shift, ntiles, hist,
+                                                                              totals, kout, vout);
     ECCKD_LAUNCH_CHECK(ctx);
     std::swap(kin, kout);
     std::swap(vin, vout);
@@ -417,15 +559,16 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
   // reorder_spectrum.cpp:245-248
   ECCKD_REQUIRE(nband > 0, ECCKD_PARAMETER_ERROR,
                 "Failure to interpret wavenumber1 and wavenumber2 as a list of band boundaries");
-  // scratch layout (slot 1): k0 | k1 | v0 | v1 | g_index | hist | band meta
+  // scratch layout (slot 1): k0 | k1 | v0 | v1 | g_index | seg | hist (+ digit totals) | band meta
   const int ntiles_max = (int)((nwav + RS_TILE - 1) / RS_TILE);
   const size_t kbytes = (size_t)nwav * sizeof(unsigned long long);
   const size_t vbytes = ((size_t)nwav * sizeof(uint32_t) + 255) & ~size_t(255);
-  const size_t hbytes = ((size_t)256 * ntiles_max * sizeof(uint32_t) + 255) & ~size_t(255);
-  const size_t mbytes = ((size_t)nband * (2 * sizeof(double) + 2 * sizeof(int)) + 2 * sizeof(unsigned long long) + 255) &
+  const size_t sbytes = ((size_t)nwav + 255) & ~size_t(255);
+  const size_t hbytes = ((size_t)256 * (ntiles_max + 1) * sizeof(uint32_t) + 255) & ~size_t(255);
+  const size_t mbytes = ((size_t)nband * (2 * sizeof(double) + 4 * sizeof(int)) + 2 * sizeof(unsigned long long) + 255) &
                         ~size_t(255);
   void* base = nullptr;
-  ECCKD_TRY(ws_reserve(ctx, 1, 2 * kbytes + 3 * vbytes + hbytes + mbytes + 1024, &base));
+  ECCKD_TRY(ws_reserve(ctx, 1, 2 * kbytes + 3 * vbytes + sbytes + hbytes + mbytes + 1024, &base));
   char* pch = static_cast<char*>(base);
   unsigned long long* k0 = reinterpret_cast<unsigned long long*>(pch);
   unsigned long long* k1 = reinterpret_cast<unsigned long long*>(pch + kbytes);
@@ -434,6 +577,8 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
   uint32_t* v1 = reinterpret_cast<uint32_t*>(pch + vbytes);
   int32_t* g_index = d_ordered_index ? d_ordered_index : reinterpret_cast<int32_t*>(pch + 2 * vbytes);
   pch += 3 * vbytes;
+  uint8_t* d_seg = reinterpret_cast<uint8_t*>(pch);
+  pch += sbytes;
   uint32_t* hist = reinterpret_cast<uint32_t*>(pch);
   pch += hbytes;
   double* d_b1 = reinterpret_cast<double*>(pch);
@@ -441,6 +586,8 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
   unsigned long long* d_bits = reinterpret_cast<unsigned long long*>(d_b2 + nband);  // [or, and]
   int* d_first = reinterpret_cast<int*>(d_bits + 2);
   int* d_last = d_first + nband;
+  int* d_sfirst = d_last + nband;  // the bands' ranges sorted by position (one-shot path)
+  int* d_slast = d_sfirst + nband;
 
   ECCKD_TRY(upload_small(ctx, d_b1, h_b1, (size_t)nband * sizeof(double)));
   ECCKD_TRY(upload_small(ctx, d_b2, h_b2, (size_t)nband * sizeof(double)));
@@ -461,9 +608,43 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
     // the reference indexes an empty vector here (reorder_spectrum.cpp:291)
     ECCKD_REQUIRE(i2 >= 0 && i1 <= i2, ECCKD_PARAMETER_ERROR, "band %d (%g-%g cm-1) contains no wavenumbers", j, h_b1[j],
                   h_b2[j]);
+  }
+  const unsigned long long bits_init[2] = {0ull, ~0ull};
+  // Bands with pairwise disjoint index ranges (the usual case: ascending wavenumbers, adjoining
+  // bands) are sorted in ONE radix sort of the whole spectrum with the band as the last digit.
+  std::vector<std::pair<int, int>> ranges(nband);
+  for (int j = 0; j < nband; ++j) ranges[j] = std::make_pair(fl[j], fl[nband + j]);
+  std::sort(ranges.begin(), ranges.end());
+  bool disjoint = nband <= 120;
+  for (int j = 1; j < nband && disjoint; ++j) disjoint = ranges[j].first > ranges[j - 1].second;
+  if (disjoint) {
+    std::vector<int> sr(2 * nband);
+    for (int j = 0; j < nband; ++j) {
+      sr[j] = ranges[j].first;
+      sr[nband + j] = ranges[j].second;
+    }
+    ECCKD_TRY(upload_small(ctx, d_sfirst, sr.data(), sr.size() * sizeof(int)));
+    ECCKD_TRY(upload_small(ctx, d_bits, bits_init, sizeof(bits_init)));
+    gather_all_kernel<<<nb, 256, 0, ctx->stream>>>(nwav, d_key, nband, d_sfirst, d_slast, k0, v0, d_seg, d_bits,
+                                                   d_bits + 1);
+    ECCKD_LAUNCH_CHECK(ctx);
+    unsigned long long bits[2];
+    ECCKD_CUDA_OK(cudaMemcpyAsync(bits, d_bits, sizeof(bits), cudaMemcpyDeviceToHost, ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long vary = bits[0] & ~bits[1];
+    uint32_t* v_sorted = nullptr;
+    // one band spanning everything needs no segment pass
+    const bool one_segment = nband == 1 && ranges[0].first == 0 && ranges[0].second == (int)(nwav - 1);
+    ECCKD_TRY(radix_sort_pairs(ctx, nwav, k0, v0, k1, v1, hist, vary, one_segment ? nullptr : d_seg, &v_sorted));
+    order_and_rank_kernel<<<nb, 256, 0, ctx->stream>>>(nwav, v_sorted, g_index, d_rank);
+    ECCKD_LAUNCH_CHECK(ctx);
+    return ECCKD_OK;
+  }
+  // overlapping bands: one after the other on g_index, as the reference's loop does
+  for (int j = 0; j < nband; ++j) {
+    const int i1 = fl[j], i2 = fl[nband + j];
     const int64_t n = (int64_t)i2 - i1 + 1;
     if (n < 2) continue;
-    const unsigned long long bits_init[2] = {0ull, ~0ull};
     ECCKD_TRY(upload_small(ctx, d_bits, bits_init, sizeof(bits_init)));
     gather_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, g_index + i1, d_key, k0, v0, d_bits,
                                                                               d_bits + 1);
@@ -473,7 +654,7 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
     ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     const unsigned long long vary = bits[0] & ~bits[1];
     uint32_t* v_sorted = nullptr;
-    ECCKD_TRY(radix_sort_pairs(ctx, n, k0, v0, k1, v1, hist, vary, &v_sorted));
+    ECCKD_TRY(radix_sort_pairs(ctx, n, k0, v0, k1, v1, hist, vary, nullptr, &v_sorted));
     write_back_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, v_sorted, g_index + i1);
     ECCKD_LAUNCH_CHECK(ctx);
   }

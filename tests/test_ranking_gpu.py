@@ -51,6 +51,44 @@ def test_rank_ties_signed_zeros_and_bands(ctx, O):
         assert np.array_equal(np.sort(got[1]), np.arange(n))
 
 
+def test_rank_overlapping_bands_follow_the_reference_loop(ctx, O):
+    """Bands whose index ranges overlap are sorted one after the other on the running order
+    (reorder_spectrum.cpp:278-294); disjoint bands take the single-sort path."""
+    rng = np.random.default_rng(8)
+    n = 30011
+    wn = np.linspace(0.5, 100.0, n)
+    key = np.round(rng.normal(size=n), 2)
+    for b1, b2 in [([0.5, 30.0], [60.0, 100.0]), ([0.5, 10.0, 5.0], [20.0, 40.0, 100.0])]:
+        got = _rank(ctx, wn, key, b1, b2)
+        ref = O.rank_bands(wn, key, b1, b2)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b)
+
+
+def test_rank_many_tiles_smooth_keys_gaps_and_unordered_bands(ctx, O):
+    """2^20+3 wavenumbers (257 tiles, ragged last tile), smooth keys (whole warps on one digit), bands
+    listed out of positional order with gaps between them and at both ends."""
+    n = (1 << 20) + 3
+    wn = np.linspace(1.0, 3000.0, n)
+    rng = np.random.default_rng(21)
+    key = 6.0 + 5.0 * np.sin(wn * 0.05) + 1e-3 * np.round(rng.normal(size=n), 1)
+    key[::9973] = key[1::9973]          # exact ties far apart
+    b1 = [1500.0, 10.0, 2200.0, 700.0]
+    b2 = [2000.0, 650.0, 2990.0, 1400.0]
+    got = _rank(ctx, wn, key, b1, b2)
+    ref = O.rank_bands(wn, key, b1, b2)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    # size-independent properties: a permutation, the identity outside the bands, sorted inside
+    ib, rank, order = got
+    assert np.array_equal(np.sort(rank), np.arange(n))
+    assert np.array_equal(order[ib < 0], np.nonzero(ib < 0)[0])
+    for j in range(4):
+        m = np.nonzero(ib == j)[0]
+        k = key[order[m[0]:m[-1] + 1]]
+        assert np.all(np.diff(k) >= 0)
+
+
 def test_rank_constant_key_is_identity(ctx):
     n = 10000
     wn = np.linspace(1.0, 2.0, n)
