@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "trans_core.cuh"
 
 namespace ecckd {
 
@@ -33,54 +34,125 @@ __device__ __forceinline__ void lw_layer_r(double tau, double& e, double& f) {
   f = (e > 1.0e-5) ? (1.0 - e * (1.0 / ECCKD_LW_DIFFUSIVITY) / tau) : (0.5 * e);
 }
 
-// per-layer constants uploaded by the host: [0..nlay] T_hl, then conv[nlay],
+// Fast element forms for the sort-key kernel (the same schemes as the flux solver and the Planck
+// weights of the spectral reduction): table exponential of trans_core.cuh, reciprocals refined by
+// two Newton steps.  Results differ from the libm forms above by a few ulp.
+__device__ __forceinline__ double rcp_newton(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));  // ~20 bits
+  r = fma(r, fma(-x, r, 1.0), r);
+  return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double planck_elem_tab(double hk_over_t, double freq, double prefactor, const TransLane& tl) {
+  // planck_function.cpp:47-53 with (h/k)/T formed on the host; exp argument capped where the result is 0 anyway
+  const double e = exp_table(fmin(freq * hk_over_t, 700.0), tl) - 1.0;
+  return prefactor * rcp_newton(e);
+}
+__device__ __forceinline__ void lw_layer_tab(double tau, const TransConst& K, const TransLane& tl, double& e, double& f) {
+  e = trans_one_minus_exp(tau, K, tl);
+  f = (e > 1.0e-5) ? (1.0 - (e * (1.0 / ECCKD_LW_DIFFUSIVITY)) * rcp_newton(tau)) : (0.5 * e);
+}
+
+// per-layer constants uploaded by the host: [0..nlay] (h/k)/T_hl, then conv[nlay],
 // dh[nlay], dhh[nlay]  (reorder_spectrum.cpp:121-124, 178-183; heating_rate.h:38)
+//
+// One thread per wavenumber, three passes over the levels with two [level][thread] arrays in shared
+// memory: (1) the Planck function of every level (independent: the exponentials pipeline), (2) the
+// upward sweep, which parks the upward fluxes and replaces the Planck function of level l+1 by the
+// layer's downward source B(l)(e-f) + B(l+1) f, (3) the downward sweep, which only needs the
+// transmittance again (one table exponential), the heating rates and the two weighted sums.  Every
+// exponential and reciprocal is evaluated once except the layer transmittance (twice); the optical
+// depths are read twice, the second time out of L2.  All 32 lanes of a warp stay in the loops (the
+// table exponential shuffles): threads past the end work on the last wavenumber and do not write.
 __global__ void sort_key_lw_kernel(int nlay, int64_t nwav, const double* __restrict__ lay, const double* __restrict__ wn,
                                    const double* __restrict__ dwn, const double* __restrict__ od, int64_t od_stride,
-                                   double thr, double* __restrict__ key, double* __restrict__ column_od) {
-  extern __shared__ double s_up[];  // [nlay+1][blockDim.x]
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwav) return;
+                                   double thr, TransConst K, double* __restrict__ key, double* __restrict__ column_od) {
+  extern __shared__ double s_lw[];
   const int bs = blockDim.x, tx = threadIdx.x;
-  const double* t_hl = lay;
+  double* s_up = s_lw;                            // [nlay+1][bs] upward flux
+  double* s_b = s_lw + (size_t)(nlay + 1) * bs;   // [nlay+1][bs] Planck function, then downward sources
+  const int64_t w_raw = (int64_t)blockIdx.x * bs + tx;
+  const bool valid = w_raw < nwav;
+  const int64_t w = valid ? w_raw : nwav - 1;
+  const TransLane tl = trans_lane_init();
+  const double* hkt = lay;
   const double* conv = lay + (nlay + 1);
   const double* dh = conv + nlay;
   const double* dhh = dh + nlay;
   const double nu = wn[w], dnu = dwn[w];
-  // upward sweep first: with surface emissivity 1 (reorder_spectrum.cpp:138-139)
+  // The optical depths of SK_G layers are loaded together, one group ahead of their use (with one
+  // load in flight per warp the kernel was bound by memory latency: 10 ms for 54 x 2^23), and the
+  // layer terms of a group are evaluated before its serial flux recurrence (independent chains).
+  constexpr int SK_G = 6;
+  double nxt[SK_G];
+  auto load_up = [&](int l0) {  // layers l0, l0-1, ...
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) nxt[j] = (l0 - j >= 0) ? od[(int64_t)(l0 - j) * od_stride + w] : 0.0;
+  };
+  auto load_dn = [&](int l0) {  // layers l0, l0+1, ...
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) nxt[j] = (l0 + j < nlay) ? od[(int64_t)(l0 + j) * od_stride + w] : 0.0;
+  };
+  load_up(nlay - 1);
+  {
+    const double h = 6.62606896e-34, c = 2.99792458e8, pi = 3.14159265358979323846;
+    const double inv_cm_2_Hz = 100.0 * c;
+    const double freq = nu * inv_cm_2_Hz;
+    const double prefactor = (dnu * 2.0 * h * inv_cm_2_Hz * pi / (c * c)) * (freq * freq * freq);
+#pragma unroll 4
+    for (int l = 0; l <= nlay; ++l) s_b[l * bs + tx] = planck_elem_tab(hkt[l], freq, prefactor, tl);
+  }
+  // upward sweep: with surface emissivity 1 (reorder_spectrum.cpp:138-139)
   // flux_up(nlay) = surf_planck*1 + (1-1)*flux_dn(nlay), independent of flux_dn
-  double b_bot = planck_elem_r(t_hl[nlay], nu, dnu);
-  double f_up = b_bot * 1.0;
+  double f_up = s_b[nlay * bs + tx];
   s_up[nlay * bs + tx] = f_up;
-  for (int l = nlay - 1; l >= 0; --l) {
-    double e, f;
-    lw_layer_r(od[(int64_t)l * od_stride + w], e, f);
-    const double b_t = planck_elem_r(t_hl[l], nu, dnu);
-    f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
-    s_up[l * bs + tx] = f_up;
-    b_bot = b_t;
+  for (int l0 = nlay - 1; l0 >= 0; l0 -= SK_G) {
+    double tau[SK_G], e[SK_G], f[SK_G];
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) tau[j] = nxt[j];
+    if (l0 - SK_G >= 0) load_up(l0 - SK_G); else load_dn(0);
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) lw_layer_tab(tau[j], K, tl, e[j], f[j]);
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) {
+      const int l = l0 - j;
+      if (l >= 0) {  // warp-uniform
+        const double b_bot = s_b[(l + 1) * bs + tx], b_t = s_b[l * bs + tx];
+        f_up = f_up * (1.0 - e[j]) + b_bot * (e[j] - f[j]) + b_t * f[j];
+        s_up[l * bs + tx] = f_up;
+        s_b[(l + 1) * bs + tx] = b_t * (e[j] - f[j]) + b_bot * f[j];  // downward source of layer l (level l+1 is done with)
+      }
+    }
   }
   // downward sweep, heating rate and the two weighted sums in ascending layer order
   double f_dn = 0.0, col = 0.0, num = 0.0, den = 0.0;
-  double b_top = b_bot;  // planck at level 0
-  for (int l = 0; l < nlay; ++l) {
-    const double tau = od[(int64_t)l * od_stride + w];
-    col += tau;
-    double e, f;
-    lw_layer_r(tau, e, f);
-    const double b_b = planck_elem_r(t_hl[l + 1], nu, dnu);
-    const double f_next = f_dn * (1.0 - e) + b_top * (e - f) + b_b * f;
-    double hr = conv[l] * (f_next - f_dn - s_up[(l + 1) * bs + tx] + s_up[l * bs + tx]);
-    if (hr > 0.0) hr = 0.0;  // reorder_spectrum.cpp:175
-    num += hr * dhh[l];
-    den += hr * dh[l];
-    f_dn = f_next;
-    b_top = b_b;
+  for (int l0 = 0; l0 < nlay; l0 += SK_G) {
+    double tau[SK_G], e[SK_G];
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) tau[j] = nxt[j];
+    if (l0 + SK_G < nlay) load_dn(l0 + SK_G);
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) e[j] = trans_one_minus_exp(tau[j], K, tl);
+#pragma unroll
+    for (int j = 0; j < SK_G; ++j) {
+      const int l = l0 + j;
+      if (l < nlay) {  // warp-uniform
+        col += tau[j];
+        const double f_next = f_dn * (1.0 - e[j]) + s_b[(l + 1) * bs + tx];
+        double hr = conv[l] * (f_next - f_dn - s_up[(l + 1) * bs + tx] + s_up[l * bs + tx]);
+        if (hr > 0.0) hr = 0.0;  // reorder_spectrum.cpp:175
+        num += hr * dhh[l];
+        den += hr * dh[l];
+        f_dn = f_next;
+      }
+    }
   }
   double k = num / den;
   if (thr > 0.0 && col < thr) k = -thr + col;  // reorder_spectrum.cpp:187-190
-  key[w] = k;
-  if (column_od) column_od[w] = col;
+  if (valid) {
+    key[w] = k;
+    if (column_od) column_od[w] = col;
+  }
 }
 
 // reorder_spectrum.cpp:197-228; lay = pseudo_height_hl[nlay+1]
@@ -503,7 +575,8 @@ ECCKD_API int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, cons
   const double x0 = log(1.0), x1 = log(100000.0), y0 = 273.15 - 100.0, y1 = 273.15 + 15.0;
   for (int i = 0; i <= nlay; ++i) {
     const double x = log(h_pressure_hl[i]);
-    lay[i] = (x <= x0) ? y0 : (x >= x1) ? y1 : y0 + (y1 - y0) * (x - x0) / (x1 - x0);
+    const double t = (x <= x0) ? y0 : (x >= x1) ? y1 : y0 + (y1 - y0) * (x - x0) / (x1 - x0);
+    lay[i] = (6.62606896e-34 / 1.3806504e-23) / t;  // (h/k)/T_hl, planck_function.cpp:29-33
   }
   double* conv = lay.data() + (nlay + 1);
   double* dh = conv + nlay;
@@ -517,11 +590,16 @@ ECCKD_API int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, cons
   void* d_lay = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 3, lay.size() * sizeof(double), &d_lay));
   ECCKD_TRY(upload_small(ctx, d_lay, lay.data(), lay.size() * sizeof(double)));
-  const int bs = 128;
-  const size_t smem = (size_t)(nlay + 1) * bs * sizeof(double);
+  // two [nlay+1][bs] arrays in shared memory: two blocks of 128 threads per SM at 54 layers
+  int bs = 128;
+  while (bs > 32 && 2 * (size_t)(nlay + 1) * bs * sizeof(double) > 110 * 1024) bs >>= 1;
+  const size_t smem = 2 * (size_t)(nlay + 1) * bs * sizeof(double);
+  ECCKD_REQUIRE(smem <= ctx->smem_optin, ECCKD_PARAMETER_ERROR, "ecckd_sort_key_lw: too many layers for shared memory");
   ECCKD_CUDA_OK(cudaFuncSetAttribute(sort_key_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  TransConst K;
+  trans_const_init(&K, ECCKD_LW_DIFFUSIVITY);
   sort_key_lw_kernel<<<(unsigned)((nwav + bs - 1) / bs), bs, smem, ctx->stream>>>(
-      nlay, nwav, static_cast<const double*>(d_lay), d_wn, d_dwn, d_od, od_stride, thr, d_key, d_column_od);
+      nlay, nwav, static_cast<const double*>(d_lay), d_wn, d_dwn, d_od, od_stride, thr, K, d_key, d_column_od);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }

@@ -46,3 +46,64 @@ def allreduce_counts(count, group=None):
 def shard_columns(ncol: int, rank: int, world: int) -> Tuple[int, int]:
     """[begin, end) of this rank's columns for the flux solver (independent columns: no exchange)."""
     return (ncol * rank) // world, (ncol * (rank + 1)) // world
+
+
+# ------------------------------------------------------------------ sort keys + ranking (SURVEY.md 8e row 2)
+def allgather_wavenumber_shards(local, nwav: int, rank: int, world: int, group=None, align: int = CHUNK):
+    """All-gather of a per-wavenumber torch vector whose rank-r piece covers shard_range(nwav, r, world):
+    every rank gets the full [nwav] vector (the sort keys of find_g_points: each rank computes the
+    keys of its range, the stable radix sort is then replicated on every rank - deterministic and
+    bit-exact, no exchange inside the sort).  Pieces differ by at most one chunk, so they are padded
+    to the longest before the collective (NCCL and gloo want equal sizes)."""
+    import torch
+    import torch.distributed as dist
+
+    spans = [shard_range(nwav, r, world, align) for r in range(world)]
+    lo, hi = spans[rank]
+    if local.numel() != hi - lo:
+        raise ValueError("local piece does not match this rank's wavenumber range")
+    if world == 1:
+        return local.clone()
+    longest = max(b - a for a, b in spans)
+    padded = torch.zeros(longest, dtype=local.dtype, device=local.device)
+    padded[: hi - lo] = local
+    pieces = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(pieces, padded, group=group)
+    return torch.cat([p[: b - a] for p, (a, b) in zip(pieces, spans)])
+
+
+def sharded_sort_keys(key_fn, nwav: int, rank: int, world: int, group=None):
+    """key_fn(lo, hi) -> torch vector of the sort keys of wavenumbers [lo, hi) (e.g. a call of
+    ecckd_sort_key_lw_dev on the column slice od[:, lo:hi] with od_stride = nwav).  Returns the full
+    key vector on every rank; rank it with rank_bands_dev (replicated)."""
+    lo, hi = shard_range(nwav, rank, world)
+    return allgather_wavenumber_shards(key_fn(lo, hi), nwav, rank, world, group)
+
+
+# ------------------------------------------------------------------ forward cost (SURVEY.md 8e row 4)
+def sharded_forward_cost(cost_fn, nprof: int, rank: int, world: int, per_profile: dict, shared: dict, group=None,
+                         device=None):
+    """optimize_lut's forward cost of one scene with its profiles (columns) sharded over the ranks:
+    cost_fn(**shared, **{name: array[lo:hi]}) is api.cost_function_ckd_lw / _sw (or, in the CPU tests
+    of this logic, the oracle) on this rank's profiles; the only exchange is ONE all-reduce of
+    {cost_total, penalty} (both are plain sums over profiles: solve_adept.cpp:107-116,157,183).
+    `per_profile` holds the arguments whose leading dimension is the profile, `shared` the rest
+    (None entries pass through).  Returns dict(cost_total, penalty, cost_profile=<this rank's>, range=(lo, hi))."""
+    import torch
+    import torch.distributed as dist
+
+    lo, hi = shard_columns(nprof, rank, world)
+    acc = torch.zeros(2, dtype=torch.float64, device=device if device is not None else "cpu")
+    local = None
+    if hi > lo:
+        kw = dict(shared)
+        for name, a in per_profile.items():
+            kw[name] = None if a is None else a[lo:hi]
+        local = cost_fn(**kw)
+        acc[0] = float(local["cost_total"])
+        acc[1] = float(local["penalty"])
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=group)
+    tot = acc.cpu().numpy()
+    return dict(cost_total=float(tot[0]), penalty=float(tot[1]),
+                cost_profile=None if local is None else local["cost_profile"], range=(lo, hi))

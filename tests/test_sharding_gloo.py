@@ -95,3 +95,97 @@ def test_two_rank_wavenumber_sharding_matches_unsharded():
         p.join(timeout=240)
         assert p.exitcode == 0
     assert q.get(timeout=10) < 1e-12
+
+
+# ------------------------------------------------------------------ sort keys and forward cost
+def _oracle_cost_fn(O, weights):
+    """The oracle standing in for api.cost_function_ckd_lw on a shard of profiles."""
+    def fn(pressure_hl, planck_hl, surf_emissivity, surf_planck, optical_depth, flux_dn, flux_up, hr):
+        costs = []
+        for i in range(pressure_hl.shape[0]):
+            lw = np.diff(np.sqrt(pressure_hl[i]))
+            costs.append(O.calc_cost_function_ckd_lw(pressure_hl[i], planck_hl[i], surf_emissivity[i], surf_planck[i],
+                                                     np.maximum(optical_depth[i], 0.0), flux_dn[i], flux_up[i], hr[i],
+                                                     *weights, lw / lw.sum()))
+        pen = 1.0e4 * float((np.minimum(optical_depth, 0.0) ** 2).sum())
+        return dict(cost_profile=np.array(costs), penalty=pen, cost_total=pen + float(np.sum(costs)))
+    return fn
+
+
+def _cost_scene(O, nprof=5, nlay=12, ng=8):
+    from tests.test_reference_sources import ckd_cost_case
+
+    cases = [ckd_cost_case(nlay=nlay, ng=ng, nband=ng, seed=900 + i) for i in range(nprof)]
+    rng = np.random.default_rng(4)
+    s = dict(pressure_hl=np.stack([c["p"] for c in cases]), planck_hl=np.stack([c["planck"] for c in cases]),
+             surf_planck=np.stack([c["surf"] for c in cases]), optical_depth=np.stack([c["od"] for c in cases]),
+             surf_emissivity=rng.uniform(0.9, 1.0, (nprof, ng)))
+    s["optical_depth"][1, 2, 3] = -0.02
+    s["optical_depth"][nprof - 1, 0, 0] = -0.3
+    dn, up, hr = [], [], []
+    for i in range(nprof):
+        a, b = O.radiative_transfer_lw(s["planck_hl"][i], np.maximum(s["optical_depth"][i], 0) * 1.1,
+                                       s["surf_emissivity"][i], s["surf_planck"][i])
+        dn.append(a), up.append(b), hr.append(O.heating_rate(s["pressure_hl"][i], a, b))
+    s.update(flux_dn=np.stack(dn), flux_up=np.stack(up), hr=np.stack(hr))
+    return s
+
+
+def _worker2(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.oracle_lib import oracle
+
+        O = oracle()
+        # (1) sort keys: each rank computes its wavenumber range, all-gather, replicated stable rank
+        c = S.lw_spectrum_case(nlay=9, nwav=5003, ng=4, nband=1, seed=8, zero_frac=0.0, vmr=1.0)
+        od = c["od"] * 3e4
+        key_full, _ = O.sort_key_lw(c["pressure_hl"], c["wavenumber"], c["d_wavenumber"], od, 0.5)
+
+        def key_fn(lo, hi):
+            k, _ = O.sort_key_lw(c["pressure_hl"], c["wavenumber"][lo:hi], c["d_wavenumber"][lo:hi],
+                                 np.ascontiguousarray(od[:, lo:hi]), 0.5)
+            return torch.from_numpy(k)
+
+        key = sharding.sharded_sort_keys(key_fn, c["nwav"], rank, world).numpy()
+        b1, b2 = [c["wavenumber"][0], c["wavenumber"][2000]], [c["wavenumber"][2000], c["wavenumber"][-1]]
+        same_key = bool(np.array_equal(key, key_full, equal_nan=True))
+        same_rank = all(np.array_equal(a, b) for a, b in zip(O.rank_bands(c["wavenumber"], key, b1, b2),
+                                                             O.rank_bands(c["wavenumber"], key_full, b1, b2)))
+        # (2) forward cost: 5 profiles over 2 ranks (2 + 3), one all-reduce of {cost_total, penalty}
+        weights = (0.2, 0.2, 0.8, 0.1)
+        fn = _oracle_cost_fn(O, weights)
+        s = _cost_scene(O)
+        got = sharding.sharded_forward_cost(fn, 5, rank, world, per_profile=s, shared={})
+        ref = fn(**s)
+        lo, hi = got["range"]
+        ok_prof = bool(np.array_equal(got["cost_profile"], ref["cost_profile"][lo:hi]))
+        if rank == 0:
+            q.put((same_key, same_rank, ok_prof, abs(got["cost_total"] - ref["cost_total"]) / ref["cost_total"],
+                   abs(got["penalty"] - ref["penalty"]) / ref["penalty"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_sort_keys_and_forward_cost_match_unsharded():
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker2, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=240)
+        assert p.exitcode == 0
+    same_key, same_rank, ok_prof, d_cost, d_pen = q.get(timeout=10)
+    assert same_key and same_rank and ok_prof
+    assert d_cost < 1e-13 and d_pen < 1e-13
