@@ -302,26 +302,49 @@ __device__ __forceinline__ int rs_digit(unsigned long long k, uint32_t v, int sh
   return (shift == RS_SEG_PASS) ? (int)seg[v] : (int)((k >> shift) & 0xFFull);
 }
 
-// per-tile digit histogram -> hist[digit][tile]
+// per-tile digit histogram -> hist[digit][tile].  Per-warp histograms in shared memory (atomics only
+// contend inside a warp); a warp whose 32 digits agree (smooth keys, constant high digits) adds once.
 __global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(int64_t n, const unsigned long long* __restrict__ keys,
                                                                 const uint32_t* __restrict__ vals,
                                                                 const uint8_t* __restrict__ seg, int shift, int ntiles,
                                                                 uint32_t* __restrict__ hist) {
-  __shared__ uint32_t s_h[256];
-  s_h[threadIdx.x] = 0;
+  __shared__ uint32_t s_h[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) s_h[w][threadIdx.x] = 0;
   __syncthreads();
   const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+  uint32_t* h = s_h[warp];
+  auto count = [&](int digit) {  // digit < 0: out of range
+    const int d0 = __shfl_sync(0xffffffffu, digit, 0);
+    if (__all_sync(0xffffffffu, digit == d0)) {
+      if (lane == 0 && d0 >= 0) h[d0] += 32u;
+      __syncwarp();
+    } else {
+      if (digit >= 0) atomicAdd(&h[digit], 1u);
+      __syncwarp();
+    }
+  };
+  if (shift != RS_SEG_PASS && base + RS_TILE <= n) {  // full tile: two keys per load
+    const ulonglong2* k2 = reinterpret_cast<const ulonglong2*>(keys + base);
 #pragma unroll 4
-  for (int r = 0; r < RS_ITEMS; ++r) {
-    const int64_t i = base + r * RS_THREADS + threadIdx.x;
-    int digit = 256 + (int)(threadIdx.x & 31);  // out of range: a group of its own, not counted
-    if (i < n) digit = rs_digit(keys[i], shift == RS_SEG_PASS ? vals[i] : 0u, shift, seg);
-    // one shared-memory atomic per distinct digit of the warp (smooth keys put whole warps on one bin)
-    const unsigned peers = __match_any_sync(0xffffffffu, digit);
-    if (digit < 256 && (peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(&s_h[digit], (uint32_t)__popc(peers));
+    for (int r = 0; r < RS_ITEMS / 2; ++r) {
+      const ulonglong2 kk = k2[r * RS_THREADS + threadIdx.x];
+      count((int)((kk.x >> shift) & 0xFFull));
+      count((int)((kk.y >> shift) & 0xFFull));
+    }
+  } else {
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; ++r) {
+      const int64_t i = base + r * RS_THREADS + threadIdx.x;
+      count((i < n) ? rs_digit(keys[i], shift == RS_SEG_PASS ? vals[i] : 0u, shift, seg) : -1);
+    }
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = s_h[threadIdx.x];
+  uint32_t t = 0;
+#pragma unroll
+  for (int w = 0; w < RS_WARPS; ++w) t += s_h[w][threadIdx.x];
+  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = t;
 }
 
 // block d: exclusive scan of hist[d][0..ntiles) in place, the digit's total to totals[d]
@@ -639,7 +662,7 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
                 "Failure to interpret wavenumber1 and wavenumber2 as a list of band boundaries");
   // scratch layout (slot 1): k0 | k1 | v0 | v1 | g_index | seg | hist (+ digit totals) | band meta
   const int ntiles_max = (int)((nwav + RS_TILE - 1) / RS_TILE);
-  const size_t kbytes = (size_t)nwav * sizeof(unsigned long long);
+  const size_t kbytes = ((size_t)nwav * sizeof(unsigned long long) + 255) & ~size_t(255);  // 16-byte loads of k1
   const size_t vbytes = ((size_t)nwav * sizeof(uint32_t) + 255) & ~size_t(255);
   const size_t sbytes = ((size_t)nwav + 255) & ~size_t(255);
   const size_t hbytes = ((size_t)256 * (ntiles_max + 1) * sizeof(uint32_t) + 255) & ~size_t(255);
