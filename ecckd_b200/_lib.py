@@ -34,6 +34,16 @@ class GasTable(C.Structure):
     ]
 
 
+class CostScene(C.Structure):
+    """struct ecckd_cost_scene (include/ecckd_b200.h)."""
+
+    _fields_ = [("nprof", C.c_int32), ("nalbedo", C.c_int32)] + [(n, C.c_void_p) for n in (
+        "d_pressure_hl", "d_optical_depth", "d_flux_dn", "d_flux_up", "d_hr", "d_spectral_flux_dn_surf",
+        "d_spectral_flux_up_toa", "d_layer_weight", "d_relative_ckd_flux_dn", "d_relative_ckd_flux_up", "d_planck_hl",
+        "d_surf_emissivity", "d_surf_planck", "d_cos_sza", "d_ssi", "h_albedo", "d_spectral_boundary_weights",
+        "d_cost_profile")]
+
+
 def header_symbols(path: str = HEADER_PATH):
     """Names of every function the header declares."""
     text = open(path).read()
@@ -135,6 +145,8 @@ def _declare(L):
                                            dbl, dbl, vp, dbl, dbl, vp, vp, vp, vp, vp, vp],
         "ecckd_cost_function_ckd_sw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dbl,
                                            dbl, dbl, vp, vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp],
+        "ecckd_cost_function_ckd_scenes_dev": [vp, i32, i32, vp, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp,
+                                               vp, vp],
     }
     for name, argtypes in sigs.items():
         if hasattr(L, name):  # symbol-completeness is asserted by tests/test_abi.py

@@ -794,3 +794,30 @@ def cost_function_ckd_sw(ctx, cos_sza, pressure_hl, ssi, albedo, optical_depth, 
     if d_pb is not None:
         out["cost_fn_per_band"] = d_pb.numpy()
     return out
+
+
+def cost_function_ckd_scenes_dev(ctx, is_sw, scenes: Sequence[dict], nlay, ng, nband, flux_weight, flux_profile_weight,
+                                 broadband_weight, spectral_boundary_weight=0.0, pressure_weight_power=0.5,
+                                 negative_od_penalty=1.0e4, d_band_mapping=None, d_cost_fn_per_band=None,
+                                 d_cost_scene=None, d_penalty_scene=None, d_cost_total=None):
+    """The forward cost of several scenes in one launch (ecckd_cost_function_ckd_scenes_dev: the scene loop of
+    solve_adept.cpp:96-199).  Every scene is a dict of the fields of struct ecckd_cost_scene without the d_/h_ prefix
+    (device arrays; `albedo` a host array), plus nprof."""
+    arr = (_lib.CostScene * len(scenes))()
+    keep = []
+    for k, sc in enumerate(scenes):
+        arr[k].nprof = int(sc["nprof"])
+        for name, _ in _lib.CostScene._fields_[2:]:
+            if name == "h_albedo":
+                continue
+            setattr(arr[k], name, _ptr(sc.get(name[2:])))
+        if sc.get("albedo") is not None:
+            a, ap = _h(np.atleast_1d(sc["albedo"]))
+            keep.append(a)
+            arr[k].h_albedo = ap
+            arr[k].nalbedo = a.size
+    check(_lib.lib().ecckd_cost_function_ckd_scenes_dev(
+        ctx.handle, int(bool(is_sw)), len(scenes), C.addressof(arr), nlay, ng, nband, float(flux_weight),
+        float(flux_profile_weight), float(broadband_weight), float(spectral_boundary_weight),
+        float(pressure_weight_power), float(negative_od_penalty), _ptr(d_band_mapping), _ptr(d_cost_fn_per_band),
+        _ptr(d_cost_scene), _ptr(d_penalty_scene), _ptr(d_cost_total)))

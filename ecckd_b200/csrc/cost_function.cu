@@ -487,9 +487,9 @@ struct CkdCostParams {
 
 // CTA = profile, thread = g point for the sweep; the (tiny) cost terms follow the reference's
 // evaluation order with sequential sums.
-__global__ void ckd_cost_kernel(const CkdCostParams p) {
+__device__ __forceinline__ void ckd_cost_body(const CkdCostParams& p, const int ip) {
   extern __shared__ double sm[];
-  const int ip = blockIdx.x, nlay = p.nlay, nlev = nlay + 1, ng = p.ng, nband = p.nband;
+  const int nlay = p.nlay, nlev = nlay + 1, ng = p.ng, nband = p.nband;
   double* fdo = sm;                          // [nlev][ng]
   double* fuo = fdo + (size_t)nlev * ng;     // [nlev][ng]
   double* fd = fuo + (size_t)nlev * ng;      // [nlev][nband]
@@ -741,6 +741,67 @@ __global__ void ckd_cost_kernel(const CkdCostParams p) {
   }
 }
 
+__global__ void ckd_cost_kernel(const CkdCostParams p) { ckd_cost_body(p, (int)blockIdx.x); }
+
+// Several scenes (LblFluxes objects of the training set, solve_adept.cpp:96-199) in one launch:
+// CTA = (scene, profile); scene_start[s] = first CTA of scene s.  The scene's parameters are copied
+// to shared memory once per CTA.
+__global__ void ckd_cost_scenes_kernel(const CkdCostParams* __restrict__ scenes, const int* __restrict__ scene_start,
+                                       int nscene) {
+  __shared__ CkdCostParams sp;
+  __shared__ int s_first;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = nscene;  // last scene with scene_start <= blockIdx.x
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (scene_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+    }
+    s_first = scene_start[lo];
+    sp = scenes[lo];
+  }
+  __syncthreads();
+  ckd_cost_body(sp, (int)blockIdx.x - s_first);
+}
+
+// per scene: penalties, then profile costs, in profile order; per-band costs of the scene
+__global__ void ckd_cost_scene_sums_kernel(const CkdCostParams* __restrict__ scenes, int nband,
+                                           double* __restrict__ cost_scene, double* __restrict__ penalty_scene,
+                                           double* __restrict__ band_scene) {
+  const CkdCostParams& p = scenes[blockIdx.x];
+  if (threadIdx.x == 0) {
+    double pen = 0.0, c = 0.0;
+    for (int i = 0; i < p.nprof; ++i) pen += p.penalty_profile[i];
+    for (int i = 0; i < p.nprof; ++i) c += p.cost_profile[i];
+    penalty_scene[blockIdx.x] = pen;
+    cost_scene[blockIdx.x] = pen + c;
+  }
+  if (band_scene && p.cost_band_profile) {
+    for (int ib = threadIdx.x; ib < nband; ib += blockDim.x) {
+      double t = 0.0;
+      for (int i = 0; i < p.nprof; ++i) t += p.cost_band_profile[(size_t)i * nband + ib];
+      band_scene[(size_t)blockIdx.x * nband + ib] = t;
+    }
+  }
+}
+
+// totals over the scenes in scene order (`cost +=` of solve_adept.cpp:157,183)
+__global__ void ckd_cost_scene_total_kernel(int nscene, int nband, const double* __restrict__ cost_scene,
+                                            const double* __restrict__ band_scene, double* __restrict__ cost_total,
+                                            double* __restrict__ cost_fn_per_band) {
+  if (threadIdx.x == 0 && cost_total) {
+    double c = 0.0;
+    for (int s = 0; s < nscene; ++s) c += cost_scene[s];
+    *cost_total = c;
+  }
+  if (cost_fn_per_band && band_scene) {
+    for (int ib = threadIdx.x; ib < nband; ib += blockDim.x) {
+      double t = cost_fn_per_band[ib];
+      for (int s = 0; s < nscene; ++s) t += band_scene[(size_t)s * nband + ib];
+      cost_fn_per_band[ib] = t;
+    }
+  }
+}
+
 // cost = sum over profiles in profile order (solve_adept.cpp:96-199 `cost +=`), penalties first per scene
 __global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __restrict__ cost_profile,
                                       const double* __restrict__ penalty_profile,
@@ -762,8 +823,8 @@ __global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __rest
   }
 }
 
-static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_profile, double* d_cost_total,
-                           double* d_penalty_total, double* d_cost_fn_per_band, const char* who) {
+// checks the dimensions of a scene and returns the dynamic shared memory its CTAs need
+static int ckd_cost_smem(ecckd_ctx* ctx, CkdCostParams& p, const char* who, size_t* smem_out) {
   const int nlev = p.nlay + 1;
   trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
   ECCKD_REQUIRE(p.nprof > 0 && p.nlay > 0 && p.ng > 0 && p.nband > 0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
@@ -772,9 +833,17 @@ static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_prof
   const size_t ndbl = (size_t)2 * nlev * p.ng + (size_t)2 * nlev * p.nband + (size_t)p.nlay * p.nband + 2 * p.nlay +
                       std::max(std::max(p.nband, nlev), p.ng) + 8 + 3 * nlev + p.nband + 2 + 256;
   const size_t smem = ndbl * sizeof(double);
-  ECCKD_REQUIRE(smem <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
+  ECCKD_REQUIRE(smem + sizeof(CkdCostParams) + 64 <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
                 "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, p.ng, nlev, smem,
                 ctx->smem_optin);
+  *smem_out = smem;
+  return ECCKD_OK;
+}
+
+static int launch_ckd_cost(ecckd_ctx* ctx, CkdCostParams& p, double* d_cost_profile, double* d_cost_total,
+                           double* d_penalty_total, double* d_cost_fn_per_band, const char* who) {
+  size_t smem = 0;
+  ECCKD_TRY(ckd_cost_smem(ctx, p, who, &smem));
   ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   void* base = nullptr;
   const size_t b_prof = ((size_t)p.nprof * sizeof(double) + 255) & ~(size_t)255;
@@ -1038,4 +1107,109 @@ ECCKD_API int ecckd_cost_function_ckd_sw_dev(
   p.broadband_weight = broadband_weight; p.negative_od_penalty = negative_od_penalty;
   p.pressure_weight_power = pressure_weight_power;
   return launch_ckd_cost(ctx, p, d_cost_profile, d_cost_total, d_penalty_total, d_cost_fn_per_band, who);
+}
+
+// ------------------------------------------------------------------ several scenes in one launch
+ECCKD_API int ecckd_cost_function_ckd_scenes_dev(ecckd_ctx* ctx, int is_sw, int nscene, const ecckd_cost_scene* scenes,
+                                                 int nlay, int ng, int nband, double flux_weight,
+                                                 double flux_profile_weight, double broadband_weight,
+                                                 double spectral_boundary_weight, double pressure_weight_power,
+                                                 double negative_od_penalty, const int32_t* d_band_mapping,
+                                                 double* d_cost_fn_per_band, double* d_cost_scene,
+                                                 double* d_penalty_scene, double* d_cost_total) {
+  const char* who = "ecckd_cost_function_ckd_scenes";
+  ECCKD_REQUIRE(ctx && scenes && nscene > 0, ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  std::vector<CkdCostParams> ps((size_t)nscene);
+  std::vector<int> start((size_t)nscene + 1, 0);
+  std::vector<double> albedos;
+  std::vector<size_t> alb_off((size_t)nscene, 0);
+  size_t smem = 0;
+  for (int k = 0; k < nscene; ++k) {
+    const ecckd_cost_scene& sc = scenes[k];
+    CkdCostParams& p = ps[k];
+    p = CkdCostParams{};
+    ECCKD_REQUIRE(sc.d_pressure_hl && sc.d_optical_depth && sc.d_flux_dn && sc.d_flux_up && sc.d_hr, ECCKD_PARAMETER_ERROR,
+                  "%s: scene %d: NULL argument", who, k);
+    ECCKD_REQUIRE((sc.d_relative_ckd_flux_dn == nullptr) == (sc.d_relative_ckd_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                  "%s: scene %d: relative-to fluxes must both be given or both be NULL", who, k);
+    p.sw = is_sw ? 1 : 0; p.nprof = sc.nprof; p.nlay = nlay; p.ng = ng; p.nband = nband;
+    p.pressure_hl = sc.d_pressure_hl; p.optical_depth = sc.d_optical_depth; p.flux_dn = sc.d_flux_dn;
+    p.flux_up = sc.d_flux_up; p.hr = sc.d_hr; p.spectral_flux_dn_surf = sc.d_spectral_flux_dn_surf;
+    p.layer_weight = sc.d_layer_weight; p.rel_dn = sc.d_relative_ckd_flux_dn; p.rel_up = sc.d_relative_ckd_flux_up;
+    p.band_mapping = d_band_mapping; p.flux_weight = flux_weight; p.flux_profile_weight = flux_profile_weight;
+    p.broadband_weight = broadband_weight; p.negative_od_penalty = negative_od_penalty;
+    p.pressure_weight_power = pressure_weight_power;
+    if (!is_sw) {
+      ECCKD_REQUIRE(sc.d_planck_hl && sc.d_surf_emissivity && sc.d_surf_planck, ECCKD_PARAMETER_ERROR,
+                    "%s: scene %d: NULL longwave argument", who, k);
+      p.nemis = d_band_mapping ? nband : ng;
+      p.up_in_bb = 1;
+      p.planck_hl = sc.d_planck_hl; p.surf_emissivity = sc.d_surf_emissivity; p.surf_planck = sc.d_surf_planck;
+      p.spectral_flux_up_toa = sc.d_spectral_flux_up_toa; p.spectral_boundary_weight = spectral_boundary_weight;
+    } else {
+      ECCKD_REQUIRE(sc.d_cos_sza && sc.d_ssi && sc.h_albedo && sc.nalbedo > 0, ECCKD_PARAMETER_ERROR,
+                    "%s: scene %d: NULL shortwave argument", who, k);
+      bool all_le0 = true, all_gt0 = true;  // calc_cost_function_sw.cpp:149,250
+      for (int j = 0; j < sc.nalbedo; ++j) {
+        if (!(sc.h_albedo[j] <= 0.0)) all_le0 = false;
+        if (!(sc.h_albedo[j] > 0.0)) all_gt0 = false;
+      }
+      ECCKD_REQUIRE(all_le0 || d_band_mapping, ECCKD_PARAMETER_ERROR,
+                    "%s: a non-zero albedo is indexed by band_mapping (calc_cost_function_sw.cpp:156)", who);
+      p.nalbedo = sc.nalbedo; p.up_in_bb = all_gt0 ? 1 : 0; p.direct_only = all_le0 ? 1 : 0;
+      p.cos_sza = sc.d_cos_sza; p.ssi = sc.d_ssi; p.spectral_boundary_weights = sc.d_spectral_boundary_weights;
+      alb_off[k] = albedos.size();
+      albedos.insert(albedos.end(), sc.h_albedo, sc.h_albedo + sc.nalbedo);
+    }
+    size_t sm_k = 0;
+    ECCKD_TRY(ckd_cost_smem(ctx, p, who, &sm_k));
+    smem = std::max(smem, sm_k);
+    start[k + 1] = start[k] + sc.nprof;
+  }
+  const int ntot = start[nscene];
+  // scratch: per-profile penalties, costs (where the caller does not want them) and per-band costs,
+  // per-scene band sums, the albedos, the scene table
+  const bool bands = is_sw && d_cost_fn_per_band;
+  const size_t b_prof = ((size_t)ntot * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_band = bands ? (((size_t)ntot * nband * sizeof(double) + 255) & ~(size_t)255) : 0;
+  const size_t b_sband = bands ? (((size_t)nscene * nband * sizeof(double) + 255) & ~(size_t)255) : 0;
+  const size_t b_alb = (albedos.size() * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_scal = (2 * (size_t)nscene * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_tab = ((size_t)nscene * sizeof(CkdCostParams) + 255) & ~(size_t)255;
+  const size_t b_start = (((size_t)nscene + 1) * sizeof(int) + 255) & ~(size_t)255;
+  void* base = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 2, 2 * b_prof + b_band + b_sband + b_alb + b_scal + b_tab + b_start, &base));
+  char* c = static_cast<char*>(base);
+  double* d_pen = reinterpret_cast<double*>(c);
+  double* d_cost = reinterpret_cast<double*>(c + b_prof);
+  double* d_band = bands ? reinterpret_cast<double*>(c + 2 * b_prof) : nullptr;
+  double* d_sband = bands ? reinterpret_cast<double*>(c + 2 * b_prof + b_band) : nullptr;
+  double* d_alb = reinterpret_cast<double*>(c + 2 * b_prof + b_band + b_sband);
+  double* d_scal = reinterpret_cast<double*>(c + 2 * b_prof + b_band + b_sband + b_alb);
+  CkdCostParams* d_tab = reinterpret_cast<CkdCostParams*>(c + 2 * b_prof + b_band + b_sband + b_alb + b_scal);
+  int* d_start = reinterpret_cast<int*>(c + 2 * b_prof + b_band + b_sband + b_alb + b_scal + b_tab);
+  for (int k = 0; k < nscene; ++k) {
+    CkdCostParams& p = ps[k];
+    p.penalty_profile = d_pen + start[k];
+    p.cost_profile = scenes[k].d_cost_profile ? scenes[k].d_cost_profile : d_cost + start[k];
+    p.cost_band_profile = bands ? d_band + (size_t)start[k] * nband : nullptr;
+    if (is_sw) p.albedo = d_alb + alb_off[k];
+  }
+  if (!albedos.empty()) ECCKD_TRY(upload_small(ctx, d_alb, albedos.data(), albedos.size() * sizeof(double)));
+  ECCKD_TRY(upload_small(ctx, d_tab, ps.data(), ps.size() * sizeof(CkdCostParams)));
+  ECCKD_TRY(upload_small(ctx, d_start, start.data(), start.size() * sizeof(int)));
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_scenes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = std::min(1024, std::max(128, (ng + 31) / 32 * 32));
+  ckd_cost_scenes_kernel<<<ntot, threads, smem, ctx->stream>>>(d_tab, d_start, nscene);
+  ECCKD_LAUNCH_CHECK(ctx);
+  double* cs = d_cost_scene ? d_cost_scene : d_scal;
+  double* pn = d_penalty_scene ? d_penalty_scene : d_scal + nscene;
+  ckd_cost_scene_sums_kernel<<<nscene, 64, 0, ctx->stream>>>(d_tab, nband, cs, pn, d_sband);
+  ECCKD_LAUNCH_CHECK(ctx);
+  if (d_cost_total || bands) {
+    ckd_cost_scene_total_kernel<<<1, 64, 0, ctx->stream>>>(nscene, nband, cs, d_sband, d_cost_total,
+                                                           bands ? d_cost_fn_per_band : nullptr);
+    ECCKD_LAUNCH_CHECK(ctx);
+  }
+  return ECCKD_OK;
 }

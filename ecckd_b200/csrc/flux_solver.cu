@@ -523,13 +523,16 @@ __host__ __device__ inline size_t run_ckd_col_smem(int nlay, int ngas) {
   return (((size_t)nlay * sizeof(Interp) + (size_t)nlay * ngas * sizeof(GasLayer)) + 15) & ~(size_t)15;
 }
 
-__global__ void run_ckd_kernel(const RunCkdParams p) {
+__global__ void __launch_bounds__(1024, 1) run_ckd_kernel(const RunCkdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ const double* s_molar_abs[RUN_CKD_MAX_GAS];
-  if (threadIdx.y == 0 && threadIdx.x < p.ngas) s_molar_abs[threadIdx.x] = p.gases[threadIdx.x].molar_abs;
+  if (threadIdx.y == 0 && threadIdx.z == 0 && threadIdx.x < p.ngas) s_molar_abs[threadIdx.x] = p.gases[threadIdx.x].molar_abs;
   // blockDim.y columns per block: neighbouring columns walk the layers at the same pace and read the
   // same LUT rows (same pressure index, a handful of temperature indices), so the gathers of the
   // block's warps hit in L1 instead of each going to L2.  A column past the end repeats the last one.
+  // blockDim.z warps share a column and take every blockDim.z-th layer: the per-column interpolation
+  // state in shared memory caps the resident columns at ~20 per SM, and one warp per column left the
+  // gathers latency-bound.
   const int icol = min((int)(blockIdx.x * blockDim.y + threadIdx.y), p.ncol - 1);
   const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
   const size_t col_bytes = run_ckd_col_smem(nlay, ngas);
@@ -541,7 +544,7 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
   // everything of ckd_model.cpp:962-1009 that does not depend on the g point, once per (layer, gas):
   // interpolation indices and weights, the concentration weight, and for a look-up-table gas its
   // concentration index (one log() per layer instead of one per layer and g point)
-  for (int l = threadIdx.x; l < nlay; l += blockDim.x) {
+  for (int l = threadIdx.z * blockDim.x + threadIdx.x; l < nlay; l += blockDim.x * blockDim.z) {
     const double t_fl = (t_hl[l] * p_hl[l] + t_hl[l + 1] * p_hl[l + 1]) / (p_hl[l] + p_hl[l + 1]);
     const Interp it = make_interp(p_hl[l], p_hl[l + 1], t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
     s_it[l] = it;
@@ -577,7 +580,7 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
   for (int g = threadIdx.x; g < ng; g += blockDim.x) {
     // optical depth: sum over gases, clamp (run_ckd.cpp:265-317).  (Keeping the table values at ip0 + 1
     // in registers for the next layer was measured slower: 7.1 vs 6.3 ms for 65536 x 54 x 32.)
-    for (int l = 0; l < nlay; ++l) {
+    for (int l = threadIdx.z; l < nlay; l += blockDim.z) {
       double tau = 0.0;
       const Interp it = s_it[l];
       const size_t o00 = it.it0 * sT + it.ip0 * sP + g;
@@ -602,17 +605,20 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
     const int64_t hl0 = (int64_t)icol * (nlay + 1) * ng + g;
     if (!p.is_sw) {
       // Planck function at half levels and surface (run_ckd.cpp:131-132)
+      if (!(p.flux_dn && p.flux_up)) {  // no sweep here: the levels are shared out over the column's warps
+        if (p.planck_hl) {
+          for (int l = threadIdx.z; l <= nlay; l += blockDim.z)
+            p.planck_hl[hl0 + (int64_t)l * ng] = planck_interp(t_hl[l], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+        }
+        if (p.planck_surf && threadIdx.z == 0)
+          p.planck_surf[(int64_t)icol * ng + g] = planck_interp(t_hl[nlay], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+        continue;
+      }
+      if (threadIdx.z != 0) continue;  // the sweeps below are serial in the layers: one warp per column
       double b_top = planck_interp(t_hl[0], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
       if (p.planck_hl) p.planck_hl[hl0] = b_top;
       const double b_surf = planck_interp(t_hl[nlay], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
       if (p.planck_surf) p.planck_surf[(int64_t)icol * ng + g] = b_surf;
-      if (!(p.flux_dn && p.flux_up)) {
-        if (p.planck_hl) {
-          for (int l = 1; l <= nlay; ++l)
-            p.planck_hl[hl0 + (int64_t)l * ng] = planck_interp(t_hl[l], p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
-        }
-        continue;
-      }
       double f_dn = 0.0;
       p.flux_dn[hl0] = 0.0;
       for (int l = 0; l < nlay; ++l) {
@@ -636,7 +642,7 @@ __global__ void run_ckd_kernel(const RunCkdParams p) {
         p.flux_up[hl0 + (int64_t)l * ng] = f_up;
         b_bot = b_t;
       }
-    } else if (p.flux_dn) {
+    } else if (p.flux_dn && threadIdx.z == 0) {
       // direct beam at mu0 = 0.5 through gas + Rayleigh (run_ckd.cpp:360-365)
       const double mu0 = 0.5;
       const double minus_sec = -1.0 / mu0;
@@ -1018,7 +1024,11 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     p.flux_dn = nullptr;
     p.flux_up = nullptr;
   }
-  run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols), col_smem * cols, ctx->stream>>>(p);
+  // warps per column (each takes every lz-th layer): fill the SM's warp slots
+  int lz = 4;  // measured on the B200 (65536 x 54 x 32): 7.1 / 6.4 / 4.6 / 4.2 ms for 1 / 2 / 3 / 4 warps per column
+  while (lz > 1 && (threads * cols * lz > 1024 || lz > nlay)) --lz;
+  if (const char* e = getenv("ECCKD_RUN_CKD_LZ")) lz = std::max(1, std::min(atoi(e), 1024 / (threads * cols)));
+  run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
   if (lw_staged) {
     if (!m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)

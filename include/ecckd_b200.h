@@ -530,6 +530,44 @@ int ecckd_cost_function_ckd_sw_dev(
     const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_profile, double* d_cost_total,
     double* d_penalty_total);
 
+/* The forward cost of several scenes of optimize_lut's training set in ONE launch: the loop over
+ * LblFluxes objects of src/ecckd/solve_adept.cpp:96-199 (each iteration = one call of the two entry
+ * points above).  A scene's kernel has only nprof CTAs (50-150) and is latency-bound on its own; the
+ * batch fills the GPU.  One struct per scene, its fields the per-scene arguments of
+ * ecckd_cost_function_ckd_lw_dev / _sw_dev (device pointers except h_albedo; the fields of the other
+ * spectral region are ignored); nlay, ng, nband, the weights and d_band_mapping are shared by the
+ * scenes, as they are in solve_adept.  Outputs (device, any may be NULL): d_cost_scene[nscene] =
+ * penalty + sum of the scene's profile costs in profile order, d_penalty_scene[nscene],
+ * d_cost_total[1] = sum of d_cost_scene in scene order, d_cost_fn_per_band[nband] (shortwave) added to. */
+typedef struct ecckd_cost_scene {
+  int32_t nprof;
+  int32_t nalbedo;                           /* shortwave */
+  const double* d_pressure_hl;               /* [nprof][nlay+1] */
+  const double* d_optical_depth;             /* [nprof][nlay][ng] */
+  const double* d_flux_dn;                   /* [nprof][nlay+1][nband] */
+  const double* d_flux_up;                   /* [nprof][nlay+1][nband] */
+  const double* d_hr;                        /* [nprof][nlay][nband] */
+  const double* d_spectral_flux_dn_surf;     /* [nprof][ng] or NULL */
+  const double* d_spectral_flux_up_toa;      /* [nprof][ng] or NULL (longwave) */
+  const double* d_layer_weight;              /* [nprof][nlay] or NULL */
+  const double* d_relative_ckd_flux_dn;      /* [nprof][nlay+1][ng] or NULL */
+  const double* d_relative_ckd_flux_up;
+  const double* d_planck_hl;                 /* longwave [nprof][nlay+1][ng] */
+  const double* d_surf_emissivity;           /* longwave [nprof][nband or ng] */
+  const double* d_surf_planck;               /* longwave [nprof][ng] */
+  const double* d_cos_sza;                   /* shortwave [nprof] */
+  const double* d_ssi;                       /* shortwave [ng] */
+  const double* h_albedo;                    /* shortwave [nalbedo], host */
+  const double* d_spectral_boundary_weights; /* shortwave [ng] or NULL */
+  double* d_cost_profile;                    /* [nprof] out, or NULL */
+} ecckd_cost_scene;
+int ecckd_cost_function_ckd_scenes_dev(ecckd_ctx* ctx, int is_sw, int nscene, const ecckd_cost_scene* scenes, int nlay,
+                                       int ng, int nband, double flux_weight, double flux_profile_weight,
+                                       double broadband_weight, double spectral_boundary_weight,
+                                       double pressure_weight_power, double negative_od_penalty,
+                                       const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_scene,
+                                       double* d_penalty_scene, double* d_cost_total);
+
 #ifdef __cplusplus
 }
 #endif

@@ -238,6 +238,71 @@ def test_cost_function_ckd_sw(ctx, O, albedo_on, weights):
     np.testing.assert_allclose(got["cost_fn_per_band"], per_band, rtol=COST_RTOL)
 
 
+def test_cost_function_scenes_batch_equals_scene_by_scene(ctx, O):
+    """ecckd_cost_function_ckd_scenes_dev (the scene loop of solve_adept.cpp:96-199 in one launch) against one call
+    of the per-scene entry points per scene (themselves held against the oracle above): same kernel body, so the
+    profile costs are bitwise equal; the totals are the sums in scene order.  Scenes of different sizes, LW and SW."""
+    nlay, ng, nband = 20, 32, 5
+    weights = (0.2, 0.2, 0.8, 0.1)
+    nprofs = [3, 1, 6, 4]
+    # ---- longwave
+    scenes, singles = [], []
+    for k, nprof in enumerate(nprofs):
+        s = _scene(nprof, nlay, ng, nband, seed=40 + k)
+        rng = s["rng"]
+        bm = s["bm"] if k == 0 else bm  # one band mapping for all scenes, as in solve_adept
+        emis = rng.uniform(0.9, 1.0, (nprof, nband))
+        dn, up, hr = rng.uniform(0, 300, (nprof, nlay + 1, nband)), rng.uniform(0, 300, (nprof, nlay + 1, nband)), \
+            rng.uniform(-1e-4, 0, (nprof, nlay, nband))
+        sfd, sfu = rng.uniform(0, 5, (nprof, ng)), rng.uniform(0, 5, (nprof, ng))
+        singles.append(E.cost_function_ckd_lw(ctx, s["p"], s["planck"], emis, s["surf"], s["od"], dn, up, hr, *weights,
+                                              spectral_flux_dn_surf=sfd, spectral_flux_up_toa=sfu, band_mapping=bm))
+        cp = ctx.empty(nprof)
+        scenes.append(dict(nprof=nprof, pressure_hl=ctx.to_device(s["p"]), optical_depth=ctx.to_device(s["od"]),
+                           flux_dn=ctx.to_device(dn), flux_up=ctx.to_device(up), hr=ctx.to_device(hr),
+                           spectral_flux_dn_surf=ctx.to_device(sfd), spectral_flux_up_toa=ctx.to_device(sfu),
+                           planck_hl=ctx.to_device(s["planck"]), surf_emissivity=ctx.to_device(emis),
+                           surf_planck=ctx.to_device(s["surf"]), cost_profile=cp))
+    d_bm = ctx.to_device(bm, np.int32)
+    d_cs, d_ps, d_ct = ctx.empty(len(nprofs)), ctx.empty(len(nprofs)), ctx.empty(1)
+    E.cost_function_ckd_scenes_dev(ctx, False, scenes, nlay, ng, nband, *weights, d_band_mapping=d_bm,
+                                   d_cost_scene=d_cs, d_penalty_scene=d_ps, d_cost_total=d_ct)
+    for k, one in enumerate(singles):
+        assert np.array_equal(scenes[k]["cost_profile"].numpy(), one["cost_profile"])
+        assert d_cs.numpy()[k] == one["cost_total"] and d_ps.numpy()[k] == one["penalty"]
+    assert abs(d_ct.numpy()[0] - sum(o["cost_total"] for o in singles)) <= 1e-13 * d_ct.numpy()[0]
+    # ---- shortwave (per-band costs added to in scene order), scene costs only in scratch
+    scenes, singles = [], []
+    per_band = np.linspace(0.1, 0.5, nband)
+    running = per_band.copy()
+    for k, nprof in enumerate(nprofs):
+        s = _scene(nprof, nlay, ng, nband, seed=60 + k, sw=True)
+        rng = s["rng"]
+        ssi, albedo, mu = rng.uniform(1.0, 100.0, ng), rng.uniform(0.05, 0.5, nband), rng.uniform(0.2, 1.0, nprof)
+        dn, up, hr = rng.uniform(0, 300, (nprof, nlay + 1, nband)), rng.uniform(0, 100, (nprof, nlay + 1, nband)), \
+            rng.uniform(0, 1e-4, (nprof, nlay, nband))
+        sbw, sfd = rng.uniform(0, 1, ng), rng.uniform(0, 5, (nprof, ng))
+        one = E.cost_function_ckd_sw(ctx, mu, s["p"], ssi, albedo, s["od"], dn, up, hr, *weights[:3],
+                                     spectral_boundary_weights=sbw, spectral_flux_dn_surf=sfd, band_mapping=bm,
+                                     cost_fn_per_band=running)
+        running = one["cost_fn_per_band"]
+        singles.append(one)
+        scenes.append(dict(nprof=nprof, pressure_hl=ctx.to_device(s["p"]), optical_depth=ctx.to_device(s["od"]),
+                           flux_dn=ctx.to_device(dn), flux_up=ctx.to_device(up), hr=ctx.to_device(hr),
+                           spectral_flux_dn_surf=ctx.to_device(sfd), cos_sza=ctx.to_device(mu), ssi=ctx.to_device(ssi),
+                           albedo=albedo, spectral_boundary_weights=ctx.to_device(sbw), cost_profile=ctx.empty(nprof)))
+    d_pb = ctx.to_device(per_band)
+    E.cost_function_ckd_scenes_dev(ctx, True, scenes, nlay, ng, nband, *weights[:3], d_band_mapping=d_bm,
+                                   d_cost_fn_per_band=d_pb, d_cost_total=d_ct)
+    for k, one in enumerate(singles):
+        assert np.array_equal(scenes[k]["cost_profile"].numpy(), one["cost_profile"])
+    np.testing.assert_allclose(d_pb.numpy(), running, rtol=1e-13)
+    assert abs(d_ct.numpy()[0] - sum(o["cost_total"] for o in singles)) <= 1e-13 * d_ct.numpy()[0]
+    with pytest.raises(E.EcckdError) as ei:
+        E.cost_function_ckd_scenes_dev(ctx, False, [dict(nprof=2)], nlay, ng, nband, *weights)
+    assert ei.value.code == 147
+
+
 def test_cost_function_errors(ctx):
     s = _scene(2, 6, 8, 3, seed=1)
     z = np.zeros((2, 7, 3))

@@ -90,6 +90,16 @@ ms = timed(cost_all, n=3, warm=1)
 out["forward_cost_lw"] = {"ms_per_100_scenes": ms, "columns_x_g_per_s": 100 * nprof * ng / (ms * 1e-3),
                           "config": "optimize_lut forward cost, 100 scenes x 50 profiles x 54 layers x 64 g points, 13 bands; "
                                     "one launch pair per scene (latency-bound: 50 CTAs per launch)"}
+# the same 100 scenes through the batched entry point (one launch for all scenes)
+scenes100 = [dict(nprof=nprof, pressure_hl=scene["p"], optical_depth=scene["od"], flux_dn=scene["dn"], flux_up=scene["up"],
+                  hr=scene["hr"], planck_hl=scene["planck"], surf_emissivity=scene["emis"], surf_planck=scene["surf"])
+             for _ in range(100)]
+cs100 = torch.empty(100, dtype=torch.float64, device=dev)
+ms = timed(lambda: E.cost_function_ckd_scenes_dev(ctx, False, scenes100, nlay, ng, nband, 0.2, 0.2, 0.8, 0.0,
+                                                  d_band_mapping=bm, d_cost_scene=cs100, d_cost_total=ct), n=5, warm=2)
+out["forward_cost_lw_scenes"] = {"ms_per_100_scenes": ms, "columns_x_g_per_s": 100 * nprof * ng / (ms * 1e-3),
+                                 "config": "the same 100 scenes x 50 profiles through ecckd_cost_function_ckd_scenes_dev "
+                                           "(one launch of 5000 CTAs + the per-scene sums)"}
 # one big scene of 5000 profiles (what a column-sharded rank would batch)
 nprof = 5000
 scene = dict(p=scene["p"][:1].repeat(nprof, 1).contiguous(), planck=r(nprof, nlay + 1, ng).add_(1.0),
