@@ -489,6 +489,49 @@ __global__ void sum_g_kernel(int64_t nrows, int ng, const double* __restrict__ f
   if (lane == 0) out[row] = s;
 }
 
+// The same sums for even ng and 16-byte aligned rows: eight lanes per row, four consecutive rows per
+// warp (one contiguous KB at ng = 32), 16-byte loads, two row quads in flight per warp.  Fixed order:
+// lane j of a row adds g = 2j, 2j+1, 2j+16, 2j+17, ... in that order, then a three-step shuffle tree.
+// (One lane per g point and one row per warp, as above, ran at a third of the HBM rate.)
+__global__ void __launch_bounds__(256) sum_g8_kernel(int64_t nrows, int ng, const double* __restrict__ flux,
+                                                     double* __restrict__ out) {
+  const int lane = threadIdx.x & 31, sub = lane & 7, rq = lane >> 3;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r0 = warp * 8; r0 < nrows; r0 += nwarps * 8) {
+    double s[2] = {0.0, 0.0};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t row = r0 + h * 4 + rq;
+      if (row < nrows) {
+        const double2* src = reinterpret_cast<const double2*>(flux + row * ng);
+        for (int g2 = sub; g2 < (ng >> 1); g2 += 8) {
+          const double2 v = src[g2];
+          s[h] += v.x;
+          s[h] += v.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+      const int64_t row = r0 + h * 4 + rq;
+      if (sub == 0 && row < nrows) out[row] = s[h];
+    }
+  }
+}
+
+static void launch_sum_g(ecckd_ctx* ctx, int64_t nrows, int ng, const double* flux, double* out) {
+  if ((ng & 1) == 0 && (reinterpret_cast<uintptr_t>(flux) & 15u) == 0) {
+    const int64_t want = (nrows + 63) / 64;  // 8 warps x 8 rows per block and trip
+    const unsigned blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)ctx->num_sms * 16));
+    sum_g8_kernel<<<blocks, 256, 0, ctx->stream>>>(nrows, ng, flux, out);
+  } else {
+    sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, ng, flux, out);
+  }
+}
+
 // Fused run_ckd core (run_ckd.cpp:119-132,261-367): block = one column,
 // thread = g point.  Interpolation state per (layer, gas) is computed once per
 // column into shared memory, then each thread walks the layers.
@@ -511,6 +554,7 @@ struct RunCkdParams {
   double* bb_flux_dn;
   double* bb_flux_up;
   double* scratch_od;  // [ncol][nlay][ng] when od == NULL
+  int vec2;            // ng even and the optical-depth array 16-byte aligned: two g points per thread
 };
 
 // g-independent part of one gas's optical depth at one (column, layer)
@@ -577,6 +621,39 @@ __global__ void __launch_bounds__(1024, 1) run_ckd_kernel(const RunCkdParams p) 
   auto bilinear = [&](const Interp& it, double k00, double k01, double k10, double k11) {
     return it.tw0 * (it.pw0 * k00 + it.pw1 * k01) + it.tw1 * (it.pw0 * k10 + it.pw1 * k11);  // as gas_od()
   };
+  if (p.vec2) {
+    // Two g points per thread (16-byte loads: one request fetches two LUT rows' worth for a warp of
+    // ng = 32), the (layer, g pair) items of the column dealt out over its threads; every layer is
+    // independent.  Same arithmetic per element as the scalar loop below.
+    const int hg = ng >> 1;
+    const int tid_c = threadIdx.z * blockDim.x + threadIdx.x, nthr_c = blockDim.x * blockDim.z;
+    for (int t = tid_c; t < nlay * hg; t += nthr_c) {
+      const int l = t / hg, g = (t - l * hg) * 2;
+      double tx = 0.0, ty = 0.0;
+      const Interp it = s_it[l];
+      const size_t o00 = it.it0 * sT + it.ip0 * sP + g;
+      for (int ig = 0; ig < ngas; ++ig) {
+        const GasLayer gl = s_gl[l * ngas + ig];
+        const int ic0 = (int)gl.cindex0;  // -1 for the gases without a concentration axis
+        const double* k = s_molar_abs[ig] + o00 + (ic0 >= 0 ? ic0 * sC : (size_t)0);
+        const double2 k00 = *reinterpret_cast<const double2*>(k), k01 = *reinterpret_cast<const double2*>(k + sP),
+                      k10 = *reinterpret_cast<const double2*>(k + sT), k11 = *reinterpret_cast<const double2*>(k + sT + sP);
+        const double ax = bilinear(it, k00.x, k01.x, k10.x, k11.x), ay = bilinear(it, k00.y, k01.y, k10.y, k11.y);
+        if (ic0 >= 0) {
+          const double cw1 = gl.cindex0 - ic0;
+          k += sC;
+          const double2 c00 = *reinterpret_cast<const double2*>(k), c01 = *reinterpret_cast<const double2*>(k + sP),
+                        c10 = *reinterpret_cast<const double2*>(k + sT), c11 = *reinterpret_cast<const double2*>(k + sT + sP);
+          tx += gl.weight * ((1.0 - cw1) * ax + cw1 * bilinear(it, c00.x, c01.x, c10.x, c11.x));
+          ty += gl.weight * ((1.0 - cw1) * ay + cw1 * bilinear(it, c00.y, c01.y, c10.y, c11.y));
+        } else {
+          tx += gl.weight * ax;
+          ty += gl.weight * ay;
+        }
+      }
+      *reinterpret_cast<double2*>(od_col + (int64_t)l * ng + g) = make_double2(fmax(tx, 0.0), fmax(ty, 0.0));
+    }
+  } else
   for (int g = threadIdx.x; g < ng; g += blockDim.x) {
     // optical depth: sum over gases, clamp (run_ckd.cpp:265-317).  (Keeping the table values at ip0 + 1
     // in registers for the next layer was measured slower: 7.1 vs 6.3 ms for 65536 x 54 x 32.)
@@ -1024,8 +1101,11 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     p.flux_dn = nullptr;
     p.flux_up = nullptr;
   }
+  p.vec2 = (m->ng % 2 == 0) && ((reinterpret_cast<uintptr_t>(d_od ? d_od : p.scratch_od) & 15u) == 0);
   // warps per column (each takes every lz-th layer): fill the SM's warp slots
-  int lz = 4;  // measured on the B200 (65536 x 54 x 32): 7.1 / 6.4 / 4.6 / 4.2 ms for 1 / 2 / 3 / 4 warps per column
+  // measured on the B200 (65536 x 54 x 32, whole run_ckd core): one g point per thread 7.1 / 6.4 / 4.6 / 4.2 ms for
+  // 1 / 2 / 3 / 4 warps per column; two g points per thread 4.5 / 3.55 / 3.8 / 3.7 ms
+  int lz = p.vec2 ? 2 : 4;
   while (lz > 1 && (threads * cols * lz > 1024 || lz > nlay)) --lz;
   if (const char* e = getenv("ECCKD_RUN_CKD_LZ")) lz = std::max(1, std::min(atoi(e), 1024 / (threads * cols)));
   run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
@@ -1042,11 +1122,11 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
   }
   const int64_t nrows = (int64_t)ncol * (nlay + 1);
   if (d_flux_dn && d_bb_flux_dn) {
-    sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, m->ng, d_flux_dn, d_bb_flux_dn);
+    launch_sum_g(ctx, nrows, m->ng, d_flux_dn, d_bb_flux_dn);
     ECCKD_LAUNCH_CHECK(ctx);
   }
   if (!m->is_sw && d_flux_up && d_bb_flux_up) {
-    sum_g_kernel<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(nrows, m->ng, d_flux_up, d_bb_flux_up);
+    launch_sum_g(ctx, nrows, m->ng, d_flux_up, d_bb_flux_up);
     ECCKD_LAUNCH_CHECK(ctx);
   }
   return ECCKD_OK;
