@@ -139,14 +139,38 @@ __global__ void interval_fit_finish_kernel(const IntervalParams p, int fit_from_
   __shared__ double s_scal[3];
   if (threadIdx.x < 3) {
     double s = 0.0;
-    for (int64_t it = it0; it < it1; ++it) s += p.part_scal[(size_t)it * 4 + threadIdx.x];
+    int64_t it = it0;
+    for (; it + 8 <= it1; it += 8) {  // tile order, eight loads in flight
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = p.part_scal[(size_t)(it + q) * 4 + threadIdx.x];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += v[q];
+    }
+    for (; it < it1; ++it) s += p.part_scal[(size_t)it * 4 + threadIdx.x];
     s_scal[threadIdx.x] = s;
     p.truth[(size_t)k * (p.nlay + 4) + p.nlay + threadIdx.x] = s;
   }
   __syncthreads();
   for (int l = threadIdx.x; l < p.nlay; l += blockDim.x) {
     double num = 0.0, den = 0.0, cnt = 0.0, hs = 0.0;
-    for (int64_t it = it0; it < it1; ++it) {
+    // tile order, eight tiles' loads in flight at a time (one load per trip made this kernel the
+    // second longest of a batch: 0.44 ms of pure latency for 1024 tiles)
+    int64_t it = it0;
+    for (; it + 8 <= it1; it += 8) {
+      double2 a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const double2* o = reinterpret_cast<const double2*>(p.part_fit + ((size_t)(it + j) * p.nlay + l) * 4);
+        a[j] = o[0];
+        b[j] = o[1];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        num += a[j].x; den += a[j].y; cnt += b[j].x; hs += b[j].y;
+      }
+    }
+    for (; it < it1; ++it) {
       const double* o = p.part_fit + ((size_t)it * p.nlay + l) * 4;
       num += o[0]; den += o[1]; cnt += o[2]; hs += o[3];
     }
@@ -355,7 +379,15 @@ __global__ void interval_error_kernel(const IntervalParams p) {
   const double* truth = p.truth ? p.truth + (size_t)k * (p.nlay + 4) : nullptr;
   for (int j = threadIdx.x; j < 2 * nlev; j += blockDim.x) {
     double s = 0.0;
-    for (int64_t it = it0; it < it1; ++it) s += p.part_flux[(size_t)it * 2 * nlev + j];
+    int64_t it = it0;
+    for (; it + 8 <= it1; it += 8) {  // tile order, eight loads in flight
+      double v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = p.part_flux[(size_t)(it + q) * 2 * nlev + j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s += v[q];
+    }
+    for (; it < it1; ++it) s += p.part_flux[(size_t)it * 2 * nlev + j];
     if (p.sw && j == 0) s = p.cos_sza * truth[p.nlay + 2];  // flux_dn(0) = cos_sza*sum(ssi), radiative_transfer_sw.cpp:134
     s_c[j] = s;
     if (p.bb_flux) p.bb_flux[(size_t)k * 2 * nlev + j] = s;
