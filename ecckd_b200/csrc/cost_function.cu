@@ -131,47 +131,66 @@ __global__ void __launch_bounds__(kTile) interval_fit_partial_kernel(const Inter
   }
 }
 
+// Fixed-order sum over the tiles of an interval: the tiles are cut into kSeg contiguous segments (a
+// function of the tile count only), every segment is added in tile order by its own thread with eight
+// loads in flight, and the segment sums are added in segment order.  Bitwise reproducible and
+// independent of the launch geometry.  (One thread walking all 1024 tiles of a 2^18-point interval
+// made the two CTA-per-interval kernels 0.76 ms of a 3.3 ms batch.)
+constexpr int kSeg = 8;
+__device__ __forceinline__ void seg_bounds(int64_t it0, int64_t it1, int seg, int64_t& a, int64_t& b) {
+  const int64_t t = it1 - it0;
+  a = it0 + (t * seg) / kSeg;
+  b = it0 + (t * (seg + 1)) / kSeg;
+}
+__device__ __forceinline__ double seg_sum(const double* __restrict__ base, size_t stride, int64_t a, int64_t b) {
+  double s = 0.0;
+  int64_t it = a;
+  for (; it + 8 <= b; it += 8) {
+    double v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = base[(size_t)(it + q) * stride];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
+  }
+  for (; it < b; ++it) s += base[(size_t)it * stride];
+  return s;
+}
+
 // ---- phase A2: add the tile partials in tile order and apply the fit formula.  CTA = interval.
+// Dynamic shared memory: kSeg*(nlay*4 + 4) doubles (+ nlay for the total-transmission fit).
 __global__ void interval_fit_finish_kernel(const IntervalParams p, int fit_from_sweep) {
+  extern __shared__ double s_dyn[];
+  double* s_seg = s_dyn;                           // [kSeg][nlay][4]
+  double* s_sseg = s_dyn + (size_t)kSeg * p.nlay * 4;  // [kSeg][4]
+  double* s_lin = s_sseg + kSeg * 4;               // [nlay]
   const int k = blockIdx.x;
   const int64_t it0 = p.item_start[k], it1 = p.item_start[k + 1];
   const int64_t npts = p.i2[k] - p.i1[k] + 1;
   __shared__ double s_scal[3];
+  for (int idx = threadIdx.x; idx < kSeg * p.nlay * 4 + kSeg * 3; idx += blockDim.x) {
+    int64_t a, b;
+    if (idx < kSeg * p.nlay * 4) {
+      const int seg = idx / (p.nlay * 4), rem = idx - seg * (p.nlay * 4);  // rem = l*4 + component
+      seg_bounds(it0, it1, seg, a, b);
+      s_seg[idx] = seg_sum(p.part_fit + rem, (size_t)p.nlay * 4, a, b);
+    } else {
+      const int j = idx - kSeg * p.nlay * 4, seg = j / 3, c = j - seg * 3;
+      seg_bounds(it0, it1, seg, a, b);
+      s_sseg[seg * 4 + c] = seg_sum(p.part_scal + c, 4, a, b);
+    }
+  }
+  __syncthreads();
   if (threadIdx.x < 3) {
     double s = 0.0;
-    int64_t it = it0;
-    for (; it + 8 <= it1; it += 8) {  // tile order, eight loads in flight
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = p.part_scal[(size_t)(it + q) * 4 + threadIdx.x];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s += v[q];
-    }
-    for (; it < it1; ++it) s += p.part_scal[(size_t)it * 4 + threadIdx.x];
+    for (int seg = 0; seg < kSeg; ++seg) s += s_sseg[seg * 4 + threadIdx.x];
     s_scal[threadIdx.x] = s;
     p.truth[(size_t)k * (p.nlay + 4) + p.nlay + threadIdx.x] = s;
   }
   __syncthreads();
   for (int l = threadIdx.x; l < p.nlay; l += blockDim.x) {
     double num = 0.0, den = 0.0, cnt = 0.0, hs = 0.0;
-    // tile order, eight tiles' loads in flight at a time (one load per trip made this kernel the
-    // second longest of a batch: 0.44 ms of pure latency for 1024 tiles)
-    int64_t it = it0;
-    for (; it + 8 <= it1; it += 8) {
-      double2 a[8], b[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double2* o = reinterpret_cast<const double2*>(p.part_fit + ((size_t)(it + j) * p.nlay + l) * 4);
-        a[j] = o[0];
-        b[j] = o[1];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        num += a[j].x; den += a[j].y; cnt += b[j].x; hs += b[j].y;
-      }
-    }
-    for (; it < it1; ++it) {
-      const double* o = p.part_fit + ((size_t)it * p.nlay + l) * 4;
+    for (int seg = 0; seg < kSeg; ++seg) {
+      const double* o = s_seg + ((size_t)seg * p.nlay + l) * 4;
       num += o[0]; den += o[1]; cnt += o[2]; hs += o[3];
     }
     p.truth[(size_t)k * (p.nlay + 4) + l] = hs;
@@ -228,7 +247,6 @@ __global__ void interval_fit_finish_kernel(const IntervalParams p, int fit_from_
     // only if a fallback happened at or before... the reference overwrites the WHOLE profile at the failing
     // layer and then continues, so layers after the failure are set individually again if they succeed.
     // Walk the layers in order, tracking what the reference's vector would contain.
-    extern __shared__ double s_lin[];
     for (int l = 0; l < p.nlay; ++l) s_lin[l] = p.fit[(size_t)k * p.nlay + l];
     for (int l = 0; l < p.nlay; ++l) p.fit[(size_t)k * p.nlay + l] = 0.0;
     for (int l = 0; l < p.nlay; ++l) {
@@ -377,17 +395,17 @@ __global__ void interval_error_kernel(const IntervalParams p) {
   double* term = up + nlev;
   const int64_t it0 = p.item_start[k], it1 = p.item_start[k + 1];
   const double* truth = p.truth ? p.truth + (size_t)k * (p.nlay + 4) : nullptr;
+  double* s_seg = term + p.nlay;  // [kSeg][2*nlev]
+  for (int idx = threadIdx.x; idx < kSeg * 2 * nlev; idx += blockDim.x) {
+    const int seg = idx / (2 * nlev), j = idx - seg * 2 * nlev;
+    int64_t a, b;
+    seg_bounds(it0, it1, seg, a, b);
+    s_seg[idx] = seg_sum(p.part_flux + j, (size_t)2 * nlev, a, b);
+  }
+  __syncthreads();
   for (int j = threadIdx.x; j < 2 * nlev; j += blockDim.x) {
     double s = 0.0;
-    int64_t it = it0;
-    for (; it + 8 <= it1; it += 8) {  // tile order, eight loads in flight
-      double v[8];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) v[q] = p.part_flux[(size_t)(it + q) * 2 * nlev + j];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) s += v[q];
-    }
-    for (; it < it1; ++it) s += p.part_flux[(size_t)it * 2 * nlev + j];
+    for (int seg = 0; seg < kSeg; ++seg) s += s_seg[seg * 2 * nlev + j];
     if (p.sw && j == 0) s = p.cos_sza * truth[p.nlay + 2];  // flux_dn(0) = cos_sza*sum(ssi), radiative_transfer_sw.cpp:134
     s_c[j] = s;
     if (p.bb_flux) p.bb_flux[(size_t)k * 2 * nlev + j] = s;
@@ -414,6 +432,8 @@ __global__ void interval_error_kernel(const IntervalParams p) {
   }
 }
 
+static inline size_t finish_smem(int nlay) { return ((size_t)kSeg * (nlay * 4 + 4) + nlay) * sizeof(double); }
+
 // Host side of a batch: item table, scratch carving, launches.
 struct IntervalBatch {
   IntervalParams p;
@@ -423,6 +443,7 @@ struct IntervalBatch {
 static int setup_batch(ecckd_ctx* ctx, IntervalParams& p, int nint, const int64_t* h_i1, const int64_t* h_i2, int64_t n,
                        const char* who) {
   ECCKD_REQUIRE(nint > 0 && h_i1 && h_i2, ECCKD_PARAMETER_ERROR, "%s: no intervals", who);
+  ECCKD_REQUIRE(finish_smem(p.nlay) <= 48 * 1024, ECCKD_PARAMETER_ERROR, "%s: more than 180 layers", who);
   std::vector<int64_t> host((size_t)3 * nint + 1);
   int64_t* i1 = host.data();
   int64_t* i2 = i1 + nint;
@@ -471,7 +492,7 @@ static int launch_flux_and_error(ecckd_ctx* ctx, const IntervalParams& p) {
   if (p.sw) interval_flux_kernel<true><<<p.nitems, kTile, smem, ctx->stream>>>(p);
   else interval_flux_kernel<false><<<p.nitems, kTile, smem, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
-  interval_error_kernel<<<p.nint, 64, (size_t)(3 * p.nlay + 2) * sizeof(double), ctx->stream>>>(p);
+  interval_error_kernel<<<p.nint, 512, (size_t)(3 * p.nlay + 2 + kSeg * 2 * (p.nlay + 1)) * sizeof(double), ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
@@ -950,7 +971,7 @@ ECCKD_API int ecckd_interval_error_batch_lw_dev(ecckd_ctx* ctx, int averaging_me
   ECCKD_TRY(setup_batch(ctx, p, nint, h_i1, h_i2, n, who));
   interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
-  interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 0);
+  interval_fit_finish_kernel<<<p.nint, 512, finish_smem(p.nlay), ctx->stream>>>(p, 0);
   ECCKD_LAUNCH_CHECK(ctx);
   return launch_flux_and_error(ctx, p);
 }
@@ -991,7 +1012,7 @@ ECCKD_API int ecckd_interval_error_batch_sw_dev(
   interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
   if (!tt) {
-    interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 0);
+    interval_fit_finish_kernel<<<p.nint, 512, finish_smem(p.nlay), ctx->stream>>>(p, 0);
     ECCKD_LAUNCH_CHECK(ctx);
     return launch_flux_and_error(ctx, p);
   }
@@ -999,7 +1020,7 @@ ECCKD_API int ecckd_interval_error_batch_sw_dev(
   const size_t smem = (size_t)2 * (nlay + 1) * kWarps * sizeof(double);
   interval_tt_sweep_kernel<<<p.nitems, kTile, smem, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
-  interval_fit_finish_kernel<<<p.nint, 64, (size_t)nlay * sizeof(double), ctx->stream>>>(p, 1);
+  interval_fit_finish_kernel<<<p.nint, 512, finish_smem(p.nlay), ctx->stream>>>(p, 1);
   ECCKD_LAUNCH_CHECK(ctx);
   p.od_scale = min_scaling;
   p.error_mode = 1;
@@ -1008,7 +1029,7 @@ ECCKD_API int ecckd_interval_error_batch_sw_dev(
   p.flux_dn_surf = d_flux_dn_surf_high; p.flux_up_toa = d_flux_up_toa_high; p.hr = d_hr_high;
   interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
-  interval_fit_finish_kernel<<<p.nint, 64, 0, ctx->stream>>>(p, 2);
+  interval_fit_finish_kernel<<<p.nint, 512, finish_smem(p.nlay), ctx->stream>>>(p, 2);
   ECCKD_LAUNCH_CHECK(ctx);
   p.od_scale = max_scaling;
   p.error_mode = 2;
@@ -1031,7 +1052,7 @@ static int bb_solver(ecckd_ctx* ctx, IntervalParams& p, const double* d_grey_od,
     p.flux_dn_surf = p.ssi; p.flux_up_toa = p.ssi; p.hr = p.bg_od; p.metric = p.bg_od; p.method = ECCKD_AVG_LINEAR;
     interval_fit_partial_kernel<<<p.nitems, kTile, 0, ctx->stream>>>(p);
     ECCKD_LAUNCH_CHECK(ctx);
-    interval_fit_finish_kernel<<<1, 64, 0, ctx->stream>>>(p, 2);
+    interval_fit_finish_kernel<<<1, 512, finish_smem(p.nlay), ctx->stream>>>(p, 2);
     ECCKD_LAUNCH_CHECK(ctx);
   } else {
     p.truth = nullptr;

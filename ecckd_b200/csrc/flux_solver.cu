@@ -1107,7 +1107,9 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
   // 1 / 2 / 3 / 4 warps per column; two g points per thread 4.5 / 3.55 / 3.8 / 3.7 ms
   int lz = p.vec2 ? 2 : 4;
   while (lz > 1 && (threads * cols * lz > 1024 || lz > nlay)) --lz;
+#ifdef ECCKD_TIMING_KNOBS  // tools/run_ckd_lz.sh
   if (const char* e = getenv("ECCKD_RUN_CKD_LZ")) lz = std::max(1, std::min(atoi(e), 1024 / (threads * cols)));
+#endif
   run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
   if (lw_staged) {
