@@ -28,6 +28,8 @@ local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local_rank)
 dev = torch.device("cuda", local_rank)
 if world > 1:
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON object)
     dist.init_process_group("nccl", device_id=dev)
 st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
