@@ -240,6 +240,19 @@ def make_spectrum(torch, wn, nlay, p_hl, seed, vmr):
 
 
 # ------------------------------------------------------------------ reference arm (CPU)
+def use_all_host_threads():
+    """The CPU arm runs on every host thread: torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would time the OpenMP oracle on one core (86 M instead of 560 M point*layers/s on the 16-thread box)."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        import ctypes
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 class CpuSample:
     """The oracle port of planck_function + average_optical_depth_to_g_point (the reference's
     per-block call pair, create_look_up_table.cpp:320-331) on a sample of the workload."""
@@ -249,6 +262,7 @@ class CpuSample:
         from tests import synthetic as S
 
         self.O = oracle()
+        use_all_host_threads()
         self.method = args.method
         self.nwav = nwav = 1 << log2_nwav
         self.nlay = nlay = args.nlay
@@ -316,10 +330,19 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: the communicator is created (first collective) with
+        # stdout pointed at stderr, so that the "NCCL version ..." banner does not land on it
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     # One explicit non-default stream for everything (torch ops, NCCL, our kernels, the timing
     # events): the legacy default stream has handle 0, which the C ABI reads as "make a private stream".
     work_stream = torch.cuda.Stream(device=dev)
