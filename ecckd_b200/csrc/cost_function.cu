@@ -488,6 +488,8 @@ static int setup_batch(ecckd_ctx* ctx, IntervalParams& p, int nint, const int64_
 }
 
 static int launch_flux_and_error(ecckd_ctx* ctx, const IntervalParams& p) {
+  // (Capping the resident CTAs per SM so that the upward sweep's re-reads hit in L2 was measured and is
+  // slower: 2.65 ms unrestricted, 3.2 / 3.6 / 4.3 / 5.6 ms at 5 / 4 / 3 / 2 CTAs per SM.)
   const size_t smem = (size_t)2 * (p.nlay + 1) * kWarps * sizeof(double) + (p.sw ? 0 : TRANS_TAB_BYTES);
   if (p.sw) interval_flux_kernel<true><<<p.nitems, kTile, smem, ctx->stream>>>(p);
   else interval_flux_kernel<false><<<p.nitems, kTile, smem, ctx->stream>>>(p);

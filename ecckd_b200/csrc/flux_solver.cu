@@ -238,8 +238,16 @@ struct RtLwStagedParams {
   const double* surf_planck;
   double* flux_dn;
   double* flux_up;
+  double* bb_dn;  // [ncol][nlay+1] sums over the n points, or NULL; only with n == 32 (lane = spectral point)
+  double* bb_up;
   TransConst tc;  // kd = LW_DIFFUSIVITY
 };
+
+__device__ __forceinline__ double warp_sum_xor(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 __device__ __forceinline__ void lw_layer_fast(double tau, const TransConst& K, const TransLane& tl, double& e, double& f) {
   e = trans_one_minus_exp(tau, K, tl);
@@ -291,8 +299,14 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
     const double bs = p.surf_planck[icol * n + i0 + lane];
     mbar_wait(bar, parity);
     parity ^= 1u;
+    // broadband sums (run_ckd.cpp:355-356) while the fluxes are in registers: with n == 32 the lanes of
+    // the warp are the g points of the column (fixed order: xor shuffle tree)
+    const bool bb = UNIT && p.bb_dn != nullptr;
+    double* bdn = bb ? p.bb_dn + icol * (nlay + 1) : nullptr;
+    double* bup = bb ? p.bb_up + icol * (nlay + 1) : nullptr;
     double f_dn = 0.0;
     dn[0] = 0.0;
+    if (bb && lane == 0) bdn[0] = 0.0;
     double b_top = s_pl[lane];
     int l = 0;
     for (; l + 4 <= nlay; l += 4) {
@@ -306,6 +320,10 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
       for (int j = 0; j < 4; ++j) {
         f_dn = f_dn * (1.0 - e[j]) + b_top * (e[j] - f[j]) + b[j] * f[j];
         dn[(int64_t)(l + j + 1) * n] = f_dn;
+        if (bb) {
+          const double sdn = warp_sum_xor(f_dn);
+          if (lane == 0) bdn[l + j + 1] = sdn;
+        }
         s_tau[(l + j) * 32 + lane] = 1.0 - e[j];
         s_pl[(l + j) * 32 + lane] = b[j] * (e[j] - f[j]) + b_top * f[j];
         b_top = b[j];
@@ -317,16 +335,28 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
       const double b_bot = s_pl[(l + 1) * 32 + lane];
       f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
       dn[(int64_t)(l + 1) * n] = f_dn;
+      if (bb) {
+        const double sdn = warp_sum_xor(f_dn);
+        if (lane == 0) bdn[l + 1] = sdn;
+      }
       s_tau[l * 32 + lane] = 1.0 - e;
       s_pl[l * 32 + lane] = b_bot * (e - f) + b_top * f;
       b_top = b_bot;
     }
     double f_up = bs * es + (1.0 - es) * f_dn;
     up[(int64_t)nlay * n] = f_up;
+    if (bb) {
+      const double sup = warp_sum_xor(f_up);
+      if (lane == 0) bup[nlay] = sup;
+    }
 #pragma unroll 6
     for (l = nlay - 1; l >= 0; --l) {
       f_up = f_up * s_tau[l * 32 + lane] + s_pl[l * 32 + lane];
       up[(int64_t)l * n] = f_up;
+      if (bb) {
+        const double sup = warp_sum_xor(f_up);
+        if (lane == 0) bup[l] = sup;
+      }
     }
     // the next item's bulk copies (async proxy) overwrite what this one wrote through the generic proxy
     fence_proxy_async();
@@ -943,9 +973,12 @@ ECCKD_API int ecckd_ckd_calc_rayleigh_optical_depth_dev(ecckd_ctx* ctx, ecckd_ck
   return ECCKD_OK;
 }
 
-ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck,
-                                              const double* d_od, const double* d_surf_emissivity,
-                                              const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+// d_bb_dn / d_bb_up (both or neither): the sums over the n spectral points, produced by the sweep
+// itself when it runs as the staged kernel with n == 32; *bb_done tells the caller whether it did.
+static int rt_lw_impl(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck, const double* d_od,
+                      const double* d_surf_emissivity, const double* d_surf_planck, double* d_flux_dn, double* d_flux_up,
+                      double* d_bb_dn, double* d_bb_up, bool* bb_done) {
+  if (bb_done) *bb_done = false;
   ECCKD_REQUIRE(ctx && d_planck && d_od && d_surf_emissivity && d_surf_planck && d_flux_dn && d_flux_up,
                 ECCKD_PARAMETER_ERROR, "ecckd_radiative_transfer_lw: NULL argument");
   const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
@@ -958,6 +991,10 @@ ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay
     RtLwStagedParams sp;
     sp.ncol = ncol; sp.nlay = nlay; sp.n = n; sp.planck = d_planck; sp.od = d_od; sp.surf_emissivity = d_surf_emissivity;
     sp.surf_planck = d_surf_planck; sp.flux_dn = d_flux_dn; sp.flux_up = d_flux_up;
+    const bool fuse_bb = n == 32 && d_bb_dn && d_bb_up;
+    sp.bb_dn = fuse_bb ? d_bb_dn : nullptr;
+    sp.bb_up = fuse_bb ? d_bb_up : nullptr;
+    if (bb_done) *bb_done = fuse_bb;
     trans_const_init(&sp.tc, ECCKD_LW_DIFFUSIVITY);
     const int per_sm = (int)std::min<size_t>(32, (ctx->smem_optin + 1024) / (staged_smem + 1024));
     const int64_t items = (int64_t)ncol * (n >> 5);
@@ -977,6 +1014,13 @@ ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay
   }
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck,
+                                              const double* d_od, const double* d_surf_emissivity,
+                                              const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+  return rt_lw_impl(ctx, ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck, d_flux_dn, d_flux_up, nullptr,
+                    nullptr, nullptr);
 }
 
 ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* h_cos_sza,
@@ -1112,6 +1156,7 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
 #endif
   run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
   ECCKD_LAUNCH_CHECK(ctx);
+  bool bb_done = false;
   if (lw_staged) {
     if (!m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)
       std::vector<double> ones(m->ng, 1.0);
@@ -1119,9 +1164,10 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
       ECCKD_CUDA_OK(cudaMemcpyAsync(m->d_ones, ones.data(), m->ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
       ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
     }
-    ECCKD_TRY(ecckd_radiative_transfer_lw_dev(ctx, ncol, nlay, m->ng, p.planck_hl, d_od ? d_od : p.scratch_od, m->d_ones,
-                                              p.planck_surf, d_flux_dn, d_flux_up));
+    ECCKD_TRY(rt_lw_impl(ctx, ncol, nlay, m->ng, p.planck_hl, d_od ? d_od : p.scratch_od, m->d_ones, p.planck_surf,
+                         d_flux_dn, d_flux_up, d_bb_flux_dn, d_bb_flux_up, &bb_done));
   }
+  if (bb_done) return ECCKD_OK;
   const int64_t nrows = (int64_t)ncol * (nlay + 1);
   if (d_flux_dn && d_bb_flux_dn) {
     launch_sum_g(ctx, nrows, m->ng, d_flux_dn, d_bb_flux_dn);
