@@ -126,7 +126,16 @@ ECCKD_API int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out) {
   ECCKD_REQUIRE(prop.major == 10, ECCKD_UNEXPECTED_EXCEPTION,
                 "ecckd_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device,
                 prop.major, prop.minor);
-  ECCKD_CUDA_OK(cudaSetDevice(device));
+  // the caller's current device is restored on return (ECCKD_DEVICE does the same in every other
+  // entry point): creating a second context must not redirect the first one's allocations
+  ecckd_ctx probe;
+  probe.device = device;
+  ECCKD_DEVICE(&probe);
+  {
+    int cur = -1;
+    ECCKD_REQUIRE(cudaGetDevice(&cur) == cudaSuccess && cur == device, ECCKD_UNEXPECTED_EXCEPTION,
+                  "ecckd_ctx_create: cannot select device %d", device);
+  }
   ecckd_ctx* ctx = new ecckd_ctx();
   ctx->device = device;
   ctx->num_sms = prop.multiProcessorCount;
@@ -146,8 +155,13 @@ ECCKD_API int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out) {
   {
     // plans and partial sums come from the stream-ordered pool (cudaMallocAsync): keep what it has
     // instead of returning it to the driver at every synchronisation (the default threshold of 0
-    // made one host-buffer call in ten pay ~300 ms for a fresh allocation)
+    // made one host-buffer call in ten pay ~300 ms for a fresh allocation).  This is a property of
+    // the DEVICE's default pool, i.e. visible to other users of cudaMallocAsync in the process
+    // (documented in include/ecckd_b200.h); ECCKD_KEEP_POOL=0 leaves the pool alone.
     cudaMemPool_t pool = nullptr;
+    const char* keep_env = getenv("ECCKD_KEEP_POOL");
+    if (keep_env && atoi(keep_env) == 0) {
+    } else
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
       uint64_t keep = ~uint64_t(0);
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -168,7 +182,7 @@ ECCKD_API int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out) {
 
 ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
   if (!ctx) return ECCKD_OK;
-  cudaSetDevice(ctx->device);
+  ECCKD_DEVICE(ctx);
   cudaStreamSynchronize(ctx->stream);
   for (auto& w : ctx->ws) {
     if (w.ptr) cudaFree(w.ptr);
@@ -185,6 +199,7 @@ ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
 }
 
 ECCKD_API int ecckd_ctx_set_stream(ecckd_ctx* ctx, void* stream) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_ctx_set_stream: ctx is NULL");
   ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (ctx->owns_stream) {
@@ -201,19 +216,21 @@ ECCKD_API int ecckd_ctx_set_stream(ecckd_ctx* ctx, void* stream) {
 }
 
 ECCKD_API int ecckd_synchronize(ecckd_ctx* ctx) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_synchronize: ctx is NULL");
   ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_device_malloc(ecckd_ctx* ctx, size_t bytes, void** d_ptr) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_ptr, ECCKD_PARAMETER_ERROR, "ecckd_device_malloc: NULL argument");
-  ECCKD_CUDA_OK(cudaSetDevice(ctx->device));
   ECCKD_CUDA_OK(cudaMalloc(d_ptr, bytes ? bytes : 1));
   return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_device_free(ecckd_ctx* ctx, void* d_ptr) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_device_free: ctx is NULL");
   if (d_ptr) {
     ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -234,12 +251,14 @@ ECCKD_API int ecckd_host_free_pinned(void* h_ptr) {
 }
 
 ECCKD_API int ecckd_memcpy_h2d(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_memcpy_h2d: ctx is NULL");
   ECCKD_CUDA_OK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_memcpy_d2h: ctx is NULL");
   ECCKD_CUDA_OK(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -249,12 +268,14 @@ ECCKD_API int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, s
 ECCKD_API int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 ECCKD_API int ecckd_ctx_set_timing(ecckd_ctx* ctx, int on) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_ctx_set_timing: ctx is NULL");
   ctx->timing = on != 0;
   return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_ctx_reduce_kernel_time(ecckd_ctx* ctx, double* total_ms, int64_t* launches) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && total_ms && launches, ECCKD_PARAMETER_ERROR, "ecckd_ctx_reduce_kernel_time: NULL argument");
   ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
   double sum = 0.0;

@@ -59,6 +59,27 @@ int upload_small(ecckd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 }  // namespace ecckd
 
+namespace ecckd {
+// Every entry point that takes a context (or an object created on one) runs with that context's
+// device current and restores the caller's device on return: one process may hold contexts on
+// several GPUs, and workspace allocation, plan/model creation and kernel launches all act on the
+// CURRENT device.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(const ecckd_ctx* ctx) {
+    if (ctx && cudaGetDevice(&prev) == cudaSuccess && prev != ctx->device)
+      switched = cudaSetDevice(ctx->device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+}  // namespace ecckd
+#define ECCKD_DEVICE(ctx) ecckd::DeviceGuard _ecckd_device_guard(ctx)
+
 #define ECCKD_CUDA_OK(expr)                                                              \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

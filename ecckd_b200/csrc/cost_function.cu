@@ -954,6 +954,7 @@ ECCKD_API int ecckd_interval_error_batch_lw_dev(ecckd_ctx* ctx, int averaging_me
                                                 const double* d_hr, double flux_weight, const double* d_layer_weight,
                                                 int nint, const int64_t* h_i1, const int64_t* h_i2, double* d_error,
                                                 double* d_optical_depth_fit) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_interval_error_batch_lw";
   ECCKD_REQUIRE(ctx && d_pressure_hl && d_planck_hl && d_surf_emissivity && d_surf_planck && d_bg_optical_depth &&
                     d_metric && d_flux_dn_surf && d_flux_up_toa && d_hr && d_layer_weight && d_error,
@@ -986,6 +987,7 @@ ECCKD_API int ecckd_interval_error_batch_sw_dev(
     const double* d_flux_up_toa_low, const double* d_hr_low, const double* d_flux_dn_surf_high,
     const double* d_flux_up_toa_high, const double* d_hr_high, double min_scaling, double max_scaling, int nint,
     const int64_t* h_i1, const int64_t* h_i2, double* d_error, double* d_optical_depth_fit) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_interval_error_batch_sw";
   ECCKD_REQUIRE(ctx && d_pressure_hl && d_ssi && d_bg_optical_depth && d_metric && d_layer_weight && d_error,
                 ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
@@ -1071,6 +1073,7 @@ ECCKD_API int ecckd_radiative_transfer_lw_bb_dev(ecckd_ctx* ctx, int nlay, int64
                                                  const double* d_planck, const double* d_spectral_od,
                                                  const double* d_grey_od, const double* d_surf_emissivity,
                                                  const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_radiative_transfer_lw_bb";
   ECCKD_REQUIRE(ctx && d_planck && d_spectral_od && d_grey_od && d_surf_emissivity && d_surf_planck && d_flux_dn &&
                     d_flux_up,
@@ -1087,6 +1090,7 @@ ECCKD_API int ecckd_radiative_transfer_sw_bb_dev(ecckd_ctx* ctx, int nlay, int64
                                                  const double* d_ssi, const double* d_spectral_od,
                                                  const double* d_grey_od, double albedo, double* d_flux_dn,
                                                  double* d_flux_up) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_radiative_transfer_sw_bb";
   ECCKD_REQUIRE(ctx && d_ssi && d_spectral_od && d_grey_od && d_flux_dn, ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
   ECCKD_REQUIRE(nlay > 0 && n > 0 && stride >= n && cos_sza > 0.0, ECCKD_PARAMETER_ERROR, "%s: bad dimensions", who);
@@ -1106,6 +1110,7 @@ ECCKD_API int ecckd_cost_function_ckd_lw_dev(
     double spectral_boundary_weight, const double* d_layer_weight, double pressure_weight_power,
     double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
     const int32_t* d_band_mapping, double* d_cost_profile, double* d_cost_total, double* d_penalty_total) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_cost_function_ckd_lw";
   ECCKD_REQUIRE(ctx && d_pressure_hl && d_planck_hl && d_surf_emissivity && d_surf_planck && d_optical_depth &&
                     d_flux_dn && d_flux_up && d_hr,
@@ -1134,6 +1139,7 @@ ECCKD_API int ecckd_cost_function_ckd_sw_dev(
     double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
     const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_profile, double* d_cost_total,
     double* d_penalty_total) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_cost_function_ckd_sw";
   (void)d_spectral_flux_up_toa;
   ECCKD_REQUIRE(ctx && d_cos_sza && d_pressure_hl && d_ssi && h_albedo && nalbedo > 0 && d_optical_depth && d_flux_dn &&
@@ -1172,6 +1178,7 @@ ECCKD_API int ecckd_cost_function_ckd_scenes_dev(ecckd_ctx* ctx, int is_sw, int 
                                                  double negative_od_penalty, const int32_t* d_band_mapping,
                                                  double* d_cost_fn_per_band, double* d_cost_scene,
                                                  double* d_penalty_scene, double* d_cost_total) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_cost_function_ckd_scenes";
   ECCKD_REQUIRE(ctx && scenes && nscene > 0, ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
   std::vector<CkdCostParams> ps((size_t)nscene);

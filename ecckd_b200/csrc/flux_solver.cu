@@ -778,6 +778,7 @@ static int upload_new(const double* h, size_t n, double** d) {
 }
 
 ECCKD_API int ecckd_ckd_model_destroy(ecckd_ckd_model* m) {
+  ECCKD_DEVICE(m ? m->ctx : nullptr);
   if (!m) return ECCKD_OK;
   if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
   for (double* p : m->d_molar_abs) cudaFree(p);
@@ -799,6 +800,7 @@ ECCKD_API int ecckd_ckd_model_create(ecckd_ctx* ctx, int ngas, const ecckd_gas_t
                                      const double* temperature_planck, const double* planck_lut,
                                      const double* solar_irradiance, const double* rayleigh_molar_scat,
                                      ecckd_ckd_model** out) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && gases && log_pressure && temperature && out, ECCKD_PARAMETER_ERROR,
                 "ecckd_ckd_model_create: NULL argument");
   ECCKD_REQUIRE(ngas > 0 && nt >= 2 && np >= 2 && ng > 0, ECCKD_PARAMETER_ERROR,
@@ -905,6 +907,7 @@ static dim3 g_block(int ng) { return dim3(ng <= 32 ? 32 : (ng <= 64 ? 64 : 128),
 ECCKD_API int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int igas, int ncol, int nlay,
                                                const double* d_pressure_hl, const double* d_temperature_fl,
                                                const double* d_vmr_fl, double* d_od, int accumulate) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_temperature_fl && d_od, ECCKD_PARAMETER_ERROR,
                 "ecckd_ckd_calc_optical_depth: NULL argument");
   ECCKD_REQUIRE(igas >= 0 && igas < m->ngas && ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR,
@@ -926,6 +929,7 @@ ECCKD_API int ecckd_ckd_calc_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* 
 ECCKD_API int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* const* h_d_vmr_fl,
                                                  int ncol, int nlay, const double* d_pressure_hl,
                                                  const double* d_temperature_hl, double* d_od) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && h_d_vmr_fl && d_pressure_hl && d_temperature_hl && d_od && ncol > 0 && nlay > 0,
                 ECCKD_PARAMETER_ERROR, "ecckd_calc_total_optical_depth: bad argument");
   const int64_t ncl = (int64_t)ncol * nlay;
@@ -949,6 +953,7 @@ ECCKD_API int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model
 
 ECCKD_API int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int64_t n,
                                                  const double* d_temperature, double* d_planck) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && d_temperature && d_planck && n > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_ckd_calc_planck_function: bad argument");
   ECCKD_REQUIRE(!m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_planck_function: shortwave model has no Planck table");
@@ -962,6 +967,7 @@ ECCKD_API int ecckd_ckd_calc_planck_function_dev(ecckd_ctx* ctx, ecckd_ckd_model
 
 ECCKD_API int ecckd_ckd_calc_rayleigh_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, int ncol, int nlay,
                                                         const double* d_pressure_hl, double* d_od) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_od && ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_ckd_calc_rayleigh_optical_depth: bad argument");
   ECCKD_REQUIRE(m->is_sw, ECCKD_PARAMETER_ERROR, "ecckd_ckd_calc_rayleigh_optical_depth: longwave model");
@@ -1019,6 +1025,7 @@ static int rt_lw_impl(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const doubl
 ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_planck,
                                               const double* d_od, const double* d_surf_emissivity,
                                               const double* d_surf_planck, double* d_flux_dn, double* d_flux_up) {
+  ECCKD_DEVICE(ctx);
   return rt_lw_impl(ctx, ncol, nlay, n, d_planck, d_od, d_surf_emissivity, d_surf_planck, d_flux_dn, d_flux_up, nullptr,
                     nullptr, nullptr);
 }
@@ -1026,6 +1033,7 @@ ECCKD_API int ecckd_radiative_transfer_lw_dev(ecckd_ctx* ctx, int ncol, int nlay
 ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* h_cos_sza,
                                               const double* d_ssi, const double* d_od, const double* d_albedo,
                                               double* d_flux_dn, double* d_flux_up) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && h_cos_sza && d_ssi && d_od && d_flux_dn, ECCKD_PARAMETER_ERROR,
                 "ecckd_radiative_transfer_sw: NULL argument");
   ECCKD_REQUIRE((d_albedo == nullptr) == (d_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
@@ -1057,6 +1065,7 @@ ECCKD_API int ecckd_radiative_transfer_sw_dev(ecckd_ctx* ctx, int ncol, int nlay
 
 ECCKD_API int ecckd_heating_rate_dev(ecckd_ctx* ctx, int ncol, int nlay, int64_t n, const double* d_pressure_hl,
                                      const double* d_flux_dn, const double* d_flux_up, double* d_hr) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_pressure_hl && d_flux_dn && d_hr, ECCKD_PARAMETER_ERROR, "ecckd_heating_rate: NULL argument");
   const int bs = n >= 128 ? 128 : (n > 32 ? 64 : 32);
   const int64_t nblk = (int64_t)ncol * nlay * ((n + bs - 1) / bs);
@@ -1072,8 +1081,15 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
                                 int ncol, int nlay, const double* d_pressure_hl, const double* d_temperature_hl,
                                 double* d_od, double* d_planck_hl, double* d_planck_surf, double* d_flux_dn,
                                 double* d_flux_up, double* d_bb_flux_dn, double* d_bb_flux_up) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && d_pressure_hl && d_temperature_hl, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: NULL argument");
   ECCKD_REQUIRE(ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: bad dimensions");
+  // The longwave sweep produces both fluxes together (radiative_transfer_lw.cpp:25-60 has no
+  // one-sided form), and a broadband sum is the sum over g of a spectral flux that was asked for.
+  ECCKD_REQUIRE(m->is_sw || ((d_flux_dn == nullptr) == (d_flux_up == nullptr)), ECCKD_PARAMETER_ERROR,
+                "ecckd_run_ckd: longwave d_flux_dn and d_flux_up must both be given or both be NULL");
+  ECCKD_REQUIRE((!d_bb_flux_dn || d_flux_dn) && (m->is_sw || !d_bb_flux_up || d_flux_up), ECCKD_PARAMETER_ERROR,
+                "ecckd_run_ckd: a broadband flux needs its spectral flux array");
   std::vector<GasDev> gd(m->ngas);
   for (int i = 0; i < m->ngas; ++i) {
     const double* v = h_d_vmr_fl ? h_d_vmr_fl[i] : nullptr;
@@ -1184,6 +1200,7 @@ ECCKD_API int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* co
                             int nlay, const double* pressure_hl, const double* temperature_hl, double* od,
                             double* planck_hl, double* planck_surf, double* flux_dn, double* flux_up,
                             double* bb_flux_dn, double* bb_flux_up) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && m && pressure_hl && temperature_hl, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: NULL argument");
   ECCKD_REQUIRE(ncol > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_run_ckd: bad dimensions");
   const int ng = m->ng, ngas = m->ngas;

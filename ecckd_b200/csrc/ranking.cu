@@ -589,6 +589,7 @@ using namespace ecckd;
 ECCKD_API int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
                                     const double* d_wn, const double* d_dwn, const double* d_od, int64_t od_stride,
                                     double thr, double* d_key, double* d_column_od) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && h_pressure_hl && d_wn && d_dwn && d_od && d_key, ECCKD_PARAMETER_ERROR,
                 "ecckd_sort_key_lw: NULL argument");
   ECCKD_REQUIRE(nlay > 0 && nlay <= 400 && nwav > 0 && od_stride >= nwav, ECCKD_PARAMETER_ERROR,
@@ -630,6 +631,7 @@ ECCKD_API int ecckd_sort_key_lw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, cons
 ECCKD_API int ecckd_sort_key_sw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, const double* h_pressure_hl,
                                     const double* d_od, int64_t od_stride, double thr, double* d_key,
                                     double* d_column_od) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && h_pressure_hl && d_od && d_key, ECCKD_PARAMETER_ERROR, "ecckd_sort_key_sw: NULL argument");
   ECCKD_REQUIRE(nlay > 0 && nwav > 0 && od_stride >= nwav, ECCKD_PARAMETER_ERROR, "ecckd_sort_key_sw: bad dimensions");
   std::vector<double> h_hl(nlay + 1);
@@ -655,6 +657,7 @@ ECCKD_API int ecckd_sort_key_sw_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, cons
 ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wn, const double* d_key, int nband,
                                    const double* h_b1, const double* h_b2, int32_t* d_iband, int32_t* d_rank,
                                    int32_t* d_ordered_index) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_wn && d_key && h_b1 && h_b2, ECCKD_PARAMETER_ERROR, "ecckd_rank_bands: NULL argument");
   ECCKD_REQUIRE(nwav > 0 && nwav < (int64_t)1 << 31, ECCKD_PARAMETER_ERROR, "ecckd_rank_bands: nwav out of range");
   // reorder_spectrum.cpp:245-248
@@ -768,6 +771,7 @@ ECCKD_API int ecckd_rank_bands_dev(ecckd_ctx* ctx, int64_t nwav, const double* d
 
 ECCKD_API int ecckd_store_g_points_dev(ecckd_ctx* ctx, int64_t nwav, const int32_t* d_rank, int ng,
                                        const int32_t* h_rank1, const int32_t* h_rank2, int32_t* d_g_point) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_rank && h_rank1 && h_rank2 && d_g_point, ECCKD_PARAMETER_ERROR,
                 "ecckd_store_g_points: NULL argument");
   ECCKD_REQUIRE(nwav > 0 && ng > 0 && ng <= 4096, ECCKD_PARAMETER_ERROR, "ecckd_store_g_points: bad dimensions");
@@ -842,6 +846,7 @@ ECCKD_API int ecckd_overlap_g_points(int ngas, int nband, const int32_t* n_g, co
 ECCKD_API int ecckd_assign_g_points_dev(ecckd_ctx* ctx, int ngas, int64_t nwav, const int32_t* d_gas_g_point, int ng,
                                         int cap, const int32_t* h_g_min, const int32_t* h_g_max, int32_t* d_g_point,
                                         int64_t* h_n_unassigned) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_gas_g_point && h_g_min && h_g_max && d_g_point, ECCKD_PARAMETER_ERROR,
                 "ecckd_assign_g_points: NULL argument");
   ECCKD_REQUIRE(ngas > 0 && nwav > 0 && ng > 0 && cap >= ng, ECCKD_PARAMETER_ERROR, "ecckd_assign_g_points: bad dimensions");

@@ -81,12 +81,15 @@ __device__ __forceinline__ void partial_begin(Partial& p, const double* __restri
 // further.  The slot loop handles 4 slots per trip and is not unrolled further: measured on the B200,
 // every variant with a bigger body (8 slots per trip, a register software pipeline, a deferred fold
 // threaded through the loop) was slower than this plain form.  `a` must come from partial_begin.
-template <int FKIND, int NR>
+// TAB64: the transmission kinds use the replicated 64-entry table (K3, lane_off = (lane & 15) << 3)
+// instead of the 256-entry one (K2).
+template <int FKIND, int NR, bool TAB64 = false>
 __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char* __restrict__ stage0,
                                            const uint16_t* __restrict__ offp, const double* __restrict__ wp,
                                            const int nv, const TransConst& K, const TransLane& tl,
                                            const bool (&is_log)[NR], const TransConst256& K2,
-                                           const unsigned char* __restrict__ tab) {
+                                           const unsigned char* __restrict__ tab,
+                                           const TransConst64* __restrict__ K3 = nullptr, const unsigned lane_off = 0u) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   // no register software pipeline: the loads of a trip are issued at its top and the other warps
   // of the scheduler cover their latency (the rotating pipeline cost 52 register moves per trip)
@@ -117,6 +120,9 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
         for (int j = 0; j < 4; ++j) {
           mn = (tau[r][j] < mn) ? tau[r][j] : mn;
           mx = (tau[r][j] > mx) ? tau[r][j] : mx;
+          // a NaN optical depth always lands here (its high word is outside every range): poison the
+          // sum, as the reference's sum() would be, instead of letting the clamps below absorb it
+          if (tau[r][j] != tau[r][j]) a[r].s0 = tau[r][j];
         }
         if (mn != a[r].mn || mx != a[r].mx) {
           a[r].mn = mn;
@@ -134,16 +140,16 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[r][j] = trans256_phase1(tau[r][j], K2);
+        for (int j = 0; j < 4; ++j) m[r][j] = TAB64 ? trans64_phase1(tau[r][j], *K3) : trans256_phase1(tau[r][j], K2);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) T[r][j] = trans256_phase2(m[r][j], tab);
+        for (int j = 0; j < 4; ++j) T[r][j] = TAB64 ? trans64_phase2(m[r][j], tab, lane_off) : trans256_phase2(m[r][j], tab);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[r][j] = trans256_phase3(m[r][j], T[r][j], K2);
+          f[r][j] = TAB64 ? trans64_phase3(m[r][j], T[r][j], *K3) : trans256_phase3(m[r][j], T[r][j], K2);
           pos[r][j] = true;
         }
     } else {

@@ -98,23 +98,24 @@ __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
 }
 
 // ------------------------------------------------------------------ plan
-// One block of `ch` threads per chunk.  Thread i owns local wavenumber i and
-// finds its (round, lane, slot): g points in ascending order, each padded to a
-// whole number of lanes; inside a g point, the k-th wavenumber goes to lane
-// (k mod L), slot (k div L), so that consecutive wavenumbers sit in consecutive
-// lanes (conflict-free shared-memory reads).
+// One block of `ch` threads per chunk (ch is a multiple of 32).  Thread i owns local wavenumber i
+// and finds its (round, lane, slot): g points in ascending order, each padded to a whole number of
+// lanes; inside a g point, the k-th wavenumber goes to lane (k mod L), slot (k div L), so that
+// consecutive wavenumbers sit in consecutive lanes.  With a window W > 0 a round is also closed
+// before the g point that would make it span W or more consecutive g indices.
 struct PlanPos {
-  int g;       // -1: belongs to no g point
-  int vlane;   // virtual lane over all rounds of the chunk
+  int g;        // -1: belongs to no g point
+  int vlane;    // virtual lane over all rounds of the chunk
   int slot;
-  int nvlanes; // total virtual lanes of the chunk
-  int kth;     // index of this wavenumber inside its g point (chunk-local)
-  int count;   // wavenumbers of its g point in the chunk
-  int L;       // lanes of its g point
+  int nvlanes;  // total virtual lanes of the chunk (with the window constraint, if any)
+  int nvfree;   // total virtual lanes without the window constraint
+  int kth;      // index of this wavenumber inside its g point (chunk-local)
+  int count;    // wavenumbers of its g point in the chunk
+  int L;        // lanes of its g point
 };
 
 __device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_point, int64_t nwav, int ng, int ch,
-                                                 int64_t c, int* sg, int* sl) {
+                                                 int64_t c, int W, int* sg, int* sred) {
   const int i = threadIdx.x;
   const int64_t w = c * ch + i;
   int g = -1;
@@ -131,39 +132,67 @@ __device__ __forceinline__ PlanPos plan_position(const int32_t* __restrict__ g_p
     k += same & (j < i);
   }
   const int L = (n + SLOTS - 1) / SLOTS;
-  sl[i] = (g >= 0 && k == 0) ? L : 0;
-  __syncthreads();
-  int a = 0, total = 0;
-  for (int j = 0; j < ch; ++j) {
-    const int lj = sl[j];
-    total += lj;
-    a += (sg[j] < g) ? lj : 0;  // sl[j] is non-zero only for valid first occurrences
+  // Walk the distinct g points of the chunk in ascending order (block-wide minimum of the g points
+  // not yet placed); every thread keeps the same running state.
+  const int lane = i & 31, warp = i >> 5, nwarps = (int)(blockDim.x >> 5);
+  int cur = -1, v = 0, v0 = 0, rgmin = -1, my_start = 0;
+  while (true) {
+    int cand = (g > cur) ? g : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cand = min(cand, __shfl_xor_sync(0xffffffffu, cand, o));
+    if (lane == 0) sred[warp] = cand;
+    __syncthreads();
+    int gn = 0x7fffffff;
+    for (int q = 0; q < nwarps; ++q) gn = min(gn, sred[q]);
+    if (gn == 0x7fffffff) break;  // block-uniform
+    if (g == gn && k == 0) sred[32] = L;
+    __syncthreads();
+    const int Lg = sred[32];
+    if (W > 0 && rgmin >= 0 && gn - rgmin >= W) {  // the round would span W g points: close it
+      v = (v + 31) & ~31;
+      rgmin = -1;
+    }
+    if (rgmin < 0) rgmin = gn;
+    const int start = v;
+    v += Lg;
+    v0 += Lg;
+    if ((v & 31) == 0) rgmin = -1;                      // the next g point opens a round
+    else if ((v >> 5) != (start >> 5)) rgmin = gn;      // this g point's tail opened the current round
+    if (g == gn) my_start = start;
+    cur = gn;
+    __syncthreads();  // sred is rewritten by the next trip
   }
   PlanPos p;
   p.g = g;
-  p.nvlanes = total;
+  p.nvlanes = v;
+  p.nvfree = v0;
   p.kth = k;
   p.count = n;
   p.L = L;
-  p.vlane = (g >= 0) ? a + (k % L) : 0;
+  p.vlane = (g >= 0) ? my_start + (k % L) : 0;
   p.slot = (g >= 0) ? (k / L) : 0;
   return p;
 }
 
-// rounds per chunk (at least one, so that every chunk visit has a ring entry) and, optionally,
-// the wavenumbers per g point
+// rounds per chunk (at least one, so that every chunk visit has a ring entry) with the window
+// constraint W (nrounds) and without it (nfree, optional), and, optionally, the wavenumbers per g point
 __global__ void __launch_bounds__(CH_MAX) plan_count_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
-                                                             uint32_t* __restrict__ nrounds,
+                                                             int W, uint32_t* __restrict__ nrounds,
+                                                             unsigned long long* __restrict__ nfree_total,
                                                              unsigned long long* __restrict__ count) {
   __shared__ int sg[CH_MAX];
-  __shared__ int sl[CH_MAX];
+  __shared__ int sred[33];
   const int64_t c = blockIdx.x;
-  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, sg, sl);
-  if (threadIdx.x == 0) nrounds[c] = (uint32_t)max(1, (p.nvlanes + 31) / 32);
+  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, W, sg, sred);
+  if (threadIdx.x == 0) {
+    nrounds[c] = (uint32_t)max(1, (p.nvlanes + 31) / 32);
+    if (nfree_total != nullptr) atomicAdd(nfree_total, (unsigned long long)max(1, (p.nvfree + 31) / 32));
+  }
   if (count != nullptr && p.g >= 0 && p.kth == 0) atomicAdd(&count[p.g], (unsigned long long)p.count);
 }
 
-__global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds) {
+__global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds, int32_t* __restrict__ rmin,
+                                 int32_t* __restrict__ rmax) {
   // unused lanes: offsets 0 (a valid address), no valid slots, meta = NO_G
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrounds * 32) return;
@@ -175,17 +204,20 @@ __global__ void plan_init_kernel(int64_t nrounds, PlanRound* __restrict__ rounds
     r.steps = 0;
     r.chunk = 0;
     r.flags = 0;
-    r.pad_ = 0;
+    r.win = 0;
+    rmin[i >> 5] = 0x7fffffff;
+    rmax[i >> 5] = -1;
   }
 }
 
 __global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __restrict__ g_point, int64_t nwav, int ng,
-                                                            const uint32_t* __restrict__ round_off,
-                                                            PlanRound* __restrict__ rounds) {
+                                                            int W, const uint32_t* __restrict__ round_off,
+                                                            PlanRound* __restrict__ rounds, int32_t* __restrict__ rmin,
+                                                            int32_t* __restrict__ rmax) {
   __shared__ int sg[CH_MAX];
-  __shared__ int sl[CH_MAX];
+  __shared__ int sred[33];
   const int64_t c = blockIdx.x;
-  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, sg, sl);
+  const PlanPos p = plan_position(g_point, nwav, ng, (int)blockDim.x, c, W, sg, sred);
   const uint32_t r0 = round_off[c], r1 = round_off[c + 1];
   if (threadIdx.x == 0) {
     for (uint32_t r = r0; r < r1; ++r) {
@@ -194,7 +226,8 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __rest
     }
   }
   if (p.g < 0) return;
-  PlanRound& rd = rounds[(size_t)r0 + (size_t)(p.vlane >> 5)];
+  const size_t rix = (size_t)r0 + (size_t)(p.vlane >> 5);
+  PlanRound& rd = rounds[rix];
   const int lane = p.vlane & 31;
   const uint16_t my = (uint16_t)(threadIdx.x * 8);
   auto slot_ref = [&](int slot) -> uint16_t& { return rd.off[slot][lane]; };
@@ -217,6 +250,29 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __rest
     const unsigned head = (lane == 0 || li == 0) ? 1u : 0u;
     rd.meta[lane] = (unsigned)p.g | ((unsigned)nv << 12) | (mask << 17) | (head << 22);
     if (steps > 0) atomicMax(&rd.steps, (uint32_t)steps);
+    atomicMin(&rmin[rix], p.g);
+    atomicMax(&rmax[rix], p.g);
+  }
+}
+
+// Windowed plans: the window base of every round, in round order (one warp; a round keeps the
+// previous window when its g points fit in it, else the window moves to the round's smallest g point).
+__global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __restrict__ rmin,
+                                   const int32_t* __restrict__ rmax, PlanRound* __restrict__ rounds) {
+  const int lane = threadIdx.x;
+  int gbase = 0;
+  for (int64_t base = 0; base < nrounds; base += 32) {
+    const int64_t r = base + lane;
+    const int mn_l = (r < nrounds) ? rmin[r] : 0x7fffffff;
+    const int mx_l = (r < nrounds) ? rmax[r] : -1;
+    int mine = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int mn = __shfl_sync(0xffffffffu, mn_l, j), mx = __shfl_sync(0xffffffffu, mx_l, j);
+      if (mn <= mx && !(mn >= gbase && mx < gbase + W)) gbase = mn;
+      if (lane == j) mine = gbase;
+    }
+    if (r < nrounds) rounds[r].win = (uint32_t)mine;
   }
 }
 
@@ -321,6 +377,130 @@ __device__ __forceinline__ bool cursor_next(Cursor& q, int ngroups, int cw, int 
   return true;
 }
 
+// The producer warps of the streaming kernels (reduce_kernel, reduce2_kernel): permuted weights +
+// plan record of every round of the CTA's piece, through the ring {wperm, PlanRound} x NSW at
+// shared-window address ring_s (generic pointer `ring`), full/empty mbarriers full_w/empty_w.
+template <int WMODE>
+__device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Cursor first, const int niter, const int pw,
+                                               const int lane, unsigned char* ring, const unsigned ring_s,
+                                               const unsigned full_w, const unsigned empty_w) {
+  const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
+  // ===================== producers: permuted weights + plan record of every round =====================
+  // Producer lane `lane` of warp pw fills wperm[k][lane] for the slots k = pw, pw + NPW, ...: the
+  // weight of the wavenumber the plan puts there (zero for padding slots).  Consecutive
+  // wavenumbers sit in consecutive lanes of a slot, so the gathers below are nearly coalesced.
+  // Software pipeline over ring entries (= plan rounds): plan offsets are fetched two entries
+  // ahead, wavenumbers / weights one entry ahead.
+  constexpr int PER = SLOTS / NPW;  // slots per producer lane per round
+  static_assert(SLOTS % NPW == 0, "slots must split evenly over the producer warps");
+  const TransLane ptl = trans_lane_init();
+  struct Entry {
+    uint32_t r;       // plan round
+    int64_t w0;       // first wavenumber of its chunk
+    int wrow;         // weight row (temperature index / matrix row)
+    bool valid;
+  };
+  Cursor q = first;
+  int visit = 0;
+  uint32_t r_cur = p.round_off[q.c], r_end = p.round_off[q.c + 1];
+  auto next_entry = [&]() {
+    Entry e;
+    e.valid = visit < niter;
+    e.r = r_cur;
+    e.w0 = (int64_t)q.c * ch;
+    e.wrow = e.valid ? p.groups[q.l].wrow : 0;
+    if (e.valid && ++r_cur == r_end) {
+      ++visit;
+      if (visit < niter) {
+        cursor_next(q, p.ngroups, p.cw, nchunks);
+        r_cur = p.round_off[q.c];
+        r_end = p.round_off[q.c + 1];
+      }
+    }
+    return e;
+  };
+  auto load_plan = [&](const Entry& e, unsigned (&off)[PER], unsigned& meta) {
+    if (!e.valid) return;
+    const PlanRound* pr = p.rounds + e.r;
+    meta = pr->meta[lane];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
+  };
+  auto load_src = [&](const Entry& e, const unsigned (&off)[PER], double (&x)[PER], double (&y)[PER]) {
+    if (!e.valid) return;
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      const int64_t w = e.w0 + (off[m] >> 3);
+      if (WMODE == W_PLANCK) {
+        x[m] = p.wn[w];
+        y[m] = p.dwn[w];
+      } else if (WMODE == W_MATRIX) {
+        x[m] = p.weight[(int64_t)e.wrow * p.w_stride + w];
+      } else {
+        x[m] = p.weight[w];
+      }
+    }
+  };
+  Entry e0 = next_entry(), e1 = next_entry();
+  unsigned off1[PER], meta0 = NO_G, meta1 = NO_G, meta2 = NO_G;
+  double x0[PER], y0[PER], x1[PER], y1[PER];
+  load_plan(e0, off1, meta0);
+  load_src(e0, off1, x0, y0);
+  load_plan(e1, off1, meta1);
+  int ws = 0, filled = 0;
+  unsigned epar = 0;
+  while (e0.valid) {
+    const Entry e2 = next_entry();
+    load_src(e1, off1, x1, y1);
+    load_plan(e2, off1, meta2);  // off1 is free again: the gathers above have their addresses
+    const int nv = (int)((meta0 >> 12) & 31u);
+    double val[PER];
+    if (WMODE == W_PLANCK) {
+      const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
+#pragma unroll
+      for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(hkt, x0[m], y0[m], ptl);
+    } else {
+#pragma unroll
+      for (int m = 0; m < PER; ++m) val[m] = x0[m];
+    }
+    unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+    double* wperm = reinterpret_cast<double*>(slot);
+    if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      const int k = pw + NPW * m;
+      wperm[k * 32 + lane] = (k < nv) ? val[m] : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (pw == 0) {
+        // (no proxy fence: the consumers only READ the old record through the generic proxy, and
+        // their release of the slot is ordered before this copy by the empty barrier)
+        mbar_arrive_expect_tx(full_w + ws * 8, (unsigned)sizeof(PlanRound));
+        bulk_g2s(ring_s + ws * RING_SLOT_BYTES + WPERM_BYTES, p.rounds + e0.r, (unsigned)sizeof(PlanRound),
+                 full_w + ws * 8);
+      } else {
+        mbar_arrive(full_w + ws * 8);
+      }
+    }
+    ++filled;
+    if (++ws == NSW) {
+      ws = 0;
+      if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
+    }
+    e0 = e1;
+    e1 = e2;
+    meta0 = meta1;
+    meta1 = meta2;
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      x0[m] = x1[m];
+      y0[m] = y1[m];
+    }
+  }
+}
+
 template <int FKIND, int WMODE>
 __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __grid_constant__ ReduceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -360,120 +540,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
   const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
 
   if (warp >= nw) {
-    // ===================== producers: permuted weights + plan record of every round =====================
-    // Producer lane `lane` of warp pw fills wperm[k][lane] for the slots k = pw, pw + NPW, ...: the
-    // weight of the wavenumber the plan puts there (zero for padding slots).  Consecutive
-    // wavenumbers sit in consecutive lanes of a slot, so the gathers below are nearly coalesced.
-    // Software pipeline over ring entries (= plan rounds): plan offsets are fetched two entries
-    // ahead, wavenumbers / weights one entry ahead.
-    const int pw = warp - nw;
-    constexpr int PER = SLOTS / NPW;  // slots per producer lane per round
-    static_assert(SLOTS % NPW == 0, "slots must split evenly over the producer warps");
-    const TransLane ptl = trans_lane_init();
-    struct Entry {
-      uint32_t r;       // plan round
-      int64_t w0;       // first wavenumber of its chunk
-      int wrow;         // weight row (temperature index / matrix row)
-      bool valid;
-    };
-    Cursor q = first;
-    int visit = 0;
-    uint32_t r_cur = p.round_off[q.c], r_end = p.round_off[q.c + 1];
-    auto next_entry = [&]() {
-      Entry e;
-      e.valid = visit < niter;
-      e.r = r_cur;
-      e.w0 = (int64_t)q.c * ch;
-      e.wrow = e.valid ? p.groups[q.l].wrow : 0;
-      if (e.valid && ++r_cur == r_end) {
-        ++visit;
-        if (visit < niter) {
-          cursor_next(q, p.ngroups, p.cw, nchunks);
-          r_cur = p.round_off[q.c];
-          r_end = p.round_off[q.c + 1];
-        }
-      }
-      return e;
-    };
-    auto load_plan = [&](const Entry& e, unsigned (&off)[PER], unsigned& meta) {
-      if (!e.valid) return;
-      const PlanRound* pr = p.rounds + e.r;
-      meta = pr->meta[lane];
-#pragma unroll
-      for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
-    };
-    auto load_src = [&](const Entry& e, const unsigned (&off)[PER], double (&x)[PER], double (&y)[PER]) {
-      if (!e.valid) return;
-#pragma unroll
-      for (int m = 0; m < PER; ++m) {
-        const int64_t w = e.w0 + (off[m] >> 3);
-        if (WMODE == W_PLANCK) {
-          x[m] = p.wn[w];
-          y[m] = p.dwn[w];
-        } else if (WMODE == W_MATRIX) {
-          x[m] = p.weight[(int64_t)e.wrow * p.w_stride + w];
-        } else {
-          x[m] = p.weight[w];
-        }
-      }
-    };
-    Entry e0 = next_entry(), e1 = next_entry();
-    unsigned off1[PER], meta0 = NO_G, meta1 = NO_G, meta2 = NO_G;
-    double x0[PER], y0[PER], x1[PER], y1[PER];
-    load_plan(e0, off1, meta0);
-    load_src(e0, off1, x0, y0);
-    load_plan(e1, off1, meta1);
-    int ws = 0, filled = 0;
-    unsigned epar = 0;
-    while (e0.valid) {
-      const Entry e2 = next_entry();
-      load_src(e1, off1, x1, y1);
-      load_plan(e2, off1, meta2);  // off1 is free again: the gathers above have their addresses
-      const int nv = (int)((meta0 >> 12) & 31u);
-      double val[PER];
-      if (WMODE == W_PLANCK) {
-        const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
-#pragma unroll
-        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(hkt, x0[m], y0[m], ptl);
-      } else {
-#pragma unroll
-        for (int m = 0; m < PER; ++m) val[m] = x0[m];
-      }
-      unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-      double* wperm = reinterpret_cast<double*>(slot);
-      if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
-#pragma unroll
-      for (int m = 0; m < PER; ++m) {
-        const int k = pw + NPW * m;
-        wperm[k * 32 + lane] = (k < nv) ? val[m] : 0.0;
-      }
-      __syncwarp();
-      if (lane == 0) {
-        if (pw == 0) {
-          // (no proxy fence: the consumers only READ the old record through the generic proxy, and
-          // their release of the slot is ordered before this copy by the empty barrier)
-          mbar_arrive_expect_tx(full_w + ws * 8, (unsigned)sizeof(PlanRound));
-          bulk_g2s(sbase + L.ring + ws * RING_SLOT_BYTES + WPERM_BYTES, p.rounds + e0.r, (unsigned)sizeof(PlanRound),
-                   full_w + ws * 8);
-        } else {
-          mbar_arrive(full_w + ws * 8);
-        }
-      }
-      ++filled;
-      if (++ws == NSW) {
-        ws = 0;
-        if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
-      }
-      e0 = e1;
-      e1 = e2;
-      meta0 = meta1;
-      meta1 = meta2;
-#pragma unroll
-      for (int m = 0; m < PER; ++m) {
-        x0[m] = x1[m];
-        y0[m] = y1[m];
-      }
-    }
+    produce_rounds<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w);
     return;
   }
 
@@ -578,6 +645,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
       mbar_wait(my_full + (set * RPW) * 8, (phase_bits >> set) & 1u);
       phase_bits ^= 1u << set;
     }
+    bool generic_fill = false;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int st = set * RPW + r;
@@ -585,6 +653,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
         const double* src = od_c[r] + (int64_t)q.c * ch;
         double* stage = reinterpret_cast<double*>(data + st * STAGE_BYTES);
         for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
+        generic_fill = true;
       }
     }
     __syncwarp();
@@ -644,8 +713,14 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
         wpar ^= 1u;
       }
     }
-    // re-arm the set for the visit after next.  No proxy fence: the stage was only READ through the
-    // generic proxy, and those loads completed before the __syncwarp above (their values were used).
+    // re-arm the set for the visit after next.  The stage was only READ through the generic proxy
+    // (those loads completed before the __syncwarp above: their values were used) unless this visit
+    // filled it with generic stores (unaligned rows, odd tails): then a proxy fence orders those
+    // stores before the asynchronous-proxy writes of the next bulk copy into the same stage.
+    if (generic_fill) {
+      fence_proxy_async();
+      __syncwarp();
+    }
     if (k + NSETS < niter) issue(set);
     if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
       flush_partial(vg);
@@ -657,6 +732,394 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce_kernel(const __
 #pragma unroll 1
   for (int k = 0; k < niter; ++k) visit(k & (NSETS - 1), k);
   if (!need_group) flush_partial(vg);
+}
+
+// ------------------------------------------------------------------ reduce, windowed plans
+// reduce2_kernel: the same streaming structure as reduce_kernel (bulk-copied stages, producer ring,
+// one (lane, slot) plan round at a time) for windowed plans and the kinds without per-row weight
+// sums (linear, transmission-k, square-root, weight sums only).  What differs is everything that
+// happens once per round, which took as long as the slot loop itself in reduce_kernel (ncu: 48 % of
+// the consumer warps' time, profiles/README.md):
+//   * no shuffle fold: a lane adds its round sums to ITS OWN shared-memory entry
+//     ent[g - window][lane] (one 16-byte read-modify-write for both rows, conflict-free, no
+//     synchronisation); the 32 lanes of an entry are only added up - butterfly, fixed order -
+//     when the window of g points moves (a band change) or the CTA's piece ends;
+//   * the running extremes of a (row, g point) AND the two words of their range check are cached in
+//     shared memory (mmv, mmb): a round starts with two loads per row instead of recomputing them,
+//     and they are only rewritten in the rare rounds in which some lane found a new extreme;
+//   * the per-(window, group) results go straight to the CTA's partial slot in global memory
+//     (no [row][ng][4] accumulators in shared memory).
+// The summation order is fixed by the plan and the launch geometry: bitwise reproducible.
+struct Smem2Layout {
+  int tab;   // replicated 2^(j/64) table (trans_core.cuh), at offset 0
+  int bars;  // mbarriers: full_d[nw][NSETS], full_w[NSW], empty_w[NSW]
+  int ring;  // ring slots [NSW]: {double wperm[SLOTS*32]; PlanRound plan}
+  int data;  // data stages [nw][NSETS*RPW][CH_MAX] doubles
+  int ent;   // [nw][WIN][32] double2: per-lane sums of the window's g points, both rows
+  int s1e;   // [WIN][32] double: per-lane weight sums (last consumer warp)
+  int mmv;   // [nw][RPW][WIN] double2 {min, max}
+  int mmb;   // [nw][RPW][WIN] uint2 {lowb, span} of the range check (reduce_rows.cuh)
+  int total;
+};
+__host__ __device__ inline Smem2Layout smem2_layout(int nw) {
+  Smem2Layout L;
+  int off = 0;
+  L.tab = off;
+  off += TRANS_TAB64_BYTES;
+  L.bars = off;
+  off += (nw * NSETS + 2 * NSW) * 8;
+  off = (off + 127) & ~127;
+  L.ring = off;
+  off += NSW * RING_SLOT_BYTES;
+  L.data = off;
+  off += nw * NSETS * RPW * STAGE_BYTES;
+  L.ent = off;
+  off += nw * WIN * 32 * 16;
+  L.s1e = off;
+  off += WIN * 32 * 8;
+  L.mmv = off;
+  off += nw * RPW * WIN * 16;
+  L.mmb = off;
+  off += nw * RPW * WIN * 8;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+// A rare round end: some lane found a new extreme.  Lane by lane (ballot order), lane 0 merges the
+// lane's extremes into the (row, entry) cache and refreshes the range-check words.
+template <int NR>
+__device__ __forceinline__ void merge_extremes(const Partial (&a)[NR], const int e, const bool used, double2* mmv,
+                                               uint2* mmb, const int lane) {
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    unsigned m = __ballot_sync(0xffffffffu, used && a[r].upd != 0);
+    while (m) {  // warp-uniform
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const int es = __shfl_sync(0xffffffffu, e, src);
+      const double mn = __shfl_sync(0xffffffffu, a[r].mn, src);
+      const double mx = __shfl_sync(0xffffffffu, a[r].mx, src);
+      if (lane == 0) {
+        double2 v = mmv[r * WIN + es];
+        v.x = (mn < v.x) ? mn : v.x;
+        v.y = (mx > v.y) ? mx : v.y;
+        mmv[r * WIN + es] = v;
+        Partial t;
+        t.mn = v.x;
+        t.mx = v.y;
+        minmax_bounds(t);
+        mmb[r * WIN + es] = make_uint2(t.lowb, t.span);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int FKIND, int WMODE>
+__global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const __grid_constant__ ReduceParams p) {
+  static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
+                "reduce2_kernel: kinds with per-row weight sums run on reduce_kernel");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nw = p.nw, ng = p.ng;
+  const Smem2Layout L = smem2_layout(nw);
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned full_d = sbase + L.bars;         // mbarriers [nw][NSETS], 8 bytes each
+  const unsigned full_w = full_d + nw * NSETS * 8; // [NSW]
+  const unsigned empty_w = full_w + NSW * 8;       // [NSW]
+  unsigned char* ring = smem_raw + L.ring;
+  constexpr bool USES_TAU = (FKIND != F_NONE);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < nw * NSETS; ++i) mbar_init(full_d + i * 8, 1);
+    for (int i = 0; i < NSW; ++i) {
+      mbar_init(full_w + i * 8, NPW);
+      mbar_init(empty_w + i * 8, nw);
+    }
+    fence_mbar_init();
+  }
+  if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
+  __syncthreads();
+  const unsigned char* tab = smem_raw + L.tab;
+
+  // this CTA's contiguous piece of the (window, group, chunk) space
+  const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
+  const int64_t T = (int64_t)p.ngroups * p.nchunks;
+  const int64_t lo = (T * blockIdx.x) / p.ncta;
+  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
+  const int niter = (int)(hi - lo);
+  if (niter == 0) return;
+  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
+  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
+
+  if (warp >= nw) {
+    produce_rounds<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w);
+    return;
+  }
+
+  // ===================== consumers: warp = RPW rows of the group =====================
+  const TransLane tl = {0, 0};  // (only the logarithmic kinds of reduce_kernel use the lane table)
+  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE_BYTES;
+  const unsigned my_full = full_d + warp * NSETS * 8;
+  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * STAGE_BYTES;
+  double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
+  double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
+  double2* mmv = reinterpret_cast<double2*>(smem_raw + L.mmv) + warp * RPW * WIN;
+  uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + warp * RPW * WIN;
+  const unsigned lane_off = (unsigned)(lane & 15) << 3;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const uint64_t pol = policy_evict_first();
+  // the weight sums do not depend on the row: the last consumer warp (the one with the fewest rows)
+  // accumulates them once per group; they end up in the s1 field of its row 0
+  const bool s1_duty = warp == nw - 1;
+
+  int gbase = -1;            // first g point of the current window (-1: none loaded)
+  double* pout = nullptr;    // this warp's rows of the current (window, group) piece: [RPW][ng][4]
+  int32_t* poutz = nullptr;
+
+  // the warp's rows of a new (window, group) piece start as {0, 0, +inf, -inf}
+  auto begin_piece = [&](int vg) {
+    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (nw * RPW) + warp * RPW;
+    pout = p.partial + slot * ng * 4;
+    poutz = p.partial_z + slot * ng;
+    for (int i = lane; i < RPW * ng; i += 32) {
+      double2* q = reinterpret_cast<double2*>(pout + (size_t)i * 4);
+      q[0] = make_double2(0.0, 0.0);
+      q[1] = make_double2(inf, -inf);
+      poutz[i] = 0;
+    }
+    __syncwarp();
+    gbase = -1;
+  };
+  // add the window's entries up over the lanes (fixed butterfly) and fold them, with the extremes,
+  // into the piece: lane e writes g point gbase + e
+  auto window_store = [&]() {
+    if (gbase < 0) return;  // warp-uniform
+    double t0 = 0.0, t1 = 0.0, ts = 0.0;
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) {
+      double2 v = ent[e * 32 + lane];
+      double s = s1_duty ? s1e[e * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        if (s1_duty) s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      if (lane == e) {
+        t0 = v.x;
+        t1 = v.y;
+        ts = s;
+      }
+    }
+    const int g = gbase + lane;
+    if (lane < WIN && g < ng) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        double* q = pout + ((size_t)r * ng + g) * 4;
+        const double2 mm = mmv[r * WIN + lane];
+        q[0] += (r == 0) ? t0 : t1;
+        q[2] = (mm.x < q[2]) ? mm.x : q[2];
+        q[3] = (mm.y > q[3]) ? mm.y : q[3];
+      }
+      if (s1_duty) pout[(size_t)g * 4 + 1] += ts;
+    }
+    __syncwarp();
+  };
+  // open the window [nb, nb + WIN): zero entries, extremes and range-check words from the piece
+  auto window_load = [&](int nb) {
+    gbase = nb;
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) ent[e * 32 + lane] = make_double2(0.0, 0.0);
+    if (s1_duty) {
+#pragma unroll
+      for (int e = 0; e < WIN; ++e) s1e[e * 32 + lane] = 0.0;
+    }
+    if (lane < WIN) {
+      const int g = nb + lane;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        Partial t;
+        t.mn = inf;
+        t.mx = -inf;
+        if (g < ng) {
+          const double* q = pout + ((size_t)r * ng + g) * 4;
+          t.mn = q[2];
+          t.mx = q[3];
+        }
+        minmax_bounds(t);
+        mmv[r * WIN + lane] = make_double2(t.mn, t.mx);
+        mmb[r * WIN + lane] = make_uint2(t.lowb, t.span);
+      }
+    }
+    __syncwarp();
+  };
+
+  // issue cursor (runs NSETS chunk visits ahead of the compute cursor)
+  Cursor qi = first;
+  const double* od_i[RPW];
+  bool bulk_i[RPW];
+  auto load_issue_group = [&]() {
+    const GroupDesc* gd = p.groups + qi.l;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int i = warp + r * nw;
+      const bool act = USES_TAU && i < gd->nrows;
+      od_i[r] = act ? gd->od[i] : nullptr;
+      bulk_i[r] = act && gd->bulk_ok[i];
+    }
+  };
+  auto issue = [&](int set) {
+    const int n_c = (qi.c == nchunks - 1) ? last_n : ch;
+    if (lane == 0 && ((n_c & 1) == 0)) {
+      // the rows of a set complete on ONE mbarrier (one wait per chunk visit instead of one per row)
+      const unsigned bar = my_full + set * 8;
+      int nb = 0;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) nb += bulk_i[r] ? 1 : 0;
+      if (nb > 0) {
+        mbar_arrive_expect_tx(bar, (unsigned)(nb * n_c * 8));
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          if (bulk_i[r])
+            bulk_g2s_hint(my_data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
+        }
+      }
+    }
+    if (cursor_next(qi, p.ngroups, p.cw, nchunks)) load_issue_group();
+  };
+  load_issue_group();
+  for (int j = 0; j < NSETS && j < niter; ++j) issue(j);
+
+  Cursor q = first;
+  int ws = 0, vg = 0;
+  unsigned wpar = 0;
+  unsigned phase_bits = 0;  // bit `set`: parity to wait for on that stage set's mbarrier
+  const double* od_c[RPW];
+  bool active[RPW], bulk_row[RPW];
+  bool need_group = true;
+
+  // the slots of one round for NR rows: range-check words and extremes from the cache, slot loop,
+  // sums into the lane's entry, extremes back into the cache if one changed
+  auto round_rows = [&](auto nr_tag, const unsigned char* stage0, const uint16_t* offp, const double* wp, const int e,
+                        const bool used) {
+    constexpr int NR = decltype(nr_tag)::value;
+    Partial a[NR];
+    bool il[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const double2 mm = mmv[r * WIN + e];
+      const uint2 b = mmb[r * WIN + e];
+      a[r].s0 = 0.0;
+      a[r].s1 = 0.0;
+      a[r].zc = 0;
+      a[r].upd = 0;
+      a[r].mn = mm.x;
+      a[r].mx = mm.y;
+      a[r].lowb = used ? b.x : 0u;          // unused lanes accept everything: no exact path, no update
+      a[r].span = used ? b.y : 0xFFFFFFFFu;
+      il[r] = false;
+    }
+    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off);
+    if (used) {
+      double2 v = ent[e * 32 + lane];
+      v.x += a[0].s0;
+      if (NR > 1) v.y += a[NR - 1].s0;
+      ent[e * 32 + lane] = v;
+    }
+    int u = 0;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) u |= a[r].upd;
+    if (__any_sync(0xffffffffu, used && u != 0)) merge_extremes<NR>(a, e, used, mmv, mmb, lane);
+  };
+
+  // one chunk visit on stage set `set`
+  auto visit = [&](const int set, const int k) {
+    if (need_group) {
+      const GroupDesc* gd = p.groups + q.l;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int i = warp + r * nw;
+        active[r] = USES_TAU && i < gd->nrows;
+        od_c[r] = active[r] ? gd->od[i] : nullptr;
+        bulk_row[r] = active[r] && gd->bulk_ok[i];
+      }
+      begin_piece(vg);
+      need_group = false;
+    }
+    const int n_c = (q.c == nchunks - 1) ? last_n : ch;
+    bool any_bulk = false;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) any_bulk = any_bulk || bulk_row[r];
+    if (any_bulk && ((n_c & 1) == 0)) {
+      mbar_wait(my_full + set * 8, (phase_bits >> set) & 1u);
+      phase_bits ^= 1u << set;
+    }
+    bool generic_fill = false;
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      const int st = set * RPW + r;
+      if (!(bulk_row[r] && ((n_c & 1) == 0)) && active[r]) {
+        const double* src = od_c[r] + (int64_t)q.c * ch;
+        double* stage = reinterpret_cast<double*>(data + st * STAGE_BYTES);
+        for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
+        generic_fill = true;
+      }
+    }
+    __syncwarp();
+    bool last_round = false;
+    while (!last_round) {
+      mbar_wait(full_w + ws * 8, wpar);
+      const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
+      const double* wp = reinterpret_cast<const double*>(slot) + lane;
+      const uint16_t* offp = &pr->off[0][lane];
+      const unsigned meta = pr->meta[lane];
+      const int wb = (int)pr->win;
+      last_round = (pr->flags & 2u) != 0;
+      if (wb != gbase) {  // warp-uniform: the window of g points moves (or the piece is new)
+        window_store();
+        window_load(wb);
+      }
+      const unsigned g = meta & 0xFFFu;
+      const bool used = g != NO_G;
+      const int e = used ? min(max((int)g - gbase, 0), WIN - 1) : 0;  // the plan keeps g inside the window
+      if (s1_duty) {
+        double s = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < SLOTS; ++kk) s += wp[kk * 32];
+        if (used) s1e[e * 32 + lane] += s;
+      }
+      if (USES_TAU && active[0]) {
+        const unsigned char* stage0 = data + (set * RPW) * STAGE_BYTES;
+        if (active[RPW - 1]) round_rows(std::integral_constant<int, RPW>{}, stage0, offp, wp, e, used);
+        else round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_w + ws * 8);
+      if (++ws == NSW) {
+        ws = 0;
+        wpar ^= 1u;
+      }
+    }
+    // re-arm the set for the visit after next (see reduce_kernel for the proxy fence)
+    if (generic_fill) {
+      fence_proxy_async();
+      __syncwarp();
+    }
+    if (k + NSETS < niter) issue(set);
+    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
+      window_store();
+      ++vg;
+      need_group = true;
+    }
+  };
+
+#pragma unroll 1
+  for (int k = 0; k < niter; ++k) visit(k & (NSETS - 1), k);
+  if (!need_group) window_store();
 }
 
 // ------------------------------------------------------------------ combine + finalize
@@ -752,6 +1215,10 @@ __global__ void finalize_kernel(const FinalizeParams p) {
     fit = 0.0;
     mn = 0.0;
     mx = 0.0;
+  } else if (s0 != s0) {
+    // a NaN optical depth poisoned the sum (reduce_rows.cuh): keep it visible instead of clamping it away
+    wflag |= ECCKD_WARN_NONFINITE;
+    fit = s0;
   } else {
     fit = fmax(mn, fmin(fit, mx));
     if (mn > fit) {
@@ -859,40 +1326,54 @@ __global__ void compact_remap_kernel(int ng, int64_t nwav, int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------ host side
-template <int FKIND, int WMODE>
+template <int FKIND, int WMODE, bool V2>
 static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta_out,
                                    bool dry_run) {
-  cudaError_t e = cudaFuncSetAttribute(reduce_kernel<FKIND, WMODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  void (*kernel)(const ReduceParams) = nullptr;
+  if constexpr (V2) kernel = reduce2_kernel<FKIND, WMODE>;
+  else kernel = reduce_kernel<FKIND, WMODE>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   if (dry_run) {
     int nb = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, reduce_kernel<FKIND, WMODE>, threads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem);
     if (e != cudaSuccess) return e;
     *ncta_out = std::max(1, nb) * ctx->num_sms;
     return cudaSuccess;
   }
-  reduce_kernel<FKIND, WMODE><<<p.ncta, threads, smem, ctx->stream>>>(p);
+  kernel<<<p.ncta, threads, smem, ctx->stream>>>(p);
   return cudaGetLastError();
 }
 
-template <int FKIND>
+template <int FKIND, bool V2>
 static cudaError_t launch_reduce_w(int wmode, ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta,
                                    bool dry) {
-  if (wmode == W_MATRIX) return launch_reduce_t<FKIND, W_MATRIX>(ctx, p, threads, smem, ncta, dry);
-  if (wmode == W_VECTOR) return launch_reduce_t<FKIND, W_VECTOR>(ctx, p, threads, smem, ncta, dry);
-  return launch_reduce_t<FKIND, W_PLANCK>(ctx, p, threads, smem, ncta, dry);
+  if (wmode == W_MATRIX) return launch_reduce_t<FKIND, W_MATRIX, V2>(ctx, p, threads, smem, ncta, dry);
+  if (wmode == W_VECTOR) return launch_reduce_t<FKIND, W_VECTOR, V2>(ctx, p, threads, smem, ncta, dry);
+  return launch_reduce_t<FKIND, W_PLANCK, V2>(ctx, p, threads, smem, ncta, dry);
 }
 
-static cudaError_t launch_reduce(int fkind, int wmode, ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem,
-                                 int* ncta, bool dry) {
+// v2: the windowed kernel (reduce2_kernel); only for the kinds reduce2_supports() names
+static bool reduce2_supports(int fkind) {
+  return fkind == F_LINEAR || fkind == F_TRANS || fkind == F_SQRT || fkind == F_NONE;
+}
+static cudaError_t launch_reduce(int fkind, int wmode, bool v2, ecckd_ctx* ctx, ReduceParams& p, int threads,
+                                 size_t smem, int* ncta, bool dry) {
+  if (v2) {
+    switch (fkind) {
+      case F_LINEAR: return launch_reduce_w<F_LINEAR, true>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_TRANS: return launch_reduce_w<F_TRANS, true>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_SQRT: return launch_reduce_w<F_SQRT, true>(wmode, ctx, p, threads, smem, ncta, dry);
+      default: return launch_reduce_w<F_NONE, true>(wmode, ctx, p, threads, smem, ncta, dry);
+    }
+  }
   switch (fkind) {
-    case F_LINEAR: return launch_reduce_w<F_LINEAR>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_TRANS: return launch_reduce_w<F_TRANS>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_SQRT: return launch_reduce_w<F_SQRT>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_LOG: return launch_reduce_w<F_LOG>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_HYBRID: return launch_reduce_w<F_HYBRID>(wmode, ctx, p, threads, smem, ncta, dry);
-    default: return launch_reduce_w<F_NONE>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_LINEAR: return launch_reduce_w<F_LINEAR, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_TRANS: return launch_reduce_w<F_TRANS, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_SQRT: return launch_reduce_w<F_SQRT, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_LOG: return launch_reduce_w<F_LOG, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_HYBRID: return launch_reduce_w<F_HYBRID, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    default: return launch_reduce_w<F_NONE, false>(wmode, ctx, p, threads, smem, ncta, dry);
   }
 }
 
@@ -919,11 +1400,13 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     longest = std::max(longest, run);
   }
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
+  // windowed plans run on reduce2_kernel (ECCKD_REDUCE_V1=1 keeps reduce_kernel, for comparisons)
+  const bool v2 = plan->windowed && reduce2_supports(fkind) && !(getenv("ECCKD_REDUCE_V1") && atoi(getenv("ECCKD_REDUCE_V1")));
+  auto smem_of = [&](int n) { return v2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total; };
   int nw = std::min(NW_MAX, (longest + RPW - 1) / RPW);
-  while (nw > 1 && (size_t)smem_layout(nw, ng).total > smem_max) --nw;
-  ECCKD_REQUIRE((size_t)smem_layout(nw, ng).total <= smem_max, ECCKD_PARAMETER_ERROR,
-                "average_optical_depth: ng = %d needs %d B of shared memory (limit %zu)", ng,
-                smem_layout(nw, ng).total, smem_max);
+  while (nw > 1 && smem_of(nw) > smem_max) --nw;
+  ECCKD_REQUIRE(smem_of(nw) <= smem_max, ECCKD_PARAMETER_ERROR,
+                "average_optical_depth: ng = %d needs %zu B of shared memory (limit %zu)", ng, smem_of(nw), smem_max);
   // balance: split a run of n rows into ceil(n/(nw*RPW)) groups of nearly equal size
   const int cap = nw * RPW;
   std::vector<GroupDesc> groups;
@@ -950,7 +1433,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   }
   const int ngroups = (int)groups.size();
   const int threads = (nw + NPW) * 32;
-  const size_t smem = (size_t)smem_layout(nw, ng).total;
+  const size_t smem = smem_of(nw);
 
   ReduceParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -969,6 +1452,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.dwn = d_dwn;
   trans_const_init(&rp.tc, kd);
   trans_const256_init(&rp.tc256, kd);
+  trans_const64_init(&rp.tc64, kd);
 #ifdef ECCKD_TIMING_KNOBS  // builds for tools/variants.sh only: the knobs skip work, the results are wrong
   if (const char* e = getenv("ECCKD_DEBUG")) rp.debug = atoi(e);
 #endif
@@ -987,7 +1471,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.cw = cw;
 
   int ncta = 0;
-  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, ctx, rp, threads, smem, &ncta, true));
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, v2, ctx, rp, threads, smem, &ncta, true));
   const int64_t T = (int64_t)ngroups * plan->nchunks;
   ncta = (int)std::min<int64_t>(ncta, std::max<int64_t>(1, T));
   // (window, group) pairs a CTA's contiguous piece can touch
@@ -1033,7 +1517,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     ECCKD_CUDA_OK(cudaEventCreate(&ev1));
     ECCKD_CUDA_OK(cudaEventRecord(ev0, ctx->stream));
   }
-  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, ctx, rp, threads, smem, &ncta, false));
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, v2, ctx, rp, threads, smem, &ncta, false));
   ctx->launches++;
   if (ctx->timing) {
     ECCKD_CUDA_OK(cudaEventRecord(ev1, ctx->stream));
@@ -1152,6 +1636,7 @@ static void plan_free(ecckd_gpoint_plan* p) {
 
 ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
                                        ecckd_gpoint_plan** out) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_g_point && out, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: NULL argument");
   ECCKD_REQUIRE(nwav > 0 && ng > 0 && ng <= MAX_NG, ECCKD_PARAMETER_ERROR,
                 "ecckd_gpoint_plan_create: need nwav > 0 and 0 < ng <= %d (got nwav=%lld ng=%d)", MAX_NG,
@@ -1164,53 +1649,83 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   // Chunk length: the plan packs every chunk into rounds of 32 lanes x 16 slots with each g point
   // padded to whole lanes, so the longest chunk whose g points still fit one round is the cheapest;
   // it depends on how many g points meet inside a chunk.  Count the rounds for a few candidates
-  // (longest first) and keep the one needing the fewest rounds per wavenumber.
+  // (longest first), with and without the window constraint of reduce2_kernel, and keep the
+  // cheapest (a windowed round costs ~0.77 of a free one: no shuffle fold).
   static const int candidates[] = {CH_MAX, 448, 384, 320, 256};
   const int64_t max_chunks = (nwav + 255) / 256;
   ECCKD_REQUIRE(max_chunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
   uint32_t* d_nrounds = nullptr;
+  unsigned long long* d_nfree = nullptr;
+  int32_t* d_rminmax = nullptr;
   cudaError_t e = cudaMallocAsync(&p->d_round_off, (size_t)(max_chunks + 1) * sizeof(uint32_t), ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nrounds, (size_t)max_chunks * sizeof(uint32_t), ctx->stream);
+  if (e == cudaSuccess) e = cudaMallocAsync(&d_nfree, sizeof(unsigned long long), ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&p->d_count, (size_t)ng * sizeof(unsigned long long), ctx->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(p->d_count, 0, (size_t)ng * sizeof(unsigned long long), ctx->stream);
   uint32_t total = 0;
   std::vector<unsigned long long> cnt(ng);
-  int best_ch = 0;
-  if (const char* env = getenv("ECCKD_CH")) best_ch = std::min(CH_MAX, std::max(2, atoi(env) & ~1));
-  auto count_rounds = [&](int ch, bool with_counts, uint32_t* h_total) {
+  int best_ch = 0, best_w = WIN;
+  int force_w = -1;  // ECCKD_PLAN_WINDOW=0: free plans only (reduce_kernel), =1: windowed plans only
+  if (const char* env = getenv("ECCKD_PLAN_WINDOW")) force_w = atoi(env) ? 1 : 0;
+  if (const char* env = getenv("ECCKD_CH")) best_ch = std::min(CH_MAX, std::max(32, atoi(env) & ~31));
+  // rounds of a plan with chunk length ch and window w (h_total), and without a window (h_free)
+  auto count_rounds = [&](int ch, int w, bool with_counts, uint32_t* h_total, unsigned long long* h_free) {
     const int64_t nch = (nwav + ch - 1) / ch;
-    plan_count_kernel<<<(unsigned)nch, ch, 0, ctx->stream>>>(d_g_point, nwav, ng, d_nrounds,
+    cudaError_t err = cudaSuccess;
+    if (h_free) err = cudaMemsetAsync(d_nfree, 0, sizeof(unsigned long long), ctx->stream);
+    if (err != cudaSuccess) return err;
+    plan_count_kernel<<<(unsigned)nch, ch, 0, ctx->stream>>>(d_g_point, nwav, ng, w, d_nrounds,
+                                                              h_free ? d_nfree : nullptr,
                                                               with_counts ? p->d_count : nullptr);
     exclusive_scan_kernel<<<1, 1024, 0, ctx->stream>>>(nch, d_nrounds, p->d_round_off);
     ctx->launches += 2;
-    cudaError_t err = cudaGetLastError();
+    err = cudaGetLastError();
     if (err == cudaSuccess)
       err = cudaMemcpyAsync(h_total, p->d_round_off + nch, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess && h_free)
+      err = cudaMemcpyAsync(h_free, d_nfree, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
     return err;
   };
+  const double windowed_round_cost = 0.77;
+  auto cost_of = [&](uint32_t tot_w, unsigned long long tot_free, int* w_out) {
+    const double cw = windowed_round_cost * (double)tot_w, cf = (double)tot_free;
+    const bool use_w = force_w < 0 ? (cw <= cf) : (force_w == 1);
+    *w_out = use_w ? WIN : 0;
+    return use_w ? cw : cf;
+  };
+  if (e == cudaSuccess && best_ch != 0) {
+    uint32_t tot = 0;
+    unsigned long long tot_free = 0;
+    e = count_rounds(best_ch, WIN, false, &tot, &tot_free);
+    if (e == cudaSuccess) cost_of(tot, tot_free, &best_w);
+  }
   if (e == cudaSuccess && best_ch == 0) {
     double best_cost = 0.0;
     for (const int& ch : candidates) {
       uint32_t tot = 0;
-      e = count_rounds(ch, false, &tot);
+      unsigned long long tot_free = 0;
+      e = count_rounds(ch, WIN, false, &tot, &tot_free);
       if (e != cudaSuccess) break;
-      const double cost = (double)tot;  // every round costs the same 32 x 16 slots per row
+      int w = 0;
+      const double cost = cost_of(tot, tot_free, &w);  // every round costs the same 32 x 16 slots per row
       if (best_ch == 0 || cost < best_cost * 0.995) {
         best_ch = ch;
         best_cost = cost;
+        best_w = w;
       }
       // the next (shorter) candidate needs at least one round per chunk: stop when that cannot win
       const size_t idx = (size_t)(&ch - candidates);
       if (idx + 1 < sizeof(candidates) / sizeof(candidates[0]) &&
-          (double)tot <= 0.995 * (double)((nwav + candidates[idx + 1] - 1) / candidates[idx + 1]))
+          best_cost <= 0.995 * windowed_round_cost * (double)((nwav + candidates[idx + 1] - 1) / candidates[idx + 1]))
         break;
     }
   }
   if (e == cudaSuccess) {
     p->ch = best_ch;
+    p->windowed = best_w > 0;
     p->nchunks = (nwav + best_ch - 1) / best_ch;
-    e = count_rounds(best_ch, true, &total);
+    e = count_rounds(best_ch, best_w, true, &total, nullptr);
   }
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(cnt.data(), p->d_count, (size_t)ng * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -1220,15 +1735,23 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
     p->nrounds = total;
     const size_t nr = std::max<size_t>(1, total);
     e = cudaMallocAsync(&p->d_rounds, (nr + 1) * sizeof(PlanRound), ctx->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_rminmax, 2 * nr * sizeof(int32_t), ctx->stream);
     if (e == cudaSuccess) {
-      plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds);
-      plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, p->d_round_off,
-                                                                          p->d_rounds);
+      plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds, d_rminmax,
+                                                                                    d_rminmax + nr);
+      plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, best_w, p->d_round_off,
+                                                                          p->d_rounds, d_rminmax, d_rminmax + nr);
       ctx->launches += 2;
+      if (best_w > 0) {
+        plan_window_kernel<<<1, 32, 0, ctx->stream>>>((int64_t)nr, best_w, d_rminmax, d_rminmax + nr, p->d_rounds);
+        ctx->launches++;
+      }
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller
   }
+  if (d_rminmax) cudaFreeAsync(d_rminmax, ctx->stream);
+  if (d_nfree) cudaFreeAsync(d_nfree, ctx->stream);
   if (d_nrounds) cudaFreeAsync(d_nrounds, ctx->stream);
   if (e != cudaSuccess) {
     set_error("ecckd_gpoint_plan_create: %s", cudaGetErrorString(e));
@@ -1241,12 +1764,16 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
 }
 
 namespace ecckd {
-__global__ void debug_eval_kernel(int which, TransConst K, TransConst256 K2, double kd, int64_t n,
+__global__ void debug_eval_kernel(int which, TransConst K, TransConst256 K2, TransConst64 K3, double kd, int64_t n,
                                   const double* __restrict__ x, double* __restrict__ out) {
   __shared__ __align__(16) double s_tab[256];
+  __shared__ __align__(16) double s_tab64[64 * 16];
   trans_tab_init(s_tab);
+  trans_tab64_init(s_tab64);
   __syncthreads();
   const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_tab);
+  const unsigned char* tab64 = reinterpret_cast<const unsigned char*>(s_tab64);
+  const unsigned lane_off = (threadIdx.x & 15u) << 3;
   const TransLane tl = trans_lane_init();
   // whole warps stay in the loop (the evaluations shuffle): pad with a harmless argument
   for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
@@ -1254,6 +1781,7 @@ __global__ void debug_eval_kernel(int which, TransConst K, TransConst256 K2, dou
     const double v = i < n ? x[i] : 1.0;
     const double r = which == 0 ? trans_one_minus_exp(v, K, tl)
                    : which == 2 ? trans256_one_minus_exp(v, K2, tab)
+                   : which == 3 ? trans64_one_minus_exp(v, K3, tab64, lane_off)
                                 : planck_elem_fast((6.62606896e-34 / 1.3806504e-23) / kd, v, 1.0, tl);
     if (i < n) out[i] = r;
   }
@@ -1261,7 +1789,8 @@ __global__ void debug_eval_kernel(int which, TransConst K, TransConst256 K2, dou
 }  // namespace ecckd
 
 ECCKD_API int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, const double* x, double* out) {
-  ECCKD_REQUIRE(ctx && x && out && n > 0 && which >= 0 && which <= 2 && kd > 0.0, ECCKD_PARAMETER_ERROR,
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && x && out && n > 0 && which >= 0 && which <= 3 && kd > 0.0, ECCKD_PARAMETER_ERROR,
                 "ecckd_debug_eval: bad argument");
   double* d = nullptr;
   ECCKD_CUDA_OK(cudaMalloc(&d, (size_t)2 * n * sizeof(double)));
@@ -1269,9 +1798,11 @@ ECCKD_API int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, 
   trans_const_init(&K, kd);
   TransConst256 K2;
   trans_const256_init(&K2, kd);
+  TransConst64 K3;
+  trans_const64_init(&K3, kd);
   cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
   if (e == cudaSuccess) {
-    debug_eval_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(which, K, K2, kd, n, d, d + n);
+    debug_eval_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 1184), 256, 0, ctx->stream>>>(which, K, K2, K3, kd, n, d, d + n);
     ctx->launches++;
     e = cudaGetLastError();
   }
@@ -1286,6 +1817,7 @@ ECCKD_API int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, 
 }
 
 ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
+  ECCKD_DEVICE(plan ? plan->ctx : nullptr);
   if (!plan) return ECCKD_OK;
   if (plan->ctx) cudaStreamSynchronize(plan->ctx->stream);
   plan_free(plan);
@@ -1293,12 +1825,14 @@ ECCKD_API int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan) {
 }
 
 ECCKD_API int ecckd_gpoint_plan_counts(ecckd_gpoint_plan* plan, int64_t* h_count) {
+  ECCKD_DEVICE(plan ? plan->ctx : nullptr);
   ECCKD_REQUIRE(plan && h_count, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_counts: NULL argument");
   for (int g = 0; g < plan->ng; ++g) h_count[g] = plan->h_count[g];
   return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_gpoint_plan_counts_dev(ecckd_gpoint_plan* plan, int64_t** d_count) {
+  ECCKD_DEVICE(plan ? plan->ctx : nullptr);
   ECCKD_REQUIRE(plan && d_count, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_counts_dev: NULL argument");
   *d_count = reinterpret_cast<int64_t*>(plan->d_count);
   return ECCKD_OK;
@@ -1307,6 +1841,7 @@ ECCKD_API int ecckd_gpoint_plan_counts_dev(ecckd_gpoint_plan* plan, int64_t** d_
 ECCKD_API int ecckd_planck_function_dev(ecckd_ctx* ctx, int nt, const double* h_temperature, int64_t nwav,
                                         const double* d_wn, const double* d_dwn, double* d_ans,
                                         int64_t ans_stride) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && h_temperature && d_wn && d_dwn && d_ans, ECCKD_PARAMETER_ERROR,
                 "ecckd_planck_function: NULL argument");
   // planck_function.cpp:40-44: output must be nt x nwav
@@ -1329,6 +1864,7 @@ ECCKD_API int ecckd_average_optical_depth_partial_dev(ecckd_ctx* ctx, ecckd_gpoi
                                                       int64_t w_stride, const double* h_temperature,
                                                       const double* d_wn, const double* d_dwn, int averaging_method,
                                                       double* d_sums, double* d_minmax) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && plan && h_pressure_fl && h_d_od && d_sums && d_minmax, ECCKD_PARAMETER_ERROR,
                 "ecckd_average_optical_depth_partial: NULL argument");
   ECCKD_REQUIRE(nspec > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: nspec and nlay must be > 0");
@@ -1363,6 +1899,7 @@ ECCKD_API int ecckd_average_optical_depth_finalize_dev(ecckd_ctx* ctx, int ng, c
                                                        const double* d_minmax, double* const* h_d_molar_abs,
                                                        double* const* h_d_min, double* const* h_d_max,
                                                        int64_t out_stride, int32_t* const* h_d_warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_count && h_reference_surface_vmr && h_pressure_fl && h_pressure_hl && d_sums && d_minmax &&
                     h_d_molar_abs,
                 ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth_finalize: NULL argument");
@@ -1397,6 +1934,7 @@ ECCKD_API int ecckd_average_optical_depth_batch_dev(
     int weight_mode, const double* d_weight, int64_t w_stride, const double* h_temperature, const double* d_wn,
     const double* d_dwn, int averaging_method, double* const* h_d_molar_abs, double* const* h_d_min,
     double* const* h_d_max, int64_t out_stride, int32_t* const* h_d_warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && plan, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: NULL argument");
   ECCKD_REQUIRE(nspec > 0 && nlay > 0, ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth: nspec and nlay must be > 0");
   // partial sums live in the plan-independent scratch slot 3 tail; sized [nrows][ng][NSUM + NMINMAX]
@@ -1424,6 +1962,7 @@ ECCKD_API int ecckd_average_optical_depth_to_g_point_dev(
     const double* h_pressure_hl, const double* d_od, int64_t od_stride, int weight_mode, const double* d_weight,
     int64_t w_stride, const double* h_temperature, const double* d_wn, const double* d_dwn, int averaging_method,
     double* d_molar_abs, double* d_min, double* d_max, int64_t out_stride, int32_t* d_warn) {
+  ECCKD_DEVICE(ctx);
   const double* ods[1] = {d_od};
   double* outs[1] = {d_molar_abs};
   double* mins[1] = {d_min};
@@ -1680,6 +2219,7 @@ ECCKD_API int ecckd_average_optical_depth_to_g_point(ecckd_ctx* ctx, int ng, dou
                                                      const char* averaging_method, double* molar_abs,
                                                      double* min_molar_abs, double* max_molar_abs, int64_t out_stride,
                                                      int32_t* warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && planck_fl && molar_abs,
                 ECCKD_PARAMETER_ERROR, "ecckd_average_optical_depth_to_g_point: NULL argument");
   return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, pressure_fl, pressure_hl, g_point, optical_depth,
@@ -1693,6 +2233,7 @@ ECCKD_API int ecckd_planck_average_optical_depth_to_g_point(
     const double* temperature_fl, const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
     const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride,
     int32_t* warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && temperature_fl && wavenumber_cm_1 &&
                     d_wavenumber_cm_1 && molar_abs,
                 ECCKD_PARAMETER_ERROR, "ecckd_planck_average_optical_depth_to_g_point: NULL argument");
@@ -1707,6 +2248,7 @@ ECCKD_API int ecckd_planck_average_optical_depth_to_g_point_f32(
     const double* temperature_fl, const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
     const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs, int64_t out_stride,
     int32_t* warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && pressure_fl && pressure_hl && g_point && optical_depth && temperature_fl && wavenumber_cm_1 &&
                     d_wavenumber_cm_1 && molar_abs,
                 ECCKD_PARAMETER_ERROR, "ecckd_planck_average_optical_depth_to_g_point_f32: NULL argument");
@@ -1727,6 +2269,7 @@ ECCKD_API int ecckd_create_lut_block(ecckd_ctx* ctx, int ng, double reference_su
                                      const double* d_wavenumber_cm_1, const double* ssi, const char* averaging_method,
                                      double* temperature_fl, double* molar_abs, double* min_molar_abs,
                                      double* max_molar_abs, int64_t out_stride, int32_t* warn) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && pressure_hl && temperature_hl && g_point && optical_depth && molar_abs && nlay > 0,
                 ECCKD_PARAMETER_ERROR, "ecckd_create_lut_block: NULL argument");
   ECCKD_REQUIRE(ssi || (wavenumber_cm_1 && d_wavenumber_cm_1), ECCKD_PARAMETER_ERROR,
@@ -1751,6 +2294,7 @@ ECCKD_API int ecckd_create_lut_block(ecckd_ctx* ctx, int ng, double reference_su
 ECCKD_API int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
                                    const double* d_od, int64_t od_stride, double scaling,
                                    const double* h_scaling_profile) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_optical_depth && d_od, ECCKD_PARAMETER_ERROR, "ecckd_merge_axpy: NULL argument");
   ECCKD_REQUIRE(nlay > 0 && nwav > 0, ECCKD_PARAMETER_ERROR, "ecckd_merge_axpy: bad dimensions");
   void* d_prof = nullptr;
@@ -1782,6 +2326,7 @@ static int check_uniform_bins(int nbin, const double* w1, const double* w2, doub
 ECCKD_API int ecckd_gpoint_fraction_dev(ecckd_ctx* ctx, int ng, int64_t nwav, const int32_t* d_g_point,
                                         const double* d_wn, const double* d_dwn, int nbin, const double* h_w1,
                                         const double* h_w2, double* d_out) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_g_point && d_wn && d_dwn && d_out, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_fraction: NULL argument");
   double bin0, dwav;
   ECCKD_TRY(check_uniform_bins(nbin, h_w1, h_w2, &bin0, &dwav));
@@ -1801,6 +2346,7 @@ ECCKD_API int ecckd_gpoint_fraction_dev(ecckd_ctx* ctx, int ng, int64_t nwav, co
 
 ECCKD_API int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wn, const double* d_ssi, int nbin,
                                       const double* h_w1, const double* h_w2, double* d_out) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_wn && d_ssi && d_out, ECCKD_PARAMETER_ERROR, "ecckd_ssi_intervals: NULL argument");
   double bin0, dwav;
   ECCKD_TRY(check_uniform_bins(nbin, h_w1, h_w2, &bin0, &dwav));
@@ -1812,6 +2358,7 @@ ECCKD_API int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double
 
 ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const double* d_wn, const double* d_dwn,
                                    int nlut, const double* h_temperature_lut, double* d_out) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && plan && d_wn && d_dwn && h_temperature_lut && d_out && nlut > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_planck_lut: bad argument");
   // sum over each g point of planck(T, nu): the reduction with f = 1 and Planck weights
@@ -1845,6 +2392,7 @@ ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, cons
 
 ECCKD_API int ecckd_compact_g_points_dev(ecckd_ctx* ctx, int ng, int64_t nwav, int32_t* d_g_point,
                                          int32_t* h_g_point_map, int* new_ng) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_g_point && h_g_point_map && new_ng && ng > 0 && nwav > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_compact_g_points: bad argument");
   void* d_tmp = nullptr;
@@ -1884,6 +2432,7 @@ ECCKD_API int ecckd_compact_g_points_dev(ecckd_ctx* ctx, int ng, int64_t nwav, i
 ECCKD_API int ecckd_planck_function(ecckd_ctx* ctx, int nt, const double* temperature, int64_t nwav,
                                     const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, double* ans,
                                     int64_t ans_stride) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && temperature && wavenumber_cm_1 && d_wavenumber_cm_1 && ans, ECCKD_PARAMETER_ERROR,
                 "ecckd_planck_function: NULL argument");
   ECCKD_REQUIRE(nt > 0 && nwav > 0 && ans_stride >= nwav, ECCKD_PARAMETER_ERROR, "ecckd_planck_function: bad dimensions");

@@ -19,6 +19,9 @@ constexpr int GROUP_ROWS = NW_MAX * RPW;
 // 17-21 "lane + 2^s belongs to the same g point in this round" for shuffle step s, 22 head lane of its g point
 constexpr unsigned NO_G = 0xFFFu;
 constexpr int MAX_NG = 4094;
+// Windowed plans (reduce2_kernel): the g points of one round span fewer than WIN consecutive
+// indices, and PlanRound::win holds the base of the round's window [win, win + WIN).
+constexpr int WIN = 8;
 
 // One round of the plan (32 lanes x 16 slots): per lane 16 byte offsets into the chunk (padding slots
 // repeat slot 0: neutral for min/max; the producers give them zero weight) and
@@ -30,7 +33,7 @@ struct PlanRound {
   uint32_t steps;
   uint32_t chunk;
   uint32_t flags;     // bit 0: first round of its chunk, bit 1: last round of its chunk
-  uint32_t pad_;
+  uint32_t win;       // windowed plans: first g point of the round's window (unused otherwise)
 };
 static_assert(sizeof(PlanRound) == 1168, "PlanRound layout");
 constexpr int WPERM_BYTES = SLOTS * 32 * 8;  // weights of a round in (slot, lane) order, zero for padding slots
@@ -102,6 +105,7 @@ struct ReduceParams {
   const double* dwn;
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
   TransConst256 tc256;        // the same for the 256-entry shared-memory table of the consumer warps
+  TransConst64 tc64;          // the same for the replicated 64-entry table of reduce2_kernel
   int debug;                  // timing experiments only (ECCKD_DEBUG): 1 skip the row evaluation, 4 skip only the slot loop
   double* partial;            // [ncta][maxg][nw*RPW][ng][4]
   int32_t* partial_z;         // [ncta][maxg][nw*RPW][ng]
@@ -143,6 +147,7 @@ struct ecckd_gpoint_plan {
   int64_t nrounds = 0;
   int ng = 0;
   int ch = 0;                            // chunk length chosen for this g-point map
+  bool windowed = false;                 // rounds obey the WIN window constraint (reduce2_kernel can run)
   uint32_t* d_round_off = nullptr;       // [nchunks+1]
   ecckd::PlanRound* d_rounds = nullptr;  // [nrounds]
   unsigned long long* d_count = nullptr; // [ng]

@@ -105,6 +105,7 @@ using namespace ecckd;
 
 ECCKD_API int ecckd_rayleigh_molar_scattering_coeff_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenumber_cm_1,
                                                         double* d_scat_coeff) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_wavenumber_cm_1 && d_scat_coeff && nwav > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_rayleigh_molar_scattering_coeff: bad argument");
   rayleigh_coeff_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(nwav, d_wavenumber_cm_1, d_scat_coeff);
@@ -115,6 +116,7 @@ ECCKD_API int ecckd_rayleigh_molar_scattering_coeff_dev(ecckd_ctx* ctx, int64_t 
 ECCKD_API int ecckd_rayleigh_molar_scat_gpoints_dev(ecckd_ctx* ctx, int ng, int nbin, const double* d_wavenumber1,
                                                     const double* d_wavenumber2, const double* d_gpoint_fraction,
                                                     const double* d_ssi_intervals, double* d_rayleigh_molar_scat) {
+  ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && d_wavenumber1 && d_wavenumber2 && d_gpoint_fraction && d_ssi_intervals && d_rayleigh_molar_scat &&
                     ng > 0 && nbin > 0,
                 ECCKD_PARAMETER_ERROR, "ecckd_rayleigh_molar_scat_gpoints: bad argument");
@@ -129,6 +131,7 @@ ECCKD_API int ecckd_split_base_g_points_dev(ecckd_ctx* ctx, int nband, const dou
                                             int nbound, const double* h_base_wavenumber_boundary, int64_t nwav,
                                             const double* d_wavenumber_cm_1, const double* d_ssi, int cap, int* ng_io,
                                             int32_t* h_band_number, int32_t* d_g_point, double* h_solar_irradiance) {
+  ECCKD_DEVICE(ctx);
   const char* who = "ecckd_split_base_g_points";
   ECCKD_REQUIRE(ctx && h_band_wn1 && h_band_wn2 && (nbound == 0 || h_base_wavenumber_boundary) && d_wavenumber_cm_1 &&
                     ng_io && h_band_number && d_g_point && nband > 0 && nwav > 0,

@@ -262,6 +262,77 @@ __device__ __forceinline__ double trans256_one_minus_exp(double tau, const Trans
   return trans256_phase3(m, trans256_phase2(m, tab), K);
 }
 
+// The same with a 64-entry table REPLICATED 16 times (8 KB of shared memory): copy c = lane & 15 of
+// entry j sits at byte ((j*16 + c)*8), so the 16 lanes of a half-warp always read 16 different
+// 8-byte bank pairs whatever their j -- the look-up is one conflict-free wavefront per half-warp,
+// where the single 256-entry table above cost ~3.  |r| <= ln2/128 needs a degree-5 polynomial
+// (r^6/720 < 3.6e-17): one FP64 instruction more per value, one integer instruction less.
+struct TransConst64 {
+  double a;        // -kd * 64/ln2
+  double b;        // ln2 / (64 kd)
+  double c[5];     // c[i] = (-kd)^(i+1) / (i+1)!
+  int32_t hi_max;  // high word of 708/kd
+  int32_t pad_;
+};
+
+inline void trans_const64_init(TransConst64* k, double kd) {
+  const long double ln2 = 0.693147180559945309417232121458176568L;
+  const long double lkd = (long double)kd;
+  k->a = (double)(-lkd * 64.0L / ln2);
+  k->b = (double)(ln2 / (64.0L * lkd));
+  long double f = 1.0L, pw = 1.0L;
+  for (int i = 0; i < 5; ++i) {
+    pw *= -lkd;
+    f *= (long double)(i + 1);
+    k->c[i] = (double)(pw / f);
+  }
+  const double tmax = 708.0 / kd;
+  uint64_t bits;
+  memcpy(&bits, &tmax, 8);
+  k->hi_max = (int32_t)(bits >> 32);
+  k->pad_ = 0;
+}
+
+constexpr int TRANS_TAB64_BYTES = 64 * 16 * 8;
+// entry (j, c) = 2^(j/64) with (j << 14) taken off its high word: adding (n << 14), n = 64 k + j,
+// applies 2^k and cancels j.  Call with all threads of the CTA.
+__device__ __forceinline__ void trans_tab64_init(double* tab) {
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+    const int j = i >> 4;
+    const double t = EXP2_256[4 * j];
+    tab[i] = __hiloint2double(__double2hiint(t) - (j << 14), __double2loint(t));
+  }
+}
+__device__ __forceinline__ TransMid trans64_phase1(double tau, const TransConst64& K) {
+  const double magic = 6755399441055744.0;
+  const double tc = __hiloint2double(min(__double2hiint(tau), K.hi_max), __double2loint(tau));
+  const double t = fma(tc, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma(t - magic, K.b, tc);
+  return m;
+}
+// lane_off = (lane & 15) << 3
+__device__ __forceinline__ double trans64_phase2(const TransMid& m, const unsigned char* __restrict__ tab,
+                                                 const unsigned lane_off) {
+  const unsigned idx = (((unsigned)m.n << 7) & 0x1f80u) | lane_off;
+  const uint2 e = *reinterpret_cast<const uint2*>(tab + idx);
+  return __hiloint2double((int)e.y + (m.n << 14), (int)e.x);
+}
+__device__ __forceinline__ double trans64_phase3(const TransMid& m, const double T, const TransConst64& K) {
+  double q = K.c[4];
+  q = fma(q, m.rho, K.c[3]);
+  q = fma(q, m.rho, K.c[2]);
+  q = fma(q, m.rho, K.c[1]);
+  q = fma(q, m.rho, K.c[0]);
+  return fma(-T, fma(q, m.rho, 1.0), 1.0);
+}
+__device__ __forceinline__ double trans64_one_minus_exp(double tau, const TransConst64& K,
+                                                        const unsigned char* __restrict__ tab, const unsigned lane_off) {
+  const TransMid m = trans64_phase1(tau, K);
+  return trans64_phase3(m, trans64_phase2(m, tab, lane_off), K);
+}
+
 // exp(x) for 0 <= x < 708 with the same table: x = (32 k + j) ln2/32 + r (two-constant
 // Cody-Waite reduction), exp(x) = 2^k 2^(j/32) (1 + p(r)).  Below 1 ulp; used for the Planck weights.
 __device__ __forceinline__ double exp_table(double x, const TransLane& tl) {

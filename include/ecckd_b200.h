@@ -72,11 +72,14 @@ enum ecckd_weight_mode {
                               the kernel (fuses planck_function.cpp:47-53)       */
 };
 
-/* per-g-point warning bits, the WARNINGs of average_optical_depth.cpp:136,154,159 */
+/* per-g-point warning bits, the WARNINGs of average_optical_depth.cpp:136,154,159; NONFINITE has no
+ * reference counterpart: a NaN optical depth in the g point's wavenumbers (the averaged value is NaN,
+ * as the reference's sum() makes it, instead of being absorbed by the min/max clamps) */
 enum ecckd_warning {
   ECCKD_WARN_EMPTY_G = 1,
   ECCKD_WARN_MIN_GT_FIT = 2,
-  ECCKD_WARN_MIN_GE_MAX = 4
+  ECCKD_WARN_MIN_GE_MAX = 4,
+  ECCKD_WARN_NONFINITE = 8
 };
 
 /* conc_dependence codes written by src/ecckd/ckd_model.cpp:409-413 */
@@ -93,7 +96,13 @@ const char* ecckd_last_error(void);
 /* Number of usable sm_100 devices (0 if none or no driver). */
 int ecckd_device_count(void);
 /* stream: a cudaStream_t to enqueue on (e.g. torch's current stream), or NULL
- * for a private non-blocking stream owned by the context. */
+ * for a private non-blocking stream owned by the context.
+ * Devices: every entry point that takes a context (or a plan / model created on one) makes the
+ * context's device current for the duration of the call and restores the caller's device on
+ * return, so one process may hold contexts on several GPUs.  Side effect on the process: the
+ * release threshold of the device's DEFAULT stream-ordered memory pool is raised to "keep
+ * everything" (plans and partial sums come from cudaMallocAsync); set ECCKD_KEEP_POOL=0 in the
+ * environment to leave the pool untouched. */
 int ecckd_ctx_create(int device, void* stream, ecckd_ctx** out);
 int ecckd_ctx_destroy(ecckd_ctx* ctx);
 int ecckd_ctx_set_stream(ecckd_ctx* ctx, void* stream);
@@ -119,7 +128,8 @@ int ecckd_ctx_reduce_kernel_time(ecckd_ctx* ctx, double* total_ms, int64_t* laun
  * averaging methods (average_optical_depth.cpp:49,53,57,61: `1.0 - exp(-D*k*optical_depth)`) and
  * their Planck weight (planck_function.cpp:47-53 with the folded constants of the fused path),
  * evaluated element-wise on host arrays so that tests can sweep their accuracy.
- * which = 0: out[i] = 1 - exp(-kd*x[i]);  which = 1: out[i] = planck(T = kd, nu = x[i], dnu = 1). */
+ * which = 0, 2, 3: out[i] = 1 - exp(-kd*x[i]) by the 32-entry lane table, the 256-entry and the
+ * replicated 64-entry shared-memory table of trans_core.cuh;  which = 1: out[i] = planck(T = kd, nu = x[i], dnu = 1). */
 int ecckd_debug_eval(ecckd_ctx* ctx, int which, double kd, int64_t n, const double* x, double* out);
 
 /* planck_function: src/ecckd/planck_function.cpp:22-54.

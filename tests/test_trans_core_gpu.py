@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 KD = [1.66, 2 * 1.66, 3 * 1.66, 10 * 1.66]  # transmission, -2, -3, -10
 
 
-@pytest.mark.parametrize("which", [0, 2])  # 0: 32-entry lane table, degree 6; 2: 256-entry shared table, degree 4
+# 0: 32-entry lane table, degree 6; 2: 256-entry shared table, degree 4; 3: replicated 64-entry table, degree 5
+@pytest.mark.parametrize("which", [0, 2, 3])
 @pytest.mark.parametrize("kd", KD)
 def test_one_minus_exp_absolute_error(ctx, kd, which):
     rng = np.random.default_rng(int(kd * 100))
@@ -26,7 +27,7 @@ def test_one_minus_exp_absolute_error(ctx, kd, which):
     assert got[len(tau) - 7] == 0.0            # tau = 0
 
 
-@pytest.mark.parametrize("which", [0, 2])
+@pytest.mark.parametrize("which", [0, 2, 3])
 def test_one_minus_exp_is_monotone_on_a_fine_grid(ctx, which):
     tau = np.linspace(0.0, 30.0, 400001)
     got = E.debug_eval(ctx, which, 1.66, tau)
