@@ -1122,20 +1122,503 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   if (!need_group) window_store();
 }
 
+// ------------------------------------------------------------------ reduce, windowed plans, one row per warp
+// reduce3_kernel: reduce2_kernel's per-round scheme (per-lane entries, cached range-check words,
+// results straight to the CTA's piece) re-cut for occupancy.  ncu on reduce2_kernel showed the
+// consumer warps issuing only a fifth of the time inside the slot loop (FP64 and shared-memory
+// latency with 2.5 consumer warps per scheduler, 168 registers): here
+//   * every consumer warp owns ONE row of the group (up to 20 consumer warps), evaluates 4 slots
+//     per trip (4 dependency chains) and stays under 88 registers: 23 warps per SM;
+//   * the extremes live in shared memory as order-preserving 64-bit keys updated with atomicMin /
+//     atomicMax on the rare exact path (no min/max registers, no cross-lane merge);
+//   * a dedicated warp issues all bulk copies (lane = consumer warp; it polls the stages' empty
+//     barriers), so the consumers' chunk visit is wait, rounds, arrive;
+//   * rows that are not 16-byte aligned and odd chunk tails are copied from the aligned address
+//     below / to the aligned length above and read at a per-row byte shift: every copy is a bulk
+//     copy (the bytes read in excess stay inside the 16-byte granules of the caller's rows).
+constexpr int NW3_MAX = GROUP_ROWS;         // consumer warps (one row each)
+constexpr int STAGE3_BYTES = STAGE_BYTES + 16;
+constexpr int THREADS3_MAX = (NW3_MAX + NPW + 1) * 32;
+
+struct Smem3Layout {
+  int tab;   // replicated 2^(j/64) table, at offset 0
+  int bars;  // mbarriers: full_d[nw][NSETS], empty_d[nw][NSETS], full_w[NSW], empty_w[NSW]
+  int ring;  // ring slots [NSW]: {double wperm[SLOTS*32]; PlanRound plan}
+  int data;  // data stages [nw][NSETS][STAGE3_BYTES]
+  int ent;   // [nw][WIN][32] double: per-lane sums of the window's g points
+  int s1e;   // [WIN][32] double: per-lane weight sums (last consumer warp)
+  int mmk;   // [nw][WIN][2] uint64: order-preserving keys of {min, max}
+  int mmb;   // [nw][WIN] uint2 {lowb, span} of the range check
+  int total;
+};
+__host__ __device__ inline Smem3Layout smem3_layout(int nw) {
+  Smem3Layout L;
+  int off = 0;
+  L.tab = off;
+  off += TRANS_TAB64_BYTES;
+  L.bars = off;
+  off += (2 * nw * NSETS + 2 * NSW) * 8;
+  off = (off + 127) & ~127;
+  L.ring = off;
+  off += NSW * RING_SLOT_BYTES;
+  L.data = off;
+  off += nw * NSETS * STAGE3_BYTES;
+  L.ent = off;
+  off += nw * WIN * 32 * 8;
+  L.s1e = off;
+  off += WIN * 32 * 8;
+  L.mmk = off;
+  off += nw * WIN * 16;
+  L.mmb = off;
+  off += nw * WIN * 8;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+// order-preserving image of a double (not NaN) as an unsigned 64-bit key, and back
+__device__ __forceinline__ unsigned long long key_of(double x) {
+  const long long b = __double_as_longlong(x);
+  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
+}
+__device__ __forceinline__ double value_of(unsigned long long k) {
+  const long long b = (long long)k;
+  return __longlong_as_double(b ^ ((((b >> 63) & 1) - 1) | (long long)0x8000000000000000LL));
+}
+
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+// The 16 slots of one row of one round, 4 per trip.  `stage` is the row's chunk in shared memory
+// (already shifted), mmk the {min, max} keys of the lane's g point.  Returns the lane's sum of
+// f(tau)*w; sets upd when the exact path ran (the range-check words must then be refreshed).
+template <int FKIND>
+__device__ __forceinline__ double row_slots3(const unsigned char* __restrict__ stage, const uint16_t* __restrict__ offp,
+                                             const double* __restrict__ wp, const unsigned lowb, const unsigned span,
+                                             unsigned long long* __restrict__ mmk, const bool used, int& upd,
+                                             const TransConst64& K, const unsigned char* __restrict__ tab,
+                                             const unsigned lane_off) {
+  double s0 = 0.0;
+#pragma unroll 1
+  for (int kk = 0; kk < SLOTS; kk += 4) {
+    double tau[4], w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned o = offp[(kk + j) * 32];
+      w[j] = wp[(kk + j) * 32];  // zero for padding slots
+      tau[j] = *reinterpret_cast<const double*>(stage + o);
+    }
+    unsigned worst = 0u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) worst = max(worst, (unsigned)__double2hiint(tau[j]) - lowb);
+    if (worst >= span) {  // rare: a value may be a new extreme (or is negative / non-finite)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double t = tau[j];
+        if (t == t) {
+          if (used) {
+            const unsigned long long k = key_of(t);
+            atomicMin(&mmk[0], k);
+            atomicMax(&mmk[1], k);
+          }
+        } else {
+          s0 = t;  // NaN: poison the sum (see reduce_rows.cuh)
+        }
+      }
+      upd = 1;
+    }
+    double f[4];
+    if (FKIND == F_TRANS) {
+      TransMid m[4];
+      double T[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[j] = trans64_phase1(tau[j], K);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) T[j] = trans64_phase2(m[j], tab, lane_off);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = trans64_phase3(m[j], T[j], K);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = (FKIND == F_LINEAR) ? tau[j] : (FKIND == F_SQRT ? sqrt(tau[j]) : 1.0);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s0 = fma(f[j], w[j], s0);
+  }
+  return s0;
+}
+
+// Lean form of produce_rounds for reduce3_kernel (88 registers): plan offsets are fetched one
+// round ahead, the sources of the current round are loaded and converted in place.
+template <int WMODE>
+__device__ __forceinline__ void produce_rounds3(const ReduceParams& p, const Cursor first, const int niter, const int pw,
+                                                const int lane, unsigned char* ring, const unsigned ring_s,
+                                                const unsigned full_w, const unsigned empty_w) {
+  const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
+  constexpr int PER = SLOTS / NPW;
+  const TransLane ptl = trans_lane_init();
+  Cursor q = first;
+  int visit = 0;
+  uint32_t r_cur = p.round_off[q.c], r_end = p.round_off[q.c + 1];
+  int ws = 0, filled = 0;
+  unsigned epar = 0;
+  // current round
+  uint32_t r = r_cur;
+  int64_t w0 = (int64_t)q.c * ch;
+  int wrow = p.groups[q.l].wrow;
+  unsigned off[PER], meta;
+  {
+    const PlanRound* pr = p.rounds + r;
+    meta = pr->meta[lane];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
+  }
+  bool valid = niter > 0;
+  while (valid) {
+    // sources of this round
+    double x[PER], y[PER];
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      const int64_t w = w0 + (off[m] >> 3);
+      if (WMODE == W_PLANCK) {
+        x[m] = p.wn[w];
+        y[m] = p.dwn[w];
+      } else if (WMODE == W_MATRIX) {
+        x[m] = p.weight[(int64_t)wrow * p.w_stride + w];
+      } else {
+        x[m] = p.weight[w];
+      }
+    }
+    const int nv = (int)((meta >> 12) & 31u);
+    const double hkt = (WMODE == W_PLANCK) ? p.temperature[wrow] : 0.0;
+    const uint32_t r_this = r;
+    // advance to the next round and fetch its plan words while the sources are in flight
+    if (++r_cur == r_end) {
+      ++visit;
+      if (visit < niter) {
+        cursor_next(q, p.ngroups, p.cw, nchunks);
+        r_cur = p.round_off[q.c];
+        r_end = p.round_off[q.c + 1];
+        wrow = p.groups[q.l].wrow;
+      } else {
+        valid = false;
+      }
+    }
+    if (valid) {
+      r = r_cur;
+      w0 = (int64_t)q.c * ch;
+      const PlanRound* pr = p.rounds + r;
+      meta = pr->meta[lane];
+#pragma unroll
+      for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
+    }
+    unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+    double* wperm = reinterpret_cast<double*>(slot);
+    if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
+#pragma unroll
+    for (int m = 0; m < PER; ++m) {
+      const int k = pw + NPW * m;
+      const double val = (WMODE == W_PLANCK) ? planck_elem_fast(hkt, x[m], y[m], ptl) : x[m];
+      wperm[k * 32 + lane] = (k < nv) ? val : 0.0;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (pw == 0) {
+        mbar_arrive_expect_tx(full_w + ws * 8, (unsigned)sizeof(PlanRound));
+        bulk_g2s(ring_s + ws * RING_SLOT_BYTES + WPERM_BYTES, p.rounds + r_this, (unsigned)sizeof(PlanRound),
+                 full_w + ws * 8);
+      } else {
+        mbar_arrive(full_w + ws * 8);
+      }
+    }
+    ++filled;
+    if (++ws == NSW) {
+      ws = 0;
+      if (filled > NSW) epar ^= 1u;
+    }
+  }
+}
+
+template <int FKIND, int WMODE>
+__global__ void __launch_bounds__(THREADS3_MAX, 1) reduce3_kernel(const __grid_constant__ ReduceParams p) {
+  static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
+                "reduce3_kernel: kinds with per-row weight sums run on reduce_kernel");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nw = p.nw, ng = p.ng;
+  const Smem3Layout L = smem3_layout(nw);
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned full_d = sbase + L.bars;            // [nw][NSETS]
+  const unsigned empty_d = full_d + nw * NSETS * 8;  // [nw][NSETS]
+  const unsigned full_w = empty_d + nw * NSETS * 8;  // [NSW]
+  const unsigned empty_w = full_w + NSW * 8;         // [NSW]
+  unsigned char* ring = smem_raw + L.ring;
+  constexpr bool USES_TAU = (FKIND != F_NONE);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * nw * NSETS; ++i) mbar_init(full_d + i * 8, 1);
+    for (int i = 0; i < NSW; ++i) {
+      mbar_init(full_w + i * 8, NPW);
+      mbar_init(empty_w + i * 8, nw);
+    }
+    fence_mbar_init();
+  }
+  if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
+  __syncthreads();
+  const unsigned char* tab = smem_raw + L.tab;
+
+  // this CTA's contiguous piece of the (window, group, chunk) space
+  const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
+  const int64_t T = (int64_t)p.ngroups * p.nchunks;
+  const int64_t lo = (T * blockIdx.x) / p.ncta;
+  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
+  const int niter = (int)(hi - lo);
+  if (niter == 0) return;
+  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
+  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
+
+  if (warp >= nw + NPW) {
+    // ===================== data producer: lane = consumer warp, all bulk copies of its row =====================
+    if (!USES_TAU || lane >= nw) return;
+    const uint64_t pol = policy_evict_first();
+    const unsigned my_full = full_d + lane * NSETS * 8, my_empty = empty_d + lane * NSETS * 8;
+    const unsigned my_data = sbase + L.data + lane * NSETS * STAGE3_BYTES;
+    Cursor q = first;
+    const double* od = nullptr;
+    bool act = false;
+    int group = -1;
+    unsigned used_sets = 0, epar = 0;
+    int k = 0, nset = 0;  // nset: copies issued so far for this row (its visits alternate the two sets)
+    while (k < niter) {
+      if (q.l != group) {
+        group = q.l;
+        const GroupDesc* gd = p.groups + group;
+        act = lane < gd->nrows;
+        od = act ? gd->od[lane] : nullptr;
+      }
+      if (act) {
+        const int set = nset & (NSETS - 1);
+        if ((used_sets >> set) & 1u) {
+          if (!mbar_test(my_empty + set * 8, (epar >> set) & 1u)) {
+            __nanosleep(64);
+            continue;  // poll again: lanes progress independently
+          }
+          epar ^= 1u << set;
+        }
+        used_sets |= 1u << set;
+        const int n_c = (q.c == nchunks - 1) ? last_n : ch;
+        const double* src = od + (int64_t)q.c * ch;
+        const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(src) & 8u);
+        const unsigned bytes = (shift + (unsigned)n_c * 8u + 15u) & ~15u;
+        const unsigned bar = my_full + set * 8;
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s_hint(my_data + set * STAGE3_BYTES, reinterpret_cast<const unsigned char*>(src) - shift, bytes, bar, pol);
+        ++nset;
+      }
+      cursor_next(q, p.ngroups, p.cw, nchunks);
+      ++k;
+    }
+    return;
+  }
+  if (warp >= nw) {
+    produce_rounds3<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w);
+    return;
+  }
+
+  // ===================== consumers: warp = one row of the group =====================
+  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * STAGE3_BYTES;
+  const unsigned my_full = full_d + warp * NSETS * 8, my_empty = empty_d + warp * NSETS * 8;
+  double* ent = reinterpret_cast<double*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
+  double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
+  unsigned long long* mmk = reinterpret_cast<unsigned long long*>(smem_raw + L.mmk) + warp * WIN * 2;
+  uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + warp * WIN;
+  const unsigned lane_off = (unsigned)(lane & 15) << 3;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  // the weight sums do not depend on the row: the last consumer warp accumulates them once per
+  // group; they end up in the s1 field of its row
+  const bool s1_duty = warp == nw - 1;
+
+  int gbase = -1;          // first g point of the current window (-1: none loaded)
+  double* pout = nullptr;  // this warp's row of the current (window, group) piece: [ng][4]
+
+  auto begin_piece = [&](int vg) {
+    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * nw + warp;
+    pout = p.partial + slot * ng * 4;
+    int32_t* poutz = p.partial_z + slot * ng;
+    for (int i = lane; i < ng; i += 32) {
+      double2* q = reinterpret_cast<double2*>(pout + (size_t)i * 4);
+      q[0] = make_double2(0.0, 0.0);
+      q[1] = make_double2(inf, -inf);
+      poutz[i] = 0;
+    }
+    __syncwarp();
+  };
+  // add the window's entries up over the lanes (fixed butterfly) and fold them, with the extremes,
+  // into the piece: lane e writes g point gbase + e
+  auto window_store = [&]() {
+    double t0 = 0.0, ts = 0.0;
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) {
+      double v = ent[e * 32 + lane];
+      double s = s1_duty ? s1e[e * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (s1_duty) s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      if (lane == e) {
+        t0 = v;
+        ts = s;
+      }
+    }
+    const int g = gbase + lane;
+    if (lane < WIN && g < ng) {
+      double* q = pout + (size_t)g * 4;
+      const double mn = value_of(mmk[lane * 2]), mx = value_of(mmk[lane * 2 + 1]);
+      q[0] += t0;
+      if (s1_duty) q[1] += ts;
+      q[2] = (mn < q[2]) ? mn : q[2];
+      q[3] = (mx > q[3]) ? mx : q[3];
+    }
+    __syncwarp();
+  };
+  auto refresh_bounds = [&]() {
+    if (lane < WIN) {
+      Partial t;
+      t.mn = value_of(mmk[lane * 2]);
+      t.mx = value_of(mmk[lane * 2 + 1]);
+      minmax_bounds(t);
+      mmb[lane] = make_uint2(t.lowb, t.span);
+    }
+    __syncwarp();
+  };
+  // open the window [nb, nb + WIN): zero entries, extremes from the piece
+  auto window_load = [&](int nb) {
+    gbase = nb;
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) ent[e * 32 + lane] = 0.0;
+    if (s1_duty) {
+#pragma unroll
+      for (int e = 0; e < WIN; ++e) s1e[e * 32 + lane] = 0.0;
+    }
+    if (lane < WIN) {
+      const int g = nb + lane;
+      double mn = inf, mx = -inf;
+      if (g < ng) {
+        mn = pout[(size_t)g * 4 + 2];
+        mx = pout[(size_t)g * 4 + 3];
+      }
+      mmk[lane * 2] = key_of(mn);
+      mmk[lane * 2 + 1] = key_of(mx);
+    }
+    __syncwarp();
+    refresh_bounds();
+  };
+
+  Cursor q = first;
+  int ws = 0, vg = 0, nset = 0;
+  unsigned wpar = 0, phase_bits = 0;
+  const double* od_c = nullptr;
+  bool active = false, need_group = true, new_piece = true;
+
+#pragma unroll 1
+  for (int k = 0; k < niter; ++k) {
+    if (need_group) {
+      const GroupDesc* gd = p.groups + q.l;
+      active = USES_TAU && warp < gd->nrows;
+      od_c = active ? gd->od[warp] : nullptr;
+      need_group = false;
+    }
+    const int set = nset & (NSETS - 1);
+    const unsigned char* stage = data + set * STAGE3_BYTES;
+    if (active) {
+      mbar_wait(my_full + set * 8, (phase_bits >> set) & 1u);
+      phase_bits ^= 1u << set;
+      stage += (unsigned)(reinterpret_cast<uintptr_t>(od_c + (int64_t)q.c * ch) & 8u);
+      ++nset;
+    }
+    bool last_round = false;
+    while (!last_round) {
+      mbar_wait(full_w + ws * 8, wpar);
+      const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
+      const double* wp = reinterpret_cast<const double*>(slot) + lane;
+      const uint16_t* offp = &pr->off[0][lane];
+      const unsigned meta = pr->meta[lane];
+      const int wb = (int)pr->win;
+      last_round = (pr->flags & 2u) != 0;
+      if (new_piece || wb != gbase) {  // warp-uniform: the window of g points moves, or the piece is new
+        if (gbase >= 0) window_store();
+        if (new_piece) {
+          begin_piece(vg);
+          new_piece = false;
+        }
+        window_load(wb);
+      }
+      const unsigned g = meta & 0xFFFu;
+      const bool used = g != NO_G;
+      const int e = used ? min(max((int)g - gbase, 0), WIN - 1) : 0;  // the plan keeps g inside the window
+      double s1 = 0.0;
+      if (s1_duty) {
+#pragma unroll
+        for (int kk = 0; kk < SLOTS; ++kk) s1 += wp[kk * 32];
+      }
+      double s0 = 0.0;
+      int upd = 0;
+      if (active) {
+        const uint2 b = mmb[e];
+        s0 = row_slots3<FKIND>(stage, offp, wp, used ? b.x : 0u, used ? b.y : 0xFFFFFFFFu, mmk + e * 2, used, upd,
+                               p.tc64, tab, lane_off);
+      }
+      if (used) {
+        if (active) ent[e * 32 + lane] += s0;
+        if (s1_duty) s1e[e * 32 + lane] += s1;
+      }
+      if (__any_sync(0xffffffffu, upd != 0)) {
+        __syncwarp();  // the other lanes' atomics on the keys are visible
+        refresh_bounds();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_w + ws * 8);
+      if (++ws == NSW) {
+        ws = 0;
+        wpar ^= 1u;
+      }
+    }
+    if (active && lane == 0) mbar_arrive(my_empty + set * 8);  // the stage may be refilled
+    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
+      ++vg;
+      need_group = true;
+      new_piece = true;
+    }
+  }
+  if (gbase >= 0) window_store();
+}
+
 // ------------------------------------------------------------------ combine + finalize
 // Add the CTA pieces of every (row, g) in fixed (window, CTA) order (deterministic).
 __global__ void combine_kernel(const CombineParams p) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)p.ngroups * p.nw * RPW * p.ng;
+  const int64_t total = (int64_t)p.ngroups * p.nw * p.rpw * p.ng;
   if (tid >= total) return;
   const int g = (int)(tid % p.ng);
-  const int i = (int)((tid / p.ng) % (p.nw * RPW));  // row of the group
-  const int grp = (int)(tid / ((int64_t)p.ng * p.nw * RPW));
+  const int i = (int)((tid / p.ng) % (p.nw * p.rpw));  // row of the group
+  const int grp = (int)(tid / ((int64_t)p.ng * p.nw * p.rpw));
   const GroupDesc* gd = p.groups + grp;
   if (i >= gd->nrows) return;
-  const int piece = (i % p.nw) * RPW + (i / p.nw);                   // (warp, row of the warp)
-  const int piece_s1 = p.shared_s1 ? (p.nw - 1) * RPW : piece;       // weight sums: last warp, row 0
-  const int nrw = p.nw * RPW;
+  const int piece = (i % p.nw) * p.rpw + (i / p.nw);                 // (warp, row of the warp)
+  const int piece_s1 = p.shared_s1 ? (p.nw - 1) * p.rpw : piece;     // weight sums: last warp, row 0
+  const int nrw = p.nw * p.rpw;
   const int nchunks = (int)p.nchunks;
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
@@ -1326,11 +1809,12 @@ __global__ void compact_remap_kernel(int ng, int64_t nwav, int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------ host side
-template <int FKIND, int WMODE, bool V2>
+template <int FKIND, int WMODE, int GEN>
 static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta_out,
                                    bool dry_run) {
   void (*kernel)(const ReduceParams) = nullptr;
-  if constexpr (V2) kernel = reduce2_kernel<FKIND, WMODE>;
+  if constexpr (GEN == 3) kernel = reduce3_kernel<FKIND, WMODE>;
+  else if constexpr (GEN == 2) kernel = reduce2_kernel<FKIND, WMODE>;
   else kernel = reduce_kernel<FKIND, WMODE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1345,35 +1829,43 @@ static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads,
   return cudaGetLastError();
 }
 
-template <int FKIND, bool V2>
+template <int FKIND, int GEN>
 static cudaError_t launch_reduce_w(int wmode, ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta,
                                    bool dry) {
-  if (wmode == W_MATRIX) return launch_reduce_t<FKIND, W_MATRIX, V2>(ctx, p, threads, smem, ncta, dry);
-  if (wmode == W_VECTOR) return launch_reduce_t<FKIND, W_VECTOR, V2>(ctx, p, threads, smem, ncta, dry);
-  return launch_reduce_t<FKIND, W_PLANCK, V2>(ctx, p, threads, smem, ncta, dry);
+  if (wmode == W_MATRIX) return launch_reduce_t<FKIND, W_MATRIX, GEN>(ctx, p, threads, smem, ncta, dry);
+  if (wmode == W_VECTOR) return launch_reduce_t<FKIND, W_VECTOR, GEN>(ctx, p, threads, smem, ncta, dry);
+  return launch_reduce_t<FKIND, W_PLANCK, GEN>(ctx, p, threads, smem, ncta, dry);
 }
 
 // v2: the windowed kernel (reduce2_kernel); only for the kinds reduce2_supports() names
 static bool reduce2_supports(int fkind) {
   return fkind == F_LINEAR || fkind == F_TRANS || fkind == F_SQRT || fkind == F_NONE;
 }
-static cudaError_t launch_reduce(int fkind, int wmode, bool v2, ecckd_ctx* ctx, ReduceParams& p, int threads,
+static cudaError_t launch_reduce(int fkind, int wmode, int gen, ecckd_ctx* ctx, ReduceParams& p, int threads,
                                  size_t smem, int* ncta, bool dry) {
-  if (v2) {
+  if (gen == 3) {
     switch (fkind) {
-      case F_LINEAR: return launch_reduce_w<F_LINEAR, true>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_TRANS: return launch_reduce_w<F_TRANS, true>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_SQRT: return launch_reduce_w<F_SQRT, true>(wmode, ctx, p, threads, smem, ncta, dry);
-      default: return launch_reduce_w<F_NONE, true>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_LINEAR: return launch_reduce_w<F_LINEAR, 3>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_TRANS: return launch_reduce_w<F_TRANS, 3>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_SQRT: return launch_reduce_w<F_SQRT, 3>(wmode, ctx, p, threads, smem, ncta, dry);
+      default: return launch_reduce_w<F_NONE, 3>(wmode, ctx, p, threads, smem, ncta, dry);
+    }
+  }
+  if (gen == 2) {
+    switch (fkind) {
+      case F_LINEAR: return launch_reduce_w<F_LINEAR, 2>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_TRANS: return launch_reduce_w<F_TRANS, 2>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_SQRT: return launch_reduce_w<F_SQRT, 2>(wmode, ctx, p, threads, smem, ncta, dry);
+      default: return launch_reduce_w<F_NONE, 2>(wmode, ctx, p, threads, smem, ncta, dry);
     }
   }
   switch (fkind) {
-    case F_LINEAR: return launch_reduce_w<F_LINEAR, false>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_TRANS: return launch_reduce_w<F_TRANS, false>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_SQRT: return launch_reduce_w<F_SQRT, false>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_LOG: return launch_reduce_w<F_LOG, false>(wmode, ctx, p, threads, smem, ncta, dry);
-    case F_HYBRID: return launch_reduce_w<F_HYBRID, false>(wmode, ctx, p, threads, smem, ncta, dry);
-    default: return launch_reduce_w<F_NONE, false>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_LINEAR: return launch_reduce_w<F_LINEAR, 1>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_TRANS: return launch_reduce_w<F_TRANS, 1>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_SQRT: return launch_reduce_w<F_SQRT, 1>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_LOG: return launch_reduce_w<F_LOG, 1>(wmode, ctx, p, threads, smem, ncta, dry);
+    case F_HYBRID: return launch_reduce_w<F_HYBRID, 1>(wmode, ctx, p, threads, smem, ncta, dry);
+    default: return launch_reduce_w<F_NONE, 1>(wmode, ctx, p, threads, smem, ncta, dry);
   }
 }
 
@@ -1400,15 +1892,24 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     longest = std::max(longest, run);
   }
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
-  // windowed plans run on reduce2_kernel (ECCKD_REDUCE_V1=1 keeps reduce_kernel, for comparisons)
-  const bool v2 = plan->windowed && reduce2_supports(fkind) && !(getenv("ECCKD_REDUCE_V1") && atoi(getenv("ECCKD_REDUCE_V1")));
-  auto smem_of = [&](int n) { return v2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total; };
-  int nw = std::min(NW_MAX, (longest + RPW - 1) / RPW);
+  // Kernel generation: windowed plans and the kinds without per-row weight sums run on
+  // reduce3_kernel (one row per consumer warp), everything else on reduce_kernel (two rows per warp,
+  // shuffle fold).  ECCKD_REDUCE_GEN=1|2|3 forces an older generation where it applies (comparisons).
+  int gen = (plan->windowed && reduce2_supports(fkind)) ? 3 : 1;
+  if (const char* env = getenv("ECCKD_REDUCE_GEN")) {
+    const int want = atoi(env);
+    if (want >= 1 && want < gen) gen = want;
+  }
+  const int rpw = (gen == 3) ? 1 : RPW;
+  auto smem_of = [&](int n) {
+    return gen == 3 ? (size_t)smem3_layout(n).total : (gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total);
+  };
+  int nw = std::min(gen == 3 ? NW3_MAX : NW_MAX, (longest + rpw - 1) / rpw);
   while (nw > 1 && smem_of(nw) > smem_max) --nw;
   ECCKD_REQUIRE(smem_of(nw) <= smem_max, ECCKD_PARAMETER_ERROR,
                 "average_optical_depth: ng = %d needs %zu B of shared memory (limit %zu)", ng, smem_of(nw), smem_max);
   // balance: split a run of n rows into ceil(n/(nw*RPW)) groups of nearly equal size
-  const int cap = nw * RPW;
+  const int cap = nw * rpw;
   std::vector<GroupDesc> groups;
   for (int i = 0; i < nrows;) {
     int j = i;
@@ -1432,7 +1933,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     i = j;
   }
   const int ngroups = (int)groups.size();
-  const int threads = (nw + NPW) * 32;
+  const int threads = (nw + NPW + (gen == 3 ? 1 : 0)) * 32;
   const size_t smem = smem_of(nw);
 
   ReduceParams rp;
@@ -1471,7 +1972,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.cw = cw;
 
   int ncta = 0;
-  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, v2, ctx, rp, threads, smem, &ncta, true));
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, gen, ctx, rp, threads, smem, &ncta, true));
   const int64_t T = (int64_t)ngroups * plan->nchunks;
   ncta = (int)std::min<int64_t>(ncta, std::max<int64_t>(1, T));
   // (window, group) pairs a CTA's contiguous piece can touch
@@ -1493,7 +1994,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   void* d_groups = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 0, (size_t)ngroups * sizeof(GroupDesc), &d_groups));
   ECCKD_TRY(upload_small(ctx, d_groups, groups.data(), (size_t)ngroups * sizeof(GroupDesc)));
-  const size_t npieces = (size_t)ncta * maxg * nw * RPW;
+  const size_t npieces = (size_t)ncta * maxg * nw * rpw;
   void* d_partial = nullptr;
   ECCKD_TRY(ws_reserve(ctx, 1, npieces * ng * 4 * sizeof(double), &d_partial));
   void* d_pz = nullptr;
@@ -1517,7 +2018,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     ECCKD_CUDA_OK(cudaEventCreate(&ev1));
     ECCKD_CUDA_OK(cudaEventRecord(ev0, ctx->stream));
   }
-  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, v2, ctx, rp, threads, smem, &ncta, false));
+  ECCKD_CUDA_OK(launch_reduce(fkind, wmode, gen, ctx, rp, threads, smem, &ncta, false));
   ctx->launches++;
   if (ctx->timing) {
     ECCKD_CUDA_OK(cudaEventRecord(ev1, ctx->stream));
@@ -1528,6 +2029,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.groups = rp.groups;
   cp.ngroups = ngroups;
   cp.nw = nw;
+  cp.rpw = rpw;
   cp.ncta = ncta;
   cp.maxg = maxg;
   cp.nwin = nwin;
@@ -1539,7 +2041,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.partial_z = rp.partial_z;
   cp.sums = d_sums;
   cp.minmax = d_minmax;
-  const int64_t nthreads = (int64_t)ngroups * nw * RPW * ng;
+  const int64_t nthreads = (int64_t)ngroups * nw * rpw * ng;
   combine_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(cp);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
@@ -1652,7 +2154,7 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   // (longest first), with and without the window constraint of reduce2_kernel, and keep the
   // cheapest (a windowed round costs ~0.77 of a free one: no shuffle fold).
   static const int candidates[] = {CH_MAX, 448, 384, 320, 256};
-  const int64_t max_chunks = (nwav + 255) / 256;
+  const int64_t max_chunks = (nwav + 31) / 32;  // the shortest chunk length ECCKD_CH may ask for
   ECCKD_REQUIRE(max_chunks < ((int64_t)1 << 31), ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: nwav too large");
   uint32_t* d_nrounds = nullptr;
   unsigned long long* d_nfree = nullptr;

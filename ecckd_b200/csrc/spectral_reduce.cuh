@@ -115,6 +115,7 @@ struct CombineParams {
   const GroupDesc* groups;
   int ngroups;
   int nw;
+  int rpw;         // rows per consumer warp of the kernel that wrote the pieces
   int ncta;
   int maxg;
   int nwin;

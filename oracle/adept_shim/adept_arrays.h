@@ -400,6 +400,8 @@ typedef Array<2, Real, true> aMatrix;
 typedef Array<3, Real, true> aArray3D;
 typedef Array<1, int, false> intVector;
 typedef Array<2, int, false> intMatrix;
+typedef Array<1, int, false> IntVector;  // Adept spells the integer arrays both ways
+typedef Array<2, int, false> IntMatrix;
 typedef Array<1, bool, false> boolVector;
 typedef Array<2, bool, false> boolMatrix;
 

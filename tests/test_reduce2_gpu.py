@@ -1,8 +1,9 @@
-"""The two generations of the streaming reduction kernel behind
-ecckd_average_optical_depth_* (average_optical_depth.cpp:22-197): reduce2_kernel on windowed plans
-and reduce_kernel on free plans must both match the oracle on the same inputs, agree with each
-other, and be bitwise reproducible whatever the launch geometry knobs say (stress of the
-mbarrier / bulk-copy pipelines: many tiny chunks, several wavenumber windows, repeated launches)."""
+"""The generations of the streaming reduction kernel behind ecckd_average_optical_depth_*
+(average_optical_depth.cpp:22-197): reduce3_kernel / reduce2_kernel on windowed plans and
+reduce_kernel on free and on windowed plans must all match the oracle on the same inputs, agree
+with each other, and be bitwise reproducible whatever the launch geometry knobs say (stress of the
+mbarrier / bulk-copy pipelines: many tiny chunks, several wavenumber windows, repeated launches,
+rows that are not 16-byte aligned, odd lengths)."""
 import numpy as np
 import pytest
 
@@ -16,6 +17,15 @@ METHODS2 = ["transmission", "transmission-10", "linear", "square-root"]  # the k
 
 def _planck(O, c):
     return O.planck_function(c["temperature_fl"], c["wavenumber"], c["d_wavenumber"])
+
+
+# (plan kind, kernel generation): free plan + reduce_kernel, windowed plan + each generation
+GENS = [("0", "1"), ("1", "1"), ("1", "2"), ("1", "3")]
+
+
+def _select(monkeypatch, gen):
+    monkeypatch.setenv("ECCKD_PLAN_WINDOW", gen[0])
+    monkeypatch.setenv("ECCKD_REDUCE_GEN", gen[1])
 
 
 def _run(ctx, c, g, ng, planck, method):
@@ -45,10 +55,11 @@ def _cases():
 CASES = _cases()
 
 
-@pytest.mark.parametrize("window", ["0", "1"])
+@pytest.mark.parametrize("gen", GENS)
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_both_kernel_generations_match_the_oracle(ctx, O, monkeypatch, case, window):
-    monkeypatch.setenv("ECCKD_PLAN_WINDOW", window)
+def test_every_kernel_generation_matches_the_oracle(ctx, O, monkeypatch, case, gen):
+    _select(monkeypatch, gen)
+    window = "/".join(gen)
     c, g, ng = CASES[case]
     planck = _planck(O, c)
     for method in METHODS2:
@@ -63,21 +74,23 @@ def test_generations_agree_and_extremes_are_identical(ctx, O, monkeypatch, case)
     c, g, ng = CASES[case]
     planck = _planck(O, c)
     res = {}
-    for window in ("0", "1"):
-        monkeypatch.setenv("ECCKD_PLAN_WINDOW", window)
-        res[window] = _run(ctx, c, g, ng, planck, "linear")
-    np.testing.assert_allclose(res["1"][0], res["0"][0], rtol=1e-13, atol=0.0)
-    assert np.array_equal(res["1"][1], res["0"][1]) and np.array_equal(res["1"][2], res["0"][2])  # selections
-    assert np.array_equal(res["1"][3], res["0"][3])
+    for gen in GENS:
+        _select(monkeypatch, gen)
+        res[gen] = _run(ctx, c, g, ng, planck, "linear")
+    base = res[GENS[0]]
+    for gen in GENS[1:]:
+        np.testing.assert_allclose(res[gen][0], base[0], rtol=1e-13, atol=0.0)
+        assert np.array_equal(res[gen][1], base[1]) and np.array_equal(res[gen][2], base[2]), gen  # selections
+        assert np.array_equal(res[gen][3], base[3]), gen
 
 
-@pytest.mark.parametrize("window", ["0", "1"])
-def test_pipeline_stress_tiny_chunks_windows_and_repeats(ctx, O, monkeypatch, window):
+@pytest.mark.parametrize("gen", GENS)
+def test_pipeline_stress_tiny_chunks_windows_and_repeats(ctx, O, monkeypatch, gen):
     """Many tiny chunks (every mbarrier phase flips thousands of times per CTA), 1..7 wavenumber
     windows, odd row lengths (generic-store fallback followed by bulk copies into the same stage),
     20 spectra in one group; every configuration is launched three times and must reproduce itself
     bit for bit, and all of them must match the oracle."""
-    monkeypatch.setenv("ECCKD_PLAN_WINDOW", window)
+    _select(monkeypatch, gen)
     nspec = 20
     c = S.lw_spectrum_case(nlay=3, nwav=30001, ng=14, nband=3, seed=5)
     rng = np.random.default_rng(3)
@@ -114,9 +127,9 @@ def test_pipeline_stress_tiny_chunks_windows_and_repeats(ctx, O, monkeypatch, wi
         plan.close()
 
 
-@pytest.mark.parametrize("window", ["0", "1"])
-def test_nan_optical_depth_is_reported_not_absorbed(ctx, O, monkeypatch, window):
-    monkeypatch.setenv("ECCKD_PLAN_WINDOW", window)
+@pytest.mark.parametrize("gen", GENS)
+def test_nan_optical_depth_is_reported_not_absorbed(ctx, O, monkeypatch, gen):
+    _select(monkeypatch, gen)
     c = S.lw_spectrum_case(nlay=4, nwav=5000, ng=6, nband=2, seed=2)
     od = c["od"].copy()
     w_bad = 1234
