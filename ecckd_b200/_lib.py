@@ -90,6 +90,7 @@ def _declare(L):
         "ecckd_gpoint_plan_create": [vp, vp, i64, i32, c_void_pp],
         "ecckd_gpoint_plan_destroy": [vp],
         "ecckd_gpoint_plan_counts": [vp, vp],
+        "ecckd_gpoint_plan_export": [vp, vp, i64, vp],
         "ecckd_gpoint_plan_counts_dev": [vp, c_void_pp],
         "ecckd_average_optical_depth_partial_dev": [vp, vp, i32, i32, vp, vp, i64, i32, vp, i64, vp, vp, vp, i32, vp,
                                                     vp],

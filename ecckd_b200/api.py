@@ -195,6 +195,16 @@ class GPointPlan:
         check(_lib.lib().ecckd_gpoint_plan_counts_dev(self.handle, C.byref(p)))
         return int(p.value)
 
+    def export(self):
+        """ecckd_gpoint_plan_export: (info dict, structured array of the plan's rounds)."""
+        info = np.zeros(4, dtype=np.int64)
+        check(_lib.lib().ecckd_gpoint_plan_export(self.handle, None, 0, info.ctypes.data))
+        dt = np.dtype([("off", np.uint16, (16, 32)), ("meta", np.uint32, (32,)), ("steps", np.uint32),
+                       ("chunk", np.uint32), ("flags", np.uint32), ("win", np.uint32)])
+        rounds = np.zeros(int(info[0]), dtype=dt)
+        check(_lib.lib().ecckd_gpoint_plan_export(self.handle, rounds.ctypes.data, rounds.size, info.ctypes.data))
+        return dict(nrounds=int(info[0]), ch=int(info[1]), windowed=bool(info[2]), balanced=bool(info[3])), rounds
+
     def close(self):
         if self.handle:
             _lib.lib().ecckd_gpoint_plan_destroy(self.handle)

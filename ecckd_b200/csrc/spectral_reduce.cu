@@ -38,6 +38,10 @@
 #include <ctime>
 #include <type_traits>
 
+// (defined with the C ABI at the end of this file)
+static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng, bool free_layout,
+                            ecckd_gpoint_plan** out);
+
 namespace ecckd {
 
 // exp(x) without branches: Cody-Waite reduction by ln 2 and a degree-11 polynomial; maximum
@@ -255,6 +259,236 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_kernel(const int32_t* __rest
   }
 }
 
+// ------------------------------------------------------------------ balanced plans
+// The slot loop of the streaming kernels is bound by shared-memory bandwidth, and a third of its
+// wavefronts were bank-conflict replays of the permuted 64-bit gathers (a warp's LDS.64 is served as
+// lanes 0-15 then 16-31, each half costing as many wavefronts as the fullest of the 16 eight-byte bank
+// pairs: tools/ubench/lds64_conflicts.cu).  reduce2/3_kernel add their lanes' sums through per-lane
+// entries, so the lanes of a g point need not be adjacent and ANY placement of a g point's
+// wavenumbers on its lanes' cells is allowed.  plan_fill_balanced_kernel uses that freedom:
+//   * the lanes of every g point of a round alternate between the two half-warps (virtual lane v ->
+//     physical lane v/2 + 16 (v & 1));
+//   * the wavenumbers of a (g point, round) are dealt to the two half-warps residue class by residue
+//     class (class = chunk index mod 16 = bank pair), by error diffusion, so that each half-warp holds
+//     its share of every class: over a round no class then exceeds 16 wavenumbers per half-warp
+//     (a chunk has at most 30 of each), except for rounding;
+//   * inside a half-warp the wavenumbers are edges of a bipartite multigraph lanes x residue classes
+//     of maximum degree 16: a proper edge colouring with 16 colours (Koenig) exists, and the colour is
+//     the slot - every slot then reads 16 different bank pairs.  It is built edge by edge with the
+//     alternating-path flip; an edge whose class already has 16 edges keeps a lane-proper colour
+//     and is the only source of conflicts left;
+//   * padding cells repeat an address another lane of the same g point reads in that slot
+//     (broadcast), else an own wavenumber of an unused class.
+// The valid slots of a lane are no longer a prefix: bits 12-27 of the lane's meta word are a slot mask.
+constexpr int BAL_TASKS = 8;  // (round, half-warp) colouring tasks per batch
+
+__global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_t* __restrict__ g_point, int64_t nwav,
+                                                                     int ng, int W,
+                                                                     const uint32_t* __restrict__ round_off,
+                                                                     PlanRound* __restrict__ rounds,
+                                                                     int32_t* __restrict__ rmin,
+                                                                     int32_t* __restrict__ rmax) {
+  __shared__ int sg[CH_MAX];
+  __shared__ int sred[33];
+  // per wavenumber: bits 0-9 chunk-local round, 10 half-warp, 11-15 physical lane, 16-19 colour (slot),
+  // 20 "half edge" (its class was full: not registered on the class side), 31 belongs to a g point
+  __shared__ unsigned sinfo[CH_MAX];
+  __shared__ short slead[CH_MAX];             // first wavenumber (thread) of the same (g point, round)
+  __shared__ unsigned char scls[CH_MAX][16];  // [leader][class]: wavenumbers of the (g point, round) per class
+  __shared__ unsigned char sa0[CH_MAX][16];   // [leader][class]: how many of them go to half-warp 0
+  __shared__ short scolL[BAL_TASKS][16][16];  // [task][lane][colour] -> wavenumber or -1
+  __shared__ short scolR[BAL_TASKS][16][16];  // [task][class][colour] -> wavenumber or -1
+  const int i = threadIdx.x;
+  const int ch = (int)blockDim.x;
+  const int64_t c = blockIdx.x;
+  const PlanPos p = plan_position(g_point, nwav, ng, ch, c, W, sg, sred);
+  const uint32_t r0 = round_off[c], r1 = round_off[c + 1];
+  if (i == 0) {
+    for (uint32_t r = r0; r < r1; ++r) {
+      rounds[r].chunk = (uint32_t)c;
+      rounds[r].flags = (r == r0 ? 1u : 0u) | (r + 1 == r1 ? 2u : 0u);
+    }
+  }
+  const bool valid = p.g >= 0;
+  // the (g point, round) of this wavenumber: the g point's capacity lanes, 16 wavenumbers each in
+  // wavenumber order, map to virtual lanes gs .. gs+L-1; round = virtual lane / 32
+  int gs = 0, rl = 0, l = 1, n = 0, a = 0;
+  if (valid) {
+    gs = p.vlane - (p.kth % p.L);
+    rl = (gs + (p.kth >> 4)) >> 5;
+    const int c0 = max(0, 32 * rl - gs);                          // capacity lanes of the g point before this round
+    l = min(gs + p.L, 32 * rl + 32) - max(gs, 32 * rl);           // its lanes in this round
+    n = min(p.count - 16 * c0, 16 * l);                           // its wavenumbers in this round
+    a = max(gs, 32 * rl) - 32 * rl;                               // virtual position of its first lane
+  }
+  sinfo[i] = valid ? (0x80000000u | (unsigned)rl) : 0u;
+  for (int q = 0; q < 16; ++q) scls[i][q] = 0;
+  __syncthreads();
+  int lead = i, t = 0, m = 0;
+  if (valid) {
+    for (int j = 0; j < ch; ++j) {
+      if (sg[j] == p.g && (sinfo[j] & 0x3ffu) == (unsigned)rl) {
+        lead = j;
+        break;
+      }
+    }
+    for (int j = (i & 15); j < ch; j += 16) {
+      const int same = (sg[j] == p.g && (sinfo[j] & 0x3ffu) == (unsigned)rl) ? 1 : 0;
+      m += same;
+      t += same & (j < i);
+    }
+  }
+  slead[i] = (short)lead;
+  if (valid && t == 0) scls[lead][i & 15] = (unsigned char)m;
+  __syncthreads();
+  const int l0 = ((a + l + 1) >> 1) - ((a + 1) >> 1);  // even virtual lanes in [a, a+l): half-warp 0
+  const int l1 = l - l0;
+  if (valid && i == lead) {
+    int n0 = (n * l0 + l / 2) / l;
+    n0 = min(max(n0, n - 16 * l1), 16 * l0);
+    int M = 0, A = 0;
+    for (int q = 0; q < 16; ++q) {
+      M += scls[i][q];
+      const int tgt = (n0 * M + n / 2) / n;  // rounded share of half-warp 0 after this class
+      sa0[i][q] = (unsigned char)(tgt - A);
+      A = tgt;
+    }
+    PlanRound& rd = rounds[r0 + rl];
+    for (int v = a; v < a + l; ++v) rd.meta[(v >> 1) + 16 * (v & 1)] = (unsigned)p.g;  // slot mask OR-ed in later
+    atomicMin(&rmin[r0 + rl], p.g);
+    atomicMax(&rmax[r0 + rl], p.g);
+  }
+  __syncthreads();
+  if (valid) {
+    const int q = i & 15;
+    const int a0 = sa0[lead][q];
+    const int h = (t < a0) ? 0 : 1;
+    int u = h ? t - a0 : t;
+    for (int qq = 0; qq < q; ++qq) u += h ? (int)scls[lead][qq] - (int)sa0[lead][qq] : (int)sa0[lead][qq];
+    const int lh = h ? l1 : l0;  // >= 1 whenever the half-warp got a wavenumber
+    const int v = a + ((a & 1) ^ h) + 2 * (u % lh);
+    const int phys = (v >> 1) + 16 * h;
+    sinfo[i] |= ((unsigned)h << 10) | ((unsigned)phys << 11);
+  }
+  __syncthreads();
+  // one colouring task per (round, half-warp), each run by lane 0 of its own warp (tasks are serial
+  // code: sharing a warp would serialise them)
+  const int ntask = 2 * (int)(r1 - r0);
+  const int ntb = min(BAL_TASKS, ch >> 5);
+  for (int base = 0; base < ntask; base += ntb) {
+    for (int x = i; x < BAL_TASKS * 256; x += ch) {
+      (&scolL[0][0][0])[x] = -1;
+      (&scolR[0][0][0])[x] = -1;
+    }
+    __syncthreads();
+    if ((i & 31) == 0 && (i >> 5) < ntb && base + (i >> 5) < ntask) {
+      const int ts = i >> 5, task = base + ts, rt = task >> 1, ht = task & 1;
+      short (*CL)[16] = scolL[ts];
+      short (*CR)[16] = scolR[ts];
+      auto colour_of = [&](int e) { return (int)((sinfo[e] >> 16) & 15u); };
+      auto is_half = [&](int e) { return ((sinfo[e] >> 20) & 1u) != 0; };
+      auto lane_of = [&](int e) { return (int)((sinfo[e] >> 11) & 15u); };
+      auto set_colour = [&](int e, int col) { sinfo[e] = (sinfo[e] & ~(15u << 16)) | ((unsigned)col << 16); };
+      for (int e = 0; e < ch; ++e) {
+        const unsigned inf = sinfo[e];
+        if (!(inf >> 31) || (inf & 0x3ffu) != (unsigned)rt || ((inf >> 10) & 1u) != (unsigned)ht) continue;
+        const int ln = (int)((inf >> 11) & 15u), q = e & 15;
+        int ca = 0, cb = 0;
+        while (ca < 16 && CL[ln][ca] >= 0) ++ca;
+        while (cb < 16 && CR[q][cb] >= 0) ++cb;
+        if (ca == 16) ca = 15;  // cannot happen: a lane holds at most 16 wavenumbers
+        if (cb == 16) {         // the class already has 16 wavenumbers in this half-warp: lane-proper only
+          CL[ln][ca] = (short)e;
+          sinfo[e] |= 1u << 20;
+          set_colour(e, ca);
+          continue;
+        }
+        if (CR[q][ca] >= 0) {
+          // colour ca is taken at the class by another lane: flip the ca/cb alternating path that
+          // starts there (it cannot reach lane ln, which has no ca edge)
+          short path[40];
+          int np = 0;
+          int x = CR[q][ca], cx = ca;
+          while (x >= 0 && np < 40) {
+            path[np++] = (short)x;
+            if (cx == ca) {
+              x = CL[lane_of(x)][cb];
+              cx = cb;
+            } else {
+              if (is_half(x)) break;
+              x = CR[x & 15][ca];
+              cx = ca;
+            }
+          }
+          for (int k = 0; k < np; ++k) {
+            const int y = path[k], cy = colour_of(y);
+            CL[lane_of(y)][cy] = -1;
+            if (!is_half(y)) CR[y & 15][cy] = -1;
+          }
+          for (int k = 0; k < np; ++k) {
+            const int y = path[k], cy = colour_of(y) == ca ? cb : ca;
+            CL[lane_of(y)][cy] = (short)y;
+            if (!is_half(y)) CR[y & 15][cy] = (short)y;
+            set_colour(y, cy);
+          }
+        }
+        if (CL[ln][ca] >= 0 || CR[q][ca] >= 0) {
+          // (defensive: the flip could not free the colour - keep the plan valid with a lane-proper colour)
+          int cf = 0;
+          while (cf < 15 && CL[ln][cf] >= 0) ++cf;
+          CL[ln][cf] = (short)e;
+          sinfo[e] |= 1u << 20;
+          set_colour(e, cf);
+          continue;
+        }
+        CL[ln][ca] = (short)e;
+        CR[q][ca] = (short)e;
+        set_colour(e, ca);
+      }
+      // write the half-warp's 16 x 16 cells
+      PlanRound& rd = rounds[r0 + rt];
+      int lane_g[16];
+      unsigned mask[16];
+      for (int ln = 0; ln < 16; ++ln) {
+        lane_g[ln] = (int)(rd.meta[ln + 16 * ht] & 0xFFFu);
+        mask[ln] = 0u;
+        bool any = false;
+        for (int s = 0; s < 16; ++s) any = any || CL[ln][s] >= 0;
+        if (!any) lane_g[ln] = (int)NO_G;
+      }
+      for (int s = 0; s < 16; ++s) {
+        for (int ln = 0; ln < 16; ++ln) {
+          if (lane_g[ln] == (int)NO_G) continue;
+          int e = CL[ln][s];
+          if (e >= 0) {
+            mask[ln] |= 1u << s;
+          } else {
+            // padding: an address another lane of this g point reads in this slot, else an own
+            // wavenumber of a class nobody reads in this slot, else any own wavenumber
+            for (int l2 = 0; l2 < 16 && e < 0; ++l2)
+              if (lane_g[l2] == lane_g[ln] && CL[l2][s] >= 0) e = CL[l2][s];
+            int own = -1;
+            for (int s2 = 0; s2 < 16 && e < 0; ++s2) {
+              const int y = CL[ln][s2];
+              if (y < 0) continue;
+              if (own < 0) own = y;
+              if (CR[y & 15][s] < 0) {
+                e = y;
+                CR[y & 15][s] = (short)y;  // the class is now read in this slot
+              }
+            }
+            if (e < 0) e = own;
+          }
+          rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
+        }
+      }
+      for (int ln = 0; ln < 16; ++ln)
+        rd.meta[ln + 16 * ht] = lane_g[ln] == (int)NO_G ? NO_G : ((unsigned)lane_g[ln] | (mask[ln] << 12));
+    }
+    __syncthreads();
+  }
+}
+
 // Windowed plans: the window base of every round, in round order (one warp; a round keeps the
 // previous window when its g points fit in it, else the window moves to the round's smallest g point).
 __global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __restrict__ rmin,
@@ -454,7 +688,8 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
     const Entry e2 = next_entry();
     load_src(e1, off1, x1, y1);
     load_plan(e2, off1, meta2);  // off1 is free again: the gathers above have their addresses
-    const int nv = (int)((meta0 >> 12) & 31u);
+    // valid slots: a prefix of nv slots, or (balanced plans) the slot mask in bits 12-27
+    const unsigned vmask = p.balanced ? ((meta0 >> 12) & 0xFFFFu) : ((1u << ((meta0 >> 12) & 31u)) - 1u);
     double val[PER];
     if (WMODE == W_PLANCK) {
       const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
@@ -470,7 +705,7 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
 #pragma unroll
     for (int m = 0; m < PER; ++m) {
       const int k = pw + NPW * m;
-      wperm[k * 32 + lane] = (k < nv) ? val[m] : 0.0;
+      wperm[k * 32 + lane] = ((vmask >> k) & 1u) ? val[m] : 0.0;
     }
     __syncwarp();
     if (lane == 0) {
@@ -1297,7 +1532,7 @@ __device__ __forceinline__ void produce_rounds3(const ReduceParams& p, const Cur
         x[m] = p.weight[w];
       }
     }
-    const int nv = (int)((meta >> 12) & 31u);
+    const unsigned vmask = p.balanced ? ((meta >> 12) & 0xFFFFu) : ((1u << ((meta >> 12) & 31u)) - 1u);
     const double hkt = (WMODE == W_PLANCK) ? p.temperature[wrow] : 0.0;
     const uint32_t r_this = r;
     // advance to the next round and fetch its plan words while the sources are in flight
@@ -1327,7 +1562,7 @@ __device__ __forceinline__ void produce_rounds3(const ReduceParams& p, const Cur
     for (int m = 0; m < PER; ++m) {
       const int k = pw + NPW * m;
       const double val = (WMODE == W_PLANCK) ? planck_elem_fast(hkt, x[m], y[m], ptl) : x[m];
-      wperm[k * 32 + lane] = (k < nv) ? val : 0.0;
+      wperm[k * 32 + lane] = ((vmask >> k) & 1u) ? val : 0.0;
     }
     __syncwarp();
     if (lane == 0) {
@@ -1900,6 +2135,10 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     const int want = atoi(env);
     if (want >= 1 && want < gen) gen = want;
   }
+  if (gen == 1 && plan->balanced) {
+    if (!plan->legacy) ECCKD_TRY(::plan_create_impl(ctx, plan->d_g_copy, plan->nwav, plan->ng, true, &plan->legacy));
+    plan = plan->legacy;
+  }
   const int rpw = (gen == 3) ? 1 : RPW;
   auto smem_of = [&](int n) {
     return gen == 3 ? (size_t)smem3_layout(n).total : (gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total);
@@ -1946,6 +2185,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.ch = plan->ch;
   rp.round_off = plan->d_round_off;
   rp.rounds = plan->d_rounds;
+  rp.balanced = plan->balanced ? 1 : 0;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
@@ -2133,12 +2373,14 @@ static void plan_free(ecckd_gpoint_plan* p) {
   if (p->d_rounds) cudaFreeAsync(p->d_rounds, st);
   if (p->d_count) cudaFreeAsync(p->d_count, st);
   if (p->d_scratch) cudaFreeAsync(p->d_scratch, st);
+  if (p->d_g_copy) cudaFreeAsync(p->d_g_copy, st);
+  if (p->legacy) plan_free(p->legacy);
   delete p;
 }
 
-ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
-                                       ecckd_gpoint_plan** out) {
-  ECCKD_DEVICE(ctx);
+// free_layout: build the plan reduce_kernel needs (no window constraint, lanes of a g point adjacent)
+static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng, bool free_layout,
+                            ecckd_gpoint_plan** out) {
   ECCKD_REQUIRE(ctx && d_g_point && out, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_create: NULL argument");
   ECCKD_REQUIRE(nwav > 0 && ng > 0 && ng <= MAX_NG, ECCKD_PARAMETER_ERROR,
                 "ecckd_gpoint_plan_create: need nwav > 0 and 0 < ng <= %d (got nwav=%lld ng=%d)", MAX_NG,
@@ -2169,6 +2411,9 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   int best_ch = 0, best_w = WIN;
   int force_w = -1;  // ECCKD_PLAN_WINDOW=0: free plans only (reduce_kernel), =1: windowed plans only
   if (const char* env = getenv("ECCKD_PLAN_WINDOW")) force_w = atoi(env) ? 1 : 0;
+  if (free_layout) force_w = 0;
+  bool balance = true;  // ECCKD_PLAN_BALANCE=0: windowed plans keep the adjacent-lane placement (comparisons)
+  if (const char* env = getenv("ECCKD_PLAN_BALANCE")) balance = atoi(env) != 0;
   if (const char* env = getenv("ECCKD_CH")) best_ch = std::min(CH_MAX, std::max(32, atoi(env) & ~31));
   // rounds of a plan with chunk length ch and window w (h_total), and without a window (h_free)
   auto count_rounds = [&](int ch, int w, bool with_counts, uint32_t* h_total, unsigned long long* h_free) {
@@ -2241,14 +2486,26 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
     if (e == cudaSuccess) {
       plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds, d_rminmax,
                                                                                     d_rminmax + nr);
-      plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, best_w, p->d_round_off,
-                                                                          p->d_rounds, d_rminmax, d_rminmax + nr);
+      p->balanced = best_w > 0 && balance;
+      if (p->balanced)
+        plan_fill_balanced_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(
+            d_g_point, nwav, ng, best_w, p->d_round_off, p->d_rounds, d_rminmax, d_rminmax + nr);
+      else
+        plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, best_w, p->d_round_off,
+                                                                            p->d_rounds, d_rminmax, d_rminmax + nr);
       ctx->launches += 2;
       if (best_w > 0) {
         plan_window_kernel<<<1, 32, 0, ctx->stream>>>((int64_t)nr, best_w, d_rminmax, d_rminmax + nr, p->d_rounds);
         ctx->launches++;
       }
       e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && p->balanced) {
+      // reduce_kernel (kinds with per-row weight sums) cannot run on a balanced plan: keep the map so
+      // that a free-layout plan can be built the first time such a kind is asked for
+      e = cudaMallocAsync(&p->d_g_copy, (size_t)nwav * sizeof(int32_t), ctx->stream);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(p->d_g_copy, d_g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller
   }
@@ -2262,6 +2519,32 @@ ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point,
   }
   p->h_count.assign(cnt.begin(), cnt.end());
   *out = p;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
+                                       ecckd_gpoint_plan** out) {
+  ECCKD_DEVICE(ctx);
+  return plan_create_impl(ctx, d_g_point, nwav, ng, false, out);
+}
+
+// Test / diagnostic hook: the plan's rounds as the kernels see them.  h_rounds receives up to
+// capacity_rounds records of 1168 bytes (uint16 off[16][32], uint32 meta[32], steps, chunk, flags, win);
+// info = {nrounds, chunk length, windowed, balanced}.
+ECCKD_API int ecckd_gpoint_plan_export(ecckd_gpoint_plan* plan, void* h_rounds, int64_t capacity_rounds,
+                                       int64_t* info) {
+  ECCKD_DEVICE(plan ? plan->ctx : nullptr);
+  ECCKD_REQUIRE(plan && info, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_plan_export: NULL argument");
+  info[0] = plan->nrounds;
+  info[1] = plan->ch;
+  info[2] = plan->windowed ? 1 : 0;
+  info[3] = plan->balanced ? 1 : 0;
+  if (h_rounds && capacity_rounds > 0) {
+    const int64_t n = std::min<int64_t>(capacity_rounds, plan->nrounds);
+    ECCKD_CUDA_OK(cudaMemcpyAsync(h_rounds, plan->d_rounds, (size_t)n * sizeof(PlanRound), cudaMemcpyDeviceToHost,
+                                  plan->ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(plan->ctx->stream));
+  }
   return ECCKD_OK;
 }
 

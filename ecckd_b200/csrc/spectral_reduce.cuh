@@ -106,6 +106,7 @@ struct ReduceParams {
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
   TransConst256 tc256;        // the same for the 256-entry shared-memory table of the consumer warps
   TransConst64 tc64;          // the same for the replicated 64-entry table of reduce2_kernel
+  int balanced;               // the plan is a balanced one: lane meta bits 12-27 are a slot mask (not a count)
   int debug;                  // timing experiments only (ECCKD_DEBUG): 1 skip the row evaluation, 4 skip only the slot loop
   double* partial;            // [ncta][maxg][nw*RPW][ng][4]
   int32_t* partial_z;         // [ncta][maxg][nw*RPW][ng]
@@ -148,7 +149,11 @@ struct ecckd_gpoint_plan {
   int64_t nrounds = 0;
   int ng = 0;
   int ch = 0;                            // chunk length chosen for this g-point map
-  bool windowed = false;                 // rounds obey the WIN window constraint (reduce2_kernel can run)
+  bool windowed = false;                 // rounds obey the WIN window constraint (reduce2/3_kernel can run)
+  bool balanced = false;                 // bank-conflict-free cell placement (reduce2/3_kernel ONLY: lanes of a g
+                                         // point are not adjacent, the lane meta word carries a slot mask)
+  int32_t* d_g_copy = nullptr;           // balanced plans keep the g-point map to build `legacy` on demand
+  ecckd_gpoint_plan* legacy = nullptr;   // free-layout plan for reduce_kernel (kinds with per-row weight sums)
   uint32_t* d_round_off = nullptr;       // [nchunks+1]
   ecckd::PlanRound* d_rounds = nullptr;  // [nrounds]
   unsigned long long* d_count = nullptr; // [ng]

@@ -149,6 +149,12 @@ int ecckd_planck_function(ecckd_ctx* ctx, int nt, const double* temperature, int
 int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
                              ecckd_gpoint_plan** out);
 int ecckd_gpoint_plan_destroy(ecckd_gpoint_plan* plan);
+/* Test / diagnostic hook (no reference counterpart): the plan's rounds as the kernels read them.
+ * h_rounds receives up to capacity_rounds records of 1168 bytes each {uint16 off[16][32] (byte
+ * offset of (slot, lane) into the chunk), uint32 meta[32] (bits 0-11 g point, 0xFFF = lane unused;
+ * bits 12-27 valid-slot mask in balanced plans, bits 12-16 valid-slot count otherwise),
+ * uint32 steps, chunk, flags, win}; info[4] = {rounds, chunk length, windowed, balanced}. */
+int ecckd_gpoint_plan_export(ecckd_gpoint_plan* plan, void* h_rounds, int64_t capacity_rounds, int64_t* info);
 /* Number of wavenumbers in each g point (h_count[ng], host). */
 int ecckd_gpoint_plan_counts(ecckd_gpoint_plan* plan, int64_t* h_count);
 /* Device pointer to the same counts as int64[ng] (for a cross-GPU sum when the

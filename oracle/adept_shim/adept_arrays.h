@@ -72,6 +72,30 @@ inline RangeIndex range(int a, EndIndex b) { RangeIndex r = {false, true, a, b.o
 inline RangeIndex range(EndIndex a, EndIndex b) { RangeIndex r = {true, true, a.offset, b.offset}; return r; }
 inline RangeIndex range(EndIndex a, int b) { RangeIndex r = {true, false, a.offset, b}; return r; }
 
+// ExpressionSize<Rank>: what `dimensions(n0, n1, ...)`, `expression_size(...)` and `a.dimensions()` return
+template <int Rank>
+struct ExpressionSize {
+  int dim[Rank > 0 ? Rank : 1];
+  int operator[](int d) const { return dim[d]; }
+  int& operator[](int d) { return dim[d]; }
+};
+inline ExpressionSize<1> dimensions(int n0) { ExpressionSize<1> e; e.dim[0] = n0; return e; }
+inline ExpressionSize<2> dimensions(int n0, int n1) { ExpressionSize<2> e; e.dim[0] = n0; e.dim[1] = n1; return e; }
+inline ExpressionSize<3> dimensions(int n0, int n1, int n2) {
+  ExpressionSize<3> e; e.dim[0] = n0; e.dim[1] = n1; e.dim[2] = n2; return e;
+}
+inline ExpressionSize<4> dimensions(int n0, int n1, int n2, int n3) {
+  ExpressionSize<4> e; e.dim[0] = n0; e.dim[1] = n1; e.dim[2] = n2; e.dim[3] = n3; return e;
+}
+inline ExpressionSize<1> expression_size(int n0) { return dimensions(n0); }
+inline ExpressionSize<2> expression_size(int n0, int n1) { return dimensions(n0, n1); }
+template <int Rank>
+std::ostream& operator<<(std::ostream& os, const ExpressionSize<Rank>& e) {
+  os << "(";
+  for (int d = 0; d < Rank; ++d) os << (d ? "," : "") << e.dim[d];
+  return os << ")";
+}
+
 template <int Rank, typename T, bool IsActive = false> class Array;
 template <int Rank, typename T, bool IsActive> class ScatterRef;
 template <int Rank, typename T, bool IsActive> class WhereRef;
@@ -132,6 +156,36 @@ class Array {
   explicit Array(int n0) : data_(0) { int n[1] = {n0}; static_assert(Rank == 1, "rank"); alloc(n); }
   Array(int n0, int n1) : data_(0) { int n[2] = {n0, n1}; static_assert(Rank == 2, "rank"); alloc(n); }
   Array(int n0, int n1, int n2) : data_(0) { int n[3] = {n0, n1, n2}; static_assert(Rank == 3, "rank"); alloc(n); }
+  Array(int n0, int n1, int n2, int n3) : data_(0) {
+    int n[4] = {n0, n1, n2, n3}; static_assert(Rank == 4, "rank"); alloc(n);
+  }
+  explicit Array(const ExpressionSize<Rank>& e) : data_(0) { alloc(e.dim); }
+  // Adept: an array that points at caller-owned, contiguous row-major memory
+  Array(T* p, const ExpressionSize<Rank>& e) : data_(p) {
+    long st = 1;
+    for (int d = Rank - 1; d >= 0; --d) { dim_[d] = e.dim[d]; stride_[d] = st; st *= e.dim[d]; }
+  }
+  // element-type conversion (Adept evaluates `const Vector& = intVector` into a temporary)
+  template <typename U, bool B, typename std::enable_if<!std::is_same<U, T>::value && std::is_arithmetic<U>::value &&
+                                                         std::is_arithmetic<T>::value, int>::type = 0>
+  Array(const Array<Rank, U, B>& o) : data_(0) {
+    for (int d = 0; d < Rank; ++d) dim_[d] = stride_[d] = 0;
+    if (!o.empty()) {
+      int n[Rank];
+      for (int d = 0; d < Rank; ++d) n[d] = o.size(d);
+      alloc(n);
+      const long tot = size();
+      for (long k = 0; k < tot; ++k) data_[k] = (T)o.flat(k);
+    }
+  }
+  // `Vector v = range(a, b)`
+  Array(const RangeIndex& r) : data_(0) {
+    static_assert(Rank == 1, "rank");
+    const int a = r.first(0), b = r.last(0);
+    int n[1] = {b >= a ? b - a + 1 : 0};
+    alloc(n);
+    for (int k = 0; k < n[0]; ++k) data_[k] = (T)(a + k);
+  }
   // wrap caller-owned memory (used by the glue; not part of Adept's API surface used by the reference)
   static Array wrap(T* p, const int* dims, const long* strides) {
     Array a;
@@ -153,6 +207,24 @@ class Array {
   void resize(int n0) { int n[1] = {n0}; static_assert(Rank == 1, "rank"); alloc(n); }
   void resize(int n0, int n1) { int n[2] = {n0, n1}; static_assert(Rank == 2, "rank"); alloc(n); }
   void resize(int n0, int n1, int n2) { int n[3] = {n0, n1, n2}; static_assert(Rank == 3, "rank"); alloc(n); }
+  void resize(int n0, int n1, int n2, int n3) { int n[4] = {n0, n1, n2, n3}; static_assert(Rank == 4, "rank"); alloc(n); }
+  void resize(const ExpressionSize<Rank>& e) { alloc(e.dim); }
+  ExpressionSize<Rank> dimensions() const { ExpressionSize<Rank> e; for (int d = 0; d < Rank; ++d) e.dim[d] = dim_[d]; return e; }
+  Array<Rank, T, false> inactive_link() const { return Array<Rank, T, false>(*this); }
+  // a contiguous vector seen as a higher-rank array sharing its storage
+  template <int R2>
+  Array<R2, T, IsActive> reshape(const ExpressionSize<R2>& e) const {
+    static_assert(Rank == 1, "reshape of a vector");
+    long tot = 1;
+    for (int d = 0; d < R2; ++d) tot *= e.dim[d];
+    if (tot != size() || (size() > 1 && stride_[0] != 1)) throw size_mismatch("adept shim: reshape");
+    long str[R2];
+    long st = 1;
+    for (int d = R2 - 1; d >= 0; --d) { str[d] = st; st *= e.dim[d]; }
+    Array<R2, T, IsActive> r = Array<R2, T, IsActive>::wrap(data_, e.dim, str);
+    r.adopt(store_);
+    return r;
+  }
   void resize_like(const int* n) { alloc(n); }
   Array soft_link() const { return *this; }
   Array& operator>>=(const Array& o) { store_ = o.store_; data_ = o.data_; copy_shape(o); return *this; }
@@ -171,6 +243,7 @@ class Array {
     for (long k = 0; k < n; ++k) flat(k) = (T)s;
     return *this;
   }
+  Array& operator=(const RangeIndex& r) { return assign(Array<1, int, false>(r)); }
 #define ECCKD_SHIM_COMPOUND(OP)                                                          \
   template <typename U, bool B>                                                          \
   Array& operator OP(const Array<Rank, U, B>& o) {                                       \
@@ -296,6 +369,34 @@ class Array {
     return view<shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value>(s);
   }
 
+  // Rank 4
+  template <typename I0, typename I1, typename I2, typename I3>
+  typename std::enable_if<shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value +
+                                  shim::sel_rank<I3>::value == 0 && Rank == 4, T&>::type
+  operator()(const I0& i0, const I1& i1, const I2& i2, const I3& i3) {
+    return data_[stride_[0] * resolve(shim::sel(i0), 0) + stride_[1] * resolve(shim::sel(i1), 1) +
+                 stride_[2] * resolve(shim::sel(i2), 2) + stride_[3] * resolve(shim::sel(i3), 3)];
+  }
+  template <typename I0, typename I1, typename I2, typename I3>
+  typename std::enable_if<shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value +
+                                  shim::sel_rank<I3>::value == 0 && Rank == 4, const T&>::type
+  operator()(const I0& i0, const I1& i1, const I2& i2, const I3& i3) const {
+    return data_[stride_[0] * resolve(shim::sel(i0), 0) + stride_[1] * resolve(shim::sel(i1), 1) +
+                 stride_[2] * resolve(shim::sel(i2), 2) + stride_[3] * resolve(shim::sel(i3), 3)];
+  }
+  template <typename I0, typename I1, typename I2, typename I3>
+  typename std::enable_if<(shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value +
+                           shim::sel_rank<I3>::value > 0) &&
+                              !shim::sel_is_list<I0>::value && !shim::sel_is_list<I1>::value &&
+                              !shim::sel_is_list<I2>::value && !shim::sel_is_list<I3>::value && Rank == 4,
+                          Array<shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value +
+                                    shim::sel_rank<I3>::value, T, IsActive> >::type
+  operator()(const I0& i0, const I1& i1, const I2& i2, const I3& i3) const {
+    shim::Sel s[4] = {shim::sel(i0), shim::sel(i1), shim::sel(i2), shim::sel(i3)};
+    return view<shim::sel_rank<I0>::value + shim::sel_rank<I1>::value + shim::sel_rank<I2>::value +
+                shim::sel_rank<I3>::value>(s);
+  }
+
   // ---- where
   template <bool B>
   WhereRef<Rank, T, IsActive> where(const Array<Rank, bool, B>& mask) {
@@ -402,6 +503,11 @@ typedef Array<1, int, false> intVector;
 typedef Array<2, int, false> intMatrix;
 typedef Array<1, int, false> IntVector;  // Adept spells the integer arrays both ways
 typedef Array<2, int, false> IntMatrix;
+typedef Array<3, Real, false> Array3;
+typedef Array<3, Real, true> aArray3;
+typedef Array<4, Real, true> aArray4D;
+typedef Array<3, int, false> intArray3D;
+typedef Array<2, Real, false> SymmMatrix;  // stored full (only the prior-covariance code of CkdModel uses it)
 typedef Array<1, bool, false> boolVector;
 typedef Array<2, bool, false> boolMatrix;
 
@@ -439,6 +545,7 @@ class ScatterRef : public Array<Rank, T, IsActive> {
     return *this;
   }
   ScatterRef& operator=(const ScatterRef& o) { return operator=(static_cast<const Base&>(o)); }
+  ScatterRef& operator=(const RangeIndex& r) { return operator=(Array<1, int, false>(r)); }
   template <typename S, typename std::enable_if<shim::is_scalar<S>::value, int>::type = 0>
   ScatterRef& operator=(S s) {
     for (size_t k = 0; k < target.size(); ++k) { *target[k] = (T)s; this->flat((long)k) = (T)s; }
@@ -742,6 +849,161 @@ Array<2, T, A> spread(const Array<1, T, A>& v, int n) {
   } else {
     r.resize(n, v.size());
     for (int j = 0; j < n; ++j) for (int i = 0; i < v.size(); ++i) r(j, i) = v(i);
+  }
+  return r;
+}
+
+// spread of an integer range (Adept treats range(a,b) as an integer vector expression)
+template <int Dim>
+Array<2, int, false> spread(const RangeIndex& r, int n) { return spread<Dim>(Array<1, int, false>(r), n); }
+// spread of a matrix to rank 3: the new dimension of length n is inserted at position Dim
+template <int Dim, typename T, bool A>
+Array<3, T, A> spread(const Array<2, T, A>& m, int n) {
+  static_assert(Dim >= 0 && Dim <= 2, "spread dimension");
+  Array<3, T, A> r;
+  if (m.empty() || n <= 0) return r;
+  const int n0 = m.size(0), n1 = m.size(1);
+  if (Dim == 0) r.resize(n, n0, n1);
+  else if (Dim == 1) r.resize(n0, n, n1);
+  else r.resize(n0, n1, n);
+  for (int k = 0; k < n; ++k)
+    for (int i = 0; i < n0; ++i)
+      for (int j = 0; j < n1; ++j) {
+        if (Dim == 0) r(k, i, j) = m(i, j);
+        else if (Dim == 1) r(i, k, j) = m(i, j);
+        else r(i, j, k) = m(i, j);
+      }
+  return r;
+}
+// arithmetic on integer ranges: `dwav * range(a, b)`
+template <typename S, typename std::enable_if<shim::is_scalar<S>::value, int>::type = 0>
+Array<1, typename shim::promote<S, int>::type, false> operator*(S a, const RangeIndex& r) {
+  return a * Array<1, int, false>(r);
+}
+
+template <int R, typename T, bool A>
+T mean(const Array<R, T, A>& x) { return sum(x) / (T)x.size(); }
+
+// sum of a rank-3 array over one dimension
+template <typename T, bool A>
+Array<2, T, A> sum(const Array<3, T, A>& x, int dim) {
+  const int n0 = x.size(0), n1 = x.size(1), n2 = x.size(2);
+  Array<2, T, A> r;
+  if (dim == 0) r.resize(n1, n2);
+  else if (dim == 1) r.resize(n0, n2);
+  else r.resize(n0, n1);
+  if (r.empty()) return r;
+  r = (T)0;
+  for (int i = 0; i < n0; ++i)
+    for (int j = 0; j < n1; ++j)
+      for (int k = 0; k < n2; ++k) {
+        if (dim == 0) r(j, k) += x(i, j, k);
+        else if (dim == 1) r(i, k) += x(i, j, k);
+        else r(i, j) += x(i, j, k);
+      }
+  return r;
+}
+
+// Piecewise-linear interpolation interp(x, y, xi): x ascending; outside [x0, xn] the end values are
+// held (the reference only interpolates inside the range; the policy outside is not pinned).
+namespace shim {
+inline void interp_locate(const Array<1, Real, false>& x, Real xi, int& i0, Real& w1) {
+  const int n = x.size();
+  if (n == 1 || xi <= x(0)) { i0 = 0; w1 = 0.0; return; }
+  if (xi >= x(n - 1)) { i0 = n - 2; w1 = 1.0; return; }
+  int lo = 0, hi = n - 1;
+  while (hi - lo > 1) { const int mid = (lo + hi) / 2; if (x(mid) <= xi) lo = mid; else hi = mid; }
+  i0 = lo;
+  w1 = (xi - x(lo)) / (x(lo + 1) - x(lo));
+}
+}  // namespace shim
+template <bool A, bool B, bool C>
+Array<1, Real, B> interp(const Array<1, Real, A>& x, const Array<1, Real, B>& y, const Array<1, Real, C>& xi) {
+  if (x.size() != y.size() || x.size() < 1) throw size_mismatch("adept shim: interp");
+  Array<1, Real, false> xs(x);
+  Array<1, Real, B> r;
+  if (xi.empty()) return r;
+  r.resize(xi.size());
+  for (int k = 0; k < xi.size(); ++k) {
+    int i0; Real w1;
+    shim::interp_locate(xs, xi(k), i0, w1);
+    r(k) = x.size() == 1 ? y(0) : (1.0 - w1) * y(i0) + w1 * y(i0 + 1);
+  }
+  return r;
+}
+// y(nx, m): every column interpolated
+template <bool A, bool B, bool C>
+Array<2, Real, B> interp(const Array<1, Real, A>& x, const Array<2, Real, B>& y, const Array<1, Real, C>& xi) {
+  if (x.size() != y.size(0) || x.size() < 1) throw size_mismatch("adept shim: interp");
+  Array<1, Real, false> xs(x);
+  Array<2, Real, B> r;
+  if (xi.empty() || y.size(1) == 0) return r;
+  r.resize(xi.size(), y.size(1));
+  for (int k = 0; k < xi.size(); ++k) {
+    int i0; Real w1;
+    shim::interp_locate(xs, xi(k), i0, w1);
+    for (int j = 0; j < y.size(1); ++j) r(k, j) = x.size() == 1 ? y(0, j) : (1.0 - w1) * y(i0, j) + w1 * y(i0 + 1, j);
+  }
+  return r;
+}
+
+// Matrix multiplication `A ** B` = A * (*B): unary * tags the right operand
+template <int R, typename T, bool A>
+struct MatMulRhs { Array<R, T, A> x; };
+template <int R, typename T, bool A>
+MatMulRhs<R, T, A> operator*(const Array<R, T, A>& x) { MatMulRhs<R, T, A> m; m.x = x.copy(); return m; }
+template <typename T, bool A, typename U, bool B>
+Array<1, typename shim::promote<T, U>::type, (A || B)> operator*(const Array<2, T, A>& m, const MatMulRhs<1, U, B>& v) {
+  if (m.size(1) != v.x.size()) throw size_mismatch("adept shim: matrix-vector product");
+  Array<1, typename shim::promote<T, U>::type, (A || B)> r;
+  if (m.size(0) == 0) return r;
+  r.resize(m.size(0));
+  for (int i = 0; i < m.size(0); ++i) {
+    typename shim::promote<T, U>::type s = 0;
+    for (int j = 0; j < m.size(1); ++j) s += m(i, j) * v.x(j);
+    r(i) = s;
+  }
+  return r;
+}
+template <typename T, bool A, typename U, bool B>
+Array<2, typename shim::promote<T, U>::type, (A || B)> operator*(const Array<2, T, A>& m, const MatMulRhs<2, U, B>& n) {
+  if (m.size(1) != n.x.size(0)) throw size_mismatch("adept shim: matrix-matrix product");
+  Array<2, typename shim::promote<T, U>::type, (A || B)> r;
+  if (m.size(0) == 0 || n.x.size(1) == 0) return r;
+  r.resize(m.size(0), n.x.size(1));
+  for (int i = 0; i < m.size(0); ++i)
+    for (int k = 0; k < n.x.size(1); ++k) {
+      typename shim::promote<T, U>::type s = 0;
+      for (int j = 0; j < m.size(1); ++j) s += m(i, j) * n.x(j, k);
+      r(i, k) = s;
+    }
+  return r;
+}
+// inverse of a (symmetric, well-conditioned) matrix by Gauss-Jordan with partial pivoting; only the
+// prior-covariance code of CkdModel calls it (outside the hot path, compiled for completeness)
+template <bool A>
+Array<2, Real, A> inv(const Array<2, Real, A>& m) {
+  const int n = m.size(0);
+  if (m.size(1) != n) throw size_mismatch("adept shim: inv of a non-square matrix");
+  Array<2, Real, A> a = m.copy(), r;
+  if (n == 0) return r;
+  r.resize(n, n);
+  r = 0.0;
+  for (int i = 0; i < n; ++i) r(i, i) = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c;
+    for (int i = c + 1; i < n; ++i) if (std::fabs(a(i, c)) > std::fabs(a(piv, c))) piv = i;
+    if (a(piv, c) == 0.0) throw std::runtime_error("adept shim: singular matrix in inv");
+    if (piv != c)
+      for (int j = 0; j < n; ++j) { std::swap(a(c, j), a(piv, j)); std::swap(r(c, j), r(piv, j)); }
+    const Real d = 1.0 / a(c, c);
+    for (int j = 0; j < n; ++j) { a(c, j) *= d; r(c, j) *= d; }
+    for (int i = 0; i < n; ++i) {
+      if (i == c) continue;
+      const Real f = a(i, c);
+      if (f == 0.0) continue;
+      for (int j = 0; j < n; ++j) { a(i, j) -= f * a(c, j); r(i, j) -= f * r(c, j); }
+    }
   }
   return r;
 }

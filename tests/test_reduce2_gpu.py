@@ -147,3 +147,70 @@ def test_nan_optical_depth_is_reported_not_absorbed(ctx, O, monkeypatch, gen):
         clean = E.average_optical_depth_to_g_point(ctx, c["ng"], c["vmr"], c["pressure_fl"], c["pressure_hl"],
                                                    c["g_point"], c["od"], planck, method)
         assert np.array_equal(got[0][ok], clean[0][ok]), method
+
+
+def _plan_check(info, rounds, g, ng):
+    """Every wavenumber of a g point sits in exactly one valid cell of a lane of that g point, padding
+    cells read a wavenumber of the lane's own g point; returns the mean shared-memory wavefronts per
+    64-bit gather under the measured bank model (a warp is served as two half-warps, each costing the
+    fullest of the 16 eight-byte bank pairs: tools/ubench/lds64_conflicts.cu)."""
+    ch = info["ch"]
+    seen = np.zeros(g.size, dtype=np.int32)
+    wavefronts = loads = 0
+    gv = np.where((g >= 0) & (g < ng), g, -1)
+    for r in rounds:
+        base = int(r["chunk"]) * ch
+        lane_g = (r["meta"] & 0xFFF).astype(np.int64)
+        used = lane_g != 0xFFF
+        if info["balanced"]:
+            mask = (r["meta"] >> 12) & 0xFFFF
+        else:
+            mask = (1 << ((r["meta"] >> 12) & 31)) - 1
+        elem = r["off"].astype(np.int64) // 8          # [slot][lane]
+        assert np.all(r["off"] % 8 == 0)
+        for lane in np.nonzero(used)[0]:
+            e = base + elem[:, lane]
+            assert np.all(e < g.size), "offset beyond the spectrum"
+            assert np.all(gv[e] == lane_g[lane]), "a cell reads a wavenumber of another g point"
+            valid = ((mask[lane] >> np.arange(16)) & 1).astype(bool)
+            np.add.at(seen, e[valid], 1)
+        for s in range(16):
+            for h in (0, 1):
+                a = elem[s, 16 * h:16 * h + 16][used[16 * h:16 * h + 16]]
+                loads += 1
+                if a.size == 0:
+                    wavefronts += 1
+                    continue
+                worst = 0
+                for q in np.unique(a % 16):
+                    worst = max(worst, np.unique(a[a % 16 == q]).size)
+                wavefronts += worst
+    assert np.array_equal(seen, (gv >= 0).astype(np.int32)), "a wavenumber is missing or visited twice"
+    return 2.0 * wavefronts / loads
+
+
+@pytest.mark.parametrize("kind", ["coherent", "incoherent", "150g"])
+def test_balanced_plan_is_valid_and_nearly_conflict_free(ctx, monkeypatch, kind):
+    monkeypatch.setenv("ECCKD_PLAN_WINDOW", "1")
+    if kind == "coherent":
+        c = S.lw_spectrum_case(nlay=1, nwav=48011, ng=22, nband=4, seed=41)
+        g, ng = c["g_point"], c["ng"]
+    elif kind == "incoherent":
+        c = S.lw_spectrum_case(nlay=1, nwav=20000, ng=12, nband=2, seed=12, coherent=False)
+        g, ng = c["g_point"], c["ng"]
+    else:
+        rng = np.random.default_rng(5)
+        g, ng = rng.integers(-1, 150, size=9000).astype(np.int32), 150
+    d_g = ctx.to_device(g, np.int32)
+    res = {}
+    for balance in ("0", "1"):
+        monkeypatch.setenv("ECCKD_PLAN_BALANCE", balance)
+        plan = E.GPointPlan(ctx, d_g, g.size, ng)
+        info, rounds = plan.export()
+        assert info["windowed"] and info["balanced"] == (balance == "1")
+        res[balance] = _plan_check(info, rounds, g, ng)
+        plan.close()
+    # the adjacent-lane placement costs 3-4 wavefronts per gather; the balanced one is close to the ideal 2
+    assert res["1"] < res["0"]
+    if kind != "150g":
+        assert res["1"] <= 2.25, res
