@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
         if (!any) lane_g[ln] = (int)NO_G;
       }
       for (int s = 0; s < 16; ++s) {
+        int shared_e = -1;  // what the unused lanes of the half-warp read: the address of a used lane (broadcast)
         for (int ln = 0; ln < 16; ++ln) {
           if (lane_g[ln] == (int)NO_G) continue;
           int e = CL[ln][s];
@@ -480,6 +481,13 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
             if (e < 0) e = own;
           }
           rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
+          if (shared_e < 0) shared_e = e;
+        }
+        // an unused lane still issues its loads (weight zero, sums discarded): offset 0 would add an
+        // address of bank pair 0 to every slot, i.e. a conflict whenever a used lane reads that pair
+        if (shared_e >= 0) {
+          for (int ln = 0; ln < 16; ++ln)
+            if (lane_g[ln] == (int)NO_G) rd.off[s][ln + 16 * ht] = (uint16_t)(shared_e * 8);
         }
       }
       for (int ln = 0; ln < 16; ++ln)
@@ -499,14 +507,21 @@ __global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __rest
     const int64_t r = base + lane;
     const int mn_l = (r < nrounds) ? rmin[r] : 0x7fffffff;
     const int mx_l = (r < nrounds) ? rmax[r] : -1;
-    int mine = 0;
+    int mine = 0, same = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int mn = __shfl_sync(0xffffffffu, mn_l, j), mx = __shfl_sync(0xffffffffu, mx_l, j);
+      const int before = gbase;
       if (mn <= mx && !(mn >= gbase && mx < gbase + W)) gbase = mn;
-      if (lane == j) mine = gbase;
+      if (lane == j) {
+        mine = gbase;
+        same = (base + j > 0 && gbase == before) ? 1 : 0;
+      }
     }
-    if (r < nrounds) rounds[r].win = (uint32_t)mine;
+    if (r < nrounds) {
+      rounds[r].win = (uint32_t)mine;
+      if (same) rounds[r].flags |= 4u;  // bit 2: same window as the round before (reduce4_kernel's fast path)
+    }
   }
 }
 
@@ -1840,6 +1855,478 @@ __global__ void __launch_bounds__(THREADS3_MAX, 1) reduce3_kernel(const __grid_c
   if (gbase >= 0) window_store();
 }
 
+// ------------------------------------------------------------------ reduce, windowed plans, two warps per row pair
+// reduce4_kernel.  What ncu showed on reduce2_kernel once the gathers were conflict-free: every
+// pipe below 55 %, and the consumer warps - ten of them, each alone with its two rows - spending
+// 5400 cycles per chunk visit on a strictly serial sequence (wait, ~200 instructions of round
+// bookkeeping at 6-9 cycles each, the slot loop, ~60 instructions of bulk-copy issue) where the copy
+// pipeline needs 3900.  reduce3_kernel's answer (one row per warp) doubled the warps but also the
+// bookkeeping per value and lost the sharing of offsets and weights between two rows.  Here the two
+// rows of a pair stay together and TWO warps serve the pair, taking the chunk visits in turn
+// (warp 2p: even visits on stage set 0, warp 2p+1: odd visits on set 1): the work per value is
+// reduce2_kernel's, each warp has two visit periods for its serial sequence, and the slot loop
+// runs 2 slots x 2 rows per trip so that 23 warps fit the register file (80 registers).
+//   * A dedicated warp issues all bulk copies (lane = pair) as the consumers release the sets.
+//   * The pair shares its entries, extremes (atomic keys, as in reduce3_kernel) and range-check
+//     words.  Its warps run their slot loops concurrently but touch the shared entries in VISIT
+//     ORDER: a warp adds its round sums after the other warp has finished the visit before
+//     (one mbarrier handshake per visit), so the sums are added in the same order in every run.
+//   * A round may read the range-check words without that handshake only when the shared state is
+//     already the one it needs: state word = (piece, window) and the plan's "same window as the
+//     round before" bit; otherwise it waits for the other warp first and does the window / piece
+//     change itself (rare: band changes, group changes).
+constexpr int NP4_MAX = NW_MAX;  // row pairs per CTA
+constexpr int THREADS4_MAX = (2 * NP4_MAX + NPW + 1) * 32;
+
+struct Smem4Layout {
+  int tab;    // replicated 2^(j/64) table, at offset 0
+  int bars;   // mbarriers: full_d[np][2], empty_d[np][2], tok[np][2], full_w[NSW], empty_w[NSW]
+  int ring;   // ring slots [NSW]: {double wperm[SLOTS*32]; PlanRound plan}
+  int data;   // data stages [np][2 sets][RPW][STAGE3_BYTES]
+  int ent;    // [np][WIN][32] double2: per-lane sums of the window's g points, both rows
+  int s1e;    // [WIN][32] double: per-lane weight sums (last pair)
+  int mmk;    // [np][RPW][WIN][2] uint64: order-preserving keys of {min, max}
+  int mmb;    // [np][RPW][WIN] uint2 {lowb, span} of the range check
+  int state;  // [np] int: (piece << 16 | window base) the pair's shared state belongs to, -1 none
+  int total;
+};
+__host__ __device__ inline Smem4Layout smem4_layout(int np) {
+  Smem4Layout L;
+  int off = 0;
+  L.tab = off;
+  off += TRANS_TAB64_BYTES;
+  L.bars = off;
+  off += (6 * np + 2 * NSW) * 8;
+  off = (off + 127) & ~127;
+  L.ring = off;
+  off += NSW * RING_SLOT_BYTES;
+  L.data = off;
+  off += np * 2 * RPW * STAGE3_BYTES;
+  L.ent = off;
+  off += np * WIN * 32 * 16;
+  L.s1e = off;
+  off += WIN * 32 * 8;
+  L.mmk = off;
+  off += np * RPW * WIN * 16;
+  L.mmb = off;
+  off += np * RPW * WIN * 8;
+  L.state = off;
+  off += np * 4;
+  L.total = (off + 15) & ~15;
+  return L;
+}
+
+// 16 slots of NR rows of one round, 2 per trip (NR = 2: four dependency chains).  stage[r] is row
+// r's chunk in shared memory (already shifted); mmk[r] the {min, max} keys of the lane's g point.
+template <int FKIND, int NR>
+__device__ __forceinline__ void rows_slots4(double (&s0)[NR], int& upd, const unsigned char* const (&stage)[NR],
+                                            const uint16_t* __restrict__ offp, const double* __restrict__ wp,
+                                            const unsigned (&lowb)[NR], const unsigned (&span)[NR],
+                                            unsigned long long* const (&mmk)[NR], const bool used,
+                                            const TransConst64& K, const unsigned char* __restrict__ tab,
+                                            const unsigned lane_off) {
+#pragma unroll 1
+  for (int kk = 0; kk < SLOTS; kk += 2) {
+    double tau[NR][2], w[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const unsigned o = offp[(kk + j) * 32];
+      w[j] = wp[(kk + j) * 32];  // zero for padding slots
+#pragma unroll
+      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage[r] + o);
+    }
+    bool outside = false;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const unsigned worst =
+          max((unsigned)__double2hiint(tau[r][0]) - lowb[r], (unsigned)__double2hiint(tau[r][1]) - lowb[r]);
+      outside = outside || (worst >= span[r]);
+    }
+    if (outside) {  // rare: a value may be a new extreme (or is negative / non-finite)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const double t = tau[r][j];
+          if (t == t) {
+            if (used) {
+              const unsigned long long key = key_of(t);
+              atomicMin(&mmk[r][0], key);
+              atomicMax(&mmk[r][1], key);
+            }
+          } else {
+            s0[r] = t;  // NaN: poison the sum (see reduce_rows.cuh)
+          }
+        }
+      }
+      upd = 1;
+    }
+    double f[NR][2];
+    if (FKIND == F_TRANS) {
+      TransMid m[NR][2];
+      double T[NR][2];
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) m[r][j] = trans64_phase1(tau[r][j], K);
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) T[r][j] = trans64_phase2(m[r][j], tab, lane_off);
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) f[r][j] = trans64_phase3(m[r][j], T[r][j], K);
+    } else {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          f[r][j] = (FKIND == F_LINEAR) ? tau[r][j] : (FKIND == F_SQRT ? sqrt(tau[r][j]) : 1.0);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s0[r] = fma(f[r][j], w[j], s0[r]);
+  }
+}
+
+template <int FKIND, int WMODE>
+__global__ void __launch_bounds__(THREADS4_MAX, 1) reduce4_kernel(const __grid_constant__ ReduceParams p) {
+  static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
+                "reduce4_kernel: kinds with per-row weight sums run on reduce_kernel");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int np = p.nw, ng = p.ng;  // p.nw: row pairs per CTA
+  const Smem4Layout L = smem4_layout(np);
+  const unsigned sbase = smem_u32(smem_raw);
+  const unsigned full_d = sbase + L.bars;        // [np][2]
+  const unsigned empty_d = full_d + np * 2 * 8;  // [np][2]
+  const unsigned tok = empty_d + np * 2 * 8;     // [np][2]: tok[p][h] completes when warp h of pair p ends a visit
+  const unsigned full_w = tok + np * 2 * 8;      // [NSW]
+  const unsigned empty_w = full_w + NSW * 8;     // [NSW]
+  unsigned char* ring = smem_raw + L.ring;
+  constexpr bool USES_TAU = (FKIND != F_NONE);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6 * np; ++i) mbar_init(full_d + i * 8, 1);
+    for (int i = 0; i < NSW; ++i) {
+      mbar_init(full_w + i * 8, NPW);
+      mbar_init(empty_w + i * 8, np);  // the rounds of a visit are consumed by one warp of every pair
+    }
+    fence_mbar_init();
+  }
+  if (threadIdx.x < np) reinterpret_cast<int*>(smem_raw + L.state)[threadIdx.x] = -1;
+  if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
+  __syncthreads();
+  const unsigned char* tab = smem_raw + L.tab;
+
+  // this CTA's contiguous piece of the (window, group, chunk) space
+  const int nchunks = (int)p.nchunks;
+  const int ch = p.ch;
+  const int64_t T = (int64_t)p.ngroups * p.nchunks;
+  const int64_t lo = (T * blockIdx.x) / p.ncta;
+  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
+  const int niter = (int)(hi - lo);
+  if (niter == 0) return;
+  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
+  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
+
+  if (warp >= 2 * np + NPW) {
+    // ===================== data producer: lane = pair, the bulk copies of its two rows, visit by visit =====================
+    if (!USES_TAU || lane >= np) return;
+    const uint64_t pol = policy_evict_first();
+    const unsigned my_full = full_d + lane * 2 * 8, my_empty = empty_d + lane * 2 * 8;
+    const unsigned my_data = sbase + L.data + lane * 2 * RPW * STAGE3_BYTES;
+    Cursor q = first;
+    const double* od[RPW] = {};
+    int group = -1;
+    unsigned epar = 0, used_sets = 0;
+    for (int k = 0; k < niter; ++k) {
+      if (q.l != group) {
+        group = q.l;
+        const GroupDesc* gd = p.groups + group;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) od[r] = (lane + r * np < gd->nrows) ? gd->od[lane + r * np] : nullptr;
+      }
+      const int set = k & 1;
+      if (od[0] != nullptr) {
+        if ((used_sets >> set) & 1u) {  // the set holds an earlier visit's chunk: wait until its warp has released it
+          while (!mbar_test(my_empty + set * 8, (epar >> set) & 1u)) __nanosleep(256);
+          epar ^= 1u << set;
+        }
+        used_sets |= 1u << set;
+        const int n_c = (q.c == nchunks - 1) ? last_n : ch;
+        unsigned bytes[RPW], shift[RPW], total = 0;
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) {
+          shift[r] = od[r] ? (unsigned)(reinterpret_cast<uintptr_t>(od[r] + (int64_t)q.c * ch) & 8u) : 0u;
+          bytes[r] = od[r] ? ((shift[r] + (unsigned)n_c * 8u + 15u) & ~15u) : 0u;
+          total += bytes[r];
+        }
+        const unsigned bar = my_full + set * 8;
+        mbar_arrive_expect_tx(bar, total);
+#pragma unroll
+        for (int r = 0; r < RPW; ++r)
+          if (od[r])
+            bulk_g2s_hint(my_data + (set * RPW + r) * STAGE3_BYTES,
+                          reinterpret_cast<const unsigned char*>(od[r] + (int64_t)q.c * ch) - shift[r], bytes[r], bar, pol);
+      }
+      cursor_next(q, p.ngroups, p.cw, nchunks);
+    }
+    return;
+  }
+  if (warp >= 2 * np) {
+    produce_rounds3<WMODE>(p, first, niter, warp - 2 * np, lane, ring, sbase + L.ring, full_w, empty_w);
+    return;
+  }
+
+  // ===================== consumers: warps 2p, 2p+1 = the two rows of pair p, alternate visits =====================
+  const int pr_ix = warp >> 1, ph = warp & 1;
+  unsigned char* data = smem_raw + L.data + (size_t)pr_ix * 2 * RPW * STAGE3_BYTES + (size_t)ph * RPW * STAGE3_BYTES;
+  const unsigned my_full = full_d + (pr_ix * 2 + ph) * 8, my_empty = empty_d + (pr_ix * 2 + ph) * 8;
+  const unsigned tok_mine = tok + (pr_ix * 2 + ph) * 8, tok_other = tok + (pr_ix * 2 + (ph ^ 1)) * 8;
+  double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)pr_ix * WIN * 32;
+  double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
+  unsigned long long* mmk = reinterpret_cast<unsigned long long*>(smem_raw + L.mmk) + pr_ix * RPW * WIN * 2;
+  uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + pr_ix * RPW * WIN;
+  volatile int* state = reinterpret_cast<volatile int*>(smem_raw + L.state) + pr_ix;
+  const unsigned lane_off = (unsigned)(lane & 15) << 3;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  // the weight sums do not depend on the row: the last pair accumulates them once per group; they end
+  // up in the s1 field of its first row
+  const bool s1_duty = pr_ix == np - 1;
+
+  auto piece_ptr = [&](int vg) {
+    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (np * RPW) + pr_ix * RPW;
+    return p.partial + slot * ng * 4;
+  };
+  // the pair's rows of a new (window, group) piece start as {0, 0, +inf, -inf}
+  auto begin_piece = [&](int vg) {
+    double* pout = piece_ptr(vg);
+    int32_t* poutz = p.partial_z + (((size_t)blockIdx.x * p.maxg + (size_t)vg) * (np * RPW) + pr_ix * RPW) * ng;
+    for (int i = lane; i < RPW * ng; i += 32) {
+      double2* q = reinterpret_cast<double2*>(pout + (size_t)i * 4);
+      q[0] = make_double2(0.0, 0.0);
+      q[1] = make_double2(inf, -inf);
+      poutz[i] = 0;
+    }
+    __syncwarp();
+  };
+  // add the window's entries up over the lanes (fixed butterfly) and fold them, with the extremes,
+  // into piece `pout`: lane e writes g point gb + e
+  auto window_store = [&](double* pout, int gb) {
+    double t0 = 0.0, t1 = 0.0, ts = 0.0;
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) {
+      double2 v = ent[e * 32 + lane];
+      double s = s1_duty ? s1e[e * 32 + lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+        if (s1_duty) s += __shfl_xor_sync(0xffffffffu, s, o);
+      }
+      if (lane == e) {
+        t0 = v.x;
+        t1 = v.y;
+        ts = s;
+      }
+    }
+    const int g = gb + lane;
+    if (lane < WIN && g < ng) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        double* q = pout + ((size_t)r * ng + g) * 4;
+        const double mn = value_of(mmk[(r * WIN + lane) * 2]), mx = value_of(mmk[(r * WIN + lane) * 2 + 1]);
+        q[0] += (r == 0) ? t0 : t1;
+        q[2] = (mn < q[2]) ? mn : q[2];
+        q[3] = (mx > q[3]) ? mx : q[3];
+      }
+      if (s1_duty) pout[(size_t)g * 4 + 1] += ts;
+    }
+    __syncwarp();
+  };
+  auto refresh_bounds = [&]() {
+    if (lane < RPW * WIN) {
+      Partial t;
+      t.mn = value_of(mmk[lane * 2]);
+      t.mx = value_of(mmk[lane * 2 + 1]);
+      minmax_bounds(t);
+      mmb[lane] = make_uint2(t.lowb, t.span);
+    }
+    __syncwarp();
+  };
+  // open the window [nb, nb + WIN) of piece vg: zero entries, extremes from the piece, then publish
+  auto window_load = [&](double* pout, int vg, int nb) {
+#pragma unroll
+    for (int e = 0; e < WIN; ++e) ent[e * 32 + lane] = make_double2(0.0, 0.0);
+    if (s1_duty) {
+#pragma unroll
+      for (int e = 0; e < WIN; ++e) s1e[e * 32 + lane] = 0.0;
+    }
+    if (lane < RPW * WIN) {
+      const int r = lane / WIN, g = nb + lane % WIN;
+      double mn = inf, mx = -inf;
+      if (g < ng) {
+        mn = pout[((size_t)r * ng + g) * 4 + 2];
+        mx = pout[((size_t)r * ng + g) * 4 + 3];
+      }
+      mmk[lane * 2] = key_of(mn);
+      mmk[lane * 2 + 1] = key_of(mx);
+    }
+    __syncwarp();
+    refresh_bounds();
+    __threadfence_block();
+    if (lane == 0) *state = (vg << 16) | nb;
+    __syncwarp();
+  };
+
+  Cursor q = first;
+  int ws = 0, vg = 0;
+  unsigned wpar = 0, dpar = 0, tpar = 0;
+  const double* od_c[RPW] = {};
+  bool active[RPW] = {};
+  bool need_group = true, new_piece = true;
+  int group_nrounds_skip = 0;
+  (void)group_nrounds_skip;
+
+#pragma unroll 1
+  for (int k = 0; k < niter; ++k) {
+    if (need_group) {
+      const GroupDesc* gd = p.groups + q.l;
+#pragma unroll
+      for (int r = 0; r < RPW; ++r) {
+        const int i = pr_ix + r * np;
+        active[r] = USES_TAU && i < gd->nrows;
+        od_c[r] = active[r] ? gd->od[i] : nullptr;
+      }
+      need_group = false;
+    }
+    const bool mine = (k & 1) == ph;
+    if (mine) {
+      const unsigned char* stage[RPW];
+#pragma unroll
+      for (int r = 0; r < RPW; ++r)
+        stage[r] = data + r * STAGE3_BYTES +
+                   (active[r] ? (unsigned)(reinterpret_cast<uintptr_t>(od_c[r] + (int64_t)q.c * ch) & 8u) : 0u);
+      if (active[0]) {
+        mbar_wait(my_full, dpar);
+        dpar ^= 1u;
+      }
+      bool held = false;  // this warp may touch the pair's shared state: the other warp ended visit k - 1
+      auto acquire = [&]() {
+        if (!held) {
+          if (k > 0) {
+            mbar_wait(tok_other, tpar);
+            tpar ^= 1u;
+          }
+          held = true;
+        }
+      };
+      bool last_round = false;
+      while (!last_round) {
+        mbar_wait(full_w + ws * 8, wpar);
+        const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
+        const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
+        const double* wp = reinterpret_cast<const double*>(slot) + lane;
+        const uint16_t* offp = &pr->off[0][lane];
+        const unsigned meta = pr->meta[lane];
+        const int wb = (int)pr->win;
+        const unsigned flags = pr->flags;
+        last_round = (flags & 2u) != 0;
+        const int want = (vg << 16) | wb;
+        if (new_piece || !(flags & 4u) || *state != want) {
+          // (warp-uniform) not provably on the state this round needs: take the turn first
+          acquire();
+          const int cur = *state;
+          if (cur != want) {
+            if (cur >= 0) window_store(piece_ptr(cur >> 16), cur & 0xFFFF);
+            if (cur < 0 || (cur >> 16) != vg) begin_piece(vg);
+            window_load(piece_ptr(vg), vg, wb);
+          }
+          new_piece = false;
+        }
+        const unsigned g = meta & 0xFFFu;
+        const bool used = g != NO_G;
+        const int e = used ? min(max((int)g - wb, 0), WIN - 1) : 0;  // the plan keeps g inside the window
+        double s1 = 0.0;
+        if (s1_duty) {
+#pragma unroll
+          for (int kk = 0; kk < SLOTS; ++kk) s1 += wp[kk * 32];
+        }
+        double s0[RPW] = {};
+        int upd = 0;
+        if (active[0]) {
+          unsigned lowb[RPW], span[RPW];
+          unsigned long long* mk[RPW];
+#pragma unroll
+          for (int r = 0; r < RPW; ++r) {
+            const uint2 b = mmb[r * WIN + e];
+            lowb[r] = used ? b.x : 0u;  // unused lanes accept everything: no exact path
+            span[r] = used ? b.y : 0xFFFFFFFFu;
+            mk[r] = mmk + (r * WIN + e) * 2;
+          }
+          if (active[RPW - 1]) {
+            rows_slots4<FKIND, RPW>(s0, upd, stage, offp, wp, lowb, span, mk, used, p.tc64, tab, lane_off);
+          } else {
+            double s01[1] = {0.0};
+            const unsigned char* st1[1] = {stage[0]};
+            const unsigned lb1[1] = {lowb[0]}, sp1[1] = {span[0]};
+            unsigned long long* mk1[1] = {mk[0]};
+            rows_slots4<FKIND, 1>(s01, upd, st1, offp, wp, lb1, sp1, mk1, used, p.tc64, tab, lane_off);
+            s0[0] = s01[0];
+          }
+        }
+        acquire();
+        if (used) {
+          if (active[0]) {
+            double2 v = ent[e * 32 + lane];
+            v.x += s0[0];
+            v.y += s0[RPW - 1];
+            ent[e * 32 + lane] = v;
+          }
+          if (s1_duty) s1e[e * 32 + lane] += s1;
+        }
+        if (__any_sync(0xffffffffu, upd != 0)) {
+          __syncwarp();  // the other lanes' atomics on the keys are visible
+          refresh_bounds();
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_w + ws * 8);
+        if (++ws == NSW) {
+          ws = 0;
+          wpar ^= 1u;
+        }
+      }
+      if (k == niter - 1) {  // the last visit of the CTA: fold what the pair still holds
+        const int cur = *state;
+        if (cur >= 0) window_store(piece_ptr(cur >> 16), cur & 0xFFFF);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(tok_mine);                    // visit k is over: the other warp may take its turn
+        if (active[0]) mbar_arrive(my_empty);     // the stage set may be refilled
+      }
+    } else {
+      // the other warp's visit: skip its rounds in the ring bookkeeping
+      const int nr = (int)(p.round_off[q.c + 1] - p.round_off[q.c]);
+      ws += nr;
+      while (ws >= NSW) {
+        ws -= NSW;
+        wpar ^= 1u;
+      }
+      new_piece = false;  // whatever state the next visit needs, its round will see the mismatch
+    }
+    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
+      ++vg;
+      need_group = true;
+      new_piece = true;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ combine + finalize
 // Add the CTA pieces of every (row, g) in fixed (window, CTA) order (deterministic).
 __global__ void combine_kernel(const CombineParams p) {
@@ -2048,7 +2535,8 @@ template <int FKIND, int WMODE, int GEN>
 static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta_out,
                                    bool dry_run) {
   void (*kernel)(const ReduceParams) = nullptr;
-  if constexpr (GEN == 3) kernel = reduce3_kernel<FKIND, WMODE>;
+  if constexpr (GEN == 4) kernel = reduce4_kernel<FKIND, WMODE>;
+  else if constexpr (GEN == 3) kernel = reduce3_kernel<FKIND, WMODE>;
   else if constexpr (GEN == 2) kernel = reduce2_kernel<FKIND, WMODE>;
   else kernel = reduce_kernel<FKIND, WMODE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -2078,6 +2566,14 @@ static bool reduce2_supports(int fkind) {
 }
 static cudaError_t launch_reduce(int fkind, int wmode, int gen, ecckd_ctx* ctx, ReduceParams& p, int threads,
                                  size_t smem, int* ncta, bool dry) {
+  if (gen == 4) {
+    switch (fkind) {
+      case F_LINEAR: return launch_reduce_w<F_LINEAR, 4>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_TRANS: return launch_reduce_w<F_TRANS, 4>(wmode, ctx, p, threads, smem, ncta, dry);
+      case F_SQRT: return launch_reduce_w<F_SQRT, 4>(wmode, ctx, p, threads, smem, ncta, dry);
+      default: return launch_reduce_w<F_NONE, 4>(wmode, ctx, p, threads, smem, ncta, dry);
+    }
+  }
   if (gen == 3) {
     switch (fkind) {
       case F_LINEAR: return launch_reduce_w<F_LINEAR, 3>(wmode, ctx, p, threads, smem, ncta, dry);
@@ -2129,8 +2625,8 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
   // Kernel generation: windowed plans and the kinds without per-row weight sums run on
   // reduce3_kernel (one row per consumer warp), everything else on reduce_kernel (two rows per warp,
-  // shuffle fold).  ECCKD_REDUCE_GEN=1|2|3 forces an older generation where it applies (comparisons).
-  int gen = (plan->windowed && reduce2_supports(fkind)) ? 3 : 1;
+  // shuffle fold).  ECCKD_REDUCE_GEN=1|2|3|4 forces an older generation where it applies (comparisons).
+  int gen = (plan->windowed && reduce2_supports(fkind)) ? 4 : 1;
   if (const char* env = getenv("ECCKD_REDUCE_GEN")) {
     const int want = atoi(env);
     if (want >= 1 && want < gen) gen = want;
@@ -2141,7 +2637,9 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   }
   const int rpw = (gen == 3) ? 1 : RPW;
   auto smem_of = [&](int n) {
-    return gen == 3 ? (size_t)smem3_layout(n).total : (gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total);
+    return gen == 4 ? (size_t)smem4_layout(n).total
+                    : gen == 3 ? (size_t)smem3_layout(n).total
+                               : (gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total);
   };
   int nw = std::min(gen == 3 ? NW3_MAX : NW_MAX, (longest + rpw - 1) / rpw);
   while (nw > 1 && smem_of(nw) > smem_max) --nw;
@@ -2172,7 +2670,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     i = j;
   }
   const int ngroups = (int)groups.size();
-  const int threads = (nw + NPW + (gen == 3 ? 1 : 0)) * 32;
+  const int threads = gen == 4 ? (2 * nw + NPW + 1) * 32 : (nw + NPW + (gen == 3 ? 1 : 0)) * 32;
   const size_t smem = smem_of(nw);
 
   ReduceParams rp;

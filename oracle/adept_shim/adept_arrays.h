@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <initializer_list>
 #include <cstddef>
 #include <iostream>
 #include <memory>
@@ -95,6 +96,10 @@ std::ostream& operator<<(std::ostream& os, const ExpressionSize<Rank>& e) {
   for (int d = 0; d < Rank; ++d) os << (d ? "," : "") << e.dim[d];
   return os << ")";
 }
+
+// stride(a, b, step): indices a, a+step, ..., <= b
+struct StrideIndex { int b, e, step; };
+inline StrideIndex stride(int a, int b, int step) { StrideIndex s = {a, b, step}; return s; }
 
 template <int Rank, typename T, bool IsActive = false> class Array;
 template <int Rank, typename T, bool IsActive> class ScatterRef;
@@ -177,6 +182,27 @@ class Array {
       const long tot = size();
       for (long k = 0; k < tot; ++k) data_[k] = (T)o.flat(k);
     }
+  }
+  // `Vector v = {a, b, ...}`
+  Array(std::initializer_list<T> il) : data_(0) {
+    static_assert(Rank == 1, "rank");
+    int n[1] = {(int)il.size()};
+    alloc(n);
+    int k = 0;
+    for (typename std::initializer_list<T>::const_iterator it = il.begin(); it != il.end(); ++it) data_[k++] = *it;
+  }
+  // strided view of a vector
+  Array operator()(const StrideIndex& si) const {
+    static_assert(Rank == 1, "rank");
+    if (si.step <= 0 || si.e < si.b) throw index_out_of_bounds("adept shim: stride");
+    const int cnt = (si.e - si.b) / si.step + 1;
+    bounds(si.b, 0);
+    bounds(si.b + (cnt - 1) * si.step, 0);
+    int dims[1] = {cnt};
+    long str[1] = {stride_[0] * si.step};
+    Array r = wrap(data_ + stride_[0] * si.b, dims, str);
+    r.adopt(store_);
+    return r;
   }
   // `Vector v = range(a, b)`
   Array(const RangeIndex& r) : data_(0) {
@@ -883,6 +909,32 @@ Array<1, typename shim::promote<S, int>::type, false> operator*(S a, const Range
 
 template <int R, typename T, bool A>
 T mean(const Array<R, T, A>& x) { return sum(x) / (T)x.size(); }
+template <int R, typename T, bool A>
+T product(const Array<R, T, A>& x) {
+  T s = 1;
+  for (long k = 0; k < (long)x.size(); ++k) s *= x.flat(k);
+  return s;
+}
+template <typename T, bool A, typename U, bool B>
+typename shim::promote<T, U>::type dot_product(const Array<1, T, A>& x, const Array<1, U, B>& y) {
+  x.check_same(y);
+  typename shim::promote<T, U>::type s = 0;
+  for (int k = 0; k < x.size(); ++k) s += x(k) * y(k);
+  return s;
+}
+// spread of a rank-3 array along a new leading dimension
+template <int Dim, typename T, bool A>
+Array<4, T, A> spread(const Array<3, T, A>& m, int n) {
+  static_assert(Dim == 0, "spread dimension");
+  Array<4, T, A> r;
+  if (m.empty() || n <= 0) return r;
+  r.resize(n, m.size(0), m.size(1), m.size(2));
+  for (int k = 0; k < n; ++k)
+    for (int i = 0; i < m.size(0); ++i)
+      for (int j = 0; j < m.size(1); ++j)
+        for (int q = 0; q < m.size(2); ++q) r(k, i, j, q) = m(i, j, q);
+  return r;
+}
 
 // sum of a rank-3 array over one dimension
 template <typename T, bool A>

@@ -1,0 +1,38 @@
+#!/bin/sh
+# Compile the reference's own TOOLS (run_ckd, create_look_up_table, reorder_spectrum, find_g_points),
+# unmodified and where they lie under $1/src, into oracle/_ref/libecckd_ref_tools.so:
+#   * array maths against the Adept API shim (oracle/adept_shim);
+#   * configuration files through the reference's own cfg engine (DataFileEngineCfg.cpp, readconfig.c);
+#   * NetCDF files through the in-memory stand-in oracle/ref_mock/mock_files.cpp (NetCDF is not
+#     installed here);  netcdf.h / config.h stubs in oracle/ref_mock.
+# Every `main` is renamed on the command line (-Dmain=ref_main_<tool>) and called through
+# oracle/ref_tools_glue.cpp.  Nothing is copied out of the reference.  Outputs only into oracle/_ref/.
+set -e
+REF="$1"
+HERE="$(cd "$(dirname "$0")" && pwd)"
+OUT="$HERE/_ref"
+mkdir -p "$OUT/tools_obj"
+FLAGS="-O2 -march=native -fPIC -std=c++11 -Wno-unknown-pragmas -DHAVE_CONFIG_H -I$HERE/ref_mock -I$HERE/adept_shim -I$REF/src/ecckd -I$REF/src/include"
+OBJS=""
+for u in average_optical_depth planck_function radiative_transfer_lw radiative_transfer_sw single_gas_data \
+         calc_cost_function_lw calc_cost_function_sw ckd_model read_spectrum read_merged_spectrum write_order \
+         equipartition; do
+  g++ $FLAGS -c "$REF/src/ecckd/$u.cpp" -o "$OUT/tools_obj/$u.o" &
+  OBJS="$OBJS $OUT/tools_obj/$u.o"
+done
+for t in run_ckd create_look_up_table reorder_spectrum find_g_points; do
+  g++ $FLAGS -Dmain=ref_main_$t -c "$REF/src/ecckd/$t.cpp" -o "$OUT/tools_obj/main_$t.o" &
+  OBJS="$OBJS $OUT/tools_obj/main_$t.o"
+done
+for u in Logging Error file_manager DataFileEngineCfg; do
+  g++ $FLAGS -c "$REF/src/tools/$u.cpp" -o "$OUT/tools_obj/$u.o" &
+  OBJS="$OBJS $OUT/tools_obj/$u.o"
+done
+gcc -O2 -fPIC -I"$HERE/ref_mock" -I"$REF/src/include" -c "$REF/src/tools/readconfig.c" -o "$OUT/tools_obj/readconfig.o" &
+OBJS="$OBJS $OUT/tools_obj/readconfig.o"
+g++ $FLAGS -c "$HERE/ref_mock/mock_files.cpp" -o "$OUT/tools_obj/mock_files.o" &
+g++ $FLAGS -c "$HERE/ref_tools_glue.cpp" -o "$OUT/tools_obj/ref_tools_glue.o" &
+wait
+g++ -shared -o "$OUT/libecckd_ref_tools.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/mock_files.o" $OBJS
+rm -rf "$OUT/tools_obj"
+echo "built $OUT/libecckd_ref_tools.so"

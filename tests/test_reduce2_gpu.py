@@ -20,7 +20,7 @@ def _planck(O, c):
 
 
 # (plan kind, kernel generation): free plan + reduce_kernel, windowed plan + each generation
-GENS = [("0", "1"), ("1", "1"), ("1", "2"), ("1", "3")]
+GENS = [("0", "1"), ("1", "1"), ("1", "2"), ("1", "3"), ("1", "4")]
 
 
 def _select(monkeypatch, gen):
@@ -176,11 +176,8 @@ def _plan_check(info, rounds, g, ng):
             np.add.at(seen, e[valid], 1)
         for s in range(16):
             for h in (0, 1):
-                a = elem[s, 16 * h:16 * h + 16][used[16 * h:16 * h + 16]]
+                a = elem[s, 16 * h:16 * h + 16]  # unused lanes load too (their weight is zero)
                 loads += 1
-                if a.size == 0:
-                    wavefronts += 1
-                    continue
                 worst = 0
                 for q in np.unique(a % 16):
                     worst = max(worst, np.unique(a[a % 16 == q]).size)
@@ -213,4 +210,4 @@ def test_balanced_plan_is_valid_and_nearly_conflict_free(ctx, monkeypatch, kind)
     # the adjacent-lane placement costs 3-4 wavefronts per gather; the balanced one is close to the ideal 2
     assert res["1"] < res["0"]
     if kind != "150g":
-        assert res["1"] <= 2.25, res
+        assert res["1"] <= 2.35, res
