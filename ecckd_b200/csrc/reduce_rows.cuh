@@ -89,7 +89,8 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
                                            const int nv, const TransConst& K, const TransLane& tl,
                                            const bool (&is_log)[NR], const TransConst256& K2,
                                            const unsigned char* __restrict__ tab,
-                                           const TransConst64* __restrict__ K3 = nullptr, const unsigned lane_off = 0u) {
+                                           const TransConst64* __restrict__ K3 = nullptr, const unsigned lane_off = 0u,
+                                           const int row_stride = STAGE_BYTES) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   // no register software pipeline: the loads of a trip are issued at its top and the other warps
   // of the scheduler cover their latency (the rotating pipeline cost 52 register moves per trip)
@@ -101,7 +102,7 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
       const unsigned o = offp[(kk + j) * 32];
       w[j] = wp[(kk + j) * 32];  // zero for padding slots
 #pragma unroll
-      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * STAGE_BYTES + o);
+      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * row_stride + o);
     }
     // extremes: one range check per value, one (rare) branch per 4 x NR values
     bool outside = false;

@@ -520,7 +520,7 @@ __global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __rest
     }
     if (r < nrounds) {
       rounds[r].win = (uint32_t)mine;
-      if (same) rounds[r].flags |= 4u;  // bit 2: same window as the round before (reduce4_kernel's fast path)
+      if (same) rounds[r].flags |= 4u;  // bit 2: same window as the round before
     }
   }
 }
@@ -1022,7 +1022,7 @@ __host__ __device__ inline Smem2Layout smem2_layout(int nw) {
   L.ring = off;
   off += NSW * RING_SLOT_BYTES;
   L.data = off;
-  off += nw * NSETS * RPW * STAGE_BYTES;
+  off += nw * NSETS * RPW * STAGE3_BYTES;
   L.ent = off;
   off += nw * WIN * 32 * 16;
   L.s1e = off;
@@ -1111,9 +1111,9 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
 
   // ===================== consumers: warp = RPW rows of the group =====================
   const TransLane tl = {0, 0};  // (only the logarithmic kinds of reduce_kernel use the lane table)
-  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE_BYTES;
+  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE3_BYTES;
   const unsigned my_full = full_d + warp * NSETS * 8;
-  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * STAGE_BYTES;
+  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * STAGE3_BYTES;
   double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
   double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
   double2* mmv = reinterpret_cast<double2*>(smem_raw + L.mmv) + warp * RPW * WIN;
@@ -1207,38 +1207,47 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
     __syncwarp();
   };
 
-  // issue cursor (runs NSETS chunk visits ahead of the compute cursor)
+  // issue cursor (runs NSETS chunk visits ahead of the compute cursor).  Every row chunk is a bulk
+  // copy: a row that is only 8-byte aligned is copied from the aligned address below it and read at
+  // a byte shift of 8, an odd tail is copied up to the next even length (the bytes read in excess
+  // stay inside the 16-byte granules of the caller's rows).
   Cursor qi = first;
-  const double* od_i[RPW];
-  bool bulk_i[RPW];
+  const unsigned char* src_i[RPW];  // next chunk of the warp's rows (nullptr: no such row in the group)
   auto load_issue_group = [&]() {
     const GroupDesc* gd = p.groups + qi.l;
 #pragma unroll
     for (int r = 0; r < RPW; ++r) {
       const int i = warp + r * nw;
-      const bool act = USES_TAU && i < gd->nrows;
-      od_i[r] = act ? gd->od[i] : nullptr;
-      bulk_i[r] = act && gd->bulk_ok[i];
+      src_i[r] = (USES_TAU && i < gd->nrows) ? reinterpret_cast<const unsigned char*>(gd->od[i] + (int64_t)qi.c * ch) : nullptr;
     }
   };
   auto issue = [&](int set) {
-    const int n_c = (qi.c == nchunks - 1) ? last_n : ch;
-    if (lane == 0 && ((n_c & 1) == 0)) {
-      // the rows of a set complete on ONE mbarrier (one wait per chunk visit instead of one per row)
-      const unsigned bar = my_full + set * 8;
-      int nb = 0;
+    if (src_i[0] != nullptr) {
+      const unsigned n_bytes = (unsigned)((qi.c == nchunks - 1) ? last_n : ch) * 8u;
+      unsigned shift[RPW], bytes[RPW], total = 0;
 #pragma unroll
-      for (int r = 0; r < RPW; ++r) nb += bulk_i[r] ? 1 : 0;
-      if (nb > 0) {
-        mbar_arrive_expect_tx(bar, (unsigned)(nb * n_c * 8));
+      for (int r = 0; r < RPW; ++r) {
+        shift[r] = (unsigned)(reinterpret_cast<uintptr_t>(src_i[r]) & 8u);
+        bytes[r] = src_i[r] ? ((shift[r] + n_bytes + 15u) & ~15u) : 0u;
+        total += bytes[r];
+      }
+      if (lane == 0) {
+        const unsigned bar = my_full + set * 8;  // the rows of a set complete on ONE mbarrier
+        mbar_arrive_expect_tx(bar, total);
 #pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-          if (bulk_i[r])
-            bulk_g2s_hint(my_data + (set * RPW + r) * STAGE_BYTES, od_i[r] + (int64_t)qi.c * ch, (unsigned)(n_c * 8), bar, pol);
-        }
+        for (int r = 0; r < RPW; ++r)
+          if (src_i[r]) bulk_g2s_hint(my_data + (set * RPW + r) * STAGE3_BYTES, src_i[r] - shift[r], bytes[r], bar, pol);
       }
     }
-    if (cursor_next(qi, p.ngroups, p.cw, nchunks)) load_issue_group();
+    if (++qi.c < qi.c_end) {
+#pragma unroll
+      for (int r = 0; r < RPW; ++r)
+        if (src_i[r]) src_i[r] += (size_t)ch * 8;
+    } else {
+      --qi.c;
+      cursor_next(qi, p.ngroups, p.cw, nchunks);
+      load_issue_group();
+    }
   };
   load_issue_group();
   for (int j = 0; j < NSETS && j < niter; ++j) issue(j);
@@ -1248,20 +1257,20 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   unsigned wpar = 0;
   unsigned phase_bits = 0;  // bit `set`: parity to wait for on that stage set's mbarrier
   const double* od_c[RPW];
-  bool active[RPW], bulk_row[RPW];
+  bool active[RPW];
   bool need_group = true;
 
   // the slots of one round for NR rows: range-check words and extremes from the cache, slot loop,
   // sums into the lane's entry, extremes back into the cache if one changed
   auto round_rows = [&](auto nr_tag, const unsigned char* stage0, const uint16_t* offp, const double* wp, const int e,
-                        const bool used) {
+                        const bool used, const int row0) {
     constexpr int NR = decltype(nr_tag)::value;
     Partial a[NR];
     bool il[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const double2 mm = mmv[r * WIN + e];
-      const uint2 b = mmb[r * WIN + e];
+      const double2 mm = mmv[(row0 + r) * WIN + e];
+      const uint2 b = mmb[(row0 + r) * WIN + e];
       a[r].s0 = 0.0;
       a[r].s1 = 0.0;
       a[r].zc = 0;
@@ -1272,17 +1281,23 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
       a[r].span = used ? b.y : 0xFFFFFFFFu;
       il[r] = false;
     }
-    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off);
+    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off, STAGE3_BYTES);
     if (used) {
       double2 v = ent[e * 32 + lane];
-      v.x += a[0].s0;
-      if (NR > 1) v.y += a[NR - 1].s0;
+      if (NR > 1) {
+        v.x += a[0].s0;
+        v.y += a[NR - 1].s0;
+      } else if (row0 == 0) {
+        v.x += a[0].s0;
+      } else {
+        v.y += a[0].s0;
+      }
       ent[e * 32 + lane] = v;
     }
     int u = 0;
 #pragma unroll
     for (int r = 0; r < NR; ++r) u |= a[r].upd;
-    if (__any_sync(0xffffffffu, used && u != 0)) merge_extremes<NR>(a, e, used, mmv, mmb, lane);
+    if (__any_sync(0xffffffffu, used && u != 0)) merge_extremes<NR>(a, e, used, mmv + row0 * WIN, mmb + row0 * WIN, lane);
   };
 
   // one chunk visit on stage set `set`
@@ -1294,31 +1309,18 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         const int i = warp + r * nw;
         active[r] = USES_TAU && i < gd->nrows;
         od_c[r] = active[r] ? gd->od[i] : nullptr;
-        bulk_row[r] = active[r] && gd->bulk_ok[i];
       }
       begin_piece(vg);
       need_group = false;
     }
-    const int n_c = (q.c == nchunks - 1) ? last_n : ch;
-    bool any_bulk = false;
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) any_bulk = any_bulk || bulk_row[r];
-    if (any_bulk && ((n_c & 1) == 0)) {
+    if (active[0]) {
       mbar_wait(my_full + set * 8, (phase_bits >> set) & 1u);
       phase_bits ^= 1u << set;
     }
-    bool generic_fill = false;
+    // byte shift of each row's chunk inside its stage (chunk lengths are even: a row's parity is fixed)
+    unsigned shift_c[RPW];
 #pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const int st = set * RPW + r;
-      if (!(bulk_row[r] && ((n_c & 1) == 0)) && active[r]) {
-        const double* src = od_c[r] + (int64_t)q.c * ch;
-        double* stage = reinterpret_cast<double*>(data + st * STAGE_BYTES);
-        for (int j = lane; j < n_c; j += 32) stage[j] = src[j];  // unaligned rows / odd tails
-        generic_fill = true;
-      }
-    }
-    __syncwarp();
+    for (int r = 0; r < RPW; ++r) shift_c[r] = (unsigned)(reinterpret_cast<uintptr_t>(od_c[r]) & 8u);
     bool last_round = false;
     while (!last_round) {
       mbar_wait(full_w + ws * 8, wpar);
@@ -1343,9 +1345,16 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         if (used) s1e[e * 32 + lane] += s;
       }
       if (USES_TAU && active[0]) {
-        const unsigned char* stage0 = data + (set * RPW) * STAGE_BYTES;
-        if (active[RPW - 1]) round_rows(std::integral_constant<int, RPW>{}, stage0, offp, wp, e, used);
-        else round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used);
+        const unsigned char* stage0 = data + (set * RPW) * STAGE3_BYTES + shift_c[0];
+        // (both rows of a pair have the same alignment in every caller of this library: spectra are
+        // [layer][nwav] arrays with one stride; a pair with different parities takes the single-row form twice)
+        if (active[RPW - 1] && shift_c[RPW - 1] == shift_c[0]) {
+          round_rows(std::integral_constant<int, RPW>{}, stage0, offp, wp, e, used, 0);
+        } else {
+          round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used, 0);
+          if (active[RPW - 1])
+            round_rows(std::integral_constant<int, 1>{}, data + (set * RPW + 1) * STAGE3_BYTES + shift_c[RPW - 1], offp, wp, e, used, 1);
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_w + ws * 8);
@@ -1354,11 +1363,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         wpar ^= 1u;
       }
     }
-    // re-arm the set for the visit after next (see reduce_kernel for the proxy fence)
-    if (generic_fill) {
-      fence_proxy_async();
-      __syncwarp();
-    }
+    // re-arm the set for the visit after next (the stage was only read through the generic proxy)
     if (k + NSETS < niter) issue(set);
     if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
       window_store();
@@ -1370,961 +1375,6 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
 #pragma unroll 1
   for (int k = 0; k < niter; ++k) visit(k & (NSETS - 1), k);
   if (!need_group) window_store();
-}
-
-// ------------------------------------------------------------------ reduce, windowed plans, one row per warp
-// reduce3_kernel: reduce2_kernel's per-round scheme (per-lane entries, cached range-check words,
-// results straight to the CTA's piece) re-cut for occupancy.  ncu on reduce2_kernel showed the
-// consumer warps issuing only a fifth of the time inside the slot loop (FP64 and shared-memory
-// latency with 2.5 consumer warps per scheduler, 168 registers): here
-//   * every consumer warp owns ONE row of the group (up to 20 consumer warps), evaluates 4 slots
-//     per trip (4 dependency chains) and stays under 88 registers: 23 warps per SM;
-//   * the extremes live in shared memory as order-preserving 64-bit keys updated with atomicMin /
-//     atomicMax on the rare exact path (no min/max registers, no cross-lane merge);
-//   * a dedicated warp issues all bulk copies (lane = consumer warp; it polls the stages' empty
-//     barriers), so the consumers' chunk visit is wait, rounds, arrive;
-//   * rows that are not 16-byte aligned and odd chunk tails are copied from the aligned address
-//     below / to the aligned length above and read at a per-row byte shift: every copy is a bulk
-//     copy (the bytes read in excess stay inside the 16-byte granules of the caller's rows).
-constexpr int NW3_MAX = GROUP_ROWS;         // consumer warps (one row each)
-constexpr int STAGE3_BYTES = STAGE_BYTES + 16;
-constexpr int THREADS3_MAX = (NW3_MAX + NPW + 1) * 32;
-
-struct Smem3Layout {
-  int tab;   // replicated 2^(j/64) table, at offset 0
-  int bars;  // mbarriers: full_d[nw][NSETS], empty_d[nw][NSETS], full_w[NSW], empty_w[NSW]
-  int ring;  // ring slots [NSW]: {double wperm[SLOTS*32]; PlanRound plan}
-  int data;  // data stages [nw][NSETS][STAGE3_BYTES]
-  int ent;   // [nw][WIN][32] double: per-lane sums of the window's g points
-  int s1e;   // [WIN][32] double: per-lane weight sums (last consumer warp)
-  int mmk;   // [nw][WIN][2] uint64: order-preserving keys of {min, max}
-  int mmb;   // [nw][WIN] uint2 {lowb, span} of the range check
-  int total;
-};
-__host__ __device__ inline Smem3Layout smem3_layout(int nw) {
-  Smem3Layout L;
-  int off = 0;
-  L.tab = off;
-  off += TRANS_TAB64_BYTES;
-  L.bars = off;
-  off += (2 * nw * NSETS + 2 * NSW) * 8;
-  off = (off + 127) & ~127;
-  L.ring = off;
-  off += NSW * RING_SLOT_BYTES;
-  L.data = off;
-  off += nw * NSETS * STAGE3_BYTES;
-  L.ent = off;
-  off += nw * WIN * 32 * 8;
-  L.s1e = off;
-  off += WIN * 32 * 8;
-  L.mmk = off;
-  off += nw * WIN * 16;
-  L.mmb = off;
-  off += nw * WIN * 8;
-  L.total = (off + 15) & ~15;
-  return L;
-}
-
-// order-preserving image of a double (not NaN) as an unsigned 64-bit key, and back
-__device__ __forceinline__ unsigned long long key_of(double x) {
-  const long long b = __double_as_longlong(x);
-  return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000LL));
-}
-__device__ __forceinline__ double value_of(unsigned long long k) {
-  const long long b = (long long)k;
-  return __longlong_as_double(b ^ ((((b >> 63) & 1) - 1) | (long long)0x8000000000000000LL));
-}
-
-__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
-  unsigned ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-
-// The 16 slots of one row of one round, 4 per trip.  `stage` is the row's chunk in shared memory
-// (already shifted), mmk the {min, max} keys of the lane's g point.  Returns the lane's sum of
-// f(tau)*w; sets upd when the exact path ran (the range-check words must then be refreshed).
-template <int FKIND>
-__device__ __forceinline__ double row_slots3(const unsigned char* __restrict__ stage, const uint16_t* __restrict__ offp,
-                                             const double* __restrict__ wp, const unsigned lowb, const unsigned span,
-                                             unsigned long long* __restrict__ mmk, const bool used, int& upd,
-                                             const TransConst64& K, const unsigned char* __restrict__ tab,
-                                             const unsigned lane_off) {
-  double s0 = 0.0;
-#pragma unroll 1
-  for (int kk = 0; kk < SLOTS; kk += 4) {
-    double tau[4], w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned o = offp[(kk + j) * 32];
-      w[j] = wp[(kk + j) * 32];  // zero for padding slots
-      tau[j] = *reinterpret_cast<const double*>(stage + o);
-    }
-    unsigned worst = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) worst = max(worst, (unsigned)__double2hiint(tau[j]) - lowb);
-    if (worst >= span) {  // rare: a value may be a new extreme (or is negative / non-finite)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double t = tau[j];
-        if (t == t) {
-          if (used) {
-            const unsigned long long k = key_of(t);
-            atomicMin(&mmk[0], k);
-            atomicMax(&mmk[1], k);
-          }
-        } else {
-          s0 = t;  // NaN: poison the sum (see reduce_rows.cuh)
-        }
-      }
-      upd = 1;
-    }
-    double f[4];
-    if (FKIND == F_TRANS) {
-      TransMid m[4];
-      double T[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) m[j] = trans64_phase1(tau[j], K);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) T[j] = trans64_phase2(m[j], tab, lane_off);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = trans64_phase3(m[j], T[j], K);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) f[j] = (FKIND == F_LINEAR) ? tau[j] : (FKIND == F_SQRT ? sqrt(tau[j]) : 1.0);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) s0 = fma(f[j], w[j], s0);
-  }
-  return s0;
-}
-
-// Lean form of produce_rounds for reduce3_kernel (88 registers): plan offsets are fetched one
-// round ahead, the sources of the current round are loaded and converted in place.
-template <int WMODE>
-__device__ __forceinline__ void produce_rounds3(const ReduceParams& p, const Cursor first, const int niter, const int pw,
-                                                const int lane, unsigned char* ring, const unsigned ring_s,
-                                                const unsigned full_w, const unsigned empty_w) {
-  const int nchunks = (int)p.nchunks;
-  const int ch = p.ch;
-  constexpr int PER = SLOTS / NPW;
-  const TransLane ptl = trans_lane_init();
-  Cursor q = first;
-  int visit = 0;
-  uint32_t r_cur = p.round_off[q.c], r_end = p.round_off[q.c + 1];
-  int ws = 0, filled = 0;
-  unsigned epar = 0;
-  // current round
-  uint32_t r = r_cur;
-  int64_t w0 = (int64_t)q.c * ch;
-  int wrow = p.groups[q.l].wrow;
-  unsigned off[PER], meta;
-  {
-    const PlanRound* pr = p.rounds + r;
-    meta = pr->meta[lane];
-#pragma unroll
-    for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
-  }
-  bool valid = niter > 0;
-  while (valid) {
-    // sources of this round
-    double x[PER], y[PER];
-#pragma unroll
-    for (int m = 0; m < PER; ++m) {
-      const int64_t w = w0 + (off[m] >> 3);
-      if (WMODE == W_PLANCK) {
-        x[m] = p.wn[w];
-        y[m] = p.dwn[w];
-      } else if (WMODE == W_MATRIX) {
-        x[m] = p.weight[(int64_t)wrow * p.w_stride + w];
-      } else {
-        x[m] = p.weight[w];
-      }
-    }
-    const unsigned vmask = p.balanced ? ((meta >> 12) & 0xFFFFu) : ((1u << ((meta >> 12) & 31u)) - 1u);
-    const double hkt = (WMODE == W_PLANCK) ? p.temperature[wrow] : 0.0;
-    const uint32_t r_this = r;
-    // advance to the next round and fetch its plan words while the sources are in flight
-    if (++r_cur == r_end) {
-      ++visit;
-      if (visit < niter) {
-        cursor_next(q, p.ngroups, p.cw, nchunks);
-        r_cur = p.round_off[q.c];
-        r_end = p.round_off[q.c + 1];
-        wrow = p.groups[q.l].wrow;
-      } else {
-        valid = false;
-      }
-    }
-    if (valid) {
-      r = r_cur;
-      w0 = (int64_t)q.c * ch;
-      const PlanRound* pr = p.rounds + r;
-      meta = pr->meta[lane];
-#pragma unroll
-      for (int m = 0; m < PER; ++m) off[m] = pr->off[pw + NPW * m][lane];
-    }
-    unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-    double* wperm = reinterpret_cast<double*>(slot);
-    if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
-#pragma unroll
-    for (int m = 0; m < PER; ++m) {
-      const int k = pw + NPW * m;
-      const double val = (WMODE == W_PLANCK) ? planck_elem_fast(hkt, x[m], y[m], ptl) : x[m];
-      wperm[k * 32 + lane] = ((vmask >> k) & 1u) ? val : 0.0;
-    }
-    __syncwarp();
-    if (lane == 0) {
-      if (pw == 0) {
-        mbar_arrive_expect_tx(full_w + ws * 8, (unsigned)sizeof(PlanRound));
-        bulk_g2s(ring_s + ws * RING_SLOT_BYTES + WPERM_BYTES, p.rounds + r_this, (unsigned)sizeof(PlanRound),
-                 full_w + ws * 8);
-      } else {
-        mbar_arrive(full_w + ws * 8);
-      }
-    }
-    ++filled;
-    if (++ws == NSW) {
-      ws = 0;
-      if (filled > NSW) epar ^= 1u;
-    }
-  }
-}
-
-template <int FKIND, int WMODE>
-__global__ void __launch_bounds__(THREADS3_MAX, 1) reduce3_kernel(const __grid_constant__ ReduceParams p) {
-  static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
-                "reduce3_kernel: kinds with per-row weight sums run on reduce_kernel");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int nw = p.nw, ng = p.ng;
-  const Smem3Layout L = smem3_layout(nw);
-  const unsigned sbase = smem_u32(smem_raw);
-  const unsigned full_d = sbase + L.bars;            // [nw][NSETS]
-  const unsigned empty_d = full_d + nw * NSETS * 8;  // [nw][NSETS]
-  const unsigned full_w = empty_d + nw * NSETS * 8;  // [NSW]
-  const unsigned empty_w = full_w + NSW * 8;         // [NSW]
-  unsigned char* ring = smem_raw + L.ring;
-  constexpr bool USES_TAU = (FKIND != F_NONE);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * nw * NSETS; ++i) mbar_init(full_d + i * 8, 1);
-    for (int i = 0; i < NSW; ++i) {
-      mbar_init(full_w + i * 8, NPW);
-      mbar_init(empty_w + i * 8, nw);
-    }
-    fence_mbar_init();
-  }
-  if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
-  __syncthreads();
-  const unsigned char* tab = smem_raw + L.tab;
-
-  // this CTA's contiguous piece of the (window, group, chunk) space
-  const int nchunks = (int)p.nchunks;
-  const int ch = p.ch;
-  const int64_t T = (int64_t)p.ngroups * p.nchunks;
-  const int64_t lo = (T * blockIdx.x) / p.ncta;
-  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
-  const int niter = (int)(hi - lo);
-  if (niter == 0) return;
-  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
-  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
-
-  if (warp >= nw + NPW) {
-    // ===================== data producer: lane = consumer warp, all bulk copies of its row =====================
-    if (!USES_TAU || lane >= nw) return;
-    const uint64_t pol = policy_evict_first();
-    const unsigned my_full = full_d + lane * NSETS * 8, my_empty = empty_d + lane * NSETS * 8;
-    const unsigned my_data = sbase + L.data + lane * NSETS * STAGE3_BYTES;
-    Cursor q = first;
-    const double* od = nullptr;
-    bool act = false;
-    int group = -1;
-    unsigned used_sets = 0, epar = 0;
-    int k = 0, nset = 0;  // nset: copies issued so far for this row (its visits alternate the two sets)
-    while (k < niter) {
-      if (q.l != group) {
-        group = q.l;
-        const GroupDesc* gd = p.groups + group;
-        act = lane < gd->nrows;
-        od = act ? gd->od[lane] : nullptr;
-      }
-      if (act) {
-        const int set = nset & (NSETS - 1);
-        if ((used_sets >> set) & 1u) {
-          if (!mbar_test(my_empty + set * 8, (epar >> set) & 1u)) {
-            __nanosleep(64);
-            continue;  // poll again: lanes progress independently
-          }
-          epar ^= 1u << set;
-        }
-        used_sets |= 1u << set;
-        const int n_c = (q.c == nchunks - 1) ? last_n : ch;
-        const double* src = od + (int64_t)q.c * ch;
-        const unsigned shift = (unsigned)(reinterpret_cast<uintptr_t>(src) & 8u);
-        const unsigned bytes = (shift + (unsigned)n_c * 8u + 15u) & ~15u;
-        const unsigned bar = my_full + set * 8;
-        mbar_arrive_expect_tx(bar, bytes);
-        bulk_g2s_hint(my_data + set * STAGE3_BYTES, reinterpret_cast<const unsigned char*>(src) - shift, bytes, bar, pol);
-        ++nset;
-      }
-      cursor_next(q, p.ngroups, p.cw, nchunks);
-      ++k;
-    }
-    return;
-  }
-  if (warp >= nw) {
-    produce_rounds3<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w);
-    return;
-  }
-
-  // ===================== consumers: warp = one row of the group =====================
-  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * STAGE3_BYTES;
-  const unsigned my_full = full_d + warp * NSETS * 8, my_empty = empty_d + warp * NSETS * 8;
-  double* ent = reinterpret_cast<double*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
-  double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
-  unsigned long long* mmk = reinterpret_cast<unsigned long long*>(smem_raw + L.mmk) + warp * WIN * 2;
-  uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + warp * WIN;
-  const unsigned lane_off = (unsigned)(lane & 15) << 3;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  // the weight sums do not depend on the row: the last consumer warp accumulates them once per
-  // group; they end up in the s1 field of its row
-  const bool s1_duty = warp == nw - 1;
-
-  int gbase = -1;          // first g point of the current window (-1: none loaded)
-  double* pout = nullptr;  // this warp's row of the current (window, group) piece: [ng][4]
-
-  auto begin_piece = [&](int vg) {
-    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * nw + warp;
-    pout = p.partial + slot * ng * 4;
-    int32_t* poutz = p.partial_z + slot * ng;
-    for (int i = lane; i < ng; i += 32) {
-      double2* q = reinterpret_cast<double2*>(pout + (size_t)i * 4);
-      q[0] = make_double2(0.0, 0.0);
-      q[1] = make_double2(inf, -inf);
-      poutz[i] = 0;
-    }
-    __syncwarp();
-  };
-  // add the window's entries up over the lanes (fixed butterfly) and fold them, with the extremes,
-  // into the piece: lane e writes g point gbase + e
-  auto window_store = [&]() {
-    double t0 = 0.0, ts = 0.0;
-#pragma unroll
-    for (int e = 0; e < WIN; ++e) {
-      double v = ent[e * 32 + lane];
-      double s = s1_duty ? s1e[e * 32 + lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (s1_duty) s += __shfl_xor_sync(0xffffffffu, s, o);
-      }
-      if (lane == e) {
-        t0 = v;
-        ts = s;
-      }
-    }
-    const int g = gbase + lane;
-    if (lane < WIN && g < ng) {
-      double* q = pout + (size_t)g * 4;
-      const double mn = value_of(mmk[lane * 2]), mx = value_of(mmk[lane * 2 + 1]);
-      q[0] += t0;
-      if (s1_duty) q[1] += ts;
-      q[2] = (mn < q[2]) ? mn : q[2];
-      q[3] = (mx > q[3]) ? mx : q[3];
-    }
-    __syncwarp();
-  };
-  auto refresh_bounds = [&]() {
-    if (lane < WIN) {
-      Partial t;
-      t.mn = value_of(mmk[lane * 2]);
-      t.mx = value_of(mmk[lane * 2 + 1]);
-      minmax_bounds(t);
-      mmb[lane] = make_uint2(t.lowb, t.span);
-    }
-    __syncwarp();
-  };
-  // open the window [nb, nb + WIN): zero entries, extremes from the piece
-  auto window_load = [&](int nb) {
-    gbase = nb;
-#pragma unroll
-    for (int e = 0; e < WIN; ++e) ent[e * 32 + lane] = 0.0;
-    if (s1_duty) {
-#pragma unroll
-      for (int e = 0; e < WIN; ++e) s1e[e * 32 + lane] = 0.0;
-    }
-    if (lane < WIN) {
-      const int g = nb + lane;
-      double mn = inf, mx = -inf;
-      if (g < ng) {
-        mn = pout[(size_t)g * 4 + 2];
-        mx = pout[(size_t)g * 4 + 3];
-      }
-      mmk[lane * 2] = key_of(mn);
-      mmk[lane * 2 + 1] = key_of(mx);
-    }
-    __syncwarp();
-    refresh_bounds();
-  };
-
-  Cursor q = first;
-  int ws = 0, vg = 0, nset = 0;
-  unsigned wpar = 0, phase_bits = 0;
-  const double* od_c = nullptr;
-  bool active = false, need_group = true, new_piece = true;
-
-#pragma unroll 1
-  for (int k = 0; k < niter; ++k) {
-    if (need_group) {
-      const GroupDesc* gd = p.groups + q.l;
-      active = USES_TAU && warp < gd->nrows;
-      od_c = active ? gd->od[warp] : nullptr;
-      need_group = false;
-    }
-    const int set = nset & (NSETS - 1);
-    const unsigned char* stage = data + set * STAGE3_BYTES;
-    if (active) {
-      mbar_wait(my_full + set * 8, (phase_bits >> set) & 1u);
-      phase_bits ^= 1u << set;
-      stage += (unsigned)(reinterpret_cast<uintptr_t>(od_c + (int64_t)q.c * ch) & 8u);
-      ++nset;
-    }
-    bool last_round = false;
-    while (!last_round) {
-      mbar_wait(full_w + ws * 8, wpar);
-      const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-      const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
-      const double* wp = reinterpret_cast<const double*>(slot) + lane;
-      const uint16_t* offp = &pr->off[0][lane];
-      const unsigned meta = pr->meta[lane];
-      const int wb = (int)pr->win;
-      last_round = (pr->flags & 2u) != 0;
-      if (new_piece || wb != gbase) {  // warp-uniform: the window of g points moves, or the piece is new
-        if (gbase >= 0) window_store();
-        if (new_piece) {
-          begin_piece(vg);
-          new_piece = false;
-        }
-        window_load(wb);
-      }
-      const unsigned g = meta & 0xFFFu;
-      const bool used = g != NO_G;
-      const int e = used ? min(max((int)g - gbase, 0), WIN - 1) : 0;  // the plan keeps g inside the window
-      double s1 = 0.0;
-      if (s1_duty) {
-#pragma unroll
-        for (int kk = 0; kk < SLOTS; ++kk) s1 += wp[kk * 32];
-      }
-      double s0 = 0.0;
-      int upd = 0;
-      if (active) {
-        const uint2 b = mmb[e];
-        s0 = row_slots3<FKIND>(stage, offp, wp, used ? b.x : 0u, used ? b.y : 0xFFFFFFFFu, mmk + e * 2, used, upd,
-                               p.tc64, tab, lane_off);
-      }
-      if (used) {
-        if (active) ent[e * 32 + lane] += s0;
-        if (s1_duty) s1e[e * 32 + lane] += s1;
-      }
-      if (__any_sync(0xffffffffu, upd != 0)) {
-        __syncwarp();  // the other lanes' atomics on the keys are visible
-        refresh_bounds();
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(empty_w + ws * 8);
-      if (++ws == NSW) {
-        ws = 0;
-        wpar ^= 1u;
-      }
-    }
-    if (active && lane == 0) mbar_arrive(my_empty + set * 8);  // the stage may be refilled
-    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
-      ++vg;
-      need_group = true;
-      new_piece = true;
-    }
-  }
-  if (gbase >= 0) window_store();
-}
-
-// ------------------------------------------------------------------ reduce, windowed plans, two warps per row pair
-// reduce4_kernel.  What ncu showed on reduce2_kernel once the gathers were conflict-free: every
-// pipe below 55 %, and the consumer warps - ten of them, each alone with its two rows - spending
-// 5400 cycles per chunk visit on a strictly serial sequence (wait, ~200 instructions of round
-// bookkeeping at 6-9 cycles each, the slot loop, ~60 instructions of bulk-copy issue) where the copy
-// pipeline needs 3900.  reduce3_kernel's answer (one row per warp) doubled the warps but also the
-// bookkeeping per value and lost the sharing of offsets and weights between two rows.  Here the two
-// rows of a pair stay together and TWO warps serve the pair, taking the chunk visits in turn
-// (warp 2p: even visits on stage set 0, warp 2p+1: odd visits on set 1): the work per value is
-// reduce2_kernel's, each warp has two visit periods for its serial sequence, and the slot loop
-// runs 2 slots x 2 rows per trip so that 23 warps fit the register file (80 registers).
-//   * A dedicated warp issues all bulk copies (lane = pair) as the consumers release the sets.
-//   * The pair shares its entries, extremes (atomic keys, as in reduce3_kernel) and range-check
-//     words.  Its warps run their slot loops concurrently but touch the shared entries in VISIT
-//     ORDER: a warp adds its round sums after the other warp has finished the visit before
-//     (one mbarrier handshake per visit), so the sums are added in the same order in every run.
-//   * A round may read the range-check words without that handshake only when the shared state is
-//     already the one it needs: state word = (piece, window) and the plan's "same window as the
-//     round before" bit; otherwise it waits for the other warp first and does the window / piece
-//     change itself (rare: band changes, group changes).
-constexpr int NP4_MAX = NW_MAX;  // row pairs per CTA
-constexpr int THREADS4_MAX = (2 * NP4_MAX + NPW + 1) * 32;
-
-struct Smem4Layout {
-  int tab;    // replicated 2^(j/64) table, at offset 0
-  int bars;   // mbarriers: full_d[np][2], empty_d[np][2], tok[np][2], full_w[NSW], empty_w[NSW]
-  int ring;   // ring slots [NSW]: {double wperm[SLOTS*32]; PlanRound plan}
-  int data;   // data stages [np][2 sets][RPW][STAGE3_BYTES]
-  int ent;    // [np][WIN][32] double2: per-lane sums of the window's g points, both rows
-  int s1e;    // [WIN][32] double: per-lane weight sums (last pair)
-  int mmk;    // [np][RPW][WIN][2] uint64: order-preserving keys of {min, max}
-  int mmb;    // [np][RPW][WIN] uint2 {lowb, span} of the range check
-  int state;  // [np] int: (piece << 16 | window base) the pair's shared state belongs to, -1 none
-  int total;
-};
-__host__ __device__ inline Smem4Layout smem4_layout(int np) {
-  Smem4Layout L;
-  int off = 0;
-  L.tab = off;
-  off += TRANS_TAB64_BYTES;
-  L.bars = off;
-  off += (6 * np + 2 * NSW) * 8;
-  off = (off + 127) & ~127;
-  L.ring = off;
-  off += NSW * RING_SLOT_BYTES;
-  L.data = off;
-  off += np * 2 * RPW * STAGE3_BYTES;
-  L.ent = off;
-  off += np * WIN * 32 * 16;
-  L.s1e = off;
-  off += WIN * 32 * 8;
-  L.mmk = off;
-  off += np * RPW * WIN * 16;
-  L.mmb = off;
-  off += np * RPW * WIN * 8;
-  L.state = off;
-  off += np * 4;
-  L.total = (off + 15) & ~15;
-  return L;
-}
-
-// 16 slots of NR rows of one round, 2 per trip (NR = 2: four dependency chains).  stage[r] is row
-// r's chunk in shared memory (already shifted); mmk[r] the {min, max} keys of the lane's g point.
-template <int FKIND, int NR>
-__device__ __forceinline__ void rows_slots4(double (&s0)[NR], int& upd, const unsigned char* const (&stage)[NR],
-                                            const uint16_t* __restrict__ offp, const double* __restrict__ wp,
-                                            const unsigned (&lowb)[NR], const unsigned (&span)[NR],
-                                            unsigned long long* const (&mmk)[NR], const bool used,
-                                            const TransConst64& K, const unsigned char* __restrict__ tab,
-                                            const unsigned lane_off) {
-#pragma unroll 1
-  for (int kk = 0; kk < SLOTS; kk += 2) {
-    double tau[NR][2], w[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const unsigned o = offp[(kk + j) * 32];
-      w[j] = wp[(kk + j) * 32];  // zero for padding slots
-#pragma unroll
-      for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage[r] + o);
-    }
-    bool outside = false;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const unsigned worst =
-          max((unsigned)__double2hiint(tau[r][0]) - lowb[r], (unsigned)__double2hiint(tau[r][1]) - lowb[r]);
-      outside = outside || (worst >= span[r]);
-    }
-    if (outside) {  // rare: a value may be a new extreme (or is negative / non-finite)
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const double t = tau[r][j];
-          if (t == t) {
-            if (used) {
-              const unsigned long long key = key_of(t);
-              atomicMin(&mmk[r][0], key);
-              atomicMax(&mmk[r][1], key);
-            }
-          } else {
-            s0[r] = t;  // NaN: poison the sum (see reduce_rows.cuh)
-          }
-        }
-      }
-      upd = 1;
-    }
-    double f[NR][2];
-    if (FKIND == F_TRANS) {
-      TransMid m[NR][2];
-      double T[NR][2];
-#pragma unroll
-      for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) m[r][j] = trans64_phase1(tau[r][j], K);
-#pragma unroll
-      for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) T[r][j] = trans64_phase2(m[r][j], tab, lane_off);
-#pragma unroll
-      for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) f[r][j] = trans64_phase3(m[r][j], T[r][j], K);
-    } else {
-#pragma unroll
-      for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          f[r][j] = (FKIND == F_LINEAR) ? tau[r][j] : (FKIND == F_SQRT ? sqrt(tau[r][j]) : 1.0);
-    }
-#pragma unroll
-    for (int r = 0; r < NR; ++r)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) s0[r] = fma(f[r][j], w[j], s0[r]);
-  }
-}
-
-template <int FKIND, int WMODE>
-__global__ void __launch_bounds__(THREADS4_MAX, 1) reduce4_kernel(const __grid_constant__ ReduceParams p) {
-  static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
-                "reduce4_kernel: kinds with per-row weight sums run on reduce_kernel");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int np = p.nw, ng = p.ng;  // p.nw: row pairs per CTA
-  const Smem4Layout L = smem4_layout(np);
-  const unsigned sbase = smem_u32(smem_raw);
-  const unsigned full_d = sbase + L.bars;        // [np][2]
-  const unsigned empty_d = full_d + np * 2 * 8;  // [np][2]
-  const unsigned tok = empty_d + np * 2 * 8;     // [np][2]: tok[p][h] completes when warp h of pair p ends a visit
-  const unsigned full_w = tok + np * 2 * 8;      // [NSW]
-  const unsigned empty_w = full_w + NSW * 8;     // [NSW]
-  unsigned char* ring = smem_raw + L.ring;
-  constexpr bool USES_TAU = (FKIND != F_NONE);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 6 * np; ++i) mbar_init(full_d + i * 8, 1);
-    for (int i = 0; i < NSW; ++i) {
-      mbar_init(full_w + i * 8, NPW);
-      mbar_init(empty_w + i * 8, np);  // the rounds of a visit are consumed by one warp of every pair
-    }
-    fence_mbar_init();
-  }
-  if (threadIdx.x < np) reinterpret_cast<int*>(smem_raw + L.state)[threadIdx.x] = -1;
-  if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
-  __syncthreads();
-  const unsigned char* tab = smem_raw + L.tab;
-
-  // this CTA's contiguous piece of the (window, group, chunk) space
-  const int nchunks = (int)p.nchunks;
-  const int ch = p.ch;
-  const int64_t T = (int64_t)p.ngroups * p.nchunks;
-  const int64_t lo = (T * blockIdx.x) / p.ncta;
-  const int64_t hi = (T * (blockIdx.x + 1)) / p.ncta;
-  const int niter = (int)(hi - lo);
-  if (niter == 0) return;
-  const Cursor first = cursor_at(lo, p.ngroups, p.cw, nchunks);
-  const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
-
-  if (warp >= 2 * np + NPW) {
-    // ===================== data producer: lane = pair, the bulk copies of its two rows, visit by visit =====================
-    if (!USES_TAU || lane >= np) return;
-    const uint64_t pol = policy_evict_first();
-    const unsigned my_full = full_d + lane * 2 * 8, my_empty = empty_d + lane * 2 * 8;
-    const unsigned my_data = sbase + L.data + lane * 2 * RPW * STAGE3_BYTES;
-    Cursor q = first;
-    const double* od[RPW] = {};
-    int group = -1;
-    unsigned epar = 0, used_sets = 0;
-    for (int k = 0; k < niter; ++k) {
-      if (q.l != group) {
-        group = q.l;
-        const GroupDesc* gd = p.groups + group;
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) od[r] = (lane + r * np < gd->nrows) ? gd->od[lane + r * np] : nullptr;
-      }
-      const int set = k & 1;
-      if (od[0] != nullptr) {
-        if ((used_sets >> set) & 1u) {  // the set holds an earlier visit's chunk: wait until its warp has released it
-          while (!mbar_test(my_empty + set * 8, (epar >> set) & 1u)) __nanosleep(256);
-          epar ^= 1u << set;
-        }
-        used_sets |= 1u << set;
-        const int n_c = (q.c == nchunks - 1) ? last_n : ch;
-        unsigned bytes[RPW], shift[RPW], total = 0;
-#pragma unroll
-        for (int r = 0; r < RPW; ++r) {
-          shift[r] = od[r] ? (unsigned)(reinterpret_cast<uintptr_t>(od[r] + (int64_t)q.c * ch) & 8u) : 0u;
-          bytes[r] = od[r] ? ((shift[r] + (unsigned)n_c * 8u + 15u) & ~15u) : 0u;
-          total += bytes[r];
-        }
-        const unsigned bar = my_full + set * 8;
-        mbar_arrive_expect_tx(bar, total);
-#pragma unroll
-        for (int r = 0; r < RPW; ++r)
-          if (od[r])
-            bulk_g2s_hint(my_data + (set * RPW + r) * STAGE3_BYTES,
-                          reinterpret_cast<const unsigned char*>(od[r] + (int64_t)q.c * ch) - shift[r], bytes[r], bar, pol);
-      }
-      cursor_next(q, p.ngroups, p.cw, nchunks);
-    }
-    return;
-  }
-  if (warp >= 2 * np) {
-    produce_rounds3<WMODE>(p, first, niter, warp - 2 * np, lane, ring, sbase + L.ring, full_w, empty_w);
-    return;
-  }
-
-  // ===================== consumers: warps 2p, 2p+1 = the two rows of pair p, alternate visits =====================
-  const int pr_ix = warp >> 1, ph = warp & 1;
-  unsigned char* data = smem_raw + L.data + (size_t)pr_ix * 2 * RPW * STAGE3_BYTES + (size_t)ph * RPW * STAGE3_BYTES;
-  const unsigned my_full = full_d + (pr_ix * 2 + ph) * 8, my_empty = empty_d + (pr_ix * 2 + ph) * 8;
-  const unsigned tok_mine = tok + (pr_ix * 2 + ph) * 8, tok_other = tok + (pr_ix * 2 + (ph ^ 1)) * 8;
-  double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)pr_ix * WIN * 32;
-  double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
-  unsigned long long* mmk = reinterpret_cast<unsigned long long*>(smem_raw + L.mmk) + pr_ix * RPW * WIN * 2;
-  uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + pr_ix * RPW * WIN;
-  volatile int* state = reinterpret_cast<volatile int*>(smem_raw + L.state) + pr_ix;
-  const unsigned lane_off = (unsigned)(lane & 15) << 3;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL);
-  // the weight sums do not depend on the row: the last pair accumulates them once per group; they end
-  // up in the s1 field of its first row
-  const bool s1_duty = pr_ix == np - 1;
-
-  auto piece_ptr = [&](int vg) {
-    const size_t slot = ((size_t)blockIdx.x * p.maxg + (size_t)vg) * (np * RPW) + pr_ix * RPW;
-    return p.partial + slot * ng * 4;
-  };
-  // the pair's rows of a new (window, group) piece start as {0, 0, +inf, -inf}
-  auto begin_piece = [&](int vg) {
-    double* pout = piece_ptr(vg);
-    int32_t* poutz = p.partial_z + (((size_t)blockIdx.x * p.maxg + (size_t)vg) * (np * RPW) + pr_ix * RPW) * ng;
-    for (int i = lane; i < RPW * ng; i += 32) {
-      double2* q = reinterpret_cast<double2*>(pout + (size_t)i * 4);
-      q[0] = make_double2(0.0, 0.0);
-      q[1] = make_double2(inf, -inf);
-      poutz[i] = 0;
-    }
-    __syncwarp();
-  };
-  // add the window's entries up over the lanes (fixed butterfly) and fold them, with the extremes,
-  // into piece `pout`: lane e writes g point gb + e
-  auto window_store = [&](double* pout, int gb) {
-    double t0 = 0.0, t1 = 0.0, ts = 0.0;
-#pragma unroll
-    for (int e = 0; e < WIN; ++e) {
-      double2 v = ent[e * 32 + lane];
-      double s = s1_duty ? s1e[e * 32 + lane] : 0.0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
-        v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
-        if (s1_duty) s += __shfl_xor_sync(0xffffffffu, s, o);
-      }
-      if (lane == e) {
-        t0 = v.x;
-        t1 = v.y;
-        ts = s;
-      }
-    }
-    const int g = gb + lane;
-    if (lane < WIN && g < ng) {
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        double* q = pout + ((size_t)r * ng + g) * 4;
-        const double mn = value_of(mmk[(r * WIN + lane) * 2]), mx = value_of(mmk[(r * WIN + lane) * 2 + 1]);
-        q[0] += (r == 0) ? t0 : t1;
-        q[2] = (mn < q[2]) ? mn : q[2];
-        q[3] = (mx > q[3]) ? mx : q[3];
-      }
-      if (s1_duty) pout[(size_t)g * 4 + 1] += ts;
-    }
-    __syncwarp();
-  };
-  auto refresh_bounds = [&]() {
-    if (lane < RPW * WIN) {
-      Partial t;
-      t.mn = value_of(mmk[lane * 2]);
-      t.mx = value_of(mmk[lane * 2 + 1]);
-      minmax_bounds(t);
-      mmb[lane] = make_uint2(t.lowb, t.span);
-    }
-    __syncwarp();
-  };
-  // open the window [nb, nb + WIN) of piece vg: zero entries, extremes from the piece, then publish
-  auto window_load = [&](double* pout, int vg, int nb) {
-#pragma unroll
-    for (int e = 0; e < WIN; ++e) ent[e * 32 + lane] = make_double2(0.0, 0.0);
-    if (s1_duty) {
-#pragma unroll
-      for (int e = 0; e < WIN; ++e) s1e[e * 32 + lane] = 0.0;
-    }
-    if (lane < RPW * WIN) {
-      const int r = lane / WIN, g = nb + lane % WIN;
-      double mn = inf, mx = -inf;
-      if (g < ng) {
-        mn = pout[((size_t)r * ng + g) * 4 + 2];
-        mx = pout[((size_t)r * ng + g) * 4 + 3];
-      }
-      mmk[lane * 2] = key_of(mn);
-      mmk[lane * 2 + 1] = key_of(mx);
-    }
-    __syncwarp();
-    refresh_bounds();
-    __threadfence_block();
-    if (lane == 0) *state = (vg << 16) | nb;
-    __syncwarp();
-  };
-
-  Cursor q = first;
-  int ws = 0, vg = 0;
-  unsigned wpar = 0, dpar = 0, tpar = 0;
-  const double* od_c[RPW] = {};
-  bool active[RPW] = {};
-  bool need_group = true, new_piece = true;
-  int group_nrounds_skip = 0;
-  (void)group_nrounds_skip;
-
-#pragma unroll 1
-  for (int k = 0; k < niter; ++k) {
-    if (need_group) {
-      const GroupDesc* gd = p.groups + q.l;
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        const int i = pr_ix + r * np;
-        active[r] = USES_TAU && i < gd->nrows;
-        od_c[r] = active[r] ? gd->od[i] : nullptr;
-      }
-      need_group = false;
-    }
-    const bool mine = (k & 1) == ph;
-    if (mine) {
-      const unsigned char* stage[RPW];
-#pragma unroll
-      for (int r = 0; r < RPW; ++r)
-        stage[r] = data + r * STAGE3_BYTES +
-                   (active[r] ? (unsigned)(reinterpret_cast<uintptr_t>(od_c[r] + (int64_t)q.c * ch) & 8u) : 0u);
-      if (active[0]) {
-        mbar_wait(my_full, dpar);
-        dpar ^= 1u;
-      }
-      bool held = false;  // this warp may touch the pair's shared state: the other warp ended visit k - 1
-      auto acquire = [&]() {
-        if (!held) {
-          if (k > 0) {
-            mbar_wait(tok_other, tpar);
-            tpar ^= 1u;
-          }
-          held = true;
-        }
-      };
-      bool last_round = false;
-      while (!last_round) {
-        mbar_wait(full_w + ws * 8, wpar);
-        const unsigned char* slot = ring + ws * RING_SLOT_BYTES;
-        const PlanRound* pr = reinterpret_cast<const PlanRound*>(slot + WPERM_BYTES);
-        const double* wp = reinterpret_cast<const double*>(slot) + lane;
-        const uint16_t* offp = &pr->off[0][lane];
-        const unsigned meta = pr->meta[lane];
-        const int wb = (int)pr->win;
-        const unsigned flags = pr->flags;
-        last_round = (flags & 2u) != 0;
-        const int want = (vg << 16) | wb;
-        if (new_piece || !(flags & 4u) || *state != want) {
-          // (warp-uniform) not provably on the state this round needs: take the turn first
-          acquire();
-          const int cur = *state;
-          if (cur != want) {
-            if (cur >= 0) window_store(piece_ptr(cur >> 16), cur & 0xFFFF);
-            if (cur < 0 || (cur >> 16) != vg) begin_piece(vg);
-            window_load(piece_ptr(vg), vg, wb);
-          }
-          new_piece = false;
-        }
-        const unsigned g = meta & 0xFFFu;
-        const bool used = g != NO_G;
-        const int e = used ? min(max((int)g - wb, 0), WIN - 1) : 0;  // the plan keeps g inside the window
-        double s1 = 0.0;
-        if (s1_duty) {
-#pragma unroll
-          for (int kk = 0; kk < SLOTS; ++kk) s1 += wp[kk * 32];
-        }
-        double s0[RPW] = {};
-        int upd = 0;
-        if (active[0]) {
-          unsigned lowb[RPW], span[RPW];
-          unsigned long long* mk[RPW];
-#pragma unroll
-          for (int r = 0; r < RPW; ++r) {
-            const uint2 b = mmb[r * WIN + e];
-            lowb[r] = used ? b.x : 0u;  // unused lanes accept everything: no exact path
-            span[r] = used ? b.y : 0xFFFFFFFFu;
-            mk[r] = mmk + (r * WIN + e) * 2;
-          }
-          if (active[RPW - 1]) {
-            rows_slots4<FKIND, RPW>(s0, upd, stage, offp, wp, lowb, span, mk, used, p.tc64, tab, lane_off);
-          } else {
-            double s01[1] = {0.0};
-            const unsigned char* st1[1] = {stage[0]};
-            const unsigned lb1[1] = {lowb[0]}, sp1[1] = {span[0]};
-            unsigned long long* mk1[1] = {mk[0]};
-            rows_slots4<FKIND, 1>(s01, upd, st1, offp, wp, lb1, sp1, mk1, used, p.tc64, tab, lane_off);
-            s0[0] = s01[0];
-          }
-        }
-        acquire();
-        if (used) {
-          if (active[0]) {
-            double2 v = ent[e * 32 + lane];
-            v.x += s0[0];
-            v.y += s0[RPW - 1];
-            ent[e * 32 + lane] = v;
-          }
-          if (s1_duty) s1e[e * 32 + lane] += s1;
-        }
-        if (__any_sync(0xffffffffu, upd != 0)) {
-          __syncwarp();  // the other lanes' atomics on the keys are visible
-          refresh_bounds();
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty_w + ws * 8);
-        if (++ws == NSW) {
-          ws = 0;
-          wpar ^= 1u;
-        }
-      }
-      if (k == niter - 1) {  // the last visit of the CTA: fold what the pair still holds
-        const int cur = *state;
-        if (cur >= 0) window_store(piece_ptr(cur >> 16), cur & 0xFFFF);
-      }
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(tok_mine);                    // visit k is over: the other warp may take its turn
-        if (active[0]) mbar_arrive(my_empty);     // the stage set may be refilled
-      }
-    } else {
-      // the other warp's visit: skip its rounds in the ring bookkeeping
-      const int nr = (int)(p.round_off[q.c + 1] - p.round_off[q.c]);
-      ws += nr;
-      while (ws >= NSW) {
-        ws -= NSW;
-        wpar ^= 1u;
-      }
-      new_piece = false;  // whatever state the next visit needs, its round will see the mismatch
-    }
-    if (cursor_next(q, p.ngroups, p.cw, nchunks)) {
-      ++vg;
-      need_group = true;
-      new_piece = true;
-    }
-  }
 }
 
 // ------------------------------------------------------------------ combine + finalize
@@ -2535,9 +1585,7 @@ template <int FKIND, int WMODE, int GEN>
 static cudaError_t launch_reduce_t(ecckd_ctx* ctx, ReduceParams& p, int threads, size_t smem, int* ncta_out,
                                    bool dry_run) {
   void (*kernel)(const ReduceParams) = nullptr;
-  if constexpr (GEN == 4) kernel = reduce4_kernel<FKIND, WMODE>;
-  else if constexpr (GEN == 3) kernel = reduce3_kernel<FKIND, WMODE>;
-  else if constexpr (GEN == 2) kernel = reduce2_kernel<FKIND, WMODE>;
+  if constexpr (GEN == 2) kernel = reduce2_kernel<FKIND, WMODE>;
   else kernel = reduce_kernel<FKIND, WMODE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -2566,22 +1614,6 @@ static bool reduce2_supports(int fkind) {
 }
 static cudaError_t launch_reduce(int fkind, int wmode, int gen, ecckd_ctx* ctx, ReduceParams& p, int threads,
                                  size_t smem, int* ncta, bool dry) {
-  if (gen == 4) {
-    switch (fkind) {
-      case F_LINEAR: return launch_reduce_w<F_LINEAR, 4>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_TRANS: return launch_reduce_w<F_TRANS, 4>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_SQRT: return launch_reduce_w<F_SQRT, 4>(wmode, ctx, p, threads, smem, ncta, dry);
-      default: return launch_reduce_w<F_NONE, 4>(wmode, ctx, p, threads, smem, ncta, dry);
-    }
-  }
-  if (gen == 3) {
-    switch (fkind) {
-      case F_LINEAR: return launch_reduce_w<F_LINEAR, 3>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_TRANS: return launch_reduce_w<F_TRANS, 3>(wmode, ctx, p, threads, smem, ncta, dry);
-      case F_SQRT: return launch_reduce_w<F_SQRT, 3>(wmode, ctx, p, threads, smem, ncta, dry);
-      default: return launch_reduce_w<F_NONE, 3>(wmode, ctx, p, threads, smem, ncta, dry);
-    }
-  }
   if (gen == 2) {
     switch (fkind) {
       case F_LINEAR: return launch_reduce_w<F_LINEAR, 2>(wmode, ctx, p, threads, smem, ncta, dry);
@@ -2624,9 +1656,9 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   }
   const size_t smem_max = ctx->smem_optin ? ctx->smem_optin : (size_t)227 * 1024;
   // Kernel generation: windowed plans and the kinds without per-row weight sums run on
-  // reduce3_kernel (one row per consumer warp), everything else on reduce_kernel (two rows per warp,
-  // shuffle fold).  ECCKD_REDUCE_GEN=1|2|3|4 forces an older generation where it applies (comparisons).
-  int gen = (plan->windowed && reduce2_supports(fkind)) ? 4 : 1;
+  // reduce2_kernel, everything else on reduce_kernel (shuffle fold, per-row weight sums).
+  // ECCKD_REDUCE_GEN=1 forces reduce_kernel (comparisons).
+  int gen = (plan->windowed && reduce2_supports(fkind)) ? 2 : 1;
   if (const char* env = getenv("ECCKD_REDUCE_GEN")) {
     const int want = atoi(env);
     if (want >= 1 && want < gen) gen = want;
@@ -2635,13 +1667,11 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     if (!plan->legacy) ECCKD_TRY(::plan_create_impl(ctx, plan->d_g_copy, plan->nwav, plan->ng, true, &plan->legacy));
     plan = plan->legacy;
   }
-  const int rpw = (gen == 3) ? 1 : RPW;
+  const int rpw = RPW;
   auto smem_of = [&](int n) {
-    return gen == 4 ? (size_t)smem4_layout(n).total
-                    : gen == 3 ? (size_t)smem3_layout(n).total
-                               : (gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total);
+    return gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total;
   };
-  int nw = std::min(gen == 3 ? NW3_MAX : NW_MAX, (longest + rpw - 1) / rpw);
+  int nw = std::min(NW_MAX, (longest + rpw - 1) / rpw);
   while (nw > 1 && smem_of(nw) > smem_max) --nw;
   ECCKD_REQUIRE(smem_of(nw) <= smem_max, ECCKD_PARAMETER_ERROR,
                 "average_optical_depth: ng = %d needs %zu B of shared memory (limit %zu)", ng, smem_of(nw), smem_max);
@@ -2670,7 +1700,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     i = j;
   }
   const int ngroups = (int)groups.size();
-  const int threads = gen == 4 ? (2 * nw + NPW + 1) * 32 : (nw + NPW + (gen == 3 ? 1 : 0)) * 32;
+  const int threads = (nw + NPW) * 32;
   const size_t smem = smem_of(nw);
 
   ReduceParams rp;

@@ -9,6 +9,7 @@ namespace ecckd {
 constexpr int SLOTS = 16;          // plan slots per lane per round
 constexpr int CH_MAX = 480;        // longest chunk (wavenumbers); chunk bytes stay a multiple of 16
 constexpr int STAGE_BYTES = CH_MAX * 8;
+constexpr int STAGE3_BYTES = STAGE_BYTES + 16;  // room for the 8-byte shift of a row that is not 16-byte aligned
 constexpr int RPW = 2;             // rows per consumer warp (they share the lane's offsets and weights)
 constexpr int NSETS = 2;           // stage sets per consumer warp: chunk visit k uses set k & 1
 constexpr int NSW = 4;             // ring slots of (weight tile, plan round) per CTA

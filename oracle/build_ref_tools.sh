@@ -17,10 +17,10 @@ OBJS=""
 for u in average_optical_depth planck_function radiative_transfer_lw radiative_transfer_sw single_gas_data \
          calc_cost_function_lw calc_cost_function_sw ckd_model read_spectrum read_merged_spectrum write_order \
          equipartition; do
-  g++ $FLAGS -c "$REF/src/ecckd/$u.cpp" -o "$OUT/tools_obj/$u.o" &
+  g++ $FLAGS -fopenmp -c "$REF/src/ecckd/$u.cpp" -o "$OUT/tools_obj/$u.o" &
   OBJS="$OBJS $OUT/tools_obj/$u.o"
 done
-for t in run_ckd create_look_up_table reorder_spectrum find_g_points; do
+for t in run_ckd create_look_up_table reorder_spectrum; do
   g++ $FLAGS -Dmain=ref_main_$t -c "$REF/src/ecckd/$t.cpp" -o "$OUT/tools_obj/main_$t.o" &
   OBJS="$OBJS $OUT/tools_obj/main_$t.o"
 done
@@ -32,7 +32,10 @@ gcc -O2 -fPIC -I"$HERE/ref_mock" -I"$REF/src/include" -c "$REF/src/tools/readcon
 OBJS="$OBJS $OUT/tools_obj/readconfig.o"
 g++ $FLAGS -c "$HERE/ref_mock/mock_files.cpp" -o "$OUT/tools_obj/mock_files.o" &
 g++ $FLAGS -c "$HERE/ref_tools_glue.cpp" -o "$OUT/tools_obj/ref_tools_glue.o" &
+# find_g_points.cpp is compiled through the glue that includes it (its fit functions and the
+# CkdEquipartition class have no header)
+g++ $FLAGS -fopenmp -c "$HERE/ref_tools_fgp_glue.cpp" -o "$OUT/tools_obj/ref_tools_fgp_glue.o" &
 wait
-g++ -shared -o "$OUT/libecckd_ref_tools.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/mock_files.o" $OBJS
+g++ -shared -fopenmp -o "$OUT/libecckd_ref_tools.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/ref_tools_fgp_glue.o" "$OUT/tools_obj/mock_files.o" $OBJS
 rm -rf "$OUT/tools_obj"
 echo "built $OUT/libecckd_ref_tools.so"

@@ -1,6 +1,6 @@
 """The generations of the streaming reduction kernel behind ecckd_average_optical_depth_*
-(average_optical_depth.cpp:22-197): reduce3_kernel / reduce2_kernel on windowed plans and
-reduce_kernel on free and on windowed plans must all match the oracle on the same inputs, agree
+(average_optical_depth.cpp:22-197): reduce2_kernel on windowed (balanced) plans and reduce_kernel
+on free plans must both match the oracle on the same inputs, agree
 with each other, and be bitwise reproducible whatever the launch geometry knobs say (stress of the
 mbarrier / bulk-copy pipelines: many tiny chunks, several wavenumber windows, repeated launches,
 rows that are not 16-byte aligned, odd lengths)."""
@@ -20,7 +20,7 @@ def _planck(O, c):
 
 
 # (plan kind, kernel generation): free plan + reduce_kernel, windowed plan + each generation
-GENS = [("0", "1"), ("1", "1"), ("1", "2"), ("1", "3"), ("1", "4")]
+GENS = [("0", "1"), ("1", "1"), ("1", "2")]
 
 
 def _select(monkeypatch, gen):
