@@ -632,7 +632,7 @@ __device__ __forceinline__ bool cursor_next(Cursor& q, int ngroups, int cw, int 
 template <int WMODE>
 __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Cursor first, const int niter, const int pw,
                                                const int lane, unsigned char* ring, const unsigned ring_s,
-                                               const unsigned full_w, const unsigned empty_w) {
+                                               const unsigned full_w, const unsigned empty_w, const int nsw = NSW) {
   const int nchunks = (int)p.nchunks;
   const int ch = p.ch;
   // ===================== producers: permuted weights + plan record of every round =====================
@@ -716,7 +716,7 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
     }
     unsigned char* slot = ring + ws * RING_SLOT_BYTES;
     double* wperm = reinterpret_cast<double*>(slot);
-    if (filled >= NSW) mbar_wait(empty_w + ws * 8, epar);
+    if (filled >= nsw) mbar_wait(empty_w + ws * 8, epar);
 #pragma unroll
     for (int m = 0; m < PER; ++m) {
       const int k = pw + NPW * m;
@@ -735,9 +735,9 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
       }
     }
     ++filled;
-    if (++ws == NSW) {
+    if (++ws == nsw) {
       ws = 0;
-      if (filled > NSW) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
+      if (filled > nsw) epar ^= 1u;  // the first pass over the ring needs no wait; parity 0 comes first
     }
     e0 = e1;
     e1 = e2;
@@ -1011,18 +1011,20 @@ struct Smem2Layout {
   int mmb;   // [nw][RPW][WIN] uint2 {lowb, span} of the range check (reduce_rows.cuh)
   int total;
 };
-__host__ __device__ inline Smem2Layout smem2_layout(int nw) {
+// nsw ring slots, stage_bytes per row chunk (chunk length of the plan x 8 + 16: a plan with shorter
+// chunks leaves room for a deeper ring)
+__host__ __device__ inline Smem2Layout smem2_layout(int nw, int nsw, int stage_bytes) {
   Smem2Layout L;
   int off = 0;
   L.tab = off;
   off += TRANS_TAB64_BYTES;
   L.bars = off;
-  off += (nw * NSETS + 2 * NSW) * 8;
+  off += (nw * NSETS + 2 * nsw) * 8;
   off = (off + 127) & ~127;
   L.ring = off;
-  off += NSW * RING_SLOT_BYTES;
+  off += nsw * RING_SLOT_BYTES;
   L.data = off;
-  off += nw * NSETS * RPW * STAGE3_BYTES;
+  off += nw * NSETS * RPW * stage_bytes;
   L.ent = off;
   off += nw * WIN * 32 * 16;
   L.s1e = off;
@@ -1073,17 +1075,18 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nw = p.nw, ng = p.ng;
-  const Smem2Layout L = smem2_layout(nw);
+  const int nsw = p.nsw, stage_bytes = p.stage_bytes;
+  const Smem2Layout L = smem2_layout(nw, nsw, stage_bytes);
   const unsigned sbase = smem_u32(smem_raw);
   const unsigned full_d = sbase + L.bars;         // mbarriers [nw][NSETS], 8 bytes each
   const unsigned full_w = full_d + nw * NSETS * 8; // [NSW]
-  const unsigned empty_w = full_w + NSW * 8;       // [NSW]
+  const unsigned empty_w = full_w + nsw * 8;       // [nsw]
   unsigned char* ring = smem_raw + L.ring;
   constexpr bool USES_TAU = (FKIND != F_NONE);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nw * NSETS; ++i) mbar_init(full_d + i * 8, 1);
-    for (int i = 0; i < NSW; ++i) {
+    for (int i = 0; i < nsw; ++i) {
       mbar_init(full_w + i * 8, NPW);
       mbar_init(empty_w + i * 8, nw);
     }
@@ -1105,15 +1108,15 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
 
   if (warp >= nw) {
-    produce_rounds<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w);
+    produce_rounds<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w, nsw);
     return;
   }
 
   // ===================== consumers: warp = RPW rows of the group =====================
   const TransLane tl = {0, 0};  // (only the logarithmic kinds of reduce_kernel use the lane table)
-  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * STAGE3_BYTES;
+  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * stage_bytes;
   const unsigned my_full = full_d + warp * NSETS * 8;
-  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * STAGE3_BYTES;
+  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * stage_bytes;
   double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
   double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
   double2* mmv = reinterpret_cast<double2*>(smem_raw + L.mmv) + warp * RPW * WIN;
@@ -1236,7 +1239,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         mbar_arrive_expect_tx(bar, total);
 #pragma unroll
         for (int r = 0; r < RPW; ++r)
-          if (src_i[r]) bulk_g2s_hint(my_data + (set * RPW + r) * STAGE3_BYTES, src_i[r] - shift[r], bytes[r], bar, pol);
+          if (src_i[r]) bulk_g2s_hint(my_data + (set * RPW + r) * stage_bytes, src_i[r] - shift[r], bytes[r], bar, pol);
       }
     }
     if (++qi.c < qi.c_end) {
@@ -1281,7 +1284,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
       a[r].span = used ? b.y : 0xFFFFFFFFu;
       il[r] = false;
     }
-    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off, STAGE3_BYTES);
+    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off, stage_bytes);
     if (used) {
       double2 v = ent[e * 32 + lane];
       if (NR > 1) {
@@ -1345,7 +1348,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         if (used) s1e[e * 32 + lane] += s;
       }
       if (USES_TAU && active[0]) {
-        const unsigned char* stage0 = data + (set * RPW) * STAGE3_BYTES + shift_c[0];
+        const unsigned char* stage0 = data + (set * RPW) * stage_bytes + shift_c[0];
         // (both rows of a pair have the same alignment in every caller of this library: spectra are
         // [layer][nwav] arrays with one stride; a pair with different parities takes the single-row form twice)
         if (active[RPW - 1] && shift_c[RPW - 1] == shift_c[0]) {
@@ -1353,12 +1356,12 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         } else {
           round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used, 0);
           if (active[RPW - 1])
-            round_rows(std::integral_constant<int, 1>{}, data + (set * RPW + 1) * STAGE3_BYTES + shift_c[RPW - 1], offp, wp, e, used, 1);
+            round_rows(std::integral_constant<int, 1>{}, data + (set * RPW + 1) * stage_bytes + shift_c[RPW - 1], offp, wp, e, used, 1);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_w + ws * 8);
-      if (++ws == NSW) {
+      if (++ws == nsw) {
         ws = 0;
         wpar ^= 1u;
       }
@@ -1668,8 +1671,9 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     plan = plan->legacy;
   }
   const int rpw = RPW;
+  const int stage2 = plan->ch * 8 + 16;  // reduce2_kernel: row-chunk stage incl. the 8-byte shift of unaligned rows
   auto smem_of = [&](int n) {
-    return gen == 2 ? (size_t)smem2_layout(n).total : (size_t)smem_layout(n, ng).total;
+    return gen == 2 ? (size_t)smem2_layout(n, NSW, stage2).total : (size_t)smem_layout(n, ng).total;
   };
   int nw = std::min(NW_MAX, (longest + rpw - 1) / rpw);
   while (nw > 1 && smem_of(nw) > smem_max) --nw;
@@ -1701,7 +1705,12 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   }
   const int ngroups = (int)groups.size();
   const int threads = (nw + NPW) * 32;
-  const size_t smem = smem_of(nw);
+  // reduce2_kernel: as many ring slots as shared memory leaves room for (the ring couples the consumer
+  // warps: a slot is refilled when ALL of them have released it, so its depth is their slack)
+  int nsw = NSW;
+  if (gen == 2)
+    while (nsw < 8 && (size_t)smem2_layout(nw, nsw + 1, stage2).total <= smem_max) ++nsw;
+  const size_t smem = gen == 2 ? (size_t)smem2_layout(nw, nsw, stage2).total : smem_of(nw);
 
   ReduceParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -1714,6 +1723,8 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.round_off = plan->d_round_off;
   rp.rounds = plan->d_rounds;
   rp.balanced = plan->balanced ? 1 : 0;
+  rp.nsw = nsw;
+  rp.stage_bytes = stage2;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;

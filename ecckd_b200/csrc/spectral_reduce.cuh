@@ -107,6 +107,8 @@ struct ReduceParams {
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
   TransConst256 tc256;        // the same for the 256-entry shared-memory table of the consumer warps
   TransConst64 tc64;          // the same for the replicated 64-entry table of reduce2_kernel
+  int nsw;                    // reduce2_kernel: ring slots
+  int stage_bytes;            // reduce2_kernel: bytes of one row-chunk stage (chunk length x 8 + 16)
   int balanced;               // the plan is a balanced one: lane meta bits 12-27 are a slot mask (not a count)
   int debug;                  // timing experiments only (ECCKD_DEBUG): 1 skip the row evaluation, 4 skip only the slot loop
   double* partial;            // [ncta][maxg][nw*RPW][ng][4]

@@ -12,3 +12,6 @@ g++ -O2 -march=native -fopenmp -fPIC -std=c++11 -I"$REF/src/ecckd" \
 if [ -f "$HERE/adept_shim/adept_arrays.h" ] && [ -f "$HERE/ref_glue.cpp" ]; then
   sh "$HERE/build_ref_shim.sh" "$REF"
 fi
+if [ -f "$HERE/ref_mock/mock_files.cpp" ] && [ -f "$HERE/ref_tools_glue.cpp" ]; then
+  sh "$HERE/build_ref_tools.sh" "$REF"
+fi

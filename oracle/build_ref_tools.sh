@@ -5,8 +5,9 @@
 #   * configuration files through the reference's own cfg engine (DataFileEngineCfg.cpp, readconfig.c);
 #   * NetCDF files through the in-memory stand-in oracle/ref_mock/mock_files.cpp (NetCDF is not
 #     installed here);  netcdf.h / config.h stubs in oracle/ref_mock.
-# Every `main` is renamed on the command line (-Dmain=ref_main_<tool>) and called through
-# oracle/ref_tools_glue.cpp.  Nothing is copied out of the reference.  Outputs only into oracle/_ref/.
+# Every tool is compiled with its `main` intact (a function called main returns 0 when control
+# reaches its end; renamed in the source it would not) and the symbol is renamed afterwards
+# (objcopy --redefine-sym main=ref_main_<tool>); the mains are called through oracle/ref_tools_glue.cpp.  Nothing is copied out of the reference.  Outputs only into oracle/_ref/.
 set -e
 REF="$1"
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -21,7 +22,8 @@ for u in average_optical_depth planck_function radiative_transfer_lw radiative_t
   OBJS="$OBJS $OUT/tools_obj/$u.o"
 done
 for t in run_ckd create_look_up_table reorder_spectrum; do
-  g++ $FLAGS -Dmain=ref_main_$t -c "$REF/src/ecckd/$t.cpp" -o "$OUT/tools_obj/main_$t.o" &
+  (g++ $FLAGS -c "$REF/src/ecckd/$t.cpp" -o "$OUT/tools_obj/main_$t.o" &&
+   objcopy --redefine-sym main=ref_main_$t "$OUT/tools_obj/main_$t.o") &
   OBJS="$OBJS $OUT/tools_obj/main_$t.o"
 done
 for u in Logging Error file_manager DataFileEngineCfg; do
@@ -34,7 +36,8 @@ g++ $FLAGS -c "$HERE/ref_mock/mock_files.cpp" -o "$OUT/tools_obj/mock_files.o" &
 g++ $FLAGS -c "$HERE/ref_tools_glue.cpp" -o "$OUT/tools_obj/ref_tools_glue.o" &
 # find_g_points.cpp is compiled through the glue that includes it (its fit functions and the
 # CkdEquipartition class have no header)
-g++ $FLAGS -fopenmp -c "$HERE/ref_tools_fgp_glue.cpp" -o "$OUT/tools_obj/ref_tools_fgp_glue.o" &
+(g++ $FLAGS -fopenmp -c "$HERE/ref_tools_fgp_glue.cpp" -o "$OUT/tools_obj/ref_tools_fgp_glue.o" &&
+ objcopy --redefine-sym main=ref_main_find_g_points "$OUT/tools_obj/ref_tools_fgp_glue.o") &
 wait
 g++ -shared -fopenmp -o "$OUT/libecckd_ref_tools.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/ref_tools_fgp_glue.o" "$OUT/tools_obj/mock_files.o" $OBJS
 rm -rf "$OUT/tools_obj"

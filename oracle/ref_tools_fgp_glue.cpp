@@ -1,21 +1,19 @@
-// ref_tools_fgp_glue.cpp - C ABI over the internals of the reference's find_g_points.cpp and over
-// CkdModel (ckd_model.cpp).
+// ref_tools_fgp_glue.cpp - C ABI over the internals of the reference's find_g_points.cpp.
 //
 // TEST INFRASTRUCTURE ONLY (see oracle/ecckd_oracle.cpp header).  No algorithm is restated here.
 // find_g_points.cpp defines fit_optical_depth_{lw,sw,sw_total_trans} and the class
 // CkdEquipartition (the `calc_error` of the partition search, :206-427) inside the translation
 // unit of the tool's main, with no header; this file therefore INCLUDES that source, where it lies
-// under /root/reference/src/ecckd, with `main` renamed, and wraps
+// under /root/reference/src/ecckd, and wraps
 //   * the three fit functions (:54-204),
 //   * CkdEquipartition::init_lw / init_sw / init_sw_extras + calc_error (:209-405),
 //   * the reference's own partition search Equipartition::equipartition_e / _n
-//     (equipartition.cpp:201-805) driven by that calc_error - the oracle of the batched GPU search,
-//   * CkdModel<false>::calc_optical_depth / calc_planck_function / calc_rayleigh_optical_depth /
-//     calc_rayleigh_molar_scat (ckd_model.cpp:923-1145, ckd_model.h:242-252, 368-385) on a model read
-//     from a mock ckd-definition file (oracle/ref_mock/mock_files.cpp).
-#define main ref_main_find_g_points
+//     (equipartition.cpp:201-805) driven by that calc_error - the oracle of the batched GPU search.
+// (CkdModel is wrapped in ref_tools_glue.cpp: ckd_model.h and single_gas_data.h each define a
+// different SingleGasData and cannot meet in one translation unit.)
+// (its `main` keeps its name here - only a function called main may reach its end without a return -
+// and is renamed to ref_main_find_g_points in the object file by oracle/build_ref_tools.sh)
 #include "find_g_points.cpp"
-#undef main
 
 #include <cstdint>
 
@@ -63,7 +61,7 @@ REF_API int ref_fit_optical_depth_sw(const char* method, int nlay, int64_t n, in
 REF_API int ref_fit_optical_depth_sw_total_trans(int nlay, int64_t n, int64_t i1, int64_t i2, const double* ssi,
                                                  const double* bg_od, const double* od, double* out) {
   return guarded([&]() {
-    Vector r = fit_optical_depth_sw_total_trans((int)i1, (int)i2, vec(ssi, n), mat(od, nlay, n), mat(bg_od, nlay, n));
+    Vector r = fit_optical_depth_sw_total_trans((int)i1, (int)i2, vec(ssi, n), mat(bg_od, nlay, n), mat(od, nlay, n));
     for (int k = 0; k < nlay; ++k) out[k] = r(k);
   });
 }
@@ -152,34 +150,3 @@ REF_API int ref_calc_error_sw(const RefBandSw* b, int nint, const double* bound1
   });
 }
 
-// ---------------------------------------------------------------- CkdModel on a mock ckd-definition file
-REF_API int ref_ckd_calc_optical_depth(const char* file, int igas, int ncol, int nlay, const double* pressure_hl,
-                                       const double* temperature_fl, const double* vmr_fl, int* ng_out, double* od,
-                                       int64_t capacity) {
-  return guarded([&]() {
-    CkdModel<false> model(file);
-    Array3 r = model.calc_optical_depth(igas, mat(pressure_hl, ncol, nlay + 1), mat(temperature_fl, ncol, nlay),
-                                        mat(vmr_fl, ncol, nlay));
-    *ng_out = r.size(2);
-    if ((int64_t)r.size() > capacity) throw 1;
-    for (long k = 0; k < (long)r.size(); ++k) od[k] = r.flat(k);
-  });
-}
-REF_API int ref_ckd_calc_planck_function(const char* file, int64_t n, const double* temperature, double* out,
-                                         int64_t capacity) {
-  return guarded([&]() {
-    CkdModel<false> model(file);
-    Matrix r = model.calc_planck_function(vec(temperature, n));
-    if ((int64_t)r.size() > capacity) throw 1;
-    for (long k = 0; k < (long)r.size(); ++k) out[k] = r.flat(k);
-  });
-}
-REF_API int ref_ckd_calc_rayleigh_optical_depth(const char* file, int ncol, int nlay, const double* pressure_hl,
-                                                double* out, int64_t capacity) {
-  return guarded([&]() {
-    CkdModel<false> model(file);
-    Array3 r = model.calc_rayleigh_optical_depth(mat(pressure_hl, ncol, nlay + 1));
-    if ((int64_t)r.size() > capacity) throw 1;
-    for (long k = 0; k < (long)r.size(); ++k) out[k] = r.flat(k);
-  });
-}
