@@ -11,6 +11,7 @@ wherever a device array is expected.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Optional, Sequence
 
 import numpy as np
@@ -100,6 +101,9 @@ class Context:
         check(_lib.lib().ecckd_ctx_create(device, stream, C.byref(h)))
         self.handle = h.value
         self.device = device
+        # objects created on this context (plans, models, device arrays) hold a pointer to it in the
+        # library: they are closed before the context is, whatever order Python drops them in
+        self._children = weakref.WeakSet()
 
     def set_stream(self, stream: Optional[int]):
         check(_lib.lib().ecckd_ctx_set_stream(self.handle, stream))
@@ -133,6 +137,11 @@ class Context:
 
     def close(self):
         if self.handle:
+            for child in list(self._children):
+                try:
+                    child.close()
+                except Exception:
+                    pass
             _lib.lib().ecckd_ctx_destroy(self.handle)
             self.handle = None
 
@@ -183,6 +192,7 @@ class GPointPlan:
         h = C.c_void_p()
         check(_lib.lib().ecckd_gpoint_plan_create(ctx.handle, _ptr(d_g_point), self.nwav, self.ng, C.byref(h)))
         self.handle = h.value
+        ctx._children.add(self)
 
     def counts(self) -> np.ndarray:
         out = np.zeros(self.ng, dtype=np.int64)
@@ -503,6 +513,7 @@ class CkdModel:
                                                 self.np, self.ng, lpp, tp, 0 if tpl is None else tpl.size, tplp, plp,
                                                 sip, rap, C.byref(h)))
         self.handle = h.value
+        ctx._children.add(self)
 
     def calc_optical_depth_dev(self, igas, ncol, nlay, d_pressure_hl, d_temperature_fl, d_vmr_fl, d_od,
                                accumulate=False):
