@@ -56,7 +56,7 @@ def parse_args():
                          "random: no spectral coherence at all (adversarial)")
     ap.add_argument("--weights", default="planck", choices=["planck", "matrix"])
     ap.add_argument("--method", default="transmission")
-    ap.add_argument("--cpu-log2-nwav", type=int, default=22, help="CPU baseline sample size")
+    ap.add_argument("--cpu-log2-nwav", type=int, default=23, help="CPU arm block size (2^23 = the GPU arm's block)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flux", action="store_true")
@@ -236,6 +236,9 @@ def make_spectrum(torch, wn, nlay, p_hl, seed, vmr):
     for l in range(nlay):  # zeros sprinkled in (exercise the zero-handling branches), row by row to bound memory
         z = torch.rand(wn.numel(), device=dev, generator=gen) < 0.02
         od[l].masked_fill_(z, 0.0)
+        # the CKDMIP spectra files store float32 (merge_spectra.cpp:108) and the reference widens on read:
+        # the float64 values of the real workload are widened floats, and so are these
+        od[l].copy_(od[l].float())
     return od
 
 
@@ -301,9 +304,12 @@ def run_reference(args, rank):
         "unit": "point*layers/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "create_look_up_table LW block: planck_function + average_optical_depth_to_g_point "
-                               f"('{args.method}'), {args.nlay} layers x 2^{args.cpu_log2_nwav} wavenumbers, 64 g points "
-                               "(bounded sample of the 2^23-wavenumber block of BASELINE configs[1])"},
+        "config": {"workload": f"create_look_up_table LW (BASELINE configs[1]), one temperature index: {args.nspec} spectra x "
+                               f"{args.nlay} layers x 2^{args.log2_nwav} wavenumbers per GPU, 64 g points / 13 bands, "
+                               f"'{args.method}', weights={args.weights}, g map={args.gmap}",
+                   "sample": "each step is ONE of the workload's %d spectra blocks (%d layers x 2^%d wavenumbers): "
+                             "planck_function + average_optical_depth_to_g_point, the reference's per-block call pair "
+                             "(create_look_up_table.cpp:320-331)" % (args.nspec, args.nlay, args.cpu_log2_nwav)},
         "cpu_baseline": {"value": value, "unit": "point*layers/s", "cores": cores, "kind": "port",
                          "sample": f"{args.nlay} x 2^{args.cpu_log2_nwav} per step; oracle/ecckd_oracle.cpp "
                                    "(C++/OpenMP restatement incl. the reference's per-g rescans), all host threads"},
@@ -444,81 +450,125 @@ def main():
     except Exception:
         traffic = None
     peak, peak_src = measured_peak_gbs()
+    kernel_name = "reduce_kernel" if os.environ.get("ECCKD_REDUCE_GEN") == "1" or os.environ.get("ECCKD_PLAN_WINDOW") == "0" \
+        or args.method not in ("linear", "transmission", "transmission-2", "transmission-3", "transmission-10", "square-root") \
+        else "reduce2_kernel"
 
-    # ---- end to end through the reference-facing host call (one block per step)
+    # ---- parity of what was just timed, at the full size: block 1 of the batch against the oracle
+    # (planck_function + average_optical_depth_to_g_point on the same arrays, all host threads); the same
+    # oracle run is the cpu_baseline sample, so that baseline and GPU arm are on the SAME block.
+    validated, cpu, oracle_ref = None, None, None
+    host = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests.oracle_lib import oracle
+        from tests import synthetic as S
+        O = oracle()
+        ncores = use_all_host_threads()
+        host = dict(od=ods[1].cpu().numpy(), wn=wn.cpu().numpy(), dwn=dwn.cpu().numpy(), g=g_point.cpu().numpy())
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            planck = O.planck_function(t_fl, host["wn"], host["dwn"])
+            oracle_ref = O.average_optical_depth_to_g_point(ng, vmrs[1], p_fl, p_hl, host["g"], host["od"], planck,
+                                                            args.method)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+            del planck
+        got = (outs[1].cpu().numpy(), mins[1].cpu().numpy(), maxs[1].cpu().numpy(), None)
+        scale = S.out_scale(dict(vmr=vmrs[1], pressure_fl=p_fl, pressure_hl=p_hl))
+        S.assert_avg_close(got, oracle_ref, method=args.method, scale=scale, what="bench output vs oracle: ")
+        fin = np.isfinite(oracle_ref[0]) & (oracle_ref[0] != 0)
+        validated = {"against": "oracle/ecckd_oracle.cpp on the timed step's block 1 (%d x 2^%d x %d g)" % (nlay, args.log2_nwav, ng),
+                     "tolerance": "1e-12 relative (+ the transmission conditioning term, tests/synthetic.py)",
+                     "max_rel_err": float(np.max(np.abs(got[0][fin] - oracle_ref[0][fin]) / np.abs(oracle_ref[0][fin]))),
+                     "min_max_exact": bool(np.array_equal(got[1], oracle_ref[1]) and np.array_equal(got[2], oracle_ref[2]))}
+        cpu = {"value": nlay * nwav / best, "unit": "point*layers/s", "cores": ncores, "kind": "port",
+               "sample": f"one block of the timed workload ({nlay} x 2^{args.log2_nwav}): planck_function + "
+                         f"average_optical_depth_to_g_point, oracle/ecckd_oracle.cpp, OpenMP all threads, {best:.2f} s"}
+
+    # ---- end to end: the create_look_up_table block loop through the C ABI with HOST buffers.
+    # ecckd_lut_builder_* holds the g-point map, its plan and the wavenumber grid on the device (the tool
+    # reads them once per gas); every step is one block: its optical depths go host->device inside the
+    # timed region, its LUT slice comes back.  Two distinct blocks alternate.  `value` is the float32
+    # path (the spectra files store float32; widened on the device, bit-identical), the float64 path and
+    # the one-shot call (map + grid uploaded, plan looked up in the cache every call) are beside it.
     e2e = None
     if not args.no_e2e:
-        h_od = torch.empty((nlay, nwav), dtype=torch.float64, pin_memory=True)
-        h_od.copy_(ods[1])
-        pin = lambda t: torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t)
-        p_wn, p_dwn, p_g = pin(wn), pin(dwn), pin(g_point)  # every input of the call sits in pinned host memory
+        pin = lambda t, dt=None: torch.empty(t.shape, dtype=dt or t.dtype, pin_memory=True).copy_(t)
+        p_wn, p_dwn, p_g = pin(wn), pin(dwn), pin(g_point)
         h_wn, h_dwn, h_g = p_wn.numpy(), p_dwn.numpy(), p_g.numpy()
-        od_np = h_od.numpy()
-        res = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32))
-        for _ in range(2):
-            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od_np, t_fl, h_wn, h_dwn,
-                                                      args.method, out=res)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e2e_steps = max(2, min(args.steps, 5))
-        e0.record()
-        for _ in range(e2e_steps):
-            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od_np, t_fl, h_wn, h_dwn,
-                                                      args.method, out=res)
-        e1.record()
-        barrier()
-        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * nlay * nwav * e2e_steps / (float(ems.item()) * 1e-3), "unit": "point*layers/s",
-               "h2d_bytes_per_step": int(nlay * nwav * 8 + nwav * (8 + 8 + 4)),
-               "d2h_bytes_per_step": int(3 * nlay * ng * 8 + ng * 4),
-               "call": "ecckd_planck_average_optical_depth_to_g_point (one [53][2^%d] block per step, pinned host "
-                       "buffers)" % args.log2_nwav,
-               "ms_per_step": float(ems.item()) / e2e_steps}
-        del h_od, od_np
-        # the same call fed the float32 values the CKDMIP files hold (widened on the device, bit-identical
-        # results): what a front-end reading the spectra files would pass.  Reported beside e2e, not as e2e.
-        h32 = torch.empty((nlay, nwav), dtype=torch.float32, pin_memory=True)
-        h32.copy_(ods[1])
-        od32 = h32.numpy()
-        for _ in range(2):
-            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od32, t_fl, h_wn, h_dwn,
-                                                      args.method, out=res)
-        barrier()
-        e0.record()
-        for _ in range(e2e_steps):
-            E.planck_average_optical_depth_to_g_point(ctx, ng, vmrs[1], p_fl, p_hl, h_g, od32, t_fl, h_wn, h_dwn,
-                                                      args.method, out=res)
-        e1.record()
-        barrier()
-        ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e["float32_spectra"] = {
-            "value": world * nlay * nwav * e2e_steps / (float(ems.item()) * 1e-3), "unit": "point*layers/s",
-            "h2d_bytes_per_step": int(nlay * nwav * 4 + nwav * (8 + 8 + 4)),
-            "call": "ecckd_planck_average_optical_depth_to_g_point_f32 (float32 optical depths as stored in the "
-                    "spectra files, widened on the device)", "ms_per_step": float(ems.item()) / e2e_steps}
-        del h32, od32
+        blocks = [1, 2 % nspec]
+        res = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32),
+               np.zeros(nlay))
+        t_hl_b = temperature_profile(p_hl)
+        builder = E.LutBuilder(ctx, ng, h_g, h_wn, h_dwn)
+        e2e_steps = max(2, min(args.steps, 6))
+
+        def timed(call):
+            for k in range(2):
+                call(k)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(e2e_steps):
+                call(k)
+            e1.record()
+            barrier()
+            ems = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            return float(ems.item()) / e2e_steps
+
+        def check_block(what):
+            if oracle_ref is not None:  # the last call of every timed loop was on block 1
+                from tests import synthetic as S
+                S.assert_avg_close(res[:3] + (None,), oracle_ref, method=args.method,
+                                   scale=S.out_scale(dict(vmr=vmrs[1], pressure_fl=p_fl, pressure_hl=p_hl)),
+                                   what=f"e2e {what} vs oracle: ")
+
+        order = blocks if (e2e_steps - 1) % 2 == 0 else blocks[::-1]  # the last timed call is on block 1
+
+        h32 = [pin(ods[b], torch.float32) for b in blocks]
+        np32 = {b: h.numpy() for b, h in zip(blocks, h32)}
+        ms32 = timed(lambda k: builder.block(vmrs[order[k % 2]], p_hl, t_hl_b, np32[order[k % 2]], args.method, out=res))
+        check_block("float32 builder")
+        res32 = [r.copy() for r in res[:3]]
+        del h32, np32
+        h64 = [pin(ods[b]) for b in blocks]
+        np64 = {b: h.numpy() for b, h in zip(blocks, h64)}
+        ms64 = timed(lambda k: builder.block(vmrs[order[k % 2]], p_hl, t_hl_b, np64[order[k % 2]], args.method, out=res))
+        check_block("float64 builder")
+        same = all(np.array_equal(a, b) for a, b in zip(res32, res[:3]))
+        res1 = res[:4]
+        ms1 = timed(lambda k: E.planck_average_optical_depth_to_g_point(
+            ctx, ng, vmrs[order[k % 2]], p_fl, p_hl, h_g, np64[order[k % 2]], t_fl, h_wn, h_dwn, args.method, out=res1))
+        check_block("one-shot call")
+        builder.close()
+        del h64, np64
+        per = lambda ms: world * nlay * nwav / (ms * 1e-3)
+        e2e = {"value": per(ms32), "unit": "point*layers/s",
+               "h2d_bytes_per_step": int(nlay * nwav * 4), "d2h_bytes_per_step": int(3 * nlay * ng * 8 + ng * 4),
+               "call": "ecckd_lut_builder_block, float32 spectra as the CKDMIP files store them (one [%d][2^%d] block per "
+                       "step from pinned host memory, two blocks alternating; g-point map, plan and wavenumber grid "
+                       "resident in the builder)" % (nlay, args.log2_nwav),
+               "ms_per_step": ms32, "float32_equals_float64_bitwise": bool(same),
+               "float64_spectra": {"value": per(ms64), "unit": "point*layers/s", "ms_per_step": ms64,
+                                   "h2d_bytes_per_step": int(nlay * nwav * 8),
+                                   "call": "ecckd_lut_builder_block, float64 spectra"},
+               "one_shot_call": {"value": per(ms1), "unit": "point*layers/s", "ms_per_step": ms1,
+                                 "h2d_bytes_per_step": int(nlay * nwav * 8 + nwav * 20),
+                                 "call": "ecckd_planck_average_optical_depth_to_g_point (float64; map and grid uploaded "
+                                         "and the cached plan verified every call)",
+                                 "plan_cache_hits_misses": list(ctx.plan_cache_stats())}}
+    host = None
 
     # ---- metric 2: CKD flux columns.g-points/s (run_ckd LW, config A LUT with columns replicated)
     flux = None
     if not args.no_flux and rank == 0:
         try:
-            flux = bench_flux(torch, E, ctx, dev, peak)
+            flux = bench_flux(torch, E, ctx, dev, peak, with_cpu=not args.no_cpu)
         except Exception as exc:  # secondary metric must not hide the primary one
             flux = {"error": repr(exc)}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        sample = CpuSample(args, args.cpu_log2_nwav)
-        sample.run()
-        dt = min(sample.run(), sample.run())
-        v = nlay * sample.nwav / dt
-        cpu = {"value": v, "unit": "point*layers/s", "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"one block of {nlay} x 2^{args.cpu_log2_nwav} (planck_function + "
-                         f"average_optical_depth_to_g_point, oracle/ecckd_oracle.cpp, OpenMP all threads), {dt:.2f} s"}
 
     if rank == 0:
         line = {
@@ -534,9 +584,10 @@ def main():
                 "reduce_partial_bytes_allreduced_per_step": int(sums.numel() * 8 + minmax.numel() * 8) if world > 1 else 0,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "reduce_kernel", "kernel_ms": k_ms, "peak_source": peak_src,
+                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg_bytes)},
             "cpu_baseline": cpu,
+            "validated": validated,
             "e2e": e2e,
             "gpu_launches": int(launches) * world,
             "clocks": clocks,
@@ -548,17 +599,23 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_flux(torch, E, ctx, dev, peak):
-    """CKD flux columns.g-points/s: fused run_ckd LW core on 2^16 columns x 54 layers x 32 g points."""
+def bench_flux(torch, E, ctx, dev, peak, with_cpu=True):
+    """Metric 2, CKD flux columns*g-points/s: the fused run_ckd longwave core (ecckd_run_ckd_dev: total
+    optical depth of 8 gases from the look-up tables, Planck function, flux sweeps, broadband sums;
+    run_ckd.cpp:119-132, 265-356) on 2^16 columns x 54 layers x 32 g points (BASELINE configs[0]'s model with
+    the columns replicated), checked against the oracle, with its own CPU baseline and host-buffer e2e."""
     from tests import synthetic as S
 
-    ncol, nlay, ng = 1 << 16, 54, 32
-    c = S.ckd_model_case(ncol=64, nlay=nlay, ng=ng, seed=1234)
+    ncol, nlay, ng, nbase = 1 << 16, 54, 32, 64
+    c = S.ckd_model_case(ncol=nbase, nlay=nlay, ng=ng, seed=1234)
     model = E.CkdModel(ctx, c["gases"], c["log_pressure"], c["temperature"], c["temperature_planck"], c["planck_lut"])
-    rep = ncol // 64
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a, (rep, 1)))).to(dev)
-    p_hl, t_hl = t(c["pressure_hl"]), t(c["temperature_hl"])
-    vmr = [None if v is None else t(v) for v in c["vmr_fl"]]
+    rep = ncol // nbase
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (rep, 1)))
+    h_p, h_t = tile(c["pressure_hl"]), tile(c["temperature_hl"])
+    h_vmr = [None if v is None else tile(v) for v in c["vmr_fl"]]
+    t = lambda a: torch.from_numpy(a).to(dev)
+    p_hl, t_hl = t(h_p), t(h_t)
+    vmr = [None if v is None else t(v) for v in h_vmr]
     od = torch.empty((ncol, nlay, ng), dtype=torch.float64, device=dev)
     plh = torch.empty((ncol, nlay + 1, ng), dtype=torch.float64, device=dev)
     pls = torch.empty((ncol, ng), dtype=torch.float64, device=dev)
@@ -566,51 +623,110 @@ def bench_flux(torch, E, ctx, dev, peak):
     bdn = torch.empty((ncol, nlay + 1), dtype=torch.float64, device=dev)
     bup = torch.empty_like(bdn)
     run = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls, dn, up, bdn, bup)
-    for _ in range(3):
-        run()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
-    e0.record()
-    for _ in range(n):
-        run()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / n
-    bytes_per = 8 * (54 + 3 * 55) + 8  # 1760 B per column.g-point
-    # the flux solver proper (radiative_transfer_lw.cpp:25-60) on resident optical depth and Planck
-    # arrays: the HBM-bound kernel the 1760 B figure describes
+
+    def timed(fn, n=10, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    launches0 = ctx.kernel_launches
+    run()
+    launches = ctx.kernel_launches - launches0
+    ms = timed(run)
+    bytes_per = 8 * (54 + 3 * 55) + 8  # 1760 B per column.g-point (OD, Planck, two fluxes written once)
+
+    # parity of the timed output: the first replica against the oracle's run_ckd, every replica against the first
+    from tests.oracle_lib import oracle
+    O = oracle()
+    ref = O.run_ckd(c, is_sw=False)
+    got = {"optical_depth": od, "planck_hl": plh, "flux_dn": dn, "flux_up": up, "bb_flux_dn": bdn, "bb_flux_up": bup}
+    worst = {}
+    for k, arr in got.items():
+        a = arr[:nbase].cpu().numpy()
+        if k == "optical_depth":
+            np.testing.assert_allclose(a, ref[k], rtol=2e-11, atol=1e-18)
+            worst[k + "_rel"] = float(np.max(np.abs(a - ref[k]) / np.maximum(np.abs(ref[k]), 1e-300)))
+        elif k == "planck_hl":
+            np.testing.assert_allclose(a, ref[k], rtol=1e-14)
+        else:
+            err = float(np.max(np.abs(a - ref[k])))
+            assert err <= 1e-6, (k, err)  # north_star: fluxes within 1e-6 W m-2
+            worst[k + "_abs_W_m2"] = err
+        assert torch.equal(arr.view(rep, nbase, *arr.shape[1:])[-1], arr[:nbase]), k
+    validated = {"against": "oracle run_ckd on the %d base columns; the %d replicas bitwise equal" % (nbase, rep), **worst}
+
+    # the flux solver alone (radiative_transfer_lw.cpp:25-60) on resident optical depth and Planck arrays
     emis = torch.ones(ng, dtype=torch.float64, device=dev)
-    rt = lambda: E.radiative_transfer_lw_dev(ctx, ncol, nlay, ng, plh, od, emis, pls, dn, up)
-    for _ in range(3):
-        rt()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(n):
-        rt()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_rt = e0.elapsed_time(e1) / n
+    ms_rt = timed(lambda: E.radiative_transfer_lw_dev(ctx, ncol, nlay, ng, plh, od, emis, pls, dn, up))
     gbs_rt = ncol * ng * bytes_per / (ms_rt * 1e-3) / 1e9
-    rt_traffic = None
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "flux_traffic.json")))
-        if (t["workload"]["ncol"], t["workload"]["nlay"], t["workload"]["ng"]) == (ncol, nlay, ng):
-            rt_traffic = t["dram_bytes_per_launch"]
-    except Exception:
-        rt_traffic = None
-    return {"metric": "CKD flux columns*g-points/s", "value": ncol * ng / (ms_rt * 1e-3), "unit": "column*g-points/s",
-            "ms_per_step": ms_rt,
-            "config": f"radiative_transfer_lw (flux solver), {ncol} columns x {nlay} layers x {ng} g points, optical depth "
-                      "and Planck arrays resident",
-            "roofline": {"bound": "hbm", "achieved": gbs_rt, "peak": peak, "unit": "GB/s", "frac": gbs_rt / peak, "traffic": rt_traffic,
-                         "kernel": "rt_lw_staged_kernel", "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
-            "fused_run_ckd": {"value": ncol * ng / (ms * 1e-3), "unit": "column*g-points/s", "ms_per_step": ms,
-                              "config": "run_ckd LW core (ecckd_run_ckd_dev): full-level temperature, LUT interpolation of 8 "
-                                        "gases (36 LUT rows per layer.g point gathered through L1/L2), clamp, Planck "
-                                        "interpolation, then the staged flux solver and the sums over g; bound by the "
-                                        "latency of the LUT gathers (288 B per optical depth), not by HBM",
-                              "hbm_GBps_of_its_outputs": ncol * ng * bytes_per / (ms * 1e-3) / 1e9}}
+    # optical depth + Planck function alone (no sweep): bytes written 8*(54+55+1) per column.g-point + inputs
+    ms_od = timed(lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls))
+    od_bytes = ncol * ng * 8 * (nlay + nlay + 2) + ncol * 8 * (2 * (nlay + 1) + 7 * nlay)
+
+    # CPU baseline: the oracle's run_ckd (a scalar restatement, like the reference's serial column loop,
+    # run_ckd.cpp:347) on every host thread, columns dealt out in chunks of 64
+    cpu = None
+    if with_cpu:
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = os.cpu_count() or 1
+        nchunk = max(nthr * 2, 8)
+        one = lambda _: O.run_ckd(c, is_sw=False)
+        with ThreadPoolExecutor(nthr) as ex:
+            list(ex.map(one, range(nthr)))
+            t0 = time.perf_counter()
+            list(ex.map(one, range(nchunk)))
+            dt = time.perf_counter() - t0
+        cpu = {"value": nchunk * nbase * ng / dt, "unit": "column*g-points/s", "cores": nthr, "kind": "port",
+               "sample": f"{nchunk} chunks of {nbase} columns x {nlay} layers x {ng} g points through oracle run_ckd "
+                         f"(orc_run_ckd, scalar per call) on {nthr} threads, {dt:.2f} s"}
+
+    # end to end: ecckd_run_ckd with HOST arrays (profiles and 7 concentration arrays up; optical depth, Planck
+    # function, spectral and broadband fluxes down), pinned
+    pinned = lambda a: torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+    hp, ht = pinned(h_p), pinned(h_t)
+    hp.copy_(torch.from_numpy(h_p))
+    ht.copy_(torch.from_numpy(h_t))
+    hv = []
+    for v in h_vmr:
+        if v is None:
+            hv.append(None)
+        else:
+            b = pinned(v)
+            b.copy_(torch.from_numpy(v))
+            hv.append(b.numpy())
+    outs = {"optical_depth": pinned(od), "planck_hl": pinned(plh), "planck_surf": pinned(pls), "flux_dn": pinned(dn),
+            "flux_up": pinned(up), "bb_flux_dn": pinned(bdn), "bb_flux_up": pinned(bup)}
+    outs_np = {k: v.numpy() for k, v in outs.items()}
+    ms_e2e = timed(lambda: model.run_ckd(hv, hp.numpy(), ht.numpy(), out=outs_np), n=3, warm=1)
+    assert np.array_equal(outs_np["flux_up"][:nbase], up[:nbase].cpu().numpy())
+    h2d = sum(a.nbytes for a in [h_p, h_t] + [v for v in h_vmr if v is not None])
+    d2h = sum(v.numel() * 8 for v in outs.values())
+    model.close()
+
+    rate = lambda m: ncol * ng / (m * 1e-3)
+    gbs = ncol * ng * bytes_per / (ms * 1e-3) / 1e9
+    return {"metric": "CKD flux columns*g-points/s", "value": rate(ms), "unit": "column*g-points/s", "ms_per_step": ms,
+            "higher_is_better": True, "dtype": "f64", "gpu_launches": int(launches),
+            "config": {"workload": f"run_ckd LW core, fused (ecckd_run_ckd_dev): {ncol} columns x {nlay} layers x {ng} g points, "
+                                   "8 gases (BASELINE configs[0] model, its columns replicated); inputs resident"},
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                         "traffic": None, "kernel": "total_od_planck_kernel + rt_lw_staged_kernel (whole fused call)",
+                         "algorithmic_bytes_per_launch": int(ncol * ng * bytes_per)},
+            "validated": validated,
+            "cpu_baseline": cpu,
+            "e2e": {"value": rate(ms_e2e), "unit": "column*g-points/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "call": "ecckd_run_ckd (host arrays, pinned)"},
+            "parts": {"optical_depth_and_planck": {"ms": ms_od, "GBps": od_bytes / (ms_od * 1e-3) / 1e9,
+                                                   "kernel": "total_od_planck_kernel"},
+                      "flux_sweep": {"ms": ms_rt, "GBps": gbs_rt, "frac": gbs_rt / peak, "kernel": "rt_lw_staged_kernel",
+                                     "note": "radiative_transfer_lw on resident optical depth and Planck arrays"}}}
 
 
 if __name__ == "__main__":

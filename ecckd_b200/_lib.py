@@ -108,6 +108,10 @@ def _declare(L):
                                                               C.c_char_p, vp, vp, vp, i64, vp],
         "ecckd_create_lut_block": [vp, i32, dbl, i32, i64, vp, vp, vp, vp, i64, vp, vp, vp, C.c_char_p, vp, vp, vp, vp,
                                    i64, vp],
+        "ecckd_lut_builder_create": [vp, i32, i64, vp, vp, vp, vp, vp],
+        "ecckd_lut_builder_block": [vp, dbl, i32, vp, vp, vp, vp, i64, C.c_char_p, vp, vp, vp, vp, i64, vp],
+        "ecckd_lut_builder_destroy": [vp],
+        "ecckd_ctx_plan_cache_stats": [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],

@@ -135,6 +135,12 @@ class Context:
     def kernel_launches(self) -> int:
         return int(_lib.lib().ecckd_kernel_launch_count(self.handle))
 
+    def plan_cache_stats(self):
+        """(hits, misses) of the host-array entry points' g-point plan cache."""
+        h, m = C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().ecckd_ctx_plan_cache_stats(self.handle, C.byref(h), C.byref(m)))
+        return int(h.value), int(m.value)
+
     def close(self):
         if self.handle:
             for child in list(self._children):
@@ -312,6 +318,57 @@ def create_lut_block(ctx: Context, ng, reference_surface_vmr, pressure_hl, tempe
         sp, averaging_method.encode(), t_fl.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
         out[3].ctypes.data))
     return out + (t_fl,)
+
+
+class LutBuilder:
+    """ecckd_lut_builder: the state of the create_look_up_table block loop on the device
+    (create_look_up_table.cpp:249-591) - g-point map, its plan and the wavenumber grid (longwave) or the
+    solar spectrum (shortwave) are uploaded once; block() then moves only that block's optical depths.
+    float32 optical depths (what the spectra files store) are widened on the device."""
+
+    def __init__(self, ctx: Context, ng, g_point, wavenumber_cm_1=None, d_wavenumber_cm_1=None, ssi=None):
+        self.ctx, self.ng, self.handle = ctx, int(ng), None
+        gp = np.ascontiguousarray(g_point, dtype=np.int32)
+        self.nwav = gp.size
+        wn, wnp = _h(wavenumber_cm_1)
+        dwn, dwnp = _h(d_wavenumber_cm_1)
+        s, sp = _h(ssi)
+        h = C.c_void_p()
+        check(_lib.lib().ecckd_lut_builder_create(ctx.handle, self.ng, self.nwav, gp.ctypes.data, wnp, dwnp, sp,
+                                                  C.byref(h)))
+        self.handle = h.value
+        ctx._children.add(self)
+
+    def block(self, reference_surface_vmr, pressure_hl, temperature_hl, optical_depth, averaging_method, out=None):
+        """-> (molar_abs, min, max, warn, temperature_fl); optical_depth [nlay][nwav] float64 or float32."""
+        od = np.asarray(optical_depth)
+        f32 = od.dtype == np.float32
+        od = np.ascontiguousarray(od, dtype=np.float32 if f32 else np.float64)
+        nlay, nwav = od.shape
+        if nwav != self.nwav:
+            raise EcckdError(147, "optical_depth does not match the builder's wavenumber grid")
+        ph, php = _h(pressure_hl)
+        th, thp = _h(temperature_hl)
+        ng = self.ng
+        if out is None:
+            out = (np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros((nlay, ng)), np.zeros(ng, dtype=np.int32),
+                   np.zeros(nlay))
+        check(_lib.lib().ecckd_lut_builder_block(
+            self.handle, float(reference_surface_vmr), nlay, php, thp, None if f32 else od.ctypes.data,
+            od.ctypes.data if f32 else None, nwav, averaging_method.encode(), out[4].ctypes.data, out[0].ctypes.data,
+            out[1].ctypes.data, out[2].ctypes.data, ng, out[3].ctypes.data))
+        return out
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_lut_builder_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def average_optical_depth_to_g_point_dev(ctx: Context, plan: GPointPlan, reference_surface_vmr, pressure_fl,
@@ -543,19 +600,28 @@ class CkdModel:
         check(_lib.lib().ecckd_calc_total_optical_depth_dev(self.ctx.handle, self.handle, p, ncol, nlay,
                                                             _ptr(d_pressure_hl), _ptr(d_temperature_hl), _ptr(d_od)))
 
-    def run_ckd(self, vmr_fl: Sequence[Optional[np.ndarray]], pressure_hl, temperature_hl, tsi=1361.0):
-        """Numerical core of run_ckd (run_ckd.cpp:119-367) on host arrays -> dict of outputs."""
+    def run_ckd(self, vmr_fl: Sequence[Optional[np.ndarray]], pressure_hl, temperature_hl, tsi=1361.0, out=None):
+        """Numerical core of run_ckd (run_ckd.cpp:119-367) on host arrays -> dict of outputs (written into
+        the C-contiguous float64 arrays of `out` when given, e.g. pinned buffers)."""
         ph = np.ascontiguousarray(pressure_hl, dtype=np.float64)
         th = np.ascontiguousarray(temperature_hl, dtype=np.float64)
         ncol, nhl = ph.shape
         nlay, ng = nhl - 1, self.ng
         keep = [None if v is None else np.ascontiguousarray(v, dtype=np.float64) for v in vmr_fl]
         arr = (C.c_void_p * len(keep))(*[None if v is None else v.ctypes.data for v in keep])
-        out = {"optical_depth": np.zeros((ncol, nlay, ng)), "flux_dn": np.zeros((ncol, nhl, ng)),
-               "bb_flux_dn": np.zeros((ncol, nhl))}
-        if not self.is_sw:
-            out.update(planck_hl=np.zeros((ncol, nhl, ng)), planck_surf=np.zeros((ncol, ng)),
-                       flux_up=np.zeros((ncol, nhl, ng)), bb_flux_up=np.zeros((ncol, nhl)))
+        if out is None:
+            out = {"optical_depth": np.zeros((ncol, nlay, ng)), "flux_dn": np.zeros((ncol, nhl, ng)),
+                   "bb_flux_dn": np.zeros((ncol, nhl))}
+            if not self.is_sw:
+                out.update(planck_hl=np.zeros((ncol, nhl, ng)), planck_surf=np.zeros((ncol, ng)),
+                           flux_up=np.zeros((ncol, nhl, ng)), bb_flux_up=np.zeros((ncol, nhl)))
+        else:
+            shapes = {"optical_depth": (ncol, nlay, ng), "flux_dn": (ncol, nhl, ng), "flux_up": (ncol, nhl, ng),
+                      "planck_hl": (ncol, nhl, ng), "planck_surf": (ncol, ng), "bb_flux_dn": (ncol, nhl),
+                      "bb_flux_up": (ncol, nhl)}
+            for k, a in out.items():
+                if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != shapes[k]:
+                    raise EcckdError(147, f"run_ckd: out[{k!r}] must be a C-contiguous float64 array of shape {shapes[k]}")
         g = lambda k: out[k].ctypes.data if k in out else None
         check(_lib.lib().ecckd_run_ckd(self.ctx.handle, self.handle, C.cast(arr, C.c_void_p).value, float(tsi), ncol,
                                        nlay, ph.ctypes.data, th.ctypes.data, g("optical_depth"), g("planck_hl"),

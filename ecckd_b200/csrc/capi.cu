@@ -184,6 +184,8 @@ ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
   if (!ctx) return ECCKD_OK;
   ECCKD_DEVICE(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->cached_plan) ecckd_gpoint_plan_destroy(ctx->cached_plan);
+  if (ctx->cached_g) cudaFree(ctx->cached_g);
   for (auto& w : ctx->ws) {
     if (w.ptr) cudaFree(w.ptr);
   }
@@ -266,6 +268,13 @@ ECCKD_API int ecckd_memcpy_d2h(ecckd_ctx* ctx, void* h_dst, const void* d_src, s
 }
 
 ECCKD_API int64_t ecckd_kernel_launch_count(ecckd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+ECCKD_API int ecckd_ctx_plan_cache_stats(ecckd_ctx* ctx, int64_t* hits, int64_t* misses) {
+  ECCKD_REQUIRE(ctx, ECCKD_PARAMETER_ERROR, "ecckd_ctx_plan_cache_stats: NULL context");
+  if (hits) *hits = ctx->plan_cache_hits;
+  if (misses) *misses = ctx->plan_cache_misses;
+  return ECCKD_OK;
+}
 
 ECCKD_API int ecckd_ctx_set_timing(ecckd_ctx* ctx, int on) {
   ECCKD_DEVICE(ctx);

@@ -47,6 +47,14 @@ struct ecckd_ctx {
   void* pinned = nullptr;   // small pinned staging buffer for descriptor uploads
   size_t pinned_bytes = 0;
   size_t pinned_off = 0;    // bump offset; wraps after a stream synchronise
+  // Host-buffer entry points keep the plan of the last g-point map they saw (and a device copy of
+  // that map to compare the next call's map with, element for element): the create_look_up_table
+  // block loop passes the same map for every block of a gas.
+  struct ecckd_gpoint_plan* cached_plan = nullptr;
+  int32_t* cached_g = nullptr;
+  int64_t cached_nwav = 0;
+  int cached_ng = 0;
+  int64_t plan_cache_hits = 0, plan_cache_misses = 0;
 };
 
 namespace ecckd {

@@ -765,6 +765,216 @@ __global__ void __launch_bounds__(1024, 1) run_ckd_kernel(const RunCkdParams p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Total optical depth and Planck function of the run_ckd core (run_ckd.cpp:119-132, 265-317;
+// ckd_model.cpp:962-1088, 1105-1145), layer-major with the look-up-table rows held in REGISTERS.
+//
+// The interpolation indices (ip0, it0) of ckd_model.cpp:962-980 belong to the (column, layer), not to
+// the gas: every gas reads the same four corners of its own table.  At one layer the columns of a tile
+// share a handful of (ip0, it0) pairs (pressure at a model level varies little between columns,
+// temperature spans one or two 20 K table intervals), so a warp (lane = g point) takes one layer of a
+// tile of 32 columns, groups the columns by (ip0, it0) with match.any, loads the 4 corner rows of every
+// gas ONCE per group (4 x ngas coalesced row reads into registers) and then produces the optical depth
+// of each column of the group with 5 FMAs per gas and no table read at all.  Gases with a
+// concentration axis (H2O: ckd_model.cpp:1001-1045) read their 8 rows per column, two columns in
+// flight.  The earlier kernel gathered 36 rows per (column, layer); this one ~28/group + 8.
+// Phase A (lane = column) computes everything that does not depend on g once per (column, layer).
+constexpr int TOD_MAXGAS = 8;
+constexpr int TOD_TILE = 32;
+
+struct TodCol {              // g-independent state of one (column, layer), in shared memory per warp
+  double c00, c01, c10, c11; // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
+  double w[TOD_MAXGAS];      // what multiplies the interpolated absorption of each gas
+  double cidx[TOD_MAXGAS];   // LUT gases: clamped concentration index ic0 + cw1
+};
+
+struct TotalOdParams {
+  const double* molar_abs[TOD_MAXGAS];
+  const double* vmr[TOD_MAXGAS];
+  double reference_vmr[TOD_MAXGAS], log_vmr0[TOD_MAXGAS], d_log_c[TOD_MAXGAS];
+  int conc_dependence[TOD_MAXGAS], nconc[TOD_MAXGAS];
+  int ngas, nt, np, ng, nlut;
+  unsigned lut_mask;  // bit ig: gas ig has a concentration axis
+  double log_p_0, d_log_p, d_t, planck_t0, planck_dt;
+  const double* temperature;  // [nt][np]
+  const double* planck_lut;   // [nlut][ng]
+  int ncol, nlay;
+  const double* pressure_hl;
+  const double* temperature_hl;
+  double* od;           // [ncol][nlay][ng]
+  double* planck_hl;    // [ncol][nlay+1][ng] or NULL
+  double* planck_surf;  // [ncol][ng] or NULL
+};
+
+template <int NGAS>
+__device__ __forceinline__ double tod_column(const TotalOdParams& p, const TodCol& tc, const double (&K)[TOD_MAXGAS][4],
+                                             const double (&L)[8], int lut_gas) {
+  double tau = 0.0;
+#pragma unroll
+  for (int ig = 0; ig < NGAS; ++ig) {
+    if (ig >= p.ngas) break;
+    double v;
+    if (ig == lut_gas) {
+      const double cidx = tc.cidx[ig];
+      const double cw1 = cidx - (double)(int)cidx;
+      const double a = tc.c00 * L[0] + tc.c01 * L[1] + tc.c10 * L[2] + tc.c11 * L[3];
+      const double b = tc.c00 * L[4] + tc.c01 * L[5] + tc.c10 * L[6] + tc.c11 * L[7];
+      v = (1.0 - cw1) * a + cw1 * b;
+    } else {
+      v = tc.c00 * K[ig][0] + tc.c01 * K[ig][1] + tc.c10 * K[ig][2] + tc.c11 * K[ig][3];
+    }
+    tau += tc.w[ig] * v;
+  }
+  return tau;
+}
+
+__global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_constant__ TotalOdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  TodCol* s_col = reinterpret_cast<TodCol*>(smem_raw) + warp * TOD_TILE;
+  const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
+  const int ntile = (p.ncol + TOD_TILE - 1) / TOD_TILE;
+  const int64_t n_od = (int64_t)ntile * nlay;
+  const int64_t n_units = n_od + (p.planck_hl || p.planck_surf ? (int64_t)ntile * (nlay + 1) : 0);
+  const size_t sP = (size_t)ng, sT = (size_t)p.np * ng, sC = (size_t)p.nt * sT;
+  // the first LUT gas is pipelined two columns at a time; further ones (none in the CKDMIP gas lists)
+  // are read inside the column loop
+  const int lut_gas = p.lut_mask ? __ffs(p.lut_mask) - 1 : -1;
+  const unsigned lut_rest = p.lut_mask & (p.lut_mask - 1);
+  for (int64_t u = (int64_t)blockIdx.x * nwarp + warp; u < n_units; u += (int64_t)gridDim.x * nwarp) {
+    if (u >= n_od) {
+      // ---- Planck function at one half level of the tile's columns (run_ckd.cpp:131-132), lane = g
+      const int64_t v = u - n_od;
+      const int tile = (int)(v / (nlay + 1)), lev = (int)(v - (int64_t)tile * (nlay + 1));
+      const int c0 = tile * TOD_TILE, nc = min(TOD_TILE, p.ncol - c0);
+      for (int g = lane; g < ng; g += 32) {
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+          const int64_t col = c0 + c;
+          const double t = p.temperature_hl[col * (nlay + 1) + lev];
+          const double b = planck_interp(t, p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
+          if (p.planck_hl) p.planck_hl[(col * (nlay + 1) + lev) * ng + g] = b;
+          if (lev == nlay && p.planck_surf) p.planck_surf[col * ng + g] = b;
+        }
+      }
+      continue;
+    }
+    const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
+    const int c0 = tile * TOD_TILE;
+    // ---- phase A: lane = column
+    int key = -1 - lane;  // columns past the end form groups of their own that nobody visits
+    const bool valid = c0 + lane < p.ncol;
+    if (valid) {
+      const int64_t col = c0 + lane;
+      const double* p_hl = p.pressure_hl + col * (nlay + 1);
+      const double* t_hl = p.temperature_hl + col * (nlay + 1);
+      const double p0 = p_hl[l], p1 = p_hl[l + 1];
+      const double t_fl = (t_hl[l] * p0 + t_hl[l + 1] * p1) / (p0 + p1);
+      const Interp it = make_interp(p0, p1, t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+      key = it.it0 * p.np + it.ip0;
+      TodCol tc;
+      tc.c00 = it.tw0 * it.pw0;
+      tc.c01 = it.tw0 * it.pw1;
+      tc.c10 = it.tw1 * it.pw0;
+      tc.c11 = it.tw1 * it.pw1;
+#pragma unroll
+      for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
+        tc.w[ig] = 0.0;
+        tc.cidx[ig] = 0.0;
+        if (ig >= ngas) continue;
+        const int cd = p.conc_dependence[ig];
+        const bool have = p.vmr[ig] != nullptr;
+        const double vmr = have ? p.vmr[ig][col * nlay + l] : 0.0;
+        double weight = 0.0;  // ckd_model.cpp:980-999
+        if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
+        if (cd == ECCKD_CONC_LUT) {
+          double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
+          tc.cidx[ig] = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+          tc.w[ig] = weight;
+        } else {
+          tc.w[ig] = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+        }
+      }
+      s_col[lane] = tc;
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    __syncwarp();
+    // ---- phase B: lane = g point, groups of columns with the same four table corners
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+      const int g = min(g0 + lane, ng - 1);
+      const bool store = g0 + lane < ng;
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        unsigned members = __shfl_sync(0xffffffffu, same, leader);
+        const int gkey = __shfl_sync(0xffffffffu, key, leader);
+        todo &= ~members;
+        const int it0 = gkey / p.np, ip0 = gkey - it0 * p.np;
+        const size_t o00 = it0 * sT + ip0 * sP + g;
+        double K[TOD_MAXGAS][4];
+#pragma unroll
+        for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
+          if (ig < ngas && !((p.lut_mask >> ig) & 1u)) {
+            const double* k = p.molar_abs[ig] + o00;
+            K[ig][0] = __ldg(k);
+            K[ig][1] = __ldg(k + sP);
+            K[ig][2] = __ldg(k + sT);
+            K[ig][3] = __ldg(k + sT + sP);
+          } else {
+            K[ig][0] = K[ig][1] = K[ig][2] = K[ig][3] = 0.0;
+          }
+        }
+        auto lut_rows = [&](int c, double (&L)[8]) {
+          if (lut_gas < 0) return;
+          const double* k = p.molar_abs[lut_gas] + (size_t)(int)s_col[c].cidx[lut_gas] * sC + o00;
+          L[0] = __ldg(k);
+          L[1] = __ldg(k + sP);
+          L[2] = __ldg(k + sT);
+          L[3] = __ldg(k + sT + sP);
+          k += sC;
+          L[4] = __ldg(k);
+          L[5] = __ldg(k + sP);
+          L[6] = __ldg(k + sT);
+          L[7] = __ldg(k + sT + sP);
+        };
+        auto finish = [&](int c, double tau) {
+          const TodCol& tc = s_col[c];
+          for (unsigned r = lut_rest ? p.lut_mask : 0u; r; r &= r - 1) {  // several LUT gases: all of them here, unpipelined
+            const int ig = __ffs(r) - 1;
+            const double cidx = tc.cidx[ig];
+            const int ic0 = (int)cidx;
+            const double cw1 = cidx - ic0;
+            const double* k = p.molar_abs[ig] + ic0 * sC + o00;
+            const double a = tc.c00 * k[0] + tc.c01 * k[sP] + tc.c10 * k[sT] + tc.c11 * k[sT + sP];
+            k += sC;
+            const double b = tc.c00 * k[0] + tc.c01 * k[sP] + tc.c10 * k[sT] + tc.c11 * k[sT + sP];
+            tau += tc.w[ig] * ((1.0 - cw1) * a + cw1 * b);
+          }
+          if (store) p.od[((int64_t)(c0 + c) * nlay + l) * ng + g] = fmax(tau, 0.0);  // run_ckd.cpp:317
+        };
+        double La[8], Lb[8];
+        while (members) {
+          const int ca = __ffs(members) - 1;
+          members &= members - 1;
+          lut_rows(ca, La);
+          if (members) {
+            const int cb = __ffs(members) - 1;
+            members &= members - 1;
+            lut_rows(cb, Lb);
+            const double ta = tod_column<TOD_MAXGAS>(p, s_col[ca], K, La, lut_rest ? -2 : lut_gas);
+            const double tb = tod_column<TOD_MAXGAS>(p, s_col[cb], K, Lb, lut_rest ? -2 : lut_gas);
+            finish(ca, ta);
+            finish(cb, tb);
+          } else {
+            finish(ca, tod_column<TOD_MAXGAS>(p, s_col[ca], K, La, lut_rest ? -2 : lut_gas));
+          }
+        }
+      }
+    }
+    __syncwarp();  // s_col is rewritten by the next unit
+  }
+}
+
 }  // namespace ecckd
 
 using namespace ecckd;
@@ -1170,18 +1380,80 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
 #ifdef ECCKD_TIMING_KNOBS  // tools/run_ckd_lz.sh
   if (const char* e = getenv("ECCKD_RUN_CKD_LZ")) lz = std::max(1, std::min(atoi(e), 1024 / (threads * cols)));
 #endif
-  run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
-  ECCKD_LAUNCH_CHECK(ctx);
+  const bool legacy_kernel = getenv("ECCKD_RUN_CKD_LEGACY") && atoi(getenv("ECCKD_RUN_CKD_LEGACY")) != 0;
+  const bool layer_major = !m->is_sw && m->ngas <= TOD_MAXGAS && !legacy_kernel;
+  if (lw_staged && !m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)
+    std::vector<double> ones(m->ng, 1.0);
+    ECCKD_CUDA_OK(cudaMalloc(&m->d_ones, m->ng * sizeof(double)));
+    ECCKD_CUDA_OK(cudaMemcpyAsync(m->d_ones, ones.data(), m->ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
   bool bb_done = false;
-  if (lw_staged) {
-    if (!m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)
-      std::vector<double> ones(m->ng, 1.0);
-      ECCKD_CUDA_OK(cudaMalloc(&m->d_ones, m->ng * sizeof(double)));
-      ECCKD_CUDA_OK(cudaMemcpyAsync(m->d_ones, ones.data(), m->ng * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-      ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double* const od_arr = d_od ? d_od : p.scratch_od;
+  if (layer_major) {
+    // longwave: optical depth and Planck function by the layer-major kernel (table rows in registers),
+    // then the staged sweep.  The two kernels run over slices of columns whose optical depth and Planck
+    // arrays fit in L2 together, so that the sweep reads them there instead of from HBM.
+    TotalOdParams q = {};
+    for (int i = 0; i < m->ngas; ++i) {
+      q.molar_abs[i] = gd[i].molar_abs;
+      q.reference_vmr[i] = gd[i].reference_vmr;
+      q.log_vmr0[i] = gd[i].log_vmr0;
+      q.d_log_c[i] = gd[i].d_log_c;
+      q.conc_dependence[i] = gd[i].conc_dependence;
+      q.nconc[i] = gd[i].nconc;
+      if (gd[i].conc_dependence == ECCKD_CONC_LUT) q.lut_mask |= 1u << i;
     }
-    ECCKD_TRY(rt_lw_impl(ctx, ncol, nlay, m->ng, p.planck_hl, d_od ? d_od : p.scratch_od, m->d_ones, p.planck_surf,
-                         d_flux_dn, d_flux_up, d_bb_flux_dn, d_bb_flux_up, &bb_done));
+    q.ngas = m->ngas;
+    q.nt = m->nt;
+    q.np = m->np;
+    q.ng = m->ng;
+    q.nlut = m->nlut;
+    q.log_p_0 = m->log_p_0;
+    q.d_log_p = m->d_log_p;
+    q.d_t = m->d_t;
+    q.planck_t0 = m->planck_t0;
+    q.planck_dt = m->planck_dt;
+    q.temperature = m->d_temperature;
+    q.planck_lut = m->d_planck_lut;
+    q.nlay = nlay;
+    int slice = ncol;
+    if (lw_staged) {
+      // bytes a slice leaves in L2 for the sweep: optical depth + Planck function per column
+      const size_t per_col = ((size_t)nlay + (nlay + 1)) * m->ng * sizeof(double);
+      size_t budget = (size_t)48 << 20;
+      if (const char* e = getenv("ECCKD_RUN_CKD_SLICE_MB")) budget = (size_t)std::max(0, atoi(e)) << 20;
+      if (budget) slice = (int)std::max<size_t>(TOD_TILE, std::min<size_t>(ncol, budget / per_col) / TOD_TILE * TOD_TILE);
+    }
+    const int nwarp = 8;
+    for (int c0 = 0; c0 < ncol; c0 += slice) {
+      const int nc = std::min(slice, ncol - c0);
+      const size_t o_fl = (size_t)c0 * nlay, o_hl = (size_t)c0 * (nlay + 1);
+      for (int i = 0; i < m->ngas; ++i) q.vmr[i] = gd[i].vmr ? gd[i].vmr + o_fl : nullptr;
+      q.ncol = nc;
+      q.pressure_hl = d_pressure_hl + o_hl;
+      q.temperature_hl = d_temperature_hl + o_hl;
+      q.od = od_arr + o_fl * m->ng;
+      q.planck_hl = p.planck_hl ? p.planck_hl + o_hl * m->ng : nullptr;
+      q.planck_surf = p.planck_surf ? p.planck_surf + (size_t)c0 * m->ng : nullptr;
+      const int64_t ntile = (nc + TOD_TILE - 1) / TOD_TILE;
+      const int64_t units = ntile * nlay + ((q.planck_hl || q.planck_surf) ? ntile * (nlay + 1) : 0);
+      const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)2 * ctx->num_sms);
+      total_od_planck_kernel<<<grid, nwarp * 32, nwarp * TOD_TILE * sizeof(TodCol), ctx->stream>>>(q);
+      ECCKD_LAUNCH_CHECK(ctx);
+      if (lw_staged) {
+        ECCKD_TRY(rt_lw_impl(ctx, nc, nlay, m->ng, q.planck_hl, q.od, m->d_ones, q.planck_surf, d_flux_dn + o_hl * m->ng,
+                             d_flux_up + o_hl * m->ng, d_bb_flux_dn ? d_bb_flux_dn + o_hl : nullptr,
+                             d_bb_flux_up ? d_bb_flux_up + o_hl : nullptr, &bb_done));
+      }
+    }
+  } else {
+    run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);
+    ECCKD_LAUNCH_CHECK(ctx);
+    if (lw_staged) {
+      ECCKD_TRY(rt_lw_impl(ctx, ncol, nlay, m->ng, p.planck_hl, od_arr, m->d_ones, p.planck_surf, d_flux_dn, d_flux_up,
+                           d_bb_flux_dn, d_bb_flux_up, &bb_done));
+    }
   }
   if (bb_done) return ECCKD_OK;
   const int64_t nrows = (int64_t)ncol * (nlay + 1);
@@ -1208,8 +1480,9 @@ ECCKD_API int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* co
   // one device arena: inputs then outputs
   size_t n_in = 2 * n_hl + (size_t)ngas * n_fl;
   size_t n_out = n_fl * ng + n_hl * ng * 3 + (size_t)ncol * ng + 2 * n_hl;
-  double* arena = nullptr;
-  ECCKD_CUDA_OK(cudaMalloc(&arena, (n_in + n_out) * sizeof(double)));
+  void* arena_v = nullptr;  // the context's host-API staging slot: kept between calls
+  ECCKD_TRY(ws_reserve(ctx, 4, (n_in + n_out) * sizeof(double), &arena_v));
+  double* arena = static_cast<double*>(arena_v);
   cudaStream_t st = ctx->stream;
   double* d_p = arena;
   double* d_t = d_p + n_hl;
@@ -1253,7 +1526,6 @@ ECCKD_API int ecckd_run_ckd(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* co
     if (!m->is_sw) back(bb_flux_up, d_bup, n_hl);
   }
   cudaError_t e2 = cudaStreamSynchronize(st);
-  cudaFree(arena);
   if (rc != ECCKD_OK) return rc;
   if (e != cudaSuccess || e2 != cudaSuccess) {
     set_error("ecckd_run_ckd: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));

@@ -2061,10 +2061,24 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
   return ECCKD_OK;
 }
 
+// The plan-shaping environment knobs (read when a plan is built) as one word: a cached plan is only
+// reused under the settings it was built with.
+static uint64_t plan_env_signature() {
+  uint64_t sig = 1469598103934665603ull;
+  for (const char* name : {"ECCKD_PLAN_WINDOW", "ECCKD_PLAN_BALANCE", "ECCKD_CH"}) {
+    const char* v = getenv(name);
+    for (const char* c = v ? v : "-"; *c; ++c) sig = (sig ^ (unsigned char)*c) * 1099511628211ull;
+    sig = (sig ^ 0xffu) * 1099511628211ull;
+  }
+  return sig;
+}
+
 ECCKD_API int ecckd_gpoint_plan_create(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng,
                                        ecckd_gpoint_plan** out) {
   ECCKD_DEVICE(ctx);
-  return plan_create_impl(ctx, d_g_point, nwav, ng, false, out);
+  const int rc = plan_create_impl(ctx, d_g_point, nwav, ng, false, out);
+  if (rc == ECCKD_OK && out && *out) (*out)->env_sig = plan_env_signature();
+  return rc;
 }
 
 // Test / diagnostic hook: the plan's rounds as the kernels see them.  h_rounds receives up to
@@ -2310,6 +2324,23 @@ __global__ void widen_f32_kernel(int64_t n, const float* __restrict__ src, doubl
   }
 }
 
+__global__ void g_point_differs_kernel(int64_t n, const int32_t* __restrict__ a, const int32_t* __restrict__ b,
+                                       int32_t* __restrict__ differs) {
+  bool d = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    d |= a[i] != b[i];
+  if (__syncthreads_or(d) && threadIdx.x == 0) *differs = 1;
+}
+
+// What an ecckd_lut_builder keeps on the device between blocks: the g-point map and its plan, and the
+// per-wavenumber weight inputs (wavenumber + spacing for Planck weights, or one weight row).
+struct ResidentGrid {
+  const int32_t* d_g;
+  const double* d_w0;  // wavenumber_cm_1, or the weight row (ssi)
+  const double* d_w1;  // d_wavenumber_cm_1 (Planck weights only)
+  ecckd_gpoint_plan* plan;
+};
+
 // Host-buffer driver shared by the two reference-facing entry points below.
 // Weights: either planck_fl (matrix, or one row when planck_stride == 0) or
 // Planck function of temperature_fl computed in the kernel.
@@ -2319,7 +2350,7 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
                         int64_t planck_stride, const double* temperature_fl, const double* wavenumber_cm_1,
                         const double* d_wavenumber_cm_1, const char* averaging_method, double* molar_abs,
                         double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn,
-                        const float* optical_depth_f32 = nullptr) {
+                        const float* optical_depth_f32 = nullptr, const ResidentGrid* grid = nullptr) {
   const int method = ecckd_averaging_method_from_string(averaging_method);
   if (method < 0) {
     set_error("averaging_method \"%s\" not understood", averaging_method ? averaging_method : "(null)");
@@ -2333,7 +2364,9 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   // device staging (even row strides so 16 B copies are legal), cached in the context
   const int64_t dstride = (nwav + 1) & ~int64_t(1);
   const size_t od_elems = (size_t)nlay * dstride;
-  const size_t w_elems = fused ? (size_t)2 * dstride : (vecw ? (size_t)dstride : (size_t)nlay * dstride);
+  const bool resident_w = grid && (fused || vecw);
+  const size_t w_elems =
+      resident_w ? 0 : (fused ? (size_t)2 * dstride : (vecw ? (size_t)dstride : (size_t)nlay * dstride));
   const size_t out_elems = (size_t)nlay * ng;
   void* arena = nullptr;
   const size_t f32_elems = optical_depth_f32 ? (od_elems + 1) / 2 : 0;  // float staging, counted in doubles
@@ -2343,9 +2376,12 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   double* d_out = d_w + w_elems;
   float* d_f32 = reinterpret_cast<float*>(d_out + 3 * out_elems);
   void* iarena = nullptr;
-  ECCKD_TRY(ws_reserve(ctx, 5, (size_t)(nwav + ng) * sizeof(int32_t), &iarena));
-  int32_t* d_g = static_cast<int32_t*>(iarena);
-  int32_t* d_warn = d_g + nwav;
+  ECCKD_TRY(ws_reserve(ctx, 5, (size_t)(nwav + ng + 1) * sizeof(int32_t), &iarena));
+  int32_t* d_g_stage = static_cast<int32_t*>(iarena);
+  int32_t* d_warn = d_g_stage + nwav;  // [ng] warnings + 1 "map differs from the cached one" flag
+  const int32_t* d_g = grid ? grid->d_g : d_g_stage;
+  const double* d_wn = resident_w ? grid->d_w0 : d_w;            // wavenumbers, or the weight row
+  const double* d_dwn = resident_w ? grid->d_w1 : d_w + dstride;
   // Layers are independent, so the optical depths (and a weight matrix) go up in slabs of layers on a
   // second stream while the slabs already there are reduced: the call costs the PCIe transfer plus one
   // slab's reduction instead of transfer + plan + reduction in sequence.
@@ -2366,9 +2402,11 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
   };
   const double t_begin = now_ms();
   cudaEvent_t small_ready = nullptr;
-  cudaError_t e = cudaMemcpyAsync(d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, cs);
-  if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)ng * sizeof(int32_t), cs);
-  if (e == cudaSuccess && fused) {
+  cudaError_t e = cudaSuccess;
+  if (!grid) e = cudaMemcpyAsync(d_g_stage, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, cs);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_warn, 0, (size_t)(ng + 1) * sizeof(int32_t), cs);
+  if (resident_w) {
+  } else if (e == cudaSuccess && fused) {
     e = cudaMemcpyAsync(d_w, wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, cs);
     if (e == cudaSuccess)
       e = cudaMemcpyAsync(d_w + dstride, d_wavenumber_cm_1, nwav * sizeof(double), cudaMemcpyHostToDevice, cs);
@@ -2440,17 +2478,62 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     if (e != cudaSuccess) break;
     if (s == 0) {
       t_enq = now_ms();
-      rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
+      if (grid) {
+        plan = grid->plan;
+      } else {
+        // the plan of the previous call is reused when the g-point map is the same, element for element
+        // (compared on the device: 2 x 4 B per wavenumber of HBM reads, ~15 us at 2^23) and so are the
+        // plan-shaping settings; the host waits here for the small inputs only, with slab 0 in flight
+        static const bool use_cache = !(getenv("ECCKD_PLAN_CACHE") && atoi(getenv("ECCKD_PLAN_CACHE")) == 0);
+        const uint64_t sig = plan_env_signature();
+        bool hit = false;
+        if (use_cache && ctx->cached_plan && ctx->cached_nwav == nwav && ctx->cached_ng == ng &&
+            ctx->cached_plan->env_sig == sig) {
+          g_point_differs_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(nwav, d_g, ctx->cached_g, d_warn + ng);
+          ctx->launches++;
+          int32_t differs = 1;
+          e = cudaMemcpyAsync(&differs, d_warn + ng, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+          if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+          if (e != cudaSuccess) break;
+          hit = differs == 0;
+        }
+        if (hit) {
+          plan = ctx->cached_plan;
+          ctx->plan_cache_hits++;
+        } else {
+          rc = ecckd_gpoint_plan_create(ctx, d_g, nwav, ng, &plan);
+          if (rc != ECCKD_OK) break;
+          ctx->plan_cache_misses++;
+          if (use_cache) {
+            if (ctx->cached_plan) ecckd_gpoint_plan_destroy(ctx->cached_plan);
+            ctx->cached_plan = nullptr;
+            if (ctx->cached_nwav != nwav || !ctx->cached_g) {
+              if (ctx->cached_g) cudaFree(ctx->cached_g);
+              ctx->cached_g = nullptr;
+              e = cudaMalloc(&ctx->cached_g, (size_t)nwav * sizeof(int32_t));
+            }
+            if (e == cudaSuccess)
+              e = cudaMemcpyAsync(ctx->cached_g, d_g, (size_t)nwav * sizeof(int32_t), cudaMemcpyDeviceToDevice, st);
+            if (e != cudaSuccess) {
+              ecckd_gpoint_plan_destroy(plan);
+              plan = nullptr;
+              break;
+            }
+            ctx->cached_plan = plan;
+            ctx->cached_nwav = nwav;
+            ctx->cached_ng = ng;
+          }
+        }
+      }
       t_plan = now_ms();
-      if (rc != ECCKD_OK) break;
     }
     e = cudaStreamWaitEvent(st, ready[s], 0);
     if (e != cudaSuccess) break;
     rc = ecckd_average_optical_depth_to_g_point_dev(
         ctx, plan, reference_surface_vmr, l1 - l0, pressure_fl + l0, pressure_hl + l0, d_od + (size_t)l0 * dstride, dstride,
         fused ? ECCKD_WEIGHT_PLANCK : (vecw ? ECCKD_WEIGHT_VECTOR : ECCKD_WEIGHT_MATRIX),
-        fused ? nullptr : (vecw ? d_w : d_w + (size_t)l0 * dstride), (fused || vecw) ? 0 : dstride,
-        fused ? temperature_fl + l0 : nullptr, fused ? d_w : nullptr, fused ? d_w + dstride : nullptr, method,
+        fused ? nullptr : (vecw ? d_wn : d_w + (size_t)l0 * dstride), (fused || vecw) ? 0 : dstride,
+        fused ? temperature_fl + l0 : nullptr, fused ? d_wn : nullptr, fused ? d_dwn : nullptr, method,
         d_out + (size_t)l0 * ng, mm ? d_out + out_elems + (size_t)l0 * ng : nullptr,
         mm ? d_out + 2 * out_elems + (size_t)l0 * ng : nullptr, ng, d_warn);
     if (trace) {
@@ -2464,7 +2547,7 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     cudaStreamSynchronize(cs);
     cudaStreamSynchronize(st);
     drop_events();
-    ecckd_gpoint_plan_destroy(plan);
+    if (plan && !grid && plan != ctx->cached_plan) ecckd_gpoint_plan_destroy(plan);
     set_error("ecckd_average_optical_depth_to_g_point: %s", cudaGetErrorString(e));
     return ECCKD_UNEXPECTED_EXCEPTION;
   }
@@ -2522,7 +2605,7 @@ static int host_average(ecckd_ctx* ctx, int ng, double reference_surface_vmr, in
     if (warn) memcpy(warn, h_warn, (size_t)ng * sizeof(int32_t));
   }
   const double t_done = now_ms();
-  ecckd_gpoint_plan_destroy(plan);
+  if (plan && !grid && plan != ctx->cached_plan) ecckd_gpoint_plan_destroy(plan);
   if (trace)
     fprintf(stderr, "host_average: enqueue copies %.2f, plan ready %.2f, launches done %.2f, copies landed %.2f, "
             "all done %.2f, plan freed %.2f ms\n", t_enq - t_begin, t_plan - t_begin, t_launched - t_begin,
@@ -2613,6 +2696,97 @@ ECCKD_API int ecckd_create_lut_block(ecckd_ctx* ctx, int ng, double reference_su
   return host_average(ctx, ng, reference_surface_vmr, nlay, nwav, p_fl.data(), pressure_hl, g_point, optical_depth,
                       od_stride, nullptr, 0, t_fl.data(), wavenumber_cm_1, d_wavenumber_cm_1, averaging_method, molar_abs,
                       min_molar_abs, max_molar_abs, out_stride, warn);
+}
+
+// The block loop of create_look_up_table (create_look_up_table.cpp:249-591) reads the g-point map once
+// (:84-148), the wavenumber grid with the first block and then calls the averaging for every (gas,
+// concentration, temperature) block with the SAME map and grid.  An ecckd_lut_builder is that loop's
+// state on the device: map, plan and grid (or the solar spectrum) are uploaded once, every block then
+// costs its own optical depths over PCIe and nothing else.
+struct ecckd_lut_builder {
+  ecckd_ctx* ctx = nullptr;
+  int ng = 0;
+  int64_t nwav = 0;
+  bool sw = false;
+  int32_t* d_g = nullptr;
+  double* d_w = nullptr;  // [2][dstride] wavenumber, spacing (longwave) or [dstride] ssi (shortwave)
+  int64_t dstride = 0;
+  ecckd_gpoint_plan* plan = nullptr;
+};
+
+ECCKD_API int ecckd_lut_builder_destroy(ecckd_lut_builder* b) {
+  if (!b) return ECCKD_OK;
+  ECCKD_DEVICE(b->ctx);
+  cudaStreamSynchronize(b->ctx->stream);
+  if (b->plan) ecckd_gpoint_plan_destroy(b->plan);
+  if (b->d_g) cudaFree(b->d_g);
+  if (b->d_w) cudaFree(b->d_w);
+  delete b;
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_lut_builder_create(ecckd_ctx* ctx, int ng, int64_t nwav, const int32_t* g_point,
+                                       const double* wavenumber_cm_1, const double* d_wavenumber_cm_1,
+                                       const double* ssi, ecckd_lut_builder** out) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && g_point && out && ng > 0 && nwav > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_lut_builder_create: NULL argument or bad dimensions");
+  ECCKD_REQUIRE(ssi || (wavenumber_cm_1 && d_wavenumber_cm_1), ECCKD_PARAMETER_ERROR,
+                "ecckd_lut_builder_create: longwave builders need the wavenumber grid, shortwave ones ssi");
+  *out = nullptr;
+  ecckd_lut_builder* b = new ecckd_lut_builder;
+  b->ctx = ctx;
+  b->ng = ng;
+  b->nwav = nwav;
+  b->sw = ssi != nullptr;
+  b->dstride = (nwav + 1) & ~int64_t(1);
+  cudaStream_t st = ctx->stream;
+  cudaError_t e = cudaMalloc(&b->d_g, (size_t)nwav * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&b->d_w, (size_t)(b->sw ? 1 : 2) * b->dstride * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_g, g_point, (size_t)nwav * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(b->d_w, b->sw ? ssi : wavenumber_cm_1, (size_t)nwav * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && !b->sw)
+    e = cudaMemcpyAsync(b->d_w + b->dstride, d_wavenumber_cm_1, (size_t)nwav * sizeof(double), cudaMemcpyHostToDevice, st);
+  int rc = ECCKD_OK;
+  if (e == cudaSuccess) rc = ecckd_gpoint_plan_create(ctx, b->d_g, nwav, ng, &b->plan);
+  if (e == cudaSuccess && rc == ECCKD_OK) e = cudaStreamSynchronize(st);  // the host arrays may go away
+  if (e != cudaSuccess || rc != ECCKD_OK) {
+    if (e != cudaSuccess) set_error("ecckd_lut_builder_create: %s", cudaGetErrorString(e));
+    ecckd_lut_builder_destroy(b);
+    return rc != ECCKD_OK ? rc : ECCKD_UNEXPECTED_EXCEPTION;
+  }
+  *out = b;
+  return ECCKD_OK;
+}
+
+// One block: the arguments of ecckd_create_lut_block minus what the builder holds.  Exactly one of
+// optical_depth (float64) and optical_depth_f32 (the float32 values the spectra files store, widened on
+// the device: same results, half the PCIe bytes) is given.
+ECCKD_API int ecckd_lut_builder_block(ecckd_lut_builder* b, double reference_surface_vmr, int nlay,
+                                      const double* pressure_hl, const double* temperature_hl,
+                                      const double* optical_depth, const float* optical_depth_f32, int64_t od_stride,
+                                      const char* averaging_method, double* temperature_fl, double* molar_abs,
+                                      double* min_molar_abs, double* max_molar_abs, int64_t out_stride, int32_t* warn) {
+  ECCKD_REQUIRE(b && pressure_hl && molar_abs && nlay > 0 && ((optical_depth != nullptr) != (optical_depth_f32 != nullptr)),
+                ECCKD_PARAMETER_ERROR, "ecckd_lut_builder_block: NULL argument, or not exactly one optical depth array");
+  ECCKD_REQUIRE(b->sw || temperature_hl, ECCKD_PARAMETER_ERROR, "ecckd_lut_builder_block: longwave blocks need temperature_hl");
+  ECCKD_DEVICE(b->ctx);
+  std::vector<double> p_fl(nlay), t_fl(nlay, 0.0);
+  for (int i = 0; i < nlay; ++i) {
+    p_fl[i] = 0.5 * (pressure_hl[i] + pressure_hl[i + 1]);  // create_look_up_table.cpp:305
+    if (temperature_hl) {                                    // :316-317
+      const double t_x_p0 = temperature_hl[i] * pressure_hl[i], t_x_p1 = temperature_hl[i + 1] * pressure_hl[i + 1];
+      t_fl[i] = 0.5 * (t_x_p0 + t_x_p1) / p_fl[i];
+    }
+    if (temperature_fl) temperature_fl[i] = t_fl[i];
+  }
+  const ResidentGrid grid{b->d_g, b->d_w, b->sw ? nullptr : b->d_w + b->dstride, b->plan};
+  // shortwave: one weight row (planck_fl = the resident ssi, stride 0); longwave: Planck weights in the kernel
+  static const double resident_row = 0.0;  // non-NULL marker: the row itself is on the device already
+  return host_average(b->ctx, b->ng, reference_surface_vmr, nlay, b->nwav, p_fl.data(), pressure_hl, nullptr, optical_depth,
+                      od_stride, b->sw ? &resident_row : nullptr, 0, b->sw ? nullptr : t_fl.data(), nullptr, nullptr,
+                      averaging_method, molar_abs, min_molar_abs, max_molar_abs, out_stride, warn, optical_depth_f32, &grid);
 }
 
 ECCKD_API int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,

@@ -155,6 +155,7 @@ struct ecckd_gpoint_plan {
   bool windowed = false;                 // rounds obey the WIN window constraint (reduce2/3_kernel can run)
   bool balanced = false;                 // bank-conflict-free cell placement (reduce2/3_kernel ONLY: lanes of a g
                                          // point are not adjacent, the lane meta word carries a slot mask)
+  uint64_t env_sig = 0;                  // plan_env_signature() at creation (the host calls' plan cache)
   int32_t* d_g_copy = nullptr;           // balanced plans keep the g-point map to build `legacy` on demand
   ecckd_gpoint_plan* legacy = nullptr;   // free-layout plan for reduce_kernel (kinds with per-row weight sums)
   uint32_t* d_round_off = nullptr;       // [nchunks+1]

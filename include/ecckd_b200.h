@@ -269,6 +269,32 @@ int ecckd_planck_average_optical_depth_to_g_point_f32(
     const char* averaging_method, double* molar_abs, double* min_molar_abs, double* max_molar_abs,
     int64_t out_stride, int32_t* warn);
 
+/* The create_look_up_table block loop's state on the device (create_look_up_table.cpp:249-591): the
+ * tool reads the g-point map once (:84-148), the wavenumber grid (or the solar spectrum, :74-83) with
+ * the first block, and then averages every (gas, concentration, temperature) block with the SAME map
+ * and grid.  A builder uploads map and grid once and keeps the map's plan; each
+ * ecckd_lut_builder_block then moves only its own optical depths over PCIe.  Longwave: wavenumber
+ * grid given, ssi NULL (Planck weights at the block's temperature_fl, :320-331); shortwave: ssi[nwav]
+ * given (:333-341).  Arguments of _block are those of ecckd_create_lut_block minus what the builder
+ * holds; exactly one of optical_depth (float64) / optical_depth_f32 (the float32 values the spectra
+ * files store, merge_spectra.cpp:108, widened on the device: bit-identical results, half the bytes)
+ * is non-NULL.  This is the documented host path for a sequence of blocks. */
+typedef struct ecckd_lut_builder ecckd_lut_builder;
+int ecckd_lut_builder_create(ecckd_ctx* ctx, int ng, int64_t nwav, const int32_t* g_point,
+                             const double* wavenumber_cm_1, const double* d_wavenumber_cm_1, const double* ssi,
+                             ecckd_lut_builder** out);
+int ecckd_lut_builder_block(ecckd_lut_builder* builder, double reference_surface_vmr, int nlay,
+                            const double* pressure_hl, const double* temperature_hl, const double* optical_depth,
+                            const float* optical_depth_f32, int64_t od_stride, const char* averaging_method,
+                            double* temperature_fl, double* molar_abs, double* min_molar_abs, double* max_molar_abs,
+                            int64_t out_stride, int32_t* warn);
+int ecckd_lut_builder_destroy(ecckd_lut_builder* builder);
+
+/* The host-array entry points above rebuild nothing they already have: the plan of the last g-point
+ * map a context saw is kept and reused when the next call passes the same map (compared element for
+ * element on the device).  hits / misses since the context was created; ECCKD_PLAN_CACHE=0 disables. */
+int ecckd_ctx_plan_cache_stats(ecckd_ctx* ctx, int64_t* hits, int64_t* misses);
+
 /* Merge of several spectra: src/ecckd/read_merged_spectrum.cpp:149-168.
  * d_optical_depth += d_od * scaling, or * h_scaling_profile[layer] if non-NULL. */
 int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,

@@ -206,3 +206,49 @@ def test_rt_sw_staged_kernel_shapes(ctx, O, ncol, nlay, n, with_up):
         else:
             dn_o = O.radiative_transfer_direct_sw(float(mu[c]), ssi, od[c])
         np.testing.assert_allclose(dn[c], dn_o, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("ng,ncol,slice_mb", [(32, 333, "1"), (64, 77, "0"), (20, 130, "1"), (32, 31, "48")])
+def test_run_ckd_layer_major_kernel_slices_and_legacy_kernel_agree(ctx, O, monkeypatch, ng, ncol, slice_mb):
+    """total_od_planck_kernel (columns grouped by their table corners, several tiles, partial tiles, column
+    slices sized for L2) against the oracle and against the column-major kernel it replaces."""
+    c = S.ckd_model_case(ncol=ncol, nlay=23, ng=ng, seed=99 + ng)
+    # make neighbouring columns share table corners in some layers and not in others
+    c["temperature_hl"][::3] += 25.0
+    m = _model(ctx, c)
+    ref = O.run_ckd(c, is_sw=False)
+    monkeypatch.setenv("ECCKD_RUN_CKD_SLICE_MB", slice_mb)
+    got = m.run_ckd(c["vmr_fl"], c["pressure_hl"], c["temperature_hl"])
+    np.testing.assert_allclose(got["optical_depth"], ref["optical_depth"], rtol=2e-11, atol=1e-18)
+    np.testing.assert_allclose(got["planck_hl"], ref["planck_hl"], rtol=1e-14)
+    np.testing.assert_allclose(got["planck_surf"], ref["planck_surf"], rtol=1e-14)
+    for k in ("flux_dn", "flux_up", "bb_flux_dn", "bb_flux_up"):
+        assert np.max(np.abs(got[k] - ref[k])) <= FLUX_ATOL, k
+    # optical depth only (no Planck output, no sweep)
+    d_p, d_t = ctx.to_device(c["pressure_hl"]), ctx.to_device(c["temperature_hl"])
+    d_v = [None if v is None else ctx.to_device(v) for v in c["vmr_fl"]]
+    d_od = ctx.empty((ncol, 23, ng))
+    m.run_ckd_dev(d_v, 1361.0, ncol, 23, d_p, d_t, d_od)
+    assert np.array_equal(d_od.numpy(), got["optical_depth"])
+    monkeypatch.setenv("ECCKD_RUN_CKD_LEGACY", "1")
+    old = m.run_ckd(c["vmr_fl"], c["pressure_hl"], c["temperature_hl"])
+    np.testing.assert_allclose(got["optical_depth"], old["optical_depth"], rtol=2e-11, atol=1e-18)
+    assert np.array_equal(got["planck_hl"], old["planck_hl"])
+
+
+def test_run_ckd_two_lut_gases_and_nine_gases(ctx, O):
+    """More than one gas with a concentration axis (unpipelined path of the layer-major kernel), and a
+    gas list longer than the kernel's register budget (falls to the column-major kernel)."""
+    c = S.ckd_model_case(ncol=40, nlay=12, ng=32, seed=5)
+    rng = np.random.default_rng(1)
+    lut2 = dict(c["gases"][1])
+    lut2["molar_abs"] = lut2["molar_abs"] * rng.uniform(0.5, 2.0, lut2["molar_abs"].shape)
+    for gases, vmr in ((c["gases"][:5] + [lut2], c["vmr_fl"][:5] + [c["vmr_fl"][1] * 0.7]),
+                       (c["gases"] + [c["gases"][2]], c["vmr_fl"] + [c["vmr_fl"][2]])):
+        cc = dict(c, gases=gases, vmr_fl=vmr)
+        m = _model(ctx, cc)
+        got = m.run_ckd(vmr, c["pressure_hl"], c["temperature_hl"])
+        ref = O.run_ckd(cc, is_sw=False)
+        np.testing.assert_allclose(got["optical_depth"], ref["optical_depth"], rtol=2e-11, atol=1e-18)
+        for k in ("flux_dn", "flux_up"):
+            assert np.max(np.abs(got[k] - ref[k])) <= FLUX_ATOL, k
