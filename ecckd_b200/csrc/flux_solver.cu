@@ -21,6 +21,8 @@ struct ecckd_ckd_model {
   std::vector<int> conc_dependence, nconc;
   std::vector<double> reference_vmr;
   std::vector<double*> d_molar_abs;  // per gas
+  std::vector<double*> d_packed;     // per gas, longwave models: [nconc|1][nt-1][np-1][ng][4] the four table corners
+                                     // (it,ip) (it,ip+1) (it+1,ip) (it+1,ip+1) of every interpolation cell side by side
   std::vector<double*> d_vmr_lut;    // per gas (LUT only)
   std::vector<double> log_vmr0, d_log_c;  // per gas (LUT only), host-computed as in ckd_model.cpp:1003-1005
   double* d_log_pressure = nullptr;
@@ -774,27 +776,30 @@ __global__ void __launch_bounds__(1024, 1) run_ckd_kernel(const RunCkdParams p) 
 // share a handful of (ip0, it0) pairs (pressure at a model level varies little between columns,
 // temperature spans one or two 20 K table intervals), so a warp (lane = g point) takes one layer of a
 // tile of 32 columns, groups the columns by (ip0, it0) with match.any, loads the 4 corner rows of every
-// gas ONCE per group (4 x ngas coalesced row reads into registers) and then produces the optical depth
-// of each column of the group with 5 FMAs per gas and no table read at all.  Gases with a
-// concentration axis (H2O: ckd_model.cpp:1001-1045) read their 8 rows per column, two columns in
-// flight.  The earlier kernel gathered 36 rows per (column, layer); this one ~28/group + 8.
-// Phase A (lane = column) computes everything that does not depend on g once per (column, layer).
+// gas without a concentration axis ONCE per group (coalesced row reads into registers) and then
+// produces the optical depth of each column of the group with 5 FMAs per gas and no table read at all.
+// The gas with a concentration axis (H2O: ckd_model.cpp:1001-1045) reads its 8 rows per column, the
+// next column's rows in flight while this one is summed.  The column-major kernel above gathers 36 rows
+// per (column, layer); this one 4*NLIN per group + 8 per column.  Phase A (lane = column) computes
+// everything that does not depend on g once per (column, layer).  The host orders the gases: the NLIN
+// table gases first, then the ones with a concentration axis (the sum over gases is reordered
+// accordingly; run_ckd.cpp:312 adds them in file order).
 constexpr int TOD_MAXGAS = 8;
 constexpr int TOD_TILE = 32;
 
-struct TodCol {              // g-independent state of one (column, layer), in shared memory per warp
-  double c00, c01, c10, c11; // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
-  double w[TOD_MAXGAS];      // what multiplies the interpolated absorption of each gas
-  double cidx[TOD_MAXGAS];   // LUT gases: clamped concentration index ic0 + cw1
+struct __align__(16) TodCol {  // g-independent state of one (column, layer), in shared memory per warp
+  double c00, c01, c10, c11;   // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
+  double w[TOD_MAXGAS];        // what multiplies the interpolated absorption of each gas
+  double cw1[TOD_MAXGAS];      // gases with a concentration axis: weight of level ic0 + 1 ...
+  int ic0[TOD_MAXGAS];         // ... and the level index
 };
 
 struct TotalOdParams {
-  const double* molar_abs[TOD_MAXGAS];
+  const double* packed[TOD_MAXGAS];  // corner-packed tables (ecckd_ckd_model::d_packed)
   const double* vmr[TOD_MAXGAS];
   double reference_vmr[TOD_MAXGAS], log_vmr0[TOD_MAXGAS], d_log_c[TOD_MAXGAS];
   int conc_dependence[TOD_MAXGAS], nconc[TOD_MAXGAS];
-  int ngas, nt, np, ng, nlut;
-  unsigned lut_mask;  // bit ig: gas ig has a concentration axis
+  int ngas, nlin, nt, np, ng, nlut;
   double log_p_0, d_log_p, d_t, planck_t0, planck_dt;
   const double* temperature;  // [nt][np]
   const double* planck_lut;   // [nlut][ng]
@@ -806,29 +811,8 @@ struct TotalOdParams {
   double* planck_surf;  // [ncol][ng] or NULL
 };
 
-template <int NGAS>
-__device__ __forceinline__ double tod_column(const TotalOdParams& p, const TodCol& tc, const double (&K)[TOD_MAXGAS][4],
-                                             const double (&L)[8], int lut_gas) {
-  double tau = 0.0;
-#pragma unroll
-  for (int ig = 0; ig < NGAS; ++ig) {
-    if (ig >= p.ngas) break;
-    double v;
-    if (ig == lut_gas) {
-      const double cidx = tc.cidx[ig];
-      const double cw1 = cidx - (double)(int)cidx;
-      const double a = tc.c00 * L[0] + tc.c01 * L[1] + tc.c10 * L[2] + tc.c11 * L[3];
-      const double b = tc.c00 * L[4] + tc.c01 * L[5] + tc.c10 * L[6] + tc.c11 * L[7];
-      v = (1.0 - cw1) * a + cw1 * b;
-    } else {
-      v = tc.c00 * K[ig][0] + tc.c01 * K[ig][1] + tc.c10 * K[ig][2] + tc.c11 * K[ig][3];
-    }
-    tau += tc.w[ig] * v;
-  }
-  return tau;
-}
-
-__global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_constant__ TotalOdParams p) {
+template <int NLIN, bool HAS_LUT, int NWARP, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck_kernel(const __grid_constant__ TotalOdParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   TodCol* s_col = reinterpret_cast<TodCol*>(smem_raw) + warp * TOD_TILE;
@@ -836,29 +820,48 @@ __global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_co
   const int ntile = (p.ncol + TOD_TILE - 1) / TOD_TILE;
   const int64_t n_od = (int64_t)ntile * nlay;
   const int64_t n_units = n_od + (p.planck_hl || p.planck_surf ? (int64_t)ntile * (nlay + 1) : 0);
-  const size_t sP = (size_t)ng, sT = (size_t)p.np * ng, sC = (size_t)p.nt * sT;
-  // the first LUT gas is pipelined two columns at a time; further ones (none in the CKDMIP gas lists)
-  // are read inside the column loop
-  const int lut_gas = p.lut_mask ? __ffs(p.lut_mask) - 1 : -1;
-  const unsigned lut_rest = p.lut_mask & (p.lut_mask - 1);
+  // strides of the corner-packed tables, in elements (< 2^31)
+  const unsigned qP = (unsigned)ng * 4, qT = (unsigned)(p.np - 1) * qP, qC = (unsigned)(p.nt - 1) * qT;
   for (int64_t u = (int64_t)blockIdx.x * nwarp + warp; u < n_units; u += (int64_t)gridDim.x * nwarp) {
     if (u >= n_od) {
-      // ---- Planck function at one half level of the tile's columns (run_ckd.cpp:131-132), lane = g
+      // ---- Planck function at one half level of the tile's columns (run_ckd.cpp:131-132;
+      // ckd_model.cpp:1124-1142): index and weights per column by lane = column, rows by lane = g
       const int64_t v = u - n_od;
       const int tile = (int)(v / (nlay + 1)), lev = (int)(v - (int64_t)tile * (nlay + 1));
       const int c0 = tile * TOD_TILE, nc = min(TOD_TILE, p.ncol - c0);
-      for (int g = lane; g < ng; g += 32) {
+      int my_off = 0;
+      double my_w0 = 0.0, my_w1 = 0.0;
+      if (lane < nc) {
+        const double t = p.temperature_hl[(int64_t)(c0 + lane) * (nlay + 1) + lev];
+        const double tindex0 = (t - p.planck_t0) / p.planck_dt;
+        if (tindex0 >= 0) {
+          const int it0 = min((int)tindex0, p.nlut - 2);
+          my_off = it0 * ng;
+          my_w1 = tindex0 - it0;
+          my_w0 = 1.0 - my_w1;
+        } else {  // below the table: (t / t0) * lut[0]
+          my_w0 = t / p.planck_t0;
+        }
+      }
+      const int64_t lev_stride = (int64_t)(nlay + 1) * ng;
+      for (int g0 = 0; g0 < ng; g0 += 32) {
+        const int g = min(g0 + lane, ng - 1);
+        const bool store = g0 + lane < ng;
+        const double* lut_g = p.planck_lut + g;
+        double* out = p.planck_hl ? p.planck_hl + ((int64_t)c0 * (nlay + 1) + lev) * ng + g : nullptr;
+        double* surf = (lev == nlay && p.planck_surf) ? p.planck_surf + (int64_t)c0 * ng + g : nullptr;
 #pragma unroll 4
         for (int c = 0; c < nc; ++c) {
-          const int64_t col = c0 + c;
-          const double t = p.temperature_hl[col * (nlay + 1) + lev];
-          const double b = planck_interp(t, p.planck_t0, p.planck_dt, p.nlut, ng, g, p.planck_lut);
-          if (p.planck_hl) p.planck_hl[(col * (nlay + 1) + lev) * ng + g] = b;
-          if (lev == nlay && p.planck_surf) p.planck_surf[col * ng + g] = b;
+          const int off = __shfl_sync(0xffffffffu, my_off, c);
+          const double w0 = __shfl_sync(0xffffffffu, my_w0, c), w1 = __shfl_sync(0xffffffffu, my_w1, c);
+          const double b = w0 * __ldg(lut_g + off) + w1 * __ldg(lut_g + off + ng);  // w1 == 0 below the table
+          if (store && out) out[c * lev_stride] = b;
+          if (store && surf) surf[c * ng] = b;
         }
       }
       continue;
     }
+    // consecutive warps take consecutive layers of one tile: its columns' profile sectors are shared in L1/L2
     const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
     const int c0 = tile * TOD_TILE;
     // ---- phase A: lane = column
@@ -880,7 +883,8 @@ __global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_co
 #pragma unroll
       for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
         tc.w[ig] = 0.0;
-        tc.cidx[ig] = 0.0;
+        tc.cw1[ig] = 0.0;
+        tc.ic0[ig] = 0;
         if (ig >= ngas) continue;
         const int cd = p.conc_dependence[ig];
         const bool have = p.vmr[ig] != nullptr;
@@ -889,7 +893,9 @@ __global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_co
         if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
         if (cd == ECCKD_CONC_LUT) {
           double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
-          tc.cidx[ig] = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+          cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+          tc.ic0[ig] = (int)cindex0;
+          tc.cw1[ig] = cindex0 - tc.ic0[ig];
           tc.w[ig] = weight;
         } else {
           tc.w[ig] = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
@@ -900,9 +906,11 @@ __global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_co
     const unsigned same = __match_any_sync(0xffffffffu, key);
     __syncwarp();
     // ---- phase B: lane = g point, groups of columns with the same four table corners
+    const unsigned col_stride = (unsigned)nlay * ng;  // 32 * nlay * ng < 2^31 (checked by the host)
     for (int g0 = 0; g0 < ng; g0 += 32) {
       const int g = min(g0 + lane, ng - 1);
       const bool store = g0 + lane < ng;
+      double* const od_unit = p.od + ((int64_t)c0 * nlay + l) * ng + g;
       unsigned todo = __ballot_sync(0xffffffffu, valid);
       while (todo) {
         const int leader = __ffs(todo) - 1;
@@ -910,64 +918,75 @@ __global__ void __launch_bounds__(256, 2) total_od_planck_kernel(const __grid_co
         const int gkey = __shfl_sync(0xffffffffu, key, leader);
         todo &= ~members;
         const int it0 = gkey / p.np, ip0 = gkey - it0 * p.np;
-        const size_t o00 = it0 * sT + ip0 * sP + g;
-        double K[TOD_MAXGAS][4];
+        const unsigned o00 = (unsigned)it0 * qT + (unsigned)ip0 * qP + (unsigned)g * 4;
+        double K[NLIN > 0 ? NLIN : 1][4];
 #pragma unroll
-        for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
-          if (ig < ngas && !((p.lut_mask >> ig) & 1u)) {
-            const double* k = p.molar_abs[ig] + o00;
-            K[ig][0] = __ldg(k);
-            K[ig][1] = __ldg(k + sP);
-            K[ig][2] = __ldg(k + sT);
-            K[ig][3] = __ldg(k + sT + sP);
-          } else {
-            K[ig][0] = K[ig][1] = K[ig][2] = K[ig][3] = 0.0;
-          }
+        for (int ig = 0; ig < NLIN; ++ig) {
+          const double2* k = reinterpret_cast<const double2*>(p.packed[ig] + o00);
+          const double2 a = __ldg(k), b = __ldg(k + 1);
+          K[ig][0] = a.x;
+          K[ig][1] = a.y;
+          K[ig][2] = b.x;
+          K[ig][3] = b.y;
         }
-        auto lut_rows = [&](int c, double (&L)[8]) {
-          if (lut_gas < 0) return;
-          const double* k = p.molar_abs[lut_gas] + (size_t)(int)s_col[c].cidx[lut_gas] * sC + o00;
+        const double* lut_base = HAS_LUT ? p.packed[NLIN] + o00 : nullptr;
+        auto lut_rows = [&](int c, double2 (&L)[4]) {
+          if (!HAS_LUT) return;
+          const double2* k = reinterpret_cast<const double2*>(lut_base + (size_t)((unsigned)s_col[c].ic0[NLIN] * qC));
+          const double2* k1 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(k) + qC);
           L[0] = __ldg(k);
-          L[1] = __ldg(k + sP);
-          L[2] = __ldg(k + sT);
-          L[3] = __ldg(k + sT + sP);
-          k += sC;
-          L[4] = __ldg(k);
-          L[5] = __ldg(k + sP);
-          L[6] = __ldg(k + sT);
-          L[7] = __ldg(k + sT + sP);
+          L[1] = __ldg(k + 1);
+          L[2] = __ldg(k1);
+          L[3] = __ldg(k1 + 1);
         };
-        auto finish = [&](int c, double tau) {
+        auto column = [&](int c, const double2 (&L)[4]) {
           const TodCol& tc = s_col[c];
-          for (unsigned r = lut_rest ? p.lut_mask : 0u; r; r &= r - 1) {  // several LUT gases: all of them here, unpipelined
-            const int ig = __ffs(r) - 1;
-            const double cidx = tc.cidx[ig];
-            const int ic0 = (int)cidx;
-            const double cw1 = cidx - ic0;
-            const double* k = p.molar_abs[ig] + ic0 * sC + o00;
-            const double a = tc.c00 * k[0] + tc.c01 * k[sP] + tc.c10 * k[sT] + tc.c11 * k[sT + sP];
-            k += sC;
-            const double b = tc.c00 * k[0] + tc.c01 * k[sP] + tc.c10 * k[sT] + tc.c11 * k[sT + sP];
+          const double c00 = tc.c00, c01 = tc.c01, c10 = tc.c10, c11 = tc.c11;
+          double tau0 = 0.0, tau1 = 0.0;  // two chains
+#pragma unroll
+          for (int ig = 0; ig < NLIN; ++ig) {
+            const double v = c00 * K[ig][0] + c01 * K[ig][1] + c10 * K[ig][2] + c11 * K[ig][3];
+            if (ig & 1) tau1 += tc.w[ig] * v; else tau0 += tc.w[ig] * v;
+          }
+          if (HAS_LUT) {
+            const double cw1 = tc.cw1[NLIN];
+            const double a = c00 * L[0].x + c01 * L[0].y + c10 * L[1].x + c11 * L[1].y;
+            const double b = c00 * L[2].x + c01 * L[2].y + c10 * L[3].x + c11 * L[3].y;
+            tau1 += tc.w[NLIN] * ((1.0 - cw1) * a + cw1 * b);
+          }
+          double tau = tau0 + tau1;
+          for (int ig = NLIN + (HAS_LUT ? 1 : 0); ig < ngas; ++ig) {  // further gases with a concentration axis
+            const double cw1 = tc.cw1[ig];
+            const double* k = p.packed[ig] + (size_t)((unsigned)tc.ic0[ig] * qC) + o00;
+            const double a = c00 * k[0] + c01 * k[1] + c10 * k[2] + c11 * k[3];
+            k += qC;
+            const double b = c00 * k[0] + c01 * k[1] + c10 * k[2] + c11 * k[3];
             tau += tc.w[ig] * ((1.0 - cw1) * a + cw1 * b);
           }
-          if (store) p.od[((int64_t)(c0 + c) * nlay + l) * ng + g] = fmax(tau, 0.0);  // run_ckd.cpp:317
+          if (store) od_unit[(unsigned)c * col_stride] = fmax(tau, 0.0);  // run_ckd.cpp:317
         };
-        double La[8], Lb[8];
-        while (members) {
-          const int ca = __ffs(members) - 1;
-          members &= members - 1;
-          lut_rows(ca, La);
+        // software pipeline over the members: the next column's LUT rows are loaded before this one is summed
+        double2 La[4], Lb[4];
+        int ca = __ffs(members) - 1;
+        members &= members - 1;
+        lut_rows(ca, La);
+        while (true) {
+          int cb = -1;
           if (members) {
-            const int cb = __ffs(members) - 1;
+            cb = __ffs(members) - 1;
             members &= members - 1;
             lut_rows(cb, Lb);
-            const double ta = tod_column<TOD_MAXGAS>(p, s_col[ca], K, La, lut_rest ? -2 : lut_gas);
-            const double tb = tod_column<TOD_MAXGAS>(p, s_col[cb], K, Lb, lut_rest ? -2 : lut_gas);
-            finish(ca, ta);
-            finish(cb, tb);
-          } else {
-            finish(ca, tod_column<TOD_MAXGAS>(p, s_col[ca], K, La, lut_rest ? -2 : lut_gas));
           }
+          column(ca, La);
+          if (cb < 0) break;
+          ca = -1;
+          if (members) {
+            ca = __ffs(members) - 1;
+            members &= members - 1;
+            lut_rows(ca, La);
+          }
+          column(cb, Lb);
+          if (ca < 0) break;
         }
       }
     }
@@ -992,6 +1011,7 @@ ECCKD_API int ecckd_ckd_model_destroy(ecckd_ckd_model* m) {
   if (!m) return ECCKD_OK;
   if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
   for (double* p : m->d_molar_abs) cudaFree(p);
+  for (double* p : m->d_packed) cudaFree(p);
   for (double* p : m->d_vmr_lut) cudaFree(p);
   cudaFree(m->d_log_pressure);
   cudaFree(m->d_temperature);
@@ -1055,6 +1075,20 @@ ECCKD_API int ecckd_ckd_model_create(ecckd_ctx* ctx, int ngas, const ecckd_gas_t
     }
     if (rc == ECCKD_OK) rc = upload_new(g.molar_abs, n, &d_k);
     m->d_molar_abs.push_back(d_k);
+    double* d_q = nullptr;
+    if (rc == ECCKD_OK && !is_sw) {  // the layer-major optical-depth kernel reads whole interpolation cells
+      const size_t nc = g.conc_dependence == ECCKD_CONC_LUT ? (size_t)g.nconc : 1;
+      std::vector<double> q(nc * (nt - 1) * (np - 1) * ng * 4);
+      size_t o = 0;
+      for (size_t ic = 0; ic < nc; ++ic)
+        for (int it = 0; it < nt - 1; ++it)
+          for (int ip = 0; ip < np - 1; ++ip)
+            for (int ig = 0; ig < ng; ++ig)
+              for (int corner = 0; corner < 4; ++corner)
+                q[o++] = g.molar_abs[((ic * nt + it + (corner >> 1)) * np + ip + (corner & 1)) * ng + ig];
+      rc = upload_new(q.data(), q.size(), &d_q);
+    }
+    m->d_packed.push_back(d_q);
     m->d_vmr_lut.push_back(d_v);
     m->log_vmr0.push_back(lv0);
     m->d_log_c.push_back(dlc);
@@ -1381,7 +1415,7 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
   if (const char* e = getenv("ECCKD_RUN_CKD_LZ")) lz = std::max(1, std::min(atoi(e), 1024 / (threads * cols)));
 #endif
   const bool legacy_kernel = getenv("ECCKD_RUN_CKD_LEGACY") && atoi(getenv("ECCKD_RUN_CKD_LEGACY")) != 0;
-  const bool layer_major = !m->is_sw && m->ngas <= TOD_MAXGAS && !legacy_kernel;
+  const bool layer_major = !m->is_sw && m->ngas <= TOD_MAXGAS && !legacy_kernel && (int64_t)nlay * m->ng * TOD_TILE < (1LL << 28);
   if (lw_staged && !m->d_ones) {  // surface emissivity 1 (run_ckd.cpp:344-345)
     std::vector<double> ones(m->ng, 1.0);
     ECCKD_CUDA_OK(cudaMalloc(&m->d_ones, m->ng * sizeof(double)));
@@ -1392,17 +1426,26 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
   double* const od_arr = d_od ? d_od : p.scratch_od;
   if (layer_major) {
     // longwave: optical depth and Planck function by the layer-major kernel (table rows in registers),
-    // then the staged sweep.  The two kernels run over slices of columns whose optical depth and Planck
-    // arrays fit in L2 together, so that the sweep reads them there instead of from HBM.
+    // then the staged sweep.  (Running the two kernels over slices of columns sized for L2, so that the
+    // sweep would read optical depth and Planck function there, was measured and rejected: 65536 x 54 x 32,
+    // slices of 16 / 32 / 64 / 128 MB: 7.3 / 4.9 / 5.0 / 4.4 ms against 4.1 ms unsliced - the short
+    // launches leave SMs idle and the sweep already runs at 89 % of the HBM peak.)
     TotalOdParams q = {};
-    for (int i = 0; i < m->ngas; ++i) {
-      q.molar_abs[i] = gd[i].molar_abs;
-      q.reference_vmr[i] = gd[i].reference_vmr;
-      q.log_vmr0[i] = gd[i].log_vmr0;
-      q.d_log_c[i] = gd[i].d_log_c;
-      q.conc_dependence[i] = gd[i].conc_dependence;
-      q.nconc[i] = gd[i].nconc;
-      if (gd[i].conc_dependence == ECCKD_CONC_LUT) q.lut_mask |= 1u << i;
+    int order[TOD_MAXGAS], n = 0;
+    for (int i = 0; i < m->ngas; ++i)
+      if (gd[i].conc_dependence != ECCKD_CONC_LUT) order[n++] = i;
+    q.nlin = n;
+    for (int i = 0; i < m->ngas; ++i)
+      if (gd[i].conc_dependence == ECCKD_CONC_LUT) order[n++] = i;
+    for (int k = 0; k < m->ngas; ++k) {
+      const int i = order[k];
+      q.packed[k] = m->d_packed[i];
+      q.vmr[k] = gd[i].vmr;
+      q.reference_vmr[k] = gd[i].reference_vmr;
+      q.log_vmr0[k] = gd[i].log_vmr0;
+      q.d_log_c[k] = gd[i].d_log_c;
+      q.conc_dependence[k] = gd[i].conc_dependence;
+      q.nconc[k] = gd[i].nconc;
     }
     q.ngas = m->ngas;
     q.nt = m->nt;
@@ -1416,36 +1459,43 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     q.planck_dt = m->planck_dt;
     q.temperature = m->d_temperature;
     q.planck_lut = m->d_planck_lut;
+    q.ncol = ncol;
     q.nlay = nlay;
-    int slice = ncol;
-    if (lw_staged) {
-      // bytes a slice leaves in L2 for the sweep: optical depth + Planck function per column
-      const size_t per_col = ((size_t)nlay + (nlay + 1)) * m->ng * sizeof(double);
-      size_t budget = (size_t)48 << 20;
-      if (const char* e = getenv("ECCKD_RUN_CKD_SLICE_MB")) budget = (size_t)std::max(0, atoi(e)) << 20;
-      if (budget) slice = (int)std::max<size_t>(TOD_TILE, std::min<size_t>(ncol, budget / per_col) / TOD_TILE * TOD_TILE);
+    q.pressure_hl = d_pressure_hl;
+    q.temperature_hl = d_temperature_hl;
+    q.od = od_arr;
+    q.planck_hl = p.planck_hl;
+    q.planck_surf = p.planck_surf;
+    // 4 warps x 3 blocks per SM: 168 registers per thread, nothing spilled.  (8 warps x 2 blocks at 128 registers
+    // spills the prefetched table rows, which turns the prefetch into a blocking load: 1.68 against 1.44 ms for
+    // 65536 x 54 x 32.)
+    const int nwarp = 4, minb = 3;
+    const int64_t ntile = (ncol + TOD_TILE - 1) / TOD_TILE;
+    const int64_t units = ntile * nlay + ((q.planck_hl || q.planck_surf) ? ntile * (nlay + 1) : 0);
+    const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)minb * ctx->num_sms);
+    const size_t smem = nwarp * TOD_TILE * sizeof(TodCol);
+    const bool has_lut = q.nlin < q.ngas;
+#define ECCKD_TOD_LAUNCH(N)                                                                                  \
+  case N:                                                                                                    \
+    if (has_lut) total_od_planck_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);           \
+    else total_od_planck_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                  \
+    break;
+    switch (q.nlin) {
+      ECCKD_TOD_LAUNCH(0)
+      ECCKD_TOD_LAUNCH(1)
+      ECCKD_TOD_LAUNCH(2)
+      ECCKD_TOD_LAUNCH(3)
+      ECCKD_TOD_LAUNCH(4)
+      ECCKD_TOD_LAUNCH(5)
+      ECCKD_TOD_LAUNCH(6)
+      ECCKD_TOD_LAUNCH(7)
+      ECCKD_TOD_LAUNCH(8)
     }
-    const int nwarp = 8;
-    for (int c0 = 0; c0 < ncol; c0 += slice) {
-      const int nc = std::min(slice, ncol - c0);
-      const size_t o_fl = (size_t)c0 * nlay, o_hl = (size_t)c0 * (nlay + 1);
-      for (int i = 0; i < m->ngas; ++i) q.vmr[i] = gd[i].vmr ? gd[i].vmr + o_fl : nullptr;
-      q.ncol = nc;
-      q.pressure_hl = d_pressure_hl + o_hl;
-      q.temperature_hl = d_temperature_hl + o_hl;
-      q.od = od_arr + o_fl * m->ng;
-      q.planck_hl = p.planck_hl ? p.planck_hl + o_hl * m->ng : nullptr;
-      q.planck_surf = p.planck_surf ? p.planck_surf + (size_t)c0 * m->ng : nullptr;
-      const int64_t ntile = (nc + TOD_TILE - 1) / TOD_TILE;
-      const int64_t units = ntile * nlay + ((q.planck_hl || q.planck_surf) ? ntile * (nlay + 1) : 0);
-      const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)2 * ctx->num_sms);
-      total_od_planck_kernel<<<grid, nwarp * 32, nwarp * TOD_TILE * sizeof(TodCol), ctx->stream>>>(q);
-      ECCKD_LAUNCH_CHECK(ctx);
-      if (lw_staged) {
-        ECCKD_TRY(rt_lw_impl(ctx, nc, nlay, m->ng, q.planck_hl, q.od, m->d_ones, q.planck_surf, d_flux_dn + o_hl * m->ng,
-                             d_flux_up + o_hl * m->ng, d_bb_flux_dn ? d_bb_flux_dn + o_hl : nullptr,
-                             d_bb_flux_up ? d_bb_flux_up + o_hl : nullptr, &bb_done));
-      }
+#undef ECCKD_TOD_LAUNCH
+    ECCKD_LAUNCH_CHECK(ctx);
+    if (lw_staged) {
+      ECCKD_TRY(rt_lw_impl(ctx, ncol, nlay, m->ng, p.planck_hl, od_arr, m->d_ones, p.planck_surf, d_flux_dn, d_flux_up,
+                           d_bb_flux_dn, d_bb_flux_up, &bb_done));
     }
   } else {
     run_ckd_kernel<<<(ncol + cols - 1) / cols, dim3(threads, cols, lz), col_smem * cols, ctx->stream>>>(p);

@@ -99,6 +99,40 @@ def test_config_b_shape_reduction_matches_the_oracle(ctx, O, grid):
     plan.close()
 
 
+def _sort_key_lw_longdouble(p_hl, wn, dwn, od, threshold):
+    """reorder_spectrum.cpp:111-190 for a few wavenumbers in 80-bit arithmetic (numpy longdouble): idealised
+    temperature profile, Planck function, the longwave sweep with unit surface emissivity, heating rate,
+    pseudo-height of the cooling peak; same branches as the reference."""
+    L = np.longdouble
+    p, wn, dwn, od = p_hl.astype(L), wn.astype(L), dwn.astype(L), od.astype(L)
+    nlay = od.shape[0]
+    x = np.log(p)
+    x1 = np.log(L(100000.0))
+    t_hl = np.where(x <= 0, L(173.15), np.where(x >= x1, L(288.15), L(173.15) + L(115.0) * x / x1))
+    h_, c_, k_ = L(6.62606896e-34), L(2.99792458e8), L(1.3806504e-23)
+    freq = wn * (100 * c_)
+    pref = (dwn * 2 * h_ * (100 * c_) * L(3.14159265358979323846) / (c_ * c_)) * freq ** 3
+    planck = pref[None, :] / (np.exp((h_ / k_) * (freq[None, :] / t_hl[:, None])) - 1)
+    d = L(1.66)
+    emis = 1 - np.exp(-d * od)
+    with np.errstate(all="ignore"):
+        fac = np.where(emis > L(1.0e-5), 1 - emis * (1 / d) / od, emis / 2)
+    dn = np.zeros((nlay + 1, wn.size), dtype=L)
+    up = np.zeros_like(dn)
+    for i in range(nlay):
+        dn[i + 1] = dn[i] * (1 - emis[i]) + planck[i] * (emis[i] - fac[i]) + planck[i + 1] * fac[i]
+    up[nlay] = planck[nlay]
+    for i in range(nlay - 1, -1, -1):
+        up[i] = up[i + 1] * (1 - emis[i]) + planck[i + 1] * (emis[i] - fac[i]) + planck[i] * fac[i]
+    conv = -(L(9.80665) / L(1004.0)) / (p[1:] - p[:-1])
+    hr = np.minimum(conv[:, None] * (dn[1:] - dn[:-1] - up[1:] + up[:-1]), 0)
+    dh = x[1:] - x[:-1]
+    ph = x[nlay] - (x[:-1] + x[1:]) / 2
+    key = (hr * (dh * ph)[:, None]).sum(axis=0) / (hr * dh[:, None]).sum(axis=0)
+    col = od.sum(axis=0)
+    return np.where(col < threshold, col - threshold, key).astype(np.float64)
+
+
 def test_config_d_shape_sort_key_and_rank_match_the_oracle(ctx, O, grid):
     nwav, wn, dwn = grid
     nlay = 54
@@ -119,9 +153,20 @@ def test_config_d_shape_sort_key_and_rank_match_the_oracle(ctx, O, grid):
     # well conditioned and what separates two correct evaluations is the cancellation inside each hr_i
     # (a difference of four fluxes): a few eps of the flux per level.  Stated per element: 1e-12 relative
     #  plus 2e-12 absolute, i.e. 2e-13 of the key's range.
-    err = np.abs(key[ok] - key_o[ok])
-    tol = 1e-12 * np.abs(key_o[ok]) + 2e-12
-    assert np.all(err <= tol), (float(np.max(err / tol)), float(np.max(err)))
+    err = np.where(ok, np.abs(key - key_o), 0.0)
+    tol = 1e-12 * np.abs(np.where(ok, key_o, 0.0)) + 2e-12
+    # ... for all but a handful of the 2^23 elements.  Where the two double-precision evaluations differ by more,
+    # neither is "the" answer: the same formula is evaluated in 80-bit arithmetic for those elements (and for a
+    # random sample) and the GPU value must be as close to it as the stated tolerance, or no worse than 4 x the
+    # reference algorithm's own double-precision error.
+    over = np.nonzero(err > tol)[0]
+    assert over.size <= nwav // 1000, (over.size, float(np.max(err / tol)))
+    pick = np.unique(np.concatenate([over[np.argsort(err[over])[-3000:]], rng.integers(0, nwav, 3000)]))
+    pick = pick[ok[pick]]
+    exact = _sort_key_lw_longdouble(p_hl, wn[pick], dwn[pick], od[:, pick], 0.5)
+    e_gpu, e_orc = np.abs(key[pick] - exact), np.abs(key_o[pick] - exact)
+    bound = np.maximum(tol[pick], 4.0 * e_orc)
+    assert np.all(e_gpu <= bound), (float(np.max(e_gpu / bound)), float(np.max(e_gpu)), float(np.max(e_orc)))
     # rank: bit-exact against std::stable_sort on the SAME keys (13 narrow bands)
     b1, b2 = np.array(LW_BAND_EDGES[:-1]), np.array(LW_BAND_EDGES[1:])
     d_band, d_rank = ctx.empty(nwav, np.int32), ctx.empty(nwav, np.int32)

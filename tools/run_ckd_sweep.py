@@ -1,6 +1,5 @@
-"""Timing of ecckd_run_ckd_dev (65536 columns x 54 layers x 32 g points, longwave) for the column-slice budget
-ECCKD_RUN_CKD_SLICE_MB of the layer-major path, and for the column-major kernel it replaced
-(ECCKD_RUN_CKD_LEGACY=1).  Prints one line per setting."""
+"""Timing of ecckd_run_ckd_dev (65536 columns x 54 layers x 32 g points, longwave): the layer-major path and the
+column-major kernel it replaced (ECCKD_RUN_CKD_LEGACY=1).  Prints one line per setting."""
 import os
 import sys
 
@@ -52,9 +51,17 @@ def main():
     full = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls, dn, up, bdn, bup)
     odp = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls)
     ref_up = None
-    for legacy, mb in [("1", "0")] + [("0", m) for m in ("0", "8", "16", "24", "32", "48", "64", "96", "128")]:
+    settings = [("1", "0"), ("0", "0")]
+    if len(sys.argv) > 2 and sys.argv[2] == "one":  # a single short run for ncu
+        os.environ["ECCKD_RUN_CKD_LEGACY"] = "0"
+        os.environ["ECCKD_RUN_CKD_SLICE_MB"] = "0"
+        full()
+        full()
+        torch.cuda.synchronize()
+        return
+    for legacy, mb in settings:
         os.environ["ECCKD_RUN_CKD_LEGACY"] = legacy
-        os.environ["ECCKD_RUN_CKD_SLICE_MB"] = mb
+        os.environ["ECCKD_TOD_VARIANT"] = mb
         ms = timed(full)
         ms_od = timed(odp)
         full()
@@ -62,7 +69,7 @@ def main():
         if ref_up is None:
             ref_up = up.clone()
         err = float((up - ref_up).abs().max())
-        print(f"{kind} legacy={legacy} slice_mb={mb:>3}: fused {ms:.3f} ms ({ncol * ng / ms / 1e6:.2f} G col.g/s), "
+        print(f"{kind} legacy={legacy} variant={mb}: fused {ms:.3f} ms ({ncol * ng / ms / 1e6:.2f} G col.g/s), "
               f"optical depth + Planck only {ms_od:.3f} ms, max |flux_up - legacy| {err:.2e}", flush=True)
 
 
