@@ -57,6 +57,11 @@ def parse_args():
     ap.add_argument("--weights", default="planck", choices=["planck", "matrix"])
     ap.add_argument("--method", default="transmission")
     ap.add_argument("--cpu-log2-nwav", type=int, default=23, help="CPU arm block size (2^23 = the GPU arm's block)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU reduces its own 2^log2-nwav range (the driver's default); strong: ONE 2^log2-nwav "
+                         "spectrum cut into --segments pieces shared out over the GPUs")
+    ap.add_argument("--segments", type=int, default=0,
+                    help="N-independent wavenumber segments per 2^log2-nwav spectrum (default 1 weak, 8 strong)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flux", action="store_true")
@@ -357,15 +362,30 @@ def main():
     assert stream != 0
     ctx = E.Context(local_rank, stream)
 
+    from ecckd_b200 import sharding
+
     nlay, nspec = args.nlay, args.nspec
-    nwav = 1 << args.log2_nwav
-    # this rank's wavenumber range of the (world * nwav)-point spectrum
-    dnu = (3260.0 - 0.0002) / (world * nwav - 1)
-    wn = 0.0002 + dnu * (torch.arange(nwav, device=dev, dtype=torch.float64) + float(rank * nwav))
+    strong = args.scaling == "strong"
+    nwav_glob = (1 << args.log2_nwav) * (1 if strong else world)
+    nseg_total = (args.segments or (8 if strong else 1)) * (1 if strong else world)
+    spans = sharding.segment_ranges(nwav_glob, nseg_total)
+    seg_begin = sharding.segment_owners(nseg_total, world)
+    my_segs = list(range(seg_begin[rank], seg_begin[rank + 1]))
+    assert my_segs, "more ranks than segments"
+    lo, hi = spans[my_segs[0]][0], spans[my_segs[-1]][1]
+    nwav = hi - lo  # this rank's wavenumbers
+    dnu = (3260.0 - 0.0002) / (nwav_glob - 1)
+    wn = 0.0002 + dnu * (torch.arange(nwav, device=dev, dtype=torch.float64) + float(lo))
     dwn = torch.full((nwav,), dnu, dtype=torch.float64, device=dev)
-    key = smooth_key(torch, wn, seed=7)
-    g_point, ng = make_g_point(torch, wn, key, args.gmap, seed=7)
-    del key
+    if strong and world > 1:  # the map of the WHOLE spectrum (ranks inside each band), this rank's slice of it
+        wn_all = 0.0002 + dnu * torch.arange(nwav_glob, device=dev, dtype=torch.float64)
+        g_all, ng = make_g_point(torch, wn_all, smooth_key(torch, wn_all, seed=7), args.gmap, seed=7)
+        g_point = g_all[lo:hi].clone()
+        del wn_all, g_all
+    else:
+        key = smooth_key(torch, wn, seed=7)
+        g_point, ng = make_g_point(torch, wn, key, args.gmap, seed=7)
+        del key
     p_hl = pressure_grid(nlay)
     p_fl = 0.5 * (p_hl[1:] + p_hl[:-1])
     t_hl = temperature_profile(p_hl)
@@ -377,24 +397,39 @@ def main():
     if args.weights == "matrix":
         weight = torch.empty((nlay, nwav), dtype=torch.float64, device=dev)
         E.planck_function_dev(ctx, t_fl, wn, dwn, nwav, weight)
-    plan = E.GPointPlan(ctx, g_point, nwav, ng)
-    count = torch.zeros(ng, dtype=torch.int64, device=dev)
-    count.copy_(torch.from_numpy(plan.counts()))
+    wmode = E.WEIGHT_PLANCK if weight is None else E.WEIGHT_MATRIX
+    # One plan per segment; a segment's partial accumulators go to its slot of seg_sums / seg_minmax, the
+    # exchange (grouped in-place NCCL broadcasts of the owners' slots, the only cross-GPU traffic) makes all
+    # slots visible everywhere and combines them in segment order: bitwise the same for any number of GPUs.
+    n3, n2 = nlay * nspec * ng * 3, nlay * nspec * ng * 2
+    seg_sums = torch.zeros((nseg_total, n3), dtype=torch.float64, device=dev)
+    seg_minmax = torch.zeros((nseg_total, n2), dtype=torch.float64, device=dev)
+    seg_count = torch.zeros((nseg_total, ng), dtype=torch.int64, device=dev)
+    seg = []  # (slot, offset into this rank's arrays, length, plan)
+    for sidx in my_segs:
+        a, b = spans[sidx][0] - lo, spans[sidx][1] - lo
+        plan_s = E.GPointPlan(ctx, g_point[a:b], b - a, ng)
+        seg_count[sidx].copy_(torch.from_numpy(plan_s.counts()))
+        seg.append((sidx, a, b - a, plan_s))
+    plan = seg[0][3]
+    comm = None
     if world > 1:
-        dist.all_reduce(count)
-    sums = torch.empty((nlay, nspec, ng, 3), dtype=torch.float64, device=dev)
-    minmax = torch.empty((nlay, nspec, ng, 2), dtype=torch.float64, device=dev)
+        comm = E.Comm(ctx, rank, world, exchange=lambda box: dist.broadcast_object_list(box, src=0))
+    sums = torch.empty(n3, dtype=torch.float64, device=dev)
+    minmax = torch.empty(n2, dtype=torch.float64, device=dev)
+    count = torch.zeros(ng, dtype=torch.int64, device=dev)
+    # the per-g wavenumber counts are exchanged once, with the map
+    E.average_optical_depth_exchange_dev(ctx, comm, seg_begin, None, None, None, None, seg_count, count)
     outs = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
     mins = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
     maxs = [torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)]
-    wmode = E.WEIGHT_PLANCK if weight is None else E.WEIGHT_MATRIX
 
     def step():
-        E.average_optical_depth_partial_dev(ctx, plan, nlay, p_fl, ods, nwav, wmode, weight, nwav, t_fl, wn, dwn,
-                                            args.method, sums, minmax)
-        if world > 1:  # the only cross-GPU traffic: per-(layer, spectrum, g) partial accumulators
-            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-            dist.all_reduce(minmax, op=dist.ReduceOp.MIN)
+        for sidx, a, n, plan_s in seg:
+            E.average_optical_depth_partial_dev(
+                ctx, plan_s, nlay, p_fl, [od[:, a:] for od in ods], nwav, wmode, None if weight is None else weight[:, a:],
+                nwav, t_fl, wn[a:], dwn[a:], args.method, seg_sums[sidx], seg_minmax[sidx])
+        E.average_optical_depth_exchange_dev(ctx, comm, seg_begin, seg_sums, seg_minmax, sums, minmax)
         E.average_optical_depth_finalize_dev(ctx, ng, count, vmrs, p_fl, p_hl, args.method, sums, minmax, outs, mins,
                                              maxs, ng)
 
@@ -424,15 +459,15 @@ def main():
     kms, klaunch = ctx.reduce_kernel_time()
     ctx.set_timing(False)
     launches = ctx.kernel_launches - launches0
-    kstat = torch.tensor([kms / max(klaunch, 1)], dtype=torch.float64, device=dev)
+    kstat = torch.tensor([kms / args.steps], dtype=torch.float64, device=dev)  # reduction kernel time per step
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(kstat, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
-    units_per_step = world * nspec * nlay * nwav
+    units_per_step = nspec * nlay * nwav_glob
     value = units_per_step * args.steps / (total_ms * 1e-3)
 
-    # roofline of the dominant kernel (reduce_kernel), algorithmic bytes per launch per GPU:
+    # roofline of the dominant kernel, algorithmic bytes per step per GPU (one launch per segment):
     # 8 B per point.layer of optical depth; per wavenumber 4 B g point + 8 B nu + 8 B dnu (Planck
     # weights recomputed) or + 8 B per point.layer of weights per distinct weight row (streamed).
     alg_bytes = nspec * nlay * nwav * 8 + nwav * 20
@@ -574,18 +609,20 @@ def main():
         line = {
             "metric": "LBL spectral points*layers/s reduced to LUT", "value": value, "unit": "point*layers/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"create_look_up_table LW (BASELINE configs[1]), one temperature index: {nspec} spectra x "
-                            f"{nlay} layers x 2^{args.log2_nwav} wavenumbers per GPU, {ng} g points / 13 bands, "
-                            f"'{args.method}', weights={args.weights}, g map={args.gmap}",
-                "sharding": "wavenumber ranges per rank; NCCL allreduce of per-g partial accumulators only",
+                            f"{nlay} layers x 2^{args.log2_nwav} wavenumbers " + ("in total" if strong else "per GPU") +
+                            f", {ng} g points / 13 bands, '{args.method}', weights={args.weights}, g map={args.gmap}",
+                "sharding": f"{nseg_total} wavenumber segments (boundaries independent of the GPU count), contiguous runs per "
+                            "rank; grouped in-place NCCL broadcasts of the per-segment partial accumulators, combined in "
+                            "segment order (ecckd_average_optical_depth_exchange_dev): bitwise independent of the GPU count",
                 "l2": "inputs (%.1f GB per GPU) exceed L2; no flush needed" % (nspec * nlay * nwav * 8 / 1e9),
-                "reduce_partial_bytes_allreduced_per_step": int(sums.numel() * 8 + minmax.numel() * 8) if world > 1 else 0,
+                "exchange_bytes_received_per_step": int((n3 + n2) * 8 * (nseg_total - len(my_segs))) if world > 1 else 0,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes)},
+                         "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "launches_per_step": len(seg), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(alg_bytes // len(seg))},
             "cpu_baseline": cpu,
             "validated": validated,
             "e2e": e2e,

@@ -112,6 +112,11 @@ def _declare(L):
         "ecckd_lut_builder_block": [vp, dbl, i32, vp, vp, vp, vp, i64, C.c_char_p, vp, vp, vp, vp, i64, vp],
         "ecckd_lut_builder_destroy": [vp],
         "ecckd_ctx_plan_cache_stats": [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)],
+        "ecckd_comm_unique_id": [vp],
+        "ecckd_comm_create": [vp, i32, i32, vp, vp],
+        "ecckd_comm_from_nccl": [vp, vp, i32, i32, vp],
+        "ecckd_comm_destroy": [vp],
+        "ecckd_average_optical_depth_exchange_dev": [vp, vp, i32, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp],
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],

@@ -75,6 +75,21 @@ class DeviceArray:
         self.ctx.synchronize()  # `a` may be a temporary
         return self
 
+    def offset(self, n: int, shape=None) -> "DeviceArray":
+        """Unowned view starting n elements into the (flattened) array; keeps nothing alive."""
+        total = self.nbytes // self.dtype.itemsize
+        if not 0 <= n <= total:
+            raise IndexError("offset outside the array")
+        return DeviceArray(self.ctx, (total - n,) if shape is None else shape, self.dtype,
+                           ptr=self.ptr + int(n) * self.dtype.itemsize)
+
+    def row(self, i: int) -> "DeviceArray":
+        """Unowned view of self[i] (C order)."""
+        per = int(np.prod(self.shape[1:], dtype=np.int64))
+        if not 0 <= i < self.shape[0]:
+            raise IndexError("row outside the array")
+        return self.offset(i * per, self.shape[1:] or (1,))
+
     def numpy(self) -> np.ndarray:
         out = np.empty(self.shape, dtype=self.dtype)
         check(_lib.lib().ecckd_memcpy_d2h(self.ctx.handle, out.ctypes.data, self.ptr, self.nbytes))
@@ -318,6 +333,55 @@ def create_lut_block(ctx: Context, ng, reference_surface_vmr, pressure_hl, tempe
         sp, averaging_method.encode(), t_fl.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
         out[3].ctypes.data))
     return out + (t_fl,)
+
+
+class Comm:
+    """ecckd_comm: the NCCL communicator of the sharded reduction (one rank per GPU).  `exchange` is a
+    callable that hands rank 0's 128-byte id to every rank, e.g.
+    ``lambda b: torch.distributed.broadcast_object_list(b, src=0)`` on a one-element list."""
+
+    def __init__(self, ctx: Context, rank: int, world: int, exchange=None, unique_id: Optional[bytes] = None):
+        self.ctx, self.rank, self.world, self.handle = ctx, int(rank), int(world), None
+        if unique_id is None:
+            box = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                check(_lib.lib().ecckd_comm_unique_id(C.cast(buf, C.c_void_p).value))
+                box[0] = buf.raw
+            if world > 1:
+                if exchange is None:
+                    raise EcckdError(147, "Comm: world > 1 needs `exchange` or `unique_id`")
+                exchange(box)
+            unique_id = box[0]
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        h = C.c_void_p()
+        check(_lib.lib().ecckd_comm_create(ctx.handle, self.world, self.rank, C.cast(buf, C.c_void_p).value, C.byref(h)))
+        self.handle = h.value
+        ctx._children.add(self)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def average_optical_depth_exchange_dev(ctx: Context, comm: Optional[Comm], seg_begin, d_seg_sums, d_seg_minmax,
+                                       d_sums, d_minmax, d_seg_count=None, d_count=None):
+    """ecckd_average_optical_depth_exchange_dev: d_seg_*[nseg_total][...] slots -> combined d_* on every rank, in
+    segment order (bitwise independent of the number of ranks).  seg_begin[nranks + 1]: first segment of each rank."""
+    sb = np.ascontiguousarray(seg_begin, dtype=np.int32)
+    nseg = int(sb[-1])
+    numel = lambda a: 0 if a is None else (int(a.numel()) if hasattr(a, "numel") else int(np.prod(a.shape)))
+    n_sums, n_mm, n_cnt = numel(d_sums), numel(d_minmax), numel(d_count)
+    check(_lib.lib().ecckd_average_optical_depth_exchange_dev(
+        ctx.handle, None if comm is None else comm.handle, nseg, sb.ctypes.data, n_sums, n_mm, n_cnt, _ptr(d_seg_sums),
+        _ptr(d_seg_minmax), _ptr(d_seg_count), _ptr(d_sums), _ptr(d_minmax), _ptr(d_count)))
 
 
 class LutBuilder:

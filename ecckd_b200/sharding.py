@@ -27,6 +27,39 @@ def shard_range(nwav: int, rank: int, world: int, align: int = CHUNK) -> Tuple[i
     return min(c0 * align, nwav), min(c1 * align, nwav)
 
 
+def segment_ranges(nwav: int, nseg: int, align: int = CHUNK):
+    """The nseg wavenumber segments [begin, end) of the N-independent decomposition (chunk-aligned
+    boundaries that depend on nwav and nseg only)."""
+    return [shard_range(nwav, s, nseg, align) for s in range(nseg)]
+
+
+def segment_owners(nseg: int, world: int):
+    """seg_begin[world + 1]: rank r owns segments [seg_begin[r], seg_begin[r + 1]) - contiguous, in rank order,
+    counts differing by at most one (ranks may own none when world > nseg)."""
+    return [(nseg * r) // world for r in range(world + 1)]
+
+
+def exchange_partials_reference(seg_sums, seg_minmax, seg_begin, rank, group=None):
+    """What ecckd_average_optical_depth_exchange_dev does, on torch CPU tensors over any backend (the gloo tests
+    of the host logic): every owner broadcasts its run of slots, then the slots are combined in segment order."""
+    import torch
+    import torch.distributed as dist
+
+    world = len(seg_begin) - 1
+    if world > 1:
+        for r in range(world):
+            a, b = seg_begin[r], seg_begin[r + 1]
+            if b > a:
+                dist.broadcast(seg_sums[a:b], src=r, group=group)
+                dist.broadcast(seg_minmax[a:b], src=r, group=group)
+    sums = seg_sums[0].clone()
+    minmax = seg_minmax[0].clone()
+    for s in range(1, seg_sums.shape[0]):
+        sums += seg_sums[s]
+        minmax = torch.minimum(minmax, seg_minmax[s])
+    return sums, minmax
+
+
 def allreduce_partials(sums, minmax, group=None):
     """In-place all-reduce of the partial accumulators (torch tensors, any backend)."""
     import torch.distributed as dist

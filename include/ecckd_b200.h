@@ -295,6 +295,32 @@ int ecckd_lut_builder_destroy(ecckd_lut_builder* builder);
  * element on the device).  hits / misses since the context was created; ECCKD_PLAN_CACHE=0 disables. */
 int ecckd_ctx_plan_cache_stats(ecckd_ctx* ctx, int64_t* hits, int64_t* misses);
 
+/* ---- the cross-GPU form of the reduction -------------------------------------
+ * The wavenumber axis is cut into nseg_total segments whose boundaries do not depend on the number
+ * of ranks.  A rank owns the contiguous run of segments [h_seg_begin[rank], h_seg_begin[rank+1]) and
+ * reduces each with its own plan, _partial_dev writing into that segment's slot of
+ *   d_seg_sums  [nseg_total][n_sums]    (n_sums   = nlay*nspec*ng*3)
+ *   d_seg_minmax[nseg_total][n_minmax]  (n_minmax = nlay*nspec*ng*2)
+ *   d_seg_count [nseg_total][n_count]   (n_count  = ng: the plans' per-g wavenumber counts; n_count may be 0)
+ * _exchange_dev makes every slot visible on every rank (one grouped in-place NCCL broadcast per
+ * owner over NVLink) and combines the slots IN SEGMENT ORDER into d_sums / d_minmax / d_count, which
+ * _finalize_dev then takes.  Every slot depends only on its segment's data and the combination order
+ * is fixed: the result is bitwise identical on every rank and for EVERY number of ranks (an all-reduce
+ * sums in an order that follows the communicator).  comm == NULL: single process, all slots are local.
+ * NCCL is bound at run time (libnccl.so.2, or ECCKD_NCCL_LIB); nothing links against it. */
+typedef struct ecckd_comm ecckd_comm;
+/* id128: 128 bytes (ncclUniqueId); created on one rank, handed to the others by the host program */
+int ecckd_comm_unique_id(void* id128);
+int ecckd_comm_create(ecckd_ctx* ctx, int nranks, int rank, const void* id128, ecckd_comm** out);
+/* adopt a communicator the host program already has (ncclComm_t); not destroyed by _destroy */
+int ecckd_comm_from_nccl(ecckd_ctx* ctx, void* nccl_comm, int nranks, int rank, ecckd_comm** out);
+int ecckd_comm_destroy(ecckd_comm* comm);
+int ecckd_average_optical_depth_exchange_dev(ecckd_ctx* ctx, ecckd_comm* comm, int nseg_total,
+                                             const int32_t* h_seg_begin, int64_t n_sums, int64_t n_minmax,
+                                             int64_t n_count, double* d_seg_sums, double* d_seg_minmax,
+                                             int64_t* d_seg_count, double* d_sums, double* d_minmax,
+                                             int64_t* d_count);
+
 /* Merge of several spectra: src/ecckd/read_merged_spectrum.cpp:149-168.
  * d_optical_depth += d_od * scaling, or * h_scaling_profile[layer] if non-NULL. */
 int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,

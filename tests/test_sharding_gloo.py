@@ -189,3 +189,71 @@ def test_two_rank_sort_keys_and_forward_cost_match_unsharded():
     same_key, same_rank, ok_prof, d_cost, d_pen = q.get(timeout=10)
     assert same_key and same_rank and ok_prof
     assert d_cost < 1e-13 and d_pen < 1e-13
+
+
+# ------------------------------------------------------------------ N-independent segments
+def test_segment_ranges_and_owners():
+    for nwav in (1, 5003, 8_388_608):
+        for nseg in (1, 6, 8):
+            spans = sharding.segment_ranges(nwav, nseg)
+            assert spans[0][0] == 0 and spans[-1][1] == nwav
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    for nseg in (1, 6, 8):
+        for world in (1, 2, 3, 8, 11):
+            sb = sharding.segment_owners(nseg, world)
+            assert sb[0] == 0 and sb[-1] == nseg and len(sb) == world + 1
+            assert all(0 <= b - a <= (nseg + world - 1) // world for a, b in zip(sb, sb[1:]))
+
+
+def _worker_segments(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle_np as N
+
+        nseg, kd = 6, 1.66
+        c = S.lw_spectrum_case(nlay=7, nwav=5003, ng=9, nband=2, seed=3)
+        c["planck"] = N.planck_function(c["temperature_fl"], c["wavenumber"], c["d_wavenumber"])
+        spans = sharding.segment_ranges(c["nwav"], nseg)
+        sb = sharding.segment_owners(nseg, world)
+        seg_s = torch.zeros((nseg, c["nlay"], 1, c["ng"], 3), dtype=torch.float64)
+        seg_m = torch.zeros((nseg, c["nlay"], 1, c["ng"], 2), dtype=torch.float64)
+        for s in range(sb[rank], sb[rank + 1]):  # this rank's segments only
+            a, b, _ = _partials(c, spans[s][0], spans[s][1], kd)
+            seg_s[s], seg_m[s] = torch.from_numpy(a), torch.from_numpy(b)
+        sums, minmax = sharding.exchange_partials_reference(seg_s, seg_m, sb, rank)
+        count = np.bincount(c["g_point"][c["g_point"] >= 0], minlength=c["ng"]).astype(np.int64)
+        out = _finalize(c, sums.numpy(), minmax.numpy(), count, kd)
+        q.put((rank, out.tobytes()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_segment_exchange_is_bitwise_independent_of_the_number_of_ranks():
+    """One, two and three gloo ranks own 6, 3+3 and 2+2+2 of the same six segments: after the exchange and the
+    fixed-order combination every rank of every world size holds the same bits."""
+    import torch.multiprocessing as mp
+
+    results = {}
+    for world in (1, 2, 3):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        procs = [ctx.Process(target=_worker_segments, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        got = [q.get(timeout=240) for _ in range(world)]
+        for p in procs:
+            p.join(timeout=240)
+            assert p.exitcode == 0
+        results[world] = dict(got)
+    base = results[1][0]
+    for world, by_rank in results.items():
+        for rank, blob in by_rank.items():
+            assert blob == base, (world, rank)
