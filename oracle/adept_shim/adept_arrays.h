@@ -228,6 +228,8 @@ class Array {
   bool empty() const { return size() == 0; }
   T* data() { return data_; }
   const T* data() const { return data_; }
+  const T* const_data() const { return data_; }
+  long offset(int d) const { return stride_[d]; }  // Adept's name for the stride of dimension d
   const std::shared_ptr<T>& storage() const { return store_; }
   void clear() { store_.reset(); data_ = 0; for (int d = 0; d < Rank; ++d) dim_[d] = stride_[d] = 0; }
   void resize(int n0) { int n[1] = {n0}; static_assert(Rank == 1, "rank"); alloc(n); }

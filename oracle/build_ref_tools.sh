@@ -40,5 +40,32 @@ g++ $FLAGS -c "$HERE/ref_tools_glue.cpp" -o "$OUT/tools_obj/ref_tools_glue.o" &
  objcopy --redefine-sym main=ref_main_find_g_points "$OUT/tools_obj/ref_tools_fgp_glue.o") &
 wait
 g++ -shared -fopenmp -o "$OUT/libecckd_ref_tools.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/ref_tools_fgp_glue.o" "$OUT/tools_obj/mock_files.o" $OBJS
-rm -rf "$OUT/tools_obj"
 echo "built $OUT/libecckd_ref_tools.so"
+
+# The same tools as a CONSUMER of the C ABI: integration/ecckd_gpu_bindings.cpp takes the place
+# of average_optical_depth.cpp and planck_function.cpp and provides radiative_transfer_lw<false>; the stock
+# radiative_transfer_lw.cpp is compiled with that one name changed so that its other functions stay.  Everything
+# else - the mains, the file layer, every other unit - is the object code of the stock build above.
+REPO="$(cd "$HERE/.." && pwd)"
+if [ -f "$REPO/ecckd_b200/lib/libecckd_b200.so" ]; then
+  g++ $FLAGS -I"$REPO/include" -c "$REPO/integration/ecckd_gpu_bindings.cpp" -o "$OUT/tools_obj/gpu_bindings.o" &
+  g++ $FLAGS -fopenmp -Dradiative_transfer_lw=radiative_transfer_lw_stock -c "$REF/src/ecckd/radiative_transfer_lw.cpp" \
+      -o "$OUT/tools_obj/radiative_transfer_lw_renamed.o" &
+  gcc -std=c99 -Wall -Werror -fsyntax-only -I"$REPO/include" -x c "$REPO/include/ecckd_b200.h" &   # the header is C
+  wait
+  GPU_OBJS=""
+  for o in $OBJS; do
+    case "$o" in
+      */average_optical_depth.o|*/planck_function.o) ;;
+      */radiative_transfer_lw.o) GPU_OBJS="$GPU_OBJS $OUT/tools_obj/radiative_transfer_lw_renamed.o" ;;
+      *) GPU_OBJS="$GPU_OBJS $o" ;;
+    esac
+  done
+  g++ -shared -fopenmp -o "$OUT/libecckd_ref_tools_gpu.so" "$OUT/tools_obj/ref_tools_glue.o" "$OUT/tools_obj/ref_tools_fgp_glue.o" \
+      "$OUT/tools_obj/mock_files.o" "$OUT/tools_obj/gpu_bindings.o" $GPU_OBJS \
+      -L"$REPO/ecckd_b200/lib" -lecckd_b200 -Wl,-rpath,'$ORIGIN/../../ecckd_b200/lib'
+  echo "built $OUT/libecckd_ref_tools_gpu.so"
+else
+  echo "libecckd_b200.so not built yet: skipping libecckd_ref_tools_gpu.so"
+fi
+rm -rf "$OUT/tools_obj"

@@ -12,8 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.environ.get("REF_TOOLS_LIB", os.path.join(ROOT, "oracle", "_ref", "libecckd_ref_tools.so"))
 
 
+GPU_LIB = os.path.join(ROOT, "oracle", "_ref", "libecckd_ref_tools_gpu.so")  # the same tools on the C ABI
+
+
 def available():
     return os.path.exists(LIB)
+
+
+def gpu_available():
+    return os.path.exists(GPU_LIB)
 
 
 def _f64(a):
@@ -41,8 +48,8 @@ class BandSw(C.Structure):
 
 
 class RefTools:
-    def __init__(self):
-        self.L = C.CDLL(LIB)
+    def __init__(self, lib=None):
+        self.L = C.CDLL(lib or LIB)
         self.L.ref_tools_build_info.restype = C.c_char_p
         self.L.ref_tool_last_exception.restype = C.c_char_p
         self._keep = []
