@@ -117,6 +117,15 @@ def _declare(L):
         "ecckd_comm_from_nccl": [vp, vp, i32, i32, vp],
         "ecckd_comm_destroy": [vp],
         "ecckd_average_optical_depth_exchange_dev": [vp, vp, i32, vp, i64, i64, i64, vp, vp, vp, vp, vp, vp],
+        "ecckd_partition_options_default": [vp],
+        "ecckd_partition_search_create": [vp, vp, vp, vp],
+        "ecckd_partition_search_destroy": [vp],
+        "ecckd_partition_search_n": [vp, i32, vp, vp, i32, vp],
+        "ecckd_partition_search_e": [vp, dbl, dbl, dbl, i32, vp, vp, vp, vp],
+        "ecckd_partition_search_stats": [vp, vp, vp, vp],
+        "ecckd_partition_search_band": [vp, i64, dbl, i32, i32, i32, vp, vp, vp, vp, vp, vp],
+        "ecckd_interval_error_lw_eval": [vp, i32, vp, vp, vp],
+        "ecckd_interval_error_sw_eval": [vp, i32, vp, vp, vp],
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],
@@ -163,6 +172,37 @@ def _declare(L):
             fn = getattr(L, name)
             fn.argtypes = argtypes
             fn.restype = C.c_int
+
+
+class PartitionOptions(C.Structure):
+    """ecckd_partition_options"""
+    _fields_ = [("partition_tolerance", C.c_double), ("next_bound_error_tolerance", C.c_double), ("resolution", C.c_double),
+                ("partition_max_iterations", C.c_int), ("line_search_max_iterations", C.c_int),
+                ("next_bound_max_iterations", C.c_int), ("minimize_frac_range", C.c_int), ("cubic_interpolation", C.c_int),
+                ("speculative_line_search", C.c_int)]
+
+
+class IntervalErrorLwArgs(C.Structure):
+    """ecckd_interval_error_lw_args"""
+    _fields_ = [("ctx", C.c_void_p), ("averaging_method", C.c_int), ("nlay", C.c_int), ("n", C.c_int64), ("stride", C.c_int64)] + [
+        (k, C.c_void_p) for k in ("d_pressure_hl", "d_planck_hl", "d_surf_emissivity", "d_surf_planck", "d_bg_optical_depth",
+                                  "d_metric", "d_flux_dn_surf", "d_flux_up_toa", "d_hr")] + [
+        ("flux_weight", C.c_double), ("d_layer_weight", C.c_void_p)]
+
+
+class IntervalErrorSwArgs(C.Structure):
+    """ecckd_interval_error_sw_args"""
+    _fields_ = [("ctx", C.c_void_p), ("averaging_method", C.c_int), ("nlay", C.c_int), ("n", C.c_int64), ("stride", C.c_int64),
+                ("cos_sza", C.c_double), ("d_pressure_hl", C.c_void_p), ("d_ssi", C.c_void_p), ("albedo", C.c_double)] + [
+        (k, C.c_void_p) for k in ("d_bg_optical_depth", "d_metric", "d_flux_dn_surf", "d_flux_up_toa", "d_hr")] + [
+        ("flux_weight", C.c_double)] + [
+        (k, C.c_void_p) for k in ("d_layer_weight", "d_flux_dn_surf_low", "d_flux_up_toa_low", "d_hr_low",
+                                  "d_flux_dn_surf_high", "d_flux_up_toa_high", "d_hr_high")] + [
+        ("min_scaling", C.c_double), ("max_scaling", C.c_double)]
+
+
+INTERVAL_ERROR_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                C.POINTER(C.c_double))
 
 
 class EcckdError(RuntimeError):

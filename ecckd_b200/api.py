@@ -17,7 +17,8 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import EcckdError, GasTable, check
+from ._lib import (INTERVAL_ERROR_FN, EcckdError, GasTable, IntervalErrorLwArgs, IntervalErrorSwArgs, PartitionOptions,
+                   check)
 
 AVERAGING_METHODS = (
     "linear",
@@ -333,6 +334,133 @@ def create_lut_block(ctx: Context, ng, reference_surface_vmr, pressure_hl, tempe
         sp, averaging_method.encode(), t_fl.ctypes.data, out[0].ctypes.data, out[1].ctypes.data, out[2].ctypes.data, ng,
         out[3].ctypes.data))
     return out + (t_fl,)
+
+
+EP_STATUS = ("success", "max-iterations-reached", "failed-to-converge", "resolution-limit-reached", "no-progress",
+             "failure", "input-error")  # EpStatus, equipartition.h:31-39
+
+
+class PartitionSearch:
+    """ecckd_partition_search: the Equipartition driver of find_g_points (equipartition.cpp:160-805) over a batched
+    evaluator.  `evaluator` is either a Python callable (bound1[n], bound2[n]) -> error[n], or the pair
+    ("lw" | "sw", filled IntervalErrorLwArgs / IntervalErrorSwArgs) selecting the device evaluators
+    ecckd_interval_error_{lw,sw}_eval (no Python in the loop).  Options: fields of ecckd_partition_options."""
+
+    def __init__(self, evaluator, **options):
+        L = _lib.lib()
+        self.handle = None
+        self.opt = PartitionOptions()
+        L.ecckd_partition_options_default(C.byref(self.opt))
+        for k, v in options.items():
+            if not hasattr(self.opt, k):
+                raise EcckdError(147, f"unknown partition option {k}")
+            setattr(self.opt, k, v)
+        self.error = None
+        if callable(evaluator):
+            def trampoline(_user, n, b1, b2, err):
+                try:
+                    out = evaluator(np.ctypeslib.as_array(b1, (n,)).copy(), np.ctypeslib.as_array(b2, (n,)).copy())
+                    np.ctypeslib.as_array(err, (n,))[:] = np.asarray(out, dtype=np.float64)
+                    return 0
+                except EcckdError as e:
+                    self.error = e
+                    return e.code if getattr(e, "code", 0) else 131
+                except Exception as e:  # noqa: BLE001 - reported to the caller of the search
+                    self.error = e
+                    return 131
+            self._cb = INTERVAL_ERROR_FN(trampoline)
+            fn, user = C.cast(self._cb, C.c_void_p).value, None
+        else:
+            kind, self._args = evaluator
+            f = L.ecckd_interval_error_lw_eval if kind == "lw" else L.ecckd_interval_error_sw_eval
+            fn, user = C.cast(f, C.c_void_p).value, C.addressof(self._args)
+        h = C.c_void_p()
+        check(L.ecckd_partition_search_create(C.addressof(self.opt), fn, user, C.byref(h)))
+        self.handle = h.value
+
+    def _done(self, rc):
+        if rc != 0 and self.error is not None:
+            e, self.error = self.error, None
+            raise e
+        check(rc)
+
+    def equipartition_n(self, bounds, error=None):
+        """-> (status string, bounds[ni+1], error[ni])"""
+        b = np.array(bounds, dtype=np.float64)
+        ni = b.size - 1
+        e = np.zeros(ni) if error is None else np.array(error, dtype=np.float64)
+        st = C.c_int(0)
+        self._done(_lib.lib().ecckd_partition_search_n(self.handle, ni, b.ctypes.data, e.ctypes.data,
+                                                      0 if error is None else 1, C.addressof(st)))
+        return EP_STATUS[st.value], b, e
+
+    def equipartition_e(self, target_error, bound0, boundn, capacity=256):
+        b, e = np.zeros(capacity + 1), np.zeros(capacity)
+        ni, st = C.c_int(0), C.c_int(0)
+        self._done(_lib.lib().ecckd_partition_search_e(self.handle, float(target_error), float(bound0), float(boundn),
+                                                      capacity, C.addressof(ni), b.ctypes.data, e.ctypes.data,
+                                                      C.addressof(st)))
+        return EP_STATUS[st.value], b[:ni.value + 1].copy(), e[:ni.value].copy()
+
+    def band(self, npoints, target_error, min_g_points=1, max_g_points=256, capacity=256):
+        """One band of find_g_points (find_g_points.cpp:1229-1256, 1396-1400) -> (status, bounds, error, rank1, rank2)"""
+        b, e = np.zeros(capacity + 1), np.zeros(capacity)
+        r1, r2 = np.zeros(capacity, dtype=np.int64), np.zeros(capacity, dtype=np.int64)
+        ng, st = C.c_int(0), C.c_int(0)
+        self._done(_lib.lib().ecckd_partition_search_band(self.handle, int(npoints), float(target_error), min_g_points,
+                                                         max_g_points, capacity, C.addressof(ng), b.ctypes.data,
+                                                         e.ctypes.data, r1.ctypes.data, r2.ctypes.data, C.addressof(st)))
+        n = ng.value
+        return EP_STATUS[st.value], b[:n + 1].copy(), e[:n].copy(), r1[:n].copy(), r2[:n].copy()
+
+    def stats(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(_lib.lib().ecckd_partition_search_stats(self.handle, C.addressof(a), C.addressof(b), C.addressof(c)))
+        return dict(batches=a.value, intervals=b.value, speculative_unused=c.value)
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ecckd_partition_search_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def interval_error_lw_evaluator(ctx, averaging_method, nlay, n, stride, d_pressure_hl, d_planck_hl, d_surf_emissivity,
+                                d_surf_planck, d_bg_od, d_metric, d_flux_dn_surf, d_flux_up_toa, d_hr, flux_weight,
+                                d_layer_weight, offset=0):
+    """The evaluator argument of PartitionSearch for one longwave band on the device: the spectral arrays are in
+    rank order, the band is the `n` points from `offset` (find_g_points.cpp:1158-1166: ibegin..iend)."""
+    o = int(offset) * 8
+
+    def sp(d):
+        return _ptr(d).value + o
+    a = IntervalErrorLwArgs(ctx.handle, _method_id(averaging_method), nlay, n, stride, _ptr(d_pressure_hl).value,
+                            sp(d_planck_hl), sp(d_surf_emissivity), sp(d_surf_planck), sp(d_bg_od), sp(d_metric),
+                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight).value)
+    return ("lw", a)
+
+
+def interval_error_sw_evaluator(ctx, averaging_method, nlay, n, stride, cos_sza, d_pressure_hl, d_ssi, albedo, d_bg_od,
+                                d_metric, d_flux_dn_surf, d_flux_up_toa, d_hr, flux_weight, d_layer_weight, low=None,
+                                high=None, min_scaling=1.0, max_scaling=1.0, offset=0):
+    """As interval_error_lw_evaluator, shortwave (low/high: the total-transmission extras, find_g_points.cpp:1175-1180)."""
+    o = int(offset) * 8
+
+    def sp(d):
+        return None if d is None else _ptr(d).value + o
+    low = low or (None, None, None)
+    high = high or (None, None, None)
+    a = IntervalErrorSwArgs(ctx.handle, _method_id(averaging_method), nlay, n, stride, float(cos_sza),
+                            _ptr(d_pressure_hl).value, sp(d_ssi), float(albedo), sp(d_bg_od), sp(d_metric),
+                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight).value,
+                            sp(low[0]), sp(low[1]), sp(low[2]), sp(high[0]), sp(high[1]), sp(high[2]),
+                            float(min_scaling), float(max_scaling))
+    return ("sw", a)
 
 
 class Comm:

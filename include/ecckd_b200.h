@@ -555,6 +555,89 @@ int ecckd_interval_error_batch_sw_dev(
     const int64_t* h_i1, const int64_t* h_i2, double* d_error, double* d_optical_depth_fit);
 
 /* ---------------------------------------------------------------------------
+ * Partition search of find_g_points: the Equipartition class of the reference
+ * (src/ecckd/equipartition.h:64-209, equipartition.cpp:160-805) as a host driver over a BATCHED interval
+ * error evaluator.  Every calc_error_all of the reference (equipartition.h:97-113, one calc_error per
+ * OpenMP thread) is one evaluator call with all its intervals; the candidates of a line search
+ * (equipartition.cpp:160-196: the proposal moved 0, 1, 2, ... times halfway back) do not depend on the
+ * errors, so `speculative_line_search` of them go into one batch.  Given an evaluator returning the
+ * same errors, bounds / errors / number of intervals / status are those of the reference, bit for bit.
+ * ------------------------------------------------------------------------- */
+enum ecckd_ep_status { /* EpStatus, equipartition.h:31-39 */
+  ECCKD_EP_SUCCESS = 0,
+  ECCKD_EP_MAX_ITERATIONS_REACHED = 1,
+  ECCKD_EP_FAILED_TO_CONVERGE = 2,
+  ECCKD_EP_RESOLUTION_LIMIT_REACHED = 3,
+  ECCKD_EP_NO_PROGRESS = 4,
+  ECCKD_EP_FAILURE = 5,
+  ECCKD_EP_INPUT_ERROR = 6
+};
+/* error[i] of the interval [bound1[i], bound2[i]], i < n; returns ECCKD_OK or the code to abort with */
+typedef int (*ecckd_interval_error_fn)(void* user, int n, const double* bound1, const double* bound2, double* error);
+typedef struct ecckd_partition_options { /* defaults: equipartition.h:187-202 */
+  double partition_tolerance;        /* 0.05; find_g_points sets it (find_g_points.cpp:1180) */
+  double next_bound_error_tolerance; /* 0.05 */
+  double resolution;                 /* 0; find_g_points: 1 / npoints (:230, :258) */
+  int partition_max_iterations;      /* 20 (:1179) */
+  int line_search_max_iterations;    /* 10 */
+  int next_bound_max_iterations;     /* 20 */
+  int minimize_frac_range;           /* 1: (max - min) / mean; 0: fractional standard deviation */
+  int cubic_interpolation;           /* 0 */
+  int speculative_line_search;       /* line-search candidates per evaluator batch (>= 1; 1 = one at a time) */
+} ecckd_partition_options;
+void ecckd_partition_options_default(ecckd_partition_options* options);
+typedef struct ecckd_partition_search ecckd_partition_search;
+int ecckd_partition_search_create(const ecckd_partition_options* options /* NULL: defaults */, ecckd_interval_error_fn fn,
+                                  void* user, ecckd_partition_search** out);
+int ecckd_partition_search_destroy(ecckd_partition_search* search);
+/* Equipartition::equipartition_n (equipartition.cpp:353-562): bounds[ni+1] in/out (ends fixed), error[ni] out
+ * (in as well when errors_given != 0, as after equipartition_e); *ep_status one of ecckd_ep_status.
+ * Returns ECCKD_OK, or what the evaluator returned when it failed. */
+int ecckd_partition_search_n(ecckd_partition_search* search, int ni, double* bounds, double* error, int errors_given,
+                             int* ep_status);
+/* Equipartition::equipartition_e (:569-623): as many intervals as a target error needs, then equal errors.
+ * bounds[capacity+1], error[capacity]; *ni out. */
+int ecckd_partition_search_e(ecckd_partition_search* search, double target_error, double bound0, double boundn,
+                             int capacity, int* ni, double* bounds, double* error, int* ep_status);
+/* One band of find_g_points without sub-bands (find_g_points.cpp:1229-1256, 1396-1400): equipartition_e on
+ * [0, 1], re-partitioned into min/max_g_points intervals from the bounds sqrt(i / ng) when the count falls
+ * outside that range; rank1/rank2[ng] (may be NULL) = the band-relative index range of every g point. */
+int ecckd_partition_search_band(ecckd_partition_search* search, int64_t npoints, double target_error, int min_g_points,
+                                int max_g_points, int capacity, int* ng, double* bounds, double* error, int64_t* rank1,
+                                int64_t* rank2, int* ep_status);
+/* evaluator calls, intervals evaluated, intervals evaluated speculatively and not needed */
+int ecckd_partition_search_stats(ecckd_partition_search* search, int64_t* batches, int64_t* intervals,
+                                 int64_t* speculative_unused);
+
+/* The evaluators of find_g_points: CkdEquipartition::calc_error (find_g_points.cpp:291-405) on a batch, i.e.
+ * ecckd_interval_bounds_to_indices + ecckd_interval_error_batch_{lw,sw}_dev + the read-back of the errors.
+ * Pass the function as `fn` and a filled argument block as `user` (fields: the arguments of the batch calls). */
+typedef struct ecckd_interval_error_lw_args {
+  ecckd_ctx* ctx;
+  int averaging_method, nlay;
+  int64_t n, stride;
+  const double *d_pressure_hl, *d_planck_hl, *d_surf_emissivity, *d_surf_planck, *d_bg_optical_depth, *d_metric,
+      *d_flux_dn_surf, *d_flux_up_toa, *d_hr;
+  double flux_weight;
+  const double* d_layer_weight;
+} ecckd_interval_error_lw_args;
+typedef struct ecckd_interval_error_sw_args {
+  ecckd_ctx* ctx;
+  int averaging_method, nlay;
+  int64_t n, stride;
+  double cos_sza;
+  const double *d_pressure_hl, *d_ssi;
+  double albedo;
+  const double *d_bg_optical_depth, *d_metric, *d_flux_dn_surf, *d_flux_up_toa, *d_hr;
+  double flux_weight;
+  const double *d_layer_weight, *d_flux_dn_surf_low, *d_flux_up_toa_low, *d_hr_low, *d_flux_dn_surf_high,
+      *d_flux_up_toa_high, *d_hr_high;
+  double min_scaling, max_scaling;
+} ecckd_interval_error_sw_args;
+int ecckd_interval_error_lw_eval(void* lw_args, int n, const double* bound1, const double* bound2, double* error);
+int ecckd_interval_error_sw_eval(void* sw_args, int n, const double* bound1, const double* bound2, double* error);
+
+/* ---------------------------------------------------------------------------
  * Forward cost of optimize_lut (rows a21-a23), batched over the profiles of a scene
  * ------------------------------------------------------------------------- */
 

@@ -16,11 +16,15 @@ mkdir -p "$OUT/tools_obj"
 FLAGS="-O2 -march=native -fPIC -std=c++11 -Wno-unknown-pragmas -DHAVE_CONFIG_H -I$HERE/ref_mock -I$HERE/adept_shim -I$REF/src/ecckd -I$REF/src/include"
 OBJS=""
 for u in average_optical_depth planck_function radiative_transfer_lw radiative_transfer_sw single_gas_data \
-         calc_cost_function_lw calc_cost_function_sw ckd_model read_spectrum read_merged_spectrum write_order \
-         equipartition; do
+         calc_cost_function_lw calc_cost_function_sw ckd_model read_spectrum read_merged_spectrum write_order; do
   g++ $FLAGS -fopenmp -c "$REF/src/ecckd/$u.cpp" -o "$OUT/tools_obj/$u.o" &
   OBJS="$OBJS $OUT/tools_obj/$u.o"
 done
+# equipartition.cpp: the partition search is a discrete iteration whose path depends on the last bit of every
+# bound, so the oracle build evaluates its formulas in strict IEEE double arithmetic (no a*b+c contraction into
+# FMAs, which -march=native would otherwise allow) - the arithmetic ecckd_partition_search_* is held to, bit for bit.
+g++ $FLAGS -fopenmp -ffp-contract=off -c "$REF/src/ecckd/equipartition.cpp" -o "$OUT/tools_obj/equipartition.o" &
+OBJS="$OBJS $OUT/tools_obj/equipartition.o"
 for t in run_ckd create_look_up_table reorder_spectrum; do
   (g++ $FLAGS -c "$REF/src/ecckd/$t.cpp" -o "$OUT/tools_obj/main_$t.o" &&
    objcopy --redefine-sym main=ref_main_$t "$OUT/tools_obj/main_$t.o") &

@@ -150,3 +150,60 @@ REF_API int ref_calc_error_sw(const RefBandSw* b, int nint, const double* bound1
   });
 }
 
+
+// The reference's Equipartition over an arbitrary interval-error function (a callback): the oracle of the
+// host driver ecckd_partition_search_* (ecckd_b200/csrc/partition_search.cu) on synthetic error functions.
+typedef double (*ref_interval_error_fn)(void* user, double bound1, double bound2);
+namespace {
+class CallbackEquipartition : public Equipartition {
+public:
+  CallbackEquipartition(ref_interval_error_fn f, void* u) : fn(f), user(u) {}
+  virtual ep_real calc_error(ep_real bound1, ep_real bound2) {
+    ++calls;
+    return fn(user, bound1, bound2);
+  }
+  ref_interval_error_fn fn;
+  void* user;
+  long calls = 0;
+};
+struct RefEpOptions {  // the setters of equipartition.h:120-175; next_bound_* have no setter (defaults stay)
+  double partition_tolerance, resolution;
+  int partition_max_iterations, line_search_max_iterations, minimize_frac_range, cubic_interpolation;
+};
+void configure(Equipartition& eq, const RefEpOptions* o) {
+  eq.set_verbose(false);
+  eq.set_parallel(false);
+  if (!o) return;
+  eq.set_partition_tolerance(o->partition_tolerance);
+  eq.set_resolution(o->resolution);
+  eq.set_partition_max_iterations(o->partition_max_iterations);
+  eq.set_line_search_max_iterations(o->line_search_max_iterations);
+  eq.set_minimize_frac_range(o->minimize_frac_range != 0);
+  eq.set_cubic_interpolation(o->cubic_interpolation != 0);
+}
+}  // namespace
+REF_API int ref_equipartition_n_callback(ref_interval_error_fn fn, void* user, const RefEpOptions* opt, int ni,
+                                         double* bounds, double* error, int* status, long* calls) {
+  return guarded([&]() {
+    CallbackEquipartition eq(fn, user);
+    configure(eq, opt);
+    *status = (int)eq.equipartition_n(ni, bounds, error);
+    if (calls) *calls = eq.calls;
+  });
+}
+REF_API int ref_equipartition_e_callback(ref_interval_error_fn fn, void* user, const RefEpOptions* opt, double target_error,
+                                         double bound0, double boundn, int max_ni, int* ni, double* bounds, double* error,
+                                         int* status, long* calls) {
+  return guarded([&]() {
+    CallbackEquipartition eq(fn, user);
+    configure(eq, opt);
+    std::vector<ep_real> bnd, e;
+    int n = 0;
+    *status = (int)eq.equipartition_e(target_error, bound0, boundn, n, bnd, e);
+    *ni = n;
+    if (calls) *calls = eq.calls;
+    if ((int)e.size() > max_ni) throw 1;
+    for (size_t k = 0; k < bnd.size(); ++k) bounds[k] = bnd[k];
+    for (size_t k = 0; k < e.size(); ++k) error[k] = e[k];
+  });
+}

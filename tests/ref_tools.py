@@ -47,6 +47,15 @@ class BandSw(C.Structure):
                     ("min_scaling", C.c_double), ("max_scaling", C.c_double)]
 
 
+class RefEpOptions(C.Structure):
+    _fields_ = [("partition_tolerance", C.c_double), ("resolution", C.c_double), ("partition_max_iterations", C.c_int),
+                ("line_search_max_iterations", C.c_int), ("minimize_frac_range", C.c_int),
+                ("cubic_interpolation", C.c_int)]
+
+
+REF_ERROR_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_double, C.c_double)
+
+
 class RefTools:
     def __init__(self, lib=None):
         self.L = C.CDLL(lib or LIB)
@@ -171,6 +180,34 @@ class RefTools:
         rc = self.L.ref_calc_error_sw(C.byref(band), C.c_int(b1.size), _p(b1), _p(b2), _p(err))
         assert rc == 0, rc
         return err
+
+    # ---- the reference's Equipartition over a Python error function (oracle of ecckd_partition_search_*)
+    def _ep_args(self, fn, options):
+        cb = REF_ERROR_FN(lambda _u, b1, b2: float(fn(b1, b2)))
+        o = RefEpOptions(options.get("partition_tolerance", 0.05), options.get("resolution", 0.0),
+                         options.get("partition_max_iterations", 20), options.get("line_search_max_iterations", 10),
+                         options.get("minimize_frac_range", 1), options.get("cubic_interpolation", 0))
+        return cb, o
+
+    def equipartition_n_callback(self, fn, bounds, **options):
+        cb, o = self._ep_args(fn, options)
+        b = np.array(bounds, dtype=np.float64)
+        e = np.zeros(b.size - 1)
+        status, calls = C.c_int(0), C.c_long(0)
+        rc = self.L.ref_equipartition_n_callback(cb, None, C.byref(o), C.c_int(b.size - 1), _p(b), _p(e), C.byref(status),
+                                                 C.byref(calls))
+        assert rc == 0, rc
+        return status.value, b, e, calls.value
+
+    def equipartition_e_callback(self, fn, target_error, bound0, boundn, max_ni=512, **options):
+        cb, o = self._ep_args(fn, options)
+        b, e = np.zeros(max_ni + 1), np.zeros(max_ni)
+        ni, status, calls = C.c_int(0), C.c_int(0), C.c_long(0)
+        rc = self.L.ref_equipartition_e_callback(cb, None, C.byref(o), C.c_double(target_error), C.c_double(bound0),
+                                                 C.c_double(boundn), C.c_int(max_ni), C.byref(ni), _p(b), _p(e),
+                                                 C.byref(status), C.byref(calls))
+        assert rc == 0, rc
+        return status.value, b[:ni.value + 1].copy(), e[:ni.value].copy(), calls.value
 
     # ---- CkdModel
     def ckd_calc_optical_depth(self, file, igas, pressure_hl, temperature_fl, vmr_fl, ng):
