@@ -438,10 +438,10 @@ def interval_error_lw_evaluator(ctx, averaging_method, nlay, n, stride, d_pressu
     o = int(offset) * 8
 
     def sp(d):
-        return _ptr(d).value + o
-    a = IntervalErrorLwArgs(ctx.handle, _method_id(averaging_method), nlay, n, stride, _ptr(d_pressure_hl).value,
+        return _ptr(d) + o
+    a = IntervalErrorLwArgs(ctx.handle, _method_id(averaging_method), nlay, n, stride, _ptr(d_pressure_hl),
                             sp(d_planck_hl), sp(d_surf_emissivity), sp(d_surf_planck), sp(d_bg_od), sp(d_metric),
-                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight).value)
+                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight))
     return ("lw", a)
 
 
@@ -452,12 +452,12 @@ def interval_error_sw_evaluator(ctx, averaging_method, nlay, n, stride, cos_sza,
     o = int(offset) * 8
 
     def sp(d):
-        return None if d is None else _ptr(d).value + o
+        return None if d is None else _ptr(d) + o
     low = low or (None, None, None)
     high = high or (None, None, None)
     a = IntervalErrorSwArgs(ctx.handle, _method_id(averaging_method), nlay, n, stride, float(cos_sza),
-                            _ptr(d_pressure_hl).value, sp(d_ssi), float(albedo), sp(d_bg_od), sp(d_metric),
-                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight).value,
+                            _ptr(d_pressure_hl), sp(d_ssi), float(albedo), sp(d_bg_od), sp(d_metric),
+                            sp(d_flux_dn_surf), sp(d_flux_up_toa), sp(d_hr), float(flux_weight), _ptr(d_layer_weight),
                             sp(low[0]), sp(low[1]), sp(low[2]), sp(high[0]), sp(high[1]), sp(high[2]),
                             float(min_scaling), float(max_scaling))
     return ("sw", a)

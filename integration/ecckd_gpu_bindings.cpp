@@ -156,3 +156,18 @@ void radiative_transfer_lw<false>(const Matrix& planck, const Matrix& optical_de
   flux_dn = dn;  // element-wise copies into the caller's (possibly sliced) arrays
   flux_up = up;
 }
+
+// The differentiated instantiation stays with the stock unit (the reverse-mode tape is Adept's): the stock
+// radiative_transfer_lw.cpp is compiled with -Dradiative_transfer_lw=radiative_transfer_lw_stock, so its
+// <true> body is reached through this forwarder.
+template <bool IsActive>
+void radiative_transfer_lw_stock(const Matrix& planck, const adept::Array<2, adept::Real, IsActive>& optical_depth,
+                                 const Vector& surf_emissivity, const Vector& surf_planck,
+                                 adept::Array<2, adept::Real, IsActive> flux_dn,
+                                 adept::Array<2, adept::Real, IsActive> flux_up);
+template <>
+void radiative_transfer_lw<true>(const Matrix& planck, const adept::Array<2, adept::Real, true>& optical_depth,
+                                 const Vector& surf_emissivity, const Vector& surf_planck,
+                                 adept::Array<2, adept::Real, true> flux_dn, adept::Array<2, adept::Real, true> flux_up) {
+  radiative_transfer_lw_stock<true>(planck, optical_depth, surf_emissivity, surf_planck, flux_dn, flux_up);
+}

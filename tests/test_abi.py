@@ -60,3 +60,17 @@ def test_no_cpu_fallback_without_gpu():
         E.Context(0)
     assert ei.value.code == 131
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_cxx_consumer_library_resolves_every_symbol():
+    """oracle/_ref/libecckd_ref_tools_gpu.so - the reference's tool mains linked against
+    integration/ecckd_gpu_bindings.cpp and libecckd_b200.so - loads with every symbol bound (RTLD_NOW), no GPU needed."""
+    import ctypes
+    import os
+
+    from tests import ref_tools as RT
+
+    if not RT.gpu_available():
+        pytest.skip("oracle/_ref/libecckd_ref_tools_gpu.so not built")
+    lib = ctypes.CDLL(RT.GPU_LIB, mode=os.RTLD_NOW)
+    assert lib.ref_tool_run is not None

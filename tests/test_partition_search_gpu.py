@@ -15,24 +15,11 @@ import pytest
 import ecckd_b200 as E
 from ecckd_b200 import api as A
 from tests import ref_tools as RT
-from tests.oracle_lib import load_oracle
 from tests.test_reference_sources import interval_case
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not RT.available(), reason="oracle/_ref/libecckd_ref_tools.so not built")]
 
 COST_RTOL = 1e-10
-
-
-@pytest.fixture(scope="module")
-def ctx():
-    c = E.Context(0)
-    yield c
-    c.close()
-
-
-@pytest.fixture(scope="module")
-def O():
-    return load_oracle()
 
 
 @pytest.fixture(scope="module")
@@ -88,7 +75,6 @@ def test_partition_search_lw_equals_the_reference_search(ctx, O, R, method, n, o
     assert 3 <= e.size <= 200, e.size
 
     # (1) the reference's Equipartition on the same GPU evaluator: bit for bit
-    one = A.PartitionSearch(ev, speculative_line_search=1, **opt)  # used as a plain batched evaluator below
     L = A._lib.lib()
 
     def gpu_error(b1, b2):
@@ -100,7 +86,6 @@ def test_partition_search_lw_equals_the_reference_search(ctx, O, R, method, n, o
     assert st == A.EP_STATUS[st_r]
     assert np.array_equal(b, b_r) and np.array_equal(e, e_r)
     assert stats["batches"] < calls  # the batches did the work of `calls` single evaluations
-    one.close()
 
     # (2) the all-CPU reference search
     st_c, b_c, e_c = R.equipartition_e_lw(band, target, max_iterations=60, tolerance_tolerance=0.02)
