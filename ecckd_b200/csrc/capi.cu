@@ -186,6 +186,7 @@ ECCKD_API int ecckd_ctx_destroy(ecckd_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->cached_plan) ecckd_gpoint_plan_destroy(ctx->cached_plan);
   if (ctx->cached_g) cudaFree(ctx->cached_g);
+  if (ctx->d_exp2tab) cudaFree(ctx->d_exp2tab);
   for (auto& w : ctx->ws) {
     if (w.ptr) cudaFree(w.ptr);
   }

@@ -55,6 +55,8 @@ struct ecckd_ctx {
   int64_t cached_nwav = 0;
   int cached_ng = 0;
   int64_t plan_cache_hits = 0, plan_cache_misses = 0;
+  double* d_exp2tab = nullptr;  // 2^(j/N) table of the transmission averaging kernels (spectral_reduce.cu)
+  int exp2tab_logn = 0;
 };
 
 namespace ecckd {

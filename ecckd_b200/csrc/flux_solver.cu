@@ -251,6 +251,26 @@ __device__ __forceinline__ double warp_sum_xor(double v) {
   return v;
 }
 
+// Sums over the 32 lanes of FOUR values per lane at once (a transposed reduction): the first two
+// steps exchange half of the values for the partner's other half, so 6 shuffles do the work of the
+// 20 that four separate xor trees take.  Afterwards lane 0 holds the sum of v[0], lane 16 of v[1],
+// lane 8 of v[2], lane 24 of v[3] (every lane of the same (bit 4, bit 3) group holds that sum too).
+// The order of the additions is fixed: bitwise reproducible.
+__device__ __forceinline__ double warp_sum4_transposed(const double (&v)[4], const int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  // step 1 (xor 16): lanes with bit 4 clear keep v[0], v[2]; the others v[1], v[3]
+  const double a0 = (hi16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, hi16 ? v[0] : v[1], 16);
+  const double a1 = (hi16 ? v[3] : v[2]) + __shfl_xor_sync(0xffffffffu, hi16 ? v[2] : v[3], 16);
+  // step 2 (xor 8): lanes with bit 3 clear keep a0, the others a1
+  double b = (hi8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi8 ? a0 : a1, 8);
+  b += __shfl_xor_sync(0xffffffffu, b, 4);
+  b += __shfl_xor_sync(0xffffffffu, b, 2);
+  b += __shfl_xor_sync(0xffffffffu, b, 1);
+  return b;
+}
+// index (0..3) of the value whose sum warp_sum4_transposed leaves in this lane
+__device__ __forceinline__ int warp_sum4_slot(const int lane) { return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1); }
+
 __device__ __forceinline__ void lw_layer_fast(double tau, const TransConst& K, const TransLane& tl, double& e, double& f) {
   e = trans_one_minus_exp(tau, K, tl);
   double r;
@@ -311,8 +331,9 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
     if (bb && lane == 0) bdn[0] = 0.0;
     double b_top = s_pl[lane];
     int l = 0;
+    const int slot4 = warp_sum4_slot(lane);
     for (; l + 4 <= nlay; l += 4) {
-      double e[4], f[4], b[4];
+      double e[4], f[4], b[4], fd[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         lw_layer_fast(s_tau[(l + j) * 32 + lane], p.tc, tl, e[j], f[j]);
@@ -322,13 +343,14 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
       for (int j = 0; j < 4; ++j) {
         f_dn = f_dn * (1.0 - e[j]) + b_top * (e[j] - f[j]) + b[j] * f[j];
         dn[(int64_t)(l + j + 1) * n] = f_dn;
-        if (bb) {
-          const double sdn = warp_sum_xor(f_dn);
-          if (lane == 0) bdn[l + j + 1] = sdn;
-        }
+        fd[j] = f_dn;
         s_tau[(l + j) * 32 + lane] = 1.0 - e[j];
         s_pl[(l + j) * 32 + lane] = b[j] * (e[j] - f[j]) + b_top * f[j];
         b_top = b[j];
+      }
+      if (bb) {  // the four levels' broadband sums together
+        const double sdn = warp_sum4_transposed(fd, lane);
+        if ((lane & 7) == 0) bdn[l + 1 + slot4] = sdn;
       }
     }
     for (; l < nlay; ++l) {
@@ -351,8 +373,21 @@ __global__ void __launch_bounds__(32) rt_lw_staged_kernel(const __grid_constant_
       const double sup = warp_sum_xor(f_up);
       if (lane == 0) bup[nlay] = sup;
     }
-#pragma unroll 6
-    for (l = nlay - 1; l >= 0; --l) {
+    l = nlay - 1;
+    for (; l >= 3; l -= 4) {  // four levels at a time: one transposed reduction for their broadband sums
+      double fu[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f_up = f_up * s_tau[(l - j) * 32 + lane] + s_pl[(l - j) * 32 + lane];
+        up[(int64_t)(l - j) * n] = f_up;
+        fu[j] = f_up;
+      }
+      if (bb) {
+        const double sup = warp_sum4_transposed(fu, lane);
+        if ((lane & 7) == 0) bup[l - slot4] = sup;
+      }
+    }
+    for (; l >= 0; --l) {
       f_up = f_up * s_tau[l * 32 + lane] + s_pl[l * 32 + lane];
       up[(int64_t)l * n] = f_up;
       if (bb) {
@@ -994,6 +1029,255 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck_kernel(const
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The same work with every long-latency load taken off the warp's critical path (ncu on the kernel
+// above, 65536 x 54 x 32: 30 % of the stall samples in phase A - the (column, layer) inputs are
+// strided loads followed by dependent arithmetic, once per unit with nothing to overlap -, 18 % in
+// the separate Planck units, and the first use of the concentration-axis rows of every column stalls
+// on their load, which was only one column ahead):
+//   * the inputs of a warp's NEXT unit (pressures, temperatures, mixing ratios of its 32 columns)
+//     travel to shared memory by per-thread asynchronous copies (cp.async, SASS LDGSTS) while the
+//     current unit is evaluated;
+//   * the Planck function of half level l is produced by the unit of layer l from the temperature it
+//     has already loaded (the unit of the last layer adds the surface level): no Planck units;
+//   * the columns of a unit are visited in one flat sequence ordered by (it0, ip0) group - the four
+//     corner rows of the table gases are reloaded when the group changes -, and the rows of the gas
+//     with a concentration axis come through a ring of asynchronous copies TOD_AHEAD columns deep.
+constexpr int TOD_AHEAD = 3;              // columns whose concentration-axis rows are in flight
+constexpr int TOD_RING = TOD_AHEAD + 1;   // ring slots (the slot refilled was read one column earlier)
+constexpr int TOD_NIN = 4 + TOD_MAXGAS;   // staged inputs per column: p(l), p(l+1), T(l), T(l+1), vmr of each gas
+
+struct Tod2Smem {  // per warp
+  TodCol col[TOD_TILE];
+  double in[TOD_NIN][TOD_TILE];
+  double2 ring[TOD_RING][4][32];
+  int key[TOD_TILE];
+  unsigned char ord[TOD_TILE];
+  unsigned char pad_[96];
+};
+
+template <int NLIN, bool HAS_LUT, int NWARP, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(const __grid_constant__ TotalOdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  Tod2Smem& S = reinterpret_cast<Tod2Smem*>(smem_raw)[warp];
+  const unsigned s_in = smem_u32(&S.in[0][0]);
+  const unsigned s_ring = smem_u32(&S.ring[0][0][0]);
+  const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
+  const int ntile = (p.ncol + TOD_TILE - 1) / TOD_TILE;
+  const int64_t n_units = (int64_t)ntile * nlay;
+  const int64_t stride = (int64_t)gridDim.x * nwarp;
+  const bool want_planck = p.planck_hl != nullptr || p.planck_surf != nullptr;
+  const unsigned qP = (unsigned)ng * 4, qT = (unsigned)(p.np - 1) * qP, qC = (unsigned)(p.nt - 1) * qT;
+
+  // asynchronous copies of unit u's inputs into S.in (one column per lane)
+  auto stage_inputs = [&](const int64_t u) {
+    if (u < n_units) {
+      const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
+      const int64_t col = (int64_t)tile * TOD_TILE + lane;
+      if (col < p.ncol) {
+        const double* p_hl = p.pressure_hl + col * (nlay + 1) + l;
+        const double* t_hl = p.temperature_hl + col * (nlay + 1) + l;
+        cp_async8(s_in + (0 * TOD_TILE + lane) * 8, p_hl);
+        cp_async8(s_in + (1 * TOD_TILE + lane) * 8, p_hl + 1);
+        cp_async8(s_in + (2 * TOD_TILE + lane) * 8, t_hl);
+        cp_async8(s_in + (3 * TOD_TILE + lane) * 8, t_hl + 1);
+#pragma unroll
+        for (int ig = 0; ig < TOD_MAXGAS; ++ig)
+          if (ig < ngas && p.vmr[ig]) cp_async8(s_in + ((4 + ig) * TOD_TILE + lane) * 8, p.vmr[ig] + col * nlay + l);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int64_t u = (int64_t)blockIdx.x * nwarp + warp;
+  stage_inputs(u);
+  for (; u < n_units; u += stride) {
+    const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
+    const int c0 = tile * TOD_TILE;
+    const int nc = min(TOD_TILE, p.ncol - c0);
+    cp_async_wait<0>();
+    // ---- phase A: lane = column (everything that does not depend on g: ckd_model.cpp:962-1009)
+    int key = 0x7fffffff;
+    const bool valid = lane < nc;
+    int pl_off = 0, pl_off1 = 0;
+    double pl_w0 = 0.0, pl_w1 = 0.0, pl1_w0 = 0.0, pl1_w1 = 0.0;
+    if (valid) {
+      const double p0 = S.in[0][lane], p1 = S.in[1][lane], t0 = S.in[2][lane], t1 = S.in[3][lane];
+      const double t_fl = (t0 * p0 + t1 * p1) / (p0 + p1);
+      const Interp it = make_interp(p0, p1, t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+      key = it.it0 * p.np + it.ip0;
+      TodCol tc;
+      tc.c00 = it.tw0 * it.pw0;
+      tc.c01 = it.tw0 * it.pw1;
+      tc.c10 = it.tw1 * it.pw0;
+      tc.c11 = it.tw1 * it.pw1;
+#pragma unroll
+      for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
+        tc.w[ig] = 0.0;
+        tc.cw1[ig] = 0.0;
+        tc.ic0[ig] = 0;
+        if (ig >= ngas) continue;
+        const int cd = p.conc_dependence[ig];
+        const bool have = p.vmr[ig] != nullptr;
+        const double vmr = have ? S.in[4 + ig][lane] : 0.0;
+        double weight = 0.0;  // ckd_model.cpp:980-999
+        if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
+        if (cd == ECCKD_CONC_LUT) {
+          double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
+          cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+          tc.ic0[ig] = (int)cindex0;
+          tc.cw1[ig] = cindex0 - tc.ic0[ig];
+          tc.w[ig] = weight;
+        } else {
+          tc.w[ig] = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+        }
+      }
+      S.col[lane] = tc;
+      S.key[lane] = key;
+      if (want_planck) {  // ckd_model.cpp:1124-1142 at half level l (and at the surface level for the last layer)
+        auto planck_index = [&](const double t, int& off, double& w0, double& w1) {
+          const double tindex0 = (t - p.planck_t0) / p.planck_dt;
+          off = 0;
+          w1 = 0.0;
+          if (tindex0 >= 0) {
+            const int it0 = min((int)tindex0, p.nlut - 2);
+            off = it0 * ng;
+            w1 = tindex0 - it0;
+            w0 = 1.0 - w1;
+          } else {  // below the table: (t / t0) * lut[0]
+            w0 = t / p.planck_t0;
+          }
+        };
+        planck_index(t0, pl_off, pl_w0, pl_w1);
+        planck_index(t1, pl_off1, pl1_w0, pl1_w1);
+      }
+    }
+    // order of the visit: columns grouped by (it0, ip0), groups by their first column
+    {
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs(same) - 1;
+      unsigned leaders = __ballot_sync(0xffffffffu, valid && lane == leader);
+      int base = 0, pos = 0;
+      while (leaders) {  // warp-uniform
+        const int L = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const unsigned members = __shfl_sync(0xffffffffu, same, L);
+        if (leader == L) pos = base + __popc(members & ((1u << lane) - 1u));
+        base += __popc(members);
+      }
+      if (valid) S.ord[pos] = (unsigned char)lane;
+    }
+    __syncwarp();
+    // the next unit's inputs travel while this one is evaluated (S.in has been read)
+    stage_inputs(u + stride);
+
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+      const int g = min(g0 + lane, ng - 1);
+      const bool store = g0 + lane < ng;
+      // ---- Planck function of the unit's half level(s): rows by lane = g, index and weights from lane = column
+      if (want_planck) {
+        const double* lut_g = p.planck_lut + g;
+        const int64_t lev_stride = (int64_t)(nlay + 1) * ng;
+        double* out = p.planck_hl ? p.planck_hl + ((int64_t)c0 * (nlay + 1) + l) * ng + g : nullptr;
+        const bool last = l == nlay - 1;
+        double* surf = (last && p.planck_surf) ? p.planck_surf + (int64_t)c0 * ng + g : nullptr;
+#pragma unroll 4
+        for (int c = 0; c < nc; ++c) {
+          const int off = __shfl_sync(0xffffffffu, pl_off, c);
+          const double w0 = __shfl_sync(0xffffffffu, pl_w0, c), w1 = __shfl_sync(0xffffffffu, pl_w1, c);
+          const double b = w0 * __ldg(lut_g + off) + w1 * __ldg(lut_g + off + ng);  // w1 == 0 below the table
+          if (store && out) out[c * lev_stride] = b;
+        }
+        if (last) {
+#pragma unroll 4
+          for (int c = 0; c < nc; ++c) {
+            const int off = __shfl_sync(0xffffffffu, pl_off1, c);
+            const double w0 = __shfl_sync(0xffffffffu, pl1_w0, c), w1 = __shfl_sync(0xffffffffu, pl1_w1, c);
+            const double b = w0 * __ldg(lut_g + off) + w1 * __ldg(lut_g + off + ng);
+            if (store && out) out[c * lev_stride + ng] = b;
+            if (store && surf) surf[c * ng] = b;
+          }
+        }
+      }
+      // ---- optical depth: lane = g point, columns in S.ord order
+      const unsigned col_stride = (unsigned)nlay * ng;  // 32 * nlay * ng < 2^31 (checked by the host)
+      double* const od_unit = p.od + ((int64_t)c0 * nlay + l) * ng + g;
+      // asynchronous copies of the concentration-axis rows of the k-th column of the visit
+      auto ring_issue = [&](const int k) {
+        if (HAS_LUT && k < nc) {
+          const int c = S.ord[k];
+          const int ky = S.key[c];
+          const int it0 = ky / p.np, ip0 = ky - it0 * p.np;
+          const double* k0 = p.packed[NLIN] + (size_t)((unsigned)S.col[c].ic0[NLIN] * qC) + (unsigned)it0 * qT + (unsigned)ip0 * qP +
+                             (unsigned)g * 4;
+          const unsigned dst = s_ring + (unsigned)(((k % TOD_RING) * 4) * 32 + lane) * 16;
+          cp_async16(dst, k0);
+          cp_async16(dst + 32 * 16, k0 + 2);
+          cp_async16(dst + 64 * 16, k0 + qC);
+          cp_async16(dst + 96 * 16, k0 + qC + 2);
+        }
+        cp_async_commit();
+      };
+#pragma unroll
+      for (int k = 0; k < TOD_AHEAD; ++k) ring_issue(k);
+      int cur_key = -1;
+      unsigned o00 = 0;
+      double K[NLIN > 0 ? NLIN : 1][4];
+#pragma unroll 1
+      for (int k = 0; k < nc; ++k) {
+        ring_issue(k + TOD_AHEAD);
+        const int c = S.ord[k];
+        const int ky = S.key[c];
+        if (ky != cur_key) {  // warp-uniform: a new (it0, ip0) group, four corner rows of every table gas
+          cur_key = ky;
+          const int it0 = ky / p.np, ip0 = ky - it0 * p.np;
+          o00 = (unsigned)it0 * qT + (unsigned)ip0 * qP + (unsigned)g * 4;
+#pragma unroll
+          for (int ig = 0; ig < NLIN; ++ig) {
+            const double2* kk = reinterpret_cast<const double2*>(p.packed[ig] + o00);
+            const double2 a = __ldg(kk), b = __ldg(kk + 1);
+            K[ig][0] = a.x;
+            K[ig][1] = a.y;
+            K[ig][2] = b.x;
+            K[ig][3] = b.y;
+          }
+        }
+        const TodCol& tc = S.col[c];
+        const double c00 = tc.c00, c01 = tc.c01, c10 = tc.c10, c11 = tc.c11;
+        double tau0 = 0.0, tau1 = 0.0;  // two chains
+#pragma unroll
+        for (int ig = 0; ig < NLIN; ++ig) {
+          const double v = c00 * K[ig][0] + c01 * K[ig][1] + c10 * K[ig][2] + c11 * K[ig][3];
+          if (ig & 1) tau1 += tc.w[ig] * v; else tau0 += tc.w[ig] * v;
+        }
+        if (HAS_LUT) {
+          cp_async_wait<TOD_AHEAD>();  // the copies of column k have landed (each lane reads what it copied itself)
+          const double2* R = &S.ring[k % TOD_RING][0][lane];
+          const double2 L0 = R[0], L1 = R[32], L2 = R[64], L3 = R[96];
+          const double cw1 = tc.cw1[NLIN];
+          const double a = c00 * L0.x + c01 * L0.y + c10 * L1.x + c11 * L1.y;
+          const double b = c00 * L2.x + c01 * L2.y + c10 * L3.x + c11 * L3.y;
+          tau1 += tc.w[NLIN] * ((1.0 - cw1) * a + cw1 * b);
+        }
+        double tau = tau0 + tau1;
+        for (int ig = NLIN + (HAS_LUT ? 1 : 0); ig < ngas; ++ig) {  // further gases with a concentration axis
+          const double cw1 = tc.cw1[ig];
+          const double* kk = p.packed[ig] + (size_t)((unsigned)tc.ic0[ig] * qC) + o00;
+          const double a = c00 * kk[0] + c01 * kk[1] + c10 * kk[2] + c11 * kk[3];
+          kk += qC;
+          const double b = c00 * kk[0] + c01 * kk[1] + c10 * kk[2] + c11 * kk[3];
+          tau += tc.w[ig] * ((1.0 - cw1) * a + cw1 * b);
+        }
+        if (store) od_unit[(unsigned)c * col_stride] = fmax(tau, 0.0);  // run_ckd.cpp:317
+      }
+    }
+    __syncwarp();  // S.col / S.ord are rewritten by the next unit
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace ecckd
 
 using namespace ecckd;
@@ -1471,14 +1755,27 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     // 65536 x 54 x 32.)
     const int nwarp = 4, minb = 3;
     const int64_t ntile = (ncol + TOD_TILE - 1) / TOD_TILE;
-    const int64_t units = ntile * nlay + ((q.planck_hl || q.planck_surf) ? ntile * (nlay + 1) : 0);
-    const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)minb * ctx->num_sms);
-    const size_t smem = nwarp * TOD_TILE * sizeof(TodCol);
+    const bool want_planck = q.planck_hl || q.planck_surf;
     const bool has_lut = q.nlin < q.ngas;
+    // total_od_planck2_kernel (asynchronous staging) unless ECCKD_TOD_VARIANT=1 asks for the first layer-major kernel
+    const bool v2 = !(getenv("ECCKD_TOD_VARIANT") && atoi(getenv("ECCKD_TOD_VARIANT")) == 1);
+    const int64_t units = v2 ? ntile * nlay : ntile * nlay + (want_planck ? ntile * (nlay + 1) : 0);
+    const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)minb * ctx->num_sms);
+    const size_t smem = v2 ? nwarp * sizeof(Tod2Smem) : nwarp * TOD_TILE * sizeof(TodCol);
 #define ECCKD_TOD_LAUNCH(N)                                                                                  \
   case N:                                                                                                    \
-    if (has_lut) total_od_planck_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);           \
-    else total_od_planck_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                  \
+    if (v2) {                                                                                                \
+      if (has_lut) {                                                                                         \
+        ECCKD_CUDA_OK(cudaFuncSetAttribute(total_od_planck2_kernel<N, true, 4, 3>,                           \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        total_od_planck2_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                  \
+      } else {                                                                                               \
+        ECCKD_CUDA_OK(cudaFuncSetAttribute(total_od_planck2_kernel<N, false, 4, 3>,                          \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        total_od_planck2_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                 \
+      }                                                                                                      \
+    } else if (has_lut) total_od_planck_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);   \
+    else total_od_planck_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                 \
     break;
     switch (q.nlin) {
       ECCKD_TOD_LAUNCH(0)

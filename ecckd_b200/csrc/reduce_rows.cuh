@@ -90,13 +90,11 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
                                            const bool (&is_log)[NR], const TransConst256& K2,
                                            const unsigned char* __restrict__ tab,
                                            const TransConst64* __restrict__ K3 = nullptr, const unsigned lane_off = 0u,
-                                           const int row_stride = STAGE_BYTES) {
+                                           const int row_stride = STAGE_BYTES,
+                                           const TransConstT* __restrict__ KT = nullptr) {
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
-  // no register software pipeline: the loads of a trip are issued at its top and the other warps
-  // of the scheduler cover their latency (the rotating pipeline cost 52 register moves per trip)
-#pragma unroll 1
-  for (int kk = 0; kk < SLOTS; kk += 4) {
-    double tau[NR][4], w[4];
+  // the loads of one trip (4 slots): plan offsets, weights, optical depths of the NR rows
+  auto load_trip = [&](double (&tau)[NR][4], double (&w)[4], const int kk) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const unsigned o = offp[(kk + j) * 32];
@@ -104,6 +102,8 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
 #pragma unroll
       for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * row_stride + o);
     }
+  };
+  auto compute_trip = [&](const double (&tau)[NR][4], const double (&w)[4], const int kk) {
     // extremes: one range check per value, one (rare) branch per 4 x NR values
     bool outside = false;
 #pragma unroll
@@ -138,21 +138,48 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
     if (FKIND == F_TRANS) {
       TransMid m[NR][4];
       double T[NR][4];
+#if defined(ECCKD_TAB_LOGN)
+      // TAB64 callers: `tab` is the 2^ECCKD_TAB_LOGR-fold replicated 2^ECCKD_TAB_LOGN-entry table
+#define ECCKD_P1(x) (TAB64 ? transT_phase1(x, *KT) : trans256_phase1(x, K2))
+#define ECCKD_P2(mm) (TAB64 ? transT_phase2<ECCKD_TAB_LOGN, ECCKD_TAB_LOGR>(mm, tab, lane_off) : trans256_phase2(mm, tab))
+#define ECCKD_P3(mm, TT) (TAB64 ? transT_phase3<ECCKD_TAB_QDEG>(mm, TT, *KT) : trans256_phase3(mm, TT, K2))
+#elif defined(ECCKD_V_TAB256)
+      // TAB64 callers: `tab` is the 8-fold replicated 256-entry table, lane_off = (lane & 7) << 3
+#define ECCKD_P1(x) (TAB64 ? ECCKD_P1_256(x) : trans256_phase1(x, K2))
+#ifdef ECCKD_V_I2F
+#define ECCKD_P1_256(x) trans256_phase1_i2f(x, K2)
+#else
+#define ECCKD_P1_256(x) trans256_phase1(x, K2)
+#endif
+#define ECCKD_P2(mm) (TAB64 ? trans256r_phase2(mm, tab, lane_off) : trans256_phase2(mm, tab))
+#define ECCKD_P3(mm, TT) trans256_phase3(mm, TT, K2)
+#else
+#ifdef ECCKD_V_I2F
+#define ECCKD_P1(x) (TAB64 ? trans64_phase1_i2f(x, *K3) : trans256_phase1(x, K2))
+#else
+#define ECCKD_P1(x) (TAB64 ? trans64_phase1(x, *K3) : trans256_phase1(x, K2))
+#endif
+#define ECCKD_P2(mm) (TAB64 ? trans64_phase2(mm, tab, lane_off) : trans256_phase2(mm, tab))
+#define ECCKD_P3(mm, TT) (TAB64 ? trans64_phase3(mm, TT, *K3) : trans256_phase3(mm, TT, K2))
+#endif
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[r][j] = TAB64 ? trans64_phase1(tau[r][j], *K3) : trans256_phase1(tau[r][j], K2);
+        for (int j = 0; j < 4; ++j) m[r][j] = ECCKD_P1(tau[r][j]);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) T[r][j] = TAB64 ? trans64_phase2(m[r][j], tab, lane_off) : trans256_phase2(m[r][j], tab);
+        for (int j = 0; j < 4; ++j) T[r][j] = ECCKD_P2(m[r][j]);
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[r][j] = TAB64 ? trans64_phase3(m[r][j], T[r][j], *K3) : trans256_phase3(m[r][j], T[r][j], K2);
+          f[r][j] = ECCKD_P3(m[r][j], T[r][j]);
           pos[r][j] = true;
         }
+#undef ECCKD_P1
+#undef ECCKD_P2
+#undef ECCKD_P3
     } else {
 #pragma unroll
       for (int r = 0; r < NR; ++r)
@@ -172,7 +199,32 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
         a[r].s0 = fma(f[r][j], we, a[r].s0);
       }
     }
+  };
+#ifdef ECCKD_V_TAUPF
+  // two register sets in turn: the loads of the next trip are in flight while this one is evaluated
+  double tA[NR][4], wA[4], tB[NR][4], wB[4];
+  load_trip(tA, wA, 0);
+#pragma unroll 1
+  for (int kk = 0; kk < SLOTS; kk += 8) {
+    load_trip(tB, wB, kk + 4);
+    compute_trip(tA, wA, kk);
+    if (kk + 8 < SLOTS) load_trip(tA, wA, kk + 8);
+    compute_trip(tB, wB, kk + 4);
   }
+#else
+  // no register software pipeline: the loads of a trip are issued at its top and the other warps
+  // of the scheduler cover their latency (a rotating pipeline cost 52 register moves per trip)
+#ifdef ECCKD_V_UNROLL4
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+  for (int kk = 0; kk < SLOTS; kk += 4) {
+    double tau[NR][4], w[4];
+    load_trip(tau, w, kk);
+    compute_trip(tau, w, kk);
+  }
+#endif
 }
 
 // Segmented suffix reduction over adjacent lanes of the same g point (lane predicates from the

@@ -1013,18 +1013,26 @@ struct Smem2Layout {
 };
 // nsw ring slots, stage_bytes per row chunk (chunk length of the plan x 8 + 16: a plan with shorter
 // chunks leaves room for a deeper ring)
-__host__ __device__ inline Smem2Layout smem2_layout(int nw, int nsw, int stage_bytes) {
+// The data stages are packed by row: warp w owns rows w and w + nw of a group, so only the first
+// max_rows - nw warps need stages for two rows.
+__host__ __device__ inline Smem2Layout smem2_layout(int nw, int nsw, int stage_bytes, int max_rows) {
   Smem2Layout L;
   int off = 0;
   L.tab = off;
+#if defined(ECCKD_TAB_LOGN)
+  off += 8 << (ECCKD_TAB_LOGN + ECCKD_TAB_LOGR);
+#elif defined(ECCKD_V_TAB256)
+  off += TRANS_TAB256R_BYTES;
+#else
   off += TRANS_TAB64_BYTES;
+#endif
   L.bars = off;
   off += (nw * NSETS + 2 * nsw) * 8;
   off = (off + 127) & ~127;
   L.ring = off;
   off += nsw * RING_SLOT_BYTES;
   L.data = off;
-  off += nw * NSETS * RPW * stage_bytes;
+  off += max_rows * NSETS * stage_bytes;
   L.ent = off;
   off += nw * WIN * 32 * 16;
   L.s1e = off;
@@ -1068,7 +1076,7 @@ __device__ __forceinline__ void merge_extremes(const Partial (&a)[NR], const int
 }
 
 template <int FKIND, int WMODE>
-__global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const __grid_constant__ ReduceParams p) {
+__global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const __grid_constant__ ReduceParams p) {
   static_assert(FKIND == F_LINEAR || FKIND == F_TRANS || FKIND == F_SQRT || FKIND == F_NONE,
                 "reduce2_kernel: kinds with per-row weight sums run on reduce_kernel");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1076,7 +1084,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   const int lane = threadIdx.x & 31;
   const int nw = p.nw, ng = p.ng;
   const int nsw = p.nsw, stage_bytes = p.stage_bytes;
-  const Smem2Layout L = smem2_layout(nw, nsw, stage_bytes);
+  const Smem2Layout L = smem2_layout(nw, nsw, stage_bytes, p.max_rows);
   const unsigned sbase = smem_u32(smem_raw);
   const unsigned full_d = sbase + L.bars;         // mbarriers [nw][NSETS], 8 bytes each
   const unsigned full_w = full_d + nw * NSETS * 8; // [NSW]
@@ -1092,7 +1100,13 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
     }
     fence_mbar_init();
   }
+#if defined(ECCKD_TAB_LOGN)
+  if (FKIND == F_TRANS) trans_tabT_init<ECCKD_TAB_LOGN, ECCKD_TAB_LOGR>(reinterpret_cast<double*>(smem_raw + L.tab), p.exp2tab);
+#elif defined(ECCKD_V_TAB256)
+  if (FKIND == F_TRANS) trans_tab256r_init(reinterpret_cast<double*>(smem_raw + L.tab));
+#else
   if (FKIND == F_TRANS) trans_tab64_init(reinterpret_cast<double*>(smem_raw + L.tab));
+#endif
   __syncthreads();
   const unsigned char* tab = smem_raw + L.tab;
 
@@ -1114,14 +1128,23 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
 
   // ===================== consumers: warp = RPW rows of the group =====================
   const TransLane tl = {0, 0};  // (only the logarithmic kinds of reduce_kernel use the lane table)
-  unsigned char* data = smem_raw + L.data + (size_t)warp * NSETS * RPW * stage_bytes;
+  const int n2 = p.max_rows - nw;               // warps 0 .. n2-1 have two rows, the others one
+  const int rpw_w = (warp < n2) ? RPW : 1;      // rows this warp has stages for
+  const int stage_first = (warp + min(warp, n2)) * NSETS;
+  unsigned char* data = smem_raw + L.data + (size_t)stage_first * stage_bytes;
   const unsigned my_full = full_d + warp * NSETS * 8;
-  const unsigned my_data = sbase + L.data + warp * NSETS * RPW * stage_bytes;
+  const unsigned my_data = sbase + L.data + stage_first * stage_bytes;
   double2* ent = reinterpret_cast<double2*>(smem_raw + L.ent) + (size_t)warp * WIN * 32;
   double* s1e = reinterpret_cast<double*>(smem_raw + L.s1e);
   double2* mmv = reinterpret_cast<double2*>(smem_raw + L.mmv) + warp * RPW * WIN;
   uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + warp * RPW * WIN;
+#if defined(ECCKD_TAB_LOGN)
+  const unsigned lane_off = (unsigned)(lane & ((1 << ECCKD_TAB_LOGR) - 1)) << 3;
+#elif defined(ECCKD_V_TAB256)
+  const unsigned lane_off = (unsigned)(lane & 7) << 3;
+#else
   const unsigned lane_off = (unsigned)(lane & 15) << 3;
+#endif
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const uint64_t pol = policy_evict_first();
   // the weight sums do not depend on the row: the last consumer warp (the one with the fewest rows)
@@ -1216,22 +1239,43 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   // stay inside the 16-byte granules of the caller's rows).
   Cursor qi = first;
   const unsigned char* src_i[RPW];  // next chunk of the warp's rows (nullptr: no such row in the group)
+  // The floating row.  A group of 2 nw - 1 rows leaves one warp with a single row, and with it one
+  // scheduler (warp w runs on scheduler w % 4) with a row less than its neighbour: 6 / 5 rows on the two
+  // schedulers without producer warps.  The group's last row therefore changes hands every chunk visit:
+  // warp nw-2 takes it on the visits of stage set 0, warp nw-1 on those of set 1 (visit k uses set k & 1,
+  // so each of the two always finds its own copies in the set it issued them into; warp nw-1 borrows
+  // warp nw-2's second-row stage of set 1, which that warp does not use).  Both schedulers then carry
+  // 5.5 rows on average and the ring's slack absorbs the alternation.  The row's two partial results
+  // (one per warp) are added up by combine_kernel.
+  bool fl_i = false;  // the issue cursor's group has a floating row
+  auto row1_of = [&](const GroupDesc* gd, bool& fl) -> int {  // index of this warp's second row, or -1
+    fl = p.float_row && gd->nrows == 2 * nw - 1 && warp >= nw - 2;
+    if (fl) return gd->nrows - 1;
+    return (warp + nw < gd->nrows) ? warp + nw : -1;
+  };
+  auto row1_on = [&](const bool fl, const int set) { return !fl || set == (warp == nw - 2 ? 0 : 1); };
   auto load_issue_group = [&]() {
     const GroupDesc* gd = p.groups + qi.l;
-#pragma unroll
-    for (int r = 0; r < RPW; ++r) {
-      const int i = warp + r * nw;
-      src_i[r] = (USES_TAU && i < gd->nrows) ? reinterpret_cast<const unsigned char*>(gd->od[i] + (int64_t)qi.c * ch) : nullptr;
-    }
+    const int i1 = row1_of(gd, fl_i);
+    src_i[0] = (USES_TAU && warp < gd->nrows) ? reinterpret_cast<const unsigned char*>(gd->od[warp] + (int64_t)qi.c * ch) : nullptr;
+    src_i[1] = (USES_TAU && i1 >= 0) ? reinterpret_cast<const unsigned char*>(gd->od[i1] + (int64_t)qi.c * ch) : nullptr;
+  };
+  // byte offset of the stage of (set, row r of this warp) from the warp's first stage
+  auto stage_off = [&](const int set, const int r) -> int {
+    if (r == 1 && rpw_w == 1)  // borrowed: warp nw-2's (set, row 1) stage, NSETS*RPW stages before ours
+      return (set * RPW + 1 - NSETS * RPW) * stage_bytes;
+    return (set * rpw_w + r) * stage_bytes;
   };
   auto issue = [&](int set) {
     if (src_i[0] != nullptr) {
       const unsigned n_bytes = (unsigned)((qi.c == nchunks - 1) ? last_n : ch) * 8u;
+      const bool on1 = src_i[1] != nullptr && row1_on(fl_i, set);
       unsigned shift[RPW], bytes[RPW], total = 0;
 #pragma unroll
       for (int r = 0; r < RPW; ++r) {
+        const bool on = r == 0 || on1;
         shift[r] = (unsigned)(reinterpret_cast<uintptr_t>(src_i[r]) & 8u);
-        bytes[r] = src_i[r] ? ((shift[r] + n_bytes + 15u) & ~15u) : 0u;
+        bytes[r] = on ? ((shift[r] + n_bytes + 15u) & ~15u) : 0u;
         total += bytes[r];
       }
       if (lane == 0) {
@@ -1239,7 +1283,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         mbar_arrive_expect_tx(bar, total);
 #pragma unroll
         for (int r = 0; r < RPW; ++r)
-          if (src_i[r]) bulk_g2s_hint(my_data + (set * RPW + r) * stage_bytes, src_i[r] - shift[r], bytes[r], bar, pol);
+          if (bytes[r]) bulk_g2s_hint(my_data + stage_off(set, r), src_i[r] - shift[r], bytes[r], bar, pol);
       }
     }
     if (++qi.c < qi.c_end) {
@@ -1260,13 +1304,14 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   unsigned wpar = 0;
   unsigned phase_bits = 0;  // bit `set`: parity to wait for on that stage set's mbarrier
   const double* od_c[RPW];
-  bool active[RPW];
+  bool have[RPW];     // the warp's rows in the current group
+  bool fl_c = false;  // ... the second of which is the floating row
   bool need_group = true;
 
   // the slots of one round for NR rows: range-check words and extremes from the cache, slot loop,
   // sums into the lane's entry, extremes back into the cache if one changed
   auto round_rows = [&](auto nr_tag, const unsigned char* stage0, const uint16_t* offp, const double* wp, const int e,
-                        const bool used, const int row0) {
+                        const bool used, const int row0, const int row_stride) {
     constexpr int NR = decltype(nr_tag)::value;
     Partial a[NR];
     bool il[NR];
@@ -1284,7 +1329,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
       a[r].span = used ? b.y : 0xFFFFFFFFu;
       il[r] = false;
     }
-    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off, stage_bytes);
+    rows_slots<FKIND, NR, true>(a, stage0, offp, wp, SLOTS, p.tc, tl, il, p.tc256, tab, &p.tc64, lane_off, row_stride, &p.tct);
     if (used) {
       double2 v = ent[e * 32 + lane];
       if (NR > 1) {
@@ -1307,15 +1352,17 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
   auto visit = [&](const int set, const int k) {
     if (need_group) {
       const GroupDesc* gd = p.groups + q.l;
-#pragma unroll
-      for (int r = 0; r < RPW; ++r) {
-        const int i = warp + r * nw;
-        active[r] = USES_TAU && i < gd->nrows;
-        od_c[r] = active[r] ? gd->od[i] : nullptr;
-      }
+      const int i1 = row1_of(gd, fl_c);
+      have[0] = USES_TAU && warp < gd->nrows;
+      have[1] = USES_TAU && i1 >= 0;
+      od_c[0] = have[0] ? gd->od[warp] : nullptr;
+      od_c[1] = have[1] ? gd->od[i1] : nullptr;
       begin_piece(vg);
       need_group = false;
     }
+    bool active[RPW];
+    active[0] = have[0];
+    active[1] = have[1] && row1_on(fl_c, set);
     if (active[0]) {
       mbar_wait(my_full + set * 8, (phase_bits >> set) & 1u);
       phase_bits ^= 1u << set;
@@ -1324,6 +1371,7 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
     unsigned shift_c[RPW];
 #pragma unroll
     for (int r = 0; r < RPW; ++r) shift_c[r] = (unsigned)(reinterpret_cast<uintptr_t>(od_c[r]) & 8u);
+    const int row_stride = stage_off(set, 1) - stage_off(set, 0);
     bool last_round = false;
     while (!last_round) {
       mbar_wait(full_w + ws * 8, wpar);
@@ -1348,15 +1396,15 @@ __global__ void __launch_bounds__((NW_MAX + NPW) * 32, 1) reduce2_kernel(const _
         if (used) s1e[e * 32 + lane] += s;
       }
       if (USES_TAU && active[0]) {
-        const unsigned char* stage0 = data + (set * RPW) * stage_bytes + shift_c[0];
+        const unsigned char* stage0 = data + stage_off(set, 0) + shift_c[0];
         // (both rows of a pair have the same alignment in every caller of this library: spectra are
         // [layer][nwav] arrays with one stride; a pair with different parities takes the single-row form twice)
         if (active[RPW - 1] && shift_c[RPW - 1] == shift_c[0]) {
-          round_rows(std::integral_constant<int, RPW>{}, stage0, offp, wp, e, used, 0);
+          round_rows(std::integral_constant<int, RPW>{}, stage0, offp, wp, e, used, 0, row_stride);
         } else {
-          round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used, 0);
+          round_rows(std::integral_constant<int, 1>{}, stage0, offp, wp, e, used, 0, 0);
           if (active[RPW - 1])
-            round_rows(std::integral_constant<int, 1>{}, data + (set * RPW + 1) * stage_bytes + shift_c[RPW - 1], offp, wp, e, used, 1);
+            round_rows(std::integral_constant<int, 1>{}, data + stage_off(set, 1) + shift_c[RPW - 1], offp, wp, e, used, 1, 0);
         }
       }
       __syncwarp();
@@ -1392,6 +1440,7 @@ __global__ void combine_kernel(const CombineParams p) {
   const GroupDesc* gd = p.groups + grp;
   if (i >= gd->nrows) return;
   const int piece = (i % p.nw) * p.rpw + (i / p.nw);                 // (warp, row of the warp)
+  const bool floating = p.float_row && gd->nrows == 2 * p.nw - 1 && i == gd->nrows - 1;
   const int piece_s1 = p.shared_s1 ? (p.nw - 1) * p.rpw : piece;     // weight sums: last warp, row 0
   const int nrw = p.nw * p.rpw;
   const int nchunks = (int)p.nchunks;
@@ -1423,6 +1472,12 @@ __global__ void combine_kernel(const CombineParams p) {
       mn = fmin(mn, a[2]);
       mx = fmax(mx, a[3]);
       zc += p.partial_z[(base + piece) * p.ng + g];
+      if (floating) {  // the floating row's other half: row 1 of the last warp (reduce2_kernel)
+        const double* a2 = p.partial + ((base + (size_t)(p.nw - 1) * p.rpw + 1) * p.ng + g) * 4;
+        s0 += a2[0];
+        mn = fmin(mn, a2[2]);
+        mx = fmax(mx, a2[3]);
+      }
     }
   }
   const int row = gd->row[i];
@@ -1527,42 +1582,173 @@ __global__ void merge_axpy_kernel(int nlay, int64_t nwav, double* __restrict__ d
 }
 
 // gpoint_fraction numerators and per-g totals (create_look_up_table.cpp:537-548)
-__global__ void gfrac_hist_kernel(int ng, int64_t nwav, const int32_t* __restrict__ g_point,
-                                  const double* __restrict__ wn, const double* __restrict__ dwn, int nbin,
-                                  double bin0, double dwav, double* __restrict__ sums,
-                                  double* __restrict__ totals) {
-  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwav) return;
-  const int g = g_point[w];
-  if (g < 0 || g >= ng) return;
-  const double nu = wn[w], d = dwn[w];
-  atomicAdd(&totals[g], d);
+// gpoint_fraction / ssi_intervals (create_look_up_table.cpp:512-561): histograms of a per-wavenumber
+// quantity over (g point, wavenumber bin) cells.  The sums are accumulated EXACTLY, as 128-bit
+// fixed-point integers whose unit 2^lsb is derived from the largest magnitude in the data: integer
+// addition is associative, so the result does not depend on the order in which threads, warps or
+// blocks arrive (bitwise reproducible, no floating-point atomics), and it is rounded to FP64 once.
+// Values more than 2^33 times smaller than the largest lose their bits below 2^lsb (an absolute
+// error below max * 2^-85 each).
+struct Fix128 {
+  unsigned long long lo;
+  long long hi;
+};
+__device__ __forceinline__ int hist_bin(double nu, int nbin, double bin0, double dwav) {
   // bin i covers (bin0 + i*dwav, bin0 + (i+1)*dwav]
   int i = (int)ceil((nu - bin0) / dwav) - 1;
   // repair rounding of the division against the exact edge tests of :544-545
   if (i >= 0 && i < nbin && !(nu > bin0 + dwav * i)) --i;
   if (i + 1 >= 0 && i + 1 < nbin && nu > bin0 + dwav * (i + 1)) ++i;
-  if (i >= 0 && i < nbin && nu > bin0 + dwav * i && nu <= bin0 + dwav * (i + 1)) {
-    atomicAdd(&sums[(size_t)g * nbin + i], d);
+  return (i >= 0 && i < nbin && nu > bin0 + dwav * i && nu <= bin0 + dwav * (i + 1)) ? i : -1;
+}
+// largest magnitude (as the bit pattern of |v|, which orders like the value) of the values that count
+__global__ void hist_max_kernel(int ng, int64_t nwav, const int32_t* __restrict__ g_point,
+                                const double* __restrict__ val, unsigned long long* __restrict__ maxbits) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long b = 0ull;
+  if (w < nwav && (!g_point || (g_point[w] >= 0 && g_point[w] < ng))) {
+    const double v = fabs(val[w]);
+    if (v == v && v <= 1.7976931348623157e308) b = (unsigned long long)__double_as_longlong(v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, b, o);
+    b = t > b ? t : b;
+  }
+  if ((threadIdx.x & 31) == 0 && b) atomicMax(maxbits, b);
+}
+// v as a multiple of 2^lsb, two's complement
+__device__ __forceinline__ Fix128 to_fix128(double v, int lsb) {
+  Fix128 r = {0ull, 0ll};
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+  const int be = (int)((bits >> 52) & 0x7ffu);
+  if (be == 0x7ff) return r;  // non-finite values are reported by the caller, not summed
+  const unsigned long long m = (bits & 0xfffffffffffffull) | (be ? 0x10000000000000ull : 0ull);
+  const int sh = (be ? be - 1075 : -1074) - lsb;  // v = m * 2^(lsb + sh)
+  unsigned long long lo = 0ull, hi = 0ull;
+  if (sh >= 64) {
+    hi = sh < 128 ? m << (sh - 64) : 0ull;
+  } else if (sh > 0) {
+    lo = m << sh;
+    hi = m >> (64 - sh);
+  } else if (sh > -64) {
+    lo = m >> (-sh);
+  }
+  if (bits >> 63) {  // negate
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  r.lo = lo;
+  r.hi = (long long)hi;
+  return r;
+}
+__device__ __forceinline__ void fix128_add(Fix128& a, const Fix128 b) {
+  const unsigned long long lo = a.lo + b.lo;
+  a.hi += b.hi + (lo < a.lo ? 1ll : 0ll);
+  a.lo = lo;
+}
+// The lanes of a warp that hit the same cell add up first (lane order; any order gives the same
+// integer), then one lane adds the group's sum to the cell: low word, then high word plus the carry
+// out of the low word - the two atomics of different threads may interleave freely, the final
+// 128-bit value is the exact sum either way.
+__device__ __forceinline__ void fix128_warp_accumulate(Fix128* __restrict__ cells, const long long key, Fix128 x) {
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  unsigned rest = peers & (peers - 1);  // the group without its leader
+  unsigned any = __ballot_sync(0xffffffffu, rest != 0u && lane == leader);
+  while (any) {  // warp-uniform: some group still has members to fold
+    const int src = rest ? __ffs(rest) - 1 : lane;
+    Fix128 y;
+    y.lo = __shfl_sync(0xffffffffu, x.lo, src);
+    y.hi = __shfl_sync(0xffffffffu, x.hi, src);
+    if (rest && lane == leader) fix128_add(x, y);
+    rest &= rest - 1;
+    any = __ballot_sync(0xffffffffu, rest != 0u && lane == leader);
+  }
+  if (lane == leader && key >= 0 && (x.lo | (unsigned long long)x.hi)) {
+    unsigned long long* c = reinterpret_cast<unsigned long long*>(cells + key);
+    const unsigned long long old = atomicAdd(c, x.lo);
+    const unsigned long long carry = (old + x.lo < old) ? 1ull : 0ull;
+    const unsigned long long h = (unsigned long long)x.hi + carry;
+    if (h) atomicAdd(c + 1, h);
   }
 }
-
-__global__ void gfrac_norm_kernel(int ng, int nbin, const double* __restrict__ sums,
-                                  const double* __restrict__ totals, double* __restrict__ out) {
+__device__ __forceinline__ int hist_lsb(const unsigned long long maxbits) {
+  // the largest value has its leading bit at 2^e; 2^40 of them still fit below bit 126
+  const int be = (int)((maxbits >> 52) & 0x7ffu);
+  const int e = be ? be - 1023 : -1022;
+  return e + 41 - 126;
+}
+// cells: [ng*nbin] (g, bin) sums, then [ng] totals
+__global__ void gfrac_hist_kernel(int ng, int64_t nwav, const int32_t* __restrict__ g_point,
+                                  const double* __restrict__ wn, const double* __restrict__ dwn, int nbin,
+                                  double bin0, double dwav, const unsigned long long* __restrict__ maxbits,
+                                  Fix128* __restrict__ cells) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lsb = hist_lsb(*maxbits);
+  long long kcell = -1, ktot = -1;
+  Fix128 x = {0ull, 0ll};
+  if (w < nwav) {
+    const int g = g_point[w];
+    if (g >= 0 && g < ng) {
+      x = to_fix128(dwn[w], lsb);
+      ktot = (long long)ng * nbin + g;
+      const int i = hist_bin(wn[w], nbin, bin0, dwav);
+      if (i >= 0) kcell = (long long)g * nbin + i;
+    }
+  }
+  fix128_warp_accumulate(cells, ktot, x);
+  fix128_warp_accumulate(cells, kcell, x);
+}
+__device__ __forceinline__ double fix128_to_double(Fix128 a, int lsb) {
+  const bool neg = a.hi < 0;
+  unsigned long long lo = a.lo, hi = (unsigned long long)a.hi;
+  if (neg) {
+    lo = ~lo + 1ull;
+    hi = ~hi + (lo == 0ull ? 1ull : 0ull);
+  }
+  // hi * 2^64 + lo, rounded once: fold the low word's top bits into a 64-bit significand with a sticky bit
+  double r;
+  if (hi == 0ull) {
+    r = scalbn(__ull2double_rn(lo), lsb);
+  } else {
+    const int z = __clzll((long long)hi);
+    unsigned long long top = z ? (hi << z) | (lo >> (64 - z)) : hi;
+    const unsigned long long below = z ? (lo << z) : lo;
+    if (below) top |= 1ull;  // sticky: the discarded bits only matter for ties
+    r = scalbn(__ull2double_rn(top), lsb + 64 - z);
+  }
+  return neg ? -r : r;
+}
+__global__ void gfrac_norm_kernel(int ng, int nbin, const Fix128* __restrict__ cells,
+                                  const unsigned long long* __restrict__ maxbits, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ng * nbin) return;
-  out[i] = sums[i] / totals[i / nbin];
+  const int lsb = hist_lsb(*maxbits);
+  out[i] = fix128_to_double(cells[i], lsb) / fix128_to_double(cells[(size_t)ng * nbin + i / nbin], lsb);
 }
 
 __global__ void ssi_hist_kernel(int64_t nwav, const double* __restrict__ wn, const double* __restrict__ ssi,
-                                int nbin, double bin0, double dwav, double* __restrict__ out) {
+                                int nbin, double bin0, double dwav, const unsigned long long* __restrict__ maxbits,
+                                Fix128* __restrict__ cells) {
   const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= nwav) return;
-  const double nu = wn[w];
-  int i = (int)ceil((nu - bin0) / dwav) - 1;
-  if (i >= 0 && i < nbin && !(nu > bin0 + dwav * i)) --i;
-  if (i + 1 >= 0 && i + 1 < nbin && nu > bin0 + dwav * (i + 1)) ++i;
-  if (i >= 0 && i < nbin && nu > bin0 + dwav * i && nu <= bin0 + dwav * (i + 1)) atomicAdd(&out[i], ssi[w]);
+  const int lsb = hist_lsb(*maxbits);
+  long long key = -1;
+  Fix128 x = {0ull, 0ll};
+  if (w < nwav) {
+    const int i = hist_bin(wn[w], nbin, bin0, dwav);
+    if (i >= 0) {
+      key = i;
+      x = to_fix128(ssi[w], lsb);
+    }
+  }
+  fix128_warp_accumulate(cells, key, x);
+}
+__global__ void fix128_out_kernel(int n, const Fix128* __restrict__ cells, const unsigned long long* __restrict__ maxbits,
+                                  double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fix128_to_double(cells[i], hist_lsb(*maxbits));
 }
 
 __global__ void compact_used_kernel(int ng, int64_t nwav, const int32_t* __restrict__ g_point,
@@ -1637,6 +1823,26 @@ static cudaError_t launch_reduce(int fkind, int wmode, int gen, ecckd_ctx* ctx, 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// 2^(j/N), j = 0 .. N-1, evaluated in extended precision on the host and rounded to FP64 once; one
+// device copy per context.
+static int exp2tab_get(ecckd_ctx* ctx, int logn, const double** out) {
+  if (!ctx->d_exp2tab || ctx->exp2tab_logn != logn) {
+    const int n = 1 << logn;
+    std::vector<double> h((size_t)n);
+    for (int j = 0; j < n; ++j) h[j] = (double)exp2l((long double)j / (long double)n);
+    if (ctx->d_exp2tab) {
+      ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+      ECCKD_CUDA_OK(cudaFree(ctx->d_exp2tab));
+      ctx->d_exp2tab = nullptr;
+    }
+    ECCKD_CUDA_OK(cudaMalloc(&ctx->d_exp2tab, (size_t)n * sizeof(double)));
+    ECCKD_CUDA_OK(cudaMemcpy(ctx->d_exp2tab, h.data(), (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->exp2tab_logn = logn;
+  }
+  *out = ctx->d_exp2tab;
+  return ECCKD_OK;
+}
+
 // Streaming stage: reduce `rows` (any mix of spectra/layers sharing one plan and
 // one weight definition) to per-(row, g) partial results in d_sums / d_minmax
 // (layouts in spectral_reduce.cuh), rows[i].row giving each row's index there.
@@ -1672,10 +1878,31 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   }
   const int rpw = RPW;
   const int stage2 = plan->ch * 8 + 16;  // reduce2_kernel: row-chunk stage incl. the 8-byte shift of unaligned rows
-  auto smem_of = [&](int n) {
-    return gen == 2 ? (size_t)smem2_layout(n, NSW, stage2).total : (size_t)smem_layout(n, ng).total;
+  // rows of the largest group when every run of rows sharing a weight row is cut into
+  // ceil(n / (nw*RPW)) pieces of nearly equal size
+  std::vector<int> runs;
+  for (int i = 0; i < nrows;) {
+    int j = i;
+    while (j < nrows && rows[j].wrow == rows[i].wrow) ++j;
+    runs.push_back(j - i);
+    i = j;
+  }
+  auto max_rows_of = [&](int n) {
+    int m = 1;
+    for (int len : runs) {
+      const int pieces = (len + n * rpw - 1) / (n * rpw);
+      m = std::max(m, (len + pieces - 1) / pieces);
+    }
+    return m;
   };
-  int nw = std::min(NW_MAX, (longest + rpw - 1) / rpw);
+  auto smem_of = [&](int n) {
+    return gen == 2 ? (size_t)smem2_layout(n, NSW, stage2, max_rows_of(n)).total : (size_t)smem_layout(n, ng).total;
+  };
+  // reduce2_kernel: one row per warp while the rows of a group fit NW_MAX2 warps, otherwise NW_MAX2
+  // warps of which the first max_rows - nw take two rows (ECCKD_REDUCE_NW overrides, timing only)
+  int nw = gen == 2 ? std::min(NW_MAX2, longest) : std::min(NW_MAX, (longest + rpw - 1) / rpw);
+  if (gen == 2)
+    if (const char* env = getenv("ECCKD_REDUCE_NW")) nw = std::max(1, std::min(NW_MAX2, atoi(env)));
   while (nw > 1 && smem_of(nw) > smem_max) --nw;
   ECCKD_REQUIRE(smem_of(nw) <= smem_max, ECCKD_PARAMETER_ERROR,
                 "average_optical_depth: ng = %d needs %zu B of shared memory (limit %zu)", ng, smem_of(nw), smem_max);
@@ -1708,9 +1935,10 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   // reduce2_kernel: as many ring slots as shared memory leaves room for (the ring couples the consumer
   // warps: a slot is refilled when ALL of them have released it, so its depth is their slack)
   int nsw = NSW;
+  const int max_rows = max_rows_of(nw);
   if (gen == 2)
-    while (nsw < 8 && (size_t)smem2_layout(nw, nsw + 1, stage2).total <= smem_max) ++nsw;
-  const size_t smem = gen == 2 ? (size_t)smem2_layout(nw, nsw, stage2).total : smem_of(nw);
+    while (nsw < 8 && (size_t)smem2_layout(nw, nsw + 1, stage2, max_rows).total <= smem_max) ++nsw;
+  const size_t smem = gen == 2 ? (size_t)smem2_layout(nw, nsw, stage2, max_rows).total : smem_of(nw);
 
   ReduceParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -1724,6 +1952,9 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   rp.rounds = plan->d_rounds;
   rp.balanced = plan->balanced ? 1 : 0;
   rp.nsw = nsw;
+  rp.max_rows = max_rows;
+  // the floating row needs warp nw-2 to own second-row stages and warp nw-1 to own none (packed stages)
+  rp.float_row = (gen == 2 && nw >= 2 && max_rows == 2 * nw - 1 && !getenv("ECCKD_NO_FLOAT_ROW")) ? 1 : 0;
   rp.stage_bytes = stage2;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
@@ -1733,6 +1964,10 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   trans_const_init(&rp.tc, kd);
   trans_const256_init(&rp.tc256, kd);
   trans_const64_init(&rp.tc64, kd);
+#if defined(ECCKD_TAB_LOGN)
+  trans_constT_init(&rp.tct, kd, ECCKD_TAB_LOGN, ECCKD_TAB_QDEG);
+  ECCKD_TRY(exp2tab_get(ctx, ECCKD_TAB_LOGN, &rp.exp2tab));
+#endif
 #ifdef ECCKD_TIMING_KNOBS  // builds for tools/variants.sh only: the knobs skip work, the results are wrong
   if (const char* e = getenv("ECCKD_DEBUG")) rp.debug = atoi(e);
 #endif
@@ -1816,6 +2051,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.nchunks = plan->nchunks;
   cp.ng = ng;
   cp.shared_s1 = !(fkind == F_LOG || fkind == F_HYBRID);
+  cp.float_row = rp.float_row;
   cp.partial = rp.partial;
   cp.partial_z = rp.partial_z;
   cp.sums = d_sums;
@@ -2828,16 +3064,19 @@ ECCKD_API int ecckd_gpoint_fraction_dev(ecckd_ctx* ctx, int ng, int64_t nwav, co
   ECCKD_REQUIRE(ctx && d_g_point && d_wn && d_dwn && d_out, ECCKD_PARAMETER_ERROR, "ecckd_gpoint_fraction: NULL argument");
   double bin0, dwav;
   ECCKD_TRY(check_uniform_bins(nbin, h_w1, h_w2, &bin0, &dwav));
+  // scratch: [ng*nbin + ng] 128-bit cells, then the largest magnitude
   void* d_tmp = nullptr;
   const size_t n = (size_t)ng * nbin + ng;
-  ECCKD_TRY(ws_reserve(ctx, 1, n * sizeof(double), &d_tmp));
-  ECCKD_CUDA_OK(cudaMemsetAsync(d_tmp, 0, n * sizeof(double), ctx->stream));
-  double* sums = static_cast<double*>(d_tmp);
-  double* totals = sums + (size_t)ng * nbin;
-  gfrac_hist_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(ng, nwav, d_g_point, d_wn, d_dwn, nbin,
-                                                                             bin0, dwav, sums, totals);
+  ECCKD_TRY(ws_reserve(ctx, 1, n * sizeof(Fix128) + 16, &d_tmp));
+  ECCKD_CUDA_OK(cudaMemsetAsync(d_tmp, 0, n * sizeof(Fix128) + 16, ctx->stream));
+  Fix128* cells = static_cast<Fix128*>(d_tmp);
+  unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(cells + n);
+  const unsigned nblk = (unsigned)((nwav + 255) / 256);
+  hist_max_kernel<<<nblk, 256, 0, ctx->stream>>>(ng, nwav, d_g_point, d_dwn, maxbits);
   ECCKD_LAUNCH_CHECK(ctx);
-  gfrac_norm_kernel<<<(ng * nbin + 255) / 256, 256, 0, ctx->stream>>>(ng, nbin, sums, totals, d_out);
+  gfrac_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(ng, nwav, d_g_point, d_wn, d_dwn, nbin, bin0, dwav, maxbits, cells);
+  ECCKD_LAUNCH_CHECK(ctx);
+  gfrac_norm_kernel<<<(ng * nbin + 255) / 256, 256, 0, ctx->stream>>>(ng, nbin, cells, maxbits, d_out);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
@@ -2848,8 +3087,17 @@ ECCKD_API int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double
   ECCKD_REQUIRE(ctx && d_wn && d_ssi && d_out, ECCKD_PARAMETER_ERROR, "ecckd_ssi_intervals: NULL argument");
   double bin0, dwav;
   ECCKD_TRY(check_uniform_bins(nbin, h_w1, h_w2, &bin0, &dwav));
-  ECCKD_CUDA_OK(cudaMemsetAsync(d_out, 0, (size_t)nbin * sizeof(double), ctx->stream));
-  ssi_hist_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(nwav, d_wn, d_ssi, nbin, bin0, dwav, d_out);
+  void* d_tmp = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, (size_t)nbin * sizeof(Fix128) + 16, &d_tmp));
+  ECCKD_CUDA_OK(cudaMemsetAsync(d_tmp, 0, (size_t)nbin * sizeof(Fix128) + 16, ctx->stream));
+  Fix128* cells = static_cast<Fix128*>(d_tmp);
+  unsigned long long* maxbits = reinterpret_cast<unsigned long long*>(cells + nbin);
+  const unsigned nblk = (unsigned)((nwav + 255) / 256);
+  hist_max_kernel<<<nblk, 256, 0, ctx->stream>>>(0, nwav, nullptr, d_ssi, maxbits);
+  ECCKD_LAUNCH_CHECK(ctx);
+  ssi_hist_kernel<<<nblk, 256, 0, ctx->stream>>>(nwav, d_wn, d_ssi, nbin, bin0, dwav, maxbits, cells);
+  ECCKD_LAUNCH_CHECK(ctx);
+  fix128_out_kernel<<<(nbin + 255) / 256, 256, 0, ctx->stream>>>(nbin, cells, maxbits, d_out);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }

@@ -4,6 +4,18 @@
 #include "common.cuh"
 #include "trans_core.cuh"
 
+// Table form of 1 - exp(-k D tau) in reduce2_kernel (trans_core.cuh): 2^ECCKD_TAB_LOGN entries replicated
+// 2^ECCKD_TAB_LOGR times, minimax q of degree ECCKD_TAB_QDEG.  Measured on the B200 (19 x 53 x 2^23,
+// kernel ms): 64 x 16 copies, Taylor degree 5 (10 FP64 instructions per value) 17.25; 256 x 8, Taylor
+// degree 4 (9) 16.10; 128 x 16, minimax q3 (9) 16.42; 1024 x 2, minimax q2 (8) 16.17; 2048 x 1, minimax
+// q2 (8) 15.71 - the consumer warps are bound by the FP64 pipe while they evaluate, so what pays is
+// fewer FP64 instructions, not fewer shared-memory wavefronts.
+#ifndef ECCKD_TAB_LOGN
+#define ECCKD_TAB_LOGN 11
+#define ECCKD_TAB_LOGR 0
+#define ECCKD_TAB_QDEG 2
+#endif
+
 namespace ecckd {
 
 constexpr int SLOTS = 16;          // plan slots per lane per round
@@ -14,8 +26,14 @@ constexpr int RPW = 2;             // rows per consumer warp (they share the lan
 constexpr int NSETS = 2;           // stage sets per consumer warp: chunk visit k uses set k & 1
 constexpr int NSW = 4;             // ring slots of (weight tile, plan round) per CTA
 constexpr int NPW = 2;             // producer (weight) warps per CTA
-constexpr int NW_MAX = 10;         // consumer warps per CTA: 12 warps x 168 registers fill the register file
-constexpr int GROUP_ROWS = NW_MAX * RPW;
+constexpr int NW_MAX = 10;         // consumer warps per CTA of reduce_kernel: 12 warps x 168 registers fill the register file
+// reduce2_kernel.  Measured on the B200 (19 x 53 x 2^23): 11 consumer warps + 2 producers (rows 2,2,1 /
+// 2,2,1 / 2,2,1 / 2,2+producers over the four schedulers instead of 6 / 5 / 4 / 4) is SLOWER, 19.6 ms
+// against 18.6 ms for 10 + 2 built with the same 416-thread bound: the round time is the latency of a
+// two-row warp, not the issue load of its scheduler, and the 152-register cap makes ptxas serialise
+// the polynomial chains (17.1 ms with 12 warps at 168 registers).
+constexpr int NW_MAX2 = 10;
+constexpr int GROUP_ROWS = NW_MAX2 * RPW;
 // lane meta word of the plan: bits 0-11 g point (0xFFF = lane unused), 12-16 valid slots (0..16),
 // 17-21 "lane + 2^s belongs to the same g point in this round" for shuffle step s, 22 head lane of its g point
 constexpr unsigned NO_G = 0xFFFu;
@@ -107,6 +125,10 @@ struct ReduceParams {
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k
   TransConst256 tc256;        // the same for the 256-entry shared-memory table of the consumer warps
   TransConst64 tc64;          // the same for the replicated 64-entry table of reduce2_kernel
+  TransConstT tct;            // the same for the general table form (trans_core.cuh)
+  const double* exp2tab;      // 2^(j/N), N entries (ecckd_ctx::d_exp2tab)
+  int max_rows;               // reduce2_kernel: rows of the largest group (data stages are packed by row)
+  int float_row;              // reduce2_kernel: groups of 2 nw - 1 rows pass their last row between the last two warps
   int nsw;                    // reduce2_kernel: ring slots
   int stage_bytes;            // reduce2_kernel: bytes of one row-chunk stage (chunk length x 8 + 16)
   int balanced;               // the plan is a balanced one: lane meta bits 12-27 are a slot mask (not a count)
@@ -127,6 +149,7 @@ struct CombineParams {
   int64_t nchunks;
   int ng;
   int shared_s1;   // weight sums are accumulated once per group (by the last consumer warp)
+  int float_row;   // reduce2_kernel's floating row: its second partial sits in row 1 of the last warp
   const double* partial;
   const int32_t* partial_z;
   double* sums;    // [nrows][ng][NSUM]

@@ -333,6 +333,119 @@ __device__ __forceinline__ double trans64_one_minus_exp(double tau, const TransC
   return trans64_phase3(m, trans64_phase2(m, tab, lane_off), K);
 }
 
+// The 256-entry table REPLICATED 8 times (16 KB): copy c = lane & 7 of entry j at byte ((j*8 + c)*8).
+// Lanes l and l + 8 of a half-warp share a copy and collide only when their j differ and have the
+// same parity (an entry row is 64 bytes, so consecutive j alternate between the two halves of the
+// banks): ~1.9 wavefronts per half-warp against 1 for the 64-entry table, in exchange for a
+// degree-4 polynomial (one FP64 instruction less per value).
+constexpr int TRANS_TAB256R_BYTES = 256 * 8 * 8;
+__device__ __forceinline__ void trans_tab256r_init(double* tab) {
+  for (int i = threadIdx.x; i < 256 * 8; i += blockDim.x) {
+    const int j = i >> 3;
+    const double t = EXP2_256[j];
+    tab[i] = __hiloint2double(__double2hiint(t) - (j << 12), __double2loint(t));
+  }
+}
+// lane_off8 = (lane & 7) << 3
+__device__ __forceinline__ double trans256r_phase2(const TransMid& m, const unsigned char* __restrict__ tab,
+                                                   const unsigned lane_off8) {
+  const unsigned idx = (((unsigned)m.n << 6) & 0x3fc0u) | lane_off8;
+  const uint2 e = *reinterpret_cast<const uint2*>(tab + idx);
+  return __hiloint2double((int)e.y + (m.n << 12), (int)e.x);
+}
+#ifdef ECCKD_V_I2F
+// range reduction with the integer -> FP64 conversion (XU pipe) in place of the FP64 subtraction
+__device__ __forceinline__ TransMid trans256_phase1_i2f(double tau, const TransConst256& K) {
+  const double magic = 6755399441055744.0;
+  const double tc = __hiloint2double(min(__double2hiint(tau), K.hi_max), __double2loint(tau));
+  const double t = fma(tc, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma((double)m.n, K.b, tc);
+  return m;
+}
+__device__ __forceinline__ TransMid trans64_phase1_i2f(double tau, const TransConst64& K) {
+  const double magic = 6755399441055744.0;
+  const double tc = __hiloint2double(min(__double2hiint(tau), K.hi_max), __double2loint(tau));
+  const double t = fma(tc, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma((double)m.n, K.b, tc);
+  return m;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// The general form: a table of N = 2^LOGN entries 2^(j/N) replicated R = 2^LOGR times in shared memory
+// (copy c = lane & (R-1) of entry j at byte ((j*R + c)*8)), and exp(x) = 1 + x q(x) on |x| <= ln2/(2N) with
+// q the MINIMAX polynomial of (e^x - 1)/x (tools/gen_expm1_minimax.py), one degree lower than the Taylor
+// polynomial of the same accuracy.  FP64 instructions per value: 3 (range reduction) + QDEG + 2.
+//   N = 128,  R = 16, q degree 3: conflict-free look-ups, |error of exp| <= 1.5e-16
+//   N = 1024, R = 2,  q degree 2: ~2.6 wavefronts per half-warp,   <= 1.4e-16
+//   N = 2048, R = 1,  q degree 2: ~3.1 wavefronts per half-warp,   <= 8.5e-18
+// The table itself (N doubles, correctly rounded on the host in extended precision) lives in global
+// memory (ecckd_ctx::d_exp2tab); a CTA adjusts and replicates it into shared memory at start-up.
+struct TransConstT {
+  double a;        // -kd * N/ln2
+  double b;        // ln2 / (N kd)
+  double c[4];     // c[i] = q_i (-kd)^(i+1)
+  int32_t hi_max;  // high word of 708/kd
+  int32_t pad_;
+};
+static const double EXPM1_Q3_128[4] = {0x1.ffffffffffe08p-1, 0x1.ffffffffffd60p-2, 0x1.55555d887706dp-3, 0x1.55555d8840eb4p-5};
+static const double EXPM1_Q2_1024[3] = {0x1.0000000000000p+0, 0x1.0000001ebfbe0p-1, 0x1.5555557e54fd5p-3};
+static const double EXPM1_Q2_2048[3] = {0x1.0000000000000p+0, 0x1.00000007afef8p-1, 0x1.5555555f953f5p-3};
+inline void trans_constT_init(TransConstT* k, double kd, int logn, int qdeg) {
+  const long double ln2 = 0.693147180559945309417232121458176568L;
+  const long double lkd = (long double)kd;
+  const long double N = (long double)(1 << logn);
+  const double* q = logn == 7 ? EXPM1_Q3_128 : (logn == 10 ? EXPM1_Q2_1024 : EXPM1_Q2_2048);
+  k->a = (double)(-lkd * N / ln2);
+  k->b = (double)(ln2 / (N * lkd));
+  long double pw = 1.0L;
+  for (int i = 0; i < 4; ++i) {
+    pw *= -lkd;
+    k->c[i] = i <= qdeg ? (double)((long double)q[i] * pw) : 0.0;
+  }
+  const double tmax = 708.0 / kd;
+  uint64_t bits;
+  memcpy(&bits, &tmax, 8);
+  k->hi_max = (int32_t)(bits >> 32);
+  k->pad_ = 0;
+}
+template <int LOGN, int LOGR>
+__device__ __forceinline__ void trans_tabT_init(double* tab, const double* __restrict__ g_exp2) {
+  for (int i = threadIdx.x; i < (1 << (LOGN + LOGR)); i += blockDim.x) {
+    const int j = i >> LOGR;
+    const double t = g_exp2[j];
+    tab[i] = __hiloint2double(__double2hiint(t) - (j << (20 - LOGN)), __double2loint(t));
+  }
+}
+__device__ __forceinline__ TransMid transT_phase1(double tau, const TransConstT& K) {
+  const double magic = 6755399441055744.0;
+  const double tc = __hiloint2double(min(__double2hiint(tau), K.hi_max), __double2loint(tau));
+  const double t = fma(tc, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma(t - magic, K.b, tc);
+  return m;
+}
+// lane_off = (lane & (R-1)) << 3
+template <int LOGN, int LOGR>
+__device__ __forceinline__ double transT_phase2(const TransMid& m, const unsigned char* __restrict__ tab,
+                                                const unsigned lane_off) {
+  const unsigned idx = (((unsigned)m.n << (3 + LOGR)) & (unsigned)(((1 << LOGN) - 1) << (3 + LOGR))) | lane_off;
+  const uint2 e = *reinterpret_cast<const uint2*>(tab + idx);
+  return __hiloint2double((int)e.y + (m.n << (20 - LOGN)), (int)e.x);
+}
+template <int QDEG>
+__device__ __forceinline__ double transT_phase3(const TransMid& m, const double T, const TransConstT& K) {
+  double q = K.c[QDEG];
+#pragma unroll
+  for (int i = QDEG - 1; i >= 0; --i) q = fma(q, m.rho, K.c[i]);
+  return fma(-T, fma(q, m.rho, 1.0), 1.0);
+}
+
 // exp(x) for 0 <= x < 708 with the same table: x = (32 k + j) ln2/32 + r (two-constant
 // Cody-Waite reduction), exp(x) = 2^k 2^(j/32) (1 + p(r)).  Below 1 ulp; used for the Planck weights.
 __device__ __forceinline__ double exp_table(double x, const TransLane& tl) {

@@ -329,12 +329,15 @@ int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optic
 
 /* gpoint_fraction: src/ecckd/create_look_up_table.cpp:512-548.
  * Bin i is (h_wavenumber1[i], h_wavenumber2[i]]; bins must be the contiguous
- * uniform grid the reference builds (:526-535).  d_out[ng][nbin]. */
+ * uniform grid the reference builds (:526-535).  d_out[ng][nbin].
+ * The sums are accumulated exactly (128-bit fixed point, rounded to FP64 once): the result is
+ * bitwise reproducible and independent of the launch geometry. */
 int ecckd_gpoint_fraction_dev(ecckd_ctx* ctx, int ng, int64_t nwav, const int32_t* d_g_point,
                               const double* d_wavenumber_cm_1, const double* d_d_wavenumber_cm_1, int nbin,
                               const double* h_wavenumber1, const double* h_wavenumber2, double* d_out);
 
-/* Solar irradiance per bin: src/ecckd/create_look_up_table.cpp:555-561. d_out[nbin]. */
+/* Solar irradiance per bin: src/ecckd/create_look_up_table.cpp:555-561. d_out[nbin].
+ * Exact sums like ecckd_gpoint_fraction_dev. */
 int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenumber_cm_1,
                             const double* d_ssi, int nbin, const double* h_wavenumber1,
                             const double* h_wavenumber2, double* d_out);

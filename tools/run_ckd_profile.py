@@ -1,15 +1,8 @@
-"""Runs the run_ckd LW core at the bench shape a few times (profiling target)."""
+"""Runs the run_ckd LW core at the bench shape a few times (profiling target): python tools/run_ckd_sweep.py does
+the timing; this wrapper only exists so that `ncu ... python tools/run_ckd_profile.py` has a short command."""
 import os
+import runpy
 import sys
 
-import torch
-
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import bench  # noqa: E402
-import ecckd_b200 as E  # noqa: E402
-
-dev = torch.device("cuda", 0)
-st = torch.cuda.Stream(device=dev)
-torch.cuda.set_stream(st)
-ctx = E.Context(0, st.cuda_stream)
-print(bench.bench_flux(torch, E, ctx, dev, 6552.3)["fused_run_ckd"])
+sys.argv = [os.path.join(os.path.dirname(os.path.abspath(__file__)), "run_ckd_sweep.py")] + sys.argv[1:]
+runpy.run_path(sys.argv[0], run_name="__main__")
