@@ -1044,17 +1044,24 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck_kernel(const
 //   * the columns of a unit are visited in one flat sequence ordered by (it0, ip0) group - the four
 //     corner rows of the table gases are reloaded when the group changes -, and the rows of the gas
 //     with a concentration axis come through a ring of asynchronous copies TOD_AHEAD columns deep.
-constexpr int TOD_AHEAD = 3;              // columns whose concentration-axis rows are in flight
-constexpr int TOD_RING = TOD_AHEAD + 1;   // ring slots (the slot refilled was read one column earlier)
+constexpr int TOD_AHEAD = 2;              // columns whose concentration-axis rows are in flight beyond the pair being evaluated
+constexpr int TOD_RING = TOD_AHEAD + 2;   // ring slots: the pair being read + the columns in flight
 constexpr int TOD_NIN = 4 + TOD_MAXGAS;   // staged inputs per column: p(l), p(l+1), T(l), T(l+1), vmr of each gas
+static_assert((TOD_RING & (TOD_RING - 1)) == 0, "ring slots: a power of two");
 
+struct __align__(16) Tod2Col {  // g-independent state of one (column, layer), stored in VISIT order
+  double c00, c01, c10, c11;    // tw0*pw0, tw0*pw1, tw1*pw0, tw1*pw1
+  double w[TOD_MAXGAS];         // what multiplies the interpolated absorption of each gas
+  double cw1[TOD_MAXGAS];       // gases with a concentration axis: weight of level ic0 + 1 ...
+  unsigned coff[TOD_MAXGAS];    // ... and the element offset ic0 * qC of level ic0 in the packed table
+  unsigned o00;                 // element offset of the (it0, ip0) corner block (without the g point)
+  int col;                      // column of the tile
+  int pad_[2];
+};
 struct Tod2Smem {  // per warp
-  TodCol col[TOD_TILE];
+  Tod2Col col[TOD_TILE];
   double in[TOD_NIN][TOD_TILE];
   double2 ring[TOD_RING][4][32];
-  int key[TOD_TILE];
-  unsigned char ord[TOD_TILE];
-  unsigned char pad_[96];
 };
 
 template <int NLIN, bool HAS_LUT, int NWARP, int MINB>
@@ -1101,41 +1108,67 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
     // ---- phase A: lane = column (everything that does not depend on g: ckd_model.cpp:962-1009)
     int key = 0x7fffffff;
     const bool valid = lane < nc;
+    Interp it = {};
+    double t0 = 0.0, t1 = 0.0;
+    if (valid) {
+      const double p0 = S.in[0][lane], p1 = S.in[1][lane];
+      t0 = S.in[2][lane];
+      t1 = S.in[3][lane];
+      const double t_fl = (t0 * p0 + t1 * p1) / (p0 + p1);
+      it = make_interp(p0, p1, t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+      key = it.it0 * p.np + it.ip0;
+    }
+    // order of the visit: columns grouped by (it0, ip0), groups by their first column; a column's
+    // record goes to its place in that order
+    int pos = 0;
+    {
+      const unsigned same = __match_any_sync(0xffffffffu, key);
+      const int leader = __ffs(same) - 1;
+      unsigned leaders = __ballot_sync(0xffffffffu, valid && lane == leader);
+      int base = 0;
+      while (leaders) {  // warp-uniform
+        const int L = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const unsigned members = __shfl_sync(0xffffffffu, same, L);
+        if (leader == L) pos = base + __popc(members & ((1u << lane) - 1u));
+        base += __popc(members);
+      }
+    }
     int pl_off = 0, pl_off1 = 0;
     double pl_w0 = 0.0, pl_w1 = 0.0, pl1_w0 = 0.0, pl1_w1 = 0.0;
     if (valid) {
-      const double p0 = S.in[0][lane], p1 = S.in[1][lane], t0 = S.in[2][lane], t1 = S.in[3][lane];
-      const double t_fl = (t0 * p0 + t1 * p1) / (p0 + p1);
-      const Interp it = make_interp(p0, p1, t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
-      key = it.it0 * p.np + it.ip0;
-      TodCol tc;
+      Tod2Col& tc = S.col[pos];
       tc.c00 = it.tw0 * it.pw0;
       tc.c01 = it.tw0 * it.pw1;
       tc.c10 = it.tw1 * it.pw0;
       tc.c11 = it.tw1 * it.pw1;
+      tc.o00 = (unsigned)it.it0 * qT + (unsigned)it.ip0 * qP;
+      tc.col = lane;
 #pragma unroll
       for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
-        tc.w[ig] = 0.0;
-        tc.cw1[ig] = 0.0;
-        tc.ic0[ig] = 0;
-        if (ig >= ngas) continue;
-        const int cd = p.conc_dependence[ig];
-        const bool have = p.vmr[ig] != nullptr;
-        const double vmr = have ? S.in[4 + ig][lane] : 0.0;
-        double weight = 0.0;  // ckd_model.cpp:980-999
-        if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
-        if (cd == ECCKD_CONC_LUT) {
-          double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
-          cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
-          tc.ic0[ig] = (int)cindex0;
-          tc.cw1[ig] = cindex0 - tc.ic0[ig];
-          tc.w[ig] = weight;
-        } else {
-          tc.w[ig] = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+        double w = 0.0, cw1 = 0.0;
+        unsigned coff = 0u;
+        if (ig < ngas) {
+          const int cd = p.conc_dependence[ig];
+          const bool have = p.vmr[ig] != nullptr;
+          const double vmr = have ? S.in[4 + ig][lane] : 0.0;
+          double weight = 0.0;  // ckd_model.cpp:980-999
+          if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
+          if (cd == ECCKD_CONC_LUT) {
+            double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
+            cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+            const int ic0 = (int)cindex0;
+            coff = (unsigned)ic0 * qC;
+            cw1 = cindex0 - ic0;
+            w = weight;
+          } else {
+            w = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+          }
         }
+        tc.w[ig] = w;
+        tc.cw1[ig] = cw1;
+        tc.coff[ig] = coff;
       }
-      S.col[lane] = tc;
-      S.key[lane] = key;
       if (want_planck) {  // ckd_model.cpp:1124-1142 at half level l (and at the surface level for the last layer)
         auto planck_index = [&](const double t, int& off, double& w0, double& w1) {
           const double tindex0 = (t - p.planck_t0) / p.planck_dt;
@@ -1154,21 +1187,6 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
         planck_index(t1, pl_off1, pl1_w0, pl1_w1);
       }
     }
-    // order of the visit: columns grouped by (it0, ip0), groups by their first column
-    {
-      const unsigned same = __match_any_sync(0xffffffffu, key);
-      const int leader = __ffs(same) - 1;
-      unsigned leaders = __ballot_sync(0xffffffffu, valid && lane == leader);
-      int base = 0, pos = 0;
-      while (leaders) {  // warp-uniform
-        const int L = __ffs(leaders) - 1;
-        leaders &= leaders - 1;
-        const unsigned members = __shfl_sync(0xffffffffu, same, L);
-        if (leader == L) pos = base + __popc(members & ((1u << lane) - 1u));
-        base += __popc(members);
-      }
-      if (valid) S.ord[pos] = (unsigned char)lane;
-    }
     __syncwarp();
     // the next unit's inputs travel while this one is evaluated (S.in has been read)
     stage_inputs(u + stride);
@@ -1183,7 +1201,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
         double* out = p.planck_hl ? p.planck_hl + ((int64_t)c0 * (nlay + 1) + l) * ng + g : nullptr;
         const bool last = l == nlay - 1;
         double* surf = (last && p.planck_surf) ? p.planck_surf + (int64_t)c0 * ng + g : nullptr;
-#pragma unroll 4
+#pragma unroll 8
         for (int c = 0; c < nc; ++c) {
           const int off = __shfl_sync(0xffffffffu, pl_off, c);
           const double w0 = __shfl_sync(0xffffffffu, pl_w0, c), w1 = __shfl_sync(0xffffffffu, pl_w1, c);
@@ -1191,7 +1209,7 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
           if (store && out) out[c * lev_stride] = b;
         }
         if (last) {
-#pragma unroll 4
+#pragma unroll 8
           for (int c = 0; c < nc; ++c) {
             const int off = __shfl_sync(0xffffffffu, pl_off1, c);
             const double w0 = __shfl_sync(0xffffffffu, pl1_w0, c), w1 = __shfl_sync(0xffffffffu, pl1_w1, c);
@@ -1201,18 +1219,15 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
           }
         }
       }
-      // ---- optical depth: lane = g point, columns in S.ord order
+      // ---- optical depth: lane = g point, columns in visit order
       const unsigned col_stride = (unsigned)nlay * ng;  // 32 * nlay * ng < 2^31 (checked by the host)
       double* const od_unit = p.od + ((int64_t)c0 * nlay + l) * ng + g;
+      const unsigned g4 = (unsigned)g * 4;
       // asynchronous copies of the concentration-axis rows of the k-th column of the visit
       auto ring_issue = [&](const int k) {
         if (HAS_LUT && k < nc) {
-          const int c = S.ord[k];
-          const int ky = S.key[c];
-          const int it0 = ky / p.np, ip0 = ky - it0 * p.np;
-          const double* k0 = p.packed[NLIN] + (size_t)((unsigned)S.col[c].ic0[NLIN] * qC) + (unsigned)it0 * qT + (unsigned)ip0 * qP +
-                             (unsigned)g * 4;
-          const unsigned dst = s_ring + (unsigned)(((k % TOD_RING) * 4) * 32 + lane) * 16;
+          const double* k0 = p.packed[NLIN] + (size_t)(S.col[k].coff[NLIN] + S.col[k].o00 + g4);
+          const unsigned dst = s_ring + (unsigned)(((k & (TOD_RING - 1)) * 4) * 32 + lane) * 16;
           cp_async16(dst, k0);
           cp_async16(dst + 32 * 16, k0 + 2);
           cp_async16(dst + 64 * 16, k0 + qC);
@@ -1222,21 +1237,24 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
       };
 #pragma unroll
       for (int k = 0; k < TOD_AHEAD; ++k) ring_issue(k);
-      int cur_key = -1;
-      unsigned o00 = 0;
+      unsigned cur = 0xffffffffu;
       double K[NLIN > 0 ? NLIN : 1][4];
+      // Two columns of the same (it0, ip0) group per trip, their loads issued together and their
+      // arithmetic interleaved (a single column is a chain of dependent FP64 instructions behind a
+      // shared-memory load: with three warps per scheduler that latency was the whole run time).
+      // At the start of a trip at column k, the rows of columns k .. k + TOD_AHEAD - 1 are in flight.
 #pragma unroll 1
-      for (int k = 0; k < nc; ++k) {
+      for (int k = 0; k < nc;) {
+        const Tod2Col& ta = S.col[k];
+        const unsigned o00 = ta.o00;
+        const bool pair = k + 1 < nc && S.col[k + 1].o00 == o00;  // warp-uniform
         ring_issue(k + TOD_AHEAD);
-        const int c = S.ord[k];
-        const int ky = S.key[c];
-        if (ky != cur_key) {  // warp-uniform: a new (it0, ip0) group, four corner rows of every table gas
-          cur_key = ky;
-          const int it0 = ky / p.np, ip0 = ky - it0 * p.np;
-          o00 = (unsigned)it0 * qT + (unsigned)ip0 * qP + (unsigned)g * 4;
+        if (pair) ring_issue(k + TOD_AHEAD + 1);
+        if (o00 != cur) {  // warp-uniform: a new (it0, ip0) group, four corner rows of every table gas
+          cur = o00;
 #pragma unroll
           for (int ig = 0; ig < NLIN; ++ig) {
-            const double2* kk = reinterpret_cast<const double2*>(p.packed[ig] + o00);
+            const double2* kk = reinterpret_cast<const double2*>(p.packed[ig] + (o00 + g4));
             const double2 a = __ldg(kk), b = __ldg(kk + 1);
             K[ig][0] = a.x;
             K[ig][1] = a.y;
@@ -1244,36 +1262,57 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
             K[ig][3] = b.y;
           }
         }
-        const TodCol& tc = S.col[c];
-        const double c00 = tc.c00, c01 = tc.c01, c10 = tc.c10, c11 = tc.c11;
-        double tau0 = 0.0, tau1 = 0.0;  // two chains
+        const Tod2Col& tb = S.col[pair ? k + 1 : k];
+        const double a00 = ta.c00, a01 = ta.c01, a10 = ta.c10, a11 = ta.c11;
+        const double b00 = tb.c00, b01 = tb.c01, b10 = tb.c10, b11 = tb.c11;
+        double sa0 = 0.0, sa1 = 0.0, sb0 = 0.0, sb1 = 0.0;  // two chains per column
 #pragma unroll
         for (int ig = 0; ig < NLIN; ++ig) {
-          const double v = c00 * K[ig][0] + c01 * K[ig][1] + c10 * K[ig][2] + c11 * K[ig][3];
-          if (ig & 1) tau1 += tc.w[ig] * v; else tau0 += tc.w[ig] * v;
+          const double va = a00 * K[ig][0] + a01 * K[ig][1] + a10 * K[ig][2] + a11 * K[ig][3];
+          const double vb = b00 * K[ig][0] + b01 * K[ig][1] + b10 * K[ig][2] + b11 * K[ig][3];
+          if (ig & 1) {
+            sa1 += ta.w[ig] * va;
+            sb1 += tb.w[ig] * vb;
+          } else {
+            sa0 += ta.w[ig] * va;
+            sb0 += tb.w[ig] * vb;
+          }
         }
         if (HAS_LUT) {
-          cp_async_wait<TOD_AHEAD>();  // the copies of column k have landed (each lane reads what it copied itself)
-          const double2* R = &S.ring[k % TOD_RING][0][lane];
-          const double2 L0 = R[0], L1 = R[32], L2 = R[64], L3 = R[96];
-          const double cw1 = tc.cw1[NLIN];
-          const double a = c00 * L0.x + c01 * L0.y + c10 * L1.x + c11 * L1.y;
-          const double b = c00 * L2.x + c01 * L2.y + c10 * L3.x + c11 * L3.y;
-          tau1 += tc.w[NLIN] * ((1.0 - cw1) * a + cw1 * b);
+          cp_async_wait<TOD_AHEAD>();  // the copies of this trip's columns have landed (a lane reads what it copied itself)
+          const double2* Ra = &S.ring[k & (TOD_RING - 1)][0][lane];
+          const double2* Rb = &S.ring[(pair ? k + 1 : k) & (TOD_RING - 1)][0][lane];
+          const double2 A0 = Ra[0], A1 = Ra[32], A2 = Ra[64], A3 = Ra[96];
+          const double2 B0 = Rb[0], B1 = Rb[32], B2 = Rb[64], B3 = Rb[96];
+          const double cwa = ta.cw1[NLIN], cwb = tb.cw1[NLIN];
+          const double xa = a00 * A0.x + a01 * A0.y + a10 * A1.x + a11 * A1.y;
+          const double ya = a00 * A2.x + a01 * A2.y + a10 * A3.x + a11 * A3.y;
+          const double xb = b00 * B0.x + b01 * B0.y + b10 * B1.x + b11 * B1.y;
+          const double yb = b00 * B2.x + b01 * B2.y + b10 * B3.x + b11 * B3.y;
+          sa1 += ta.w[NLIN] * ((1.0 - cwa) * xa + cwa * ya);
+          sb1 += tb.w[NLIN] * ((1.0 - cwb) * xb + cwb * yb);
         }
-        double tau = tau0 + tau1;
+        double tau_a = sa0 + sa1, tau_b = sb0 + sb1;
         for (int ig = NLIN + (HAS_LUT ? 1 : 0); ig < ngas; ++ig) {  // further gases with a concentration axis
-          const double cw1 = tc.cw1[ig];
-          const double* kk = p.packed[ig] + (size_t)((unsigned)tc.ic0[ig] * qC) + o00;
-          const double a = c00 * kk[0] + c01 * kk[1] + c10 * kk[2] + c11 * kk[3];
-          kk += qC;
-          const double b = c00 * kk[0] + c01 * kk[1] + c10 * kk[2] + c11 * kk[3];
-          tau += tc.w[ig] * ((1.0 - cw1) * a + cw1 * b);
+          const double* ka = p.packed[ig] + (size_t)(ta.coff[ig] + o00 + g4);
+          const double* kb = p.packed[ig] + (size_t)(tb.coff[ig] + o00 + g4);
+          const double xa = a00 * ka[0] + a01 * ka[1] + a10 * ka[2] + a11 * ka[3];
+          const double xb = b00 * kb[0] + b01 * kb[1] + b10 * kb[2] + b11 * kb[3];
+          ka += qC;
+          kb += qC;
+          const double ya = a00 * ka[0] + a01 * ka[1] + a10 * ka[2] + a11 * ka[3];
+          const double yb = b00 * kb[0] + b01 * kb[1] + b10 * kb[2] + b11 * kb[3];
+          tau_a += ta.w[ig] * ((1.0 - ta.cw1[ig]) * xa + ta.cw1[ig] * ya);
+          tau_b += tb.w[ig] * ((1.0 - tb.cw1[ig]) * xb + tb.cw1[ig] * yb);
         }
-        if (store) od_unit[(unsigned)c * col_stride] = fmax(tau, 0.0);  // run_ckd.cpp:317
+        if (store) {  // run_ckd.cpp:317
+          od_unit[(unsigned)ta.col * col_stride] = fmax(tau_a, 0.0);
+          if (pair) od_unit[(unsigned)tb.col * col_stride] = fmax(tau_b, 0.0);
+        }
+        k += pair ? 2 : 1;
       }
     }
-    __syncwarp();  // S.col / S.ord are rewritten by the next unit
+    __syncwarp();  // S.col is rewritten by the next unit
   }
   cp_async_wait<0>();
 }
@@ -1757,8 +1796,12 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     const int64_t ntile = (ncol + TOD_TILE - 1) / TOD_TILE;
     const bool want_planck = q.planck_hl || q.planck_surf;
     const bool has_lut = q.nlin < q.ngas;
-    // total_od_planck2_kernel (asynchronous staging) unless ECCKD_TOD_VARIANT=1 asks for the first layer-major kernel
-    const bool v2 = !(getenv("ECCKD_TOD_VARIANT") && atoi(getenv("ECCKD_TOD_VARIANT")) == 1);
+    // ECCKD_TOD_VARIANT=2 selects total_od_planck2_kernel (asynchronous staging of every long-latency load, two
+    // columns per trip).  Measured on the B200 (65536 x 54 x 32) it takes 1.70-1.76 ms against 1.44 ms for
+    // total_od_planck_kernel: its long-scoreboard stalls are gone (3.2 -> 1.3 per issue) but the per-column records
+    // and rows now come through shared memory (short-scoreboard 1.0 -> 3.2 per issue) with the same three warps per
+    // scheduler, so it stays an experiment.
+    const bool v2 = getenv("ECCKD_TOD_VARIANT") && atoi(getenv("ECCKD_TOD_VARIANT")) == 2;
     const int64_t units = v2 ? ntile * nlay : ntile * nlay + (want_planck ? ntile * (nlay + 1) : 0);
     const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)minb * ctx->num_sms);
     const size_t smem = v2 ? nwarp * sizeof(Tod2Smem) : nwarp * TOD_TILE * sizeof(TodCol);

@@ -211,6 +211,23 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
     if (kk + 8 < SLOTS) load_trip(tA, wA, kk + 8);
     compute_trip(tB, wB, kk + 4);
   }
+#elif defined(ECCKD_V_ROT)
+  // rotating pipeline: the next trip's loads are issued before this trip is evaluated, one code copy
+  // (the register moves at the end of a trip are the price)
+  double tau[NR][4], w[4];
+  load_trip(tau, w, 0);
+#pragma unroll 1
+  for (int kk = 0; kk < SLOTS; kk += 4) {
+    double tn[NR][4], wn[4];
+    load_trip(tn, wn, (kk + 4) & (SLOTS - 1));  // (the last trip re-reads trip 0: unused)
+    compute_trip(tau, w, kk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = wn[j];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) tau[r][j] = tn[r][j];
+    }
+  }
 #else
   // no register software pipeline: the loads of a trip are issued at its top and the other warps
   // of the scheduler cover their latency (a rotating pipeline cost 52 register moves per trip)
