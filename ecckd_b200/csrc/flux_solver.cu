@@ -1317,6 +1317,237 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck2_kernel(cons
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// total_od_planck3_kernel: the column loop of total_od_planck_kernel (table rows in registers, the
+// concentration-axis rows of the next column in flight) with the two changes of the kernel above
+// that paid: the inputs of a warp's next unit staged by asynchronous copies while the current one
+// is evaluated, and the Planck function of half level l produced by the unit of layer l.
+struct Tod3Smem {  // per warp
+  TodCol col[TOD_TILE];
+  double in[TOD_NIN][TOD_TILE];
+};
+
+template <int NLIN, bool HAS_LUT, int NWARP, int MINB>
+__global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck3_kernel(const __grid_constant__ TotalOdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  Tod3Smem& S = reinterpret_cast<Tod3Smem*>(smem_raw)[warp];
+  TodCol* s_col = S.col;
+  const unsigned s_in = smem_u32(&S.in[0][0]);
+  const int nlay = p.nlay, ng = p.ng, ngas = p.ngas;
+  const int ntile = (p.ncol + TOD_TILE - 1) / TOD_TILE;
+  const int64_t n_units = (int64_t)ntile * nlay;
+  const int64_t stride = (int64_t)gridDim.x * nwarp;
+  const bool want_planck = p.planck_hl != nullptr || p.planck_surf != nullptr;
+  // strides of the corner-packed tables, in elements (< 2^31)
+  const unsigned qP = (unsigned)ng * 4, qT = (unsigned)(p.np - 1) * qP, qC = (unsigned)(p.nt - 1) * qT;
+
+  // asynchronous copies of unit u's inputs into S.in (one column per lane)
+  auto stage_inputs = [&](const int64_t u) {
+    if (u < n_units) {
+      const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
+      const int64_t col = (int64_t)tile * TOD_TILE + lane;
+      if (col < p.ncol) {
+        const double* p_hl = p.pressure_hl + col * (nlay + 1) + l;
+        const double* t_hl = p.temperature_hl + col * (nlay + 1) + l;
+        cp_async8(s_in + (0 * TOD_TILE + lane) * 8, p_hl);
+        cp_async8(s_in + (1 * TOD_TILE + lane) * 8, p_hl + 1);
+        cp_async8(s_in + (2 * TOD_TILE + lane) * 8, t_hl);
+        cp_async8(s_in + (3 * TOD_TILE + lane) * 8, t_hl + 1);
+#pragma unroll
+        for (int ig = 0; ig < TOD_MAXGAS; ++ig)
+          if (ig < ngas && p.vmr[ig]) cp_async8(s_in + ((4 + ig) * TOD_TILE + lane) * 8, p.vmr[ig] + col * nlay + l);
+      }
+    }
+    cp_async_commit();
+  };
+
+  int64_t u = (int64_t)blockIdx.x * nwarp + warp;
+  stage_inputs(u);
+  for (; u < n_units; u += stride) {
+    // consecutive warps take consecutive layers of one tile: its columns' profile sectors are shared in L1/L2
+    const int tile = (int)(u / nlay), l = (int)(u - (int64_t)tile * nlay);
+    const int c0 = tile * TOD_TILE;
+    const int nc = min(TOD_TILE, p.ncol - c0);
+    cp_async_wait<0>();
+    // ---- phase A: lane = column
+    int key = -1 - lane;  // columns past the end form groups of their own that nobody visits
+    const bool valid = c0 + lane < p.ncol;
+    int pl_off = 0, pl_off1 = 0;
+    double pl_w0 = 0.0, pl_w1 = 0.0, pl1_w0 = 0.0, pl1_w1 = 0.0;
+    if (valid) {
+      const double p0 = S.in[0][lane], p1 = S.in[1][lane], t0 = S.in[2][lane], t1 = S.in[3][lane];
+      const double t_fl = (t0 * p0 + t1 * p1) / (p0 + p1);
+      const Interp it = make_interp(p0, p1, t_fl, p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+      key = it.it0 * p.np + it.ip0;
+      TodCol tc;
+      tc.c00 = it.tw0 * it.pw0;
+      tc.c01 = it.tw0 * it.pw1;
+      tc.c10 = it.tw1 * it.pw0;
+      tc.c11 = it.tw1 * it.pw1;
+#pragma unroll
+      for (int ig = 0; ig < TOD_MAXGAS; ++ig) {
+        tc.w[ig] = 0.0;
+        tc.cw1[ig] = 0.0;
+        tc.ic0[ig] = 0;
+        if (ig >= ngas) continue;
+        const int cd = p.conc_dependence[ig];
+        const bool have = p.vmr[ig] != nullptr;
+        const double vmr = have ? S.in[4 + ig][lane] : 0.0;
+        double weight = 0.0;  // ckd_model.cpp:980-999
+        if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
+        if (cd == ECCKD_CONC_LUT) {
+          double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];  // :1003-1009
+          cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+          tc.ic0[ig] = (int)cindex0;
+          tc.cw1[ig] = cindex0 - tc.ic0[ig];
+          tc.w[ig] = weight;
+        } else {
+          tc.w[ig] = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+        }
+      }
+      s_col[lane] = tc;
+      if (want_planck) {  // ckd_model.cpp:1124-1142 at half level l (and at the surface level for the last layer)
+        auto planck_index = [&](const double t, int& off, double& w0, double& w1) {
+          const double tindex0 = (t - p.planck_t0) / p.planck_dt;
+          off = 0;
+          w1 = 0.0;
+          if (tindex0 >= 0) {
+            const int it0 = min((int)tindex0, p.nlut - 2);
+            off = it0 * ng;
+            w1 = tindex0 - it0;
+            w0 = 1.0 - w1;
+          } else {  // below the table: (t / t0) * lut[0]
+            w0 = t / p.planck_t0;
+          }
+        };
+        planck_index(t0, pl_off, pl_w0, pl_w1);
+        planck_index(t1, pl_off1, pl1_w0, pl1_w1);
+      }
+    }
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    __syncwarp();
+    // the next unit's inputs travel while this one is evaluated (S.in has been read)
+    stage_inputs(u + stride);
+    // ---- Planck function of the unit's half level(s): rows by lane = g, index and weights from lane = column
+    if (want_planck) {
+      const int64_t lev_stride = (int64_t)(nlay + 1) * ng;
+      const bool last = l == nlay - 1;
+      for (int g0 = 0; g0 < ng; g0 += 32) {
+        const int g = min(g0 + lane, ng - 1);
+        const bool store = g0 + lane < ng;
+        const double* lut_g = p.planck_lut + g;
+        double* out = p.planck_hl ? p.planck_hl + ((int64_t)c0 * (nlay + 1) + l) * ng + g : nullptr;
+        double* surf = (last && p.planck_surf) ? p.planck_surf + (int64_t)c0 * ng + g : nullptr;
+#pragma unroll 8
+        for (int c = 0; c < nc; ++c) {
+          const int off = __shfl_sync(0xffffffffu, pl_off, c);
+          const double w0 = __shfl_sync(0xffffffffu, pl_w0, c), w1 = __shfl_sync(0xffffffffu, pl_w1, c);
+          const double b = w0 * __ldg(lut_g + off) + w1 * __ldg(lut_g + off + ng);  // w1 == 0 below the table
+          if (store && out) out[c * lev_stride] = b;
+        }
+        if (last) {
+#pragma unroll 8
+          for (int c = 0; c < nc; ++c) {
+            const int off = __shfl_sync(0xffffffffu, pl_off1, c);
+            const double w0 = __shfl_sync(0xffffffffu, pl1_w0, c), w1 = __shfl_sync(0xffffffffu, pl1_w1, c);
+            const double b = w0 * __ldg(lut_g + off) + w1 * __ldg(lut_g + off + ng);
+            if (store && out) out[c * lev_stride + ng] = b;
+            if (store && surf) surf[c * ng] = b;
+          }
+        }
+      }
+    }
+    // ---- phase B: lane = g point, groups of columns with the same four table corners
+    const unsigned col_stride = (unsigned)nlay * ng;  // 32 * nlay * ng < 2^31 (checked by the host)
+    for (int g0 = 0; g0 < ng; g0 += 32) {
+      const int g = min(g0 + lane, ng - 1);
+      const bool store = g0 + lane < ng;
+      double* const od_unit = p.od + ((int64_t)c0 * nlay + l) * ng + g;
+      unsigned todo = __ballot_sync(0xffffffffu, valid);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        unsigned members = __shfl_sync(0xffffffffu, same, leader);
+        const int gkey = __shfl_sync(0xffffffffu, key, leader);
+        todo &= ~members;
+        const int it0 = gkey / p.np, ip0 = gkey - it0 * p.np;
+        const unsigned o00 = (unsigned)it0 * qT + (unsigned)ip0 * qP + (unsigned)g * 4;
+        double K[NLIN > 0 ? NLIN : 1][4];
+#pragma unroll
+        for (int ig = 0; ig < NLIN; ++ig) {
+          const double2* k = reinterpret_cast<const double2*>(p.packed[ig] + o00);
+          const double2 a = __ldg(k), b = __ldg(k + 1);
+          K[ig][0] = a.x;
+          K[ig][1] = a.y;
+          K[ig][2] = b.x;
+          K[ig][3] = b.y;
+        }
+        const double* lut_base = HAS_LUT ? p.packed[NLIN] + o00 : nullptr;
+        auto lut_rows = [&](int c, double2 (&L)[4]) {
+          if (!HAS_LUT) return;
+          const double2* k = reinterpret_cast<const double2*>(lut_base + (size_t)((unsigned)s_col[c].ic0[NLIN] * qC));
+          const double2* k1 = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(k) + qC);
+          L[0] = __ldg(k);
+          L[1] = __ldg(k + 1);
+          L[2] = __ldg(k1);
+          L[3] = __ldg(k1 + 1);
+        };
+        auto column = [&](int c, const double2 (&L)[4]) {
+          const TodCol& tc = s_col[c];
+          const double c00 = tc.c00, c01 = tc.c01, c10 = tc.c10, c11 = tc.c11;
+          double tau0 = 0.0, tau1 = 0.0;  // two chains
+#pragma unroll
+          for (int ig = 0; ig < NLIN; ++ig) {
+            const double v = c00 * K[ig][0] + c01 * K[ig][1] + c10 * K[ig][2] + c11 * K[ig][3];
+            if (ig & 1) tau1 += tc.w[ig] * v; else tau0 += tc.w[ig] * v;
+          }
+          if (HAS_LUT) {
+            const double cw1 = tc.cw1[NLIN];
+            const double a = c00 * L[0].x + c01 * L[0].y + c10 * L[1].x + c11 * L[1].y;
+            const double b = c00 * L[2].x + c01 * L[2].y + c10 * L[3].x + c11 * L[3].y;
+            tau1 += tc.w[NLIN] * ((1.0 - cw1) * a + cw1 * b);
+          }
+          double tau = tau0 + tau1;
+          for (int ig = NLIN + (HAS_LUT ? 1 : 0); ig < ngas; ++ig) {  // further gases with a concentration axis
+            const double cw1 = tc.cw1[ig];
+            const double* k = p.packed[ig] + (size_t)((unsigned)tc.ic0[ig] * qC) + o00;
+            const double a = c00 * k[0] + c01 * k[1] + c10 * k[2] + c11 * k[3];
+            k += qC;
+            const double b = c00 * k[0] + c01 * k[1] + c10 * k[2] + c11 * k[3];
+            tau += tc.w[ig] * ((1.0 - cw1) * a + cw1 * b);
+          }
+          if (store) od_unit[(unsigned)c * col_stride] = fmax(tau, 0.0);  // run_ckd.cpp:317
+        };
+        // software pipeline over the members: the next column's LUT rows are loaded before this one is summed
+        double2 La[4], Lb[4];
+        int ca = __ffs(members) - 1;
+        members &= members - 1;
+        lut_rows(ca, La);
+        while (true) {
+          int cb = -1;
+          if (members) {
+            cb = __ffs(members) - 1;
+            members &= members - 1;
+            lut_rows(cb, Lb);
+          }
+          column(ca, La);
+          if (cb < 0) break;
+          ca = -1;
+          if (members) {
+            ca = __ffs(members) - 1;
+            members &= members - 1;
+            lut_rows(ca, La);
+          }
+          column(cb, Lb);
+          if (ca < 0) break;
+        }
+      }
+    }
+    __syncwarp();  // s_col is rewritten by the next unit
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace ecckd
 
 using namespace ecckd;
@@ -1796,15 +2027,17 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
     const int64_t ntile = (ncol + TOD_TILE - 1) / TOD_TILE;
     const bool want_planck = q.planck_hl || q.planck_surf;
     const bool has_lut = q.nlin < q.ngas;
-    // ECCKD_TOD_VARIANT=2 selects total_od_planck2_kernel (asynchronous staging of every long-latency load, two
-    // columns per trip).  Measured on the B200 (65536 x 54 x 32) it takes 1.70-1.76 ms against 1.44 ms for
-    // total_od_planck_kernel: its long-scoreboard stalls are gone (3.2 -> 1.3 per issue) but the per-column records
-    // and rows now come through shared memory (short-scoreboard 1.0 -> 3.2 per issue) with the same three warps per
-    // scheduler, so it stays an experiment.
-    const bool v2 = getenv("ECCKD_TOD_VARIANT") && atoi(getenv("ECCKD_TOD_VARIANT")) == 2;
-    const int64_t units = v2 ? ntile * nlay : ntile * nlay + (want_planck ? ntile * (nlay + 1) : 0);
+    // Kernel choice (65536 x 54 x 32 on the B200, optical depth + Planck function): total_od_planck3_kernel 1.28 ms
+    // (default); ECCKD_TOD_VARIANT=1 total_od_planck_kernel 1.45 ms (synchronous loads of the per-unit inputs,
+    // separate Planck units); ECCKD_TOD_VARIANT=2 total_od_planck2_kernel 1.70-1.76 ms (everything through shared
+    // memory: its long-scoreboard stalls are gone, 3.2 -> 1.3 per issue, but the per-column records and rows now
+    // cost short-scoreboard stalls, 1.0 -> 3.2 per issue, with the same three warps per scheduler).
+    const int tod_variant = getenv("ECCKD_TOD_VARIANT") ? atoi(getenv("ECCKD_TOD_VARIANT")) : 3;
+    const bool v2 = tod_variant == 2;
+    const bool v3 = tod_variant != 1 && tod_variant != 2;
+    const int64_t units = (v2 || v3) ? ntile * nlay : ntile * nlay + (want_planck ? ntile * (nlay + 1) : 0);
     const unsigned grid = (unsigned)std::min<int64_t>((units + nwarp - 1) / nwarp, (int64_t)minb * ctx->num_sms);
-    const size_t smem = v2 ? nwarp * sizeof(Tod2Smem) : nwarp * TOD_TILE * sizeof(TodCol);
+    const size_t smem = v2 ? nwarp * sizeof(Tod2Smem) : (v3 ? nwarp * sizeof(Tod3Smem) : nwarp * TOD_TILE * sizeof(TodCol));
 #define ECCKD_TOD_LAUNCH(N)                                                                                  \
   case N:                                                                                                    \
     if (v2) {                                                                                                \
@@ -1817,6 +2050,9 @@ ECCKD_API int ecckd_run_ckd_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         total_od_planck2_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                 \
       }                                                                                                      \
+    } else if (v3) {                                                                                         \
+      if (has_lut) total_od_planck3_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);       \
+      else total_od_planck3_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);              \
     } else if (has_lut) total_od_planck_kernel<N, true, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);   \
     else total_od_planck_kernel<N, false, 4, 3><<<grid, nwarp * 32, smem, ctx->stream>>>(q);                 \
     break;

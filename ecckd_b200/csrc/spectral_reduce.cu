@@ -89,6 +89,50 @@ __device__ __forceinline__ double planck_elem_fast(double hk_over_t, double nu, 
   return prefactor * x;
 }
 
+// The form the producers of reduce2_kernel use (they are FP64-bound next to two consumer warps on
+// their scheduler): the per-wavenumber factor dnu c1 (nu c)^3 comes precomputed (planck_prefactor_kernel,
+// same operations in the same order as above), the exponential from the consumers' 2^(j/2048) table
+// in shared memory with the minimax polynomial of (e^r - 1)/r (relative error < 1e-17) and a two-constant
+// Cody-Waite reduction, and the reciprocal from one cubically convergent step on the 23-bit
+// approximation (error eps^3 < 2^-69): 13 FP64 instructions per weight instead of ~23.
+// hkc_over_t = (h/k) (100 c) / T, formed on the host.
+#if ECCKD_TAB_LOGN == 11 && ECCKD_TAB_LOGR == 0
+#define ECCKD_PLANCK_TAB 1
+__device__ __forceinline__ double planck_weight_tab(double hkc_over_t, double nu, double pref,
+                                                    const unsigned char* __restrict__ tab) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52
+  const double x = nu * hkc_over_t;
+  const double t = fma(x, 0x1.71547652b82fep+11, magic);  // 2048/ln2
+  const int n = __double2loint(t);
+  const double nf = t - magic;
+  double r = fma(nf, -0x1.62e42fee00000p-12, x);  // -ln2/2048, high part (21 trailing zero bits)
+  r = fma(nf, -0x1.a39ef35793c76p-44, r);         // low part
+  double q = fma(EXPM1_Q2_2048_D[2], r, EXPM1_Q2_2048_D[1]);
+  q = fma(q, r, EXPM1_Q2_2048_D[0]);
+  const double P = fma(q, r, 1.0);
+  const uint2 e = *reinterpret_cast<const uint2*>(tab + (((unsigned)n << 3) & 0x3ff8u));
+  const double T = __hiloint2double((int)e.y + (n << 9), (int)e.x);
+  const double em1 = fma(T, P, -1.0);
+  double r0;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(em1));  // relative error eps <= 2^-23
+  const double eps = fma(-em1, r0, 1.0);
+  const double r1 = fma(r0, fma(eps, eps, eps), r0);  // r0 (1 + eps + eps^2) = (1 - eps^3) / em1
+  return pref * r1;
+}
+#endif
+__global__ void planck_prefactor_kernel(int64_t n, const double* __restrict__ wn, const double* __restrict__ dwn,
+                                        double* __restrict__ pref) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double h = 6.62606896e-34;
+  const double c = 2.99792458e8;
+  const double inv_cm_2_Hz = 100.0 * c;
+  const double pi = 3.14159265358979323846;
+  const double c1 = 2.0 * h * inv_cm_2_Hz * pi / (c * c);
+  const double freq = wn[i] * inv_cm_2_Hz;
+  pref[i] = (dwn[i] * c1) * (freq * freq * freq);
+}
+
 // exact evaluation order of planck_function.cpp:47-53 (used by the standalone planck kernel)
 __device__ __forceinline__ double planck_elem(double t, double nu, double dnu) {
   const double h = 6.62606896e-34;
@@ -629,10 +673,11 @@ __device__ __forceinline__ bool cursor_next(Cursor& q, int ngroups, int cw, int 
 // The producer warps of the streaming kernels (reduce_kernel, reduce2_kernel): permuted weights +
 // plan record of every round of the CTA's piece, through the ring {wperm, PlanRound} x NSW at
 // shared-window address ring_s (generic pointer `ring`), full/empty mbarriers full_w/empty_w.
-template <int WMODE>
+template <int WMODE, bool PLANCK_TAB = false>
 __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Cursor first, const int niter, const int pw,
                                                const int lane, unsigned char* ring, const unsigned ring_s,
-                                               const unsigned full_w, const unsigned empty_w, const int nsw = NSW) {
+                                               const unsigned full_w, const unsigned empty_w, const int nsw = NSW,
+                                               const unsigned char* tab = nullptr) {
   const int nchunks = (int)p.nchunks;
   const int ch = p.ch;
   // ===================== producers: permuted weights + plan record of every round =====================
@@ -683,7 +728,7 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
       const int64_t w = e.w0 + (off[m] >> 3);
       if (WMODE == W_PLANCK) {
         x[m] = p.wn[w];
-        y[m] = p.dwn[w];
+        y[m] = PLANCK_TAB ? p.pref[w] : p.dwn[w];
       } else if (WMODE == W_MATRIX) {
         x[m] = p.weight[(int64_t)e.wrow * p.w_stride + w];
       } else {
@@ -707,9 +752,18 @@ __device__ __forceinline__ void produce_rounds(const ReduceParams& p, const Curs
     const unsigned vmask = p.balanced ? ((meta0 >> 12) & 0xFFFFu) : ((1u << ((meta0 >> 12) & 31u)) - 1u);
     double val[PER];
     if (WMODE == W_PLANCK) {
-      const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
+#ifdef ECCKD_PLANCK_TAB
+      if (PLANCK_TAB) {
+        const double hkct = p.temperature2[e0.wrow];  // (h/k)(100 c)/T, formed on the host
 #pragma unroll
-      for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(hkt, x0[m], y0[m], ptl);
+        for (int m = 0; m < PER; ++m) val[m] = planck_weight_tab(hkct, x0[m], y0[m], tab);
+      } else
+#endif
+      {
+        const double hkt = p.temperature[e0.wrow];  // (h/k)/T, formed on the host
+#pragma unroll
+        for (int m = 0; m < PER; ++m) val[m] = planck_elem_fast(hkt, x0[m], y0[m], ptl);
+      }
     } else {
 #pragma unroll
       for (int m = 0; m < PER; ++m) val[m] = x0[m];
@@ -1122,7 +1176,12 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
   const int last_n = (int)(p.nwav - (int64_t)(nchunks - 1) * ch);  // length of the last chunk of a row
 
   if (warp >= nw) {
+#ifdef ECCKD_PLANCK_TAB
+    produce_rounds<WMODE, (WMODE == W_PLANCK && FKIND == F_TRANS)>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w,
+                                                                   empty_w, nsw, smem_raw + L.tab);
+#else
     produce_rounds<WMODE>(p, first, niter, warp - nw, lane, ring, sbase + L.ring, full_w, empty_w, nsw);
+#endif
     return;
   }
 
@@ -2020,6 +2079,19 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
     std::vector<double> hkt((size_t)n_temperature);
     for (int i = 0; i < n_temperature; ++i) hkt[i] = (6.62606896e-34 / 1.3806504e-23) / h_temperature[i];
     ECCKD_TRY(upload_small(ctx, d_temp, hkt.data(), (size_t)n_temperature * sizeof(double)));
+    if (gen == 2 && fkind == F_TRANS) {  // the producers' table form (planck_weight_tab)
+      void* d_temp2 = nullptr;
+      ECCKD_TRY(ws_reserve(ctx, 6, (size_t)n_temperature * sizeof(double), &d_temp2));
+      for (int i = 0; i < n_temperature; ++i)
+        hkt[i] = (double)(((long double)6.62606896e-34 / (long double)1.3806504e-23) * (100.0L * 2.99792458e8L) / (long double)h_temperature[i]);
+      ECCKD_TRY(upload_small(ctx, d_temp2, hkt.data(), (size_t)n_temperature * sizeof(double)));
+      rp.temperature2 = static_cast<const double*>(d_temp2);
+      void* d_pref = nullptr;
+      ECCKD_TRY(ws_reserve(ctx, 7, (size_t)nwav * sizeof(double), &d_pref));
+      planck_prefactor_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(nwav, d_wn, d_dwn, static_cast<double*>(d_pref));
+      ECCKD_LAUNCH_CHECK(ctx);
+      rp.pref = static_cast<const double*>(d_pref);
+    }
   }
   rp.groups = static_cast<const GroupDesc*>(d_groups);
   rp.temperature = static_cast<const double*>(d_temp);

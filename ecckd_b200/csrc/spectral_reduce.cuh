@@ -119,7 +119,9 @@ struct ReduceParams {
   const double* weight;       // MATRIX: [wrow][nwav] (stride w_stride); VECTOR: [nwav]
   int64_t w_stride;
   int weight_bulk_ok;
-  const double* temperature;  // PLANCK: device [n weight rows]
+  const double* temperature;  // PLANCK: device [n weight rows], (h/k)/T
+  const double* temperature2; // PLANCK, reduce2_kernel: (h/k)(100 c)/T
+  const double* pref;         // PLANCK, reduce2_kernel: dnu c1 (nu c)^3 per wavenumber (planck_prefactor_kernel)
   const double* wn;
   const double* dwn;
   TransConst tc;              // constants of 1 - exp(-kd tau), kd = LW_DIFFUSIVITY*OD_SCALING*k

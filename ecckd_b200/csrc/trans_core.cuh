@@ -395,6 +395,7 @@ struct TransConstT {
 static const double EXPM1_Q3_128[4] = {0x1.ffffffffffe08p-1, 0x1.ffffffffffd60p-2, 0x1.55555d887706dp-3, 0x1.55555d8840eb4p-5};
 static const double EXPM1_Q2_1024[3] = {0x1.0000000000000p+0, 0x1.0000001ebfbe0p-1, 0x1.5555557e54fd5p-3};
 static const double EXPM1_Q2_2048[3] = {0x1.0000000000000p+0, 0x1.00000007afef8p-1, 0x1.5555555f953f5p-3};
+__constant__ double EXPM1_Q2_2048_D[3] = {0x1.0000000000000p+0, 0x1.00000007afef8p-1, 0x1.5555555f953f5p-3};
 inline void trans_constT_init(TransConstT* k, double kd, int logn, int qdeg) {
   const long double ln2 = 0.693147180559945309417232121458176568L;
   const long double lkd = (long double)kd;

@@ -164,6 +164,18 @@ def out_scale(case):
     return np.ones(nlay)
 
 
+def avg_tolerance(ref_molar_abs, method="linear", scale=None, rtol=AVG_RTOL):
+    """The tolerance array assert_avg_close applies to the averaged value (see there)."""
+    b = ref_molar_abs
+    tol = rtol * np.abs(b)
+    kd = _KD.get(method)
+    if kd is not None:
+        sc = np.ones(b.shape[0]) if scale is None else scale
+        tau = np.abs(b) / sc[:, None]
+        tol = tol + 16 * EPS * np.exp(np.minimum(kd * tau, 700.0)) / kd * sc[:, None]
+    return tol
+
+
 def assert_avg_close(got, ref, method="linear", scale=None, rtol=AVG_RTOL, what="", planck_scale=None):
     """Compare (molar_abs, min, max, warn) tuples against the oracle.
 

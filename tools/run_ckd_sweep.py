@@ -51,10 +51,10 @@ def main():
     full = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls, dn, up, bdn, bup)
     odp = lambda: model.run_ckd_dev(vmr, 1361.0, ncol, nlay, p_hl, t_hl, od, plh, pls)
     ref_up = None
-    settings = [("1", "0"), ("0", "0"), ("0", "2")]  # column-major kernel, layer-major kernel, its cp.async variant
+    settings = [("1", "1"), ("0", "1"), ("0", "2"), ("0", "3")]  # column-major kernel; layer-major kernels 1, 2, 3 (the default)
     if len(sys.argv) > 2 and sys.argv[2] == "one":  # a single short run for ncu
         os.environ["ECCKD_RUN_CKD_LEGACY"] = "0"
-        os.environ["ECCKD_RUN_CKD_SLICE_MB"] = "0"
+        os.environ.pop("ECCKD_TOD_VARIANT", None)
         full()
         full()
         torch.cuda.synchronize()
