@@ -139,9 +139,10 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
       TransMid m[NR][4];
       double T[NR][4];
 #if defined(ECCKD_TAB_LOGN)
-      // TAB64 callers: `tab` is the 2^ECCKD_TAB_LOGR-fold replicated 2^ECCKD_TAB_LOGN-entry table
+      // TAB64 callers: the 2^ECCKD_TAB_LOGR-fold replicated 2^ECCKD_TAB_LOGN-entry table; `lane_off` is its
+      // shared-window address + the lane's copy offset
 #define ECCKD_P1(x) (TAB64 ? transT_phase1(x, *KT) : trans256_phase1(x, K2))
-#define ECCKD_P2(mm) (TAB64 ? transT_phase2<ECCKD_TAB_LOGN, ECCKD_TAB_LOGR>(mm, tab, lane_off) : trans256_phase2(mm, tab))
+#define ECCKD_P2(mm) (TAB64 ? transT_phase2<ECCKD_TAB_LOGN, ECCKD_TAB_LOGR>(mm, lane_off) : trans256_phase2(mm, tab))
 #define ECCKD_P3(mm, TT) (TAB64 ? transT_phase3<ECCKD_TAB_QDEG>(mm, TT, *KT) : trans256_phase3(mm, TT, K2))
 #elif defined(ECCKD_V_TAB256)
       // TAB64 callers: `tab` is the 8-fold replicated 256-entry table, lane_off = (lane & 7) << 3

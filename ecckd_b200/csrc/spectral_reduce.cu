@@ -1198,7 +1198,7 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
   double2* mmv = reinterpret_cast<double2*>(smem_raw + L.mmv) + warp * RPW * WIN;
   uint2* mmb = reinterpret_cast<uint2*>(smem_raw + L.mmb) + warp * RPW * WIN;
 #if defined(ECCKD_TAB_LOGN)
-  const unsigned lane_off = (unsigned)(lane & ((1 << ECCKD_TAB_LOGR) - 1)) << 3;
+  const unsigned lane_off = sbase + L.tab + ((unsigned)(lane & ((1 << ECCKD_TAB_LOGR) - 1)) << 3);  // shared-window address
 #elif defined(ECCKD_V_TAB256)
   const unsigned lane_off = (unsigned)(lane & 7) << 3;
 #else
@@ -1208,7 +1208,9 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
   const uint64_t pol = policy_evict_first();
   // the weight sums do not depend on the row: the last consumer warp (the one with the fewest rows)
   // accumulates them once per group; they end up in the s1 field of its row 0
-  const bool s1_duty = warp == nw - 1;
+  // (with a floating row the last two warps sit on the producer-free schedulers, which carry 5.5 rows
+  // each: the duty then goes to a warp on a scheduler with a producer and 4 rows)
+  const bool s1_duty = warp == p.s1_warp;
 
   int gbase = -1;            // first g point of the current window (-1: none loaded)
   double* pout = nullptr;    // this warp's rows of the current (window, group) piece: [RPW][ng][4]
@@ -1500,7 +1502,7 @@ __global__ void combine_kernel(const CombineParams p) {
   if (i >= gd->nrows) return;
   const int piece = (i % p.nw) * p.rpw + (i / p.nw);                 // (warp, row of the warp)
   const bool floating = p.float_row && gd->nrows == 2 * p.nw - 1 && i == gd->nrows - 1;
-  const int piece_s1 = p.shared_s1 ? (p.nw - 1) * p.rpw : piece;     // weight sums: last warp, row 0
+  const int piece_s1 = p.shared_s1 ? p.s1_warp * p.rpw : piece;      // weight sums: row 0 of the warp with that duty
   const int nrw = p.nw * p.rpw;
   const int nchunks = (int)p.nchunks;
   const int64_t T = (int64_t)p.ngroups * p.nchunks;
@@ -2015,6 +2017,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   // the floating row needs warp nw-2 to own second-row stages and warp nw-1 to own none (packed stages)
   rp.float_row = (gen == 2 && nw >= 2 && max_rows == 2 * nw - 1 && !getenv("ECCKD_NO_FLOAT_ROW")) ? 1 : 0;
   rp.stage_bytes = stage2;
+  rp.s1_warp = (rp.float_row && nw >= 4 && !getenv("ECCKD_S1_LAST")) ? nw - 3 : nw - 1;
   rp.weight = d_weight;
   rp.w_stride = w_stride;
   rp.weight_bulk_ok = (wmode != W_PLANCK && aligned16(d_weight) && (wmode == W_VECTOR || (w_stride % 2) == 0)) ? 1 : 0;
@@ -2124,6 +2127,7 @@ static int reduce_partial(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const std::ve
   cp.ng = ng;
   cp.shared_s1 = !(fkind == F_LOG || fkind == F_HYBRID);
   cp.float_row = rp.float_row;
+  cp.s1_warp = rp.s1_warp;
   cp.partial = rp.partial;
   cp.partial_z = rp.partial_z;
   cp.sums = d_sums;

@@ -131,6 +131,7 @@ struct ReduceParams {
   const double* exp2tab;      // 2^(j/N), N entries (ecckd_ctx::d_exp2tab)
   int max_rows;               // reduce2_kernel: rows of the largest group (data stages are packed by row)
   int float_row;              // reduce2_kernel: groups of 2 nw - 1 rows pass their last row between the last two warps
+  int s1_warp;                // the consumer warp that accumulates the weight sums of a group
   int nsw;                    // reduce2_kernel: ring slots
   int stage_bytes;            // reduce2_kernel: bytes of one row-chunk stage (chunk length x 8 + 16)
   int balanced;               // the plan is a balanced one: lane meta bits 12-27 are a slot mask (not a count)
@@ -152,6 +153,7 @@ struct CombineParams {
   int ng;
   int shared_s1;   // weight sums are accumulated once per group (by the last consumer warp)
   int float_row;   // reduce2_kernel's floating row: its second partial sits in row 1 of the last warp
+  int s1_warp;     // the consumer warp whose row 0 holds the weight sums
   const double* partial;
   const int32_t* partial_z;
   double* sums;    // [nrows][ng][NSUM]

@@ -431,13 +431,17 @@ __device__ __forceinline__ TransMid transT_phase1(double tau, const TransConstT&
   m.rho = fma(t - magic, K.b, tc);
   return m;
 }
-// lane_off = (lane & (R-1)) << 3
+// tab_lane = shared-window address of the table + ((lane & (R-1)) << 3).  Mask, then scale-and-add
+// (LOP3 + IMAD/LEA) and a load through the shared window: written in PTX because the compiler turns the
+// C form into shift, mask and a separate add of the base.
 template <int LOGN, int LOGR>
-__device__ __forceinline__ double transT_phase2(const TransMid& m, const unsigned char* __restrict__ tab,
-                                                const unsigned lane_off) {
-  const unsigned idx = (((unsigned)m.n << (3 + LOGR)) & (unsigned)(((1 << LOGN) - 1) << (3 + LOGR))) | lane_off;
-  const uint2 e = *reinterpret_cast<const uint2*>(tab + idx);
-  return __hiloint2double((int)e.y + (m.n << (20 - LOGN)), (int)e.x);
+__device__ __forceinline__ double transT_phase2(const TransMid& m, const unsigned tab_lane) {
+  unsigned addr, lo, hi;
+  asm("{\n\t.reg .u32 j;\n\tand.b32 j, %1, %2;\n\tmad.lo.u32 %0, j, %3, %4;\n\t}\n"
+      : "=r"(addr)
+      : "r"(m.n), "n"((1 << LOGN) - 1), "n"(8 << LOGR), "r"(tab_lane));
+  asm("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(lo), "=r"(hi) : "r"(addr));
+  return __hiloint2double((int)hi + (m.n << (20 - LOGN)), (int)lo);
 }
 template <int QDEG>
 __device__ __forceinline__ double transT_phase3(const TransMid& m, const double T, const TransConstT& K) {
