@@ -65,6 +65,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-flux", action="store_true")
+    ap.add_argument("--no-full", action="store_true", help="skip the full look-up-table build leg (N = 1 only)")
     return ap.parse_args()
 
 
@@ -607,6 +608,20 @@ def main():
                                  "plan_cache_hits_misses": list(ctx.plan_cache_stats())}}
     host = None
 
+    # ---- the FULL look-up-table build of config B on one GPU (north_star's target sentence): g-point
+    # compaction, plan, then for each of the 6 temperature indices the composite block merged from its
+    # constituents (read_merged_spectrum.cpp:149-168) and the reduction of the 19 blocks with that index's
+    # Planck weights, then gpoint_fraction and the Planck look-up table (create_look_up_table.cpp:111-160,
+    # 293-505, 512-591).  The 405 GB of the whole config do not fit one GPU: the 6 temperature steps re-read
+    # the resident 67.6 GB (every byte still comes from HBM, the spectra being far larger than L2).
+    full = None
+    if rank == 0 and world == 1 and not args.no_full and not strong and args.weights == "planck":
+        try:
+            full = bench_full_build(torch, E, ctx, dev, args, nlay, nspec, nwav, ng, wn, dwn, g_point, ods, vmrs, p_fl,
+                                    p_hl, t_fl)
+        except Exception as exc:  # a secondary leg must not hide the primary metric
+            full = {"error": repr(exc)}
+
     # ---- metric 2: CKD flux columns.g-points/s (run_ckd LW, config A LUT with columns replicated)
     flux = None
     if not args.no_flux and rank == 0:
@@ -641,9 +656,74 @@ def main():
         }
         if flux is not None:
             line["flux_solver"] = flux
+        if full is not None:
+            line["full_build"] = full
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_full_build(torch, E, ctx, dev, args, nlay, nspec, nwav, ng, wn, dwn, g_point, ods, vmrs, p_fl, p_hl, t_fl):
+    """The whole LW look-up-table build (BASELINE configs[1]) as one timed sequence on one GPU; see the call site."""
+    nt = 6
+    g_work = g_point.clone()
+    comp = torch.empty_like(ods[0])  # the composite block of a temperature index, merged from two constituents
+    n_merge = 2
+    outs = [[torch.empty((nlay, ng), dtype=torch.float64, device=dev) for _ in range(nspec)] for _ in range(3)]
+    w1 = np.arange(0.0, 3260.0, 50.0)
+    w2 = w1 + 50.0
+    d_frac = torch.empty((ng, w1.size), dtype=torch.float64, device=dev)
+    t_lut = np.arange(120.0, 351.0)
+    d_plut = torch.empty((t_lut.size, ng), dtype=torch.float64, device=dev)
+    state = {}
+
+    def build():
+        g_work.copy_(g_point)
+        ng2, _ = E.compact_g_points_dev(ctx, ng, nwav, g_work)  # a4
+        assert ng2 == ng
+        plan = E.GPointPlan(ctx, g_work, nwav, ng)
+        for it in range(nt):
+            comp.zero_()
+            for k in range(n_merge):  # a8
+                E.merge_axpy_dev(ctx, nlay, nwav, comp, nwav, ods[(13 + k) % nspec], nwav, scaling=0.5 + 0.25 * k)
+            E.average_optical_depth_batch_dev(ctx, plan, vmrs, p_fl, p_hl, [comp] + ods[1:], nwav, E.WEIGHT_PLANCK, None,
+                                              nwav, t_fl + 20.0 * (it - 2.5), wn, dwn, args.method, outs[0], outs[1],
+                                              outs[2], ng)
+        E.gpoint_fraction_dev(ctx, ng, nwav, g_work, wn, dwn, w1, w2, d_frac)  # a5
+        E.planck_lut_dev(ctx, plan, wn, dwn, t_lut, d_plut)  # a6
+        state["plan"] = plan
+
+    build()  # warm-up (workspaces, plan kernels' first launch)
+    torch.cuda.synchronize()
+    state["plan"].close()
+    ctx.set_timing(True)
+    ctx.reduce_kernel_time()
+    l0 = ctx.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    build()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    kms, _ = ctx.reduce_kernel_time()
+    ctx.set_timing(False)
+    launches = ctx.kernel_launches - l0
+    # checks: the composite block's first layer against the same merge on the host, gpoint_fraction rows sum to 1
+    h = sum((0.5 + 0.25 * k) * ods[(13 + k) % nspec][0].cpu().numpy() for k in range(n_merge))
+    merge_ok = bool(np.allclose(comp[0].cpu().numpy(), h, rtol=1e-15, atol=0.0))
+    frac = d_frac.cpu().numpy()
+    frac_ok = bool(np.allclose(frac.sum(axis=1), 1.0, rtol=1e-12))
+    state["plan"].close()
+    units = nt * nspec * nlay * nwav
+    return {"metric": "LBL spectral points*layers/s reduced to LUT, whole build", "value": units / (ms * 1e-3),
+            "unit": "point*layers/s", "ms": ms, "blocks": nt * nspec, "gpu_launches": int(launches),
+            "reduce_kernel_ms": kms, "reduce_kernel_share": kms / ms,
+            "optical_depth_bytes_read": int(units * 8 + nt * n_merge * nlay * nwav * 8),
+            "config": {"workload": f"create_look_up_table LW, all {nt} temperature indices x {nspec} blocks of {nlay} x 2^{args.log2_nwav}: "
+                                   f"g-point compaction + plan + per index [merge of the composite block from {n_merge} constituents + "
+                                   "reduction of the 19 blocks] + gpoint_fraction + Planck look-up table (231 temperatures); "
+                                   "the resident 67.6 GB re-read per temperature index"},
+            "validated": {"composite_merge_layer0_equals_host": merge_ok, "gpoint_fraction_rows_sum_to_1": frac_ok}}
 
 
 def bench_flux(torch, E, ctx, dev, peak, with_cpu=True):

@@ -211,3 +211,53 @@ def test_balanced_plan_is_valid_and_nearly_conflict_free(ctx, monkeypatch, kind)
     assert res["1"] < res["0"]
     if kind != "150g":
         assert res["1"] <= 2.35, res
+
+
+@pytest.mark.parametrize("method", ["transmission", "linear"])
+def test_group_of_19_spectra_with_the_floating_row(ctx, O, monkeypatch, method):
+    """A LUT temperature index is a group of 19 spectra sharing one Planck weight row: 10 consumer warps, of
+    which the last two pass the 19th row between them every chunk visit (reduce2_kernel's floating row, whose
+    two partial results combine_kernel adds).  Every row - the floating one included - must match the oracle,
+    the call must be bitwise reproducible, and the min/max must not depend on whether the row floats."""
+    nspec, nlay, nwav = 19, 3, 14011  # odd length, several chunk visits per CTA piece
+    c = S.lw_spectrum_case(nlay=nlay, nwav=nwav, ng=22, nband=4, seed=5)
+    rng = np.random.default_rng(19)
+    ods = [c["od"] * np.exp(rng.normal(0.0, 1.0, (nlay, 1))) * (0.2 + 0.15 * s) for s in range(nspec)]
+    vmrs = [c["vmr"] * (1.0 + 0.1 * s) for s in range(nspec)]
+    planck = _planck(O, c)
+    d_g = ctx.to_device(c["g_point"], np.int32)
+    d_wn, d_dwn = ctx.to_device(c["wavenumber"]), ctx.to_device(c["d_wavenumber"])
+    d_ods = [ctx.to_device(od) for od in ods]
+
+    def run():
+        plan = E.GPointPlan(ctx, d_g, nwav, c["ng"])
+        outs = [ctx.empty((nlay, c["ng"])) for _ in range(nspec)]
+        mins = [ctx.empty((nlay, c["ng"])) for _ in range(nspec)]
+        maxs = [ctx.empty((nlay, c["ng"])) for _ in range(nspec)]
+        E.average_optical_depth_batch_dev(ctx, plan, vmrs, c["pressure_fl"], c["pressure_hl"], d_ods, nwav,
+                                          E.WEIGHT_PLANCK, None, 0, c["temperature_fl"], d_wn, d_dwn, method, outs, mins,
+                                          maxs, c["ng"])
+        res = [(o.numpy(), a.numpy(), b.numpy()) for o, a, b in zip(outs, mins, maxs)]
+        plan.close()
+        return res
+
+    got = run()
+    again = run()
+    for s in range(nspec):
+        ref = O.average_optical_depth_to_g_point(c["ng"], vmrs[s], c["pressure_fl"], c["pressure_hl"], c["g_point"],
+                                                 ods[s], planck, method)
+        cs = dict(vmr=vmrs[s], pressure_fl=c["pressure_fl"], pressure_hl=c["pressure_hl"])
+        S.assert_avg_close(got[s] + (None,), ref, method=method, scale=S.out_scale(cs), what=f"spectrum {s}: ")
+        for a, b in zip(got[s], again[s]):
+            assert np.array_equal(a, b), f"spectrum {s}: not reproducible"
+    monkeypatch.setenv("ECCKD_NO_FLOAT_ROW", "1")
+    fixed = run()
+    for s in range(nspec):
+        assert np.array_equal(got[s][1], fixed[s][1]) and np.array_equal(got[s][2], fixed[s][2]), s
+        if s < nspec - 1:  # rows that never float are summed in the same order either way
+            assert np.array_equal(got[s][0], fixed[s][0]), s
+        else:
+            cs = dict(vmr=vmrs[s], pressure_fl=c["pressure_fl"], pressure_hl=c["pressure_hl"])
+            ref = O.average_optical_depth_to_g_point(c["ng"], vmrs[s], c["pressure_fl"], c["pressure_hl"],
+                                                     c["g_point"], ods[s], planck, method)
+            S.assert_avg_close(fixed[s] + (None,), ref, method=method, scale=S.out_scale(cs), what="fixed rows: ")
