@@ -132,6 +132,10 @@ def _declare(L):
         "ecckd_gpoint_fraction_dev": [vp, i32, i64, vp, vp, vp, i32, vp, vp, vp],
         "ecckd_ssi_intervals_dev": [vp, i64, vp, vp, i32, vp, vp, vp],
         "ecckd_planck_lut_dev": [vp, vp, vp, vp, i32, vp, vp],
+        "ecckd_gpoint_sum_dev": [vp, vp, i32, vp, i64, vp],
+        "ecckd_row_sum_dev": [vp, i32, i64, vp, i64, vp],
+        "ecckd_lw_spectra_profile_dev": [vp, vp, i32, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp],
+        "ecckd_scale_lut_scaling": [i32, i32, dbl, vp, vp, vp, vp],
         "ecckd_compact_g_points_dev": [vp, i32, i64, vp, vp, C.POINTER(C.c_int)],
         "ecckd_sort_key_lw_dev": [vp, i32, i64, vp, vp, vp, vp, i64, dbl, vp, vp],
         "ecckd_sort_key_sw_dev": [vp, i32, i64, vp, vp, i64, dbl, vp, vp],

@@ -659,6 +659,46 @@ def planck_lut_dev(ctx: Context, plan: GPointPlan, d_wavenumber, d_d_wavenumber,
                                           _ptr(d_out)))
 
 
+def gpoint_sum_dev(ctx: Context, plan: GPointPlan, nrow, d_values, stride, d_out):
+    """out[row][g] = sum of values[row][w] over the wavenumbers w of g point g (lw_spectra.cpp:250-255,
+    scale_lut.cpp:119-123)."""
+    check(_lib.lib().ecckd_gpoint_sum_dev(ctx.handle, plan.handle, nrow, _ptr(d_values), stride, _ptr(d_out)))
+
+
+def row_sum_dev(ctx: Context, nrow, n, d_values, stride, d_out):
+    """out[row] = sum of values[row][:n] (sum(x, 1) of lw_spectra.cpp:230-231)."""
+    check(_lib.lib().ecckd_row_sum_dev(ctx.handle, nrow, n, _ptr(d_values), stride, _ptr(d_out)))
+
+
+def lw_spectra_profile(ctx: Context, plan: GPointPlan, d_wavenumber, d_d_wavenumber, pressure_hl, temperature_hl,
+                       d_optical_depth, nwav):
+    """The per-profile body of the lw_spectra tool (lw_spectra.cpp:208-255).  Returns a dict of host arrays:
+    flux_dn_lw, flux_up_lw [nlay+1]; optical_depth [nlay][ng]; spectral_flux_dn_lw, spectral_flux_up_lw [nlay+1][ng]."""
+    ph, php = _h(pressure_hl)
+    th, thp = _h(temperature_hl)
+    nlay = ph.size - 1
+    ng = plan.ng
+    bdn, bup = ctx.empty(nlay + 1), ctx.empty(nlay + 1)
+    sod, sdn, sup = ctx.empty((nlay, ng)), ctx.empty((nlay + 1, ng)), ctx.empty((nlay + 1, ng))
+    check(_lib.lib().ecckd_lw_spectra_profile_dev(ctx.handle, plan.handle, nlay, _ptr(d_wavenumber), _ptr(d_d_wavenumber),
+                                                  php, thp, _ptr(d_optical_depth), nwav, _ptr(bdn), _ptr(bup), _ptr(sod),
+                                                  _ptr(sdn), _ptr(sup)))
+    return dict(flux_dn_lw=bdn.numpy(), flux_up_lw=bup.numpy(), optical_depth=sod.numpy(),
+                spectral_flux_dn_lw=sdn.numpy(), spectral_flux_up_lw=sup.numpy())
+
+
+def scale_lut_scaling(mu0, flux_dn_gpoint, od_total=None):
+    """scale_lut.cpp:117-133, 180-181: (od_best, scaling) from the per-g-point direct fluxes [nz+1][ng]."""
+    f, fp = _h(flux_dn_gpoint)
+    nz, ng = f.shape[0] - 1, f.shape[1]
+    best = np.zeros((nz, ng))
+    scaling = np.zeros((nz, ng)) if od_total is not None else None
+    t, tp = _h(od_total)
+    check(_lib.lib().ecckd_scale_lut_scaling(nz, ng, float(mu0), fp, tp, best.ctypes.data,
+                                             scaling.ctypes.data if scaling is not None else None))
+    return best, scaling
+
+
 def compact_g_points_dev(ctx: Context, ng, nwav, d_g_point):
     """Returns (new_ng, g_point_map[new_ng]); d_g_point renumbered in place."""
     gmap = np.zeros(ng, dtype=np.int32)

@@ -3178,6 +3178,158 @@ ECCKD_API int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double
   return ECCKD_OK;
 }
 
+// Sums of nrow per-wavenumber rows over the wavenumbers of each g point (lw_spectra.cpp:250-255,
+// scale_lut.cpp:119-123: sum(flux(__, find(g_point == ig)), 1)): the reduction with f = 1 and the rows as
+// the weight matrix, i.e. the same fixed-order kernels as the averaging.
+ECCKD_API int ecckd_gpoint_sum_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nrow, const double* d_values,
+                                   int64_t stride, double* d_out) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && plan && d_values && d_out && nrow > 0 && stride >= plan->nwav, ECCKD_PARAMETER_ERROR,
+                "ecckd_gpoint_sum: bad argument");
+  std::vector<RowDesc> rows(nrow);
+  std::vector<OutDesc> outs(nrow);
+  for (int t = 0; t < nrow; ++t) {
+    RowDesc& r = rows[t];
+    r.od = d_values;  // any valid row: F_NONE ignores the values
+    r.method = M_SUMW;
+    r.wrow = t;
+    r.row = t;
+    r.pad_ = 0;
+    OutDesc& o = outs[t];
+    memset(&o, 0, sizeof(o));
+    o.out = d_out + (int64_t)t * plan->ng;
+    o.method = M_SUMW;
+  }
+  void* scratch = nullptr;
+  const size_t nrg = (size_t)nrow * plan->ng;
+  ECCKD_CUDA_OK(cudaMalloc(&scratch, nrg * (NSUM + NMINMAX) * sizeof(double)));
+  double* d_sums = static_cast<double*>(scratch);
+  double* d_minmax = d_sums + nrg * NSUM;
+  int rc = reduce_partial(ctx, plan, rows, F_NONE, 1.0, W_MATRIX, d_values, stride, nullptr, 0, nullptr, nullptr, d_sums,
+                          d_minmax);
+  if (rc == ECCKD_OK)
+    rc = finalize_rows(ctx, plan->ng, reinterpret_cast<const long long*>(plan->d_count), outs, 1.0, d_sums, d_minmax);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(scratch);
+  return rc;
+}
+
+// Sum of every row over ALL its n elements (sum(flux, 1) of lw_spectra.cpp:233-234) in a fixed order:
+// 256 blocks per row each add a contiguous slice (fixed per-thread strides, fixed tree), one more block
+// adds the 256 partial sums in order.
+constexpr int ROWSUM_BLOCKS = 256;
+__global__ void __launch_bounds__(256) row_sum_partial_kernel(int64_t n, const double* __restrict__ v, int64_t stride,
+                                                              double* __restrict__ partial) {
+  const int row = blockIdx.y;
+  const int64_t per = (n + ROWSUM_BLOCKS - 1) / ROWSUM_BLOCKS;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = min(n, lo + per);
+  const double* x = v + (int64_t)row * stride;
+  double s = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s += x[i];
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[(size_t)row * ROWSUM_BLOCKS + blockIdx.x] = sh[0];
+}
+__global__ void row_sum_final_kernel(int nrow, const double* __restrict__ partial, double* __restrict__ out) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nrow) return;
+  double s = 0.0;
+  for (int b = 0; b < ROWSUM_BLOCKS; ++b) s += partial[(size_t)row * ROWSUM_BLOCKS + b];
+  out[row] = s;
+}
+ECCKD_API int ecckd_row_sum_dev(ecckd_ctx* ctx, int nrow, int64_t n, const double* d_values, int64_t stride, double* d_out) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && d_values && d_out && nrow > 0 && n > 0 && stride >= n, ECCKD_PARAMETER_ERROR, "ecckd_row_sum: bad argument");
+  void* d_partial = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, (size_t)nrow * ROWSUM_BLOCKS * sizeof(double), &d_partial));
+  row_sum_partial_kernel<<<dim3(ROWSUM_BLOCKS, nrow), 256, 0, ctx->stream>>>(n, d_values, stride, static_cast<double*>(d_partial));
+  ECCKD_LAUNCH_CHECK(ctx);
+  row_sum_final_kernel<<<(nrow + 63) / 64, 64, 0, ctx->stream>>>(nrow, static_cast<const double*>(d_partial), d_out);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
+// The per-profile body of the lw_spectra tool (lw_spectra.cpp:208-255, the branch with g points): Planck
+// function at the half levels, the longwave sweep over every wavenumber with unit surface emissivity,
+// broadband fluxes, the transmission-averaged optical depth per g point (reference_surface_vmr = 0: raw
+// optical depth, Planck weights at the pressure-weighted layer temperatures) and the fluxes summed over
+// each g point's wavenumbers.  Scratch: 3 arrays of [nlay+1][nwav] + [nwav] doubles.
+__global__ void fill_ones_kernel(int64_t n, double* __restrict__ x) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = 1.0;
+}
+ECCKD_API int ecckd_lw_spectra_profile_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nlay, const double* d_wn,
+                                           const double* d_dwn, const double* h_pressure_hl, const double* h_temperature_hl,
+                                           const double* d_optical_depth, int64_t od_stride, double* d_flux_dn_lw,
+                                           double* d_flux_up_lw, double* d_spectral_od, double* d_spectral_flux_dn,
+                                           double* d_spectral_flux_up) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && plan && d_wn && d_dwn && h_pressure_hl && h_temperature_hl && d_optical_depth && nlay > 0,
+                ECCKD_PARAMETER_ERROR, "ecckd_lw_spectra_profile: bad argument");
+  ECCKD_REQUIRE(od_stride == plan->nwav, ECCKD_PARAMETER_ERROR,
+                "ecckd_lw_spectra_profile: optical_depth must be a contiguous [nlay][nwav] array (the flux solver's layout)");
+  const int64_t nwav = plan->nwav;
+  const int ng = plan->ng;
+  const size_t nhl = (size_t)(nlay + 1) * nwav;
+  double* scratch = nullptr;
+  ECCKD_CUDA_OK(cudaMalloc(&scratch, (3 * nhl + (size_t)nwav) * sizeof(double)));
+  double* planck_hl = scratch;
+  double* flux_dn = planck_hl + nhl;
+  double* flux_up = flux_dn + nhl;
+  double* ones = flux_up + nhl;
+  int rc = ecckd_planck_function_dev(ctx, nlay + 1, h_temperature_hl, nwav, d_wn, d_dwn, planck_hl, nwav);  // :211-216
+  if (rc == ECCKD_OK) {
+    fill_ones_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(nwav, ones);  // :217-218
+    ctx->launches++;
+    // surf_planck = planck_function(temperature_hl(end)) = the last row of planck_hl
+    rc = ecckd_radiative_transfer_lw_dev(ctx, 1, nlay, nwav, planck_hl, d_optical_depth, ones, planck_hl + (size_t)nlay * nwav,
+                                         flux_dn, flux_up);  // :223-224 (od_stride must equal nwav for the solver)
+  }
+  if (rc == ECCKD_OK && d_flux_dn_lw) rc = ecckd_row_sum_dev(ctx, nlay + 1, nwav, flux_dn, nwav, d_flux_dn_lw);  // :230
+  if (rc == ECCKD_OK && d_flux_up_lw) rc = ecckd_row_sum_dev(ctx, nlay + 1, nwav, flux_up, nwav, d_flux_up_lw);  // :231
+  if (rc == ECCKD_OK && d_spectral_od) {  // :241-249
+    std::vector<double> p_fl(nlay), t_fl(nlay);
+    for (int l = 0; l < nlay; ++l) {
+      p_fl[l] = 0.5 * (h_pressure_hl[l] + h_pressure_hl[l + 1]);
+      t_fl[l] = 0.5 * (h_temperature_hl[l] * h_pressure_hl[l] + h_temperature_hl[l + 1] * h_pressure_hl[l + 1]) / p_fl[l];
+    }
+    rc = ecckd_average_optical_depth_to_g_point_dev(ctx, plan, 0.0, nlay, p_fl.data(), h_pressure_hl, d_optical_depth, od_stride,
+                                                    ECCKD_WEIGHT_PLANCK, nullptr, 0, t_fl.data(), d_wn, d_dwn,
+                                                    ECCKD_AVG_TRANSMISSION, d_spectral_od, nullptr, nullptr, ng, nullptr);
+  }
+  if (rc == ECCKD_OK && d_spectral_flux_dn) rc = ecckd_gpoint_sum_dev(ctx, plan, nlay + 1, flux_dn, nwav, d_spectral_flux_dn);  // :250-255
+  if (rc == ECCKD_OK && d_spectral_flux_up) rc = ecckd_gpoint_sum_dev(ctx, plan, nlay + 1, flux_up, nwav, d_spectral_flux_up);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(scratch);
+  return rc;
+}
+
+// scale_lut.cpp:117-133 and :180-181 on the per-g flux sums of ecckd_gpoint_sum_dev (host-sized arrays):
+// od_best(iz, ig) = -mu0 log(flux(iz+1, ig) / flux(iz, ig)), or -1 where the flux at the layer base is not
+// positive; scaling = od_best / od_total, 1 where od_best <= 0.
+ECCKD_API int ecckd_scale_lut_scaling(int nz, int ng, double mu0, const double* h_flux_dn_gpoint, const double* h_od_total,
+                                      double* h_od_best, double* h_scaling) {
+  ECCKD_REQUIRE(nz > 0 && ng > 0 && h_flux_dn_gpoint && h_od_best, ECCKD_PARAMETER_ERROR, "ecckd_scale_lut_scaling: bad argument");
+  for (int ig = 0; ig < ng; ++ig) {
+    double flux_top = h_flux_dn_gpoint[ig];
+    for (int iz = 0; iz < nz; ++iz) {
+      const double flux_base = h_flux_dn_gpoint[(size_t)(iz + 1) * ng + ig];
+      h_od_best[(size_t)iz * ng + ig] = (flux_base <= 0.0) ? -1.0 : -mu0 * std::log(flux_base / flux_top);
+      flux_top = flux_base;
+    }
+  }
+  if (h_scaling) {
+    ECCKD_REQUIRE(h_od_total != nullptr, ECCKD_PARAMETER_ERROR, "ecckd_scale_lut_scaling: od_total missing");
+    for (size_t i = 0; i < (size_t)nz * ng; ++i) h_scaling[i] = (h_od_best[i] <= 0.0) ? 1.0 : h_od_best[i] / h_od_total[i];
+  }
+  return ECCKD_OK;
+}
+
 ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const double* d_wn, const double* d_dwn,
                                    int nlut, const double* h_temperature_lut, double* d_out) {
   ECCKD_DEVICE(ctx);

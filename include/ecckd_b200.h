@@ -342,6 +342,31 @@ int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double* d_wavenu
                             const double* d_ssi, int nbin, const double* h_wavenumber1,
                             const double* h_wavenumber2, double* d_out);
 
+/* Sums of nrow per-wavenumber rows over the wavenumbers of each g point:
+ * sum(x(row, find(g_point == ig))) of src/ecckd/lw_spectra.cpp:250-255 and src/ecckd/scale_lut.cpp:119-123.
+ * d_values[nrow][nwav] (row stride `stride`), d_out[nrow][ng]; fixed summation order. */
+int ecckd_gpoint_sum_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nrow, const double* d_values, int64_t stride,
+                         double* d_out);
+/* sum(x, 1): every row over all its n elements (src/ecckd/lw_spectra.cpp:230-231), fixed order. d_out[nrow]. */
+int ecckd_row_sum_dev(ecckd_ctx* ctx, int nrow, int64_t n, const double* d_values, int64_t stride, double* d_out);
+/* The per-profile body of the lw_spectra tool, src/ecckd/lw_spectra.cpp:208-255: Planck
+ * function at the half levels, radiative_transfer_lw over every wavenumber with unit surface emissivity,
+ * broadband fluxes d_flux_dn_lw / d_flux_up_lw[nlay+1], and for the plan's g points the transmission-averaged
+ * optical depth d_spectral_od[nlay][ng] (raw optical depth, Planck weights at the pressure-weighted layer
+ * temperatures) and the fluxes summed over each g point, d_spectral_flux_dn / _up[nlay+1][ng].
+ * d_optical_depth[nlay][nwav] contiguous (od_stride == nwav); any output may be NULL. */
+int ecckd_lw_spectra_profile_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nlay, const double* d_wavenumber_cm_1,
+                                 const double* d_d_wavenumber_cm_1, const double* h_pressure_hl,
+                                 const double* h_temperature_hl, const double* d_optical_depth, int64_t od_stride,
+                                 double* d_flux_dn_lw, double* d_flux_up_lw, double* d_spectral_od,
+                                 double* d_spectral_flux_dn, double* d_spectral_flux_up);
+/* scale_lut, src/ecckd/scale_lut.cpp:117-133, 180-181, on the per-g-point sums of the direct solar flux
+ * (ecckd_gpoint_sum_dev of spectral_flux_dn_direct_sw[nz+1][nwav]): h_od_best[nz][ng] = -mu0 log(flux(iz+1) /
+ * flux(iz)), -1 where the flux at the layer base is not positive; h_scaling[nz][ng] (may be NULL) =
+ * od_best / h_od_total, 1 where od_best <= 0.  Host arrays (they are [nz][ng] small). */
+int ecckd_scale_lut_scaling(int nz, int ng, double mu0, const double* h_flux_dn_gpoint, const double* h_od_total,
+                            double* h_od_best, double* h_scaling);
+
 /* Planck look-up table per g point: src/ecckd/create_look_up_table.cpp:579-591.
  * d_out[nlut][ng] = sum over the g point's wavenumbers of planck(T_lut, nu). */
 int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const double* d_wavenumber_cm_1,

@@ -74,3 +74,30 @@ def test_cxx_consumer_library_resolves_every_symbol():
         pytest.skip("oracle/_ref/libecckd_ref_tools_gpu.so not built")
     lib = ctypes.CDLL(RT.GPU_LIB, mode=os.RTLD_NOW)
     assert lib.ref_tool_run is not None
+
+
+def test_scale_lut_scaling_matches_the_tool_formulas():
+    """scale_lut.cpp:117-133, 180-181 (host-sized arithmetic: no device needed by the call itself)."""
+    import numpy as np
+
+    import ecckd_b200 as E
+
+    rng = np.random.default_rng(11)
+    nz, ng, mu0 = 12, 7, 0.6
+    flux = np.cumprod(rng.uniform(0.3, 1.0, size=(nz + 1, ng)), axis=0)
+    flux[9:, 2] = 0.0  # the beam is extinguished in g point 2
+    od_total = rng.uniform(0.1, 3.0, size=(nz, ng))
+    best, scaling = E.scale_lut_scaling(mu0, flux, od_total)
+    ref = np.full((nz, ng), -1.0)
+    for ig in range(ng):
+        top = flux[0, ig]
+        for iz in range(nz):
+            base = flux[iz + 1, ig]
+            with np.errstate(all="ignore"):
+                ref[iz, ig] = -1.0 if base <= 0.0 else -mu0 * np.log(base / top)
+            top = base
+    # (0/0 after extinction is NaN in the tool as well: log(0/0); compare where defined)
+    ok = np.isfinite(ref)
+    np.testing.assert_allclose(best[ok], ref[ok], rtol=1e-15)
+    ref_s = np.where(ref <= 0.0, 1.0, ref / od_total)
+    np.testing.assert_allclose(scaling[ok], ref_s[ok], rtol=1e-15)
