@@ -45,12 +45,14 @@ struct Partial {
   int upd;  // this lane found a new extreme in this round
 };
 
-__device__ __forceinline__ void minmax_bounds(Partial& p) {
-  const unsigned mnhi = (unsigned)__double2hiint(p.mn), mxhi = (unsigned)__double2hiint(p.mx);
+// hi_cap: high words at or above it never pass the range check (reduce2_kernel's transmission kinds send
+// optical depths beyond 708/kD to the exact path, which clamps them; see rows_slots)
+__device__ __forceinline__ void minmax_bounds(Partial& p, const unsigned hi_cap = 0x7ff00000u) {
+  const unsigned mnhi = (unsigned)__double2hiint(p.mn), mxhi = min((unsigned)__double2hiint(p.mx), hi_cap);
   // +0.0 cannot be undercut by a non-negative value: let high word 0 pass as "inside"
   const unsigned lowb = (p.mn == 0.0 && mnhi == 0u) ? 0u : mnhi + 1u;
   // negative or not yet initialised extremes (sign bit set / mn = +inf, mx = -inf): no fast path
-  const bool ok = (int)(mnhi | mxhi) >= 0 && mxhi > lowb;
+  const bool ok = (int)(mnhi | (unsigned)__double2hiint(p.mx)) >= 0 && mxhi > lowb;
   p.lowb = lowb;
   p.span = ok ? mxhi - lowb : 0u;
 }
@@ -92,6 +94,13 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
                                            const TransConst64* __restrict__ K3 = nullptr, const unsigned lane_off = 0u,
                                            const int row_stride = STAGE_BYTES,
                                            const TransConstT* __restrict__ KT = nullptr) {
+#if defined(ECCKD_V_NOCLAMP) && defined(ECCKD_TAB_LOGN)
+  // the transmission kinds of reduce2_kernel: no clamp of the optical depth on the fast path
+  constexpr bool NOCLAMP = TAB64 && FKIND == F_TRANS;
+#else
+  constexpr bool NOCLAMP = false;
+#endif
+  const unsigned hi_cap = NOCLAMP ? (unsigned)KT->hi_max : 0x7ff00000u;
   constexpr bool LOGKIND = (FKIND == F_LOG || FKIND == F_HYBRID);
   // the loads of one trip (4 slots): plan offsets, weights, optical depths of the NR rows
   auto load_trip = [&](double (&tau)[NR][4], double (&w)[4], const int kk) {
@@ -103,7 +112,7 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
       for (int r = 0; r < NR; ++r) tau[r][j] = *reinterpret_cast<const double*>(stage0 + r * row_stride + o);
     }
   };
-  auto compute_trip = [&](const double (&tau)[NR][4], const double (&w)[4], const int kk) {
+  auto compute_trip = [&](double (&tau)[NR][4], const double (&w)[4], const int kk) {
     // extremes: one range check per value, one (rare) branch per 4 x NR values
     bool outside = false;
 #pragma unroll
@@ -129,7 +138,12 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
           a[r].mn = mn;
           a[r].mx = mx;
           a[r].upd = 1;
-          minmax_bounds(a[r]);
+          minmax_bounds(a[r], hi_cap);
+        }
+        if (NOCLAMP) {  // optical depths beyond 708/kD (exp underflows: f = 1) come through here: clamp them now
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tau[r][j] = __hiloint2double(min(__double2hiint(tau[r][j]), KT->hi_max), __double2loint(tau[r][j]));
         }
       }
     }
@@ -141,7 +155,7 @@ __device__ __forceinline__ void rows_slots(Partial (&a)[NR], const unsigned char
 #if defined(ECCKD_TAB_LOGN)
       // TAB64 callers: the 2^ECCKD_TAB_LOGR-fold replicated 2^ECCKD_TAB_LOGN-entry table; `lane_off` is its
       // shared-window address + the lane's copy offset
-#define ECCKD_P1(x) (TAB64 ? transT_phase1(x, *KT) : trans256_phase1(x, K2))
+#define ECCKD_P1(x) (TAB64 ? (NOCLAMP ? transT_phase1_noclamp(x, *KT) : transT_phase1(x, *KT)) : trans256_phase1(x, K2))
 #define ECCKD_P2(mm) (TAB64 ? transT_phase2<ECCKD_TAB_LOGN, ECCKD_TAB_LOGR>(mm, lane_off) : trans256_phase2(mm, tab))
 #define ECCKD_P3(mm, TT) (TAB64 ? transT_phase3<ECCKD_TAB_QDEG>(mm, TT, *KT) : trans256_phase3(mm, TT, K2))
 #elif defined(ECCKD_V_TAB256)

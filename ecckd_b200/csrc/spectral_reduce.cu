@@ -1103,7 +1103,7 @@ __host__ __device__ inline Smem2Layout smem2_layout(int nw, int nsw, int stage_b
 // lane's extremes into the (row, entry) cache and refreshes the range-check words.
 template <int NR>
 __device__ __forceinline__ void merge_extremes(const Partial (&a)[NR], const int e, const bool used, double2* mmv,
-                                               uint2* mmb, const int lane) {
+                                               uint2* mmb, const int lane, const unsigned hi_cap = 0x7ff00000u) {
 #pragma unroll
   for (int r = 0; r < NR; ++r) {
     unsigned m = __ballot_sync(0xffffffffu, used && a[r].upd != 0);
@@ -1121,7 +1121,7 @@ __device__ __forceinline__ void merge_extremes(const Partial (&a)[NR], const int
         Partial t;
         t.mn = v.x;
         t.mx = v.y;
-        minmax_bounds(t);
+        minmax_bounds(t, hi_cap);
         mmb[r * WIN + es] = make_uint2(t.lowb, t.span);
       }
       __syncwarp();
@@ -1163,6 +1163,11 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
 #endif
   __syncthreads();
   const unsigned char* tab = smem_raw + L.tab;
+#if defined(ECCKD_V_NOCLAMP) && defined(ECCKD_TAB_LOGN)
+  const unsigned hi_cap2 = FKIND == F_TRANS ? (unsigned)p.tct.hi_max : 0x7ff00000u;  // see rows_slots
+#else
+  const unsigned hi_cap2 = 0x7ff00000u;
+#endif
 
   // this CTA's contiguous piece of the (window, group, chunk) space
   const int nchunks = (int)p.nchunks;
@@ -1286,7 +1291,7 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
           t.mn = q[2];
           t.mx = q[3];
         }
-        minmax_bounds(t);
+        minmax_bounds(t, hi_cap2);
         mmv[r * WIN + lane] = make_double2(t.mn, t.mx);
         mmb[r * WIN + lane] = make_uint2(t.lowb, t.span);
       }
@@ -1406,7 +1411,7 @@ __global__ void __launch_bounds__((NW_MAX2 + NPW) * 32, 1) reduce2_kernel(const 
     int u = 0;
 #pragma unroll
     for (int r = 0; r < NR; ++r) u |= a[r].upd;
-    if (__any_sync(0xffffffffu, used && u != 0)) merge_extremes<NR>(a, e, used, mmv + row0 * WIN, mmb + row0 * WIN, lane);
+    if (__any_sync(0xffffffffu, used && u != 0)) merge_extremes<NR>(a, e, used, mmv + row0 * WIN, mmb + row0 * WIN, lane, hi_cap2);
   };
 
   // one chunk visit on stage set `set`

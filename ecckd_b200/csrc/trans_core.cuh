@@ -431,6 +431,15 @@ __device__ __forceinline__ TransMid transT_phase1(double tau, const TransConstT&
   m.rho = fma(t - magic, K.b, tc);
   return m;
 }
+// (the caller guarantees tau < 708/kd * (1 + 2^-20))
+__device__ __forceinline__ TransMid transT_phase1_noclamp(double tau, const TransConstT& K) {
+  const double magic = 6755399441055744.0;
+  const double t = fma(tau, K.a, magic);
+  TransMid m;
+  m.n = __double2loint(t);
+  m.rho = fma(t - magic, K.b, tau);
+  return m;
+}
 // tab_lane = shared-window address of the table + ((lane & (R-1)) << 3).  Mask, then scale-and-add
 // (LOP3 + IMAD/LEA) and a load through the shared window: written in PTX because the compiler turns the
 // C form into shift, mask and a separate add of the base.
