@@ -647,7 +647,13 @@ def main():
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": kernel_name, "kernel_ms": k_ms, "launches_per_step": len(seg), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": int(alg_bytes // len(seg))},
+                         "algorithmic_bytes_per_launch": int(alg_bytes // len(seg)),
+                         "basis": "8 B per point.layer + 20 B per wavenumber per launch: the per-wavenumber data are "
+                                  "shared by the %d spectra of the launch (%.2f B per point.layer); SURVEY.md 8d's "
+                                  "per-unit figure for a single spectrum is 8.4 B, on which this kernel time is "
+                                  "%.3f of the peak (its 70 %% target: 546 G point.layers/s per GPU)"
+                                  % (nspec, alg_bytes / (nspec * nlay * nwav), 8.4 * nspec * nlay * nwav / (k_ms * 1e-3) / 1e9 / peak)
+                         if weight is None else "8 B per point.layer + 8 B per point.layer of each distinct weight row"},
             "cpu_baseline": cpu,
             "validated": validated,
             "e2e": e2e,
