@@ -683,20 +683,32 @@ def bench_full_build(torch, E, ctx, dev, args, nlay, nspec, nwav, ng, wn, dwn, g
     d_plut = torch.empty((t_lut.size, ng), dtype=torch.float64, device=dev)
     state = {}
 
+    marks = []
+
+    def mark(name):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        marks.append((name, e))
+
     def build():
+        del marks[:]
+        mark("start")
         g_work.copy_(g_point)
         ng2, _ = E.compact_g_points_dev(ctx, ng, nwav, g_work)  # a4
         assert ng2 == ng
         plan = E.GPointPlan(ctx, g_work, nwav, ng)
+        mark("compaction_and_plan")
         for it in range(nt):
-            comp.zero_()
-            for k in range(n_merge):  # a8
-                E.merge_axpy_dev(ctx, nlay, nwav, comp, nwav, ods[(13 + k) % nspec], nwav, scaling=0.5 + 0.25 * k)
+            E.merge_spectra_dev(ctx, nlay, nwav, [ods[(13 + k) % nspec] for k in range(n_merge)], [nwav] * n_merge,
+                                [0.5 + 0.25 * k for k in range(n_merge)], comp, nwav)  # a8, one pass
             E.average_optical_depth_batch_dev(ctx, plan, vmrs, p_fl, p_hl, [comp] + ods[1:], nwav, E.WEIGHT_PLANCK, None,
                                               nwav, t_fl + 20.0 * (it - 2.5), wn, dwn, args.method, outs[0], outs[1],
                                               outs[2], ng)
+        mark("merges_and_reductions")
         E.gpoint_fraction_dev(ctx, ng, nwav, g_work, wn, dwn, w1, w2, d_frac)  # a5
+        mark("gpoint_fraction")
         E.planck_lut_dev(ctx, plan, wn, dwn, t_lut, d_plut)  # a6
+        mark("planck_lut")
         state["plan"] = plan
 
     build()  # warm-up (workspaces, plan kernels' first launch)
@@ -724,6 +736,7 @@ def bench_full_build(torch, E, ctx, dev, args, nlay, nspec, nwav, ng, wn, dwn, g
     return {"metric": "LBL spectral points*layers/s reduced to LUT, whole build", "value": units / (ms * 1e-3),
             "unit": "point*layers/s", "ms": ms, "blocks": nt * nspec, "gpu_launches": int(launches),
             "reduce_kernel_ms": kms, "reduce_kernel_share": kms / ms,
+            "phases_ms": {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])},
             "optical_depth_bytes_read": int(units * 8 + nt * n_merge * nlay * nwav * 8),
             "config": {"workload": f"create_look_up_table LW, all {nt} temperature indices x {nspec} blocks of {nlay} x 2^{args.log2_nwav}: "
                                    f"g-point compaction + plan + per index [merge of the composite block from {n_merge} constituents + "

@@ -129,6 +129,7 @@ def _declare(L):
         "ecckd_ctx_set_timing": [vp, i32],
         "ecckd_ctx_reduce_kernel_time": [vp, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
         "ecckd_merge_axpy_dev": [vp, i32, i64, vp, i64, vp, i64, dbl, vp],
+        "ecckd_merge_spectra_dev": [vp, i32, i64, i32, vp, vp, vp, vp, i64],
         "ecckd_gpoint_fraction_dev": [vp, i32, i64, vp, vp, vp, i32, vp, vp, vp],
         "ecckd_ssi_intervals_dev": [vp, i64, vp, vp, i32, vp, vp, vp],
         "ecckd_planck_lut_dev": [vp, vp, vp, vp, i32, vp, vp],

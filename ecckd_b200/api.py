@@ -638,6 +638,16 @@ def merge_axpy_dev(ctx: Context, nlay, nwav, d_optical_depth, stride, d_od, od_s
                                           float(scaling), spp))
 
 
+def merge_spectra_dev(ctx: Context, nlay, nwav, d_ods: Sequence, od_strides: Sequence[int], scalings: Sequence[float],
+                      d_optical_depth, stride):
+    """read_merged_spectrum.cpp:149-168 for scalar scalings, all sources in one pass."""
+    a_od, p_od = _ptr_array(d_ods)
+    st, stp = _h(od_strides, np.int64)
+    sc, scp = _h(scalings)
+    check(_lib.lib().ecckd_merge_spectra_dev(ctx.handle, nlay, nwav, len(d_ods), p_od, stp, scp, _ptr(d_optical_depth),
+                                             stride))
+
+
 def gpoint_fraction_dev(ctx: Context, ng, nwav, d_g_point, d_wavenumber, d_d_wavenumber, wavenumber1, wavenumber2,
                         d_out):
     w1, w1p = _h(wavenumber1)

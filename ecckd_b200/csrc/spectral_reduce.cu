@@ -3186,6 +3186,55 @@ ECCKD_API int ecckd_ssi_intervals_dev(ecckd_ctx* ctx, int64_t nwav, const double
 // Sums of nrow per-wavenumber rows over the wavenumbers of each g point (lw_spectra.cpp:250-255,
 // scale_lut.cpp:119-123: sum(flux(__, find(g_point == ig)), 1)): the reduction with f = 1 and the rows as
 // the weight matrix, i.e. the same fixed-order kernels as the averaging.
+// The merge loop of read_merged_spectrum.cpp:149-168 for sources with a scalar scaling, in ONE pass:
+// optical_depth = 0, then += od_k * scaling_k (or += od_k when scaling_k == 1) for k = 0 .. nsrc-1 in that
+// order - the same operations in the same order as the loop of AXPY calls, without re-reading and
+// re-writing the running sum nsrc times.
+constexpr int MERGE_MAX_SRC = 8;
+struct MergeSrc {
+  const double* od[MERGE_MAX_SRC];
+  int64_t stride[MERGE_MAX_SRC];
+  double scaling[MERGE_MAX_SRC];
+  int nsrc;
+};
+__global__ void merge_spectra_kernel(int nlay, int64_t nwav, double* __restrict__ dst, int64_t stride, const MergeSrc m) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwav) return;
+  for (int l = blockIdx.y; l < nlay; l += gridDim.y) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < MERGE_MAX_SRC; ++k) {
+      if (k < m.nsrc) {
+        const double v = m.od[k][(int64_t)l * m.stride[k] + w];
+        acc += (m.scaling[k] != 1.0) ? v * m.scaling[k] : v;  // read_merged_spectrum.cpp:160-167
+      }
+    }
+    dst[(int64_t)l * stride + w] = acc;
+  }
+}
+ECCKD_API int ecckd_merge_spectra_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, int nsrc, const double* const* h_d_od,
+                                      const int64_t* h_od_stride, const double* h_scaling, double* d_optical_depth,
+                                      int64_t stride) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && h_d_od && h_od_stride && h_scaling && d_optical_depth, ECCKD_PARAMETER_ERROR,
+                "ecckd_merge_spectra: NULL argument");
+  ECCKD_REQUIRE(nlay > 0 && nwav > 0 && nsrc > 0 && nsrc <= MERGE_MAX_SRC && stride >= nwav, ECCKD_PARAMETER_ERROR,
+                "ecckd_merge_spectra: bad dimensions (1 to %d sources)", MERGE_MAX_SRC);
+  MergeSrc m;
+  memset(&m, 0, sizeof(m));
+  m.nsrc = nsrc;
+  for (int k = 0; k < nsrc; ++k) {
+    ECCKD_REQUIRE(h_d_od[k] != nullptr && h_od_stride[k] >= nwav, ECCKD_PARAMETER_ERROR, "ecckd_merge_spectra: source %d", k);
+    m.od[k] = h_d_od[k];
+    m.stride[k] = h_od_stride[k];
+    m.scaling[k] = h_scaling[k] < 0.0 ? 1.0 : h_scaling[k];  // :146-148
+  }
+  dim3 grid((unsigned)((nwav + 255) / 256), (unsigned)std::min(nlay, 64));
+  merge_spectra_kernel<<<grid, 256, 0, ctx->stream>>>(nlay, nwav, d_optical_depth, stride, m);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
+}
+
 ECCKD_API int ecckd_gpoint_sum_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, int nrow, const double* d_values,
                                    int64_t stride, double* d_out) {
   ECCKD_DEVICE(ctx);

@@ -326,6 +326,12 @@ int ecckd_average_optical_depth_exchange_dev(ecckd_ctx* ctx, ecckd_comm* comm, i
 int ecckd_merge_axpy_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, double* d_optical_depth, int64_t stride,
                          const double* d_od, int64_t od_stride, double scaling,
                          const double* h_scaling_profile);
+/* The same loop for nsrc (<= 8) sources with scalar scalings in one pass: d_optical_depth = 0, then
+ * += h_d_od[k] * h_scaling[k] (plain += when the scaling is 1; < 0 means 1, :146-148) in source order -
+ * bitwise what the sequence of ecckd_merge_axpy_dev calls on a zeroed array gives. */
+int ecckd_merge_spectra_dev(ecckd_ctx* ctx, int nlay, int64_t nwav, int nsrc, const double* const* h_d_od,
+                            const int64_t* h_od_stride, const double* h_scaling, double* d_optical_depth,
+                            int64_t stride);
 
 /* gpoint_fraction: src/ecckd/create_look_up_table.cpp:512-548.
  * Bin i is (h_wavenumber1[i], h_wavenumber2[i]]; bins must be the contiguous

@@ -34,6 +34,28 @@ def test_merge_axpy(ctx, O):
         np.testing.assert_allclose(d_a.numpy(), ref, rtol=2.3e-16)
 
 
+def test_merge_spectra_one_pass_equals_the_axpy_sequence_bitwise(ctx, O):
+    """read_merged_spectrum.cpp:149-168: the fused merge must give the bits of the loop of AXPYs on a zeroed array
+    (and of the oracle's loop), for scalings of 1, below 0 (= 1) and arbitrary ones, with row strides."""
+    rng = np.random.default_rng(1)
+    nlay, nwav, pad = 5, 2999, 7
+    srcs = [rng.uniform(0, 3, (nlay, nwav + pad)) for _ in range(4)]
+    scalings = [1.0, 0.37, -1.0, 2.5]
+    d_srcs = [ctx.to_device(a) for a in srcs]
+    d_out = ctx.zeros((nlay, nwav + 3))
+    E.merge_spectra_dev(ctx, nlay, nwav, d_srcs, [nwav + pad] * 4, scalings, d_out, nwav + 3)
+    seq = ctx.zeros((nlay, nwav))
+    ref = np.zeros((nlay, nwav))
+    for a, d_a, sc in zip(srcs, d_srcs, scalings):
+        sc = 1.0 if sc < 0.0 else sc
+        E.merge_axpy_dev(ctx, nlay, nwav, seq, nwav, d_a, nwav + pad, sc, None)
+        ref = O.merge_axpy(ref, np.ascontiguousarray(a[:, :nwav]), sc, None)
+    got = d_out.numpy()[:, :nwav]
+    assert np.array_equal(got, seq.numpy())
+    assert np.array_equal(got, ref)
+    assert np.all(d_out.numpy()[:, nwav:] == 0.0)  # nothing written past the row
+
+
 def test_gpoint_fraction_ssi_intervals_planck_lut(ctx, O):
     c = S.lw_spectrum_case(nlay=3, nwav=30000, ng=14, nband=3, seed=8)
     w1, w2 = O.gpoint_fraction_grid(False, [0.0, 500.0, 1500.0], [500.0, 1500.0, 3260.0])

@@ -12,7 +12,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c
   python bench.py --steps 2 --warmup 3 --no-cpu > ${O}_ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:reduce2_kernel -s 3 -c 1 -o ${O}_reduce2 -f \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --no-flux > ${O}_ncu_reduce2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'total_od_planck_kernel|rt_lw_staged_kernel' -s 2 -c 2 -o ${O}_run_ckd -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'total_od_planck3_kernel|rt_lw_staged_kernel' -s 2 -c 2 -o ${O}_run_ckd -f \
   python tools/run_ckd_sweep.py synthetic one > ${O}_ncu_run_ckd.log 2>&1
 timeout 600 python tools/bench_extra.py > ${O}_bench_extra.json 2> ${O}_bench_extra.err; tail -c 600 ${O}_bench_extra.json
 ls -la gpurun_out | grep r02f
