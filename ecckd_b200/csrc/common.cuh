@@ -119,3 +119,25 @@ struct DeviceGuard {
     int _rc = (expr);              \
     if (_rc != ECCKD_OK) return _rc; \
   } while (0)
+
+namespace ecckd {
+// Sums over the 32 lanes of FOUR values per lane at once (a transposed reduction): the first two
+// steps exchange half of the values for the partner's other half, so 6 shuffles do the work of the
+// 20 that four separate xor trees take.  Afterwards lane 0 holds the sum of v[0], lane 16 of v[1],
+// lane 8 of v[2], lane 24 of v[3] (every lane of the same (bit 4, bit 3) group holds that sum too).
+// The order of the additions is fixed: bitwise reproducible.
+__device__ __forceinline__ double warp_sum4_transposed(const double (&v)[4], const int lane) {
+  const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+  // step 1 (xor 16): lanes with bit 4 clear keep v[0], v[2]; the others v[1], v[3]
+  const double a0 = (hi16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, hi16 ? v[0] : v[1], 16);
+  const double a1 = (hi16 ? v[3] : v[2]) + __shfl_xor_sync(0xffffffffu, hi16 ? v[2] : v[3], 16);
+  // step 2 (xor 8): lanes with bit 3 clear keep a0, the others a1
+  double b = (hi8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, hi8 ? a0 : a1, 8);
+  b += __shfl_xor_sync(0xffffffffu, b, 4);
+  b += __shfl_xor_sync(0xffffffffu, b, 2);
+  b += __shfl_xor_sync(0xffffffffu, b, 1);
+  return b;
+}
+// index (0..3) of the value whose sum warp_sum4_transposed leaves in this lane
+__device__ __forceinline__ int warp_sum4_slot(const int lane) { return ((lane >> 4) & 1) | (((lane >> 3) & 1) << 1); }
+}  // namespace ecckd
