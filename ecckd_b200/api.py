@@ -1099,6 +1099,29 @@ def cost_function_ckd_lw(ctx, pressure_hl, planck_hl, surf_emissivity, surf_plan
     return dict(cost_profile=cp.numpy(), cost_total=float(ct.numpy()[0]), penalty=float(pt.numpy()[0]))
 
 
+def cost_function_ckd_lw_grad(ctx, pressure_hl, planck_hl, surf_emissivity, surf_planck, optical_depth, flux_dn, flux_up, hr,
+                              flux_weight, flux_profile_weight, broadband_weight, spectral_boundary_weight,
+                              layer_weight=None, pressure_weight_power=0.5, negative_od_penalty=1.0e4,
+                              spectral_flux_dn_surf=None, spectral_flux_up_toa=None, rel_dn=None, rel_up=None,
+                              band_mapping=None):
+    """Gradient of the scene's longwave cost (sum of calc_cost_function_ckd_lw over the profiles + the
+    negative-optical-depth penalty, solve_adept.cpp:96-184) with respect to optical_depth[nprof][nlay][ng]: the
+    hand-written reverse mode that stands in for the Adept tape (solve_adept.cpp:91, 201-203)."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nprof, nlay, ng = od.shape
+    nband = np.asarray(flux_dn).shape[-1]
+    d = [_dev(ctx, a) for a in (pressure_hl, planck_hl, surf_emissivity, surf_planck, od, flux_dn, flux_up, hr,
+                                spectral_flux_dn_surf, spectral_flux_up_toa, layer_weight, rel_dn, rel_up)]
+    d_bm = _dev(ctx, band_mapping, np.int32)
+    grad = ctx.empty((nprof, nlay, ng))
+    check(_lib.lib().ecckd_cost_function_ckd_lw_grad_dev(
+        ctx.handle, nprof, nlay, ng, nband, d[0].ptr, d[1].ptr, d[2].ptr, d[3].ptr, d[4].ptr, d[5].ptr, d[6].ptr,
+        d[7].ptr, _ptr(d[8]), _ptr(d[9]), float(flux_weight), float(flux_profile_weight), float(broadband_weight),
+        float(spectral_boundary_weight), _ptr(d[10]), float(pressure_weight_power), float(negative_od_penalty),
+        _ptr(d[11]), _ptr(d[12]), _ptr(d_bm), grad.ptr))
+    return grad.numpy()
+
+
 def cost_function_ckd_sw(ctx, cos_sza, pressure_hl, ssi, albedo, optical_depth, flux_dn, flux_up, hr, flux_weight,
                          flux_profile_weight, broadband_weight, layer_weight=None, pressure_weight_power=0.5,
                          negative_od_penalty=1.0e4, spectral_boundary_weights=None, spectral_flux_dn_surf=None,

@@ -879,6 +879,218 @@ __global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __rest
 }
 
 // checks the dimensions of a scene and returns the dynamic shared memory its CTAs need
+// ---------------------------------------------------------------------------------------------
+// Reverse mode of the longwave forward cost (first part): the gradient of
+// calc_cost_function_ckd_lw (calc_cost_function_lw.cpp:115-232) plus the negative-optical-depth penalty
+// (solve_adept.cpp:107-116) with respect to the optical depth of every (profile, layer, g point) - what the
+// Adept tape of solve_adept.cpp:91, 201-203 delivers up to the look-up-table interpolation.  Written by hand:
+//   forward sweep (as ckd_cost_body) -> band sums -> heating rates -> residuals;
+//   dJ/d(band flux) from the quadratic terms (spectral and broadband parts, boundary and interior
+//   fluxes, heating rates through their difference stencil), dJ/d(g-point flux) = its band's + the
+//   spectral boundary term;
+//   adjoint of the upward recurrence walked downwards (level 0 -> surface), the surface reflection
+//   (1 - emissivity), adjoint of the downward recurrence walked upwards; per layer the adjoints of the
+//   transmittance and of the two sources give dJ/de and dJ/df, and with de/dtau = D (1 - e),
+//   df/dtau = (e / tau - de/dtau) / (D tau)  [e > 1e-5]  or  de/dtau / 2, the derivative in tau.
+// Clamped (negative) optical depths only carry the penalty's derivative.  CTA = profile, thread = g point.
+__global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restrict__ grad) {
+  extern __shared__ double sm[];
+  const int ip = blockIdx.x;
+  const int nlay = p.nlay, nlev = nlay + 1, ng = p.ng, nband = p.nband;
+  double* fdo = sm;                          // [nlev][ng] forward flux down (relative-to flux subtracted)
+  double* fuo = fdo + (size_t)nlev * ng;     // [nlev][ng] ... up; later dJ/de partial sums
+  double* gd = fuo + (size_t)nlev * ng;      // [nlev][nband] band flux down -> dJ/d(band flux down)
+  double* gu = gd + (size_t)nlev * nband;    // [nlev][nband]
+  double* hrf = gu + (size_t)nlev * nband;   // [nlay][nband] heating-rate residual -> dJ/d(heating rate)
+  double* lw = hrf + (size_t)nlay * nband;   // [nlay]
+  double* iw = lw + nlay;                    // [nlay]
+  double* sdn = iw + nlay;                   // [nlev] band sums of the residuals
+  double* sup = sdn + nlev;                  // [nlev]
+  double* shr = sup + nlev;                  // [nlay]
+  double* s_tab = shr + nlay;                // 2^(j/256) table
+  const double* p_hl = p.pressure_hl + (size_t)ip * nlev;
+  const double* od = p.optical_depth + (size_t)ip * nlay * ng;
+  double* g_out = grad + (size_t)ip * nlay * ng;
+  const double hr_weight = 3600.0 * 24.0;
+  const double D = ECCKD_LW_DIFFUSIVITY;
+  trans_tab_init(s_tab);
+  const unsigned char* tab = reinterpret_cast<const unsigned char*>(s_tab);
+  if (threadIdx.x == 0) {  // layer weights (solve_adept.cpp:133-145), as ckd_cost_body
+    if (p.layer_weight) {
+      for (int l = 0; l < nlay; ++l) lw[l] = p.layer_weight[(size_t)ip * nlay + l];
+    } else {
+      double s = 0.0;
+      for (int l = 0; l < nlay; ++l) {
+        double v;
+        if (p.pressure_weight_power == 0.5) v = sqrt(p_hl[l + 1]) - sqrt(p_hl[l]);
+        else if (p.pressure_weight_power == 1.0) v = p_hl[l + 1] - p_hl[l];
+        else v = pow(p_hl[l + 1], p.pressure_weight_power) - pow(p_hl[l], p.pressure_weight_power);
+        lw[l] = v;
+        s += v;
+      }
+      for (int l = 0; l < nlay; ++l) lw[l] /= s;
+    }
+    for (int l = 0; l + 1 < nlay; ++l) iw[l] = p.flux_profile_weight * 0.5 * (lw[l] + lw[l + 1]);
+  }
+  __syncthreads();
+  // ---- forward fluxes per g point
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    const double* pl = p.planck_hl + (size_t)ip * nlev * ng + g;
+    double f_dn = 0.0, b_top = pl[0];
+    fdo[g] = 0.0;
+    for (int l = 0; l < nlay; ++l) {
+      const double tau = fmax(od[(size_t)l * ng + g], 0.0);
+      double e, f;
+      lw_layer_tab(tau, p.tc, tab, e, f);
+      const double b_bot = pl[(size_t)(l + 1) * ng];
+      f_dn = f_dn * (1.0 - e) + b_top * (e - f) + b_bot * f;
+      fdo[(size_t)(l + 1) * ng + g] = f_dn;
+      b_top = b_bot;
+    }
+    const int ie = p.band_mapping ? p.band_mapping[g] : g;
+    const double es = p.surf_emissivity[(size_t)ip * p.nemis + ie];
+    double f_up = p.surf_planck[(size_t)ip * ng + g] * es + (1.0 - es) * f_dn;
+    fuo[(size_t)nlay * ng + g] = f_up;
+    double b_bot = b_top;
+    for (int l = nlay - 1; l >= 0; --l) {
+      const double tau = fmax(od[(size_t)l * ng + g], 0.0);
+      double e, f;
+      lw_layer_tab(tau, p.tc, tab, e, f);
+      const double b_t = pl[(size_t)l * ng];
+      f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
+      fuo[(size_t)l * ng + g] = f_up;
+      b_bot = b_t;
+    }
+    if (p.rel_dn) {
+      const double* rd = p.rel_dn + (size_t)ip * nlev * ng + g;
+      const double* ru = p.rel_up + (size_t)ip * nlev * ng + g;
+      for (int l = 0; l < nlev; ++l) {
+        fdo[(size_t)l * ng + g] -= rd[(size_t)l * ng];
+        fuo[(size_t)l * ng + g] -= ru[(size_t)l * ng];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- band flux residuals, heating-rate residuals
+  const double* t_dn = p.flux_dn + (size_t)ip * nlev * nband;
+  const double* t_up = p.flux_up + (size_t)ip * nlev * nband;
+  const double* t_hr = p.hr + (size_t)ip * nlay * nband;
+  for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
+    const int l = j / nband, ib = j - l * nband;
+    double sd = 0.0, su = 0.0;
+    if (!p.band_mapping) {
+      sd = fdo[(size_t)l * ng + ib];
+      su = fuo[(size_t)l * ng + ib];
+    } else {
+      for (int g = 0; g < ng; ++g)
+        if (p.band_mapping[g] == ib) { sd += fdo[(size_t)l * ng + g]; su += fuo[(size_t)l * ng + g]; }
+    }
+    gd[j] = sd;
+    gu[j] = su;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nlay * nband; j += blockDim.x) {
+    const int l = j / nband, ib = j - l * nband;
+    const double conv = -(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l + 1] - p_hl[l]);
+    const size_t a = (size_t)l * nband + ib;
+    hrf[j] = conv * (gd[a + nband] - gd[a] - gu[a + nband] + gu[a]) - t_hr[j];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {  // flux residuals in place
+    gd[j] -= t_dn[j];
+    gu[j] -= t_up[j];
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < nlev; l += blockDim.x) {  // band sums of the residuals (band order)
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int ib = 0; ib < nband; ++ib) {
+      a += gd[(size_t)l * nband + ib];
+      b += gu[(size_t)l * nband + ib];
+      if (l < nlay) c += hrf[(size_t)l * nband + ib];
+    }
+    sdn[l] = a;
+    sup[l] = b;
+    if (l < nlay) shr[l] = c;
+  }
+  __syncthreads();
+  // ---- dJ/d(heating rate), dJ/d(band flux) of the quadratic terms (calc_cost_function_lw.cpp:194-222)
+  const double bw = p.broadband_weight, c1 = (1.0 - bw) / nband;
+  for (int j = threadIdx.x; j < nlay * nband; j += blockDim.x) {
+    const int l = j / nband;
+    hrf[j] = 2.0 * hr_weight * hr_weight * lw[l] * (c1 * hrf[j] + bw * shr[l]);
+  }
+  for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
+    const int l = j / nband;
+    double wd = 0.0, wu = 0.0;  // weight of this level's squared flux error
+    if (l == nlay) wd = p.flux_weight;
+    if (l == 0) wu = p.flux_weight;
+    if (l >= 1 && l <= nlay - 1 && p.flux_profile_weight > 0.0) wd = wu = iw[l - 1];
+    gd[j] = 2.0 * wd * (c1 * gd[j] + bw * sdn[l]);
+    gu[j] = 2.0 * wu * (c1 * gu[j] + bw * sup[l]);
+  }
+  __syncthreads();
+  // heating rate -> fluxes (heating_rate.h:38-48): hr(l) = conv (dn(l+1) - dn(l) - up(l+1) + up(l))
+  for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
+    const int l = j / nband, ib = j - l * nband;
+    double a = 0.0;  // dJ/d dn(l) from the heating rates of the layers above and below
+    if (l >= 1) a += (-(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l] - p_hl[l - 1])) * hrf[(size_t)(l - 1) * nband + ib];
+    if (l < nlay) a -= (-(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l + 1] - p_hl[l])) * hrf[(size_t)l * nband + ib];
+    gd[j] += a;
+    gu[j] -= a;
+  }
+  __syncthreads();
+  // ---- reverse sweeps per g point
+  for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    const double* pl = p.planck_hl + (size_t)ip * nlev * ng + g;
+    const int ib = p.band_mapping ? p.band_mapping[g] : g;
+    const double* rd = p.rel_dn ? p.rel_dn + (size_t)ip * nlev * ng + g : nullptr;
+    const double* ru = p.rel_up ? p.rel_up + (size_t)ip * nlev * ng + g : nullptr;
+    const bool sb = p.spectral_boundary_weight > 0.0 && p.spectral_flux_dn_surf && p.spectral_flux_up_toa;
+    // adjoint of the upward recurrence: level 0 down to the surface
+    double a = gu[ib];
+    if (sb) a += 2.0 * p.spectral_boundary_weight * (fuo[g] - p.spectral_flux_up_toa[(size_t)ip * ng + g]);
+    for (int l = 0; l < nlay; ++l) {
+      const double tau = fmax(od[(size_t)l * ng + g], 0.0);
+      double e, f;
+      lw_layer_tab(tau, p.tc, tab, e, f);
+      const double up_next = fuo[(size_t)(l + 1) * ng + g] + (ru ? ru[(size_t)(l + 1) * ng] : 0.0);  // raw flux_up(l+1)
+      const double b_t = pl[(size_t)l * ng], b_b = pl[(size_t)(l + 1) * ng];
+      // up(l) = up(l+1) (1 - e) + b_b (e - f) + b_t f
+      fuo[(size_t)l * ng + g] = a * (b_b - up_next);  // dJ/de so far (fuo(l) is no longer needed)
+      g_out[(size_t)l * ng + g] = a * (b_t - b_b);     // dJ/df so far
+      a = a * (1.0 - e) + gu[(size_t)(l + 1) * nband + ib];
+    }
+    // surface: up(nlay) = surf_planck emissivity + (1 - emissivity) dn(nlay)
+    const int ie = p.band_mapping ? p.band_mapping[g] : g;
+    const double es = p.surf_emissivity[(size_t)ip * p.nemis + ie];
+    double d = gd[(size_t)nlay * nband + ib] + a * (1.0 - es);
+    if (sb) d += 2.0 * p.spectral_boundary_weight * (fdo[(size_t)nlay * ng + g] - p.spectral_flux_dn_surf[(size_t)ip * ng + g]);
+    // adjoint of the downward recurrence: surface up to level 0
+    for (int l = nlay - 1; l >= 0; --l) {
+      const double tau_raw = od[(size_t)l * ng + g];
+      const double tau = fmax(tau_raw, 0.0);
+      double e, f;
+      lw_layer_tab(tau, p.tc, tab, e, f);
+      const double dn_l = fdo[(size_t)l * ng + g] + (rd ? rd[(size_t)l * ng] : 0.0);  // raw flux_dn(l)
+      const double b_t = pl[(size_t)l * ng], b_b = pl[(size_t)(l + 1) * ng];
+      // dn(l+1) = dn(l) (1 - e) + b_t (e - f) + b_b f
+      const double de = fuo[(size_t)l * ng + g] + d * (b_t - dn_l);
+      const double df = g_out[(size_t)l * ng + g] + d * (b_b - b_t);
+      const double dedt = D * (1.0 - e);
+      double dfdt;
+      if (e > 1.0e-5) {
+        dfdt = (e / tau - dedt) / (D * tau);  // f = 1 - e / (D tau)
+      } else {
+        dfdt = 0.5 * dedt;
+      }
+      double gt = de * dedt + df * dfdt;
+      if (tau_raw < 0.0) gt = 2.0 * p.negative_od_penalty * tau_raw;  // clamped: only the penalty depends on it
+      g_out[(size_t)l * ng + g] = gt;
+      d = d * (1.0 - e) + gd[(size_t)l * nband + ib];
+    }
+  }
+}
+
 static int ckd_cost_smem(ecckd_ctx* ctx, CkdCostParams& p, const char* who, size_t* smem_out) {
   const int nlev = p.nlay + 1;
   trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
@@ -1128,6 +1340,47 @@ ECCKD_API int ecckd_cost_function_ckd_lw_dev(
   p.broadband_weight = broadband_weight; p.spectral_boundary_weight = spectral_boundary_weight;
   p.negative_od_penalty = negative_od_penalty; p.pressure_weight_power = pressure_weight_power;
   return launch_ckd_cost(ctx, p, d_cost_profile, d_cost_total, d_penalty_total, nullptr, who);
+}
+
+ECCKD_API int ecckd_cost_function_ckd_lw_grad_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_pressure_hl, const double* d_planck_hl,
+    const double* d_surf_emissivity, const double* d_surf_planck, const double* d_optical_depth,
+    const double* d_flux_dn, const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    double spectral_boundary_weight, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_grad_optical_depth) {
+  ECCKD_DEVICE(ctx);
+  const char* who = "ecckd_cost_function_ckd_lw_grad";
+  ECCKD_REQUIRE(ctx && d_pressure_hl && d_planck_hl && d_surf_emissivity && d_surf_planck && d_optical_depth &&
+                    d_flux_dn && d_flux_up && d_hr && d_grad_optical_depth,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE((d_relative_ckd_flux_dn == nullptr) == (d_relative_ckd_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                "%s: relative-to fluxes must both be given or both be NULL", who);
+  ECCKD_REQUIRE(nprof > 0 && nlay > 0 && ng > 0 && nband > 0 && (d_band_mapping || nband == ng), ECCKD_PARAMETER_ERROR,
+                "%s: bad dimensions", who);
+  CkdCostParams p = {};
+  trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
+  p.sw = 0; p.nprof = nprof; p.nlay = nlay; p.ng = ng; p.nband = nband; p.nemis = d_band_mapping ? nband : ng;
+  p.up_in_bb = 1;
+  p.pressure_hl = d_pressure_hl; p.planck_hl = d_planck_hl; p.surf_emissivity = d_surf_emissivity;
+  p.surf_planck = d_surf_planck; p.optical_depth = d_optical_depth; p.flux_dn = d_flux_dn; p.flux_up = d_flux_up;
+  p.hr = d_hr; p.spectral_flux_dn_surf = d_spectral_flux_dn_surf; p.spectral_flux_up_toa = d_spectral_flux_up_toa;
+  p.layer_weight = d_layer_weight; p.rel_dn = d_relative_ckd_flux_dn; p.rel_up = d_relative_ckd_flux_up;
+  p.band_mapping = d_band_mapping; p.flux_weight = flux_weight; p.flux_profile_weight = flux_profile_weight;
+  p.broadband_weight = broadband_weight; p.spectral_boundary_weight = spectral_boundary_weight;
+  p.negative_od_penalty = negative_od_penalty; p.pressure_weight_power = pressure_weight_power;
+  const int nlev = nlay + 1;
+  const size_t ndbl = (size_t)2 * nlev * ng + (size_t)2 * nlev * nband + (size_t)nlay * nband + 2 * nlay + 2 * nlev + nlay + 256;
+  const size_t smem = ndbl * sizeof(double);
+  ECCKD_REQUIRE(smem + sizeof(CkdCostParams) + 64 <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
+                "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, ng, nlev, smem,
+                ctx->smem_optin);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_lw_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = std::min(1024, std::max(128, (ng + 31) / 32 * 32));
+  ckd_cost_lw_grad_kernel<<<nprof, threads, smem, ctx->stream>>>(p, d_grad_optical_depth);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
 }
 
 ECCKD_API int ecckd_cost_function_ckd_sw_dev(

@@ -702,6 +702,21 @@ int ecckd_cost_function_ckd_lw_dev(
     double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
     const int32_t* d_band_mapping, double* d_cost_profile, double* d_cost_total, double* d_penalty_total);
 
+/* Reverse mode of the above (first part): d_grad_optical_depth[nprof][nlay][ng] = the
+ * derivative of (sum over the profiles of calc_cost_function_ckd_lw + the negative-optical-depth penalty of
+ * solve_adept.cpp:107-116) with respect to d_optical_depth - what the Adept tape of solve_adept.cpp:91, 201-203
+ * yields up to the look-up-table interpolation, written by hand: adjoints of the quadratic cost terms, of the
+ * heating-rate stencil (heating_rate.h:38-48) and of the two flux recurrences of radiative_transfer_lw.cpp:25-60.
+ * Same arguments as the forward call.  Clamped (negative) optical depths carry only the penalty's derivative. */
+int ecckd_cost_function_ckd_lw_grad_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_pressure_hl, const double* d_planck_hl,
+    const double* d_surf_emissivity, const double* d_surf_planck, const double* d_optical_depth,
+    const double* d_flux_dn, const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf,
+    const double* d_spectral_flux_up_toa, double flux_weight, double flux_profile_weight, double broadband_weight,
+    double spectral_boundary_weight, const double* d_layer_weight, double pressure_weight_power,
+    double negative_od_penalty, const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up,
+    const int32_t* d_band_mapping, double* d_grad_optical_depth);
+
 /* calc_cost_function_ckd_sw (forward value): src/ecckd/calc_cost_function_sw.cpp:115-277.
  * d_cos_sza[nprof], d_ssi[ng] (already scaled to the scene's TSI, solve_adept.cpp:160-166),
  * h_albedo[nalbedo] indexed by band_mapping; d_cost_fn_per_band[nband] (may be NULL) is added to. */

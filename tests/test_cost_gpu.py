@@ -351,3 +351,78 @@ def test_rayleigh_coefficients(ctx, O):
     ssi_int = S.solar_spectrum(0.5 * (w1 + w2))
     np.testing.assert_allclose(E.rayleigh_molar_scat_gpoints(ctx, w1, w2, gf, ssi_int),
                                O.rayleigh_molar_scat_gpoints(w1, w2, gf, ssi_int), rtol=1e-12)
+
+
+@pytest.mark.parametrize("banded", [True, False])
+@pytest.mark.parametrize("weights", [(0.2, 0.2, 0.8, 0.1), (0.5, 0.0, 0.0, 0.0)])
+def test_cost_function_ckd_lw_gradient_matches_finite_differences(ctx, O, banded, weights):
+    """the hand-written reverse mode of the longwave cost (calc_cost_function_lw.cpp:115-232 +
+    the penalty of solve_adept.cpp:107-116) against central differences of the ORACLE's forward cost (the function
+    Adept would differentiate, pinned to the reference's own translation unit) and of the device's forward cost:
+    random directions for the whole gradient, single entries for a sample of (profile, layer, g point)."""
+    nprof, nlay, ng, nb = 3, 20, 16, 5
+    s = _scene(nprof, nlay, ng, nb, seed=9)
+    rng = s["rng"]
+    nband = nb if banded else ng
+    bm = s["bm"] if banded else None
+    emis = rng.uniform(0.9, 1.0, (nprof, nband))
+    od = np.abs(s["od"]) * rng.choice([1e-4, 1e-2, 1.0, 5.0], size=s["od"].shape)  # thin (f = e/2 branch) to thick layers
+    od[0, 3, 2] = -0.01   # clamped entries: only the penalty depends on them
+    od[2, 7, 5] = -0.003
+    t_dn, t_up, hr, lws = [], [], [], []
+    for i in range(nprof):
+        eg = emis[i][bm] if banded else emis[i]
+        dn, up = O.radiative_transfer_lw(s["planck"][i], np.maximum(od[i], 0) * 1.3, eg, s["surf"][i])
+        if banded:
+            dn = np.stack([dn[:, bm == b].sum(1) for b in range(nband)], 1)
+            up = np.stack([up[:, bm == b].sum(1) for b in range(nband)], 1)
+        t_dn.append(dn), t_up.append(up), hr.append(O.heating_rate(s["p"][i], dn, up))
+        lw = np.diff(np.sqrt(s["p"][i]))
+        lws.append(lw / lw.sum())
+    t_dn, t_up, hr, lws = np.stack(t_dn), np.stack(t_up), np.stack(hr), np.stack(lws)
+    sfd, sfu = rng.uniform(0, 5, (nprof, ng)), rng.uniform(0, 5, (nprof, ng))
+    rel = rng.uniform(0, 1, (2, nprof, nlay + 1, ng))
+    pen = 50.0
+    kw = dict(layer_weight=lws, negative_od_penalty=pen, spectral_flux_dn_surf=sfd, spectral_flux_up_toa=sfu,
+              rel_dn=rel[0], rel_up=rel[1], band_mapping=bm)
+
+    def cost_oracle(x):
+        c = pen * float((np.minimum(x, 0.0) ** 2).sum())
+        for i in range(nprof):
+            c += O.calc_cost_function_ckd_lw(s["p"][i], s["planck"][i], emis[i], s["surf"][i], np.maximum(x[i], 0.0),
+                                             t_dn[i], t_up[i], hr[i], *weights, lws[i], spectral_flux_dn_surf=sfd[i],
+                                             spectral_flux_up_toa=sfu[i], rel_dn=rel[0][i], rel_up=rel[1][i],
+                                             band_mapping=bm)
+        return c
+
+    def cost_device(x):
+        return E.cost_function_ckd_lw(ctx, s["p"], s["planck"], emis, s["surf"], x, t_dn, t_up, hr, *weights, **kw)["cost_total"]
+
+    grad = E.cost_function_ckd_lw_grad(ctx, s["p"], s["planck"], emis, s["surf"], od, t_dn, t_up, hr, *weights, **kw)
+    assert grad.shape == od.shape and np.all(np.isfinite(grad))
+    assert grad[0, 3, 2] == 2 * pen * od[0, 3, 2] and grad[2, 7, 5] == 2 * pen * od[2, 7, 5]
+    # directional derivatives (relative steps: the entries span four decades); clamped entries are kept out of the
+    # direction, a central difference across the kink at zero is not a derivative
+    # ... and so are the entries next to the reference's own branch point (emissivity = 1e-5, i.e. tau = 6.0e-6,
+    # radiative_transfer_lw.cpp:41-43), where its two expressions for the Planck-gradient factor differ by ~1e-11:
+    # a jump of that size over a step of 1e-6 tau is not a derivative either
+    free = (od > 0.0) & ~((od > 2.0e-6) & (od < 2.0e-5))
+    for k in range(4):
+        v = rng.normal(size=od.shape) * od * free
+        h = 1.0e-4  # relative step (v is proportional to od): truncation ~h^2, rounding ~1e-14 cost / h
+        for cost in (cost_oracle, cost_device):
+            fd = (cost(od + h * v) - cost(od - h * v)) / (2 * h)
+            an = float((grad * v).sum())
+            assert abs(fd - an) <= 5.0e-6 * max(abs(an), abs(fd)) + 2e-9 * abs(cost(od)), (k, cost.__name__, fd, an)
+    # single entries (those big enough for a central difference of a cost of O(100) to resolve the step)
+    for _ in range(40):
+        i, l, g = rng.integers(nprof), rng.integers(nlay), rng.integers(ng)
+        if not free[i, l, g] or od[i, l, g] < 1.0e-3:
+            continue
+        h = 1.0e-4 * od[i, l, g]
+        xp, xm = od.copy(), od.copy()
+        xp[i, l, g] += h
+        xm[i, l, g] -= h
+        fd = (cost_oracle(xp) - cost_oracle(xm)) / (2 * h)
+        scale = np.abs(grad[i]).max()
+        assert abs(fd - grad[i, l, g]) <= 1.0e-5 * abs(grad[i, l, g]) + 1e-7 * scale, (i, l, g, fd, grad[i, l, g])
