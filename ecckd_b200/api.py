@@ -842,6 +842,17 @@ class CkdModel:
         check(_lib.lib().ecckd_calc_total_optical_depth_dev(self.ctx.handle, self.handle, p, ncol, nlay,
                                                             _ptr(d_pressure_hl), _ptr(d_temperature_hl), _ptr(d_od)))
 
+    def calc_total_optical_depth_adjoint_dev(self, d_vmr_fl: Sequence, ncol, nlay, d_pressure_hl, d_temperature_hl, d_grad_od,
+                                             d_grad_molar_abs: Sequence, accumulate=False):
+        """Adjoint of calc_total_optical_depth: d_grad_molar_abs[igas] (device array shaped like the gas's table, or
+        None) += / = sum over (column, layer) of d_grad_od times the interpolation coefficients (ckd_model.cpp:962-1088
+        transposed)."""
+        arr, p = _ptr_array(d_vmr_fl)
+        garr, gp = _ptr_array(d_grad_molar_abs)
+        check(_lib.lib().ecckd_calc_total_optical_depth_adjoint_dev(
+            self.ctx.handle, self.handle, p, ncol, nlay, _ptr(d_pressure_hl), _ptr(d_temperature_hl), _ptr(d_grad_od), gp,
+            1 if accumulate else 0))
+
     def run_ckd(self, vmr_fl: Sequence[Optional[np.ndarray]], pressure_hl, temperature_hl, tsi=1361.0, out=None):
         """Numerical core of run_ckd (run_ckd.cpp:119-367) on host arrays -> dict of outputs (written into
         the C-contiguous float64 arrays of `out` when given, e.g. pinned buffers)."""

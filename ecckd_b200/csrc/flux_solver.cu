@@ -1528,6 +1528,129 @@ __global__ void __launch_bounds__(NWARP * 32, MINB) total_od_planck3_kernel(cons
   cp_async_wait<0>();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Adjoint of the look-up-table interpolation: the optical depth is linear in the table,
+//   tau(cl, g) = sum_gas W_gas(cl) sum_corners c(cl, corner) [sum_conc cw] K_gas(node, g)   (ckd_model.cpp:962-1088),
+// so dJ/dK_gas(node, g) = sum over the (column, layer) pairs cl whose interpolation cell touches the node of
+// dJ/dtau(cl, g) times that coefficient - the transpose of the forward gather, done as a GATHER per table node so
+// that every sum has a fixed order (no floating-point atomics): kernel 1 writes the g-independent record of every
+// cl; kernel 2 runs one block per node (it, ip): its warps scan fixed contiguous ranges of cl in ascending order,
+// add the contributions of the cl in the (up to) four adjacent cells into per-warp accumulators in shared memory
+// (lane = g point) and the warps' partial sums are added in warp order.
+constexpr int ADJ_MAXGAS = TOD_MAXGAS;
+struct AdjParams {
+  const double* vmr[ADJ_MAXGAS];
+  double reference_vmr[ADJ_MAXGAS], log_vmr0[ADJ_MAXGAS], d_log_c[ADJ_MAXGAS];
+  int conc_dependence[ADJ_MAXGAS], nconc[ADJ_MAXGAS], present[ADJ_MAXGAS], acc_off[ADJ_MAXGAS];
+  double* grad[ADJ_MAXGAS];  // [nconc|1][nt][np][ng] or NULL
+  int ngas, nt, np, ng, nacc;
+  double log_p_0, d_log_p, d_t;
+  const double* temperature;
+  int ncol, nlay;
+  const double* pressure_hl;
+  const double* temperature_fl;
+  const double* grad_od;  // [ncol][nlay][ng]
+  // records, one per cl
+  int* key;               // it0 * np + ip0
+  double* corner;         // [4][ncl]: tw0 pw0, tw0 pw1, tw1 pw0, tw1 pw1
+  double* w;              // [ngas][ncl] what multiplies the interpolated absorption of the gas (0: gas absent)
+  double* cw1;            // [ngas][ncl]
+  int* ic0;               // [ngas][ncl]
+  int accumulate;
+};
+
+__global__ void od_adjoint_records_kernel(const AdjParams p) {
+  const int64_t ncl = (int64_t)p.ncol * p.nlay;
+  const int64_t cl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cl >= ncl) return;
+  const int icol = (int)(cl / p.nlay), il = (int)(cl - (int64_t)icol * p.nlay);
+  const double p0 = p.pressure_hl[(int64_t)icol * (p.nlay + 1) + il];
+  const double p1 = p.pressure_hl[(int64_t)icol * (p.nlay + 1) + il + 1];
+  const Interp it = make_interp(p0, p1, p.temperature_fl[cl], p.log_p_0, p.d_log_p, p.d_t, p.nt, p.np, p.temperature);
+  p.key[cl] = it.it0 * p.np + it.ip0;
+  p.corner[0 * ncl + cl] = it.tw0 * it.pw0;
+  p.corner[1 * ncl + cl] = it.tw0 * it.pw1;
+  p.corner[2 * ncl + cl] = it.tw1 * it.pw0;
+  p.corner[3 * ncl + cl] = it.tw1 * it.pw1;
+  for (int ig = 0; ig < p.ngas; ++ig) {
+    double w = 0.0, cw1 = 0.0;
+    int ic0 = 0;
+    if (p.present[ig]) {  // as gas_od
+      const bool have = p.vmr[ig] != nullptr;
+      const double vmr = have ? p.vmr[ig][cl] : 0.0;
+      const int cd = p.conc_dependence[ig];
+      double weight = 0.0;
+      if (have) weight = (cd == ECCKD_CONC_RELATIVE_LINEAR) ? it.simple_weight * (vmr - p.reference_vmr[ig]) : it.simple_weight * vmr;
+      if (cd == ECCKD_CONC_LUT) {
+        double cindex0 = (log(vmr) - p.log_vmr0[ig]) / p.d_log_c[ig];
+        cindex0 = fmax(0.0, fmin(cindex0, p.nconc[ig] - 1.0001));
+        ic0 = (int)cindex0;
+        cw1 = cindex0 - ic0;
+        w = weight;
+      } else {
+        w = (cd == ECCKD_CONC_NONE) ? it.simple_weight : weight;
+      }
+    }
+    p.w[(int64_t)ig * ncl + cl] = w;
+    p.cw1[(int64_t)ig * ncl + cl] = cw1;
+    p.ic0[(int64_t)ig * ncl + cl] = ic0;
+  }
+}
+
+constexpr int ADJ_WARPS = 8;
+__global__ void __launch_bounds__(ADJ_WARPS * 32) od_adjoint_gather_kernel(const AdjParams p) {
+  extern __shared__ double s_acc[];  // [ADJ_WARPS][nacc][32]
+  const int node = blockIdx.x, it = node / p.np, ip = node - it * p.np;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ncl = (int64_t)p.ncol * p.nlay;
+  const int64_t per = (ncl + ADJ_WARPS - 1) / ADJ_WARPS;
+  const int64_t lo = min(ncl, (int64_t)warp * per), hi = min(ncl, lo + per);
+  double* acc = s_acc + (size_t)warp * p.nacc * 32;
+  for (int g0 = 0; g0 < p.ng; g0 += 32) {
+    const int g = min(g0 + lane, p.ng - 1);
+    for (int a = 0; a < p.nacc; ++a) acc[a * 32 + lane] = 0.0;
+    __syncwarp();
+    for (int64_t cl = lo; cl < hi; ++cl) {
+      const int key = p.key[cl];  // warp-uniform
+      const int it0 = key / p.np, ip0 = key - it0 * p.np;
+      const int dt = it - it0, dp = ip - ip0;
+      if ((unsigned)dt > 1u || (unsigned)dp > 1u) continue;  // the cell of this cl does not touch the node
+      const double c = p.corner[(int64_t)(dt * 2 + dp) * ncl + cl];
+      const double gt = p.grad_od[cl * p.ng + g] * c;
+      for (int ig = 0; ig < p.ngas; ++ig) {
+        if (!p.grad[ig]) continue;
+        const double w = p.w[(int64_t)ig * ncl + cl];
+        double* a = acc + (size_t)p.acc_off[ig] * 32 + lane;
+        if (p.conc_dependence[ig] == ECCKD_CONC_LUT) {
+          const int ic0 = p.ic0[(int64_t)ig * ncl + cl];
+          const double cw1 = p.cw1[(int64_t)ig * ncl + cl];
+          a[(size_t)ic0 * 32] += gt * (w * (1.0 - cw1));
+          a[(size_t)(ic0 + 1) * 32] += gt * (w * cw1);
+        } else {
+          a[0] += gt * w;
+        }
+      }
+    }
+    __syncthreads();
+    // warps' partial sums in warp order, one (accumulator, g) per thread
+    for (int j = threadIdx.x; j < p.nacc * 32; j += blockDim.x) {
+      const int a = j >> 5, l = j & 31;
+      if (g0 + l >= p.ng) continue;
+      double sum = 0.0;
+      for (int w = 0; w < ADJ_WARPS; ++w) sum += s_acc[((size_t)w * p.nacc + a) * 32 + l];
+      // which gas / concentration level is accumulator a
+      int ig = 0;
+      while (ig + 1 < p.ngas && (!p.grad[ig] || a >= p.acc_off[ig] + (p.conc_dependence[ig] == ECCKD_CONC_LUT ? p.nconc[ig] : 1))) ++ig;
+      if (!p.grad[ig]) continue;
+      const int ic = a - p.acc_off[ig];
+      double* dst = p.grad[ig] + (((size_t)ic * p.nt + it) * p.np + ip) * p.ng + g0 + l;
+      *dst = p.accumulate ? (*dst + sum) : sum;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace ecckd
 
 using namespace ecckd;
@@ -1726,6 +1849,66 @@ ECCKD_API int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model
     ECCKD_TRY(ecckd_ckd_calc_optical_depth_dev(ctx, m, igas, ncol, nlay, d_pressure_hl, static_cast<double*>(d_tfl),
                                                h_d_vmr_fl[igas], d_od, 1));
   }
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_calc_total_optical_depth_adjoint_dev(ecckd_ctx* ctx, ecckd_ckd_model* m, const double* const* h_d_vmr_fl,
+                                                         int ncol, int nlay, const double* d_pressure_hl,
+                                                         const double* d_temperature_hl, const double* d_grad_od,
+                                                         double* const* h_d_grad_molar_abs, int accumulate) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && m && h_d_vmr_fl && d_pressure_hl && d_temperature_hl && d_grad_od && h_d_grad_molar_abs && ncol > 0 &&
+                    nlay > 0,
+                ECCKD_PARAMETER_ERROR, "ecckd_calc_total_optical_depth_adjoint: bad argument");
+  ECCKD_REQUIRE(m->ngas <= ADJ_MAXGAS, ECCKD_PARAMETER_ERROR, "ecckd_calc_total_optical_depth_adjoint: more than %d gases",
+                ADJ_MAXGAS);
+  const int64_t ncl = (int64_t)ncol * nlay;
+  AdjParams p;
+  memset(&p, 0, sizeof(p));
+  int nacc = 0;
+  for (int i = 0; i < m->ngas; ++i) {
+    p.vmr[i] = h_d_vmr_fl[i];
+    p.reference_vmr[i] = m->reference_vmr[i];
+    p.log_vmr0[i] = m->log_vmr0[i];
+    p.d_log_c[i] = m->d_log_c[i];
+    p.conc_dependence[i] = m->conc_dependence[i];
+    p.nconc[i] = m->nconc[i];
+    // solve_adept.cpp:62-66: a gas the training scene does not hold is skipped unless it has no concentration dependence
+    p.present[i] = (h_d_vmr_fl[i] || m->conc_dependence[i] == ECCKD_CONC_NONE) ? 1 : 0;
+    p.grad[i] = p.present[i] ? h_d_grad_molar_abs[i] : nullptr;
+    p.acc_off[i] = nacc;
+    if (p.grad[i]) nacc += (m->conc_dependence[i] == ECCKD_CONC_LUT) ? m->nconc[i] : 1;
+  }
+  if (nacc == 0) return ECCKD_OK;
+  p.ngas = m->ngas; p.nt = m->nt; p.np = m->np; p.ng = m->ng; p.nacc = nacc;
+  p.log_p_0 = m->log_p_0; p.d_log_p = m->d_log_p; p.d_t = m->d_t; p.temperature = m->d_temperature;
+  p.ncol = ncol; p.nlay = nlay; p.pressure_hl = d_pressure_hl; p.grad_od = d_grad_od; p.accumulate = accumulate ? 1 : 0;
+  // scratch: layer temperatures, then the records
+  const size_t b_t = ((size_t)ncl * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_key = ((size_t)ncl * sizeof(int) + 255) & ~(size_t)255;
+  const size_t b_c = ((size_t)4 * ncl * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_w = ((size_t)m->ngas * ncl * sizeof(double) + 255) & ~(size_t)255;
+  const size_t b_i = ((size_t)m->ngas * ncl * sizeof(int) + 255) & ~(size_t)255;
+  void* base = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 1, b_t + b_key + b_c + 2 * b_w + b_i, &base));
+  char* c = static_cast<char*>(base);
+  double* d_tfl = reinterpret_cast<double*>(c);
+  p.temperature_fl = d_tfl;
+  p.key = reinterpret_cast<int*>(c + b_t);
+  p.corner = reinterpret_cast<double*>(c + b_t + b_key);
+  p.w = reinterpret_cast<double*>(c + b_t + b_key + b_c);
+  p.cw1 = reinterpret_cast<double*>(c + b_t + b_key + b_c + b_w);
+  p.ic0 = reinterpret_cast<int*>(c + b_t + b_key + b_c + 2 * b_w);
+  temperature_fl_kernel<<<(unsigned)((ncl + 255) / 256), 256, 0, ctx->stream>>>(ncol, nlay, d_temperature_hl, d_pressure_hl, d_tfl);
+  ECCKD_LAUNCH_CHECK(ctx);
+  od_adjoint_records_kernel<<<(unsigned)((ncl + 127) / 128), 128, 0, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
+  const size_t smem = (size_t)ADJ_WARPS * nacc * 32 * sizeof(double);
+  ECCKD_REQUIRE(smem <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
+                "ecckd_calc_total_optical_depth_adjoint: %d accumulators need %zu B of shared memory", nacc, smem);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(od_adjoint_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  od_adjoint_gather_kernel<<<m->nt * m->np, ADJ_WARPS * 32, smem, ctx->stream>>>(p);
+  ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
 

@@ -683,6 +683,19 @@ int ecckd_calc_total_optical_depth_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, c
                                        int ncol, int nlay, const double* d_pressure_hl,
                                        const double* d_temperature_hl, double* d_od);
 
+/* Adjoint of the above: the optical depth is linear in the look-up tables, and
+ * h_d_grad_molar_abs[igas] (device, laid out like the gas's table: [nconc][nt][np][ng] with a concentration axis,
+ * [nt][np][ng] without; NULL: not wanted) receives sum over (column, layer) of d_grad_od[ncol][nlay][ng] times the
+ * interpolation coefficient of that table entry (ckd_model.cpp:962-1088 transposed) - with d_grad_od from
+ * ecckd_cost_function_ckd_lw_grad_dev this is dJ/d(molar absorption), what the Adept tape of solve_adept.cpp:91,
+ * 201-203 yields for the state vector of optimize_lut.  A gather per table node in a fixed order: bitwise
+ * reproducible, no floating-point atomics.  accumulate != 0 adds to what the arrays hold (the loop over training
+ * scenes, solve_adept.cpp:96).  Gases the scene does not hold are skipped as in the forward call. */
+int ecckd_calc_total_optical_depth_adjoint_dev(ecckd_ctx* ctx, ecckd_ckd_model* model, const double* const* h_d_vmr_fl,
+                                               int ncol, int nlay, const double* d_pressure_hl,
+                                               const double* d_temperature_hl, const double* d_grad_od,
+                                               double* const* h_d_grad_molar_abs, int accumulate);
+
 /* calc_cost_function_ckd_lw (forward value): src/ecckd/calc_cost_function_lw.cpp:115-232, for
  * every profile of a training scene as solve_adept.cpp:96-184 drives it, including the layer
  * weights (d_layer_weight[nprof][nlay], or NULL: computed from pressure_weight_power and

@@ -426,3 +426,62 @@ def test_cost_function_ckd_lw_gradient_matches_finite_differences(ctx, O, banded
         fd = (cost_oracle(xp) - cost_oracle(xm)) / (2 * h)
         scale = np.abs(grad[i]).max()
         assert abs(fd - grad[i, l, g]) <= 1.0e-5 * abs(grad[i, l, g]) + 1e-7 * scale, (i, l, g, fd, grad[i, l, g])
+
+
+def test_gradient_with_respect_to_the_look_up_tables_end_to_end(ctx, O):
+    """SURVEY.md 8f item 2, the chain of optimize_lut for a longwave scene: tables -> calc_total_optical_depth ->
+    cost, and back: ecckd_cost_function_ckd_lw_grad_dev then ecckd_calc_total_optical_depth_adjoint_dev.  Central
+    differences of the device's forward chain in single table entries (models re-created with the entry moved)."""
+    from tests import synthetic as S
+    ncol, nlay, ng = 4, 20, 16
+    c = S.ckd_model_case(ncol=ncol, nlay=nlay, ng=ng, seed=41)
+    rng = np.random.default_rng(8)
+    d_vmr = [None if v is None else ctx.to_device(v) for v in c["vmr_fl"]]
+    d_p, d_t = ctx.to_device(c["pressure_hl"]), ctx.to_device(c["temperature_hl"])
+    planck = rng.uniform(5.0, 30.0, (ncol, nlay + 1, ng)) * np.linspace(0.5, 1.5, nlay + 1)[None, :, None]
+    emis, surf = rng.uniform(0.9, 1.0, (ncol, ng)), planck[:, -1, :] * 1.02
+    weights = (0.2, 0.2, 0.8, 0.0)
+
+    def model_of(gases):
+        return E.CkdModel(ctx, gases, c["log_pressure"], c["temperature"], c["temperature_planck"], c["planck_lut"])
+
+    def od_of(m):
+        d_od = ctx.empty((ncol, nlay, ng))
+        m.calc_total_optical_depth_dev(d_vmr, ncol, nlay, d_p, d_t, d_od)
+        return d_od.numpy()
+
+    m0 = model_of(c["gases"])
+    od0 = od_of(m0)
+    t_dn, t_up, hr = [], [], []
+    for i in range(ncol):  # "truth": the fluxes of somewhat different optical depths
+        dn, up = O.radiative_transfer_lw(planck[i], od0[i] * 1.2, emis[i], surf[i])
+        t_dn.append(dn), t_up.append(up), hr.append(O.heating_rate(c["pressure_hl"][i], dn, up))
+    t_dn, t_up, hr = np.stack(t_dn), np.stack(t_up), np.stack(hr)
+
+    def cost_of(od):
+        return E.cost_function_ckd_lw(ctx, c["pressure_hl"], planck, emis, surf, od, t_dn, t_up, hr, *weights)["cost_total"]
+
+    g_od = E.cost_function_ckd_lw_grad(ctx, c["pressure_hl"], planck, emis, surf, od0, t_dn, t_up, hr, *weights)
+    grads = [ctx.zeros(np.asarray(g["molar_abs"]).shape) for g in c["gases"]]
+    m0.calc_total_optical_depth_adjoint_dev(d_vmr, ncol, nlay, d_p, d_t, ctx.to_device(g_od), grads)
+    grads = [g.numpy() for g in grads]
+    checked = 0
+    for igas in (1, 2, 4):  # h2o (concentration axis), o3 (linear), ch4 (relative-linear)
+        gk = grads[igas]
+        for idx in np.argsort(np.abs(gk).ravel())[::-1][:2]:  # the entries that matter most
+            tab = np.asarray(c["gases"][igas]["molar_abs"])
+            h = 1.0e-4 * tab.ravel()[idx]
+            costs = []
+            for sgn in (+1, -1):
+                t2 = tab.copy()
+                t2.ravel()[idx] += sgn * h
+                gases = [dict(g) for g in c["gases"]]
+                gases[igas]["molar_abs"] = t2
+                m = model_of(gases)
+                costs.append(cost_of(od_of(m)))
+                m.close()
+            fd = (costs[0] - costs[1]) / (2 * h)
+            an = gk.ravel()[idx]
+            assert abs(fd - an) <= 1.0e-5 * abs(an) + 1e-9 * abs(costs[0]) / abs(h), (igas, idx, fd, an)
+            checked += 1
+    assert checked == 6

@@ -251,3 +251,45 @@ def test_run_ckd_two_lut_gases_and_nine_gases(ctx, O):
         np.testing.assert_allclose(got["optical_depth"], ref["optical_depth"], rtol=2e-11, atol=1e-18)
         for k in ("flux_dn", "flux_up"):
             assert np.max(np.abs(got[k] - ref[k])) <= FLUX_ATOL, k
+
+
+@pytest.mark.parametrize("ng", [32, 40])
+def test_calc_total_optical_depth_adjoint_is_the_transpose_of_the_forward(ctx, O, ng):
+    """calc_total_optical_depth (solve_adept.cpp:23-69, ckd_model.cpp:962-1088) is linear in
+    the look-up tables, tau = A K, so its reverse mode is A^T.  For random c and a second random set of tables K':
+    <c, A K'> == <A^T c, K'> - the forward is the oracle-checked device call on a model holding K', the adjoint
+    never sees K'.  Also: an absent gas gets nothing, accumulate adds, and the call is bitwise reproducible."""
+    ncol, nlay = 37, 23
+    c = S.ckd_model_case(ncol=ncol, nlay=nlay, ng=ng, seed=29)
+    rng = np.random.default_rng(5)
+    m = _model(ctx, c, sw=False)
+    vmr = list(c["vmr_fl"])
+    absent = [i for i, g in enumerate(c["gases"]) if g["conc_dependence"] != E.CONC_NONE][-1]
+    vmr[absent] = None  # "not present in LBL file": skipped by the forward, so by its transpose
+    d_vmr = [None if v is None else ctx.to_device(v) for v in vmr]
+    d_p, d_t = ctx.to_device(c["pressure_hl"]), ctx.to_device(c["temperature_hl"])
+    cvec = rng.normal(size=(ncol, nlay, ng))
+    d_c = ctx.to_device(cvec)
+    grads = [ctx.zeros(np.asarray(g["molar_abs"]).shape) for g in c["gases"]]
+    m.calc_total_optical_depth_adjoint_dev(d_vmr, ncol, nlay, d_p, d_t, d_c, grads)
+    g1 = [g.numpy() for g in grads]
+    assert not np.any(g1[absent])
+    # a second model with other tables
+    c2 = dict(c)
+    c2["gases"] = [dict(g, molar_abs=np.asarray(g["molar_abs"]) * rng.uniform(0.2, 3.0, np.asarray(g["molar_abs"]).shape))
+                   for g in c["gases"]]
+    m2 = _model(ctx, c2, sw=False)
+    d_od = ctx.empty((ncol, nlay, ng))
+    m2.calc_total_optical_depth_dev(d_vmr, ncol, nlay, d_p, d_t, d_od)
+    lhs = float((cvec * d_od.numpy()).sum())
+    rhs = float(sum((a * np.asarray(g["molar_abs"])).sum() for a, g in zip(g1, c2["gases"])))
+    scale = float(sum(np.abs(a * np.asarray(g["molar_abs"])).sum() for a, g in zip(g1, c2["gases"])))
+    assert abs(lhs - rhs) <= 1e-12 * scale, (lhs, rhs, scale)
+    # reproducible, and accumulate = True adds
+    m.calc_total_optical_depth_adjoint_dev(d_vmr, ncol, nlay, d_p, d_t, d_c, grads, accumulate=True)
+    for a, g in zip(g1, grads):
+        assert np.array_equal(g.numpy(), a + a)
+    only = [None] * len(grads)
+    only[1] = ctx.zeros(g1[1].shape)  # a subset of the gases
+    m.calc_total_optical_depth_adjoint_dev(d_vmr, ncol, nlay, d_p, d_t, d_c, only)
+    assert np.array_equal(only[1].numpy(), g1[1])
