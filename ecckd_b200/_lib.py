@@ -170,6 +170,8 @@ def _declare(L):
         "ecckd_calc_total_optical_depth_adjoint_dev": [vp, vp, vp, i32, i32, vp, vp, vp, vp, i32],
         "ecckd_cost_function_ckd_lw_grad_dev": [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, dbl, dbl,
                                                 dbl, dbl, vp, dbl, dbl, vp, vp, vp, vp],
+        "ecckd_cost_function_ckd_sw_grad_dev": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, dbl, dbl,
+                                                dbl, vp, vp, dbl, dbl, vp, vp, vp, vp],
         "ecckd_cost_function_ckd_sw_dev": [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, dbl,
                                            dbl, dbl, vp, vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp],
         "ecckd_cost_function_ckd_scenes_dev": [vp, i32, i32, vp, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp,

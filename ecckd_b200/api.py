@@ -1159,6 +1159,29 @@ def cost_function_ckd_sw(ctx, cos_sza, pressure_hl, ssi, albedo, optical_depth, 
     return out
 
 
+def cost_function_ckd_sw_grad(ctx, cos_sza, pressure_hl, ssi, albedo, optical_depth, flux_dn, flux_up, hr, flux_weight,
+                              flux_profile_weight, broadband_weight, layer_weight=None, pressure_weight_power=0.5,
+                              negative_od_penalty=1.0e4, spectral_boundary_weights=None, spectral_flux_dn_surf=None,
+                              rel_dn=None, rel_up=None, band_mapping=None):
+    """Gradient of the scene's shortwave cost (calc_cost_function_sw.cpp:115-277 over the profiles + the
+    negative-optical-depth penalty) with respect to optical_depth[nprof][nlay][ng]."""
+    od = np.ascontiguousarray(optical_depth, dtype=np.float64)
+    nprof, nlay, ng = od.shape
+    nband = np.asarray(flux_dn).shape[-1]
+    mu = np.broadcast_to(np.asarray(cos_sza, dtype=np.float64), (nprof,))
+    d = [_dev(ctx, a) for a in (mu, pressure_hl, ssi, od, flux_dn, flux_up, hr, spectral_flux_dn_surf,
+                                spectral_boundary_weights, layer_weight, rel_dn, rel_up)]
+    d_bm = _dev(ctx, band_mapping, np.int32)
+    alb, albp = _h(np.atleast_1d(albedo))
+    grad = ctx.empty((nprof, nlay, ng))
+    check(_lib.lib().ecckd_cost_function_ckd_sw_grad_dev(
+        ctx.handle, nprof, nlay, ng, nband, d[0].ptr, d[1].ptr, d[2].ptr, alb.size, albp, d[3].ptr, d[4].ptr, d[5].ptr,
+        d[6].ptr, _ptr(d[7]), float(flux_weight), float(flux_profile_weight), float(broadband_weight), _ptr(d[8]),
+        _ptr(d[9]), float(pressure_weight_power), float(negative_od_penalty), _ptr(d[10]), _ptr(d[11]), _ptr(d_bm),
+        grad.ptr))
+    return grad.numpy()
+
+
 def cost_function_ckd_scenes_dev(ctx, is_sw, scenes: Sequence[dict], nlay, ng, nband, flux_weight, flux_profile_weight,
                                  broadband_weight, spectral_boundary_weight=0.0, pressure_weight_power=0.5,
                                  negative_od_penalty=1.0e4, d_band_mapping=None, d_cost_fn_per_band=None,

@@ -893,7 +893,7 @@ __global__ void ckd_cost_total_kernel(int nprof, int nband, const double* __rest
 //   transmittance and of the two sources give dJ/de and dJ/df, and with de/dtau = D (1 - e),
 //   df/dtau = (e / tau - de/dtau) / (D tau)  [e > 1e-5]  or  de/dtau / 2, the derivative in tau.
 // Clamped (negative) optical depths only carry the penalty's derivative.  CTA = profile, thread = g point.
-__global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restrict__ grad) {
+__global__ void ckd_cost_grad_kernel(const CkdCostParams p, double* __restrict__ grad) {
   extern __shared__ double sm[];
   const int ip = blockIdx.x;
   const int nlay = p.nlay, nlev = nlay + 1, ng = p.ng, nband = p.nband;
@@ -935,6 +935,26 @@ __global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restric
   __syncthreads();
   // ---- forward fluxes per g point
   for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    if (p.sw) {  // radiative_transfer_sw.cpp:24-77 (direct beam, Lambertian return without Rayleigh), as ckd_cost_body
+      const double mu0 = p.cos_sza[ip];
+      const double minus_sec_sza = -1.0 / mu0;
+      double f = mu0 * p.ssi[g];
+      fdo[g] = f;
+      for (int l = 0; l < nlay; ++l) {
+        f = f * exp(minus_sec_sza * fmax(od[(size_t)l * ng + g], 0.0));
+        fdo[(size_t)(l + 1) * ng + g] = f;
+      }
+      if (p.direct_only) {
+        for (int l = 0; l < nlev; ++l) fuo[(size_t)l * ng + g] = 0.0;
+      } else {
+        f = f * p.albedo[p.band_mapping[g]];
+        fuo[(size_t)nlay * ng + g] = f;
+        for (int l = nlay - 1; l >= 0; --l) {
+          f = f * exp(-2.0 * fmax(od[(size_t)l * ng + g], 0.0));
+          fuo[(size_t)l * ng + g] = f;
+        }
+      }
+    } else {
     const double* pl = p.planck_hl + (size_t)ip * nlev * ng + g;
     double f_dn = 0.0, b_top = pl[0];
     fdo[g] = 0.0;
@@ -960,6 +980,7 @@ __global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restric
       f_up = f_up * (1.0 - e) + b_bot * (e - f) + b_t * f;
       fuo[(size_t)l * ng + g] = f_up;
       b_bot = b_t;
+    }
     }
     if (p.rel_dn) {
       const double* rd = p.rel_dn + (size_t)ip * nlev * ng + g;
@@ -993,7 +1014,7 @@ __global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restric
     const int l = j / nband, ib = j - l * nband;
     const double conv = -(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l + 1] - p_hl[l]);
     const size_t a = (size_t)l * nband + ib;
-    hrf[j] = conv * (gd[a + nband] - gd[a] - gu[a + nband] + gu[a]) - t_hr[j];
+    hrf[j] = (p.sw ? conv * (gd[a + nband] - gd[a]) : conv * (gd[a + nband] - gd[a] - gu[a + nband] + gu[a])) - t_hr[j];
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {  // flux residuals in place
@@ -1014,19 +1035,24 @@ __global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restric
   }
   __syncthreads();
   // ---- dJ/d(heating rate), dJ/d(band flux) of the quadratic terms (calc_cost_function_lw.cpp:194-222)
-  const double bw = p.broadband_weight, c1 = (1.0 - bw) / nband;
+  // (shortwave, calc_cost_function_sw.cpp:209-269: the spectral part is only divided by nband when there is a
+  // broadband part; the TOA upwelling error counts 20-fold in the spectral part; the upwelling enters the broadband
+  // part only when every albedo is positive)
+  const double bw = p.broadband_weight;
+  const double c1 = (!p.sw || bw > 0.0) ? (1.0 - bw) / nband : 1.0;
+  const double up_bb = (!p.sw || p.up_in_bb) ? bw : 0.0;
   for (int j = threadIdx.x; j < nlay * nband; j += blockDim.x) {
     const int l = j / nband;
     hrf[j] = 2.0 * hr_weight * hr_weight * lw[l] * (c1 * hrf[j] + bw * shr[l]);
   }
   for (int j = threadIdx.x; j < nlev * nband; j += blockDim.x) {
     const int l = j / nband;
-    double wd = 0.0, wu = 0.0;  // weight of this level's squared flux error
+    double wd = 0.0, wu = 0.0, wus = 1.0;  // weights of this level's squared flux errors
     if (l == nlay) wd = p.flux_weight;
-    if (l == 0) wu = p.flux_weight;
+    if (l == 0) { wu = p.flux_weight; wus = p.sw ? 20.0 : 1.0; }
     if (l >= 1 && l <= nlay - 1 && p.flux_profile_weight > 0.0) wd = wu = iw[l - 1];
     gd[j] = 2.0 * wd * (c1 * gd[j] + bw * sdn[l]);
-    gu[j] = 2.0 * wu * (c1 * gu[j] + bw * sup[l]);
+    gu[j] = 2.0 * wu * (wus * c1 * gu[j] + up_bb * sup[l]);
   }
   __syncthreads();
   // heating rate -> fluxes (heating_rate.h:38-48): hr(l) = conv (dn(l+1) - dn(l) - up(l+1) + up(l))
@@ -1036,11 +1062,42 @@ __global__ void ckd_cost_lw_grad_kernel(const CkdCostParams p, double* __restric
     if (l >= 1) a += (-(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l] - p_hl[l - 1])) * hrf[(size_t)(l - 1) * nband + ib];
     if (l < nlay) a -= (-(ECCKD_ACCEL_GRAVITY / ECCKD_SPECIFIC_HEAT_AIR) / (p_hl[l + 1] - p_hl[l])) * hrf[(size_t)l * nband + ib];
     gd[j] += a;
-    gu[j] -= a;
+    if (!p.sw) gu[j] -= a;  // heating_rate.h:38-42: the shortwave passes an empty upwelling
   }
   __syncthreads();
   // ---- reverse sweeps per g point
   for (int g = threadIdx.x; g < ng; g += blockDim.x) {
+    if (p.sw) {
+      const int ib = p.band_mapping ? p.band_mapping[g] : g;
+      const double* rd = p.rel_dn ? p.rel_dn + (size_t)ip * nlev * ng + g : nullptr;
+      const double* ru = p.rel_up ? p.rel_up + (size_t)ip * nlev * ng + g : nullptr;
+      const double inv_mu0 = 1.0 / p.cos_sza[ip];
+      double a = 0.0;
+      // up(l) = up(l+1) exp(-2 tau(l)): d up(l) / d tau(l) = -2 up(l); walked from the top down
+      if (!p.direct_only) {
+        a = gu[ib];
+        for (int l = 0; l < nlay; ++l) {
+          const double up_l = fuo[(size_t)l * ng + g] + (ru ? ru[(size_t)l * ng] : 0.0);  // raw flux_up(l)
+          g_out[(size_t)l * ng + g] = -2.0 * a * up_l;
+          a = a * exp(-2.0 * fmax(od[(size_t)l * ng + g], 0.0)) + gu[(size_t)(l + 1) * nband + ib];
+        }
+      } else {
+        for (int l = 0; l < nlay; ++l) g_out[(size_t)l * ng + g] = 0.0;
+      }
+      // up(nlay) = albedo dn(nlay); dn(l+1) = dn(l) exp(-tau(l) / mu0): d dn(l+1) / d tau(l) = -dn(l+1) / mu0
+      double d = gd[(size_t)nlay * nband + ib] + (p.direct_only ? 0.0 : a * p.albedo[p.band_mapping[g]]);
+      if (p.spectral_boundary_weights && p.spectral_flux_dn_surf)
+        d += 2.0 * p.spectral_boundary_weights[g] * (fdo[(size_t)nlay * ng + g] - p.spectral_flux_dn_surf[(size_t)ip * ng + g]);
+      for (int l = nlay - 1; l >= 0; --l) {
+        const double tau_raw = od[(size_t)l * ng + g];
+        const double dn_next = fdo[(size_t)(l + 1) * ng + g] + (rd ? rd[(size_t)(l + 1) * ng] : 0.0);  // raw flux_dn(l+1)
+        double gt = g_out[(size_t)l * ng + g] - d * dn_next * inv_mu0;
+        if (tau_raw < 0.0) gt = 2.0 * p.negative_od_penalty * tau_raw;
+        g_out[(size_t)l * ng + g] = gt;
+        d = d * exp(-inv_mu0 * fmax(tau_raw, 0.0)) + gd[(size_t)l * nband + ib];
+      }
+      continue;
+    }
     const double* pl = p.planck_hl + (size_t)ip * nlev * ng + g;
     const int ib = p.band_mapping ? p.band_mapping[g] : g;
     const double* rd = p.rel_dn ? p.rel_dn + (size_t)ip * nlev * ng + g : nullptr;
@@ -1376,9 +1433,9 @@ ECCKD_API int ecckd_cost_function_ckd_lw_grad_dev(
   ECCKD_REQUIRE(smem + sizeof(CkdCostParams) + 64 <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
                 "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, ng, nlev, smem,
                 ctx->smem_optin);
-  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_lw_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int threads = std::min(1024, std::max(128, (ng + 31) / 32 * 32));
-  ckd_cost_lw_grad_kernel<<<nprof, threads, smem, ctx->stream>>>(p, d_grad_optical_depth);
+  ckd_cost_grad_kernel<<<nprof, threads, smem, ctx->stream>>>(p, d_grad_optical_depth);
   ECCKD_LAUNCH_CHECK(ctx);
   return ECCKD_OK;
 }
@@ -1421,6 +1478,57 @@ ECCKD_API int ecckd_cost_function_ckd_sw_dev(
   p.broadband_weight = broadband_weight; p.negative_od_penalty = negative_od_penalty;
   p.pressure_weight_power = pressure_weight_power;
   return launch_ckd_cost(ctx, p, d_cost_profile, d_cost_total, d_penalty_total, d_cost_fn_per_band, who);
+}
+
+ECCKD_API int ecckd_cost_function_ckd_sw_grad_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_cos_sza, const double* d_pressure_hl,
+    const double* d_ssi, int nalbedo, const double* h_albedo, const double* d_optical_depth, const double* d_flux_dn,
+    const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf, double flux_weight,
+    double flux_profile_weight, double broadband_weight, const double* d_spectral_boundary_weights,
+    const double* d_layer_weight, double pressure_weight_power, double negative_od_penalty,
+    const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up, const int32_t* d_band_mapping,
+    double* d_grad_optical_depth) {
+  ECCKD_DEVICE(ctx);
+  const char* who = "ecckd_cost_function_ckd_sw_grad";
+  ECCKD_REQUIRE(ctx && d_cos_sza && d_pressure_hl && d_ssi && h_albedo && nalbedo > 0 && d_optical_depth && d_flux_dn &&
+                    d_flux_up && d_hr && d_grad_optical_depth,
+                ECCKD_PARAMETER_ERROR, "%s: NULL argument", who);
+  ECCKD_REQUIRE((d_relative_ckd_flux_dn == nullptr) == (d_relative_ckd_flux_up == nullptr), ECCKD_PARAMETER_ERROR,
+                "%s: relative-to fluxes must both be given or both be NULL", who);
+  ECCKD_REQUIRE(nprof > 0 && nlay > 0 && ng > 0 && nband > 0 && (d_band_mapping || nband == ng), ECCKD_PARAMETER_ERROR,
+                "%s: bad dimensions", who);
+  bool all_le0 = true, all_gt0 = true;  // calc_cost_function_sw.cpp:149,250
+  for (int k = 0; k < nalbedo; ++k) {
+    if (!(h_albedo[k] <= 0.0)) all_le0 = false;
+    if (!(h_albedo[k] > 0.0)) all_gt0 = false;
+  }
+  ECCKD_REQUIRE(all_le0 || d_band_mapping, ECCKD_PARAMETER_ERROR,
+                "%s: a non-zero albedo is indexed by band_mapping (calc_cost_function_sw.cpp:156)", who);
+  void* d_alb = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 3, (size_t)nalbedo * sizeof(double), &d_alb));
+  ECCKD_TRY(upload_small(ctx, d_alb, h_albedo, (size_t)nalbedo * sizeof(double)));
+  CkdCostParams p = {};
+  trans_const256_init(&p.tc, ECCKD_LW_DIFFUSIVITY);
+  p.sw = 1; p.nprof = nprof; p.nlay = nlay; p.ng = ng; p.nband = nband; p.nalbedo = nalbedo;
+  p.up_in_bb = all_gt0 ? 1 : 0; p.direct_only = all_le0 ? 1 : 0;
+  p.cos_sza = d_cos_sza; p.pressure_hl = d_pressure_hl; p.ssi = d_ssi; p.albedo = static_cast<double*>(d_alb);
+  p.optical_depth = d_optical_depth; p.flux_dn = d_flux_dn; p.flux_up = d_flux_up; p.hr = d_hr;
+  p.spectral_flux_dn_surf = d_spectral_flux_dn_surf; p.spectral_boundary_weights = d_spectral_boundary_weights;
+  p.layer_weight = d_layer_weight; p.rel_dn = d_relative_ckd_flux_dn; p.rel_up = d_relative_ckd_flux_up;
+  p.band_mapping = d_band_mapping; p.flux_weight = flux_weight; p.flux_profile_weight = flux_profile_weight;
+  p.broadband_weight = broadband_weight; p.negative_od_penalty = negative_od_penalty;
+  p.pressure_weight_power = pressure_weight_power;
+  const int nlev = nlay + 1;
+  const size_t ndbl = (size_t)2 * nlev * ng + (size_t)2 * nlev * nband + (size_t)nlay * nband + 2 * nlay + 2 * nlev + nlay + 256;
+  const size_t smem = ndbl * sizeof(double);
+  ECCKD_REQUIRE(smem + sizeof(CkdCostParams) + 64 <= ctx->smem_optin, ECCKD_PARAMETER_ERROR,
+                "%s: %d g points x %d levels need %zu B of shared memory per profile (limit %zu)", who, ng, nlev, smem,
+                ctx->smem_optin);
+  ECCKD_CUDA_OK(cudaFuncSetAttribute(ckd_cost_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = std::min(1024, std::max(128, (ng + 31) / 32 * 32));
+  ckd_cost_grad_kernel<<<nprof, threads, smem, ctx->stream>>>(p, d_grad_optical_depth);
+  ECCKD_LAUNCH_CHECK(ctx);
+  return ECCKD_OK;
 }
 
 // ------------------------------------------------------------------ several scenes in one launch

@@ -743,6 +743,20 @@ int ecckd_cost_function_ckd_sw_dev(
     const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_profile, double* d_cost_total,
     double* d_penalty_total);
 
+/* Reverse mode of the above: d_grad_optical_depth[nprof][nlay][ng] = derivative of (sum over the profiles of
+ * calc_cost_function_ckd_sw, src/ecckd/calc_cost_function_sw.cpp:115-277, + the negative-optical-depth penalty) with
+ * respect to d_optical_depth: adjoints of the quadratic terms (the 20-fold TOA upwelling term, the broadband part only
+ * when broadband_weight > 0, the upwelling in it only when every albedo is positive), of the direct-beam heating rate
+ * and of the two exponential recurrences of radiative_transfer_sw.cpp:24-77. */
+int ecckd_cost_function_ckd_sw_grad_dev(
+    ecckd_ctx* ctx, int nprof, int nlay, int ng, int nband, const double* d_cos_sza, const double* d_pressure_hl,
+    const double* d_ssi, int nalbedo, const double* h_albedo, const double* d_optical_depth, const double* d_flux_dn,
+    const double* d_flux_up, const double* d_hr, const double* d_spectral_flux_dn_surf, double flux_weight,
+    double flux_profile_weight, double broadband_weight, const double* d_spectral_boundary_weights,
+    const double* d_layer_weight, double pressure_weight_power, double negative_od_penalty,
+    const double* d_relative_ckd_flux_dn, const double* d_relative_ckd_flux_up, const int32_t* d_band_mapping,
+    double* d_grad_optical_depth);
+
 /* The forward cost of several scenes of optimize_lut's training set in ONE launch: the loop over
  * LblFluxes objects of src/ecckd/solve_adept.cpp:96-199 (each iteration = one call of the two entry
  * points above).  A scene's kernel has only nprof CTAs (50-150) and is latency-bound on its own; the

@@ -485,3 +485,55 @@ def test_gradient_with_respect_to_the_look_up_tables_end_to_end(ctx, O):
             assert abs(fd - an) <= 1.0e-5 * abs(an) + 1e-9 * abs(costs[0]) / abs(h), (igas, idx, fd, an)
             checked += 1
     assert checked == 6
+
+
+@pytest.mark.parametrize("albedo_on", [True, False])
+@pytest.mark.parametrize("weights", [(0.2, 0.2, 0.8), (0.5, 0.0, 0.0)])
+def test_cost_function_ckd_sw_gradient_matches_finite_differences(ctx, O, albedo_on, weights):
+    """The hand-written reverse mode of the shortwave cost (calc_cost_function_sw.cpp:115-277 + the penalty of
+    solve_adept.cpp:107-116) against central differences of the pinned oracle's forward cost and of the device's:
+    with and without the Lambertian return, with and without the broadband part (no division by nband then)."""
+    nprof, nlay, ng, nband = 3, 18, 16, 5
+    s = _scene(nprof, nlay, ng, nband, seed=15, sw=True)
+    rng, bm = s["rng"], s["bm"]
+    ssi = rng.uniform(1.0, 100.0, ng)
+    albedo = rng.uniform(0.05, 0.5, nband) if albedo_on else np.zeros(nband)
+    mu = rng.uniform(0.2, 1.0, nprof)
+    od = np.abs(s["od"]) * rng.choice([1e-3, 1e-1, 1.0], size=s["od"].shape)
+    od[1, 4, 3] = -0.02  # clamped: only the penalty depends on it
+    t_dn, t_up, hr, lws = [], [], [], []
+    for i in range(nprof):
+        dn, up = O.radiative_transfer_norayleigh_sw(mu[i], ssi, np.maximum(od[i], 0) * 1.2, albedo[bm])
+        dn = np.stack([dn[:, bm == b].sum(1) for b in range(nband)], 1)
+        up = np.stack([up[:, bm == b].sum(1) for b in range(nband)], 1)
+        t_dn.append(dn), t_up.append(up), hr.append(O.heating_rate(s["p"][i], dn, None))
+        lw = np.diff(np.sqrt(s["p"][i]))
+        lws.append(lw / lw.sum())
+    t_dn, t_up, hr, lws = np.stack(t_dn), np.stack(t_up), np.stack(hr), np.stack(lws)
+    sbw, sfd = rng.uniform(0, 1, ng), rng.uniform(0, 5, (nprof, ng))
+    pen = 30.0
+    kw = dict(layer_weight=lws, negative_od_penalty=pen, spectral_boundary_weights=sbw, spectral_flux_dn_surf=sfd,
+              band_mapping=bm)
+
+    def cost_oracle(x):
+        c = pen * float((np.minimum(x, 0.0) ** 2).sum())
+        for i in range(nprof):
+            c += O.calc_cost_function_ckd_sw(mu[i], s["p"][i], ssi, albedo, np.maximum(x[i], 0.0), t_dn[i], t_up[i], hr[i],
+                                             *weights, lws[i], spectral_boundary_weights=sbw, spectral_flux_dn_surf=sfd[i],
+                                             spectral_flux_up_toa=sfd[i], band_mapping=bm)
+        return c
+
+    def cost_device(x):
+        return E.cost_function_ckd_sw(ctx, mu, s["p"], ssi, albedo, x, t_dn, t_up, hr, *weights, **kw)["cost_total"]
+
+    grad = E.cost_function_ckd_sw_grad(ctx, mu, s["p"], ssi, albedo, od, t_dn, t_up, hr, *weights, **kw)
+    assert grad.shape == od.shape and np.all(np.isfinite(grad))
+    assert grad[1, 4, 3] == 2 * pen * od[1, 4, 3]
+    free = od > 0.0
+    for k in range(4):
+        v = rng.normal(size=od.shape) * od * free
+        h = 1.0e-4
+        for cost in (cost_oracle, cost_device):
+            fd = (cost(od + h * v) - cost(od - h * v)) / (2 * h)
+            an = float((grad * v).sum())
+            assert abs(fd - an) <= 5.0e-6 * max(abs(an), abs(fd)) + 2e-9 * abs(cost(od)), (k, cost.__name__, fd, an)
