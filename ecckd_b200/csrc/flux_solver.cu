@@ -1611,24 +1611,45 @@ __global__ void __launch_bounds__(ADJ_WARPS * 32) od_adjoint_gather_kernel(const
     const int g = min(g0 + lane, p.ng - 1);
     for (int a = 0; a < p.nacc; ++a) acc[a * 32 + lane] = 0.0;
     __syncwarp();
-    for (int64_t cl = lo; cl < hi; ++cl) {
-      const int key = p.key[cl];  // warp-uniform
-      const int it0 = key / p.np, ip0 = key - it0 * p.np;
-      const int dt = it - it0, dp = ip - ip0;
-      if ((unsigned)dt > 1u || (unsigned)dp > 1u) continue;  // the cell of this cl does not touch the node
-      const double c = p.corner[(int64_t)(dt * 2 + dp) * ncl + cl];
-      const double gt = p.grad_od[cl * p.ng + g] * c;
-      for (int ig = 0; ig < p.ngas; ++ig) {
-        if (!p.grad[ig]) continue;
-        const double w = p.w[(int64_t)ig * ncl + cl];
-        double* a = acc + (size_t)p.acc_off[ig] * 32 + lane;
-        if (p.conc_dependence[ig] == ECCKD_CONC_LUT) {
-          const int ic0 = p.ic0[(int64_t)ig * ncl + cl];
-          const double cw1 = p.cw1[(int64_t)ig * ncl + cl];
-          a[(size_t)ic0 * 32] += gt * (w * (1.0 - cw1));
-          a[(size_t)(ic0 + 1) * 32] += gt * (w * cw1);
-        } else {
-          a[0] += gt * w;
+    // 32 records are tested at a time (lane = record), the ones whose cell touches the node are then taken in
+    // ascending order (lane = g point): the order of the additions is that of a serial scan
+    for (int64_t base = lo; base < hi; base += 32) {
+      const int64_t mine = base + lane;
+      int corner_of = -1;
+      if (mine < hi) {
+        const int key = p.key[mine];
+        const int it0 = key / p.np, ip0 = key - it0 * p.np;
+        const int dt = it - it0, dp = ip - ip0;
+        if ((unsigned)dt <= 1u && (unsigned)dp <= 1u) corner_of = dt * 2 + dp;
+      }
+      unsigned hits = __ballot_sync(0xffffffffu, corner_of >= 0);
+      while (hits) {  // warp-uniform
+        const int j = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int64_t cl = base + j;
+        const int cn = __shfl_sync(0xffffffffu, corner_of, j);
+        const double c = p.corner[(int64_t)cn * ncl + cl];
+        const double gt = p.grad_od[cl * p.ng + g] * c;
+        // the per-gas fields of the record: lane ig fetches gas ig's (one memory latency for all gases), then broadcast
+        double w_l = 0.0, cw_l = 0.0;
+        int ic_l = 0;
+        if (lane < p.ngas) {
+          w_l = p.w[(int64_t)lane * ncl + cl];
+          cw_l = p.cw1[(int64_t)lane * ncl + cl];
+          ic_l = p.ic0[(int64_t)lane * ncl + cl];
+        }
+        for (int ig = 0; ig < p.ngas; ++ig) {
+          const double w = __shfl_sync(0xffffffffu, w_l, ig);
+          const double cw1 = __shfl_sync(0xffffffffu, cw_l, ig);
+          const int ic0 = __shfl_sync(0xffffffffu, ic_l, ig);
+          if (!p.grad[ig]) continue;  // warp-uniform
+          double* a = acc + (size_t)p.acc_off[ig] * 32 + lane;
+          if (p.conc_dependence[ig] == ECCKD_CONC_LUT) {
+            a[(size_t)ic0 * 32] += gt * (w * (1.0 - cw1));
+            a[(size_t)(ic0 + 1) * 32] += gt * (w * cw1);
+          } else {
+            a[0] += gt * w;
+          }
         }
       }
     }

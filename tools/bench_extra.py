@@ -110,6 +110,39 @@ ms = timed(cost_scene, n=10, warm=2)
 out["forward_cost_lw_batched"] = {"ms_per_5000_profiles": ms, "columns_x_g_per_s": nprof * ng / (ms * 1e-3),
                                   "config": "the same 5000 profiles as one batch"}
 
+# ---- the reverse mode of the same 5000 profiles: dJ/dtau, then its transpose of the look-up-table
+# interpolation into the tables of an 8-gas model
+grad_od = torch.empty((nprof, nlay, ng), dtype=torch.float64, device=dev)
+
+
+def grad_scene():
+    s = scene
+    E.check(L.ecckd_cost_function_ckd_lw_grad_dev(
+        ctx.handle, nprof, nlay, ng, nband, s["p"].data_ptr(), s["planck"].data_ptr(), s["emis"].data_ptr(),
+        s["surf"].data_ptr(), s["od"].data_ptr(), s["dn"].data_ptr(), s["up"].data_ptr(), s["hr"].data_ptr(), None, None,
+        0.2, 0.2, 0.8, 0.0, None, 0.5, 1.0e4, None, None, bm.data_ptr(), grad_od.data_ptr()))
+
+
+ms = timed(grad_scene, n=10, warm=2)
+out["gradient_cost_lw_batched"] = {"ms_per_5000_profiles": ms, "columns_x_g_per_s": nprof * ng / (ms * 1e-3),
+                                   "config": "ecckd_cost_function_ckd_lw_grad_dev on the same 5000 profiles x 54 layers x 64 g points"}
+try:
+    from tests import synthetic as S
+    ck = S.ckd_model_case(ncol=64, nlay=nlay, ng=ng, seed=1234)
+    model = E.CkdModel(ctx, ck["gases"], ck["log_pressure"], ck["temperature"], ck["temperature_planck"], ck["planck_lut"])
+    rep = (nprof + 63) // 64
+    tile = lambda a: torch.from_numpy(np.ascontiguousarray(np.tile(a, (rep, 1))[:nprof])).to(dev)
+    p_hl, t_hl = tile(ck["pressure_hl"]), tile(ck["temperature_hl"])
+    vmr = [None if v is None else tile(v) for v in ck["vmr_fl"]]
+    grads = [torch.zeros(np.asarray(g["molar_abs"]).shape, dtype=torch.float64, device=dev) for g in ck["gases"]]
+    ms = timed(lambda: model.calc_total_optical_depth_adjoint_dev(vmr, nprof, nlay, p_hl, t_hl, grad_od, grads), n=5, warm=2)
+    out["gradient_lut_adjoint"] = {"ms_per_5000_profiles": ms,
+                                   "config": "ecckd_calc_total_optical_depth_adjoint_dev: dJ/dtau of 5000 profiles x 54 layers x 64 g "
+                                             "points gathered into the tables of 8 gases (one with 12 concentrations), fixed order"}
+    model.close()
+except Exception as exc:  # noqa: BLE001
+    out["gradient_lut_adjoint"] = {"error": repr(exc)}
+
 # ---- ranking (config D): 2^23 keys, 13 bands
 nw = 1 << 23
 wn = torch.linspace(0.0002, 3260.0, nw, dtype=torch.float64, device=dev)
