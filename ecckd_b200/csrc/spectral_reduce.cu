@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
                                                                      const uint32_t* __restrict__ round_off,
                                                                      PlanRound* __restrict__ rounds,
                                                                      int32_t* __restrict__ rmin,
-                                                                     int32_t* __restrict__ rmax) {
+                                                                     int32_t* __restrict__ rmax,
+                                                                     unsigned* __restrict__ g_sinfo) {
   __shared__ int sg[CH_MAX];
   __shared__ int sred[33];
   // per wavenumber: bits 0-9 chunk-local round, 10 half-warp, 11-15 physical lane, 16-19 colour (slot),
@@ -340,8 +341,6 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
   __shared__ short slead[CH_MAX];             // first wavenumber (thread) of the same (g point, round)
   __shared__ unsigned char scls[CH_MAX][16];  // [leader][class]: wavenumbers of the (g point, round) per class
   __shared__ unsigned char sa0[CH_MAX][16];   // [leader][class]: how many of them go to half-warp 0
-  __shared__ short scolL[BAL_TASKS][16][16];  // [task][lane][colour] -> wavenumber or -1
-  __shared__ short scolR[BAL_TASKS][16][16];  // [task][class][colour] -> wavenumber or -1
   const int i = threadIdx.x;
   const int ch = (int)blockDim.x;
   const int64_t c = blockIdx.x;
@@ -415,129 +414,164 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
     sinfo[i] |= ((unsigned)h << 10) | ((unsigned)phys << 11);
   }
   __syncthreads();
-  // one colouring task per (round, half-warp), each run by lane 0 of its own warp (tasks are serial
-  // code: sharing a warp would serialise them)
-  const int ntask = 2 * (int)(r1 - r0);
-  const int ntb = min(BAL_TASKS, ch >> 5);
-  for (int base = 0; base < ntask; base += ntb) {
-    for (int x = i; x < BAL_TASKS * 256; x += ch) {
-      (&scolL[0][0][0])[x] = -1;
-      (&scolR[0][0][0])[x] = -1;
-    }
-    __syncthreads();
-    if ((i & 31) == 0 && (i >> 5) < ntb && base + (i >> 5) < ntask) {
-      const int ts = i >> 5, task = base + ts, rt = task >> 1, ht = task & 1;
-      short (*CL)[16] = scolL[ts];
-      short (*CR)[16] = scolR[ts];
-      auto colour_of = [&](int e) { return (int)((sinfo[e] >> 16) & 15u); };
-      auto is_half = [&](int e) { return ((sinfo[e] >> 20) & 1u) != 0; };
-      auto lane_of = [&](int e) { return (int)((sinfo[e] >> 11) & 15u); };
-      auto set_colour = [&](int e, int col) { sinfo[e] = (sinfo[e] & ~(15u << 16)) | ((unsigned)col << 16); };
-      for (int e = 0; e < ch; ++e) {
-        const unsigned inf = sinfo[e];
-        if (!(inf >> 31) || (inf & 0x3ffu) != (unsigned)rt || ((inf >> 10) & 1u) != (unsigned)ht) continue;
-        const int ln = (int)((inf >> 11) & 15u), q = e & 15;
-        int ca = 0, cb = 0;
-        while (ca < 16 && CL[ln][ca] >= 0) ++ca;
-        while (cb < 16 && CR[q][cb] >= 0) ++cb;
-        if (ca == 16) ca = 15;  // cannot happen: a lane holds at most 16 wavenumbers
-        if (cb == 16) {         // the class already has 16 wavenumbers in this half-warp: lane-proper only
-          CL[ln][ca] = (short)e;
-          sinfo[e] |= 1u << 20;
-          set_colour(e, ca);
-          continue;
-        }
-        if (CR[q][ca] >= 0) {
-          // colour ca is taken at the class by another lane: flip the ca/cb alternating path that
-          // starts there (it cannot reach lane ln, which has no ca edge)
-          short path[40];
-          int np = 0;
-          int x = CR[q][ca], cx = ca;
-          while (x >= 0 && np < 40) {
-            path[np++] = (short)x;
-            if (cx == ca) {
-              x = CL[lane_of(x)][cb];
-              cx = cb;
-            } else {
-              if (is_half(x)) break;
-              x = CR[x & 15][ca];
-              cx = ca;
-            }
-          }
-          for (int k = 0; k < np; ++k) {
-            const int y = path[k], cy = colour_of(y);
-            CL[lane_of(y)][cy] = -1;
-            if (!is_half(y)) CR[y & 15][cy] = -1;
-          }
-          for (int k = 0; k < np; ++k) {
-            const int y = path[k], cy = colour_of(y) == ca ? cb : ca;
-            CL[lane_of(y)][cy] = (short)y;
-            if (!is_half(y)) CR[y & 15][cy] = (short)y;
-            set_colour(y, cy);
-          }
-        }
-        if (CL[ln][ca] >= 0 || CR[q][ca] >= 0) {
-          // (defensive: the flip could not free the colour - keep the plan valid with a lane-proper colour)
-          int cf = 0;
-          while (cf < 15 && CL[ln][cf] >= 0) ++cf;
-          CL[ln][cf] = (short)e;
-          sinfo[e] |= 1u << 20;
-          set_colour(e, cf);
-          continue;
-        }
+  // the colouring of the (round, half-warp) cells is serial per cell set: plan_colour_kernel gives every set a warp
+  g_sinfo[(size_t)c * ch + i] = sinfo[i];
+}
+
+// One (round, half-warp) colouring task per warp: lane 0 runs the serial edge colouring and writes the cells, the
+// other lanes only help to stage the chunk's per-wavenumber words and to clear the colour tables.  (Inside
+// plan_fill_balanced_kernel the two tasks of a chunk kept 14 warps of its block waiting at a barrier - 80 % of the
+// kernel's stall samples - and only 4 tasks ran per SM; here up to 32 do.)
+constexpr int COL_WARPS = 8;
+__global__ void __launch_bounds__(COL_WARPS * 32) plan_colour_kernel(int64_t nrounds, int ch,
+                                                                       const uint32_t* __restrict__ round_off,
+                                                                       PlanRound* __restrict__ rounds,
+                                                                       const unsigned* __restrict__ g_sinfo) {
+  __shared__ unsigned s_info[COL_WARPS][CH_MAX];
+  __shared__ short scolL[COL_WARPS][16][16];  // [warp][lane][colour] -> wavenumber or -1
+  __shared__ short scolR[COL_WARPS][16][16];  // [warp][class][colour] -> wavenumber or -1
+  __shared__ unsigned sused[COL_WARPS][32];   // [warp][lane | 16 + class]: bit mask of the colours taken (the occupancy of
+                                              // scolL / scolR as bits, so that "lowest free colour" is one find-first-set)
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t task = (int64_t)blockIdx.x * COL_WARPS + wib;
+  if (task >= 2 * nrounds) return;
+  const int64_t r = task >> 1;
+  const int ht = (int)(task & 1);
+  const int64_t c = rounds[r].chunk;
+  const uint32_t r0 = round_off[c];
+  const int rt = (int)(r - r0);
+  unsigned* sinfo = s_info[wib];
+  for (int x = lane; x < ch; x += 32) sinfo[x] = g_sinfo[(size_t)c * ch + x];
+  for (int x = lane; x < 256; x += 32) {
+    (&scolL[wib][0][0])[x] = -1;
+    (&scolR[wib][0][0])[x] = -1;
+  }
+  __syncwarp();
+  if (lane != 0) return;
+  {
+    short (*CL)[16] = scolL[wib];
+    short (*CR)[16] = scolR[wib];
+    unsigned* UL = sused[wib];
+    unsigned* UR = sused[wib] + 16;
+    for (int x = 0; x < 32; ++x) UL[x] = 0u;
+    auto colour_of = [&](int e) { return (int)((sinfo[e] >> 16) & 15u); };
+    auto is_half = [&](int e) { return ((sinfo[e] >> 20) & 1u) != 0; };
+    auto lane_of = [&](int e) { return (int)((sinfo[e] >> 11) & 15u); };
+    auto set_colour = [&](int e, int col) { sinfo[e] = (sinfo[e] & ~(15u << 16)) | ((unsigned)col << 16); };
+    for (int e = 0; e < ch; ++e) {
+      const unsigned inf = sinfo[e];
+      if (!(inf >> 31) || (inf & 0x3ffu) != (unsigned)rt || ((inf >> 10) & 1u) != (unsigned)ht) continue;
+      const int ln = (int)((inf >> 11) & 15u), q = e & 15;
+      int ca = __ffs(~UL[ln] & 0xffffu) - 1, cb = __ffs(~UR[q] & 0xffffu) - 1;  // lowest free colour at the lane / class
+      if (cb < 0) cb = 16;
+      if (ca < 0) ca = 15;  // cannot happen: a lane holds at most 16 wavenumbers
+      if (cb == 16) {         // the class already has 16 wavenumbers in this half-warp: lane-proper only
         CL[ln][ca] = (short)e;
-        CR[q][ca] = (short)e;
+        UL[ln] |= 1u << ca;
+        sinfo[e] |= 1u << 20;
         set_colour(e, ca);
+        continue;
       }
-      // write the half-warp's 16 x 16 cells
-      PlanRound& rd = rounds[r0 + rt];
-      int lane_g[16];
-      unsigned mask[16];
-      for (int ln = 0; ln < 16; ++ln) {
-        lane_g[ln] = (int)(rd.meta[ln + 16 * ht] & 0xFFFu);
-        mask[ln] = 0u;
-        bool any = false;
-        for (int s = 0; s < 16; ++s) any = any || CL[ln][s] >= 0;
-        if (!any) lane_g[ln] = (int)NO_G;
-      }
-      for (int s = 0; s < 16; ++s) {
-        int shared_e = -1;  // what the unused lanes of the half-warp read: the address of a used lane (broadcast)
-        for (int ln = 0; ln < 16; ++ln) {
-          if (lane_g[ln] == (int)NO_G) continue;
-          int e = CL[ln][s];
-          if (e >= 0) {
-            mask[ln] |= 1u << s;
+      if (CR[q][ca] >= 0) {
+        // colour ca is taken at the class by another lane: flip the ca/cb alternating path that
+        // starts there (it cannot reach lane ln, which has no ca edge)
+        short path[40];
+        int np = 0;
+        int x = CR[q][ca], cx = ca;
+        while (x >= 0 && np < 40) {
+          path[np++] = (short)x;
+          if (cx == ca) {
+            x = CL[lane_of(x)][cb];
+            cx = cb;
           } else {
-            // padding: an address another lane of this g point reads in this slot, else an own
-            // wavenumber of a class nobody reads in this slot, else any own wavenumber
-            for (int l2 = 0; l2 < 16 && e < 0; ++l2)
-              if (lane_g[l2] == lane_g[ln] && CL[l2][s] >= 0) e = CL[l2][s];
-            int own = -1;
-            for (int s2 = 0; s2 < 16 && e < 0; ++s2) {
-              const int y = CL[ln][s2];
-              if (y < 0) continue;
-              if (own < 0) own = y;
-              if (CR[y & 15][s] < 0) {
-                e = y;
-                CR[y & 15][s] = (short)y;  // the class is now read in this slot
-              }
-            }
-            if (e < 0) e = own;
+            if (is_half(x)) break;
+            x = CR[x & 15][ca];
+            cx = ca;
           }
-          rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
-          if (shared_e < 0) shared_e = e;
         }
-        // an unused lane still issues its loads (weight zero, sums discarded): offset 0 would add an
-        // address of bank pair 0 to every slot, i.e. a conflict whenever a used lane reads that pair
-        if (shared_e >= 0) {
-          for (int ln = 0; ln < 16; ++ln)
-            if (lane_g[ln] == (int)NO_G) rd.off[s][ln + 16 * ht] = (uint16_t)(shared_e * 8);
+        for (int k = 0; k < np; ++k) {
+          const int y = path[k], cy = colour_of(y);
+          CL[lane_of(y)][cy] = -1;
+          UL[lane_of(y)] &= ~(1u << cy);
+          if (!is_half(y)) {
+            CR[y & 15][cy] = -1;
+            UR[y & 15] &= ~(1u << cy);
+          }
+        }
+        for (int k = 0; k < np; ++k) {
+          const int y = path[k], cy = colour_of(y) == ca ? cb : ca;
+          CL[lane_of(y)][cy] = (short)y;
+          UL[lane_of(y)] |= 1u << cy;
+          if (!is_half(y)) {
+            CR[y & 15][cy] = (short)y;
+            UR[y & 15] |= 1u << cy;
+          }
+          set_colour(y, cy);
         }
       }
-      for (int ln = 0; ln < 16; ++ln)
-        rd.meta[ln + 16 * ht] = lane_g[ln] == (int)NO_G ? NO_G : ((unsigned)lane_g[ln] | (mask[ln] << 12));
+      if (CL[ln][ca] >= 0 || CR[q][ca] >= 0) {
+        // (defensive: the flip could not free the colour - keep the plan valid with a lane-proper colour)
+        int cf = __ffs(~UL[ln] & 0x7fffu) - 1;
+        if (cf < 0) cf = 15;
+        CL[ln][cf] = (short)e;
+        UL[ln] |= 1u << cf;
+        sinfo[e] |= 1u << 20;
+        set_colour(e, cf);
+        continue;
+      }
+      CL[ln][ca] = (short)e;
+      CR[q][ca] = (short)e;
+      UL[ln] |= 1u << ca;
+      UR[q] |= 1u << ca;
+      set_colour(e, ca);
     }
-    __syncthreads();
+    // write the half-warp's 16 x 16 cells
+    PlanRound& rd = rounds[r0 + rt];
+    int lane_g[16];
+    unsigned mask[16];
+    for (int ln = 0; ln < 16; ++ln) {
+      lane_g[ln] = (int)(rd.meta[ln + 16 * ht] & 0xFFFu);
+      mask[ln] = 0u;
+      bool any = false;
+      for (int s = 0; s < 16; ++s) any = any || CL[ln][s] >= 0;
+      if (!any) lane_g[ln] = (int)NO_G;
+    }
+    for (int s = 0; s < 16; ++s) {
+      int shared_e = -1;  // what the unused lanes of the half-warp read: the address of a used lane (broadcast)
+      for (int ln = 0; ln < 16; ++ln) {
+        if (lane_g[ln] == (int)NO_G) continue;
+        int e = CL[ln][s];
+        if (e >= 0) {
+          mask[ln] |= 1u << s;
+        } else {
+          // padding: an address another lane of this g point reads in this slot, else an own
+          // wavenumber of a class nobody reads in this slot, else any own wavenumber
+          for (int l2 = 0; l2 < 16 && e < 0; ++l2)
+            if (lane_g[l2] == lane_g[ln] && CL[l2][s] >= 0) e = CL[l2][s];
+          int own = -1;
+          for (int s2 = 0; s2 < 16 && e < 0; ++s2) {
+            const int y = CL[ln][s2];
+            if (y < 0) continue;
+            if (own < 0) own = y;
+            if (CR[y & 15][s] < 0) {
+              e = y;
+              CR[y & 15][s] = (short)y;  // the class is now read in this slot
+            }
+          }
+          if (e < 0) e = own;
+        }
+        rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
+        if (shared_e < 0) shared_e = e;
+      }
+      // an unused lane still issues its loads (weight zero, sums discarded): offset 0 would add an
+      // address of bank pair 0 to every slot, i.e. a conflict whenever a used lane reads that pair
+      if (shared_e >= 0) {
+        for (int ln = 0; ln < 16; ++ln)
+          if (lane_g[ln] == (int)NO_G) rd.off[s][ln + 16 * ht] = (uint16_t)(shared_e * 8);
+      }
+    }
+    for (int ln = 0; ln < 16; ++ln)
+      rd.meta[ln + 16 * ht] = lane_g[ln] == (int)NO_G ? NO_G : ((unsigned)lane_g[ln] | (mask[ln] << 12));
   }
 }
 
@@ -2257,6 +2291,7 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
   uint32_t* d_nrounds = nullptr;
   unsigned long long* d_nfree = nullptr;
   int32_t* d_rminmax = nullptr;
+  unsigned* d_sinfo = nullptr;  // balanced plans: the per-wavenumber words handed from the fill to the colouring kernel
   cudaError_t e = cudaMallocAsync(&p->d_round_off, (size_t)(max_chunks + 1) * sizeof(uint32_t), ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nrounds, (size_t)max_chunks * sizeof(uint32_t), ctx->stream);
   if (e == cudaSuccess) e = cudaMallocAsync(&d_nfree, sizeof(unsigned long long), ctx->stream);
@@ -2343,10 +2378,16 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
       plan_init_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, ctx->stream>>>((int64_t)nr, p->d_rounds, d_rminmax,
                                                                                     d_rminmax + nr);
       p->balanced = best_w > 0 && balance;
-      if (p->balanced)
-        plan_fill_balanced_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(
-            d_g_point, nwav, ng, best_w, p->d_round_off, p->d_rounds, d_rminmax, d_rminmax + nr);
-      else
+      if (p->balanced) {
+        e = cudaMallocAsync(&d_sinfo, (size_t)p->nchunks * best_ch * sizeof(unsigned), ctx->stream);
+        if (e == cudaSuccess) {
+          plan_fill_balanced_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(
+              d_g_point, nwav, ng, best_w, p->d_round_off, p->d_rounds, d_rminmax, d_rminmax + nr, d_sinfo);
+          plan_colour_kernel<<<(unsigned)((2 * nr + COL_WARPS - 1) / COL_WARPS), COL_WARPS * 32, 0, ctx->stream>>>(
+              (int64_t)total, best_ch, p->d_round_off, p->d_rounds, d_sinfo);
+          ctx->launches++;
+        }
+      } else
         plan_fill_kernel<<<(unsigned)p->nchunks, best_ch, 0, ctx->stream>>>(d_g_point, nwav, ng, best_w, p->d_round_off,
                                                                             p->d_rounds, d_rminmax, d_rminmax + nr);
       ctx->launches += 2;
@@ -2366,6 +2407,7 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // d_g_point may be freed by the caller
   }
   if (d_rminmax) cudaFreeAsync(d_rminmax, ctx->stream);
+  if (d_sinfo) cudaFreeAsync(d_sinfo, ctx->stream);
   if (d_nfree) cudaFreeAsync(d_nfree, ctx->stream);
   if (d_nrounds) cudaFreeAsync(d_nrounds, ctx->stream);
   if (e != cudaSuccess) {
