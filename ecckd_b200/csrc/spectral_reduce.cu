@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(CH_MAX) plan_fill_balanced_kernel(const int32_
   g_sinfo[(size_t)c * ch + i] = sinfo[i];
 }
 
-// One (round, half-warp) colouring task per warp: lane 0 runs the serial edge colouring and writes the cells, the
-// other lanes only help to stage the chunk's per-wavenumber words and to clear the colour tables.  (Inside
+// One (round, half-warp) colouring task per warp: lane 0 runs the serial edge colouring, then 16 lanes write the
+// cells of one slot each.  (Inside
 // plan_fill_balanced_kernel the two tasks of a chunk kept 14 warps of its block waiting at a barrier - 80 % of the
 // kernel's stall samples - and only 4 tasks ran per SM; here up to 32 do.)
 constexpr int COL_WARPS = 8;
@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) plan_colour_kernel(int64_t nro
   __shared__ unsigned s_info[COL_WARPS][CH_MAX];
   __shared__ short scolL[COL_WARPS][16][16];  // [warp][lane][colour] -> wavenumber or -1
   __shared__ short scolR[COL_WARPS][16][16];  // [warp][class][colour] -> wavenumber or -1
+  __shared__ int slane_g[COL_WARPS][16];      // [warp][lane]: g point of the lane, NO_G when unused
   __shared__ unsigned sused[COL_WARPS][32];   // [warp][lane | 16 + class]: bit mask of the colours taken (the occupancy of
                                               // scolL / scolR as bits, so that "lowest free colour" is one find-first-set)
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -447,8 +448,7 @@ __global__ void __launch_bounds__(COL_WARPS * 32) plan_colour_kernel(int64_t nro
     (&scolR[wib][0][0])[x] = -1;
   }
   __syncwarp();
-  if (lane != 0) return;
-  {
+  if (lane == 0) {
     short (*CL)[16] = scolL[wib];
     short (*CR)[16] = scolR[wib];
     unsigned* UL = sused[wib];
@@ -525,54 +525,55 @@ __global__ void __launch_bounds__(COL_WARPS * 32) plan_colour_kernel(int64_t nro
       UR[q] |= 1u << ca;
       set_colour(e, ca);
     }
-    // write the half-warp's 16 x 16 cells
-    PlanRound& rd = rounds[r0 + rt];
-    int lane_g[16];
-    unsigned mask[16];
-    for (int ln = 0; ln < 16; ++ln) {
-      lane_g[ln] = (int)(rd.meta[ln + 16 * ht] & 0xFFFu);
-      mask[ln] = 0u;
-      bool any = false;
-      for (int s = 0; s < 16; ++s) any = any || CL[ln][s] >= 0;
-      if (!any) lane_g[ln] = (int)NO_G;
-    }
-    for (int s = 0; s < 16; ++s) {
-      int shared_e = -1;  // what the unused lanes of the half-warp read: the address of a used lane (broadcast)
-      for (int ln = 0; ln < 16; ++ln) {
-        if (lane_g[ln] == (int)NO_G) continue;
-        int e = CL[ln][s];
-        if (e >= 0) {
-          mask[ln] |= 1u << s;
-        } else {
-          // padding: an address another lane of this g point reads in this slot, else an own
-          // wavenumber of a class nobody reads in this slot, else any own wavenumber
-          for (int l2 = 0; l2 < 16 && e < 0; ++l2)
-            if (lane_g[l2] == lane_g[ln] && CL[l2][s] >= 0) e = CL[l2][s];
-          int own = -1;
-          for (int s2 = 0; s2 < 16 && e < 0; ++s2) {
-            const int y = CL[ln][s2];
-            if (y < 0) continue;
-            if (own < 0) own = y;
-            if (CR[y & 15][s] < 0) {
-              e = y;
-              CR[y & 15][s] = (short)y;  // the class is now read in this slot
-            }
-          }
-          if (e < 0) e = own;
-        }
-        rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
-        if (shared_e < 0) shared_e = e;
-      }
-      // an unused lane still issues its loads (weight zero, sums discarded): offset 0 would add an
-      // address of bank pair 0 to every slot, i.e. a conflict whenever a used lane reads that pair
-      if (shared_e >= 0) {
-        for (int ln = 0; ln < 16; ++ln)
-          if (lane_g[ln] == (int)NO_G) rd.off[s][ln + 16 * ht] = (uint16_t)(shared_e * 8);
-      }
-    }
-    for (int ln = 0; ln < 16; ++ln)
-      rd.meta[ln + 16 * ht] = lane_g[ln] == (int)NO_G ? NO_G : ((unsigned)lane_g[ln] | (mask[ln] << 12));
   }
+  __syncwarp();
+  // write the half-warp's 16 x 16 cells: the slots are independent of each other (a slot reads the colour tables of
+  // all the lanes but writes only its own column of the class table), so that lane s takes slot s
+  short (*CL)[16] = scolL[wib];
+  short (*CR)[16] = scolR[wib];
+  const unsigned* UL = sused[wib];
+  int* lane_g = slane_g[wib];
+  PlanRound& rd = rounds[r0 + rt];
+  if (lane < 16)  // a lane of the round without a wavenumber in this half-warp is unused
+    lane_g[lane] = UL[lane] ? (int)(rd.meta[lane + 16 * ht] & 0xFFFu) : (int)NO_G;
+  __syncwarp();
+  if (lane >= 16) return;
+  {
+    const int s = lane;
+    int shared_e = -1;  // what the unused lanes of the half-warp read: the address of a used lane (broadcast)
+    for (int ln = 0; ln < 16; ++ln) {
+      if (lane_g[ln] == (int)NO_G) continue;
+      int e = CL[ln][s];
+      if (e < 0) {
+        // padding: an address another lane of this g point reads in this slot, else an own
+        // wavenumber of a class nobody reads in this slot, else any own wavenumber
+        for (int l2 = 0; l2 < 16 && e < 0; ++l2)
+          if (lane_g[l2] == lane_g[ln] && CL[l2][s] >= 0) e = CL[l2][s];
+        int own = -1;
+        for (int s2 = 0; s2 < 16 && e < 0; ++s2) {
+          const int y = CL[ln][s2];
+          if (y < 0) continue;
+          if (own < 0) own = y;
+          if (CR[y & 15][s] < 0) {
+            e = y;
+            CR[y & 15][s] = (short)y;  // the class is now read in this slot
+          }
+        }
+        if (e < 0) e = own;
+      }
+      rd.off[s][ln + 16 * ht] = (uint16_t)(e * 8);
+      if (shared_e < 0) shared_e = e;
+    }
+    // an unused lane still issues its loads (weight zero, sums discarded): offset 0 would add an
+    // address of bank pair 0 to every slot, i.e. a conflict whenever a used lane reads that pair
+    if (shared_e >= 0) {
+      for (int ln = 0; ln < 16; ++ln)
+        if (lane_g[ln] == (int)NO_G) rd.off[s][ln + 16 * ht] = (uint16_t)(shared_e * 8);
+    }
+  }
+  // the mask of the slots that hold a wavenumber of the lane is the occupancy word of its colours
+  rd.meta[lane + 16 * ht] =
+      lane_g[lane] == (int)NO_G ? NO_G : ((unsigned)lane_g[lane] | ((UL[lane] & 0xffffu) << 12));
 }
 
 // Windowed plans: the window base of every round, in round order (one warp; a round keeps the
@@ -581,10 +582,15 @@ __global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __rest
                                    const int32_t* __restrict__ rmax, PlanRound* __restrict__ rounds) {
   const int lane = threadIdx.x;
   int gbase = 0;
+  // the chain over the rounds is serial: keep the memory latencies off it (the next 32 bounds are fetched while the
+  // current ones are folded, and the flag is set by a reduction that nobody waits for)
+  int mn_n = (lane < nrounds) ? rmin[lane] : 0x7fffffff;
+  int mx_n = (lane < nrounds) ? rmax[lane] : -1;
   for (int64_t base = 0; base < nrounds; base += 32) {
     const int64_t r = base + lane;
-    const int mn_l = (r < nrounds) ? rmin[r] : 0x7fffffff;
-    const int mx_l = (r < nrounds) ? rmax[r] : -1;
+    const int mn_l = mn_n, mx_l = mx_n;
+    mn_n = (r + 32 < nrounds) ? rmin[r + 32] : 0x7fffffff;
+    mx_n = (r + 32 < nrounds) ? rmax[r + 32] : -1;
     int mine = 0, same = 0;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -598,7 +604,7 @@ __global__ void plan_window_kernel(int64_t nrounds, int W, const int32_t* __rest
     }
     if (r < nrounds) {
       rounds[r].win = (uint32_t)mine;
-      if (same) rounds[r].flags |= 4u;  // bit 2: same window as the round before
+      if (same) atomicOr(&rounds[r].flags, 4u);  // bit 2: same window as the round before
     }
   }
 }
@@ -3426,11 +3432,141 @@ ECCKD_API int ecckd_scale_lut_scaling(int nz, int ng, double mu0, const double* 
   return ECCKD_OK;
 }
 
+#ifdef ECCKD_PLANCK_TAB
+// The Planck look-up table (create_look_up_table.cpp:565-587) is a reduction whose weights differ in every row
+// (one temperature each) and whose values are all 1: on reduce2_kernel every row is a group of its own, fed by two
+// producer warps (14.3 ms for 231 temperatures x 2^23 wavenumbers).  Here the temperatures are the lanes: a warp
+// walks a range of wavenumbers, every lane evaluates the weight at its own temperature (planck_weight_tab, the
+// per-wavenumber factor and the g point are warp-uniform and come staged in shared memory) and adds it to its own
+// column of the warp's [g point][lane] sums - no two lanes share a cell, the order of the additions is the order of
+// the wavenumbers.  A block takes PL_RANGE wavenumbers (fixed, so that the sums do not depend on the grid) for up to
+// 8 tiles of 32 temperatures; planck_lut_combine_kernel adds the blocks' sums in block order.
+constexpr int PL_STAGE = 1024;
+constexpr int PL_RANGE = 8192;
+constexpr int PL_TAB_BYTES = (1 << ECCKD_TAB_LOGN) * 8;
+__global__ void __launch_bounds__(256) planck_lut_kernel(int64_t nwav, int ng, int nt, int ntp,
+                                                          const int32_t* __restrict__ g_point,
+                                                          const double* __restrict__ wn, const double* __restrict__ pref,
+                                                          const double* __restrict__ hkct,
+                                                          const double* __restrict__ exp2tab,
+                                                          double* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char pl_smem[];
+  unsigned char* tab = pl_smem;
+  double* s_nu = reinterpret_cast<double*>(pl_smem + PL_TAB_BYTES);
+  double* s_pf = s_nu + PL_STAGE;
+  int* s_g = reinterpret_cast<int*>(s_pf + PL_STAGE);
+  double* bins_all = reinterpret_cast<double*>(s_g + PL_STAGE);
+  const int nwarp = (int)blockDim.x >> 5, warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
+  trans_tabT_init<ECCKD_TAB_LOGN, 0>(reinterpret_cast<double*>(tab), exp2tab);  // the producers' form of the table
+  double* bins = bins_all + (size_t)warp * ng * 32 + lane;  // [g point][lane]
+  for (int g = 0; g < ng; ++g) bins[g * 32] = 0.0;
+  const int t = ((int)blockIdx.y * nwarp + warp) * 32 + lane;
+  const double hk = hkct[t < nt ? t : nt - 1];
+  const int64_t w0 = (int64_t)blockIdx.x * PL_RANGE;
+  const int64_t w1 = w0 + PL_RANGE < nwav ? w0 + PL_RANGE : nwav;
+  for (int64_t base = w0; base < w1; base += PL_STAGE) {
+    const int n = (int)(w1 - base < PL_STAGE ? w1 - base : PL_STAGE);
+    __syncthreads();
+    for (int i = threadIdx.x; i < PL_STAGE; i += blockDim.x) {
+      const bool in = i < n;
+      const int g = in ? g_point[base + i] : -1;
+      // a wavenumber outside the map (or past the end) keeps a harmless argument and adds to nobody
+      s_nu[i] = in ? wn[base + i] : 1.0;
+      s_pf[i] = in ? pref[base + i] : 0.0;
+      s_g[i] = (g >= 0 && g < ng) ? g * 32 : -1;
+    }
+    __syncthreads();
+    // four independent evaluations in flight, then the four additions in wavenumber order
+    for (int i = 0; i < PL_STAGE; i += 4) {
+      if (i >= n) break;
+      double w[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) w[m] = planck_weight_tab(hk, s_nu[i + m], s_pf[i + m], tab);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int o = s_g[i + m];
+        if (o >= 0) bins[o] += w[m];
+      }
+    }
+  }
+  if (t < nt) {
+    double* out = partial + (size_t)blockIdx.x * ng * ntp + t;  // [block][g point][temperature]
+    for (int g = 0; g < ng; ++g) out[(size_t)g * ntp] = bins[g * 32];
+  }
+}
+__global__ void planck_lut_combine_kernel(int nblk, int ng, int nt, int ntp, const double* __restrict__ partial,
+                                          double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // g * ntp + t
+  if (i >= ng * ntp) return;
+  const int g = i / ntp, t = i - g * ntp;
+  if (t >= nt) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * ng * ntp + i];
+  out[(size_t)t * ng + g] = s;
+}
+static int planck_lut_tiled(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng, const double* d_wn,
+                            const double* d_dwn, int nlut, const double* h_temperature_lut, double* d_out, bool* done) {
+  *done = false;
+  int dev = 0, smem_max = 0;
+  ECCKD_CUDA_OK(cudaGetDevice(&dev));
+  ECCKD_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t fixed = (size_t)PL_TAB_BYTES + (size_t)PL_STAGE * 20;
+  const size_t per_warp = (size_t)ng * 32 * sizeof(double);
+  if (fixed + per_warp > (size_t)smem_max) return ECCKD_OK;  // too many g points for one warp's sums: the general path
+  const int ntile = (nlut + 31) / 32;
+  int nwarp = (int)std::min<size_t>(8, ((size_t)smem_max - fixed) / per_warp);
+  nwarp = std::min(nwarp, ntile);
+  const int ny = (ntile + nwarp - 1) / nwarp;
+  const int ntp = ny * nwarp * 32;
+  const int64_t nblk = (nwav + PL_RANGE - 1) / PL_RANGE;
+  const size_t smem = fixed + per_warp * nwarp;
+  std::vector<double> hkct((size_t)nlut);
+  for (int i = 0; i < nlut; ++i)  // (h/k)(100 c)/T, as for the producers of reduce2_kernel
+    hkct[i] = (double)(((long double)6.62606896e-34 / (long double)1.3806504e-23) * (100.0L * 2.99792458e8L) /
+                       (long double)h_temperature_lut[i]);
+  void* d_hk = nullptr;
+  void* d_pref = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 6, (size_t)nlut * sizeof(double), &d_hk));
+  ECCKD_TRY(ws_reserve(ctx, 7, (size_t)nwav * sizeof(double), &d_pref));
+  ECCKD_TRY(upload_small(ctx, d_hk, hkct.data(), (size_t)nlut * sizeof(double)));
+  const double* d_tab = nullptr;
+  ECCKD_TRY(exp2tab_get(ctx, ECCKD_TAB_LOGN, &d_tab));
+  double* d_partial = nullptr;
+  ECCKD_CUDA_OK(cudaMallocAsync(&d_partial, (size_t)nblk * ng * ntp * sizeof(double), ctx->stream));
+  planck_prefactor_kernel<<<(unsigned)((nwav + 255) / 256), 256, 0, ctx->stream>>>(nwav, d_wn, d_dwn,
+                                                                                   static_cast<double*>(d_pref));
+  cudaError_t e = cudaFuncSetAttribute(planck_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    planck_lut_kernel<<<dim3((unsigned)nblk, (unsigned)ny), nwarp * 32, smem, ctx->stream>>>(
+        nwav, ng, nlut, ntp, d_g_point, d_wn, static_cast<const double*>(d_pref), static_cast<const double*>(d_hk),
+        d_tab, d_partial);
+    planck_lut_combine_kernel<<<(unsigned)((ng * ntp + 255) / 256), 256, 0, ctx->stream>>>((int)nblk, ng, nlut, ntp,
+                                                                                         d_partial, d_out);
+    ctx->launches += 3;
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(d_partial, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  ECCKD_CUDA_OK(e);
+  *done = true;
+  return ECCKD_OK;
+}
+#endif
+
 ECCKD_API int ecckd_planck_lut_dev(ecckd_ctx* ctx, ecckd_gpoint_plan* plan, const double* d_wn, const double* d_dwn,
                                    int nlut, const double* h_temperature_lut, double* d_out) {
   ECCKD_DEVICE(ctx);
   ECCKD_REQUIRE(ctx && plan && d_wn && d_dwn && h_temperature_lut && d_out && nlut > 0, ECCKD_PARAMETER_ERROR,
                 "ecckd_planck_lut: bad argument");
+#ifdef ECCKD_PLANCK_TAB
+  // temperatures across the lanes (planck_lut_kernel) when the plan kept its g-point map
+  if (plan->d_g_copy && !getenv("ECCKD_PLANCK_LUT_GENERAL")) {
+    bool done = false;
+    ECCKD_TRY(planck_lut_tiled(ctx, plan->d_g_copy, plan->nwav, plan->ng, d_wn, d_dwn, nlut, h_temperature_lut, d_out,
+                               &done));
+    if (done) return ECCKD_OK;
+  }
+#endif
   // sum over each g point of planck(T, nu): the reduction with f = 1 and Planck weights
   std::vector<RowDesc> rows(nlut);
   std::vector<OutDesc> outs(nlut);
