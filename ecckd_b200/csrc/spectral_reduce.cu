@@ -3443,6 +3443,10 @@ ECCKD_API int ecckd_scale_lut_scaling(int nz, int ng, double mu0, const double* 
 // 8 tiles of 32 temperatures; planck_lut_combine_kernel adds the blocks' sums in block order.
 constexpr int PL_STAGE = 1024;
 constexpr int PL_RANGE = 8192;
+#ifndef ECCKD_PL_ILP
+#define ECCKD_PL_ILP 8
+#endif
+constexpr int PL_ILP = ECCKD_PL_ILP;
 constexpr int PL_TAB_BYTES = (1 << ECCKD_TAB_LOGN) * 8;
 __global__ void __launch_bounds__(256) planck_lut_kernel(int64_t nwav, int ng, int nt, int ntp,
                                                           const int32_t* __restrict__ g_point,
@@ -3452,9 +3456,8 @@ __global__ void __launch_bounds__(256) planck_lut_kernel(int64_t nwav, int ng, i
                                                           double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char pl_smem[];
   unsigned char* tab = pl_smem;
-  double* s_nu = reinterpret_cast<double*>(pl_smem + PL_TAB_BYTES);
-  double* s_pf = s_nu + PL_STAGE;
-  int* s_g = reinterpret_cast<int*>(s_pf + PL_STAGE);
+  double2* s_np = reinterpret_cast<double2*>(pl_smem + PL_TAB_BYTES);  // (wavenumber, prefactor)
+  int* s_g = reinterpret_cast<int*>(s_np + PL_STAGE);
   double* bins_all = reinterpret_cast<double*>(s_g + PL_STAGE);
   const int nwarp = (int)blockDim.x >> 5, warp = (int)threadIdx.x >> 5, lane = (int)threadIdx.x & 31;
   trans_tabT_init<ECCKD_TAB_LOGN, 0>(reinterpret_cast<double*>(tab), exp2tab);  // the producers' form of the table
@@ -3471,22 +3474,29 @@ __global__ void __launch_bounds__(256) planck_lut_kernel(int64_t nwav, int ng, i
       const bool in = i < n;
       const int g = in ? g_point[base + i] : -1;
       // a wavenumber outside the map (or past the end) keeps a harmless argument and adds to nobody
-      s_nu[i] = in ? wn[base + i] : 1.0;
-      s_pf[i] = in ? pref[base + i] : 0.0;
+      s_np[i] = make_double2(in ? wn[base + i] : 1.0, in ? pref[base + i] : 0.0);
       s_g[i] = (g >= 0 && g < ng) ? g * 32 : -1;
     }
     __syncthreads();
-    // four independent evaluations in flight, then the four additions in wavenumber order
-    for (int i = 0; i < PL_STAGE; i += 4) {
+    // PL_ILP independent evaluations in flight (two warps per scheduler cannot hide the latency of one chain), then
+    // their additions in wavenumber order
+    for (int i = 0; i < PL_STAGE; i += PL_ILP) {
       if (i >= n) break;
-      double w[4];
+      double w[PL_ILP];
+      int o[PL_ILP];
 #pragma unroll
-      for (int m = 0; m < 4; ++m) w[m] = planck_weight_tab(hk, s_nu[i + m], s_pf[i + m], tab);
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int o = s_g[i + m];
-        if (o >= 0) bins[o] += w[m];
+      for (int m = 0; m < PL_ILP; m += 4) {
+        const int4 q = *reinterpret_cast<const int4*>(s_g + i + m);
+        o[m] = q.x, o[m + 1] = q.y, o[m + 2] = q.z, o[m + 3] = q.w;
       }
+#pragma unroll
+      for (int m = 0; m < PL_ILP; ++m) {
+        const double2 a = s_np[i + m];
+        w[m] = planck_weight_tab(hk, a.x, a.y, tab);
+      }
+#pragma unroll
+      for (int m = 0; m < PL_ILP; ++m)
+        if (o[m] >= 0) bins[o[m]] += w[m];
     }
   }
   if (t < nt) {
@@ -3494,14 +3504,25 @@ __global__ void __launch_bounds__(256) planck_lut_kernel(int64_t nwav, int ng, i
     for (int g = 0; g < ng; ++g) out[(size_t)g * ntp] = bins[g * 32];
   }
 }
-__global__ void planck_lut_combine_kernel(int nblk, int ng, int nt, int ntp, const double* __restrict__ partial,
-                                          double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // g * ntp + t
-  if (i >= ng * ntp) return;
+// the blocks' sums in block order: eight contiguous runs of blocks per cell, then the eight run sums in run order
+__global__ void __launch_bounds__(256) planck_lut_combine_kernel(int nblk, int ng, int nt, int ntp,
+                                                                  const double* __restrict__ partial,
+                                                                  double* __restrict__ out) {
+  __shared__ double s_part[8][32];
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;  // g * ntp + t
+  const int per = (nblk + 7) / 8;
+  const int b0 = part * per, b1 = min(nblk, b0 + per);
+  double s = 0.0;
+  if (i < ng * ntp)
+    for (int b = b0; b < b1; ++b) s += partial[(size_t)b * ng * ntp + i];
+  s_part[part][lane] = s;
+  __syncthreads();
+  if (part != 0 || i >= ng * ntp) return;
   const int g = i / ntp, t = i - g * ntp;
   if (t >= nt) return;
-  double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += partial[(size_t)b * ng * ntp + i];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) s += s_part[k][lane];
   out[(size_t)t * ng + g] = s;
 }
 static int planck_lut_tiled(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nwav, int ng, const double* d_wn,
@@ -3540,7 +3561,7 @@ static int planck_lut_tiled(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
     planck_lut_kernel<<<dim3((unsigned)nblk, (unsigned)ny), nwarp * 32, smem, ctx->stream>>>(
         nwav, ng, nlut, ntp, d_g_point, d_wn, static_cast<const double*>(d_pref), static_cast<const double*>(d_hk),
         d_tab, d_partial);
-    planck_lut_combine_kernel<<<(unsigned)((ng * ntp + 255) / 256), 256, 0, ctx->stream>>>((int)nblk, ng, nlut, ntp,
+    planck_lut_combine_kernel<<<(unsigned)((ng * ntp + 31) / 32), 256, 0, ctx->stream>>>((int)nblk, ng, nlut, ntp,
                                                                                          d_partial, d_out);
     ctx->launches += 3;
     e = cudaGetLastError();
