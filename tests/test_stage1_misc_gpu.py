@@ -34,11 +34,13 @@ def test_merge_axpy(ctx, O):
         np.testing.assert_allclose(d_a.numpy(), ref, rtol=2.3e-16)
 
 
-def test_merge_spectra_one_pass_equals_the_axpy_sequence_bitwise(ctx, O):
+@pytest.mark.parametrize("nwav,pad", [(2999, 7), (3000, 7), (5121, 1), (1, 1)])
+def test_merge_spectra_one_pass_equals_the_axpy_sequence_bitwise(ctx, O, nwav, pad):
     """read_merged_spectrum.cpp:149-168: the fused merge must give the bits of the loop of AXPYs on a zeroed array
-    (and of the oracle's loop), for scalings of 1, below 0 (= 1) and arbitrary ones, with row strides."""
+    (and of the oracle's loop), for scalings of 1, below 0 (= 1) and arbitrary ones, with row strides (even strides
+    take the two-wavenumbers-per-load kernel, with an odd last wavenumber; odd ones the scalar kernel)."""
     rng = np.random.default_rng(1)
-    nlay, nwav, pad = 5, 2999, 7
+    nlay = 5
     srcs = [rng.uniform(0, 3, (nlay, nwav + pad)) for _ in range(4)]
     scalings = [1.0, 0.37, -1.0, 2.5]
     d_srcs = [ctx.to_device(a) for a in srcs]
@@ -77,6 +79,30 @@ def test_gpoint_fraction_ssi_intervals_planck_lut(ctx, O):
     E.planck_lut_dev(ctx, plan, d_wn, d_dwn, t_lut, d_lut)
     ref = O.planck_lut(c["ng"], c["g_point"], c["wavenumber"], c["d_wavenumber"], t_lut)
     np.testing.assert_allclose(d_lut.numpy(), ref, rtol=1e-12)
+
+
+@pytest.mark.parametrize("nwav,ng,nt", [(8192 * 3 + 77, 14, 231), (20011, 300, 40), (9000, 700, 33), (1, 1, 1)])
+def test_planck_lut_with_the_temperatures_across_the_lanes(ctx, O, monkeypatch, nwav, ng, nt):
+    """planck_lut_kernel (temperatures on the lanes, create_look_up_table.cpp:565-587) against the oracle and against
+    the reduction path it replaces: ragged last block, fewer warps per block as ng grows, nt not a multiple of 32."""
+    rng = np.random.default_rng(nwav + ng)
+    wn = np.sort(rng.uniform(0.5, 3260.0, nwav))
+    dwn = rng.uniform(0.5e-3, 2e-3, nwav)
+    g = rng.integers(0, ng, nwav).astype(np.int32)
+    g[:ng] = np.arange(ng)[:nwav]  # every g point used
+    t_lut = np.linspace(120.0, 350.0, nt)
+    d_g, d_wn, d_dwn = ctx.to_device(g, np.int32), ctx.to_device(wn), ctx.to_device(dwn)
+    plan = E.GPointPlan(ctx, d_g, nwav, ng)
+    d_lut = ctx.empty((nt, ng))
+    E.planck_lut_dev(ctx, plan, d_wn, d_dwn, t_lut, d_lut)
+    got = d_lut.numpy().copy()
+    np.testing.assert_allclose(got, O.planck_lut(ng, g, wn, dwn, t_lut), rtol=1e-12)
+    monkeypatch.setenv("ECCKD_PLANCK_LUT_GENERAL", "1")
+    E.planck_lut_dev(ctx, plan, d_wn, d_dwn, t_lut, d_lut)
+    np.testing.assert_allclose(got, d_lut.numpy(), rtol=1e-13)
+    monkeypatch.delenv("ECCKD_PLANCK_LUT_GENERAL")
+    E.planck_lut_dev(ctx, plan, d_wn, d_dwn, t_lut, d_lut)
+    assert np.array_equal(got, d_lut.numpy())  # the same bits on every call
 
 
 def test_gpoint_fraction_bin_edges_exact(ctx, O):
