@@ -2314,9 +2314,18 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
   if (const char* env = getenv("ECCKD_PLAN_BALANCE")) balance = atoi(env) != 0;
   if (const char* env = getenv("ECCKD_CH")) best_ch = std::min(CH_MAX, std::max(32, atoi(env) & ~31));
   // rounds of a plan with chunk length ch and window w (h_total), and without a window (h_free)
+  // (the wavenumbers per g point do not depend on ch: they are counted by the first pass only; the round offsets
+  // left by the last pass are those of (last_ch, last_w))
+  bool counted = false;
+  int last_ch = 0, last_w = -1;
+  uint32_t last_total = 0;
   auto count_rounds = [&](int ch, int w, bool with_counts, uint32_t* h_total, unsigned long long* h_free) {
     const int64_t nch = (nwav + ch - 1) / ch;
     cudaError_t err = cudaSuccess;
+    with_counts = !counted;
+    counted = true;
+    last_ch = ch;
+    last_w = w;
     if (h_free) err = cudaMemsetAsync(d_nfree, 0, sizeof(unsigned long long), ctx->stream);
     if (err != cudaSuccess) return err;
     plan_count_kernel<<<(unsigned)nch, ch, 0, ctx->stream>>>(d_g_point, nwav, ng, w, d_nrounds,
@@ -2330,6 +2339,7 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
     if (err == cudaSuccess && h_free)
       err = cudaMemcpyAsync(h_free, d_nfree, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+    if (err == cudaSuccess) last_total = *h_total;
     return err;
   };
   const double windowed_round_cost = 0.77;
@@ -2370,7 +2380,10 @@ static int plan_create_impl(ecckd_ctx* ctx, const int32_t* d_g_point, int64_t nw
     p->ch = best_ch;
     p->windowed = best_w > 0;
     p->nchunks = (nwav + best_ch - 1) / best_ch;
-    e = count_rounds(best_ch, best_w, true, &total, nullptr);
+    if (last_ch == best_ch && last_w == best_w)
+      total = last_total;  // the pass that chose this plan left its offsets
+    else
+      e = count_rounds(best_ch, best_w, true, &total, nullptr);
   }
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(cnt.data(), p->d_count, (size_t)ng * sizeof(unsigned long long), cudaMemcpyDeviceToHost,

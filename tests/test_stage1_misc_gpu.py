@@ -81,8 +81,9 @@ def test_gpoint_fraction_ssi_intervals_planck_lut(ctx, O):
     np.testing.assert_allclose(d_lut.numpy(), ref, rtol=1e-12)
 
 
-@pytest.mark.parametrize("nwav,ng,nt", [(8192 * 3 + 77, 14, 231), (20011, 300, 40), (9000, 700, 33), (1, 1, 1)])
-def test_planck_lut_with_the_temperatures_across_the_lanes(ctx, O, monkeypatch, nwav, ng, nt):
+@pytest.mark.parametrize("nwav,ng,nt,holes", [(8192 * 3 + 77, 14, 231, False), (20011, 300, 40, False),
+                                               (9000, 700, 33, False), (1, 1, 1, False), (70001, 40, 65, True)])
+def test_planck_lut_with_the_temperatures_across_the_lanes(ctx, O, monkeypatch, nwav, ng, nt, holes):
     """planck_lut_kernel (temperatures on the lanes, create_look_up_table.cpp:565-587) against the oracle and against
     the reduction path it replaces: ragged last block, fewer warps per block as ng grows, nt not a multiple of 32."""
     rng = np.random.default_rng(nwav + ng)
@@ -90,6 +91,9 @@ def test_planck_lut_with_the_temperatures_across_the_lanes(ctx, O, monkeypatch, 
     dwn = rng.uniform(0.5e-3, 2e-3, nwav)
     g = rng.integers(0, ng, nwav).astype(np.int32)
     g[:ng] = np.arange(ng)[:nwav]  # every g point used
+    if holes:  # wavenumbers of no g point, and a g point without wavenumbers (its sums are 0)
+        g[rng.random(nwav) < 0.1] = -1
+        g[g == 3] = 4
     t_lut = np.linspace(120.0, 350.0, nt)
     d_g, d_wn, d_dwn = ctx.to_device(g, np.int32), ctx.to_device(wn), ctx.to_device(dwn)
     plan = E.GPointPlan(ctx, d_g, nwav, ng)
