@@ -465,6 +465,9 @@ __global__ void __launch_bounds__(COL_WARPS * 32) plan_colour_kernel(int64_t nro
       int ca = __ffs(~UL[ln] & 0xffffu) - 1, cb = __ffs(~UR[q] & 0xffffu) - 1;  // lowest free colour at the lane / class
       if (cb < 0) cb = 16;
       if (ca < 0) ca = 15;  // cannot happen: a lane holds at most 16 wavenumbers
+      // a colour free at both ends needs no alternating-path flip (with the lowest colour free at the lane alone,
+      // 53 % of the edges flipped a path and the kernel took three times as long)
+      if (const unsigned both = ~UL[ln] & ~UR[q] & 0xffffu) ca = __ffs(both) - 1;
       if (cb == 16) {         // the class already has 16 wavenumbers in this half-warp: lane-proper only
         CL[ln][ca] = (short)e;
         UL[ln] |= 1u << ca;
