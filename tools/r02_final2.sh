@@ -16,4 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:p
 timeout 300 python tools/planck_lut_probe.py > ${O}_planck_probe.log 2>&1; tail -8 ${O}_planck_probe.log
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:planck_lut_kernel -s 1 -c 1 -o ${O}_plut -f \
   python tools/planck_lut_probe.py > ${O}_ncu_plut.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:plan_colour_kernel -s 2 -c 1 -o ${O}_colour -f \
+  python tools/plan_hash.py > ${O}_ncu_colour.log 2>&1
 ls -la gpurun_out | grep r02g
