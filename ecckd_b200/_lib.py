@@ -176,6 +176,8 @@ def _declare(L):
                                            dbl, dbl, vp, vp, dbl, dbl, vp, vp, vp, vp, vp, vp, vp],
         "ecckd_cost_function_ckd_scenes_dev": [vp, i32, i32, vp, i32, i32, i32, dbl, dbl, dbl, dbl, dbl, dbl, vp, vp, vp,
                                                vp, vp],
+        "ecckd_background_cost_gas_dev": [vp, i32, i32, vp, vp, vp, vp, vp],
+        "ecckd_background_cost_rayleigh_dev": [vp, i32, vp, vp, vp],
     }
     for name, argtypes in sigs.items():
         if hasattr(L, name):  # symbol-completeness is asserted by tests/test_abi.py

@@ -1182,6 +1182,25 @@ def cost_function_ckd_sw_grad(ctx, cos_sza, pressure_hl, ssi, albedo, optical_de
     return grad.numpy()
 
 
+def background_cost_gas_dev(ctx: Context, nx: int, ng: int, d_inv_background_shape, d_background_error, d_delta_x,
+                            d_gradient=None) -> float:
+    """Background (prior) term of one active gas, CkdModel<true>::calc_background_cost_function
+    (ckd_model.cpp:838-866): returns the gas's cost and adds its term to d_gradient [nx][ng] (None = cost only)."""
+    cost = C.c_double(0.0)
+    check(_lib.lib().ecckd_background_cost_gas_dev(ctx.handle, int(nx), int(ng), _ptr(d_inv_background_shape),
+                                                   _ptr(d_background_error), _ptr(d_delta_x), _ptr(d_gradient),
+                                                   C.byref(cost)))
+    return cost.value
+
+
+def background_cost_rayleigh_dev(ctx: Context, ng: int, d_rayleigh_inv_background, d_delta_x) -> float:
+    """The Rayleigh part of the background term (ckd_model.cpp:868-873): cost only, as in the reference."""
+    cost = C.c_double(0.0)
+    check(_lib.lib().ecckd_background_cost_rayleigh_dev(ctx.handle, int(ng), _ptr(d_rayleigh_inv_background),
+                                                        _ptr(d_delta_x), C.byref(cost)))
+    return cost.value
+
+
 def cost_function_ckd_scenes_dev(ctx, is_sw, scenes: Sequence[dict], nlay, ng, nband, flux_weight, flux_profile_weight,
                                  broadband_weight, spectral_boundary_weight=0.0, pressure_weight_power=0.5,
                                  negative_od_penalty=1.0e4, d_band_mapping=None, d_cost_fn_per_band=None,

@@ -1636,3 +1636,91 @@ ECCKD_API int ecckd_cost_function_ckd_scenes_dev(ecckd_ctx* ctx, int is_sw, int 
   }
   return ECCKD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Background (prior) term of the optimize_lut cost function, CkdModel<true>::calc_background_cost_function
+// (ckd_model.cpp:838-877).  A gas's slice of the state vector is [nx][ng], g point fastest (:851-855).
+// background_grad_kernel: one thread per (row i, g point): the row of inv_background_shape times the g point's column
+// of delta_x in ascending j (coalesced over g, the matrix row broadcast), scaled by 1/error(g)^2 (:857-858), added to
+// the gradient (:861); the product delta_x * gradient_local goes to a scratch array.  background_cost_kernel: one
+// thread per g point adds its column of products in ascending i (the dot_product of :859), thread 0 then adds the
+// per-g halves in ascending g (:864): fixed order, no atomics.
+namespace ecckd {
+__global__ void background_grad_kernel(int nx, int ng, const double* __restrict__ shape, const double* __restrict__ err,
+                                       const double* __restrict__ dx, double* __restrict__ grad,
+                                       double* __restrict__ prod) {
+  const int ig = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (ig >= ng) return;
+  const double* row = shape + (size_t)i * nx;
+  double s = 0.0;
+  for (int j = 0; j < nx; ++j) s += row[j] * dx[(size_t)j * ng + ig];
+  const double e = err[ig];
+  const double gl = (1.0 / (e * e)) * s;
+  const size_t k = (size_t)i * ng + ig;
+  if (grad) grad[k] += gl;
+  prod[k] = dx[k] * gl;
+}
+__global__ void __launch_bounds__(1024) background_cost_kernel(int nx, int ng, const double* __restrict__ prod,
+                                                                double* __restrict__ cost) {
+  extern __shared__ double s_half[];  // [ng]
+  for (int ig = threadIdx.x; ig < ng; ig += blockDim.x) {
+    double d = 0.0;
+    for (int i = 0; i < nx; ++i) d += prod[(size_t)i * ng + ig];
+    s_half[ig] = 0.5 * d;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double c = 0.0;
+    for (int ig = 0; ig < ng; ++ig) c += s_half[ig];
+    *cost = c;
+  }
+}
+// the Rayleigh part (:868-873): 0.5 * sum_g delta_x(g) * (inv_background(g) * delta_x(g)) in ascending g
+__global__ void background_rayleigh_kernel(int ng, const double* __restrict__ inv_b, const double* __restrict__ dx,
+                                           double* __restrict__ cost) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double d = 0.0;
+  for (int ig = 0; ig < ng; ++ig) d += dx[ig] * (inv_b[ig] * dx[ig]);
+  *cost = 0.5 * d;
+}
+}  // namespace ecckd
+
+ECCKD_API int ecckd_background_cost_rayleigh_dev(ecckd_ctx* ctx, int ng, const double* d_rayleigh_inv_background,
+                                                 const double* d_delta_x, double* h_cost) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && d_rayleigh_inv_background && d_delta_x && h_cost && ng > 0, ECCKD_PARAMETER_ERROR,
+                "ecckd_background_cost_rayleigh: bad argument");
+  void* d_tmp = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 4, sizeof(double), &d_tmp));
+  ecckd::background_rayleigh_kernel<<<1, 32, 0, ctx->stream>>>(ng, d_rayleigh_inv_background, d_delta_x,
+                                                                static_cast<double*>(d_tmp));
+  ECCKD_LAUNCH_CHECK(ctx);
+  ECCKD_CUDA_OK(cudaMemcpyAsync(h_cost, d_tmp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return ECCKD_OK;
+}
+
+ECCKD_API int ecckd_background_cost_gas_dev(ecckd_ctx* ctx, int nx, int ng, const double* d_inv_background_shape,
+                                            const double* d_background_error, const double* d_delta_x,
+                                            double* d_gradient, double* h_cost) {
+  ECCKD_DEVICE(ctx);
+  ECCKD_REQUIRE(ctx && d_inv_background_shape && d_background_error && d_delta_x && h_cost, ECCKD_PARAMETER_ERROR,
+                "ecckd_background_cost_gas: NULL argument");
+  ECCKD_REQUIRE(nx > 0 && ng > 0 && nx <= 65535 && (size_t)ng * sizeof(double) <= 48 * 1024, ECCKD_PARAMETER_ERROR,
+                "ecckd_background_cost_gas: bad dimensions");
+  void* d_tmp = nullptr;
+  ECCKD_TRY(ws_reserve(ctx, 4, ((size_t)nx * ng + 1) * sizeof(double), &d_tmp));
+  double* d_prod = static_cast<double*>(d_tmp);
+  double* d_cost = d_prod + (size_t)nx * ng;
+  const int bs = ng >= 128 ? 128 : 32 * ((ng + 31) / 32);
+  ecckd::background_grad_kernel<<<dim3((unsigned)((ng + bs - 1) / bs), (unsigned)nx), bs, 0, ctx->stream>>>(
+      nx, ng, d_inv_background_shape, d_background_error, d_delta_x, d_gradient, d_prod);
+  ecckd::background_cost_kernel<<<1, std::min(1024, 32 * ((ng + 31) / 32)), (size_t)ng * sizeof(double), ctx->stream>>>(
+      nx, ng, d_prod, d_cost);
+  ctx->launches += 1;
+  ECCKD_LAUNCH_CHECK(ctx);
+  ECCKD_CUDA_OK(cudaMemcpyAsync(h_cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  ECCKD_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return ECCKD_OK;
+}

@@ -795,6 +795,23 @@ int ecckd_cost_function_ckd_scenes_dev(ecckd_ctx* ctx, int is_sw, int nscene, co
                                        const int32_t* d_band_mapping, double* d_cost_fn_per_band, double* d_cost_scene,
                                        double* d_penalty_scene, double* d_cost_total);
 
+/* Background (prior) term of the optimize_lut cost function for one active gas:
+ * CkdModel<true>::calc_background_cost_function, src/ecckd/ckd_model.cpp:838-866.  d_delta_x and d_gradient are the
+ * gas's [nx][ng] slice of the state vector and of its gradient (g point fastest, :851-855), d_inv_background_shape
+ * the gas's [nx][nx] inverse background shape matrix (row-major), d_background_error [ng].  Per g point:
+ * gradient_local = (1 / background_error(g)^2) * (inv_background_shape ** delta_x_local) (:857-858);
+ * d_gradient += gradient_local (:861; NULL = cost only; the caller zeroes the gradient once before the first gas as
+ * :842 does); *h_cost = sum over g of 0.5 * dot_product(delta_x_local, gradient_local) (:859,864), fixed order. */
+int ecckd_background_cost_gas_dev(ecckd_ctx* ctx, int nx, int ng, const double* d_inv_background_shape,
+                                  const double* d_background_error, const double* d_delta_x, double* d_gradient,
+                                  double* h_cost);
+
+/* The Rayleigh part of the same function (ckd_model.cpp:868-873): *h_cost = 0.5 * sum_g delta_x(g) *
+ * (rayleigh_inv_background(g) * delta_x(g)).  As in the reference, it contributes to the cost only: the reference
+ * forms gradient_local and does not add it to the gradient. */
+int ecckd_background_cost_rayleigh_dev(ecckd_ctx* ctx, int ng, const double* d_rayleigh_inv_background,
+                                       const double* d_delta_x, double* h_cost);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1494,3 +1494,39 @@ ORC_API int orc_calc_cost_function_ckd_sw(int nlay, int ng, int nband, double co
   *cost = c;
   return ORC_OK;
 }
+
+// Background (prior) term of the optimize_lut cost function for one active gas:
+// CkdModel<true>::calc_background_cost_function, ckd_model.cpp:838-866.  The gas's slice of the state vector is
+// [nx][ng] with the g point the fastest index (:851-855); per g point
+//   gradient_local = (1 / background_error(g)^2) * (inv_background_shape ** delta_x_local)      (:857-858)
+//   cost          += 0.5 * dot_product(delta_x_local, gradient_local)                           (:859,864)
+//   gradient      += gradient_local                                                             (:861)
+// gradient is accumulated into (the reference zeroes the whole vector once, :842, before the gas loop).
+ORC_API int orc_background_cost_gas(int nx, int ng, const double* inv_background_shape, const double* background_error,
+                                    const double* delta_x, double* gradient, double* cost) {
+  double c = 0.0;
+  std::vector<double> gl((size_t)nx);
+  for (int ig = 0; ig < ng; ++ig) {
+    const double inv_err2 = 1.0 / (background_error[ig] * background_error[ig]);
+    for (int i = 0; i < nx; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < nx; ++j) s += inv_background_shape[(size_t)i * nx + j] * delta_x[(size_t)j * ng + ig];
+      gl[i] = inv_err2 * s;
+    }
+    double d = 0.0;
+    for (int i = 0; i < nx; ++i) d += delta_x[(size_t)i * ng + ig] * gl[i];
+    c += 0.5 * d;
+    for (int i = 0; i < nx; ++i) gradient[(size_t)i * ng + ig] += gl[i];
+  }
+  *cost = c;
+  return ORC_OK;
+}
+
+// The Rayleigh part, ckd_model.cpp:868-873: the cost only (the reference forms gradient_local and drops it).
+ORC_API int orc_background_cost_rayleigh(int ng, const double* rayleigh_inv_background, const double* delta_x,
+                                         double* cost) {
+  double d = 0.0;
+  for (int ig = 0; ig < ng; ++ig) d += delta_x[ig] * (rayleigh_inv_background[ig] * delta_x[ig]);
+  *cost = 0.5 * d;
+  return ORC_OK;
+}

@@ -379,6 +379,27 @@ class Oracle:
             raise RuntimeError(rc)
         return od
 
+    def background_cost_gas(self, inv_background_shape, background_error, delta_x, gradient):
+        """ckd_model.cpp:838-866 for one gas: returns the cost, adds the gas's term to `gradient` [nx][ng] in place."""
+        sh, err, dx = _f64(inv_background_shape), _f64(background_error), _f64(delta_x)
+        nx, ng = dx.shape
+        assert sh.shape == (nx, nx) and err.shape == (ng,)
+        assert gradient.dtype == np.float64 and gradient.flags.c_contiguous and gradient.shape == (nx, ng)
+        cost = C.c_double(0.0)
+        rc = self.L.orc_background_cost_gas(C.c_int(nx), C.c_int(ng), C.c_void_p(_p(sh)), C.c_void_p(_p(err)),
+                                            C.c_void_p(_p(dx)), C.c_void_p(_p(gradient)), C.byref(cost))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return cost.value
+
+    def background_cost_rayleigh(self, rayleigh_inv_background, delta_x):
+        ib, dx = _f64(rayleigh_inv_background), _f64(delta_x)
+        cost = C.c_double(0.0)
+        rc = self.L.orc_background_cost_rayleigh(C.c_int(dx.size), C.c_void_p(_p(ib)), C.c_void_p(_p(dx)), C.byref(cost))
+        if rc != 0:
+            raise RuntimeError(rc)
+        return cost.value
+
     def ckd_calc_planck_function(self, temperature_planck, planck_lut, temperature):
         tp, pl, t = _f64(temperature_planck), _f64(planck_lut), _f64(temperature)
         out = np.zeros(t.shape + (pl.shape[1],))

@@ -537,3 +537,34 @@ def test_cost_function_ckd_sw_gradient_matches_finite_differences(ctx, O, albedo
             fd = (cost(od + h * v) - cost(od - h * v)) / (2 * h)
             an = float((grad * v).sum())
             assert abs(fd - an) <= 5.0e-6 * max(abs(an), abs(fd)) + 2e-9 * abs(cost(od)), (k, cost.__name__, fd, an)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx,ng", [(1, 1), (7, 5), (318, 32), (636, 200)])
+def test_background_cost_matches_the_oracle(ctx, O, nx, ng):
+    """CkdModel<true>::calc_background_cost_function (ckd_model.cpp:838-873) for one gas and for the Rayleigh part:
+    cost and accumulated gradient against the oracle, the same bits on every call."""
+    rng = np.random.default_rng(nx * 1000 + ng)
+    a = rng.standard_normal((nx, nx))
+    shape = a @ a.T / nx + np.eye(nx)
+    err = rng.uniform(0.5, 4.0, ng)
+    dx = rng.standard_normal((nx, ng))
+    grad0 = rng.standard_normal((nx, ng))
+    ref_grad = grad0.copy()
+    ref_cost = O.background_cost_gas(shape, err, dx, ref_grad)
+    d_shape, d_err, d_dx = ctx.to_device(shape), ctx.to_device(err), ctx.to_device(dx)
+    d_grad = ctx.to_device(grad0)
+    cost = E.background_cost_gas_dev(ctx, nx, ng, d_shape, d_err, d_dx, d_grad)
+    np.testing.assert_allclose(cost, ref_cost, rtol=1e-13)
+    scale = np.abs(ref_grad - grad0).max()
+    np.testing.assert_allclose(d_grad.numpy(), ref_grad, rtol=1e-12, atol=1e-13 * scale)
+    d_grad2 = ctx.to_device(grad0)
+    cost2 = E.background_cost_gas_dev(ctx, nx, ng, d_shape, d_err, d_dx, d_grad2)
+    assert cost2 == cost and np.array_equal(d_grad2.numpy(), d_grad.numpy())
+    assert E.background_cost_gas_dev(ctx, nx, ng, d_shape, d_err, d_dx, None) == cost  # cost only
+    inv_b = 1.0 / err ** 2
+    d_inv = ctx.to_device(inv_b)
+    got = E.background_cost_rayleigh_dev(ctx, ng, d_inv, d_dx)  # the first row of dx as the Rayleigh slice
+    np.testing.assert_allclose(got, O.background_cost_rayleigh(inv_b, dx[0]), rtol=1e-14)
+    with pytest.raises(E.EcckdError):
+        E.background_cost_gas_dev(ctx, 0, ng, d_shape, d_err, d_dx, None)

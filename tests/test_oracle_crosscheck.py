@@ -210,3 +210,33 @@ def test_gpoint_fraction_and_planck_lut(O):
     t = np.arange(120.0, 351.0, 23.0)
     np.testing.assert_allclose(O.planck_lut(c["ng"], c["g_point"], c["wavenumber"], c["d_wavenumber"], t),
                                N.planck_lut(c["ng"], c["g_point"], c["wavenumber"], c["d_wavenumber"], t), rtol=1e-13)
+
+
+def _background_case(nx, ng, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.standard_normal((nx, nx))
+    shape = a @ a.T / nx + np.eye(nx)  # symmetric positive definite, like an inverse covariance
+    err = rng.uniform(0.5, 4.0, ng)
+    dx = rng.standard_normal((nx, ng))
+    grad0 = rng.standard_normal((nx, ng))
+    return shape, err, dx, grad0
+
+
+@pytest.mark.parametrize("nx,ng", [(1, 1), (7, 5), (318, 32)])
+def test_background_cost_cpp_vs_numpy(O, nx, ng):
+    """ckd_model.cpp:838-873: J_b = 1/2 sum_g dx_g^T (S / err_g^2) dx_g, gradient += (S dx_g) / err_g^2 per gas;
+    the Rayleigh part adds to the cost only."""
+    shape, err, dx, grad0 = _background_case(nx, ng, nx + ng)
+    grad = grad0.copy()
+    cost = O.background_cost_gas(shape, err, dx, grad)
+    gl = (shape @ dx) / err[None, :] ** 2
+    np.testing.assert_allclose(cost, 0.5 * np.sum(dx * gl), rtol=1e-13)
+    np.testing.assert_allclose(grad - grad0, gl, rtol=1e-12, atol=1e-13 * np.abs(gl).max())
+    # the gradient is the derivative of the cost: central differences along a random direction
+    d = np.random.default_rng(1).standard_normal(dx.shape)
+    h = 1e-6
+    cp = O.background_cost_gas(shape, err, dx + h * d, np.zeros_like(dx))
+    cm = O.background_cost_gas(shape, err, dx - h * d, np.zeros_like(dx))
+    np.testing.assert_allclose((cp - cm) / (2 * h), np.sum(gl * d), rtol=1e-7)
+    inv_b = 1.0 / err ** 2
+    np.testing.assert_allclose(O.background_cost_rayleigh(inv_b, dx[0]), 0.5 * np.sum(inv_b * dx[0] ** 2), rtol=1e-14)
